@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — rays/s (TriMesh::cast_ray) and contact pairs/s on B200 vs the host CPU (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic input. The headline line (`metric` = rays/s) is
+BASELINE config[3]'s per-GPU shard — 2^23 incoherent rays vs the 8,000,000-triangle terrain TriMesh, BVH replicated
+per GPU, weak scaling (2^26 rays at 8 GPUs) — because it is the ray configuration whose inputs exceed L2. The other
+single-GPU configurations (1M rays vs 1M-triangle sphere, 4M convex pairs, 1M-collider broadphase) are measured in
+the same run and reported under "also".
+
+  value : rays/s with rays + outputs resident in HBM (CUDA events on the library's stream, max over ranks)
+  e2e   : rays/s through the C ABI with HOST buffers (pinned), H2D + kernels + D2H inside the timed region
+  --impl reference : the CPU restatement of parry3d's algorithm (oracle/, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FMAX = float(np.finfo(np.float32).max)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+
+    def run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------- workloads
+def terrain_scene():
+    from harness import scenes
+    v, i = scenes.terrain(2001, 2001)
+    return v, i
+
+
+def cpu_rays(v, i, rays, threads, repeat=1):
+    """Times the oracle (C++ restatement of TriMesh::cast_ray) on `rays`; returns (rays/s, seconds, build seconds)."""
+    from harness import oracle
+    t0 = time.perf_counter()
+    om = oracle.TriMesh(v, i)
+    t_build = time.perf_counter() - t0
+    best = None
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        om.cast_rays(None, rays, FMAX, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return len(rays) / best, best, t_build, om
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; parry3d itself cannot be built offline: no cargo,
+    nalgebra not vendored) with all host threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from harness import oracle, scenes
+    oracle.build()
+    threads = oracle.hardware_threads()
+    v, i = terrain_scene()
+    sample = 1 << 19
+    rays = scenes.terrain_rays(sample, seed=6)
+    om = oracle.TriMesh(v, i)
+    for _ in range(args.warmup):
+        om.cast_rays(None, rays, FMAX, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        om.cast_rays(None, rays, FMAX, threads=threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample / dt
+    line = {
+        "impl": "reference", "metric": "rays/s (TriMesh::cast_ray)", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "2^23 incoherent rays per GPU vs 8,000,000-triangle terrain TriMesh (BASELINE config[3] shard)",
+                   "triangles": int(len(i)), "sample_rays_per_step": sample},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
+                         "sample": "%d rays of the same seeded ray set per step, all host threads" % sample},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays-log2", type=int, default=23, help="rays per GPU = 2^k")
+    ap.add_argument("--skip-also", action="store_true", help="only the headline workload")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import parry_b200
+    from harness import scenes
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = parry_b200.Context(local_rank)
+    stream = ctx.torch_stream()
+    hbm_peak, peak_src = load_peaks()
+
+    # ------------------------------------------------------------------ headline: terrain rays
+    v, i = terrain_scene()
+    mesh = parry_b200.TriMesh(ctx, v, i)
+    m = 1 << args.rays_log2
+    rays_h = scenes.terrain_rays(m, seed=6 + rank)  # each rank casts its own shard of the 2^26-ray set
+    rays_d = torch.from_numpy(rays_h).cuda()
+    toi_d = torch.empty(m, dtype=torch.float32, device="cuda")
+    tri_d = torch.empty(m, dtype=torch.int32, device="cuda")
+    gather_buf = None
+    if world > 1:
+        rec = torch.empty((m, 2), dtype=torch.int32, device="cuda")
+        gather_buf = torch.empty((world * m, 2), dtype=torch.int32, device="cuda")
+
+    def step_device():
+        mesh.cast_local_ray(rays_d, FMAX, out=(toi_d, tri_d))
+        if world > 1:
+            # the path's only collective: all-gather of the fixed-size hit records (toi bits, triangle id)
+            with torch.cuda.stream(stream):
+                rec[:, 0] = toi_d.view(torch.int32)
+                rec[:, 1] = tri_d
+                dist.all_gather_into_tensor(gather_buf, rec)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, ctx.launch_count - l0
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, launches = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.finish()
+    value = world * m / (ms_dev * 1e-3)
+
+    # kernel-only duration for the roofline (same launches, events on the launching stream, no collective)
+    def step_kernel():
+        mesh.cast_local_ray(rays_d, FMAX, out=(toi_d, tri_d))
+    ms_kernel, _ = timed(step_kernel, args.steps, 1)
+
+    # end-to-end: host (pinned) buffers through the C ABI, copies inside the timed region
+    rays_pin = torch.from_numpy(rays_h).pin_memory()
+    toi_pin = torch.empty(m, dtype=torch.float32).pin_memory()
+    tri_pin = torch.empty(m, dtype=torch.int32).pin_memory()
+    rays_np, toi_np, tri_np = rays_pin.numpy(), toi_pin.numpy(), tri_pin.numpy().view(np.uint32)
+
+    def step_e2e():
+        mesh.cast_local_ray(rays_np, FMAX, out=(toi_np, tri_np))
+
+    for _ in range(2):
+        step_e2e()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        step_e2e()
+    dt_e2e = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([dt_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_e2e = float(t.item())
+    e2e_val = world * m / dt_e2e
+    # sanity: device-resident and host paths agree
+    assert (toi_d.cpu().numpy().view(np.uint32) == toi_np.view(np.uint32)).all()
+
+    nt, nv = len(i), len(v)
+    scene_bytes = 64 * (nt - 1) + 48 * nt  # node array + pre-gathered triangles, read at least once per launch
+    alg_bytes = m * 32 + scene_bytes       # 24 B ray in + 8 B (toi, id) out per ray
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    line = {
+        "metric": "rays/s (TriMesh::cast_ray)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "2^%d incoherent rays per GPU vs 8,000,000-triangle terrain TriMesh (BASELINE config[3] shard), "
+                               "BVH replicated per GPU" % args.rays_log2,
+                   "triangles": nt, "rays_per_gpu": m, "l2": "inputs larger than L2 (rays %d MB, scene %d MB)" % (m * 24 >> 20, scene_bytes >> 20),
+                   "collective": "all_gather of (toi,id) records inside the timed region" if world > 1 else "none (N=1)"},
+        "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": m * 24, "d2h_bytes_per_step": m * 8,
+                "ms_per_step": dt_e2e * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "kernel": "k_raycast_trimesh<false>", "kernel_ms": ms_kernel,
+                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+    }
+
+    also = {}
+    if rank == 0 and not args.skip_also:
+        also.update(bench_also(ctx, stream, args, hbm_peak))
+    if also:
+        line["also"] = also
+
+    if rank == 0 and not args.skip_cpu:
+        from harness import oracle
+        oracle.build()
+        threads = oracle.hardware_threads()
+        sample = 1 << 18
+        val, secs, t_build, _ = cpu_rays(v, i, rays_h[:sample], threads)
+        line["cpu_baseline"] = {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
+                                "sample": "first %d rays of rank 0's shard, same mesh; %.2f s cast + %.2f s Bvh build (1 thread)"
+                                          % (sample, secs, t_build)}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def bench_also(ctx, stream, args, hbm_peak):
+    """Secondary single-GPU configurations, device-timed the same way (inputs resident, CUDA events)."""
+    import torch
+    import parry_b200
+    from harness import scenes
+    out = {}
+
+    def timed(fn, steps=10, warmup=3, flush=None):
+        for _ in range(warmup):
+            fn()
+        ctx.synchronize()
+        tot = 0.0
+        for _ in range(steps):
+            if flush is not None:
+                flush.zero_()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            ctx.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / steps
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    # 1M rays vs 1M-triangle sphere (north_star target configuration); inputs fit in L2 => flush between iterations
+    v, i = scenes.uv_sphere(708, 707)
+    mesh = parry_b200.TriMesh(ctx, v, i)
+    m = 1 << 20
+    rays = torch.from_numpy(scenes.sphere_rays(m, seed=1)).cuda()
+    toi = torch.empty(m, dtype=torch.float32, device="cuda")
+    tri = torch.empty(m, dtype=torch.int32, device="cuda")
+    ms = timed(lambda: mesh.cast_local_ray(rays, FMAX, out=(toi, tri)), flush=flush)
+    alg = m * 32 + 64 * (len(i) - 1) + 48 * len(i)
+    out["rays_1M_vs_1M_tri_sphere"] = {"value": m / (ms * 1e-3), "unit": "rays/s", "ms": ms, "l2": "flushed between iterations",
+                                       "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+    v, i = scenes.uv_sphere(224, 224)
+    mesh2 = parry_b200.TriMesh(ctx, v, i)
+    ms = timed(lambda: mesh2.cast_local_ray(rays, FMAX, out=(toi, tri)), flush=flush)
+    alg = m * 32 + 64 * (len(i) - 1) + 48 * len(i)
+    out["rays_1M_vs_100k_tri_sphere"] = {"value": m / (ms * 1e-3), "unit": "rays/s", "ms": ms, "l2": "flushed between iterations",
+                                         "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+    del mesh, mesh2
+    for name, fn in EXTRA_ALSO:
+        try:
+            out[name] = fn(ctx, stream, timed, flush, hbm_peak)
+        except Exception as e:  # a secondary workload must not take the headline down
+            out[name] = {"error": repr(e)}
+    return out
+
+
+EXTRA_ALSO = []
+
+if __name__ == "__main__":
+    main()

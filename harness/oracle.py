@@ -1,0 +1,223 @@
+"""ctypes loader for the CPU oracle (oracle/liboracle.so). TEST INFRASTRUCTURE ONLY: imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs — never by parry_b200/."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
+
+_lib = None
+P, u32, u64, f32, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float, C.c_int
+
+
+def build(force=False):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cpp", ".hpp"))]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs):
+        return LIB_PATH
+    subprocess.check_call(["make", "-C", ORACLE_DIR, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        l = C.CDLL(LIB_PATH)
+        l.pb2o_hardware_threads.restype = i32
+        l.pb2o_trimesh_create.restype = P
+        l.pb2o_trimesh_create.argtypes = [P, u32, P, u32, i32]
+        l.pb2o_trimesh_destroy.argtypes = [P]
+        l.pb2o_trimesh_num_nodes.restype = u32
+        l.pb2o_trimesh_num_nodes.argtypes = [P]
+        l.pb2o_trimesh_copy_nodes.argtypes = [P, P]
+        l.pb2o_trimesh_cast_rays.argtypes = [P, P, P, u32, f32, i32, i32, i32, P, P, P, P]
+        l.pb2o_bvh_create.restype = P
+        l.pb2o_bvh_create.argtypes = [P, u32, i32]
+        l.pb2o_bvh_destroy.argtypes = [P]
+        l.pb2o_bvh_num_nodes.restype = u32
+        l.pb2o_bvh_num_nodes.argtypes = [P]
+        l.pb2o_bvh_copy_nodes.argtypes = [P, P]
+        l.pb2o_bvh_copy_parents.argtypes = [P, P]
+        l.pb2o_bvh_copy_leaf_node_indices.argtypes = [P, P]
+        l.pb2o_bvh_update_leaves.argtypes = [P, P, P, u32, f32]
+        l.pb2o_bvh_refit.argtypes = [P]
+        l.pb2o_bvh_refit_without_opt.argtypes = [P]
+        l.pb2o_bvh_intersect_aabbs.restype = u64
+        l.pb2o_bvh_intersect_aabbs.argtypes = [P, P, u32, i32, P, P, u64]
+        l.pb2o_bvh_self_pairs.restype = u64
+        l.pb2o_bvh_self_pairs.argtypes = [P, i32, P, u64]
+        l.pb2o_bvh_leaf_pairs.restype = u64
+        l.pb2o_bvh_leaf_pairs.argtypes = [P, P, P, u64]
+        l.pb2o_bvh_cast_rays_shapes.argtypes = [P, P, P, P, P, u32, f32, i32, i32, P, P, P, P]
+        l.pb2o_shape_cast_ray.restype = i32
+        l.pb2o_shape_cast_ray.argtypes = [i32, P, P, P, f32, i32, P, P, P]
+        l.pb2o_shape_cast_ray_toi.restype = i32
+        l.pb2o_shape_cast_ray_toi.argtypes = [i32, P, P, P, f32, i32, P]
+        for name, res, args in _EXTRA:
+            fn = getattr(l, name, None)
+            if fn is not None:
+                fn.restype = res
+                fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+_EXTRA = []  # (name, restype, argtypes) registered by later sections
+
+
+def hardware_threads():
+    return int(lib().pb2o_hardware_threads())
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+NODE_HALF = np.dtype([("mins", np.float32, (3,)), ("children", np.uint32), ("maxs", np.float32, (3,)), ("data", np.uint32)])
+NODE_WIDE = np.dtype([("left", NODE_HALF), ("right", NODE_HALF)])
+
+
+class TriMesh:
+    def __init__(self, vertices, indices, strategy=0):
+        self.v, self.i = _f32(vertices), _u32(indices)
+        self.nt = self.i.shape[0]
+        self.h = lib().pb2o_trimesh_create(self.v.ctypes.data, self.v.shape[0], self.i.ctypes.data, self.nt, strategy)
+
+    def nodes(self):
+        n = lib().pb2o_trimesh_num_nodes(self.h)
+        out = np.zeros(n, dtype=NODE_WIDE)
+        lib().pb2o_trimesh_copy_nodes(self.h, out.ctypes.data)
+        return out
+
+    def cast_rays(self, pose, rays, max_toi, solid=True, with_normal=False, mode=0, threads=1):
+        rays = _f32(rays)
+        m = rays.shape[0]
+        pose = None if pose is None else _f32(pose)
+        toi = np.zeros(m, dtype=np.float32)
+        tri = np.zeros(m, dtype=np.uint32)
+        normal = np.zeros((m, 3), dtype=np.float32) if with_normal else None
+        feature = np.zeros(m, dtype=np.uint32) if with_normal else None
+        lib().pb2o_trimesh_cast_rays(self.h, None if pose is None else pose.ctypes.data, rays.ctypes.data, m, max_toi, int(solid),
+                                     mode, threads, toi.ctypes.data, tri.ctypes.data,
+                                     None if normal is None else normal.ctypes.data,
+                                     None if feature is None else feature.ctypes.data)
+        return (toi, tri, normal, feature) if with_normal else (toi, tri)
+
+    def __del__(self):
+        try:
+            lib().pb2o_trimesh_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Bvh:
+    def __init__(self, aabbs, strategy=0):
+        self.aabbs = _f32(aabbs).reshape(-1, 6)
+        self.n = self.aabbs.shape[0]
+        self.h = lib().pb2o_bvh_create(self.aabbs.ctypes.data, self.n, strategy)
+
+    def nodes(self):
+        n = lib().pb2o_bvh_num_nodes(self.h)
+        out = np.zeros(n, dtype=NODE_WIDE)
+        if n:
+            lib().pb2o_bvh_copy_nodes(self.h, out.ctypes.data)
+        return out
+
+    def parents(self):
+        n = lib().pb2o_bvh_num_nodes(self.h)
+        out = np.zeros(n, dtype=np.uint64)
+        if n:
+            lib().pb2o_bvh_copy_parents(self.h, out.ctypes.data)
+        return out
+
+    def leaf_node_indices(self):
+        out = np.zeros(self.n, dtype=np.uint64)
+        if self.n:
+            lib().pb2o_bvh_copy_leaf_node_indices(self.h, out.ctypes.data)
+        return out
+
+    def update_leaves(self, aabbs, ids=None, margin=0.0):
+        a = _f32(aabbs)
+        i = None if ids is None else _u32(ids)
+        lib().pb2o_bvh_update_leaves(self.h, None if i is None else i.ctypes.data, a.ctypes.data, a.shape[0], margin)
+
+    def refit(self):
+        lib().pb2o_bvh_refit(self.h)
+
+    def refit_without_opt(self):
+        lib().pb2o_bvh_refit_without_opt(self.h)
+
+    def intersect_aabbs(self, queries, threads=1):
+        q = _f32(queries).reshape(-1, 6)
+        m = q.shape[0]
+        offs = np.zeros(m + 1, dtype=np.uint32)
+        total = lib().pb2o_bvh_intersect_aabbs(self.h, q.ctypes.data, m, threads, offs.ctypes.data, None, 0)
+        ids = np.zeros(max(1, total), dtype=np.uint32)
+        lib().pb2o_bvh_intersect_aabbs(self.h, q.ctypes.data, m, threads, offs.ctypes.data, ids.ctypes.data, total)
+        return offs, ids[:total]
+
+    def self_pairs(self, change_detection=False):
+        total = lib().pb2o_bvh_self_pairs(self.h, int(change_detection), None, 0)
+        pairs = np.zeros((max(1, total), 2), dtype=np.uint32)
+        lib().pb2o_bvh_self_pairs(self.h, int(change_detection), pairs.ctypes.data, total)
+        return pairs[:total]
+
+    def leaf_pairs(self, other):
+        total = lib().pb2o_bvh_leaf_pairs(self.h, other.h, None, 0)
+        pairs = np.zeros((max(1, total), 2), dtype=np.uint32)
+        lib().pb2o_bvh_leaf_pairs(self.h, other.h, pairs.ctypes.data, total)
+        return pairs[:total]
+
+    def cast_rays_shapes(self, kinds, params, poses, rays, max_toi, solid=True, with_normal=False, threads=1):
+        rays = _f32(rays)
+        m = rays.shape[0]
+        kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+        params = _f32(params).reshape(-1, 3)
+        poses = _f32(poses)
+        toi = np.zeros(m, dtype=np.float32)
+        leaf = np.zeros(m, dtype=np.uint32)
+        normal = np.zeros((m, 3), dtype=np.float32) if with_normal else None
+        feature = np.zeros(m, dtype=np.uint32) if with_normal else None
+        lib().pb2o_bvh_cast_rays_shapes(self.h, kinds.ctypes.data, params.ctypes.data, poses.ctypes.data, rays.ctypes.data, m, max_toi,
+                                        int(solid), threads, toi.ctypes.data, leaf.ctypes.data,
+                                        None if normal is None else normal.ctypes.data,
+                                        None if feature is None else feature.ctypes.data)
+        return (toi, leaf, normal, feature) if with_normal else (toi, leaf)
+
+    def __del__(self):
+        try:
+            lib().pb2o_bvh_destroy(self.h)
+        except Exception:
+            pass
+
+
+def shape_cast_ray(kind, params, pose, ray, max_toi, solid=True):
+    """RayCast::cast_ray_and_get_normal for a single Ball(0)/Cuboid(1)/Triangle(2). Returns None or (toi, normal, feature)."""
+    p = _f32(params).ravel()
+    r = _f32(ray).ravel()
+    po = None if pose is None else _f32(pose).ravel()
+    toi = C.c_float(0)
+    n = np.zeros(3, dtype=np.float32)
+    f = C.c_uint32(0)
+    hit = lib().pb2o_shape_cast_ray(kind, p.ctypes.data, None if po is None else po.ctypes.data, r.ctypes.data, max_toi, int(solid),
+                                    C.addressof(toi), n.ctypes.data, C.addressof(f))
+    return (toi.value, n, f.value) if hit else None
+
+
+def shape_cast_ray_toi(kind, params, pose, ray, max_toi, solid=True):
+    p = _f32(params).ravel()
+    r = _f32(ray).ravel()
+    po = None if pose is None else _f32(pose).ravel()
+    toi = C.c_float(0)
+    hit = lib().pb2o_shape_cast_ray_toi(kind, p.ctypes.data, None if po is None else po.ctypes.data, r.ctypes.data, max_toi, int(solid),
+                                        C.addressof(toi))
+    return toi.value if hit else None

@@ -1,0 +1,172 @@
+/* parry_b200 — C ABI of the B200-native (sm_100a) implementation of parry3d's data-parallel query hot path.
+ *
+ * parry3d (reference, 100 % Rust) has no FFI of its own; the boundary it exposes for this path is its public
+ * Rust API. Every entry point below is the *batched* form of one reference call and cites the reference
+ * interface it replaces (paths relative to the parry checkout). INTEGRATION.md shows the Rust `extern "C"`
+ * bindings + the shim types (`Bvh`, `TriMesh: RayCast`, `B200Dispatcher: QueryDispatcher`) built on them.
+ *
+ * Conventions
+ *  - All functions return PB2_OK (0) or a negative pb2_status. Nothing throws / panics across the boundary.
+ *  - `mem` says where EVERY data pointer of that call lives: PB2_MEM_HOST (the library stages through HBM and
+ *    synchronises before returning) or PB2_MEM_DEVICE (pointers are device pointers on ctx's device; the call
+ *    is enqueued on ctx's stream and returns without synchronising).
+ *  - Layouts are the reference's `#[repr(C)]` ones: Aabb = {mins[3], maxs[3]} (24 B, bounding_volume/aabb.rs:110),
+ *    Ray = {origin[3], dir[3]} (24 B, query/ray/ray.rs:74-88), Isometry3<f32> = {qi,qj,qk,qw, tx,ty,tz} (28 B,
+ *    nalgebra field order), BvhNodeWide = 64 B (partitioning/bvh/bvh_tree.rs:263-266).
+ *  - Output buffers are caller-owned with a capacity; the true count is always reported so overflow is
+ *    detectable (PB2_ERR_OVERFLOW is returned, the first `cap` entries are valid).
+ *  - A pb2_ctx is bound to one CUDA device + one stream and is not re-entrant; distinct ctxs are independent
+ *    (mirrors `&self` readers / `&mut self` writers of the Rust API).
+ *  - There is NO CPU fallback: without a CUDA device pb2_ctx_create fails with PB2_ERR_CUDA.
+ */
+#ifndef PARRY_B200_H
+#define PARRY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pb2_status {
+    PB2_OK = 0,
+    PB2_ERR_INVALID = -1,     /* bad argument */
+    PB2_ERR_CUDA = -2,        /* CUDA runtime error; see pb2_last_error */
+    PB2_ERR_OVERFLOW = -3,    /* output capacity too small; *count holds the required size */
+    PB2_ERR_UNSUPPORTED = -4  /* mirrors query::Unsupported (query/error.rs) */
+} pb2_status;
+
+typedef enum pb2_mem { PB2_MEM_HOST = 0, PB2_MEM_DEVICE = 1 } pb2_mem;
+
+/* BvhBuildStrategy (partitioning/bvh/bvh_tree.rs:58-78). Both map onto the GPU builder (Morton LBVH +
+ * SAH treelet refinement); the value is recorded so a shim can round-trip it. */
+typedef enum pb2_build_strategy { PB2_BUILD_BINNED = 0, PB2_BUILD_PLOC = 1 } pb2_build_strategy;
+
+/* Shape kinds known to the typed-leaf / contact kernels (shape/shape.rs ShapeType subset on the hot path). */
+typedef enum pb2_shape_kind { PB2_SHAPE_BALL = 0, PB2_SHAPE_CUBOID = 1, PB2_SHAPE_CONVEX = 2 } pb2_shape_kind;
+
+typedef struct pb2_ctx pb2_ctx;
+typedef struct pb2_bvh pb2_bvh;
+typedef struct pb2_trimesh pb2_trimesh;
+typedef struct pb2_shapes pb2_shapes;
+
+#define PB2_INVALID_U32 0xffffffffu
+
+/* Contact (query/contact/contact.rs:71-105): point1, point2, normal1, normal2, dist = 13 f32 = 52 B. */
+typedef struct pb2_contact {
+    float point1[3];
+    float point2[3];
+    float normal1[3];
+    float normal2[3];
+    float dist;
+} pb2_contact;
+
+/* ------------------------------------------------------------------ context */
+int pb2_version(void);
+/* Number of visible CUDA devices (0 => nothing in this library can run). */
+int pb2_device_count(void);
+/* Creates a context on `device` with its own non-blocking stream. */
+int pb2_ctx_create(int device, pb2_ctx** out);
+/* Same, but enqueue on a caller-owned cudaStream_t (passed as void*). */
+int pb2_ctx_create_on_stream(int device, void* cuda_stream, pb2_ctx** out);
+int pb2_ctx_destroy(pb2_ctx* ctx);
+int pb2_ctx_synchronize(pb2_ctx* ctx);
+/* The cudaStream_t the context enqueues on (so callers can record events on it). */
+void* pb2_ctx_stream(pb2_ctx* ctx);
+const char* pb2_last_error(pb2_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py `gpu_launches`). */
+uint64_t pb2_ctx_launch_count(pb2_ctx* ctx);
+
+/* ------------------------------------------------------------------ Bvh (partitioning/bvh) */
+/* Bvh::from_leaves(strategy, &[Aabb]) — bvh_tree.rs:1835 (leaf id = index). n may be 0, 1, 2 (special-cased like
+ * bvh_tree.rs:1914-1932). */
+int pb2_bvh_build(pb2_ctx* ctx, const float* aabbs /* n x 6 */, uint32_t n, int strategy, int mem, pb2_bvh** out);
+int pb2_bvh_destroy(pb2_ctx* ctx, pb2_bvh* bvh);
+/* Bvh::leaf_count — bvh_tree.rs:2295 */
+uint32_t pb2_bvh_leaf_count(const pb2_bvh* bvh);
+/* number of BvhNodeWide entries (`nodes.len()`) */
+uint32_t pb2_bvh_node_count(const pb2_bvh* bvh);
+/* Bvh::insert_or_update_partially(aabb, leaf_index, change_detection_margin) for n existing leaves —
+ * bvh_insert.rs:209-231. ids == NULL means ids[i] = i. */
+int pb2_bvh_update_leaves(pb2_ctx* ctx, pb2_bvh* bvh, const uint32_t* ids, const float* aabbs, uint32_t n, float margin, int mem);
+/* Bvh::refit(&mut workspace) — bvh_refit.rs:170-180 (internal AABBs, leaf counts, change-flag resolution). */
+int pb2_bvh_refit(pb2_ctx* ctx, pb2_bvh* bvh);
+/* Bvh::rebuild(&mut workspace, strategy) — bvh_binned_build.rs:11 (same leaves, new topology). */
+int pb2_bvh_rebuild(pb2_ctx* ctx, pb2_bvh* bvh, int strategy);
+/* Copies `nodes` out in the reference's BvhNodeWide layout (root at index 0; leaf `children` = leaf id;
+ * `data` = leaf_count | change flags) so the Rust `Bvh` stays inspectable. parents / leaf_node_indices are
+ * BvhNodeIndex values ((node << 1) | is_right, bvh_tree.rs:1284-1420) as u32; either may be NULL. */
+int pb2_bvh_download(pb2_ctx* ctx, const pb2_bvh* bvh, void* nodes64, uint32_t* parents, uint32_t* leaf_node_indices, int mem);
+/* Bvh::root_aabb — bvh_tree.rs:1991 (host pointer, 6 floats). */
+int pb2_bvh_root_aabb(pb2_ctx* ctx, const pb2_bvh* bvh, float* aabb6);
+
+/* Bvh::intersect_aabb(&aabb) for m query boxes — bvh_queries.rs:203-205. Two-pass CSR output:
+ * offsets[m+1] (exclusive scan of per-query counts), leaf_ids[cap] grouped by query (order inside a group is
+ * unspecified, like the reference's iterator order is tree-dependent). *count = total hits. */
+int pb2_bvh_intersect_aabbs(pb2_ctx* ctx, const pb2_bvh* bvh, const float* queries /* m x 6 */, uint32_t m,
+                            uint32_t* offsets, uint32_t* leaf_ids, uint64_t cap, uint64_t* count, int mem);
+/* Bvh::traverse_bvtt_single_tree::<CHANGE_DETECTION>(ws, f) — bvh_traverse_bvtt.rs:19-31. Emits each unordered
+ * overlapping leaf pair exactly once as (min id, max id); order unspecified. `count` is a HOST pointer. */
+int pb2_bvh_self_pairs(pb2_ctx* ctx, const pb2_bvh* bvh, int change_detection, uint32_t* pairs /* cap x 2 */,
+                       uint64_t cap, uint64_t* count, int mem);
+/* Bvh::leaf_pairs(&other, |a, b| a.intersects(b)) — bvh_traverse_bvtt.rs:210-316 (leaf of a, leaf of b). */
+int pb2_bvh_leaf_pairs(pb2_ctx* ctx, const pb2_bvh* a, const pb2_bvh* b, uint32_t* pairs, uint64_t cap,
+                       uint64_t* count, int mem);
+
+/* ------------------------------------------------------------------ TriMesh + RayCast (shape/trimesh.rs, query/ray) */
+/* TriMesh::new(vertices, indices) — shape/trimesh.rs:607 / rebuild_bvh :1159-1171. nt == 0 is PB2_ERR_INVALID
+ * (TriMeshBuilderError::EmptyIndices, trimesh.rs:724). */
+int pb2_trimesh_create(pb2_ctx* ctx, const float* vertices /* nv x 3 */, uint32_t nv, const uint32_t* indices /* nt x 3 */,
+                       uint32_t nt, int mem, pb2_trimesh** out);
+int pb2_trimesh_destroy(pb2_ctx* ctx, pb2_trimesh* mesh);
+/* TriMesh::bvh() — borrowed handle, owned by the mesh. */
+const pb2_bvh* pb2_trimesh_bvh(const pb2_trimesh* mesh);
+/* RayCast::cast_ray / cast_ray_and_get_normal for TriMesh over m rays — query/ray/ray.rs:381-411,
+ * ray_trimesh.rs:8-36, ray_composite_shape.rs:20-62, bvh_traverse.rs:335-417, ray_aabb.rs:12-49,
+ * ray_triangle.rs:49-152.  pose7 may be NULL (identity / cast_local_ray*).  Outputs per ray: toi (0 on miss),
+ * tri = hit triangle index or PB2_INVALID_U32 (None).  normal (m x 3) and feature (m; FeatureId::Face(i) or
+ * Face(i + nt) for back faces; PB2_INVALID_U32 on miss) may both be NULL => toi-only variant.
+ * Ties: among bit-equal minimal toi the smallest triangle index wins (documented rule). */
+int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays /* m x 6 */,
+                          uint32_t m, float max_toi, int solid, float* toi, uint32_t* tri, float* normal,
+                          uint32_t* feature, int mem);
+
+/* ------------------------------------------------------------------ typed shape tables */
+/* A table of shapes referenced by index from ray / contact batches. kinds[n] (pb2_shape_kind), params[n x 4]:
+ * ball {r,-,-,-}; cuboid {hx,hy,hz,-}; convex {first_point, num_points (as u32 bit patterns), -, -} into
+ * `points` (np x 3, ConvexPolyhedron::points(), shape/convex_polyhedron.rs:172-185). Always HOST pointers. */
+int pb2_shapes_create(pb2_ctx* ctx, const uint8_t* kinds, const float* params, uint32_t n, const float* points,
+                      uint32_t np, pb2_shapes** out);
+int pb2_shapes_destroy(pb2_ctx* ctx, pb2_shapes* shapes);
+
+/* Shape::compute_aabb(pos) for n colliders (shape/shape.rs:369; aabb_ball.rs:25, aabb_cuboid.rs:9-16,
+ * aabb_convex_polyhedron.rs:8) -> aabbs (n x 6). */
+int pb2_shapes_compute_aabbs(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape_ids, const float* poses7,
+                             uint32_t n, float* aabbs, int mem);
+
+/* Bvh::cast_ray with typed leaves (bvh_queries.rs:260-271 + RayCast for Ball ray_ball.rs:8-98 / Cuboid
+ * ray_cuboid.rs:6-25 + ray_aabb.rs:52-92 + clip_aabb_line.rs:79-187): leaf i of `bvh` is shape shape_ids[i]
+ * at poses7[i]. Convex leaves are PB2_ERR_UNSUPPORTED. normal/feature may be NULL. */
+int pb2_bvh_cast_rays_shapes(pb2_ctx* ctx, const pb2_bvh* bvh, const pb2_shapes* shapes, const uint32_t* shape_ids,
+                             const float* poses7, const float* rays, uint32_t m, float max_toi, int solid, float* toi,
+                             uint32_t* leaf, float* normal, uint32_t* feature, int mem);
+
+/* ------------------------------------------------------------------ query::contact (query/contact, gjk, epa) */
+/* query::contact(pos1, g1, pos2, g2, prediction) for n pairs — contact_shape_shape.rs:123-138 through
+ * DefaultQueryDispatcher::contact (default_query_dispatcher.rs:302-356). Pair k uses shapes shape1[k] /
+ * shape2[k] at poses pos1[k] / pos2[k]. status[k]: 0 = Ok(None), 1 = Ok(Some(contact)) (out[k] valid),
+ * 2 = Err(Unsupported).  *num_contacts (HOST pointer, may be NULL) = number of status==1. */
+int pb2_contact_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
+                      const float* pos1 /* n x 7 */, const float* pos2 /* n x 7 */, float prediction, uint32_t n,
+                      pb2_contact* out, uint8_t* status, uint64_t* num_contacts, int mem);
+/* Compacted variant: writes only the Some(contact) records, each tagged with its pair index, through
+ * warp-aggregated atomics (order unspecified). */
+int pb2_contact_batch_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
+                              const float* pos1, const float* pos2, float prediction, uint32_t n, pb2_contact* out,
+                              uint32_t* pair_index, uint64_t cap, uint64_t* count, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARRY_B200_H */

@@ -1,0 +1,181 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. C entry points for ctypes (tests/, __graft_entry__.smoke(),
+// bench.py cpu_baseline / --impl reference). The product library never links this file.
+#include "ray.hpp"
+#include <thread>
+#include <algorithm>
+
+using namespace pb2o;
+
+template <class F>
+static void parallel_for(size_t n, int nthreads, F f) {
+    if (nthreads <= 1 || n < 2) { f(0, n); return; }
+    std::vector<std::thread> th;
+    size_t chunk = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        size_t lo = std::min(n, t * chunk), hi = std::min(n, lo + chunk);
+        if (lo < hi) th.emplace_back([=] { f(lo, hi); });
+    }
+    for (auto& t : th) t.join();
+}
+
+static inline Vec3 ld3(const float* p) { return Vec3(p[0], p[1], p[2]); }
+static inline void st3(float* p, const Vec3& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+
+extern "C" {
+
+int pb2o_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+// ---------------- TriMesh ----------------
+void* pb2o_trimesh_create(const float* verts, uint32_t nv, const uint32_t* idx, uint32_t nt, int strategy) {
+    TriMesh* m = new TriMesh();
+    m->build(verts, nv, idx, nt, (BuildStrategy)strategy);
+    return m;
+}
+void pb2o_trimesh_destroy(void* m) { delete (TriMesh*)m; }
+uint32_t pb2o_trimesh_num_nodes(void* m) { return (uint32_t)((TriMesh*)m)->bvh.nodes.size(); }
+void pb2o_trimesh_copy_nodes(void* m, void* out) {
+    TriMesh* t = (TriMesh*)m;
+    memcpy(out, t->bvh.nodes.data(), t->bvh.nodes.size() * sizeof(BvhNodeWide));
+}
+
+// mode 0: reference traversal (RayCast::cast_ray / cast_ray_and_get_normal on TriMesh, ray.rs:381-411)
+// mode 1: brute force over all triangles (tie/ulp adjudication, min index on ties)
+// tri[i] = u32::MAX on miss. normal/feature may be NULL (=> toi-only variant, which post-filters toi < max_toi).
+void pb2o_trimesh_cast_rays(void* mesh, const float* pose7, const float* rays, uint32_t m, float max_toi, int solid,
+                            int mode, int nthreads, float* toi, uint32_t* tri, float* normal, uint32_t* feature) {
+    const TriMesh* t = (const TriMesh*)mesh;
+    bool has_pose = pose7 != nullptr;
+    Iso pose = has_pose ? Iso::from7(pose7) : Iso();
+    parallel_for(m, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            Ray ray(ld3(rays + 6 * i), ld3(rays + 6 * i + 3));
+            if (has_pose) ray = ray.inverse_transform_by(pose);
+            uint32_t id = UINT32_MAX; RayIntersection ri; ri.time_of_impact = 0; ri.feature = UINT32_MAX;
+            bool hit;
+            if (mode == 1) hit = t->brute_force(ray, max_toi, id, ri);
+            else if (normal || feature) hit = t->cast_local_ray_and_get_normal(ray, max_toi, solid != 0, id, ri);
+            else { Real tt = 0; hit = t->cast_local_ray(ray, max_toi, solid != 0, id, tt); ri.time_of_impact = tt; }
+            if (!hit) { toi[i] = 0.0f; tri[i] = UINT32_MAX; if (normal) st3(normal + 3 * i, Vec3()); if (feature) feature[i] = UINT32_MAX; continue; }
+            toi[i] = ri.time_of_impact; tri[i] = id;
+            if (normal) st3(normal + 3 * i, has_pose ? pose.transform_vector(ri.normal) : ri.normal);
+            if (feature) feature[i] = ri.feature;
+        }
+    });
+}
+
+// ---------------- Bvh ----------------
+void* pb2o_bvh_create(const float* aabbs, uint32_t n, int strategy) {
+    Bvh* b = new Bvh(Bvh::from_leaves((BuildStrategy)strategy, (const Aabb*)aabbs, n));
+    return b;
+}
+void pb2o_bvh_destroy(void* b) { delete (Bvh*)b; }
+uint32_t pb2o_bvh_num_nodes(void* b) { return (uint32_t)((Bvh*)b)->nodes.size(); }
+void pb2o_bvh_copy_nodes(void* b, void* out) {
+    Bvh* t = (Bvh*)b;
+    memcpy(out, t->nodes.data(), t->nodes.size() * sizeof(BvhNodeWide));
+}
+// parents / leaf_node_indices as u64 (BvhNodeIndex = usize)
+void pb2o_bvh_copy_parents(void* b, uint64_t* out) { Bvh* t = (Bvh*)b; for (size_t i = 0; i < t->parents.size(); ++i) out[i] = t->parents[i].v; }
+void pb2o_bvh_copy_leaf_node_indices(void* b, uint64_t* out) { Bvh* t = (Bvh*)b; for (size_t i = 0; i < t->leaf_node_indices.size(); ++i) out[i] = t->leaf_node_indices[i].v; }
+void pb2o_bvh_update_leaves(void* b, const uint32_t* ids, const float* aabbs, uint32_t n, float margin) {
+    Bvh* t = (Bvh*)b;
+    for (uint32_t i = 0; i < n; ++i) t->insert_or_update_partially(((const Aabb*)aabbs)[i], ids ? ids[i] : i, margin);
+}
+void pb2o_bvh_refit(void* b) { ((Bvh*)b)->refit(); }
+void pb2o_bvh_refit_without_opt(void* b) { ((Bvh*)b)->refit_without_opt(); }
+
+// Bvh::intersect_aabb for a batch. offsets has m+1 entries. Returns total count (leaf_ids filled up to cap,
+// in the reference's iteration order per query).
+uint64_t pb2o_bvh_intersect_aabbs(void* b, const float* q, uint32_t m, int nthreads, uint32_t* offsets, uint32_t* leaf_ids, uint64_t cap) {
+    const Bvh* t = (const Bvh*)b;
+    std::vector<std::vector<uint32_t>> res(m);
+    parallel_for(m, nthreads, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) t->intersect_aabb(((const Aabb*)q)[i], res[i]);
+    });
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < m; ++i) {
+        offsets[i] = (uint32_t)total;
+        for (uint32_t id : res[i]) { if (total < cap) leaf_ids[total] = id; total++; }
+    }
+    offsets[m] = (uint32_t)total;
+    return total;
+}
+// Bvh::traverse_bvtt_single_tree::<CHANGE_DETECTION>; pairs in the reference's emission order and orientation.
+uint64_t pb2o_bvh_self_pairs(void* b, int change_detection, uint32_t* pairs, uint64_t cap) {
+    const Bvh* t = (const Bvh*)b;
+    uint64_t count = 0;
+    auto f = [&](uint32_t a, uint32_t c) { if (count < cap) { pairs[2 * count] = a; pairs[2 * count + 1] = c; } count++; };
+    if (change_detection) t->traverse_bvtt_single_tree<true>(f); else t->traverse_bvtt_single_tree<false>(f);
+    return count;
+}
+// Bvh::leaf_pairs(other, |a, b| a.intersects(b))
+uint64_t pb2o_bvh_leaf_pairs(void* b1, void* b2, uint32_t* pairs, uint64_t cap) {
+    const Bvh* t1 = (const Bvh*)b1; const Bvh* t2 = (const Bvh*)b2;
+    uint64_t count = 0;
+    auto f = [&](uint32_t a, uint32_t c) { if (count < cap) { pairs[2 * count] = a; pairs[2 * count + 1] = c; } count++; };
+    t1->leaf_pairs(*t2, [](const BvhNode& a, const BvhNode& c) { return a.intersects(c); }, f);
+    return count;
+}
+
+// Bvh::cast_ray with typed leaves: kind 0 = Ball (param = radius), kind 1 = Cuboid (param = half extents).
+// leaf i: pose7[i], kinds[i], params[3*i..]. toi-only when normal == NULL.
+void pb2o_bvh_cast_rays_shapes(void* b, const uint8_t* kinds, const float* params, const float* poses7, const float* rays,
+                               uint32_t m, float max_toi, int solid, int nthreads, float* toi, uint32_t* leaf, float* normal, uint32_t* feature) {
+    const Bvh* t = (const Bvh*)b;
+    parallel_for(m, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            Ray ray(ld3(rays + 6 * i), ld3(rays + 6 * i + 3));
+            uint32_t id = UINT32_MAX; RayIntersection best; best.time_of_impact = 0; best.feature = UINT32_MAX;
+            bool hit = t->find_best<RayIntersection>(max_toi,
+                [&](const BvhNode& n, Real bsf) { return node_cast_ray(n, ray, bsf); },
+                [&](uint32_t prim, Real bsf, RayIntersection& ri) {
+                    Iso pose = Iso::from7(poses7 + 7 * prim);
+                    Ray ls = ray.inverse_transform_by(pose);
+                    bool h;
+                    if (normal) {
+                        h = kinds[prim] == 0 ? ball_cast_local_ray_and_get_normal(params[3 * prim], ls, bsf, solid != 0, ri)
+                                             : cuboid_cast_local_ray_and_get_normal(ld3(params + 3 * prim), ls, bsf, solid != 0, ri);
+                        if (h) ri.normal = pose.transform_vector(ri.normal);
+                    } else {
+                        Real tt = 0;
+                        h = kinds[prim] == 0 ? ball_cast_local_ray(params[3 * prim], ls, bsf, solid != 0, tt)
+                                             : cuboid_cast_local_ray(ld3(params + 3 * prim), ls, bsf, solid != 0, tt);
+                        ri.time_of_impact = tt; ri.feature = 0;
+                    }
+                    return h;
+                }, id, best);
+            if (!hit) { toi[i] = 0.0f; leaf[i] = UINT32_MAX; if (normal) st3(normal + 3 * i, Vec3()); if (feature) feature[i] = UINT32_MAX; continue; }
+            toi[i] = best.time_of_impact; leaf[i] = id;
+            if (normal) st3(normal + 3 * i, best.normal);
+            if (feature) feature[i] = best.feature;
+        }
+    });
+}
+
+// Single-shape ray casts (RayCast for Ball / Cuboid / Triangle), world-space with pose (ray.rs:381-411).
+// kind 0 ball (p[0]=r), 1 cuboid (p=he), 2 triangle (p = a,b,c: 9 floats). returns 1 on hit.
+int pb2o_shape_cast_ray(int kind, const float* p, const float* pose7, const float* ray6, float max_toi, int solid, float* toi, float* normal, uint32_t* feature) {
+    Iso pose = pose7 ? Iso::from7(pose7) : Iso();
+    Ray ray(ld3(ray6), ld3(ray6 + 3));
+    Ray ls = pose7 ? ray.inverse_transform_by(pose) : ray;
+    RayIntersection ri; bool h;
+    if (kind == 0) h = ball_cast_local_ray_and_get_normal(p[0], ls, max_toi, solid != 0, ri);
+    else if (kind == 1) h = cuboid_cast_local_ray_and_get_normal(ld3(p), ls, max_toi, solid != 0, ri);
+    else h = triangle_cast_local_ray_and_get_normal(ld3(p), ld3(p + 3), ld3(p + 6), ls, max_toi, ri);
+    if (!h) return 0;
+    *toi = ri.time_of_impact; if (normal) st3(normal, pose7 ? pose.transform_vector(ri.normal) : ri.normal); if (feature) *feature = ri.feature;
+    return 1;
+}
+// toi-only single-shape casts (separate code path in the reference for ball/cuboid)
+int pb2o_shape_cast_ray_toi(int kind, const float* p, const float* pose7, const float* ray6, float max_toi, int solid, float* toi) {
+    Iso pose = pose7 ? Iso::from7(pose7) : Iso();
+    Ray ray(ld3(ray6), ld3(ray6 + 3));
+    Ray ls = pose7 ? ray.inverse_transform_by(pose) : ray;
+    if (kind == 0) return ball_cast_local_ray(p[0], ls, max_toi, solid != 0, *toi);
+    if (kind == 1) return cuboid_cast_local_ray(ld3(p), ls, max_toi, solid != 0, *toi);
+    RayIntersection ri;
+    if (!triangle_cast_local_ray_and_get_normal(ld3(p), ld3(p + 3), ld3(p + 6), ls, max_toi, ri)) return 0;
+    *toi = ri.time_of_impact; return 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// parry_b200 — context management and small host helpers of the C ABI (include/parry_b200.h).
+#include "common.cuh"
+
+int pb2_scratch_reserve(pb2_ctx* ctx, Scratch* s, size_t bytes) {
+    if (bytes <= s->cap) return PB2_OK;
+    if (s->ptr) {
+        PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PB2_CUDA(ctx, cudaFree(s->ptr));
+        s->ptr = nullptr;
+        s->cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    PB2_CUDA(ctx, cudaMalloc(&s->ptr, want));
+    s->cap = want;
+    return PB2_OK;
+}
+
+extern "C" {
+
+int pb2_version(void) { return 100; }
+
+int pb2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static int ctx_init(int device, cudaStream_t stream, bool own, pb2_ctx** out) {
+    if (!out) return PB2_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return PB2_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return PB2_ERR_CUDA;
+    pb2_ctx* ctx = new pb2_ctx();
+    ctx->device = device;
+    ctx->own_stream = own;
+    if (own) {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PB2_ERR_CUDA; }
+    } else {
+        ctx->stream = stream;
+    }
+    int sm = 0;
+    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sm > 0) ctx->sm_count = sm;
+    if (cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(uint64_t)) != cudaSuccess) { delete ctx; return PB2_ERR_CUDA; }
+    if (cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(uint64_t)) != cudaSuccess) { delete ctx; return PB2_ERR_CUDA; }
+    *out = ctx;
+    return PB2_OK;
+}
+
+int pb2_ctx_create(int device, pb2_ctx** out) { return ctx_init(device, nullptr, true, out); }
+int pb2_ctx_create_on_stream(int device, void* cuda_stream, pb2_ctx** out) {
+    return ctx_init(device, (cudaStream_t)cuda_stream, false, out);
+}
+
+int pb2_ctx_destroy(pb2_ctx* ctx) {
+    if (!ctx) return PB2_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->stage) if (s.ptr) cudaFree(s.ptr);
+    for (auto& s : ctx->scratch) if (s.ptr) cudaFree(s.ptr);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PB2_OK;
+}
+
+int pb2_ctx_synchronize(pb2_ctx* ctx) {
+    if (!ctx) return PB2_ERR_INVALID;
+    PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB2_OK;
+}
+
+void* pb2_ctx_stream(pb2_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+const char* pb2_last_error(pb2_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+uint64_t pb2_ctx_launch_count(pb2_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

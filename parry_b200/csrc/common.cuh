@@ -1,0 +1,189 @@
+// parry_b200 — shared device/host definitions. Compiled with --fmad=false: every a*b+c stays un-fused so f32
+// results are bit-identical to the reference's (Rust never contracts), with IEEE div/sqrt (nvcc defaults
+// -prec-div=true -prec-sqrt=true, -ftz=false).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <float.h>
+#include "../../include/parry_b200.h"
+
+#define PB2_SM_COUNT_FALLBACK 148
+
+struct Scratch {
+    void* ptr = nullptr;
+    size_t cap = 0;
+};
+
+struct pb2_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = PB2_SM_COUNT_FALLBACK;
+    uint64_t launches = 0;
+    char err[512] = {0};
+    // grow-only device staging for PB2_MEM_HOST calls + misc scratch
+    Scratch stage[8];
+    Scratch scratch[4];
+    // pinned host bounce buffer for small readbacks (counters)
+    uint64_t* h_counters = nullptr;  // 16 x u64 pinned
+    uint64_t* d_counters = nullptr;  // 16 x u64 device
+};
+
+#define PB2_CUDA(ctx, expr)                                                                             \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s -> %s", __FILE__, __LINE__, #expr,       \
+                     cudaGetErrorString(_e));                                                           \
+            return PB2_ERR_CUDA;                                                                        \
+        }                                                                                               \
+    } while (0)
+
+#define PB2_CHECK(expr)            \
+    do {                           \
+        int _s = (expr);           \
+        if (_s != PB2_OK) return _s; \
+    } while (0)
+
+#define PB2_FAIL(ctx, code, ...)                                \
+    do {                                                        \
+        snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);  \
+        return (code);                                          \
+    } while (0)
+
+int pb2_scratch_reserve(pb2_ctx* ctx, Scratch* s, size_t bytes);
+static inline unsigned pb2_blocks(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+#define PB2_LAUNCHED(ctx) ((ctx)->launches++)
+
+// ---------------------------------------------------------------- node layout (== BvhNodeWide, 64 B)
+// child = { mins.xyz, children:u32, maxs.xyz, data:u32 }; data low 30 bits = leaf_count, top 2 = change flags.
+struct __align__(16) NodeHalf {
+    float mnx, mny, mnz;
+    uint32_t children;
+    float mxx, mxy, mxz;
+    uint32_t data;
+};
+struct __align__(64) NodeWide {
+    NodeHalf left, right;
+};
+#define PB2_LEAF_COUNT_MASK 0x3fffffffu
+#define PB2_CHANGED (1u << 30)
+#define PB2_CHANGE_PENDING (3u << 30)
+
+struct pb2_bvh {
+    uint32_t n_leaves = 0;
+    uint32_t n_nodes = 0;      // number of wide nodes (max(1, n-1); 0 when empty)
+    int strategy = 0;
+    NodeWide* nodes = nullptr; // leaf `children` = sorted position (see leaf_order), internal = wide node index
+    uint32_t* parents = nullptr;     // per wide node: (parent << 1) | is_right ; parents[0] = 0 (dummy)
+    uint32_t* leaf_slot = nullptr;   // per leaf id: (node << 1) | is_right  (== leaf_node_indices)
+    uint32_t* leaf_order = nullptr;  // sorted position -> leaf id
+    uint32_t* counters = nullptr;    // per wide node arrival counters for bottom-up passes
+    uint32_t cap_leaves = 0;
+};
+
+// ---------------------------------------------------------------- device math (nalgebra op order)
+struct V3 {
+    float x, y, z;
+};
+__host__ __device__ __forceinline__ V3 mk3(float x, float y, float z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
+__host__ __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ __forceinline__ V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
+__host__ __device__ __forceinline__ V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ __forceinline__ V3 operator/(V3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+__host__ __device__ __forceinline__ float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__host__ __device__ __forceinline__ V3 cross3(V3 a, V3 b) {
+    return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__host__ __device__ __forceinline__ float nrm2(V3 a) { return dot3(a, a); }
+__device__ __forceinline__ float nrm(V3 a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ V3 normalize3(V3 a) { return a / nrm(a); }
+__device__ __forceinline__ V3 vmin3(V3 a, V3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
+__device__ __forceinline__ V3 vmax3(V3 a, V3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+__device__ __forceinline__ float comp(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+struct Q4 {
+    float i, j, k, w;
+};
+struct Iso7 {
+    Q4 q;
+    V3 t;
+};
+__device__ __forceinline__ Iso7 load_iso(const float* p) {
+    Iso7 m;
+    m.q.i = p[0]; m.q.j = p[1]; m.q.k = p[2]; m.q.w = p[3];
+    m.t = mk3(p[4], p[5], p[6]);
+    return m;
+}
+__device__ __forceinline__ Q4 qconj(Q4 q) { Q4 r; r.i = -q.i; r.j = -q.j; r.k = -q.k; r.w = q.w; return r; }
+// UnitQuaternion * Vector3: t = (q.xyz x v) * 2 ; t * w + (q.xyz x t) + v
+__device__ __forceinline__ V3 qrot(Q4 q, V3 v) {
+    V3 u = mk3(q.i, q.j, q.k);
+    V3 t = cross3(u, v) * 2.0f;
+    V3 c = cross3(u, t);
+    return (t * q.w + c) + v;
+}
+__device__ __forceinline__ V3 qirot(Q4 q, V3 v) { return qrot(qconj(q), v); }
+__device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
+    Q4 r;
+    r.i = a.w * b.i + a.i * b.w + a.j * b.k - a.k * b.j;
+    r.j = a.w * b.j - a.i * b.k + a.j * b.w + a.k * b.i;
+    r.k = a.w * b.k + a.i * b.j - a.j * b.i + a.k * b.w;
+    r.w = a.w * b.w - a.i * b.i - a.j * b.j - a.k * b.k;
+    return r;
+}
+__device__ __forceinline__ V3 iso_point(const Iso7& m, V3 p) { return qrot(m.q, p) + m.t; }
+__device__ __forceinline__ V3 iso_vec(const Iso7& m, V3 v) { return qrot(m.q, v); }
+__device__ __forceinline__ V3 iso_inv_point(const Iso7& m, V3 p) { return qirot(m.q, p - m.t); }
+__device__ __forceinline__ V3 iso_inv_vec(const Iso7& m, V3 v) { return qirot(m.q, v); }
+__device__ __forceinline__ Iso7 iso_inv_mul(const Iso7& a, const Iso7& b) {
+    Iso7 r;
+    Q4 inv = qconj(a.q);
+    r.t = qrot(inv, b.t - a.t);
+    r.q = qmul(inv, b.q);
+    return r;
+}
+__device__ __forceinline__ Iso7 iso_inverse(const Iso7& a) {
+    Iso7 r;
+    r.q = qconj(a.q);
+    r.t = -qrot(r.q, a.t);
+    return r;
+}
+
+// slab test == Aabb::cast_local_ray(ray, max_toi, solid = true) (query/ray/ray_aabb.rs:12-49) with
+// FLT_MAX for None (BvhNode::cast_ray, bvh_tree.rs:1177-1181). inv = 1/dir (only read where dir != 0).
+__device__ __forceinline__ float slab_cost(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, V3 o, V3 d,
+                                           V3 inv, float tmax) {
+    float tmin = 0.0f;
+    if (d.x == 0.0f) {
+        if (o.x < mnx || o.x > mxx) return FLT_MAX;
+    } else {
+        float n = (mnx - o.x) * inv.x, f = (mxx - o.x) * inv.x;
+        if (n > f) { float t = n; n = f; f = t; }
+        tmin = fmaxf(tmin, n);
+        tmax = fminf(tmax, f);
+        if (tmin > tmax) return FLT_MAX;
+    }
+    if (d.y == 0.0f) {
+        if (o.y < mny || o.y > mxy) return FLT_MAX;
+    } else {
+        float n = (mny - o.y) * inv.y, f = (mxy - o.y) * inv.y;
+        if (n > f) { float t = n; n = f; f = t; }
+        tmin = fmaxf(tmin, n);
+        tmax = fminf(tmax, f);
+        if (tmin > tmax) return FLT_MAX;
+    }
+    if (d.z == 0.0f) {
+        if (o.z < mnz || o.z > mxz) return FLT_MAX;
+    } else {
+        float n = (mnz - o.z) * inv.z, f = (mxz - o.z) * inv.z;
+        if (n > f) { float t = n; n = f; f = t; }
+        tmin = fmaxf(tmin, n);
+        tmax = fminf(tmax, f);
+        if (tmin > tmax) return FLT_MAX;
+    }
+    return tmin;
+}

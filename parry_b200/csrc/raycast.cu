@@ -1,0 +1,245 @@
+// parry_b200 — batched ray casts.
+//
+// Replaces (reference, file:line): RayCast::cast_ray / cast_ray_and_get_normal (query/ray/ray.rs:381-411) for TriMesh
+// (query/ray/ray_trimesh.rs:8-36 -> ray_composite_shape.rs:20-62 -> Bvh::cast_ray bvh_queries.rs:260-271 ->
+// Bvh::find_best bvh_traverse.rs:335-417), BvhNode::cast_ray (bvh_tree.rs:1177-1181) = Aabb::cast_local_ray
+// (ray_aabb.rs:12-49), Triangle ray test (ray_triangle.rs:49-152), TriMesh::triangle (shape/trimesh.rs:1896-1903).
+//
+// One thread per ray, ordered depth-first descent with a short per-thread stack (nearer child first, farther child
+// pushed), pruning against the best hit so far exactly like find_best. Triangles are pre-gathered in BVH leaf
+// order as 3 x float4 (48 B, 16-B aligned vector loads) so a leaf visit costs no index indirection.
+#include "common.cuh"
+#include "traverse.cuh"
+
+int pb2_bvh_build_device(pb2_ctx* ctx, pb2_bvh* b, const float* d_aabbs, uint32_t n, bool resolve_flags);
+int pb2_stage_in(pb2_ctx* ctx, int slot, const void* src, size_t bytes, int mem, const void** out);
+int pb2_stage_out(pb2_ctx* ctx, int slot, void* dst, size_t bytes, int mem, void** out);
+int pb2_stage_back(pb2_ctx* ctx, void* dst, const void* dev, size_t bytes, int mem);
+
+struct pb2_trimesh {
+    pb2_bvh bvh;
+    uint32_t nt = 0, nv = 0;
+    float4* tris = nullptr;  // [3 * sorted position]: {a, id}, {b, -}, {c, -}
+};
+
+
+// Triangle::local_aabb (bounding_volume/aabb_triangle.rs:16-30)
+__global__ void k_triangle_aabbs(const float* __restrict__ v, const uint32_t* __restrict__ idx, uint32_t nt, uint32_t nv,
+                                 float* __restrict__ aabbs, uint32_t* __restrict__ bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    uint32_t ia = idx[3ull * i], ib = idx[3ull * i + 1], ic = idx[3ull * i + 2];
+    if (ia >= nv || ib >= nv || ic >= nv) { atomicAdd(bad, 1u); ia = ib = ic = 0; }
+    float* o = aabbs + 6ull * i;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float a = v[3ull * ia + d], b = v[3ull * ib + d], c = v[3ull * ic + d];
+        o[d] = fminf(fminf(a, b), c);
+        o[3 + d] = fmaxf(fmaxf(a, b), c);
+    }
+}
+
+__global__ void k_gather_triangles(const float* __restrict__ v, const uint32_t* __restrict__ idx, uint32_t nt,
+                                   const uint32_t* __restrict__ order, float4* __restrict__ tris) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nt) return;
+    uint32_t id = order[p];
+    uint32_t ia = idx[3ull * id], ib = idx[3ull * id + 1], ic = idx[3ull * id + 2];
+    tris[3ull * p + 0] = make_float4(v[3ull * ia], v[3ull * ia + 1], v[3ull * ia + 2], __uint_as_float(id));
+    tris[3ull * p + 1] = make_float4(v[3ull * ib], v[3ull * ib + 1], v[3ull * ib + 2], 0.0f);
+    tris[3ull * p + 2] = make_float4(v[3ull * ic], v[3ull * ic + 1], v[3ull * ic + 2], 0.0f);
+}
+
+// local_ray_intersection_with_triangle (ray_triangle.rs:70-152) — toi, face side (0 front / 1 back) and the
+// un-normalised oriented normal. Returns false for None.
+__device__ __forceinline__ bool ray_triangle(V3 a, V3 b, V3 c, V3 o, V3 dir, float& toi, uint32_t& fid, V3& n_out) {
+    V3 ab = b - a, ac = c - a;
+    V3 n = cross3(ab, ac);
+    float d = dot3(n, dir);
+    if (d == 0.0f) return false;
+    V3 ap = o - a;
+    float t = dot3(ap, n);
+    if ((t < 0.0f && d < 0.0f) || (t > 0.0f && d > 0.0f)) return false;
+    fid = d < 0.0f ? 0u : 1u;
+    d = fabsf(d);
+    V3 e = -cross3(dir, ap);
+    float v, w;
+    if (t < 0.0f) {
+        v = -dot3(ac, e);
+        if (v < 0.0f || v > d) return false;
+        w = dot3(ab, e);
+        if (w < 0.0f || v + w > d) return false;
+        float invd = 1.0f / d;
+        toi = -t * invd;
+        n_out = n;
+        fid |= 2u;  // bit 1: normal = -(n.normalize()) — negate after normalising
+    } else {
+        v = dot3(ac, e);
+        if (v < 0.0f || v > d) return false;
+        w = -dot3(ab, e);
+        if (w < 0.0f || v + w > d) return false;
+        float invd = 1.0f / d;
+        toi = t * invd;
+        n_out = n;
+    }
+    return true;
+}
+
+template <bool WITH_NORMAL>
+__global__ void __launch_bounds__(128) k_raycast_trimesh(const NodeWide* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_leaves,
+                                  uint32_t nt, const float* __restrict__ pose7, const float* __restrict__ rays, uint32_t m,
+                                  float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
+                                  float* __restrict__ out_normal, uint32_t* __restrict__ out_feature) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    V3 o = mk3(rays[6ull * r], rays[6ull * r + 1], rays[6ull * r + 2]);
+    V3 d = mk3(rays[6ull * r + 3], rays[6ull * r + 4], rays[6ull * r + 5]);
+    Iso7 pose;
+    if (pose7) {  // Ray::inverse_transform_by (ray.rs:167-172)
+        pose = load_iso(pose7);
+        o = iso_inv_point(pose, o);
+        d = iso_inv_vec(pose, d);
+    }
+    V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+
+    float best = max_toi;
+    uint32_t best_id = PB2_INVALID_U32;
+    uint32_t best_fid = 0;
+    V3 best_n = mk3(0.f, 0.f, 0.f);
+    bool found = false;
+
+    auto leaf_test = [&](uint32_t pos) {
+        float4 ta = __ldg(&tris[3ull * pos]), tb = __ldg(&tris[3ull * pos + 1]), tc = __ldg(&tris[3ull * pos + 2]);
+        float toi; uint32_t fid; V3 n;
+        if (!ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n)) return;
+        if (!(toi <= best)) return;  // Triangle::cast_local_ray_and_get_normal: toi <= max_toi(=best so far)
+        uint32_t id = __float_as_uint(ta.w);
+        // find_best keeps strictly better hits; exact ties resolve to the smallest triangle index.
+        if (toi < best || (found && toi == best && id < best_id)) {
+            best = toi; best_id = id; best_fid = fid; best_n = n; found = true;
+        }
+    };
+
+    bvh_find_best(nodes, n_leaves, o, d, inv, max_toi, best, found, leaf_test);
+
+    // CompositeShapeRef::cast_local_ray post-filter `toi < max_toi` holds by construction (strict accept vs
+    // the initial best = max_toi).
+    out_toi[r] = found ? best : 0.0f;
+    out_tri[r] = best_id;
+    if (WITH_NORMAL) {
+        V3 n = mk3(0.f, 0.f, 0.f);
+        uint32_t feat = PB2_INVALID_U32;
+        if (found) {
+            n = normalize3(best_n);
+            if (best_fid & 2u) n = -n;
+            if (pose7) n = iso_vec(pose, n);  // RayIntersection::transform_by (ray.rs:327-333)
+            // ray_trimesh.rs:28-32: back face => Face(i + num_triangles)
+            feat = (best_fid & 1u) ? best_id + nt : best_id;
+        }
+        if (out_normal) { out_normal[3ull * r] = n.x; out_normal[3ull * r + 1] = n.y; out_normal[3ull * r + 2] = n.z; }
+        if (out_feature) out_feature[r] = feat;
+    }
+}
+
+extern "C" {
+
+int pb2_trimesh_create(pb2_ctx* ctx, const float* vertices, uint32_t nv, const uint32_t* indices, uint32_t nt, int mem,
+                       pb2_trimesh** out) {
+    if (!ctx || !out || !vertices || !indices) return PB2_ERR_INVALID;
+    if (nt == 0 || nv == 0) PB2_FAIL(ctx, PB2_ERR_INVALID, "TriMeshBuilderError::EmptyIndices");
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_v = nullptr, *d_i = nullptr;
+    PB2_CHECK(pb2_stage_in(ctx, 0, vertices, (size_t)nv * 12, mem, &d_v));
+    PB2_CHECK(pb2_stage_in(ctx, 1, indices, (size_t)nt * 12, mem, &d_i));
+    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[1], (size_t)nt * 24));
+    float* aabbs = (float*)ctx->scratch[1].ptr;
+    uint32_t* bad = (uint32_t*)ctx->d_counters;
+    PB2_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, ctx->stream));
+    k_triangle_aabbs<<<pb2_blocks(nt, 256), 256, 0, ctx->stream>>>((const float*)d_v, (const uint32_t*)d_i, nt, nv, aabbs, bad);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*(uint32_t*)ctx->h_counters != 0) PB2_FAIL(ctx, PB2_ERR_INVALID, "triangle index out of bounds");
+
+    pb2_trimesh* mesh = new pb2_trimesh();
+    mesh->nt = nt; mesh->nv = nv;
+    pb2_bvh* b = &mesh->bvh;
+    b->strategy = PB2_BUILD_BINNED;
+    b->n_leaves = nt;
+    b->n_nodes = nt <= 2 ? 1 : nt - 1;
+    b->cap_leaves = nt;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->nodes, (size_t)b->n_nodes * sizeof(NodeWide));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->parents, (size_t)b->n_nodes * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->counters, (size_t)b->n_nodes * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->leaf_slot, (size_t)nt * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->leaf_order, (size_t)nt * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&mesh->tris, (size_t)nt * 48);
+    int s = PB2_OK;
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh alloc: %s", cudaGetErrorString(e)); s = PB2_ERR_CUDA; }
+    if (s == PB2_OK) s = pb2_bvh_build_device(ctx, b, aabbs, nt, true);
+    if (s == PB2_OK) {
+        k_gather_triangles<<<pb2_blocks(nt, 256), 256, 0, ctx->stream>>>((const float*)d_v, (const uint32_t*)d_i, nt, b->leaf_order, mesh->tris);
+        PB2_LAUNCHED(ctx);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh build: %s", cudaGetErrorString(e)); s = PB2_ERR_CUDA; }
+    }
+    if (s != PB2_OK) { pb2_trimesh_destroy(ctx, mesh); return s; }
+    *out = mesh;
+    return PB2_OK;
+}
+
+int pb2_trimesh_destroy(pb2_ctx* ctx, pb2_trimesh* mesh) {
+    if (!ctx || !mesh) return PB2_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    pb2_bvh* b = &mesh->bvh;
+    if (b->nodes) cudaFree(b->nodes);
+    if (b->parents) cudaFree(b->parents);
+    if (b->counters) cudaFree(b->counters);
+    if (b->leaf_slot) cudaFree(b->leaf_slot);
+    if (b->leaf_order) cudaFree(b->leaf_order);
+    if (mesh->tris) cudaFree(mesh->tris);
+    delete mesh;
+    return PB2_OK;
+}
+
+const pb2_bvh* pb2_trimesh_bvh(const pb2_trimesh* mesh) { return mesh ? &mesh->bvh : nullptr; }
+
+int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays, uint32_t m,
+                          float max_toi, int solid, float* toi, uint32_t* tri, float* normal, uint32_t* feature, int mem) {
+    (void)solid;  // ignored by the 3D triangle test (ray_triangle.rs:53)
+    if (!ctx || !mesh || (m && (!rays || !toi || !tri))) return PB2_ERR_INVALID;
+    if (m == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_rays = nullptr, *d_pose = nullptr;
+    void *d_toi = nullptr, *d_tri = nullptr, *d_n = nullptr, *d_f = nullptr;
+    PB2_CHECK(pb2_stage_in(ctx, 0, rays, (size_t)m * 24, mem, &d_rays));
+    // the pose is tiny: always staged from host memory when given in host mode
+    PB2_CHECK(pb2_stage_in(ctx, 1, pose7, 28, mem, &d_pose));
+    PB2_CHECK(pb2_stage_out(ctx, 2, toi, (size_t)m * 4, mem, &d_toi));
+    PB2_CHECK(pb2_stage_out(ctx, 3, tri, (size_t)m * 4, mem, &d_tri));
+    PB2_CHECK(pb2_stage_out(ctx, 4, normal, (size_t)m * 12, mem, &d_n));
+    PB2_CHECK(pb2_stage_out(ctx, 5, feature, (size_t)m * 4, mem, &d_f));
+    const pb2_bvh* b = &mesh->bvh;
+    unsigned blocks = pb2_blocks(m, 128);
+    if (normal || feature)
+        k_raycast_trimesh<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
+                                                                 (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
+                                                                 (float*)d_n, (uint32_t*)d_f);
+    else
+        k_raycast_trimesh<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
+                                                                  (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
+                                                                  nullptr, nullptr);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(pb2_stage_back(ctx, toi, d_toi, (size_t)m * 4, mem));
+    PB2_CHECK(pb2_stage_back(ctx, tri, d_tri, (size_t)m * 4, mem));
+    PB2_CHECK(pb2_stage_back(ctx, normal, d_n, (size_t)m * 12, mem));
+    PB2_CHECK(pb2_stage_back(ctx, feature, d_f, (size_t)m * 4, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,319 @@
+// parry_b200 — typed shape table, per-collider AABBs and Bvh ray casts with Ball / Cuboid leaves.
+//
+// Replaces (reference, file:line): Ball::aabb (bounding_volume/aabb_ball.rs:8-33), Cuboid::aabb (aabb_cuboid.rs:9-16 +
+// utils/isometry_ops.rs:16-18), ConvexPolyhedron::aabb (aabb_convex_polyhedron.rs:8-16 -> aabb_utils.rs:66-87);
+// Bvh::cast_ray (bvh_queries.rs:260-271) with leaves = RayCast for Ball (query/ray/ray_ball.rs:8-98) and
+// Cuboid (ray_cuboid.rs:6-25 -> ray_aabb.rs:12-92 -> query/clip/clip_aabb_line.rs:79-187).
+#include "shapes.cuh"
+#include "traverse.cuh"
+
+int pb2_stage_in(pb2_ctx* ctx, int slot, const void* src, size_t bytes, int mem, const void** out);
+int pb2_stage_out(pb2_ctx* ctx, int slot, void* dst, size_t bytes, int mem, void** out);
+int pb2_stage_back(pb2_ctx* ctx, void* dst, const void* dev, size_t bytes, int mem);
+
+__global__ void k_compute_aabbs(const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float* __restrict__ points,
+                                uint32_t n_shapes, const uint32_t* __restrict__ shape_ids, const float* __restrict__ poses, uint32_t n,
+                                float* __restrict__ out, uint32_t* __restrict__ bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t sid = shape_ids ? shape_ids[i] : i;
+    if (sid >= n_shapes) { atomicAdd(bad, 1u); return; }
+    Iso7 pos = load_iso(poses + 7ull * i);
+    float4 pr = params[sid];
+    V3 mn, mx;
+    uint8_t kind = kinds[sid];
+    if (kind == PB2_SHAPE_BALL) {
+        // ball_aabb: center + repeat(-r), center + repeat(r)
+        float r = pr.x;
+        mn = mk3(pos.t.x + (-r), pos.t.y + (-r), pos.t.z + (-r));
+        mx = mk3(pos.t.x + r, pos.t.y + r, pos.t.z + r);
+    } else if (kind == PB2_SHAPE_CUBOID) {
+        // |R| * half_extents with R = to_rotation_matrix(), gemv accumulated column by column
+        float qi = pos.q.i, qj = pos.q.j, qk = pos.q.k, qw = pos.q.w;
+        float ww = qw * qw, ii = qi * qi, jj = qj * qj, kk = qk * qk;
+        float ij = qi * qj * 2.0f, wk = qw * qk * 2.0f, wj = qw * qj * 2.0f;
+        float ik = qi * qk * 2.0f, jk = qj * qk * 2.0f, wi = qw * qi * 2.0f;
+        float m00 = fabsf(ww + ii - jj - kk), m01 = fabsf(ij - wk), m02 = fabsf(wj + ik);
+        float m10 = fabsf(wk + ij), m11 = fabsf(ww - ii + jj - kk), m12 = fabsf(jk - wi);
+        float m20 = fabsf(ik - wj), m21 = fabsf(wi + jk), m22 = fabsf(ww - ii - jj + kk);
+        V3 he = mk3((m00 * pr.x + m01 * pr.y) + m02 * pr.z, (m10 * pr.x + m11 * pr.y) + m12 * pr.z,
+                    (m20 * pr.x + m21 * pr.y) + m22 * pr.z);
+        mn = pos.t - he;  // Aabb::from_half_extents(center, he)
+        mx = pos.t + he;
+    } else {
+        uint32_t first = __float_as_uint(pr.x), cnt = __float_as_uint(pr.y);
+        const float* p = points + 3ull * first;
+        V3 w0 = iso_point(pos, mk3(p[0], p[1], p[2]));
+        mn = w0; mx = w0;
+        for (uint32_t k = 1; k < cnt; ++k) {
+            V3 w = iso_point(pos, mk3(p[3 * k], p[3 * k + 1], p[3 * k + 2]));
+            mn = vmin3(mn, w);
+            mx = vmax3(mx, w);
+        }
+    }
+    float* o = out + 6ull * i;
+    o[0] = mn.x; o[1] = mn.y; o[2] = mn.z; o[3] = mx.x; o[4] = mx.y; o[5] = mx.z;
+}
+
+// ---------------------------------------------------------------- single-shape ray casts (local space)
+// ray_toi_with_ball (ray_ball.rs:33-77), ball at the origin of its local frame
+__device__ __forceinline__ bool ray_ball(float radius, V3 o, V3 dir, bool solid, bool& inside, float& toi) {
+    V3 dcenter = o - mk3(0.f, 0.f, 0.f);
+    float a = nrm2(dir);
+    float b = dot3(dcenter, dir);
+    float c = nrm2(dcenter) - radius * radius;
+    if (a == 0.0f) {
+        if (c > 0.0f) { inside = false; return false; }
+        inside = true; toi = 0.0f; return true;
+    }
+    if (c > 0.0f && b > 0.0f) { inside = false; return false; }
+    float delta = b * b - a * c;
+    if (delta < 0.0f) { inside = false; return false; }
+    float t = (-b - sqrtf(delta)) / a;
+    if (t <= 0.0f) {
+        inside = true;
+        toi = solid ? 0.0f : (-b + sqrtf(delta)) / a;
+        return true;
+    }
+    inside = false; toi = t; return true;
+}
+
+// Aabb::cast_local_ray (ray_aabb.rs:12-49) on [-he, he]
+__device__ __forceinline__ bool ray_cuboid_toi(V3 he, V3 o, V3 d, float max_toi, bool solid, float& toi) {
+    float tmin = 0.0f, tmax = max_toi;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float di = comp(d, i), oi = comp(o, i), h = comp(he, i);
+        if (di == 0.0f) {
+            if (oi < -h || oi > h) return false;
+        } else {
+            float denom = 1.0f / di;
+            float n = (-h - oi) * denom, f = (h - oi) * denom;
+            if (n > f) { float t = n; n = f; f = t; }
+            tmin = fmaxf(tmin, n);
+            tmax = fminf(tmax, f);
+            if (tmin > tmax) return false;
+        }
+    }
+    toi = (tmin == 0.0f && !solid) ? tmax : tmin;
+    return true;
+}
+
+struct ClipHit { float t; V3 n; int side; };
+// clip_aabb_line (clip_aabb_line.rs:79-187) on [-he, he]
+__device__ __forceinline__ bool clip_cuboid_line(V3 he, V3 o, V3 d, ClipHit& near, ClipHit& far) {
+    float tmax = FLT_MAX, tmin = -FLT_MAX;
+    int near_side = 0, far_side = 0;
+    bool near_diag = false, far_diag = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float di = comp(d, i), oi = comp(o, i), h = comp(he, i);
+        if (di == 0.0f) {
+            if (oi < -h || oi > h) return false;
+        } else {
+            float denom = 1.0f / di;
+            bool flip;
+            float n = (-h - oi) * denom, f = (h - oi) * denom;
+            if (n > f) { flip = true; float t = n; n = f; f = t; } else flip = false;
+            if (n > tmin) { tmin = n; near_side = flip ? -(i + 1) : (i + 1); near_diag = false; }
+            else if (n == tmin) near_diag = true;
+            if (f < tmax) { tmax = f; far_side = !flip ? -(i + 1) : (i + 1); far_diag = false; }
+            else if (f == tmax) far_diag = true;
+            if (tmax < 0.0f || tmin > tmax) return false;
+        }
+    }
+    bool contains = -he.x <= o.x && -he.y <= o.y && -he.z <= o.z && o.x <= he.x && o.y <= he.y && o.z <= he.z;
+    ClipHit zero; zero.t = 0.0f; zero.n = mk3(0.f, 0.f, 0.f); zero.side = 0;
+    if (near_diag) { near.t = tmin; near.n = -normalize3(d); near.side = near_side; }
+    else {
+        if (near_side == 0) { near = zero; far = zero; return contains; }
+        float v[3] = {0.f, 0.f, 0.f};
+        if (near_side < 0) v[-near_side - 1] = 1.0f; else v[near_side - 1] = -1.0f;
+        near.t = tmin; near.n = mk3(v[0], v[1], v[2]); near.side = near_side;
+    }
+    if (far_diag) { far.t = tmax; far.n = -normalize3(d); far.side = far_side; }
+    else {
+        if (far_side == 0) { near = zero; far = zero; return contains; }
+        float v[3] = {0.f, 0.f, 0.f};
+        if (far_side < 0) v[-far_side - 1] = -1.0f; else v[far_side - 1] = 1.0f;
+        far.t = tmax; far.n = mk3(v[0], v[1], v[2]); far.side = far_side;
+    }
+    return true;
+}
+// Aabb::cast_local_ray_and_get_normal (ray_aabb.rs:52-92)
+__device__ __forceinline__ bool ray_cuboid_normal(V3 he, V3 o, V3 d, float max_toi, bool solid, float& toi, V3& n, uint32_t& feat) {
+    ClipHit near, far, r;
+    if (!clip_cuboid_line(he, o, d, near, far)) return false;
+    if (near.t < 0.0f) {
+        if (solid) { r.t = 0.0f; r.n = mk3(0.f, 0.f, 0.f); r.side = far.side; }
+        else if (far.t <= max_toi) r = far;
+        else return false;
+    } else if (near.t <= max_toi) r = near;
+    else return false;
+    toi = r.t; n = r.n;
+    feat = r.side < 0 ? (uint32_t)(-r.side) - 1u + 3u : (uint32_t)r.side - 1u;
+    return true;
+}
+
+template <bool WITH_NORMAL>
+__global__ void __launch_bounds__(128) k_raycast_shapes(const NodeWide* __restrict__ nodes, const uint32_t* __restrict__ order, uint32_t n_leaves,
+                                 const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
+                                 const uint32_t* __restrict__ shape_ids, const float* __restrict__ poses, const float* __restrict__ rays,
+                                 uint32_t m, float max_toi, bool solid, float* __restrict__ out_toi, uint32_t* __restrict__ out_leaf,
+                                 float* __restrict__ out_normal, uint32_t* __restrict__ out_feature) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    V3 o = mk3(rays[6ull * r], rays[6ull * r + 1], rays[6ull * r + 2]);
+    V3 d = mk3(rays[6ull * r + 3], rays[6ull * r + 4], rays[6ull * r + 5]);
+    V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    float best = max_toi;
+    bool found = false;
+    uint32_t best_id = PB2_INVALID_U32, best_feat = PB2_INVALID_U32;
+    V3 best_n = mk3(0.f, 0.f, 0.f);
+    auto leaf = [&](uint32_t pos) {
+        uint32_t id = order[pos];
+        uint32_t sid = shape_ids ? shape_ids[id] : id;
+        Iso7 pose = load_iso(poses + 7ull * id);
+        V3 lo = iso_inv_point(pose, o), ld = iso_inv_vec(pose, d);  // RayCast::cast_ray (ray.rs:381-390)
+        float4 pr = params[sid];
+        float toi; V3 n = mk3(0.f, 0.f, 0.f); uint32_t feat = 0;
+        bool hit;
+        if (kinds[sid] == PB2_SHAPE_BALL) {
+            bool inside;
+            hit = ray_ball(pr.x, lo, ld, solid, inside, toi);
+            if (hit && WITH_NORMAL) {  // ray_toi_and_normal_with_ball (ray_ball.rs:81-98)
+                V3 p = (lo + ld * toi) - mk3(0.f, 0.f, 0.f);
+                n = normalize3(p);
+                if (inside) n = -n;
+            }
+            hit = hit && toi <= best;
+        } else {
+            V3 he = mk3(pr.x, pr.y, pr.z);
+            if (WITH_NORMAL) hit = ray_cuboid_normal(he, lo, ld, best, solid, toi, n, feat);
+            else hit = ray_cuboid_toi(he, lo, ld, best, solid, toi);
+        }
+        if (!hit) return;
+        if (toi < best || (found && toi == best && id < best_id)) {
+            best = toi; best_id = id; found = true;
+            if (WITH_NORMAL) { best_n = iso_vec(pose, n); best_feat = feat; }
+        }
+    };
+    bvh_find_best(nodes, n_leaves, o, d, inv, max_toi, best, found, leaf);
+    out_toi[r] = found ? best : 0.0f;
+    out_leaf[r] = best_id;
+    if (WITH_NORMAL) {
+        if (out_normal) { out_normal[3ull * r] = best_n.x; out_normal[3ull * r + 1] = best_n.y; out_normal[3ull * r + 2] = best_n.z; }
+        if (out_feature) out_feature[r] = found ? best_feat : PB2_INVALID_U32;
+    }
+}
+
+extern "C" {
+
+int pb2_shapes_create(pb2_ctx* ctx, const uint8_t* kinds, const float* params, uint32_t n, const float* points, uint32_t np,
+                      pb2_shapes** out) {
+    if (!ctx || !out || (n && (!kinds || !params)) || (np && !points)) return PB2_ERR_INVALID;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    bool has_convex = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (kinds[i] > PB2_SHAPE_CONVEX) PB2_FAIL(ctx, PB2_ERR_INVALID, "shape %u: unknown kind %u", i, kinds[i]);
+        if (kinds[i] == PB2_SHAPE_CONVEX) {
+            uint32_t first, cnt;
+            memcpy(&first, params + 4 * i, 4);
+            memcpy(&cnt, params + 4 * i + 1, 4);
+            if (cnt == 0 || (uint64_t)first + cnt > np) PB2_FAIL(ctx, PB2_ERR_INVALID, "shape %u: bad point range", i);
+            has_convex = true;
+        }
+    }
+    pb2_shapes* s = new pb2_shapes();
+    s->n = n; s->np = np; s->has_convex = has_convex;
+    size_t nn = n ? n : 1, npp = np ? np : 1;
+    cudaError_t e = cudaMalloc((void**)&s->kinds, nn);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->params, nn * 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->points, npp * 12);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(s->kinds, kinds, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(s->params, params, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && np) e = cudaMemcpyAsync(s->points, points, (size_t)np * 12, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "shapes_create: %s", cudaGetErrorString(e));
+        pb2_shapes_destroy(ctx, s);
+        return PB2_ERR_CUDA;
+    }
+    *out = s;
+    return PB2_OK;
+}
+
+int pb2_shapes_destroy(pb2_ctx* ctx, pb2_shapes* s) {
+    if (!ctx || !s) return PB2_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (s->kinds) cudaFree(s->kinds);
+    if (s->params) cudaFree(s->params);
+    if (s->points) cudaFree(s->points);
+    delete s;
+    return PB2_OK;
+}
+
+int pb2_shapes_compute_aabbs(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape_ids, const float* poses7, uint32_t n,
+                             float* aabbs, int mem) {
+    if (!ctx || !shapes || (n && (!poses7 || !aabbs))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_ids = nullptr, *d_poses = nullptr;
+    void* d_out = nullptr;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape_ids, (size_t)n * 4, mem, &d_ids));
+    PB2_CHECK(pb2_stage_in(ctx, 1, poses7, (size_t)n * 28, mem, &d_poses));
+    PB2_CHECK(pb2_stage_out(ctx, 2, aabbs, (size_t)n * 24, mem, &d_out));
+    uint32_t* bad = (uint32_t*)(ctx->d_counters + 2);
+    PB2_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, ctx->stream));
+    k_compute_aabbs<<<pb2_blocks(n, 128), 128, 0, ctx->stream>>>(shapes->kinds, shapes->params, shapes->points, shapes->n,
+                                                                (const uint32_t*)d_ids, (const float*)d_poses, n, (float*)d_out, bad);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(pb2_stage_back(ctx, aabbs, d_out, (size_t)n * 24, mem));
+    if (mem == PB2_MEM_HOST) {
+        PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 2, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (*(uint32_t*)(ctx->h_counters + 2)) PB2_FAIL(ctx, PB2_ERR_INVALID, "compute_aabbs: shape id out of range");
+    }
+    return PB2_OK;
+}
+
+int pb2_bvh_cast_rays_shapes(pb2_ctx* ctx, const pb2_bvh* bvh, const pb2_shapes* shapes, const uint32_t* shape_ids,
+                             const float* poses7, const float* rays, uint32_t m, float max_toi, int solid, float* toi, uint32_t* leaf,
+                             float* normal, uint32_t* feature, int mem) {
+    if (!ctx || !bvh || !shapes || !poses7 || (m && (!rays || !toi || !leaf))) return PB2_ERR_INVALID;
+    if (shapes->has_convex) PB2_FAIL(ctx, PB2_ERR_UNSUPPORTED, "ray casts on ConvexPolyhedron leaves are out of scope");
+    if (m == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t nl = bvh->n_leaves;
+    const void *d_rays = nullptr, *d_ids = nullptr, *d_poses = nullptr;
+    void *d_toi = nullptr, *d_leaf = nullptr, *d_n = nullptr, *d_f = nullptr;
+    PB2_CHECK(pb2_stage_in(ctx, 0, rays, (size_t)m * 24, mem, &d_rays));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape_ids, (size_t)nl * 4, mem, &d_ids));
+    PB2_CHECK(pb2_stage_in(ctx, 6, poses7, (size_t)nl * 28, mem, &d_poses));
+    PB2_CHECK(pb2_stage_out(ctx, 2, toi, (size_t)m * 4, mem, &d_toi));
+    PB2_CHECK(pb2_stage_out(ctx, 3, leaf, (size_t)m * 4, mem, &d_leaf));
+    PB2_CHECK(pb2_stage_out(ctx, 4, normal, (size_t)m * 12, mem, &d_n));
+    PB2_CHECK(pb2_stage_out(ctx, 5, feature, (size_t)m * 4, mem, &d_f));
+    unsigned blocks = pb2_blocks(m, 128);
+    if (normal || feature)
+        k_raycast_shapes<true><<<blocks, 128, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_order, nl, shapes->kinds, shapes->params,
+                                                                (const uint32_t*)d_ids, (const float*)d_poses, (const float*)d_rays, m,
+                                                                max_toi, solid != 0, (float*)d_toi, (uint32_t*)d_leaf, (float*)d_n,
+                                                                (uint32_t*)d_f);
+    else
+        k_raycast_shapes<false><<<blocks, 128, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_order, nl, shapes->kinds, shapes->params,
+                                                                 (const uint32_t*)d_ids, (const float*)d_poses, (const float*)d_rays, m,
+                                                                 max_toi, solid != 0, (float*)d_toi, (uint32_t*)d_leaf, nullptr, nullptr);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(pb2_stage_back(ctx, toi, d_toi, (size_t)m * 4, mem));
+    PB2_CHECK(pb2_stage_back(ctx, leaf, d_leaf, (size_t)m * 4, mem));
+    PB2_CHECK(pb2_stage_back(ctx, normal, d_n, (size_t)m * 12, mem));
+    PB2_CHECK(pb2_stage_back(ctx, feature, d_f, (size_t)m * 4, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB2_OK;
+}
+
+}  // extern "C"

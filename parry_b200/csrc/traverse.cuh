@@ -1,0 +1,55 @@
+// parry_b200 — ordered best-first Bvh descent shared by the ray kernels.
+// Mirrors Bvh::find_best (partitioning/bvh/bvh_traverse.rs:335-417) with aabb_cost = BvhNode::cast_ray
+// (bvh_tree.rs:1177-1181): both children scored against the best hit so far, nearer child first, farther child
+// pushed on a short per-thread stack, prune when score >= best.
+#pragma once
+#include "common.cuh"
+
+#define PB2_STACK 64
+
+// `leaf(pos)` tests the primitive at sorted position `pos` and updates `best` / `found` itself.
+// Deviation from the reference (documented tie rule): once a hit exists, nodes whose score == best are
+// still visited so that every bit-equal tie is seen and the smallest leaf id can win.
+template <class Leaf>
+__device__ __forceinline__ void bvh_find_best(const NodeWide* __restrict__ nodes, uint32_t n_leaves, V3 o, V3 d, V3 inv,
+                                              float max_toi, float& best, bool& found, Leaf leaf) {
+    if (n_leaves == 1) {
+        // partial root (bvh_traverse.rs:349-358)
+        const float4* np = reinterpret_cast<const float4*>(&nodes[0]);
+        float4 l0 = __ldg(np), l1 = __ldg(np + 1);
+        if (slab_cost(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, o, d, inv, max_toi) < max_toi) leaf(__float_as_uint(l0.w));
+        return;
+    }
+    if (n_leaves < 2) return;
+    uint32_t stack[PB2_STACK];
+    int sp = 0;
+    uint32_t curr = 0;
+    for (;;) {
+        const float4* np = reinterpret_cast<const float4*>(&nodes[curr]);
+        float4 l0 = __ldg(np), l1 = __ldg(np + 1), r0 = __ldg(np + 2), r1 = __ldg(np + 3);
+        float ls = slab_cost(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, o, d, inv, best);
+        float rs = slab_cost(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, o, d, inv, best);
+        uint32_t lc = __float_as_uint(l0.w), rc = __float_as_uint(r0.w);
+        bool lleaf = (__float_as_uint(l1.w) & PB2_LEAF_COUNT_MASK) == 1u;
+        bool rleaf = (__float_as_uint(r1.w) & PB2_LEAF_COUNT_MASK) == 1u;
+        if (ls > rs) {
+            float ts = ls; ls = rs; rs = ts;
+            uint32_t tc = lc; lc = rc; rc = tc;
+            bool tl = lleaf; lleaf = rleaf; rleaf = tl;
+        }
+        bool found_next = false;
+        if (ls != FLT_MAX && (ls < best || (found && ls == best))) {
+            if (lleaf) leaf(lc);
+            else { curr = lc; found_next = true; }
+        }
+        if (rs != FLT_MAX && (rs < best || (found && rs == best))) {
+            if (rleaf) leaf(rc);
+            else if (found_next) { if (sp < PB2_STACK) stack[sp++] = rc; }
+            else { curr = rc; found_next = true; }
+        }
+        if (!found_next) {
+            if (sp == 0) break;
+            curr = stack[--sp];
+        }
+    }
+}

@@ -1,0 +1,422 @@
+"""Host-side mirror of the reference's API for the hot path, over the C ABI. Names follow parry3d:
+`Bvh::from_leaves / refit / intersect_aabb / traverse_bvtt_single_tree / leaf_pairs` (src/partitioning/bvh),
+`TriMesh::cast_ray / cast_ray_and_get_normal / cast_local_ray*` (src/query/ray/ray.rs:359-411),
+`query::contact` (src/query/contact/contact_shape_shape.rs:123). Every call is the batched form; arrays may be
+numpy (host; results come back as numpy) or torch CUDA tensors (device resident; results are CUDA tensors and the
+call is asynchronous on the context's stream)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import MEM_DEVICE, MEM_HOST, Pb2Error, Unsupported
+
+try:  # torch is plumbing only (device memory + streams); the library itself never sees torch types
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+class BvhBuildStrategy:
+    """partitioning/bvh/bvh_tree.rs:58-78"""
+    Binned = 0
+    Ploc = 1
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _prep(x, dtype, mem=None):
+    """Returns (keepalive, address, mem) for an input array."""
+    if x is None:
+        return None, None, mem
+    if _is_torch(x):
+        tdt = {np.float32: torch.float32, np.uint32: torch.int32, np.uint8: torch.uint8}[dtype]
+        if x.dtype != tdt:
+            if dtype is np.uint32 and x.dtype in (torch.int64, torch.uint32):
+                x = x.to(torch.int32)
+            else:
+                x = x.to(tdt)
+        x = x.contiguous()
+        if x.is_cuda:
+            return x, x.data_ptr(), MEM_DEVICE
+        x = x.numpy()
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return a, a.ctypes.data, MEM_HOST
+
+
+def _empty(shape, dtype, mem, device):
+    if mem == MEM_DEVICE:
+        tdt = {np.float32: torch.float32, np.uint32: torch.int32, np.uint8: torch.uint8}[dtype]
+        t = torch.empty(shape, dtype=tdt, device=device)
+        return t, t.data_ptr()
+    a = np.empty(shape, dtype=dtype)
+    return a, a.ctypes.data
+
+
+class Context:
+    """One CUDA device + one stream (pb2_ctx). With `stream=` (a torch.cuda.Stream) work is enqueued there."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = _ffi.lib()
+        self.device = int(device)
+        h = C.c_void_p()
+        if stream is not None:
+            st = self._lib.pb2_ctx_create_on_stream(self.device, C.c_void_p(stream.cuda_stream), C.byref(h))
+        else:
+            st = self._lib.pb2_ctx_create(self.device, C.byref(h))
+        if st != 0:
+            raise Pb2Error(st, "pb2_ctx_create failed: no usable CUDA device %d (no CPU fallback)" % self.device)
+        self.h = h
+        self.torch_device = "cuda:%d" % self.device
+
+    def check(self, st):
+        if st == 0:
+            return
+        msg = self._lib.pb2_last_error(self.h)
+        msg = msg.decode() if msg else ""
+        if st == _ffi.PB2_ERR_UNSUPPORTED:
+            raise Unsupported(st, msg)
+        raise Pb2Error(st, msg)
+
+    def synchronize(self):
+        self.check(self._lib.pb2_ctx_synchronize(self.h))
+
+    @property
+    def stream_ptr(self):
+        return self._lib.pb2_ctx_stream(self.h)
+
+    def torch_stream(self):
+        return torch.cuda.ExternalStream(self.stream_ptr, device=self.torch_device)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.pb2_ctx_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self._lib.pb2_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Bvh:
+    """partitioning::Bvh"""
+
+    def __init__(self, ctx, handle, owned=True, keep=None):
+        self.ctx, self.h, self.owned, self._keep = ctx, handle, owned, keep
+
+    @staticmethod
+    def from_leaves(ctx, strategy, aabbs):
+        """Bvh::from_leaves (bvh_tree.rs:1835). aabbs: (n, 6) [mins, maxs]."""
+        n = 0 if aabbs is None else int(aabbs.shape[0])
+        keep, ptr, mem = _prep(aabbs, np.float32)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.pb2_bvh_build(ctx.h, ptr, n, int(strategy), mem if mem is not None else MEM_HOST, C.byref(h)))
+        return Bvh(ctx, h)
+
+    def leaf_count(self):
+        return int(self.ctx._lib.pb2_bvh_leaf_count(self.h))
+
+    def node_count(self):
+        return int(self.ctx._lib.pb2_bvh_node_count(self.h))
+
+    def is_empty(self):
+        return self.leaf_count() == 0
+
+    def root_aabb(self):
+        out = np.empty(6, dtype=np.float32)
+        self.ctx.check(self.ctx._lib.pb2_bvh_root_aabb(self.ctx.h, self.h, out.ctypes.data))
+        return out
+
+    def insert_or_update_partially(self, aabbs, leaf_indices=None, change_detection_margin=0.0):
+        """Batched Bvh::insert_or_update_partially for existing leaves (bvh_insert.rs:209-231)."""
+        k1, p1, mem = _prep(aabbs, np.float32)
+        k2, p2, _ = _prep(leaf_indices, np.uint32, mem)
+        self.ctx.check(self.ctx._lib.pb2_bvh_update_leaves(self.ctx.h, self.h, p2, p1, int(aabbs.shape[0]),
+                                                          float(change_detection_margin), mem))
+
+    def refit(self):
+        self.ctx.check(self.ctx._lib.pb2_bvh_refit(self.ctx.h, self.h))
+
+    def rebuild(self, strategy=BvhBuildStrategy.Binned):
+        self.ctx.check(self.ctx._lib.pb2_bvh_rebuild(self.ctx.h, self.h, int(strategy)))
+
+    def download(self):
+        """(nodes, parents, leaf_node_indices): nodes as a structured array in the BvhNodeWide layout."""
+        nn, nl = self.node_count(), self.leaf_count()
+        nodes = np.zeros(nn, dtype=NODE_WIDE_DTYPE)
+        parents = np.zeros(nn, dtype=np.uint32)
+        leaf_idx = np.zeros(nl, dtype=np.uint32)
+        if nn:
+            self.ctx.check(self.ctx._lib.pb2_bvh_download(self.ctx.h, self.h, nodes.ctypes.data, parents.ctypes.data,
+                                                         leaf_idx.ctypes.data, MEM_HOST))
+        return nodes, parents, leaf_idx
+
+    def intersect_aabb(self, queries, capacity=None):
+        """Batched Bvh::intersect_aabb (bvh_queries.rs:203). Returns (offsets[m+1], leaf_ids[count])."""
+        m = int(queries.shape[0])
+        kq, pq, mem = _prep(queries, np.float32)
+        dev = self.ctx.torch_device
+        cap = int(capacity) if capacity is not None else max(1024, 16 * m)
+        while True:
+            offs, po = _empty((m + 1,), np.uint32, mem, dev)
+            ids, pi = _empty((cap,), np.uint32, mem, dev)
+            cnt = C.c_uint64(0)
+            st = self.ctx._lib.pb2_bvh_intersect_aabbs(self.ctx.h, self.h, pq, m, po, pi, cap, C.byref(cnt), mem)
+            if st == _ffi.PB2_ERR_OVERFLOW:
+                cap = int(cnt.value)
+                continue
+            self.ctx.check(st)
+            return offs, ids[: int(cnt.value)]
+
+    def traverse_bvtt_single_tree(self, change_detection=False, capacity=None, like=None):
+        """Bvh::traverse_bvtt_single_tree (bvh_traverse_bvtt.rs:19): all overlapping leaf pairs, (count, 2)."""
+        mem = MEM_DEVICE if (like is not None and _is_torch(like) and like.is_cuda) else MEM_HOST
+        cap = int(capacity) if capacity is not None else max(1024, 8 * self.leaf_count())
+        while True:
+            pairs, pp = _empty((cap, 2), np.uint32, mem, self.ctx.torch_device)
+            cnt = C.c_uint64(0)
+            st = self.ctx._lib.pb2_bvh_self_pairs(self.ctx.h, self.h, int(bool(change_detection)), pp, cap, C.byref(cnt), mem)
+            if st == _ffi.PB2_ERR_OVERFLOW:
+                cap = int(cnt.value)
+                continue
+            self.ctx.check(st)
+            return pairs[: int(cnt.value)]
+
+    def leaf_pairs(self, other, capacity=None, like=None):
+        """Bvh::leaf_pairs(other, |a, b| a.intersects(b)) (bvh_traverse_bvtt.rs:210)."""
+        mem = MEM_DEVICE if (like is not None and _is_torch(like) and like.is_cuda) else MEM_HOST
+        cap = int(capacity) if capacity is not None else max(1024, 8 * max(self.leaf_count(), other.leaf_count()))
+        while True:
+            pairs, pp = _empty((cap, 2), np.uint32, mem, self.ctx.torch_device)
+            cnt = C.c_uint64(0)
+            st = self.ctx._lib.pb2_bvh_leaf_pairs(self.ctx.h, self.h, other.h, pp, cap, C.byref(cnt), mem)
+            if st == _ffi.PB2_ERR_OVERFLOW:
+                cap = int(cnt.value)
+                continue
+            self.ctx.check(st)
+            return pairs[: int(cnt.value)]
+
+    def cast_ray(self, shapes, shape_ids, poses, rays, max_time_of_impact, solid=True, with_normal=False):
+        """Batched Bvh::cast_ray with typed Ball/Cuboid leaves (bvh_queries.rs:260)."""
+        m = int(rays.shape[0])
+        kr, pr, mem = _prep(rays, np.float32)
+        ks, ps, _ = _prep(shape_ids, np.uint32, mem)
+        kp, pp, _ = _prep(poses, np.float32, mem)
+        dev = self.ctx.torch_device
+        toi, pt = _empty((m,), np.float32, mem, dev)
+        leaf, pl = _empty((m,), np.uint32, mem, dev)
+        normal = feature = None
+        pn = pf = None
+        if with_normal:
+            normal, pn = _empty((m, 3), np.float32, mem, dev)
+            feature, pf = _empty((m,), np.uint32, mem, dev)
+        self.ctx.check(self.ctx._lib.pb2_bvh_cast_rays_shapes(self.ctx.h, self.h, shapes.h, ps, pp, pr, m, float(max_time_of_impact),
+                                                             int(bool(solid)), pt, pl, pn, pf, mem))
+        return (toi, leaf, normal, feature) if with_normal else (toi, leaf)
+
+    def close(self):
+        if self.owned and self.h:
+            self.ctx._lib.pb2_bvh_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+NODE_HALF_FIELDS = [("mins", np.float32, (3,)), ("children", np.uint32), ("maxs", np.float32, (3,)), ("data", np.uint32)]
+NODE_WIDE_DTYPE = np.dtype([("left", np.dtype(NODE_HALF_FIELDS)), ("right", np.dtype(NODE_HALF_FIELDS))])
+assert NODE_WIDE_DTYPE.itemsize == 64
+
+
+class TriMesh:
+    """shape::TriMesh (vertices + indices + Bvh) with the RayCast impl (query/ray/ray_trimesh.rs)."""
+
+    def __init__(self, ctx, vertices, indices):
+        """TriMesh::new (shape/trimesh.rs:607)."""
+        self.ctx = ctx
+        kv, pv, mem = _prep(vertices, np.float32)
+        ki, pi, _ = _prep(indices, np.uint32, mem)
+        self.num_vertices = int(vertices.shape[0])
+        self.num_triangles = int(indices.shape[0])
+        h = C.c_void_p()
+        ctx.check(ctx._lib.pb2_trimesh_create(ctx.h, pv, self.num_vertices, pi, self.num_triangles, mem, C.byref(h)))
+        self.h = h
+
+    def bvh(self):
+        return Bvh(self.ctx, C.c_void_p(self.ctx._lib.pb2_trimesh_bvh(self.h)), owned=False, keep=self)
+
+    def _cast(self, pose, rays, max_toi, solid, with_normal, out=None):
+        m = int(rays.shape[0])
+        kr, pr, mem = _prep(rays, np.float32)
+        kp, pp, _ = _prep(pose, np.float32, mem)
+        dev = self.ctx.torch_device
+        if out is not None:
+            toi, tri = out[0], out[1]
+            pt = toi.data_ptr() if _is_torch(toi) else toi.ctypes.data
+            pl = tri.data_ptr() if _is_torch(tri) else tri.ctypes.data
+        else:
+            toi, pt = _empty((m,), np.float32, mem, dev)
+            tri, pl = _empty((m,), np.uint32, mem, dev)
+        normal = feature = None
+        pn = pf = None
+        if with_normal:
+            if out is not None and len(out) == 4:
+                normal, feature = out[2], out[3]
+                pn = normal.data_ptr() if _is_torch(normal) else normal.ctypes.data
+                pf = feature.data_ptr() if _is_torch(feature) else feature.ctypes.data
+            else:
+                normal, pn = _empty((m, 3), np.float32, mem, dev)
+                feature, pf = _empty((m,), np.uint32, mem, dev)
+        self.ctx.check(self.ctx._lib.pb2_trimesh_cast_rays(self.ctx.h, self.h, pp, pr, m, float(max_toi), int(bool(solid)),
+                                                          pt, pl, pn, pf, mem))
+        return (toi, tri, normal, feature) if with_normal else (toi, tri)
+
+    def cast_ray(self, m, rays, max_time_of_impact, solid=True, out=None):
+        """RayCast::cast_ray (ray.rs:381-390), batched: returns (toi, tri); tri == INVALID_U32 means None."""
+        return self._cast(m, rays, max_time_of_impact, solid, False, out)
+
+    def cast_ray_and_get_normal(self, m, rays, max_time_of_impact, solid=True, out=None):
+        """RayCast::cast_ray_and_get_normal (ray.rs:393-404): (toi, tri, normal, feature)."""
+        return self._cast(m, rays, max_time_of_impact, solid, True, out)
+
+    def cast_local_ray(self, rays, max_time_of_impact, solid=True, out=None):
+        return self._cast(None, rays, max_time_of_impact, solid, False, out)
+
+    def cast_local_ray_and_get_normal(self, rays, max_time_of_impact, solid=True, out=None):
+        return self._cast(None, rays, max_time_of_impact, solid, True, out)
+
+    def close(self):
+        if self.h:
+            self.ctx._lib.pb2_trimesh_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Ball:
+    """shape::Ball (shape/ball.rs:50)"""
+    kind = 0
+
+    def __init__(self, radius):
+        self.radius = float(radius)
+
+
+class Cuboid:
+    """shape::Cuboid (shape/cuboid.rs:69)"""
+    kind = 1
+
+    def __init__(self, half_extents):
+        self.half_extents = np.asarray(half_extents, dtype=np.float32)
+
+
+class ConvexPolyhedron:
+    """shape::ConvexPolyhedron — only `points()` matters on this path (shape/convex_polyhedron.rs:172-185)."""
+    kind = 2
+
+    def __init__(self, points):
+        self.points = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+
+
+class Shapes:
+    """A table of shapes living on the device; batches reference shapes by index (pb2_shapes)."""
+
+    def __init__(self, ctx, shapes):
+        self.ctx = ctx
+        n = len(shapes)
+        kinds = np.zeros(n, dtype=np.uint8)
+        params = np.zeros((n, 4), dtype=np.float32)
+        pu = params.view(np.uint32)
+        pts = []
+        npts = 0
+        for i, s in enumerate(shapes):
+            kinds[i] = s.kind
+            if s.kind == 0:
+                params[i, 0] = s.radius
+            elif s.kind == 1:
+                params[i, :3] = s.half_extents
+            else:
+                pu[i, 0] = npts
+                pu[i, 1] = len(s.points)
+                pts.append(s.points)
+                npts += len(s.points)
+        points = np.concatenate(pts, axis=0).astype(np.float32) if pts else np.zeros((0, 3), dtype=np.float32)
+        self.kinds, self.params, self.points = kinds, params, np.ascontiguousarray(points)
+        self.n = n
+        h = C.c_void_p()
+        ctx.check(ctx._lib.pb2_shapes_create(ctx.h, kinds.ctypes.data, params.ctypes.data, n,
+                                             self.points.ctypes.data if npts else None, npts, C.byref(h)))
+        self.h = h
+
+    def compute_aabbs(self, shape_ids, poses):
+        """Shape::compute_aabb(pos), batched (shape/shape.rs:369)."""
+        n = int(poses.shape[0])
+        kp, pp, mem = _prep(poses, np.float32)
+        ks, ps, _ = _prep(shape_ids, np.uint32, mem)
+        out, po = _empty((n, 6), np.float32, mem, self.ctx.torch_device)
+        self.ctx.check(self.ctx._lib.pb2_shapes_compute_aabbs(self.ctx.h, self.h, ps, pp, n, po, mem))
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx._lib.pb2_shapes_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+CONTACT_DTYPE = np.dtype([("point1", np.float32, (3,)), ("point2", np.float32, (3,)), ("normal1", np.float32, (3,)),
+                          ("normal2", np.float32, (3,)), ("dist", np.float32)])
+assert CONTACT_DTYPE.itemsize == 52
+
+
+def contact(shapes, shape1, pos1, shape2, pos2, prediction):
+    """query::contact(pos1, g1, pos2, g2, prediction), batched (contact_shape_shape.rs:123-138).
+    Returns (contacts (n, 13) f32 [point1, point2, normal1, normal2, dist], status (n,) u8: 0 None, 1 Some,
+    2 Unsupported)."""
+    ctx = shapes.ctx
+    n = int(pos1.shape[0])
+    k1, p1, mem = _prep(pos1, np.float32)
+    k2, p2, _ = _prep(pos2, np.float32, mem)
+    ks1, ps1, _ = _prep(shape1, np.uint32, mem)
+    ks2, ps2, _ = _prep(shape2, np.uint32, mem)
+    out, po = _empty((n, 13), np.float32, mem, ctx.torch_device)
+    status, pst = _empty((n,), np.uint8, mem, ctx.torch_device)
+    ctx.check(ctx._lib.pb2_contact_batch(ctx.h, shapes.h, ps1, ps2, p1, p2, float(prediction), n, po, pst, None, mem))
+    return out, status
+
+
+def contact_compact(shapes, shape1, pos1, shape2, pos2, prediction, capacity=None):
+    """Same query, compacted output: (contacts (count, 13), pair_index (count,))."""
+    ctx = shapes.ctx
+    n = int(pos1.shape[0])
+    k1, p1, mem = _prep(pos1, np.float32)
+    k2, p2, _ = _prep(pos2, np.float32, mem)
+    ks1, ps1, _ = _prep(shape1, np.uint32, mem)
+    ks2, ps2, _ = _prep(shape2, np.uint32, mem)
+    cap = int(capacity) if capacity is not None else n
+    out, po = _empty((cap, 13), np.float32, mem, ctx.torch_device)
+    idx, pi = _empty((cap,), np.uint32, mem, ctx.torch_device)
+    cnt = C.c_uint64(0)
+    ctx.check(ctx._lib.pb2_contact_batch_compact(ctx.h, shapes.h, ps1, ps2, p1, p2, float(prediction), n, po, pi, cap,
+                                                 C.byref(cnt), mem))
+    c = int(cnt.value)
+    return out[:c], idx[:c]
