@@ -221,3 +221,22 @@ def shape_cast_ray_toi(kind, params, pose, ray, max_toi, solid=True):
     hit = lib().pb2o_shape_cast_ray_toi(kind, p.ctypes.data, None if po is None else po.ctypes.data, r.ctypes.data, max_toi, int(solid),
                                         C.addressof(toi))
     return toi.value if hit else None
+
+
+_EXTRA.append(("pb2o_shape_aabbs", None, [P, P, P, P, P, P, u32, P]))
+
+
+def shape_aabbs(kinds, params, poses, points=None, first=None, count=None):
+    """Shape::compute_aabb(pos) per collider. params: (n,3); convex: points (np,3), first/count per collider."""
+    kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+    params = _f32(params).reshape(-1, 3)
+    poses = _f32(poses)
+    n = len(kinds)
+    out = np.zeros((n, 6), dtype=np.float32)
+    pts = None if points is None else _f32(points)
+    fi = None if first is None else _u32(first)
+    ct = None if count is None else _u32(count)
+    lib().pb2o_shape_aabbs(kinds.ctypes.data, params.ctypes.data, None if pts is None else pts.ctypes.data,
+                           None if fi is None else fi.ctypes.data, None if ct is None else ct.ctypes.data, poses.ctypes.data, n,
+                           out.ctypes.data)
+    return out

@@ -179,3 +179,25 @@ int pb2o_shape_cast_ray_toi(int kind, const float* p, const float* pose7, const 
 }
 
 }  // extern "C"
+
+// ---------------- per-shape AABBs (Shape::compute_aabb) ----------------
+extern "C" void pb2o_shape_aabbs(const uint8_t* kinds, const float* params /* n x 3 */, const float* points, const uint32_t* first,
+                                 const uint32_t* count, const float* poses7, uint32_t n, float* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        Iso pos = Iso::from7(poses7 + 7 * i);
+        Aabb a;
+        if (kinds[i] == 0) {  // aabb_ball.rs:8-33
+            Real r = params[3 * i];
+            a = Aabb(pos.tra + Vec3(-r, -r, -r), pos.tra + Vec3(r, r, r));
+        } else if (kinds[i] == 1) {  // aabb_cuboid.rs:9-16
+            Vec3 he = pos.absolute_transform_vector(ld3(params + 3 * i));
+            a = Aabb(pos.tra - he, pos.tra + he);
+        } else {  // aabb_convex_polyhedron.rs:8 -> aabb_utils.rs:66-87
+            const float* p = points + 3 * first[i];
+            Vec3 w0 = pos.transform_point(ld3(p));
+            a = Aabb(w0, w0);
+            for (uint32_t k = 1; k < count[i]; ++k) { Vec3 w = pos.transform_point(ld3(p + 3 * k)); a.mins = vinf(a.mins, w); a.maxs = vsup(a.maxs, w); }
+        }
+        st3(out + 6 * i, a.mins); st3(out + 6 * i + 3, a.maxs);
+    }
+}

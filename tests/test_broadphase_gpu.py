@@ -1,0 +1,241 @@
+"""GPU parity: Bvh build / refit / intersect_aabb / traverse_bvtt_single_tree / leaf_pairs and typed-leaf ray casts
+through the C ABI vs the CPU oracle. Pair and hit *sets* must be identical (order is tree-dependent in the reference too)."""
+import numpy as np
+import pytest
+
+from harness import scenes
+from helpers import INVALID, assert_well_formed, check_ray_parity, sorted_pairs
+
+pytestmark = pytest.mark.gpu
+FMAX = float(np.finfo(np.float32).max)
+
+
+def make_colliders(n, seed, side=None):
+    kinds, params, poses, _ = scenes.colliders(n, side=side, seed=seed)
+    return kinds, params, poses
+
+
+def make_shapes(ctx, kinds, params):
+    import parry_b200
+    shapes = [parry_b200.Ball(p[0]) if k == 0 else parry_b200.Cuboid(p) for k, p in zip(kinds, params)]
+    return parry_b200.Shapes(ctx, shapes)
+
+
+def brute_pairs(aabbs):
+    a = aabbs.astype(np.float64)
+    n = len(a)
+    out = []
+    for i in range(n):
+        m = ((a[i, 0] <= a[i + 1:, 3]) & (a[i, 1] <= a[i + 1:, 4]) & (a[i, 2] <= a[i + 1:, 5]) &
+             (a[i, 3] >= a[i + 1:, 0]) & (a[i, 4] >= a[i + 1:, 1]) & (a[i, 5] >= a[i + 1:, 2]))
+        j = np.nonzero(m)[0] + i + 1
+        out.append(np.stack([np.full(len(j), i), j], axis=1))
+    return np.concatenate(out) if out else np.zeros((0, 2), np.int64)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 7, 100, 1000])
+def test_build_well_formed_and_pairs_small(ctx, oracle, n):
+    import parry_b200
+    g0 = scenes.rng(200 + n)
+    c = g0.random((n, 3)) * max(1.0, n ** (1 / 3))
+    h = g0.random((n, 3)) * 0.5 + 0.1
+    aabbs = np.concatenate([c - h, c + h], axis=1).astype(np.float32)
+    gb = parry_b200.Bvh.from_leaves(ctx, parry_b200.BvhBuildStrategy.Binned, aabbs)
+    assert gb.leaf_count() == n
+    nodes, parents, leaf_idx = gb.download()
+    assert_well_formed(nodes, parents, leaf_idx)
+    ob = oracle.Bvh(aabbs)
+    gp = gb.traverse_bvtt_single_tree()
+    op = ob.self_pairs()
+    assert (sorted_pairs(gp) == sorted_pairs(op)).all()
+    assert (sorted_pairs(gp) == sorted_pairs(brute_pairs(aabbs))).all() if n > 1 else len(gp) == 0
+
+
+def test_shape_aabbs_bit_exact_and_pair_set(ctx, oracle):
+    import parry_b200
+    n = 20000
+    kinds, params, poses = make_colliders(n, seed=2)
+    shapes = make_shapes(ctx, kinds, params)
+    aabbs = shapes.compute_aabbs(np.arange(n, dtype=np.uint32), poses)
+    ref = oracle.shape_aabbs(kinds, params, poses)
+    assert (aabbs.view(np.uint32) == ref.view(np.uint32)).all()
+    gb = parry_b200.Bvh.from_leaves(ctx, 0, aabbs)
+    ob = oracle.Bvh(aabbs)
+    gp, op = gb.traverse_bvtt_single_tree(), ob.self_pairs()
+    assert len(gp) == len(op) > n
+    assert (sorted_pairs(gp) == sorted_pairs(op)).all()
+    assert (gp[:, 0] < gp[:, 1]).all()
+    # overflow is reported, not UB
+    with pytest.raises(parry_b200.Pb2Error):
+        import ctypes as C
+        cnt = C.c_uint64(0)
+        buf = np.zeros((10, 2), np.uint32)
+        ctx.check(ctx._lib.pb2_bvh_self_pairs(ctx.h, gb.h, 0, buf.ctypes.data, 10, C.byref(cnt), 0))
+    assert cnt.value == len(op)
+
+
+def test_intersect_aabb_batch(ctx, oracle):
+    import parry_b200
+    n = 30000
+    kinds, params, poses = make_colliders(n, seed=21)
+    shapes = make_shapes(ctx, kinds, params)
+    aabbs = shapes.compute_aabbs(None, poses) if False else shapes.compute_aabbs(np.arange(n, dtype=np.uint32), poses)
+    gb, ob = parry_b200.Bvh.from_leaves(ctx, 0, aabbs), oracle.Bvh(aabbs)
+    g0 = scenes.rng(22)
+    side = n ** (1 / 3)
+    c = g0.random((5000, 3)) * side
+    h = g0.random((5000, 3)) * 1.5
+    q = np.concatenate([c - h, c + h], axis=1).astype(np.float32)
+    q[0] = [-1e9, -1e9, -1e9, -1e8, -1e8, -1e8]  # empty result
+    goff, gids = gb.intersect_aabb(q)
+    ooff, oids = ob.intersect_aabbs(q, threads=8)
+    assert (goff == ooff).all()
+    for k in range(len(q)):
+        assert (np.sort(gids[goff[k]:goff[k + 1]]) == np.sort(oids[ooff[k]:ooff[k + 1]])).all()
+
+
+def test_update_refit_matches_rebuild_and_oracle(ctx, oracle):
+    """One broad-phase frame: insert_or_update_partially on every leaf + refit, then the full pair set."""
+    import parry_b200
+    n = 20000
+    kinds, params, poses = make_colliders(n, seed=23)
+    shapes = make_shapes(ctx, kinds, params)
+    ids = np.arange(n, dtype=np.uint32)
+    aabbs0 = shapes.compute_aabbs(ids, poses)
+    gb, ob = parry_b200.Bvh.from_leaves(ctx, 0, aabbs0), oracle.Bvh(aabbs0)
+    g0 = scenes.rng(24)
+    for frame in range(3):
+        poses = poses.copy()
+        poses[:, 4:] += (g0.random((n, 3)).astype(np.float32) - 0.5) * 0.2
+        aabbs = shapes.compute_aabbs(ids, poses)
+        gb.insert_or_update_partially(aabbs, ids, 0.0)
+        gb.refit()
+        ob.update_leaves(aabbs, ids, 0.0)
+        ob.refit()
+        nodes, parents, leaf_idx = gb.download()
+        assert_well_formed(nodes, parents, leaf_idx)
+        # root box identical to the oracle's (min/max are exact)
+        on = ob.nodes()
+        oroot = np.concatenate([np.minimum(on[0]["left"]["mins"], on[0]["right"]["mins"]), np.maximum(on[0]["left"]["maxs"], on[0]["right"]["maxs"])])
+        assert (gb.root_aabb() == oroot).all()
+        gp, op = gb.traverse_bvtt_single_tree(), ob.self_pairs()
+        assert (sorted_pairs(gp) == sorted_pairs(op)).all()
+    gb.rebuild()
+    nodes, parents, leaf_idx = gb.download()
+    assert_well_formed(nodes, parents, leaf_idx)
+    assert (sorted_pairs(gb.traverse_bvtt_single_tree()) == sorted_pairs(op)).all()
+
+
+def test_change_detection_pairs(ctx, oracle):
+    import parry_b200
+    n = 5000
+    kinds, params, poses = make_colliders(n, seed=25)
+    shapes = make_shapes(ctx, kinds, params)
+    ids = np.arange(n, dtype=np.uint32)
+    aabbs = shapes.compute_aabbs(ids, poses)
+    gb, ob = parry_b200.Bvh.from_leaves(ctx, 0, aabbs), oracle.Bvh(aabbs)
+    margin = 0.05
+    # frame 0: everything is flagged changed by construction
+    assert (sorted_pairs(gb.traverse_bvtt_single_tree(True)) == sorted_pairs(ob.self_pairs(True))).all()
+    g0 = scenes.rng(26)
+    for frame in range(3):
+        moved = g0.random(n) < 0.1
+        poses = poses.copy()
+        poses[moved, 4:] += (g0.random((int(moved.sum()), 3)).astype(np.float32) - 0.5) * 0.5
+        aabbs = shapes.compute_aabbs(ids, poses)
+        gb.insert_or_update_partially(aabbs, ids, margin)
+        gb.refit()
+        ob.update_leaves(aabbs, ids, margin)
+        ob.refit()
+        gp, op = gb.traverse_bvtt_single_tree(True), ob.self_pairs(True)
+        assert 0 < len(op) < len(ob.self_pairs(False))
+        assert (sorted_pairs(gp) == sorted_pairs(op)).all()
+        assert (sorted_pairs(gb.traverse_bvtt_single_tree(False)) == sorted_pairs(ob.self_pairs(False))).all()
+
+
+@pytest.mark.parametrize("na,nb", [(1, 1), (2, 2), (1, 2), (50, 1), (1, 50), (3000, 2500)])
+def test_leaf_pairs_two_trees(ctx, oracle, na, nb):
+    import parry_b200
+    g0 = scenes.rng(300 + na + nb)
+    def boxes(n):
+        c = g0.random((n, 3)) * 8.0
+        h = g0.random((n, 3)) * 0.6 + 0.05
+        return np.concatenate([c - h, c + h], axis=1).astype(np.float32)
+    a, b = boxes(na), boxes(nb)
+    ga, gb = parry_b200.Bvh.from_leaves(ctx, 0, a), parry_b200.Bvh.from_leaves(ctx, 0, b)
+    oa, ob = oracle.Bvh(a), oracle.Bvh(b)
+    gp, op = ga.leaf_pairs(gb), oa.leaf_pairs(ob)
+    def key(p):
+        p = np.asarray(p).astype(np.int64).reshape(-1, 2)
+        return np.sort(p[:, 0] * (1 << 32) + p[:, 1])
+    if na <= 2 and nb <= 2 or (na > 2 and nb > 2):
+        assert (key(gp) == key(op)).all()
+    else:
+        # the reference yields root-level leaf/leaf pairs unchecked (bvh_traverse_bvtt.rs:215-237), which depends on
+        # its tree topology; every checked pair must match and extras must be exactly such unchecked root pairs.
+        gk, ok = set(key(gp).tolist()), set(key(op).tolist())
+        assert gk <= ok and len(ok - gk) <= 2
+
+
+def test_bvh_cast_ray_ball_cuboid_leaves(ctx, oracle):
+    import parry_b200
+    n = 3000
+    kinds, params, poses = make_colliders(n, seed=27)
+    shapes = make_shapes(ctx, kinds, params)
+    ids = np.arange(n, dtype=np.uint32)
+    aabbs = shapes.compute_aabbs(ids, poses)
+    gb, ob = parry_b200.Bvh.from_leaves(ctx, 0, aabbs), oracle.Bvh(aabbs)
+    g0 = scenes.rng(28)
+    side = n ** (1 / 3)
+    o = g0.random((20000, 3)) * side
+    d = g0.standard_normal((20000, 3))
+    rays = np.concatenate([o, d], axis=1).astype(np.float32)
+    def adjudicate(g, r, max_toi, solid):
+        # toi is bit-exact everywhere; ids may differ only on exact ties (rays starting inside several overlapping
+        # solids all report toi == 0): the GPU then returns the smallest tied leaf id (documented rule).
+        assert (g[0].view(np.uint32) == r[0].view(np.uint32)).all()
+        diff = np.nonzero(g[1] != r[1])[0]
+        assert len(diff) < 0.1 * len(g[1])
+        for k in diff:
+            assert g[1][k] < r[1][k]
+            t = oracle.shape_cast_ray_toi(int(kinds[g[1][k]]), params[g[1][k]], poses[g[1][k]], rays[k], max_toi, solid)
+            assert t is not None and np.float32(t) == g[0][k]
+        return g[1] == r[1]
+
+    for solid in (True, False):
+        g = gb.cast_ray(shapes, ids, poses, rays, FMAX, solid=solid, with_normal=True)
+        r = ob.cast_rays_shapes(kinds, params, poses, rays, FMAX, solid=solid, with_normal=True, threads=8)
+        assert (r[1] != INVALID).mean() > 0.3
+        same = adjudicate(g, r, FMAX, solid)
+        np.testing.assert_allclose(g[2][same], r[2][same], rtol=1e-5, atol=1e-7)
+        assert (g[3][same] == r[3][same]).all()
+        g2 = gb.cast_ray(shapes, ids, poses, rays, 2.0, solid=solid)
+        r2 = ob.cast_rays_shapes(kinds, params, poses, rays, 2.0, solid=solid, threads=8)
+        adjudicate(g2, r2, 2.0, solid)
+
+
+def test_full_size_config2_frame(ctx):
+    """BASELINE config[1]: 2^20 dynamic AABBs. Properties at full size: the pair set equals the sort-and-sweep
+    brute force on a spatial slab, no duplicates, and refit after a no-op update is idempotent."""
+    import parry_b200
+    n = 1 << 20
+    kinds, params, poses = make_colliders(n, seed=2)
+    shapes = make_shapes(ctx, kinds, params)
+    ids = np.arange(n, dtype=np.uint32)
+    aabbs = shapes.compute_aabbs(ids, poses)
+    gb = parry_b200.Bvh.from_leaves(ctx, 0, aabbs)
+    p1 = gb.traverse_bvtt_single_tree()
+    k1 = sorted_pairs(p1)
+    assert len(np.unique(k1)) == len(k1)
+    gb.insert_or_update_partially(aabbs, ids, 0.0)
+    gb.refit()
+    k2 = sorted_pairs(gb.traverse_bvtt_single_tree())
+    assert (k1 == k2).all()
+    # brute force inside a slab
+    sel = np.nonzero(aabbs[:, 3] < 4.0)[0]
+    bp = brute_pairs(aabbs[sel])
+    bk = sorted_pairs(np.stack([sel[bp[:, 0]], sel[bp[:, 1]]], axis=1))
+    insel = np.zeros(n, bool)
+    insel[sel] = True
+    mask = insel[p1[:, 0]] & insel[p1[:, 1]]
+    assert (sorted_pairs(p1[mask]) == bk).all()
