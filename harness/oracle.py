@@ -240,3 +240,61 @@ def shape_aabbs(kinds, params, poses, points=None, first=None, count=None):
                            None if fi is None else fi.ctypes.data, None if ct is None else ct.ctypes.data, poses.ctypes.data, n,
                            out.ctypes.data)
     return out
+
+
+# ---------------------------------------------------------------- query::contact
+_EXTRA.append(("pb2o_contact_batch", None, [P, P, P, P, P, P, P, f32, u32, i32, P, P, P]))
+_EXTRA.append(("pb2o_dispatch_contact", i32, [P, P, P, u32, u32, P, f32, P]))
+_EXTRA.append(("pb2o_gjk_closest_points", i32, [P, P, P, u32, u32, P, f32, P]))
+
+
+class ShapeTable:
+    """Same table layout as pb2_shapes_create: kinds[n], params[n,4], points[np,3]. shapes: list of ('ball', r) /
+    ('cuboid', he) / ('convex', pts)."""
+
+    def __init__(self, shapes):
+        n = len(shapes)
+        self.kinds = np.zeros(n, dtype=np.uint8)
+        self.params = np.zeros((n, 4), dtype=np.float32)
+        pu = self.params.view(np.uint32)
+        pts, npts = [], 0
+        for i, (k, v) in enumerate(shapes):
+            if k == "ball":
+                self.kinds[i] = 0
+                self.params[i, 0] = v
+            elif k == "cuboid":
+                self.kinds[i] = 1
+                self.params[i, :3] = v
+            else:
+                self.kinds[i] = 2
+                p = np.ascontiguousarray(v, dtype=np.float32).reshape(-1, 3)
+                pu[i, 0], pu[i, 1] = npts, len(p)
+                pts.append(p)
+                npts += len(p)
+        self.points = np.ascontiguousarray(np.concatenate(pts) if pts else np.zeros((1, 3), np.float32), dtype=np.float32)
+
+    def contact(self, shape1, pos1, shape2, pos2, prediction, threads=1, with_stats=False):
+        s1, s2, p1, p2 = _u32(shape1), _u32(shape2), _f32(pos1), _f32(pos2)
+        n = len(s1)
+        out = np.zeros((n, 13), dtype=np.float32)
+        status = np.zeros(n, dtype=np.uint8)
+        stats = np.zeros((n, 6), dtype=np.int32) if with_stats else None
+        lib().pb2o_contact_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, s1.ctypes.data, s2.ctypes.data,
+                                 p1.ctypes.data, p2.ctypes.data, prediction, n, threads, out.ctypes.data, status.ctypes.data,
+                                 None if stats is None else stats.ctypes.data)
+        return (out, status, stats) if with_stats else (out, status)
+
+    def dispatch_contact(self, s1, s2, pos12, prediction):
+        """DefaultQueryDispatcher::contact(pos12, g1, g2, prediction): (status, contact[13]) in local frames."""
+        out = np.zeros(13, dtype=np.float32)
+        p = _f32(pos12)
+        st = lib().pb2o_dispatch_contact(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, s1, s2, p.ctypes.data,
+                                         prediction, out.ctypes.data)
+        return st, out
+
+    def gjk_closest_points(self, s1, s2, pos12, max_dist):
+        out = np.zeros(9, dtype=np.float32)
+        p = _f32(pos12)
+        kind = lib().pb2o_gjk_closest_points(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, s1, s2, p.ctypes.data,
+                                             max_dist, out.ctypes.data)
+        return kind, out

@@ -201,3 +201,61 @@ extern "C" void pb2o_shape_aabbs(const uint8_t* kinds, const float* params /* n 
         st3(out + 6 * i, a.mins); st3(out + 6 * i + 3, a.maxs);
     }
 }
+
+// ---------------- query::contact ----------------
+#include "contact.hpp"
+
+static inline ShapeRef make_shape(const uint8_t* kinds, const float* params4, const float* points, uint32_t id) {
+    ShapeRef s; s.kind = kinds[id]; s.radius = params4[4 * id]; s.half_extents = ld3(params4 + 4 * id); s.points = nullptr; s.num_points = 0;
+    if (s.kind == SHAPE_CONVEX) {
+        uint32_t first, cnt; memcpy(&first, params4 + 4 * id, 4); memcpy(&cnt, params4 + 4 * id + 1, 4);
+        s.points = points + 3 * first; s.num_points = cnt;
+    }
+    return s;
+}
+
+extern "C" {
+// query::contact for n pairs. Shape table layout == pb2_shapes_create's. out: n x 13 floats; status: 0/1/2/3.
+// stats (optional, n x 6 ints): gjk iters, used_epa, epa iters, max faces, max vertices, max heap.
+void pb2o_contact_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* shape1, const uint32_t* shape2,
+                        const float* pos1, const float* pos2, float prediction, uint32_t n, int nthreads, float* out, uint8_t* status, int32_t* stats) {
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            ShapeRef s1 = make_shape(kinds, params4, points, shape1[k]), s2 = make_shape(kinds, params4, points, shape2[k]);
+            Contact c; memset(&c, 0, sizeof(c));
+            GjkEpaStats gs;
+            int st = query_contact(Iso::from7(pos1 + 7 * k), s1, Iso::from7(pos2 + 7 * k), s2, prediction, c, &gs);
+            status[k] = (uint8_t)st;
+            float* o = out + 13 * k;
+            if (st == CONTACT_SOME) { st3(o, c.point1); st3(o + 3, c.point2); st3(o + 6, c.normal1); st3(o + 9, c.normal2); o[12] = c.dist; }
+            else for (int i = 0; i < 13; ++i) o[i] = 0.0f;
+            if (stats) {
+                int32_t* s = stats + 6 * k;
+                s[0] = gs.gjk_iters; s[1] = gs.used_epa; s[2] = gs.epa.niter; s[3] = (int32_t)gs.epa.max_faces; s[4] = (int32_t)gs.epa.max_vertices; s[5] = (int32_t)gs.epa.max_heap;
+            }
+        }
+    });
+}
+// DefaultQueryDispatcher::contact(pos12, ...) — results in the local frames of shape 1 / shape 2.
+int pb2o_dispatch_contact(const uint8_t* kinds, const float* params4, const float* points, uint32_t s1, uint32_t s2, const float* pos12, float prediction, float* out13) {
+    ShapeRef a = make_shape(kinds, params4, points, s1), b = make_shape(kinds, params4, points, s2);
+    Contact c; memset(&c, 0, sizeof(c));
+    int st = dispatch_contact(Iso::from7(pos12), a, b, prediction, c);
+    if (st == CONTACT_SOME) { st3(out13, c.point1); st3(out13 + 3, c.point2); st3(out13 + 6, c.normal1); st3(out13 + 9, c.normal2); out13[12] = c.dist; }
+    return st;
+}
+// gjk::closest_points between two support shapes (epa3.rs tests use the ClosestPoints query); returns GJKResult kind,
+// out = p1, p2 (both in shape-1 space), dir.
+int pb2o_gjk_closest_points(const uint8_t* kinds, const float* params4, const float* points, uint32_t s1, uint32_t s2, const float* pos12, float max_dist, float* out9) {
+    ShapeRef a = make_shape(kinds, params4, points, s1), b = make_shape(kinds, params4, points, s2);
+    Iso p = Iso::from7(pos12);
+    VoronoiSimplex simplex;
+    Vec3 dir;
+    if (!try_normalize(p.tra, DEFAULT_EPSILON, dir)) dir = Vec3(1, 0, 0);
+    SupportShape g1 = a.support(), g2 = b.support();
+    simplex.reset(CSOPoint::from_shapes(p, g1, g2, dir));
+    GJKResult r = gjk_closest_points(p, g1, g2, max_dist, simplex);
+    st3(out9, r.p1); st3(out9 + 3, r.p2); st3(out9 + 6, r.dir);
+    return (int)r.kind;
+}
+}

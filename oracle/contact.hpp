@@ -1,0 +1,194 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see math.hpp header).
+// Restatement of parry3d src/query/contact/{contact_shape_shape,contact_ball_ball,contact_ball_convex_polyhedron,
+// contact_support_map_support_map}.rs, DefaultQueryDispatcher::contact (default_query_dispatcher.rs:302-356),
+// src/query/point/{point_aabb,point_cuboid,point_support_map}.rs and Cuboid::feature_normal (shape/cuboid.rs:401-448).
+#pragma once
+#include "epa.hpp"
+
+namespace pb2o {
+
+struct Contact { Vec3 point1, point2, normal1, normal2; Real dist; };
+
+enum ShapeKind { SHAPE_BALL = 0, SHAPE_CUBOID = 1, SHAPE_CONVEX = 2 };
+struct ShapeRef {
+    int kind;
+    Real radius;
+    Vec3 half_extents;
+    const float* points;
+    uint32_t num_points;
+    SupportShape support() const { return kind == SHAPE_CUBOID ? SupportShape::cuboid(half_extents) : SupportShape::convex(points, num_points); }
+};
+
+enum ContactStatus { CONTACT_NONE = 0, CONTACT_SOME = 1, CONTACT_UNSUPPORTED = 2, CONTACT_NEEDS_TOPOLOGY = 3 };
+
+// contact_ball_ball.rs:9-42
+static inline bool contact_ball_ball(const Iso& pos12, Real r1, Real r2, Real prediction, Contact& c) {
+    Vec3 center2_1 = pos12.tra;
+    Real d2 = norm_squared(center2_1);
+    Real sum_radius = r1 + r2;
+    Real sre = sum_radius + prediction;
+    if (d2 < sre * sre) {
+        Vec3 normal1 = d2 != 0.0f ? normalize(center2_1) : Vec3(1, 0, 0);
+        Vec3 normal2 = -pos12.inverse_transform_vector(normal1);
+        c.point1 = normal1 * r1; c.point2 = normal2 * r2; c.normal1 = normal1; c.normal2 = normal2;
+        c.dist = sqrtf(d2) - sum_radius;
+        return true;
+    }
+    return false;
+}
+
+// FeatureId on a cuboid: kind 0 vertex, 1 edge, 2 face, 3 unknown
+struct Feature { int kind; uint32_t id; };
+
+// point_aabb.rs:9-132 on [-he, he] (point_cuboid.rs:6-37): project_local_point_and_get_feature (solid = false)
+static inline void cuboid_project_point_and_get_feature(const Vec3& he, const Vec3& pt, Vec3& proj, bool& inside, Feature& feat) {
+    Vec3 mins = -he, maxs = he;
+    Vec3 mins_pt = mins - pt, pt_maxs = pt - maxs;
+    Vec3 zero;
+    Vec3 shift = vsup(mins_pt, zero) - vsup(pt_maxs, zero);
+    inside = shift.x == 0.0f && shift.y == 0.0f && shift.z == 0.0f;
+    if (!inside) { proj = pt + shift; }
+    else {
+        Real best = -REAL_MAX; bool is_mins = false; int best_id = 0;
+        for (int i = 0; i < 3; ++i) {
+            Real a = mins_pt[i], b = pt_maxs[i];
+            if (a < b) { if (b > best) { best_id = i; is_mins = false; best = b; } }
+            else if (a > best) { best_id = i; is_mins = true; best = a; }
+        }
+        shift = Vec3();
+        shift[best_id] = is_mins ? best : -best;
+        proj = pt + shift;
+    }
+    int nzero = 0, last_zero = 0, last_not_zero = 0;
+    for (int i = 0; i < 3; ++i) { if (shift[i] == 0.0f) { nzero++; last_zero = i; } else last_not_zero = i; }
+    Vec3 ctr = center(mins, maxs);
+    if (nzero == 3) {
+        for (int i = 0; i < 3; ++i) {
+            if (proj[i] > maxs[i] - DEFAULT_EPSILON) { feat = Feature{2, (uint32_t)i}; return; }
+            if (proj[i] <= mins[i] + DEFAULT_EPSILON) { feat = Feature{2, (uint32_t)(i + 3)}; return; }
+        }
+        feat = Feature{3, 0};
+    } else if (nzero == 2) {
+        feat = proj[last_not_zero] < ctr[last_not_zero] ? Feature{2, (uint32_t)(last_not_zero + 3)} : Feature{2, (uint32_t)last_not_zero};
+    } else {
+        uint32_t id = 0;
+        for (int i = 0; i < 3; ++i) if (proj[i] < ctr[i]) id |= 1u << i;
+        feat = nzero == 0 ? Feature{0, id} : Feature{1, (id << 2) | (uint32_t)last_zero};
+    }
+}
+// cuboid.rs:401-448
+static inline bool cuboid_feature_normal(const Feature& f, Vec3& n) {
+    Vec3 dir;
+    if (f.kind == 2) { if (f.id < 3) dir[f.id] = 1.0f; else dir[f.id - 3] = -1.0f; n = dir; return true; }
+    if (f.kind == 1) {
+        uint32_t edge = f.id & 3u, face1 = (edge + 1) % 3, face2 = (edge + 2) % 3, signs = f.id >> 2;
+        dir[face1] = (signs & (1u << face1)) ? -1.0f : 1.0f;
+        dir[face2] = (signs & (1u << face2)) ? -1.0f : 1.0f;
+        n = normalize(dir); return true;
+    }
+    if (f.kind == 0) {
+        for (int i = 0; i < 3; ++i) dir[i] = (f.id & (1u << i)) ? -1.0f : 1.0f;
+        n = normalize(dir); return true;
+    }
+    return false;
+}
+
+// point_support_map.rs:17-52 local_point_projection_on_support_map(shape, simplex, point, solid = false)
+static inline void hull_project_point(const SupportShape& shape, const Vec3& point, Vec3& proj, bool& inside) {
+    Iso m(Quat(), -point), m_inv(Quat(), point);
+    Vec3 dir;
+    if (!try_normalize(-m.tra, DEFAULT_EPSILON, dir)) dir = Vec3(1, 0, 0);
+    SupportShape origin = SupportShape::constant_origin();
+    VoronoiSimplex simplex;
+    simplex.reset(CSOPoint::from_shapes(m_inv, shape, origin, dir));
+    // gjk::project_origin(&m, shape, simplex) (gjk.rs:306-324)
+    Iso minv = m.inverse();
+    GJKResult r = gjk_closest_points(minv, shape, origin, REAL_MAX, simplex);
+    if (r.kind == GJKResult::CLOSEST_POINTS) { proj = r.p1; inside = false; return; }
+    assert(r.kind == GJKResult::INTERSECTION);
+    EPA epa;
+    Vec3 p1, p2, n;
+    if (epa.closest_points(minv, shape, origin, simplex, p1, p2, n)) { proj = p1; inside = true; return; }
+    proj = point; inside = true;
+}
+
+// contact_ball_convex_polyhedron.rs:26-63
+static inline int contact_convex_polyhedron_ball(const Iso& pos12, const ShapeRef& shape1, Real radius2, Real prediction, Contact& c) {
+    Vec3 center2_1 = pos12.tra;
+    Vec3 proj; bool inside; Feature f1{3, 0};
+    if (shape1.kind == SHAPE_CUBOID) cuboid_project_point_and_get_feature(shape1.half_extents, center2_1, proj, inside, f1);
+    else hull_project_point(shape1.support(), center2_1, proj, inside);
+    Real dist; Vec3 normal1, dir1; Real len;
+    if (try_normalize_and_get(proj - center2_1, DEFAULT_EPSILON, dir1, len)) {
+        if (inside) { dist = -len - radius2; normal1 = dir1; }
+        else { dist = len - radius2; normal1 = -dir1; }
+    } else {
+        dist = -radius2;
+        if (shape1.kind != SHAPE_CUBOID) return CONTACT_NEEDS_TOPOLOGY;  // ConvexPolyhedron::feature_normal needs the hull topology
+        if (!cuboid_feature_normal(f1, normal1)) {
+            if (!try_normalize(proj, DEFAULT_EPSILON, normal1)) normal1 = Vec3(0, 1, 0);
+        }
+    }
+    if (dist <= prediction) {
+        Vec3 normal2 = pos12.inverse_transform_vector(-normal1);
+        c.point2 = normal2 * radius2; c.point1 = proj; c.normal1 = normal1; c.normal2 = normal2; c.dist = dist;
+        return CONTACT_SOME;
+    }
+    return CONTACT_NONE;
+}
+// contact_ball_convex_polyhedron.rs:12-20
+static inline int contact_ball_convex_polyhedron(const Iso& pos12, Real radius1, const ShapeRef& shape2, Real prediction, Contact& c) {
+    int st = contact_convex_polyhedron_ball(pos12.inverse(), shape2, radius1, prediction, c);
+    if (st == CONTACT_SOME) { std::swap(c.point1, c.point2); std::swap(c.normal1, c.normal2); }
+    return st;
+}
+
+struct GjkEpaStats { int gjk_iters = 0; bool used_epa = false; EpaStats epa; };
+
+// contact_support_map_support_map.rs:10-77
+static inline int contact_support_map_support_map(const Iso& pos12, const SupportShape& g1, const SupportShape& g2, Real prediction, Contact& c,
+                                                  GjkEpaStats* stats = nullptr) {
+    VoronoiSimplex simplex;
+    Vec3 dir;
+    if (!try_normalize(pos12.tra, DEFAULT_EPSILON, dir)) dir = Vec3(1, 0, 0);
+    simplex.reset(CSOPoint::from_shapes(pos12, g1, g2, dir));
+    GJKResult r = gjk_closest_points(pos12, g1, g2, prediction, simplex);
+    if (stats) stats->gjk_iters = r.niter;
+    Vec3 p1, p2_1, n1;
+    if (r.kind == GJKResult::INTERSECTION) {
+        EPA epa;
+        bool ok = epa.closest_points(pos12, g1, g2, simplex, p1, p2_1, n1);
+        if (stats) { stats->used_epa = true; stats->epa = epa.stats; }
+        if (!ok) return CONTACT_NONE;  // "Everything failed" => NoIntersection => None
+    } else if (r.kind == GJKResult::CLOSEST_POINTS) { p1 = r.p1; p2_1 = r.p2; n1 = r.dir; }
+    else return CONTACT_NONE;
+    c.dist = dot(p2_1 - p1, n1);
+    c.point1 = p1;
+    c.point2 = pos12.inverse_transform_point(p2_1);
+    c.normal1 = n1;
+    c.normal2 = pos12.inverse_transform_vector(-n1);
+    return CONTACT_SOME;
+}
+
+// DefaultQueryDispatcher::contact (default_query_dispatcher.rs:302-356), shapes restricted to Ball/Cuboid/ConvexPolyhedron
+static inline int dispatch_contact(const Iso& pos12, const ShapeRef& s1, const ShapeRef& s2, Real prediction, Contact& c, GjkEpaStats* stats = nullptr) {
+    if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_BALL) return contact_ball_ball(pos12, s1.radius, s2.radius, prediction, c) ? CONTACT_SOME : CONTACT_NONE;
+    if (s1.kind == SHAPE_BALL) return contact_ball_convex_polyhedron(pos12, s1.radius, s2, prediction, c);
+    if (s2.kind == SHAPE_BALL) return contact_convex_polyhedron_ball(pos12, s1, s2.radius, prediction, c);
+    return contact_support_map_support_map(pos12, s1.support(), s2.support(), prediction, c, stats);
+}
+
+// query::contact (contact_shape_shape.rs:123-138)
+static inline int query_contact(const Iso& pos1, const ShapeRef& g1, const Iso& pos2, const ShapeRef& g2, Real prediction, Contact& c, GjkEpaStats* stats = nullptr) {
+    Iso pos12 = pos1.inv_mul(pos2);
+    int st = dispatch_contact(pos12, g1, g2, prediction, c, stats);
+    if (st == CONTACT_SOME) {  // Contact::transform_by_mut (contact.rs:171)
+        c.point1 = pos1.transform_point(c.point1);
+        c.point2 = pos2.transform_point(c.point2);
+        c.normal1 = pos1.transform_vector(c.normal1);
+        c.normal2 = pos2.transform_vector(c.normal2);
+    }
+    return st;
+}
+
+}  // namespace pb2o

@@ -1,15 +1,693 @@
-// parry_b200 — query::contact batch (placeholder until the GJK/EPA kernels land).
-#include "shapes.cuh"
+// parry_b200 — batched query::contact.
+//
+// Replaces (reference, file:line): query::contact (query/contact/contact_shape_shape.rs:123-138), Contact (contact.rs:71-105,
+// flip :156, transform_by_mut :171), DefaultQueryDispatcher::contact (query/default_query_dispatcher.rs:302-356),
+// contact_ball_ball (contact_ball_ball.rs:9-42), contact_ball_convex_polyhedron / contact_convex_polyhedron_ball
+// (contact_ball_convex_polyhedron.rs:12-63) with Cuboid point projection (query/point/point_aabb.rs:9-132, point_cuboid.rs,
+// shape/cuboid.rs:401-448) and ConvexPolyhedron point projection (query/point/point_support_map.rs:17-77),
+// contact_support_map_support_map (contact_support_map_support_map.rs:10-77), EPA (query/epa/epa3.rs:18-675) with the
+// sift rules of Rust's BinaryHeap, ccw_face_normal (utils/ccw_face_normal.rs:21-27), Triangle::is_affinely_dependent
+// (shape/triangle.rs:534-540).
+//
+// B200 design: phase 1 (k_contact_gjk) runs one pair per thread: pose composition, dispatch, the closed forms and the
+// GJK loop; pairs whose GJK ends in `Intersection` park their simplex in a compact queue (warp-aggregated append).
+// Phase 2 (k_contact_epa) is a persistent grid that pulls queued pairs and runs the expanding polytope with a bounded
+// per-thread arena (vertices / faces / heap) so that divergence of the rare, long EPA runs does not stall the
+// closed-form and separated pairs. Contacts are written either densely (status per pair) or compacted.
+#include "gjk.cuh"
+
+int pb2_stage_in(pb2_ctx* ctx, int slot, const void* src, size_t bytes, int mem, const void** out);
+int pb2_stage_out(pb2_ctx* ctx, int slot, void* dst, size_t bytes, int mem, void** out);
+int pb2_stage_back(pb2_ctx* ctx, void* dst, const void* dev, size_t bytes, int mem);
+
+enum { ST_NONE = 0, ST_SOME = 1, ST_UNSUPPORTED = 2, ST_NEEDS_HOST = 3 };
+
+#define EPA_MAX_VERTS 112   // 4 (simplex) + <= 102 expansions
+#define EPA_MAX_FACES 320
+#define EPA_MAX_SIL 64
+#define EPA_STACK 96
+
+struct ContactOut {
+    V3 p1, p2, n1, n2;
+    float dist;
+};
+
+struct EpaJob {
+    uint32_t pair;
+    uint32_t dim;
+    float o1[4][3];
+    float o2[4][3];
+};
+
+// ------------------------------------------------------------------------------------------- closed forms
+// contact_ball_ball.rs:9-42
+__device__ __forceinline__ bool d_contact_ball_ball(const Iso7& pos12, float r1, float r2, float prediction, ContactOut& c) {
+    V3 center2_1 = pos12.t;
+    float d2 = nrm2(center2_1);
+    float sum_radius = r1 + r2;
+    float sre = sum_radius + prediction;
+    if (d2 < sre * sre) {
+        V3 normal1 = d2 != 0.0f ? normalize3(center2_1) : mk3(1.f, 0.f, 0.f);
+        V3 normal2 = -iso_inv_vec(pos12, normal1);
+        c.p1 = normal1 * r1; c.p2 = normal2 * r2; c.n1 = normal1; c.n2 = normal2;
+        c.dist = sqrtf(d2) - sum_radius;
+        return true;
+    }
+    return false;
+}
+
+struct Feat { int kind; uint32_t id; };  // 0 vertex 1 edge 2 face 3 unknown
+__device__ __forceinline__ void setc(V3& v, int i, float x) { if (i == 0) v.x = x; else if (i == 1) v.y = x; else v.z = x; }
+
+// point_aabb.rs:9-132 on [-he, he]
+__device__ __forceinline__ void d_cuboid_project(V3 he, V3 pt, V3& proj, bool& inside, Feat& feat) {
+    V3 mins = -he, maxs = he;
+    V3 mins_pt = mins - pt, pt_maxs = pt - maxs;
+    V3 zero = mk3(0.f, 0.f, 0.f);
+    V3 shift = vmax3(mins_pt, zero) - vmax3(pt_maxs, zero);
+    inside = shift.x == 0.0f && shift.y == 0.0f && shift.z == 0.0f;
+    if (!inside) proj = pt + shift;
+    else {
+        float best = -FLT_MAX; bool is_mins = false; int best_id = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float a = comp(mins_pt, i), b = comp(pt_maxs, i);
+            if (a < b) { if (b > best) { best_id = i; is_mins = false; best = b; } }
+            else if (a > best) { best_id = i; is_mins = true; best = a; }
+        }
+        shift = zero;
+        setc(shift, best_id, is_mins ? best : -best);
+        proj = pt + shift;
+    }
+    int nzero = 0, last_zero = 0, last_not_zero = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { if (comp(shift, i) == 0.0f) { nzero++; last_zero = i; } else last_not_zero = i; }
+    V3 ctr = (mins + maxs) * 0.5f;
+    if (nzero == 3) {
+        feat.kind = 3; feat.id = 0;
+        for (int i = 0; i < 3; ++i) {
+            if (comp(proj, i) > comp(maxs, i) - PB2_EPS) { feat.kind = 2; feat.id = (uint32_t)i; return; }
+            if (comp(proj, i) <= comp(mins, i) + PB2_EPS) { feat.kind = 2; feat.id = (uint32_t)(i + 3); return; }
+        }
+    } else if (nzero == 2) {
+        feat.kind = 2;
+        feat.id = comp(proj, last_not_zero) < comp(ctr, last_not_zero) ? (uint32_t)(last_not_zero + 3) : (uint32_t)last_not_zero;
+    } else {
+        uint32_t id = 0;
+        for (int i = 0; i < 3; ++i) if (comp(proj, i) < comp(ctr, i)) id |= 1u << i;
+        if (nzero == 0) { feat.kind = 0; feat.id = id; } else { feat.kind = 1; feat.id = (id << 2) | (uint32_t)last_zero; }
+    }
+}
+// cuboid.rs:401-448
+__device__ __forceinline__ bool d_cuboid_feature_normal(Feat f, V3& n) {
+    V3 dir = mk3(0.f, 0.f, 0.f);
+    if (f.kind == 2) { if (f.id < 3) setc(dir, (int)f.id, 1.0f); else setc(dir, (int)f.id - 3, -1.0f); n = dir; return true; }
+    if (f.kind == 1) {
+        uint32_t edge = f.id & 3u, face1 = (edge + 1) % 3, face2 = (edge + 2) % 3, signs = f.id >> 2;
+        setc(dir, (int)face1, (signs & (1u << face1)) ? -1.0f : 1.0f);
+        setc(dir, (int)face2, (signs & (1u << face2)) ? -1.0f : 1.0f);
+        n = normalize3(dir); return true;
+    }
+    if (f.kind == 0) {
+        for (int i = 0; i < 3; ++i) setc(dir, i, (f.id & (1u << i)) ? -1.0f : 1.0f);
+        n = normalize3(dir); return true;
+    }
+    return false;
+}
+
+// Tail of contact_convex_polyhedron_ball (contact_ball_convex_polyhedron.rs:34-62) once the projection is known.
+__device__ __forceinline__ int d_convex_ball_finish(const Iso7& pos12, bool is_cuboid, Feat f1, V3 proj, bool inside, float radius2,
+                                                    float prediction, ContactOut& c) {
+    V3 center2_1 = pos12.t;
+    float dist; V3 normal1, dir1; float len;
+    if (try_normalize_get(proj - center2_1, PB2_EPS, dir1, len)) {
+        if (inside) { dist = -len - radius2; normal1 = dir1; }
+        else { dist = len - radius2; normal1 = -dir1; }
+    } else {
+        dist = -radius2;
+        if (!is_cuboid) return ST_NEEDS_HOST;  // ConvexPolyhedron::feature_normal_at_point needs the hull topology
+        if (!d_cuboid_feature_normal(f1, normal1)) {
+            float n;
+            if (!try_normalize_get(proj, PB2_EPS, normal1, n)) normal1 = mk3(0.f, 1.f, 0.f);
+        }
+    }
+    if (dist <= prediction) {
+        V3 normal2 = iso_inv_vec(pos12, -normal1);
+        c.p2 = normal2 * radius2; c.p1 = proj; c.n1 = normal1; c.n2 = normal2; c.dist = dist;
+        return ST_SOME;
+    }
+    return ST_NONE;
+}
+
+__device__ __forceinline__ void flip_contact(ContactOut& c) {
+    V3 t = c.p1; c.p1 = c.p2; c.p2 = t;
+    t = c.n1; c.n1 = c.n2; c.n2 = t;
+}
+
+__device__ __forceinline__ DShape make_dshape(uint8_t kind, float4 pr, const float4* pts) {
+    DShape s;
+    s.kind = kind == PB2_SHAPE_CUBOID ? DS_CUBOID : DS_CONVEX;
+    s.he = mk3(pr.x, pr.y, pr.z);
+    s.pts = pts + __float_as_uint(pr.x);
+    s.n = __float_as_uint(pr.y);
+    return s;
+}
+__device__ __forceinline__ DShape origin_dshape() { DShape s; s.kind = DS_ORIGIN; s.he = mk3(0.f, 0.f, 0.f); s.pts = nullptr; s.n = 0; return s; }
+
+// Per-pair setup shared by both phases: everything is recomputed from the inputs with identical arithmetic, so the
+// EPA phase only needs the parked simplex.
+struct PairSetup {
+    Iso7 pos1, pos2, pos12;
+    uint8_t k1, k2;
+    float4 pr1, pr2;
+    // GJK problem (when mode != 0): gpos12, g1, g2
+    int mode;  // 0 closed form / nothing, 1 support-map pair, 2 convex(shape1)-ball(shape2), 3 ball(shape1)-convex(shape2)
+    Iso7 gpos12;
+    Iso7 cb_pos12;  // pos12 seen by contact_convex_polyhedron_ball (mode 2: pos12, mode 3: pos12.inverse())
+    DShape g1, g2;
+};
+
+__device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* params, const float4* pts, const uint32_t* shape1,
+                                           const uint32_t* shape2, const float* pos1, const float* pos2, uint32_t k, PairSetup& ps) {
+    uint32_t s1 = shape1[k], s2 = shape2[k];
+    ps.k1 = kinds[s1]; ps.k2 = kinds[s2];
+    ps.pr1 = params[s1]; ps.pr2 = params[s2];
+    ps.pos1 = load_iso(pos1 + 7ull * k);
+    ps.pos2 = load_iso(pos2 + 7ull * k);
+    ps.pos12 = iso_inv_mul(ps.pos1, ps.pos2);  // contact_shape_shape.rs:130
+    ps.mode = 0;
+    bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
+    if (!b1 && !b2) {
+        ps.mode = 1;
+        ps.gpos12 = ps.pos12;
+        ps.g1 = make_dshape(ps.k1, ps.pr1, pts);
+        ps.g2 = make_dshape(ps.k2, ps.pr2, pts);
+    } else if (b1 != b2) {
+        bool convex_first = b2;
+        ps.cb_pos12 = convex_first ? ps.pos12 : iso_inverse(ps.pos12);
+        uint8_t kc = convex_first ? ps.k1 : ps.k2;
+        if (kc == PB2_SHAPE_CONVEX) {
+            ps.mode = convex_first ? 2 : 3;
+            // local_point_projection_on_support_map (point_support_map.rs:17-33): m = Isometry(-point), gjk runs with m.inverse()
+            V3 point = ps.cb_pos12.t;
+            Iso7 m; m.q.i = 0.f; m.q.j = 0.f; m.q.k = 0.f; m.q.w = 1.f; m.t = -point;
+            ps.gpos12 = iso_inverse(m);
+            ps.g1 = make_dshape(kc, convex_first ? ps.pr1 : ps.pr2, pts);
+            ps.g2 = origin_dshape();
+        }
+    }
+}
+
+// Epilogue for a GJK/EPA result (p1, p2_1, n1 in shape-1 space) -> local-frame contact or projection-based contact.
+__device__ __forceinline__ int finish_gjk_pair(const PairSetup& ps, bool from_epa, V3 p1, V3 p2_1, V3 n1, float prediction, ContactOut& c) {
+    if (ps.mode == 1) {
+        // contact_support_map_support_map.rs:21-27
+        c.dist = dot3(p2_1 - p1, n1);
+        c.p1 = p1;
+        c.p2 = iso_inv_point(ps.pos12, p2_1);
+        c.n1 = n1;
+        c.n2 = iso_inv_vec(ps.pos12, -n1);
+        return ST_SOME;
+    }
+    // modes 2/3: p1 is the projection of the ball centre on the hull; inside iff it came from EPA
+    Feat f; f.kind = 3; f.id = 0;
+    float radius = ps.mode == 2 ? ps.pr2.x : ps.pr1.x;
+    int st = d_convex_ball_finish(ps.cb_pos12, false, f, p1, from_epa, radius, prediction, c);
+    if (st == ST_SOME && ps.mode == 3) flip_contact(c);
+    return st;
+}
+
+__device__ __forceinline__ void to_world(const PairSetup& ps, ContactOut& c) {  // Contact::transform_by_mut
+    c.p1 = iso_point(ps.pos1, c.p1);
+    c.p2 = iso_point(ps.pos2, c.p2);
+    c.n1 = iso_vec(ps.pos1, c.n1);
+    c.n2 = iso_vec(ps.pos2, c.n2);
+}
+
+__device__ __forceinline__ unsigned long long warp_append1(unsigned long long* counter) {
+    unsigned mask = __activemask();
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+struct OutSinks {
+    float* dense;        // n x 13 or NULL
+    uint8_t* status;     // n or NULL
+    float* compact;      // cap x 13 or NULL
+    uint32_t* pair_index;
+    unsigned long long cap;
+    unsigned long long* compact_count;
+    unsigned long long* some_count;
+};
+
+__device__ __forceinline__ void store_contact(float* o, const ContactOut& c) {
+    o[0] = c.p1.x; o[1] = c.p1.y; o[2] = c.p1.z; o[3] = c.p2.x; o[4] = c.p2.y; o[5] = c.p2.z;
+    o[6] = c.n1.x; o[7] = c.n1.y; o[8] = c.n1.z; o[9] = c.n2.x; o[10] = c.n2.y; o[11] = c.n2.z; o[12] = c.dist;
+}
+
+__device__ __forceinline__ void emit(const OutSinks& out, uint32_t k, int st, const ContactOut& c) {
+    if (out.status) out.status[k] = (uint8_t)st;
+    if (out.dense) {
+        float* o = out.dense + 13ull * k;
+        if (st == ST_SOME) store_contact(o, c);
+        else { for (int i = 0; i < 13; ++i) o[i] = 0.0f; }
+    }
+    if (st == ST_SOME) {
+        if (out.compact) {
+            unsigned long long at = warp_append1(out.compact_count);
+            if (at < out.cap) { store_contact(out.compact + 13ull * at, c); out.pair_index[at] = k; }
+        } else if (out.some_count) {
+            (void)warp_append1(out.some_count);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- phase 1
+__global__ void __launch_bounds__(128) k_contact_gjk(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
+                              const float4* __restrict__ pts, uint32_t n_shapes, const uint32_t* __restrict__ shape1,
+                              const uint32_t* __restrict__ shape2, const float* __restrict__ pos1, const float* __restrict__ pos2,
+                              float prediction, uint32_t n, OutSinks out, EpaJob* __restrict__ jobs, unsigned long long* job_count) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    ContactOut c;
+    if (shape1[k] >= n_shapes || shape2[k] >= n_shapes) { emit(out, k, ST_UNSUPPORTED, c); return; }
+    PairSetup ps;
+    pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, k, ps);
+    int st;
+    if (ps.mode == 0) {
+        bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
+        if (b1 && b2) st = d_contact_ball_ball(ps.pos12, ps.pr1.x, ps.pr2.x, prediction, c) ? ST_SOME : ST_NONE;
+        else {
+            // ball <-> cuboid (closed-form projection)
+            bool convex_first = b2;
+            float4 prc = convex_first ? ps.pr1 : ps.pr2;
+            float radius = convex_first ? ps.pr2.x : ps.pr1.x;
+            V3 proj; bool inside; Feat f;
+            d_cuboid_project(mk3(prc.x, prc.y, prc.z), ps.cb_pos12.t, proj, inside, f);
+            st = d_convex_ball_finish(ps.cb_pos12, true, f, proj, inside, radius, prediction, c);
+            if (st == ST_SOME && !convex_first) flip_contact(c);
+        }
+    } else {
+        Simplex s;
+        V3 dir; float nn;
+        if (ps.mode == 1) {
+            // contact_support_map_support_map_with_params (contact_support_map_support_map.rs:40-61)
+            if (!try_normalize_get(ps.pos12.t, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
+            sx_reset(s, cso_from_shapes(ps.gpos12, ps.g1, ps.g2, dir));
+        } else {
+            // point_support_map.rs:26-31: dir = normalize(point) or +x; support with m_inv = Isometry(point)
+            V3 point = ps.cb_pos12.t;
+            if (!try_normalize_get(point, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
+            Iso7 m_inv; m_inv.q.i = 0.f; m_inv.q.j = 0.f; m_inv.q.k = 0.f; m_inv.q.w = 1.f; m_inv.t = point;
+            sx_reset(s, cso_from_shapes(m_inv, ps.g1, ps.g2, dir));
+        }
+        V3 p1, p2, n1;
+        float max_dist = ps.mode == 1 ? prediction : FLT_MAX;
+        int r = gjk_closest_points(ps.gpos12, ps.g1, ps.g2, max_dist, s, p1, p2, n1);
+        if (r == GJK_INTERSECTION) {
+            unsigned long long at = warp_append1(job_count);
+            EpaJob* j = &jobs[at];
+            j->pair = k; j->dim = (uint32_t)s.dim;
+            for (int i = 0; i <= s.dim; ++i) {
+                j->o1[i][0] = s.v[i].o1.x; j->o1[i][1] = s.v[i].o1.y; j->o1[i][2] = s.v[i].o1.z;
+                j->o2[i][0] = s.v[i].o2.x; j->o2[i][1] = s.v[i].o2.y; j->o2[i][2] = s.v[i].o2.z;
+            }
+            return;  // finished by phase 2
+        } else if (r == GJK_CLOSEST_POINTS) {
+            st = finish_gjk_pair(ps, false, p1, p2, n1, prediction, c);
+        } else {
+            st = ST_NONE;
+        }
+    }
+    if (st == ST_SOME) to_world(ps, c);
+    emit(out, k, st, c);
+}
+
+// ------------------------------------------------------------------------------------------- phase 2: EPA
+struct EFace {
+    V3 normal;
+    float bc[3];
+    uint16_t adj[3];
+    uint8_t pts[3];
+    uint8_t deleted;
+};
+struct HeapEnt { float neg_dist; uint32_t id; };
+
+struct EpaArena {
+    CSO verts[EPA_MAX_VERTS];
+    EFace faces[EPA_MAX_FACES];
+    HeapEnt heap[EPA_MAX_FACES];
+    uint16_t sil_face[EPA_MAX_SIL];
+    uint8_t sil_opp[EPA_MAX_SIL];
+    uint16_t stk_face[EPA_STACK];
+    uint8_t stk_opp[EPA_STACK];
+    int nverts, nfaces, nheap, nsil;
+    bool overflow;
+};
+
+// Rust BinaryHeap<FaceId> (max-heap on neg_dist): sift_up / sift_down_to_bottom
+__device__ __forceinline__ bool he_le(const HeapEnt& a, const HeapEnt& b) { return !(a.neg_dist > b.neg_dist); }
+__device__ __forceinline__ void heap_sift_up(EpaArena& A, int start, int pos) {
+    HeapEnt elt = A.heap[pos];
+    while (pos > start) {
+        int parent = (pos - 1) / 2;
+        if (he_le(elt, A.heap[parent])) break;
+        A.heap[pos] = A.heap[parent];
+        pos = parent;
+    }
+    A.heap[pos] = elt;
+}
+__device__ __forceinline__ void heap_push(EpaArena& A, uint32_t id, float neg_dist) {
+    int old = A.nheap;
+    A.heap[old].id = id; A.heap[old].neg_dist = neg_dist;
+    A.nheap = old + 1;
+    heap_sift_up(A, 0, old);
+}
+__device__ __forceinline__ HeapEnt heap_pop(EpaArena& A) {
+    HeapEnt item = A.heap[A.nheap - 1];
+    A.nheap -= 1;
+    if (A.nheap > 0) {
+        HeapEnt t = item; item = A.heap[0]; A.heap[0] = t;
+        int end = A.nheap, pos = 0;
+        HeapEnt elt = A.heap[0];
+        int child = 1;
+        while (end >= 2 && child <= end - 2) {
+            if (he_le(A.heap[child], A.heap[child + 1])) child += 1;
+            A.heap[pos] = A.heap[child];
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (child == end - 1) { A.heap[pos] = A.heap[child]; pos = child; }
+        A.heap[pos] = elt;
+        heap_sift_up(A, 0, pos);
+    }
+    return item;
+}
+
+// Face::new (epa3.rs:96-118) + new_with_proj (:65-94)
+__device__ __forceinline__ bool epa_face_new(EpaArena& A, int slot, int p0, int p1, int p2, int a0, int a1, int a2) {
+    V3 va = A.verts[p0].point, vb = A.verts[p1].point, vc = A.verts[p2].point;
+    Proj p;
+    project_on_triangle(va, vb, vc, mk3(0.f, 0.f, 0.f), p);
+    bool inside;
+    float bc[3] = {0.f, 0.f, 0.f};
+    if (p.kind == 0) { bc[p.idx] = 1.0f; }
+    if (p.kind == 1) {
+        int i0 = p.idx == 1 ? 1 : 0, i1 = p.idx == 0 ? 1 : 2;
+        bc[i0] = p.bc[0]; bc[i1] = p.bc[1];
+    }
+    if (p.kind == 0 || p.kind == 1) {
+        const float eps_tol = PB2_EPS * 100.0f;
+        inside = p.inside || nrm2(p.point - mk3(0.f, 0.f, 0.f)) < eps_tol * eps_tol;
+    } else if (p.kind == 2) { bc[0] = p.bc[0]; bc[1] = p.bc[1]; bc[2] = p.bc[2]; inside = true; }
+    else inside = false;
+    EFace f;
+    V3 n; float nn;
+    if (!try_normalize_get(cross3(vb - va, vc - va), PB2_EPS, n, nn)) n = mk3(0.f, 0.f, 0.f);  // ccw_face_normal
+    f.normal = n;
+    f.bc[0] = bc[0]; f.bc[1] = bc[1]; f.bc[2] = bc[2];
+    f.pts[0] = (uint8_t)p0; f.pts[1] = (uint8_t)p1; f.pts[2] = (uint8_t)p2;
+    f.adj[0] = (uint16_t)a0; f.adj[1] = (uint16_t)a1; f.adj[2] = (uint16_t)a2;
+    f.deleted = 0;
+    A.faces[slot] = f;
+    return inside;
+}
+__device__ __forceinline__ int epa_next_ccw(const EFace& f, int id) {
+    if (f.pts[0] == id) return 1;
+    if (f.pts[1] == id) return 2;
+    return 0;
+}
+__device__ __forceinline__ bool epa_can_be_seen_by(const EpaArena& A, const EFace& f, int point, int opp) {
+    V3 p0 = A.verts[f.pts[opp]].point;
+    V3 p1 = A.verts[f.pts[(opp + 1) % 3]].point;
+    V3 p2 = A.verts[f.pts[(opp + 2) % 3]].point;
+    V3 pt = A.verts[point].point;
+    if (dot3(pt - p0, f.normal) >= -PB2_GJK_EPS_TOL) return true;
+    // Triangle::new(p1, p2, pt).is_affinely_dependent()
+    const float EPS = PB2_EPS * 100.0f;
+    return rel_eq(nrm2(cross3(p2 - p1, pt - p1)), 0.0f, EPS * EPS, PB2_EPS);
+}
+// compute_silhouette (epa3.rs:653-675): the reference recursion (adj1 fully, then adj2) as an explicit DFS stack.
+__device__ __forceinline__ void epa_silhouette(EpaArena& A, int point, int id, int opp) {
+    int sp = 0;
+    A.stk_face[sp] = (uint16_t)id; A.stk_opp[sp] = (uint8_t)opp; sp++;
+    while (sp > 0) {
+        --sp;
+        int fid = A.stk_face[sp], fo = A.stk_opp[sp];
+        EFace& f = A.faces[fid];
+        if (f.deleted) continue;
+        if (!epa_can_be_seen_by(A, f, point, fo)) {
+            if (A.nsil >= EPA_MAX_SIL) { A.overflow = true; return; }
+            A.sil_face[A.nsil] = (uint16_t)fid; A.sil_opp[A.nsil] = (uint8_t)fo; A.nsil++;
+        } else {
+            f.deleted = 1;
+            int i1 = (fo + 2) % 3, i2 = fo;
+            int adj1 = f.adj[i1], adj2 = f.adj[i2];
+            int o1 = epa_next_ccw(A.faces[adj1], f.pts[i1]);
+            int o2 = epa_next_ccw(A.faces[adj2], f.pts[i2]);
+            if (sp + 2 > EPA_STACK) { A.overflow = true; return; }
+            // push adj2 first so adj1 is processed (fully) first
+            A.stk_face[sp] = (uint16_t)adj2; A.stk_opp[sp] = (uint8_t)o2; sp++;
+            A.stk_face[sp] = (uint16_t)adj1; A.stk_opp[sp] = (uint8_t)o1; sp++;
+        }
+    }
+}
+__device__ __forceinline__ void epa_face_closest(const EpaArena& A, const EFace& f, V3& p1, V3& p2) {
+    p1 = A.verts[f.pts[0]].o1 * f.bc[0] + A.verts[f.pts[1]].o1 * f.bc[1] + A.verts[f.pts[2]].o1 * f.bc[2];
+    p2 = A.verts[f.pts[0]].o2 * f.bc[0] + A.verts[f.pts[1]].o2 * f.bc[1] + A.verts[f.pts[2]].o2 * f.bc[2];
+}
+
+// EPA::closest_points (epa3.rs:428-651). Returns 1 Some, 0 None, -1 arena overflow.
+__device__ int epa_closest_points(EpaArena& A, const Iso7& pos12, const DShape& g1, const DShape& g2, int dim, V3& out_p1, V3& out_p2,
+                                  V3& out_n) {
+    const float eps = PB2_EPS;
+    const float eps_tol = eps * 100.0f;
+    A.nfaces = 0; A.nheap = 0; A.nsil = 0; A.overflow = false;
+    if (dim == 0) { out_p1 = mk3(0.f, 0.f, 0.f); out_p2 = out_p1; out_n = mk3(0.f, 1.f, 0.f); return 1; }
+    if (dim == 3) {
+        V3 dp1 = A.verts[1].point - A.verts[0].point, dp2 = A.verts[2].point - A.verts[0].point, dp3 = A.verts[3].point - A.verts[0].point;
+        if (dot3(cross3(dp1, dp2), dp3) > 0.0f) { CSO t = A.verts[1]; A.verts[1] = A.verts[2]; A.verts[2] = t; }
+        bool in0 = epa_face_new(A, 0, 0, 1, 2, 3, 1, 2);
+        bool in1 = epa_face_new(A, 1, 1, 3, 2, 3, 2, 0);
+        bool in2 = epa_face_new(A, 2, 0, 2, 3, 0, 1, 3);
+        bool in3 = epa_face_new(A, 3, 0, 3, 1, 2, 1, 0);
+        A.nfaces = 4;
+        bool ins[4] = {in0, in1, in2, in3};
+        for (int k = 0; k < 4; ++k) {
+            if (ins[k]) {
+                float dist = dot3(A.faces[k].normal, A.verts[k].point);
+                if (-dist > PB2_GJK_EPS_TOL) return 0;  // FaceId::new(..)?
+                heap_push(A, (uint32_t)k, -dist);
+            }
+        }
+        if (!(in0 || in1 || in2 || in3)) return 0;
+    } else {
+        if (dim == 1) {
+            V3 dpt = A.verts[1].point - A.verts[0].point;
+            V3 a = fabsf(dpt.x) > fabsf(dpt.y) ? mk3(dpt.z, 0.0f, -dpt.x) : mk3(0.0f, -dpt.z, dpt.y);
+            a = normalize3(a);
+            V3 dir = cross3(a, dpt);
+            A.verts[A.nverts++] = cso_from_shapes(pos12, g1, g2, dir);
+        }
+        epa_face_new(A, 0, 0, 1, 2, 1, 1, 1);
+        epa_face_new(A, 1, 0, 2, 1, 0, 0, 0);
+        A.nfaces = 2;
+        heap_push(A, 0u, 0.0f);
+        heap_push(A, 1u, 0.0f);
+    }
+    int niter = 0;
+    float max_dist = FLT_MAX;
+    if (A.nheap == 0) return 0;
+    HeapEnt best_face = A.heap[0];
+    float old_dist = 0.0f;
+    while (A.nheap > 0) {
+        HeapEnt face_id = heap_pop(A);
+        EFace face = A.faces[face_id.id];
+        if (face.deleted) continue;
+        if (A.nverts >= EPA_MAX_VERTS) return -1;
+        CSO cso = cso_from_shapes(pos12, g1, g2, face.normal);
+        int support_id = A.nverts;
+        A.verts[A.nverts++] = cso;
+        float candidate = dot3(cso.point, face.normal);
+        if (candidate < max_dist) { best_face = face_id; max_dist = candidate; }
+        float curr_dist = -face_id.neg_dist;
+        if (max_dist - curr_dist < eps_tol || (fabsf(curr_dist - old_dist) < eps && candidate < max_dist)) {
+            const EFace& bf = A.faces[best_face.id];
+            epa_face_closest(A, bf, out_p1, out_p2); out_n = bf.normal;
+            return 1;
+        }
+        old_dist = curr_dist;
+        A.faces[face_id.id].deleted = 1;
+        int o1 = epa_next_ccw(A.faces[face.adj[0]], face.pts[0]);
+        int o2 = epa_next_ccw(A.faces[face.adj[1]], face.pts[1]);
+        int o3 = epa_next_ccw(A.faces[face.adj[2]], face.pts[2]);
+        epa_silhouette(A, support_id, face.adj[0], o1);
+        epa_silhouette(A, support_id, face.adj[1], o2);
+        epa_silhouette(A, support_id, face.adj[2], o3);
+        if (A.overflow) return -1;
+        int first_new = A.nfaces;
+        if (A.nsil == 0) return 0;
+        for (int e = 0; e < A.nsil; ++e) {
+            int efid = A.sil_face[e], eopp = A.sil_opp[e];
+            if (!A.faces[efid].deleted) {
+                int new_id = A.nfaces;
+                if (new_id >= EPA_MAX_FACES) return -1;
+                int pt1 = A.faces[efid].pts[(eopp + 2) % 3], pt2 = A.faces[efid].pts[(eopp + 1) % 3];
+                bool inside = epa_face_new(A, new_id, pt1, pt2, support_id, efid, new_id + 1, new_id - 1);
+                A.faces[efid].adj[(eopp + 1) % 3] = (uint16_t)new_id;
+                A.nfaces = new_id + 1;
+                if (inside) {
+                    V3 pt = A.verts[A.faces[new_id].pts[0]].point;
+                    float dist = dot3(A.faces[new_id].normal, pt);
+                    if (dist < curr_dist) { epa_face_closest(A, face, out_p1, out_p2); out_n = face.normal; return 1; }
+                    if (-dist > PB2_GJK_EPS_TOL) return 0;
+                    heap_push(A, (uint32_t)new_id, -dist);
+                }
+            }
+        }
+        if (first_new == A.nfaces) return 0;
+        A.faces[first_new].adj[2] = (uint16_t)(A.nfaces - 1);
+        A.faces[A.nfaces - 1].adj[1] = (uint16_t)first_new;
+        A.nsil = 0;
+        niter += 1;
+        if (niter > 100) break;
+    }
+    const EFace& bf = A.faces[best_face.id];
+    epa_face_closest(A, bf, out_p1, out_p2); out_n = bf.normal;
+    return 1;
+}
+
+__global__ void __launch_bounds__(64) k_contact_epa(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
+                             const float4* __restrict__ pts, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2,
+                             const float* __restrict__ pos1, const float* __restrict__ pos2, float prediction, OutSinks out,
+                             const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
+                             unsigned long long* __restrict__ next_job, EpaArena* __restrict__ arenas) {
+    EpaArena& A = arenas[blockIdx.x * blockDim.x + threadIdx.x];
+    unsigned long long total = *job_count;
+    for (;;) {
+        unsigned long long j = atomicAdd(next_job, 1ull);
+        if (j >= total) break;
+        const EpaJob& job = jobs[j];
+        uint32_t k = job.pair;
+        PairSetup ps;
+        pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, k, ps);
+        int dim = (int)job.dim;
+        for (int i = 0; i <= dim; ++i) {
+            V3 o1 = mk3(job.o1[i][0], job.o1[i][1], job.o1[i][2]), o2 = mk3(job.o2[i][0], job.o2[i][1], job.o2[i][2]);
+            A.verts[i] = cso_make(o1, o2);
+        }
+        A.nverts = dim + 1;
+        V3 p1, p2, n1;
+        int r = epa_closest_points(A, ps.gpos12, ps.g1, ps.g2, dim, p1, p2, n1);
+        ContactOut c;
+        int st;
+        if (r < 0) st = ST_NEEDS_HOST;
+        else if (r == 0) {
+            // support-map pair: "Everything failed" => NoIntersection => None. Hull projection: PointProjection(true, point).
+            if (ps.mode == 1) st = ST_NONE;
+            else st = finish_gjk_pair(ps, true, ps.cb_pos12.t, p2, n1, prediction, c);
+        } else st = finish_gjk_pair(ps, true, p1, p2, n1, prediction, c);
+        if (st == ST_SOME) to_world(ps, c);
+        emit(out, k, st, c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
+                        const float* pos2, float prediction, uint32_t n, OutSinks sinks) {
+    cudaStream_t st = ctx->stream;
+    // EPA job queue (worst case: every pair) + arenas for the persistent EPA grid
+    int epa_threads = 64, epa_blocks = ctx->sm_count * 4;
+    size_t jobs_bytes = (size_t)n * sizeof(EpaJob);
+    size_t arena_bytes = (size_t)epa_threads * epa_blocks * sizeof(EpaArena);
+    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[3], jobs_bytes));
+    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], arena_bytes));
+    EpaJob* jobs = (EpaJob*)ctx->scratch[3].ptr;
+    EpaArena* arenas = (EpaArena*)ctx->scratch[2].ptr;
+    unsigned long long* job_count = (unsigned long long*)(ctx->d_counters + 4);
+    unsigned long long* next_job = (unsigned long long*)(ctx->d_counters + 5);
+    PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 4, 0, 16, st));
+    k_contact_gjk<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, shape1, shape2, pos1, pos2,
+                                                     prediction, n, sinks, jobs, job_count);
+    PB2_LAUNCHED(ctx);
+    k_contact_epa<<<epa_blocks, epa_threads, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction,
+                                                     sinks, jobs, job_count, next_job, arenas);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    return PB2_OK;
+}
 
 extern "C" {
-int pb2_contact_batch(pb2_ctx* ctx, const pb2_shapes*, const uint32_t*, const uint32_t*, const float*, const float*, float, uint32_t,
-                      pb2_contact*, uint8_t*, uint64_t*, int) {
-    if (!ctx) return PB2_ERR_INVALID;
-    PB2_FAIL(ctx, PB2_ERR_UNSUPPORTED, "contact kernels not built yet");
+
+int pb2_contact_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
+                      const float* pos2, float prediction, uint32_t n, pb2_contact* out, uint8_t* status, uint64_t* num_contacts, int mem) {
+    if (!ctx || !shapes || (n && (!shape1 || !shape2 || !pos1 || !pos2 || !out || !status))) return PB2_ERR_INVALID;
+    if (num_contacts) *num_contacts = 0;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_s1, *d_s2, *d_p1, *d_p2;
+    void *d_out, *d_status;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape1, (size_t)n * 4, mem, &d_s1));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape2, (size_t)n * 4, mem, &d_s2));
+    PB2_CHECK(pb2_stage_in(ctx, 2, pos1, (size_t)n * 28, mem, &d_p1));
+    PB2_CHECK(pb2_stage_in(ctx, 3, pos2, (size_t)n * 28, mem, &d_p2));
+    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_status));
+    OutSinks sinks;
+    sinks.dense = (float*)d_out; sinks.status = (uint8_t*)d_status; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
+    sinks.compact_count = nullptr;
+    sinks.some_count = num_contacts ? (unsigned long long*)(ctx->d_counters + 6) : nullptr;
+    if (num_contacts) PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 6, 0, 8, ctx->stream));
+    PB2_CHECK(run_contacts(ctx, shapes, (const uint32_t*)d_s1, (const uint32_t*)d_s2, (const float*)d_p1, (const float*)d_p2, prediction, n, sinks));
+    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_status, (size_t)n, mem));
+    if (num_contacts) {
+        PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 6, ctx->d_counters + 6, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *num_contacts = ctx->h_counters[6];
+    } else if (mem == PB2_MEM_HOST) {
+        PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return PB2_OK;
 }
-int pb2_contact_batch_compact(pb2_ctx* ctx, const pb2_shapes*, const uint32_t*, const uint32_t*, const float*, const float*, float,
-                              uint32_t, pb2_contact*, uint32_t*, uint64_t, uint64_t*, int) {
-    if (!ctx) return PB2_ERR_INVALID;
-    PB2_FAIL(ctx, PB2_ERR_UNSUPPORTED, "contact kernels not built yet");
+
+int pb2_contact_batch_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
+                              const float* pos2, float prediction, uint32_t n, pb2_contact* out, uint32_t* pair_index, uint64_t cap,
+                              uint64_t* count, int mem) {
+    if (!ctx || !shapes || !count || (n && (!shape1 || !shape2 || !pos1 || !pos2))) return PB2_ERR_INVALID;
+    *count = 0;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_s1, *d_s2, *d_p1, *d_p2;
+    void *d_out = nullptr, *d_idx = nullptr;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape1, (size_t)n * 4, mem, &d_s1));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape2, (size_t)n * 4, mem, &d_s2));
+    PB2_CHECK(pb2_stage_in(ctx, 2, pos1, (size_t)n * 28, mem, &d_p1));
+    PB2_CHECK(pb2_stage_in(ctx, 3, pos2, (size_t)n * 28, mem, &d_p2));
+    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)cap * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, pair_index, (size_t)cap * 4, mem, &d_idx));
+    if (!d_out || !d_idx) cap = 0;
+    OutSinks sinks;
+    sinks.dense = nullptr; sinks.status = nullptr; sinks.compact = (float*)d_out; sinks.pair_index = (uint32_t*)d_idx; sinks.cap = cap;
+    sinks.compact_count = (unsigned long long*)(ctx->d_counters + 6);
+    sinks.some_count = nullptr;
+    if (cap == 0) { sinks.compact = nullptr; sinks.some_count = sinks.compact_count; }
+    PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 6, 0, 8, ctx->stream));
+    PB2_CHECK(run_contacts(ctx, shapes, (const uint32_t*)d_s1, (const uint32_t*)d_s2, (const float*)d_p1, (const float*)d_p2, prediction, n, sinks));
+    PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 6, ctx->d_counters + 6, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t total = ctx->h_counters[6];
+    *count = total;
+    uint64_t valid = total < cap ? total : cap;
+    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)valid * 52, mem));
+    PB2_CHECK(pb2_stage_back(ctx, pair_index, d_idx, (size_t)valid * 4, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (total > cap) PB2_FAIL(ctx, PB2_ERR_OVERFLOW, "contact_batch_compact: %llu contacts > capacity %llu", (unsigned long long)total, (unsigned long long)cap);
+    return PB2_OK;
 }
-}
+
+}  // extern "C"

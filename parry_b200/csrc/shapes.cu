@@ -207,6 +207,11 @@ __global__ void __launch_bounds__(128) k_raycast_shapes(const NodeWide* __restri
     }
 }
 
+__global__ void k_pad_points(const float* __restrict__ p, uint32_t np, float4* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) out[i] = make_float4(p[3ull * i], p[3ull * i + 1], p[3ull * i + 2], 0.0f);
+}
+
 extern "C" {
 
 int pb2_shapes_create(pb2_ctx* ctx, const uint8_t* kinds, const float* params, uint32_t n, const float* points, uint32_t np,
@@ -230,9 +235,15 @@ int pb2_shapes_create(pb2_ctx* ctx, const uint8_t* kinds, const float* params, u
     cudaError_t e = cudaMalloc((void**)&s->kinds, nn);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->params, nn * 16);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->points, npp * 12);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->points4, npp * 16);
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(s->kinds, kinds, n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(s->params, params, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && np) e = cudaMemcpyAsync(s->points, points, (size_t)np * 12, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && np) {
+        k_pad_points<<<pb2_blocks(np, 256), 256, 0, ctx->stream>>>(s->points, np, s->points4);
+        PB2_LAUNCHED(ctx);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         snprintf(ctx->err, sizeof(ctx->err), "shapes_create: %s", cudaGetErrorString(e));
@@ -250,6 +261,7 @@ int pb2_shapes_destroy(pb2_ctx* ctx, pb2_shapes* s) {
     if (s->kinds) cudaFree(s->kinds);
     if (s->params) cudaFree(s->params);
     if (s->points) cudaFree(s->points);
+    if (s->points4) cudaFree(s->points4);
     delete s;
     return PB2_OK;
 }
