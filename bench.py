@@ -127,7 +127,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays-log2", type=int, default=23, help="rays per GPU = 2^k")
@@ -269,7 +269,7 @@ def main():
         from harness import oracle
         oracle.build()
         threads = oracle.hardware_threads()
-        sample = 1 << 18
+        sample = min(m, 1 << 23)
         val, secs, t_build, _ = cpu_rays(v, i, rays_h[:sample], threads)
         line["cpu_baseline"] = {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": "first %d rays of rank 0's shard, same mesh; %.2f s cast + %.2f s Bvh build (1 thread)"
@@ -333,7 +333,75 @@ def bench_also(ctx, stream, args, hbm_peak):
     return out
 
 
-EXTRA_ALSO = []
+def also_contacts(ctx, stream, timed, flush, hbm_peak):
+    """BASELINE config[2]: 2^22 ConvexPolyhedron pairs (32-vertex hulls from a pool of 4096), prediction 0.01."""
+    import torch
+    import parry_b200
+    from harness import scenes
+    pts, radii = scenes.hull_pool(4096)
+    G = parry_b200.Shapes(ctx, [parry_b200.ConvexPolyhedron(p) for p in pts])
+    n = 1 << 22
+    a, b, p1, p2 = scenes.hull_pairs(n, radii, seed=4)
+    da, db = torch.from_numpy(a.astype(np.int32)).cuda(), torch.from_numpy(b.astype(np.int32)).cuda()
+    dp1, dp2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+    res = {}
+
+    def run():
+        res["out"] = parry_b200.contact(G, da, dp1, db, dp2, 0.01)
+    ms = timed(run, steps=5, warmup=3)  # inputs+outputs = 2^22 * 120 B = 503 MB > L2
+    st = res["out"][1]
+    frac_some = float((st == 1).float().mean().item())
+    alg = n * 120
+    r = {"value": n / (ms * 1e-3), "unit": "pairs/s", "ms": ms, "pairs": n, "contacts_fraction": frac_some,
+         "l2": "inputs+outputs (503 MB) larger than L2", "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
+         "algorithmic_bytes_per_pair": 120}
+    # end to end with host buffers
+    t0 = time.perf_counter()
+    for _ in range(3):
+        parry_b200.contact(G, a, p1, b, p2, 0.01)
+    r["e2e_value"] = n / ((time.perf_counter() - t0) / 3)
+    return r
+
+
+def also_broadphase(ctx, stream, timed, flush, hbm_peak):
+    """BASELINE config[1]: 2^20 dynamic colliders (balls + cuboids): per frame AABBs -> Bvh (rebuild, or update + refit)
+    -> full self-pair set."""
+    import torch
+    import parry_b200
+    from harness import scenes
+    n = 1 << 20
+    kinds, params, poses, _ = scenes.colliders(n, seed=2)
+    shapes = parry_b200.Shapes(ctx, [parry_b200.Ball(p[0]) if k == 0 else parry_b200.Cuboid(p) for k, p in zip(kinds, params)])
+    ids = torch.arange(n, dtype=torch.int32, device="cuda")
+    dposes = torch.from_numpy(poses).cuda()
+    aabbs = shapes.compute_aabbs(ids, dposes)
+    bvh = parry_b200.Bvh.from_leaves(ctx, 0, aabbs)
+    cap = 16 * n
+    state = {}
+
+    def frame_rebuild():
+        a = shapes.compute_aabbs(ids, dposes)
+        bvh.insert_or_update_partially(a, ids, 0.0)
+        bvh.rebuild()
+        state["pairs"] = bvh.traverse_bvtt_single_tree(capacity=cap, like=a)
+
+    def frame_refit():
+        a = shapes.compute_aabbs(ids, dposes)
+        bvh.insert_or_update_partially(a, ids, 0.0)
+        bvh.refit()
+        state["pairs"] = bvh.traverse_bvtt_single_tree(capacity=cap, like=a)
+
+    ms_rebuild = timed(frame_rebuild, steps=5, warmup=3, flush=flush)
+    npairs = int(state["pairs"].shape[0])
+    ms_refit = timed(frame_refit, steps=5, warmup=3, flush=flush)
+    alg = 24 * n + 8 * npairs
+    return {"value": n / (ms_rebuild * 1e-3), "unit": "AABBs/s (frame: AABBs + rebuild + self pairs)", "ms": ms_rebuild,
+            "pairs_per_frame": npairs, "pairs_per_s": npairs / (ms_rebuild * 1e-3),
+            "refit_frame_ms": ms_refit, "refit_frame_aabbs_per_s": n / (ms_refit * 1e-3), "l2": "flushed between iterations",
+            "roofline_frac": alg / (ms_rebuild * 1e-3) / 1e9 / hbm_peak}
+
+
+EXTRA_ALSO = [("contact_pairs_4M_hulls", also_contacts), ("broadphase_1M_colliders", also_broadphase)]
 
 if __name__ == "__main__":
     main()

@@ -266,7 +266,7 @@ class ShapeTable:
                 self.kinds[i] = 1
                 self.params[i, :3] = v
             else:
-                self.kinds[i] = 2
+                self.kinds[i] = 3 if k == "triangle" else 2
                 p = np.ascontiguousarray(v, dtype=np.float32).reshape(-1, 3)
                 pu[i, 0], pu[i, 1] = npts, len(p)
                 pts.append(p)

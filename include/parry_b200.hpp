@@ -1,0 +1,157 @@
+// parry_b200 — header-only C++ mirror of the reference's Rust API for the hot path, over the C ABI (parry_b200.h).
+// Names and argument meaning follow parry3d: Bvh (partitioning/bvh), TriMesh + RayCast (shape/trimesh.rs, query/ray/ray.rs),
+// query::contact (query/contact/contact_shape_shape.rs). Every call is the batched form; host pointers only.
+// Errors: pb2::Error (status + message); query::Unsupported surfaces per pair in the status array, like
+// Result<Option<Contact>, Unsupported>.
+#pragma once
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "parry_b200.h"
+
+namespace pb2 {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int st, const std::string& msg) : std::runtime_error("parry_b200 status " + std::to_string(st) + ": " + msg), status(st) {}
+};
+
+struct Aabb { float mins[3], maxs[3]; };                 // bounding_volume/aabb.rs:110
+struct Ray { float origin[3], dir[3]; };                 // query/ray/ray.rs:74-88
+struct Isometry { float rotation[4], translation[3]; };  // nalgebra Isometry3<f32>: (i, j, k, w), (x, y, z)
+struct RayIntersection { float time_of_impact; float normal[3]; uint32_t feature; };  // ray.rs:293-315 (Face id)
+enum class BvhBuildStrategy { Binned = PB2_BUILD_BINNED, Ploc = PB2_BUILD_PLOC };     // bvh_tree.rs:58-78
+
+class Context {
+public:
+    explicit Context(int device = 0) {
+        int st = pb2_ctx_create(device, &ctx_);
+        if (st != PB2_OK) throw Error(st, "no usable CUDA device (there is no CPU fallback)");
+    }
+    ~Context() { if (ctx_) pb2_ctx_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    pb2_ctx* get() const { return ctx_; }
+    void check(int st) const { if (st != PB2_OK) throw Error(st, pb2_last_error(ctx_)); }
+    void synchronize() const { check(pb2_ctx_synchronize(ctx_)); }
+private:
+    pb2_ctx* ctx_ = nullptr;
+};
+
+class Bvh {
+public:
+    // Bvh::from_leaves(strategy, &[Aabb])
+    static Bvh from_leaves(const Context& c, BvhBuildStrategy s, const std::vector<Aabb>& leaves) {
+        Bvh b(c);
+        c.check(pb2_bvh_build(c.get(), leaves.empty() ? nullptr : leaves[0].mins, (uint32_t)leaves.size(), (int)s, PB2_MEM_HOST, &b.h_));
+        return b;
+    }
+    Bvh(Bvh&& o) noexcept : c_(o.c_), h_(o.h_) { o.h_ = nullptr; }
+    ~Bvh() { if (h_) pb2_bvh_destroy(c_->get(), h_); }
+    uint32_t leaf_count() const { return pb2_bvh_leaf_count(h_); }
+    bool is_empty() const { return leaf_count() == 0; }
+    Aabb root_aabb() const { Aabb a; c_->check(pb2_bvh_root_aabb(c_->get(), h_, a.mins)); return a; }
+    // Bvh::insert_or_update_partially for existing leaves (batched)
+    void insert_or_update_partially(const std::vector<Aabb>& aabbs, const std::vector<uint32_t>& leaf_indices, float change_detection_margin) {
+        c_->check(pb2_bvh_update_leaves(c_->get(), h_, leaf_indices.data(), aabbs[0].mins, (uint32_t)aabbs.size(), change_detection_margin, PB2_MEM_HOST));
+    }
+    void refit() { c_->check(pb2_bvh_refit(c_->get(), h_)); c_->synchronize(); }
+    void rebuild(BvhBuildStrategy s) { c_->check(pb2_bvh_rebuild(c_->get(), h_, (int)s)); c_->synchronize(); }
+    // Bvh::intersect_aabb for a batch: CSR (offsets, leaf ids)
+    std::pair<std::vector<uint32_t>, std::vector<uint32_t>> intersect_aabb(const std::vector<Aabb>& queries) const {
+        std::vector<uint32_t> offs(queries.size() + 1), ids(16 * queries.size() + 1024);
+        uint64_t count = 0;
+        int st = pb2_bvh_intersect_aabbs(c_->get(), h_, queries[0].mins, (uint32_t)queries.size(), offs.data(), ids.data(), ids.size(), &count, PB2_MEM_HOST);
+        if (st == PB2_ERR_OVERFLOW) {
+            ids.resize(count);
+            st = pb2_bvh_intersect_aabbs(c_->get(), h_, queries[0].mins, (uint32_t)queries.size(), offs.data(), ids.data(), ids.size(), &count, PB2_MEM_HOST);
+        }
+        c_->check(st);
+        ids.resize(count);
+        return {offs, ids};
+    }
+    // Bvh::traverse_bvtt_single_tree::<CHANGE_DETECTION>: f(a, b) for every overlapping leaf pair
+    template <class F>
+    void traverse_bvtt_single_tree(bool change_detection, F f) const {
+        std::vector<uint32_t> pairs(2 * (8 * (size_t)leaf_count() + 1024));
+        uint64_t count = 0;
+        int st = pb2_bvh_self_pairs(c_->get(), h_, change_detection, pairs.data(), pairs.size() / 2, &count, PB2_MEM_HOST);
+        if (st == PB2_ERR_OVERFLOW) {
+            pairs.resize(2 * count);
+            st = pb2_bvh_self_pairs(c_->get(), h_, change_detection, pairs.data(), count, &count, PB2_MEM_HOST);
+        }
+        c_->check(st);
+        for (uint64_t i = 0; i < count; ++i) f(pairs[2 * i], pairs[2 * i + 1]);
+    }
+    // Bvh::leaf_pairs(other, |a, b| a.intersects(b))
+    std::vector<std::pair<uint32_t, uint32_t>> leaf_pairs(const Bvh& other) const {
+        std::vector<uint32_t> pairs(2 * (8 * (size_t)(leaf_count() + other.leaf_count()) + 1024));
+        uint64_t count = 0;
+        int st = pb2_bvh_leaf_pairs(c_->get(), h_, other.h_, pairs.data(), pairs.size() / 2, &count, PB2_MEM_HOST);
+        if (st == PB2_ERR_OVERFLOW) {
+            pairs.resize(2 * count);
+            st = pb2_bvh_leaf_pairs(c_->get(), h_, other.h_, pairs.data(), count, &count, PB2_MEM_HOST);
+        }
+        c_->check(st);
+        std::vector<std::pair<uint32_t, uint32_t>> out(count);
+        for (uint64_t i = 0; i < count; ++i) out[i] = {pairs[2 * i], pairs[2 * i + 1]};
+        return out;
+    }
+    pb2_bvh* get() const { return h_; }
+private:
+    explicit Bvh(const Context& c) : c_(&c) {}
+    const Context* c_;
+    pb2_bvh* h_ = nullptr;
+};
+
+class TriMesh {
+public:
+    // TriMesh::new(vertices, indices)
+    TriMesh(const Context& c, const std::vector<float>& vertices_xyz, const std::vector<uint32_t>& indices) : c_(&c), nt_((uint32_t)indices.size() / 3) {
+        c.check(pb2_trimesh_create(c.get(), vertices_xyz.data(), (uint32_t)vertices_xyz.size() / 3, indices.data(), nt_, PB2_MEM_HOST, &h_));
+    }
+    ~TriMesh() { if (h_) pb2_trimesh_destroy(c_->get(), h_); }
+    TriMesh(const TriMesh&) = delete;
+    // RayCast::cast_ray(m, ray, max_toi, solid) for a batch: toi[i] valid iff tri[i] != PB2_INVALID_U32 (None)
+    void cast_ray(const Isometry* m, const std::vector<Ray>& rays, float max_time_of_impact, bool solid, std::vector<float>& toi,
+                  std::vector<uint32_t>& tri) const {
+        toi.resize(rays.size()); tri.resize(rays.size());
+        c_->check(pb2_trimesh_cast_rays(c_->get(), h_, m ? m->rotation : nullptr, rays[0].origin, (uint32_t)rays.size(), max_time_of_impact, solid,
+                                        toi.data(), tri.data(), nullptr, nullptr, PB2_MEM_HOST));
+    }
+    // RayCast::cast_ray_and_get_normal
+    std::vector<RayIntersection> cast_ray_and_get_normal(const Isometry* m, const std::vector<Ray>& rays, float max_time_of_impact, bool solid,
+                                                         std::vector<uint32_t>& tri) const {
+        size_t n = rays.size();
+        std::vector<float> toi(n), normal(3 * n);
+        std::vector<uint32_t> feature(n);
+        tri.resize(n);
+        c_->check(pb2_trimesh_cast_rays(c_->get(), h_, m ? m->rotation : nullptr, rays[0].origin, (uint32_t)n, max_time_of_impact, solid, toi.data(),
+                                        tri.data(), normal.data(), feature.data(), PB2_MEM_HOST));
+        std::vector<RayIntersection> out(n);
+        for (size_t i = 0; i < n; ++i) out[i] = RayIntersection{toi[i], {normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]}, feature[i]};
+        return out;
+    }
+    uint32_t num_triangles() const { return nt_; }
+private:
+    const Context* c_;
+    pb2_trimesh* h_ = nullptr;
+    uint32_t nt_;
+};
+
+namespace query {
+// query::contact(pos1, g1, pos2, g2, prediction) for n pairs; status[k]: 0 Ok(None), 1 Ok(Some), 2 Err(Unsupported), 3 host fallback
+inline void contact(const Context& c, const pb2_shapes* shapes, const std::vector<uint32_t>& g1, const std::vector<Isometry>& pos1,
+                    const std::vector<uint32_t>& g2, const std::vector<Isometry>& pos2, float prediction, std::vector<pb2_contact>& out,
+                    std::vector<uint8_t>& status) {
+    out.resize(g1.size()); status.resize(g1.size());
+    c.check(pb2_contact_batch(c.get(), shapes, g1.data(), g2.data(), pos1[0].rotation, pos2[0].rotation, prediction, (uint32_t)g1.size(), out.data(),
+                              status.data(), nullptr, PB2_MEM_HOST));
+}
+}  // namespace query
+
+}  // namespace pb2

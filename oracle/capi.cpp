@@ -207,7 +207,7 @@ extern "C" void pb2o_shape_aabbs(const uint8_t* kinds, const float* params /* n 
 
 static inline ShapeRef make_shape(const uint8_t* kinds, const float* params4, const float* points, uint32_t id) {
     ShapeRef s; s.kind = kinds[id]; s.radius = params4[4 * id]; s.half_extents = ld3(params4 + 4 * id); s.points = nullptr; s.num_points = 0;
-    if (s.kind == SHAPE_CONVEX) {
+    if (s.kind == SHAPE_CONVEX || s.kind == SHAPE_TRIANGLE) {
         uint32_t first, cnt; memcpy(&first, params4 + 4 * id, 4); memcpy(&cnt, params4 + 4 * id + 1, 4);
         s.points = points + 3 * first; s.num_points = cnt;
     }
@@ -222,7 +222,7 @@ void pb2o_contact_batch(const uint8_t* kinds, const float* params4, const float*
     parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
         for (size_t k = lo; k < hi; ++k) {
             ShapeRef s1 = make_shape(kinds, params4, points, shape1[k]), s2 = make_shape(kinds, params4, points, shape2[k]);
-            Contact c; memset(&c, 0, sizeof(c));
+            Contact c = Contact();
             GjkEpaStats gs;
             int st = query_contact(Iso::from7(pos1 + 7 * k), s1, Iso::from7(pos2 + 7 * k), s2, prediction, c, &gs);
             status[k] = (uint8_t)st;
@@ -239,7 +239,7 @@ void pb2o_contact_batch(const uint8_t* kinds, const float* params4, const float*
 // DefaultQueryDispatcher::contact(pos12, ...) — results in the local frames of shape 1 / shape 2.
 int pb2o_dispatch_contact(const uint8_t* kinds, const float* params4, const float* points, uint32_t s1, uint32_t s2, const float* pos12, float prediction, float* out13) {
     ShapeRef a = make_shape(kinds, params4, points, s1), b = make_shape(kinds, params4, points, s2);
-    Contact c; memset(&c, 0, sizeof(c));
+    Contact c = Contact();
     int st = dispatch_contact(Iso::from7(pos12), a, b, prediction, c);
     if (st == CONTACT_SOME) { st3(out13, c.point1); st3(out13 + 3, c.point2); st3(out13 + 6, c.normal1); st3(out13 + 9, c.normal2); out13[12] = c.dist; }
     return st;

@@ -9,14 +9,18 @@ namespace pb2o {
 
 struct Contact { Vec3 point1, point2, normal1, normal2; Real dist; };
 
-enum ShapeKind { SHAPE_BALL = 0, SHAPE_CUBOID = 1, SHAPE_CONVEX = 2 };
+enum ShapeKind { SHAPE_BALL = 0, SHAPE_CUBOID = 1, SHAPE_CONVEX = 2, SHAPE_TRIANGLE = 3 /* oracle-only, for the reference's EPA regression test */ };
 struct ShapeRef {
     int kind;
     Real radius;
     Vec3 half_extents;
     const float* points;
     uint32_t num_points;
-    SupportShape support() const { return kind == SHAPE_CUBOID ? SupportShape::cuboid(half_extents) : SupportShape::convex(points, num_points); }
+    SupportShape support() const {
+        if (kind == SHAPE_CUBOID) return SupportShape::cuboid(half_extents);
+        if (kind == SHAPE_TRIANGLE) return SupportShape::triangle(points);
+        return SupportShape::convex(points, num_points);
+    }
 };
 
 enum ContactStatus { CONTACT_NONE = 0, CONTACT_SOME = 1, CONTACT_UNSUPPORTED = 2, CONTACT_NEEDS_TOPOLOGY = 3 };

@@ -11,13 +11,14 @@ namespace pb2o {
 
 // ---------------------------------------------------------------- support maps (shape/support_map.rs:213-467)
 struct SupportShape {
-    enum Kind { CUBOID, CONVEX, CONSTANT_ORIGIN } kind;
+    enum Kind { CUBOID, CONVEX, CONSTANT_ORIGIN, TRIANGLE } kind;
     Vec3 half_extents;       // CUBOID
     const float* points;     // CONVEX: xyz packed
     uint32_t num_points;
 
     static SupportShape cuboid(const Vec3& he) { SupportShape s; s.kind = CUBOID; s.half_extents = he; s.points = nullptr; s.num_points = 0; return s; }
     static SupportShape convex(const float* p, uint32_t n) { SupportShape s; s.kind = CONVEX; s.points = p; s.num_points = n; return s; }
+    static SupportShape triangle(const float* p) { SupportShape s; s.kind = TRIANGLE; s.points = p; s.num_points = 3; return s; }
     static SupportShape constant_origin() { SupportShape s; s.kind = CONSTANT_ORIGIN; s.points = nullptr; s.num_points = 0; return s; }
 
     Vec3 local_support_point(const Vec3& dir) const {
@@ -32,6 +33,12 @@ struct SupportShape {
                     if (d > best_dot) { best_dot = d; best = i; }
                 }
                 return Vec3(points[3 * best], points[3 * best + 1], points[3 * best + 2]);
+            }
+            case TRIANGLE: {  // shape/triangle.rs:697-716 (its own tie-breaking, used by the epa3.rs regression test)
+                Vec3 a(points[0], points[1], points[2]), b(points[3], points[4], points[5]), c(points[6], points[7], points[8]);
+                Real d1 = dot(a, dir), d2 = dot(b, dir), d3 = dot(c, dir);
+                if (d1 > d2) return d1 > d3 ? a : c;
+                return d2 > d3 ? b : c;
             }
             default:  // special_support_maps.rs ConstantOrigin
                 return Vec3();

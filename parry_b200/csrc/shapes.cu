@@ -78,9 +78,11 @@ __device__ __forceinline__ bool ray_ball(float radius, V3 o, V3 dir, bool solid,
     inside = false; toi = t; return true;
 }
 
-// Aabb::cast_local_ray (ray_aabb.rs:12-49) on [-he, he]
+// Aabb::cast_local_ray (ray_aabb.rs:12-49) on [-he, he]. Quirk: for a non-solid cast from inside, the reference returns
+// tmax = min(max_toi, exit time), i.e. Some(max_toi) when the exit lies beyond max_toi. find_best never accepts that value
+// (strict `<` against best == max_toi), so it is reported as a miss here — otherwise the tie rule could mistake it for a tie.
 __device__ __forceinline__ bool ray_cuboid_toi(V3 he, V3 o, V3 d, float max_toi, bool solid, float& toi) {
-    float tmin = 0.0f, tmax = max_toi;
+    float tmin = 0.0f, tmax = max_toi, texit = FLT_MAX;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         float di = comp(d, i), oi = comp(o, i), h = comp(he, i);
@@ -92,10 +94,14 @@ __device__ __forceinline__ bool ray_cuboid_toi(V3 he, V3 o, V3 d, float max_toi,
             if (n > f) { float t = n; n = f; f = t; }
             tmin = fmaxf(tmin, n);
             tmax = fminf(tmax, f);
+            texit = fminf(texit, f);
             if (tmin > tmax) return false;
         }
     }
-    toi = (tmin == 0.0f && !solid) ? tmax : tmin;
+    if (tmin == 0.0f && !solid) {
+        if (texit > max_toi) return false;
+        toi = tmax;
+    } else toi = tmin;
     return true;
 }
 

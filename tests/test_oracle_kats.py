@@ -1,0 +1,182 @@
+"""CPU: pins the oracle (C++ restatement of parry3d) against every known-answer the reference's own tests, examples and
+doc-tests hold for the hot path. These are the only reference-provided vectors: parry3d itself cannot be
+compiled here (no cargo, nalgebra not vendored)."""
+import numpy as np
+
+from harness import scenes
+
+FMAX = float(np.finfo(np.float32).max)
+I4 = [0.0, 0.0, 0.0, 1.0]
+INVALID = 0xFFFFFFFF
+
+
+def test_cuboid_cuboid_epa_exact(oracle):
+    """crates/parry3d/tests/geometry/epa3.rs:8-23 — exact equality, as in the reference's assert_eq!."""
+    T = oracle.ShapeTable([("cuboid", [2, 1, 1])])
+    st, c = T.dispatch_contact(0, 0, I4 + [-3.5, 0, 0], 10.0)  # m1.inv_mul(m2), m1 = translation(3.5,0,0)
+    assert st == 1 and c[12] == np.float32(-0.5) and (c[6:9] == [-1, 0, 0]).all()
+    st, c = T.dispatch_contact(0, 0, I4 + [0, -0.2, 0], 10.0)
+    assert st == 1 and c[12] == np.float32(-1.8) and (c[6:9] == [0, -1, 0]).all()
+
+
+def test_triangle_vertex_touches_triangle_edge_epa(oracle):
+    """epa3.rs:25-59 (issues #253/#246): must produce ClosestPoints with a.y ~ 1.0 and a.x ~ -2.349647 (1e-3)."""
+    t1 = [[-13.174434, 1.0, 8.736801], [3.5251038, 1.0, 12.1], [3.2048466, 1.0, 12.218325]]
+    t2 = [[-1.63, 0.0, 11.19], [-2.349647, 0.0, 11.037681], [-2.349647, 1.0, 11.037681]]
+    T = oracle.ShapeTable([("triangle", t1), ("triangle", t2)])
+    st, c = T.dispatch_contact(0, 1, I4 + [0, 0, 0], 0.00999999977)
+    assert st == 1
+    assert abs(c[1] - 1.0) < 1e-3 and abs(c[0] - (-2.349647)) < 1e-3
+
+
+def test_contact_query3d_example(oracle):
+    """crates/parry3d/examples/contact_query3d.rs: ball (r=1) vs unit cube, prediction 1."""
+    T = oracle.ShapeTable([("ball", 1.0), ("cuboid", [1, 1, 1])])
+    ident = np.array([I4 + [0, 0, 0]], np.float32)
+    out, st = T.contact([0], [I4 + [1, 1, 1]], [1], ident, 1.0)
+    assert st[0] == 1 and out[0, 12] <= 0.0
+    out, st = T.contact([0], [I4 + [2, 2, 2]], [1], ident, 1.0)
+    assert st[0] == 1 and out[0, 12] >= 0.0
+    out, st = T.contact([0], [I4 + [3, 3, 3]], [1], ident, 1.0)
+    assert st[0] == 0
+
+
+def test_contact_doc_examples(oracle):
+    """contact_shape_shape.rs doc (two r=0.5 balls, gap 2.2) and contact.rs:37-63 (overlapping balls => dist < 0)."""
+    T = oracle.ShapeTable([("ball", 0.5), ("ball", 1.0)])
+    p1, p2 = [I4 + [0, 0, 0]], [I4 + [3.2, 0, 0]]
+    assert T.contact([0], p1, [0], p2, 0.0)[1][0] == 0
+    assert T.contact([0], p1, [0], p2, 0.5)[1][0] == 0
+    out, st = T.contact([0], p1, [0], p2, 3.0)
+    assert st[0] == 1 and 0 < out[0, 12] <= 3.0
+    out, st = T.contact([1], p1, [1], [I4 + [1.5, 0, 0]], 0.0)
+    assert st[0] == 1 and out[0, 12] < 0
+    assert np.allclose(out[0, 6:9], [1, 0, 0]) and np.allclose(out[0, 9:12], [-1, 0, 0])
+
+
+def test_ball_cuboid_both_argument_orders(oracle):
+    """crates/parry2d/tests/geometry/ball_cuboid_contact.rs semantics (3D flavour): a contact must exist in both orders."""
+    T = oracle.ShapeTable([("ball", 0.5), ("cuboid", [1, 1, 1])])
+    for t in ([1.2, 0, 0], [0, 1.4, 0.1], [0.9, 0.9, 0.9]):
+        a = T.contact([0], [I4 + t], [1], [I4 + [0, 0, 0]], 0.0)
+        b = T.contact([1], [I4 + [0, 0, 0]], [0], [I4 + t], 0.0)
+        assert a[1][0] == 1 and b[1][0] == 1
+        assert np.allclose(a[0][0, 12], b[0][0, 12])
+        assert np.allclose(a[0][0, 0:3], b[0][0, 3:6], atol=1e-6)
+
+
+def test_solid_ray_cast3d_example(oracle):
+    """crates/parry3d/examples/solid_ray_cast3d.rs: cuboid (1,2,1)."""
+    he = [1, 2, 1]
+    inside = [0, 0, 0, 0, 1, 0]
+    miss = [2, 2, 2, 1, 1, 1]
+    assert oracle.shape_cast_ray_toi(1, he, I4 + [0, 0, 0], inside, FMAX, True) == 0.0
+    assert oracle.shape_cast_ray_toi(1, he, I4 + [0, 0, 0], inside, FMAX, False) == 2.0
+    assert oracle.shape_cast_ray_toi(1, he, I4 + [0, 0, 0], miss, FMAX, False) is None
+    assert oracle.shape_cast_ray_toi(1, he, I4 + [0, 0, 0], miss, FMAX, True) is None
+
+
+def test_bvh_node_cast_ray_doc(oracle):
+    """bvh_tree.rs:1155-1171 doc-test: node box [5,6]x[-1,1]^2, ray from the origin along +x => toi == 5.0."""
+    b = oracle.Bvh(np.array([[5, -1, -1, 6, 1, 1]], np.float32))
+    toi, leaf = b.cast_rays_shapes([1], [[0.5, 1, 1]], [I4 + [5.5, 0, 0]], [[0, 0, 0, 1, 0, 0]], FMAX)
+    assert leaf[0] == 0 and toi[0] == 5.0
+
+
+def test_intersect_aabb_doc_examples(oracle):
+    """bvh_queries.rs:130-155 doc-test: the far object is culled."""
+    boxes = np.array([[0, 0, 0, 1, 1, 1], [2, 0, 0, 3, 1, 1], [100, 0, 0, 101, 1, 1]], np.float32)
+    b = oracle.Bvh(boxes)
+    offs, ids = b.intersect_aabbs(np.array([[-10, -10, -10, 10, 10, 10]], np.float32))
+    assert sorted(ids.tolist()) == [0, 1]
+    b2 = oracle.Bvh(np.array([[0, 0, 0, 1, 1, 1], [1.5, 0, 0, 2.5, 1, 1], [100, 0, 0, 101, 1, 1]], np.float32))
+    offs, ids = b2.intersect_aabbs(np.array([[-2, -2, -2, 3, 3, 3]], np.float32))
+    assert sorted(ids.tolist()) == [0, 1]
+
+
+def test_shape_ray_cast_points_to_surface(oracle):
+    """crates/parry3d/tests/geometry/cuboid_ray_cast.rs:7-90 property (issue #242) with our seeded RNG: the hit point,
+    nudged outward along the normal and re-cast away from the shape, must not hit again; nudged inward it is inside."""
+    g = scenes.rng(42)
+    shapes = [(0, [1.0, 0, 0]), (1, [1, 1, 1]), (1, [1, 1, 0.5]), (1, [0.5, 1, 0.5])]
+    for kind, p in shapes:
+        for _ in range(1000):
+            o = g.random(3)
+            o = o / np.linalg.norm(o) * 5.0
+            ray = np.concatenate([o, -o]).astype(np.float32)
+            q = g.random(4)
+            q = np.array([0, 0, 0, 1.0]) if g.random() < 0.01 else q / np.linalg.norm(q)
+            pose = np.concatenate([q, [0, 0, 0]]).astype(np.float32)
+            hit = oracle.shape_cast_ray(kind, p, pose, ray, FMAX, True)
+            assert hit is not None
+            toi, n, _ = hit
+            pt = ray[:3] + ray[3:] * np.float32(toi)
+            out = pt + n * np.float32(0.001)
+            new_ray = np.concatenate([out, ray[:3] - out]).astype(np.float32)
+            assert oracle.shape_cast_ray(kind, p, pose, new_ray, FMAX, True) is None
+            inn = pt - n * np.float32(0.001)
+            # contains_point: a ray starting inside a solid shape reports toi == 0
+            assert oracle.shape_cast_ray_toi(kind, p, pose, np.concatenate([inn, [1, 0, 0]]).astype(np.float32), FMAX, True) == 0.0
+
+
+def test_single_triangle_mesh_faces(oracle):
+    """ray_trimesh.rs:187-212 scene (one triangle, rays from both sides): front face => Face(0), back face => Face(0 + 1)."""
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    i = np.array([[0, 1, 2]], np.uint32)
+    m = oracle.TriMesh(v, i)
+    up = np.array([[0.1, 0.1, -1, 0, 0, 1]], np.float32)     # along +z: hits the back face (normal is +z)
+    down = np.array([[0.1, 0.1, 1, 0, 0, -1]], np.float32)
+    toi, tri, n, f = m.cast_rays(None, up, 1000.0, with_normal=True)
+    assert tri[0] == 0 and toi[0] == 1.0 and f[0] == 1 and (n[0] == [0, 0, -1]).all()
+    toi, tri, n, f = m.cast_rays(None, down, 1000.0, with_normal=True)
+    assert tri[0] == 0 and toi[0] == 1.0 and f[0] == 0 and (n[0] == [0, 0, 1]).all()
+    # toi-only variant post-filters toi < max_toi (ray_composite_shape.rs:38)
+    assert m.cast_rays(None, down, 1.0)[1][0] == INVALID
+    assert m.cast_rays(None, down, 1.0001)[1][0] == 0
+
+
+def test_bvh_build_well_formed_all_sizes(oracle):
+    """bvh_tests.rs:34-123 (build part): Binned and Ploc, len 1..=100, assert_well_formed (bvh_validation.rs:61-134)."""
+    from helpers import assert_well_formed
+    g = scenes.rng(7)
+    for strategy in (0, 1):
+        for n in list(range(1, 101)) + [1000]:
+            c = g.random((n, 3)) * 10
+            aabbs = np.concatenate([c - 0.5, c + 0.5], axis=1).astype(np.float32)
+            b = oracle.Bvh(aabbs, strategy)
+            nodes = b.nodes()
+            assert len(nodes) == (1 if n <= 2 else n - 1)
+            if n > 2:
+                assert_well_formed(nodes, b.parents(), b.leaf_node_indices())
+            # every leaf reachable through intersect_aabb with an all-enclosing box (test_leaves_iteration analogue)
+            offs, ids = b.intersect_aabbs(np.array([[-100, -100, -100, 100, 100, 100]], np.float32))
+            assert sorted(ids.tolist()) == list(range(n))
+
+
+def test_pairs_match_brute_force(oracle):
+    from helpers import sorted_pairs
+    g = scenes.rng(8)
+    for n in (2, 3, 10, 500):
+        c = g.random((n, 3)) * (n ** (1 / 3)) * 1.2
+        h = g.random((n, 3)) * 0.6 + 0.1
+        a = np.concatenate([c - h, c + h], axis=1).astype(np.float32)
+        for strategy in (0, 1):
+            b = oracle.Bvh(a, strategy)
+            got = sorted_pairs(b.self_pairs())
+            ref = []
+            for i in range(n):
+                for j in range(i + 1, n):
+                    if (a[i, :3] <= a[j, 3:]).all() and (a[i, 3:] >= a[j, :3]).all():
+                        ref.append((i, j))
+            assert (got == sorted_pairs(np.array(ref).reshape(-1, 2))).all()
+
+
+def test_ray_ball_analytic(oracle):
+    """Unit ball, axis rays: closed-form distances (ray_ball.rs)."""
+    assert oracle.shape_cast_ray_toi(0, [1.0], None, [-3, 0, 0, 1, 0, 0], FMAX, True) == 2.0
+    assert oracle.shape_cast_ray_toi(0, [1.0], None, [0, 0, 0, 1, 0, 0], FMAX, True) == 0.0
+    assert oracle.shape_cast_ray_toi(0, [1.0], None, [0, 0, 0, 1, 0, 0], FMAX, False) == 1.0
+    assert oracle.shape_cast_ray_toi(0, [1.0], None, [-3, 0, 0, -1, 0, 0], FMAX, True) is None
+    assert oracle.shape_cast_ray_toi(0, [1.0], None, [-3, 0, 0, 1, 0, 0], 1.5, True) is None
+    t, n, f = oracle.shape_cast_ray(0, [1.0], None, [-3, 0, 0, 1, 0, 0], FMAX, True)
+    assert (n == [-1, 0, 0]).all() and f == 0
