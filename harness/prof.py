@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Small single-workload driver for ncu captures / quick timings: python harness/prof.py <workload> [iters]
+workloads: rays_terrain, rays_sphere1m, contacts, broadphase"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+FMAX = float(np.finfo(np.float32).max)
+
+
+def main():
+    import torch
+    import parry_b200
+    from harness import scenes
+    wl = sys.argv[1]
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    ctx = parry_b200.Context(0)
+    stream = ctx.torch_stream()
+
+    def timeit(fn, name):
+        fn()
+        ctx.synchronize()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            ctx.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        print("%s: min %.3f ms  med %.3f ms" % (name, min(ts), float(np.median(ts))))
+        return min(ts)
+
+    if wl.startswith("rays"):
+        if wl == "rays_terrain":
+            v, i = scenes.terrain(2001, 2001)
+            m = 1 << 23
+            rays = scenes.terrain_rays(m, seed=6)
+        else:
+            v, i = scenes.uv_sphere(708, 707)
+            m = 1 << 20
+            rays = scenes.sphere_rays(m, seed=1)
+        mesh = parry_b200.TriMesh(ctx, v, i)
+        rd = torch.from_numpy(rays).cuda()
+        toi = torch.empty(m, dtype=torch.float32, device="cuda")
+        tri = torch.empty(m, dtype=torch.int32, device="cuda")
+        sweep = os.environ.get("PB2_SWEEP")
+        configs = [None]
+        if sweep:
+            configs = [(0, 0, 0), (1, 32, 8), (2, 32, 8), (2, 8, 8), (2, 32, 16), (2, 64, 8), (2, 16, 4)]
+        for cfg in configs:
+            if cfg is not None:
+                os.environ["PB2_RAY_VARIANT"], os.environ["PB2_RAY_STEPS"], os.environ["PB2_RAY_REFILL"] = map(str, cfg)
+            ms = timeit(lambda: mesh.cast_local_ray(rd, FMAX, out=(toi, tri)), "%s %s" % (wl, cfg))
+            print("   %.1f Mrays/s  checksum %d %.6f" % (m / ms / 1e3, int(tri.to(torch.int64).sum().item()), float(toi.double().sum().item())))
+    elif wl == "contacts":
+        pts, radii = scenes.hull_pool(4096)
+        G = parry_b200.Shapes(ctx, [parry_b200.ConvexPolyhedron(p) for p in pts])
+        n = 1 << 22
+        a, b, p1, p2 = scenes.hull_pairs(n, radii, seed=4)
+        da, db = torch.from_numpy(a.astype(np.int32)).cuda(), torch.from_numpy(b.astype(np.int32)).cuda()
+        dp1, dp2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
+        res = {}
+
+        def run():
+            res["o"] = parry_b200.contact(G, da, dp1, db, dp2, 0.01)
+        ms = timeit(run, wl)
+        print("%.1f Mpairs/s" % (n / ms / 1e3))
+        out, st = res["o"]
+        print("checksum", int(st.to(torch.int64).sum().item()), float(out.double().nan_to_num().sum().item()))
+    elif wl == "broadphase":
+        n = 1 << 20
+        kinds, params, poses, _ = scenes.colliders(n, seed=2)
+        shapes = parry_b200.Shapes(ctx, [parry_b200.Ball(p[0]) if k == 0 else parry_b200.Cuboid(p) for k, p in zip(kinds, params)])
+        ids = torch.arange(n, dtype=torch.int32, device="cuda")
+        dposes = torch.from_numpy(poses).cuda()
+        aabbs = shapes.compute_aabbs(ids, dposes)
+        bvh = parry_b200.Bvh.from_leaves(ctx, 0, aabbs)
+        st = {}
+
+        def frame():
+            a = shapes.compute_aabbs(ids, dposes)
+            bvh.insert_or_update_partially(a, ids, 0.0)
+            bvh.rebuild()
+            st["p"] = bvh.traverse_bvtt_single_tree(capacity=16 * n, like=a)
+        ms = timeit(frame, wl)
+        print("%.1f MAABB/s, %d pairs" % (n / ms / 1e3, st["p"].shape[0]))
+
+
+if __name__ == "__main__":
+    main()

@@ -187,3 +187,22 @@ __device__ __forceinline__ float slab_cost(float mnx, float mny, float mnz, floa
     }
     return tmin;
 }
+
+// Branch-free form of slab_cost: identical values for every input (IEEE inf/NaN arithmetic reproduces the reference's
+// dir == 0 special case: inv = +-inf gives (-inf, +inf) inside the slab, a same-signed infinite pair outside, and NaN —
+// ignored by fmaxf/fminf exactly like Rust's f32::max/min — on the boundary). The per-axis early-outs of the reference
+// are equivalent to one final test because tmin only grows and tmax only shrinks.
+__device__ __forceinline__ float slab_cost_bf(float4 lo, float4 hi, V3 o, V3 inv, float tmax) {
+    float tmin = 0.0f;
+    float n, f, a, b;
+    n = (lo.x - o.x) * inv.x; f = (hi.x - o.x) * inv.x;
+    a = n > f ? f : n; b = n > f ? n : f;
+    tmin = fmaxf(tmin, a); tmax = fminf(tmax, b);
+    n = (lo.y - o.y) * inv.y; f = (hi.y - o.y) * inv.y;
+    a = n > f ? f : n; b = n > f ? n : f;
+    tmin = fmaxf(tmin, a); tmax = fminf(tmax, b);
+    n = (lo.z - o.z) * inv.z; f = (hi.z - o.z) * inv.z;
+    a = n > f ? f : n; b = n > f ? n : f;
+    tmin = fmaxf(tmin, a); tmax = fminf(tmax, b);
+    return tmin > tmax ? FLT_MAX : tmin;
+}

@@ -10,6 +10,8 @@
 // order as 3 x float4 (48 B, 16-B aligned vector loads) so a leaf visit costs no index indirection.
 #include "common.cuh"
 #include "traverse.cuh"
+#include <stdlib.h>
+#include <cub/device/device_radix_sort.cuh>
 
 int pb2_bvh_build_device(pb2_ctx* ctx, pb2_bvh* b, const float* d_aabbs, uint32_t n, bool resolve_flags);
 int pb2_stage_in(pb2_ctx* ctx, int slot, const void* src, size_t bytes, int mem, const void** out);
@@ -141,6 +143,155 @@ __global__ void __launch_bounds__(128) k_raycast_trimesh(const NodeWide* __restr
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant (n_leaves >= 2): one lane = one ray at a time, warps pull new rays from a global counter as
+// lanes retire (dynamic fetch), so a few long rays no longer hold 31 idle lanes hostage; leaf tests of both children
+// share one call site so lanes that reach a leaf on different sides stay converged. Same arithmetic, same tie rule.
+template <bool WITH_NORMAL>
+__global__ void __launch_bounds__(128) k_raycast_trimesh_persistent(const NodeWide* __restrict__ nodes, const float4* __restrict__ tris,
+                                  uint32_t nt, const float* __restrict__ pose7, const float* __restrict__ rays,
+                                  const uint32_t* __restrict__ perm, uint32_t m, float max_toi, float* __restrict__ out_toi,
+                                  uint32_t* __restrict__ out_tri, float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
+                                  unsigned int* __restrict__ next_ray, int steps, int refill) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    Iso7 pose;
+    if (pose7) pose = load_iso(pose7);
+    V3 o = mk3(0.f, 0.f, 0.f), d = o, inv = o, best_n = o;
+    float best = 0.f;
+    uint32_t best_id = PB2_INVALID_U32, best_fid = 0, r = 0, curr = PB2_INVALID_U32;
+    bool found = false, active = false;
+    uint32_t stack[PB2_STACK];
+    int sp = 0;
+    bool exhausted = false;
+    for (;;) {
+        __syncwarp();
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (!exhausted && (idle == FULL || __popc(idle) >= refill)) {
+            unsigned base = 0;
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(next_ray, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base >= m) exhausted = true;
+            if (!active) {
+                uint32_t slot = base + __popc(idle & ((1u << lane) - 1u));
+                if (slot < m) {
+                    r = perm ? perm[slot] : slot;
+                    o = mk3(rays[6ull * r], rays[6ull * r + 1], rays[6ull * r + 2]);
+                    d = mk3(rays[6ull * r + 3], rays[6ull * r + 4], rays[6ull * r + 5]);
+                    if (pose7) { o = iso_inv_point(pose, o); d = iso_inv_vec(pose, d); }
+                    inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                    best = max_toi; best_id = PB2_INVALID_U32; best_fid = 0; found = false;
+                    curr = 0; sp = 0; active = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) break;
+#pragma unroll 1
+        for (int it = 0; it < steps; ++it) {
+            if (curr != PB2_INVALID_U32) {
+                const float4* np = reinterpret_cast<const float4*>(&nodes[curr]);
+                float4 l0 = __ldg(np), l1 = __ldg(np + 1), r0 = __ldg(np + 2), r1 = __ldg(np + 3);
+                float ls = slab_cost_bf(l0, l1, o, inv, best);
+                float rs = slab_cost_bf(r0, r1, o, inv, best);
+                uint32_t lc = __float_as_uint(l0.w), rc = __float_as_uint(r0.w);
+                bool lleaf = (__float_as_uint(l1.w) & PB2_LEAF_COUNT_MASK) == 1u;
+                bool rleaf = (__float_as_uint(r1.w) & PB2_LEAF_COUNT_MASK) == 1u;
+                bool sw = ls > rs;
+                float s0 = sw ? rs : ls, s1 = sw ? ls : rs;
+                uint32_t c0 = sw ? rc : lc, c1 = sw ? lc : rc;
+                bool f0 = sw ? rleaf : lleaf, f1 = sw ? lleaf : rleaf;
+                if (f0 | f1) {
+                    // leaves first (near, then far), one call site
+#pragma unroll 1
+                    for (int k = 0; k < 2; ++k) {
+                        float sc = k ? s1 : s0;
+                        bool isleaf = k ? f1 : f0;
+                        if (isleaf && sc != FLT_MAX && (sc < best || (found && sc == best))) {
+                            uint32_t pos = k ? c1 : c0;
+                            float4 ta = __ldg(&tris[3ull * pos]), tb = __ldg(&tris[3ull * pos + 1]), tc = __ldg(&tris[3ull * pos + 2]);
+                            float toi; uint32_t fid; V3 n;
+                            if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n) && toi <= best) {
+                                uint32_t id = __float_as_uint(ta.w);
+                                if (toi < best || (found && toi == best && id < best_id)) {
+                                    best = toi; best_id = id; best_fid = fid; found = true;
+                                    if (WITH_NORMAL) best_n = n;
+                                }
+                            }
+                        }
+                    }
+                }
+                bool go0 = !f0 && s0 != FLT_MAX && (s0 < best || (found && s0 == best));
+                bool go1 = !f1 && s1 != FLT_MAX && (s1 < best || (found && s1 == best));
+                if (go0 && go1 && sp < PB2_STACK) stack[sp++] = c1;
+                uint32_t nxt = go0 ? c0 : c1;
+                if (!(go0 || go1)) {
+                    nxt = PB2_INVALID_U32;
+                    if (sp > 0) nxt = stack[--sp];
+                }
+                curr = nxt;
+            }
+        }
+        if (active && curr == PB2_INVALID_U32) {
+            out_toi[r] = found ? best : 0.0f;
+            out_tri[r] = best_id;
+            if (WITH_NORMAL) {
+                V3 n = mk3(0.f, 0.f, 0.f);
+                uint32_t feat = PB2_INVALID_U32;
+                if (found) {
+                    n = normalize3(best_n);
+                    if (best_fid & 2u) n = -n;
+                    if (pose7) n = iso_vec(pose, n);
+                    feat = (best_fid & 1u) ? best_id + nt : best_id;
+                }
+                if (out_normal) { out_normal[3ull * r] = n.x; out_normal[3ull * r + 1] = n.y; out_normal[3ull * r + 2] = n.z; }
+                if (out_feature) out_feature[r] = feat;
+            }
+            active = false;
+        }
+    }
+}
+
+
+// Coherence key for ray reordering (results are scattered back by ray index, so outputs are order-independent):
+// [direction octant : 3][Morton of the origin quantised to 6 bits/axis over the root box : 18][direction quantised 3 bits/axis : 9].
+__device__ __forceinline__ uint32_t spread3_10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void k_ray_keys(const NodeWide* __restrict__ nodes, const float* __restrict__ pose7, const float* __restrict__ rays, uint32_t m,
+                           uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    V3 o = mk3(rays[6ull * r], rays[6ull * r + 1], rays[6ull * r + 2]);
+    V3 d = mk3(rays[6ull * r + 3], rays[6ull * r + 4], rays[6ull * r + 5]);
+    if (pose7) { Iso7 pose = load_iso(pose7); o = iso_inv_point(pose, o); d = iso_inv_vec(pose, d); }
+    const float4* np = reinterpret_cast<const float4*>(&nodes[0]);
+    float4 l0 = __ldg(np), l1 = __ldg(np + 1), r0 = __ldg(np + 2), r1 = __ldg(np + 3);
+    V3 mn = mk3(fminf(l0.x, r0.x), fminf(l0.y, r0.y), fminf(l0.z, r0.z));
+    V3 mx = mk3(fmaxf(l1.x, r1.x), fmaxf(l1.y, r1.y), fmaxf(l1.z, r1.z));
+    V3 ext = mx - mn;
+    float e = fmaxf(fmaxf(ext.x, ext.y), fmaxf(ext.z, 1e-30f));
+    // origins may lie outside the scene box: quantise over the box grown by its largest extent on each side
+    float sc = 64.0f / (3.0f * e);
+    uint32_t qx = (uint32_t)fminf(fmaxf((o.x - mn.x + e) * sc, 0.0f), 63.0f);
+    uint32_t qy = (uint32_t)fminf(fmaxf((o.y - mn.y + e) * sc, 0.0f), 63.0f);
+    uint32_t qz = (uint32_t)fminf(fmaxf((o.z - mn.z + e) * sc, 0.0f), 63.0f);
+    float dl = fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), 1e-30f));
+    uint32_t dx = (uint32_t)fminf(fabsf(d.x) / dl * 7.999f, 7.0f), dy = (uint32_t)fminf(fabsf(d.y) / dl * 7.999f, 7.0f),
+             dz = (uint32_t)fminf(fabsf(d.z) / dl * 7.999f, 7.0f);
+    uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    uint32_t om = spread3_10(qx) | (spread3_10(qy) << 1) | (spread3_10(qz) << 2);
+    uint32_t dm = spread3_10(dx) | (spread3_10(dy) << 1) | (spread3_10(dz) << 2);
+    keys[r] = (oct << 27) | ((om & 0x3ffffu) << 9) | (dm & 0x1ffu);
+    vals[r] = r;
+}
+
 extern "C" {
 
 int pb2_trimesh_create(pb2_ctx* ctx, const float* vertices, uint32_t nv, const uint32_t* indices, uint32_t nt, int mem,
@@ -223,15 +374,58 @@ int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* po
     PB2_CHECK(pb2_stage_out(ctx, 4, normal, (size_t)m * 12, mem, &d_n));
     PB2_CHECK(pb2_stage_out(ctx, 5, feature, (size_t)m * 4, mem, &d_f));
     const pb2_bvh* b = &mesh->bvh;
-    unsigned blocks = pb2_blocks(m, 128);
-    if (normal || feature)
-        k_raycast_trimesh<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
-                                                                 (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
-                                                                 (float*)d_n, (uint32_t*)d_f);
-    else
-        k_raycast_trimesh<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
-                                                                  (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
-                                                                  nullptr, nullptr);
+    bool with_normal = normal || feature;
+    // ray reordering pays off once the node array no longer fits in L2 (126 MB); below that the sort costs more than it saves
+    int variant = ((size_t)b->n_nodes * sizeof(NodeWide) > (size_t)(100u << 20)) ? 2 : 1, steps = 16, refill = 8;
+    {   // tuning knobs (read per call; cheap)
+        const char* e = getenv("PB2_RAY_VARIANT");
+        if (e) variant = atoi(e);
+        if ((e = getenv("PB2_RAY_STEPS"))) steps = atoi(e);
+        if ((e = getenv("PB2_RAY_REFILL"))) refill = atoi(e);
+    }
+    if (variant == 0 || b->n_leaves < 2 || m < 4096) {
+        unsigned blocks = pb2_blocks(m, 128);
+        if (with_normal)
+            k_raycast_trimesh<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
+                                                                     (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
+                                                                     (float*)d_n, (uint32_t*)d_f);
+        else
+            k_raycast_trimesh<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
+                                                                      (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
+                                                                      nullptr, nullptr);
+    } else {
+        unsigned int* next_ray = (unsigned int*)(ctx->d_counters + 8);
+        PB2_CUDA(ctx, cudaMemsetAsync(next_ray, 0, 4, ctx->stream));
+        const uint32_t* perm = nullptr;
+        if (variant >= 2 && m >= 65536) {
+            size_t cub_bytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                            (uint32_t*)nullptr, (int)m, 0, 30, ctx->stream);
+            size_t arr = ((size_t)m * 4 + 255) & ~(size_t)255;
+            PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[0], 4 * arr + cub_bytes));
+            char* base = (char*)ctx->scratch[0].ptr;
+            uint32_t *k_in = (uint32_t*)base, *k_out = (uint32_t*)(base + arr), *v_in = (uint32_t*)(base + 2 * arr), *v_out = (uint32_t*)(base + 3 * arr);
+            k_ray_keys<<<pb2_blocks(m, 256), 256, 0, ctx->stream>>>(b->nodes, (const float*)d_pose, (const float*)d_rays, m, k_in, v_in);
+            PB2_LAUNCHED(ctx);
+            PB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + 4 * arr, cub_bytes, (const uint32_t*)k_in, k_out, (const uint32_t*)v_in, v_out,
+                                                          (int)m, 0, 30, ctx->stream));
+            ctx->launches += 3;
+            perm = v_out;
+        }
+        int per_sm = 0;
+        if (with_normal) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_trimesh_persistent<true>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_trimesh_persistent<false>, 128, 0);
+        if (per_sm < 1) per_sm = 1;
+        unsigned blocks = (unsigned)(ctx->sm_count * per_sm);
+        unsigned need = pb2_blocks(m, 128);
+        if (blocks > need) blocks = need;
+        if (with_normal)
+            k_raycast_trimesh_persistent<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
+                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, (float*)d_n, (uint32_t*)d_f, next_ray, steps, refill);
+        else
+            k_raycast_trimesh_persistent<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
+                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, nullptr, nullptr, next_ray, steps, refill);
+    }
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
     PB2_CHECK(pb2_stage_back(ctx, toi, d_toi, (size_t)m * 4, mem));
