@@ -15,6 +15,7 @@
 // per-thread arena (vertices / faces / heap) so that divergence of the rare, long EPA runs does not stall the
 // closed-form and separated pairs. Contacts are written either densely (status per pair) or compacted.
 #include "gjk.cuh"
+#include <stdlib.h>
 
 int pb2_stage_in(pb2_ctx* ctx, int slot, const void* src, size_t bytes, int mem, const void** out);
 int pb2_stage_out(pb2_ctx* ctx, int slot, void* dst, size_t bytes, int mem, void** out);
@@ -596,26 +597,399 @@ __global__ void __launch_bounds__(64) k_contact_epa(const uint8_t* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------- phase 2, flattened
+// Warp-convergent EPA: every lane owns one parked pair; ONE loop whose trip is "one expansion step" for every lane, with
+// job fetch / initial-polytope construction folded into the same phases (pop -> support -> test -> silhouette -> faces ->
+// finish). Lanes refill individually, so a long run never holds finished lanes idle (the first version waited at the end
+// of the per-job loop: 8.6 of 32 lanes active). Hot arena per lane: faces 16 B (normal + packed pts/deleted), adjacency
+// 8 B, heap 8 B, vertex point 16 B; witness points (orig1/orig2) live in a cold array and the barycentric coordinates of
+// the winning face are recomputed at the end by the same deterministic projection.
+#define E2_MAX_VERTS 112
+#define E2_MAX_FACES 256
+#define E2_MAX_SIL 64
+#define E2_STACK 96
+
+struct Epa2Arena {
+    float4 face[E2_MAX_FACES];   // normal.xyz ; w = pts0 | pts1 << 8 | pts2 << 16 | deleted << 24
+    uint2 adj[E2_MAX_FACES];     // x = adj0 | adj1 << 16 ; y = adj2
+    float2 heap[E2_MAX_FACES];   // neg_dist ; face id (bits)
+    float4 vp[E2_MAX_VERTS];     // CSO point
+    float4 vo1[E2_MAX_VERTS];    // orig1 (cold)
+    float4 vo2[E2_MAX_VERTS];    // orig2 (cold)
+    uint32_t sil[E2_MAX_SIL];    // face | opp << 16
+    uint32_t stk[E2_STACK];
+};
+
+__device__ __forceinline__ uint32_t f_pts(float4 f, int i) { return (__float_as_uint(f.w) >> (8 * i)) & 0xffu; }
+__device__ __forceinline__ bool f_deleted(float4 f) { return (__float_as_uint(f.w) >> 24) != 0u; }
+__device__ __forceinline__ uint32_t a_get(uint2 a, int i) { return i == 0 ? (a.x & 0xffffu) : (i == 1 ? (a.x >> 16) : a.y); }
+__device__ __forceinline__ void a_set(uint2& a, int i, uint32_t v) {
+    if (i == 0) a.x = (a.x & 0xffff0000u) | v; else if (i == 1) a.x = (a.x & 0xffffu) | (v << 16); else a.y = v;
+}
+__device__ __forceinline__ V3 v3of(float4 f) { return mk3(f.x, f.y, f.z); }
+__device__ __forceinline__ int e2_next_ccw(float4 f, uint32_t id) {
+    if (f_pts(f, 0) == id) return 1;
+    if (f_pts(f, 1) == id) return 2;
+    return 0;
+}
+__device__ __forceinline__ bool h2_le(float a, float b) { return !(a > b); }
+__device__ __forceinline__ void h2_sift_up(Epa2Arena& A, int start, int pos) {
+    float2 elt = A.heap[pos];
+    while (pos > start) {
+        int parent = (pos - 1) / 2;
+        float2 pe = A.heap[parent];
+        if (h2_le(elt.x, pe.x)) break;
+        A.heap[pos] = pe;
+        pos = parent;
+    }
+    A.heap[pos] = elt;
+}
+__device__ __forceinline__ void h2_push(Epa2Arena& A, int& nheap, uint32_t id, float neg_dist) {
+    int old = nheap;
+    A.heap[old] = make_float2(neg_dist, __uint_as_float(id));
+    nheap = old + 1;
+    h2_sift_up(A, 0, old);
+}
+__device__ __forceinline__ float2 h2_pop(Epa2Arena& A, int& nheap) {
+    float2 item = A.heap[nheap - 1];
+    nheap -= 1;
+    if (nheap > 0) {
+        float2 t = item; item = A.heap[0];
+        int end = nheap, pos = 0;
+        float2 elt = t;
+        int child = 1;
+        while (end >= 2 && child <= end - 2) {
+            float2 c0 = A.heap[child], c1 = A.heap[child + 1];
+            if (h2_le(c0.x, c1.x)) { child += 1; c0 = c1; }
+            A.heap[pos] = c0;
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (child == end - 1) { A.heap[pos] = A.heap[child]; pos = child; }
+        A.heap[pos] = elt;
+        h2_sift_up(A, 0, pos);
+    }
+    return item;
+}
+// Barycentric coordinates Face::new would store for (va, vb, vc) + whether the origin projects inside.
+__device__ __forceinline__ bool e2_face_bc(V3 va, V3 vb, V3 vc, float bc[3]) {
+    Proj p;
+    project_on_triangle(va, vb, vc, mk3(0.f, 0.f, 0.f), p);
+    bc[0] = bc[1] = bc[2] = 0.f;
+    if (p.kind == 0) { bc[p.idx] = 1.0f; }
+    else if (p.kind == 1) { int i0 = p.idx == 1 ? 1 : 0, i1 = p.idx == 0 ? 1 : 2; bc[i0] = p.bc[0]; bc[i1] = p.bc[1]; }
+    if (p.kind == 0 || p.kind == 1) {
+        const float eps_tol = PB2_EPS * 100.0f;
+        return p.inside || nrm2(p.point - mk3(0.f, 0.f, 0.f)) < eps_tol * eps_tol;
+    }
+    if (p.kind == 2) { bc[0] = p.bc[0]; bc[1] = p.bc[1]; bc[2] = p.bc[2]; return true; }
+    return false;
+}
+
+enum { E2_IDLE = 0, E2_INIT = 1, E2_RUN = 2 };
+enum { FIN_NOT = 0, FIN_FACE = 1, FIN_NONE = 2, FIN_OVERFLOW = 3, FIN_DIM0 = 4 };
+
+__global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
+                              const float4* __restrict__ pts, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2,
+                              const float* __restrict__ pos1, const float* __restrict__ pos2, float prediction, OutSinks out,
+                              const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
+                              unsigned long long* __restrict__ next_job, Epa2Arena* __restrict__ arenas, int refill) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    Epa2Arena& A = arenas[blockIdx.x * blockDim.x + threadIdx.x];
+    const unsigned long long total = *job_count;
+    const float eps = PB2_EPS, eps_tol = PB2_EPS * 100.0f;
+
+    int state = E2_IDLE;
+    uint32_t pair = 0;
+    Iso7 gpos12;
+    DShape g1, g2;
+    g1.kind = g2.kind = DS_ORIGIN; g1.n = g2.n = 0; g1.pts = g2.pts = nullptr; g1.he = g2.he = mk3(0.f, 0.f, 0.f);
+    gpos12.q.i = gpos12.q.j = gpos12.q.k = 0.f; gpos12.q.w = 1.f; gpos12.t = mk3(0.f, 0.f, 0.f);
+    int dim = 0, nverts = 0, nfaces = 0, nheap = 0, niter = 0;
+    float max_dist = FLT_MAX, old_dist = 0.0f, best_neg = 0.0f;
+    uint32_t best_id = 0;
+    bool exhausted = false;
+
+    for (;;) {
+        __syncwarp();
+        unsigned idle = __ballot_sync(FULL, state == E2_IDLE);
+        if (!exhausted && (idle == FULL || __popc(idle) >= refill)) {
+            unsigned long long base = 0;
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(next_job, (unsigned long long)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base >= total) exhausted = true;
+            if (state == E2_IDLE) {
+                unsigned long long j = base + __popc(idle & ((1u << lane) - 1u));
+                if (j < total) {
+                    const EpaJob& job = jobs[j];
+                    pair = job.pair;
+                    PairSetup ps;
+                    pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, pair, ps);
+                    gpos12 = ps.gpos12; g1 = ps.g1; g2 = ps.g2;
+                    dim = (int)job.dim;
+                    for (int i = 0; i <= dim; ++i) {
+                        V3 o1 = mk3(job.o1[i][0], job.o1[i][1], job.o1[i][2]), o2 = mk3(job.o2[i][0], job.o2[i][1], job.o2[i][2]);
+                        V3 p = o1 - o2;
+                        A.vp[i] = make_float4(p.x, p.y, p.z, 0.f);
+                        A.vo1[i] = make_float4(o1.x, o1.y, o1.z, 0.f);
+                        A.vo2[i] = make_float4(o2.x, o2.y, o2.z, 0.f);
+                    }
+                    nverts = dim + 1; nfaces = 0; nheap = 0; niter = 0;
+                    max_dist = FLT_MAX; old_dist = 0.0f;
+                    state = E2_INIT;
+                }
+            }
+        }
+        if (!__any_sync(FULL, state != E2_IDLE)) break;
+
+        int fin = FIN_NOT;
+        uint32_t fin_face = 0;
+        bool need_support = false, run_step = false;
+        V3 sdir = mk3(0.f, 0.f, 0.f);
+        float4 face = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint2 face_adj = make_uint2(0u, 0u);
+        uint32_t face_id = 0;
+        float face_neg = 0.0f, curr_dist = 0.0f;
+        int npend = 0;
+
+        // ---- phase A: pop the closest live face (RUN) / seed the initial polytope (INIT)
+        if (state == E2_RUN) {
+            bool got = false;
+            while (nheap > 0) {
+                float2 ent = h2_pop(A, nheap);
+                face_id = __float_as_uint(ent.y); face_neg = ent.x;
+                face = A.face[face_id];
+                if (!f_deleted(face)) { got = true; break; }
+            }
+            if (got) { need_support = true; run_step = true; sdir = v3of(face); face_adj = A.adj[face_id]; }
+            else { fin = FIN_FACE; fin_face = best_id; }
+        } else if (state == E2_INIT) {
+            if (dim == 0) fin = FIN_DIM0;
+            else if (dim == 3) {
+                V3 v0 = v3of(A.vp[0]), v1 = v3of(A.vp[1]), v2 = v3of(A.vp[2]), v3 = v3of(A.vp[3]);
+                if (dot3(cross3(v1 - v0, v2 - v0), v3 - v0) > 0.0f) {
+                    float4 t = A.vp[1]; A.vp[1] = A.vp[2]; A.vp[2] = t;
+                    t = A.vo1[1]; A.vo1[1] = A.vo1[2]; A.vo1[2] = t;
+                    t = A.vo2[1]; A.vo2[1] = A.vo2[2]; A.vo2[2] = t;
+                }
+                npend = 4;
+            } else {
+                if (dim == 1) {
+                    V3 dpt = v3of(A.vp[1]) - v3of(A.vp[0]);
+                    V3 a = fabsf(dpt.x) > fabsf(dpt.y) ? mk3(dpt.z, 0.0f, -dpt.x) : mk3(0.0f, -dpt.z, dpt.y);
+                    a = normalize3(a);
+                    sdir = cross3(a, dpt);
+                    need_support = true;
+                }
+                npend = 2;
+            }
+        }
+        // ---- phase B: one support point of the Minkowski difference
+        uint32_t support_id = 0;
+        V3 sp_point = mk3(0.f, 0.f, 0.f);
+        if (need_support) {
+            if (nverts >= E2_MAX_VERTS) { fin = FIN_OVERFLOW; run_step = false; npend = 0; }
+            else {
+                CSO cso = cso_from_shapes(gpos12, g1, g2, sdir);
+                support_id = (uint32_t)nverts;
+                A.vp[nverts] = make_float4(cso.point.x, cso.point.y, cso.point.z, 0.f);
+                A.vo1[nverts] = make_float4(cso.o1.x, cso.o1.y, cso.o1.z, 0.f);
+                A.vo2[nverts] = make_float4(cso.o2.x, cso.o2.y, cso.o2.z, 0.f);
+                nverts++;
+                sp_point = cso.point;
+            }
+        }
+        // ---- phase C/D: convergence test, then the silhouette of the faces visible from the new point
+        if (run_step) {
+            V3 fnormal = v3of(face);
+            float candidate = dot3(sp_point, fnormal);
+            if (candidate < max_dist) { best_id = face_id; best_neg = face_neg; max_dist = candidate; }
+            curr_dist = -face_neg;
+            if (max_dist - curr_dist < eps_tol || (fabsf(curr_dist - old_dist) < eps && candidate < max_dist)) {
+                fin = FIN_FACE; fin_face = best_id; run_step = false;
+            } else {
+                old_dist = curr_dist;
+                A.face[face_id].w = __uint_as_float(__float_as_uint(face.w) | (1u << 24));
+                int nsil = 0, sp = 0;
+                bool ovf = false;
+                // three compute_silhouette calls (adj[0], adj[1], adj[2]) as one DFS stack: push in reverse order
+#pragma unroll 1
+                for (int k = 2; k >= 0; --k) {
+                    uint32_t af = a_get(face_adj, k);
+                    int opp = e2_next_ccw(A.face[af], f_pts(face, k));
+                    A.stk[sp++] = af | ((uint32_t)opp << 16);
+                }
+                V3 pt = sp_point;
+                while (sp > 0) {
+                    uint32_t e = A.stk[--sp];
+                    uint32_t fid = e & 0xffffu; int fo = (int)(e >> 16);
+                    float4 f = A.face[fid];
+                    if (f_deleted(f)) continue;
+                    V3 p0 = v3of(A.vp[f_pts(f, fo)]);
+                    bool seen = dot3(pt - p0, v3of(f)) >= -PB2_GJK_EPS_TOL;
+                    if (!seen) {
+                        V3 p1 = v3of(A.vp[f_pts(f, (fo + 1) % 3)]), p2 = v3of(A.vp[f_pts(f, (fo + 2) % 3)]);
+                        const float EPS = PB2_EPS * 100.0f;
+                        seen = rel_eq(nrm2(cross3(p2 - p1, pt - p1)), 0.0f, EPS * EPS, PB2_EPS);
+                    }
+                    if (!seen) {
+                        if (nsil >= E2_MAX_SIL) { ovf = true; break; }
+                        A.sil[nsil++] = e;
+                    } else {
+                        A.face[fid].w = __uint_as_float(__float_as_uint(f.w) | (1u << 24));
+                        int i1 = (fo + 2) % 3, i2 = fo;
+                        uint2 fa = A.adj[fid];
+                        uint32_t adj1 = a_get(fa, i1), adj2 = a_get(fa, i2);
+                        int o1 = e2_next_ccw(A.face[adj1], f_pts(f, i1));
+                        int o2 = e2_next_ccw(A.face[adj2], f_pts(f, i2));
+                        if (sp + 2 > E2_STACK) { ovf = true; break; }
+                        A.stk[sp++] = adj2 | ((uint32_t)o2 << 16);
+                        A.stk[sp++] = adj1 | ((uint32_t)o1 << 16);
+                    }
+                }
+                if (ovf) { fin = FIN_OVERFLOW; run_step = false; }
+                else if (nsil == 0) { fin = FIN_NONE; run_step = false; }
+                else npend = nsil;
+            }
+        }
+        // ---- phase E: create the pending faces (initial polytope or the fan around the silhouette)
+        int first_new = nfaces;
+        if (fin == FIN_NOT && npend > 0) {
+#pragma unroll 1
+            for (int e = 0; e < npend; ++e) {
+                int p0, p1, p2, a0, a1, a2, dv;
+                int new_id = nfaces;
+                if (state == E2_INIT) {
+                    if (npend == 4) {
+                        // pts {0,1,2},{1,3,2},{0,2,3},{0,3,1}; adj {3,1,2},{3,2,0},{0,1,3},{2,1,0}; dist uses vertex e
+                        p0 = (e == 1) ? 1 : 0; p1 = (e == 0) ? 1 : ((e == 2) ? 2 : 3); p2 = (e == 0) ? 2 : ((e == 1) ? 2 : ((e == 2) ? 3 : 1));
+                        a0 = (e == 0 || e == 1) ? 3 : ((e == 2) ? 0 : 2); a1 = (e == 1) ? 2 : 1; a2 = (e == 0) ? 2 : ((e == 2) ? 3 : 0);
+                        dv = e;
+                    } else {
+                        p0 = 0; p1 = e == 0 ? 1 : 2; p2 = e == 0 ? 2 : 1;
+                        a0 = a1 = a2 = e == 0 ? 1 : 0;
+                        dv = 0;
+                    }
+                } else {
+                    uint32_t ed = A.sil[e];
+                    uint32_t efid = ed & 0xffffu; int eopp = (int)(ed >> 16);
+                    float4 ef = A.face[efid];
+                    if (f_deleted(ef)) continue;
+                    if (new_id >= E2_MAX_FACES) { fin = FIN_OVERFLOW; break; }
+                    p0 = (int)f_pts(ef, (eopp + 2) % 3); p1 = (int)f_pts(ef, (eopp + 1) % 3); p2 = (int)support_id;
+                    a0 = (int)efid; a1 = new_id + 1; a2 = new_id - 1;
+                    dv = p0;
+                    uint2 ea = A.adj[efid];
+                    a_set(ea, (eopp + 1) % 3, (uint32_t)new_id);
+                    A.adj[efid] = ea;
+                }
+                V3 va = v3of(A.vp[p0]), vb = v3of(A.vp[p1]), vc = v3of(A.vp[p2]);
+                float bc[3];
+                bool inside = e2_face_bc(va, vb, vc, bc);
+                V3 n; float nn;
+                if (!try_normalize_get(cross3(vb - va, vc - va), PB2_EPS, n, nn)) n = mk3(0.f, 0.f, 0.f);
+                A.face[new_id] = make_float4(n.x, n.y, n.z, __uint_as_float((uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16)));
+                A.adj[new_id] = make_uint2((uint32_t)a0 | ((uint32_t)a1 << 16), (uint32_t)a2);
+                nfaces = new_id + 1;
+                if (state == E2_INIT) {
+                    if (npend == 4) {
+                        if (inside) {
+                            float dist = dot3(n, v3of(A.vp[dv]));
+                            if (-dist > PB2_GJK_EPS_TOL) { fin = FIN_NONE; break; }
+                            h2_push(A, nheap, (uint32_t)new_id, -dist);
+                        }
+                    } else {
+                        h2_push(A, nheap, (uint32_t)new_id, 0.0f);
+                    }
+                } else if (inside) {
+                    float dist = dot3(n, v3of(A.vp[dv]));
+                    if (dist < curr_dist) { fin = FIN_FACE; fin_face = face_id; break; }
+                    if (-dist > PB2_GJK_EPS_TOL) { fin = FIN_NONE; break; }
+                    h2_push(A, nheap, (uint32_t)new_id, -dist);
+                }
+            }
+            if (fin == FIN_NOT) {
+                if (state == E2_INIT) {
+                    // `*self.heap.peek()?` and the "failed to project the origin on the initial simplex" exit
+                    if (nheap == 0) fin = FIN_NONE;
+                    else { float2 top = A.heap[0]; best_id = __float_as_uint(top.y); best_neg = top.x; state = E2_RUN; }
+                } else {
+                    if (first_new == nfaces) fin = FIN_NONE;
+                    else {
+                        uint2 fa = A.adj[first_new]; a_set(fa, 2, (uint32_t)(nfaces - 1)); A.adj[first_new] = fa;
+                        uint2 la = A.adj[nfaces - 1]; a_set(la, 1, (uint32_t)first_new); A.adj[nfaces - 1] = la;
+                        niter += 1;
+                        if (niter > 100) { fin = FIN_FACE; fin_face = best_id; }
+                    }
+                }
+            }
+        }
+        // ---- phase F: finished lanes build the contact and go idle
+        if (fin != FIN_NOT) {
+            PairSetup ps;
+            pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, pair, ps);
+            ContactOut c;
+            int st;
+            V3 p1 = mk3(0.f, 0.f, 0.f), p2 = p1, n1 = mk3(0.f, 1.f, 0.f);
+            if (fin == FIN_FACE) {
+                float4 f = A.face[fin_face];
+                uint32_t i0 = f_pts(f, 0), i1 = f_pts(f, 1), i2 = f_pts(f, 2);
+                float bc[3];
+                e2_face_bc(v3of(A.vp[i0]), v3of(A.vp[i1]), v3of(A.vp[i2]), bc);
+                p1 = v3of(A.vo1[i0]) * bc[0] + v3of(A.vo1[i1]) * bc[1] + v3of(A.vo1[i2]) * bc[2];
+                p2 = v3of(A.vo2[i0]) * bc[0] + v3of(A.vo2[i1]) * bc[1] + v3of(A.vo2[i2]) * bc[2];
+                n1 = v3of(f);
+            }
+            if (fin == FIN_OVERFLOW) st = ST_NEEDS_HOST;
+            else if (fin == FIN_NONE) {
+                if (ps.mode == 1) st = ST_NONE;
+                else st = finish_gjk_pair(ps, true, ps.cb_pos12.t, p2, n1, prediction, c);
+            } else st = finish_gjk_pair(ps, true, p1, p2, n1, prediction, c);
+            if (st == ST_SOME) to_world(ps, c);
+            emit(out, pair, st, c);
+            state = E2_IDLE;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
                         const float* pos2, float prediction, uint32_t n, OutSinks sinks) {
     cudaStream_t st = ctx->stream;
     // EPA job queue (worst case: every pair) + arenas for the persistent EPA grid
-    int epa_threads = 64, epa_blocks = ctx->sm_count * 4;
+    int epa_variant = 2, refill = 8;
+    {
+        const char* e = getenv("PB2_EPA_VARIANT");
+        if (e) epa_variant = atoi(e);
+        if ((e = getenv("PB2_EPA_REFILL"))) refill = atoi(e);
+    }
     size_t jobs_bytes = (size_t)n * sizeof(EpaJob);
-    size_t arena_bytes = (size_t)epa_threads * epa_blocks * sizeof(EpaArena);
     PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[3], jobs_bytes));
-    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], arena_bytes));
     EpaJob* jobs = (EpaJob*)ctx->scratch[3].ptr;
-    EpaArena* arenas = (EpaArena*)ctx->scratch[2].ptr;
     unsigned long long* job_count = (unsigned long long*)(ctx->d_counters + 4);
     unsigned long long* next_job = (unsigned long long*)(ctx->d_counters + 5);
     PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 4, 0, 16, st));
     k_contact_gjk<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, shape1, shape2, pos1, pos2,
                                                      prediction, n, sinks, jobs, job_count);
     PB2_LAUNCHED(ctx);
-    k_contact_epa<<<epa_blocks, epa_threads, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction,
-                                                     sinks, jobs, job_count, next_job, arenas);
+    if (epa_variant == 1) {
+        int epa_threads = 64, epa_blocks = ctx->sm_count * 4;
+        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)epa_threads * epa_blocks * sizeof(EpaArena)));
+        k_contact_epa<<<epa_blocks, epa_threads, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction,
+                                                         sinks, jobs, job_count, next_job, (EpaArena*)ctx->scratch[2].ptr);
+    } else {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contact_epa2, 128, 0);
+        if (per_sm < 1) per_sm = 1;
+        int epa_blocks = ctx->sm_count * per_sm;
+        int need = (int)pb2_blocks(n, 128);
+        if (epa_blocks > need) epa_blocks = need;
+        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)128 * epa_blocks * sizeof(Epa2Arena)));
+        k_contact_epa2<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction, sinks,
+                                                  jobs, job_count, next_job, (Epa2Arena*)ctx->scratch[2].ptr, refill);
+    }
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
     return PB2_OK;

@@ -81,43 +81,51 @@ struct Proj {
     bool inside;
 };
 
-// point_triangle.rs:58-290 (pt is a general point; `solid` true on the GJK/EPA paths)
-__device__ __noinline__ void project_on_triangle(V3 a, V3 b, V3 c, V3 pt, Proj& r) {
-    r.bc[0] = r.bc[1] = r.bc[2] = 0.f; r.idx = 0;
+// point_triangle.rs:58-290 (pt is a general point; `solid` true on the GJK/EPA paths).
+// Branch-free restatement: every intermediate of the reference is a pure function of the inputs, so all of them are
+// evaluated eagerly, the Voronoi region is picked by the same cascade of comparisons, and the single division of the
+// chosen region runs on selected operands — bit-identical results with no divergent paths inside a warp.
+__device__ __forceinline__ void project_on_triangle(V3 a, V3 b, V3 c, V3 pt, Proj& r) {
     V3 ab = b - a, ac = c - a, ap = pt - a;
     float ab_ap = dot3(ab, ap), ac_ap = dot3(ac, ap);
-    if (ab_ap <= 0.0f && ac_ap <= 0.0f) { r.point = a; r.inside = rel_eq3(a, pt); r.kind = 0; r.idx = 0; return; }
     V3 bp = pt - b;
     float ab_bp = dot3(ab, bp), ac_bp = dot3(ac, bp);
-    if (ab_bp >= 0.0f && ac_bp <= ab_bp) { r.point = b; r.inside = rel_eq3(b, pt); r.kind = 0; r.idx = 1; return; }
     V3 cp = pt - c;
     float ab_cp = dot3(ab, cp), ac_cp = dot3(ac, cp);
-    if (ac_cp >= 0.0f && ab_cp <= ac_cp) { r.point = c; r.inside = rel_eq3(c, pt); r.kind = 0; r.idx = 2; return; }
     V3 bc = c - b;
     V3 n = cross3(ab, ac);
     float vc = dot3(n, cross3(ab, ap));
-    if (vc < 0.0f && ab_ap >= 0.0f && ab_bp <= 0.0f) {
-        float v = ab_ap / nrm2(ab);
-        r.bc[0] = 1.0f - v; r.bc[1] = v; r.point = a + ab * v; r.inside = rel_eq3(r.point, pt); r.kind = 1; r.idx = 0; return;
-    }
     float vb = -dot3(n, cross3(ac, cp));
-    if (vb < 0.0f && ac_ap >= 0.0f && ac_cp <= 0.0f) {
-        float w = ac_ap / nrm2(ac);
-        r.bc[0] = 1.0f - w; r.bc[1] = w; r.point = a + ac * w; r.inside = rel_eq3(r.point, pt); r.kind = 1; r.idx = 2; return;
-    }
     float va = dot3(n, cross3(bc, bp));
-    if (va < 0.0f && ac_bp - ab_bp >= 0.0f && ab_cp - ac_cp >= 0.0f) {
-        float w = dot3(bc, bp) / nrm2(bc);
-        r.bc[0] = 1.0f - w; r.bc[1] = w; r.point = b + bc * w; r.inside = rel_eq3(r.point, pt); r.kind = 1; r.idx = 1; return;
-    }
-    uint32_t face_side = dot3(n, ap) >= 0.0f ? 0u : 1u;
-    if (va + vb + vc != 0.0f) {
-        float denom = 1.0f / (va + vb + vc);
-        float v = vb * denom, w = vc * denom;
-        r.bc[0] = 1.0f - v - w; r.bc[1] = v; r.bc[2] = w;
-        r.point = a + ab * v + ac * w; r.inside = rel_eq3(r.point, pt); r.kind = 2; r.idx = face_side; return;
-    }
-    r.point = pt; r.inside = true; r.kind = 3;  // solid
+    bool rA = ab_ap <= 0.0f && ac_ap <= 0.0f;
+    bool rB = !rA && (ab_bp >= 0.0f && ac_bp <= ab_bp);
+    bool rC = !rA && !rB && (ac_cp >= 0.0f && ab_cp <= ac_cp);
+    bool vtx = rA || rB || rC;
+    bool rAB = !vtx && (vc < 0.0f && ab_ap >= 0.0f && ab_bp <= 0.0f);
+    bool rAC = !vtx && !rAB && (vb < 0.0f && ac_ap >= 0.0f && ac_cp <= 0.0f);
+    bool rBC = !vtx && !rAB && !rAC && (va < 0.0f && ac_bp - ab_bp >= 0.0f && ab_cp - ac_cp >= 0.0f);
+    bool edge = rAB || rAC || rBC;
+    float sum = va + vb + vc;
+    bool face = !vtx && !edge && sum != 0.0f;
+    float num = rAB ? ab_ap : (rAC ? ac_ap : (rBC ? dot3(bc, bp) : 1.0f));
+    float den = rAB ? nrm2(ab) : (rAC ? nrm2(ac) : (rBC ? nrm2(bc) : sum));
+    float q = num / den;
+    // edge: base + dir * q
+    V3 base = rBC ? b : a;
+    V3 dirv = rAB ? ab : (rAC ? ac : bc);
+    V3 pe = base + dirv * q;
+    // face: a + ab * v + ac * w
+    float v = vb * q, w = vc * q;
+    V3 pf = a + ab * v + ac * w;
+    V3 pv = rA ? a : (rB ? b : c);
+    V3 point = vtx ? pv : (edge ? pe : (face ? pf : pt));
+    r.point = point;
+    r.kind = vtx ? 0 : (edge ? 1 : (face ? 2 : 3));
+    r.idx = vtx ? (rA ? 0u : (rB ? 1u : 2u)) : (edge ? (rAB ? 0u : (rAC ? 2u : 1u)) : (dot3(n, ap) >= 0.0f ? 0u : 1u));
+    r.bc[0] = edge ? 1.0f - q : (face ? 1.0f - v - w : 0.0f);
+    r.bc[1] = edge ? q : (face ? v : 0.0f);
+    r.bc[2] = face ? w : 0.0f;
+    r.inside = (vtx || edge || face) ? rel_eq3(point, pt) : true;
 }
 
 // point_tetrahedron.rs check_edge
