@@ -29,7 +29,13 @@ struct pb2_ctx {
     // pinned host bounce buffer for small readbacks (counters)
     uint64_t* h_counters = nullptr;  // 16 x u64 pinned
     uint64_t* d_counters = nullptr;  // 16 x u64 device
+    // copy/compute pipeline for PB2_MEM_HOST batches: H2D stream, D2H stream, event pool
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev[64] = {nullptr};
+    int ev_next = 0;
 };
+int pb2_pipeline_init(pb2_ctx* ctx);
+static inline cudaEvent_t pb2_next_event(pb2_ctx* ctx) { cudaEvent_t e = ctx->ev[ctx->ev_next]; ctx->ev_next = (ctx->ev_next + 1) % 64; return e; }
 
 #define PB2_CUDA(ctx, expr)                                                                             \
     do {                                                                                                \

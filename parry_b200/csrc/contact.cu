@@ -1003,22 +1003,45 @@ int pb2_contact_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* sh
     if (num_contacts) *num_contacts = 0;
     if (n == 0) return PB2_OK;
     PB2_CUDA(ctx, cudaSetDevice(ctx->device));
-    const void *d_s1, *d_s2, *d_p1, *d_p2;
-    void *d_out, *d_status;
-    PB2_CHECK(pb2_stage_in(ctx, 0, shape1, (size_t)n * 4, mem, &d_s1));
-    PB2_CHECK(pb2_stage_in(ctx, 1, shape2, (size_t)n * 4, mem, &d_s2));
-    PB2_CHECK(pb2_stage_in(ctx, 2, pos1, (size_t)n * 28, mem, &d_p1));
-    PB2_CHECK(pb2_stage_in(ctx, 3, pos2, (size_t)n * 28, mem, &d_p2));
-    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * 52, mem, &d_out));
-    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_status));
     OutSinks sinks;
-    sinks.dense = (float*)d_out; sinks.status = (uint8_t*)d_status; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
-    sinks.compact_count = nullptr;
+    sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0; sinks.compact_count = nullptr;
     sinks.some_count = num_contacts ? (unsigned long long*)(ctx->d_counters + 6) : nullptr;
     if (num_contacts) PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 6, 0, 8, ctx->stream));
-    PB2_CHECK(run_contacts(ctx, shapes, (const uint32_t*)d_s1, (const uint32_t*)d_s2, (const float*)d_p1, (const float*)d_p2, prediction, n, sinks));
-    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
-    PB2_CHECK(pb2_stage_back(ctx, status, d_status, (size_t)n, mem));
+    if (mem == PB2_MEM_DEVICE) {
+        sinks.dense = (float*)out; sinks.status = status;
+        PB2_CHECK(run_contacts(ctx, shapes, shape1, shape2, pos1, pos2, prediction, n, sinks));
+    } else {
+        // Host buffers: chunked H2D / kernels / D2H pipeline (see pb2_trimesh_cast_rays).
+        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->stage[0], (size_t)n * 4));
+        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->stage[1], (size_t)n * 4));
+        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->stage[2], (size_t)n * 28));
+        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->stage[3], (size_t)n * 28));
+        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->stage[4], (size_t)n * 52));
+        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->stage[5], (size_t)n));
+        uint32_t *d_s1 = (uint32_t*)ctx->stage[0].ptr, *d_s2 = (uint32_t*)ctx->stage[1].ptr;
+        float *d_p1 = (float*)ctx->stage[2].ptr, *d_p2 = (float*)ctx->stage[3].ptr, *d_out = (float*)ctx->stage[4].ptr;
+        uint8_t* d_status = (uint8_t*)ctx->stage[5].ptr;
+        PB2_CHECK(pb2_pipeline_init(ctx));
+        // make sure the job queue / arenas are sized before the pipeline starts (no reallocation mid-flight)
+        const uint32_t CHUNK = 1u << 19;
+        for (uint32_t lo = 0; lo < n; lo += CHUNK) {
+            uint32_t cnt = n - lo < CHUNK ? n - lo : CHUNK;
+            cudaEvent_t e_in = pb2_next_event(ctx), e_k = pb2_next_event(ctx);
+            PB2_CUDA(ctx, cudaMemcpyAsync(d_s1 + lo, shape1 + lo, (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+            PB2_CUDA(ctx, cudaMemcpyAsync(d_s2 + lo, shape2 + lo, (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+            PB2_CUDA(ctx, cudaMemcpyAsync(d_p1 + 7ull * lo, pos1 + 7ull * lo, (size_t)cnt * 28, cudaMemcpyHostToDevice, ctx->copy_in));
+            PB2_CUDA(ctx, cudaMemcpyAsync(d_p2 + 7ull * lo, pos2 + 7ull * lo, (size_t)cnt * 28, cudaMemcpyHostToDevice, ctx->copy_in));
+            PB2_CUDA(ctx, cudaEventRecord(e_in, ctx->copy_in));
+            PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e_in, 0));
+            sinks.dense = d_out + 13ull * lo; sinks.status = d_status + lo;
+            PB2_CHECK(run_contacts(ctx, shapes, d_s1 + lo, d_s2 + lo, d_p1 + 7ull * lo, d_p2 + 7ull * lo, prediction, cnt, sinks));
+            PB2_CUDA(ctx, cudaEventRecord(e_k, ctx->stream));
+            PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, e_k, 0));
+            PB2_CUDA(ctx, cudaMemcpyAsync((float*)out + 13ull * lo, d_out + 13ull * lo, (size_t)cnt * 52, cudaMemcpyDeviceToHost, ctx->copy_out));
+            PB2_CUDA(ctx, cudaMemcpyAsync(status + lo, d_status + lo, (size_t)cnt, cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
+        PB2_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    }
     if (num_contacts) {
         PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 6, ctx->d_counters + 6, 8, cudaMemcpyDeviceToHost, ctx->stream));
         PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

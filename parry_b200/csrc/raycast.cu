@@ -292,6 +292,66 @@ __global__ void k_ray_keys(const NodeWide* __restrict__ nodes, const float* __re
     vals[r] = r;
 }
 
+// Enqueues the ray kernels for m device-resident rays on ctx->stream.
+static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d_pose, const void* d_rays, uint32_t m, float max_toi,
+                            void* d_toi, void* d_tri, void* d_n, void* d_f, bool with_normal) {
+    const pb2_bvh* b = &mesh->bvh;
+    // ray reordering pays off once the node array no longer fits in L2 (126 MB); below that the sort costs more than it saves
+    int variant = ((size_t)b->n_nodes * sizeof(NodeWide) > (size_t)(100u << 20)) ? 2 : 1, steps = 16, refill = 8;
+    {   // tuning knobs (read per call; cheap)
+        const char* e = getenv("PB2_RAY_VARIANT");
+        if (e) variant = atoi(e);
+        if ((e = getenv("PB2_RAY_STEPS"))) steps = atoi(e);
+        if ((e = getenv("PB2_RAY_REFILL"))) refill = atoi(e);
+    }
+    if (variant == 0 || b->n_leaves < 2 || m < 4096) {
+        unsigned blocks = pb2_blocks(m, 128);
+        if (with_normal)
+            k_raycast_trimesh<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
+                                                                     (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
+                                                                     (float*)d_n, (uint32_t*)d_f);
+        else
+            k_raycast_trimesh<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
+                                                                      (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
+                                                                      nullptr, nullptr);
+    } else {
+        unsigned int* next_ray = (unsigned int*)(ctx->d_counters + 8);
+        PB2_CUDA(ctx, cudaMemsetAsync(next_ray, 0, 4, ctx->stream));
+        const uint32_t* perm = nullptr;
+        if (variant >= 2 && m >= 65536) {
+            size_t cub_bytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                            (uint32_t*)nullptr, (int)m, 0, 30, ctx->stream);
+            size_t arr = ((size_t)m * 4 + 255) & ~(size_t)255;
+            PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[0], 4 * arr + cub_bytes));
+            char* base = (char*)ctx->scratch[0].ptr;
+            uint32_t *k_in = (uint32_t*)base, *k_out = (uint32_t*)(base + arr), *v_in = (uint32_t*)(base + 2 * arr), *v_out = (uint32_t*)(base + 3 * arr);
+            k_ray_keys<<<pb2_blocks(m, 256), 256, 0, ctx->stream>>>(b->nodes, (const float*)d_pose, (const float*)d_rays, m, k_in, v_in);
+            PB2_LAUNCHED(ctx);
+            PB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + 4 * arr, cub_bytes, (const uint32_t*)k_in, k_out, (const uint32_t*)v_in, v_out,
+                                                          (int)m, 0, 30, ctx->stream));
+            ctx->launches += 3;
+            perm = v_out;
+        }
+        int per_sm = 0;
+        if (with_normal) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_trimesh_persistent<true>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_trimesh_persistent<false>, 128, 0);
+        if (per_sm < 1) per_sm = 1;
+        unsigned blocks = (unsigned)(ctx->sm_count * per_sm);
+        unsigned need = pb2_blocks(m, 128);
+        if (blocks > need) blocks = need;
+        if (with_normal)
+            k_raycast_trimesh_persistent<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
+                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, (float*)d_n, (uint32_t*)d_f, next_ray, steps, refill);
+        else
+            k_raycast_trimesh_persistent<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
+                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, nullptr, nullptr, next_ray, steps, refill);
+    }
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    return PB2_OK;
+}
+
 extern "C" {
 
 int pb2_trimesh_create(pb2_ctx* ctx, const float* vertices, uint32_t nv, const uint32_t* indices, uint32_t nt, int mem,
@@ -364,75 +424,42 @@ int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* po
     if (!ctx || !mesh || (m && (!rays || !toi || !tri))) return PB2_ERR_INVALID;
     if (m == 0) return PB2_OK;
     PB2_CUDA(ctx, cudaSetDevice(ctx->device));
-    const void *d_rays = nullptr, *d_pose = nullptr;
-    void *d_toi = nullptr, *d_tri = nullptr, *d_n = nullptr, *d_f = nullptr;
-    PB2_CHECK(pb2_stage_in(ctx, 0, rays, (size_t)m * 24, mem, &d_rays));
-    // the pose is tiny: always staged from host memory when given in host mode
-    PB2_CHECK(pb2_stage_in(ctx, 1, pose7, 28, mem, &d_pose));
+    bool with_normal = normal || feature;
+    if (mem == PB2_MEM_DEVICE)
+        return cast_rays_device(ctx, mesh, pose7, rays, m, max_toi, toi, tri, normal, feature, with_normal);
+    // Host buffers: stage through HBM in chunks so that H2D copies, traversal and D2H copies of neighbouring chunks overlap
+    // (full-duplex PCIe + compute; needs page-locked host memory to be truly asynchronous, pageable memory still works).
+    void *d_rays = nullptr, *d_pose = nullptr, *d_toi = nullptr, *d_tri = nullptr, *d_n = nullptr, *d_f = nullptr;
+    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->stage[0], (size_t)m * 24));
+    d_rays = ctx->stage[0].ptr;
+    if (pose7) {
+        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->stage[1], 28));
+        d_pose = ctx->stage[1].ptr;
+        PB2_CUDA(ctx, cudaMemcpyAsync(d_pose, pose7, 28, cudaMemcpyHostToDevice, ctx->stream));
+    }
     PB2_CHECK(pb2_stage_out(ctx, 2, toi, (size_t)m * 4, mem, &d_toi));
     PB2_CHECK(pb2_stage_out(ctx, 3, tri, (size_t)m * 4, mem, &d_tri));
     PB2_CHECK(pb2_stage_out(ctx, 4, normal, (size_t)m * 12, mem, &d_n));
     PB2_CHECK(pb2_stage_out(ctx, 5, feature, (size_t)m * 4, mem, &d_f));
-    const pb2_bvh* b = &mesh->bvh;
-    bool with_normal = normal || feature;
-    // ray reordering pays off once the node array no longer fits in L2 (126 MB); below that the sort costs more than it saves
-    int variant = ((size_t)b->n_nodes * sizeof(NodeWide) > (size_t)(100u << 20)) ? 2 : 1, steps = 16, refill = 8;
-    {   // tuning knobs (read per call; cheap)
-        const char* e = getenv("PB2_RAY_VARIANT");
-        if (e) variant = atoi(e);
-        if ((e = getenv("PB2_RAY_STEPS"))) steps = atoi(e);
-        if ((e = getenv("PB2_RAY_REFILL"))) refill = atoi(e);
+    PB2_CHECK(pb2_pipeline_init(ctx));
+    const uint32_t CHUNK = 1u << 20;
+    for (uint32_t lo = 0; lo < m; lo += CHUNK) {
+        uint32_t cnt = m - lo < CHUNK ? m - lo : CHUNK;
+        cudaEvent_t e_in = pb2_next_event(ctx), e_k = pb2_next_event(ctx);
+        PB2_CUDA(ctx, cudaMemcpyAsync((char*)d_rays + (size_t)lo * 24, rays + (size_t)lo * 6, (size_t)cnt * 24, cudaMemcpyHostToDevice, ctx->copy_in));
+        PB2_CUDA(ctx, cudaEventRecord(e_in, ctx->copy_in));
+        PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e_in, 0));
+        PB2_CHECK(cast_rays_device(ctx, mesh, d_pose, (char*)d_rays + (size_t)lo * 24, cnt, max_toi, (float*)d_toi + lo, (uint32_t*)d_tri + lo,
+                                   d_n ? (float*)d_n + 3ull * lo : nullptr, d_f ? (uint32_t*)d_f + lo : nullptr, with_normal));
+        PB2_CUDA(ctx, cudaEventRecord(e_k, ctx->stream));
+        PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, e_k, 0));
+        PB2_CUDA(ctx, cudaMemcpyAsync(toi + lo, (float*)d_toi + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+        PB2_CUDA(ctx, cudaMemcpyAsync(tri + lo, (uint32_t*)d_tri + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (normal) PB2_CUDA(ctx, cudaMemcpyAsync(normal + 3ull * lo, (float*)d_n + 3ull * lo, (size_t)cnt * 12, cudaMemcpyDeviceToHost, ctx->copy_out));
+        if (feature) PB2_CUDA(ctx, cudaMemcpyAsync(feature + lo, (uint32_t*)d_f + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
     }
-    if (variant == 0 || b->n_leaves < 2 || m < 4096) {
-        unsigned blocks = pb2_blocks(m, 128);
-        if (with_normal)
-            k_raycast_trimesh<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
-                                                                     (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
-                                                                     (float*)d_n, (uint32_t*)d_f);
-        else
-            k_raycast_trimesh<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
-                                                                      (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
-                                                                      nullptr, nullptr);
-    } else {
-        unsigned int* next_ray = (unsigned int*)(ctx->d_counters + 8);
-        PB2_CUDA(ctx, cudaMemsetAsync(next_ray, 0, 4, ctx->stream));
-        const uint32_t* perm = nullptr;
-        if (variant >= 2 && m >= 65536) {
-            size_t cub_bytes = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                            (uint32_t*)nullptr, (int)m, 0, 30, ctx->stream);
-            size_t arr = ((size_t)m * 4 + 255) & ~(size_t)255;
-            PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[0], 4 * arr + cub_bytes));
-            char* base = (char*)ctx->scratch[0].ptr;
-            uint32_t *k_in = (uint32_t*)base, *k_out = (uint32_t*)(base + arr), *v_in = (uint32_t*)(base + 2 * arr), *v_out = (uint32_t*)(base + 3 * arr);
-            k_ray_keys<<<pb2_blocks(m, 256), 256, 0, ctx->stream>>>(b->nodes, (const float*)d_pose, (const float*)d_rays, m, k_in, v_in);
-            PB2_LAUNCHED(ctx);
-            PB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + 4 * arr, cub_bytes, (const uint32_t*)k_in, k_out, (const uint32_t*)v_in, v_out,
-                                                          (int)m, 0, 30, ctx->stream));
-            ctx->launches += 3;
-            perm = v_out;
-        }
-        int per_sm = 0;
-        if (with_normal) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_trimesh_persistent<true>, 128, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_trimesh_persistent<false>, 128, 0);
-        if (per_sm < 1) per_sm = 1;
-        unsigned blocks = (unsigned)(ctx->sm_count * per_sm);
-        unsigned need = pb2_blocks(m, 128);
-        if (blocks > need) blocks = need;
-        if (with_normal)
-            k_raycast_trimesh_persistent<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
-                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, (float*)d_n, (uint32_t*)d_f, next_ray, steps, refill);
-        else
-            k_raycast_trimesh_persistent<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
-                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, nullptr, nullptr, next_ray, steps, refill);
-    }
-    PB2_LAUNCHED(ctx);
-    PB2_CUDA(ctx, cudaGetLastError());
-    PB2_CHECK(pb2_stage_back(ctx, toi, d_toi, (size_t)m * 4, mem));
-    PB2_CHECK(pb2_stage_back(ctx, tri, d_tri, (size_t)m * 4, mem));
-    PB2_CHECK(pb2_stage_back(ctx, normal, d_n, (size_t)m * 12, mem));
-    PB2_CHECK(pb2_stage_back(ctx, feature, d_f, (size_t)m * 4, mem));
-    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PB2_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB2_OK;
 }
 

@@ -388,7 +388,7 @@ CONTACT_DTYPE = np.dtype([("point1", np.float32, (3,)), ("point2", np.float32, (
 assert CONTACT_DTYPE.itemsize == 52
 
 
-def contact(shapes, shape1, pos1, shape2, pos2, prediction):
+def contact(shapes, shape1, pos1, shape2, pos2, prediction, out=None):
     """query::contact(pos1, g1, pos2, g2, prediction), batched (contact_shape_shape.rs:123-138).
     Returns (contacts (n, 13) f32 [point1, point2, normal1, normal2, dist], status (n,) u8: 0 None, 1 Some,
     2 Unsupported)."""
@@ -398,8 +398,13 @@ def contact(shapes, shape1, pos1, shape2, pos2, prediction):
     k2, p2, _ = _prep(pos2, np.float32, mem)
     ks1, ps1, _ = _prep(shape1, np.uint32, mem)
     ks2, ps2, _ = _prep(shape2, np.uint32, mem)
-    out, po = _empty((n, 13), np.float32, mem, ctx.torch_device)
-    status, pst = _empty((n,), np.uint8, mem, ctx.torch_device)
+    if out is not None:  # caller-owned (e.g. page-locked) output buffers: (contacts (n, 13) f32, status (n,) u8)
+        out, status = out
+        po = out.data_ptr() if _is_torch(out) else out.ctypes.data
+        pst = status.data_ptr() if _is_torch(status) else status.ctypes.data
+    else:
+        out, po = _empty((n, 13), np.float32, mem, ctx.torch_device)
+        status, pst = _empty((n,), np.uint8, mem, ctx.torch_device)
     ctx.check(ctx._lib.pb2_contact_batch(ctx.h, shapes.h, ps1, ps2, p1, p2, float(prediction), n, po, pst, None, mem))
     return out, status
 
