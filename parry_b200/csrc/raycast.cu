@@ -8,7 +8,7 @@
 // One thread per ray, ordered depth-first descent with a short per-thread stack (nearer child first, farther child
 // pushed), pruning against the best hit so far exactly like find_best. Triangles are pre-gathered in BVH leaf
 // order as 3 x float4 (48 B, 16-B aligned vector loads) so a leaf visit costs no index indirection.
-#include "common.cuh"
+#include "trimesh.cuh"
 #include "traverse.cuh"
 #include <stdlib.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -18,11 +18,6 @@ int pb2_stage_in(pb2_ctx* ctx, int slot, const void* src, size_t bytes, int mem,
 int pb2_stage_out(pb2_ctx* ctx, int slot, void* dst, size_t bytes, int mem, void** out);
 int pb2_stage_back(pb2_ctx* ctx, void* dst, const void* dev, size_t bytes, int mem);
 
-struct pb2_trimesh {
-    pb2_bvh bvh;
-    uint32_t nt = 0, nv = 0;
-    float4* tris = nullptr;  // [3 * sorted position]: {a, id}, {b, -}, {c, -}
-};
 
 
 // Triangle::local_aabb (bounding_volume/aabb_triangle.rs:16-30)
@@ -50,41 +45,6 @@ __global__ void k_gather_triangles(const float* __restrict__ v, const uint32_t* 
     tris[3ull * p + 0] = make_float4(v[3ull * ia], v[3ull * ia + 1], v[3ull * ia + 2], __uint_as_float(id));
     tris[3ull * p + 1] = make_float4(v[3ull * ib], v[3ull * ib + 1], v[3ull * ib + 2], 0.0f);
     tris[3ull * p + 2] = make_float4(v[3ull * ic], v[3ull * ic + 1], v[3ull * ic + 2], 0.0f);
-}
-
-// local_ray_intersection_with_triangle (ray_triangle.rs:70-152) — toi, face side (0 front / 1 back) and the
-// un-normalised oriented normal. Returns false for None.
-__device__ __forceinline__ bool ray_triangle(V3 a, V3 b, V3 c, V3 o, V3 dir, float& toi, uint32_t& fid, V3& n_out) {
-    V3 ab = b - a, ac = c - a;
-    V3 n = cross3(ab, ac);
-    float d = dot3(n, dir);
-    if (d == 0.0f) return false;
-    V3 ap = o - a;
-    float t = dot3(ap, n);
-    if ((t < 0.0f && d < 0.0f) || (t > 0.0f && d > 0.0f)) return false;
-    fid = d < 0.0f ? 0u : 1u;
-    d = fabsf(d);
-    V3 e = -cross3(dir, ap);
-    float v, w;
-    if (t < 0.0f) {
-        v = -dot3(ac, e);
-        if (v < 0.0f || v > d) return false;
-        w = dot3(ab, e);
-        if (w < 0.0f || v + w > d) return false;
-        float invd = 1.0f / d;
-        toi = -t * invd;
-        n_out = n;
-        fid |= 2u;  // bit 1: normal = -(n.normalize()) — negate after normalising
-    } else {
-        v = dot3(ac, e);
-        if (v < 0.0f || v > d) return false;
-        w = -dot3(ab, e);
-        if (w < 0.0f || v + w > d) return false;
-        float invd = 1.0f / d;
-        toi = t * invd;
-        n_out = n;
-    }
-    return true;
 }
 
 template <bool WITH_NORMAL>
@@ -297,7 +257,9 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
                             void* d_toi, void* d_tri, void* d_n, void* d_f, bool with_normal) {
     const pb2_bvh* b = &mesh->bvh;
     // ray reordering pays off once the node array no longer fits in L2 (126 MB); below that the sort costs more than it saves
-    int variant = ((size_t)b->n_nodes * sizeof(NodeWide) > (size_t)(100u << 20)) ? 2 : 1, steps = 16, refill = 8;
+    // variants: 0 one thread per ray, 1 persistent binary, 2 = 1 + ray reordering, 3 compressed 8-wide tree, 4 = 3 + ray reordering
+    bool big = (size_t)b->n_nodes * sizeof(NodeWide) > (size_t)(100u << 20);
+    int variant = mesh->n_nodes8 ? (big ? 4 : 3) : (big ? 2 : 1), steps = 16, refill = 8;
     {   // tuning knobs (read per call; cheap)
         const char* e = getenv("PB2_RAY_VARIANT");
         if (e) variant = atoi(e);
@@ -318,7 +280,8 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
         unsigned int* next_ray = (unsigned int*)(ctx->d_counters + 8);
         PB2_CUDA(ctx, cudaMemsetAsync(next_ray, 0, 4, ctx->stream));
         const uint32_t* perm = nullptr;
-        if (variant >= 2 && m >= 65536) {
+        if (variant >= 3 && !mesh->n_nodes8) variant -= 2;
+        if ((variant == 2 || variant == 4) && m >= 65536) {
             size_t cub_bytes = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                             (uint32_t*)nullptr, (int)m, 0, 30, ctx->stream);
@@ -340,7 +303,10 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
         unsigned blocks = (unsigned)(ctx->sm_count * per_sm);
         unsigned need = pb2_blocks(m, 128);
         if (blocks > need) blocks = need;
-        if (with_normal)
+        if (variant >= 3)
+            PB2_CHECK(pb2_wide_cast(ctx, mesh, (const float*)d_pose, (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
+                                    (float*)d_n, (uint32_t*)d_f, with_normal, steps, refill));
+        else if (with_normal)
             k_raycast_trimesh_persistent<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
                 (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, (float*)d_n, (uint32_t*)d_f, next_ray, steps, refill);
         else
@@ -396,6 +362,7 @@ int pb2_trimesh_create(pb2_ctx* ctx, const float* vertices, uint32_t nv, const u
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh build: %s", cudaGetErrorString(e)); s = PB2_ERR_CUDA; }
     }
+    if (s == PB2_OK) s = pb2_wide_build(ctx, mesh);
     if (s != PB2_OK) { pb2_trimesh_destroy(ctx, mesh); return s; }
     *out = mesh;
     return PB2_OK;
@@ -412,6 +379,8 @@ int pb2_trimesh_destroy(pb2_ctx* ctx, pb2_trimesh* mesh) {
     if (b->leaf_slot) cudaFree(b->leaf_slot);
     if (b->leaf_order) cudaFree(b->leaf_order);
     if (mesh->tris) cudaFree(mesh->tris);
+    if (mesh->nodes8) cudaFree(mesh->nodes8);
+    if (mesh->tris8) cudaFree(mesh->tris8);
     delete mesh;
     return PB2_OK;
 }

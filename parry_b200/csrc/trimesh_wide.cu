@@ -1,0 +1,422 @@
+// parry_b200 — compressed 8-wide traversal tree for TriMesh ray casts.
+//
+// Same query as raycast.cu (TriMesh::cast_ray -> Bvh::cast_ray -> Bvh::find_best, query/ray/ray_trimesh.rs:8-36,
+// partitioning/bvh/bvh_queries.rs:260-271, bvh_traverse.rs:335-417), different memory shape. The ncu captures of the
+// binary-tree kernels (profiles/r1_rays_v*_full.json) show the L1/TEX pipe at 70-82 % with incoherent rays: every lane
+// touches its own 64-byte node, four 16-byte loads per two child boxes. Here every binary subtree of up to eight
+// children is collapsed into one 80-byte node (five 16-byte loads per eight child boxes) whose boxes are quantised to
+// 8 bits per plane relative to the node's own origin and per-axis power-of-two scale (the compressed wide BVH of
+// Ylitie, Karras & Laine, HPG 2017, restated from the paper; octant-ordered child slots give a front-to-back order
+// without sorting).
+//
+// Parity: the quantised boxes only decide WHICH triangles get looked at. They are conservative by construction —
+// quantised planes are rounded outward at build time (verified in double), the dequantised slab bounds are evaluated
+// with directed rounding (lower bound for entries, upper bound for exits) and the interval test carries a relative
+// slack of 2^-20 that covers the reference's own two f32 roundings — so every leaf whose exact AABB passes the
+// reference's slab test is reached. Each reached triangle is then filtered by the reference's arithmetic: exact leaf
+// AABB (Triangle::local_aabb, aabb_triangle.rs:16-30, recomputed from the vertices) slab-tested like
+// BvhNode::cast_ray (bvh_tree.rs:1177-1181), then local_ray_intersection_with_triangle (ray_triangle.rs:70-152).
+// Accept / tie rules are those of raycast.cu.
+#include "trimesh.cuh"
+#include <cub/device/device_scan.cuh>
+
+#define W8_LEAF 0x80000000u
+#define W8_STACK 32
+#define W8_GAMMA 1.00000095367431640625f  // 1 + 2^-20
+
+// ------------------------------------------------------------------------------------------------ build
+// One thread per wide node of the current BFS level. wroot[w] = binary (Karras) node collapsed into wide node w.
+__global__ void k_collapse8(const NodeWide* __restrict__ nodes, uint32_t* __restrict__ wroot, uint32_t w_begin, uint32_t w_end,
+                            uint32_t* __restrict__ total, float4* __restrict__ nodes8, uint32_t* __restrict__ leafpos,
+                            uint32_t* __restrict__ nleaf) {
+    uint32_t w = w_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= w_end) return;
+    uint32_t ref[8];
+    float lo[8][3], hi[8][3];
+    int cnt = 0;
+    auto add_half = [&](int at, float4 a, float4 b) {
+        bool leaf = (__float_as_uint(b.w) & PB2_LEAF_COUNT_MASK) == 1u;
+        ref[at] = leaf ? (__float_as_uint(a.w) | W8_LEAF) : __float_as_uint(a.w);
+        lo[at][0] = a.x; lo[at][1] = a.y; lo[at][2] = a.z;
+        hi[at][0] = b.x; hi[at][1] = b.y; hi[at][2] = b.z;
+    };
+    {
+        const float4* np = reinterpret_cast<const float4*>(&nodes[wroot[w]]);
+        add_half(0, np[0], np[1]);
+        add_half(1, np[2], np[3]);
+        cnt = 2;
+    }
+    // greedy collapse: open the internal child with the largest surface area until eight children or only leaves
+    while (cnt < 8) {
+        int k = -1;
+        float best_area = -1.0f;
+        for (int c = 0; c < cnt; ++c) {
+            if (ref[c] & W8_LEAF) continue;
+            float ex = hi[c][0] - lo[c][0], ey = hi[c][1] - lo[c][1], ez = hi[c][2] - lo[c][2];
+            float area = ex * ey + ey * ez + ez * ex;
+            if (area > best_area) { best_area = area; k = c; }
+        }
+        if (k < 0) break;
+        const float4* np = reinterpret_cast<const float4*>(&nodes[ref[k]]);
+        float4 a0 = np[0], a1 = np[1], b0 = np[2], b1 = np[3];
+        add_half(k, a0, a1);
+        add_half(cnt, b0, b1);
+        cnt++;
+    }
+    // node frame
+    double plo[3], phi[3];
+    for (int a = 0; a < 3; ++a) {
+        float mn = lo[0][a], mx = hi[0][a];
+        for (int c = 1; c < cnt; ++c) { mn = fminf(mn, lo[c][a]); mx = fmaxf(mx, hi[c][a]); }
+        plo[a] = (double)mn; phi[a] = (double)mx;
+    }
+    // octant slots: child c goes to the free slot s whose sign vector (bit a of s set = +axis a) best matches the
+    // direction from the node centre to the child centre (greedy on the 8x8 cost table)
+    int slot_of[8];
+    {
+        float cost[8][8];
+        for (int c = 0; c < cnt; ++c) {
+            float v[3];
+            for (int a = 0; a < 3; ++a) v[a] = (float)(((double)lo[c][a] + (double)hi[c][a]) * 0.5 - (plo[a] + phi[a]) * 0.5);
+            for (int s = 0; s < 8; ++s)
+                cost[c][s] = ((s & 1) ? v[0] : -v[0]) + ((s & 2) ? v[1] : -v[1]) + ((s & 4) ? v[2] : -v[2]);
+        }
+        uint32_t used_c = 0, used_s = 0;
+        for (int it = 0; it < cnt; ++it) {
+            int bc = -1, bs = -1;
+            float bv = -FLT_MAX;
+            for (int c = 0; c < cnt; ++c) {
+                if (used_c & (1u << c)) continue;
+                for (int s = 0; s < 8; ++s) {
+                    if (used_s & (1u << s)) continue;
+                    if (bc < 0 || cost[c][s] > bv) { bv = cost[c][s]; bc = c; bs = s; }
+                }
+            }
+            slot_of[bc] = bs;
+            used_c |= 1u << bc;
+            used_s |= 1u << bs;
+        }
+    }
+    // per-axis power-of-two scale and outward-rounded 8-bit planes; every plane is verified in double
+    uint32_t qlo[3][8], qhi[3][8], ebits[3];
+    for (int a = 0; a < 3; ++a) {
+        for (int s = 0; s < 8; ++s) { qlo[a][s] = 255u; qhi[a][s] = 0u; }  // empty slots never pass (valid masks also say so)
+        double ext = phi[a] - plo[a];
+        int e = -141;
+        if (ext > 0.0) { frexp(ext / 255.0, &e); }
+        if (e < -141) e = -141;
+        if (e > 112) e = 112;
+        for (;;) {
+            double S = ldexp(1.0, e);
+            bool ok = true;
+            for (int c = 0; c < cnt; ++c) {
+                double l = (double)lo[c][a], h = (double)hi[c][a];
+                double ql = floor((l - plo[a]) / S), qh = ceil((h - plo[a]) / S);
+                if (ql < 0.0) ql = 0.0;
+                if (ql > 255.0) ql = 255.0;
+                while (ql > 0.0 && plo[a] + ql * S > l) ql -= 1.0;
+                if (qh < 0.0) qh = 0.0;
+                while (qh <= 255.0 && plo[a] + qh * S < h) qh += 1.0;
+                if (qh > 255.0) { ok = false; break; }
+                qlo[a][slot_of[c]] = (uint32_t)ql;
+                qhi[a][slot_of[c]] = (uint32_t)qh;
+            }
+            if (ok || e >= 112) break;
+            e++;
+        }
+        ebits[a] = (uint32_t)(e + 15 + 127);  // biased exponent of 2^(e+15): the kernel scales (1 + q * 2^-15)
+    }
+    uint32_t imask = 0, lmask = 0;
+    uint32_t cref[8];
+    for (int c = 0; c < cnt; ++c) {
+        int s = slot_of[c];
+        cref[s] = ref[c];
+        if (ref[c] & W8_LEAF) lmask |= 1u << s;
+        else imask |= 1u << s;
+    }
+    uint32_t base = 0;
+    if (imask) base = atomicAdd(total, (uint32_t)__popc(imask));
+    for (int s = 0; s < 8; ++s) {
+        if (imask & (1u << s)) wroot[base + __popc(imask & ((1u << s) - 1u))] = cref[s];
+        leafpos[8ull * w + s] = (lmask & (1u << s)) ? (cref[s] & ~W8_LEAF) : 0xffffffffu;
+    }
+    nleaf[w] = (uint32_t)__popc(lmask);
+    auto pack4 = [](const uint32_t* q) { return q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24); };
+    float4* out = nodes8 + 5ull * w;
+    out[0] = make_float4((float)plo[0], (float)plo[1], (float)plo[2],
+                         __uint_as_float(ebits[0] | (ebits[1] << 8) | (ebits[2] << 16) | (imask << 24)));
+    out[1] = make_float4(__uint_as_float(base), __uint_as_float(0u), __uint_as_float(lmask), 0.0f);
+    out[2] = make_float4(__uint_as_float(pack4(&qlo[0][0])), __uint_as_float(pack4(&qlo[0][4])),
+                         __uint_as_float(pack4(&qlo[1][0])), __uint_as_float(pack4(&qlo[1][4])));
+    out[3] = make_float4(__uint_as_float(pack4(&qlo[2][0])), __uint_as_float(pack4(&qlo[2][4])),
+                         __uint_as_float(pack4(&qhi[0][0])), __uint_as_float(pack4(&qhi[0][4])));
+    out[4] = make_float4(__uint_as_float(pack4(&qhi[1][0])), __uint_as_float(pack4(&qhi[1][4])),
+                         __uint_as_float(pack4(&qhi[2][0])), __uint_as_float(pack4(&qhi[2][4])));
+}
+
+// Writes each node's first-triangle index and gathers the triangles into (wide node, slot) order.
+__global__ void k_finalize8(uint32_t n8, const uint32_t* __restrict__ tri_base, const uint32_t* __restrict__ leafpos,
+                            const float4* __restrict__ tris, float4* __restrict__ nodes8, float4* __restrict__ tris8) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n8) return;
+    uint32_t tb = tri_base[w];
+    reinterpret_cast<uint32_t*>(nodes8 + 5ull * w + 1)[1] = tb;
+    uint32_t r = 0;
+    for (int s = 0; s < 8; ++s) {
+        uint32_t pos = leafpos[8ull * w + s];
+        if (pos == 0xffffffffu) continue;
+        const float4* src = tris + 3ull * pos;
+        float4* dst = tris8 + 3ull * (tb + r);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        r++;
+    }
+}
+
+int pb2_wide_build(pb2_ctx* ctx, pb2_trimesh* mesh) {
+    pb2_bvh* b = &mesh->bvh;
+    mesh->n_nodes8 = 0;
+    if (b->n_leaves < 3) return PB2_OK;
+    const char* off = getenv("PB2_NO_WIDE");
+    if (off && atoi(off)) return PB2_OK;
+    cudaStream_t st = ctx->stream;
+    uint32_t nn = b->n_nodes;
+    uint32_t *wroot = nullptr, *leafpos = nullptr, *nleaf = nullptr, *tbase = nullptr, *total = nullptr;
+    float4* tmp8 = nullptr;
+    void* cub_tmp = nullptr;
+    int s = PB2_OK;
+    auto fail = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && s == PB2_OK) { snprintf(ctx->err, sizeof(ctx->err), "wide build (%s): %s", what, cudaGetErrorString(e)); s = PB2_ERR_CUDA; }
+        return e != cudaSuccess;
+    };
+    do {
+        if (fail(cudaMalloc((void**)&wroot, (size_t)nn * 4), "alloc")) break;
+        if (fail(cudaMalloc((void**)&leafpos, (size_t)nn * 32), "alloc")) break;
+        if (fail(cudaMalloc((void**)&nleaf, (size_t)nn * 4), "alloc")) break;
+        if (fail(cudaMalloc((void**)&tbase, (size_t)nn * 4), "alloc")) break;
+        if (fail(cudaMalloc((void**)&total, 4), "alloc")) break;
+        if (fail(cudaMalloc((void**)&tmp8, (size_t)nn * 80), "alloc")) break;
+        uint32_t one = 1, zero = 0;
+        if (fail(cudaMemcpyAsync(total, &one, 4, cudaMemcpyHostToDevice, st), "init")) break;
+        if (fail(cudaMemcpyAsync(wroot, &zero, 4, cudaMemcpyHostToDevice, st), "init")) break;
+        uint32_t begin = 0, end = 1;
+        int levels = 0;
+        while (begin < end) {
+            k_collapse8<<<pb2_blocks(end - begin, 128), 128, 0, st>>>(b->nodes, wroot, begin, end, total, tmp8, leafpos, nleaf);
+            PB2_LAUNCHED(ctx);
+            uint32_t t = 0;
+            if (fail(cudaMemcpyAsync(&t, total, 4, cudaMemcpyDeviceToHost, st), "level")) break;
+            if (fail(cudaStreamSynchronize(st), "level")) break;
+            begin = end;
+            end = t;
+            levels++;
+        }
+        if (s != PB2_OK) break;
+        if (levels > W8_STACK) break;  // degenerate (very deep) tree: keep the binary-tree kernels
+        uint32_t n8 = end;
+        size_t cub_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n8, st);
+        if (fail(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 1), "alloc")) break;
+        if (fail(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, nleaf, tbase, (int)n8, st), "scan")) break;
+        ctx->launches += 2;
+        if (fail(cudaMalloc((void**)&mesh->nodes8, (size_t)n8 * 80), "alloc")) break;
+        if (fail(cudaMalloc((void**)&mesh->tris8, (size_t)mesh->nt * 48), "alloc")) break;
+        if (fail(cudaMemcpyAsync(mesh->nodes8, tmp8, (size_t)n8 * 80, cudaMemcpyDeviceToDevice, st), "copy")) break;
+        k_finalize8<<<pb2_blocks(n8, 128), 128, 0, st>>>(n8, tbase, leafpos, mesh->tris, mesh->nodes8, mesh->tris8);
+        PB2_LAUNCHED(ctx);
+        if (fail(cudaGetLastError(), "finalize")) break;
+        if (fail(cudaStreamSynchronize(st), "finalize")) break;
+        mesh->n_nodes8 = n8;
+    } while (0);
+    cudaFree(wroot); cudaFree(leafpos); cudaFree(nleaf); cudaFree(tbase); cudaFree(total); cudaFree(tmp8); cudaFree(cub_tmp);
+    if (s != PB2_OK || mesh->n_nodes8 == 0) {
+        if (mesh->nodes8) cudaFree(mesh->nodes8);
+        if (mesh->tris8) cudaFree(mesh->tris8);
+        mesh->nodes8 = nullptr; mesh->tris8 = nullptr; mesh->n_nodes8 = 0;
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------ traversal
+// bit s of an 8-bit slot mask -> bit (s ^ x)
+__device__ __forceinline__ uint32_t perm8(uint32_t m, uint32_t x) {
+    uint32_t t;
+    t = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u); m = (x & 1u) ? t : m;
+    t = ((m & 0x33u) << 2) | ((m >> 2) & 0x33u); m = (x & 2u) ? t : m;
+    t = ((m & 0x0fu) << 4) | ((m >> 4) & 0x0fu); m = (x & 4u) ? t : m;
+    return m;
+}
+
+// Directed-rounding constants of one axis: entry >= fma_rd(u, Kn, cn), exit <= fma_ru(u, Kf, cf) with u = 1 + q * 2^-15.
+struct AxisK {
+    float Kn, Kf, cn, cf;
+};
+__device__ __forceinline__ AxisK axis_setup(float p, float o, float inv, bool neg, uint32_t ebyte) {
+    float S = __uint_as_float(ebyte << 23);
+    AxisK k;
+    k.Kn = __fmul_rd(S, inv);
+    k.Kf = __fmul_ru(S, inv);
+    float slo = __fsub_rd(p, o), shi = __fsub_ru(p, o);
+    float an = neg ? shi : slo, af = neg ? slo : shi;
+    k.cn = __fsub_rd(__fmul_rd(an, inv), k.Kf);
+    k.cf = __fsub_ru(__fmul_ru(af, inv), k.Kn);
+    return k;
+}
+
+#define W8_U(word, k) __uint_as_float(__byte_perm((word), 0x3F800000u, 0x7604u | ((k) << 4)))
+#define W8_CHILD(j, nxw, nyw, nzw, fxw, fyw, fzw)                                                   \
+    {                                                                                               \
+        float tnx = __fmaf_rd(W8_U(nxw, (j) & 3), kx.Kn, kx.cn), tfx = __fmaf_ru(W8_U(fxw, (j) & 3), kx.Kf, kx.cf); \
+        float tny = __fmaf_rd(W8_U(nyw, (j) & 3), ky.Kn, ky.cn), tfy = __fmaf_ru(W8_U(fyw, (j) & 3), ky.Kf, ky.cf); \
+        float tnz = __fmaf_rd(W8_U(nzw, (j) & 3), kz.Kn, kz.cn), tfz = __fmaf_ru(W8_U(fzw, (j) & 3), kz.Kf, kz.cf); \
+        float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), 0.0f);                                      \
+        float tmax = fminf(fminf(fminf(tfx, tfy), tfz), best) * W8_GAMMA;                           \
+        if (tmin <= tmax) hit8 |= 1u << (j);                                                        \
+    }
+
+template <bool WITH_NORMAL>
+__global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
+                                  const float* __restrict__ pose7, const float* __restrict__ rays, const uint32_t* __restrict__ perm,
+                                  uint32_t m, float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
+                                  float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
+                                  unsigned int* __restrict__ next_ray, int steps, int refill) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    Iso7 pose;
+    if (pose7) pose = load_iso(pose7);
+    V3 o = mk3(0.f, 0.f, 0.f), d = o, inv = o, best_n = o;
+    float best = 0.f;
+    uint32_t best_id = PB2_INVALID_U32, best_fid = 0, r = 0;
+    uint32_t oct = 0;          // bit a set <=> d[a] < 0 (sign bit)
+    uint32_t g_base = 0, g_bits = 0;  // current node group: first child index, (pending hits in priority order << 24) | imask
+    bool found = false, active = false;
+    uint2 stack[W8_STACK];
+    int sp = 0;
+    bool exhausted = false;
+    for (;;) {
+        __syncwarp();
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (!exhausted && (idle == FULL || __popc(idle) >= refill)) {
+            unsigned base = 0;
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(next_ray, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base >= m) exhausted = true;
+            if (!active) {
+                uint32_t slot = base + __popc(idle & ((1u << lane) - 1u));
+                if (slot < m) {
+                    r = perm ? perm[slot] : slot;
+                    o = mk3(rays[6ull * r], rays[6ull * r + 1], rays[6ull * r + 2]);
+                    d = mk3(rays[6ull * r + 3], rays[6ull * r + 4], rays[6ull * r + 5]);
+                    if (pose7) { o = iso_inv_point(pose, o); d = iso_inv_vec(pose, d); }
+                    inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                    oct = (__float_as_uint(d.x) >> 31) | ((__float_as_uint(d.y) >> 31) << 1) | ((__float_as_uint(d.z) >> 31) << 2);
+                    best = max_toi; best_id = PB2_INVALID_U32; best_fid = 0; found = false;
+                    // root group: one internal child (wide node 0) in slot 0
+                    g_base = 0;
+                    g_bits = ((1u << (7u ^ oct)) << 24) | 1u;
+                    sp = 0; active = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) break;
+        const uint32_t pxor = 7u ^ oct;
+#pragma unroll 1
+        for (int it = 0; it < steps; ++it) {
+            if (g_bits >> 24) {
+                uint32_t hits = g_bits >> 24;
+                uint32_t bsel = 31u - (uint32_t)__clz(hits);
+                hits &= ~(1u << bsel);
+                uint32_t slot = bsel ^ pxor;
+                uint32_t pim = g_bits & 0xffu;
+                uint32_t idx = g_base + (uint32_t)__popc(pim & ((1u << slot) - 1u));
+                if (hits) { stack[sp] = make_uint2(g_base, (hits << 24) | pim); sp++; }
+                const float4* np = nodes8 + 5ull * idx;
+                float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                uint32_t ew = __float_as_uint(n0.w);
+                AxisK kx = axis_setup(n0.x, o.x, inv.x, oct & 1u, ew & 0xffu);
+                AxisK ky = axis_setup(n0.y, o.y, inv.y, oct & 2u, (ew >> 8) & 0xffu);
+                AxisK kz = axis_setup(n0.z, o.z, inv.z, oct & 4u, (ew >> 16) & 0xffu);
+                uint32_t lx0 = __float_as_uint(n2.x), lx1 = __float_as_uint(n2.y), ly0 = __float_as_uint(n2.z), ly1 = __float_as_uint(n2.w);
+                uint32_t lz0 = __float_as_uint(n3.x), lz1 = __float_as_uint(n3.y), hx0 = __float_as_uint(n3.z), hx1 = __float_as_uint(n3.w);
+                uint32_t hy0 = __float_as_uint(n4.x), hy1 = __float_as_uint(n4.y), hz0 = __float_as_uint(n4.z), hz1 = __float_as_uint(n4.w);
+                // entry planes are the low planes for a positive direction, the high planes for a negative one
+                uint32_t nx0 = (oct & 1u) ? hx0 : lx0, nx1 = (oct & 1u) ? hx1 : lx1, fx0 = (oct & 1u) ? lx0 : hx0, fx1 = (oct & 1u) ? lx1 : hx1;
+                uint32_t ny0 = (oct & 2u) ? hy0 : ly0, ny1 = (oct & 2u) ? hy1 : ly1, fy0 = (oct & 2u) ? ly0 : hy0, fy1 = (oct & 2u) ? ly1 : hy1;
+                uint32_t nz0 = (oct & 4u) ? hz0 : lz0, nz1 = (oct & 4u) ? hz1 : lz1, fz0 = (oct & 4u) ? lz0 : hz0, fz1 = (oct & 4u) ? lz1 : hz1;
+                uint32_t hit8 = 0;
+                W8_CHILD(0, nx0, ny0, nz0, fx0, fy0, fz0)
+                W8_CHILD(1, nx0, ny0, nz0, fx0, fy0, fz0)
+                W8_CHILD(2, nx0, ny0, nz0, fx0, fy0, fz0)
+                W8_CHILD(3, nx0, ny0, nz0, fx0, fy0, fz0)
+                W8_CHILD(4, nx1, ny1, nz1, fx1, fy1, fz1)
+                W8_CHILD(5, nx1, ny1, nz1, fx1, fy1, fz1)
+                W8_CHILD(6, nx1, ny1, nz1, fx1, fy1, fz1)
+                W8_CHILD(7, nx1, ny1, nz1, fx1, fy1, fz1)
+                uint32_t imask = ew >> 24, lmask = __float_as_uint(n1.z);
+                uint32_t cbase = __float_as_uint(n1.x), tbase = __float_as_uint(n1.y);
+                // triangles of this node first: they may shorten the ray before any child is opened
+                uint32_t lh = hit8 & lmask;
+                while (lh) {
+                    uint32_t s = (uint32_t)__ffs(lh) - 1u;
+                    lh &= lh - 1u;
+                    uint32_t t = tbase + (uint32_t)__popc(lmask & ((1u << s) - 1u));
+                    float4 ta = __ldg(&tris8[3ull * t]), tb = __ldg(&tris8[3ull * t + 1]), tc = __ldg(&tris8[3ull * t + 2]);
+                    // exact leaf AABB (Triangle::local_aabb) and the reference's node test against the best hit so far
+                    float4 blo = make_float4(fminf(fminf(ta.x, tb.x), tc.x), fminf(fminf(ta.y, tb.y), tc.y), fminf(fminf(ta.z, tb.z), tc.z), 0.f);
+                    float4 bhi = make_float4(fmaxf(fmaxf(ta.x, tb.x), tc.x), fmaxf(fmaxf(ta.y, tb.y), tc.y), fmaxf(fmaxf(ta.z, tb.z), tc.z), 0.f);
+                    float sc = slab_cost_bf(blo, bhi, o, inv, best);
+                    if (sc != FLT_MAX && (sc < best || (found && sc == best))) {
+                        float toi; uint32_t fid; V3 n;
+                        if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n) && toi <= best) {
+                            uint32_t id = __float_as_uint(ta.w);
+                            if (toi < best || (found && toi == best && id < best_id)) {
+                                best = toi; best_id = id; best_fid = fid; found = true;
+                                if (WITH_NORMAL) best_n = n;
+                            }
+                        }
+                    }
+                }
+                uint32_t ih = perm8(hit8 & imask, pxor);
+                if (ih) { g_base = cbase; g_bits = (ih << 24) | imask; }
+                else if (sp > 0) { sp--; uint2 e = stack[sp]; g_base = e.x; g_bits = e.y; }
+                else g_bits = 0;
+            }
+        }
+        if (active && (g_bits >> 24) == 0) {
+            out_toi[r] = found ? best : 0.0f;
+            out_tri[r] = best_id;
+            if (WITH_NORMAL) {
+                V3 n = mk3(0.f, 0.f, 0.f);
+                uint32_t feat = PB2_INVALID_U32;
+                if (found) {
+                    n = normalize3(best_n);
+                    if (best_fid & 2u) n = -n;
+                    if (pose7) n = iso_vec(pose, n);
+                    feat = (best_fid & 1u) ? best_id + nt : best_id;
+                }
+                if (out_normal) { out_normal[3ull * r] = n.x; out_normal[3ull * r + 1] = n.y; out_normal[3ull * r + 2] = n.z; }
+                if (out_feature) out_feature[r] = feat;
+            }
+            active = false;
+        }
+    }
+}
+
+int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, const float* d_rays, const uint32_t* d_perm, uint32_t m,
+                  float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int steps, int refill) {
+    unsigned int* next_ray = (unsigned int*)(ctx->d_counters + 8);
+    int per_sm = 0;
+    if (with_normal) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_wide<true>, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_wide<false>, 128, 0);
+    if (per_sm < 1) per_sm = 1;
+    unsigned blocks = (unsigned)(ctx->sm_count * per_sm);
+    unsigned need = pb2_blocks(m, 128);
+    if (blocks > need) blocks = need;
+    if (with_normal)
+        k_raycast_wide<true><<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi,
+                                                              d_toi, d_tri, d_n, d_f, next_ray, steps, refill);
+    else
+        k_raycast_wide<false><<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi,
+                                                               d_toi, d_tri, nullptr, nullptr, next_ray, steps, refill);
+    return PB2_OK;
+}
