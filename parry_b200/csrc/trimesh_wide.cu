@@ -22,6 +22,7 @@
 
 #define W8_LEAF 0x80000000u
 #define W8_STACK 32
+#define W8_TQ 16  // per-lane triangle queue entries (power of two)
 #define W8_GAMMA 1.00000095367431640625f  // 1 + 2^-20
 
 // ------------------------------------------------------------------------------------------------ build
@@ -145,7 +146,9 @@ __global__ void k_collapse8(const NodeWide* __restrict__ nodes, uint32_t* __rest
     float4* out = nodes8 + 5ull * w;
     out[0] = make_float4((float)plo[0], (float)plo[1], (float)plo[2],
                          __uint_as_float(ebits[0] | (ebits[1] << 8) | (ebits[2] << 16) | (imask << 24)));
-    out[1] = make_float4(__uint_as_float(base), __uint_as_float(0u), __uint_as_float(lmask), 0.0f);
+    // .w = 1.0f: the kernel ORs the quantised bytes into this word's mantissa; reading it from the node (instead of an
+    // immediate) leaves PRMT's only flexible operand slot to the byte selector
+    out[1] = make_float4(__uint_as_float(base), __uint_as_float(0u), __uint_as_float(lmask), 1.0f);
     out[2] = make_float4(__uint_as_float(pack4(&qlo[0][0])), __uint_as_float(pack4(&qlo[0][4])),
                          __uint_as_float(pack4(&qlo[1][0])), __uint_as_float(pack4(&qlo[1][4])));
     out[3] = make_float4(__uint_as_float(pack4(&qlo[2][0])), __uint_as_float(pack4(&qlo[2][4])),
@@ -262,7 +265,7 @@ __device__ __forceinline__ AxisK axis_setup(float p, float o, float inv, bool ne
     return k;
 }
 
-#define W8_U(word, k) __uint_as_float(__byte_perm((word), 0x3F800000u, 0x7604u | ((k) << 4)))
+#define W8_U(word, k) __uint_as_float(__byte_perm((word), onef, 0x7604u | ((k) << 4)))
 #define W8_CHILD(j, nxw, nyw, nzw, fxw, fyw, fzw)                                                   \
     {                                                                                               \
         float tnx = __fmaf_rd(W8_U(nxw, (j) & 3), kx.Kn, kx.cn), tfx = __fmaf_ru(W8_U(fxw, (j) & 3), kx.Kf, kx.cf); \
@@ -273,12 +276,22 @@ __device__ __forceinline__ AxisK axis_setup(float p, float o, float inv, bool ne
         if (tmin <= tmax) hit8 |= 1u << (j);                                                        \
     }
 
+// Persistent warps, one ray per lane, three phases per iteration:
+//   refill   — lanes whose ray is finished pull new rays from a global counter once `refill` of them are idle;
+//   node     — every lane with traversal work opens one wide node, tests its eight quantised child boxes, queues the
+//              triangles whose box was hit (per-lane FIFO in shared memory) and picks the next node (octant order);
+//   triangle — run only when enough lanes have queued triangles (or nothing else can make progress), so that the exact
+//              leaf-box + triangle test executes with many lanes active instead of one or two (the first version of this
+//              kernel ran it inline: 40 % of all issued instructions at 1.9 active lanes, profiles/r1_rays_v4_*).
+// Queued triangles delay the update of `best`; the lane meanwhile keeps traversing against its older bound, which can
+// only add node visits, never remove a candidate.
 template <bool WITH_NORMAL>
 __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
                                   const float* __restrict__ pose7, const float* __restrict__ rays, const uint32_t* __restrict__ perm,
                                   uint32_t m, float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
                                   float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
-                                  unsigned int* __restrict__ next_ray, int steps, int refill) {
+                                  unsigned int* __restrict__ next_ray, int tri_lanes, int refill) {
+    __shared__ uint32_t tq[W8_TQ][128];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     Iso7 pose;
@@ -288,19 +301,19 @@ __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__
     uint32_t best_id = PB2_INVALID_U32, best_fid = 0, r = 0;
     uint32_t oct = 0;          // bit a set <=> d[a] < 0 (sign bit)
     uint32_t g_base = 0, g_bits = 0;  // current node group: first child index, (pending hits in priority order << 24) | imask
+    uint32_t qh = 0, nq = 0;   // triangle queue head / length
     bool found = false, active = false;
     uint2 stack[W8_STACK];
     int sp = 0;
     bool exhausted = false;
     for (;;) {
-        __syncwarp();
         unsigned idle = __ballot_sync(FULL, !active);
         if (!exhausted && (idle == FULL || __popc(idle) >= refill)) {
             unsigned base = 0;
             int leader = __ffs(idle) - 1;
             if (lane == leader) base = atomicAdd(next_ray, (unsigned)__popc(idle));
             base = __shfl_sync(FULL, base, leader);
-            if (base >= m) exhausted = true;
+            if (base + __popc(idle) >= m) exhausted = true;
             if (!active) {
                 uint32_t slot = base + __popc(idle & ((1u << lane) - 1u));
                 if (slot < m) {
@@ -314,75 +327,92 @@ __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__
                     // root group: one internal child (wide node 0) in slot 0
                     g_base = 0;
                     g_bits = ((1u << (7u ^ oct)) << 24) | 1u;
-                    sp = 0; active = true;
+                    sp = 0; qh = 0; nq = 0; active = true;
                 }
             }
+            idle = __ballot_sync(FULL, !active);
         }
-        if (!__any_sync(FULL, active)) break;
+        if (idle == FULL) break;
         const uint32_t pxor = 7u ^ oct;
-#pragma unroll 1
-        for (int it = 0; it < steps; ++it) {
-            if (g_bits >> 24) {
-                uint32_t hits = g_bits >> 24;
-                uint32_t bsel = 31u - (uint32_t)__clz(hits);
-                hits &= ~(1u << bsel);
-                uint32_t slot = bsel ^ pxor;
-                uint32_t pim = g_bits & 0xffu;
-                uint32_t idx = g_base + (uint32_t)__popc(pim & ((1u << slot) - 1u));
-                if (hits) { stack[sp] = make_uint2(g_base, (hits << 24) | pim); sp++; }
-                const float4* np = nodes8 + 5ull * idx;
-                float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-                uint32_t ew = __float_as_uint(n0.w);
-                AxisK kx = axis_setup(n0.x, o.x, inv.x, oct & 1u, ew & 0xffu);
-                AxisK ky = axis_setup(n0.y, o.y, inv.y, oct & 2u, (ew >> 8) & 0xffu);
-                AxisK kz = axis_setup(n0.z, o.z, inv.z, oct & 4u, (ew >> 16) & 0xffu);
-                uint32_t lx0 = __float_as_uint(n2.x), lx1 = __float_as_uint(n2.y), ly0 = __float_as_uint(n2.z), ly1 = __float_as_uint(n2.w);
-                uint32_t lz0 = __float_as_uint(n3.x), lz1 = __float_as_uint(n3.y), hx0 = __float_as_uint(n3.z), hx1 = __float_as_uint(n3.w);
-                uint32_t hy0 = __float_as_uint(n4.x), hy1 = __float_as_uint(n4.y), hz0 = __float_as_uint(n4.z), hz1 = __float_as_uint(n4.w);
-                // entry planes are the low planes for a positive direction, the high planes for a negative one
-                uint32_t nx0 = (oct & 1u) ? hx0 : lx0, nx1 = (oct & 1u) ? hx1 : lx1, fx0 = (oct & 1u) ? lx0 : hx0, fx1 = (oct & 1u) ? lx1 : hx1;
-                uint32_t ny0 = (oct & 2u) ? hy0 : ly0, ny1 = (oct & 2u) ? hy1 : ly1, fy0 = (oct & 2u) ? ly0 : hy0, fy1 = (oct & 2u) ? ly1 : hy1;
-                uint32_t nz0 = (oct & 4u) ? hz0 : lz0, nz1 = (oct & 4u) ? hz1 : lz1, fz0 = (oct & 4u) ? lz0 : hz0, fz1 = (oct & 4u) ? lz1 : hz1;
-                uint32_t hit8 = 0;
-                W8_CHILD(0, nx0, ny0, nz0, fx0, fy0, fz0)
-                W8_CHILD(1, nx0, ny0, nz0, fx0, fy0, fz0)
-                W8_CHILD(2, nx0, ny0, nz0, fx0, fy0, fz0)
-                W8_CHILD(3, nx0, ny0, nz0, fx0, fy0, fz0)
-                W8_CHILD(4, nx1, ny1, nz1, fx1, fy1, fz1)
-                W8_CHILD(5, nx1, ny1, nz1, fx1, fy1, fz1)
-                W8_CHILD(6, nx1, ny1, nz1, fx1, fy1, fz1)
-                W8_CHILD(7, nx1, ny1, nz1, fx1, fy1, fz1)
-                uint32_t imask = ew >> 24, lmask = __float_as_uint(n1.z);
-                uint32_t cbase = __float_as_uint(n1.x), tbase = __float_as_uint(n1.y);
-                // triangles of this node first: they may shorten the ray before any child is opened
-                uint32_t lh = hit8 & lmask;
-                while (lh) {
-                    uint32_t s = (uint32_t)__ffs(lh) - 1u;
-                    lh &= lh - 1u;
-                    uint32_t t = tbase + (uint32_t)__popc(lmask & ((1u << s) - 1u));
-                    float4 ta = __ldg(&tris8[3ull * t]), tb = __ldg(&tris8[3ull * t + 1]), tc = __ldg(&tris8[3ull * t + 2]);
-                    // exact leaf AABB (Triangle::local_aabb) and the reference's node test against the best hit so far
-                    float4 blo = make_float4(fminf(fminf(ta.x, tb.x), tc.x), fminf(fminf(ta.y, tb.y), tc.y), fminf(fminf(ta.z, tb.z), tc.z), 0.f);
-                    float4 bhi = make_float4(fmaxf(fmaxf(ta.x, tb.x), tc.x), fmaxf(fmaxf(ta.y, tb.y), tc.y), fmaxf(fmaxf(ta.z, tb.z), tc.z), 0.f);
-                    float sc = slab_cost_bf(blo, bhi, o, inv, best);
-                    if (sc != FLT_MAX && (sc < best || (found && sc == best))) {
-                        float toi; uint32_t fid; V3 n;
-                        if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n) && toi <= best) {
-                            uint32_t id = __float_as_uint(ta.w);
-                            if (toi < best || (found && toi == best && id < best_id)) {
-                                best = toi; best_id = id; best_fid = fid; found = true;
-                                if (WITH_NORMAL) best_n = n;
+        // ------------------------------------------------------------------ node phase
+        if ((g_bits >> 24) && nq <= W8_TQ - 8) {
+            uint32_t hits = g_bits >> 24;
+            uint32_t bsel = 31u - (uint32_t)__clz(hits);
+            hits &= ~(1u << bsel);
+            uint32_t slot = bsel ^ pxor;
+            uint32_t pim = g_bits & 0xffu;
+            uint32_t idx = g_base + (uint32_t)__popc(pim & ((1u << slot) - 1u));
+            if (hits) { stack[sp] = make_uint2(g_base, (hits << 24) | pim); sp++; }
+            const float4* np = nodes8 + 5ull * idx;
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            uint32_t ew = __float_as_uint(n0.w);
+            const uint32_t onef = __float_as_uint(n1.w);  // 0x3F800000, see k_collapse8
+            AxisK kx = axis_setup(n0.x, o.x, inv.x, oct & 1u, ew & 0xffu);
+            AxisK ky = axis_setup(n0.y, o.y, inv.y, oct & 2u, (ew >> 8) & 0xffu);
+            AxisK kz = axis_setup(n0.z, o.z, inv.z, oct & 4u, (ew >> 16) & 0xffu);
+            uint32_t lx0 = __float_as_uint(n2.x), lx1 = __float_as_uint(n2.y), ly0 = __float_as_uint(n2.z), ly1 = __float_as_uint(n2.w);
+            uint32_t lz0 = __float_as_uint(n3.x), lz1 = __float_as_uint(n3.y), hx0 = __float_as_uint(n3.z), hx1 = __float_as_uint(n3.w);
+            uint32_t hy0 = __float_as_uint(n4.x), hy1 = __float_as_uint(n4.y), hz0 = __float_as_uint(n4.z), hz1 = __float_as_uint(n4.w);
+            // entry planes are the low planes for a positive direction, the high planes for a negative one
+            uint32_t nx0 = (oct & 1u) ? hx0 : lx0, nx1 = (oct & 1u) ? hx1 : lx1, fx0 = (oct & 1u) ? lx0 : hx0, fx1 = (oct & 1u) ? lx1 : hx1;
+            uint32_t ny0 = (oct & 2u) ? hy0 : ly0, ny1 = (oct & 2u) ? hy1 : ly1, fy0 = (oct & 2u) ? ly0 : hy0, fy1 = (oct & 2u) ? ly1 : hy1;
+            uint32_t nz0 = (oct & 4u) ? hz0 : lz0, nz1 = (oct & 4u) ? hz1 : lz1, fz0 = (oct & 4u) ? lz0 : hz0, fz1 = (oct & 4u) ? lz1 : hz1;
+            uint32_t hit8 = 0;
+            W8_CHILD(0, nx0, ny0, nz0, fx0, fy0, fz0)
+            W8_CHILD(1, nx0, ny0, nz0, fx0, fy0, fz0)
+            W8_CHILD(2, nx0, ny0, nz0, fx0, fy0, fz0)
+            W8_CHILD(3, nx0, ny0, nz0, fx0, fy0, fz0)
+            W8_CHILD(4, nx1, ny1, nz1, fx1, fy1, fz1)
+            W8_CHILD(5, nx1, ny1, nz1, fx1, fy1, fz1)
+            W8_CHILD(6, nx1, ny1, nz1, fx1, fy1, fz1)
+            W8_CHILD(7, nx1, ny1, nz1, fx1, fy1, fz1)
+            uint32_t imask = ew >> 24, lmask = __float_as_uint(n1.z);
+            uint32_t cbase = __float_as_uint(n1.x), tbase = __float_as_uint(n1.y);
+            // queue the triangles whose box was hit (at most eight; lanes with fuller queues do not walk)
+            uint32_t lh = hit8 & lmask;
+            while (lh) {
+                uint32_t s = (uint32_t)__ffs(lh) - 1u;
+                lh &= lh - 1u;
+                tq[(qh + nq) & (W8_TQ - 1)][threadIdx.x] = tbase + (uint32_t)__popc(lmask & ((1u << s) - 1u));
+                nq++;
+            }
+            uint32_t ih = perm8(hit8 & imask, pxor);
+            if (ih) { g_base = cbase; g_bits = (ih << 24) | imask; }
+            else if (sp > 0) { sp--; uint2 e = stack[sp]; g_base = e.x; g_bits = e.y; }
+            else g_bits = 0;
+        }
+        // ------------------------------------------------------------------ triangle phase
+        {
+            unsigned has = __ballot_sync(FULL, nq > 0);
+            if (has) {
+                unsigned full = __ballot_sync(FULL, nq > W8_TQ - 8);
+                unsigned walking = __ballot_sync(FULL, (g_bits >> 24) != 0 && nq <= W8_TQ - 8);
+                int nh = __popc(has);
+                if (nh >= tri_lanes || full || !walking || 2 * nh >= __popc(~idle)) {
+                    if (nq > 0) {
+                        uint32_t t = tq[qh & (W8_TQ - 1)][threadIdx.x];
+                        qh++; nq--;
+                        float4 ta = __ldg(&tris8[3ull * t]), tb = __ldg(&tris8[3ull * t + 1]), tc = __ldg(&tris8[3ull * t + 2]);
+                        // exact leaf AABB (Triangle::local_aabb) and the reference's node test against the best hit so far
+                        float4 blo = make_float4(fminf(fminf(ta.x, tb.x), tc.x), fminf(fminf(ta.y, tb.y), tc.y), fminf(fminf(ta.z, tb.z), tc.z), 0.f);
+                        float4 bhi = make_float4(fmaxf(fmaxf(ta.x, tb.x), tc.x), fmaxf(fmaxf(ta.y, tb.y), tc.y), fmaxf(fmaxf(ta.z, tb.z), tc.z), 0.f);
+                        float sc = slab_cost_bf(blo, bhi, o, inv, best);
+                        if (sc != FLT_MAX && (sc < best || (found && sc == best))) {
+                            float toi; uint32_t fid; V3 n;
+                            if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n) && toi <= best) {
+                                uint32_t id = __float_as_uint(ta.w);
+                                if (toi < best || (found && toi == best && id < best_id)) {
+                                    best = toi; best_id = id; best_fid = fid; found = true;
+                                    if (WITH_NORMAL) best_n = n;
+                                }
                             }
                         }
                     }
                 }
-                uint32_t ih = perm8(hit8 & imask, pxor);
-                if (ih) { g_base = cbase; g_bits = (ih << 24) | imask; }
-                else if (sp > 0) { sp--; uint2 e = stack[sp]; g_base = e.x; g_bits = e.y; }
-                else g_bits = 0;
             }
         }
-        if (active && (g_bits >> 24) == 0) {
+        // ------------------------------------------------------------------ retire
+        if (active && (g_bits >> 24) == 0 && nq == 0) {
             out_toi[r] = found ? best : 0.0f;
             out_tri[r] = best_id;
             if (WITH_NORMAL) {
@@ -403,7 +433,7 @@ __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__
 }
 
 int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, const float* d_rays, const uint32_t* d_perm, uint32_t m,
-                  float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int steps, int refill) {
+                  float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int tri_lanes, int refill) {
     unsigned int* next_ray = (unsigned int*)(ctx->d_counters + 8);
     int per_sm = 0;
     if (with_normal) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_wide<true>, 128, 0);
@@ -414,9 +444,9 @@ int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, co
     if (blocks > need) blocks = need;
     if (with_normal)
         k_raycast_wide<true><<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi,
-                                                              d_toi, d_tri, d_n, d_f, next_ray, steps, refill);
+                                                              d_toi, d_tri, d_n, d_f, next_ray, tri_lanes, refill);
     else
         k_raycast_wide<false><<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi,
-                                                               d_toi, d_tri, nullptr, nullptr, next_ray, steps, refill);
+                                                               d_toi, d_tri, nullptr, nullptr, next_ray, tri_lanes, refill);
     return PB2_OK;
 }
