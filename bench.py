@@ -259,7 +259,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": PROFILED_TRAFFIC.get("rays_terrain"), "kernel": "k_raycast_trimesh_persistent<false> (+ ray-key sort)", "kernel_ms": ms_kernel,
+                     "traffic": PROFILED_TRAFFIC.get("rays_terrain"), "kernel": "k_raycast_wide<false, 0>", "kernel_ms": ms_kernel,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
     }
 

@@ -21,8 +21,9 @@
 #include <cub/device/device_scan.cuh>
 
 #define W8_LEAF 0x80000000u
-#define W8_STACK 32
-#define W8_TQ 16  // per-lane triangle queue entries (power of two)
+#define W8_STACK 96        // per-lane traversal stack entries; a visit pushes at most 7, so depth <= 7 * levels
+#define W8_MAX_LEVELS 13
+#define W8_TQ 8   // per-lane queue of triangle groups (power of two)
 #define W8_GAMMA 1.00000095367431640625f  // 1 + 2^-20
 
 // ------------------------------------------------------------------------------------------------ build
@@ -32,36 +33,55 @@ __global__ void k_collapse8(const NodeWide* __restrict__ nodes, uint32_t* __rest
                             uint32_t* __restrict__ nleaf) {
     uint32_t w = w_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= w_end) return;
-    uint32_t ref[8];
+    uint32_t ref[8], lc[8];  // lc = leaves below the child; bit 31 = "being flattened" (see below)
     float lo[8][3], hi[8][3];
     int cnt = 0;
-    auto add_half = [&](int at, float4 a, float4 b) {
-        bool leaf = (__float_as_uint(b.w) & PB2_LEAF_COUNT_MASK) == 1u;
-        ref[at] = leaf ? (__float_as_uint(a.w) | W8_LEAF) : __float_as_uint(a.w);
+    auto add_half = [&](int at, float4 a, float4 b, uint32_t flag) {
+        uint32_t n = __float_as_uint(b.w) & PB2_LEAF_COUNT_MASK;
+        ref[at] = n == 1u ? (__float_as_uint(a.w) | W8_LEAF) : __float_as_uint(a.w);
+        lc[at] = n | flag;
         lo[at][0] = a.x; lo[at][1] = a.y; lo[at][2] = a.z;
         hi[at][0] = b.x; hi[at][1] = b.y; hi[at][2] = b.z;
     };
     {
         const float4* np = reinterpret_cast<const float4*>(&nodes[wroot[w]]);
-        add_half(0, np[0], np[1]);
-        add_half(1, np[2], np[3]);
+        add_half(0, np[0], np[1], 0u);
+        add_half(1, np[2], np[3], 0u);
         cnt = 2;
     }
-    // greedy collapse: open the internal child with the largest surface area until eight children or only leaves
+    // Greedy collapse. Subtrees with more than eight leaves are opened largest-surface-area first. A subtree with at
+    // most eight leaves is either flattened completely into this node (when all its leaves fit into the free slots) or
+    // left whole, so that it becomes one full leaf node of its own: opening it half-way would leave a litter of
+    // two- and three-triangle nodes at the bottom of the tree (the first version did: 3.1 triangles per node).
     while (cnt < 8) {
         int k = -1;
-        float best_area = -1.0f;
-        for (int c = 0; c < cnt; ++c) {
-            if (ref[c] & W8_LEAF) continue;
-            float ex = hi[c][0] - lo[c][0], ey = hi[c][1] - lo[c][1], ez = hi[c][2] - lo[c][2];
-            float area = ex * ey + ey * ez + ez * ex;
-            if (area > best_area) { best_area = area; k = c; }
+        float best_key = -1.0f;
+        for (int c = 0; c < cnt; ++c) {  // a subtree already being flattened goes first
+            if (!(ref[c] & W8_LEAF) && (lc[c] & 0x80000000u)) { k = c; break; }
+        }
+        if (k < 0) {
+            for (int c = 0; c < cnt; ++c) {
+                if ((ref[c] & W8_LEAF) || lc[c] <= 8u) continue;
+                float ex = hi[c][0] - lo[c][0], ey = hi[c][1] - lo[c][1], ez = hi[c][2] - lo[c][2];
+                float area = ex * ey + ey * ez + ez * ex;
+                if (area > best_key) { best_key = area; k = c; }
+            }
+        }
+        uint32_t flag = 0u;
+        if (k < 0) {
+            for (int c = 0; c < cnt; ++c) {  // the largest small subtree whose leaves all fit
+                if ((ref[c] & W8_LEAF) || cnt - 1 + (int)lc[c] > 8) continue;
+                if ((float)lc[c] > best_key) { best_key = (float)lc[c]; k = c; }
+            }
+            flag = 0x80000000u;
+        } else if (lc[k] & 0x80000000u) {
+            flag = 0x80000000u;
         }
         if (k < 0) break;
         const float4* np = reinterpret_cast<const float4*>(&nodes[ref[k]]);
         float4 a0 = np[0], a1 = np[1], b0 = np[2], b1 = np[3];
-        add_half(k, a0, a1);
-        add_half(cnt, b0, b1);
+        add_half(k, a0, a1, flag);
+        add_half(cnt, b0, b1, flag);
         cnt++;
     }
     // node frame
@@ -214,7 +234,7 @@ int pb2_wide_build(pb2_ctx* ctx, pb2_trimesh* mesh) {
             levels++;
         }
         if (s != PB2_OK) break;
-        if (levels > W8_STACK) break;  // degenerate (very deep) tree: keep the binary-tree kernels
+        if (levels > W8_MAX_LEVELS) break;  // degenerate (very deep) tree: keep the binary-tree kernels
         uint32_t n8 = end;
         size_t cub_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n8, st);
@@ -273,25 +293,32 @@ __device__ __forceinline__ AxisK axis_setup(float p, float o, float inv, bool ne
         float tnz = __fmaf_rd(W8_U(nzw, (j) & 3), kz.Kn, kz.cn), tfz = __fmaf_ru(W8_U(fzw, (j) & 3), kz.Kf, kz.cf); \
         float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), 0.0f);                                      \
         float tmax = fminf(fminf(fminf(tfx, tfy), tfz), best) * W8_GAMMA;                           \
+        if (MODE == 1) tent[j][threadIdx.x] = tmin;                                                 \
         if (tmin <= tmax) hit8 |= 1u << (j);                                                        \
     }
 
 // Persistent warps, one ray per lane, three phases per iteration:
 //   refill   — lanes whose ray is finished pull new rays from a global counter once `refill` of them are idle;
-//   node     — every lane with traversal work opens one wide node, tests its eight quantised child boxes, queues the
-//              triangles whose box was hit (per-lane FIFO in shared memory) and picks the next node (octant order);
+//   node     — every lane with traversal work opens one wide node and tests its eight quantised child boxes. Hit
+//              triangles are queued as a group. MODE 0 (default): the hit inner children form a group that is walked in
+//              octant order (child slots were assigned by octant at build time), the rest of a group waits on the
+//              lane's stack. MODE 1 (PB2_RAY_MODE=1, kept for comparison): the nearest hit child is opened next and
+//              every other one is pushed with its entry distance so that stale entries are dropped at pop time; it
+//              saves 10 % of the node visits (15.7 vs 17.4 per ray on the 8M-triangle terrain) but its per-visit
+//              overhead (eight shared-memory stores + two short divergent loops) costs more than that;
 //   triangle — run only when enough lanes have queued triangles (or nothing else can make progress), so that the exact
-//              leaf-box + triangle test executes with many lanes active instead of one or two (the first version of this
-//              kernel ran it inline: 40 % of all issued instructions at 1.9 active lanes, profiles/r1_rays_v4_*).
+//              leaf-box + triangle test executes with many lanes active instead of one or two (run inline it took 40 %
+//              of all issued instructions at 1.9 active lanes, profiles/r1_rays_v4_*).
 // Queued triangles delay the update of `best`; the lane meanwhile keeps traversing against its older bound, which can
 // only add node visits, never remove a candidate.
-template <bool WITH_NORMAL>
+template <bool WITH_NORMAL, int MODE>
 __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
                                   const float* __restrict__ pose7, const float* __restrict__ rays, const uint32_t* __restrict__ perm,
                                   uint32_t m, float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
                                   float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
-                                  unsigned int* __restrict__ next_ray, int tri_lanes, int refill) {
-    __shared__ uint32_t tq[W8_TQ][128];
+                                  unsigned int* __restrict__ next_ray, int tri_lanes, int refill, unsigned long long* __restrict__ stats) {
+    __shared__ uint2 tq[W8_TQ][128];   // queued triangle groups: {first triangle, leaf mask | hit mask << 8}
+    __shared__ float tent[MODE == 1 ? 8 : 1][128];  // entry distances of the node being tested
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     Iso7 pose;
@@ -299,11 +326,13 @@ __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__
     V3 o = mk3(0.f, 0.f, 0.f), d = o, inv = o, best_n = o;
     float best = 0.f;
     uint32_t best_id = PB2_INVALID_U32, best_fid = 0, r = 0;
-    uint32_t oct = 0;          // bit a set <=> d[a] < 0 (sign bit)
-    uint32_t g_base = 0, g_bits = 0;  // current node group: first child index, (pending hits in priority order << 24) | imask
-    uint32_t qh = 0, nq = 0;   // triangle queue head / length
+    uint32_t oct = 0;                    // bit a set <=> d[a] < 0 (sign bit)
+    uint32_t cur = PB2_INVALID_U32;      // wide node to open next
+    uint32_t g_base = 0, g_bits = 0;     // MODE 0: node group {first child, (pending hits in octant priority order << 24) | imask}
+    uint32_t tg_base = 0, tg_bits = 0;   // triangle group being worked on (bits: leaf mask | pending hits << 8)
+    uint32_t qh = 0, nq = 0;             // further queued groups: ring head / length
     bool found = false, active = false;
-    uint2 stack[W8_STACK];
+    uint2 stack[W8_STACK];               // {wide node, entry distance}
     int sp = 0;
     bool exhausted = false;
     for (;;) {
@@ -324,26 +353,29 @@ __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__
                     inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
                     oct = (__float_as_uint(d.x) >> 31) | ((__float_as_uint(d.y) >> 31) << 1) | ((__float_as_uint(d.z) >> 31) << 2);
                     best = max_toi; best_id = PB2_INVALID_U32; best_fid = 0; found = false;
-                    // root group: one internal child (wide node 0) in slot 0
-                    g_base = 0;
-                    g_bits = ((1u << (7u ^ oct)) << 24) | 1u;
-                    sp = 0; qh = 0; nq = 0; active = true;
+                    cur = 0; sp = 0; qh = 0; nq = 0; tg_bits = 0; active = true;
+                    g_base = 0; g_bits = ((1u << (7u ^ oct)) << 24) | 1u;  // root group: wide node 0 in slot 0
                 }
             }
             idle = __ballot_sync(FULL, !active);
         }
         if (idle == FULL) break;
-        const uint32_t pxor = 7u ^ oct;
         // ------------------------------------------------------------------ node phase
-        if ((g_bits >> 24) && nq <= W8_TQ - 8) {
-            uint32_t hits = g_bits >> 24;
-            uint32_t bsel = 31u - (uint32_t)__clz(hits);
-            hits &= ~(1u << bsel);
-            uint32_t slot = bsel ^ pxor;
-            uint32_t pim = g_bits & 0xffu;
-            uint32_t idx = g_base + (uint32_t)__popc(pim & ((1u << slot) - 1u));
-            if (hits) { stack[sp] = make_uint2(g_base, (hits << 24) | pim); sp++; }
-            const float4* np = nodes8 + 5ull * idx;
+        const uint32_t pxor = 7u ^ oct;
+        if (MODE == 0) {  // pick the highest-priority pending child of the current group
+            cur = PB2_INVALID_U32;
+            if ((g_bits >> 24) && nq < W8_TQ) {
+                uint32_t hits = g_bits >> 24;
+                uint32_t bsel = 31u - (uint32_t)__clz(hits);
+                hits &= ~(1u << bsel);
+                uint32_t pim = g_bits & 0xffu;
+                cur = g_base + (uint32_t)__popc(pim & ((1u << (bsel ^ pxor)) - 1u));
+                g_bits = (hits << 24) | pim;
+                if (hits) { stack[sp] = make_uint2(g_base, g_bits); sp++; }
+            }
+        }
+        if (cur != PB2_INVALID_U32 && nq < W8_TQ) {
+            const float4* np = nodes8 + 5ull * cur;
             float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
             uint32_t ew = __float_as_uint(n0.w);
             const uint32_t onef = __float_as_uint(n1.w);  // 0x3F800000, see k_collapse8
@@ -368,35 +400,83 @@ __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__
             W8_CHILD(7, nx1, ny1, nz1, fx1, fy1, fz1)
             uint32_t imask = ew >> 24, lmask = __float_as_uint(n1.z);
             uint32_t cbase = __float_as_uint(n1.x), tbase = __float_as_uint(n1.y);
-            // queue the triangles whose box was hit (at most eight; lanes with fuller queues do not walk)
-            uint32_t lh = hit8 & lmask;
-            while (lh) {
-                uint32_t s = (uint32_t)__ffs(lh) - 1u;
-                lh &= lh - 1u;
-                tq[(qh + nq) & (W8_TQ - 1)][threadIdx.x] = tbase + (uint32_t)__popc(lmask & ((1u << s) - 1u));
-                nq++;
+            if (stats) {  // debug counters (PB2_RAY_STATS): visits, visits without any hit, inner hits, leaf hits
+                atomicAdd(&stats[0], 1ull);
+                if (hit8 == 0) atomicAdd(&stats[1], 1ull);
+                atomicAdd(&stats[2], (unsigned long long)__popc(hit8 & imask));
+                atomicAdd(&stats[3], (unsigned long long)__popc(hit8 & lmask));
             }
-            uint32_t ih = perm8(hit8 & imask, pxor);
-            if (ih) { g_base = cbase; g_bits = (ih << 24) | imask; }
-            else if (sp > 0) { sp--; uint2 e = stack[sp]; g_base = e.x; g_bits = e.y; }
-            else g_bits = 0;
+            // triangles whose box was hit: one group
+            uint32_t lh = hit8 & lmask;
+            if (lh) {
+                uint32_t bits = lmask | (lh << 8);
+                if (tg_bits >> 8) { tq[(qh + nq) & (W8_TQ - 1)][threadIdx.x] = make_uint2(tbase, bits); nq++; }
+                else { tg_base = tbase; tg_bits = bits; }
+            }
+            // hit inner children: open the nearest next, push the others with their entry distance
+            uint32_t ih = hit8 & imask;
+            if (MODE == 0) {
+                ih = perm8(ih, pxor);
+                if (ih) { g_base = cbase; g_bits = (ih << 24) | imask; }
+                else if (sp > 0) { sp--; uint2 e = stack[sp]; g_base = e.x; g_bits = e.y; }
+                else g_bits = 0;
+            } else if (ih) {
+                uint32_t ns = (uint32_t)__ffs(ih) - 1u;
+                uint32_t rest = ih & (ih - 1u);
+                if (rest) {
+                    float ntm = tent[ns][threadIdx.x];
+                    do {
+                        uint32_t s = (uint32_t)__ffs(rest) - 1u;
+                        rest &= rest - 1u;
+                        float t = tent[s][threadIdx.x];
+                        bool nearer = t < ntm;
+                        uint32_t ps = nearer ? ns : s;
+                        float pt = nearer ? ntm : t;
+                        ns = nearer ? s : ns;
+                        ntm = nearer ? t : ntm;
+                        stack[sp] = make_uint2(cbase + (uint32_t)__popc(imask & ((1u << ps) - 1u)), __float_as_uint(pt));
+                        sp++;
+                    } while (rest);
+                }
+                cur = cbase + (uint32_t)__popc(imask & ((1u << ns) - 1u));
+            } else {
+                cur = PB2_INVALID_U32;
+            }
+        }
+        // pop: entries farther than the current bound are dropped (same test as the box test that recorded them)
+        if (MODE == 1 && cur == PB2_INVALID_U32 && sp > 0) {
+            float bg = best * W8_GAMMA;
+            do {
+                sp--;
+                uint2 e = stack[sp];
+                if (__uint_as_float(e.y) <= bg) { cur = e.x; break; }
+            } while (sp > 0);
         }
         // ------------------------------------------------------------------ triangle phase
         {
-            unsigned has = __ballot_sync(FULL, nq > 0);
+            unsigned has = __ballot_sync(FULL, (tg_bits >> 8) != 0);
             if (has) {
-                unsigned full = __ballot_sync(FULL, nq > W8_TQ - 8);
-                unsigned walking = __ballot_sync(FULL, (g_bits >> 24) != 0 && nq <= W8_TQ - 8);
+                unsigned full = __ballot_sync(FULL, nq >= W8_TQ);
+                unsigned walking = __ballot_sync(FULL, (MODE == 0 ? (g_bits >> 24) != 0 : cur != PB2_INVALID_U32) && nq < W8_TQ);
                 int nh = __popc(has);
                 if (nh >= tri_lanes || full || !walking || 2 * nh >= __popc(~idle)) {
-                    if (nq > 0) {
-                        uint32_t t = tq[qh & (W8_TQ - 1)][threadIdx.x];
-                        qh++; nq--;
+                    if (tg_bits >> 8) {
+                        uint32_t lh = tg_bits >> 8, lmask = tg_bits & 0xffu;
+                        uint32_t s = (uint32_t)__ffs(lh) - 1u;
+                        lh &= lh - 1u;
+                        uint32_t t = tg_base + (uint32_t)__popc(lmask & ((1u << s) - 1u));
+                        tg_bits = lmask | (lh << 8);
+                        if (lh == 0 && nq > 0) {
+                            uint2 g = tq[qh & (W8_TQ - 1)][threadIdx.x];
+                            qh++; nq--;
+                            tg_base = g.x; tg_bits = g.y;
+                        }
                         float4 ta = __ldg(&tris8[3ull * t]), tb = __ldg(&tris8[3ull * t + 1]), tc = __ldg(&tris8[3ull * t + 2]);
                         // exact leaf AABB (Triangle::local_aabb) and the reference's node test against the best hit so far
                         float4 blo = make_float4(fminf(fminf(ta.x, tb.x), tc.x), fminf(fminf(ta.y, tb.y), tc.y), fminf(fminf(ta.z, tb.z), tc.z), 0.f);
                         float4 bhi = make_float4(fmaxf(fmaxf(ta.x, tb.x), tc.x), fmaxf(fmaxf(ta.y, tb.y), tc.y), fmaxf(fmaxf(ta.z, tb.z), tc.z), 0.f);
                         float sc = slab_cost_bf(blo, bhi, o, inv, best);
+                        if (stats) { atomicAdd(&stats[4], 1ull); if (sc != FLT_MAX && sc <= best) atomicAdd(&stats[5], 1ull); }
                         if (sc != FLT_MAX && (sc < best || (found && sc == best))) {
                             float toi; uint32_t fid; V3 n;
                             if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n) && toi <= best) {
@@ -412,7 +492,7 @@ __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__
             }
         }
         // ------------------------------------------------------------------ retire
-        if (active && (g_bits >> 24) == 0 && nq == 0) {
+        if (active && (MODE == 0 ? (g_bits >> 24) == 0 : (cur == PB2_INVALID_U32 && sp == 0)) && (tg_bits >> 8) == 0) {
             out_toi[r] = found ? best : 0.0f;
             out_tri[r] = best_id;
             if (WITH_NORMAL) {
@@ -435,18 +515,31 @@ __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__
 int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, const float* d_rays, const uint32_t* d_perm, uint32_t m,
                   float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int tri_lanes, int refill) {
     unsigned int* next_ray = (unsigned int*)(ctx->d_counters + 8);
+    int mode = 0;
+    { const char* e = getenv("PB2_RAY_MODE"); if (e) mode = atoi(e) ? 1 : 0; }
+    auto kern = with_normal ? (mode ? k_raycast_wide<true, 1> : k_raycast_wide<true, 0>) : (mode ? k_raycast_wide<false, 1> : k_raycast_wide<false, 0>);
     int per_sm = 0;
-    if (with_normal) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_wide<true>, 128, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_wide<false>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
     if (per_sm < 1) per_sm = 1;
     unsigned blocks = (unsigned)(ctx->sm_count * per_sm);
     unsigned need = pb2_blocks(m, 128);
     if (blocks > need) blocks = need;
-    if (with_normal)
-        k_raycast_wide<true><<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi,
-                                                              d_toi, d_tri, d_n, d_f, next_ray, tri_lanes, refill);
-    else
-        k_raycast_wide<false><<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi,
-                                                               d_toi, d_tri, nullptr, nullptr, next_ray, tri_lanes, refill);
+    unsigned long long* stats = nullptr;
+    const char* se = getenv("PB2_RAY_STATS");
+    if (se && atoi(se)) {
+        static unsigned long long* d_stats = nullptr;
+        if (!d_stats) cudaMalloc((void**)&d_stats, 64);
+        cudaMemsetAsync(d_stats, 0, 64, ctx->stream);
+        stats = d_stats;
+    }
+    kern<<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi, d_toi, d_tri,
+                                          with_normal ? d_n : nullptr, with_normal ? d_f : nullptr, next_ray, tri_lanes, refill, stats);
+    if (stats) {
+        unsigned long long h[8];
+        cudaMemcpyAsync(h, stats, 64, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "[pb2 ray stats] rays %u nodes8 %u | visits %llu (%.2f/ray) empty %llu inner-hits %llu leaf-hits %llu | tri tests %llu slab-pass %llu\n",
+                m, mesh->n_nodes8, h[0], (double)h[0] / m, h[1], h[2], h[3], h[4], h[5]);
+    }
     return PB2_OK;
 }
