@@ -689,16 +689,14 @@ __device__ __forceinline__ bool e2_face_bc(V3 va, V3 vb, V3 vc, float bc[3]) {
 enum { E2_IDLE = 0, E2_INIT = 1, E2_RUN = 2 };
 enum { FIN_NOT = 0, FIN_FACE = 1, FIN_NONE = 2, FIN_OVERFLOW = 3, FIN_DIM0 = 4 };
 
-template <bool LOCAL, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_contact_epa2(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
+__global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
                               const float4* __restrict__ pts, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2,
                               const float* __restrict__ pos1, const float* __restrict__ pos2, float prediction, OutSinks out,
                               const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
                               unsigned long long* __restrict__ next_job, Epa2Arena* __restrict__ arenas, int refill) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    Epa2Arena A_local;
-    Epa2Arena& A = LOCAL ? A_local : arenas[blockIdx.x * blockDim.x + threadIdx.x];
+    Epa2Arena& A = arenas[blockIdx.x * blockDim.x + threadIdx.x];
     const unsigned long long total = *job_count;
     const float eps = PB2_EPS, eps_tol = PB2_EPS * 100.0f;
 
@@ -956,442 +954,12 @@ __global__ void __launch_bounds__(128, MINB) k_contact_epa2(const uint8_t* __res
     }
 }
 
-// ------------------------------------------------------------------------------------------- phase 2, group-cooperative
-// k_contact_epa3<G>: G lanes (8, 16 or 32) share ONE parked pair and its polytope lives in shared memory.
-// Why: the per-thread kernels above keep ~14 KB of polytope per thread in local memory — 1 GB for the resident grid, so
-// the arena streams through HBM (ncu, profiles/r1_contacts_epa2_full.json: 28.8 GB of DRAM traffic for 1.4 M runs, issue
-// slots 25 % busy at 9 of 32 lanes). Here a 5.5 KB arena per pair sits in shared memory, and the two steps that are data
-// parallel are spread over the group's lanes:
-//   * support points — one hull vertex per lane, arg-max by shuffles (first maximum wins on ties, like the scalar scan of
-//     utils/point_cloud_support_point.rs:5-20);
-//   * the fan of new faces around the silhouette — one face per lane (normal, origin projection, distance); the heap
-//     pushes and the early exits are then replayed in silhouette order so that the reference's sequence of decisions
-//     (epa3.rs:597-635) is unchanged.
-// Everything else (heap sifts with Rust's BinaryHeap rules, the silhouette DFS) is executed redundantly by all lanes of
-// the group: same code, same data, no communication. The loop is the flattened state machine of k_contact_epa2 (one trip
-// = one expansion step for every group of the warp). Witness points are not stored: every polytope vertex remembers which
-// hull vertices produced it (8+8 bits) and the winning face's witnesses are recomputed with the same arithmetic.
-// Runs that outgrow the arena (> 128 faces / 64 vertices / 64 silhouette edges) are re-queued for k_contact_epa2.
-#define E3_F 128
-#define E3_V 64
-#define E3_SIL 64
-#define E3_STK 96
-
-struct __align__(16) Epa3Arena {
-    float4 face[E3_F];      // normal.xyz ; w = pts0 | pts1 << 8 | pts2 << 16 | deleted << 24
-    float4 vp[E3_V];        // CSO point ; w = support vertex ids (shape1 | shape2 << 16)
-    float4 vo[8];           // orig1 / orig2 of the parked simplex vertices (2 i, 2 i + 1)
-    float2 heap[E3_F];      // neg_dist ; face id (bits)
-    uint16_t adj[E3_F][4];  // three used
-    uint16_t sil[E3_SIL];   // face | opp << 14
-    uint16_t stk[E3_STK];
-};
-
-__device__ __forceinline__ void h3_sift_up(Epa3Arena& A, int start, int pos) {
-    float2 elt = A.heap[pos];
-    while (pos > start) {
-        int parent = (pos - 1) / 2;
-        float2 pe = A.heap[parent];
-        if (h2_le(elt.x, pe.x)) break;
-        A.heap[pos] = pe;
-        pos = parent;
-    }
-    A.heap[pos] = elt;
-}
-__device__ __forceinline__ void h3_push(Epa3Arena& A, int& nheap, uint32_t id, float neg_dist) {
-    int old = nheap;
-    A.heap[old] = make_float2(neg_dist, __uint_as_float(id));
-    nheap = old + 1;
-    h3_sift_up(A, 0, old);
-}
-__device__ __forceinline__ float2 h3_pop(Epa3Arena& A, int& nheap) {
-    float2 item = A.heap[nheap - 1];
-    nheap -= 1;
-    if (nheap > 0) {
-        float2 t = item; item = A.heap[0];
-        int end = nheap, pos = 0;
-        float2 elt = t;
-        int child = 1;
-        while (end >= 2 && child <= end - 2) {
-            float2 c0 = A.heap[child], c1 = A.heap[child + 1];
-            if (h2_le(c0.x, c1.x)) { child += 1; c0 = c1; }
-            A.heap[pos] = c0;
-            pos = child;
-            child = 2 * pos + 1;
-        }
-        if (child == end - 1) { A.heap[pos] = A.heap[child]; pos = child; }
-        A.heap[pos] = elt;
-        h3_sift_up(A, 0, pos);
-    }
-    return item;
-}
-
-// Local support point of `s` along `dir`, computed by the G lanes of a group. id: hull vertex index / cuboid sign bits.
-template <int G>
-__device__ __forceinline__ V3 group_local_support(const DShape& s, V3 dir, int gl, unsigned gmask, uint32_t& id) {
-    id = 0;
-    if (s.kind == DS_CUBOID) {
-        id = (__float_as_uint(dir.x) >> 31) | ((__float_as_uint(dir.y) >> 31) << 1) | ((__float_as_uint(dir.z) >> 31) << 2);
-        return mk3(copysignf(s.he.x, dir.x), copysignf(s.he.y, dir.y), copysignf(s.he.z, dir.z));
-    }
-    if (s.kind == DS_CONVEX) {
-        float bd = 0.0f;
-        uint32_t bi = 0xffffffffu;
-        for (uint32_t i = (uint32_t)gl; i < s.n; i += G) {
-            float4 q = __ldg(&s.pts[i]);
-            float d = dot3(mk3(q.x, q.y, q.z), dir);
-            if (bi == 0xffffffffu || d > bd) { bd = d; bi = i; }
-        }
-#pragma unroll
-        for (int off = G / 2; off > 0; off >>= 1) {
-            float od = __shfl_xor_sync(gmask, bd, off);
-            uint32_t oi = __shfl_xor_sync(gmask, bi, off);
-            if (oi != 0xffffffffu && (bi == 0xffffffffu || od > bd || (od == bd && oi < bi))) { bd = od; bi = oi; }
-        }
-        id = bi;
-        float4 q = __ldg(&s.pts[bi]);
-        return mk3(q.x, q.y, q.z);
-    }
-    return mk3(0.f, 0.f, 0.f);
-}
-__device__ __forceinline__ V3 local_support_from_id(const DShape& s, uint32_t id) {
-    if (s.kind == DS_CUBOID)
-        return mk3(copysignf(s.he.x, (id & 1u) ? -1.0f : 1.0f), copysignf(s.he.y, (id & 2u) ? -1.0f : 1.0f), copysignf(s.he.z, (id & 4u) ? -1.0f : 1.0f));
-    if (s.kind == DS_CONVEX) { float4 q = __ldg(&s.pts[id]); return mk3(q.x, q.y, q.z); }
-    return mk3(0.f, 0.f, 0.f);
-}
-
-template <int G>
-__global__ void __launch_bounds__(128) k_contact_epa3(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
-                              const float4* __restrict__ pts, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2,
-                              const float* __restrict__ pos1, const float* __restrict__ pos2, float prediction, OutSinks out,
-                              const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
-                              unsigned long long* __restrict__ next_job, EpaJob* __restrict__ ovf_jobs,
-                              unsigned long long* __restrict__ ovf_count) {
-    extern __shared__ __align__(16) unsigned char e3_smem[];
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int gl = lane % G;                       // lane within the group
-    const int gbase = lane - gl;                   // first lane of the group
-    const unsigned gmask = G == 32 ? FULL : (((1u << G) - 1u) << gbase);
-    Epa3Arena& A = reinterpret_cast<Epa3Arena*>(e3_smem)[threadIdx.x / G];
-    const unsigned long long total = *job_count;
-    const float eps = PB2_EPS, eps_tol = PB2_EPS * 100.0f;
-
-    int state = E2_IDLE;
-    uint32_t pair = 0;
-    unsigned long long job_idx = 0;
-    Iso7 gpos12;
-    DShape g1, g2;
-    g1.kind = g2.kind = DS_ORIGIN; g1.n = g2.n = 0; g1.pts = g2.pts = nullptr; g1.he = g2.he = mk3(0.f, 0.f, 0.f);
-    gpos12.q.i = gpos12.q.j = gpos12.q.k = 0.f; gpos12.q.w = 1.f; gpos12.t = mk3(0.f, 0.f, 0.f);
-    int dim = 0, nverts = 0, nfaces = 0, nheap = 0, niter = 0;
-    float max_dist = FLT_MAX, old_dist = 0.0f;
-    uint32_t best_id = 0;
-    bool exhausted = false;
-
-    for (;;) {
-        __syncwarp();
-        // ---- refill: every idle group pulls one parked pair
-        if (state == E2_IDLE && !exhausted) {
-            unsigned long long j = 0;
-            if (gl == 0) j = atomicAdd(next_job, 1ull);
-            j = __shfl_sync(gmask, j, gbase);
-            if (j >= total) exhausted = true;
-            else {
-                const EpaJob& job = jobs[j];
-                job_idx = j;
-                pair = job.pair;
-                PairSetup ps;
-                pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, pair, ps);
-                gpos12 = ps.gpos12; g1 = ps.g1; g2 = ps.g2;
-                dim = (int)job.dim;
-                for (int i = 0; i <= dim; ++i) {
-                    V3 o1 = mk3(job.o1[i][0], job.o1[i][1], job.o1[i][2]), o2 = mk3(job.o2[i][0], job.o2[i][1], job.o2[i][2]);
-                    V3 p = o1 - o2;
-                    A.vp[i] = make_float4(p.x, p.y, p.z, 0.f);
-                    A.vo[2 * i] = make_float4(o1.x, o1.y, o1.z, 0.f);
-                    A.vo[2 * i + 1] = make_float4(o2.x, o2.y, o2.z, 0.f);
-                }
-                nverts = dim + 1; nfaces = 0; nheap = 0; niter = 0;
-                max_dist = FLT_MAX; old_dist = 0.0f;
-                state = E2_INIT;
-            }
-        }
-        if (!__any_sync(FULL, state != E2_IDLE)) break;
-
-        int fin = FIN_NOT;
-        uint32_t fin_face = 0;
-        bool need_support = false, run_step = false;
-        V3 sdir = mk3(0.f, 0.f, 0.f);
-        float4 face = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t face_id = 0;
-        float face_neg = 0.0f, curr_dist = 0.0f;
-        int npend = 0;
-
-        // ---- phase A: pop the closest live face (RUN) / seed the initial polytope (INIT).
-        // Lane 0 of the group owns every in-place structure (heap, DFS stack, silhouette list) and `nheap`.
-        if (state == E2_RUN) {
-            int got = 0;
-            if (gl == 0) {
-                while (nheap > 0) {
-                    float2 ent = h3_pop(A, nheap);
-                    face_id = __float_as_uint(ent.y); face_neg = ent.x;
-                    if (!f_deleted(A.face[face_id])) { got = 1; break; }
-                }
-            }
-            __syncwarp(gmask);
-            got = __shfl_sync(gmask, got, gbase);
-            face_id = __shfl_sync(gmask, face_id, gbase);
-            face_neg = __shfl_sync(gmask, face_neg, gbase);
-            if (got) { face = A.face[face_id]; need_support = true; run_step = true; sdir = v3of(face); }
-            else { fin = FIN_FACE; fin_face = best_id; }
-        } else if (state == E2_INIT) {
-            if (dim == 0) fin = FIN_DIM0;
-            else if (dim == 3) {
-                V3 v0 = v3of(A.vp[0]), v1 = v3of(A.vp[1]), v2 = v3of(A.vp[2]), v3 = v3of(A.vp[3]);
-                bool swap12 = dot3(cross3(v1 - v0, v2 - v0), v3 - v0) > 0.0f;
-                __syncwarp(gmask);
-                if (swap12 && gl == 0) {
-                    float4 t1 = A.vp[1], t2 = A.vp[2];
-                    float4 a1 = A.vo[2], b1 = A.vo[3], a2 = A.vo[4], b2 = A.vo[5];
-                    A.vp[1] = t2; A.vp[2] = t1;
-                    A.vo[2] = a2; A.vo[3] = b2; A.vo[4] = a1; A.vo[5] = b1;
-                }
-                __syncwarp(gmask);
-                npend = 4;
-            } else {
-                if (dim == 1) {
-                    V3 dpt = v3of(A.vp[1]) - v3of(A.vp[0]);
-                    V3 a = fabsf(dpt.x) > fabsf(dpt.y) ? mk3(dpt.z, 0.0f, -dpt.x) : mk3(0.0f, -dpt.z, dpt.y);
-                    a = normalize3(a);
-                    sdir = cross3(a, dpt);
-                    need_support = true;
-                }
-                npend = 2;
-            }
-        }
-        // ---- phase B: one support point of the Minkowski difference (hull vertices spread over the group's lanes)
-        uint32_t support_id = 0;
-        V3 sp_point = mk3(0.f, 0.f, 0.f);
-        if (need_support) {
-            if (nverts >= E3_V) { fin = FIN_OVERFLOW; run_step = false; npend = 0; }
-            else {
-                uint32_t id1 = 0, id2 = 0;
-                V3 sp1 = group_local_support<G>(g1, sdir, gl, gmask, id1);
-                V3 sp2;
-                if (g2.kind == DS_ORIGIN) sp2 = gpos12.t;
-                else {
-                    V3 ld = iso_inv_vec(gpos12, -sdir);
-                    sp2 = iso_point(gpos12, group_local_support<G>(g2, ld, gl, gmask, id2));
-                }
-                V3 p = sp1 - sp2;
-                support_id = (uint32_t)nverts;
-                A.vp[nverts] = make_float4(p.x, p.y, p.z, __uint_as_float(id1 | (id2 << 16)));
-                nverts++;
-                sp_point = p;
-            }
-        }
-        // ---- phase C/D: convergence test, then the silhouette of the faces visible from the new point
-        if (run_step) {
-            V3 fnormal = v3of(face);
-            float candidate = dot3(sp_point, fnormal);
-            if (candidate < max_dist) { best_id = face_id; max_dist = candidate; }
-            curr_dist = -face_neg;
-            if (max_dist - curr_dist < eps_tol || (fabsf(curr_dist - old_dist) < eps && candidate < max_dist)) {
-                fin = FIN_FACE; fin_face = best_id; run_step = false;
-            } else {
-                old_dist = curr_dist;
-                int nsil = 0;
-                int ovf = 0;
-                __syncwarp(gmask);
-                if (gl == 0) {
-                A.face[face_id].w = __uint_as_float(__float_as_uint(face.w) | (1u << 24));
-                int sp = 0;
-#pragma unroll 1
-                for (int k = 2; k >= 0; --k) {
-                    uint32_t af = A.adj[face_id][k];
-                    int opp = e2_next_ccw(A.face[af], f_pts(face, k));
-                    A.stk[sp++] = (uint16_t)(af | ((uint32_t)opp << 14));
-                }
-                V3 pt = sp_point;
-                while (sp > 0) {
-                    uint32_t e = A.stk[--sp];
-                    uint32_t fid = e & 0x3fffu; int fo = (int)(e >> 14);
-                    float4 f = A.face[fid];
-                    if (f_deleted(f)) continue;
-                    V3 p0 = v3of(A.vp[f_pts(f, fo)]);
-                    bool seen = dot3(pt - p0, v3of(f)) >= -PB2_GJK_EPS_TOL;
-                    if (!seen) {
-                        V3 p1 = v3of(A.vp[f_pts(f, (fo + 1) % 3)]), p2 = v3of(A.vp[f_pts(f, (fo + 2) % 3)]);
-                        const float EPS = PB2_EPS * 100.0f;
-                        seen = rel_eq(nrm2(cross3(p2 - p1, pt - p1)), 0.0f, EPS * EPS, PB2_EPS);
-                    }
-                    if (!seen) {
-                        if (nsil >= E3_SIL) { ovf = 1; break; }
-                        A.sil[nsil++] = (uint16_t)e;
-                    } else {
-                        A.face[fid].w = __uint_as_float(__float_as_uint(f.w) | (1u << 24));
-                        int i1 = (fo + 2) % 3, i2 = fo;
-                        uint32_t adj1 = A.adj[fid][i1], adj2 = A.adj[fid][i2];
-                        int o1 = e2_next_ccw(A.face[adj1], f_pts(f, i1));
-                        int o2 = e2_next_ccw(A.face[adj2], f_pts(f, i2));
-                        if (sp + 2 > E3_STK) { ovf = 1; break; }
-                        A.stk[sp++] = (uint16_t)(adj2 | ((uint32_t)o2 << 14));
-                        A.stk[sp++] = (uint16_t)(adj1 | ((uint32_t)o1 << 14));
-                    }
-                }
-                }
-                __syncwarp(gmask);
-                nsil = __shfl_sync(gmask, nsil, gbase);
-                ovf = __shfl_sync(gmask, ovf, gbase);
-                if (ovf) { fin = FIN_OVERFLOW; run_step = false; }
-                else if (nsil == 0) { fin = FIN_NONE; run_step = false; }
-                else npend = nsil;
-            }
-        }
-        // ---- phase E: create the pending faces (initial polytope or the fan around the silhouette), one per lane
-        int first_new = nfaces;
-        if (fin == FIN_NOT && npend > 0) {
-            __syncwarp(gmask);
-            const bool init = state == E2_INIT;
-            for (int e0 = 0; e0 < npend && fin == FIN_NOT; e0 += G) {
-                int e = e0 + gl;
-                bool valid = e < npend;
-                int p0 = 0, p1 = 0, p2 = 0, a0 = 0, dv = 0;
-                uint32_t efid = 0; int eopp = 0;
-                bool skip = !valid;
-                if (valid && !init) {
-                    uint32_t ed = A.sil[e];
-                    efid = ed & 0x3fffu; eopp = (int)(ed >> 14);
-                    float4 ef = A.face[efid];
-                    if (f_deleted(ef)) skip = true;
-                    p0 = (int)f_pts(ef, (eopp + 2) % 3); p1 = (int)f_pts(ef, (eopp + 1) % 3); p2 = (int)support_id;
-                    a0 = (int)efid; dv = p0;
-                }
-                unsigned live = (__ballot_sync(gmask, !skip) >> gbase) & (G == 32 ? FULL : ((1u << G) - 1u));
-                int new_id = nfaces + __popc(live & ((1u << gl) - 1u));
-                int n_new = __popc(live);
-                if (nfaces + n_new > E3_F) { fin = FIN_OVERFLOW; break; }
-                int a1 = new_id + 1, a2 = new_id - 1;
-                if (valid && init) {
-                    if (npend == 4) {
-                        p0 = (e == 1) ? 1 : 0; p1 = (e == 0) ? 1 : ((e == 2) ? 2 : 3); p2 = (e == 0) ? 2 : ((e == 1) ? 2 : ((e == 2) ? 3 : 1));
-                        a0 = (e == 0 || e == 1) ? 3 : ((e == 2) ? 0 : 2); a1 = (e == 1) ? 2 : 1; a2 = (e == 0) ? 2 : ((e == 2) ? 3 : 0);
-                        dv = e;
-                    } else {
-                        p0 = 0; p1 = e == 0 ? 1 : 2; p2 = e == 0 ? 2 : 1;
-                        a0 = a1 = a2 = e == 0 ? 1 : 0;
-                        dv = 0;
-                    }
-                }
-                bool inside = false;
-                float dist = 0.0f;
-                if (!skip) {
-                    if (!init) A.adj[efid][(eopp + 1) % 3] = (uint16_t)new_id;
-                    V3 va = v3of(A.vp[p0]), vb = v3of(A.vp[p1]), vc = v3of(A.vp[p2]);
-                    float bc[3];
-                    inside = e2_face_bc(va, vb, vc, bc);
-                    V3 n; float nn;
-                    if (!try_normalize_get(cross3(vb - va, vc - va), PB2_EPS, n, nn)) n = mk3(0.f, 0.f, 0.f);
-                    A.face[new_id] = make_float4(n.x, n.y, n.z, __uint_as_float((uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16)));
-                    A.adj[new_id][0] = (uint16_t)a0; A.adj[new_id][1] = (uint16_t)a1; A.adj[new_id][2] = (uint16_t)a2;
-                    dist = dot3(n, v3of(A.vp[dv]));
-                }
-                __syncwarp(gmask);
-                // replay the sequential decisions in silhouette order
-                int cnt = npend - e0 < G ? npend - e0 : G;
-                for (int k = 0; k < cnt; ++k) {
-                    bool k_skip = __shfl_sync(gmask, (int)skip, gbase + k) != 0;
-                    bool k_inside = __shfl_sync(gmask, (int)inside, gbase + k) != 0;
-                    float k_dist = __shfl_sync(gmask, dist, gbase + k);
-                    int k_id = __shfl_sync(gmask, new_id, gbase + k);
-                    if (k_skip) continue;
-                    if (init) {
-                        if (npend == 4) {
-                            if (k_inside) {
-                                if (-k_dist > PB2_GJK_EPS_TOL) { fin = FIN_NONE; break; }
-                                if (gl == 0) h3_push(A, nheap, (uint32_t)k_id, -k_dist);
-                            }
-                        } else {
-                            if (gl == 0) h3_push(A, nheap, (uint32_t)k_id, 0.0f);
-                        }
-                    } else if (k_inside) {
-                        if (k_dist < curr_dist) { fin = FIN_FACE; fin_face = face_id; break; }
-                        if (-k_dist > PB2_GJK_EPS_TOL) { fin = FIN_NONE; break; }
-                        if (gl == 0) h3_push(A, nheap, (uint32_t)k_id, -k_dist);
-                    }
-                }
-                nfaces += n_new;
-            }
-            __syncwarp(gmask);
-            if (fin == FIN_NOT) {
-                if (init) {
-                    int nh = __shfl_sync(gmask, nheap, gbase);
-                    if (nh == 0) fin = FIN_NONE;
-                    else { float2 top = A.heap[0]; best_id = __float_as_uint(top.y); state = E2_RUN; }
-                } else {
-                    if (first_new == nfaces) fin = FIN_NONE;
-                    else {
-                        A.adj[first_new][2] = (uint16_t)(nfaces - 1);
-                        A.adj[nfaces - 1][1] = (uint16_t)first_new;
-                        niter += 1;
-                        if (niter > 100) { fin = FIN_FACE; fin_face = best_id; }
-                    }
-                }
-            }
-        }
-        // ---- phase F: finished groups build the contact (lane 0 writes) and go idle
-        if (fin != FIN_NOT) {
-            if (fin == FIN_OVERFLOW) {
-                if (gl == 0) {
-                    unsigned long long at = atomicAdd(ovf_count, 1ull);
-                    ovf_jobs[at] = jobs[job_idx];
-                }
-            } else {
-                PairSetup ps;
-                pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, pair, ps);
-                ContactOut c;
-                int st;
-                V3 p1 = mk3(0.f, 0.f, 0.f), p2 = p1, n1 = mk3(0.f, 1.f, 0.f);
-                if (fin == FIN_FACE) {
-                    float4 f = A.face[fin_face];
-                    uint32_t ids[3] = {f_pts(f, 0), f_pts(f, 1), f_pts(f, 2)};
-                    float bc[3];
-                    e2_face_bc(v3of(A.vp[ids[0]]), v3of(A.vp[ids[1]]), v3of(A.vp[ids[2]]), bc);
-                    V3 w1[3], w2[3];
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        uint32_t vi = ids[q];
-                        if ((int)vi <= dim) { w1[q] = v3of(A.vo[2 * vi]); w2[q] = v3of(A.vo[2 * vi + 1]); }
-                        else {
-                            uint32_t sid = __float_as_uint(A.vp[vi].w);
-                            w1[q] = local_support_from_id(g1, sid & 0xffffu);
-                            w2[q] = g2.kind == DS_ORIGIN ? gpos12.t : iso_point(gpos12, local_support_from_id(g2, sid >> 16));
-                        }
-                    }
-                    p1 = w1[0] * bc[0] + w1[1] * bc[1] + w1[2] * bc[2];
-                    p2 = w2[0] * bc[0] + w2[1] * bc[1] + w2[2] * bc[2];
-                    n1 = v3of(f);
-                }
-                if (fin == FIN_NONE) {
-                    if (ps.mode == 1) st = ST_NONE;
-                    else st = finish_gjk_pair(ps, true, ps.cb_pos12.t, p2, n1, prediction, c);
-                } else st = finish_gjk_pair(ps, true, p1, p2, n1, prediction, c);
-                if (st == ST_SOME) to_world(ps, c);
-                if (gl == 0) emit(out, pair, st, c);
-            }
-            state = E2_IDLE;
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------- host side
 static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
                         const float* pos2, float prediction, uint32_t n, OutSinks sinks) {
     cudaStream_t st = ctx->stream;
     // EPA job queue (worst case: every pair) + arenas for the persistent EPA grid
-    int epa_variant = 2, refill = 8;  // 1, 2: per-thread kernels; 3 / 4 / 5: group-cooperative with 8 / 16 / 32 lanes per pair (slower)
+    int epa_variant = 2, refill = 8;
     {
         const char* e = getenv("PB2_EPA_VARIANT");
         if (e) epa_variant = atoi(e);
@@ -1411,57 +979,16 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
         PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)epa_threads * epa_blocks * sizeof(EpaArena)));
         k_contact_epa<<<epa_blocks, epa_threads, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction,
                                                          sinks, jobs, job_count, next_job, (EpaArena*)ctx->scratch[2].ptr);
-    } else if (epa_variant == 2) {
-        int minb = 4;
-        { const char* me = getenv("PB2_EPA_MINB"); if (me) minb = atoi(me); }
-        auto kern2 = minb >= 8 ? k_contact_epa2<false, 8> : (minb >= 6 ? k_contact_epa2<false, 6> : k_contact_epa2<false, 4>);
+    } else {
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern2, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contact_epa2, 128, 0);
         if (per_sm < 1) per_sm = 1;
         int epa_blocks = ctx->sm_count * per_sm;
         int need = (int)pb2_blocks(n, 128);
         if (epa_blocks > need) epa_blocks = need;
         PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)128 * epa_blocks * sizeof(Epa2Arena)));
-        const char* le = getenv("PB2_EPA_LOCAL");
-        if (le && atoi(le))
-            k_contact_epa2<true, 4><<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction, sinks,
+        k_contact_epa2<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction, sinks,
                                                   jobs, job_count, next_job, (Epa2Arena*)ctx->scratch[2].ptr, refill);
-        else
-        kern2<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction, sinks,
-                                                  jobs, job_count, next_job, (Epa2Arena*)ctx->scratch[2].ptr, refill);
-    } else {
-        // group-cooperative kernel (shared-memory polytopes) + the per-thread kernel for the runs that outgrow its arena
-        int G = epa_variant == 3 ? 8 : (epa_variant == 4 ? 16 : 32);
-        void (*kern)(const uint8_t*, const float4*, const float4*, const uint32_t*, const uint32_t*, const float*, const float*, float, OutSinks,
-                     const EpaJob*, const unsigned long long*, unsigned long long*, EpaJob*, unsigned long long*) =
-            G == 8 ? k_contact_epa3<8> : (G == 16 ? k_contact_epa3<16> : k_contact_epa3<32>);
-        size_t smem = (size_t)(128 / G) * sizeof(Epa3Arena);
-        PB2_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
-        if (per_sm < 1) per_sm = 1;
-        int epa_blocks = ctx->sm_count * per_sm;
-        unsigned long long* ovf_count = (unsigned long long*)(ctx->d_counters + 10);
-        unsigned long long* next_job2 = (unsigned long long*)(ctx->d_counters + 11);
-        PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 10, 0, 16, st));
-        int fb_blocks = ctx->sm_count;
-        size_t fb_arena = (size_t)128 * fb_blocks * sizeof(Epa2Arena);
-        size_t ovf_off = (fb_arena + 255) & ~(size_t)255;
-        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], ovf_off + jobs_bytes));
-        EpaJob* ovf_jobs = (EpaJob*)((char*)ctx->scratch[2].ptr + ovf_off);
-        kern<<<epa_blocks, 128, smem, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction, sinks,
-                                            jobs, job_count, next_job, ovf_jobs, ovf_count);
-        PB2_LAUNCHED(ctx);
-        k_contact_epa2<false, 4><<<fb_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction, sinks,
-                                                 ovf_jobs, ovf_count, next_job2, (Epa2Arena*)ctx->scratch[2].ptr, refill);
-        const char* se = getenv("PB2_EPA_STATS");
-        if (se && atoi(se)) {
-            unsigned long long h[2] = {0, 0};
-            cudaStreamSynchronize(st);
-            cudaMemcpy(&h[0], job_count, 8, cudaMemcpyDeviceToHost);
-            cudaMemcpy(&h[1], ovf_count, 8, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[pb2 epa stats] pairs %u parked %llu re-queued for the per-thread kernel %llu (G=%d, %d blocks, %zu B smem)\n", n, h[0], h[1], G, epa_blocks, smem);
-        }
     }
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
