@@ -169,19 +169,18 @@ def main():
     rays_d = torch.from_numpy(rays_h).cuda()
     toi_d = torch.empty(m, dtype=torch.float32, device="cuda")
     tri_d = torch.empty(m, dtype=torch.int32, device="cuda")
-    gather_buf = None
+    gather = None
     if world > 1:
-        rec = torch.empty((m, 2), dtype=torch.int32, device="cuda")
-        gather_buf = torch.empty((world * m, 2), dtype=torch.int32, device="cuda")
+        from parry_b200 import sharding
+        gather = sharding.OverlappedHitGather(m, "cuda", chunks=4)
 
     def step_device():
-        mesh.cast_local_ray(rays_d, FMAX, out=(toi_d, tri_d))
-        if world > 1:
-            # the path's only collective: all-gather of the fixed-size hit records (toi bits, triangle id)
-            with torch.cuda.stream(stream):
-                rec[:, 0] = toi_d.view(torch.int32)
-                rec[:, 1] = tri_d
-                dist.all_gather_into_tensor(gather_buf, rec)
+        if world == 1:
+            mesh.cast_local_ray(rays_d, FMAX, out=(toi_d, tri_d))
+        else:
+            # the path's only collective: all-gather of the fixed-size hit records, piece c gathered on a side stream
+            # while piece c + 1 is being traversed
+            gather.run(lambda lo, hi, t, k: mesh.cast_local_ray(rays_d[lo:hi], FMAX, out=(t, k)), stream)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -240,7 +239,8 @@ def main():
         dt_e2e = float(t.item())
     e2e_val = world * m / dt_e2e
     # sanity: device-resident and host paths agree
-    assert (toi_d.cpu().numpy().view(np.uint32) == toi_np.view(np.uint32)).all()
+    toi_chk = gather.toi if world > 1 else toi_d
+    assert (toi_chk.cpu().numpy().view(np.uint32) == toi_np.view(np.uint32)).all()
 
     nt, nv = len(i), len(v)
     scene_bytes = 64 * (nt - 1) + 48 * nt  # node array + pre-gathered triangles, read at least once per launch
@@ -253,7 +253,7 @@ def main():
         "config": {"workload": "2^%d incoherent rays per GPU vs 8,000,000-triangle terrain TriMesh (BASELINE config[3] shard), "
                                "BVH replicated per GPU" % args.rays_log2,
                    "triangles": nt, "rays_per_gpu": m, "l2": "inputs larger than L2 (rays %d MB, scene %d MB)" % (m * 24 >> 20, scene_bytes >> 20),
-                   "collective": "all_gather of (toi,id) records inside the timed region" if world > 1 else "none (N=1)"},
+                   "collective": "all_gather of (toi,id) results inside the timed region, 4 pieces overlapped with traversal" if world > 1 else "none (N=1)"},
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": m * 24, "d2h_bytes_per_step": m * 8,
                 "ms_per_step": dt_e2e * 1e3},
         "gpu_launches": int(launches),
@@ -409,7 +409,46 @@ def also_broadphase(ctx, stream, timed, flush, hbm_peak):
             "roofline_frac": alg / (ms_rebuild * 1e-3) / 1e9 / hbm_peak}
 
 
-EXTRA_ALSO = [("contact_pairs_4M_hulls", also_contacts), ("broadphase_1M_colliders", also_broadphase)]
+def also_mixed(ctx, stream, timed, flush, hbm_peak):
+    """BASELINE config[4]: 2^21 ball / cuboid / 32-vertex-hull colliders; per frame leaf AABBs -> Bvh build -> self pair
+    set -> query::contact on every pair (compacted contacts), all device resident."""
+    import torch
+    import parry_b200
+    from harness import scenes
+    n, H = 1 << 21, 4096
+    kinds, params, poses, hull_ids = scenes.colliders(n, seed=8, hull_fraction=1.0 / 3.0, n_hulls=H)
+    pts, _ = scenes.hull_pool(H, 32, seed=9)
+    pts = np.asarray(pts, dtype=np.float32) * 0.5
+    tk = np.concatenate([np.full(H, 2, np.uint8), np.where(kinds == 2, 0, kinds).astype(np.uint8)])
+    tp = np.concatenate([np.zeros((H, 3), np.float32), params])
+    first = np.concatenate([np.arange(H, dtype=np.uint32) * 32, np.zeros(n, np.uint32)])
+    count = np.concatenate([np.full(H, 32, np.uint32), np.zeros(n, np.uint32)])
+    G = parry_b200.Shapes.from_arrays(ctx, tk, tp, pts.reshape(-1, 3), first, count)
+    cs = torch.from_numpy(np.where(kinds == 2, hull_ids, H + np.arange(n)).astype(np.uint32).view(np.int32)).cuda()
+    dposes = torch.from_numpy(poses).cuda()
+    aabbs = G.compute_aabbs(cs, dposes)
+    bvh = parry_b200.Bvh.from_leaves(ctx, 0, aabbs)
+    state = {}
+
+    def frame():
+        a = G.compute_aabbs(cs, dposes)
+        bvh.insert_or_update_partially(a, torch.arange(n, dtype=torch.int32, device="cuda"), 0.0)
+        bvh.rebuild()
+        pr = bvh.traverse_bvtt_single_tree(capacity=16 * n, like=a)
+        state["pairs"] = int(pr.shape[0])
+        out, idx = parry_b200.contact_pairs_compact(G, cs, dposes, pr, 0.01)
+        state["contacts"] = int(out.shape[0])
+
+    ms = timed(frame, steps=5, warmup=2, flush=flush)
+    P, Cn = state["pairs"], state["contacts"]
+    alg = 24 * n + 8 * P + P * 8 + Cn * 56
+    return {"value": n / (ms * 1e-3), "unit": "colliders/s (frame: AABBs + Bvh build + self pairs + contacts)", "ms": ms,
+            "colliders": n, "pairs_per_frame": P, "contacts_per_frame": Cn, "pairs_per_s": P / (ms * 1e-3),
+            "l2": "flushed between iterations", "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+
+
+EXTRA_ALSO = [("contact_pairs_4M_hulls", also_contacts), ("broadphase_1M_colliders", also_broadphase),
+              ("mixed_2M_colliders_pipeline", also_mixed)]
 
 if __name__ == "__main__":
     main()

@@ -166,6 +166,17 @@ int pb2_contact_batch_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint
                               const float* pos1, const float* pos2, float prediction, uint32_t n, pb2_contact* out,
                               uint32_t* pair_index, uint64_t cap, uint64_t* count, int mem);
 
+/* Narrow phase straight from a broad-phase pair list (BASELINE config 5: Bvh pair query feeding per-pair contacts; the
+ * loop a caller such as rapier runs over the pairs reported by Bvh::traverse_bvtt_single_tree /
+ * Bvh::leaf_pairs, bvh_traverse_bvtt.rs:19,210, calling query::contact, contact_shape_shape.rs:123, on each):
+ * pair k = colliders (pairs[2k], pairs[2k+1]); collider i has shape collider_shape[i] at pose collider_pose[i].
+ * Shapes and poses are read through the pair list inside the kernel (no gathered per-pair copies). Output as in
+ * pb2_contact_batch_compact; pair_index[j] = k. Pairs naming a collider >= n_colliders are skipped. */
+int pb2_contact_pairs_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* collider_shape /* n_colliders */,
+                              const float* collider_pose /* n_colliders x 7 */, uint32_t n_colliders,
+                              const uint32_t* pairs /* n x 2 */, uint32_t n, float prediction, pb2_contact* out,
+                              uint32_t* pair_index, uint64_t cap, uint64_t* count, int mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,13 +168,18 @@ struct PairSetup {
     DShape g1, g2;
 };
 
+// `ab` (optional): candidate pairs as collider indices (2 per pair, e.g. straight from pb2_bvh_self_pairs); shapes and poses
+// are then per-collider tables indexed through it instead of per-pair arrays.
 __device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* params, const float4* pts, const uint32_t* shape1,
-                                           const uint32_t* shape2, const float* pos1, const float* pos2, uint32_t k, PairSetup& ps) {
-    uint32_t s1 = shape1[k], s2 = shape2[k];
+                                           const uint32_t* shape2, const float* pos1, const float* pos2, const uint32_t* ab, uint32_t k,
+                                           PairSetup& ps) {
+    uint32_t i1 = k, i2 = k;
+    if (ab) { i1 = ab[2ull * k]; i2 = ab[2ull * k + 1]; }
+    uint32_t s1 = shape1[i1], s2 = shape2[i2];
     ps.k1 = kinds[s1]; ps.k2 = kinds[s2];
     ps.pr1 = params[s1]; ps.pr2 = params[s2];
-    ps.pos1 = load_iso(pos1 + 7ull * k);
-    ps.pos2 = load_iso(pos2 + 7ull * k);
+    ps.pos1 = load_iso(pos1 + 7ull * i1);
+    ps.pos2 = load_iso(pos2 + 7ull * i2);
     ps.pos12 = iso_inv_mul(ps.pos1, ps.pos2);  // contact_shape_shape.rs:130
     ps.mode = 0;
     bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
@@ -271,13 +276,18 @@ __device__ __forceinline__ void emit(const OutSinks& out, uint32_t k, int st, co
 __global__ void __launch_bounds__(128) k_contact_gjk(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
                               const float4* __restrict__ pts, uint32_t n_shapes, const uint32_t* __restrict__ shape1,
                               const uint32_t* __restrict__ shape2, const float* __restrict__ pos1, const float* __restrict__ pos2,
-                              float prediction, uint32_t n, OutSinks out, EpaJob* __restrict__ jobs, unsigned long long* job_count) {
+                              const uint32_t* __restrict__ ab, uint32_t n_colliders, float prediction, uint32_t n, OutSinks out,
+                              EpaJob* __restrict__ jobs, unsigned long long* job_count) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     ContactOut c;
-    if (shape1[k] >= n_shapes || shape2[k] >= n_shapes) { emit(out, k, ST_UNSUPPORTED, c); return; }
+    {
+        uint32_t i1 = k, i2 = k;
+        if (ab) { i1 = ab[2ull * k]; i2 = ab[2ull * k + 1]; }
+        if ((ab && (i1 >= n_colliders || i2 >= n_colliders)) || shape1[i1] >= n_shapes || shape2[i2] >= n_shapes) { emit(out, k, ST_UNSUPPORTED, c); return; }
+    }
     PairSetup ps;
-    pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, k, ps);
+    pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, k, ps);
     int st;
     if (ps.mode == 0) {
         bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
@@ -564,7 +574,7 @@ __device__ int epa_closest_points(EpaArena& A, const Iso7& pos12, const DShape& 
 
 __global__ void __launch_bounds__(64) k_contact_epa(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
                              const float4* __restrict__ pts, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2,
-                             const float* __restrict__ pos1, const float* __restrict__ pos2, float prediction, OutSinks out,
+                             const float* __restrict__ pos1, const float* __restrict__ pos2, const uint32_t* __restrict__ ab, float prediction, OutSinks out,
                              const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
                              unsigned long long* __restrict__ next_job, EpaArena* __restrict__ arenas) {
     EpaArena& A = arenas[blockIdx.x * blockDim.x + threadIdx.x];
@@ -575,7 +585,7 @@ __global__ void __launch_bounds__(64) k_contact_epa(const uint8_t* __restrict__ 
         const EpaJob& job = jobs[j];
         uint32_t k = job.pair;
         PairSetup ps;
-        pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, k, ps);
+        pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, k, ps);
         int dim = (int)job.dim;
         for (int i = 0; i <= dim; ++i) {
             V3 o1 = mk3(job.o1[i][0], job.o1[i][1], job.o1[i][2]), o2 = mk3(job.o2[i][0], job.o2[i][1], job.o2[i][2]);
@@ -691,7 +701,7 @@ enum { FIN_NOT = 0, FIN_FACE = 1, FIN_NONE = 2, FIN_OVERFLOW = 3, FIN_DIM0 = 4 }
 
 __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
                               const float4* __restrict__ pts, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2,
-                              const float* __restrict__ pos1, const float* __restrict__ pos2, float prediction, OutSinks out,
+                              const float* __restrict__ pos1, const float* __restrict__ pos2, const uint32_t* __restrict__ ab, float prediction, OutSinks out,
                               const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
                               unsigned long long* __restrict__ next_job, Epa2Arena* __restrict__ arenas, int refill) {
     const unsigned FULL = 0xffffffffu;
@@ -726,7 +736,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                     const EpaJob& job = jobs[j];
                     pair = job.pair;
                     PairSetup ps;
-                    pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, pair, ps);
+                    pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, pair, ps);
                     gpos12 = ps.gpos12; g1 = ps.g1; g2 = ps.g2;
                     dim = (int)job.dim;
                     for (int i = 0; i <= dim; ++i) {
@@ -929,7 +939,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
         // ---- phase F: finished lanes build the contact and go idle
         if (fin != FIN_NOT) {
             PairSetup ps;
-            pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, pair, ps);
+            pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, pair, ps);
             ContactOut c;
             int st;
             V3 p1 = mk3(0.f, 0.f, 0.f), p2 = p1, n1 = mk3(0.f, 1.f, 0.f);
@@ -956,7 +966,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
 
 // ------------------------------------------------------------------------------------------- host side
 static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
-                        const float* pos2, float prediction, uint32_t n, OutSinks sinks) {
+                        const float* pos2, float prediction, uint32_t n, OutSinks sinks, const uint32_t* ab = nullptr, uint32_t n_colliders = 0) {
     cudaStream_t st = ctx->stream;
     // EPA job queue (worst case: every pair) + arenas for the persistent EPA grid
     int epa_variant = 2, refill = 8;
@@ -972,12 +982,12 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
     unsigned long long* next_job = (unsigned long long*)(ctx->d_counters + 5);
     PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 4, 0, 16, st));
     k_contact_gjk<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, shape1, shape2, pos1, pos2,
-                                                     prediction, n, sinks, jobs, job_count);
+                                                     ab, n_colliders, prediction, n, sinks, jobs, job_count);
     PB2_LAUNCHED(ctx);
     if (epa_variant == 1) {
         int epa_threads = 64, epa_blocks = ctx->sm_count * 4;
         PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)epa_threads * epa_blocks * sizeof(EpaArena)));
-        k_contact_epa<<<epa_blocks, epa_threads, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction,
+        k_contact_epa<<<epa_blocks, epa_threads, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, ab, prediction,
                                                          sinks, jobs, job_count, next_job, (EpaArena*)ctx->scratch[2].ptr);
     } else {
         int per_sm = 0;
@@ -987,7 +997,7 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
         int need = (int)pb2_blocks(n, 128);
         if (epa_blocks > need) epa_blocks = need;
         PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)128 * epa_blocks * sizeof(Epa2Arena)));
-        k_contact_epa2<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, prediction, sinks,
+        k_contact_epa2<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, ab, prediction, sinks,
                                                   jobs, job_count, next_job, (Epa2Arena*)ctx->scratch[2].ptr, refill);
     }
     PB2_LAUNCHED(ctx);
@@ -1084,6 +1094,41 @@ int pb2_contact_batch_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint
     PB2_CHECK(pb2_stage_back(ctx, pair_index, d_idx, (size_t)valid * 4, mem));
     if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (total > cap) PB2_FAIL(ctx, PB2_ERR_OVERFLOW, "contact_batch_compact: %llu contacts > capacity %llu", (unsigned long long)total, (unsigned long long)cap);
+    return PB2_OK;
+}
+
+int pb2_contact_pairs_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* collider_shape, const float* collider_pose,
+                              uint32_t n_colliders, const uint32_t* pairs, uint32_t n, float prediction, pb2_contact* out,
+                              uint32_t* pair_index, uint64_t cap, uint64_t* count, int mem) {
+    if (!ctx || !shapes || !count || (n && (!collider_shape || !collider_pose || !pairs))) return PB2_ERR_INVALID;
+    *count = 0;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_s, *d_p, *d_ab;
+    void *d_out = nullptr, *d_idx = nullptr;
+    PB2_CHECK(pb2_stage_in(ctx, 0, collider_shape, (size_t)n_colliders * 4, mem, &d_s));
+    PB2_CHECK(pb2_stage_in(ctx, 2, collider_pose, (size_t)n_colliders * 28, mem, &d_p));
+    PB2_CHECK(pb2_stage_in(ctx, 1, pairs, (size_t)n * 8, mem, &d_ab));
+    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)cap * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, pair_index, (size_t)cap * 4, mem, &d_idx));
+    if (!d_out || !d_idx) cap = 0;
+    OutSinks sinks;
+    sinks.dense = nullptr; sinks.status = nullptr; sinks.compact = (float*)d_out; sinks.pair_index = (uint32_t*)d_idx; sinks.cap = cap;
+    sinks.compact_count = (unsigned long long*)(ctx->d_counters + 6);
+    sinks.some_count = nullptr;
+    if (cap == 0) { sinks.compact = nullptr; sinks.some_count = sinks.compact_count; }
+    PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 6, 0, 8, ctx->stream));
+    PB2_CHECK(run_contacts(ctx, shapes, (const uint32_t*)d_s, (const uint32_t*)d_s, (const float*)d_p, (const float*)d_p, prediction, n, sinks,
+                           (const uint32_t*)d_ab, n_colliders));
+    PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 6, ctx->d_counters + 6, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t total = ctx->h_counters[6];
+    *count = total;
+    uint64_t valid = total < cap ? total : cap;
+    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)valid * 52, mem));
+    PB2_CHECK(pb2_stage_back(ctx, pair_index, d_idx, (size_t)valid * 4, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (total > cap) PB2_FAIL(ctx, PB2_ERR_OVERFLOW, "contact_pairs_compact: %llu contacts > capacity %llu", (unsigned long long)total, (unsigned long long)cap);
     return PB2_OK;
 }
 

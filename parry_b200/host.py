@@ -362,6 +362,30 @@ class Shapes:
                                              self.points.ctypes.data if npts else None, npts, C.byref(h)))
         self.h = h
 
+    @classmethod
+    def from_arrays(cls, ctx, kinds, params, hull_points=None, hull_first=None, hull_count=None):
+        """Bulk constructor: kinds (n,) u8 (0 ball, 1 cuboid, 2 convex), params (n, 3): radius / half extents; convex
+        shape i uses hull_points[hull_first[i] : hull_first[i] + hull_count[i]]."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+        n = len(kinds)
+        p4 = np.zeros((n, 4), dtype=np.float32)
+        p4[:, :3] = np.asarray(params, dtype=np.float32).reshape(n, -1)[:, :3]
+        cv = kinds == 2
+        if cv.any():
+            pu = p4.view(np.uint32)
+            pu[cv, 0] = np.asarray(hull_first, dtype=np.uint32)[cv]
+            pu[cv, 1] = np.asarray(hull_count, dtype=np.uint32)[cv]
+            p4[cv, 2] = 0.0
+        points = np.ascontiguousarray(hull_points, dtype=np.float32).reshape(-1, 3) if hull_points is not None else np.zeros((0, 3), np.float32)
+        self.kinds, self.params, self.points, self.n = kinds, p4, points, n
+        h = C.c_void_p()
+        ctx.check(ctx._lib.pb2_shapes_create(ctx.h, kinds.ctypes.data, p4.ctypes.data, n,
+                                             points.ctypes.data if len(points) else None, len(points), C.byref(h)))
+        self.h = h
+        return self
+
     def compute_aabbs(self, shape_ids, poses):
         """Shape::compute_aabb(pos), batched (shape/shape.rs:369)."""
         n = int(poses.shape[0])
@@ -423,5 +447,24 @@ def contact_compact(shapes, shape1, pos1, shape2, pos2, prediction, capacity=Non
     cnt = C.c_uint64(0)
     ctx.check(ctx._lib.pb2_contact_batch_compact(ctx.h, shapes.h, ps1, ps2, p1, p2, float(prediction), n, po, pi, cap,
                                                  C.byref(cnt), mem))
+    c = int(cnt.value)
+    return out[:c], idx[:c]
+
+
+def contact_pairs_compact(shapes, collider_shape, collider_pose, pairs, prediction, capacity=None):
+    """query::contact for every broad-phase pair (a, b) of `pairs` ((n, 2) collider indices, e.g. the output of
+    Bvh.traverse_bvtt_single_tree): collider i is shape collider_shape[i] at pose collider_pose[i]. Compacted output:
+    (contacts (count, 13), pair_index (count,)) with pair_index pointing into `pairs`."""
+    ctx = shapes.ctx
+    n = int(pairs.shape[0])
+    nc = int(collider_pose.shape[0])
+    kp, pp, mem = _prep(collider_pose, np.float32)
+    ks, ps, _ = _prep(collider_shape, np.uint32, mem)
+    kab, pab, _ = _prep(pairs, np.uint32, mem)
+    cap = int(capacity) if capacity is not None else n
+    out, po = _empty((cap, 13), np.float32, mem, ctx.torch_device)
+    idx, pi = _empty((cap,), np.uint32, mem, ctx.torch_device)
+    cnt = C.c_uint64(0)
+    ctx.check(ctx._lib.pb2_contact_pairs_compact(ctx.h, shapes.h, ps, pp, nc, pab, n, float(prediction), po, pi, cap, C.byref(cnt), mem))
     c = int(cnt.value)
     return out[:c], idx[:c]

@@ -57,3 +57,53 @@ def all_gather_varlen(rows, group=None):
     dist.all_gather_into_tensor(out, buf, group=group)
     out = out.view(world, pad, k)
     return torch.cat([out[r, : int(counts[r])] for r in range(world)], dim=0), counts
+
+
+class OverlappedHitGather:
+    """Range-split ray batch whose per-rank result all-gather overlaps the traversal: the local shard is cast in
+    `chunks` pieces on the compute stream, and as soon as piece c is done its (toi, tri) slices are all-gathered on a
+    side stream while piece c + 1 is being traversed. Only the last piece's gather is exposed. Buffers are allocated
+    once. `full()` returns rank-major (world * m_local) views of the gathered results.
+
+    cast_fn(lo, hi, toi_out, tri_out) must enqueue the cast of local rays [lo, hi) on `compute_stream` (CUDA) or run it
+    synchronously (CPU / gloo tests)."""
+
+    def __init__(self, m_local, device, chunks=4, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.m = int(m_local)
+        chunks = max(1, min(int(chunks), self.m)) if self.m else 1
+        base, rem = divmod(self.m, chunks)
+        self.spans, lo = [], 0
+        for c in range(chunks):
+            hi = lo + base + (1 if c < rem else 0)
+            self.spans.append((lo, hi))
+            lo = hi
+        self.toi = torch.empty(self.m, dtype=torch.float32, device=device)
+        self.tri = torch.empty(self.m, dtype=torch.int32, device=device)
+        self.g_toi = [torch.empty(self.world * (hi - lo), dtype=torch.float32, device=device) for lo, hi in self.spans]
+        self.g_tri = [torch.empty(self.world * (hi - lo), dtype=torch.int32, device=device) for lo, hi in self.spans]
+        self.cuda = torch.device(device).type == "cuda"
+        self.comm = torch.cuda.Stream(device=device) if self.cuda else None
+        self.events = [torch.cuda.Event() for _ in self.spans] if self.cuda else None
+
+    def run(self, cast_fn, compute_stream=None):
+        for c, (lo, hi) in enumerate(self.spans):
+            cast_fn(lo, hi, self.toi[lo:hi], self.tri[lo:hi])
+            if self.cuda:
+                self.events[c].record(compute_stream)
+                self.comm.wait_event(self.events[c])
+                with torch.cuda.stream(self.comm):
+                    dist.all_gather_into_tensor(self.g_toi[c], self.toi[lo:hi], group=self.group)
+                    dist.all_gather_into_tensor(self.g_tri[c], self.tri[lo:hi], group=self.group)
+            else:
+                dist.all_gather_into_tensor(self.g_toi[c], self.toi[lo:hi].contiguous(), group=self.group)
+                dist.all_gather_into_tensor(self.g_tri[c], self.tri[lo:hi].contiguous(), group=self.group)
+        if self.cuda:
+            (compute_stream or torch.cuda.current_stream()).wait_stream(self.comm)
+
+    def full(self):
+        """(toi, tri) of all ranks, rank-major: element r * m_local + i is ray i of rank r (all ranks hold m_local rays)."""
+        toi = torch.cat([g.view(self.world, -1) for g in self.g_toi], dim=1).reshape(-1)
+        tri = torch.cat([g.view(self.world, -1) for g in self.g_tri], dim=1).reshape(-1)
+        return toi, tri

@@ -54,6 +54,19 @@ def _worker(rank, world, port, ret):
         got = allrows.numpy()
         ok_contacts = bool(int(counts.sum()) == len(ridx) and (got[:, 0].astype(np.int64) == ridx).all()
                            and (got[:, 1:].astype(np.float32).view(np.uint32) == rout[ridx].view(np.uint32)).all())
+        # chunk-overlapped gather (same code path as bench.py --gpus N, minus the CUDA streams)
+        m_local = 2500
+        lo = rank * m_local
+        og = sharding.OverlappedHitGather(m_local, "cpu", chunks=3)
+
+        def cast(clo, chi, toi_out, tri_out):
+            t, k = mesh.cast_rays(None, rays[lo + clo:lo + chi], FMAX)
+            toi_out.copy_(torch.from_numpy(t))
+            tri_out.copy_(torch.from_numpy(k.astype(np.int32)))
+        og.run(cast)
+        gt, gk = og.full()
+        ok_rays = ok_rays and bool((gt.numpy().view(np.uint32) == rtoi[:world * m_local].view(np.uint32)).all()
+                                   and (gk.numpy().view(np.uint32) == rtri[:world * m_local]).all())
         cnt = sharding.all_gather_counts(len(idx), "cpu")
         ok_counts = bool(int(cnt[rank]) == len(idx) and int(cnt.sum()) == len(ridx))
         ret[rank] = (ok_rays, ok_contacts, ok_counts)
