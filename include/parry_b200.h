@@ -91,6 +91,13 @@ uint32_t pb2_bvh_node_count(const pb2_bvh* bvh);
  * bvh_insert.rs:209-231. ids == NULL means ids[i] = i. */
 int pb2_bvh_update_leaves(pb2_ctx* ctx, pb2_bvh* bvh, const uint32_t* ids, const float* aabbs, uint32_t n, float margin, int mem);
 /* Bvh::refit(&mut workspace) — bvh_refit.rs:170-180 (internal AABBs, leaf counts, change-flag resolution). */
+/* Bvh::remove(leaf_index) (bvh_tree.rs:2360-2427), batched: the leaves stop taking part in every query (their slot keeps
+ * Aabb::new_invalid()) and the ancestor boxes are re-fitted. Unknown ids are ignored, like the reference. */
+int pb2_bvh_remove_leaves(pb2_ctx* ctx, pb2_bvh* bvh, const uint32_t* ids, uint32_t n, int mem);
+/* Grows the leaf index space to new_n leaves; new indices start removed. Bvh::insert(aabb, leaf_index)
+ * (bvh_insert.rs:126-197) for a new index = pb2_bvh_resize + pb2_bvh_update_leaves + pb2_bvh_rebuild: structural edits
+ * are whole-tree rebuilds on the GPU. */
+int pb2_bvh_resize(pb2_ctx* ctx, pb2_bvh* bvh, uint32_t new_n);
 int pb2_bvh_refit(pb2_ctx* ctx, pb2_bvh* bvh);
 /* Bvh::rebuild(&mut workspace, strategy) — bvh_binned_build.rs:11 (same leaves, new topology). */
 int pb2_bvh_rebuild(pb2_ctx* ctx, pb2_bvh* bvh, int strategy);
@@ -131,6 +138,14 @@ const pb2_bvh* pb2_trimesh_bvh(const pb2_trimesh* mesh);
 int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays /* m x 6 */,
                           uint32_t m, float max_toi, int solid, float* toi, uint32_t* tri, float* normal,
                           uint32_t* feature, int mem);
+/* TriMesh::cast_ray_with_culling / cast_local_ray_with_culling (ray_trimesh.rs:139-178, RayCullingMode :50-65): same
+ * query, but a triangle is only considered when its scaled normal faces the ray the allowed way. Always the
+ * `_and_get_normal` flavour in the reference; normal / feature may still be NULL here. */
+#define PB2_CULL_IGNORE_BACKFACES 1
+#define PB2_CULL_IGNORE_FRONTFACES 2
+int pb2_trimesh_cast_rays_with_culling(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays /* m x 6 */,
+                                       uint32_t m, float max_toi, int culling, float* toi, uint32_t* tri, float* normal,
+                                       uint32_t* feature, int mem);
 
 /* ------------------------------------------------------------------ typed shape tables */
 /* A table of shapes referenced by index from ray / contact batches. kinds[n] (pb2_shape_kind), params[n x 4]:

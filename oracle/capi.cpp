@@ -41,6 +41,7 @@ void pb2o_trimesh_copy_nodes(void* m, void* out) {
 // mode 0: reference traversal (RayCast::cast_ray / cast_ray_and_get_normal on TriMesh, ray.rs:381-411)
 // mode 1: brute force over all triangles (tie/ulp adjudication, min index on ties)
 // tri[i] = u32::MAX on miss. normal/feature may be NULL (=> toi-only variant, which post-filters toi < max_toi).
+// mode 2 / 3: TriMesh::cast_ray_with_culling with IgnoreBackfaces / IgnoreFrontfaces (ray_trimesh.rs:139-178)
 void pb2o_trimesh_cast_rays(void* mesh, const float* pose7, const float* rays, uint32_t m, float max_toi, int solid,
                             int mode, int nthreads, float* toi, uint32_t* tri, float* normal, uint32_t* feature) {
     const TriMesh* t = (const TriMesh*)mesh;
@@ -53,6 +54,7 @@ void pb2o_trimesh_cast_rays(void* mesh, const float* pose7, const float* rays, u
             uint32_t id = UINT32_MAX; RayIntersection ri; ri.time_of_impact = 0; ri.feature = UINT32_MAX;
             bool hit;
             if (mode == 1) hit = t->brute_force(ray, max_toi, id, ri);
+            else if (mode == 2 || mode == 3) hit = t->cast_local_ray_with_culling(ray, max_toi, mode - 1, id, ri);
             else if (normal || feature) hit = t->cast_local_ray_and_get_normal(ray, max_toi, solid != 0, id, ri);
             else { Real tt = 0; hit = t->cast_local_ray(ray, max_toi, solid != 0, id, tt); ri.time_of_impact = tt; }
             if (!hit) { toi[i] = 0.0f; tri[i] = UINT32_MAX; if (normal) st3(normal + 3 * i, Vec3()); if (feature) feature[i] = UINT32_MAX; continue; }

@@ -223,6 +223,22 @@ struct TriMesh {
         out.feature = (out.feature == 1) ? id + (uint32_t)num_triangles() : id;
         return true;
     }
+    // TriMesh::cast_local_ray_with_culling (ray_trimesh.rs:155-178): TriMeshWithCulling maps a part only when
+    // RayCullingMode::check(tri.scaled_normal(), ray.dir) holds (:58-65, :104-111). culling: 1 IgnoreBackfaces, 2 IgnoreFrontfaces.
+    bool cast_local_ray_with_culling(const Ray& ray, Real max_toi, int culling, uint32_t& id, RayIntersection& out) const {
+        bool hit = bvh.find_best<RayIntersection>(max_toi,
+            [&](const BvhNode& n, Real best_so_far) { return node_cast_ray(n, ray, best_so_far); },
+            [&](uint32_t prim, Real best_so_far, RayIntersection& ri) {
+                const uint32_t* t = &indices[3 * prim];
+                Vec3 sn = cross(vertices[t[1]] - vertices[t[0]], vertices[t[2]] - vertices[t[0]]);  // Triangle::scaled_normal
+                Real dd = dot(sn, ray.dir);
+                if (!(culling == 1 ? dd < 0.0f : dd > 0.0f)) return false;
+                return triangle_cast_local_ray_and_get_normal(vertices[t[0]], vertices[t[1]], vertices[t[2]], ray, best_so_far, ri);
+            }, id, out);
+        if (!hit) return false;
+        out.feature = (out.feature == 1) ? id + (uint32_t)num_triangles() : id;
+        return true;
+    }
     // Brute force over all triangles: argmin toi with "own-AABB passes" filter off; ties -> min index.
     // Used by tests to adjudicate tie / ulp cases.
     bool brute_force(const Ray& ray, Real max_toi, uint32_t& id, RayIntersection& out) const {

@@ -32,6 +32,8 @@ SIGNATURES = {
     "pb2_bvh_node_count": (c_u32, [c_void_p]),
     "pb2_bvh_update_leaves": (c_int, [c_void_p, c_void_p, P, P, c_u32, c_float, c_int]),
     "pb2_bvh_refit": (c_int, [c_void_p, c_void_p]),
+    "pb2_bvh_remove_leaves": (c_int, [c_void_p, c_void_p, P, c_u32, c_int]),
+    "pb2_bvh_resize": (c_int, [c_void_p, c_void_p, c_u32]),
     "pb2_bvh_rebuild": (c_int, [c_void_p, c_void_p, c_int]),
     "pb2_bvh_download": (c_int, [c_void_p, c_void_p, P, P, P, c_int]),
     "pb2_bvh_root_aabb": (c_int, [c_void_p, c_void_p, P]),
@@ -42,6 +44,7 @@ SIGNATURES = {
     "pb2_trimesh_destroy": (c_int, [c_void_p, c_void_p]),
     "pb2_trimesh_bvh": (c_void_p, [c_void_p]),
     "pb2_trimesh_cast_rays": (c_int, [c_void_p, c_void_p, P, P, c_u32, c_float, c_int, P, P, P, P, c_int]),
+    "pb2_trimesh_cast_rays_with_culling": (c_int, [c_void_p, c_void_p, P, P, c_u32, c_float, c_int, P, P, P, P, c_int]),
     "pb2_shapes_create": (c_int, [c_void_p, P, P, c_u32, P, c_u32, C.POINTER(c_void_p)]),
     "pb2_shapes_destroy": (c_int, [c_void_p, c_void_p]),
     "pb2_shapes_compute_aabbs": (c_int, [c_void_p, c_void_p, P, P, c_u32, P, c_int]),

@@ -418,6 +418,68 @@ int pb2_bvh_rebuild(pb2_ctx* ctx, pb2_bvh* bvh, int strategy) {
     return pb2_bvh_build_device(ctx, bvh, aabbs, n, true);
 }
 
+// Leaves that are not (or no longer) part of the tree keep a slot with Aabb::new_invalid() (mins = +MAX, maxs = -MAX):
+// the neutral element of the box merge, never overlapped, never hit by a ray — inert in every query.
+__global__ void k_fill_invalid_aabbs(float* __restrict__ aabbs, uint32_t lo, uint32_t hi) {
+    uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    float* a = aabbs + 6ull * i;
+    a[0] = a[1] = a[2] = FLT_MAX;
+    a[3] = a[4] = a[5] = -FLT_MAX;
+}
+__global__ void k_invalidate_leaves(const uint32_t* __restrict__ ids, uint32_t n, const uint32_t* __restrict__ leaf_slot, uint32_t n_leaves,
+                                    NodeWide* __restrict__ nodes) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t id = ids[k];
+    if (id >= n_leaves) return;
+    uint32_t slot = leaf_slot[id];
+    NodeHalf* h = (slot & 1u) ? &nodes[slot >> 1].right : &nodes[slot >> 1].left;
+    h->mnx = h->mny = h->mnz = FLT_MAX;
+    h->mxx = h->mxy = h->mxz = -FLT_MAX;
+}
+
+// Bvh::remove (bvh_tree.rs:2360-2427), batched: the leaves become inert and every ancestor box is re-fitted bottom-up
+// (the reference splices the sibling into the parent and refits the ancestors; query results are the same).
+int pb2_bvh_remove_leaves(pb2_ctx* ctx, pb2_bvh* bvh, const uint32_t* ids, uint32_t n, int mem) {
+    if (!ctx || !bvh || (n && !ids)) return PB2_ERR_INVALID;
+    if (n == 0 || bvh->n_leaves == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* d_ids = nullptr;
+    PB2_CHECK(pb2_stage_in(ctx, 1, ids, (size_t)n * 4, mem, &d_ids));
+    k_invalidate_leaves<<<pb2_blocks(n, 256), 256, 0, ctx->stream>>>((const uint32_t*)d_ids, n, bvh->leaf_slot, bvh->n_leaves, bvh->nodes);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(bvh_refit_device(ctx, bvh));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB2_OK;
+}
+
+// Grows the leaf-id space to new_n (Bvh::insert of a new leaf index, bvh_insert.rs:126-197, is resize + update + rebuild:
+// structural edits are whole-tree rebuilds here, ~1 ms per million leaves, instead of the reference's SAH descent with
+// rotations). New ids start inert; existing leaves keep their boxes.
+int pb2_bvh_resize(pb2_ctx* ctx, pb2_bvh* bvh, uint32_t new_n) {
+    if (!ctx || !bvh) return PB2_ERR_INVALID;
+    if (new_n > PB2_LEAF_COUNT_MASK) PB2_FAIL(ctx, PB2_ERR_INVALID, "too many leaves");
+    if (new_n < bvh->n_leaves) PB2_FAIL(ctx, PB2_ERR_INVALID, "pb2_bvh_resize cannot shrink (remove leaves instead)");
+    if (new_n == bvh->n_leaves) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t old_n = bvh->n_leaves;
+    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[1], (size_t)new_n * 24));
+    float* aabbs = (float*)ctx->scratch[1].ptr;
+    if (old_n) {
+        k_gather_leaf_aabbs<<<pb2_blocks(old_n, 256), 256, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_slot, old_n, aabbs);
+        PB2_LAUNCHED(ctx);
+    }
+    k_fill_invalid_aabbs<<<pb2_blocks(new_n - old_n, 256), 256, 0, ctx->stream>>>(aabbs, old_n, new_n);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bvh_free(bvh);
+    PB2_CHECK(bvh_alloc(ctx, bvh, new_n));
+    return pb2_bvh_build_device(ctx, bvh, aabbs, new_n, true);
+}
+
 int pb2_bvh_download(pb2_ctx* ctx, const pb2_bvh* bvh, void* nodes64, uint32_t* parents, uint32_t* leaf_node_indices, int mem) {
     if (!ctx || !bvh) return PB2_ERR_INVALID;
     PB2_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -51,7 +51,7 @@ template <bool WITH_NORMAL>
 __global__ void __launch_bounds__(128) k_raycast_trimesh(const NodeWide* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_leaves,
                                   uint32_t nt, const float* __restrict__ pose7, const float* __restrict__ rays, uint32_t m,
                                   float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
-                                  float* __restrict__ out_normal, uint32_t* __restrict__ out_feature) {
+                                  float* __restrict__ out_normal, uint32_t* __restrict__ out_feature, uint32_t cull) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     V3 o = mk3(rays[6ull * r], rays[6ull * r + 1], rays[6ull * r + 2]);
@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(128) k_raycast_trimesh(const NodeWide* __restr
         float toi; uint32_t fid; V3 n;
         if (!ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n)) return;
         if (!(toi <= best)) return;  // Triangle::cast_local_ray_and_get_normal: toi <= max_toi(=best so far)
+        if (cull && (fid & 1u) != cull - 1u) return;  // RayCullingMode::check (ray_trimesh.rs:58-65): 1 front faces only, 2 back faces only
         uint32_t id = __float_as_uint(ta.w);
         // find_best keeps strictly better hits; exact ties resolve to the smallest triangle index.
         if (toi < best || (found && toi == best && id < best_id)) {
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(128) k_raycast_trimesh_persistent(const NodeWi
                                   uint32_t nt, const float* __restrict__ pose7, const float* __restrict__ rays,
                                   const uint32_t* __restrict__ perm, uint32_t m, float max_toi, float* __restrict__ out_toi,
                                   uint32_t* __restrict__ out_tri, float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
-                                  unsigned int* __restrict__ next_ray, int steps, int refill) {
+                                  unsigned int* __restrict__ next_ray, int steps, int refill, uint32_t cull) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     Iso7 pose;
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(128) k_raycast_trimesh_persistent(const NodeWi
                             uint32_t pos = k ? c1 : c0;
                             float4 ta = __ldg(&tris[3ull * pos]), tb = __ldg(&tris[3ull * pos + 1]), tc = __ldg(&tris[3ull * pos + 2]);
                             float toi; uint32_t fid; V3 n;
-                            if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n) && toi <= best) {
+                            if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n) && toi <= best &&
+                                (cull == 0u || (fid & 1u) == cull - 1u)) {
                                 uint32_t id = __float_as_uint(ta.w);
                                 if (toi < best || (found && toi == best && id < best_id)) {
                                     best = toi; best_id = id; best_fid = fid; found = true;
@@ -254,7 +256,7 @@ __global__ void k_ray_keys(const NodeWide* __restrict__ nodes, const float* __re
 
 // Enqueues the ray kernels for m device-resident rays on ctx->stream.
 static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d_pose, const void* d_rays, uint32_t m, float max_toi,
-                            void* d_toi, void* d_tri, void* d_n, void* d_f, bool with_normal) {
+                            void* d_toi, void* d_tri, void* d_n, void* d_f, bool with_normal, uint32_t cull) {
     const pb2_bvh* b = &mesh->bvh;
     // ray reordering pays off once the node array no longer fits in L2 (126 MB); below that the sort costs more than it saves
     // variants: 0 one thread per ray, 1 persistent binary, 2 = 1 + ray reordering, 3 compressed 8-wide tree, 4 = 3 + ray reordering
@@ -272,11 +274,11 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
         if (with_normal)
             k_raycast_trimesh<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
                                                                      (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
-                                                                     (float*)d_n, (uint32_t*)d_f);
+                                                                     (float*)d_n, (uint32_t*)d_f, cull);
         else
             k_raycast_trimesh<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
                                                                       (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
-                                                                      nullptr, nullptr);
+                                                                      nullptr, nullptr, cull);
     } else {
         unsigned int* next_ray = (unsigned int*)(ctx->d_counters + 8);
         PB2_CUDA(ctx, cudaMemsetAsync(next_ray, 0, 4, ctx->stream));
@@ -306,13 +308,13 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
         if (blocks > need) blocks = need;
         if (variant >= 3)
             PB2_CHECK(pb2_wide_cast(ctx, mesh, (const float*)d_pose, (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
-                                    (float*)d_n, (uint32_t*)d_f, with_normal, steps, refill));
+                                    (float*)d_n, (uint32_t*)d_f, with_normal, steps, refill, cull));
         else if (with_normal)
             k_raycast_trimesh_persistent<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
-                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, (float*)d_n, (uint32_t*)d_f, next_ray, steps, refill);
+                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, (float*)d_n, (uint32_t*)d_f, next_ray, steps, refill, cull);
         else
             k_raycast_trimesh_persistent<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
-                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, nullptr, nullptr, next_ray, steps, refill);
+                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, nullptr, nullptr, next_ray, steps, refill, cull);
     }
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
@@ -388,15 +390,14 @@ int pb2_trimesh_destroy(pb2_ctx* ctx, pb2_trimesh* mesh) {
 
 const pb2_bvh* pb2_trimesh_bvh(const pb2_trimesh* mesh) { return mesh ? &mesh->bvh : nullptr; }
 
-int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays, uint32_t m,
-                          float max_toi, int solid, float* toi, uint32_t* tri, float* normal, uint32_t* feature, int mem) {
-    (void)solid;  // ignored by the 3D triangle test (ray_triangle.rs:53)
+static int trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays, uint32_t m,
+                             float max_toi, uint32_t cull, float* toi, uint32_t* tri, float* normal, uint32_t* feature, int mem) {
     if (!ctx || !mesh || (m && (!rays || !toi || !tri))) return PB2_ERR_INVALID;
     if (m == 0) return PB2_OK;
     PB2_CUDA(ctx, cudaSetDevice(ctx->device));
     bool with_normal = normal || feature;
     if (mem == PB2_MEM_DEVICE)
-        return cast_rays_device(ctx, mesh, pose7, rays, m, max_toi, toi, tri, normal, feature, with_normal);
+        return cast_rays_device(ctx, mesh, pose7, rays, m, max_toi, toi, tri, normal, feature, with_normal, cull);
     // Host buffers: stage through HBM in chunks so that H2D copies, traversal and D2H copies of neighbouring chunks overlap
     // (full-duplex PCIe + compute; needs page-locked host memory to be truly asynchronous, pageable memory still works).
     void *d_rays = nullptr, *d_pose = nullptr, *d_toi = nullptr, *d_tri = nullptr, *d_n = nullptr, *d_f = nullptr;
@@ -420,7 +421,7 @@ int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* po
         PB2_CUDA(ctx, cudaEventRecord(e_in, ctx->copy_in));
         PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e_in, 0));
         PB2_CHECK(cast_rays_device(ctx, mesh, d_pose, (char*)d_rays + (size_t)lo * 24, cnt, max_toi, (float*)d_toi + lo, (uint32_t*)d_tri + lo,
-                                   d_n ? (float*)d_n + 3ull * lo : nullptr, d_f ? (uint32_t*)d_f + lo : nullptr, with_normal));
+                                   d_n ? (float*)d_n + 3ull * lo : nullptr, d_f ? (uint32_t*)d_f + lo : nullptr, with_normal, cull));
         PB2_CUDA(ctx, cudaEventRecord(e_k, ctx->stream));
         PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, e_k, 0));
         PB2_CUDA(ctx, cudaMemcpyAsync(toi + lo, (float*)d_toi + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
@@ -431,6 +432,18 @@ int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* po
     PB2_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
     PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB2_OK;
+}
+
+int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays, uint32_t m,
+                          float max_toi, int solid, float* toi, uint32_t* tri, float* normal, uint32_t* feature, int mem) {
+    (void)solid;  // ignored by the 3D triangle test (ray_triangle.rs:53)
+    return trimesh_cast_rays(ctx, mesh, pose7, rays, m, max_toi, 0u, toi, tri, normal, feature, mem);
+}
+
+int pb2_trimesh_cast_rays_with_culling(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays, uint32_t m,
+                                       float max_toi, int culling, float* toi, uint32_t* tri, float* normal, uint32_t* feature, int mem) {
+    if (culling != PB2_CULL_IGNORE_BACKFACES && culling != PB2_CULL_IGNORE_FRONTFACES) return PB2_ERR_INVALID;
+    return trimesh_cast_rays(ctx, mesh, pose7, rays, m, max_toi, (uint32_t)culling, toi, tri, normal, feature, mem);
 }
 
 }  // extern "C"

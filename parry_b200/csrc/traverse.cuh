@@ -17,7 +17,7 @@ __device__ __forceinline__ void bvh_find_best(const NodeWide* __restrict__ nodes
         // partial root (bvh_traverse.rs:349-358)
         const float4* np = reinterpret_cast<const float4*>(&nodes[0]);
         float4 l0 = __ldg(np), l1 = __ldg(np + 1);
-        if (slab_cost(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, o, d, inv, max_toi) < max_toi) leaf(__float_as_uint(l0.w));
+        if (!(l0.x > l1.x) && slab_cost(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, o, d, inv, max_toi) < max_toi) leaf(__float_as_uint(l0.w));
         return;
     }
     if (n_leaves < 2) return;
@@ -29,6 +29,10 @@ __device__ __forceinline__ void bvh_find_best(const NodeWide* __restrict__ nodes
         float4 l0 = __ldg(np), l1 = __ldg(np + 1), r0 = __ldg(np + 2), r1 = __ldg(np + 3);
         float ls = slab_cost(l0.x, l0.y, l0.z, l1.x, l1.y, l1.z, o, d, inv, best);
         float rs = slab_cost(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, o, d, inv, best);
+        // removed leaves / emptied subtrees keep Aabb::new_invalid() (mins > maxs): the slab test would sort the two
+        // planes and walk in, so they are excluded explicitly (pb2_bvh_remove_leaves)
+        if (l0.x > l1.x) ls = FLT_MAX;
+        if (r0.x > r1.x) rs = FLT_MAX;
         uint32_t lc = __float_as_uint(l0.w), rc = __float_as_uint(r0.w);
         bool lleaf = (__float_as_uint(l1.w) & PB2_LEAF_COUNT_MASK) == 1u;
         bool rleaf = (__float_as_uint(r1.w) & PB2_LEAF_COUNT_MASK) == 1u;

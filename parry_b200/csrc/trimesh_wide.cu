@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__
                                   const float* __restrict__ pose7, const float* __restrict__ rays, const uint32_t* __restrict__ perm,
                                   uint32_t m, float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
                                   float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
-                                  unsigned int* __restrict__ next_ray, int tri_lanes, int refill, unsigned long long* __restrict__ stats) {
+                                  unsigned int* __restrict__ next_ray, int tri_lanes, int refill, uint32_t cull,
+                                  unsigned long long* __restrict__ stats) {
     __shared__ uint2 tq[W8_TQ][128];   // queued triangle groups: {first triangle, leaf mask | hit mask << 8}
     __shared__ float tent[MODE == 1 ? 8 : 1][128];  // entry distances of the node being tested
     const unsigned FULL = 0xffffffffu;
@@ -479,7 +480,8 @@ __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__
                         if (stats) { atomicAdd(&stats[4], 1ull); if (sc != FLT_MAX && sc <= best) atomicAdd(&stats[5], 1ull); }
                         if (sc != FLT_MAX && (sc < best || (found && sc == best))) {
                             float toi; uint32_t fid; V3 n;
-                            if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n) && toi <= best) {
+                            if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n) && toi <= best &&
+                                (cull == 0u || (fid & 1u) == cull - 1u)) {  // RayCullingMode::check (ray_trimesh.rs:58-65)
                                 uint32_t id = __float_as_uint(ta.w);
                                 if (toi < best || (found && toi == best && id < best_id)) {
                                     best = toi; best_id = id; best_fid = fid; found = true;
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__
 }
 
 int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, const float* d_rays, const uint32_t* d_perm, uint32_t m,
-                  float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int tri_lanes, int refill) {
+                  float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int tri_lanes, int refill, uint32_t cull) {
     unsigned int* next_ray = (unsigned int*)(ctx->d_counters + 8);
     int mode = 0;
     { const char* e = getenv("PB2_RAY_MODE"); if (e) mode = atoi(e) ? 1 : 0; }
@@ -533,7 +535,7 @@ int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, co
         stats = d_stats;
     }
     kern<<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi, d_toi, d_tri,
-                                          with_normal ? d_n : nullptr, with_normal ? d_f : nullptr, next_ray, tri_lanes, refill, stats);
+                                          with_normal ? d_n : nullptr, with_normal ? d_f : nullptr, next_ray, tri_lanes, refill, cull, stats);
     if (stats) {
         unsigned long long h[8];
         cudaMemcpyAsync(h, stats, 64, cudaMemcpyDeviceToHost, ctx->stream);

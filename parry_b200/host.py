@@ -142,6 +142,21 @@ class Bvh:
         self.ctx.check(self.ctx._lib.pb2_bvh_update_leaves(self.ctx.h, self.h, p2, p1, int(aabbs.shape[0]),
                                                           float(change_detection_margin), mem))
 
+    def insert(self, aabbs, leaf_indices):
+        """Batched Bvh::insert (bvh_insert.rs:126-197): new leaf indices grow the tree, known ones are updated; the
+        tree is rebuilt (structural edits are whole-tree rebuilds on the GPU)."""
+        ids = leaf_indices
+        top = int(ids.max().item() if _is_torch(ids) else np.asarray(ids).max()) + 1 if int(aabbs.shape[0]) else 0
+        if top > self.leaf_count():
+            self.ctx.check(self.ctx._lib.pb2_bvh_resize(self.ctx.h, self.h, top))
+        self.insert_or_update_partially(aabbs, leaf_indices, 0.0)
+        self.rebuild()
+
+    def remove(self, leaf_indices):
+        """Batched Bvh::remove (bvh_tree.rs:2360-2427)."""
+        k, p, mem = _prep(leaf_indices, np.uint32)
+        self.ctx.check(self.ctx._lib.pb2_bvh_remove_leaves(self.ctx.h, self.h, p, int(leaf_indices.shape[0]), mem))
+
     def refit(self):
         self.ctx.check(self.ctx._lib.pb2_bvh_refit(self.ctx.h, self.h))
 
@@ -256,7 +271,7 @@ class TriMesh:
     def bvh(self):
         return Bvh(self.ctx, C.c_void_p(self.ctx._lib.pb2_trimesh_bvh(self.h)), owned=False, keep=self)
 
-    def _cast(self, pose, rays, max_toi, solid, with_normal, out=None):
+    def _cast(self, pose, rays, max_toi, solid, with_normal, out=None, culling=0):
         m = int(rays.shape[0])
         kr, pr, mem = _prep(rays, np.float32)
         kp, pp, _ = _prep(pose, np.float32, mem)
@@ -278,9 +293,23 @@ class TriMesh:
             else:
                 normal, pn = _empty((m, 3), np.float32, mem, dev)
                 feature, pf = _empty((m,), np.uint32, mem, dev)
-        self.ctx.check(self.ctx._lib.pb2_trimesh_cast_rays(self.ctx.h, self.h, pp, pr, m, float(max_toi), int(bool(solid)),
-                                                          pt, pl, pn, pf, mem))
+        if culling:
+            self.ctx.check(self.ctx._lib.pb2_trimesh_cast_rays_with_culling(self.ctx.h, self.h, pp, pr, m, float(max_toi), int(culling),
+                                                                           pt, pl, pn, pf, mem))
+        else:
+            self.ctx.check(self.ctx._lib.pb2_trimesh_cast_rays(self.ctx.h, self.h, pp, pr, m, float(max_toi), int(bool(solid)),
+                                                              pt, pl, pn, pf, mem))
         return (toi, tri, normal, feature) if with_normal else (toi, tri)
+
+    IGNORE_BACKFACES, IGNORE_FRONTFACES = 1, 2  # RayCullingMode (ray_trimesh.rs:50-56)
+
+    def cast_ray_with_culling(self, m, rays, max_time_of_impact, culling, out=None):
+        """TriMesh::cast_ray_with_culling (ray_trimesh.rs:139-150): (toi, tri, normal, feature)."""
+        return self._cast(m, rays, max_time_of_impact, True, True, out, culling)
+
+    def cast_local_ray_with_culling(self, rays, max_time_of_impact, culling, out=None):
+        """TriMesh::cast_local_ray_with_culling (ray_trimesh.rs:155-178)."""
+        return self._cast(None, rays, max_time_of_impact, True, True, out, culling)
 
     def cast_ray(self, m, rays, max_time_of_impact, solid=True, out=None):
         """RayCast::cast_ray (ray.rs:381-390), batched: returns (toi, tri); tri == INVALID_U32 means None."""

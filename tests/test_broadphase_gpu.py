@@ -126,6 +126,70 @@ def test_update_refit_matches_rebuild_and_oracle(ctx, oracle):
     assert (sorted_pairs(gb.traverse_bvtt_single_tree()) == sorted_pairs(op)).all()
 
 
+def test_insert_and_remove_leaves(ctx, oracle):
+    """Bvh::insert / Bvh::remove (bvh_insert.rs:126-197, bvh_tree.rs:2360-2427): after any sequence of edits every query
+    answers like a reference Bvh built from the surviving leaves (pair sets / intersect_aabb are tree independent)."""
+    import parry_b200
+    n = 6000
+    kinds, params, poses = make_colliders(n, seed=31)
+    shapes = make_shapes(ctx, kinds, params)
+    aabbs = shapes.compute_aabbs(np.arange(n, dtype=np.uint32), poses)
+    gb = parry_b200.Bvh.from_leaves(ctx, 0, aabbs[:4000])
+    present = np.zeros(n, bool)
+    present[:4000] = True
+
+    def check():
+        ids = np.nonzero(present)[0]
+        ob = oracle.Bvh(aabbs[ids])
+        gp = np.asarray(gb.traverse_bvtt_single_tree()).astype(np.int64)
+        op = ids[np.asarray(ob.self_pairs()).astype(np.int64)]
+        assert (sorted_pairs(gp) == sorted_pairs(op)).all()
+        q = aabbs[::37]
+        goff, gids = gb.intersect_aabb(q)
+        ooff, oids = ob.intersect_aabbs(q)
+        assert (np.asarray(goff) == np.asarray(ooff)).all()
+        for k in range(len(q)):
+            assert sorted(np.asarray(gids)[goff[k]:goff[k + 1]].tolist()) == sorted(ids[np.asarray(oids)[ooff[k]:ooff[k + 1]]].tolist())
+
+    check()
+    rm = np.arange(0, 4000, 3, dtype=np.uint32)
+    gb.remove(rm)
+    present[rm] = False
+    check()
+    new = np.arange(4000, n, dtype=np.uint32)           # new indices + re-insertion of removed ones
+    back = rm[::2]
+    ins = np.concatenate([new, back])
+    gb.insert(aabbs[ins], ins)
+    present[ins] = True
+    assert gb.leaf_count() == n
+    check()
+    gb.remove(np.array([n + 5, 1], dtype=np.uint32))     # unknown index ignored
+    present[1] = False
+    check()
+    nodes, parents, leaf_idx = gb.download()
+    assert_well_formed(nodes, parents, leaf_idx, check_geometry=False)
+    # rays never hit a removed collider, and hit the survivors exactly like a reference Bvh over the survivors
+    ids = np.nonzero(present)[0]
+    g0 = scenes.rng(32)
+    side = float(n) ** (1.0 / 3.0)
+    o = g0.random((20000, 3)) * side
+    rays = np.concatenate([o, g0.standard_normal((20000, 3))], axis=1).astype(np.float32)
+    g = gb.cast_ray(shapes, np.arange(n, dtype=np.uint32), poses, rays, FMAX)
+    ob = oracle.Bvh(aabbs[ids])
+    r = ob.cast_rays_shapes(kinds[ids], params[ids], poses[ids], rays, FMAX, threads=8)
+    gl, rl = np.asarray(g[1]).astype(np.uint32), np.asarray(r[1]).astype(np.uint32)
+    hit = rl != INVALID
+    assert hit.mean() > 0.3 and ((gl != INVALID) == hit).all()
+    assert present[gl[hit]].all()
+    gt, rt = np.asarray(g[0])[hit], np.asarray(r[0])[hit]
+    assert (gt.view(np.uint32) == rt.view(np.uint32)).mean() > 0.9995
+    same = gl[hit] == ids[rl[hit]]
+    # rays starting inside several overlapping colliders tie at toi == 0: smallest index wins on the GPU (documented rule)
+    tie = ~same
+    assert (gt[tie] == rt[tie]).all() and (gl[hit][tie] < ids[rl[hit]][tie]).all()
+    assert same.mean() > 0.9
+
+
 def test_change_detection_pairs(ctx, oracle):
     import parry_b200
     n = 5000

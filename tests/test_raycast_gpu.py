@@ -117,6 +117,36 @@ def test_tie_stress_axis_aligned_grid(ctx, oracle):
     assert (gi <= r[1]).all()
 
 
+def test_cast_ray_with_culling(sphere, ctx, oracle):
+    """TriMesh::cast_ray_with_culling: the reference's own test (ray_trimesh.rs:187-212) and oracle parity on the sphere
+    for both culling modes, small (thread-per-ray kernel) and large (wide-tree kernel) batches, with a pose."""
+    import parry_b200
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    tm = parry_b200.TriMesh(ctx, v, np.array([[0, 1, 2]], np.uint32))
+    up = np.array([[0, 0, -1, 0, 0, 1]], np.float32)
+    down = np.array([[0, 0, 1, 0, 0, -1]], np.float32)
+    hit = lambda rays, mode: tm.cast_local_ray_with_culling(rays, 1000.0, mode)[1][0] != INVALID
+    assert hit(up, tm.IGNORE_FRONTFACES) and not hit(down, tm.IGNORE_FRONTFACES)
+    assert not hit(up, tm.IGNORE_BACKFACES) and hit(down, tm.IGNORE_BACKFACES)
+    vs, i, gmesh, omesh = sphere
+    g0 = scenes.rng(16)
+    q = np.array([0.1, 0.7, -0.2, 0.6]); q /= np.linalg.norm(q)
+    pose = np.concatenate([q, [0.05, 0.1, -0.2]]).astype(np.float32)
+    for m in (3000, 40000):
+        o = (g0.random((m, 3)) - 0.5) * 2.4          # origins inside and outside the sphere
+        rays = np.concatenate([o, g0.standard_normal((m, 3))], axis=1).astype(np.float32)
+        for mode in (1, 2):
+            g = gmesh.cast_ray_with_culling(pose, rays, FMAX, mode)
+            r = omesh.cast_rays(pose, rays, FMAX, with_normal=True, mode=1 + mode, threads=8)
+            hitm = np.asarray(r[1]) != INVALID
+            assert 0.05 < hitm.mean() < 0.95
+            same = (np.asarray(g[1]).astype(np.uint32) == r[1]) & (np.asarray(g[0]).view(np.uint32) == r[0].view(np.uint32))
+            assert same.mean() > 0.9995, same.mean()
+            back = np.asarray(g[3]).astype(np.uint32)[hitm & same] >= len(i)
+            assert back.all() if mode == 2 else not back.any()
+            np.testing.assert_allclose(np.asarray(g[2])[same], r[2][same], rtol=1e-5, atol=1e-7)
+
+
 @pytest.mark.parametrize("nt", [1, 2, 3, 5])
 def test_tiny_meshes(ctx, oracle, nt):
     import parry_b200
