@@ -59,6 +59,18 @@ public:
     void insert_or_update_partially(const std::vector<Aabb>& aabbs, const std::vector<uint32_t>& leaf_indices, float change_detection_margin) {
         c_->check(pb2_bvh_update_leaves(c_->get(), h_, leaf_indices.data(), aabbs[0].mins, (uint32_t)aabbs.size(), change_detection_margin, PB2_MEM_HOST));
     }
+    // Bvh::insert (bvh_insert.rs:126-197), batched: unknown indices grow the tree; structural edits rebuild it
+    void insert(const std::vector<Aabb>& aabbs, const std::vector<uint32_t>& leaf_indices) {
+        uint32_t top = 0;
+        for (uint32_t i : leaf_indices) top = i + 1 > top ? i + 1 : top;
+        if (top > leaf_count()) c_->check(pb2_bvh_resize(c_->get(), h_, top));
+        insert_or_update_partially(aabbs, leaf_indices, 0.0f);
+        rebuild(BvhBuildStrategy::Binned);
+    }
+    // Bvh::remove (bvh_tree.rs:2360-2427), batched
+    void remove(const std::vector<uint32_t>& leaf_indices) {
+        c_->check(pb2_bvh_remove_leaves(c_->get(), h_, leaf_indices.data(), (uint32_t)leaf_indices.size(), PB2_MEM_HOST));
+    }
     void refit() { c_->check(pb2_bvh_refit(c_->get(), h_)); c_->synchronize(); }
     void rebuild(BvhBuildStrategy s) { c_->check(pb2_bvh_rebuild(c_->get(), h_, (int)s)); c_->synchronize(); }
     // Bvh::intersect_aabb for a batch: CSR (offsets, leaf ids)
@@ -136,6 +148,19 @@ public:
         for (size_t i = 0; i < n; ++i) out[i] = RayIntersection{toi[i], {normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]}, feature[i]};
         return out;
     }
+    // TriMesh::cast_ray_with_culling (ray_trimesh.rs:139-150); culling: PB2_CULL_IGNORE_BACKFACES / PB2_CULL_IGNORE_FRONTFACES
+    std::vector<RayIntersection> cast_ray_with_culling(const Isometry* m, const std::vector<Ray>& rays, float max_time_of_impact, int culling,
+                                                       std::vector<uint32_t>& tri) const {
+        size_t n = rays.size();
+        std::vector<float> toi(n), normal(3 * n);
+        std::vector<uint32_t> feature(n);
+        tri.resize(n);
+        c_->check(pb2_trimesh_cast_rays_with_culling(c_->get(), h_, m ? m->rotation : nullptr, rays[0].origin, (uint32_t)n, max_time_of_impact,
+                                                     culling, toi.data(), tri.data(), normal.data(), feature.data(), PB2_MEM_HOST));
+        std::vector<RayIntersection> out(n);
+        for (size_t i = 0; i < n; ++i) out[i] = RayIntersection{toi[i], {normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]}, feature[i]};
+        return out;
+    }
     uint32_t num_triangles() const { return nt_; }
 private:
     const Context* c_;
@@ -151,6 +176,17 @@ inline void contact(const Context& c, const pb2_shapes* shapes, const std::vecto
     out.resize(g1.size()); status.resize(g1.size());
     c.check(pb2_contact_batch(c.get(), shapes, g1.data(), g2.data(), pos1[0].rotation, pos2[0].rotation, prediction, (uint32_t)g1.size(), out.data(),
                               status.data(), nullptr, PB2_MEM_HOST));
+}
+// The narrow-phase loop over a broad-phase pair list: query::contact(pos[a], g[a], pos[b], g[b], prediction) for every
+// (a, b) of `pairs`; returns the Some(contact) records, pair_index[j] = index into `pairs`.
+inline void contact_pairs(const Context& c, const pb2_shapes* shapes, const std::vector<uint32_t>& collider_shape, const std::vector<Isometry>& collider_pose,
+                          const std::vector<uint32_t>& pairs /* 2 per pair */, float prediction, std::vector<pb2_contact>& out,
+                          std::vector<uint32_t>& pair_index) {
+    uint64_t n = pairs.size() / 2, count = 0;
+    out.resize(n); pair_index.resize(n);
+    c.check(pb2_contact_pairs_compact(c.get(), shapes, collider_shape.data(), collider_pose[0].rotation, (uint32_t)collider_shape.size(), pairs.data(),
+                                      (uint32_t)n, prediction, out.data(), pair_index.data(), n, &count, PB2_MEM_HOST));
+    out.resize(count); pair_index.resize(count);
 }
 }  // namespace query
 
