@@ -964,12 +964,391 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------- phase 2, compact arena
+// Same state machine as k_contact_epa2, different memory shape. The ncu capture of k_contact_epa2
+// (profiles/r1_contacts_epa2_full.json) shows 28.8 GB of DRAM traffic for 2.83 M runs — 10 KB per run although a run
+// touches ~2 KB: 75 k resident threads x ~17 touched 128-byte lines = 166 MB of hot polytope state, more than the 126 MB
+// L2, so lines are evicted and re-fetched several times per run, as scattered 32-byte sectors. This version halves the
+// hot set: a face is 8 bytes (three vertex ids, three neighbour ids, deleted bit) — its normal is recomputed from the
+// vertices when needed, bit-identically, instead of being stored —, witness points are replaced by the two hull-vertex
+// ids that produced each polytope vertex (recomputed for the winning face), silhouette / DFS entries are 16-bit.
+#define C2_MAX_VERTS 112
+#define C2_MAX_FACES 255
+#define C2_MAX_SIL 64
+#define C2_STACK 96
+
+struct __align__(128) EpaCArena {
+    float4 vo[8];                // orig1 / orig2 of the parked simplex vertices (2 i, 2 i + 1)
+    float4 vp[C2_MAX_VERTS];     // CSO point ; w = support ids (shape1 | shape2 << 16)
+    uint2 face[C2_MAX_FACES + 1];// x = pts0 | pts1 << 8 | pts2 << 16 | deleted << 24 ; y = adj0 | adj1 << 8 | adj2 << 16
+    float2 heap[C2_MAX_FACES + 1];// neg_dist ; face id (bits)
+    uint16_t sil[C2_MAX_SIL];    // face | opp << 8
+    uint16_t stk[C2_STACK];
+};
+
+__device__ __forceinline__ uint32_t c_pts(uint2 f, int i) { return (f.x >> (8 * i)) & 0xffu; }
+__device__ __forceinline__ bool c_deleted(uint2 f) { return (f.x >> 24) != 0u; }
+__device__ __forceinline__ uint32_t c_adj(uint2 f, int i) { return (f.y >> (8 * i)) & 0xffu; }
+__device__ __forceinline__ int c_next_ccw(uint2 f, uint32_t id) {
+    if (c_pts(f, 0) == id) return 1;
+    if (c_pts(f, 1) == id) return 2;
+    return 0;
+}
+// Face::new's normal (epa3.rs:96-118 -> utils::ccw_face_normal), recomputed from the three vertices
+__device__ __forceinline__ V3 c_normal(const EpaCArena& A, uint2 f) {
+    V3 va = v3of(A.vp[c_pts(f, 0)]), vb = v3of(A.vp[c_pts(f, 1)]), vc = v3of(A.vp[c_pts(f, 2)]);
+    V3 n; float nn;
+    if (!try_normalize_get(cross3(vb - va, vc - va), PB2_EPS, n, nn)) n = mk3(0.f, 0.f, 0.f);
+    return n;
+}
+__device__ __forceinline__ void hc_sift_up(EpaCArena& A, int start, int pos) {
+    float2 elt = A.heap[pos];
+    while (pos > start) {
+        int parent = (pos - 1) / 2;
+        float2 pe = A.heap[parent];
+        if (h2_le(elt.x, pe.x)) break;
+        A.heap[pos] = pe;
+        pos = parent;
+    }
+    A.heap[pos] = elt;
+}
+__device__ __forceinline__ void hc_push(EpaCArena& A, int& nheap, uint32_t id, float neg_dist) {
+    int old = nheap;
+    A.heap[old] = make_float2(neg_dist, __uint_as_float(id));
+    nheap = old + 1;
+    hc_sift_up(A, 0, old);
+}
+__device__ __forceinline__ float2 hc_pop(EpaCArena& A, int& nheap) {
+    float2 item = A.heap[nheap - 1];
+    nheap -= 1;
+    if (nheap > 0) {
+        float2 t = item; item = A.heap[0];
+        int end = nheap, pos = 0;
+        float2 elt = t;
+        int child = 1;
+        while (end >= 2 && child <= end - 2) {
+            float2 c0 = A.heap[child], c1 = A.heap[child + 1];
+            if (h2_le(c0.x, c1.x)) { child += 1; c0 = c1; }
+            A.heap[pos] = c0;
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (child == end - 1) { A.heap[pos] = A.heap[child]; pos = child; }
+        A.heap[pos] = elt;
+        hc_sift_up(A, 0, pos);
+    }
+    return item;
+}
+// support point with the ids of the hull vertices that produced it (cuboid: sign bits)
+__device__ __forceinline__ V3 ds_local_support_id(const DShape& s, V3 dir, uint32_t& id) {
+    id = 0;
+    if (s.kind == DS_CUBOID) {
+        id = (__float_as_uint(dir.x) >> 31) | ((__float_as_uint(dir.y) >> 31) << 1) | ((__float_as_uint(dir.z) >> 31) << 2);
+        return mk3(copysignf(s.he.x, dir.x), copysignf(s.he.y, dir.y), copysignf(s.he.z, dir.z));
+    }
+    if (s.kind == DS_CONVEX) {
+        float4 p = __ldg(&s.pts[0]);
+        V3 best = mk3(p.x, p.y, p.z);
+        float best_dot = dot3(best, dir);
+        for (uint32_t i = 1; i < s.n; ++i) {
+            float4 q = __ldg(&s.pts[i]);
+            V3 v = mk3(q.x, q.y, q.z);
+            float d = dot3(v, dir);
+            if (d > best_dot) { best_dot = d; best = v; id = i; }
+        }
+        return best;
+    }
+    return mk3(0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ V3 ds_local_support_from_id(const DShape& s, uint32_t id) {
+    if (s.kind == DS_CUBOID)
+        return mk3(copysignf(s.he.x, (id & 1u) ? -1.0f : 1.0f), copysignf(s.he.y, (id & 2u) ? -1.0f : 1.0f), copysignf(s.he.z, (id & 4u) ? -1.0f : 1.0f));
+    if (s.kind == DS_CONVEX) { float4 q = __ldg(&s.pts[id]); return mk3(q.x, q.y, q.z); }
+    return mk3(0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(128, 4) k_contact_epac(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
+                              const float4* __restrict__ pts, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2,
+                              const float* __restrict__ pos1, const float* __restrict__ pos2, const uint32_t* __restrict__ ab, float prediction, OutSinks out,
+                              const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
+                              unsigned long long* __restrict__ next_job, EpaCArena* __restrict__ arenas, int refill) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    EpaCArena& A = arenas[blockIdx.x * blockDim.x + threadIdx.x];
+    const unsigned long long total = *job_count;
+    const float eps = PB2_EPS, eps_tol = PB2_EPS * 100.0f;
+
+    int state = E2_IDLE;
+    uint32_t pair = 0;
+    Iso7 gpos12;
+    DShape g1, g2;
+    g1.kind = g2.kind = DS_ORIGIN; g1.n = g2.n = 0; g1.pts = g2.pts = nullptr; g1.he = g2.he = mk3(0.f, 0.f, 0.f);
+    gpos12.q.i = gpos12.q.j = gpos12.q.k = 0.f; gpos12.q.w = 1.f; gpos12.t = mk3(0.f, 0.f, 0.f);
+    int dim = 0, nverts = 0, nfaces = 0, nheap = 0, niter = 0;
+    float max_dist = FLT_MAX, old_dist = 0.0f;
+    uint32_t best_id = 0;
+    bool exhausted = false;
+
+    for (;;) {
+        __syncwarp();
+        unsigned idle = __ballot_sync(FULL, state == E2_IDLE);
+        if (!exhausted && (idle == FULL || __popc(idle) >= refill)) {
+            unsigned long long base = 0;
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(next_job, (unsigned long long)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base >= total) exhausted = true;
+            if (state == E2_IDLE) {
+                unsigned long long j = base + __popc(idle & ((1u << lane) - 1u));
+                if (j < total) {
+                    const EpaJob& job = jobs[j];
+                    pair = job.pair;
+                    PairSetup ps;
+                    pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, pair, ps);
+                    gpos12 = ps.gpos12; g1 = ps.g1; g2 = ps.g2;
+                    dim = (int)job.dim;
+                    for (int i = 0; i <= dim; ++i) {
+                        V3 o1 = mk3(job.o1[i][0], job.o1[i][1], job.o1[i][2]), o2 = mk3(job.o2[i][0], job.o2[i][1], job.o2[i][2]);
+                        V3 p = o1 - o2;
+                        A.vp[i] = make_float4(p.x, p.y, p.z, 0.f);
+                        A.vo[2 * i] = make_float4(o1.x, o1.y, o1.z, 0.f);
+                        A.vo[2 * i + 1] = make_float4(o2.x, o2.y, o2.z, 0.f);
+                    }
+                    nverts = dim + 1; nfaces = 0; nheap = 0; niter = 0;
+                    max_dist = FLT_MAX; old_dist = 0.0f;
+                    state = E2_INIT;
+                }
+            }
+        }
+        if (!__any_sync(FULL, state != E2_IDLE)) break;
+
+        int fin = FIN_NOT;
+        uint32_t fin_face = 0;
+        bool need_support = false, run_step = false;
+        V3 sdir = mk3(0.f, 0.f, 0.f);
+        uint2 face = make_uint2(0u, 0u);
+        V3 fnormal = mk3(0.f, 0.f, 0.f);
+        uint32_t face_id = 0;
+        float face_neg = 0.0f, curr_dist = 0.0f;
+        int npend = 0;
+
+        // ---- phase A: pop the closest live face (RUN) / seed the initial polytope (INIT)
+        if (state == E2_RUN) {
+            bool got = false;
+            while (nheap > 0) {
+                float2 ent = hc_pop(A, nheap);
+                face_id = __float_as_uint(ent.y); face_neg = ent.x;
+                face = A.face[face_id];
+                if (!c_deleted(face)) { got = true; break; }
+            }
+            if (got) { need_support = true; run_step = true; fnormal = c_normal(A, face); sdir = fnormal; }
+            else { fin = FIN_FACE; fin_face = best_id; }
+        } else if (state == E2_INIT) {
+            if (dim == 0) fin = FIN_DIM0;
+            else if (dim == 3) {
+                V3 v0 = v3of(A.vp[0]), v1 = v3of(A.vp[1]), v2 = v3of(A.vp[2]), v3 = v3of(A.vp[3]);
+                if (dot3(cross3(v1 - v0, v2 - v0), v3 - v0) > 0.0f) {
+                    float4 t = A.vp[1]; A.vp[1] = A.vp[2]; A.vp[2] = t;
+                    float4 a1 = A.vo[2], b1 = A.vo[3];
+                    A.vo[2] = A.vo[4]; A.vo[3] = A.vo[5]; A.vo[4] = a1; A.vo[5] = b1;
+                }
+                npend = 4;
+            } else {
+                if (dim == 1) {
+                    V3 dpt = v3of(A.vp[1]) - v3of(A.vp[0]);
+                    V3 a = fabsf(dpt.x) > fabsf(dpt.y) ? mk3(dpt.z, 0.0f, -dpt.x) : mk3(0.0f, -dpt.z, dpt.y);
+                    a = normalize3(a);
+                    sdir = cross3(a, dpt);
+                    need_support = true;
+                }
+                npend = 2;
+            }
+        }
+        // ---- phase B: one support point of the Minkowski difference
+        uint32_t support_id = 0;
+        V3 sp_point = mk3(0.f, 0.f, 0.f);
+        if (need_support) {
+            if (nverts >= C2_MAX_VERTS) { fin = FIN_OVERFLOW; run_step = false; npend = 0; }
+            else {
+                uint32_t id1 = 0, id2 = 0;
+                V3 sp1 = ds_local_support_id(g1, sdir, id1);
+                V3 sp2;
+                if (g2.kind == DS_ORIGIN) sp2 = gpos12.t;
+                else sp2 = iso_point(gpos12, ds_local_support_id(g2, iso_inv_vec(gpos12, -sdir), id2));
+                V3 p = sp1 - sp2;
+                support_id = (uint32_t)nverts;
+                A.vp[nverts] = make_float4(p.x, p.y, p.z, __uint_as_float(id1 | (id2 << 16)));
+                nverts++;
+                sp_point = p;
+            }
+        }
+        // ---- phase C/D: convergence test, then the silhouette of the faces visible from the new point
+        if (run_step) {
+            float candidate = dot3(sp_point, fnormal);
+            if (candidate < max_dist) { best_id = face_id; max_dist = candidate; }
+            curr_dist = -face_neg;
+            if (max_dist - curr_dist < eps_tol || (fabsf(curr_dist - old_dist) < eps && candidate < max_dist)) {
+                fin = FIN_FACE; fin_face = best_id; run_step = false;
+            } else {
+                old_dist = curr_dist;
+                A.face[face_id].x = face.x | (1u << 24);
+                int nsil = 0, sp = 0;
+                bool ovf = false;
+#pragma unroll 1
+                for (int k = 2; k >= 0; --k) {
+                    uint32_t af = c_adj(face, k);
+                    int opp = c_next_ccw(A.face[af], c_pts(face, k));
+                    A.stk[sp++] = (uint16_t)(af | ((uint32_t)opp << 8));
+                }
+                V3 pt = sp_point;
+                while (sp > 0) {
+                    uint32_t e = A.stk[--sp];
+                    uint32_t fid = e & 0xffu; int fo = (int)(e >> 8);
+                    uint2 f = A.face[fid];
+                    if (c_deleted(f)) continue;
+                    V3 q0 = v3of(A.vp[c_pts(f, 0)]), q1 = v3of(A.vp[c_pts(f, 1)]), q2 = v3of(A.vp[c_pts(f, 2)]);
+                    V3 fn; float fnn;
+                    if (!try_normalize_get(cross3(q1 - q0, q2 - q0), PB2_EPS, fn, fnn)) fn = mk3(0.f, 0.f, 0.f);
+                    V3 p0 = fo == 0 ? q0 : (fo == 1 ? q1 : q2);
+                    bool seen = dot3(pt - p0, fn) >= -PB2_GJK_EPS_TOL;
+                    if (!seen) {
+                        V3 p1 = fo == 0 ? q1 : (fo == 1 ? q2 : q0), p2 = fo == 0 ? q2 : (fo == 1 ? q0 : q1);
+                        const float EPS = PB2_EPS * 100.0f;
+                        seen = rel_eq(nrm2(cross3(p2 - p1, pt - p1)), 0.0f, EPS * EPS, PB2_EPS);
+                    }
+                    if (!seen) {
+                        if (nsil >= C2_MAX_SIL) { ovf = true; break; }
+                        A.sil[nsil++] = (uint16_t)e;
+                    } else {
+                        A.face[fid].x = f.x | (1u << 24);
+                        int i1 = (fo + 2) % 3, i2 = fo;
+                        uint32_t adj1 = c_adj(f, i1), adj2 = c_adj(f, i2);
+                        int o1 = c_next_ccw(A.face[adj1], c_pts(f, i1));
+                        int o2 = c_next_ccw(A.face[adj2], c_pts(f, i2));
+                        if (sp + 2 > C2_STACK) { ovf = true; break; }
+                        A.stk[sp++] = (uint16_t)(adj2 | ((uint32_t)o2 << 8));
+                        A.stk[sp++] = (uint16_t)(adj1 | ((uint32_t)o1 << 8));
+                    }
+                }
+                if (ovf) { fin = FIN_OVERFLOW; run_step = false; }
+                else if (nsil == 0) { fin = FIN_NONE; run_step = false; }
+                else npend = nsil;
+            }
+        }
+        // ---- phase E: create the pending faces (initial polytope or the fan around the silhouette)
+        int first_new = nfaces;
+        if (fin == FIN_NOT && npend > 0) {
+#pragma unroll 1
+            for (int e = 0; e < npend; ++e) {
+                int p0, p1, p2, a0, a1, a2, dv;
+                int new_id = nfaces;
+                if (state == E2_INIT) {
+                    if (npend == 4) {
+                        p0 = (e == 1) ? 1 : 0; p1 = (e == 0) ? 1 : ((e == 2) ? 2 : 3); p2 = (e == 0) ? 2 : ((e == 1) ? 2 : ((e == 2) ? 3 : 1));
+                        a0 = (e == 0 || e == 1) ? 3 : ((e == 2) ? 0 : 2); a1 = (e == 1) ? 2 : 1; a2 = (e == 0) ? 2 : ((e == 2) ? 3 : 0);
+                        dv = e;
+                    } else {
+                        p0 = 0; p1 = e == 0 ? 1 : 2; p2 = e == 0 ? 2 : 1;
+                        a0 = a1 = a2 = e == 0 ? 1 : 0;
+                        dv = 0;
+                    }
+                } else {
+                    uint32_t ed = A.sil[e];
+                    uint32_t efid = ed & 0xffu; int eopp = (int)(ed >> 8);
+                    uint2 ef = A.face[efid];
+                    if (c_deleted(ef)) continue;
+                    if (new_id >= C2_MAX_FACES) { fin = FIN_OVERFLOW; break; }
+                    p0 = (int)c_pts(ef, (eopp + 2) % 3); p1 = (int)c_pts(ef, (eopp + 1) % 3); p2 = (int)support_id;
+                    a0 = (int)efid; a1 = new_id + 1; a2 = new_id - 1;
+                    dv = p0;
+                    int sh = 8 * ((eopp + 1) % 3);
+                    A.face[efid].y = (ef.y & ~(0xffu << sh)) | ((uint32_t)new_id << sh);
+                }
+                V3 va = v3of(A.vp[p0]), vb = v3of(A.vp[p1]), vc = v3of(A.vp[p2]);
+                float bc[3];
+                bool inside = e2_face_bc(va, vb, vc, bc);
+                V3 n; float nn;
+                if (!try_normalize_get(cross3(vb - va, vc - va), PB2_EPS, n, nn)) n = mk3(0.f, 0.f, 0.f);
+                A.face[new_id] = make_uint2((uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16),
+                                            ((uint32_t)a0 & 0xffu) | (((uint32_t)a1 & 0xffu) << 8) | (((uint32_t)a2 & 0xffu) << 16));
+                nfaces = new_id + 1;
+                if (state == E2_INIT) {
+                    if (npend == 4) {
+                        if (inside) {
+                            float dist = dot3(n, v3of(A.vp[dv]));
+                            if (-dist > PB2_GJK_EPS_TOL) { fin = FIN_NONE; break; }
+                            hc_push(A, nheap, (uint32_t)new_id, -dist);
+                        }
+                    } else {
+                        hc_push(A, nheap, (uint32_t)new_id, 0.0f);
+                    }
+                } else if (inside) {
+                    float dist = dot3(n, v3of(A.vp[dv]));
+                    if (dist < curr_dist) { fin = FIN_FACE; fin_face = face_id; break; }
+                    if (-dist > PB2_GJK_EPS_TOL) { fin = FIN_NONE; break; }
+                    hc_push(A, nheap, (uint32_t)new_id, -dist);
+                }
+            }
+            if (fin == FIN_NOT) {
+                if (state == E2_INIT) {
+                    if (nheap == 0) fin = FIN_NONE;
+                    else { float2 top = A.heap[0]; best_id = __float_as_uint(top.y); state = E2_RUN; }
+                } else {
+                    if (first_new == nfaces) fin = FIN_NONE;
+                    else {
+                        A.face[first_new].y = (A.face[first_new].y & ~(0xffu << 16)) | ((uint32_t)(nfaces - 1) << 16);
+                        A.face[nfaces - 1].y = (A.face[nfaces - 1].y & ~(0xffu << 8)) | ((uint32_t)first_new << 8);
+                        niter += 1;
+                        if (niter > 100) { fin = FIN_FACE; fin_face = best_id; }
+                    }
+                }
+            }
+        }
+        // ---- phase F: finished lanes build the contact and go idle
+        if (fin != FIN_NOT) {
+            PairSetup ps;
+            pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, pair, ps);
+            ContactOut c;
+            int st;
+            V3 p1 = mk3(0.f, 0.f, 0.f), p2 = p1, n1 = mk3(0.f, 1.f, 0.f);
+            if (fin == FIN_FACE) {
+                uint2 f = A.face[fin_face];
+                uint32_t ids[3] = {c_pts(f, 0), c_pts(f, 1), c_pts(f, 2)};
+                float bc[3];
+                e2_face_bc(v3of(A.vp[ids[0]]), v3of(A.vp[ids[1]]), v3of(A.vp[ids[2]]), bc);
+                V3 w1[3], w2[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    uint32_t vi = ids[q];
+                    if ((int)vi <= dim) { w1[q] = v3of(A.vo[2 * vi]); w2[q] = v3of(A.vo[2 * vi + 1]); }
+                    else {
+                        uint32_t sid = __float_as_uint(A.vp[vi].w);
+                        w1[q] = ds_local_support_from_id(g1, sid & 0xffffu);
+                        w2[q] = g2.kind == DS_ORIGIN ? gpos12.t : iso_point(gpos12, ds_local_support_from_id(g2, sid >> 16));
+                    }
+                }
+                p1 = w1[0] * bc[0] + w1[1] * bc[1] + w1[2] * bc[2];
+                p2 = w2[0] * bc[0] + w2[1] * bc[1] + w2[2] * bc[2];
+                n1 = c_normal(A, f);
+            }
+            if (fin == FIN_OVERFLOW) st = ST_NEEDS_HOST;
+            else if (fin == FIN_NONE) {
+                if (ps.mode == 1) st = ST_NONE;
+                else st = finish_gjk_pair(ps, true, ps.cb_pos12.t, p2, n1, prediction, c);
+            } else st = finish_gjk_pair(ps, true, p1, p2, n1, prediction, c);
+            if (st == ST_SOME) to_world(ps, c);
+            emit(out, pair, st, c);
+            state = E2_IDLE;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
                         const float* pos2, float prediction, uint32_t n, OutSinks sinks, const uint32_t* ab = nullptr, uint32_t n_colliders = 0) {
     cudaStream_t st = ctx->stream;
     // EPA job queue (worst case: every pair) + arenas for the persistent EPA grid
-    int epa_variant = 2, refill = 8;
+    int epa_variant = 2, refill = 8;  // 1, 2 (default): 14 KB arenas; 3: compact arena — 4x less DRAM traffic, same time
     {
         const char* e = getenv("PB2_EPA_VARIANT");
         if (e) epa_variant = atoi(e);
@@ -989,6 +1368,17 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
         PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)epa_threads * epa_blocks * sizeof(EpaArena)));
         k_contact_epa<<<epa_blocks, epa_threads, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, ab, prediction,
                                                          sinks, jobs, job_count, next_job, (EpaArena*)ctx->scratch[2].ptr);
+    } else if (epa_variant == 3) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contact_epac, 128, 0);
+        if (per_sm < 1) per_sm = 1;
+        { const char* pe = getenv("PB2_EPA_PER_SM"); if (pe && atoi(pe) > 0 && atoi(pe) < per_sm) per_sm = atoi(pe); }
+        int epa_blocks = ctx->sm_count * per_sm;
+        int need = (int)pb2_blocks(n, 128);
+        if (epa_blocks > need) epa_blocks = need;
+        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)128 * epa_blocks * sizeof(EpaCArena)));
+        k_contact_epac<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, ab, prediction, sinks,
+                                                  jobs, job_count, next_job, (EpaCArena*)ctx->scratch[2].ptr, refill);
     } else {
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contact_epa2, 128, 0);
