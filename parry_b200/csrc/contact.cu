@@ -697,6 +697,9 @@ __device__ __forceinline__ bool e2_face_bc(V3 va, V3 vb, V3 vc, float bc[3]) {
 }
 
 enum { E2_IDLE = 0, E2_INIT = 1, E2_RUN = 2 };
+#ifdef PB2_EPA_DEBUG
+__device__ unsigned long long g_epa_dbg[8];
+#endif
 enum { FIN_NOT = 0, FIN_FACE = 1, FIN_NONE = 2, FIN_OVERFLOW = 3, FIN_DIM0 = 4 };
 
 __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
@@ -753,6 +756,16 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
             }
         }
         if (!__any_sync(FULL, state != E2_IDLE)) break;
+#ifdef PB2_EPA_DEBUG
+        {
+            unsigned r_ = __ballot_sync(FULL, state == E2_RUN), i_ = __ballot_sync(FULL, state == E2_INIT), d_ = __ballot_sync(FULL, state == E2_IDLE);
+            if (lane == 0) {
+                atomicAdd(&g_epa_dbg[0], 1ull); atomicAdd(&g_epa_dbg[1], (unsigned long long)__popc(r_));
+                atomicAdd(&g_epa_dbg[2], (unsigned long long)__popc(i_)); atomicAdd(&g_epa_dbg[3], (unsigned long long)__popc(d_));
+                if (exhausted) atomicAdd(&g_epa_dbg[4], 1ull);
+            }
+        }
+#endif
 
         int fin = FIN_NOT;
         uint32_t fin_face = 0;
@@ -1392,6 +1405,17 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
     }
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
+#ifdef PB2_EPA_DEBUG
+    {
+        unsigned long long h[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_epa_dbg, sizeof(h));
+        fprintf(stderr, "[epa dbg] warp-trips %llu run %.2f init %.2f idle %.2f lanes/trip, exhausted trips %llu\n", h[0], (double)h[1] / h[0],
+                (double)h[2] / h[0], (double)h[3] / h[0], h[4]);
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_epa_dbg, z, sizeof(z));
+    }
+#endif
     return PB2_OK;
 }
 
