@@ -28,7 +28,7 @@ FMAX = float(np.finfo(np.float32).max)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full captures
 # (profiles/*.json); None when no capture of the current kernel version exists.
-PROFILED_TRAFFIC = {}
+PROFILED_TRAFFIC = {"rays_terrain": 5309194616}  # profiles/r1_rays_v6_wide8_terrain8M_full.json (k_raycast_wide<false, 0>, this workload)
 
 
 def load_peaks():
@@ -264,9 +264,19 @@ def main():
     }
 
     also = {}
-    if rank == 0 and not args.skip_also:
-        also.update(bench_also(ctx, stream, args, hbm_peak))
-    if also:
+    if not args.skip_also:
+        if world > 1:
+            # the second named metric (contact pairs/s) at N GPUs: every rank runs its own 2^22-pair shard (weak scaling,
+            # no data-path collective), device time = max over ranks
+            r = also_contacts(ctx, stream, make_timed(ctx, stream), None, hbm_peak, seed=4 + rank, e2e=False)
+            t = torch.tensor([r["ms"]], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            also["contact_pairs_4M_hulls_per_gpu_all_ranks"] = {"value": world * r["pairs"] / (ms * 1e-3), "unit": "pairs/s", "ms": ms,
+                                                                "pairs_per_gpu": r["pairs"], "n_gpus": world, "scaling": "weak"}
+        if rank == 0:
+            also.update(bench_also(ctx, stream, args, hbm_peak))
+    if also and rank == 0:
         line["also"] = also
 
     if rank == 0 and not args.skip_cpu:
@@ -283,6 +293,28 @@ def main():
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line))
+
+
+def make_timed(ctx, stream):
+    import torch
+
+    def timed(fn, steps=10, warmup=3, flush=None):
+        for _ in range(warmup):
+            fn()
+        ctx.synchronize()
+        tot = 0.0
+        for _ in range(steps):
+            if flush is not None:
+                flush.zero_()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            ctx.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / steps
+    return timed
 
 
 def bench_also(ctx, stream, args, hbm_peak):
@@ -337,7 +369,7 @@ def bench_also(ctx, stream, args, hbm_peak):
     return out
 
 
-def also_contacts(ctx, stream, timed, flush, hbm_peak):
+def also_contacts(ctx, stream, timed, flush, hbm_peak, seed=4, e2e=True):
     """BASELINE config[2]: 2^22 ConvexPolyhedron pairs (32-vertex hulls from a pool of 4096), prediction 0.01."""
     import torch
     import parry_b200
@@ -345,7 +377,7 @@ def also_contacts(ctx, stream, timed, flush, hbm_peak):
     pts, radii = scenes.hull_pool(4096)
     G = parry_b200.Shapes(ctx, [parry_b200.ConvexPolyhedron(p) for p in pts])
     n = 1 << 22
-    a, b, p1, p2 = scenes.hull_pairs(n, radii, seed=4)
+    a, b, p1, p2 = scenes.hull_pairs(n, radii, seed=seed)
     da, db = torch.from_numpy(a.astype(np.int32)).cuda(), torch.from_numpy(b.astype(np.int32)).cuda()
     dp1, dp2 = torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda()
     res = {}
@@ -359,6 +391,8 @@ def also_contacts(ctx, stream, timed, flush, hbm_peak):
     r = {"value": n / (ms * 1e-3), "unit": "pairs/s", "ms": ms, "pairs": n, "contacts_fraction": frac_some,
          "l2": "inputs+outputs (503 MB) larger than L2", "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
          "algorithmic_bytes_per_pair": 120}
+    if not e2e:
+        return r
     # end to end through the C ABI with pinned host buffers (H2D + kernels + D2H inside the timed region)
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
     ha, hb, hp1, hp2 = pin(a.astype(np.uint32).view(np.int32)).view(np.uint32), pin(b.astype(np.uint32).view(np.int32)).view(np.uint32), pin(p1), pin(p2)
