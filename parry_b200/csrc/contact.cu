@@ -696,6 +696,46 @@ __device__ __forceinline__ bool e2_face_bc(V3 va, V3 vb, V3 vc, float bc[3]) {
     return false;
 }
 
+// The boolean e2_face_bc returns, without the barycentric coordinates: same comparisons on the same intermediates as
+// project_on_triangle (point_triangle.rs:58-290) with pt = origin, but the projected point (one IEEE division) is only
+// formed for the vertex / edge regions where the answer depends on it. Face::new runs once per new polytope face
+// (epa3.rs:96-118) and only needs this flag there; the coordinates are recomputed for the single winning face.
+__device__ __forceinline__ bool e2_face_inside(V3 a, V3 b, V3 c) {
+    const V3 pt = mk3(0.f, 0.f, 0.f);
+    V3 ab = b - a, ac = c - a, ap = pt - a;
+    float ab_ap = dot3(ab, ap), ac_ap = dot3(ac, ap);
+    V3 bp = pt - b;
+    float ab_bp = dot3(ab, bp), ac_bp = dot3(ac, bp);
+    V3 cp = pt - c;
+    float ab_cp = dot3(ab, cp), ac_cp = dot3(ac, cp);
+    V3 bc = c - b;
+    V3 n = cross3(ab, ac);
+    float vc = dot3(n, cross3(ab, ap));
+    float vb = -dot3(n, cross3(ac, cp));
+    float va = dot3(n, cross3(bc, bp));
+    bool rA = ab_ap <= 0.0f && ac_ap <= 0.0f;
+    bool rB = !rA && (ab_bp >= 0.0f && ac_bp <= ab_bp);
+    bool rC = !rA && !rB && (ac_cp >= 0.0f && ab_cp <= ac_cp);
+    bool vtx = rA || rB || rC;
+    bool rAB = !vtx && (vc < 0.0f && ab_ap >= 0.0f && ab_bp <= 0.0f);
+    bool rAC = !vtx && !rAB && (vb < 0.0f && ac_ap >= 0.0f && ac_cp <= 0.0f);
+    bool rBC = !vtx && !rAB && !rAC && (va < 0.0f && ac_bp - ab_bp >= 0.0f && ab_cp - ac_cp >= 0.0f);
+    bool edge = rAB || rAC || rBC;
+    if (!vtx && !edge) return (va + vb + vc) != 0.0f;  // face region: inside; degenerate (kind 3): not
+    V3 point;
+    if (vtx) point = rA ? a : (rB ? b : c);
+    else {
+        float num = rAB ? ab_ap : (rAC ? ac_ap : dot3(bc, bp));
+        float den = rAB ? nrm2(ab) : (rAC ? nrm2(ac) : nrm2(bc));
+        float q = num / den;
+        V3 base = rBC ? b : a;
+        V3 dirv = rAB ? ab : (rAC ? ac : bc);
+        point = base + dirv * q;
+    }
+    const float eps_tol = PB2_EPS * 100.0f;
+    return rel_eq3(point, pt) || nrm2(point - pt) < eps_tol * eps_tol;
+}
+
 enum { E2_IDLE = 0, E2_INIT = 1, E2_RUN = 2 };
 #ifdef PB2_EPA_DEBUG
 __device__ unsigned long long g_epa_dbg[8];
@@ -909,8 +949,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                     A.adj[efid] = ea;
                 }
                 V3 va = v3of(A.vp[p0]), vb = v3of(A.vp[p1]), vc = v3of(A.vp[p2]);
-                float bc[3];
-                bool inside = e2_face_bc(va, vb, vc, bc);
+                bool inside = e2_face_inside(va, vb, vc);
                 V3 n; float nn;
                 if (!try_normalize_get(cross3(vb - va, vc - va), PB2_EPS, n, nn)) n = mk3(0.f, 0.f, 0.f);
                 A.face[new_id] = make_float4(n.x, n.y, n.z, __uint_as_float((uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16)));
@@ -1278,8 +1317,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epac(const uint8_t* __restri
                     A.face[efid].y = (ef.y & ~(0xffu << sh)) | ((uint32_t)new_id << sh);
                 }
                 V3 va = v3of(A.vp[p0]), vb = v3of(A.vp[p1]), vc = v3of(A.vp[p2]);
-                float bc[3];
-                bool inside = e2_face_bc(va, vb, vc, bc);
+                bool inside = e2_face_inside(va, vb, vc);
                 V3 n; float nn;
                 if (!try_normalize_get(cross3(vb - va, vc - va), PB2_EPS, n, nn)) n = mk3(0.f, 0.f, 0.f);
                 A.face[new_id] = make_uint2((uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16),
