@@ -36,6 +36,8 @@ def lib():
         l.pb2o_trimesh_num_nodes.argtypes = [P]
         l.pb2o_trimesh_copy_nodes.argtypes = [P, P]
         l.pb2o_trimesh_cast_rays.argtypes = [P, P, P, u32, f32, i32, i32, i32, P, P, P, P]
+        l.pb2o_trimesh_contact_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, i32, P, P, P]
+        l.pb2o_trimesh_contact_batch.restype = None
         l.pb2o_bvh_create.restype = P
         l.pb2o_bvh_create.argtypes = [P, u32, i32]
         l.pb2o_bvh_destroy.argtypes = [P]
@@ -111,6 +113,18 @@ class TriMesh:
                                      None if normal is None else normal.ctypes.data,
                                      None if feature is None else feature.ctypes.data)
         return (toi, tri, normal, feature) if with_normal else (toi, tri)
+
+    def contact_shapes(self, mesh_pose, table, shape2, pos2, prediction, threads=1, min_index_ties=False):
+        """query::contact(mesh_pose, mesh, pos2[k], shape2[k], prediction): (contacts (n,13), status, part)."""
+        s2, p2, mp = _u32(shape2), _f32(pos2), _f32(mesh_pose)
+        n = len(s2)
+        out = np.zeros((n, 13), dtype=np.float32)
+        status = np.zeros(n, dtype=np.uint8)
+        part = np.zeros(n, dtype=np.uint32)
+        lib().pb2o_trimesh_contact_batch(self.h, mp.ctypes.data, table.kinds.ctypes.data, table.params.ctypes.data, table.points.ctypes.data,
+                                         s2.ctypes.data, p2.ctypes.data, prediction, n, threads, int(min_index_ties), out.ctypes.data,
+                                         status.ctypes.data, part.ctypes.data)
+        return out, status, part
 
     def __del__(self):
         try:

@@ -192,6 +192,17 @@ int pb2_contact_pairs_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint
                               const uint32_t* pairs /* n x 2 */, uint32_t n, float prediction, pb2_contact* out,
                               uint32_t* pair_index, uint64_t cap, uint64_t* count, int mem);
 
+/* query::contact(mesh_pose, &TriMesh, poses7[k], shape k, prediction) for n shapes against ONE mesh: the composite arm of
+ * DefaultQueryDispatcher::contact (default_query_dispatcher.rs:343-346) = contact_composite_shape_shape /
+ * CompositeShapeRef::contact_with_shape (contact_composite_shape_shape.rs:14-61): the mesh Bvh is queried with
+ * shape.compute_aabb(pose12).loosened(prediction), every reported triangle is dispatched as a shape::Triangle (ball:
+ * contact_convex_polyhedron_ball on the triangle's point projection; cuboid / convex: GJK + EPA with the triangle's own
+ * support map, shape/triangle.rs:697-716) and the contact with the smallest dist is kept. part[k] = winning triangle
+ * (UINT32_MAX when status[k] != 1); equal dists resolve to the smallest triangle index. Contacts are in world space. */
+int pb2_trimesh_contact_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* mesh_pose7, const pb2_shapes* shapes,
+                               const uint32_t* shape_ids /* n */, const float* poses7 /* n x 7 */, uint32_t n, float prediction,
+                               pb2_contact* out, uint8_t* status, uint32_t* part, int mem);
+
 #ifdef __cplusplus
 }
 #endif

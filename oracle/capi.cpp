@@ -238,6 +238,32 @@ void pb2o_contact_batch(const uint8_t* kinds, const float* params4, const float*
         }
     });
 }
+// query::contact(pos1, &TriMesh, pos2[k], shape2[k], prediction) for n shapes against one mesh (composite arm of
+// DefaultQueryDispatcher::contact -> contact_composite_shape_shape). mesh_pose7: one pose. part[k] = winning triangle or
+// u32::MAX. ties != 0: equal-dist ties go to the smallest triangle index (the GPU's documented rule) instead of BVH order.
+void pb2o_trimesh_contact_batch(void* mesh, const float* mesh_pose7, const uint8_t* kinds, const float* params4, const float* points,
+                                const uint32_t* shape2, const float* pos2, float prediction, uint32_t n, int nthreads, int ties, float* out,
+                                uint8_t* status, uint32_t* part) {
+    const TriMesh* tm = (const TriMesh*)mesh;
+    Iso pos1 = Iso::from7(mesh_pose7);
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            ShapeRef s2 = make_shape(kinds, params4, points, shape2[k]);
+            Iso p2 = Iso::from7(pos2 + 7 * k);
+            Iso pos12 = pos1.inv_mul(p2);
+            Contact c = Contact();
+            uint32_t id = UINT32_MAX;
+            int st = contact_trimesh_shape(pos12, *tm, s2, prediction, c, id, ties != 0);
+            status[k] = (uint8_t)st; part[k] = st == CONTACT_SOME ? id : UINT32_MAX;
+            float* o = out + 13 * k;
+            if (st == CONTACT_SOME) {
+                c.point1 = pos1.transform_point(c.point1); c.point2 = p2.transform_point(c.point2);
+                c.normal1 = pos1.transform_vector(c.normal1); c.normal2 = p2.transform_vector(c.normal2);
+                st3(o, c.point1); st3(o + 3, c.point2); st3(o + 6, c.normal1); st3(o + 9, c.normal2); o[12] = c.dist;
+            } else for (int i = 0; i < 13; ++i) o[i] = 0.0f;
+        }
+    });
+}
 // DefaultQueryDispatcher::contact(pos12, ...) — results in the local frames of shape 1 / shape 2.
 int pb2o_dispatch_contact(const uint8_t* kinds, const float* params4, const float* points, uint32_t s1, uint32_t s2, const float* pos12, float prediction, float* out13) {
     ShapeRef a = make_shape(kinds, params4, points, s1), b = make_shape(kinds, params4, points, s2);

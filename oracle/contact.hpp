@@ -121,6 +121,11 @@ static inline int contact_convex_polyhedron_ball(const Iso& pos12, const ShapeRe
     Vec3 center2_1 = pos12.tra;
     Vec3 proj; bool inside; Feature f1{3, 0};
     if (shape1.kind == SHAPE_CUBOID) cuboid_project_point_and_get_feature(shape1.half_extents, center2_1, proj, inside, f1);
+    else if (shape1.kind == SHAPE_TRIANGLE) {
+        // PointQuery for Triangle: project_local_point_and_get_feature = ..._and_get_location(pt, solid = true) (point_triangle.rs:27-47)
+        TriProj p = project_on_triangle(ld3(shape1.points), ld3(shape1.points + 3), ld3(shape1.points + 6), center2_1, true);
+        proj = p.point; inside = p.inside;
+    }
     else hull_project_point(shape1.support(), center2_1, proj, inside);
     Real dist; Vec3 normal1, dir1; Real len;
     if (try_normalize_and_get(proj - center2_1, DEFAULT_EPSILON, dir1, len)) {
@@ -128,9 +133,17 @@ static inline int contact_convex_polyhedron_ball(const Iso& pos12, const ShapeRe
         else { dist = len - radius2; normal1 = -dir1; }
     } else {
         dist = -radius2;
+        if (shape1.kind == SHAPE_TRIANGLE) {
+            // Triangle::feature_normal_at_point = Triangle::normal() for every feature (shape.rs:919-928, triangle.rs:226-228,626-628)
+            Vec3 a = ld3(shape1.points), b = ld3(shape1.points + 3), c3 = ld3(shape1.points + 6);
+            if (!try_normalize(cross(b - a, c3 - a), DEFAULT_EPSILON, normal1)) {
+                if (!try_normalize(proj, DEFAULT_EPSILON, normal1)) normal1 = Vec3(0, 1, 0);
+            }
+        } else {
         if (shape1.kind != SHAPE_CUBOID) return CONTACT_NEEDS_TOPOLOGY;  // ConvexPolyhedron::feature_normal needs the hull topology
         if (!cuboid_feature_normal(f1, normal1)) {
             if (!try_normalize(proj, DEFAULT_EPSILON, normal1)) normal1 = Vec3(0, 1, 0);
+        }
         }
     }
     if (dist <= prediction) {
@@ -193,6 +206,40 @@ static inline int query_contact(const Iso& pos1, const ShapeRef& g1, const Iso& 
         c.normal2 = pos2.transform_vector(c.normal2);
     }
     return st;
+}
+
+// Shape::compute_aabb(pos) for the supported shapes (aabb_ball.rs:8-33, aabb_cuboid.rs:9-16, aabb_convex_polyhedron.rs:8-16)
+static inline Aabb shape_compute_aabb(const ShapeRef& s, const Iso& pos) {
+    if (s.kind == SHAPE_BALL) { Real r = s.radius; return Aabb(pos.tra + Vec3(-r, -r, -r), pos.tra + Vec3(r, r, r)); }
+    if (s.kind == SHAPE_CUBOID) { Vec3 he = pos.absolute_transform_vector(s.half_extents); return Aabb(pos.tra - he, pos.tra + he); }
+    Vec3 w0 = pos.transform_point(ld3(s.points));
+    Aabb a(w0, w0);
+    for (uint32_t k = 1; k < s.num_points; ++k) { Vec3 w = pos.transform_point(ld3(s.points + 3 * k)); a.mins = vinf(a.mins, w); a.maxs = vsup(a.maxs, w); }
+    return a;
+}
+
+// CompositeShapeRef::contact_with_shape for a TriMesh (contact_composite_shape_shape.rs:14-45): every triangle whose leaf
+// AABB intersects shape2's loosened AABB is dispatched, the first strictly smaller dist wins (BVH iteration order).
+// Result in the local frames of the mesh / shape2. part = winning triangle.
+static inline int contact_trimesh_shape(const Iso& pos12, const TriMesh& mesh, const ShapeRef& shape2, Real prediction, Contact& best,
+                                        uint32_t& part, bool min_index_ties = false) {
+    Aabb ls = shape_compute_aabb(shape2, pos12);
+    ls.mins = ls.mins - Vec3(prediction, prediction, prediction);  // Aabb::loosened (aabb.rs)
+    ls.maxs = ls.maxs + Vec3(prediction, prediction, prediction);
+    std::vector<uint32_t> parts;
+    mesh.bvh.intersect_aabb(ls, parts);
+    bool have = false;
+    for (uint32_t id : parts) {
+        float tri[9];
+        const uint32_t* t = &mesh.indices[3 * id];
+        for (int k = 0; k < 3; ++k) { tri[3 * k] = mesh.vertices[t[k]].x; tri[3 * k + 1] = mesh.vertices[t[k]].y; tri[3 * k + 2] = mesh.vertices[t[k]].z; }
+        ShapeRef s1; s1.kind = SHAPE_TRIANGLE; s1.radius = 0; s1.points = tri; s1.num_points = 3;
+        Contact c = Contact();
+        if (dispatch_contact(pos12, s1, shape2, prediction, c) != CONTACT_SOME) continue;
+        bool replace = !have || c.dist < best.dist || (min_index_ties && c.dist == best.dist && id < part);
+        if (replace) { best = c; part = id; have = true; }
+    }
+    return have ? CONTACT_SOME : CONTACT_NONE;
 }
 
 }  // namespace pb2o

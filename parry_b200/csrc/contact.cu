@@ -15,6 +15,7 @@
 // per-thread arena (vertices / faces / heap) so that divergence of the rare, long EPA runs does not stall the
 // closed-form and separated pairs. Contacts are written either densely (status per pair) or compacted.
 #include "gjk.cuh"
+#include "trimesh.cuh"
 #include <stdlib.h>
 
 int pb2_stage_in(pb2_ctx* ctx, int slot, const void* src, size_t bytes, int mem, const void** out);
@@ -117,8 +118,9 @@ __device__ __forceinline__ bool d_cuboid_feature_normal(Feat f, V3& n) {
 }
 
 // Tail of contact_convex_polyhedron_ball (contact_ball_convex_polyhedron.rs:34-62) once the projection is known.
+__device__ __forceinline__ V3 v3of4(float4 f) { return mk3(f.x, f.y, f.z); }
 __device__ __forceinline__ int d_convex_ball_finish(const Iso7& pos12, bool is_cuboid, Feat f1, V3 proj, bool inside, float radius2,
-                                                    float prediction, ContactOut& c) {
+                                                    float prediction, ContactOut& c, const float4* tri = nullptr) {
     V3 center2_1 = pos12.t;
     float dist; V3 normal1, dir1; float len;
     if (try_normalize_get(proj - center2_1, PB2_EPS, dir1, len)) {
@@ -126,10 +128,17 @@ __device__ __forceinline__ int d_convex_ball_finish(const Iso7& pos12, bool is_c
         else { dist = len - radius2; normal1 = -dir1; }
     } else {
         dist = -radius2;
+        float n;
+        if (tri) {  // Triangle::normal() = Unit::try_new(scaled_normal, eps)
+            V3 ta = v3of4(tri[0]), tb = v3of4(tri[1]), tc = v3of4(tri[2]);
+            if (!try_normalize_get(cross3(tb - ta, tc - ta), PB2_EPS, normal1, n)) {
+                if (!try_normalize_get(proj, PB2_EPS, normal1, n)) normal1 = mk3(0.f, 1.f, 0.f);
+            }
+        } else {
         if (!is_cuboid) return ST_NEEDS_HOST;  // ConvexPolyhedron::feature_normal_at_point needs the hull topology
         if (!d_cuboid_feature_normal(f1, normal1)) {
-            float n;
             if (!try_normalize_get(proj, PB2_EPS, normal1, n)) normal1 = mk3(0.f, 1.f, 0.f);
+        }
         }
     }
     if (dist <= prediction) {
@@ -166,27 +175,53 @@ struct PairSetup {
     Iso7 gpos12;
     Iso7 cb_pos12;  // pos12 seen by contact_convex_polyhedron_ball (mode 2: pos12, mode 3: pos12.inverse())
     DShape g1, g2;
+    const float4* tri;  // shape 1 is this TriMesh triangle (k1 == PB2_SHAPE_TRIANGLE_INTERNAL), else NULL
 };
 
-// `ab` (optional): candidate pairs as collider indices (2 per pair, e.g. straight from pb2_bvh_self_pairs); shapes and poses
-// are then per-collider tables indexed through it instead of per-pair arrays.
-__device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* params, const float4* pts, const uint32_t* shape1,
-                                           const uint32_t* shape2, const float* pos1, const float* pos2, const uint32_t* ab, uint32_t k,
+// Where the pairs come from. Plain mode: pair k = (shape1[k] at pos1[k], shape2[k] at pos2[k]). `ab` (optional): pairs as
+// index couples (2 per pair, e.g. straight from pb2_bvh_self_pairs): shapes and poses are then per-collider tables read
+// through it. `mesh_tris` (optional, with `ab`): shape 1 of pair k is the TriMesh triangle stored at mesh_tris[3 * ab[2k]]
+// (three float4, .w of the first = triangle id) at the single pose pos1[0]; shape 2 is shape2[ab[2k+1]] at pos2[ab[2k+1]].
+struct PairSrc {
+    const uint32_t* shape1;
+    const uint32_t* shape2;
+    const float* pos1;
+    const float* pos2;
+    const uint32_t* ab;
+    const float4* mesh_tris;
+    uint32_t n_first, n_second;   // index bounds for ab[2k] / ab[2k+1]
+};
+#define PB2_SHAPE_TRIANGLE_INTERNAL 3   // a TriMesh part (shape::Triangle), never in a shape table
+
+__device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* params, const float4* pts, const PairSrc& src, uint32_t k,
                                            PairSetup& ps) {
     uint32_t i1 = k, i2 = k;
-    if (ab) { i1 = ab[2ull * k]; i2 = ab[2ull * k + 1]; }
-    uint32_t s1 = shape1[i1], s2 = shape2[i2];
-    ps.k1 = kinds[s1]; ps.k2 = kinds[s2];
-    ps.pr1 = params[s1]; ps.pr2 = params[s2];
-    ps.pos1 = load_iso(pos1 + 7ull * i1);
-    ps.pos2 = load_iso(pos2 + 7ull * i2);
+    if (src.ab) { i1 = src.ab[2ull * k]; i2 = src.ab[2ull * k + 1]; }
+    uint32_t s2 = src.shape2[i2];
+    ps.k2 = kinds[s2];
+    ps.pr2 = params[s2];
+    ps.pos2 = load_iso(src.pos2 + 7ull * i2);
+    const float4* tri = nullptr;
+    if (src.mesh_tris) {
+        tri = src.mesh_tris + 3ull * i1;
+        ps.k1 = PB2_SHAPE_TRIANGLE_INTERNAL;
+        ps.pr1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        ps.pos1 = load_iso(src.pos1);
+    } else {
+        uint32_t s1 = src.shape1[i1];
+        ps.k1 = kinds[s1];
+        ps.pr1 = params[s1];
+        ps.pos1 = load_iso(src.pos1 + 7ull * i1);
+    }
+    ps.tri = tri;
     ps.pos12 = iso_inv_mul(ps.pos1, ps.pos2);  // contact_shape_shape.rs:130
     ps.mode = 0;
     bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
     if (!b1 && !b2) {
         ps.mode = 1;
         ps.gpos12 = ps.pos12;
-        ps.g1 = make_dshape(ps.k1, ps.pr1, pts);
+        if (tri) { ps.g1.kind = DS_TRIANGLE; ps.g1.he = mk3(0.f, 0.f, 0.f); ps.g1.pts = tri; ps.g1.n = 3; }
+        else ps.g1 = make_dshape(ps.k1, ps.pr1, pts);
         ps.g2 = make_dshape(ps.k2, ps.pr2, pts);
     } else if (b1 != b2) {
         bool convex_first = b2;
@@ -274,32 +309,42 @@ __device__ __forceinline__ void emit(const OutSinks& out, uint32_t k, int st, co
 
 // ------------------------------------------------------------------------------------------- phase 1
 __global__ void __launch_bounds__(128) k_contact_gjk(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
-                              const float4* __restrict__ pts, uint32_t n_shapes, const uint32_t* __restrict__ shape1,
-                              const uint32_t* __restrict__ shape2, const float* __restrict__ pos1, const float* __restrict__ pos2,
-                              const uint32_t* __restrict__ ab, uint32_t n_colliders, float prediction, uint32_t n, OutSinks out,
+                              const float4* __restrict__ pts, uint32_t n_shapes, PairSrc src, float prediction, uint32_t n, OutSinks out,
                               EpaJob* __restrict__ jobs, unsigned long long* job_count) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     ContactOut c;
     {
         uint32_t i1 = k, i2 = k;
-        if (ab) { i1 = ab[2ull * k]; i2 = ab[2ull * k + 1]; }
-        if ((ab && (i1 >= n_colliders || i2 >= n_colliders)) || shape1[i1] >= n_shapes || shape2[i2] >= n_shapes) { emit(out, k, ST_UNSUPPORTED, c); return; }
+        if (src.ab) { i1 = src.ab[2ull * k]; i2 = src.ab[2ull * k + 1]; }
+        bool bad = src.ab && (i1 >= src.n_first || i2 >= src.n_second);
+        if (!bad) bad = src.shape2[i2] >= n_shapes || (!src.mesh_tris && src.shape1[i1] >= n_shapes);
+        if (bad) { emit(out, k, ST_UNSUPPORTED, c); return; }
     }
     PairSetup ps;
-    pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, k, ps);
+    pair_setup(kinds, params, pts, src, k, ps);
     int st;
     if (ps.mode == 0) {
         bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
         if (b1 && b2) st = d_contact_ball_ball(ps.pos12, ps.pr1.x, ps.pr2.x, prediction, c) ? ST_SOME : ST_NONE;
         else {
-            // ball <-> cuboid (closed-form projection)
+            // ball <-> cuboid / TriMesh triangle (closed-form projections)
             bool convex_first = b2;
             float4 prc = convex_first ? ps.pr1 : ps.pr2;
             float radius = convex_first ? ps.pr2.x : ps.pr1.x;
             V3 proj; bool inside; Feat f;
-            d_cuboid_project(mk3(prc.x, prc.y, prc.z), ps.cb_pos12.t, proj, inside, f);
-            st = d_convex_ball_finish(ps.cb_pos12, true, f, proj, inside, radius, prediction, c);
+            if (ps.tri) {
+                // PointQuery for Triangle (point_triangle.rs:27-47: location with solid = true); the feature normal of a
+                // triangle is its normal whatever the feature (shape.rs:919-928, triangle.rs:226-228)
+                V3 ta = v3of4(ps.tri[0]), tb = v3of4(ps.tri[1]), tc = v3of4(ps.tri[2]);
+                Proj pr;
+                project_on_triangle(ta, tb, tc, ps.cb_pos12.t, pr);
+                f.kind = 4; f.id = 0;
+                st = d_convex_ball_finish(ps.cb_pos12, false, f, pr.point, pr.inside, radius, prediction, c, ps.tri);
+            } else {
+                d_cuboid_project(mk3(prc.x, prc.y, prc.z), ps.cb_pos12.t, proj, inside, f);
+                st = d_convex_ball_finish(ps.cb_pos12, true, f, proj, inside, radius, prediction, c);
+            }
             if (st == ST_SOME && !convex_first) flip_contact(c);
         }
     } else {
@@ -573,8 +618,7 @@ __device__ int epa_closest_points(EpaArena& A, const Iso7& pos12, const DShape& 
 }
 
 __global__ void __launch_bounds__(64) k_contact_epa(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
-                             const float4* __restrict__ pts, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2,
-                             const float* __restrict__ pos1, const float* __restrict__ pos2, const uint32_t* __restrict__ ab, float prediction, OutSinks out,
+                             const float4* __restrict__ pts, PairSrc src, float prediction, OutSinks out,
                              const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
                              unsigned long long* __restrict__ next_job, EpaArena* __restrict__ arenas) {
     EpaArena& A = arenas[blockIdx.x * blockDim.x + threadIdx.x];
@@ -585,7 +629,7 @@ __global__ void __launch_bounds__(64) k_contact_epa(const uint8_t* __restrict__ 
         const EpaJob& job = jobs[j];
         uint32_t k = job.pair;
         PairSetup ps;
-        pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, k, ps);
+        pair_setup(kinds, params, pts, src, k, ps);
         int dim = (int)job.dim;
         for (int i = 0; i <= dim; ++i) {
             V3 o1 = mk3(job.o1[i][0], job.o1[i][1], job.o1[i][2]), o2 = mk3(job.o2[i][0], job.o2[i][1], job.o2[i][2]);
@@ -743,8 +787,7 @@ __device__ unsigned long long g_epa_dbg[8];
 enum { FIN_NOT = 0, FIN_FACE = 1, FIN_NONE = 2, FIN_OVERFLOW = 3, FIN_DIM0 = 4 };
 
 __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
-                              const float4* __restrict__ pts, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2,
-                              const float* __restrict__ pos1, const float* __restrict__ pos2, const uint32_t* __restrict__ ab, float prediction, OutSinks out,
+                              const float4* __restrict__ pts, PairSrc src, float prediction, OutSinks out,
                               const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
                               unsigned long long* __restrict__ next_job, Epa2Arena* __restrict__ arenas, int refill) {
     const unsigned FULL = 0xffffffffu;
@@ -779,7 +822,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                     const EpaJob& job = jobs[j];
                     pair = job.pair;
                     PairSetup ps;
-                    pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, pair, ps);
+                    pair_setup(kinds, params, pts, src, pair, ps);
                     gpos12 = ps.gpos12; g1 = ps.g1; g2 = ps.g2;
                     dim = (int)job.dim;
                     for (int i = 0; i <= dim; ++i) {
@@ -991,7 +1034,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
         // ---- phase F: finished lanes build the contact and go idle
         if (fin != FIN_NOT) {
             PairSetup ps;
-            pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, pair, ps);
+            pair_setup(kinds, params, pts, src, pair, ps);
             ContactOut c;
             int st;
             V3 p1 = mk3(0.f, 0.f, 0.f), p2 = p1, n1 = mk3(0.f, 1.f, 0.f);
@@ -1110,18 +1153,25 @@ __device__ __forceinline__ V3 ds_local_support_id(const DShape& s, V3 dir, uint3
         }
         return best;
     }
+    if (s.kind == DS_TRIANGLE) {
+        float4 pa = __ldg(&s.pts[0]), pb = __ldg(&s.pts[1]), pc = __ldg(&s.pts[2]);
+        V3 a = mk3(pa.x, pa.y, pa.z), b = mk3(pb.x, pb.y, pb.z), c = mk3(pc.x, pc.y, pc.z);
+        float d1 = dot3(a, dir), d2 = dot3(b, dir), d3 = dot3(c, dir);
+        if (d1 > d2) { if (d1 > d3) { id = 0; return a; } id = 2; return c; }
+        if (d2 > d3) { id = 1; return b; }
+        id = 2; return c;
+    }
     return mk3(0.f, 0.f, 0.f);
 }
 __device__ __forceinline__ V3 ds_local_support_from_id(const DShape& s, uint32_t id) {
     if (s.kind == DS_CUBOID)
         return mk3(copysignf(s.he.x, (id & 1u) ? -1.0f : 1.0f), copysignf(s.he.y, (id & 2u) ? -1.0f : 1.0f), copysignf(s.he.z, (id & 4u) ? -1.0f : 1.0f));
-    if (s.kind == DS_CONVEX) { float4 q = __ldg(&s.pts[id]); return mk3(q.x, q.y, q.z); }
+    if (s.kind == DS_CONVEX || s.kind == DS_TRIANGLE) { float4 q = __ldg(&s.pts[id]); return mk3(q.x, q.y, q.z); }
     return mk3(0.f, 0.f, 0.f);
 }
 
 __global__ void __launch_bounds__(128, 4) k_contact_epac(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
-                              const float4* __restrict__ pts, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2,
-                              const float* __restrict__ pos1, const float* __restrict__ pos2, const uint32_t* __restrict__ ab, float prediction, OutSinks out,
+                              const float4* __restrict__ pts, PairSrc src, float prediction, OutSinks out,
                               const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
                               unsigned long long* __restrict__ next_job, EpaCArena* __restrict__ arenas, int refill) {
     const unsigned FULL = 0xffffffffu;
@@ -1156,7 +1206,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epac(const uint8_t* __restri
                     const EpaJob& job = jobs[j];
                     pair = job.pair;
                     PairSetup ps;
-                    pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, pair, ps);
+                    pair_setup(kinds, params, pts, src, pair, ps);
                     gpos12 = ps.gpos12; g1 = ps.g1; g2 = ps.g2;
                     dim = (int)job.dim;
                     for (int i = 0; i <= dim; ++i) {
@@ -1358,7 +1408,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epac(const uint8_t* __restri
         // ---- phase F: finished lanes build the contact and go idle
         if (fin != FIN_NOT) {
             PairSetup ps;
-            pair_setup(kinds, params, pts, shape1, shape2, pos1, pos2, ab, pair, ps);
+            pair_setup(kinds, params, pts, src, pair, ps);
             ContactOut c;
             int st;
             V3 p1 = mk3(0.f, 0.f, 0.f), p2 = p1, n1 = mk3(0.f, 1.f, 0.f);
@@ -1396,7 +1446,11 @@ __global__ void __launch_bounds__(128, 4) k_contact_epac(const uint8_t* __restri
 
 // ------------------------------------------------------------------------------------------- host side
 static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
-                        const float* pos2, float prediction, uint32_t n, OutSinks sinks, const uint32_t* ab = nullptr, uint32_t n_colliders = 0) {
+                        const float* pos2, float prediction, uint32_t n, OutSinks sinks, const uint32_t* ab = nullptr, uint32_t n_colliders = 0,
+                        const float4* mesh_tris = nullptr, uint32_t n_tris = 0) {
+    PairSrc src;
+    src.shape1 = shape1; src.shape2 = shape2; src.pos1 = pos1; src.pos2 = pos2; src.ab = ab; src.mesh_tris = mesh_tris;
+    src.n_first = mesh_tris ? n_tris : n_colliders; src.n_second = n_colliders;
     cudaStream_t st = ctx->stream;
     // EPA job queue (worst case: every pair) + arenas for the persistent EPA grid
     int epa_variant = 2, refill = 8;  // 1, 2 (default): 14 KB arenas; 3: compact arena — 4x less DRAM traffic, same time
@@ -1411,13 +1465,13 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
     unsigned long long* job_count = (unsigned long long*)(ctx->d_counters + 4);
     unsigned long long* next_job = (unsigned long long*)(ctx->d_counters + 5);
     PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 4, 0, 16, st));
-    k_contact_gjk<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, shape1, shape2, pos1, pos2,
-                                                     ab, n_colliders, prediction, n, sinks, jobs, job_count);
+    k_contact_gjk<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, src,
+                                                     prediction, n, sinks, jobs, job_count);
     PB2_LAUNCHED(ctx);
     if (epa_variant == 1) {
         int epa_threads = 64, epa_blocks = ctx->sm_count * 4;
         PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)epa_threads * epa_blocks * sizeof(EpaArena)));
-        k_contact_epa<<<epa_blocks, epa_threads, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, ab, prediction,
+        k_contact_epa<<<epa_blocks, epa_threads, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction,
                                                          sinks, jobs, job_count, next_job, (EpaArena*)ctx->scratch[2].ptr);
     } else if (epa_variant == 3) {
         int per_sm = 0;
@@ -1428,7 +1482,7 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
         int need = (int)pb2_blocks(n, 128);
         if (epa_blocks > need) epa_blocks = need;
         PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)128 * epa_blocks * sizeof(EpaCArena)));
-        k_contact_epac<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, ab, prediction, sinks,
+        k_contact_epac<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction, sinks,
                                                   jobs, job_count, next_job, (EpaCArena*)ctx->scratch[2].ptr, refill);
     } else {
         int per_sm = 0;
@@ -1438,7 +1492,7 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
         int need = (int)pb2_blocks(n, 128);
         if (epa_blocks > need) epa_blocks = need;
         PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)128 * epa_blocks * sizeof(Epa2Arena)));
-        k_contact_epa2<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shape1, shape2, pos1, pos2, ab, prediction, sinks,
+        k_contact_epa2<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction, sinks,
                                                   jobs, job_count, next_job, (Epa2Arena*)ctx->scratch[2].ptr, refill);
     }
     PB2_LAUNCHED(ctx);
@@ -1581,6 +1635,126 @@ int pb2_contact_pairs_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint
     PB2_CHECK(pb2_stage_back(ctx, pair_index, d_idx, (size_t)valid * 4, mem));
     if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (total > cap) PB2_FAIL(ctx, PB2_ERR_OVERFLOW, "contact_pairs_compact: %llu contacts > capacity %llu", (unsigned long long)total, (unsigned long long)cap);
+    return PB2_OK;
+}
+
+// ------------------------------------------------------------------------------------------- TriMesh vs shapes
+}  // extern "C"
+
+extern "C" int pb2_intersect_csr_device(pb2_ctx* ctx, const pb2_bvh* bvh, const float* d_queries, uint32_t m, bool positions,
+                                        uint32_t* d_offsets, uint32_t** d_items, uint64_t* total_out);
+
+// shape2.compute_aabb(pose12).loosened(prediction) in the mesh's frame (contact_composite_shape_shape.rs:21)
+__global__ void k_mesh_query_aabbs(const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float* __restrict__ points,
+                                   uint32_t n_shapes, const uint32_t* __restrict__ shape_ids, const float* __restrict__ poses,
+                                   const float* __restrict__ mesh_pose, uint32_t n, float prediction, float* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* o = out + 6ull * i;
+    uint32_t sid = shape_ids[i];
+    if (sid >= n_shapes) { o[0] = o[1] = o[2] = FLT_MAX; o[3] = o[4] = o[5] = -FLT_MAX; return; }  // no candidates: reported by the reduce
+    Iso7 pos12 = iso_inv_mul(load_iso(mesh_pose), load_iso(poses + 7ull * i));
+    V3 mn, mx;
+    shape_aabb_dev(kinds[sid], params[sid], points, pos12, mn, mx);
+    o[0] = mn.x + (-prediction); o[1] = mn.y + (-prediction); o[2] = mn.z + (-prediction);
+    o[3] = mx.x + prediction; o[4] = mx.y + prediction; o[5] = mx.z + prediction;
+}
+
+__global__ void k_expand_candidates(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ items, uint32_t n, uint32_t* __restrict__ ab) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    for (uint32_t j = offsets[q]; j < offsets[q + 1]; ++j) { ab[2ull * j] = items[j]; ab[2ull * j + 1] = q; }
+}
+
+// CompositeShapeRef::contact_with_shape's reduction (contact_composite_shape_shape.rs:26-41): the contact with the smallest
+// dist wins; equal dists go to the smallest triangle index (the reference keeps the first in its own tree's order).
+__global__ void k_mesh_reduce(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ items, const float4* __restrict__ tris,
+                              const float* __restrict__ cand, const uint8_t* __restrict__ cand_status, const uint32_t* __restrict__ shape_ids,
+                              uint32_t n_shapes, uint32_t n, float* __restrict__ out, uint8_t* __restrict__ status, uint32_t* __restrict__ part) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int st = shape_ids[q] >= n_shapes ? ST_UNSUPPORTED : ST_NONE;
+    uint32_t best_j = 0, best_id = PB2_INVALID_U32;
+    float best_d = 0.0f;
+    for (uint32_t j = offsets[q]; j < offsets[q + 1]; ++j) {
+        int cs = cand_status[j];
+        if (cs == ST_SOME) {
+            float d = cand[13ull * j + 12];
+            uint32_t id = __float_as_uint(tris[3ull * items[j]].w);
+            if (best_id == PB2_INVALID_U32 || d < best_d || (d == best_d && id < best_id)) { best_d = d; best_id = id; best_j = j; }
+        } else if (cs >= ST_UNSUPPORTED && st == ST_NONE) st = cs;
+    }
+    float* o = out + 13ull * q;
+    if (best_id != PB2_INVALID_U32) {
+        for (int i = 0; i < 13; ++i) o[i] = cand[13ull * best_j + i];
+        status[q] = (uint8_t)ST_SOME;
+    } else {
+        for (int i = 0; i < 13; ++i) o[i] = 0.0f;
+        status[q] = (uint8_t)st;
+    }
+    part[q] = best_id;
+}
+
+extern "C" {
+
+int pb2_trimesh_contact_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* mesh_pose7, const pb2_shapes* shapes, const uint32_t* shape_ids,
+                               const float* poses7, uint32_t n, float prediction, pb2_contact* out, uint8_t* status, uint32_t* part, int mem) {
+    if (!ctx || !mesh || !shapes || !mesh_pose7 || (n && (!shape_ids || !poses7 || !out || !status || !part))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_ids, *d_poses, *d_mpose;
+    void *d_out, *d_status, *d_part;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape_ids, (size_t)n * 4, mem, &d_ids));
+    PB2_CHECK(pb2_stage_in(ctx, 2, poses7, (size_t)n * 28, mem, &d_poses));
+    PB2_CHECK(pb2_stage_in(ctx, 3, mesh_pose7, 28, mem, &d_mpose));
+    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_status));
+    PB2_CHECK(pb2_stage_out(ctx, 6, part, (size_t)n * 4, mem, &d_part));
+    float* d_q = nullptr;
+    uint32_t *d_off = nullptr, *d_items = nullptr, *d_ab = nullptr;
+    float* d_cand = nullptr;
+    uint8_t* d_cst = nullptr;
+    int rc = PB2_OK;
+    do {
+        if (cudaMallocAsync((void**)&d_q, (size_t)n * 24, st) != cudaSuccess || cudaMallocAsync((void**)&d_off, ((size_t)n + 1) * 4, st) != cudaSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_shapes: out of memory"); rc = PB2_ERR_CUDA; break;
+        }
+        k_mesh_query_aabbs<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points, shapes->n, (const uint32_t*)d_ids,
+                                                              (const float*)d_poses, (const float*)d_mpose, n, prediction, d_q);
+        PB2_LAUNCHED(ctx);
+        uint64_t total = 0;
+        if ((rc = pb2_intersect_csr_device(ctx, &mesh->bvh, d_q, n, true, d_off, &d_items, &total)) != PB2_OK) break;
+        if (total > 0xffffffffull) { snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_shapes: too many candidates"); rc = PB2_ERR_OVERFLOW; break; }
+        if (total) {
+            if (cudaMallocAsync((void**)&d_ab, total * 8, st) != cudaSuccess || cudaMallocAsync((void**)&d_cand, total * 52, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_cst, total, st) != cudaSuccess) {
+                snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_shapes: out of memory (%llu candidates)", (unsigned long long)total); rc = PB2_ERR_CUDA; break;
+            }
+            k_expand_candidates<<<pb2_blocks(n, 128), 128, 0, st>>>(d_off, d_items, n, d_ab);
+            PB2_LAUNCHED(ctx);
+            OutSinks sinks;
+            sinks.dense = d_cand; sinks.status = d_cst; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
+            sinks.compact_count = nullptr; sinks.some_count = nullptr;
+            if ((rc = run_contacts(ctx, shapes, nullptr, (const uint32_t*)d_ids, (const float*)d_mpose, (const float*)d_poses, prediction,
+                                   (uint32_t)total, sinks, d_ab, n, mesh->tris, mesh->nt)) != PB2_OK) break;
+        }
+        k_mesh_reduce<<<pb2_blocks(n, 128), 128, 0, st>>>(d_off, d_items, mesh->tris, d_cand, d_cst, (const uint32_t*)d_ids, shapes->n, n,
+                                                         (float*)d_out, (uint8_t*)d_status, (uint32_t*)d_part);
+        PB2_LAUNCHED(ctx);
+        if (cudaGetLastError() != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_shapes: launch failed"); rc = PB2_ERR_CUDA; break; }
+    } while (0);
+    if (d_q) cudaFreeAsync(d_q, st);
+    if (d_off) cudaFreeAsync(d_off, st);
+    if (d_items) cudaFreeAsync(d_items, st);
+    if (d_ab) cudaFreeAsync(d_ab, st);
+    if (d_cand) cudaFreeAsync(d_cand, st);
+    if (d_cst) cudaFreeAsync(d_cst, st);
+    if (rc != PB2_OK) return rc;
+    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_status, (size_t)n, mem));
+    PB2_CHECK(pb2_stage_back(ctx, part, d_part, (size_t)n * 4, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(st));
     return PB2_OK;
 }
 

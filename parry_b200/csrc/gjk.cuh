@@ -12,7 +12,7 @@
 #define PB2_EPS 1.1920929e-7f          // f32::EPSILON (DEFAULT_EPSILON, src/lib.rs:102)
 #define PB2_GJK_EPS_TOL (PB2_EPS * 10.0f)
 
-enum { DS_CUBOID = 0, DS_CONVEX = 1, DS_ORIGIN = 2 };
+enum { DS_CUBOID = 0, DS_CONVEX = 1, DS_ORIGIN = 2, DS_TRIANGLE = 3 };
 struct DShape {
     int kind;
     V3 he;
@@ -34,6 +34,14 @@ __device__ __forceinline__ V3 ds_local_support(const DShape& s, V3 dir) {
             if (d > best_dot) { best_dot = d; best = v; }
         }
         return best;
+    }
+    if (s.kind == DS_TRIANGLE) {
+        // SupportMap for Triangle (shape/triangle.rs:697-716): its own comparison cascade, not the point-cloud scan
+        float4 pa = __ldg(&s.pts[0]), pb = __ldg(&s.pts[1]), pc = __ldg(&s.pts[2]);
+        V3 a = mk3(pa.x, pa.y, pa.z), b = mk3(pb.x, pb.y, pb.z), c = mk3(pc.x, pc.y, pc.z);
+        float d1 = dot3(a, dir), d2 = dot3(b, dir), d3 = dot3(c, dir);
+        if (d1 > d2) return d1 > d3 ? a : c;
+        return d2 > d3 ? b : c;
     }
     return mk3(0.f, 0.f, 0.f);
 }

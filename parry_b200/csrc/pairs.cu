@@ -47,7 +47,7 @@ __global__ void k_intersect_aabbs(const NodeWide* __restrict__ nodes, const uint
     uint32_t cnt = 0;
     uint64_t base = WRITE ? offsets[qi] : 0;
     auto emit = [&](uint32_t pos) {
-        if (WRITE) { if (base + cnt < cap) out[base + cnt] = order[pos]; }
+        if (WRITE) { if (base + cnt < cap) out[base + cnt] = order ? order[pos] : pos; }  // order == NULL: sorted positions
         cnt++;
     };
     if (n_leaves == 1) {
@@ -200,6 +200,38 @@ static int read_counter(pb2_ctx* ctx, uint64_t* count) {
 }
 
 extern "C" {
+
+// Device-resident CSR for internal callers (TriMesh-vs-shape contacts): d_offsets has m + 1 entries (caller-owned);
+// *d_items is allocated here with cudaMallocAsync on ctx->stream (caller frees with cudaFreeAsync) and holds leaf ids,
+// or sorted leaf positions when `positions` is set. Synchronises the stream once (to size the item list).
+int pb2_intersect_csr_device(pb2_ctx* ctx, const pb2_bvh* bvh, const float* d_queries, uint32_t m, bool positions, uint32_t* d_offsets,
+                             uint32_t** d_items, uint64_t* total_out) {
+    cudaStream_t st = ctx->stream;
+    *d_items = nullptr; *total_out = 0;
+    if (m == 0) return PB2_OK;
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)(m + 1), st);
+    size_t counts_bytes = (((size_t)m + 1) * 4 + 255) & ~(size_t)255;
+    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], counts_bytes + cub_bytes));
+    uint32_t* counts = (uint32_t*)ctx->scratch[2].ptr;
+    void* cub_tmp = (char*)ctx->scratch[2].ptr + counts_bytes;
+    PB2_CUDA(ctx, cudaMemsetAsync(counts + m, 0, 4, st));
+    k_intersect_aabbs<false><<<pb2_blocks(m, 128), 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->n_leaves, d_queries, m, counts, nullptr, nullptr, 0);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, counts, d_offsets, (int)(m + 1), st));
+    ctx->launches += 2;
+    PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, d_offsets + m, 4, cudaMemcpyDeviceToHost, st));
+    PB2_CUDA(ctx, cudaStreamSynchronize(st));
+    uint64_t total = *(uint32_t*)ctx->h_counters;
+    *total_out = total;
+    if (total == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaMallocAsync((void**)d_items, total * 4, st));
+    k_intersect_aabbs<true><<<pb2_blocks(m, 128), 128, 0, st>>>(bvh->nodes, positions ? nullptr : bvh->leaf_order, bvh->n_leaves, d_queries, m,
+                                                               nullptr, d_offsets, *d_items, total);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    return PB2_OK;
+}
 
 int pb2_bvh_intersect_aabbs(pb2_ctx* ctx, const pb2_bvh* bvh, const float* queries, uint32_t m, uint32_t* offsets,
                             uint32_t* leaf_ids, uint64_t cap, uint64_t* count, int mem) {

@@ -19,38 +19,8 @@ __global__ void k_compute_aabbs(const uint8_t* __restrict__ kinds, const float4*
     uint32_t sid = shape_ids ? shape_ids[i] : i;
     if (sid >= n_shapes) { atomicAdd(bad, 1u); return; }
     Iso7 pos = load_iso(poses + 7ull * i);
-    float4 pr = params[sid];
     V3 mn, mx;
-    uint8_t kind = kinds[sid];
-    if (kind == PB2_SHAPE_BALL) {
-        // ball_aabb: center + repeat(-r), center + repeat(r)
-        float r = pr.x;
-        mn = mk3(pos.t.x + (-r), pos.t.y + (-r), pos.t.z + (-r));
-        mx = mk3(pos.t.x + r, pos.t.y + r, pos.t.z + r);
-    } else if (kind == PB2_SHAPE_CUBOID) {
-        // |R| * half_extents with R = to_rotation_matrix(), gemv accumulated column by column
-        float qi = pos.q.i, qj = pos.q.j, qk = pos.q.k, qw = pos.q.w;
-        float ww = qw * qw, ii = qi * qi, jj = qj * qj, kk = qk * qk;
-        float ij = qi * qj * 2.0f, wk = qw * qk * 2.0f, wj = qw * qj * 2.0f;
-        float ik = qi * qk * 2.0f, jk = qj * qk * 2.0f, wi = qw * qi * 2.0f;
-        float m00 = fabsf(ww + ii - jj - kk), m01 = fabsf(ij - wk), m02 = fabsf(wj + ik);
-        float m10 = fabsf(wk + ij), m11 = fabsf(ww - ii + jj - kk), m12 = fabsf(jk - wi);
-        float m20 = fabsf(ik - wj), m21 = fabsf(wi + jk), m22 = fabsf(ww - ii - jj + kk);
-        V3 he = mk3((m00 * pr.x + m01 * pr.y) + m02 * pr.z, (m10 * pr.x + m11 * pr.y) + m12 * pr.z,
-                    (m20 * pr.x + m21 * pr.y) + m22 * pr.z);
-        mn = pos.t - he;  // Aabb::from_half_extents(center, he)
-        mx = pos.t + he;
-    } else {
-        uint32_t first = __float_as_uint(pr.x), cnt = __float_as_uint(pr.y);
-        const float* p = points + 3ull * first;
-        V3 w0 = iso_point(pos, mk3(p[0], p[1], p[2]));
-        mn = w0; mx = w0;
-        for (uint32_t k = 1; k < cnt; ++k) {
-            V3 w = iso_point(pos, mk3(p[3 * k], p[3 * k + 1], p[3 * k + 2]));
-            mn = vmin3(mn, w);
-            mx = vmax3(mx, w);
-        }
-    }
+    shape_aabb_dev(kinds[sid], params[sid], points, pos, mn, mx);
     float* o = out + 6ull * i;
     o[0] = mn.x; o[1] = mn.y; o[2] = mn.z; o[3] = mx.x; o[4] = mx.y; o[5] = mx.z;
 }

@@ -10,3 +10,37 @@ struct pb2_shapes {
     float* points = nullptr;    // ConvexPolyhedron::points(), xyz packed
     float4* points4 = nullptr;  // same points padded to 16 B for vector loads in the support-map loop
 };
+
+// Shape::compute_aabb(pos) (shape/shape.rs:369): aabb_ball.rs:8-33, aabb_cuboid.rs:9-16 + utils/isometry_ops.rs:16-18,
+// aabb_convex_polyhedron.rs:8-16 + aabb_utils.rs:66-87.
+__device__ __forceinline__ void shape_aabb_dev(uint8_t kind, float4 pr, const float* __restrict__ points, const Iso7& pos, V3& mn, V3& mx) {
+    if (kind == PB2_SHAPE_BALL) {
+        // ball_aabb: center + repeat(-r), center + repeat(r)
+        float r = pr.x;
+        mn = mk3(pos.t.x + (-r), pos.t.y + (-r), pos.t.z + (-r));
+        mx = mk3(pos.t.x + r, pos.t.y + r, pos.t.z + r);
+    } else if (kind == PB2_SHAPE_CUBOID) {
+        // |R| * half_extents with R = to_rotation_matrix(), gemv accumulated column by column
+        float qi = pos.q.i, qj = pos.q.j, qk = pos.q.k, qw = pos.q.w;
+        float ww = qw * qw, ii = qi * qi, jj = qj * qj, kk = qk * qk;
+        float ij = qi * qj * 2.0f, wk = qw * qk * 2.0f, wj = qw * qj * 2.0f;
+        float ik = qi * qk * 2.0f, jk = qj * qk * 2.0f, wi = qw * qi * 2.0f;
+        float m00 = fabsf(ww + ii - jj - kk), m01 = fabsf(ij - wk), m02 = fabsf(wj + ik);
+        float m10 = fabsf(wk + ij), m11 = fabsf(ww - ii + jj - kk), m12 = fabsf(jk - wi);
+        float m20 = fabsf(ik - wj), m21 = fabsf(wi + jk), m22 = fabsf(ww - ii - jj + kk);
+        V3 he = mk3((m00 * pr.x + m01 * pr.y) + m02 * pr.z, (m10 * pr.x + m11 * pr.y) + m12 * pr.z,
+                    (m20 * pr.x + m21 * pr.y) + m22 * pr.z);
+        mn = pos.t - he;  // Aabb::from_half_extents(center, he)
+        mx = pos.t + he;
+    } else {
+        uint32_t first = __float_as_uint(pr.x), cnt = __float_as_uint(pr.y);
+        const float* p = points + 3ull * first;
+        V3 w0 = iso_point(pos, mk3(p[0], p[1], p[2]));
+        mn = w0; mx = w0;
+        for (uint32_t k = 1; k < cnt; ++k) {
+            V3 w = iso_point(pos, mk3(p[3 * k], p[3 * k + 1], p[3 * k + 2]));
+            mn = vmin3(mn, w);
+            mx = vmax3(mx, w);
+        }
+    }
+}

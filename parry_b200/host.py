@@ -325,6 +325,20 @@ class TriMesh:
     def cast_local_ray_and_get_normal(self, rays, max_time_of_impact, solid=True, out=None):
         return self._cast(None, rays, max_time_of_impact, solid, True, out)
 
+    def contact_shapes(self, mesh_pose, shapes, shape_ids, poses, prediction):
+        """query::contact(mesh_pose, self, poses[k], shapes[shape_ids[k]], prediction) for every k (the composite-shape arm,
+        contact_composite_shape_shape.rs:14-61). Returns (contacts (n, 13), status (n,), part (n,) winning triangle)."""
+        n = int(poses.shape[0])
+        kp, pp, mem = _prep(poses, np.float32)
+        ks, ps, _ = _prep(shape_ids, np.uint32, mem)
+        km, pm, _ = _prep(mesh_pose, np.float32, mem)
+        dev = self.ctx.torch_device
+        out, po = _empty((n, 13), np.float32, mem, dev)
+        status, pst = _empty((n,), np.uint8, mem, dev)
+        part, ppart = _empty((n,), np.uint32, mem, dev)
+        self.ctx.check(self.ctx._lib.pb2_trimesh_contact_shapes(self.ctx.h, self.h, pm, shapes.h, ps, pp, n, float(prediction), po, pst, ppart, mem))
+        return out, status, part
+
     def close(self):
         if self.h:
             self.ctx._lib.pb2_trimesh_destroy(self.ctx.h, self.h)
