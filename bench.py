@@ -481,8 +481,43 @@ def also_mixed(ctx, stream, timed, flush, hbm_peak):
             "l2": "flushed between iterations", "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
 
 
+def also_mesh_contacts(ctx, stream, timed, flush, hbm_peak):
+    """2^20 ball / cuboid / hull colliders resting on or near the 8,000,000-triangle terrain TriMesh:
+    query::contact(mesh, collider) for every collider (mesh Bvh query + per-triangle narrow phase + min reduction)."""
+    import torch
+    import parry_b200
+    from harness import scenes
+    v, i = terrain_scene()
+    mesh = parry_b200.TriMesh(ctx, v, i)
+    n, H = 1 << 20, 4096
+    g = scenes.rng(11)
+    pts, _ = scenes.hull_pool(H, 32, seed=12)
+    pts = np.asarray(pts, dtype=np.float32) * 0.4
+    kinds = g.integers(0, 3, n).astype(np.uint8)
+    params = (g.random((n, 3)) * 0.3 + 0.15).astype(np.float32)
+    tk = np.concatenate([np.full(H, 2, np.uint8), np.where(kinds == 2, 0, kinds).astype(np.uint8)])
+    tp = np.concatenate([np.zeros((H, 3), np.float32), params])
+    first = np.concatenate([np.arange(H, dtype=np.uint32) * 32, np.zeros(n, np.uint32)])
+    count = np.concatenate([np.full(H, 32, np.uint32), np.zeros(n, np.uint32)])
+    G = parry_b200.Shapes.from_arrays(ctx, tk, tp, pts.reshape(-1, 3), first, count)
+    sid = np.where(kinds == 2, g.integers(0, H, n), H + np.arange(n)).astype(np.uint32)
+    anchor = v[g.integers(0, len(v), n)]
+    t = anchor + np.stack([g.standard_normal(n) * 0.2, (g.random(n) - 0.3) * 0.8, g.standard_normal(n) * 0.2], axis=1)
+    poses = np.concatenate([scenes.random_unit_quaternions(g, n), t], axis=1).astype(np.float32)
+    dsid, dposes = torch.from_numpy(sid.view(np.int32)).cuda(), torch.from_numpy(poses).cuda()
+    mpose = torch.tensor([0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0], dtype=torch.float32, device="cuda")
+    res = {}
+
+    def run():
+        res["o"] = mesh.contact_shapes(mpose, G, dsid, dposes, 0.02)
+    ms = timed(run, steps=5, warmup=2, flush=flush)
+    st = res["o"][1]
+    return {"value": n / (ms * 1e-3), "unit": "colliders/s (TriMesh-vs-shape contacts, 8M-triangle terrain)", "ms": ms, "colliders": n,
+            "contacts_fraction": float((st == 1).float().mean().item()), "l2": "flushed between iterations"}
+
+
 EXTRA_ALSO = [("contact_pairs_4M_hulls", also_contacts), ("broadphase_1M_colliders", also_broadphase),
-              ("mixed_2M_colliders_pipeline", also_mixed)]
+              ("mixed_2M_colliders_pipeline", also_mixed), ("trimesh_contacts_1M_colliders", also_mesh_contacts)]
 
 if __name__ == "__main__":
     main()

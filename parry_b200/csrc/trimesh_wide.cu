@@ -312,7 +312,7 @@ __device__ __forceinline__ AxisK axis_setup(float p, float o, float inv, bool ne
 // Queued triangles delay the update of `best`; the lane meanwhile keeps traversing against its older bound, which can
 // only add node visits, never remove a candidate.
 template <bool WITH_NORMAL, int MODE>
-__global__ void __launch_bounds__(128) k_raycast_wide(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
+__global__ void __launch_bounds__(128, 7) k_raycast_wide(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
                                   const float* __restrict__ pose7, const float* __restrict__ rays, const uint32_t* __restrict__ perm,
                                   uint32_t m, float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
                                   float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
