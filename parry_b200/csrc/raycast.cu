@@ -280,7 +280,7 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
                                                                       (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
                                                                       nullptr, nullptr, cull);
     } else {
-        unsigned int* next_ray = (unsigned int*)(ctx->d_counters + 8);
+        unsigned int* next_ray = (unsigned int*)(ctx->d_counters + ctx->ray_slot);
         PB2_CUDA(ctx, cudaMemsetAsync(next_ray, 0, 4, ctx->stream));
         const uint32_t* perm = nullptr;
         if (variant >= 3 && !mesh->n_nodes8) variant -= 2;
@@ -413,9 +413,34 @@ static int trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float*
     PB2_CHECK(pb2_stage_out(ctx, 4, normal, (size_t)m * 12, mem, &d_n));
     PB2_CHECK(pb2_stage_out(ctx, 5, feature, (size_t)m * 4, mem, &d_f));
     PB2_CHECK(pb2_pipeline_init(ctx));
-    const uint32_t CHUNK = 1u << 20;
-    for (uint32_t lo = 0; lo < m; lo += CHUNK) {
-        uint32_t cnt = m - lo < CHUNK ? m - lo : CHUNK;
+    // Chunks: H2D (24 B/ray at ~53 GB/s) runs at about the kernel's own rate, so chunk c + 1 is uploaded while chunk c is
+    // traversed and chunk c - 1 is downloaded. Measured on 2^23 rays (harness/e2e_sweep.py): one chunk 8.3 ms; 2^20-ray chunks on
+    // one compute stream 5.2 ms; 2^19-ray chunks alternating between two compute streams 4.5 ms.
+    uint32_t sizes[64];
+    int n_chunks = 0;
+    const bool dual = mesh->n_nodes8 != 0 && getenv("PB2_RAY_VARIANT") == nullptr && getenv("PB2_RAY_SINGLE_STREAM") == nullptr;
+    {
+        uint32_t c = dual ? (1u << 19) : (1u << 20);
+        const char* e = getenv("PB2_RAY_CHUNK_LOG2");
+        if (e && atoi(e) >= 12 && atoi(e) <= 30) c = 1u << atoi(e);
+        while ((uint64_t)c * 60 < m) c <<= 1;
+        uint32_t rem = m;
+        while (rem) { uint32_t k = rem < c ? rem : c; sizes[n_chunks++] = k; rem -= k; }
+    }
+    // two compute streams, alternating: the tail of one chunk's persistent launch (a few long rays) overlaps the start of the
+    // next. Only for the wide-tree kernel, which needs no per-call scratch besides its fetch counter.
+    cudaStream_t main_stream = ctx->stream;
+    if (dual) {  // the second stream starts after everything already queued on the main one (pose upload, earlier calls)
+        cudaEvent_t e0 = pb2_next_event(ctx);
+        PB2_CUDA(ctx, cudaEventRecord(e0, main_stream));
+        PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->compute2, e0, 0));
+    }
+    int rc = PB2_OK;
+    uint32_t lo = 0;
+    for (int ci = 0; ci < n_chunks && rc == PB2_OK; lo += sizes[ci], ++ci) {
+        uint32_t cnt = sizes[ci];
+        if (dual) { ctx->stream = (ci & 1) ? ctx->compute2 : main_stream; ctx->ray_slot = (ci & 1) ? 12 : 8; }
+        rc = [&]() -> int {
         cudaEvent_t e_in = pb2_next_event(ctx), e_k = pb2_next_event(ctx);
         PB2_CUDA(ctx, cudaMemcpyAsync((char*)d_rays + (size_t)lo * 24, rays + (size_t)lo * 6, (size_t)cnt * 24, cudaMemcpyHostToDevice, ctx->copy_in));
         PB2_CUDA(ctx, cudaEventRecord(e_in, ctx->copy_in));
@@ -428,8 +453,13 @@ static int trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float*
         PB2_CUDA(ctx, cudaMemcpyAsync(tri + lo, (uint32_t*)d_tri + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
         if (normal) PB2_CUDA(ctx, cudaMemcpyAsync(normal + 3ull * lo, (float*)d_n + 3ull * lo, (size_t)cnt * 12, cudaMemcpyDeviceToHost, ctx->copy_out));
         if (feature) PB2_CUDA(ctx, cudaMemcpyAsync(feature + lo, (uint32_t*)d_f + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+        return PB2_OK;
+        }();
     }
+    ctx->stream = main_stream; ctx->ray_slot = 8;
+    if (rc != PB2_OK) { cudaStreamSynchronize(ctx->copy_out); cudaStreamSynchronize(main_stream); if (dual) cudaStreamSynchronize(ctx->compute2); return rc; }
     PB2_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    if (dual) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->compute2));
     PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB2_OK;
 }

@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide(const float4* __restric
 
 int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, const float* d_rays, const uint32_t* d_perm, uint32_t m,
                   float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int tri_lanes, int refill, uint32_t cull) {
-    unsigned int* next_ray = (unsigned int*)(ctx->d_counters + 8);
+    unsigned int* next_ray = (unsigned int*)(ctx->d_counters + ctx->ray_slot);
     int mode = 0;
     { const char* e = getenv("PB2_RAY_MODE"); if (e) mode = atoi(e) ? 1 : 0; }
     auto kern = with_normal ? (mode ? k_raycast_wide<true, 1> : k_raycast_wide<true, 0>) : (mode ? k_raycast_wide<false, 1> : k_raycast_wide<false, 0>);
