@@ -414,7 +414,7 @@ static int trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float*
     PB2_CHECK(pb2_stage_out(ctx, 5, feature, (size_t)m * 4, mem, &d_f));
     PB2_CHECK(pb2_pipeline_init(ctx));
     // Chunks: H2D (24 B/ray at ~53 GB/s) runs at about the kernel's own rate, so chunk c + 1 is uploaded while chunk c is
-    // traversed and chunk c - 1 is downloaded. Measured on 2^23 rays (harness/e2e_sweep.py): one chunk 8.3 ms; 2^20-ray chunks on
+    // traversed and chunk c - 1 is downloaded. Measured on 2^23 rays (chunk-size sweep): one chunk 8.3 ms; 2^20-ray chunks on
     // one compute stream 5.2 ms; 2^19-ray chunks alternating between two compute streams 4.5 ms.
     uint32_t sizes[64];
     int n_chunks = 0;
