@@ -11,6 +11,7 @@
 // BvhNodeWide layout so it can be handed back verbatim (pb2_bvh_download). Karras' numbering puts the two
 // children of a node at adjacent indices (split, split+1) => sibling nodes share a 128-byte line.
 #include "common.cuh"
+#include <stdlib.h>
 #include <cub/device/device_radix_sort.cuh>
 
 // ---------------------------------------------------------------- helpers
@@ -61,16 +62,22 @@ __device__ __forceinline__ uint64_t split3(uint32_t a) {
 }
 
 __global__ void k_morton(const float* __restrict__ aabbs, uint32_t n, const uint32_t* __restrict__ bounds,
-                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, bool cubic) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* a = aabbs + 6ull * i;
     uint32_t q[3];
+    // One scale for the three axes (the largest centroid extent): Morton cells are cubes, so a flat scene (terrain: 1000 x 40
+    // x 1000) is split along its long axes first instead of being sliced into overlapping height bands. The reference's own
+    // Morton helper normalises per axis (utils/morton.rs:33-40, PLOC only); query results do not depend on the tree.
+    float emax = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) emax = fmaxf(emax, ord2f(bounds[3 + d]) - ord2f(bounds[d]));
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        float lo = ord2f(bounds[d]), hi = ord2f(bounds[3 + d]);
+        float lo = ord2f(bounds[d]);
         float c = (a[d] + a[3 + d]) * 0.5f;
-        float e = hi - lo;
+        float e = cubic ? emax : ord2f(bounds[3 + d]) - lo;
         float u = e > 0.0f ? (c - lo) / e : 0.0f;
         u = fminf(fmaxf(u, 0.0f), 1.0f);
         uint32_t v = (uint32_t)(u * 2097152.0f);
@@ -305,7 +312,9 @@ int pb2_bvh_build_device(pb2_ctx* ctx, pb2_bvh* b, const float* d_aabbs, uint32_
     if ((uint64_t)grid * 256 > n) grid = (int)pb2_blocks(n, 256);
     k_centroid_bounds<<<grid, 256, 0, st>>>(d_aabbs, n, bounds);
     PB2_LAUNCHED(ctx);
-    k_morton<<<pb2_blocks(n, 256), 256, 0, st>>>(d_aabbs, n, bounds, keys_in, vals_in);
+    bool cubic = true;
+    { const char* e = getenv("PB2_MORTON_PER_AXIS"); if (e && atoi(e)) cubic = false; }
+    k_morton<<<pb2_blocks(n, 256), 256, 0, st>>>(d_aabbs, n, bounds, keys_in, vals_in, cubic);
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const uint64_t*)keys_in, keys_out, (const uint32_t*)vals_in,
                                                   b->leaf_order, (int)n, 0, 63, st));
