@@ -51,7 +51,7 @@ def main():
         sweep = os.environ.get("PB2_SWEEP")
         configs = [None]
         if sweep:
-            configs = [(2, 16, 8), (3, 12, 4), (3, 8, 4), (3, 16, 4), (3, 24, 4), (3, 12, 2), (3, 12, 8), (3, 6, 4), (4, 12, 4)]
+            configs = [(3, 8, 4), (3, 6, 4), (3, 12, 4), (3, 16, 4), (3, 8, 2), (3, 8, 6), (3, 8, 8), (3, 4, 4)]
         for cfg in configs:
             if cfg is not None:
                 os.environ["PB2_RAY_VARIANT"], os.environ["PB2_RAY_STEPS"], os.environ["PB2_RAY_REFILL"] = map(str, cfg)

@@ -262,7 +262,7 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
     // variants: 0 one thread per ray, 1 persistent binary, 2 = 1 + ray reordering, 3 compressed 8-wide tree, 4 = 3 + ray reordering
     bool big = (size_t)b->n_nodes * sizeof(NodeWide) > (size_t)(100u << 20);
     int variant = mesh->n_nodes8 ? 3 : (big ? 2 : 1), steps = 16, refill = 8;
-    if (variant >= 3) { steps = 8; refill = 4; }  // wide kernel: `steps` = lanes with queued triangles that trigger a triangle pass
+    if (variant >= 3) { steps = 8; refill = 6; }  // wide kernel: `steps` = lanes with queued triangles that trigger a triangle pass
     {   // tuning knobs (read per call; cheap)
         const char* e = getenv("PB2_RAY_VARIANT");
         if (e) variant = atoi(e);
