@@ -169,17 +169,26 @@ def main():
     rays_d = torch.from_numpy(rays_h).cuda()
     toi_d = torch.empty(m, dtype=torch.float32, device="cuda")
     tri_d = torch.empty(m, dtype=torch.int32, device="cuda")
-    gather = None
+    gather, gather_kind, peer = None, "none (N=1)", False
     if world > 1:
         from parry_b200 import sharding
-        gather = sharding.OverlappedHitGather(m, "cuda", chunks=4)
+        try:
+            if os.environ.get("PB2_BENCH_NCCL_GATHER"):
+                raise RuntimeError("forced")
+            gather = sharding.PeerHitGather(m, torch.device("cuda", local_rank), chunks=4)
+            gather_kind = ("all-gather of the (toi,id) results inside the timed region: 4 pieces pushed into every peer's symmetric-memory "
+                           "buffer by copy engines over NVLink while the next piece is traversed, then a cross-rank barrier")
+        except Exception as e:  # no symmetric memory on this box: NCCL all_gather per piece on a side stream
+            gather = sharding.OverlappedHitGather(m, "cuda", chunks=4)
+            gather_kind = "all_gather (NCCL) of the (toi,id) results inside the timed region, 4 pieces on a side stream (%s)" % type(e).__name__
+        peer = isinstance(gather, sharding.PeerHitGather)
 
     def step_device():
         if world == 1:
             mesh.cast_local_ray(rays_d, FMAX, out=(toi_d, tri_d))
+        elif peer:
+            gather.run(mesh, rays_d, FMAX, stream)
         else:
-            # the path's only collective: all-gather of the fixed-size hit records, piece c gathered on a side stream
-            # while piece c + 1 is being traversed
             gather.run(lambda lo, hi, t, k: mesh.cast_local_ray(rays_d[lo:hi], FMAX, out=(t, k)), stream)
 
     def timed(fn, steps, warmup):
@@ -239,8 +248,17 @@ def main():
         dt_e2e = float(t.item())
     e2e_val = world * m / dt_e2e
     # sanity: device-resident and host paths agree
-    toi_chk = gather.toi if world > 1 else toi_d
+    toi_chk = (gather.local()[0] if peer else gather.toi) if world > 1 else toi_d
     assert (toi_chk.cpu().numpy().view(np.uint32) == toi_np.view(np.uint32)).all()
+    if world > 1:
+        # every rank must hold every rank's results: compare per-shard checksums of the gathered arrays with the owners' own
+        ft, fk = gather.full()
+        torch.cuda.synchronize()
+        mine = torch.tensor([int(fk[rank * m:(rank + 1) * m].to(torch.int64).sum().item())], device="cuda")
+        owners = torch.empty(world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(owners, mine)
+        seen = torch.stack([fk[r * m:(r + 1) * m].to(torch.int64).sum() for r in range(world)])
+        assert bool((seen == owners).all()), "gathered results differ from the owners' results"
 
     nt, nv = len(i), len(v)
     scene_bytes = 64 * (nt - 1) + 48 * nt  # node array + pre-gathered triangles, read at least once per launch
@@ -253,7 +271,7 @@ def main():
         "config": {"workload": "2^%d incoherent rays per GPU vs 8,000,000-triangle terrain TriMesh (BASELINE config[3] shard), "
                                "BVH replicated per GPU" % args.rays_log2,
                    "triangles": nt, "rays_per_gpu": m, "l2": "inputs larger than L2 (rays %d MB, scene %d MB)" % (m * 24 >> 20, scene_bytes >> 20),
-                   "collective": "all_gather of (toi,id) results inside the timed region, 4 pieces overlapped with traversal" if world > 1 else "none (N=1)"},
+                   "collective": gather_kind},
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": m * 24, "d2h_bytes_per_step": m * 8,
                 "ms_per_step": dt_e2e * 1e3},
         "gpu_launches": int(launches),

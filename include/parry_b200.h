@@ -138,6 +138,17 @@ const pb2_bvh* pb2_trimesh_bvh(const pb2_trimesh* mesh);
 int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays /* m x 6 */,
                           uint32_t m, float max_toi, int solid, float* toi, uint32_t* tri, float* normal,
                           uint32_t* feature, int mem);
+/* Multi-GPU form of pb2_trimesh_cast_rays for a range-split batch with the mesh replicated per GPU (the
+ * path's only exchange is the all-gather of the fixed-size (toi, tri) hit records). Everything is device memory. The local
+ * shard of m rays is traversed in `chunks` pieces; as soon as a piece is done its results — written straight into this
+ * rank's gather buffers at element offset `elem_offset` — are pushed into the same place of every peer's buffers with
+ * device-to-device copies over NVLink (copy engines), while the next piece is traversed. peer_toi[p] / peer_tri[p]: rank
+ * p's gather buffers as mapped in THIS process (CUDA IPC / symmetric memory; entry `self` is the local one). Asynchronous
+ * on the context's stream; the caller runs a cross-rank barrier before reading peers' slices. */
+int pb2_trimesh_cast_rays_allgather(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays /* m x 6, device */,
+                                    uint32_t m, float max_toi, void* const* peer_toi, void* const* peer_tri, int n_peers, int self,
+                                    uint64_t elem_offset, int chunks);
+
 /* TriMesh::cast_ray_with_culling / cast_local_ray_with_culling (ray_trimesh.rs:139-178, RayCullingMode :50-65): same
  * query, but a triangle is only considered when its scaled normal faces the ray the allowed way. Always the
  * `_and_get_normal` flavour in the reference; normal / feature may still be NULL here. */

@@ -476,4 +476,54 @@ int pb2_trimesh_cast_rays_with_culling(pb2_ctx* ctx, const pb2_trimesh* mesh, co
     return trimesh_cast_rays(ctx, mesh, pose7, rays, m, max_toi, (uint32_t)culling, toi, tri, normal, feature, mem);
 }
 
+int pb2_trimesh_cast_rays_allgather(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays, uint32_t m, float max_toi,
+                                    void* const* peer_toi, void* const* peer_tri, int n_peers, int self, uint64_t elem_offset, int chunks) {
+    if (!ctx || !mesh || !peer_toi || !peer_tri || n_peers < 1 || self < 0 || self >= n_peers || (m && !rays)) return PB2_ERR_INVALID;
+    if (m == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    PB2_CHECK(pb2_pipeline_init(ctx));
+    if (chunks < 1) chunks = 1;
+    if (chunks > 16) chunks = 16;
+    float* my_toi = (float*)peer_toi[self] + elem_offset;
+    uint32_t* my_tri = (uint32_t*)peer_tri[self] + elem_offset;
+    const bool dual = mesh->n_nodes8 != 0 && getenv("PB2_RAY_VARIANT") == nullptr && chunks > 1;
+    cudaStream_t main_stream = ctx->stream;
+    cudaEvent_t e0 = pb2_next_event(ctx);
+    PB2_CUDA(ctx, cudaEventRecord(e0, main_stream));
+    if (dual) PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->compute2, e0, 0));
+    int rc = PB2_OK;
+    uint32_t base = m / (uint32_t)chunks, rem = m % (uint32_t)chunks, lo = 0;
+    for (int ci = 0; ci < chunks && rc == PB2_OK; ++ci) {
+        uint32_t cnt = base + ((uint32_t)ci < rem ? 1u : 0u);
+        if (cnt == 0) continue;
+        if (dual) { ctx->stream = (ci & 1) ? ctx->compute2 : main_stream; ctx->ray_slot = (ci & 1) ? 12 : 8; }
+        rc = [&]() -> int {
+            PB2_CHECK(cast_rays_device(ctx, mesh, pose7, rays + 6ull * lo, cnt, max_toi, my_toi + lo, my_tri + lo, nullptr, nullptr, false, 0u));
+            cudaEvent_t e_k = pb2_next_event(ctx);
+            PB2_CUDA(ctx, cudaEventRecord(e_k, ctx->stream));
+            // push this slice into every peer's gather buffers: device-to-device copies over NVLink on the copy engines (no SM is
+            // taken from the persistent traversal kernel, which an NCCL kernel would have to wait for)
+            PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, e_k, 0));
+            PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, e_k, 0));
+            for (int p = 0; p < n_peers; ++p) {
+                if (p == self) continue;
+                cudaStream_t cs = (p & 1) ? ctx->copy_out : ctx->copy_in;
+                PB2_CUDA(ctx, cudaMemcpyAsync((float*)peer_toi[p] + elem_offset + lo, my_toi + lo, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, cs));
+                PB2_CUDA(ctx, cudaMemcpyAsync((uint32_t*)peer_tri[p] + elem_offset + lo, my_tri + lo, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, cs));
+            }
+            return PB2_OK;
+        }();
+        lo += cnt;
+    }
+    ctx->stream = main_stream; ctx->ray_slot = 8;
+    // everything this call enqueued joins the context's stream again
+    cudaEvent_t e1 = pb2_next_event(ctx), e2 = pb2_next_event(ctx), e3 = pb2_next_event(ctx);
+    cudaEventRecord(e1, ctx->copy_in); cudaStreamWaitEvent(main_stream, e1, 0);
+    cudaEventRecord(e2, ctx->copy_out); cudaStreamWaitEvent(main_stream, e2, 0);
+    if (dual) { cudaEventRecord(e3, ctx->compute2); cudaStreamWaitEvent(main_stream, e3, 0); }
+    if (rc != PB2_OK) return rc;
+    PB2_CUDA(ctx, cudaGetLastError());
+    return PB2_OK;
+}
+
 }  // extern "C"

@@ -325,6 +325,18 @@ class TriMesh:
     def cast_local_ray_and_get_normal(self, rays, max_time_of_impact, solid=True, out=None):
         return self._cast(None, rays, max_time_of_impact, solid, True, out)
 
+    def cast_local_ray_allgather(self, rays, max_time_of_impact, peer_toi_ptrs, peer_tri_ptrs, rank, elem_offset, chunks=4):
+        """Range-split batch on several GPUs: casts this rank's (device-resident) rays and pushes the results into every
+        rank's gather buffers over NVLink while traversing (pb2_trimesh_cast_rays_allgather). peer_*_ptrs: ctypes arrays of
+        device pointers, one per rank (parry_b200.sharding.PeerHitGather builds them from symmetric memory)."""
+        m = int(rays.shape[0])
+        kr, pr, mem = _prep(rays, np.float32)
+        if mem != MEM_DEVICE:
+            raise ValueError("cast_local_ray_allgather needs device-resident rays")
+        self.ctx.check(self.ctx._lib.pb2_trimesh_cast_rays_allgather(self.ctx.h, self.h, None, pr, m, float(max_time_of_impact),
+                                                                    peer_toi_ptrs, peer_tri_ptrs, len(peer_toi_ptrs), int(rank),
+                                                                    int(elem_offset), int(chunks)))
+
     def contact_shapes(self, mesh_pose, shapes, shape_ids, poses, prediction):
         """query::contact(mesh_pose, self, poses[k], shapes[shape_ids[k]], prediction) for every k (the composite-shape arm,
         contact_composite_shape_shape.rs:14-61). Returns (contacts (n, 13), status (n,), part (n,) winning triangle)."""

@@ -107,3 +107,40 @@ class OverlappedHitGather:
         toi = torch.cat([g.view(self.world, -1) for g in self.g_toi], dim=1).reshape(-1)
         tri = torch.cat([g.view(self.world, -1) for g in self.g_tri], dim=1).reshape(-1)
         return toi, tri
+
+
+class PeerHitGather:
+    """Same job as OverlappedHitGather, without NCCL kernels: the gather buffers are symmetric memory (every rank's buffer
+    is mapped into every process), and the library pushes each finished piece of the local shard into all peers' buffers
+    with copy-engine transfers over NVLink while the next piece is traversed (pb2_trimesh_cast_rays_allgather). A persistent
+    traversal kernel fills every SM, so an NCCL all-gather kernel only gets to run once the traversal is over; DMA copies
+    overlap for real. `run` ends with a cross-rank barrier on the compute stream. Raises if symmetric memory is unavailable
+    (callers fall back to OverlappedHitGather)."""
+
+    def __init__(self, m_local, device, chunks=4, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.m = int(m_local)
+        self.chunks = int(chunks)
+        n = self.world * self.m
+        self.toi = symm_mem.empty(n, dtype=torch.float32, device=device)
+        self.tri = symm_mem.empty(n, dtype=torch.int32, device=device)
+        self.h_toi = symm_mem.rendezvous(self.toi, self.group)
+        self.h_tri = symm_mem.rendezvous(self.tri, self.group)
+        self.p_toi = (C.c_void_p * self.world)(*[int(p) for p in self.h_toi.buffer_ptrs])
+        self.p_tri = (C.c_void_p * self.world)(*[int(p) for p in self.h_tri.buffer_ptrs])
+
+    def run(self, mesh, rays, max_toi, compute_stream):
+        mesh.cast_local_ray_allgather(rays, max_toi, self.p_toi, self.p_tri, self.rank, self.rank * self.m, self.chunks)
+        with torch.cuda.stream(compute_stream):
+            self.h_toi.barrier()
+
+    def local(self):
+        lo = self.rank * self.m
+        return self.toi[lo:lo + self.m], self.tri[lo:lo + self.m]
+
+    def full(self):
+        return self.toi, self.tri
