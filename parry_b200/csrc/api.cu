@@ -20,6 +20,7 @@ int pb2_pipeline_init(pb2_ctx* ctx) {
     PB2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     PB2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
     PB2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; ++i) PB2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_peer[i], cudaStreamNonBlocking));
     for (int i = 0; i < 64; ++i) PB2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
     return PB2_OK;
 }
@@ -69,7 +70,7 @@ int pb2_ctx_destroy(pb2_ctx* ctx) {
     for (auto& s : ctx->scratch) if (s.ptr) cudaFree(s.ptr);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
-    if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); cudaStreamDestroy(ctx->copy_out); if (ctx->compute2) cudaStreamDestroy(ctx->compute2); for (int i = 0; i < 64; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]); }
+    if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); cudaStreamDestroy(ctx->copy_out); if (ctx->compute2) cudaStreamDestroy(ctx->compute2); for (int i = 0; i < 6; ++i) if (ctx->copy_peer[i]) cudaStreamDestroy(ctx->copy_peer[i]); for (int i = 0; i < 64; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PB2_OK;

@@ -31,6 +31,7 @@ struct pb2_ctx {
     uint64_t* d_counters = nullptr;  // 16 x u64 device
     // copy/compute pipeline for PB2_MEM_HOST batches: H2D stream, D2H stream, event pool
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t copy_peer[6] = {nullptr};  // peer pushes of the multi-GPU gather: one DMA queue per group of peers
     cudaStream_t compute2 = nullptr;  // second compute stream: consecutive host-mode ray chunks alternate so that one chunk's tail overlaps the next one's start
     int ray_slot = 8;                 // d_counters slot of the persistent ray kernels' fetch counter (8 or 12, one per compute stream)
     cudaEvent_t ev[64] = {nullptr};

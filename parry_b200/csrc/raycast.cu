@@ -503,11 +503,10 @@ int pb2_trimesh_cast_rays_allgather(pb2_ctx* ctx, const pb2_trimesh* mesh, const
             PB2_CUDA(ctx, cudaEventRecord(e_k, ctx->stream));
             // push this slice into every peer's gather buffers: device-to-device copies over NVLink on the copy engines (no SM is
             // taken from the persistent traversal kernel, which an NCCL kernel would have to wait for)
-            PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, e_k, 0));
-            PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, e_k, 0));
+            for (int q = 0; q < 6; ++q) PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_peer[q], e_k, 0));
             for (int p = 0; p < n_peers; ++p) {
                 if (p == self) continue;
-                cudaStream_t cs = (p & 1) ? ctx->copy_out : ctx->copy_in;
+                cudaStream_t cs = ctx->copy_peer[((p - self + n_peers) % n_peers) % 6];  // spread peers over the DMA queues
                 PB2_CUDA(ctx, cudaMemcpyAsync((float*)peer_toi[p] + elem_offset + lo, my_toi + lo, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, cs));
                 PB2_CUDA(ctx, cudaMemcpyAsync((uint32_t*)peer_tri[p] + elem_offset + lo, my_tri + lo, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, cs));
             }
@@ -517,10 +516,8 @@ int pb2_trimesh_cast_rays_allgather(pb2_ctx* ctx, const pb2_trimesh* mesh, const
     }
     ctx->stream = main_stream; ctx->ray_slot = 8;
     // everything this call enqueued joins the context's stream again
-    cudaEvent_t e1 = pb2_next_event(ctx), e2 = pb2_next_event(ctx), e3 = pb2_next_event(ctx);
-    cudaEventRecord(e1, ctx->copy_in); cudaStreamWaitEvent(main_stream, e1, 0);
-    cudaEventRecord(e2, ctx->copy_out); cudaStreamWaitEvent(main_stream, e2, 0);
-    if (dual) { cudaEventRecord(e3, ctx->compute2); cudaStreamWaitEvent(main_stream, e3, 0); }
+    for (int q = 0; q < 6; ++q) { cudaEvent_t e = pb2_next_event(ctx); cudaEventRecord(e, ctx->copy_peer[q]); cudaStreamWaitEvent(main_stream, e, 0); }
+    if (dual) { cudaEvent_t e3 = pb2_next_event(ctx); cudaEventRecord(e3, ctx->compute2); cudaStreamWaitEvent(main_stream, e3, 0); }
     if (rc != PB2_OK) return rc;
     PB2_CUDA(ctx, cudaGetLastError());
     return PB2_OK;
