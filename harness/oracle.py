@@ -259,6 +259,8 @@ def shape_aabbs(kinds, params, poses, points=None, first=None, count=None):
 # ---------------------------------------------------------------- query::contact
 _EXTRA.append(("pb2o_contact_batch", None, [P, P, P, P, P, P, P, f32, u32, i32, P, P, P]))
 _EXTRA.append(("pb2o_dispatch_contact", i32, [P, P, P, u32, u32, P, f32, P]))
+_EXTRA.append(("pb2o_distance_batch", None, [P, P, P, u32, P, P, P, P, u32, i32, P, P]))
+_EXTRA.append(("pb2o_intersection_test_batch", None, [P, P, P, u32, P, P, P, P, u32, i32, P, P]))
 _EXTRA.append(("pb2o_gjk_closest_points", i32, [P, P, P, u32, u32, P, f32, P]))
 
 
@@ -297,6 +299,27 @@ class ShapeTable:
                                  p1.ctypes.data, p2.ctypes.data, prediction, n, threads, out.ctypes.data, status.ctypes.data,
                                  None if stats is None else stats.ctypes.data)
         return (out, status, stats) if with_stats else (out, status)
+
+    def distance(self, shape1, pos1, shape2, pos2, threads=1):
+        """query::distance per pair: (dist (n,), status (n,): 0 Ok, 2 Unsupported, 3 cuboid-cuboid)."""
+        s1, s2, p1, p2 = _u32(shape1), _u32(shape2), _f32(pos1), _f32(pos2)
+        n = len(s1)
+        out = np.zeros(n, dtype=np.float32)
+        status = np.zeros(n, dtype=np.uint8)
+        lib().pb2o_distance_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, len(self.kinds), s1.ctypes.data,
+                                  s2.ctypes.data, p1.ctypes.data, p2.ctypes.data, n, threads, out.ctypes.data, status.ctypes.data)
+        return out, status
+
+    def intersection_test(self, shape1, pos1, shape2, pos2, threads=1):
+        """query::intersection_test per pair: (hit (n,) u8, status (n,))."""
+        s1, s2, p1, p2 = _u32(shape1), _u32(shape2), _f32(pos1), _f32(pos2)
+        n = len(s1)
+        out = np.zeros(n, dtype=np.uint8)
+        status = np.zeros(n, dtype=np.uint8)
+        lib().pb2o_intersection_test_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, len(self.kinds),
+                                           s1.ctypes.data, s2.ctypes.data, p1.ctypes.data, p2.ctypes.data, n, threads, out.ctypes.data,
+                                           status.ctypes.data)
+        return out, status
 
     def dispatch_contact(self, s1, s2, pos12, prediction):
         """DefaultQueryDispatcher::contact(pos12, g1, g2, prediction): (status, contact[13]) in local frames."""

@@ -192,6 +192,16 @@ int pb2_contact_batch_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint
                               const float* pos1, const float* pos2, float prediction, uint32_t n, pb2_contact* out,
                               uint32_t* pair_index, uint64_t cap, uint64_t* count, int mem);
 
+/* query::distance(pos1, g1, pos2, g2) (query/distance/distance.rs:89-97) and query::intersection_test (query/intersection_test/
+ * intersection_test.rs:88-96) for n pairs, through the same arms as DefaultQueryDispatcher (default_query_dispatcher.rs:104-236):
+ * ball-ball closed forms, ball vs cuboid / hull by point projection, support-map pairs by GJK. status[k]: 0 = Ok (dist[k] /
+ * hit[k] valid), 2 = Err(Unsupported) (unknown shape), 3 = cuboid-cuboid pair: the reference's SAT arm is not built here, the
+ * host answers it (dispatcher chain). */
+int pb2_distance_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1 /* n x 7 */,
+                       const float* pos2 /* n x 7 */, uint32_t n, float* dist, uint8_t* status, int mem);
+int pb2_intersection_test_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
+                                const float* pos2, uint32_t n, uint8_t* hit, uint8_t* status, int mem);
+
 /* Narrow phase straight from a broad-phase pair list (BASELINE config 5: Bvh pair query feeding per-pair contacts; the
  * loop a caller such as rapier runs over the pairs reported by Bvh::traverse_bvtt_single_tree /
  * Bvh::leaf_pairs, bvh_traverse_bvtt.rs:19,210, calling query::contact, contact_shape_shape.rs:123, on each):

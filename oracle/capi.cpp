@@ -264,6 +264,37 @@ void pb2o_trimesh_contact_batch(void* mesh, const float* mesh_pose7, const uint8
         }
     });
 }
+// query::distance / query::intersection_test for n pairs (distance.rs:89-97, intersection_test.rs:88-96). status: 0 Ok, 2 Unsupported
+// (bad shape id), 3 cuboid-cuboid (SAT arm, not restated).
+void pb2o_distance_batch(const uint8_t* kinds, const float* params4, const float* points, uint32_t n_shapes, const uint32_t* shape1,
+                         const uint32_t* shape2, const float* pos1, const float* pos2, uint32_t n, int nthreads, float* out, uint8_t* status) {
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            out[k] = 0.0f;
+            if (shape1[k] >= n_shapes || shape2[k] >= n_shapes) { status[k] = QUERY_UNSUPPORTED; continue; }
+            ShapeRef s1 = make_shape(kinds, params4, points, shape1[k]), s2 = make_shape(kinds, params4, points, shape2[k]);
+            Iso pos12 = Iso::from7(pos1 + 7 * k).inv_mul(Iso::from7(pos2 + 7 * k));
+            Real d = 0;
+            status[k] = (uint8_t)dispatch_distance(pos12, s1, s2, d);
+            out[k] = d;
+        }
+    });
+}
+void pb2o_intersection_test_batch(const uint8_t* kinds, const float* params4, const float* points, uint32_t n_shapes, const uint32_t* shape1,
+                                  const uint32_t* shape2, const float* pos1, const float* pos2, uint32_t n, int nthreads, uint8_t* out,
+                                  uint8_t* status) {
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            out[k] = 0;
+            if (shape1[k] >= n_shapes || shape2[k] >= n_shapes) { status[k] = QUERY_UNSUPPORTED; continue; }
+            ShapeRef s1 = make_shape(kinds, params4, points, shape1[k]), s2 = make_shape(kinds, params4, points, shape2[k]);
+            Iso pos12 = Iso::from7(pos1 + 7 * k).inv_mul(Iso::from7(pos2 + 7 * k));
+            bool b = false;
+            status[k] = (uint8_t)dispatch_intersection_test(pos12, s1, s2, b);
+            out[k] = b ? 1 : 0;
+        }
+    });
+}
 // DefaultQueryDispatcher::contact(pos12, ...) — results in the local frames of shape 1 / shape 2.
 int pb2o_dispatch_contact(const uint8_t* kinds, const float* params4, const float* points, uint32_t s1, uint32_t s2, const float* pos12, float prediction, float* out13) {
     ShapeRef a = make_shape(kinds, params4, points, s1), b = make_shape(kinds, params4, points, s2);

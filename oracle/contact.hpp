@@ -208,6 +208,92 @@ static inline int query_contact(const Iso& pos1, const ShapeRef& g1, const Iso& 
     return st;
 }
 
+// PointQuery::project_local_point(pt, solid = true) for Cuboid (point_cuboid.rs:8-12 -> point_aabb.rs:9-60) and ConvexPolyhedron
+// (point_support_map.rs:17-52: GJK projection; an inside point projects on itself when solid).
+static inline void project_local_point_solid(const ShapeRef& s, const Vec3& pt, Vec3& proj, bool& inside) {
+    if (s.kind == SHAPE_CUBOID) {
+        Vec3 mins = -s.half_extents, maxs = s.half_extents, zero;
+        Vec3 shift = vsup(mins - pt, zero) - vsup(pt - maxs, zero);
+        inside = shift.x == 0.0f && shift.y == 0.0f && shift.z == 0.0f;
+        proj = inside ? pt : pt + shift;
+        return;
+    }
+    SupportShape shape = s.support();
+    Iso m(Quat(), -pt), m_inv(Quat(), pt);
+    Vec3 dir;
+    if (!try_normalize(-m.tra, DEFAULT_EPSILON, dir)) dir = Vec3(1, 0, 0);
+    SupportShape origin = SupportShape::constant_origin();
+    VoronoiSimplex simplex;
+    simplex.reset(CSOPoint::from_shapes(m_inv, shape, origin, dir));
+    GJKResult r = gjk_closest_points(m.inverse(), shape, origin, REAL_MAX, simplex);
+    if (r.kind == GJKResult::CLOSEST_POINTS) { proj = r.p1; inside = false; }
+    else { proj = pt; inside = true; }
+}
+
+enum QueryStatus { QUERY_OK = 0, QUERY_UNSUPPORTED = 2, QUERY_NEEDS_HOST = 3 };
+
+// DefaultQueryDispatcher::distance (default_query_dispatcher.rs:177-236) for Ball / Cuboid / ConvexPolyhedron. The cuboid-cuboid
+// arm (SAT + segment closest points, distance_cuboid_cuboid.rs) is not restated: QUERY_NEEDS_HOST.
+static inline int dispatch_distance(const Iso& pos12, const ShapeRef& s1, const ShapeRef& s2, Real& out) {
+    out = 0.0f;
+    if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_BALL) {  // distance_ball_ball.rs
+        Real d2 = norm_squared(pos12.tra), sum = s1.radius + s2.radius;
+        out = d2 <= sum * sum ? 0.0f : sqrtf(d2) - sum;
+        return QUERY_OK;
+    }
+    if (s1.kind == SHAPE_BALL || s2.kind == SHAPE_BALL) {  // distance_ball_convex_polyhedron.rs
+        bool ball_first = s1.kind == SHAPE_BALL;
+        Iso p = ball_first ? pos12.inverse() : pos12;
+        const ShapeRef& cv = ball_first ? s2 : s1;
+        Real r = ball_first ? s1.radius : s2.radius;
+        Vec3 center = p.tra, proj; bool inside;
+        project_local_point_solid(cv, center, proj, inside);
+        Real d = norm(center - proj) - r;     // na::distance(&proj.point, &center2_1)
+        out = d > 0.0f ? d : 0.0f;             // .max(0.0)
+        return QUERY_OK;
+    }
+    if (s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_CUBOID) return QUERY_NEEDS_HOST;
+    // distance_support_map_support_map.rs
+    SupportShape g1 = s1.support(), g2 = s2.support();
+    VoronoiSimplex simplex;
+    Vec3 dir;
+    if (!try_normalize(-pos12.tra, DEFAULT_EPSILON, dir)) dir = Vec3(1, 0, 0);
+    simplex.reset(CSOPoint::from_shapes(pos12, g1, g2, dir));
+    GJKResult r = gjk_closest_points(pos12, g1, g2, REAL_MAX, simplex);
+    out = r.kind == GJKResult::CLOSEST_POINTS ? norm(r.p2 - r.p1) : 0.0f;
+    return QUERY_OK;
+}
+
+// DefaultQueryDispatcher::intersection_test (default_query_dispatcher.rs:104-175), same shapes, same restriction.
+static inline int dispatch_intersection_test(const Iso& pos12, const ShapeRef& s1, const ShapeRef& s2, bool& out) {
+    out = false;
+    if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_BALL) {  // intersection_test_ball_ball.rs
+        Real d2 = norm_squared(pos12.tra), sum = s1.radius + s2.radius;
+        out = d2 <= sum * sum;
+        return QUERY_OK;
+    }
+    if (s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_CUBOID) return QUERY_NEEDS_HOST;
+    if (s1.kind == SHAPE_BALL || s2.kind == SHAPE_BALL) {  // intersection_test_ball_point_query.rs
+        bool ball_first = s1.kind == SHAPE_BALL;
+        Iso p = ball_first ? pos12.inverse() : pos12;
+        const ShapeRef& pq = ball_first ? s2 : s1;
+        Real r = ball_first ? s1.radius : s2.radius;
+        Vec3 c = p.tra, proj; bool inside;
+        project_local_point_solid(pq, c, proj, inside);
+        out = inside || norm_squared(c - proj) <= r * r;
+        return QUERY_OK;
+    }
+    // intersection_test_support_map_support_map.rs
+    SupportShape g1 = s1.support(), g2 = s2.support();
+    VoronoiSimplex simplex;
+    Vec3 dir;
+    if (!try_normalize(pos12.tra, DEFAULT_EPSILON, dir)) dir = Vec3(1, 0, 0);
+    simplex.reset(CSOPoint::from_shapes(pos12, g1, g2, dir));
+    GJKResult r = gjk_closest_points(pos12, g1, g2, 0.0f, simplex, false);
+    out = r.kind == GJKResult::INTERSECTION;
+    return QUERY_OK;
+}
+
 // Shape::compute_aabb(pos) for the supported shapes (aabb_ball.rs:8-33, aabb_cuboid.rs:9-16, aabb_convex_polyhedron.rs:8-16)
 static inline Aabb shape_compute_aabb(const ShapeRef& s, const Iso& pos) {
     if (s.kind == SHAPE_BALL) { Real r = s.radius; return Aabb(pos.tra + Vec3(-r, -r, -r), pos.tra + Vec3(r, r, r)); }

@@ -344,7 +344,9 @@ static inline void gjk_result(const VoronoiSimplex& s, bool prev, Vec3& r0, Vec3
 }
 
 // gjk.rs:353-453 with exact_dist = true
-static inline GJKResult gjk_closest_points(const Iso& pos12, const SupportShape& g1, const SupportShape& g2, Real max_dist, VoronoiSimplex& simplex) {
+// gjk.rs:353-453. exact_dist = false (intersection_test) answers PROXIMITY as soon as a separating direction is known.
+static inline GJKResult gjk_closest_points(const Iso& pos12, const SupportShape& g1, const SupportShape& g2, Real max_dist, VoronoiSimplex& simplex,
+                                           bool exact_dist = true) {
     const Real eps_tol = gjk_eps_tol();
     const Real eps_rel = sqrtf(eps_tol);
     GJKResult res;
@@ -363,22 +365,27 @@ static inline GJKResult gjk_closest_points(const Iso& pos12, const SupportShape&
         if (try_normalize_and_get(-proj, eps_tol, dir, dist)) max_bound = dist;
         else { res.kind = GJKResult::INTERSECTION; res.niter = niter; return res; }
         if (max_bound >= old_max_bound) {
+            if (!exact_dist) { res.kind = GJKResult::PROXIMITY; res.dir = old_dir; res.niter = niter; return res; }
             res.kind = GJKResult::CLOSEST_POINTS; gjk_result(simplex, true, res.p1, res.p2); res.dir = old_dir; res.niter = niter; return res;
         }
         CSOPoint cso = CSOPoint::from_shapes(pos12, g1, g2, dir);
         Real min_bound = -dot(dir, cso.point);
         assert(std::isfinite(min_bound));
         if (min_bound > max_dist) { res.kind = GJKResult::NO_INTERSECTION; res.dir = dir; res.niter = niter; return res; }
+        else if (!exact_dist && min_bound > 0.0f && max_bound <= max_dist) { res.kind = GJKResult::PROXIMITY; res.dir = old_dir; res.niter = niter; return res; }
         else if (max_bound - min_bound <= eps_rel * max_bound) {
+            if (!exact_dist) { res.kind = GJKResult::PROXIMITY; res.dir = dir; res.niter = niter; return res; }
             res.kind = GJKResult::CLOSEST_POINTS; gjk_result(simplex, false, res.p1, res.p2); res.dir = dir; res.niter = niter; return res;
         }
         if (!simplex.add_point(cso)) {
+            if (!exact_dist) { res.kind = GJKResult::PROXIMITY; res.dir = dir; res.niter = niter; return res; }
             res.kind = GJKResult::CLOSEST_POINTS; gjk_result(simplex, false, res.p1, res.p2); res.dir = dir; res.niter = niter; return res;
         }
         old_dir = dir;
         proj = simplex.project_origin_and_reduce();
         if (simplex.dimension() == 3) {
             if (min_bound >= eps_tol) {
+                if (!exact_dist) { res.kind = GJKResult::PROXIMITY; res.dir = old_dir; res.niter = niter; return res; }
                 res.kind = GJKResult::CLOSEST_POINTS; gjk_result(simplex, true, res.p1, res.p2); res.dir = old_dir; res.niter = niter; return res;
             }
             res.kind = GJKResult::INTERSECTION; res.niter = niter; return res;

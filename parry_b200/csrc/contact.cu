@@ -11,9 +11,11 @@
 //
 // B200 design: phase 1 (k_contact_gjk) runs one pair per thread: pose composition, dispatch, the closed forms and the
 // GJK loop; pairs whose GJK ends in `Intersection` park their simplex in a compact queue (warp-aggregated append).
-// Phase 2 (k_contact_epa) is a persistent grid that pulls queued pairs and runs the expanding polytope with a bounded
-// per-thread arena (vertices / faces / heap) so that divergence of the rare, long EPA runs does not stall the
-// closed-form and separated pairs. Contacts are written either densely (status per pair) or compacted.
+// Phase 2 (k_contact_epa2) is a persistent grid that pulls queued pairs and runs the expanding polytope with a bounded
+// per-thread arena (vertices / faces / heap) as a flattened state machine, so that divergence of the long EPA runs
+// does not stall the closed-form and separated pairs. Contacts are written either densely (status per pair) or
+// compacted. The same two phases serve per-pair arrays, broad-phase pair lists (collider tables read through the list)
+// and TriMesh-vs-shape candidates (shape 1 = a mesh triangle), see PairSrc.
 #include "gjk.cuh"
 #include "trimesh.cuh"
 #include <stdlib.h>
@@ -24,10 +26,6 @@ int pb2_stage_back(pb2_ctx* ctx, void* dst, const void* dev, size_t bytes, int m
 
 enum { ST_NONE = 0, ST_SOME = 1, ST_UNSUPPORTED = 2, ST_NEEDS_HOST = 3 };
 
-#define EPA_MAX_VERTS 112   // 4 (simplex) + <= 102 expansions
-#define EPA_MAX_FACES 320
-#define EPA_MAX_SIL 64
-#define EPA_STACK 96
 
 struct ContactOut {
     V3 p1, p2, n1, n2;
@@ -381,274 +379,6 @@ __global__ void __launch_bounds__(128) k_contact_gjk(const uint8_t* __restrict__
     }
     if (st == ST_SOME) to_world(ps, c);
     emit(out, k, st, c);
-}
-
-// ------------------------------------------------------------------------------------------- phase 2: EPA
-struct EFace {
-    V3 normal;
-    float bc[3];
-    uint16_t adj[3];
-    uint8_t pts[3];
-    uint8_t deleted;
-};
-struct HeapEnt { float neg_dist; uint32_t id; };
-
-struct EpaArena {
-    CSO verts[EPA_MAX_VERTS];
-    EFace faces[EPA_MAX_FACES];
-    HeapEnt heap[EPA_MAX_FACES];
-    uint16_t sil_face[EPA_MAX_SIL];
-    uint8_t sil_opp[EPA_MAX_SIL];
-    uint16_t stk_face[EPA_STACK];
-    uint8_t stk_opp[EPA_STACK];
-    int nverts, nfaces, nheap, nsil;
-    bool overflow;
-};
-
-// Rust BinaryHeap<FaceId> (max-heap on neg_dist): sift_up / sift_down_to_bottom
-__device__ __forceinline__ bool he_le(const HeapEnt& a, const HeapEnt& b) { return !(a.neg_dist > b.neg_dist); }
-__device__ __forceinline__ void heap_sift_up(EpaArena& A, int start, int pos) {
-    HeapEnt elt = A.heap[pos];
-    while (pos > start) {
-        int parent = (pos - 1) / 2;
-        if (he_le(elt, A.heap[parent])) break;
-        A.heap[pos] = A.heap[parent];
-        pos = parent;
-    }
-    A.heap[pos] = elt;
-}
-__device__ __forceinline__ void heap_push(EpaArena& A, uint32_t id, float neg_dist) {
-    int old = A.nheap;
-    A.heap[old].id = id; A.heap[old].neg_dist = neg_dist;
-    A.nheap = old + 1;
-    heap_sift_up(A, 0, old);
-}
-__device__ __forceinline__ HeapEnt heap_pop(EpaArena& A) {
-    HeapEnt item = A.heap[A.nheap - 1];
-    A.nheap -= 1;
-    if (A.nheap > 0) {
-        HeapEnt t = item; item = A.heap[0]; A.heap[0] = t;
-        int end = A.nheap, pos = 0;
-        HeapEnt elt = A.heap[0];
-        int child = 1;
-        while (end >= 2 && child <= end - 2) {
-            if (he_le(A.heap[child], A.heap[child + 1])) child += 1;
-            A.heap[pos] = A.heap[child];
-            pos = child;
-            child = 2 * pos + 1;
-        }
-        if (child == end - 1) { A.heap[pos] = A.heap[child]; pos = child; }
-        A.heap[pos] = elt;
-        heap_sift_up(A, 0, pos);
-    }
-    return item;
-}
-
-// Face::new (epa3.rs:96-118) + new_with_proj (:65-94)
-__device__ __forceinline__ bool epa_face_new(EpaArena& A, int slot, int p0, int p1, int p2, int a0, int a1, int a2) {
-    V3 va = A.verts[p0].point, vb = A.verts[p1].point, vc = A.verts[p2].point;
-    Proj p;
-    project_on_triangle(va, vb, vc, mk3(0.f, 0.f, 0.f), p);
-    bool inside;
-    float bc[3] = {0.f, 0.f, 0.f};
-    if (p.kind == 0) { bc[p.idx] = 1.0f; }
-    if (p.kind == 1) {
-        int i0 = p.idx == 1 ? 1 : 0, i1 = p.idx == 0 ? 1 : 2;
-        bc[i0] = p.bc[0]; bc[i1] = p.bc[1];
-    }
-    if (p.kind == 0 || p.kind == 1) {
-        const float eps_tol = PB2_EPS * 100.0f;
-        inside = p.inside || nrm2(p.point - mk3(0.f, 0.f, 0.f)) < eps_tol * eps_tol;
-    } else if (p.kind == 2) { bc[0] = p.bc[0]; bc[1] = p.bc[1]; bc[2] = p.bc[2]; inside = true; }
-    else inside = false;
-    EFace f;
-    V3 n; float nn;
-    if (!try_normalize_get(cross3(vb - va, vc - va), PB2_EPS, n, nn)) n = mk3(0.f, 0.f, 0.f);  // ccw_face_normal
-    f.normal = n;
-    f.bc[0] = bc[0]; f.bc[1] = bc[1]; f.bc[2] = bc[2];
-    f.pts[0] = (uint8_t)p0; f.pts[1] = (uint8_t)p1; f.pts[2] = (uint8_t)p2;
-    f.adj[0] = (uint16_t)a0; f.adj[1] = (uint16_t)a1; f.adj[2] = (uint16_t)a2;
-    f.deleted = 0;
-    A.faces[slot] = f;
-    return inside;
-}
-__device__ __forceinline__ int epa_next_ccw(const EFace& f, int id) {
-    if (f.pts[0] == id) return 1;
-    if (f.pts[1] == id) return 2;
-    return 0;
-}
-__device__ __forceinline__ bool epa_can_be_seen_by(const EpaArena& A, const EFace& f, int point, int opp) {
-    V3 p0 = A.verts[f.pts[opp]].point;
-    V3 p1 = A.verts[f.pts[(opp + 1) % 3]].point;
-    V3 p2 = A.verts[f.pts[(opp + 2) % 3]].point;
-    V3 pt = A.verts[point].point;
-    if (dot3(pt - p0, f.normal) >= -PB2_GJK_EPS_TOL) return true;
-    // Triangle::new(p1, p2, pt).is_affinely_dependent()
-    const float EPS = PB2_EPS * 100.0f;
-    return rel_eq(nrm2(cross3(p2 - p1, pt - p1)), 0.0f, EPS * EPS, PB2_EPS);
-}
-// compute_silhouette (epa3.rs:653-675): the reference recursion (adj1 fully, then adj2) as an explicit DFS stack.
-__device__ __forceinline__ void epa_silhouette(EpaArena& A, int point, int id, int opp) {
-    int sp = 0;
-    A.stk_face[sp] = (uint16_t)id; A.stk_opp[sp] = (uint8_t)opp; sp++;
-    while (sp > 0) {
-        --sp;
-        int fid = A.stk_face[sp], fo = A.stk_opp[sp];
-        EFace& f = A.faces[fid];
-        if (f.deleted) continue;
-        if (!epa_can_be_seen_by(A, f, point, fo)) {
-            if (A.nsil >= EPA_MAX_SIL) { A.overflow = true; return; }
-            A.sil_face[A.nsil] = (uint16_t)fid; A.sil_opp[A.nsil] = (uint8_t)fo; A.nsil++;
-        } else {
-            f.deleted = 1;
-            int i1 = (fo + 2) % 3, i2 = fo;
-            int adj1 = f.adj[i1], adj2 = f.adj[i2];
-            int o1 = epa_next_ccw(A.faces[adj1], f.pts[i1]);
-            int o2 = epa_next_ccw(A.faces[adj2], f.pts[i2]);
-            if (sp + 2 > EPA_STACK) { A.overflow = true; return; }
-            // push adj2 first so adj1 is processed (fully) first
-            A.stk_face[sp] = (uint16_t)adj2; A.stk_opp[sp] = (uint8_t)o2; sp++;
-            A.stk_face[sp] = (uint16_t)adj1; A.stk_opp[sp] = (uint8_t)o1; sp++;
-        }
-    }
-}
-__device__ __forceinline__ void epa_face_closest(const EpaArena& A, const EFace& f, V3& p1, V3& p2) {
-    p1 = A.verts[f.pts[0]].o1 * f.bc[0] + A.verts[f.pts[1]].o1 * f.bc[1] + A.verts[f.pts[2]].o1 * f.bc[2];
-    p2 = A.verts[f.pts[0]].o2 * f.bc[0] + A.verts[f.pts[1]].o2 * f.bc[1] + A.verts[f.pts[2]].o2 * f.bc[2];
-}
-
-// EPA::closest_points (epa3.rs:428-651). Returns 1 Some, 0 None, -1 arena overflow.
-__device__ int epa_closest_points(EpaArena& A, const Iso7& pos12, const DShape& g1, const DShape& g2, int dim, V3& out_p1, V3& out_p2,
-                                  V3& out_n) {
-    const float eps = PB2_EPS;
-    const float eps_tol = eps * 100.0f;
-    A.nfaces = 0; A.nheap = 0; A.nsil = 0; A.overflow = false;
-    if (dim == 0) { out_p1 = mk3(0.f, 0.f, 0.f); out_p2 = out_p1; out_n = mk3(0.f, 1.f, 0.f); return 1; }
-    if (dim == 3) {
-        V3 dp1 = A.verts[1].point - A.verts[0].point, dp2 = A.verts[2].point - A.verts[0].point, dp3 = A.verts[3].point - A.verts[0].point;
-        if (dot3(cross3(dp1, dp2), dp3) > 0.0f) { CSO t = A.verts[1]; A.verts[1] = A.verts[2]; A.verts[2] = t; }
-        bool in0 = epa_face_new(A, 0, 0, 1, 2, 3, 1, 2);
-        bool in1 = epa_face_new(A, 1, 1, 3, 2, 3, 2, 0);
-        bool in2 = epa_face_new(A, 2, 0, 2, 3, 0, 1, 3);
-        bool in3 = epa_face_new(A, 3, 0, 3, 1, 2, 1, 0);
-        A.nfaces = 4;
-        bool ins[4] = {in0, in1, in2, in3};
-        for (int k = 0; k < 4; ++k) {
-            if (ins[k]) {
-                float dist = dot3(A.faces[k].normal, A.verts[k].point);
-                if (-dist > PB2_GJK_EPS_TOL) return 0;  // FaceId::new(..)?
-                heap_push(A, (uint32_t)k, -dist);
-            }
-        }
-        if (!(in0 || in1 || in2 || in3)) return 0;
-    } else {
-        if (dim == 1) {
-            V3 dpt = A.verts[1].point - A.verts[0].point;
-            V3 a = fabsf(dpt.x) > fabsf(dpt.y) ? mk3(dpt.z, 0.0f, -dpt.x) : mk3(0.0f, -dpt.z, dpt.y);
-            a = normalize3(a);
-            V3 dir = cross3(a, dpt);
-            A.verts[A.nverts++] = cso_from_shapes(pos12, g1, g2, dir);
-        }
-        epa_face_new(A, 0, 0, 1, 2, 1, 1, 1);
-        epa_face_new(A, 1, 0, 2, 1, 0, 0, 0);
-        A.nfaces = 2;
-        heap_push(A, 0u, 0.0f);
-        heap_push(A, 1u, 0.0f);
-    }
-    int niter = 0;
-    float max_dist = FLT_MAX;
-    if (A.nheap == 0) return 0;
-    HeapEnt best_face = A.heap[0];
-    float old_dist = 0.0f;
-    while (A.nheap > 0) {
-        HeapEnt face_id = heap_pop(A);
-        EFace face = A.faces[face_id.id];
-        if (face.deleted) continue;
-        if (A.nverts >= EPA_MAX_VERTS) return -1;
-        CSO cso = cso_from_shapes(pos12, g1, g2, face.normal);
-        int support_id = A.nverts;
-        A.verts[A.nverts++] = cso;
-        float candidate = dot3(cso.point, face.normal);
-        if (candidate < max_dist) { best_face = face_id; max_dist = candidate; }
-        float curr_dist = -face_id.neg_dist;
-        if (max_dist - curr_dist < eps_tol || (fabsf(curr_dist - old_dist) < eps && candidate < max_dist)) {
-            const EFace& bf = A.faces[best_face.id];
-            epa_face_closest(A, bf, out_p1, out_p2); out_n = bf.normal;
-            return 1;
-        }
-        old_dist = curr_dist;
-        A.faces[face_id.id].deleted = 1;
-        int o1 = epa_next_ccw(A.faces[face.adj[0]], face.pts[0]);
-        int o2 = epa_next_ccw(A.faces[face.adj[1]], face.pts[1]);
-        int o3 = epa_next_ccw(A.faces[face.adj[2]], face.pts[2]);
-        epa_silhouette(A, support_id, face.adj[0], o1);
-        epa_silhouette(A, support_id, face.adj[1], o2);
-        epa_silhouette(A, support_id, face.adj[2], o3);
-        if (A.overflow) return -1;
-        int first_new = A.nfaces;
-        if (A.nsil == 0) return 0;
-        for (int e = 0; e < A.nsil; ++e) {
-            int efid = A.sil_face[e], eopp = A.sil_opp[e];
-            if (!A.faces[efid].deleted) {
-                int new_id = A.nfaces;
-                if (new_id >= EPA_MAX_FACES) return -1;
-                int pt1 = A.faces[efid].pts[(eopp + 2) % 3], pt2 = A.faces[efid].pts[(eopp + 1) % 3];
-                bool inside = epa_face_new(A, new_id, pt1, pt2, support_id, efid, new_id + 1, new_id - 1);
-                A.faces[efid].adj[(eopp + 1) % 3] = (uint16_t)new_id;
-                A.nfaces = new_id + 1;
-                if (inside) {
-                    V3 pt = A.verts[A.faces[new_id].pts[0]].point;
-                    float dist = dot3(A.faces[new_id].normal, pt);
-                    if (dist < curr_dist) { epa_face_closest(A, face, out_p1, out_p2); out_n = face.normal; return 1; }
-                    if (-dist > PB2_GJK_EPS_TOL) return 0;
-                    heap_push(A, (uint32_t)new_id, -dist);
-                }
-            }
-        }
-        if (first_new == A.nfaces) return 0;
-        A.faces[first_new].adj[2] = (uint16_t)(A.nfaces - 1);
-        A.faces[A.nfaces - 1].adj[1] = (uint16_t)first_new;
-        A.nsil = 0;
-        niter += 1;
-        if (niter > 100) break;
-    }
-    const EFace& bf = A.faces[best_face.id];
-    epa_face_closest(A, bf, out_p1, out_p2); out_n = bf.normal;
-    return 1;
-}
-
-__global__ void __launch_bounds__(64) k_contact_epa(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
-                             const float4* __restrict__ pts, PairSrc src, float prediction, OutSinks out,
-                             const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
-                             unsigned long long* __restrict__ next_job, EpaArena* __restrict__ arenas) {
-    EpaArena& A = arenas[blockIdx.x * blockDim.x + threadIdx.x];
-    unsigned long long total = *job_count;
-    for (;;) {
-        unsigned long long j = atomicAdd(next_job, 1ull);
-        if (j >= total) break;
-        const EpaJob& job = jobs[j];
-        uint32_t k = job.pair;
-        PairSetup ps;
-        pair_setup(kinds, params, pts, src, k, ps);
-        int dim = (int)job.dim;
-        for (int i = 0; i <= dim; ++i) {
-            V3 o1 = mk3(job.o1[i][0], job.o1[i][1], job.o1[i][2]), o2 = mk3(job.o2[i][0], job.o2[i][1], job.o2[i][2]);
-            A.verts[i] = cso_make(o1, o2);
-        }
-        A.nverts = dim + 1;
-        V3 p1, p2, n1;
-        int r = epa_closest_points(A, ps.gpos12, ps.g1, ps.g2, dim, p1, p2, n1);
-        ContactOut c;
-        int st;
-        if (r < 0) st = ST_NEEDS_HOST;
-        else if (r == 0) {
-            // support-map pair: "Everything failed" => NoIntersection => None. Hull projection: PointProjection(true, point).
-            if (ps.mode == 1) st = ST_NONE;
-            else st = finish_gjk_pair(ps, true, ps.cb_pos12.t, p2, n1, prediction, c);
-        } else st = finish_gjk_pair(ps, true, p1, p2, n1, prediction, c);
-        if (st == ST_SOME) to_world(ps, c);
-        emit(out, k, st, c);
-    }
 }
 
 // ------------------------------------------------------------------------------------------- phase 2, flattened
@@ -1453,7 +1183,7 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
     src.n_first = mesh_tris ? n_tris : n_colliders; src.n_second = n_colliders;
     cudaStream_t st = ctx->stream;
     // EPA job queue (worst case: every pair) + arenas for the persistent EPA grid
-    int epa_variant = 2, refill = 8;  // 1, 2 (default): 14 KB arenas; 3: compact arena — 4x less DRAM traffic, same time
+    int epa_variant = 2, refill = 8;  // 2 (default): 14 KB arenas; 3: compact arena — 4x less DRAM traffic, same time
     {
         const char* e = getenv("PB2_EPA_VARIANT");
         if (e) epa_variant = atoi(e);
@@ -1468,12 +1198,7 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
     k_contact_gjk<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, src,
                                                      prediction, n, sinks, jobs, job_count);
     PB2_LAUNCHED(ctx);
-    if (epa_variant == 1) {
-        int epa_threads = 64, epa_blocks = ctx->sm_count * 4;
-        PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)epa_threads * epa_blocks * sizeof(EpaArena)));
-        k_contact_epa<<<epa_blocks, epa_threads, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction,
-                                                         sinks, jobs, job_count, next_job, (EpaArena*)ctx->scratch[2].ptr);
-    } else if (epa_variant == 3) {
+    if (epa_variant == 3) {
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contact_epac, 128, 0);
         if (per_sm < 1) per_sm = 1;
@@ -1636,6 +1361,120 @@ int pb2_contact_pairs_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint
     if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (total > cap) PB2_FAIL(ctx, PB2_ERR_OVERFLOW, "contact_pairs_compact: %llu contacts > capacity %llu", (unsigned long long)total, (unsigned long long)cap);
     return PB2_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------- distance / intersection_test
+// query::distance (distance.rs:89-97 -> DefaultQueryDispatcher::distance, default_query_dispatcher.rs:177-236) and
+// query::intersection_test (intersection_test.rs:88-96 -> :104-175) for Ball / Cuboid / ConvexPolyhedron pairs: closed forms
+// for ball-ball (distance_ball_ball.rs, intersection_test_ball_ball.rs), point projection with solid = true for ball vs
+// cuboid / hull (distance_ball_convex_polyhedron.rs, intersection_test_ball_point_query.rs, point_aabb.rs:9-60,
+// point_support_map.rs:17-52) and GJK for the support-map pairs (distance_support_map_support_map.rs — initial direction
+// -pos12.translation; intersection_test_support_map_support_map.rs — max_dist 0, exact_dist false). The cuboid-cuboid arm is
+// SAT based in the reference and not built: status 3 (host fallback through the dispatcher chain).
+template <bool DIST>
+__global__ void __launch_bounds__(128) k_query_pairs(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
+                              const float4* __restrict__ pts, uint32_t n_shapes, PairSrc src, uint32_t n, float* __restrict__ out_dist,
+                              uint8_t* __restrict__ out_hit, uint8_t* __restrict__ status) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (DIST) out_dist[k] = 0.0f; else out_hit[k] = 0;
+    if (src.shape1[k] >= n_shapes || src.shape2[k] >= n_shapes) { status[k] = (uint8_t)ST_UNSUPPORTED; return; }
+    PairSetup ps;
+    pair_setup(kinds, params, pts, src, k, ps);
+    bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
+    float dist = 0.0f;
+    bool hit = false;
+    int st = ST_NONE;  // 0 = Ok
+    if (b1 && b2) {
+        float d2 = nrm2(ps.pos12.t), sum = ps.pr1.x + ps.pr2.x;
+        hit = d2 <= sum * sum;
+        dist = hit ? 0.0f : sqrtf(d2) - sum;
+    } else if (b1 || b2) {
+        // ball vs point query: project the ball centre (in the other shape's frame) with solid = true
+        float4 prc = b2 ? ps.pr1 : ps.pr2;
+        uint8_t kc = b2 ? ps.k1 : ps.k2;
+        float radius = b2 ? ps.pr2.x : ps.pr1.x;
+        V3 c = ps.cb_pos12.t, proj;
+        bool inside;
+        if (kc == PB2_SHAPE_CUBOID) {
+            V3 he = mk3(prc.x, prc.y, prc.z), zero = mk3(0.f, 0.f, 0.f);
+            V3 shift = vmax3((-he) - c, zero) - vmax3(c - he, zero);
+            inside = shift.x == 0.0f && shift.y == 0.0f && shift.z == 0.0f;
+            proj = inside ? c : c + shift;
+        } else {
+            Simplex s;
+            V3 dir; float nn;
+            if (!try_normalize_get(c, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
+            Iso7 m_inv; m_inv.q.i = 0.f; m_inv.q.j = 0.f; m_inv.q.k = 0.f; m_inv.q.w = 1.f; m_inv.t = c;
+            sx_reset(s, cso_from_shapes(m_inv, ps.g1, ps.g2, dir));
+            V3 p1, p2, n1;
+            int r = gjk_closest_points<true>(ps.gpos12, ps.g1, ps.g2, FLT_MAX, s, p1, p2, n1);
+            inside = r != GJK_CLOSEST_POINTS;
+            proj = inside ? c : p1;
+        }
+        if (DIST) { float d = nrm(c - proj) - radius; dist = d > 0.0f ? d : 0.0f; }
+        else hit = inside || nrm2(c - proj) <= radius * radius;
+    } else if (ps.k1 == PB2_SHAPE_CUBOID && ps.k2 == PB2_SHAPE_CUBOID) {
+        st = ST_NEEDS_HOST;
+    } else {
+        Simplex s;
+        V3 dir; float nn;
+        V3 d0 = DIST ? -ps.pos12.t : ps.pos12.t;
+        if (!try_normalize_get(d0, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
+        sx_reset(s, cso_from_shapes(ps.gpos12, ps.g1, ps.g2, dir));
+        V3 p1, p2, n1;
+        if (DIST) {
+            int r = gjk_closest_points<true>(ps.gpos12, ps.g1, ps.g2, FLT_MAX, s, p1, p2, n1);
+            dist = r == GJK_CLOSEST_POINTS ? nrm(p2 - p1) : 0.0f;
+        } else {
+            hit = gjk_closest_points<false>(ps.gpos12, ps.g1, ps.g2, 0.0f, s, p1, p2, n1) == GJK_INTERSECTION;
+        }
+    }
+    if (DIST) out_dist[k] = dist; else out_hit[k] = hit ? 1 : 0;
+    status[k] = (uint8_t)st;
+}
+
+static int run_query_pairs(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
+                           const float* pos2, uint32_t n, void* out, size_t out_elem, uint8_t* status, int mem, bool dist) {
+    if (!ctx || !shapes || (n && (!shape1 || !shape2 || !pos1 || !pos2 || !out || !status))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_s1, *d_s2, *d_p1, *d_p2;
+    void *d_out, *d_st;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape1, (size_t)n * 4, mem, &d_s1));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape2, (size_t)n * 4, mem, &d_s2));
+    PB2_CHECK(pb2_stage_in(ctx, 2, pos1, (size_t)n * 28, mem, &d_p1));
+    PB2_CHECK(pb2_stage_in(ctx, 3, pos2, (size_t)n * 28, mem, &d_p2));
+    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * out_elem, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_st));
+    PairSrc src;
+    src.shape1 = (const uint32_t*)d_s1; src.shape2 = (const uint32_t*)d_s2; src.pos1 = (const float*)d_p1; src.pos2 = (const float*)d_p2;
+    src.ab = nullptr; src.mesh_tris = nullptr; src.n_first = src.n_second = 0;
+    if (dist)
+        k_query_pairs<true><<<pb2_blocks(n, 128), 128, 0, ctx->stream>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, src, n, (float*)d_out,
+                                                                        nullptr, (uint8_t*)d_st);
+    else
+        k_query_pairs<false><<<pb2_blocks(n, 128), 128, 0, ctx->stream>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, src, n, nullptr,
+                                                                         (uint8_t*)d_out, (uint8_t*)d_st);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * out_elem, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_st, (size_t)n, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB2_OK;
+}
+
+extern "C" {
+
+int pb2_distance_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1, const float* pos2,
+                       uint32_t n, float* dist, uint8_t* status, int mem) {
+    return run_query_pairs(ctx, shapes, shape1, shape2, pos1, pos2, n, dist, 4, status, mem, true);
+}
+int pb2_intersection_test_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
+                                const float* pos2, uint32_t n, uint8_t* hit, uint8_t* status, int mem) {
+    return run_query_pairs(ctx, shapes, shape1, shape2, pos1, pos2, n, hit, 1, status, mem, false);
 }
 
 // ------------------------------------------------------------------------------------------- TriMesh vs shapes

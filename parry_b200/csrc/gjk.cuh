@@ -312,9 +312,11 @@ __device__ __forceinline__ void gjk_witness(const Simplex& s, bool prev, V3& r0,
     }
 }
 
-enum { GJK_INTERSECTION = 0, GJK_CLOSEST_POINTS = 1, GJK_NO_INTERSECTION = 3 };
+enum { GJK_INTERSECTION = 0, GJK_CLOSEST_POINTS = 1, GJK_PROXIMITY = 2, GJK_NO_INTERSECTION = 3 };
 
-// gjk::closest_points(pos12, g1, g2, max_dist, exact_dist = true, simplex)
+// gjk::closest_points(pos12, g1, g2, max_dist, exact_dist = EXACT, simplex). EXACT = false (intersection_test) answers
+// GJK_PROXIMITY as soon as a separating direction is known (gjk.rs:397-443).
+template <bool EXACT = true>
 __device__ __forceinline__ int gjk_closest_points(const Iso7& pos12, const DShape& g1, const DShape& g2, float max_dist, Simplex& s,
                                                   V3& p1, V3& p2, V3& out_dir) {
     const float eps_tol = PB2_GJK_EPS_TOL;
@@ -333,16 +335,29 @@ __device__ __forceinline__ int gjk_closest_points(const Iso7& pos12, const DShap
         float dist;
         if (try_normalize_get(-proj, eps_tol, dir, dist)) max_bound = dist;
         else return GJK_INTERSECTION;
-        if (max_bound >= old_max_bound) { gjk_witness(s, true, p1, p2); out_dir = old_dir; return GJK_CLOSEST_POINTS; }
+        if (max_bound >= old_max_bound) {
+            if (!EXACT) { out_dir = old_dir; return GJK_PROXIMITY; }
+            gjk_witness(s, true, p1, p2); out_dir = old_dir; return GJK_CLOSEST_POINTS;
+        }
         CSO cso = cso_from_shapes(pos12, g1, g2, dir);
         float min_bound = -dot3(dir, cso.point);
         if (min_bound > max_dist) { out_dir = dir; return GJK_NO_INTERSECTION; }
-        else if (max_bound - min_bound <= eps_rel * max_bound) { gjk_witness(s, false, p1, p2); out_dir = dir; return GJK_CLOSEST_POINTS; }
-        if (!sx_add_point(s, cso)) { gjk_witness(s, false, p1, p2); out_dir = dir; return GJK_CLOSEST_POINTS; }
+        else if (!EXACT && min_bound > 0.0f && max_bound <= max_dist) { out_dir = old_dir; return GJK_PROXIMITY; }
+        else if (max_bound - min_bound <= eps_rel * max_bound) {
+            if (!EXACT) { out_dir = dir; return GJK_PROXIMITY; }
+            gjk_witness(s, false, p1, p2); out_dir = dir; return GJK_CLOSEST_POINTS;
+        }
+        if (!sx_add_point(s, cso)) {
+            if (!EXACT) { out_dir = dir; return GJK_PROXIMITY; }
+            gjk_witness(s, false, p1, p2); out_dir = dir; return GJK_CLOSEST_POINTS;
+        }
         old_dir = dir;
         proj = sx_project_origin_and_reduce(s);
         if (s.dim == 3) {
-            if (min_bound >= eps_tol) { gjk_witness(s, true, p1, p2); out_dir = old_dir; return GJK_CLOSEST_POINTS; }
+            if (min_bound >= eps_tol) {
+                if (!EXACT) { out_dir = old_dir; return GJK_PROXIMITY; }
+                gjk_witness(s, true, p1, p2); out_dir = old_dir; return GJK_CLOSEST_POINTS;
+            }
             return GJK_INTERSECTION;
         }
         niter += 1;

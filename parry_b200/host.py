@@ -523,3 +523,27 @@ def contact_pairs_compact(shapes, collider_shape, collider_pose, pairs, predicti
     ctx.check(ctx._lib.pb2_contact_pairs_compact(ctx.h, shapes.h, ps, pp, nc, pab, n, float(prediction), po, pi, cap, C.byref(cnt), mem))
     c = int(cnt.value)
     return out[:c], idx[:c]
+
+
+def _pair_query(fn_name, out_dtype, shapes, shape1, pos1, shape2, pos2):
+    ctx = shapes.ctx
+    n = int(pos1.shape[0])
+    k1, p1, mem = _prep(pos1, np.float32)
+    k2, p2, _ = _prep(pos2, np.float32, mem)
+    ks1, ps1, _ = _prep(shape1, np.uint32, mem)
+    ks2, ps2, _ = _prep(shape2, np.uint32, mem)
+    out, po = _empty((n,), out_dtype, mem, ctx.torch_device)
+    status, pst = _empty((n,), np.uint8, mem, ctx.torch_device)
+    ctx.check(getattr(ctx._lib, fn_name)(ctx.h, shapes.h, ps1, ps2, p1, p2, n, po, pst, mem))
+    return out, status
+
+
+def distance(shapes, shape1, pos1, shape2, pos2):
+    """query::distance(pos1, g1, pos2, g2), batched (query/distance/distance.rs:89-97): (dist (n,) f32, status (n,) u8: 0 Ok,
+    2 Unsupported, 3 cuboid-cuboid -> host)."""
+    return _pair_query("pb2_distance_batch", np.float32, shapes, shape1, pos1, shape2, pos2)
+
+
+def intersection_test(shapes, shape1, pos1, shape2, pos2):
+    """query::intersection_test(pos1, g1, pos2, g2), batched (intersection_test.rs:88-96): (hit (n,) u8, status (n,) u8)."""
+    return _pair_query("pb2_intersection_test_batch", np.uint8, shapes, shape1, pos1, shape2, pos2)

@@ -1,0 +1,86 @@
+"""query::distance / query::intersection_test: oracle pins from the reference's examples and doc-tests (CPU) and
+GPU parity through the C ABI."""
+import numpy as np
+import pytest
+
+from harness import scenes
+
+I4 = [0.0, 0.0, 0.0, 1.0]
+
+
+def P(t):
+    return np.array([I4 + list(t)], np.float32)
+
+
+def test_oracle_pins_from_reference_examples():
+    from harness import oracle
+    oracle.build()
+    T = oracle.ShapeTable([("ball", 1.0), ("cuboid", [1, 1, 1]), ("ball", 2.0), ("cuboid", [0.5, 0.5, 0.5])])
+    # examples/distance_query3d.rs
+    assert T.distance([0], P([0, 1, 0]), [1], P([0, 0, 0]))[0][0] == 0.0
+    assert abs(T.distance([0], P([0, 3, 0]), [1], P([0, 0, 0]))[0][0] - 1.0) <= 1e-7
+    # examples/proximity_query3d.rs
+    assert T.intersection_test([0], P([1, 1, 1]), [1], P([0, 0, 0]))[0][0] == 1
+    assert T.intersection_test([0], P([3, 3, 3]), [1], P([0, 0, 0]))[0][0] == 0
+    # distance.rs doc-test: balls r = 1 and r = 2, centres 10 apart => exactly 7
+    assert T.distance([0], P([0, 0, 0]), [2], P([10, 0, 0]))[0][0] == np.float32(7.0)
+    # intersection_test.rs doc-test: two unit balls 1.5 apart intersect, 5 apart do not
+    assert T.intersection_test([0], P([0, 0, 0]), [0], P([1.5, 0, 0]))[0][0] == 1
+    assert T.intersection_test([0], P([0, 0, 0]), [0], P([5.0, 0, 0]))[0][0] == 0
+    # cuboid-cuboid is the SAT arm: flagged for the host
+    assert T.distance([1], P([0, 0, 0]), [3], P([5, 0, 0]))[1][0] == 3
+
+
+def make_pairs(seed, n):
+    g = scenes.rng(seed)
+    pts, _ = scenes.hull_pool(12, 32, seed=seed + 1)
+    spec = [("ball", float(r)) for r in g.random(6) * 0.5 + 0.3]
+    spec += [("cuboid", list(h)) for h in g.random((6, 3)) * 0.6 + 0.2]
+    spec += [("convex", p) for p in pts]
+    a = g.integers(0, len(spec), n).astype(np.uint32)
+    b = g.integers(0, len(spec), n).astype(np.uint32)
+    q1, q2 = scenes.random_unit_quaternions(g, n), scenes.random_unit_quaternions(g, n)
+    t1 = (g.random((n, 3)) - 0.5) * 10
+    t2 = t1 + g.standard_normal((n, 3)) * 1.2
+    return spec, a, b, np.concatenate([q1, t1], 1).astype(np.float32), np.concatenate([q2, t2], 1).astype(np.float32)
+
+
+@pytest.mark.gpu
+def test_distance_and_intersection_match_oracle(ctx, oracle):
+    import parry_b200
+    spec, a, b, p1, p2 = make_pairs(91, 80000)
+    gshapes = [parry_b200.Ball(v) if k == "ball" else parry_b200.Cuboid(v) if k == "cuboid" else parry_b200.ConvexPolyhedron(v) for k, v in spec]
+    G, O = parry_b200.Shapes(ctx, gshapes), oracle.ShapeTable(spec)
+    gd, gds = parry_b200.distance(G, a, p1, b, p2)
+    od, ods = O.distance(a, p1, b, p2, threads=8)
+    assert (np.asarray(gds) == ods).all()
+    ok = ods == 0
+    assert 0.05 < (ods == 3).mean() < 0.2           # cuboid-cuboid pairs are flagged for the host
+    assert 0.2 < (od[ok] > 0).mean() < 0.9
+    np.testing.assert_allclose(np.asarray(gd)[ok], od[ok], rtol=1e-5, atol=1e-6)
+    assert (np.asarray(gd)[ok].view(np.uint32) == od[ok].view(np.uint32)).mean() > 0.999
+    gi, gis = parry_b200.intersection_test(G, a, p1, b, p2)
+    oi, ois = O.intersection_test(a, p1, b, p2, threads=8)
+    assert (np.asarray(gis) == ois).all()
+    assert (np.asarray(gi) == oi).all()              # boolean answers: exact
+    ok = ois == 0
+    # consistency of the two queries (same GJK, different exit rules): intersecting <=> distance 0 up to grazing cases
+    agree = (oi[ok] == 1) == (od[ok] == 0.0)
+    assert agree.mean() > 0.999
+    # bad shape id
+    d, st = parry_b200.distance(G, np.array([999], np.uint32), p1[:1], b[:1], p2[:1])
+    assert np.asarray(st)[0] == 2
+
+
+@pytest.mark.gpu
+def test_distance_device_resident(ctx, oracle):
+    import torch
+    import parry_b200
+    spec, a, b, p1, p2 = make_pairs(92, 20000)
+    gshapes = [parry_b200.Ball(v) if k == "ball" else parry_b200.Cuboid(v) if k == "cuboid" else parry_b200.ConvexPolyhedron(v) for k, v in spec]
+    G = parry_b200.Shapes(ctx, gshapes)
+    h = parry_b200.distance(G, a, p1, b, p2)
+    T = lambda x: torch.from_numpy(x.view(np.int32) if x.dtype == np.uint32 else x).cuda()
+    d = parry_b200.distance(G, T(a), T(p1), T(b), T(p2))
+    ctx.synchronize()
+    assert (d[0].cpu().numpy().view(np.uint32) == h[0].view(np.uint32)).all() and (d[1].cpu().numpy() == h[1]).all()
