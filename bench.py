@@ -28,7 +28,7 @@ FMAX = float(np.finfo(np.float32).max)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full captures
 # (profiles/*.json); None when no capture of the current kernel version exists.
-PROFILED_TRAFFIC = {"rays_terrain": 5309194616}  # profiles/r1_rays_v6_wide8_terrain8M_full.json (k_raycast_wide<false, 0>, this workload)
+PROFILED_TRAFFIC = {"rays_terrain": 4570920904}  # profiles/r1_rays_v7_cubic_lbvh_terrain8M_full.json (k_raycast_wide<false, 0>, this workload)
 
 
 def load_peaks():
