@@ -48,7 +48,48 @@ def main():
     out, st = T.contact(a, p1, bb, p2, 0.02)
     np.savez_compressed(os.path.join(HERE, "contacts_mixed_3000.npz"), kinds=T.kinds, params=T.params, points=T.points, shape1=a, shape2=bb,
                         pos1=p1, pos2=p2, prediction=np.float32(0.02), contacts=out, status=st)
+    more()
     print("golden vectors written")
+
+
+def more():
+    """Later additions (culling ray casts, distance / intersection_test, TriMesh-vs-shape contacts); separate files so that the
+    first set stays byte-identical."""
+    z = np.load(os.path.join(HERE, "rays_sphere24x16.npz"))
+    m = oracle.TriMesh(z["vertices"], z["indices"])
+    g = scenes.rng(105)
+    o = (g.random((2000, 3)) - 0.5) * 2.4
+    rays = np.concatenate([o, g.standard_normal((2000, 3))], axis=1).astype(np.float32)
+    res = {}
+    for mode, name in ((1, "ignore_backfaces"), (2, "ignore_frontfaces")):
+        toi, tri, n, f = m.cast_rays(None, rays, FMAX, with_normal=True, mode=1 + mode)
+        res.update({name + "_toi": toi, name + "_tri": tri, name + "_normal": n, name + "_feature": f})
+    np.savez_compressed(os.path.join(HERE, "rays_culling_sphere24x16.npz"), rays=rays, **res)
+    z = np.load(os.path.join(HERE, "contacts_mixed_3000.npz"))
+    T = oracle.ShapeTable([])
+    T.kinds, T.params, T.points = z["kinds"].copy(), z["params"].copy(), np.ascontiguousarray(z["points"])
+    d, ds = T.distance(z["shape1"], z["pos1"], z["shape2"], z["pos2"])
+    h, hs = T.intersection_test(z["shape1"], z["pos1"], z["shape2"], z["pos2"])
+    np.savez_compressed(os.path.join(HERE, "distance_mixed_3000.npz"), dist=d, dist_status=ds, hit=h, hit_status=hs)
+    # TriMesh-vs-shape contacts on a small terrain
+    v, i = scenes.terrain(17, 17, extent=12.0)
+    v = v.copy(); v[:, 1] *= 0.1
+    pts, _ = scenes.hull_pool(4, 32, seed=106)
+    g = scenes.rng(107)
+    spec = [("ball", float(r)) for r in g.random(3) * 0.4 + 0.2] + [("cuboid", list(h_)) for h_ in g.random((3, 3)) * 0.4 + 0.15]
+    spec += [("convex", np.asarray(q, np.float32) * 0.5) for q in pts]
+    T2 = oracle.ShapeTable(spec)
+    n = 1500
+    sid = g.integers(0, len(spec), n).astype(np.uint32)
+    t = v[g.integers(0, len(v), n)] + np.stack([g.standard_normal(n) * 0.2, (g.random(n) - 0.35) * 1.2, g.standard_normal(n) * 0.2], axis=1)
+    poses = np.concatenate([scenes.random_unit_quaternions(g, n), t], axis=1).astype(np.float32)
+    mesh_pose = np.array([0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0], np.float32)
+    om = oracle.TriMesh(v, i)
+    out, st, part = om.contact_shapes(mesh_pose, T2, sid, poses, 0.05)
+    out2, st2, part2 = om.contact_shapes(mesh_pose, T2, sid, poses, 0.05, min_index_ties=True)
+    np.savez_compressed(os.path.join(HERE, "mesh_contacts_1500.npz"), vertices=v, indices=i, kinds=T2.kinds, params=T2.params, points=T2.points,
+                        shape=sid, poses=poses, mesh_pose=mesh_pose, prediction=np.float32(0.05), contacts=out, status=st, part=part,
+                        contacts_min_index=out2, part_min_index=part2)
 
 
 if __name__ == "__main__":

@@ -112,3 +112,32 @@ def test_wide_tree_axis_aligned_and_degenerate_rays(terrain, variant):
         g = gm.cast_local_ray_and_get_normal(rays, FMAX)
     r = om.cast_rays(None, rays, FMAX, with_normal=True, threads=8)
     check_ray_parity(g, r, _brute(om, rays, FMAX))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 3])
+def test_duplicate_and_degenerate_triangles(ctx, oracle, variant):
+    """Exact duplicates (bit-equal toi: smallest index must win), zero-area triangles (never hit, zero-extent boxes) and a
+    far-away outlier (huge root box, coarse quantisation at the top of the wide tree)."""
+    import parry_b200
+    v, i = scenes.terrain(33, 33, extent=60.0)
+    nv = len(v)
+    dup = i[:200].copy()
+    degen = np.stack([i[300:340, 0], i[300:340, 0], i[300:340, 1]], axis=1)          # a == b
+    line = np.stack([i[400:440, 0], i[400:440, 1], i[400:440, 0]], axis=1)           # c == a
+    far = np.array([[1e4, 5e3, -2e4], [1e4 + 1, 5e3, -2e4], [1e4, 5e3 + 1, -2e4]], np.float32)
+    v2 = np.concatenate([v, far]).astype(np.float32)
+    i2 = np.concatenate([i, dup, degen, line, np.array([[nv, nv + 1, nv + 2]], np.uint32)]).astype(np.uint32)
+    gm, om = parry_b200.TriMesh(ctx, v2, i2), oracle.TriMesh(v2, i2)
+    rays = scenes.terrain_rays(30000, extent=60.0, seed=24)
+    rays[:, 1] = rays[:, 1] * 0.2 + 10.0
+    with _Variant(variant):
+        g = gm.cast_local_ray_and_get_normal(rays, FMAX)
+    r = om.cast_rays(None, rays, FMAX, with_normal=True, threads=8)
+    b = om.cast_rays(None, rays, FMAX, with_normal=True, mode=1, threads=8)
+    # rays through a duplicated triangle tie exactly: the reference keeps the first in its own tree order, the GPU the smallest index
+    check_ray_parity(g, r, _brute(om, rays, FMAX), max_ulp_cases=0.05)
+    gi = np.asarray(g[1]).astype(np.uint32)
+    hit = gi != INVALID
+    assert hit.mean() > 0.3
+    assert (gi[hit] < len(i)).all()                      # duplicates and degenerate triangles never win
+    assert (gi == b[1]).mean() > 0.999                   # == brute force with min-index ties
