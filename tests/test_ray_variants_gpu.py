@@ -141,3 +141,25 @@ def test_duplicate_and_degenerate_triangles(ctx, oracle, variant):
     assert hit.mean() > 0.3
     assert (gi[hit] < len(i)).all()                      # duplicates and degenerate triangles never win
     assert (gi == b[1]).mean() > 0.999                   # == brute force with min-index ties
+
+
+@pytest.mark.parametrize("scale,offset", [(1e-3, 0.0), (1.0, 3.0e4), (100.0, -7.0e5), (1.0e-2, 2.5e3)])
+def test_wide_tree_far_from_origin_and_tiny_scenes(ctx, oracle, scale, offset):
+    """The quantised-box filter must stay conservative when coordinates are huge compared with the boxes (few f32 bits left for
+    the geometry) or tiny: directed rounding + relative slack, trimesh_wide.cu. Checked against the oracle, bit for bit."""
+    import parry_b200
+    v, i = scenes.terrain(65, 65, extent=100.0)
+    rays = scenes.terrain_rays(40000, extent=100.0, seed=25)
+    rays[:, 1] = rays[:, 1] * 0.3 + 20.0
+    off = np.array([offset, -0.5 * offset, 0.25 * offset])
+    v2 = (v.astype(np.float64) * scale + off).astype(np.float32)
+    r2 = rays.astype(np.float64)
+    r2[:, :3] = r2[:, :3] * scale + off
+    r2[:, 3:] *= scale
+    r2 = r2.astype(np.float32)
+    gm, om = parry_b200.TriMesh(ctx, v2, i), oracle.TriMesh(v2, i)
+    with _Variant(3):
+        g = gm.cast_local_ray_and_get_normal(r2, FMAX)
+    r = om.cast_rays(None, r2, FMAX, with_normal=True, threads=8)
+    assert (np.asarray(r[1]) != INVALID).mean() > 0.2
+    check_ray_parity(g, r, _brute(om, r2, FMAX), max_ulp_cases=0.002)
