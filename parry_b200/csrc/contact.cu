@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(128, MINB) k_contact_gjk(const uint8_t* __rest
 #define E2_MAX_FACES 256
 #define E2_MAX_SIL 64
 #define E2_STACK 96
+#define E2_STACK_SMEM 64   // DFS stack entries kept in shared memory by k_contact_epa2 (deeper walks: status 3)
 
 struct Epa2Arena {
     float4 face[E2_MAX_FACES];   // normal.xyz ; w = pts0 | pts1 << 8 | pts2 << 16 | deleted << 24
@@ -401,8 +402,6 @@ struct Epa2Arena {
     float4 vp[E2_MAX_VERTS];     // CSO point
     float4 vo1[E2_MAX_VERTS];    // orig1 (cold)
     float4 vo2[E2_MAX_VERTS];    // orig2 (cold)
-    uint32_t sil[E2_MAX_SIL];    // face | opp << 16
-    uint32_t stk[E2_STACK];
 };
 
 __device__ __forceinline__ uint32_t f_pts(float4 f, int i) { return (__float_as_uint(f.w) >> (8 * i)) & 0xffu; }
@@ -418,41 +417,58 @@ __device__ __forceinline__ int e2_next_ccw(float4 f, uint32_t id) {
     return 0;
 }
 __device__ __forceinline__ bool h2_le(float a, float b) { return !(a > b); }
-__device__ __forceinline__ void h2_sift_up(Epa2Arena& A, int start, int pos) {
-    float2 elt = A.heap[pos];
+// Heap storage of k_contact_epa2: the first E2_HEAP_SMEM entries of every thread's heap sit in shared memory ([entry][thread],
+// f32 key + u8 face id), the rest in the thread's arena. Rust's BinaryHeap sift rules (sift_up / sift_down_to_bottom) below.
+#define E2_HEAP_SMEM 32
+#define E2_SMEM_BYTES (E2_HEAP_SMEM * 128 * 5 + (E2_STACK_SMEM + E2_MAX_SIL) * 128 * 2)
+struct Heap2 {
+    float (*key)[128];
+    uint8_t (*id)[128];
+    float2* spill;
+    __device__ __forceinline__ float2 get(int i) const {
+        if (i < E2_HEAP_SMEM) return make_float2(key[i][threadIdx.x], __uint_as_float((uint32_t)id[i][threadIdx.x]));
+        return spill[i];
+    }
+    __device__ __forceinline__ void set(int i, float2 v) const {
+        if (i < E2_HEAP_SMEM) { key[i][threadIdx.x] = v.x; id[i][threadIdx.x] = (uint8_t)__float_as_uint(v.y); }
+        else spill[i] = v;
+    }
+};
+__device__ __forceinline__ void h2_sift_up(const Heap2& H, int start, int pos) {
+    float2 elt = H.get(pos);
     while (pos > start) {
         int parent = (pos - 1) / 2;
-        float2 pe = A.heap[parent];
+        float2 pe = H.get(parent);
         if (h2_le(elt.x, pe.x)) break;
-        A.heap[pos] = pe;
+        H.set(pos, pe);
         pos = parent;
     }
-    A.heap[pos] = elt;
+    H.set(pos, elt);
 }
-__device__ __forceinline__ void h2_push(Epa2Arena& A, int& nheap, uint32_t id, float neg_dist) {
+__device__ __forceinline__ void h2_push(const Heap2& H, int& nheap, uint32_t id, float neg_dist) {
     int old = nheap;
-    A.heap[old] = make_float2(neg_dist, __uint_as_float(id));
+    H.set(old, make_float2(neg_dist, __uint_as_float(id)));
     nheap = old + 1;
-    h2_sift_up(A, 0, old);
+    h2_sift_up(H, 0, old);
 }
-__device__ __forceinline__ float2 h2_pop(Epa2Arena& A, int& nheap) {
-    float2 item = A.heap[nheap - 1];
+__device__ __forceinline__ float2 h2_pop(const Heap2& H, int& nheap) {
+    float2 item = H.get(nheap - 1);
     nheap -= 1;
     if (nheap > 0) {
-        float2 t = item; item = A.heap[0];
+        float2 t = item; item = H.get(0);
         int end = nheap, pos = 0;
         float2 elt = t;
         int child = 1;
         while (end >= 2 && child <= end - 2) {
-            float2 c0 = A.heap[child], c1 = A.heap[child + 1];
+            float2 c0 = H.get(child), c1 = H.get(child + 1);
             if (h2_le(c0.x, c1.x)) { child += 1; c0 = c1; }
-            A.heap[pos] = c0;
+            H.set(pos, c0);
             pos = child;
             child = 2 * pos + 1;
         }
-        if (child == end - 1) { A.heap[pos] = A.heap[child]; pos = child; }
-        A.heap[pos] = elt;
-        h2_sift_up(A, 0, pos);
+        if (child == end - 1) { H.set(pos, H.get(child)); pos = child; }
+        H.set(pos, elt);
+        h2_sift_up(H, 0, pos);
     }
     return item;
 }
@@ -521,9 +537,18 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                               const float4* __restrict__ pts, PairSrc src, float prediction, OutSinks out,
                               const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
                               unsigned long long* __restrict__ next_job, Epa2Arena* __restrict__ arenas, int refill) {
+    // DFS stack and silhouette list live in shared memory ([entry][thread]: conflict free): they are written and read back
+    // within one trip, and global stores do not allocate in L1, so every pop used to be an L2 round trip
+    extern __shared__ __align__(16) unsigned char e2_smem[];   // E2_SMEM_BYTES, carved below
+    float (*s_hkey)[128] = reinterpret_cast<float (*)[128]>(e2_smem);
+    uint16_t (*s_stk)[128] = reinterpret_cast<uint16_t (*)[128]>(e2_smem + E2_HEAP_SMEM * 128 * 4);   // face | opp << 8
+    uint16_t (*s_sil)[128] = reinterpret_cast<uint16_t (*)[128]>(e2_smem + E2_HEAP_SMEM * 128 * 4 + E2_STACK_SMEM * 128 * 2);
+    uint8_t (*s_hid)[128] = reinterpret_cast<uint8_t (*)[128]>(e2_smem + E2_HEAP_SMEM * 128 * 4 + (E2_STACK_SMEM + E2_MAX_SIL) * 128 * 2);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     Epa2Arena& A = arenas[blockIdx.x * blockDim.x + threadIdx.x];
+    Heap2 H;
+    H.key = s_hkey; H.id = s_hid; H.spill = A.heap;
     const unsigned long long total = *job_count;
     const float eps = PB2_EPS, eps_tol = PB2_EPS * 100.0f;
 
@@ -595,7 +620,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
         if (state == E2_RUN) {
             bool got = false;
             while (nheap > 0) {
-                float2 ent = h2_pop(A, nheap);
+                float2 ent = h2_pop(H, nheap);
                 face_id = __float_as_uint(ent.y); face_neg = ent.x;
                 face = A.face[face_id];
                 if (!f_deleted(face)) { got = true; break; }
@@ -656,12 +681,12 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                 for (int k = 2; k >= 0; --k) {
                     uint32_t af = a_get(face_adj, k);
                     int opp = e2_next_ccw(A.face[af], f_pts(face, k));
-                    A.stk[sp++] = af | ((uint32_t)opp << 16);
+                    s_stk[sp++][threadIdx.x] = (uint16_t)(af | ((uint32_t)opp << 8));
                 }
                 V3 pt = sp_point;
                 while (sp > 0) {
-                    uint32_t e = A.stk[--sp];
-                    uint32_t fid = e & 0xffffu; int fo = (int)(e >> 16);
+                    uint32_t e = s_stk[--sp][threadIdx.x];
+                    uint32_t fid = e & 0xffu; int fo = (int)(e >> 8);
                     float4 f = A.face[fid];
                     if (f_deleted(f)) continue;
                     V3 p0 = v3of(A.vp[f_pts(f, fo)]);
@@ -673,7 +698,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                     }
                     if (!seen) {
                         if (nsil >= E2_MAX_SIL) { ovf = true; break; }
-                        A.sil[nsil++] = e;
+                        s_sil[nsil++][threadIdx.x] = (uint16_t)e;
                     } else {
                         A.face[fid].w = __uint_as_float(__float_as_uint(f.w) | (1u << 24));
                         int i1 = (fo + 2) % 3, i2 = fo;
@@ -681,9 +706,9 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                         uint32_t adj1 = a_get(fa, i1), adj2 = a_get(fa, i2);
                         int o1 = e2_next_ccw(A.face[adj1], f_pts(f, i1));
                         int o2 = e2_next_ccw(A.face[adj2], f_pts(f, i2));
-                        if (sp + 2 > E2_STACK) { ovf = true; break; }
-                        A.stk[sp++] = adj2 | ((uint32_t)o2 << 16);
-                        A.stk[sp++] = adj1 | ((uint32_t)o1 << 16);
+                        if (sp + 2 > E2_STACK_SMEM) { ovf = true; break; }
+                        s_stk[sp++][threadIdx.x] = (uint16_t)(adj2 | ((uint32_t)o2 << 8));
+                        s_stk[sp++][threadIdx.x] = (uint16_t)(adj1 | ((uint32_t)o1 << 8));
                     }
                 }
                 if (ovf) { fin = FIN_OVERFLOW; run_step = false; }
@@ -710,8 +735,8 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                         dv = 0;
                     }
                 } else {
-                    uint32_t ed = A.sil[e];
-                    uint32_t efid = ed & 0xffffu; int eopp = (int)(ed >> 16);
+                    uint32_t ed = s_sil[e][threadIdx.x];
+                    uint32_t efid = ed & 0xffu; int eopp = (int)(ed >> 8);
                     float4 ef = A.face[efid];
                     if (f_deleted(ef)) continue;
                     if (new_id >= E2_MAX_FACES) { fin = FIN_OVERFLOW; break; }
@@ -734,23 +759,23 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                         if (inside) {
                             float dist = dot3(n, v3of(A.vp[dv]));
                             if (-dist > PB2_GJK_EPS_TOL) { fin = FIN_NONE; break; }
-                            h2_push(A, nheap, (uint32_t)new_id, -dist);
+                            h2_push(H, nheap, (uint32_t)new_id, -dist);
                         }
                     } else {
-                        h2_push(A, nheap, (uint32_t)new_id, 0.0f);
+                        h2_push(H, nheap, (uint32_t)new_id, 0.0f);
                     }
                 } else if (inside) {
                     float dist = dot3(n, v3of(A.vp[dv]));
                     if (dist < curr_dist) { fin = FIN_FACE; fin_face = face_id; break; }
                     if (-dist > PB2_GJK_EPS_TOL) { fin = FIN_NONE; break; }
-                    h2_push(A, nheap, (uint32_t)new_id, -dist);
+                    h2_push(H, nheap, (uint32_t)new_id, -dist);
                 }
             }
             if (fin == FIN_NOT) {
                 if (state == E2_INIT) {
                     // `*self.heap.peek()?` and the "failed to project the origin on the initial simplex" exit
                     if (nheap == 0) fin = FIN_NONE;
-                    else { float2 top = A.heap[0]; best_id = __float_as_uint(top.y); best_neg = top.x; state = E2_RUN; }
+                    else { float2 top = H.get(0); best_id = __float_as_uint(top.y); best_neg = top.x; state = E2_RUN; }
                 } else {
                     if (first_new == nfaces) fin = FIN_NONE;
                     else {
@@ -1214,13 +1239,14 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
                                                   jobs, job_count, next_job, (EpaCArena*)ctx->scratch[2].ptr, refill);
     } else {
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contact_epa2, 128, 0);
+        PB2_CUDA(ctx, cudaFuncSetAttribute(k_contact_epa2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E2_SMEM_BYTES));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contact_epa2, 128, E2_SMEM_BYTES);
         if (per_sm < 1) per_sm = 1;
         int epa_blocks = ctx->sm_count * per_sm;
         int need = (int)pb2_blocks(n, 128);
         if (epa_blocks > need) epa_blocks = need;
         PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)128 * epa_blocks * sizeof(Epa2Arena)));
-        k_contact_epa2<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction, sinks,
+        k_contact_epa2<<<epa_blocks, 128, E2_SMEM_BYTES, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction, sinks,
                                                   jobs, job_count, next_job, (Epa2Arena*)ctx->scratch[2].ptr, refill);
     }
     PB2_LAUNCHED(ctx);
