@@ -648,6 +648,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                 npend = 2;
             }
         }
+        __syncwarp();  // lanes leave the previous phase's loops at different times: make them walk the next phase together
         // ---- phase B: one support point of the Minkowski difference
         uint32_t support_id = 0;
         V3 sp_point = mk3(0.f, 0.f, 0.f);
@@ -663,7 +664,10 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                 sp_point = cso.point;
             }
         }
+        __syncwarp();  // lanes leave the previous phase's loops at different times: make them walk the next phase together
         // ---- phase C/D: convergence test, then the silhouette of the faces visible from the new point
+        int nsil = 0, sp = 0;
+        bool ovf = false, dfs = false;
         if (run_step) {
             V3 fnormal = v3of(face);
             float candidate = dot3(sp_point, fnormal);
@@ -674,8 +678,6 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
             } else {
                 old_dist = curr_dist;
                 A.face[face_id].w = __uint_as_float(__float_as_uint(face.w) | (1u << 24));
-                int nsil = 0, sp = 0;
-                bool ovf = false;
                 // three compute_silhouette calls (adj[0], adj[1], adj[2]) as one DFS stack: push in reverse order
 #pragma unroll 1
                 for (int k = 2; k >= 0; --k) {
@@ -683,46 +685,62 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                     int opp = e2_next_ccw(A.face[af], f_pts(face, k));
                     s_stk[sp++][threadIdx.x] = (uint16_t)(af | ((uint32_t)opp << 8));
                 }
-                V3 pt = sp_point;
-                while (sp > 0) {
+                dfs = true;
+            }
+        }
+        // The walk itself, in lockstep: one visit per trip of the loop for every lane that still has entries, so that lanes with
+        // short walks wait at the loop head instead of drifting into their own copies of the loop body.
+        const unsigned m_dfs = __ballot_sync(FULL, dfs);
+        if (dfs) {
+            V3 pt = sp_point;
+            while (__any_sync(m_dfs, sp > 0 && !ovf)) {
+                if (sp > 0 && !ovf) {
                     uint32_t e = s_stk[--sp][threadIdx.x];
                     uint32_t fid = e & 0xffu; int fo = (int)(e >> 8);
                     float4 f = A.face[fid];
-                    if (f_deleted(f)) continue;
-                    V3 p0 = v3of(A.vp[f_pts(f, fo)]);
-                    bool seen = dot3(pt - p0, v3of(f)) >= -PB2_GJK_EPS_TOL;
-                    if (!seen) {
-                        V3 p1 = v3of(A.vp[f_pts(f, (fo + 1) % 3)]), p2 = v3of(A.vp[f_pts(f, (fo + 2) % 3)]);
-                        const float EPS = PB2_EPS * 100.0f;
-                        seen = rel_eq(nrm2(cross3(p2 - p1, pt - p1)), 0.0f, EPS * EPS, PB2_EPS);
-                    }
-                    if (!seen) {
-                        if (nsil >= E2_MAX_SIL) { ovf = true; break; }
-                        s_sil[nsil++][threadIdx.x] = (uint16_t)e;
-                    } else {
-                        A.face[fid].w = __uint_as_float(__float_as_uint(f.w) | (1u << 24));
-                        int i1 = (fo + 2) % 3, i2 = fo;
-                        uint2 fa = A.adj[fid];
-                        uint32_t adj1 = a_get(fa, i1), adj2 = a_get(fa, i2);
-                        int o1 = e2_next_ccw(A.face[adj1], f_pts(f, i1));
-                        int o2 = e2_next_ccw(A.face[adj2], f_pts(f, i2));
-                        if (sp + 2 > E2_STACK_SMEM) { ovf = true; break; }
-                        s_stk[sp++][threadIdx.x] = (uint16_t)(adj2 | ((uint32_t)o2 << 8));
-                        s_stk[sp++][threadIdx.x] = (uint16_t)(adj1 | ((uint32_t)o1 << 8));
+                    if (!f_deleted(f)) {
+                        V3 p0 = v3of(A.vp[f_pts(f, fo)]);
+                        bool seen = dot3(pt - p0, v3of(f)) >= -PB2_GJK_EPS_TOL;
+                        if (!seen) {
+                            V3 p1 = v3of(A.vp[f_pts(f, (fo + 1) % 3)]), p2 = v3of(A.vp[f_pts(f, (fo + 2) % 3)]);
+                            const float EPS = PB2_EPS * 100.0f;
+                            seen = rel_eq(nrm2(cross3(p2 - p1, pt - p1)), 0.0f, EPS * EPS, PB2_EPS);
+                        }
+                        if (!seen) {
+                            if (nsil >= E2_MAX_SIL) ovf = true;
+                            else s_sil[nsil++][threadIdx.x] = (uint16_t)e;
+                        } else {
+                            A.face[fid].w = __uint_as_float(__float_as_uint(f.w) | (1u << 24));
+                            int i1 = (fo + 2) % 3, i2 = fo;
+                            uint2 fa = A.adj[fid];
+                            uint32_t adj1 = a_get(fa, i1), adj2 = a_get(fa, i2);
+                            int o1 = e2_next_ccw(A.face[adj1], f_pts(f, i1));
+                            int o2 = e2_next_ccw(A.face[adj2], f_pts(f, i2));
+                            if (sp + 2 > E2_STACK_SMEM) ovf = true;
+                            else {
+                                s_stk[sp++][threadIdx.x] = (uint16_t)(adj2 | ((uint32_t)o2 << 8));
+                                s_stk[sp++][threadIdx.x] = (uint16_t)(adj1 | ((uint32_t)o1 << 8));
+                            }
+                        }
                     }
                 }
-                if (ovf) { fin = FIN_OVERFLOW; run_step = false; }
-                else if (nsil == 0) { fin = FIN_NONE; run_step = false; }
-                else npend = nsil;
             }
+            if (ovf) { fin = FIN_OVERFLOW; run_step = false; }
+            else if (nsil == 0) { fin = FIN_NONE; run_step = false; }
+            else npend = nsil;
         }
+        __syncwarp();  // lanes leave the previous phase's loops at different times: make them walk the next phase together
         // ---- phase E: create the pending faces (initial polytope or the fan around the silhouette)
         int first_new = nfaces;
-        if (fin == FIN_NOT && npend > 0) {
+        const bool making = fin == FIN_NOT && npend > 0;
+        const unsigned m_mk = __ballot_sync(FULL, making);
+        if (making) {
 #pragma unroll 1
-            for (int e = 0; e < npend; ++e) {
-                int p0, p1, p2, a0, a1, a2, dv;
+            for (int e = 0; __any_sync(m_mk, e < npend && fin == FIN_NOT); ++e) {   // lockstep, one face per lane per trip
+                if (!(e < npend && fin == FIN_NOT)) continue;
+                int p0 = 0, p1 = 0, p2 = 0, a0 = 0, a1 = 0, a2 = 0, dv = 0;
                 int new_id = nfaces;
+                bool skip = false;
                 if (state == E2_INIT) {
                     if (npend == 4) {
                         // pts {0,1,2},{1,3,2},{0,2,3},{0,3,1}; adj {3,1,2},{3,2,0},{0,1,3},{2,1,0}; dist uses vertex e
@@ -738,15 +756,18 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                     uint32_t ed = s_sil[e][threadIdx.x];
                     uint32_t efid = ed & 0xffu; int eopp = (int)(ed >> 8);
                     float4 ef = A.face[efid];
-                    if (f_deleted(ef)) continue;
-                    if (new_id >= E2_MAX_FACES) { fin = FIN_OVERFLOW; break; }
-                    p0 = (int)f_pts(ef, (eopp + 2) % 3); p1 = (int)f_pts(ef, (eopp + 1) % 3); p2 = (int)support_id;
-                    a0 = (int)efid; a1 = new_id + 1; a2 = new_id - 1;
-                    dv = p0;
-                    uint2 ea = A.adj[efid];
-                    a_set(ea, (eopp + 1) % 3, (uint32_t)new_id);
-                    A.adj[efid] = ea;
+                    if (f_deleted(ef)) skip = true;
+                    else if (new_id >= E2_MAX_FACES) { fin = FIN_OVERFLOW; skip = true; }
+                    else {
+                        p0 = (int)f_pts(ef, (eopp + 2) % 3); p1 = (int)f_pts(ef, (eopp + 1) % 3); p2 = (int)support_id;
+                        a0 = (int)efid; a1 = new_id + 1; a2 = new_id - 1;
+                        dv = p0;
+                        uint2 ea = A.adj[efid];
+                        a_set(ea, (eopp + 1) % 3, (uint32_t)new_id);
+                        A.adj[efid] = ea;
+                    }
                 }
+                if (skip) continue;
                 V3 va = v3of(A.vp[p0]), vb = v3of(A.vp[p1]), vc = v3of(A.vp[p2]);
                 bool inside = e2_face_inside(va, vb, vc);
                 V3 n; float nn;
@@ -758,17 +779,17 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                     if (npend == 4) {
                         if (inside) {
                             float dist = dot3(n, v3of(A.vp[dv]));
-                            if (-dist > PB2_GJK_EPS_TOL) { fin = FIN_NONE; break; }
-                            h2_push(H, nheap, (uint32_t)new_id, -dist);
+                            if (-dist > PB2_GJK_EPS_TOL) fin = FIN_NONE;
+                            else h2_push(H, nheap, (uint32_t)new_id, -dist);
                         }
                     } else {
                         h2_push(H, nheap, (uint32_t)new_id, 0.0f);
                     }
                 } else if (inside) {
                     float dist = dot3(n, v3of(A.vp[dv]));
-                    if (dist < curr_dist) { fin = FIN_FACE; fin_face = face_id; break; }
-                    if (-dist > PB2_GJK_EPS_TOL) { fin = FIN_NONE; break; }
-                    h2_push(H, nheap, (uint32_t)new_id, -dist);
+                    if (dist < curr_dist) { fin = FIN_FACE; fin_face = face_id; }
+                    else if (-dist > PB2_GJK_EPS_TOL) fin = FIN_NONE;
+                    else h2_push(H, nheap, (uint32_t)new_id, -dist);
                 }
             }
             if (fin == FIN_NOT) {
@@ -787,6 +808,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                 }
             }
         }
+        __syncwarp();  // lanes leave the previous phase's loops at different times: make them walk the next phase together
         // ---- phase F: finished lanes build the contact and go idle
         if (fin != FIN_NOT) {
             PairSetup ps;
