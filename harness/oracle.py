@@ -38,6 +38,8 @@ def lib():
         l.pb2o_trimesh_cast_rays.argtypes = [P, P, P, u32, f32, i32, i32, i32, P, P, P, P]
         l.pb2o_trimesh_contact_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, i32, P, P, P]
         l.pb2o_trimesh_contact_batch.restype = None
+        l.pb2o_trimesh_project_points.argtypes = [P, P, P, u32, i32, i32, i32, P, P, P]
+        l.pb2o_trimesh_project_points.restype = None
         l.pb2o_bvh_create.restype = P
         l.pb2o_bvh_create.argtypes = [P, u32, i32]
         l.pb2o_bvh_destroy.argtypes = [P]
@@ -113,6 +115,18 @@ class TriMesh:
                                      None if normal is None else normal.ctypes.data,
                                      None if feature is None else feature.ctypes.data)
         return (toi, tri, normal, feature) if with_normal else (toi, tri)
+
+    def project_points(self, pose, points, solid=True, mode=0, threads=1):
+        """PointQuery::project_point on the mesh: (proj (n,3), inside (n,) u8, tri (n,) u32). mode 1 = brute force, min-index ties."""
+        pts = _f32(points)
+        n = pts.shape[0]
+        pose = None if pose is None else _f32(pose)
+        proj = np.zeros((n, 3), dtype=np.float32)
+        inside = np.zeros(n, dtype=np.uint8)
+        tri = np.zeros(n, dtype=np.uint32)
+        lib().pb2o_trimesh_project_points(self.h, None if pose is None else pose.ctypes.data, pts.ctypes.data, n, int(solid), mode, threads,
+                                          proj.ctypes.data, inside.ctypes.data, tri.ctypes.data)
+        return proj, inside, tri
 
     def contact_shapes(self, mesh_pose, table, shape2, pos2, prediction, threads=1, min_index_ties=False):
         """query::contact(mesh_pose, mesh, pos2[k], shape2[k], prediction): (contacts (n,13), status, part)."""

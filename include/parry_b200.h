@@ -138,6 +138,14 @@ const pb2_bvh* pb2_trimesh_bvh(const pb2_trimesh* mesh);
 int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays /* m x 6 */,
                           uint32_t m, float max_toi, int solid, float* toi, uint32_t* tri, float* normal,
                           uint32_t* feature, int mem);
+/* PointQuery::project_point(m, pt, solid) on a TriMesh, batched (query/point/point_query.rs:147-151 ->
+ * point_composite_shape.rs:164-186,49-72: Bvh::find_best on the distance to the node boxes, point_triangle.rs at the
+ * leaves). proj: m x 3 projected points (world space), inside[k]: PointProjection::is_inside, tri[k]: the triangle the
+ * point was projected on (FeatureId::Face of project_point_and_get_feature); equal distances resolve to the smallest
+ * triangle index. */
+int pb2_trimesh_project_points(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* points /* m x 3 */, uint32_t m,
+                               int solid, float* proj, uint8_t* inside, uint32_t* tri, int mem);
+
 /* Multi-GPU form of pb2_trimesh_cast_rays for a range-split batch with the mesh replicated per GPU (the
  * path's only exchange is the all-gather of the fixed-size (toi, tri) hit records). Everything is device memory. The local
  * shard of m rays is traversed in `chunks` pieces; as soon as a piece is done its results — written straight into this

@@ -264,6 +264,25 @@ void pb2o_trimesh_contact_batch(void* mesh, const float* mesh_pose7, const uint8
         }
     });
 }
+// PointQuery::project_point(m, pt, solid) / project_local_point on a TriMesh (query/point/point_query.rs:147-151: local projection
+// of m^-1 * pt, transformed back). mode 0: reference traversal; mode 1: brute force, ties to the smallest triangle index.
+void pb2o_trimesh_project_points(void* mesh, const float* pose7, const float* points, uint32_t n, int solid, int mode, int nthreads,
+                                 float* proj, uint8_t* inside, uint32_t* tri) {
+    const TriMesh* tm = (const TriMesh*)mesh;
+    bool has_pose = pose7 != nullptr;
+    Iso pose = has_pose ? Iso::from7(pose7) : Iso();
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            Vec3 pt = ld3(points + 3 * k);
+            if (has_pose) pt = pose.inverse_transform_point(pt);
+            uint32_t id = UINT32_MAX; Vec3 p; bool in = false;
+            bool ok = trimesh_project_local_point(*tm, pt, solid != 0, mode == 1, id, p, in);
+            if (!ok) { st3(proj + 3 * k, Vec3()); inside[k] = 0; tri[k] = UINT32_MAX; continue; }
+            if (has_pose) p = pose.transform_point(p);
+            st3(proj + 3 * k, p); inside[k] = in ? 1 : 0; tri[k] = id;
+        }
+    });
+}
 // query::distance / query::intersection_test for n pairs (distance.rs:89-97, intersection_test.rs:88-96). status: 0 Ok, 2 Unsupported
 // (bad shape id), 3 cuboid-cuboid (SAT arm, not restated).
 void pb2o_distance_batch(const uint8_t* kinds, const float* params4, const float* points, uint32_t n_shapes, const uint32_t* shape1,

@@ -328,4 +328,35 @@ static inline int contact_trimesh_shape(const Iso& pos12, const TriMesh& mesh, c
     return have ? CONTACT_SOME : CONTACT_NONE;
 }
 
+// PointQuery for TriMesh without pseudo-normals (point_composite_shape.rs:164-186 -> CompositeShapeRef::project_local_point,
+// :49-72): Bvh::find_best with aabb cost = Aabb::distance_to_local_point(pt, solid = true) (point_aabb.rs:135-146: the norm of
+// the per-axis shift) and leaf cost = distance to the projection on the triangle (point_triangle.rs).
+struct ProjCost { Real d; Vec3 point; bool inside; Real cost() const { return d; } };
+static inline bool trimesh_project_local_point(const TriMesh& mesh, const Vec3& pt, bool solid, bool min_index_ties, uint32_t& id, Vec3& proj, bool& inside) {
+    ProjCost best;
+    auto aabb_cost = [&](const BvhNode& n, Real) {
+        Vec3 zero;
+        Vec3 shift = vsup(vsup(n.aabb().mins - pt, pt - n.aabb().maxs), zero);
+        return norm(shift);
+    };
+    auto leaf = [&](uint32_t prim, Real, ProjCost& out) {
+        const uint32_t* t = &mesh.indices[3 * prim];
+        TriProj p = project_on_triangle(mesh.vertices[t[0]], mesh.vertices[t[1]], mesh.vertices[t[2]], pt, solid);
+        out.point = p.point; out.inside = p.inside; out.d = norm(pt - p.point);
+        return true;
+    };
+    if (!min_index_ties) {
+        if (!mesh.bvh.find_best<ProjCost>(REAL_MAX, aabb_cost, leaf, id, best)) return false;
+    } else {  // brute force over all triangles, equal distances resolve to the smallest index
+        bool have = false;
+        for (uint32_t k = 0; k < (uint32_t)mesh.num_triangles(); ++k) {
+            ProjCost c; leaf(k, 0, c);
+            if (!have || c.d < best.d) { best = c; id = k; have = true; }
+        }
+        if (!have) return false;
+    }
+    proj = best.point; inside = best.inside;
+    return true;
+}
+
 }  // namespace pb2o

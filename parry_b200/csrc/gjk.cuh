@@ -174,7 +174,7 @@ __device__ __forceinline__ bool tet_face(uint32_t i, V3 a, V3 b, V3 c, V3 ap, V3
     return false;
 }
 // point_tetrahedron.rs:32-339, pt = origin, solid = true
-__device__ __noinline__ void project_origin_on_tetrahedron(V3 a, V3 b, V3 c, V3 d, Proj& r) {
+static __device__ __noinline__ void project_origin_on_tetrahedron(V3 a, V3 b, V3 c, V3 d, Proj& r) {
     V3 pt = mk3(0.f, 0.f, 0.f);
     r.bc[0] = r.bc[1] = r.bc[2] = 0.f; r.idx = 0; r.inside = false;
     V3 ab = b - a, ac = c - a, ad = d - a, ap = pt - a;

@@ -254,6 +254,72 @@ __global__ void k_ray_keys(const NodeWide* __restrict__ nodes, const float* __re
     vals[r] = r;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// PointQuery for TriMesh (query/point/point_composite_shape.rs:164-186, no pseudo-normals): CompositeShapeRef::project_local_point
+// (:49-72) = Bvh::find_best with aabb cost Aabb::distance_to_local_point(pt, true) (point_aabb.rs:135-146) and leaf cost
+// na::distance(projection on the triangle, pt) (point_triangle.rs:58-290). Same ordered descent and tie rule as the ray
+// kernels: among bit-equal minimal distances (a point closest to a shared edge or vertex: one third of random points) the
+// smallest triangle index wins, so nodes whose cost equals the best are still opened once a candidate exists.
+__device__ __forceinline__ float aabb_point_dist(float4 lo, float4 hi, V3 p) {
+    V3 shift = vmax3(vmax3(mk3(lo.x, lo.y, lo.z) - p, p - mk3(hi.x, hi.y, hi.z)), mk3(0.f, 0.f, 0.f));
+    return nrm(shift);
+}
+
+#include "gjk.cuh"
+
+__global__ void __launch_bounds__(128) k_project_points_trimesh(const NodeWide* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_leaves,
+                                  const float* __restrict__ pose7, const float* __restrict__ points, uint32_t m,
+                                  float* __restrict__ out_proj, uint8_t* __restrict__ out_inside, uint32_t* __restrict__ out_tri) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    V3 p = mk3(points[3ull * k], points[3ull * k + 1], points[3ull * k + 2]);
+    Iso7 pose;
+    if (pose7) { pose = load_iso(pose7); p = iso_inv_point(pose, p); }
+    float best = FLT_MAX;
+    uint32_t best_id = PB2_INVALID_U32;
+    V3 best_pt = mk3(0.f, 0.f, 0.f);
+    bool best_in = false, found = false;
+    auto leaf = [&](uint32_t pos) {
+        float4 ta = __ldg(&tris[3ull * pos]), tb = __ldg(&tris[3ull * pos + 1]), tc = __ldg(&tris[3ull * pos + 2]);
+        Proj pr;
+        project_on_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), p, pr);
+        float d = nrm(p - pr.point);
+        uint32_t id = __float_as_uint(ta.w);
+        if (d < best || (found && d == best && id < best_id)) { best = d; best_id = id; best_pt = pr.point; best_in = pr.inside; found = true; }
+    };
+    if (n_leaves == 1) {
+        const float4* np = reinterpret_cast<const float4*>(&nodes[0]);
+        float4 l0 = __ldg(np), l1 = __ldg(np + 1);
+        if (aabb_point_dist(l0, l1, p) < FLT_MAX) leaf(__float_as_uint(l0.w));
+    } else if (n_leaves >= 2) {
+        uint32_t stack[PB2_STACK];
+        int sp = 0;
+        uint32_t curr = 0;
+        for (;;) {
+            const float4* np = reinterpret_cast<const float4*>(&nodes[curr]);
+            float4 l0 = __ldg(np), l1 = __ldg(np + 1), r0 = __ldg(np + 2), r1 = __ldg(np + 3);
+            float ls = aabb_point_dist(l0, l1, p), rs = aabb_point_dist(r0, r1, p);
+            uint32_t lc = __float_as_uint(l0.w), rc = __float_as_uint(r0.w);
+            bool lleaf = (__float_as_uint(l1.w) & PB2_LEAF_COUNT_MASK) == 1u, rleaf = (__float_as_uint(r1.w) & PB2_LEAF_COUNT_MASK) == 1u;
+            if (ls > rs) { float ts = ls; ls = rs; rs = ts; uint32_t tc = lc; lc = rc; rc = tc; bool tl = lleaf; lleaf = rleaf; rleaf = tl; }
+            bool next = false;
+            if (ls != FLT_MAX && (ls < best || (found && ls == best))) {
+                if (lleaf) leaf(lc); else { curr = lc; next = true; }
+            }
+            if (rs != FLT_MAX && (rs < best || (found && rs == best))) {
+                if (rleaf) leaf(rc);
+                else if (next) { if (sp < PB2_STACK) stack[sp++] = rc; }
+                else { curr = rc; next = true; }
+            }
+            if (!next) { if (sp == 0) break; curr = stack[--sp]; }
+        }
+    }
+    if (found && pose7) best_pt = iso_point(pose, best_pt);  // PointProjection::transform_by
+    out_proj[3ull * k] = best_pt.x; out_proj[3ull * k + 1] = best_pt.y; out_proj[3ull * k + 2] = best_pt.z;
+    out_inside[k] = best_in ? 1 : 0;
+    out_tri[k] = best_id;
+}
+
 // Enqueues the ray kernels for m device-resident rays on ctx->stream.
 static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d_pose, const void* d_rays, uint32_t m, float max_toi,
                             void* d_toi, void* d_tri, void* d_n, void* d_f, bool with_normal, uint32_t cull) {
@@ -520,6 +586,30 @@ int pb2_trimesh_cast_rays_allgather(pb2_ctx* ctx, const pb2_trimesh* mesh, const
     if (dual) { cudaEvent_t e3 = pb2_next_event(ctx); cudaEventRecord(e3, ctx->compute2); cudaStreamWaitEvent(main_stream, e3, 0); }
     if (rc != PB2_OK) return rc;
     PB2_CUDA(ctx, cudaGetLastError());
+    return PB2_OK;
+}
+
+int pb2_trimesh_project_points(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* points, uint32_t m, int solid,
+                               float* proj, uint8_t* inside, uint32_t* tri, int mem) {
+    (void)solid;  // only matters for a degenerate triangle in 3D, where the device projection already returns the point itself
+    if (!ctx || !mesh || (m && (!points || !proj || !inside || !tri))) return PB2_ERR_INVALID;
+    if (m == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_pts, *d_pose = nullptr;
+    void *d_proj, *d_in, *d_tri;
+    PB2_CHECK(pb2_stage_in(ctx, 0, points, (size_t)m * 12, mem, &d_pts));
+    if (pose7) PB2_CHECK(pb2_stage_in(ctx, 1, pose7, 28, mem, &d_pose));
+    PB2_CHECK(pb2_stage_out(ctx, 2, proj, (size_t)m * 12, mem, &d_proj));
+    PB2_CHECK(pb2_stage_out(ctx, 3, inside, (size_t)m, mem, &d_in));
+    PB2_CHECK(pb2_stage_out(ctx, 4, tri, (size_t)m * 4, mem, &d_tri));
+    k_project_points_trimesh<<<pb2_blocks(m, 128), 128, 0, ctx->stream>>>(mesh->bvh.nodes, mesh->tris, mesh->bvh.n_leaves, (const float*)d_pose,
+                                                                         (const float*)d_pts, m, (float*)d_proj, (uint8_t*)d_in, (uint32_t*)d_tri);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(pb2_stage_back(ctx, proj, d_proj, (size_t)m * 12, mem));
+    PB2_CHECK(pb2_stage_back(ctx, inside, d_in, (size_t)m, mem));
+    PB2_CHECK(pb2_stage_back(ctx, tri, d_tri, (size_t)m * 4, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB2_OK;
 }
 

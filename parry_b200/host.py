@@ -337,6 +337,21 @@ class TriMesh:
                                                                     peer_toi_ptrs, peer_tri_ptrs, len(peer_toi_ptrs), int(rank),
                                                                     int(elem_offset), int(chunks)))
 
+    def project_point(self, m, points, solid=True):
+        """PointQuery::project_point(m, pt, solid), batched: (proj (n, 3), is_inside (n,) u8, triangle (n,) u32)."""
+        n = int(points.shape[0])
+        kp, pp, mem = _prep(points, np.float32)
+        km, pm, _ = _prep(m, np.float32, mem)
+        dev = self.ctx.torch_device
+        proj, ppr = _empty((n, 3), np.float32, mem, dev)
+        inside, pin = _empty((n,), np.uint8, mem, dev)
+        tri, ptr = _empty((n,), np.uint32, mem, dev)
+        self.ctx.check(self.ctx._lib.pb2_trimesh_project_points(self.ctx.h, self.h, pm, pp, n, int(bool(solid)), ppr, pin, ptr, mem))
+        return proj, inside, tri
+
+    def project_local_point(self, points, solid=True):
+        return self.project_point(None, points, solid)
+
     def contact_shapes(self, mesh_pose, shapes, shape_ids, poses, prediction):
         """query::contact(mesh_pose, self, poses[k], shapes[shape_ids[k]], prediction) for every k (the composite-shape arm,
         contact_composite_shape_shape.rs:14-61). Returns (contacts (n, 13), status (n,), part (n,) winning triangle)."""
