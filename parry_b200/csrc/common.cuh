@@ -25,7 +25,7 @@ struct pb2_ctx {
     char err[512] = {0};
     // grow-only device staging for PB2_MEM_HOST calls + misc scratch
     Scratch stage[8];
-    Scratch scratch[4];
+    Scratch scratch[5];
     // pinned host bounce buffer for small readbacks (counters)
     uint64_t* h_counters = nullptr;  // 16 x u64 pinned
     uint64_t* d_counters = nullptr;  // 16 x u64 device

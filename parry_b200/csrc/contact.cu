@@ -533,10 +533,23 @@ __device__ unsigned long long g_epa_dbg[8];
 #endif
 enum { FIN_NOT = 0, FIN_FACE = 1, FIN_NONE = 2, FIN_OVERFLOW = 3, FIN_DIM0 = 4 };
 
+// EPA outcome -> contact (contact_support_map_support_map.rs:54-86 after gjk/epa): shared by the EPA kernels' phase F.
+__device__ __forceinline__ int epa_result_to_contact(const PairSetup& ps, int fin, V3 p1, V3 p2, V3 n1, float prediction, ContactOut& c) {
+    int st;
+    if (fin == FIN_OVERFLOW) st = ST_NEEDS_HOST;
+    else if (fin == FIN_NONE) {
+        if (ps.mode == 1) st = ST_NONE;
+        else st = finish_gjk_pair(ps, true, ps.cb_pos12.t, p2, n1, prediction, c);
+    } else st = finish_gjk_pair(ps, true, p1, p2, n1, prediction, c);
+    if (st == ST_SOME) to_world(ps, c);
+    return st;
+}
+
 __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
                               const float4* __restrict__ pts, PairSrc src, float prediction, OutSinks out,
                               const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
-                              unsigned long long* __restrict__ next_job, Epa2Arena* __restrict__ arenas, int refill) {
+                              unsigned long long* __restrict__ next_job, Epa2Arena* __restrict__ arenas, int refill,
+                              float4* __restrict__ fin_recs, unsigned long long* __restrict__ fin_count) {
     // DFS stack and silhouette list live in shared memory ([entry][thread]: conflict free): they are written and read back
     // within one trip, and global stores do not allocate in L1, so every pop used to be an L2 round trip
     extern __shared__ __align__(16) unsigned char e2_smem[];   // E2_SMEM_BYTES, carved below
@@ -811,10 +824,6 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
         __syncwarp();  // lanes leave the previous phase's loops at different times: make them walk the next phase together
         // ---- phase F: finished lanes build the contact and go idle
         if (fin != FIN_NOT) {
-            PairSetup ps;
-            pair_setup(kinds, params, pts, src, pair, ps);
-            ContactOut c;
-            int st;
             V3 p1 = mk3(0.f, 0.f, 0.f), p2 = p1, n1 = mk3(0.f, 1.f, 0.f);
             if (fin == FIN_FACE) {
                 float4 f = A.face[fin_face];
@@ -825,16 +834,41 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                 p2 = v3of(A.vo2[i0]) * bc[0] + v3of(A.vo2[i1]) * bc[1] + v3of(A.vo2[i2]) * bc[2];
                 n1 = v3of(f);
             }
-            if (fin == FIN_OVERFLOW) st = ST_NEEDS_HOST;
-            else if (fin == FIN_NONE) {
-                if (ps.mode == 1) st = ST_NONE;
-                else st = finish_gjk_pair(ps, true, ps.cb_pos12.t, p2, n1, prediction, c);
-            } else st = finish_gjk_pair(ps, true, p1, p2, n1, prediction, c);
-            if (st == ST_SOME) to_world(ps, c);
-            emit(out, pair, st, c);
+            if (fin_recs) {
+                // Only ~3 lanes of a warp finish in the same trip, and building the contact (pair setup, two isometry
+                // products, the compacted append) is ~150 instructions: hand the witness points to k_contact_finish,
+                // which does that part with full warps
+                unsigned long long at = warp_append1(fin_count);
+                float4* r = fin_recs + 3ull * at;
+                r[0] = make_float4(__uint_as_float(pair), __uint_as_float((uint32_t)fin), p1.x, p1.y);
+                r[1] = make_float4(p1.z, p2.x, p2.y, p2.z);
+                r[2] = make_float4(n1.x, n1.y, n1.z, 0.0f);
+            } else {
+                PairSetup ps;
+                pair_setup(kinds, params, pts, src, pair, ps);
+                ContactOut c;
+                int st = epa_result_to_contact(ps, fin, p1, p2, n1, prediction, c);
+                emit(out, pair, st, c);
+            }
             state = E2_IDLE;
         }
     }
+}
+
+// Second half of phase F for k_contact_epa2: one thread per finished EPA run.
+__global__ void __launch_bounds__(128) k_contact_finish(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
+                              const float4* __restrict__ pts, PairSrc src, float prediction, OutSinks out,
+                              const float4* __restrict__ fin_recs, const unsigned long long* __restrict__ fin_count) {
+    unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *fin_count) return;
+    float4 r0 = fin_recs[3 * k], r1 = fin_recs[3 * k + 1], r2 = fin_recs[3 * k + 2];
+    uint32_t pair = __float_as_uint(r0.x);
+    int fin = (int)__float_as_uint(r0.y);
+    PairSetup ps;
+    pair_setup(kinds, params, pts, src, pair, ps);
+    ContactOut c;
+    int st = epa_result_to_contact(ps, fin, mk3(r0.z, r0.w, r1.x), mk3(r1.y, r1.z, r1.w), mk3(r2.x, r2.y, r2.z), prediction, c);
+    emit(out, pair, st, c);
 }
 
 // ------------------------------------------------------------------------------------------- phase 2, compact arena
@@ -1243,6 +1277,7 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
     unsigned long long* job_count = (unsigned long long*)(ctx->d_counters + 4);
     unsigned long long* next_job = (unsigned long long*)(ctx->d_counters + 5);
     PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 4, 0, 16, st));
+    PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 7, 0, 8, st));   // finished-run records (slot 6 is the callers' contact count)
     int gjk_minb = 4;  // 128 registers, 4 CTAs per SM: 0.7 ms faster than the unconstrained 151-register build on the 4M-pair config
     { const char* e = getenv("PB2_GJK_MINB"); if (e) gjk_minb = atoi(e); }
     auto gjk = gjk_minb >= 5 ? k_contact_gjk<5> : (gjk_minb == 4 ? k_contact_gjk<4> : k_contact_gjk<3>);
@@ -1268,8 +1303,21 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
         int need = (int)pb2_blocks(n, 128);
         if (epa_blocks > need) epa_blocks = need;
         PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)128 * epa_blocks * sizeof(Epa2Arena)));
+        const bool split_finish = !getenv("PB2_EPA_INLINE_FINISH");
+        float4* fin_recs = nullptr;
+        unsigned long long* fin_count = (unsigned long long*)(ctx->d_counters + 7);
+        if (split_finish) {
+            PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[4], (size_t)n * 48));
+            fin_recs = (float4*)ctx->scratch[4].ptr;
+        }
         k_contact_epa2<<<epa_blocks, 128, E2_SMEM_BYTES, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction, sinks,
-                                                  jobs, job_count, next_job, (Epa2Arena*)ctx->scratch[2].ptr, refill);
+                                                  jobs, job_count, next_job, (Epa2Arena*)ctx->scratch[2].ptr, refill, fin_recs, fin_count);
+        if (split_finish) {
+            PB2_LAUNCHED(ctx);
+            // grid sized for the worst case (every pair went to EPA); blocks past the record count exit on their first load
+            k_contact_finish<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction, sinks,
+                                                             fin_recs, fin_count);
+        }
     }
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
