@@ -48,13 +48,18 @@ def main():
         rd = torch.from_numpy(rays).cuda()
         toi = torch.empty(m, dtype=torch.float32, device="cuda")
         tri = torch.empty(m, dtype=torch.int32, device="cuda")
+        # PB2_SWEEP="K=V,K=V;K=V;..." runs one timing per ';'-separated group of environment settings
         sweep = os.environ.get("PB2_SWEEP")
-        configs = [None]
-        if sweep:
-            configs = [(3, 8, 4), (3, 6, 4), (3, 12, 4), (3, 16, 4), (3, 8, 2), (3, 8, 6), (3, 8, 8), (3, 4, 4)]
+        configs = [None] + (sweep.split(";") if sweep else [])
+        touched = set()
         for cfg in configs:
-            if cfg is not None:
-                os.environ["PB2_RAY_VARIANT"], os.environ["PB2_RAY_STEPS"], os.environ["PB2_RAY_REFILL"] = map(str, cfg)
+            for k in touched:
+                os.environ.pop(k, None)
+            if cfg:
+                for kv in cfg.split(","):
+                    k, v = kv.split("=")
+                    os.environ[k] = v
+                    touched.add(k)
             ms = timeit(lambda: mesh.cast_local_ray(rd, FMAX, out=(toi, tri)), "%s %s" % (wl, cfg))
             print("   %.1f Mrays/s  checksum %d %.6f" % (m / ms / 1e3, int(tri.to(torch.int64).sum().item()), float(toi.double().sum().item())))
     elif wl == "contacts":

@@ -325,9 +325,10 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
                             void* d_toi, void* d_tri, void* d_n, void* d_f, bool with_normal, uint32_t cull) {
     const pb2_bvh* b = &mesh->bvh;
     // ray reordering pays off once the node array no longer fits in L2 (126 MB); below that the sort costs more than it saves
-    // variants: 0 one thread per ray, 1 persistent binary, 2 = 1 + ray reordering, 3 compressed 8-wide tree, 4 = 3 + ray reordering
+    // variants: 0 one thread per ray, 1 persistent binary, 2 = 1 + ray reordering, 3 compressed 8-wide tree, 4 = 3 + ray reordering,
+    // 5 = 3 with the warp-shared triangle phase, 6 = 5 + ray reordering
     bool big = (size_t)b->n_nodes * sizeof(NodeWide) > (size_t)(100u << 20);
-    int variant = mesh->n_nodes8 ? 3 : (big ? 2 : 1), steps = 16, refill = 8;
+    int variant = mesh->n_nodes8 ? 5 : (big ? 2 : 1), steps = 16, refill = 8;
     if (variant >= 3) { steps = 8; refill = 6; }  // wide kernel: `steps` = lanes with queued triangles that trigger a triangle pass
     {   // tuning knobs (read per call; cheap)
         const char* e = getenv("PB2_RAY_VARIANT");
@@ -349,8 +350,8 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
         unsigned int* next_ray = (unsigned int*)(ctx->d_counters + ctx->ray_slot);
         PB2_CUDA(ctx, cudaMemsetAsync(next_ray, 0, 4, ctx->stream));
         const uint32_t* perm = nullptr;
-        if (variant >= 3 && !mesh->n_nodes8) variant -= 2;
-        if ((variant == 2 || variant == 4) && m >= 65536) {
+        if (variant >= 3 && !mesh->n_nodes8) variant = 1 + (variant & 1 ? 0 : 1);
+        if ((variant == 2 || variant == 4 || variant == 6) && m >= 65536) {
             size_t cub_bytes = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                             (uint32_t*)nullptr, (int)m, 0, 30, ctx->stream);
@@ -374,7 +375,7 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
         if (blocks > need) blocks = need;
         if (variant >= 3)
             PB2_CHECK(pb2_wide_cast(ctx, mesh, (const float*)d_pose, (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
-                                    (float*)d_n, (uint32_t*)d_f, with_normal, steps, refill, cull));
+                                    (float*)d_n, (uint32_t*)d_f, with_normal, steps, refill, cull, variant >= 5));
         else if (with_normal)
             k_raycast_trimesh_persistent<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
                 (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, (float*)d_n, (uint32_t*)d_f, next_ray, steps, refill, cull);

@@ -514,14 +514,250 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide(const float4* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------ shared triangle phase
+// Same traversal as k_raycast_wide<., 0>, different triangle phase. The ncu source page of that kernel
+// (profiles/r1_rays_v7_*) shows the exact leaf-box + triangle tests taking 20 % of the issued instructions with 8-10 of 32
+// lanes active: a lane only ever tests its own ray's triangles, one per trip. Here the hit triangle groups of all lanes
+// go to one per-warp queue, and when the queue is processed its triangles are dealt out to the 32 lanes regardless of
+// which lane's ray they belong to: the ray (origin, direction, reciprocal) sits in shared memory, and the per-ray best hit
+// is a 64-bit shared-memory word {|toi| bits, triangle id} updated with atomicMin — which is exactly the documented tie
+// rule (smallest toi, then smallest triangle id). The lane that owns the winning candidate then stores the payload (exact
+// toi bits, feature, normal) for the ray's owner.
+#define W8C_GQ 64   // queued groups per warp (a node phase adds at most 32)
+template <bool WITH_NORMAL>
+__global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
+                                  const float* __restrict__ pose7, const float* __restrict__ rays, const uint32_t* __restrict__ perm,
+                                  uint32_t m, float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
+                                  float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
+                                  unsigned int* __restrict__ next_ray, int tri_groups, int refill, uint32_t cull, int blocked_max,
+                                  unsigned long long* __restrict__ stats) {
+    __shared__ float s_ray[9][128];                // o, d, 1/d of the ray each thread owns
+    __shared__ unsigned long long s_key[128];      // best hit so far: |toi| bits << 32 | triangle id (id INVALID: none yet)
+    __shared__ uint2 s_pay[128];                   // {exact toi bits, feature bits} of that hit
+    __shared__ float s_nrm[WITH_NORMAL ? 3 : 1][128];
+    __shared__ uint2 s_gq[4][W8C_GQ];              // {first triangle, leaf mask | hit mask << 8 | owner lane << 16}
+    __shared__ uint16_t s_items[4][256];           // queue slot << 3 | child slot, one per triangle to test
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
+    const unsigned lt = (1u << lane) - 1u;
+    Iso7 pose;
+    if (pose7) pose = load_iso(pose7);
+    V3 o = mk3(0.f, 0.f, 0.f), inv = o;
+    float best = 0.f;
+    uint32_t r = 0, oct = 0, cur = PB2_INVALID_U32;
+    uint32_t g_base = 0, g_bits = 0;
+    bool active = false, pend = false;
+    uint2 stack[W8_STACK];
+    int sp = 0;
+    uint32_t G = 0;                                // groups in this warp's queue (warp uniform)
+    bool exhausted = false;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (!exhausted && (idle == FULL || __popc(idle) >= refill)) {
+            unsigned base = 0;
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(next_ray, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base + __popc(idle) >= m) exhausted = true;
+            if (!active) {
+                uint32_t slot = base + __popc(idle & lt);
+                if (slot < m) {
+                    r = perm ? perm[slot] : slot;
+                    o = mk3(rays[6ull * r], rays[6ull * r + 1], rays[6ull * r + 2]);
+                    V3 d = mk3(rays[6ull * r + 3], rays[6ull * r + 4], rays[6ull * r + 5]);
+                    if (pose7) { o = iso_inv_point(pose, o); d = iso_inv_vec(pose, d); }
+                    inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                    oct = (__float_as_uint(d.x) >> 31) | ((__float_as_uint(d.y) >> 31) << 1) | ((__float_as_uint(d.z) >> 31) << 2);
+                    best = max_toi;
+                    sp = 0; active = true; pend = false;
+                    g_base = 0; g_bits = ((1u << (7u ^ oct)) << 24) | 1u;
+                    s_ray[0][threadIdx.x] = o.x; s_ray[1][threadIdx.x] = o.y; s_ray[2][threadIdx.x] = o.z;
+                    s_ray[3][threadIdx.x] = d.x; s_ray[4][threadIdx.x] = d.y; s_ray[5][threadIdx.x] = d.z;
+                    s_ray[6][threadIdx.x] = inv.x; s_ray[7][threadIdx.x] = inv.y; s_ray[8][threadIdx.x] = inv.z;
+                    s_key[threadIdx.x] = ((unsigned long long)__float_as_uint(max_toi) << 32) | 0xffffffffull;
+                }
+            }
+            idle = __ballot_sync(FULL, !active);
+        }
+        if (idle == FULL) break;
+        // ------------------------------------------------------------------ node phase
+        const uint32_t pxor = 7u ^ oct;
+        cur = PB2_INVALID_U32;
+        if (g_bits >> 24) {
+            uint32_t hits = g_bits >> 24;
+            uint32_t bsel = 31u - (uint32_t)__clz(hits);
+            hits &= ~(1u << bsel);
+            uint32_t pim = g_bits & 0xffu;
+            cur = g_base + (uint32_t)__popc(pim & ((1u << (bsel ^ pxor)) - 1u));
+            g_bits = (hits << 24) | pim;
+            if (hits) { stack[sp] = make_uint2(g_base, g_bits); sp++; }
+        }
+        uint32_t lh = 0, q_tbase = 0, q_lmask = 0;
+        if (cur != PB2_INVALID_U32) {
+            const int MODE = 0;
+            float (*tent)[128] = nullptr;
+            (void)tent;
+            const float4* np = nodes8 + 5ull * cur;
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            uint32_t ew = __float_as_uint(n0.w);
+            const uint32_t onef = __float_as_uint(n1.w);
+            AxisK kx = axis_setup(n0.x, o.x, inv.x, oct & 1u, ew & 0xffu);
+            AxisK ky = axis_setup(n0.y, o.y, inv.y, oct & 2u, (ew >> 8) & 0xffu);
+            AxisK kz = axis_setup(n0.z, o.z, inv.z, oct & 4u, (ew >> 16) & 0xffu);
+            uint32_t lx0 = __float_as_uint(n2.x), lx1 = __float_as_uint(n2.y), ly0 = __float_as_uint(n2.z), ly1 = __float_as_uint(n2.w);
+            uint32_t lz0 = __float_as_uint(n3.x), lz1 = __float_as_uint(n3.y), hx0 = __float_as_uint(n3.z), hx1 = __float_as_uint(n3.w);
+            uint32_t hy0 = __float_as_uint(n4.x), hy1 = __float_as_uint(n4.y), hz0 = __float_as_uint(n4.z), hz1 = __float_as_uint(n4.w);
+            uint32_t nx0 = (oct & 1u) ? hx0 : lx0, nx1 = (oct & 1u) ? hx1 : lx1, fx0 = (oct & 1u) ? lx0 : hx0, fx1 = (oct & 1u) ? lx1 : hx1;
+            uint32_t ny0 = (oct & 2u) ? hy0 : ly0, ny1 = (oct & 2u) ? hy1 : ly1, fy0 = (oct & 2u) ? ly0 : hy0, fy1 = (oct & 2u) ? ly1 : hy1;
+            uint32_t nz0 = (oct & 4u) ? hz0 : lz0, nz1 = (oct & 4u) ? hz1 : lz1, fz0 = (oct & 4u) ? lz0 : hz0, fz1 = (oct & 4u) ? lz1 : hz1;
+            uint32_t hit8 = 0;
+            W8_CHILD(0, nx0, ny0, nz0, fx0, fy0, fz0)
+            W8_CHILD(1, nx0, ny0, nz0, fx0, fy0, fz0)
+            W8_CHILD(2, nx0, ny0, nz0, fx0, fy0, fz0)
+            W8_CHILD(3, nx0, ny0, nz0, fx0, fy0, fz0)
+            W8_CHILD(4, nx1, ny1, nz1, fx1, fy1, fz1)
+            W8_CHILD(5, nx1, ny1, nz1, fx1, fy1, fz1)
+            W8_CHILD(6, nx1, ny1, nz1, fx1, fy1, fz1)
+            W8_CHILD(7, nx1, ny1, nz1, fx1, fy1, fz1)
+            uint32_t imask = ew >> 24;
+            q_lmask = __float_as_uint(n1.z);
+            q_tbase = __float_as_uint(n1.y);
+            lh = hit8 & q_lmask;
+            if (stats) {
+                atomicAdd(&stats[0], 1ull);
+                if (hit8 == 0) atomicAdd(&stats[1], 1ull);
+                atomicAdd(&stats[2], (unsigned long long)__popc(hit8 & imask));
+                atomicAdd(&stats[3], (unsigned long long)__popc(lh));
+            }
+            uint32_t ih = perm8(hit8 & imask, pxor);
+            if (ih) { g_base = __float_as_uint(n1.x); g_bits = (ih << 24) | imask; }
+            else if (sp > 0) { sp--; uint2 e = stack[sp]; g_base = e.x; g_bits = e.y; }
+            else g_bits = 0;
+        }
+        // hit triangle groups go to the warp's queue
+        {
+            unsigned pm = __ballot_sync(FULL, lh != 0);
+            if (lh) {
+                s_gq[w][G + __popc(pm & lt)] = make_uint2(q_tbase, q_lmask | (lh << 8) | ((uint32_t)lane << 16));
+                pend = true;
+            }
+            G += (uint32_t)__popc(pm);
+        }
+        // ------------------------------------------------------------------ triangle phase
+        if (G) {
+            unsigned walking = __ballot_sync(FULL, active && (g_bits >> 24) != 0);
+            unsigned blocked = __ballot_sync(FULL, active && pend && (g_bits >> 24) == 0);
+            if ((int)G >= tri_groups || G > W8C_GQ - 32 || !walking || __popc(blocked) >= blocked_max) {
+                __syncwarp();
+                for (uint32_t gb = 0; gb < G; gb += 32) {
+                    // deal the triangles of up to 32 groups out as items
+                    uint32_t gi = gb + (uint32_t)lane, glh = 0;
+                    if (gi < G) glh = (s_gq[w][gi].y >> 8) & 0xffu;
+                    int c = __popc(glh), pre = c;
+#pragma unroll
+                    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                        int v = __shfl_up_sync(FULL, pre, dlt);
+                        if (lane >= dlt) pre += v;
+                    }
+                    const int T = __shfl_sync(FULL, pre, 31);
+                    int at = pre - c;
+                    while (glh) {
+                        uint32_t sl = (uint32_t)__ffs(glh) - 1u;
+                        glh &= glh - 1u;
+                        s_items[w][at++] = (uint16_t)((lane << 3) | sl);
+                    }
+                    __syncwarp();
+                    for (int j0 = 0; j0 < T; j0 += 32) {
+                        const int j = j0 + lane;
+                        bool cand = false;
+                        unsigned long long mine = 0;
+                        int own = 0;
+                        uint32_t c_toi = 0, c_fid = 0;
+                        V3 c_n = mk3(0.f, 0.f, 0.f);
+                        if (j < T) {
+                            uint32_t it = s_items[w][j];
+                            uint2 ge = s_gq[w][gb + (it >> 3)];
+                            own = wbase + (int)(ge.y >> 16);
+                            uint32_t t = ge.x + (uint32_t)__popc(ge.y & 0xffu & ((1u << (it & 7u)) - 1u));
+                            float4 ta = __ldg(&tris8[3ull * t]), tb = __ldg(&tris8[3ull * t + 1]), tc = __ldg(&tris8[3ull * t + 2]);
+                            unsigned long long k0 = s_key[own];
+                            float sbest = __uint_as_float((uint32_t)(k0 >> 32));
+                            uint32_t sid = (uint32_t)k0;
+                            bool sfound = sid != PB2_INVALID_U32;
+                            V3 ro = mk3(s_ray[0][own], s_ray[1][own], s_ray[2][own]);
+                            V3 rinv = mk3(s_ray[6][own], s_ray[7][own], s_ray[8][own]);
+                            // exact leaf AABB (Triangle::local_aabb) and the reference's node test against the best hit so far
+                            float4 blo = make_float4(fminf(fminf(ta.x, tb.x), tc.x), fminf(fminf(ta.y, tb.y), tc.y), fminf(fminf(ta.z, tb.z), tc.z), 0.f);
+                            float4 bhi = make_float4(fmaxf(fmaxf(ta.x, tb.x), tc.x), fmaxf(fmaxf(ta.y, tb.y), tc.y), fmaxf(fmaxf(ta.z, tb.z), tc.z), 0.f);
+                            float sc = slab_cost_bf(blo, bhi, ro, rinv, sbest);
+                            if (stats) { atomicAdd(&stats[4], 1ull); if (sc != FLT_MAX && sc <= sbest) atomicAdd(&stats[5], 1ull); }
+                            if (sc != FLT_MAX && (sc < sbest || (sfound && sc == sbest))) {
+                                V3 rd = mk3(s_ray[3][own], s_ray[4][own], s_ray[5][own]);
+                                float toi; uint32_t fid; V3 n;
+                                if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), ro, rd, toi, fid, n) && toi <= sbest &&
+                                    (cull == 0u || (fid & 1u) == cull - 1u)) {  // RayCullingMode::check (ray_trimesh.rs:58-65)
+                                    uint32_t id = __float_as_uint(ta.w);
+                                    if (toi < sbest || (sfound && toi == sbest && id < sid)) {
+                                        cand = true;
+                                        mine = ((unsigned long long)__float_as_uint(fabsf(toi)) << 32) | id;
+                                        c_toi = __float_as_uint(toi); c_fid = fid; c_n = n;
+                                        atomicMin(&s_key[own], mine);
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (cand && s_key[own] == mine) {
+                            s_pay[own] = make_uint2(c_toi, c_fid);
+                            if (WITH_NORMAL) { s_nrm[0][own] = c_n.x; s_nrm[1][own] = c_n.y; s_nrm[2][own] = c_n.z; }
+                        }
+                        __syncwarp();
+                    }
+                }
+                G = 0;
+                pend = false;
+                best = __uint_as_float((uint32_t)(s_key[threadIdx.x] >> 32));
+            }
+        }
+        // ------------------------------------------------------------------ retire
+        if (active && (g_bits >> 24) == 0 && !pend) {
+            unsigned long long k = s_key[threadIdx.x];
+            uint32_t best_id = (uint32_t)k;
+            bool found = best_id != PB2_INVALID_U32;
+            uint2 pay = s_pay[threadIdx.x];
+            out_toi[r] = found ? __uint_as_float(pay.x) : 0.0f;
+            out_tri[r] = best_id;
+            if (WITH_NORMAL) {
+                V3 n = mk3(0.f, 0.f, 0.f);
+                uint32_t feat = PB2_INVALID_U32;
+                if (found) {
+                    n = normalize3(mk3(s_nrm[0][threadIdx.x], s_nrm[1][threadIdx.x], s_nrm[2][threadIdx.x]));
+                    if (pay.y & 2u) n = -n;
+                    if (pose7) n = iso_vec(pose, n);
+                    feat = (pay.y & 1u) ? best_id + nt : best_id;
+                }
+                if (out_normal) { out_normal[3ull * r] = n.x; out_normal[3ull * r + 1] = n.y; out_normal[3ull * r + 2] = n.z; }
+                if (out_feature) out_feature[r] = feat;
+            }
+            active = false;
+        }
+    }
+}
+
 int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, const float* d_rays, const uint32_t* d_perm, uint32_t m,
-                  float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int tri_lanes, int refill, uint32_t cull) {
+                  float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int tri_lanes, int refill, uint32_t cull,
+                  int shared_tri) {
     unsigned int* next_ray = (unsigned int*)(ctx->d_counters + ctx->ray_slot);
     int mode = 0;
     { const char* e = getenv("PB2_RAY_MODE"); if (e) mode = atoi(e) ? 1 : 0; }
     auto kern = with_normal ? (mode ? k_raycast_wide<true, 1> : k_raycast_wide<true, 0>) : (mode ? k_raycast_wide<false, 1> : k_raycast_wide<false, 0>);
+    auto kern_shared = with_normal ? k_raycast_wide_shared<true> : k_raycast_wide_shared<false>;
+    int tri_groups = 12, blocked_max = 8;
+    { const char* e = getenv("PB2_RAY_TRI_GROUPS"); if (e) tri_groups = atoi(e); }
+    { const char* e = getenv("PB2_RAY_BLOCKED"); if (e) blocked_max = atoi(e); }
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
+    if (shared_tri) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_shared, 128, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
     if (per_sm < 1) per_sm = 1;
     unsigned blocks = (unsigned)(ctx->sm_count * per_sm);
     unsigned need = pb2_blocks(m, 128);
@@ -534,8 +770,13 @@ int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, co
         cudaMemsetAsync(d_stats, 0, 64, ctx->stream);
         stats = d_stats;
     }
-    kern<<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi, d_toi, d_tri,
-                                          with_normal ? d_n : nullptr, with_normal ? d_f : nullptr, next_ray, tri_lanes, refill, cull, stats);
+    if (shared_tri)
+        kern_shared<<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi, d_toi, d_tri,
+                                                     with_normal ? d_n : nullptr, with_normal ? d_f : nullptr, next_ray, tri_groups, refill, cull,
+                                                     blocked_max, stats);
+    else
+        kern<<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi, d_toi, d_tri,
+                                              with_normal ? d_n : nullptr, with_normal ? d_f : nullptr, next_ray, tri_lanes, refill, cull, stats);
     if (stats) {
         unsigned long long h[8];
         cudaMemcpyAsync(h, stats, 64, cudaMemcpyDeviceToHost, ctx->stream);

@@ -1,5 +1,5 @@
 """GPU parity of every ray-kernel variant (PB2_RAY_VARIANT: 0 thread-per-ray, 1 persistent binary tree, 2 = 1 + ray
-reordering, 3 compressed 8-wide tree, 4 = 3 + ray reordering) against the CPU oracle and against each other."""
+reordering, 3 compressed 8-wide tree, 4 = 3 + ray reordering, 5 = 3 with the warp-shared triangle phase, 6 = 5 + ray reordering) against the CPU oracle and against each other."""
 import os
 
 import numpy as np
@@ -10,7 +10,7 @@ from helpers import INVALID, check_ray_parity
 
 pytestmark = pytest.mark.gpu
 FMAX = float(np.finfo(np.float32).max)
-VARIANTS = [0, 1, 2, 3, 4]
+VARIANTS = [0, 1, 2, 3, 4, 5, 6]
 
 
 class _Variant:
@@ -67,7 +67,7 @@ def test_variants_agree_bit_for_bit(terrain):
         assert diff.sum() <= 2, int(diff.sum())
 
 
-@pytest.mark.parametrize("variant", [1, 3])
+@pytest.mark.parametrize("variant", [1, 3, 5])
 def test_tie_stress_large_batch(ctx, oracle, variant):
     """Exact toi ties (rays through shared edges / vertices) in batches large enough to take the persistent kernels."""
     import parry_b200
@@ -91,7 +91,7 @@ def test_tie_stress_large_batch(ctx, oracle, variant):
     assert (gi == b[1]).all()  # smallest index among bit-equal minimal toi
 
 
-@pytest.mark.parametrize("variant", [3])
+@pytest.mark.parametrize("variant", [3, 5])
 def test_wide_tree_axis_aligned_and_degenerate_rays(terrain, variant):
     """Directions with zero components (1/0 = inf in the slab test), rays starting inside leaf boxes, zero-length
     directions: the quantised tree must stay a superset of the reference's culling."""
@@ -114,7 +114,7 @@ def test_wide_tree_axis_aligned_and_degenerate_rays(terrain, variant):
     check_ray_parity(g, r, _brute(om, rays, FMAX))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 5])
 def test_duplicate_and_degenerate_triangles(ctx, oracle, variant):
     """Exact duplicates (bit-equal toi: smallest index must win), zero-area triangles (never hit, zero-extent boxes) and a
     far-away outlier (huge root box, coarse quantisation at the top of the wide tree)."""
