@@ -28,7 +28,7 @@ FMAX = float(np.finfo(np.float32).max)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full captures
 # (profiles/*.json); None when no capture of the current kernel version exists.
-PROFILED_TRAFFIC = {"rays_terrain": 4570920904}  # profiles/r1_rays_v7_cubic_lbvh_terrain8M_full.json (k_raycast_wide<false, 0>, this workload)
+PROFILED_TRAFFIC = {"rays_terrain": 4502166952}  # profiles/r1_rays_v8_shared_tri_terrain8M_full.json (k_raycast_wide_shared<false>, this workload)
 
 
 def load_peaks():
@@ -277,7 +277,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": PROFILED_TRAFFIC.get("rays_terrain"), "kernel": "k_raycast_wide<false, 0>", "kernel_ms": ms_kernel,
+                     "traffic": PROFILED_TRAFFIC.get("rays_terrain"), "kernel": "k_raycast_wide_shared<false>", "kernel_ms": ms_kernel,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
     }
 

@@ -53,6 +53,15 @@ static int ctx_init(int device, cudaStream_t stream, bool own, pb2_ctx** out) {
     if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sm > 0) ctx->sm_count = sm;
     if (cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(uint64_t)) != cudaSuccess) { delete ctx; return PB2_ERR_CUDA; }
     if (cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(uint64_t)) != cudaSuccess) { delete ctx; return PB2_ERR_CUDA; }
+    {   // temporaries of the pair / candidate lists come from the stream-ordered pool: keep what it has grown to across
+        // synchronisations (the default threshold of 0 gives the memory back at every sync and re-maps it on the next call,
+        // which showed up as 3-8 ms of idle GPU per TriMesh-contact call); trimmed again in pb2_ctx_destroy
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     *out = ctx;
     return PB2_OK;
 }
@@ -68,6 +77,7 @@ int pb2_ctx_destroy(pb2_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->stage) if (s.ptr) cudaFree(s.ptr);
     for (auto& s : ctx->scratch) if (s.ptr) cudaFree(s.ptr);
+    { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); cudaStreamDestroy(ctx->copy_out); if (ctx->compute2) cudaStreamDestroy(ctx->compute2); for (int i = 0; i < 6; ++i) if (ctx->copy_peer[i]) cudaStreamDestroy(ctx->copy_peer[i]); for (int i = 0; i < 64; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]); }

@@ -306,6 +306,60 @@ __device__ __forceinline__ void emit(const OutSinks& out, uint32_t k, int st, co
 }
 
 // ------------------------------------------------------------------------------------------- phase 1
+// Pairs without a GJK problem (PairSetup::mode == 0): ball-ball and ball <-> cuboid / TriMesh triangle closed forms.
+__device__ __forceinline__ int closed_form_pair(const PairSetup& ps, float prediction, ContactOut& c) {
+    int st;
+    bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
+    if (b1 && b2) st = d_contact_ball_ball(ps.pos12, ps.pr1.x, ps.pr2.x, prediction, c) ? ST_SOME : ST_NONE;
+    else {
+        bool convex_first = b2;
+        float4 prc = convex_first ? ps.pr1 : ps.pr2;
+        float radius = convex_first ? ps.pr2.x : ps.pr1.x;
+        V3 proj; bool inside; Feat f;
+        if (ps.tri) {
+            // PointQuery for Triangle (point_triangle.rs:27-47: location with solid = true); the feature normal of a
+            // triangle is its normal whatever the feature (shape.rs:919-928, triangle.rs:226-228)
+            V3 ta = v3of4(ps.tri[0]), tb = v3of4(ps.tri[1]), tc = v3of4(ps.tri[2]);
+            Proj pr;
+            project_on_triangle(ta, tb, tc, ps.cb_pos12.t, pr);
+            f.kind = 4; f.id = 0;
+            st = d_convex_ball_finish(ps.cb_pos12, false, f, pr.point, pr.inside, radius, prediction, c, ps.tri);
+        } else {
+            d_cuboid_project(mk3(prc.x, prc.y, prc.z), ps.cb_pos12.t, proj, inside, f);
+            st = d_convex_ball_finish(ps.cb_pos12, true, f, proj, inside, radius, prediction, c);
+        }
+        if (st == ST_SOME && !convex_first) flip_contact(c);
+    }
+    return st;
+}
+
+// First simplex of the pair's GJK problem.
+__device__ __forceinline__ void gjk_start(const PairSetup& ps, Simplex& s) {
+    V3 dir; float nn;
+    if (ps.mode == 1) {
+        // contact_support_map_support_map_with_params (contact_support_map_support_map.rs:40-61)
+        if (!try_normalize_get(ps.pos12.t, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
+        sx_reset(s, cso_from_shapes(ps.gpos12, ps.g1, ps.g2, dir));
+    } else {
+        // point_support_map.rs:26-31: dir = normalize(point) or +x; support with m_inv = Isometry(point)
+        V3 point = ps.cb_pos12.t;
+        if (!try_normalize_get(point, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
+        Iso7 m_inv; m_inv.q.i = 0.f; m_inv.q.j = 0.f; m_inv.q.k = 0.f; m_inv.q.w = 1.f; m_inv.t = point;
+        sx_reset(s, cso_from_shapes(m_inv, ps.g1, ps.g2, dir));
+    }
+}
+
+// GJK answered Intersection: the simplex goes to the EPA queue.
+__device__ __forceinline__ void park_epa_job(EpaJob* __restrict__ jobs, unsigned long long* job_count, uint32_t k, const Simplex& s) {
+    unsigned long long at = warp_append1(job_count);
+    EpaJob* j = &jobs[at];
+    j->pair = k; j->dim = (uint32_t)s.dim;
+    for (int i = 0; i <= s.dim; ++i) {
+        j->o1[i][0] = s.v[i].o1.x; j->o1[i][1] = s.v[i].o1.y; j->o1[i][2] = s.v[i].o1.z;
+        j->o2[i][0] = s.v[i].o2.x; j->o2[i][1] = s.v[i].o2.y; j->o2[i][2] = s.v[i].o2.z;
+    }
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_contact_gjk(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
                               const float4* __restrict__ pts, uint32_t n_shapes, PairSrc src, float prediction, uint32_t n, OutSinks out,
@@ -324,53 +378,15 @@ __global__ void __launch_bounds__(128, MINB) k_contact_gjk(const uint8_t* __rest
     pair_setup(kinds, params, pts, src, k, ps);
     int st;
     if (ps.mode == 0) {
-        bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
-        if (b1 && b2) st = d_contact_ball_ball(ps.pos12, ps.pr1.x, ps.pr2.x, prediction, c) ? ST_SOME : ST_NONE;
-        else {
-            // ball <-> cuboid / TriMesh triangle (closed-form projections)
-            bool convex_first = b2;
-            float4 prc = convex_first ? ps.pr1 : ps.pr2;
-            float radius = convex_first ? ps.pr2.x : ps.pr1.x;
-            V3 proj; bool inside; Feat f;
-            if (ps.tri) {
-                // PointQuery for Triangle (point_triangle.rs:27-47: location with solid = true); the feature normal of a
-                // triangle is its normal whatever the feature (shape.rs:919-928, triangle.rs:226-228)
-                V3 ta = v3of4(ps.tri[0]), tb = v3of4(ps.tri[1]), tc = v3of4(ps.tri[2]);
-                Proj pr;
-                project_on_triangle(ta, tb, tc, ps.cb_pos12.t, pr);
-                f.kind = 4; f.id = 0;
-                st = d_convex_ball_finish(ps.cb_pos12, false, f, pr.point, pr.inside, radius, prediction, c, ps.tri);
-            } else {
-                d_cuboid_project(mk3(prc.x, prc.y, prc.z), ps.cb_pos12.t, proj, inside, f);
-                st = d_convex_ball_finish(ps.cb_pos12, true, f, proj, inside, radius, prediction, c);
-            }
-            if (st == ST_SOME && !convex_first) flip_contact(c);
-        }
+        st = closed_form_pair(ps, prediction, c);
     } else {
         Simplex s;
-        V3 dir; float nn;
-        if (ps.mode == 1) {
-            // contact_support_map_support_map_with_params (contact_support_map_support_map.rs:40-61)
-            if (!try_normalize_get(ps.pos12.t, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
-            sx_reset(s, cso_from_shapes(ps.gpos12, ps.g1, ps.g2, dir));
-        } else {
-            // point_support_map.rs:26-31: dir = normalize(point) or +x; support with m_inv = Isometry(point)
-            V3 point = ps.cb_pos12.t;
-            if (!try_normalize_get(point, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
-            Iso7 m_inv; m_inv.q.i = 0.f; m_inv.q.j = 0.f; m_inv.q.k = 0.f; m_inv.q.w = 1.f; m_inv.t = point;
-            sx_reset(s, cso_from_shapes(m_inv, ps.g1, ps.g2, dir));
-        }
+        gjk_start(ps, s);
         V3 p1, p2, n1;
         float max_dist = ps.mode == 1 ? prediction : FLT_MAX;
         int r = gjk_closest_points(ps.gpos12, ps.g1, ps.g2, max_dist, s, p1, p2, n1);
         if (r == GJK_INTERSECTION) {
-            unsigned long long at = warp_append1(job_count);
-            EpaJob* j = &jobs[at];
-            j->pair = k; j->dim = (uint32_t)s.dim;
-            for (int i = 0; i <= s.dim; ++i) {
-                j->o1[i][0] = s.v[i].o1.x; j->o1[i][1] = s.v[i].o1.y; j->o1[i][2] = s.v[i].o1.z;
-                j->o2[i][0] = s.v[i].o2.x; j->o2[i][1] = s.v[i].o2.y; j->o2[i][2] = s.v[i].o2.z;
-            }
+            park_epa_job(jobs, job_count, k, s);
             return;  // finished by phase 2
         } else if (r == GJK_CLOSEST_POINTS) {
             st = finish_gjk_pair(ps, false, p1, p2, n1, prediction, c);
@@ -380,6 +396,124 @@ __global__ void __launch_bounds__(128, MINB) k_contact_gjk(const uint8_t* __rest
     }
     if (st == ST_SOME) to_world(ps, c);
     emit(out, k, st, c);
+}
+
+
+// Phase 1, persistent form: warps pull pairs from a counter and every trip runs ONE GJK iteration per lane, so a pair that
+// needs ten iterations no longer holds the lanes of pairs that needed three (k_contact_gjk runs at 15.9 of 32 active
+// lanes on the 4M hull-pair config). Lanes whose GJK has answered wait as "pending"; once `refill` lanes are pending or
+// idle, one pass builds the pending lanes' contacts (or parks their simplex for EPA) and hands all of them new pairs —
+// so the epilogue and the pair setup also run with many lanes. Same arithmetic as gjk_closest_points, flattened.
+enum { G_IDLE = 0, G_RUN = 1, G_PEND = 2 };
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_contact_gjk_persistent(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
+                              const float4* __restrict__ pts, uint32_t n_shapes, PairSrc src, float prediction, uint32_t n, OutSinks out,
+                              EpaJob* __restrict__ jobs, unsigned long long* job_count, unsigned long long* __restrict__ next_pair, int refill) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const float eps_tol = PB2_GJK_EPS_TOL;
+    const float eps_rel = sqrtf(eps_tol);
+    int state = G_IDLE, res = GJK_NO_INTERSECTION, niter = 0;
+    bool wit_prev = false, exhausted = false;
+    uint32_t k = 0;
+    Simplex s;
+    Iso7 gpos12;
+    DShape g1, g2;
+    g1 = origin_dshape(); g2 = origin_dshape();
+    gpos12.q.i = gpos12.q.j = gpos12.q.k = 0.f; gpos12.q.w = 1.f; gpos12.t = mk3(0.f, 0.f, 0.f);
+    V3 proj = mk3(0.f, 0.f, 0.f), old_dir = proj, res_dir = proj;
+    float max_bound = FLT_MAX, max_dist = 0.0f;
+    for (;;) {
+        unsigned running = __ballot_sync(FULL, state == G_RUN);
+        unsigned pend = __ballot_sync(FULL, state == G_PEND);
+        if ((32 - __popc(running) >= refill || running == 0u) && (pend != 0u || !exhausted)) {
+            if (state == G_PEND) {
+                if (res == GJK_INTERSECTION) {
+                    park_epa_job(jobs, job_count, k, s);
+                } else {
+                    PairSetup ps;
+                    pair_setup(kinds, params, pts, src, k, ps);
+                    ContactOut c;
+                    int st = ST_NONE;
+                    if (res == GJK_CLOSEST_POINTS) {
+                        V3 p1, p2;
+                        gjk_witness(s, wit_prev, p1, p2);
+                        st = finish_gjk_pair(ps, false, p1, p2, res_dir, prediction, c);
+                    }
+                    if (st == ST_SOME) to_world(ps, c);
+                    emit(out, k, st, c);
+                }
+                state = G_IDLE;
+            }
+            if (!exhausted) {
+                unsigned idle = __ballot_sync(FULL, state == G_IDLE);
+                unsigned long long base = 0;
+                int leader = __ffs(idle) - 1;
+                if (lane == leader) base = atomicAdd(next_pair, (unsigned long long)__popc(idle));
+                base = __shfl_sync(FULL, base, leader);
+                if (base + __popc(idle) >= n) exhausted = true;
+                unsigned long long slot = base + __popc(idle & ((1u << lane) - 1u));
+                if (state == G_IDLE && slot < n) {
+                    k = (uint32_t)slot;
+                    ContactOut c;
+                    uint32_t i1 = k, i2 = k;
+                    if (src.ab) { i1 = src.ab[2ull * k]; i2 = src.ab[2ull * k + 1]; }
+                    bool bad = src.ab && (i1 >= src.n_first || i2 >= src.n_second);
+                    if (!bad) bad = src.shape2[i2] >= n_shapes || (!src.mesh_tris && src.shape1[i1] >= n_shapes);
+                    if (bad) {
+                        emit(out, k, ST_UNSUPPORTED, c);
+                    } else {
+                        PairSetup ps;
+                        pair_setup(kinds, params, pts, src, k, ps);
+                        if (ps.mode == 0) {
+                            int st = closed_form_pair(ps, prediction, c);
+                            if (st == ST_SOME) to_world(ps, c);
+                            emit(out, k, st, c);
+                        } else {
+                            gjk_start(ps, s);
+                            gpos12 = ps.gpos12; g1 = ps.g1; g2 = ps.g2;
+                            max_dist = ps.mode == 1 ? prediction : FLT_MAX;
+                            proj = sx_project_origin_and_reduce(s);
+                            V3 pd; float nn;
+                            if (try_normalize_get(proj, 0.0f, pd, nn)) { old_dir = -pd; state = G_RUN; max_bound = FLT_MAX; niter = 0; }
+                            else { res = GJK_INTERSECTION; state = G_PEND; }
+                        }
+                    }
+                }
+            }
+            running = __ballot_sync(FULL, state == G_RUN);
+            pend = __ballot_sync(FULL, state == G_PEND);
+        }
+        if (running == 0u && pend == 0u && exhausted) break;
+        if (state == G_RUN) {  // one trip of the loop in gjk::closest_points (gjk.rs:371-447)
+            float old_max_bound = max_bound;
+            V3 dir; float dist;
+            if (!try_normalize_get(-proj, eps_tol, dir, dist)) { res = GJK_INTERSECTION; state = G_PEND; }
+            else {
+                max_bound = dist;
+                if (max_bound >= old_max_bound) { res = GJK_CLOSEST_POINTS; wit_prev = true; res_dir = old_dir; state = G_PEND; }
+                else {
+                    CSO cso = cso_from_shapes(gpos12, g1, g2, dir);
+                    float min_bound = -dot3(dir, cso.point);
+                    if (min_bound > max_dist) { res = GJK_NO_INTERSECTION; state = G_PEND; }
+                    else if (max_bound - min_bound <= eps_rel * max_bound || !sx_add_point(s, cso)) {
+                        res = GJK_CLOSEST_POINTS; wit_prev = false; res_dir = dir; state = G_PEND;
+                    } else {
+                        old_dir = dir;
+                        proj = sx_project_origin_and_reduce(s);
+                        if (s.dim == 3) {
+                            if (min_bound >= eps_tol) { res = GJK_CLOSEST_POINTS; wit_prev = true; res_dir = old_dir; }
+                            else res = GJK_INTERSECTION;
+                            state = G_PEND;
+                        } else {
+                            niter += 1;
+                            if (niter == 100) { res = GJK_NO_INTERSECTION; state = G_PEND; }
+                        }
+                    }
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------- phase 2, flattened
@@ -1281,7 +1415,23 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
     int gjk_minb = 4;  // 128 registers, 4 CTAs per SM: 0.7 ms faster than the unconstrained 151-register build on the 4M-pair config
     { const char* e = getenv("PB2_GJK_MINB"); if (e) gjk_minb = atoi(e); }
     auto gjk = gjk_minb >= 5 ? k_contact_gjk<5> : (gjk_minb == 4 ? k_contact_gjk<4> : k_contact_gjk<3>);
-    gjk<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, src, prediction, n, sinks, jobs, job_count);
+    int gjk_persistent = 0, gjk_refill = 12;  // measured: no gain on hull pairs (31.9 vs 31.4 ms), 2.7x slower on TriMesh candidates
+    { const char* e = getenv("PB2_GJK_PERSISTENT"); if (e) gjk_persistent = atoi(e); }
+    { const char* e = getenv("PB2_GJK_REFILL"); if (e) gjk_refill = atoi(e); }
+    if (gjk_persistent && n >= 4096) {
+        auto gjkp = gjk_minb >= 5 ? k_contact_gjk_persistent<5> : (gjk_minb == 4 ? k_contact_gjk_persistent<4> : k_contact_gjk_persistent<3>);
+        unsigned long long* next_pair = (unsigned long long*)(ctx->d_counters + 9);
+        PB2_CUDA(ctx, cudaMemsetAsync(next_pair, 0, 8, st));
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjkp, 128, 0);
+        if (per_sm < 1) per_sm = 1;
+        unsigned blocks = (unsigned)(ctx->sm_count * per_sm), need = pb2_blocks(n, 128);
+        if (blocks > need) blocks = need;
+        gjkp<<<blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, src, prediction, n, sinks, jobs, job_count,
+                                     next_pair, gjk_refill);
+    } else {
+        gjk<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, src, prediction, n, sinks, jobs, job_count);
+    }
     PB2_LAUNCHED(ctx);
     if (epa_variant == 3) {
         int per_sm = 0;
