@@ -58,6 +58,9 @@ def lib():
         l.pb2o_bvh_leaf_pairs.restype = u64
         l.pb2o_bvh_leaf_pairs.argtypes = [P, P, P, u64]
         l.pb2o_bvh_cast_rays_shapes.argtypes = [P, P, P, P, P, u32, f32, i32, i32, P, P, P, P]
+        l.pb2o_bvh_cast_rays_shapes2.argtypes = [P, P, P, P, P, P, P, P, u32, f32, i32, i32, P, P, P, P]
+        l.pb2o_convex_cast_ray.restype = i32
+        l.pb2o_convex_cast_ray.argtypes = [P, u32, P, P, f32, i32, P, P]
         l.pb2o_shape_cast_ray.restype = i32
         l.pb2o_shape_cast_ray.argtypes = [i32, P, P, P, f32, i32, P, P, P]
         l.pb2o_shape_cast_ray_toi.restype = i32
@@ -205,7 +208,9 @@ class Bvh:
         lib().pb2o_bvh_leaf_pairs(self.h, other.h, pairs.ctypes.data, total)
         return pairs[:total]
 
-    def cast_rays_shapes(self, kinds, params, poses, rays, max_toi, solid=True, with_normal=False, threads=1):
+    def cast_rays_shapes(self, kinds, params, poses, rays, max_toi, solid=True, with_normal=False, threads=1, points=None, first=None,
+                         count=None):
+        """Leaf i = shape kinds[i] (0 ball, 1 cuboid, 2 ConvexPolyhedron = points[first[i] : first[i] + count[i]]) at poses[i]."""
         rays = _f32(rays)
         m = rays.shape[0]
         kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
@@ -215,10 +220,18 @@ class Bvh:
         leaf = np.zeros(m, dtype=np.uint32)
         normal = np.zeros((m, 3), dtype=np.float32) if with_normal else None
         feature = np.zeros(m, dtype=np.uint32) if with_normal else None
-        lib().pb2o_bvh_cast_rays_shapes(self.h, kinds.ctypes.data, params.ctypes.data, poses.ctypes.data, rays.ctypes.data, m, max_toi,
-                                        int(solid), threads, toi.ctypes.data, leaf.ctypes.data,
-                                        None if normal is None else normal.ctypes.data,
-                                        None if feature is None else feature.ctypes.data)
+        if points is not None:
+            points = _f32(points).reshape(-1, 3)
+            first = np.ascontiguousarray(first, dtype=np.uint32)
+            count = np.ascontiguousarray(count, dtype=np.uint32)
+        else:
+            assert not (kinds == 2).any()
+        lib().pb2o_bvh_cast_rays_shapes2(self.h, kinds.ctypes.data, params.ctypes.data,
+                                         None if points is None else points.ctypes.data, None if points is None else first.ctypes.data,
+                                         None if points is None else count.ctypes.data, poses.ctypes.data, rays.ctypes.data, m, max_toi,
+                                         int(solid), threads, toi.ctypes.data, leaf.ctypes.data,
+                                         None if normal is None else normal.ctypes.data,
+                                         None if feature is None else feature.ctypes.data)
         return (toi, leaf, normal, feature) if with_normal else (toi, leaf)
 
     def __del__(self):
@@ -226,6 +239,18 @@ class Bvh:
             lib().pb2o_bvh_destroy(self.h)
         except Exception:
             pass
+
+
+def convex_cast_ray(points, pose, ray, max_toi, solid=True):
+    """RayCast::cast_ray_and_get_normal for one ConvexPolyhedron (ray_support_map.rs:163-181). Returns None or (toi, normal)."""
+    p = _f32(points).reshape(-1, 3)
+    po = None if pose is None else _f32(pose)
+    r = _f32(ray)
+    toi = C.c_float(0.0)
+    n = np.zeros(3, dtype=np.float32)
+    hit = lib().pb2o_convex_cast_ray(p.ctypes.data, p.shape[0], None if po is None else po.ctypes.data, r.ctypes.data, max_toi, int(solid),
+                                     C.byref(toi), n.ctypes.data)
+    return (np.float32(toi.value), n) if hit else None
 
 
 def shape_cast_ray(kind, params, pose, ray, max_toi, solid=True):

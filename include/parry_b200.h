@@ -180,8 +180,10 @@ int pb2_shapes_compute_aabbs(pb2_ctx* ctx, const pb2_shapes* shapes, const uint3
                              uint32_t n, float* aabbs, int mem);
 
 /* Bvh::cast_ray with typed leaves (bvh_queries.rs:260-271 + RayCast for Ball ray_ball.rs:8-98 / Cuboid
- * ray_cuboid.rs:6-25 + ray_aabb.rs:52-92 + clip_aabb_line.rs:79-187): leaf i of `bvh` is shape shape_ids[i]
- * at poses7[i]. Convex leaves are PB2_ERR_UNSUPPORTED. normal/feature may be NULL. */
+ * ray_cuboid.rs:6-25 + ray_aabb.rs:52-92 + clip_aabb_line.rs:79-187 / ConvexPolyhedron ray_support_map.rs:19-72,163-181
+ * + gjk.rs:519-534,660-795): leaf i of `bvh` is shape shape_ids[i] at poses7[i]. feature: Face(i) as i for ball / cuboid
+ * leaves, PB2_FEATURE_UNKNOWN (FeatureId::Unknown) for convex leaves, 0xFFFFFFFF on a miss. normal/feature may be NULL. */
+#define PB2_FEATURE_UNKNOWN 0xFFFFFFFEu
 int pb2_bvh_cast_rays_shapes(pb2_ctx* ctx, const pb2_bvh* bvh, const pb2_shapes* shapes, const uint32_t* shape_ids,
                              const float* poses7, const float* rays, uint32_t m, float max_toi, int solid, float* toi,
                              uint32_t* leaf, float* normal, uint32_t* feature, int mem);

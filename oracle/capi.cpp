@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY. C entry points for ctypes (tests/, __graft_entry__.smoke(),
 // bench.py cpu_baseline / --impl reference). The product library never links this file.
 #include "ray.hpp"
+#include "ray_support_map.hpp"
 #include <thread>
 #include <algorithm>
 
@@ -119,10 +120,12 @@ uint64_t pb2o_bvh_leaf_pairs(void* b1, void* b2, uint32_t* pairs, uint64_t cap) 
     return count;
 }
 
-// Bvh::cast_ray with typed leaves: kind 0 = Ball (param = radius), kind 1 = Cuboid (param = half extents).
+// Bvh::cast_ray with typed leaves: kind 0 = Ball (param = radius), kind 1 = Cuboid (param = half extents), kind 2 =
+// ConvexPolyhedron (points + 3 * first[i], count[i] points; ray_support_map.rs:163-181).
 // leaf i: pose7[i], kinds[i], params[3*i..]. toi-only when normal == NULL.
-void pb2o_bvh_cast_rays_shapes(void* b, const uint8_t* kinds, const float* params, const float* poses7, const float* rays,
-                               uint32_t m, float max_toi, int solid, int nthreads, float* toi, uint32_t* leaf, float* normal, uint32_t* feature) {
+void pb2o_bvh_cast_rays_shapes2(void* b, const uint8_t* kinds, const float* params, const float* points, const uint32_t* first,
+                                const uint32_t* count, const float* poses7, const float* rays, uint32_t m, float max_toi, int solid,
+                                int nthreads, float* toi, uint32_t* leaf, float* normal, uint32_t* feature) {
     const Bvh* t = (const Bvh*)b;
     parallel_for(m, nthreads, [=](size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; ++i) {
@@ -134,7 +137,12 @@ void pb2o_bvh_cast_rays_shapes(void* b, const uint8_t* kinds, const float* param
                     Iso pose = Iso::from7(poses7 + 7 * prim);
                     Ray ls = ray.inverse_transform_by(pose);
                     bool h;
-                    if (normal) {
+                    if (kinds[prim] == 2) {
+                        // RayCast::cast_local_ray defaults to the normal variant (ray.rs:362-371)
+                        h = support_map_cast_local_ray_and_get_normal(SupportShape::convex(points + 3 * (size_t)first[prim], count[prim]), ls, bsf,
+                                                                      solid != 0, ri);
+                        if (h && normal) ri.normal = pose.transform_vector(ri.normal);
+                    } else if (normal) {
                         h = kinds[prim] == 0 ? ball_cast_local_ray_and_get_normal(params[3 * prim], ls, bsf, solid != 0, ri)
                                              : cuboid_cast_local_ray_and_get_normal(ld3(params + 3 * prim), ls, bsf, solid != 0, ri);
                         if (h) ri.normal = pose.transform_vector(ri.normal);
@@ -152,6 +160,21 @@ void pb2o_bvh_cast_rays_shapes(void* b, const uint8_t* kinds, const float* param
             if (feature) feature[i] = best.feature;
         }
     });
+}
+void pb2o_bvh_cast_rays_shapes(void* b, const uint8_t* kinds, const float* params, const float* poses7, const float* rays,
+                               uint32_t m, float max_toi, int solid, int nthreads, float* toi, uint32_t* leaf, float* normal, uint32_t* feature) {
+    pb2o_bvh_cast_rays_shapes2(b, kinds, params, nullptr, nullptr, nullptr, poses7, rays, m, max_toi, solid, nthreads, toi, leaf, normal, feature);
+}
+// RayCast for ConvexPolyhedron, one shape (world-space ray, pose7 may be NULL). returns 1 on hit.
+int pb2o_convex_cast_ray(const float* points, uint32_t n, const float* pose7, const float* ray6, float max_toi, int solid, float* toi, float* normal) {
+    Iso pose = pose7 ? Iso::from7(pose7) : Iso();
+    Ray ray(ld3(ray6), ld3(ray6 + 3));
+    Ray ls = pose7 ? ray.inverse_transform_by(pose) : ray;
+    RayIntersection ri;
+    if (!support_map_cast_local_ray_and_get_normal(SupportShape::convex(points, n), ls, max_toi, solid != 0, ri)) return 0;
+    *toi = ri.time_of_impact;
+    if (normal) st3(normal, pose7 ? pose.transform_vector(ri.normal) : ri.normal);
+    return 1;
 }
 
 // Single-shape ray casts (RayCast for Ball / Cuboid / Triangle), world-space with pose (ray.rs:381-411).

@@ -364,3 +364,93 @@ __device__ __forceinline__ int gjk_closest_points(const Iso7& pos12, const DShap
         if (niter == 100) { out_dir = mk3(1.f, 0.f, 0.f); return GJK_NO_INTERSECTION; }
     }
 }
+
+// ---- ray casts on support-mapped shapes
+// gjk::cast_local_ray (gjk.rs:519-534) = minkowski_ray_cast (gjk.rs:660-795) with g2 = ConstantOrigin, pos12 = identity;
+// ray_toi_with_halfspace (ray_halfspace.rs:9-39) inlined. Returns the hit as (toi, outward normal).
+__device__ __forceinline__ bool gjk_cast_local_ray(const DShape& shape, Simplex& s, V3 ro, V3 rd, float max_toi, float& toi, V3& normal) {
+    const float eps_tol = PB2_GJK_EPS_TOL;
+    const float eps_rel = sqrtf(eps_tol);
+    float ray_length = nrm(rd);
+    if (rel_eq(ray_length, 0.0f, PB2_EPS, PB2_EPS)) return false;
+    float ltoi = 0.0f;
+    V3 co = ro, cd = rd / ray_length;
+    V3 dir = -cd, ldir = dir;
+    {
+        V3 sp = ds_local_support(shape, dir);
+        CSO c0 = cso_make(sp, mk3(0.f, 0.f, 0.f));
+        c0.point = c0.point + (-co);
+        sx_reset(s, c0);
+    }
+    V3 proj = sx_project_origin_and_reduce(s);
+    float max_bound = FLT_MAX;
+    int niter = 0;
+    bool last_chance = false;
+    for (;;) {
+        float old_max_bound = max_bound;
+        float dist;
+        if (try_normalize_get(-proj, eps_tol, dir, dist)) max_bound = dist;
+        else { toi = ltoi / ray_length; normal = ldir; return true; }
+        CSO sp;
+        if (max_bound >= old_max_bound) {
+            last_chance = true;
+            V3 p = proj + co;
+            sp.point = p; sp.o1 = p; sp.o2 = mk3(0.f, 0.f, 0.f);
+        } else {
+            sp = cso_make(ds_local_support(shape, dir), mk3(0.f, 0.f, 0.f));
+        }
+        if (last_chance && ltoi > 0.0f) { toi = ltoi / ray_length; normal = ldir; return true; }
+        float denom = dot3(dir, cd);
+        bool some = false;
+        float t = 0.0f;
+        if (!rel_eq(denom, 0.0f, PB2_EPS, PB2_EPS)) {
+            t = dot3(dir, sp.point - co) / denom;
+            some = t >= 0.0f;
+        }
+        if (some) {
+            if (dot3(dir, cd) < 0.0f && t > 0.0f) {
+                ldir = dir;
+                ltoi += t;
+                if (ltoi / ray_length > max_toi) return false;
+                V3 shift = cd * t;
+                co = co + shift;
+                max_bound = FLT_MAX;
+                for (int i = 0; i <= s.dim; ++i) s.v[i].point = s.v[i].point + (-shift);
+                last_chance = false;
+            }
+        } else if (dot3(dir, cd) > eps_tol) {
+            return false;
+        }
+        if (last_chance) return false;
+        float min_bound = -dot3(dir, sp.point - co);
+        if (max_bound - min_bound <= eps_rel * max_bound) return false;
+        sp.point = sp.point + (-co);
+        (void)sx_add_point(s, sp);
+        proj = sx_project_origin_and_reduce(s);
+        if (s.dim == 3) {
+            if (min_bound >= eps_tol) return false;
+            toi = ltoi / ray_length; normal = ldir; return true;
+        }
+        niter += 1;
+        if (niter == 100) return false;
+    }
+}
+
+// local_ray_intersection_with_support_map_with_params (ray_support_map.rs:19-72); the feature is FeatureId::Unknown.
+__device__ __forceinline__ bool ray_support_map(const DShape& shape, V3 ro, V3 rd, float max_toi, bool solid, float& toi, V3& normal) {
+    Simplex s;
+    if (!gjk_cast_local_ray(shape, s, ro, rd, max_toi, toi, normal)) return false;
+    if (!solid && toi == 0.0f) {
+        // the ray starts inside the shape: cast it back from beyond the far side
+        V3 ndir = rd / nrm(rd);
+        V3 supp = ds_local_support(shape, ndir);
+        const float eps = 0.001f;
+        float shift = dot3(supp - ro, ndir) + eps;
+        float t2; V3 n2;
+        if (!gjk_cast_local_ray(shape, s, ro + ndir * shift, -rd, shift + eps, t2, n2)) return false;
+        float t = shift - t2;
+        if (!(t <= max_toi)) return false;
+        toi = t; normal = -n2;
+    }
+    return true;
+}

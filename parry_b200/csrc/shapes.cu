@@ -5,6 +5,7 @@
 // Bvh::cast_ray (bvh_queries.rs:260-271) with leaves = RayCast for Ball (query/ray/ray_ball.rs:8-98) and
 // Cuboid (ray_cuboid.rs:6-25 -> ray_aabb.rs:12-92 -> query/clip/clip_aabb_line.rs:79-187).
 #include "shapes.cuh"
+#include "gjk.cuh"
 #include "traverse.cuh"
 
 int pb2_stage_in(pb2_ctx* ctx, int slot, const void* src, size_t bytes, int mem, const void** out);
@@ -133,7 +134,7 @@ __device__ __forceinline__ bool ray_cuboid_normal(V3 he, V3 o, V3 d, float max_t
 
 template <bool WITH_NORMAL>
 __global__ void __launch_bounds__(128) k_raycast_shapes(const NodeWide* __restrict__ nodes, const uint32_t* __restrict__ order, uint32_t n_leaves,
-                                 const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
+                                 const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float4* __restrict__ pts,
                                  const uint32_t* __restrict__ shape_ids, const float* __restrict__ poses, const float* __restrict__ rays,
                                  uint32_t m, float max_toi, bool solid, float* __restrict__ out_toi, uint32_t* __restrict__ out_leaf,
                                  float* __restrict__ out_normal, uint32_t* __restrict__ out_feature) {
@@ -163,10 +164,16 @@ __global__ void __launch_bounds__(128) k_raycast_shapes(const NodeWide* __restri
                 if (inside) n = -n;
             }
             hit = hit && toi <= best;
-        } else {
+        } else if (kinds[sid] == PB2_SHAPE_CUBOID) {
             V3 he = mk3(pr.x, pr.y, pr.z);
             if (WITH_NORMAL) hit = ray_cuboid_normal(he, lo, ld, best, solid, toi, n, feat);
             else hit = ray_cuboid_toi(he, lo, ld, best, solid, toi);
+        } else {
+            // RayCast for ConvexPolyhedron (ray_support_map.rs:163-181): GJK ray cast, FeatureId::Unknown
+            DShape g;
+            g.kind = DS_CONVEX; g.he = mk3(0.f, 0.f, 0.f); g.pts = pts + __float_as_uint(pr.x); g.n = __float_as_uint(pr.y);
+            hit = ray_support_map(g, lo, ld, best, solid, toi, n);
+            feat = PB2_FEATURE_UNKNOWN;
         }
         if (!hit) return;
         if (toi < best || (found && toi == best && id < best_id)) {
@@ -271,7 +278,6 @@ int pb2_bvh_cast_rays_shapes(pb2_ctx* ctx, const pb2_bvh* bvh, const pb2_shapes*
                              const float* poses7, const float* rays, uint32_t m, float max_toi, int solid, float* toi, uint32_t* leaf,
                              float* normal, uint32_t* feature, int mem) {
     if (!ctx || !bvh || !shapes || !poses7 || (m && (!rays || !toi || !leaf))) return PB2_ERR_INVALID;
-    if (shapes->has_convex) PB2_FAIL(ctx, PB2_ERR_UNSUPPORTED, "ray casts on ConvexPolyhedron leaves are out of scope");
     if (m == 0) return PB2_OK;
     PB2_CUDA(ctx, cudaSetDevice(ctx->device));
     uint32_t nl = bvh->n_leaves;
@@ -286,12 +292,12 @@ int pb2_bvh_cast_rays_shapes(pb2_ctx* ctx, const pb2_bvh* bvh, const pb2_shapes*
     PB2_CHECK(pb2_stage_out(ctx, 5, feature, (size_t)m * 4, mem, &d_f));
     unsigned blocks = pb2_blocks(m, 128);
     if (normal || feature)
-        k_raycast_shapes<true><<<blocks, 128, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_order, nl, shapes->kinds, shapes->params,
+        k_raycast_shapes<true><<<blocks, 128, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_order, nl, shapes->kinds, shapes->params, shapes->points4,
                                                                 (const uint32_t*)d_ids, (const float*)d_poses, (const float*)d_rays, m,
                                                                 max_toi, solid != 0, (float*)d_toi, (uint32_t*)d_leaf, (float*)d_n,
                                                                 (uint32_t*)d_f);
     else
-        k_raycast_shapes<false><<<blocks, 128, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_order, nl, shapes->kinds, shapes->params,
+        k_raycast_shapes<false><<<blocks, 128, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_order, nl, shapes->kinds, shapes->params, shapes->points4,
                                                                  (const uint32_t*)d_ids, (const float*)d_poses, (const float*)d_rays, m,
                                                                  max_toi, solid != 0, (float*)d_toi, (uint32_t*)d_leaf, nullptr, nullptr);
     PB2_LAUNCHED(ctx);

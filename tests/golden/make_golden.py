@@ -92,5 +92,38 @@ def more():
                         contacts_min_index=out2, part_min_index=part2)
 
 
+def shape_rays():
+    """Bvh::cast_ray over ball / cuboid / ConvexPolyhedron leaves (solid and non-solid), 400 colliders, 3000 rays."""
+    n, H = 400, 16
+    g = scenes.rng(201)
+    hulls, _ = scenes.hull_pool(H, 16, seed=202)
+    hulls = (hulls * 0.5).astype(np.float32)
+    kinds = g.integers(0, 3, n).astype(np.uint8)
+    params = (g.random((n, 3)) * 0.3 + 0.15).astype(np.float32)
+    hid = g.integers(0, H, n)
+    side = (n ** (1 / 3)) * 1.2
+    poses = np.concatenate([scenes.random_unit_quaternions(g, n), g.random((n, 3)) * side], axis=1).astype(np.float32)
+    points = np.concatenate([hulls[h] for h in hid]).astype(np.float32)
+    first = (np.arange(n) * 16).astype(np.uint32)
+    count = np.full(n, 16, np.uint32)
+    aabbs = oracle.shape_aabbs(kinds, params, poses, points, first, count)
+    ob = oracle.Bvh(aabbs)
+    d = g.standard_normal((3000, 3))
+    d[::2] /= np.linalg.norm(d[::2], axis=1, keepdims=True)
+    rays = np.concatenate([g.random((3000, 3)) * side, d], axis=1).astype(np.float32)
+    res = {}
+    for solid in (True, False):
+        toi, leaf, nrm, feat = ob.cast_rays_shapes(kinds, params, poses, rays, FMAX, solid=solid, with_normal=True, points=points, first=first,
+                                                   count=count)
+        tag = "solid" if solid else "hollow"
+        res.update({tag + "_toi": toi, tag + "_leaf": leaf, tag + "_normal": nrm, tag + "_feature": feat})
+    np.savez_compressed(os.path.join(HERE, "rays_shapes_400.npz"), kinds=kinds, params=params, poses=poses, points=points, first=first, count=count,
+                        aabbs=aabbs, rays=rays, **res)
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if "shape_rays" in sys.argv:
+        shape_rays()
+    else:
+        main()

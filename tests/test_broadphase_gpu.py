@@ -303,3 +303,47 @@ def test_full_size_config2_frame(ctx):
     insel[sel] = True
     mask = insel[p1[:, 0]] & insel[p1[:, 1]]
     assert (sorted_pairs(p1[mask]) == bk).all()
+
+
+def test_bvh_cast_ray_convex_leaves(ctx, oracle):
+    """SURVEY §8 f3 (ray vs hull): Bvh::cast_ray over ball / cuboid / ConvexPolyhedron leaves; the convex leaves go through
+    the GJK ray cast (ray_support_map.rs:19-72, gjk.rs:660-795). Ids exact (ties: smallest id), toi / normals 1e-5."""
+    import parry_b200
+    n, H = 1500, 64
+    g0 = scenes.rng(61)
+    hulls, _ = scenes.hull_pool(H, 16, seed=62)
+    hulls = (hulls * 0.5).astype(np.float32)
+    kinds = g0.integers(0, 3, n).astype(np.uint8)
+    params = (g0.random((n, 3)) * 0.3 + 0.15).astype(np.float32)
+    hid = g0.integers(0, H, n)
+    side = (n ** (1 / 3)) * 1.2
+    poses = np.concatenate([scenes.random_unit_quaternions(g0, n), g0.random((n, 3)) * side], axis=1).astype(np.float32)
+    shapes = parry_b200.Shapes(ctx, [parry_b200.Ball(p[0]) if k == 0 else parry_b200.Cuboid(p) if k == 1 else parry_b200.ConvexPolyhedron(hulls[h])
+                                     for k, p, h in zip(kinds, params, hid)])
+    ids = np.arange(n, dtype=np.uint32)
+    aabbs = shapes.compute_aabbs(ids, poses)
+    gb, ob = parry_b200.Bvh.from_leaves(ctx, 0, aabbs), oracle.Bvh(aabbs)
+    points = np.concatenate([hulls[h] for h in hid])
+    first = (np.arange(n) * 16).astype(np.uint32)
+    count = np.full(n, 16, np.uint32)
+    o = g0.random((20000, 3)) * side
+    d = g0.standard_normal((20000, 3))
+    d[::2] /= np.linalg.norm(d[::2], axis=1, keepdims=True)
+    rays = np.concatenate([o, d], axis=1).astype(np.float32)
+    for solid in (True, False):
+        for max_toi in (FMAX, 1.5):
+            g = gb.cast_ray(shapes, ids, poses, rays, max_toi, solid=solid, with_normal=True)
+            r = ob.cast_rays_shapes(kinds, params, poses, rays, max_toi, solid=solid, with_normal=True, threads=8, points=points, first=first,
+                                    count=count)
+            hit = r[1] != INVALID
+            assert hit.mean() > 0.2 and (kinds[r[1][hit]] == 2).mean() > 0.15
+            assert ((g[1] != INVALID) == hit).all()
+            np.testing.assert_allclose(g[0], r[0], rtol=1e-5, atol=1e-7)
+            diff = np.nonzero(g[1] != r[1])[0]
+            assert len(diff) < 0.05 * len(rays)
+            for k in diff:  # exact ties only (rays starting inside overlapping solids): smallest leaf id
+                assert g[1][k] < r[1][k] and g[0][k] == r[0][k]
+            same = g[1] == r[1]
+            np.testing.assert_allclose(g[2][same], r[2][same], rtol=1e-5, atol=1e-6)
+            assert (g[3][same] == r[3][same]).all()
+            assert (g[3][same & hit & (kinds[np.minimum(r[1], n - 1)] == 2)] == 0xFFFFFFFE).all()

@@ -180,3 +180,50 @@ def test_ray_ball_analytic(oracle):
     assert oracle.shape_cast_ray_toi(0, [1.0], None, [-3, 0, 0, 1, 0, 0], 1.5, True) is None
     t, n, f = oracle.shape_cast_ray(0, [1.0], None, [-3, 0, 0, 1, 0, 0], FMAX, True)
     assert (n == [-1, 0, 0]).all() and f == 0
+
+
+def test_convex_ray_cast_matches_cuboid_closed_form(oracle):
+    """No reference test pins ray casts on a ConvexPolyhedron (ray_support_map.rs); the restatement of the GJK ray cast
+    (gjk.rs:660-795) is cross-checked against the closed-form cuboid cast on the hull of a cuboid's corners: same hit/miss,
+    toi within GJK's tolerance, for solid and non-solid casts (unit directions: the non-solid branch of
+    ray_support_map.rs:31-56 mixes distance and ray-parameter units otherwise, which the restatement keeps)."""
+    g = scenes.rng(5)
+    he = np.array([0.7, 0.4, 1.1], np.float32)
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float32) * he
+    hits = 0
+    for solid in (True, False):
+        for k in range(1500):
+            o = (g.random(3) - 0.5) * (1.0 if k % 4 == 0 else 6.0)
+            d = g.standard_normal(3)
+            d /= np.linalg.norm(d)
+            ray = np.concatenate([o, d]).astype(np.float32)
+            pose = np.concatenate([scenes.random_unit_quaternions(g, 1)[0], g.random(3) - 0.5]).astype(np.float32)
+            a = oracle.convex_cast_ray(corners, pose, ray, FMAX, solid)
+            b = oracle.shape_cast_ray(1, he, pose, ray, FMAX, solid)
+            assert (a is None) == (b is None)
+            if a is not None:
+                hits += 1
+                assert abs(float(a[0]) - float(b[0])) < 2e-3
+    assert hits > 500
+
+
+def test_convex_ray_cast_points_to_surface(oracle):
+    """cuboid_ray_cast.rs:7-90 property on random 16-point hulls: the hit point nudged outward and re-cast away from the
+    shape does not hit again; nudged inward, a solid cast from there reports toi == 0."""
+    g = scenes.rng(43)
+    pts, _ = scenes.hull_pool(8, 16, seed=44)
+    for h in range(8):
+        for _ in range(150):
+            o = g.standard_normal(3)
+            o = o / np.linalg.norm(o) * 5.0
+            ray = np.concatenate([o, -o]).astype(np.float32)
+            pose = np.concatenate([scenes.random_unit_quaternions(g, 1)[0], [0, 0, 0]]).astype(np.float32)
+            hit = oracle.convex_cast_ray(pts[h], pose, ray, FMAX, True)
+            assert hit is not None
+            toi, n = hit
+            pt = ray[:3] + ray[3:] * np.float32(toi)
+            out = pt + n * np.float32(0.002)
+            assert oracle.convex_cast_ray(pts[h], pose, np.concatenate([out, ray[:3] - out]).astype(np.float32), FMAX, True) is None
+            inn = pt - n * np.float32(0.002)
+            back = oracle.convex_cast_ray(pts[h], pose, np.concatenate([inn, [1, 0, 0]]).astype(np.float32), FMAX, True)
+            assert back is not None and back[0] == 0.0
