@@ -59,6 +59,7 @@ def lib():
         l.pb2o_bvh_leaf_pairs.argtypes = [P, P, P, u64]
         l.pb2o_bvh_cast_rays_shapes.argtypes = [P, P, P, P, P, u32, f32, i32, i32, P, P, P, P]
         l.pb2o_bvh_cast_rays_shapes2.argtypes = [P, P, P, P, P, P, P, P, u32, f32, i32, i32, P, P, P, P]
+        l.pb2o_cast_shapes_batch.argtypes = [P, P, P, P, P, P, P, P, P, f32, f32, i32, i32, u32, i32, P, P]
         l.pb2o_convex_cast_ray.restype = i32
         l.pb2o_convex_cast_ray.argtypes = [P, u32, P, P, f32, i32, P, P]
         l.pb2o_shape_cast_ray.restype = i32
@@ -338,6 +339,21 @@ class ShapeTable:
                                  p1.ctypes.data, p2.ctypes.data, prediction, n, threads, out.ctypes.data, status.ctypes.data,
                                  None if stats is None else stats.ctypes.data)
         return (out, status, stats) if with_stats else (out, status)
+
+    def cast_shapes(self, shape1, pos1, vel1, shape2, pos2, vel2, max_time_of_impact=float(np.finfo(np.float32).max), target_distance=0.0,
+                    stop_at_penetration=True, compute_impact_geometry_on_penetration=True, threads=1):
+        """query::cast_shapes per pair: (out (n,13) = witness1, witness2, normal1, normal2 (local frames), toi; status: 0 None,
+        1 Converged, 2 PenetratingOrWithinTargetDist)."""
+        s1, s2, p1, p2 = _u32(shape1), _u32(shape2), _f32(pos1), _f32(pos2)
+        v1, v2 = _f32(vel1).reshape(-1, 3), _f32(vel2).reshape(-1, 3)
+        n = len(s1)
+        out = np.zeros((n, 13), dtype=np.float32)
+        status = np.zeros(n, dtype=np.uint8)
+        lib().pb2o_cast_shapes_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, s1.ctypes.data, s2.ctypes.data,
+                                     p1.ctypes.data, v1.ctypes.data, p2.ctypes.data, v2.ctypes.data, max_time_of_impact, target_distance,
+                                     int(stop_at_penetration), int(compute_impact_geometry_on_penetration), n, threads, out.ctypes.data,
+                                     status.ctypes.data)
+        return out, status
 
     def distance(self, shape1, pos1, shape2, pos2, threads=1):
         """query::distance per pair: (dist (n,), status (n,): 0 Ok, 2 Unsupported, 3 cuboid-cuboid)."""

@@ -234,6 +234,22 @@ int pb2_trimesh_contact_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const floa
                                const uint32_t* shape_ids /* n */, const float* poses7 /* n x 7 */, uint32_t n, float prediction,
                                pb2_contact* out, uint8_t* status, uint32_t* part, int mem);
 
+/* query::cast_shapes for n pairs (query/shape_cast/shape_cast.rs:268-286 -> DefaultQueryDispatcher::cast_shapes,
+ * default_query_dispatcher.rs:434-515: ball-ball shape_cast_ball_ball.rs:10-69, every other Ball / Cuboid / ConvexPolyhedron
+ * pair shape_cast_support_map_support_map.rs:11-69 + gjk::directional_distance gjk.rs:632-795). vel1 / vel2: n x 3
+ * (world space). The four scalars are ShapeCastOptions (shape_cast.rs:196-243). out: n x 13 floats {witness1, witness2,
+ * normal1, normal2, time_of_impact}, witness / normal i in the local frame of shape i as in ShapeCastHit; status:
+ * PB2_CAST_*. */
+#define PB2_CAST_NONE 0
+#define PB2_CAST_CONVERGED 1       /* ShapeCastStatus::Converged */
+#define PB2_CAST_PENETRATING 2     /* ShapeCastStatus::PenetratingOrWithinTargetDist */
+#define PB2_CAST_UNSUPPORTED 3     /* shape id out of range */
+#define PB2_CAST_NEEDS_HOST 4      /* the penetration contact overflowed the EPA arena */
+int pb2_cast_shapes_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
+                          const float* pos1 /* n x 7 */, const float* vel1 /* n x 3 */, const float* pos2, const float* vel2,
+                          float max_time_of_impact, float target_distance, int stop_at_penetration,
+                          int compute_impact_geometry_on_penetration, uint32_t n, float* out /* n x 13 */, uint8_t* status, int mem);
+
 #ifdef __cplusplus
 }
 #endif

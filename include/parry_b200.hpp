@@ -188,6 +188,21 @@ inline void contact_pairs(const Context& c, const pb2_shapes* shapes, const std:
                                       (uint32_t)n, prediction, out.data(), pair_index.data(), n, &count, PB2_MEM_HOST));
     out.resize(count); pair_index.resize(count);
 }
+// query::cast_shapes(pos1, vel1, g1, pos2, vel2, g2, options) for n pairs (shape_cast.rs:268-286); status[k]: PB2_CAST_*
+struct ShapeCastOptions {   // shape_cast.rs:196-243, same defaults
+    float max_time_of_impact = 3.402823466e+38f, target_distance = 0.0f;
+    bool stop_at_penetration = true, compute_impact_geometry_on_penetration = true;
+};
+struct ShapeCastHit { float witness1[3], witness2[3], normal1[3], normal2[3], time_of_impact; };  // shape_cast.rs:30-60 (local frames)
+struct Vector { float x, y, z; };
+inline void cast_shapes(const Context& c, const pb2_shapes* shapes, const std::vector<uint32_t>& g1, const std::vector<Isometry>& pos1,
+                        const std::vector<Vector>& vel1, const std::vector<uint32_t>& g2, const std::vector<Isometry>& pos2,
+                        const std::vector<Vector>& vel2, const ShapeCastOptions& o, std::vector<ShapeCastHit>& out, std::vector<uint8_t>& status) {
+    out.resize(g1.size()); status.resize(g1.size());
+    c.check(pb2_cast_shapes_batch(c.get(), shapes, g1.data(), g2.data(), pos1[0].rotation, &vel1[0].x, pos2[0].rotation, &vel2[0].x,
+                                  o.max_time_of_impact, o.target_distance, o.stop_at_penetration, o.compute_impact_geometry_on_penetration,
+                                  (uint32_t)g1.size(), out[0].witness1, status.data(), PB2_MEM_HOST));
+}
 }  // namespace query
 
 }  // namespace pb2

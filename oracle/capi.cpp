@@ -229,6 +229,7 @@ extern "C" void pb2o_shape_aabbs(const uint8_t* kinds, const float* params /* n 
 
 // ---------------- query::contact ----------------
 #include "contact.hpp"
+#include "shape_cast.hpp"
 
 static inline ShapeRef make_shape(const uint8_t* kinds, const float* params4, const float* points, uint32_t id) {
     ShapeRef s; s.kind = kinds[id]; s.radius = params4[4 * id]; s.half_extents = ld3(params4 + 4 * id); s.points = nullptr; s.num_points = 0;
@@ -257,6 +258,32 @@ void pb2o_contact_batch(const uint8_t* kinds, const float* params4, const float*
             if (stats) {
                 int32_t* s = stats + 6 * k;
                 s[0] = gs.gjk_iters; s[1] = gs.used_epa; s[2] = gs.epa.niter; s[3] = (int32_t)gs.epa.max_faces; s[4] = (int32_t)gs.epa.max_vertices; s[5] = (int32_t)gs.epa.max_heap;
+            }
+        }
+    });
+}
+// query::cast_shapes for n pairs (shape_cast.rs:268-286). vel1/vel2: n x 3. out: n x 13 floats {witness1, witness2, normal1,
+// normal2, time_of_impact} (witness/normal i in the local frame of shape i, as the reference returns them);
+// status: 0 None, 1 Converged, 2 PenetratingOrWithinTargetDist.
+void pb2o_cast_shapes_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* shape1, const uint32_t* shape2,
+                            const float* pos1, const float* vel1, const float* pos2, const float* vel2, float max_toi, float target_distance,
+                            int stop_at_penetration, int compute_impact_geometry_on_penetration, uint32_t n, int nthreads, float* out,
+                            uint8_t* status) {
+    ShapeCastOptions o;
+    o.max_time_of_impact = max_toi; o.target_distance = target_distance; o.stop_at_penetration = stop_at_penetration != 0;
+    o.compute_impact_geometry_on_penetration = compute_impact_geometry_on_penetration != 0;
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            ShapeRef s1 = make_shape(kinds, params4, points, shape1[k]), s2 = make_shape(kinds, params4, points, shape2[k]);
+            ShapeCastHit h;
+            bool some = cast_shapes(Iso::from7(pos1 + 7 * k), ld3(vel1 + 3 * k), s1, Iso::from7(pos2 + 7 * k), ld3(vel2 + 3 * k), s2, o, h);
+            float* q = out + 13 * k;
+            if (some) {
+                st3(q, h.witness1); st3(q + 3, h.witness2); st3(q + 6, h.normal1); st3(q + 9, h.normal2); q[12] = h.time_of_impact;
+                status[k] = h.status == CAST_PENETRATING ? 2 : 1;
+            } else {
+                for (int i = 0; i < 13; ++i) q[i] = 0.0f;
+                status[k] = 0;
             }
         }
     });

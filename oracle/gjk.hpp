@@ -11,10 +11,15 @@ namespace pb2o {
 
 // ---------------------------------------------------------------- support maps (shape/support_map.rs:213-467)
 struct SupportShape {
-    enum Kind { CUBOID, CONVEX, CONSTANT_ORIGIN, TRIANGLE } kind;
+    enum Kind { CUBOID, CONVEX, CONSTANT_ORIGIN, TRIANGLE, BALL } kind;
     Vec3 half_extents;       // CUBOID
     const float* points;     // CONVEX: xyz packed
     uint32_t num_points;
+    Real radius = 0.0f;         // BALL (shape/ball.rs:230-250)
+    Real border_radius = 0.0f;  // > 0: RoundShapeRef around the shape (shape/round_shape.rs:317-350), local support only
+
+    static SupportShape ball(Real r) { SupportShape s; s.kind = BALL; s.points = nullptr; s.num_points = 0; s.radius = r; return s; }
+    SupportShape rounded(Real border) const { SupportShape s = *this; s.border_radius = border; return s; }
 
     static SupportShape cuboid(const Vec3& he) { SupportShape s; s.kind = CUBOID; s.half_extents = he; s.points = nullptr; s.num_points = 0; return s; }
     static SupportShape convex(const float* p, uint32_t n) { SupportShape s; s.kind = CONVEX; s.points = p; s.num_points = n; return s; }
@@ -22,7 +27,14 @@ struct SupportShape {
     static SupportShape constant_origin() { SupportShape s; s.kind = CONSTANT_ORIGIN; s.points = nullptr; s.num_points = 0; return s; }
 
     Vec3 local_support_point(const Vec3& dir) const {
+        if (border_radius > 0.0f) {  // RoundShapeRef: inner.local_support_point_toward(unit dir) + unit dir * border_radius
+            Vec3 nd = normalize(dir);
+            SupportShape inner = *this; inner.border_radius = 0.0f;
+            return inner.local_support_point(nd) + nd * border_radius;
+        }
         switch (kind) {
+            case BALL:  // local_support_point_toward(Unit::new_normalize(dir)) = dir * radius
+                return normalize(dir) * radius;
             case CUBOID:  // cuboid.rs:452-457: dir.copy_sign_to(half_extents)
                 return Vec3(copysignf(half_extents.x, dir.x), copysignf(half_extents.y, dir.y), copysignf(half_extents.z, dir.z));
             case CONVEX: {  // convex_polyhedron.rs:952-957 -> point_cloud_support_point_id (first max, strict >)
@@ -47,6 +59,7 @@ struct SupportShape {
     // SupportMap::support_point (support_map.rs:380-383); ConstantOrigin overrides it (translation only).
     Vec3 support_point(const Iso& m, const Vec3& dir) const {
         if (kind == CONSTANT_ORIGIN) return m.tra;
+        if (kind == BALL) return m.tra + normalize(dir) * radius;  // ball.rs:232-239 (its own override: no rotation involved)
         Vec3 local_dir = m.inverse_transform_vector(dir);
         return m.transform_point(local_support_point(local_dir));
     }

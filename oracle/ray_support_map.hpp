@@ -18,19 +18,18 @@ static inline bool ray_toi_with_halfspace(const Vec3& center, const Vec3& normal
     return t >= 0.0f;
 }
 
-// gjk.rs:660-795 with g2 = ConstantOrigin, pos12 = identity (cast_local_ray, gjk.rs:519-534)
-static inline bool gjk_cast_local_ray(const SupportShape& shape, VoronoiSimplex& simplex, const Ray& ray, Real max_toi, Real& toi, Vec3& normal) {
+// minkowski_ray_cast (gjk.rs:660-795): ray cast on the Minkowski difference g1 - pos12 * g2
+static inline bool minkowski_ray_cast(const Iso& pos12, const SupportShape& g1, const SupportShape& g2, const Ray& ray, Real max_toi,
+                                      VoronoiSimplex& simplex, Real& toi, Vec3& normal) {
     const Real eps_tol = gjk_eps_tol();
     const Real eps_rel = sqrtf(eps_tol);
-    const Iso id;
-    const SupportShape g2 = SupportShape::constant_origin();
     Real ray_length = norm(ray.dir);
     if (relative_eq(ray_length, 0.0f)) return false;
     Real ltoi = 0.0f;
     Ray curr_ray(ray.origin, ray.dir / ray_length);
     Vec3 dir0 = -curr_ray.dir;
     Vec3 ldir = dir0;
-    CSOPoint sp0 = CSOPoint::from_shapes(id, shape, g2, dir0);
+    CSOPoint sp0 = CSOPoint::from_shapes(pos12, g1, g2, dir0);
     sp0.point = sp0.point + (-curr_ray.origin);  // translate(&-origin)
     simplex.reset(sp0);
     Vec3 proj = simplex.project_origin_and_reduce();
@@ -49,7 +48,7 @@ static inline bool gjk_cast_local_ray(const SupportShape& shape, VoronoiSimplex&
             Vec3 p = proj + curr_ray.origin;
             support_point.point = p; support_point.orig1 = p; support_point.orig2 = Vec3();  // single_point
         } else {
-            support_point = CSOPoint::from_shapes(id, shape, g2, dir);
+            support_point = CSOPoint::from_shapes(pos12, g1, g2, dir);
         }
         if (last_chance && ltoi > 0.0f) { toi = ltoi / ray_length; normal = ldir; return true; }
         Real t;
@@ -82,6 +81,21 @@ static inline bool gjk_cast_local_ray(const SupportShape& shape, VoronoiSimplex&
         niter += 1;
         if (niter == 100) return false;
     }
+}
+
+// gjk::cast_local_ray (gjk.rs:519-534): g2 = ConstantOrigin, pos12 = identity
+static inline bool gjk_cast_local_ray(const SupportShape& shape, VoronoiSimplex& simplex, const Ray& ray, Real max_toi, Real& toi, Vec3& normal) {
+    return minkowski_ray_cast(Iso(), shape, SupportShape::constant_origin(), ray, max_toi, simplex, toi, normal);
+}
+
+// gjk::directional_distance (gjk.rs:632-657)
+static inline bool gjk_directional_distance(const Iso& pos12, const SupportShape& g1, const SupportShape& g2, const Vec3& dir, VoronoiSimplex& simplex,
+                                            Real& toi, Vec3& normal, Vec3& w1, Vec3& w2) {
+    Ray ray(Vec3(), dir);
+    if (!minkowski_ray_cast(pos12, g1, g2, ray, REAL_MAX, simplex, toi, normal)) return false;
+    if (toi != 0.0f) gjk_result(simplex, simplex.dimension() == 3, w1, w2);
+    else { w1 = Vec3(); w2 = Vec3(); }  // penetration: witness points undefined
+    return true;
 }
 
 #define PB2O_FEATURE_UNKNOWN 0xFFFFFFFEu  // FeatureId::Unknown in the u32 feature column

@@ -174,6 +174,7 @@ struct PairSetup {
     Iso7 cb_pos12;  // pos12 seen by contact_convex_polyhedron_ball (mode 2: pos12, mode 3: pos12.inverse())
     DShape g1, g2;
     const float4* tri;  // shape 1 is this TriMesh triangle (k1 == PB2_SHAPE_TRIANGLE_INTERNAL), else NULL
+    bool local_frames;
 };
 
 // Where the pairs come from. Plain mode: pair k = (shape1[k] at pos1[k], shape2[k] at pos2[k]). `ab` (optional): pairs as
@@ -188,7 +189,11 @@ struct PairSrc {
     const uint32_t* ab;
     const float4* mesh_tris;
     uint32_t n_first, n_second;   // index bounds for ab[2k] / ab[2k+1]
+    uint32_t flags = 0;           // PAIR_* below
 };
+#define PAIR_SUPPORT_MAPS_ONLY 1u  // no ball arms: balls take part in GJK/EPA through their support map (what
+                                   // cast_shapes_support_map_support_map calls: contact_support_map_support_map on any pair)
+#define PAIR_LOCAL_FRAMES 2u       // leave the contact in the shapes' local frames (no Contact::transform_by_mut)
 #define PB2_SHAPE_TRIANGLE_INTERNAL 3   // a TriMesh part (shape::Triangle), never in a shape table
 
 __device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* params, const float4* pts, const PairSrc& src, uint32_t k,
@@ -214,8 +219,16 @@ __device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* p
     ps.tri = tri;
     ps.pos12 = iso_inv_mul(ps.pos1, ps.pos2);  // contact_shape_shape.rs:130
     ps.mode = 0;
+    ps.local_frames = (src.flags & PAIR_LOCAL_FRAMES) != 0;
     bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
-    if (!b1 && !b2) {
+    if (src.flags & PAIR_SUPPORT_MAPS_ONLY) {
+        ps.mode = 1;
+        ps.gpos12 = ps.pos12;
+        ps.g1 = make_dshape(ps.k1, ps.pr1, pts);
+        ps.g2 = make_dshape(ps.k2, ps.pr2, pts);
+        if (b1) ps.g1.kind = DS_BALL;
+        if (b2) ps.g2.kind = DS_BALL;
+    } else if (!b1 && !b2) {
         ps.mode = 1;
         ps.gpos12 = ps.pos12;
         if (tri) { ps.g1.kind = DS_TRIANGLE; ps.g1.he = mk3(0.f, 0.f, 0.f); ps.g1.pts = tri; ps.g1.n = 3; }
@@ -257,6 +270,7 @@ __device__ __forceinline__ int finish_gjk_pair(const PairSetup& ps, bool from_ep
 }
 
 __device__ __forceinline__ void to_world(const PairSetup& ps, ContactOut& c) {  // Contact::transform_by_mut
+    if (ps.local_frames) return;
     c.p1 = iso_point(ps.pos1, c.p1);
     c.p2 = iso_point(ps.pos2, c.p2);
     c.n1 = iso_vec(ps.pos1, c.n1);
@@ -1393,8 +1407,9 @@ __global__ void __launch_bounds__(128, 4) k_contact_epac(const uint8_t* __restri
 // ------------------------------------------------------------------------------------------- host side
 static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
                         const float* pos2, float prediction, uint32_t n, OutSinks sinks, const uint32_t* ab = nullptr, uint32_t n_colliders = 0,
-                        const float4* mesh_tris = nullptr, uint32_t n_tris = 0) {
+                        const float4* mesh_tris = nullptr, uint32_t n_tris = 0, uint32_t flags = 0) {
     PairSrc src;
+    src.flags = flags;
     src.shape1 = shape1; src.shape2 = shape2; src.pos1 = pos1; src.pos2 = pos2; src.ab = ab; src.mesh_tris = mesh_tris;
     src.n_first = mesh_tris ? n_tris : n_colliders; src.n_second = n_colliders;
     cudaStream_t st = ctx->stream;
@@ -1728,6 +1743,205 @@ int pb2_intersection_test_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const ui
 
 // ------------------------------------------------------------------------------------------- TriMesh vs shapes
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------- query::cast_shapes
+// query::cast_shapes (shape_cast.rs:268-286) -> DefaultQueryDispatcher::cast_shapes (default_query_dispatcher.rs:434-515):
+// ball-ball closed form (shape_cast_ball_ball.rs:10-69), everything else cast_shapes_support_map_support_map
+// (shape_cast_support_map_support_map.rs:11-69) = gjk::directional_distance (gjk.rs:632-657) on the Minkowski difference,
+// with RoundShapeRef (round_shape.rs:317-350) around shape 1 when target_distance > 0. Hits that start penetrating and need
+// the impact geometry (toi < 1e-5) are parked: their contact comes from the GJK/EPA contact kernels (second phase).
+enum { CAST_NONE = 0, CAST_CONVERGED = 1, CAST_PENETRATING = 2, CAST_UNSUPPORTED = 3, CAST_NEEDS_HOST = 4, CAST_PARKED = 250 };
+struct CastOpts { float max_toi, target_distance; int stop_at_penetration, compute_geometry; };
+
+// ray_toi_with_ball (ray_ball.rs:33-77) with dcenter = ray.origin - center already formed
+__device__ __forceinline__ bool ray_ball_at(V3 dcenter, float radius, V3 dir, bool solid, bool& inside, float& toi) {
+    float a = nrm2(dir);
+    float b = dot3(dcenter, dir);
+    float c = nrm2(dcenter) - radius * radius;
+    if (a == 0.0f) {
+        if (c > 0.0f) { inside = false; return false; }
+        inside = true; toi = 0.0f; return true;
+    }
+    if (c > 0.0f && b > 0.0f) { inside = false; return false; }
+    float delta = b * b - a * c;
+    if (delta < 0.0f) { inside = false; return false; }
+    float t = (-b - sqrtf(delta)) / a;
+    if (t <= 0.0f) {
+        inside = true;
+        toi = solid ? 0.0f : (-b + sqrtf(delta)) / a;
+        return true;
+    }
+    inside = false; toi = t; return true;
+}
+
+__device__ __forceinline__ DShape cast_dshape(uint8_t kind, float4 pr, const float4* pts) {
+    DShape g = make_dshape(kind, pr, pts);
+    if (kind == PB2_SHAPE_BALL) g.kind = DS_BALL;
+    return g;
+}
+
+__global__ void __launch_bounds__(128) k_cast_shapes(const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float4* __restrict__ pts,
+                              uint32_t n_shapes, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2,
+                              const float* __restrict__ pos1, const float* __restrict__ vel1, const float* __restrict__ pos2,
+                              const float* __restrict__ vel2, CastOpts o, uint32_t n, float* __restrict__ out, uint8_t* __restrict__ status,
+                              uint32_t* __restrict__ parked, unsigned long long* parked_count) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float* q = out + 13ull * k;
+    uint32_t s1 = shape1[k], s2 = shape2[k];
+    int st = CAST_NONE;
+    V3 w1 = mk3(0.f, 0.f, 0.f), w2 = w1, n1 = w1, n2 = w1;
+    float toi = 0.0f;
+    if (s1 >= n_shapes || s2 >= n_shapes) st = CAST_UNSUPPORTED;
+    else {
+        Iso7 p1 = load_iso(pos1 + 7ull * k), p2 = load_iso(pos2 + 7ull * k);
+        Iso7 pos12 = iso_inv_mul(p1, p2);
+        V3 v1 = mk3(vel1[3ull * k], vel1[3ull * k + 1], vel1[3ull * k + 2]), v2 = mk3(vel2[3ull * k], vel2[3ull * k + 1], vel2[3ull * k + 2]);
+        V3 vel12 = iso_inv_vec(p1, v2 - v1);
+        uint8_t k1 = kinds[s1], k2 = kinds[s2];
+        float4 pr1 = params[s1], pr2 = params[s2];
+        if (k1 == PB2_SHAPE_BALL && k2 == PB2_SHAPE_BALL) {
+            float rsum = pr1.x + pr2.x + o.target_distance;
+            V3 center = -pos12.t;
+            // ray_toi_with_ball(center, radius, Ray(origin, vel12), solid = true): dcenter = origin - center
+            bool inside;
+            if (ray_ball_at(mk3(0.f, 0.f, 0.f) - center, rsum, vel12, true, inside, toi) && !(toi > o.max_toi)) {
+                V3 dpt = (mk3(0.f, 0.f, 0.f) + vel12 * toi) - center;
+                if (rsum == 0.0f) {
+                    n1 = mk3(1.f, 0.f, 0.f); n2 = iso_inv_vec(pos12, -n1);
+                } else {
+                    n1 = dpt / rsum; n2 = iso_inv_vec(pos12, -n1);
+                    w1 = n1 * pr1.x; w2 = n2 * pr2.x;
+                }
+                if (!(!o.stop_at_penetration && toi < 1.0e-5f && dot3(n1, vel12) >= 0.0f))
+                    st = (inside && nrm2(center) < rsum * rsum) ? CAST_PENETRATING : CAST_CONVERGED;
+            }
+        } else {
+            DShape g1 = cast_dshape(k1, pr1, pts), g2 = cast_dshape(k2, pr2, pts);
+            const float border = o.target_distance;
+            Simplex s;
+            V3 normal1;
+            auto cso = [&](V3 dir) {
+                V3 sp1;
+                if (border > 0.0f) { V3 nd = dir / nrm(dir); sp1 = ds_local_support(g1, nd) + nd * border; }
+                else sp1 = ds_local_support(g1, dir);
+                return cso_make(sp1, ds_support_point(g2, pos12, -dir));
+            };
+            if (minkowski_ray_cast(cso, s, mk3(0.f, 0.f, 0.f), vel12, FLT_MAX, toi, normal1) && !(toi > o.max_toi)) {
+                if ((o.compute_geometry || !o.stop_at_penetration) && toi < 1.0e-5f) {
+                    st = CAST_PARKED;
+                } else {
+                    V3 r0 = mk3(0.f, 0.f, 0.f), r1 = r0;
+                    if (toi != 0.0f) gjk_witness(s, s.dim == 3, r0, r1);
+                    n1 = normal1;
+                    n2 = iso_inv_vec(pos12, -normal1);
+                    w1 = r0 - normal1 * border;
+                    w2 = iso_inv_point(pos12, r1);
+                    st = toi == 0.0f ? CAST_PENETRATING : CAST_CONVERGED;
+                }
+            }
+        }
+    }
+    if (st == CAST_PARKED) parked[warp_append1(parked_count)] = k;
+    bool some = st == CAST_CONVERGED || st == CAST_PENETRATING;
+    if (!some && st != CAST_PARKED) { w1 = w2 = n1 = n2 = mk3(0.f, 0.f, 0.f); toi = 0.0f; }
+    q[0] = w1.x; q[1] = w1.y; q[2] = w1.z; q[3] = w2.x; q[4] = w2.y; q[5] = w2.z;
+    q[6] = n1.x; q[7] = n1.y; q[8] = n1.z; q[9] = n2.x; q[10] = n2.y; q[11] = n2.z; q[12] = toi;
+    status[k] = (uint8_t)st;
+}
+
+// Second half of the penetrating branch of cast_shapes_support_map_support_map (:36-57), once the parked pairs' contacts exist.
+__global__ void k_cast_merge(const uint32_t* __restrict__ parked, uint32_t count, const float* __restrict__ contacts, const uint8_t* __restrict__ cstatus,
+                             const float* __restrict__ pos1, const float* __restrict__ vel1, const float* __restrict__ vel2, int stop_at_penetration,
+                             float* __restrict__ out, uint8_t* __restrict__ status) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t k = parked[i];
+    float* q = out + 13ull * k;
+    const float* c = contacts + 13ull * i;
+    int st = CAST_NONE;
+    if (cstatus[i] == ST_NEEDS_HOST) st = CAST_NEEDS_HOST;
+    else if (cstatus[i] == ST_SOME) {
+        Iso7 p1 = load_iso(pos1 + 7ull * k);
+        V3 v1 = mk3(vel1[3ull * k], vel1[3ull * k + 1], vel1[3ull * k + 2]), v2 = mk3(vel2[3ull * k], vel2[3ull * k + 1], vel2[3ull * k + 2]);
+        V3 vel12 = iso_inv_vec(p1, v2 - v1);
+        float normal_vel = dot3(mk3(c[6], c[7], c[8]), vel12);
+        if (!(!stop_at_penetration && normal_vel >= 0.0f)) st = CAST_PENETRATING;
+    }
+    if (st == CAST_PENETRATING) { for (int j = 0; j < 12; ++j) q[j] = c[j]; }
+    else { for (int j = 0; j < 13; ++j) q[j] = 0.0f; }
+    status[k] = (uint8_t)st;
+}
+
+__global__ void k_pair_up(const uint32_t* __restrict__ idx, uint32_t count, uint32_t* __restrict__ ab) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) { ab[2ull * i] = idx[i]; ab[2ull * i + 1] = idx[i]; }
+}
+
+extern "C" int pb2_cast_shapes_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
+                                     const float* vel1, const float* pos2, const float* vel2, float max_time_of_impact, float target_distance,
+                                     int stop_at_penetration, int compute_impact_geometry_on_penetration, uint32_t n, float* out, uint8_t* status,
+                                     int mem) {
+    if (!ctx || !shapes || (n && (!shape1 || !shape2 || !pos1 || !pos2 || !vel1 || !vel2 || !out || !status))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_s1, *d_s2, *d_p1, *d_p2, *d_v1, *d_v2;
+    void *d_out, *d_st;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape1, (size_t)n * 4, mem, &d_s1));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape2, (size_t)n * 4, mem, &d_s2));
+    PB2_CHECK(pb2_stage_in(ctx, 2, pos1, (size_t)n * 28, mem, &d_p1));
+    PB2_CHECK(pb2_stage_in(ctx, 3, pos2, (size_t)n * 28, mem, &d_p2));
+    PB2_CHECK(pb2_stage_in(ctx, 4, vel1, (size_t)n * 12, mem, &d_v1));
+    PB2_CHECK(pb2_stage_in(ctx, 5, vel2, (size_t)n * 12, mem, &d_v2));
+    PB2_CHECK(pb2_stage_out(ctx, 6, out, (size_t)n * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 7, status, (size_t)n, mem, &d_st));
+    uint32_t *d_parked = nullptr, *d_ab = nullptr;
+    float* d_c = nullptr;
+    uint8_t* d_cst = nullptr;
+    int rc = PB2_OK;
+    if (cudaMallocAsync((void**)&d_parked, (size_t)n * 4, st) != cudaSuccess) PB2_FAIL(ctx, PB2_ERR_CUDA, "cast_shapes: out of device memory");
+    unsigned long long* parked_count = (unsigned long long*)(ctx->d_counters + 10);
+    cudaMemsetAsync(parked_count, 0, 8, st);
+    CastOpts o;
+    o.max_toi = max_time_of_impact; o.target_distance = target_distance; o.stop_at_penetration = stop_at_penetration;
+    o.compute_geometry = compute_impact_geometry_on_penetration;
+    k_cast_shapes<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, (const uint32_t*)d_s1,
+                                                      (const uint32_t*)d_s2, (const float*)d_p1, (const float*)d_v1, (const float*)d_p2,
+                                                      (const float*)d_v2, o, n, (float*)d_out, (uint8_t*)d_st, d_parked, parked_count);
+    PB2_LAUNCHED(ctx);
+    cudaMemcpyAsync(ctx->h_counters + 10, parked_count, 8, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { rc = PB2_ERR_CUDA; goto done; }
+    {
+        uint32_t cnt = (uint32_t)ctx->h_counters[10];
+        if (cnt) {
+            if (cudaMallocAsync((void**)&d_ab, (size_t)cnt * 8, st) != cudaSuccess || cudaMallocAsync((void**)&d_c, (size_t)cnt * 52, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_cst, cnt, st) != cudaSuccess) { rc = PB2_ERR_CUDA; goto done; }
+            k_pair_up<<<pb2_blocks(cnt, 256), 256, 0, st>>>(d_parked, cnt, d_ab);
+            PB2_LAUNCHED(ctx);
+            OutSinks sinks;
+            sinks.dense = d_c; sinks.status = d_cst; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
+            sinks.compact_count = nullptr; sinks.some_count = nullptr;
+            rc = run_contacts(ctx, shapes, (const uint32_t*)d_s1, (const uint32_t*)d_s2, (const float*)d_p1, (const float*)d_p2, FLT_MAX, cnt, sinks,
+                              d_ab, n, nullptr, 0, PAIR_SUPPORT_MAPS_ONLY | PAIR_LOCAL_FRAMES);
+            if (rc != PB2_OK) goto done;
+            k_cast_merge<<<pb2_blocks(cnt, 128), 128, 0, st>>>(d_parked, cnt, d_c, d_cst, (const float*)d_p1, (const float*)d_v1, (const float*)d_v2,
+                                                               stop_at_penetration, (float*)d_out, (uint8_t*)d_st);
+            PB2_LAUNCHED(ctx);
+        }
+    }
+    if (cudaGetLastError() != cudaSuccess) { rc = PB2_ERR_CUDA; goto done; }
+    rc = pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem);
+    if (rc == PB2_OK) rc = pb2_stage_back(ctx, status, d_st, (size_t)n, mem);
+    if (rc == PB2_OK && mem == PB2_MEM_HOST && cudaStreamSynchronize(st) != cudaSuccess) rc = PB2_ERR_CUDA;
+done:
+    if (d_parked) cudaFreeAsync(d_parked, st);
+    if (d_ab) cudaFreeAsync(d_ab, st);
+    if (d_c) cudaFreeAsync(d_c, st);
+    if (d_cst) cudaFreeAsync(d_cst, st);
+    return rc;
+}
+
 
 extern "C" int pb2_intersect_csr_device(pb2_ctx* ctx, const pb2_bvh* bvh, const float* d_queries, uint32_t m, bool positions,
                                         uint32_t* d_offsets, uint32_t** d_items, uint64_t* total_out);

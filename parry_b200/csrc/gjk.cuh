@@ -12,7 +12,7 @@
 #define PB2_EPS 1.1920929e-7f          // f32::EPSILON (DEFAULT_EPSILON, src/lib.rs:102)
 #define PB2_GJK_EPS_TOL (PB2_EPS * 10.0f)
 
-enum { DS_CUBOID = 0, DS_CONVEX = 1, DS_ORIGIN = 2, DS_TRIANGLE = 3 };
+enum { DS_CUBOID = 0, DS_CONVEX = 1, DS_ORIGIN = 2, DS_TRIANGLE = 3, DS_BALL = 4 /* radius in he.x (shape/ball.rs:230-250) */ };
 struct DShape {
     int kind;
     V3 he;
@@ -43,10 +43,12 @@ __device__ __forceinline__ V3 ds_local_support(const DShape& s, V3 dir) {
         if (d1 > d2) return d1 > d3 ? a : c;
         return d2 > d3 ? b : c;
     }
+    if (s.kind == DS_BALL) return (dir / nrm(dir)) * s.he.x;  // local_support_point_toward(Unit::new_normalize(dir))
     return mk3(0.f, 0.f, 0.f);
 }
 __device__ __forceinline__ V3 ds_support_point(const DShape& s, const Iso7& m, V3 dir) {
     if (s.kind == DS_ORIGIN) return m.t;
+    if (s.kind == DS_BALL) return m.t + (dir / nrm(dir)) * s.he.x;  // Ball overrides support_point: translation only
     V3 ld = iso_inv_vec(m, dir);
     return iso_point(m, ds_local_support(s, ld));
 }
@@ -366,9 +368,11 @@ __device__ __forceinline__ int gjk_closest_points(const Iso7& pos12, const DShap
 }
 
 // ---- ray casts on support-mapped shapes
-// gjk::cast_local_ray (gjk.rs:519-534) = minkowski_ray_cast (gjk.rs:660-795) with g2 = ConstantOrigin, pos12 = identity;
-// ray_toi_with_halfspace (ray_halfspace.rs:9-39) inlined. Returns the hit as (toi, outward normal).
-__device__ __forceinline__ bool gjk_cast_local_ray(const DShape& shape, Simplex& s, V3 ro, V3 rd, float max_toi, float& toi, V3& normal) {
+// minkowski_ray_cast (gjk.rs:660-795): ray cast on a Minkowski difference given by its support function `cso(dir)`;
+// ray_toi_with_halfspace (ray_halfspace.rs:9-39) inlined. Returns the hit as (toi, outward normal); the simplex is left as
+// the reference leaves it (directional_distance reads the witness points from it).
+template <class CsoFn>
+__device__ __forceinline__ bool minkowski_ray_cast(CsoFn cso, Simplex& s, V3 ro, V3 rd, float max_toi, float& toi, V3& normal) {
     const float eps_tol = PB2_GJK_EPS_TOL;
     const float eps_rel = sqrtf(eps_tol);
     float ray_length = nrm(rd);
@@ -377,8 +381,7 @@ __device__ __forceinline__ bool gjk_cast_local_ray(const DShape& shape, Simplex&
     V3 co = ro, cd = rd / ray_length;
     V3 dir = -cd, ldir = dir;
     {
-        V3 sp = ds_local_support(shape, dir);
-        CSO c0 = cso_make(sp, mk3(0.f, 0.f, 0.f));
+        CSO c0 = cso(dir);
         c0.point = c0.point + (-co);
         sx_reset(s, c0);
     }
@@ -397,7 +400,7 @@ __device__ __forceinline__ bool gjk_cast_local_ray(const DShape& shape, Simplex&
             V3 p = proj + co;
             sp.point = p; sp.o1 = p; sp.o2 = mk3(0.f, 0.f, 0.f);
         } else {
-            sp = cso_make(ds_local_support(shape, dir), mk3(0.f, 0.f, 0.f));
+            sp = cso(dir);
         }
         if (last_chance && ltoi > 0.0f) { toi = ltoi / ray_length; normal = ldir; return true; }
         float denom = dot3(dir, cd);
@@ -434,6 +437,11 @@ __device__ __forceinline__ bool gjk_cast_local_ray(const DShape& shape, Simplex&
         niter += 1;
         if (niter == 100) return false;
     }
+}
+
+// gjk::cast_local_ray (gjk.rs:519-534): g2 = ConstantOrigin, pos12 = identity
+__device__ __forceinline__ bool gjk_cast_local_ray(const DShape& shape, Simplex& s, V3 ro, V3 rd, float max_toi, float& toi, V3& normal) {
+    return minkowski_ray_cast([&](V3 dir) { return cso_make(ds_local_support(shape, dir), mk3(0.f, 0.f, 0.f)); }, s, ro, rd, max_toi, toi, normal);
 }
 
 // local_ray_intersection_with_support_map_with_params (ray_support_map.rs:19-72); the feature is FeatureId::Unknown.

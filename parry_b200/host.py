@@ -562,3 +562,38 @@ def distance(shapes, shape1, pos1, shape2, pos2):
 def intersection_test(shapes, shape1, pos1, shape2, pos2):
     """query::intersection_test(pos1, g1, pos2, g2), batched (intersection_test.rs:88-96): (hit (n,) u8, status (n,) u8)."""
     return _pair_query("pb2_intersection_test_batch", np.uint8, shapes, shape1, pos1, shape2, pos2)
+
+
+class ShapeCastOptions:
+    """query::ShapeCastOptions (shape_cast.rs:196-243), same defaults."""
+
+    def __init__(self, max_time_of_impact=float(np.finfo(np.float32).max), target_distance=0.0, stop_at_penetration=True,
+                 compute_impact_geometry_on_penetration=True):
+        self.max_time_of_impact = float(max_time_of_impact)
+        self.target_distance = float(target_distance)
+        self.stop_at_penetration = bool(stop_at_penetration)
+        self.compute_impact_geometry_on_penetration = bool(compute_impact_geometry_on_penetration)
+
+    @classmethod
+    def with_max_time_of_impact(cls, max_time_of_impact):
+        return cls(max_time_of_impact=max_time_of_impact)
+
+
+def cast_shapes(shapes, shape1, pos1, vel1, shape2, pos2, vel2, options=None):
+    """query::cast_shapes(pos1, vel1, g1, pos2, vel2, g2, options), batched (shape_cast.rs:268-286). Returns (hits (n, 13) f32 =
+    witness1, witness2, normal1, normal2 in the shapes' local frames and time_of_impact last; status (n,) u8: 0 None,
+    1 Converged, 2 PenetratingOrWithinTargetDist, 3 unknown shape, 4 host fallback)."""
+    o = options or ShapeCastOptions()
+    ctx = shapes.ctx
+    n = int(pos1.shape[0])
+    k1, p1, mem = _prep(pos1, np.float32)
+    k2, p2, _ = _prep(pos2, np.float32, mem)
+    kv1, v1, _ = _prep(vel1, np.float32, mem)
+    kv2, v2, _ = _prep(vel2, np.float32, mem)
+    ks1, ps1, _ = _prep(shape1, np.uint32, mem)
+    ks2, ps2, _ = _prep(shape2, np.uint32, mem)
+    out, po = _empty((n, 13), np.float32, mem, ctx.torch_device)
+    status, pst = _empty((n,), np.uint8, mem, ctx.torch_device)
+    ctx.check(ctx._lib.pb2_cast_shapes_batch(ctx.h, shapes.h, ps1, ps2, p1, v1, p2, v2, o.max_time_of_impact, o.target_distance,
+                                             int(o.stop_at_penetration), int(o.compute_impact_geometry_on_penetration), n, po, pst, mem))
+    return out, status

@@ -227,3 +227,49 @@ def test_convex_ray_cast_points_to_surface(oracle):
             inn = pt - n * np.float32(0.002)
             back = oracle.convex_cast_ray(pts[h], pose, np.concatenate([inn, [1, 0, 0]]).astype(np.float32), FMAX, True)
             assert back is not None and back[0] == 0.0
+
+
+def _pose(t):
+    return np.array([0, 0, 0, 1] + list(t), np.float32)
+
+
+def test_cast_shapes_reference_tests(oracle):
+    """crates/parry3d/tests/geometry/ball_ball_toi.rs (exact 0.9), time_of_impact3.rs (Some(0.0), relative_eq value, None) and
+    still_objects_toi.rs (issue #141: None, None, Some)."""
+    T = oracle.ShapeTable([("ball", 0.5)])
+    out, st = T.cast_shapes([0], [_pose([0, 0, 0])], [[0, 10, 0]], [0], [_pose([0, 10, 0])], [[0, 0, 0]])
+    assert st[0] == 1 and out[0, 12] == np.float32(0.9)
+    T = oracle.ShapeTable([("ball", 1.0), ("cuboid", [1, 1, 1])])
+    out, st = T.cast_shapes([0, 0, 0], [_pose([1, 1, 1]), _pose([2, 2, 2]), _pose([3, 3, 3])], [[2, 2, 2], [-.5, -.5, -.5], [2, 2, 2]],
+                            [1, 1, 1], [_pose([0, 0, 0])] * 3, [[-1, 1, 1], [1, 1, 1], [-1, 1, 1]])
+    assert st[0] != 0 and out[0, 12] == 0.0
+    expect = (np.sqrt(np.float32(3.0)) - np.float32(1.0)) / np.linalg.norm(np.array([-1.5, -1.5, -1.5], np.float32))
+    assert st[1] == 1 and abs(out[1, 12] - expect) <= np.finfo(np.float32).eps * max(abs(expect), abs(out[1, 12]))
+    assert st[2] == 0
+    T = oracle.ShapeTable([("cuboid", [.5, .5, .5])])
+    got = [T.cast_shapes([0], [_pose([0, 1.1, 0])], [[0, vy, 0]], [0], [_pose([0, 0, 0])], [[0, 0, 0]])[1][0] for vy in (0.0, 1.0, -1.0)]
+    assert got[0] == 0 and got[1] == 0 and got[2] != 0
+
+
+def test_cast_shapes_hit_configuration_touches(oracle):
+    """Property at the oracle level: advancing both shapes to the reported time of impact leaves them at distance ~
+    target_distance, and the witnesses (local frames) coincide in world space up to that distance."""
+    g = scenes.rng(71)
+    pts, radii = scenes.hull_pool(8, 16, seed=72)
+    T = oracle.ShapeTable([("ball", 0.4), ("cuboid", [0.3, 0.5, 0.4])] + [("convex", p) for p in pts])
+    n = 400
+    s1, s2 = g.integers(0, 10, n), g.integers(0, 10, n)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - 0.5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * 4.0], axis=1).astype(np.float32)
+    v1 = (d * 3.0 + g.standard_normal((n, 3)) * 0.4).astype(np.float32)
+    v2 = np.zeros((n, 3), np.float32)
+    for target in (0.0, 0.05):
+        out, st = T.cast_shapes(s1, p1, v1, s2, p2, v2, target_distance=target)
+        hit = st == 1
+        assert hit.mean() > 0.4
+        q1, q2 = p1[hit].copy(), p2[hit].copy()
+        q1[:, 4:] += v1[hit] * out[hit, 12:13]
+        dist, ds = T.distance(s1[hit], q1, s2[hit], q2)
+        ok = ds == 0
+        assert np.abs(dist[ok] - target).max() < 5e-3
