@@ -60,6 +60,7 @@ def lib():
         l.pb2o_bvh_cast_rays_shapes.argtypes = [P, P, P, P, P, u32, f32, i32, i32, P, P, P, P]
         l.pb2o_bvh_cast_rays_shapes2.argtypes = [P, P, P, P, P, P, P, P, u32, f32, i32, i32, P, P, P, P]
         l.pb2o_cast_shapes_batch.argtypes = [P, P, P, P, P, P, P, P, P, f32, f32, i32, i32, u32, i32, P, P]
+        l.pb2o_compound_contact_batch.argtypes = [P, P, P, P, P, P, P, P, P, P, P, f32, i32, u32, i32, P, P, P]
         l.pb2o_convex_cast_ray.restype = i32
         l.pb2o_convex_cast_ray.argtypes = [P, u32, P, P, f32, i32, P, P]
         l.pb2o_shape_cast_ray.restype = i32
@@ -354,6 +355,21 @@ class ShapeTable:
                                      int(stop_at_penetration), int(compute_impact_geometry_on_penetration), n, threads, out.ctypes.data,
                                      status.ctypes.data)
         return out, status
+
+    def contact_compound(self, comp_first, comp_count, part_shape, part_pose, compound_id, pos_c, shape, pos_s, prediction,
+                         compound_second=False, threads=1):
+        """query::contact(pos_c, Compound, pos_s, shape) per pair (or the flipped call when compound_second): (out (n,13), status,
+        part). Compound c = parts comp_first[c] .. + comp_count[c] of (part_shape -> this table, part_pose)."""
+        cf, cc, psid, cid, sid = _u32(comp_first), _u32(comp_count), _u32(part_shape), _u32(compound_id), _u32(shape)
+        pp, pc, ps = _f32(part_pose), _f32(pos_c), _f32(pos_s)
+        n = len(cid)
+        out = np.zeros((n, 13), dtype=np.float32)
+        status = np.zeros(n, dtype=np.uint8)
+        part = np.zeros(n, dtype=np.uint32)
+        lib().pb2o_compound_contact_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, cf.ctypes.data, cc.ctypes.data,
+                                          psid.ctypes.data, pp.ctypes.data, cid.ctypes.data, pc.ctypes.data, sid.ctypes.data, ps.ctypes.data,
+                                          prediction, int(compound_second), n, threads, out.ctypes.data, status.ctypes.data, part.ctypes.data)
+        return out, status, part
 
     def distance(self, shape1, pos1, shape2, pos2, threads=1):
         """query::distance per pair: (dist (n,), status (n,): 0 Ok, 2 Unsupported, 3 cuboid-cuboid)."""

@@ -50,6 +50,7 @@ typedef struct pb2_ctx pb2_ctx;
 typedef struct pb2_bvh pb2_bvh;
 typedef struct pb2_trimesh pb2_trimesh;
 typedef struct pb2_shapes pb2_shapes;
+typedef struct pb2_compounds pb2_compounds;
 
 #define PB2_INVALID_U32 0xffffffffu
 
@@ -233,6 +234,22 @@ int pb2_contact_pairs_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint
 int pb2_trimesh_contact_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* mesh_pose7, const pb2_shapes* shapes,
                                const uint32_t* shape_ids /* n */, const float* poses7 /* n x 7 */, uint32_t n, float prediction,
                                pb2_contact* out, uint8_t* status, uint32_t* part, int mem);
+
+/* Compound shapes (shape/compound.rs:113-144): compound c = parts comp_first[c] .. comp_first[c] + comp_count[c] - 1 of a part
+ * table, part i = shape part_shape[i] of `shapes` at part_pose7[i] in the compound's frame. HOST pointers; `shapes` must
+ * outlive the handle. Empty compounds are PB2_ERR_INVALID (Compound::new panics on them). */
+int pb2_compounds_create(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* comp_first, const uint32_t* comp_count, uint32_t nc,
+                         const uint32_t* part_shape, const float* part_pose7, uint32_t np, pb2_compounds** out);
+int pb2_compounds_destroy(pb2_ctx* ctx, pb2_compounds* compounds);
+
+/* query::contact with a Compound on one side, n pairs (composite arms of DefaultQueryDispatcher::contact,
+ * default_query_dispatcher.rs:338-351 -> contact_composite_shape_shape.rs:14-76): pair k = compound compound_ids[k] at
+ * compound_poses7[k] and shape shape_ids[k] at shape_poses7[k]. compound_second = 0: contact(compound, shape);
+ * != 0: contact(shape, compound) (pose12.inverse() + Contact::flipped(), :63-76). out / status as pb2_contact_batch; part[k]
+ * = index of the winning part inside its compound (equal dists: smallest index) or 0xFFFFFFFF. */
+int pb2_compound_contact_shapes(pb2_ctx* ctx, const pb2_compounds* compounds, const uint32_t* compound_ids, const float* compound_poses7,
+                                const uint32_t* shape_ids, const float* shape_poses7, uint32_t n, float prediction, int compound_second,
+                                pb2_contact* out, uint8_t* status, uint32_t* part, int mem);
 
 /* query::cast_shapes for n pairs (query/shape_cast/shape_cast.rs:268-286 -> DefaultQueryDispatcher::cast_shapes,
  * default_query_dispatcher.rs:434-515: ball-ball shape_cast_ball_ball.rs:10-69, every other Ball / Cuboid / ConvexPolyhedron

@@ -262,6 +262,33 @@ void pb2o_contact_batch(const uint8_t* kinds, const float* params4, const float*
         }
     });
 }
+// query::contact between Compound compound_id[k] (parts comp_first[c] .. + comp_count[c] of the part table: part_shape = index
+// into the shape table, part_pose7) and shape[k]. pos_c / pos_s: poses of the compound and of the shape. compound_second != 0:
+// the call was contact(pos_s, shape, pos_c, compound) (result flipped accordingly). part[k] = winning part (index within
+// the compound) or u32::MAX.
+void pb2o_compound_contact_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* comp_first,
+                                 const uint32_t* comp_count, const uint32_t* part_shape, const float* part_pose7, const uint32_t* compound_id,
+                                 const float* pos_c, const uint32_t* shape, const float* pos_s, float prediction, int compound_second, uint32_t n,
+                                 int nthreads, float* out, uint8_t* status, uint32_t* part) {
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        std::vector<ShapeRef> ps; std::vector<Iso> pp;
+        for (size_t k = lo; k < hi; ++k) {
+            uint32_t c = compound_id[k], f = comp_first[c], cnt = comp_count[c];
+            ps.resize(cnt); pp.resize(cnt);
+            for (uint32_t i = 0; i < cnt; ++i) { ps[i] = make_shape(kinds, params4, points, part_shape[f + i]); pp[i] = Iso::from7(part_pose7 + 7 * (size_t)(f + i)); }
+            CompoundRef comp{ps.data(), pp.data(), cnt};
+            ShapeRef s2 = make_shape(kinds, params4, points, shape[k]);
+            Iso pc = Iso::from7(pos_c + 7 * k), psh = Iso::from7(pos_s + 7 * k);
+            Contact ct = Contact(); uint32_t id = UINT32_MAX;
+            int st = compound_second ? query_contact_compound(psh, pc, comp, s2, true, prediction, ct, id)
+                                     : query_contact_compound(pc, psh, comp, s2, false, prediction, ct, id);
+            status[k] = (uint8_t)st; part[k] = st == CONTACT_SOME ? id : UINT32_MAX;
+            float* o = out + 13 * k;
+            if (st == CONTACT_SOME) { st3(o, ct.point1); st3(o + 3, ct.point2); st3(o + 6, ct.normal1); st3(o + 9, ct.normal2); o[12] = ct.dist; }
+            else for (int i = 0; i < 13; ++i) o[i] = 0.0f;
+        }
+    });
+}
 // query::cast_shapes for n pairs (shape_cast.rs:268-286). vel1/vel2: n x 3. out: n x 13 floats {witness1, witness2, normal1,
 // normal2, time_of_impact} (witness/normal i in the local frame of shape i, as the reference returns them);
 // status: 0 None, 1 Converged, 2 PenetratingOrWithinTargetDist.

@@ -328,6 +328,45 @@ static inline int contact_trimesh_shape(const Iso& pos12, const TriMesh& mesh, c
     return have ? CONTACT_SOME : CONTACT_NONE;
 }
 
+// CompositeShapeRef::contact_with_shape for a Compound (contact_composite_shape_shape.rs:14-45, shape/compound.rs:113-144,
+// map_part_at :181-193): parts whose AABB (part shape at its pose) intersects shape2's loosened AABB are dispatched with
+// part_pos1.inv_mul(pose12); the first strictly smaller dist wins and is moved to the compound's frame with
+// transform1_by_mut. Parts are visited in index order, i.e. equal dists go to the smallest part index (the reference visits
+// them in its binned tree's order); the candidate set is the same as Bvh::intersect_aabb's (leaf test = Aabb::intersects).
+struct CompoundRef { const ShapeRef* shapes; const Iso* poses; uint32_t n; };
+static inline int contact_compound_shape(const Iso& pos12, const CompoundRef& comp, const ShapeRef& shape2, Real prediction, Contact& best,
+                                         uint32_t& part) {
+    Aabb ls = shape_compute_aabb(shape2, pos12);
+    ls.mins = ls.mins - Vec3(prediction, prediction, prediction);
+    ls.maxs = ls.maxs + Vec3(prediction, prediction, prediction);
+    bool have = false;
+    for (uint32_t i = 0; i < comp.n; ++i) {
+        if (!shape_compute_aabb(comp.shapes[i], comp.poses[i]).intersects(ls)) continue;
+        Contact c = Contact();
+        if (dispatch_contact(comp.poses[i].inv_mul(pos12), comp.shapes[i], shape2, prediction, c) != CONTACT_SOME) continue;
+        if (!have || c.dist < best.dist) {
+            c.point1 = comp.poses[i].transform_point(c.point1);   // transform1_by_mut(part_pos1)
+            c.normal1 = comp.poses[i].transform_vector(c.normal1);
+            best = c; part = i; have = true;
+        }
+    }
+    return have ? CONTACT_SOME : CONTACT_NONE;
+}
+// query::contact with a Compound on one side (default_query_dispatcher.rs:338-351): compound first = composite arm; compound
+// second (flipped) = contact_shape_composite_shape (contact_composite_shape_shape.rs:63-76): pose12.inverse(), then flipped().
+static inline int query_contact_compound(const Iso& pos1, const Iso& pos2, const CompoundRef& comp, const ShapeRef& shape, bool compound_second,
+                                         Real prediction, Contact& c, uint32_t& part) {
+    Iso pos12 = pos1.inv_mul(pos2);
+    int st = contact_compound_shape(compound_second ? pos12.inverse() : pos12, comp, shape, prediction, c, part);
+    if (st != CONTACT_SOME) return st;
+    if (compound_second) { std::swap(c.point1, c.point2); std::swap(c.normal1, c.normal2); }
+    c.point1 = pos1.transform_point(c.point1);
+    c.point2 = pos2.transform_point(c.point2);
+    c.normal1 = pos1.transform_vector(c.normal1);
+    c.normal2 = pos2.transform_vector(c.normal2);
+    return st;
+}
+
 // PointQuery for TriMesh without pseudo-normals (point_composite_shape.rs:164-186 -> CompositeShapeRef::project_local_point,
 // :49-72): Bvh::find_best with aabb cost = Aabb::distance_to_local_point(pt, solid = true) (point_aabb.rs:135-146: the norm of
 // the per-axis shift) and leaf cost = distance to the projection on the triangle (point_triangle.rs).

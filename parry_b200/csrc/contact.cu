@@ -19,6 +19,7 @@
 #include "gjk.cuh"
 #include "trimesh.cuh"
 #include <stdlib.h>
+#include <cub/cub.cuh>
 
 int pb2_stage_in(pb2_ctx* ctx, int slot, const void* src, size_t bytes, int mem, const void** out);
 int pb2_stage_out(pb2_ctx* ctx, int slot, void* dst, size_t bytes, int mem, void** out);
@@ -190,10 +191,14 @@ struct PairSrc {
     const float4* mesh_tris;
     uint32_t n_first, n_second;   // index bounds for ab[2k] / ab[2k+1]
     uint32_t flags = 0;           // PAIR_* below
+    const float* part_pose = nullptr;  // Compound mode (with `ab` = {part, pair}): shape 1 of candidate k is part ab[2k] (shape
+                                       // shape1[part] at part_pose[part] inside the compound posed at pos1[pair]); shape 2 is
+                                       // shape2[pair] at pos2[pair]. Implies local frames (of the part and of shape 2).
 };
 #define PAIR_SUPPORT_MAPS_ONLY 1u  // no ball arms: balls take part in GJK/EPA through their support map (what
                                    // cast_shapes_support_map_support_map calls: contact_support_map_support_map on any pair)
 #define PAIR_LOCAL_FRAMES 2u       // leave the contact in the shapes' local frames (no Contact::transform_by_mut)
+#define PAIR_COMPOUND_SECOND 4u    // Compound mode: the user's call was contact(shape, compound): pose12 = inv_mul(pos2, pos1).inverse()
 #define PB2_SHAPE_TRIANGLE_INTERNAL 3   // a TriMesh part (shape::Triangle), never in a shape table
 
 __device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* params, const float4* pts, const PairSrc& src, uint32_t k,
@@ -214,12 +219,19 @@ __device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* p
         uint32_t s1 = src.shape1[i1];
         ps.k1 = kinds[s1];
         ps.pr1 = params[s1];
-        ps.pos1 = load_iso(src.pos1 + 7ull * i1);
+        ps.pos1 = load_iso((src.part_pose ? src.part_pose : src.pos1) + 7ull * i1);
     }
     ps.tri = tri;
     ps.pos12 = iso_inv_mul(ps.pos1, ps.pos2);  // contact_shape_shape.rs:130
+    if (src.part_pose) {
+        // contact_composite_shape_shape.rs:27: dispatcher.contact(&part_pos1.inv_mul(pose12), part1, shape2, ..); pose12 is the
+        // user's pos12, or its inverse when the compound is the second shape (contact_shape_composite_shape, :74)
+        Iso7 pc = load_iso(src.pos1 + 7ull * i2);
+        Iso7 pose12 = (src.flags & PAIR_COMPOUND_SECOND) ? iso_inverse(iso_inv_mul(ps.pos2, pc)) : iso_inv_mul(pc, ps.pos2);
+        ps.pos12 = iso_inv_mul(ps.pos1, pose12);
+    }
     ps.mode = 0;
-    ps.local_frames = (src.flags & PAIR_LOCAL_FRAMES) != 0;
+    ps.local_frames = (src.flags & PAIR_LOCAL_FRAMES) != 0 || src.part_pose != nullptr;
     bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
     if (src.flags & PAIR_SUPPORT_MAPS_ONLY) {
         ps.mode = 1;
@@ -1407,11 +1419,13 @@ __global__ void __launch_bounds__(128, 4) k_contact_epac(const uint8_t* __restri
 // ------------------------------------------------------------------------------------------- host side
 static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
                         const float* pos2, float prediction, uint32_t n, OutSinks sinks, const uint32_t* ab = nullptr, uint32_t n_colliders = 0,
-                        const float4* mesh_tris = nullptr, uint32_t n_tris = 0, uint32_t flags = 0) {
+                        const float4* mesh_tris = nullptr, uint32_t n_tris = 0, uint32_t flags = 0, const float* part_pose = nullptr,
+                        uint32_t n_parts = 0) {
     PairSrc src;
     src.flags = flags;
+    src.part_pose = part_pose;
     src.shape1 = shape1; src.shape2 = shape2; src.pos1 = pos1; src.pos2 = pos2; src.ab = ab; src.mesh_tris = mesh_tris;
-    src.n_first = mesh_tris ? n_tris : n_colliders; src.n_second = n_colliders;
+    src.n_first = mesh_tris ? n_tris : (part_pose ? n_parts : n_colliders); src.n_second = n_colliders;
     cudaStream_t st = ctx->stream;
     // EPA job queue (worst case: every pair) + arenas for the persistent EPA grid
     int epa_variant = 2, refill = 8;  // 2 (default): 14 KB arenas; 3: compact arena — 4x less DRAM traffic, same time
@@ -2049,6 +2063,239 @@ int pb2_trimesh_contact_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const floa
     if (d_q) cudaFreeAsync(d_q, st);
     if (d_off) cudaFreeAsync(d_off, st);
     if (d_items) cudaFreeAsync(d_items, st);
+    if (d_ab) cudaFreeAsync(d_ab, st);
+    if (d_cand) cudaFreeAsync(d_cand, st);
+    if (d_cst) cudaFreeAsync(d_cst, st);
+    if (rc != PB2_OK) return rc;
+    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_status, (size_t)n, mem));
+    PB2_CHECK(pb2_stage_back(ctx, part, d_part, (size_t)n * 4, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(st));
+    return PB2_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------- Compound vs shapes
+// query::contact with a Compound on one side (default_query_dispatcher.rs:338-351 -> contact_composite_shape_shape.rs:14-76):
+// the candidate parts are those whose AABB (Compound::new, compound.rs:122-127: part.compute_aabb(part_pose)) intersects
+// shape2.compute_aabb(pose12).loosened(prediction) — the leaf test of Bvh::intersect_aabb; compounds are a handful of parts,
+// so the boxes are tested directly instead of walking a per-compound tree (same candidate set) —, every candidate runs
+// through the contact kernels in the part's frame, and the smallest dist wins (equal dists: smallest part index).
+struct pb2_compounds {
+    uint32_t nc = 0, np = 0;
+    uint32_t *first = nullptr, *count = nullptr, *part_shape = nullptr;
+    float* part_pose = nullptr;
+    float* part_aabb = nullptr;   // np x 6, in the compound's frame
+    const pb2_shapes* shapes = nullptr;
+};
+
+__device__ __forceinline__ Iso7 compound_pose12(const float* pos_c, const float* pos_s, uint32_t k, bool second) {
+    Iso7 pc = load_iso(pos_c + 7ull * k), ps = load_iso(pos_s + 7ull * k);
+    return second ? iso_inverse(iso_inv_mul(ps, pc)) : iso_inv_mul(pc, ps);
+}
+
+// pass 0: counts[k] = number of candidate parts; pass 1 (offsets given): ab[j] = {global part, k}
+template <bool FILL>
+__global__ void k_compound_candidates(const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float* __restrict__ points,
+                                      uint32_t n_shapes, const uint32_t* __restrict__ comp_first, const uint32_t* __restrict__ comp_count, uint32_t nc,
+                                      const float* __restrict__ part_aabb, const uint32_t* __restrict__ compound_id, const float* __restrict__ pos_c,
+                                      const uint32_t* __restrict__ shape_ids, const float* __restrict__ pos_s, uint32_t n, float prediction, bool second,
+                                      uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ ab) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t c = compound_id[k], sid = shape_ids[k], cnt = 0;
+    if (c < nc && sid < n_shapes) {
+        Iso7 pose12 = compound_pose12(pos_c, pos_s, k, second);
+        V3 mn, mx;
+        shape_aabb_dev(kinds[sid], params[sid], points, pose12, mn, mx);
+        mn = mk3(mn.x + (-prediction), mn.y + (-prediction), mn.z + (-prediction));   // Aabb::loosened
+        mx = mk3(mx.x + prediction, mx.y + prediction, mx.z + prediction);
+        uint32_t f = comp_first[c], m = comp_count[c];
+        uint32_t at = FILL ? offsets[k] : 0;
+        for (uint32_t i = 0; i < m; ++i) {
+            const float* b = part_aabb + 6ull * (f + i);
+            // Aabb::intersects (aabb.rs:951-953): inclusive on every axis
+            bool hit = b[0] <= mx.x && b[1] <= mx.y && b[2] <= mx.z && mn.x <= b[3] && mn.y <= b[4] && mn.z <= b[5];
+            if (hit) {
+                if (FILL) { ab[2ull * (at + cnt)] = f + i; ab[2ull * (at + cnt) + 1] = k; }
+                cnt++;
+            }
+        }
+    }
+    if (!FILL) counts[k] = cnt;
+}
+
+__global__ void k_compound_part_aabbs(const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float* __restrict__ points,
+                                      const uint32_t* __restrict__ part_shape, const float* __restrict__ part_pose, uint32_t np, float* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    uint32_t sid = part_shape[i];
+    V3 mn, mx;
+    shape_aabb_dev(kinds[sid], params[sid], points, load_iso(part_pose + 7ull * i), mn, mx);
+    float* o = out + 6ull * i;
+    o[0] = mn.x; o[1] = mn.y; o[2] = mn.z; o[3] = mx.x; o[4] = mx.y; o[5] = mx.z;
+}
+
+__global__ void k_compound_reduce(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ab, const float* __restrict__ cand,
+                                  const uint8_t* __restrict__ cand_status, const uint32_t* __restrict__ comp_first, uint32_t nc,
+                                  const float* __restrict__ part_pose, const uint32_t* __restrict__ compound_id, const float* __restrict__ pos_c,
+                                  const uint32_t* __restrict__ shape_ids, uint32_t n_shapes, const float* __restrict__ pos_s, uint32_t n, bool second,
+                                  float* __restrict__ out, uint8_t* __restrict__ status, uint32_t* __restrict__ part) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    uint32_t c = compound_id[q];
+    int st = (c >= nc || shape_ids[q] >= n_shapes) ? ST_UNSUPPORTED : ST_NONE;
+    uint32_t best_j = 0;
+    float best = 0.0f;
+    bool needs_host = false;
+    if (st == ST_NONE) {
+        for (uint32_t j = offsets[q]; j < offsets[q + 1]; ++j) {
+            if (cand_status[j] == ST_NEEDS_HOST) needs_host = true;
+            if (cand_status[j] != ST_SOME) continue;
+            float d = cand[13ull * j + 12];
+            if (st != ST_SOME || d < best) { best = d; best_j = j; st = ST_SOME; }   // candidates are in part order: first minimum wins
+        }
+        if (needs_host) st = ST_NEEDS_HOST;
+    }
+    float* o = out + 13ull * q;
+    if (st == ST_SOME) {
+        const float* cj = cand + 13ull * best_j;
+        uint32_t gp = ab[2ull * best_j];
+        Iso7 pp = load_iso(part_pose + 7ull * gp);
+        ContactOut ct;
+        ct.p1 = iso_point(pp, mk3(cj[0], cj[1], cj[2]));   // Contact::transform1_by_mut(part_pos1)
+        ct.n1 = iso_vec(pp, mk3(cj[6], cj[7], cj[8]));
+        ct.p2 = mk3(cj[3], cj[4], cj[5]);
+        ct.n2 = mk3(cj[9], cj[10], cj[11]);
+        ct.dist = cj[12];
+        Iso7 pc = load_iso(pos_c + 7ull * q), ps = load_iso(pos_s + 7ull * q);
+        if (second) {   // Contact::flipped, then the user's (pos1, pos2) = (shape, compound)
+            flip_contact(ct);
+            ct.p1 = iso_point(ps, ct.p1); ct.n1 = iso_vec(ps, ct.n1); ct.p2 = iso_point(pc, ct.p2); ct.n2 = iso_vec(pc, ct.n2);
+        } else {
+            ct.p1 = iso_point(pc, ct.p1); ct.n1 = iso_vec(pc, ct.n1); ct.p2 = iso_point(ps, ct.p2); ct.n2 = iso_vec(ps, ct.n2);
+        }
+        store_contact(o, ct);
+        part[q] = gp - comp_first[c];
+    } else {
+        for (int i = 0; i < 13; ++i) o[i] = 0.0f;
+        part[q] = PB2_INVALID_U32;
+    }
+    status[q] = (uint8_t)st;
+}
+
+extern "C" {
+
+int pb2_compounds_create(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* comp_first, const uint32_t* comp_count, uint32_t nc,
+                         const uint32_t* part_shape, const float* part_pose7, uint32_t np, pb2_compounds** out) {
+    if (!ctx || !shapes || !out || !comp_first || !comp_count || !part_shape || !part_pose7 || nc == 0 || np == 0) return PB2_ERR_INVALID;
+    *out = nullptr;
+    for (uint32_t c = 0; c < nc; ++c) {
+        // Compound::new asserts !shapes.is_empty() (compound.rs:114-117)
+        if (comp_count[c] == 0 || (uint64_t)comp_first[c] + comp_count[c] > np) PB2_FAIL(ctx, PB2_ERR_INVALID, "compounds_create: empty compound or part range out of bounds");
+    }
+    for (uint32_t i = 0; i < np; ++i)
+        if (part_shape[i] >= shapes->n) PB2_FAIL(ctx, PB2_ERR_INVALID, "compounds_create: part shape id out of range");
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    pb2_compounds* cp = new pb2_compounds();
+    cp->nc = nc; cp->np = np; cp->shapes = shapes;
+    cudaStream_t st = ctx->stream;
+    bool ok = cudaMalloc((void**)&cp->first, (size_t)nc * 4) == cudaSuccess && cudaMalloc((void**)&cp->count, (size_t)nc * 4) == cudaSuccess &&
+              cudaMalloc((void**)&cp->part_shape, (size_t)np * 4) == cudaSuccess && cudaMalloc((void**)&cp->part_pose, (size_t)np * 28) == cudaSuccess &&
+              cudaMalloc((void**)&cp->part_aabb, (size_t)np * 24) == cudaSuccess;
+    if (ok) {
+        cudaMemcpyAsync(cp->first, comp_first, (size_t)nc * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(cp->count, comp_count, (size_t)nc * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(cp->part_shape, part_shape, (size_t)np * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(cp->part_pose, part_pose7, (size_t)np * 28, cudaMemcpyHostToDevice, st);
+        k_compound_part_aabbs<<<pb2_blocks(np, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points, cp->part_shape, cp->part_pose, np,
+                                                                   cp->part_aabb);
+        PB2_LAUNCHED(ctx);
+        ok = cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    if (!ok) {
+        cudaFree(cp->first); cudaFree(cp->count); cudaFree(cp->part_shape); cudaFree(cp->part_pose); cudaFree(cp->part_aabb);
+        delete cp;
+        PB2_FAIL(ctx, PB2_ERR_CUDA, "compounds_create: device allocation or upload failed");
+    }
+    *out = cp;
+    return PB2_OK;
+}
+
+int pb2_compounds_destroy(pb2_ctx* ctx, pb2_compounds* cp) {
+    if (!ctx || !cp) return PB2_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(cp->first); cudaFree(cp->count); cudaFree(cp->part_shape); cudaFree(cp->part_pose); cudaFree(cp->part_aabb);
+    delete cp;
+    return PB2_OK;
+}
+
+int pb2_compound_contact_shapes(pb2_ctx* ctx, const pb2_compounds* compounds, const uint32_t* compound_ids, const float* compound_poses7,
+                                const uint32_t* shape_ids, const float* shape_poses7, uint32_t n, float prediction, int compound_second,
+                                pb2_contact* out, uint8_t* status, uint32_t* part, int mem) {
+    if (!ctx || !compounds || (n && (!compound_ids || !compound_poses7 || !shape_ids || !shape_poses7 || !out || !status || !part))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    const pb2_shapes* shapes = compounds->shapes;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_cid, *d_pc, *d_sid, *d_ps;
+    void *d_out, *d_status, *d_part;
+    PB2_CHECK(pb2_stage_in(ctx, 0, compound_ids, (size_t)n * 4, mem, &d_cid));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape_ids, (size_t)n * 4, mem, &d_sid));
+    PB2_CHECK(pb2_stage_in(ctx, 2, compound_poses7, (size_t)n * 28, mem, &d_pc));
+    PB2_CHECK(pb2_stage_in(ctx, 3, shape_poses7, (size_t)n * 28, mem, &d_ps));
+    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_status));
+    PB2_CHECK(pb2_stage_out(ctx, 6, part, (size_t)n * 4, mem, &d_part));
+    const bool second = compound_second != 0;
+    uint32_t *d_cnt = nullptr, *d_off = nullptr, *d_ab = nullptr;
+    float* d_cand = nullptr;
+    uint8_t* d_cst = nullptr;
+    void* d_tmp = nullptr;
+    int rc = PB2_OK;
+    do {
+        size_t cub_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n + 1, st);
+        if (cudaMallocAsync((void**)&d_cnt, ((size_t)n + 1) * 4, st) != cudaSuccess || cudaMallocAsync((void**)&d_off, ((size_t)n + 1) * 4, st) != cudaSuccess ||
+            cudaMallocAsync(&d_tmp, cub_bytes, st) != cudaSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), "compound_contact_shapes: out of memory"); rc = PB2_ERR_CUDA; break;
+        }
+        cudaMemsetAsync(d_cnt + n, 0, 4, st);
+        k_compound_candidates<false><<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points, shapes->n, compounds->first,
+            compounds->count, compounds->nc, compounds->part_aabb, (const uint32_t*)d_cid, (const float*)d_pc, (const uint32_t*)d_sid,
+            (const float*)d_ps, n, prediction, second, d_cnt, nullptr, nullptr);
+        PB2_LAUNCHED(ctx);
+        cub::DeviceScan::ExclusiveSum(d_tmp, cub_bytes, (const uint32_t*)d_cnt, d_off, (int)n + 1, st);
+        ctx->launches += 1;
+        uint32_t total = 0;
+        cudaMemcpyAsync(&total, d_off + n, 4, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "compound_contact_shapes: candidate pass failed"); rc = PB2_ERR_CUDA; break; }
+        if (total) {
+            if (cudaMallocAsync((void**)&d_ab, (size_t)total * 8, st) != cudaSuccess || cudaMallocAsync((void**)&d_cand, (size_t)total * 52, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_cst, total, st) != cudaSuccess) {
+                snprintf(ctx->err, sizeof(ctx->err), "compound_contact_shapes: out of memory (%u candidates)", total); rc = PB2_ERR_CUDA; break;
+            }
+            k_compound_candidates<true><<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points, shapes->n, compounds->first,
+                compounds->count, compounds->nc, compounds->part_aabb, (const uint32_t*)d_cid, (const float*)d_pc, (const uint32_t*)d_sid,
+                (const float*)d_ps, n, prediction, second, nullptr, d_off, d_ab);
+            PB2_LAUNCHED(ctx);
+            OutSinks sinks;
+            sinks.dense = d_cand; sinks.status = d_cst; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
+            sinks.compact_count = nullptr; sinks.some_count = nullptr;
+            if ((rc = run_contacts(ctx, shapes, compounds->part_shape, (const uint32_t*)d_sid, (const float*)d_pc, (const float*)d_ps, prediction, total,
+                                   sinks, d_ab, n, nullptr, 0, second ? PAIR_COMPOUND_SECOND : 0u, compounds->part_pose, compounds->np)) != PB2_OK) break;
+        }
+        k_compound_reduce<<<pb2_blocks(n, 128), 128, 0, st>>>(d_off, d_ab, d_cand, d_cst, compounds->first, compounds->nc, compounds->part_pose,
+            (const uint32_t*)d_cid, (const float*)d_pc, (const uint32_t*)d_sid, shapes->n, (const float*)d_ps, n, second, (float*)d_out,
+            (uint8_t*)d_status, (uint32_t*)d_part);
+        PB2_LAUNCHED(ctx);
+        if (cudaGetLastError() != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "compound_contact_shapes: launch failed"); rc = PB2_ERR_CUDA; break; }
+    } while (0);
+    if (d_cnt) cudaFreeAsync(d_cnt, st);
+    if (d_off) cudaFreeAsync(d_off, st);
+    if (d_tmp) cudaFreeAsync(d_tmp, st);
     if (d_ab) cudaFreeAsync(d_ab, st);
     if (d_cand) cudaFreeAsync(d_cand, st);
     if (d_cst) cudaFreeAsync(d_cst, st);

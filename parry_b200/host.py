@@ -477,6 +477,57 @@ class Shapes:
             pass
 
 
+class Compounds:
+    """A table of Compound shapes (shape/compound.rs:113-144) over a Shapes table: compound c = the parts
+    [(pose, shapes[shape_id]), ...] given as `compounds[c]`. `contact_shapes` is query::contact with the compound on one side."""
+
+    def __init__(self, ctx, shapes, compounds):
+        self.ctx, self.shapes = ctx, shapes
+        first, count, part_shape, part_pose = [], [], [], []
+        for parts in compounds:
+            first.append(len(part_shape))
+            count.append(len(parts))
+            for pose, sid in parts:
+                part_pose.append(np.asarray(pose, dtype=np.float32).reshape(7))
+                part_shape.append(int(sid))
+        self.first = np.asarray(first, dtype=np.uint32)
+        self.count = np.asarray(count, dtype=np.uint32)
+        self.part_shape = np.asarray(part_shape, dtype=np.uint32)
+        self.part_pose = np.ascontiguousarray(np.stack(part_pose) if part_pose else np.zeros((0, 7)), dtype=np.float32)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.pb2_compounds_create(ctx.h, shapes.h, self.first.ctypes.data, self.count.ctypes.data, len(self.first),
+                                                self.part_shape.ctypes.data, self.part_pose.ctypes.data, len(self.part_shape), C.byref(h)))
+        self.h = h
+
+    def contact_shapes(self, compound_ids, compound_poses, shape_ids, shape_poses, prediction, compound_second=False):
+        """query::contact(compound_poses[k], compound k, shape_poses[k], shape k, prediction) — or, with compound_second,
+        query::contact(shape_poses[k], shape k, compound_poses[k], compound k, prediction) — for every k
+        (contact_composite_shape_shape.rs:14-76). Returns (contacts (n, 13), status (n,), part (n,) winning part index)."""
+        n = int(compound_poses.shape[0])
+        kc, pc, mem = _prep(compound_poses, np.float32)
+        ks, ps, _ = _prep(shape_poses, np.float32, mem)
+        kci, pci, _ = _prep(compound_ids, np.uint32, mem)
+        ksi, psi, _ = _prep(shape_ids, np.uint32, mem)
+        dev = self.ctx.torch_device
+        out, po = _empty((n, 13), np.float32, mem, dev)
+        status, pst = _empty((n,), np.uint8, mem, dev)
+        part, ppart = _empty((n,), np.uint32, mem, dev)
+        self.ctx.check(self.ctx._lib.pb2_compound_contact_shapes(self.ctx.h, self.h, pci, pc, psi, ps, n, float(prediction), int(compound_second),
+                                                                 po, pst, ppart, mem))
+        return out, status, part
+
+    def close(self):
+        if self.h:
+            self.ctx._lib.pb2_compounds_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 CONTACT_DTYPE = np.dtype([("point1", np.float32, (3,)), ("point2", np.float32, (3,)), ("normal1", np.float32, (3,)),
                           ("normal2", np.float32, (3,)), ("dist", np.float32)])
 assert CONTACT_DTYPE.itemsize == 52

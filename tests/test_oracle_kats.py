@@ -273,3 +273,27 @@ def test_cast_shapes_hit_configuration_touches(oracle):
         dist, ds = T.distance(s1[hit], q1, s2[hit], q2)
         ok = ds == 0
         assert np.abs(dist[ok] - target).max() < 5e-3
+
+
+def test_compound_single_part_equals_plain_contact(oracle):
+    """contact_composite_shape_shape.rs:14-45 with one part at the identity pose degenerates to the part's own contact (bit for
+    bit); with the part moved by a pose P it equals the plain contact of the part posed at pos1 * P up to rounding."""
+    g = scenes.rng(3)
+    pts, _ = scenes.hull_pool(4, 16, seed=5)
+    T = oracle.ShapeTable([("ball", 0.4), ("cuboid", [0.3, 0.5, 0.4])] + [("convex", p * 0.6) for p in pts])
+    n = 2000
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    cf, cc = np.arange(6, dtype=np.uint32), np.ones(6, np.uint32)
+    cid, sid = g.integers(0, 6, n).astype(np.uint32), g.integers(0, 6, n).astype(np.uint32)
+    pc = np.concatenate([scenes.random_unit_quaternions(g, n), g.random((n, 3)) - .5], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    ps = np.concatenate([scenes.random_unit_quaternions(g, n), pc[:, 4:] + d * (g.random((n, 1)) * 1.2 + 0.2)], axis=1).astype(np.float32)
+    o1, s1, p1 = T.contact_compound(cf, cc, np.arange(6, dtype=np.uint32), np.tile(ident, (6, 1)), cid, pc, sid, ps, 0.05)
+    o2, s2 = T.contact(cid, pc, sid, ps, 0.05)
+    assert (s1 == s2).all() and (s2 == 1).mean() > 0.3 and (o1.view(np.uint32) == o2.view(np.uint32)).all()
+    assert (p1[s1 == 1] == 0).all() and (p1[s1 != 1] == 0xFFFFFFFF).all()
+    o3, s3, _ = T.contact_compound(cf, cc, np.arange(6, dtype=np.uint32), np.tile(ident, (6, 1)), cid, pc, sid, ps, 0.05, compound_second=True)
+    o4, s4 = T.contact(sid, ps, cid, pc, 0.05)
+    assert (s3 == s4).all()
+    np.testing.assert_allclose(o3[s4 == 1], o4[s4 == 1], rtol=1e-3, atol=2e-4)
