@@ -175,7 +175,7 @@ def main():
         try:
             if os.environ.get("PB2_BENCH_NCCL_GATHER"):
                 raise RuntimeError("forced")
-            gather = sharding.PeerHitGather(m, torch.device("cuda", local_rank), chunks=int(os.environ.get("PB2_BENCH_GATHER_CHUNKS", "8")))
+            gather = sharding.PeerHitGather(m, torch.device("cuda", local_rank), chunks=int(os.environ.get("PB2_BENCH_GATHER_CHUNKS", "4" if world <= 2 else "8")))
             gather_kind = ("all-gather of the (toi,id) results inside the timed region: pieces pushed into every peer's symmetric-memory "
                            "buffer by copy engines over NVLink while the next piece is traversed, then a cross-rank barrier")
         except Exception as e:  # no symmetric memory on this box: NCCL all_gather per piece on a side stream

@@ -22,6 +22,13 @@ int pb2_pipeline_init(pb2_ctx* ctx) {
     PB2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
     for (int i = 0; i < 6; ++i) PB2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_peer[i], cudaStreamNonBlocking));
     for (int i = 0; i < 64; ++i) PB2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+    PB2_CUDA(ctx, cudaMalloc((void**)&ctx->d_pieces, 64 * sizeof(unsigned int)));
+    {   // stream memory operations come from the driver API; resolved through the runtime so that nothing links against libcuda
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) ctx->wait_value32 = fn;
+        (void)cudaGetLastError();
+    }
     return PB2_OK;
 }
 
@@ -80,6 +87,7 @@ int pb2_ctx_destroy(pb2_ctx* ctx) {
     { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_pieces) cudaFree(ctx->d_pieces);
     if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); cudaStreamDestroy(ctx->copy_out); if (ctx->compute2) cudaStreamDestroy(ctx->compute2); for (int i = 0; i < 6; ++i) if (ctx->copy_peer[i]) cudaStreamDestroy(ctx->copy_peer[i]); for (int i = 0; i < 64; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

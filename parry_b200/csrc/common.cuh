@@ -36,7 +36,10 @@ struct pb2_ctx {
     int ray_slot = 8;                 // d_counters slot of the persistent ray kernels' fetch counter (8 or 12, one per compute stream)
     cudaEvent_t ev[64] = {nullptr};
     int ev_next = 0;
+    unsigned int* d_pieces = nullptr;  // 2 x 32 u32: per-piece retired-ray counters and completion flags of a piece-signalling ray cast
+    void* wait_value32 = nullptr;      // cuStreamWaitValue32, resolved once (NULL: not available -> piece-wise launches)
 };
+struct PieceSignal { uint32_t size; unsigned int* done; unsigned int* flag; uint32_t flush_every; };
 int pb2_pipeline_init(pb2_ctx* ctx);
 static inline cudaEvent_t pb2_next_event(pb2_ctx* ctx) { cudaEvent_t e = ctx->ev[ctx->ev_next]; ctx->ev_next = (ctx->ev_next + 1) % 64; return e; }
 

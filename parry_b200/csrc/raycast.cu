@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(128) k_project_points_trimesh(const NodeWide* 
 
 // Enqueues the ray kernels for m device-resident rays on ctx->stream.
 static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d_pose, const void* d_rays, uint32_t m, float max_toi,
-                            void* d_toi, void* d_tri, void* d_n, void* d_f, bool with_normal, uint32_t cull) {
+                            void* d_toi, void* d_tri, void* d_n, void* d_f, bool with_normal, uint32_t cull, const PieceSignal* pieces = nullptr) {
     const pb2_bvh* b = &mesh->bvh;
     // ray reordering pays off once the node array no longer fits in L2 (126 MB); below that the sort costs more than it saves
     // variants: 0 one thread per ray, 1 persistent binary, 2 = 1 + ray reordering, 3 compressed 8-wide tree, 4 = 3 + ray reordering,
@@ -336,6 +336,7 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
         if ((e = getenv("PB2_RAY_STEPS"))) steps = atoi(e);
         if ((e = getenv("PB2_RAY_REFILL"))) refill = atoi(e);
     }
+    if (pieces && (variant != 5 || b->n_leaves < 2 || m < 4096)) return PB2_ERR_INVALID;  // callers check pb2_can_signal_pieces first
     if (variant == 0 || b->n_leaves < 2 || m < 4096) {
         unsigned blocks = pb2_blocks(m, 128);
         if (with_normal)
@@ -375,7 +376,7 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
         if (blocks > need) blocks = need;
         if (variant >= 3)
             PB2_CHECK(pb2_wide_cast(ctx, mesh, (const float*)d_pose, (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
-                                    (float*)d_n, (uint32_t*)d_f, with_normal, steps, refill, cull, variant >= 5));
+                                    (float*)d_n, (uint32_t*)d_f, with_normal, steps, refill, cull, variant >= 5, pieces));
         else if (with_normal)
             k_raycast_trimesh_persistent<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
                 (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, (float*)d_n, (uint32_t*)d_f, next_ray, steps, refill, cull);
@@ -553,8 +554,51 @@ int pb2_trimesh_cast_rays_allgather(pb2_ctx* ctx, const pb2_trimesh* mesh, const
     if (chunks > 16) chunks = 16;
     float* my_toi = (float*)peer_toi[self] + elem_offset;
     uint32_t* my_tri = (uint32_t*)peer_tri[self] + elem_offset;
-    const bool dual = mesh->n_nodes8 != 0 && getenv("PB2_RAY_VARIANT") == nullptr && chunks > 1;
     cudaStream_t main_stream = ctx->stream;
+    if (mesh->n_nodes8 != 0 && getenv("PB2_RAY_VARIANT") == nullptr && chunks > 1 && chunks <= 32 && m >= 4096 && mesh->bvh.n_leaves >= 2 &&
+        ctx->wait_value32 != nullptr && getenv("PB2_RAY_PIECEWISE") == nullptr) {
+        // One launch for the whole shard; the kernel publishes the completion of each range of results (PieceSignal), and the
+        // copy-engine streams wait on those flags before pushing the range to the peers.
+        typedef int (*wait_fn_t)(cudaStream_t, unsigned long long, unsigned int, unsigned int);   // CUresult cuStreamWaitValue32(CUstream, CUdeviceptr, cuuint32_t, unsigned)
+        wait_fn_t wait_value = (wait_fn_t)ctx->wait_value32;
+        PieceSignal ps;
+        ps.size = (m + (uint32_t)chunks - 1u) / (uint32_t)chunks;
+        ps.done = ctx->d_pieces; ps.flag = ctx->d_pieces + 32;
+        ps.flush_every = 32;  // refills between two publications of a warp's retired-ray counts
+        { const char* e = getenv("PB2_RAY_PIECE_FLUSH"); if (e && atoi(e) > 0) ps.flush_every = (uint32_t)atoi(e); }
+        PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_pieces, 0, 64 * sizeof(unsigned int), main_stream));
+        cudaEvent_t e0 = pb2_next_event(ctx);
+        PB2_CUDA(ctx, cudaEventRecord(e0, main_stream));
+        for (int q = 0; q < 6; ++q) PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_peer[q], e0, 0));   // flags are reset before anybody waits on them
+        ctx->ray_slot = 8;
+        PB2_CHECK(cast_rays_device(ctx, mesh, pose7, rays, m, max_toi, my_toi, my_tri, nullptr, nullptr, false, 0u, &ps));
+        const uint32_t n_pieces = (m + ps.size - 1u) / ps.size;
+        cudaEvent_t e_done = pb2_next_event(ctx);
+        PB2_CUDA(ctx, cudaEventRecord(e_done, main_stream));
+        for (uint32_t ci = 0; ci < n_pieces; ++ci) {
+            uint32_t lo = ci * ps.size, cnt = m - lo < ps.size ? m - lo : ps.size;
+            bool waited[6] = {false, false, false, false, false, false};
+            if (ci + 1 == n_pieces) {   // the last range completes with the kernel: an ordinary event wakes the copy streams sooner than a polled flag
+                for (int q = 0; q < 6; ++q) { PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_peer[q], e_done, 0)); waited[q] = true; }
+            }
+            for (int p = 0; p < n_peers; ++p) {
+                if (p == self) continue;
+                int q = ((p - self + n_peers) % n_peers) % 6;
+                cudaStream_t cs = ctx->copy_peer[q];
+                if (!waited[q]) {
+                    if (wait_value(cs, (unsigned long long)(uintptr_t)(ps.flag + ci), 1u, 0x0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
+                        PB2_FAIL(ctx, PB2_ERR_CUDA, "cuStreamWaitValue32 failed");
+                    waited[q] = true;
+                }
+                PB2_CUDA(ctx, cudaMemcpyAsync((float*)peer_toi[p] + elem_offset + lo, my_toi + lo, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, cs));
+                PB2_CUDA(ctx, cudaMemcpyAsync((uint32_t*)peer_tri[p] + elem_offset + lo, my_tri + lo, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, cs));
+            }
+        }
+        for (int q = 0; q < 6; ++q) { cudaEvent_t e = pb2_next_event(ctx); cudaEventRecord(e, ctx->copy_peer[q]); cudaStreamWaitEvent(main_stream, e, 0); }
+        PB2_CUDA(ctx, cudaGetLastError());
+        return PB2_OK;
+    }
+    const bool dual = mesh->n_nodes8 != 0 && getenv("PB2_RAY_VARIANT") == nullptr && chunks > 1;
     cudaEvent_t e0 = pb2_next_event(ctx);
     PB2_CUDA(ctx, cudaEventRecord(e0, main_stream));
     if (dual) PB2_CUDA(ctx, cudaStreamWaitEvent(ctx->compute2, e0, 0));

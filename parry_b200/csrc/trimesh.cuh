@@ -50,4 +50,4 @@ __device__ __forceinline__ bool ray_triangle(V3 a, V3 b, V3 c, V3 o, V3 dir, flo
 
 int pb2_wide_build(pb2_ctx* ctx, pb2_trimesh* mesh);
 int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, const float* d_rays, const uint32_t* d_perm, uint32_t m,
-                  float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int tri_lanes, int refill, uint32_t cull, int shared_tri);
+                  float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int tri_lanes, int refill, uint32_t cull, int shared_tri, const PieceSignal* pieces = nullptr);

@@ -524,13 +524,18 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide(const float4* __restric
 // rule (smallest toi, then smallest triangle id). The lane that owns the winning candidate then stores the payload (exact
 // toi bits, feature, normal) for the ray's owner.
 #define W8C_GQ 64   // queued groups per warp (a node phase adds at most 32)
-template <bool WITH_NORMAL>
+// PIECES: the batch is split into ranges of `pieces.size` rays whose completion is published while the kernel runs — each
+// warp counts the rays it has retired per range when it refills (and at exit) and, every 8 refills, fences its result
+// stores and adds the count to pieces.done[range]; whoever completes a range sets pieces.flag[range], which copy-engine streams wait on
+// (cuStreamWaitValue32) to push that range of results to the peer GPUs. One launch keeps the SMs full across range
+// boundaries, which separate launches per range cannot (each boundary cost ~40 us of ramp-down, harness/pieces_probe.py).
+template <bool WITH_NORMAL, bool PIECES>
 __global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
                                   const float* __restrict__ pose7, const float* __restrict__ rays, const uint32_t* __restrict__ perm,
                                   uint32_t m, float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
                                   float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
                                   unsigned int* __restrict__ next_ray, int tri_groups, int refill, uint32_t cull, int blocked_max,
-                                  unsigned long long* __restrict__ stats) {
+                                  unsigned long long* __restrict__ stats, PieceSignal pieces) {
     __shared__ float s_ray[9][128];                // o, d, 1/d of the ray each thread owns
     __shared__ unsigned long long s_key[128];      // best hit so far: |toi| bits << 32 | triangle id (id INVALID: none yet)
     __shared__ uint2 s_pay[128];                   // {exact toi bits, feature bits} of that hit
@@ -540,6 +545,7 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
     const unsigned lt = (1u << lane) - 1u;
+    const int pieces_flush_every = PIECES ? (int)pieces.flush_every : 0;
     Iso7 pose;
     if (pose7) pose = load_iso(pose7);
     V3 o = mk3(0.f, 0.f, 0.f), inv = o;
@@ -551,9 +557,44 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __
     int sp = 0;
     uint32_t G = 0;                                // groups in this warp's queue (warp uniform)
     bool exhausted = false;
+    // PIECES: retired rays not yet published, for the two ranges a warp can hold rays of around a range boundary
+    uint32_t pz_piece = PB2_INVALID_U32, pz_count = 0, pz_piece2 = PB2_INVALID_U32, pz_count2 = 0, pz_since = 0;
+    auto pz_publish = [&](uint32_t piece, uint32_t count) {   // lane 0, after the warp's fence
+        uint32_t lo_r = piece * pieces.size;
+        uint32_t total = m - lo_r < pieces.size ? m - lo_r : pieces.size;
+        unsigned prev = atomicAdd(&pieces.done[piece], count);
+        if (prev + count == total) { __threadfence(); atomicExch(&pieces.flag[piece], 1u); }
+    };
+    auto pz_flush = [&]() {
+        __threadfence();   // every lane's result stores are visible before the counts are
+        __syncwarp();
+        if (lane == 0) {
+            if (pz_count) pz_publish(pz_piece, pz_count);
+            if (pz_count2) pz_publish(pz_piece2, pz_count2);
+        }
+        pz_count = 0; pz_count2 = 0; pz_since = 0;
+    };
+    // rays retired since the last refill are counted when their lane is handed a new ray (and at exit): nothing per trip
+    uint32_t rp = PB2_INVALID_U32;   // range of the ray this lane holds or has retired but not yet counted
+    auto pz_collect = [&]() {
+        unsigned cm = __ballot_sync(FULL, !active && rp != PB2_INVALID_U32);
+        while (cm) {   // usually one range
+            uint32_t p0 = __shfl_sync(FULL, rp, __ffs(cm) - 1);
+            unsigned grp = __ballot_sync(FULL, !active && rp == p0);
+            cm &= ~grp;
+            uint32_t c = (uint32_t)__popc(grp);
+            if (p0 == pz_piece) pz_count += c;
+            else if (p0 == pz_piece2) pz_count2 += c;
+            else if (pz_count == 0) { pz_piece = p0; pz_count = c; }
+            else if (pz_count2 == 0) { pz_piece2 = p0; pz_count2 = c; }
+            else { pz_flush(); pz_piece = p0; pz_count = c; }
+        }
+        if (!active) rp = PB2_INVALID_U32;
+    };
     for (;;) {
         unsigned idle = __ballot_sync(FULL, !active);
         if (!exhausted && (idle == FULL || __popc(idle) >= refill)) {
+            if (PIECES) { pz_collect(); if (++pz_since >= (uint32_t)pieces_flush_every && (pz_count | pz_count2)) pz_flush(); }
             unsigned base = 0;
             int leader = __ffs(idle) - 1;
             if (lane == leader) base = atomicAdd(next_ray, (unsigned)__popc(idle));
@@ -575,6 +616,7 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __
                     s_ray[3][threadIdx.x] = d.x; s_ray[4][threadIdx.x] = d.y; s_ray[5][threadIdx.x] = d.z;
                     s_ray[6][threadIdx.x] = inv.x; s_ray[7][threadIdx.x] = inv.y; s_ray[8][threadIdx.x] = inv.z;
                     s_key[threadIdx.x] = ((unsigned long long)__float_as_uint(max_toi) << 32) | 0xffffffffull;
+                    if (PIECES) rp = r / pieces.size;
                 }
             }
             idle = __ballot_sync(FULL, !active);
@@ -742,16 +784,20 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __
             active = false;
         }
     }
+    if (PIECES) { pz_collect(); if (pz_count | pz_count2) pz_flush(); }
 }
 
 int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, const float* d_rays, const uint32_t* d_perm, uint32_t m,
                   float max_toi, float* d_toi, uint32_t* d_tri, float* d_n, uint32_t* d_f, bool with_normal, int tri_lanes, int refill, uint32_t cull,
-                  int shared_tri) {
+                  int shared_tri, const PieceSignal* pieces) {
     unsigned int* next_ray = (unsigned int*)(ctx->d_counters + ctx->ray_slot);
     int mode = 0;
     { const char* e = getenv("PB2_RAY_MODE"); if (e) mode = atoi(e) ? 1 : 0; }
     auto kern = with_normal ? (mode ? k_raycast_wide<true, 1> : k_raycast_wide<true, 0>) : (mode ? k_raycast_wide<false, 1> : k_raycast_wide<false, 0>);
-    auto kern_shared = with_normal ? k_raycast_wide_shared<true> : k_raycast_wide_shared<false>;
+    const bool pz = pieces != nullptr && shared_tri && !with_normal && d_perm == nullptr;
+    if (pieces && !pz) return PB2_ERR_INVALID;
+    auto kern_shared = pz ? k_raycast_wide_shared<false, true> : (with_normal ? k_raycast_wide_shared<true, false> : k_raycast_wide_shared<false, false>);
+    PieceSignal no_pieces = {0u, nullptr, nullptr, 0u};
     int tri_groups = 12, blocked_max = 8;
     { const char* e = getenv("PB2_RAY_TRI_GROUPS"); if (e) tri_groups = atoi(e); }
     { const char* e = getenv("PB2_RAY_BLOCKED"); if (e) blocked_max = atoi(e); }
@@ -773,7 +819,7 @@ int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, co
     if (shared_tri)
         kern_shared<<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi, d_toi, d_tri,
                                                      with_normal ? d_n : nullptr, with_normal ? d_f : nullptr, next_ray, tri_groups, refill, cull,
-                                                     blocked_max, stats);
+                                                     blocked_max, stats, pz ? *pieces : no_pieces);
     else
         kern<<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi, d_toi, d_tri,
                                               with_normal ? d_n : nullptr, with_normal ? d_f : nullptr, next_ray, tri_lanes, refill, cull, stats);
