@@ -18,6 +18,7 @@
 // BvhNode::cast_ray (bvh_tree.rs:1177-1181), then local_ray_intersection_with_triangle (ray_triangle.rs:70-152).
 // Accept / tie rules are those of raycast.cu.
 #include "trimesh.cuh"
+#include <string.h>
 #include <cub/device/device_scan.cuh>
 
 #define W8_LEAF 0x80000000u
@@ -816,6 +817,32 @@ int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, co
         cudaMemsetAsync(d_stats, 0, 64, ctx->stream);
         stats = d_stats;
     }
+    // Optional L2 residency hint for the node array (PB2_RAY_L2_PERSIST = percent of the persisting carve-out to use, 0 = off):
+    // triangles (3x the bytes of the nodes) and, on several GPUs, the gathered results stream through L2 and evict nodes.
+    int l2_pct = 0;
+    { const char* e = getenv("PB2_RAY_L2_PERSIST"); if (e) l2_pct = atoi(e); }
+    bool l2_set = false;
+    if (l2_pct > 0) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+        if (max_persist > 0 && max_window > 0) {
+            size_t carve = (size_t)max_persist * (size_t)(l2_pct > 100 ? 100 : l2_pct) / 100;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+            size_t bytes = (size_t)mesh->n_nodes8 * 80;
+            if (bytes > (size_t)max_window) bytes = (size_t)max_window;
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.accessPolicyWindow.base_ptr = (void*)mesh->nodes8;
+            attr.accessPolicyWindow.num_bytes = bytes;
+            attr.accessPolicyWindow.hitRatio = carve >= bytes ? 1.0f : (float)((double)carve / (double)bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            l2_set = cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+            if (getenv("PB2_RAY_L2_VERBOSE")) fprintf(stderr, "[pb2] L2 persist: carve %zu of max %d, window %zu (max %d), hit ratio %.2f, set %d\n", carve, max_persist, bytes, max_window, attr.accessPolicyWindow.hitRatio, (int)l2_set);
+            (void)cudaGetLastError();
+        }
+    }
     if (shared_tri)
         kern_shared<<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi, d_toi, d_tri,
                                                      with_normal ? d_n : nullptr, with_normal ? d_f : nullptr, next_ray, tri_groups, refill, cull,
@@ -823,6 +850,11 @@ int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, co
     else
         kern<<<blocks, 128, 0, ctx->stream>>>(mesh->nodes8, mesh->tris8, mesh->nt, d_pose, d_rays, d_perm, m, max_toi, d_toi, d_tri,
                                               with_normal ? d_n : nullptr, with_normal ? d_f : nullptr, next_ray, tri_lanes, refill, cull, stats);
+    if (l2_set) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);   // num_bytes = 0 disables the window
+    }
     if (stats) {
         unsigned long long h[8];
         cudaMemcpyAsync(h, stats, 64, cudaMemcpyDeviceToHost, ctx->stream);
