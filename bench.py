@@ -549,7 +549,36 @@ def also_mesh_contacts(ctx, stream, timed, flush, hbm_peak):
             "contacts_fraction": float((st == 1).float().mean().item()), "l2": "flushed between iterations"}
 
 
-EXTRA_ALSO = [("contact_pairs_4M_hulls", also_contacts), ("broadphase_1M_colliders", also_broadphase),
+def also_manifolds(ctx, stream, timed, flush, hbm_peak):
+    """SURVEY §8 f1 (closed-form arms): 2^22 ball / cuboid pairs -> contact manifolds (ball-ball, ball-cuboid, cuboid-cuboid SAT +
+    face clipping), first frame, up to 8 points per manifold."""
+    import torch
+    import parry_b200
+    from harness import scenes
+    n = 1 << 22
+    g = scenes.rng(21)
+    G = parry_b200.Shapes(ctx, [parry_b200.Ball(0.4), parry_b200.Ball(0.25), parry_b200.Cuboid([0.3, 0.5, 0.4]), parry_b200.Cuboid([0.6, 0.2, 0.2]),
+                                parry_b200.Cuboid([0.5, 0.5, 0.5])])
+    s1, s2 = g.integers(0, 5, n).astype(np.int32), g.integers(0, 5, n).astype(np.int32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 20], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 1.3 + 0.2)], axis=1).astype(np.float32)
+    ds1, ds2, dp1, dp2 = (torch.from_numpy(x).cuda() for x in (s1, s2, p1, p2))
+    res = {}
+
+    def run():
+        res["o"] = parry_b200.contact_manifolds(G, ds1, dp1, ds2, dp2, 0.05, max_points=8)
+    ms = timed(run, steps=5, warmup=2, flush=flush)
+    cnt = res["o"][1]
+    npts = int(cnt.to(torch.int64).sum().item())
+    alg = n * (8 + 56 + 24 + 4 + 1) + npts * 36
+    return {"value": n / (ms * 1e-3), "unit": "pairs/s (ball / cuboid contact manifolds)", "ms": ms, "pairs": n,
+            "manifolds_with_points": float((cnt > 0).float().mean().item()), "points": npts, "l2": "flushed between iterations",
+            "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+
+
+EXTRA_ALSO = [("contact_pairs_4M_hulls", also_contacts), ("manifolds_4M_ball_cuboid_pairs", also_manifolds), ("broadphase_1M_colliders", also_broadphase),
               ("mixed_2M_colliders_pipeline", also_mixed), ("trimesh_contacts_1M_colliders", also_mesh_contacts)]
 
 if __name__ == "__main__":

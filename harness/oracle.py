@@ -61,6 +61,7 @@ def lib():
         l.pb2o_bvh_cast_rays_shapes2.argtypes = [P, P, P, P, P, P, P, P, u32, f32, i32, i32, P, P, P, P]
         l.pb2o_cast_shapes_batch.argtypes = [P, P, P, P, P, P, P, P, P, f32, f32, i32, i32, u32, i32, P, P]
         l.pb2o_compound_contact_batch.argtypes = [P, P, P, P, P, P, P, P, P, P, P, f32, i32, u32, i32, P, P, P]
+        l.pb2o_contact_manifolds_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, u32, i32, P, P, P, P]
         l.pb2o_convex_cast_ray.restype = i32
         l.pb2o_convex_cast_ray.argtypes = [P, u32, P, P, f32, i32, P, P]
         l.pb2o_shape_cast_ray.restype = i32
@@ -370,6 +371,20 @@ class ShapeTable:
                                           psid.ctypes.data, pp.ctypes.data, cid.ctypes.data, pc.ctypes.data, sid.ctypes.data, ps.ctypes.data,
                                           prediction, int(compound_second), n, threads, out.ctypes.data, status.ctypes.data, part.ctypes.data)
         return out, status, part
+
+    def contact_manifolds(self, shape1, pos1, shape2, pos2, prediction, max_points=16, threads=1):
+        """contact_manifolds per pair, first frame: (normals (n,6), counts (n,), points (n,max_points,9) f32 with fid1/fid2 as u32 bit
+        patterns in the last two columns, status (n,): 0 ok, 2 unsupported pair, 4 more than max_points)."""
+        s1, s2, p1, p2 = _u32(shape1), _u32(shape2), _f32(pos1), _f32(pos2)
+        n = len(s1)
+        normals = np.zeros((n, 6), dtype=np.float32)
+        counts = np.zeros(n, dtype=np.uint32)
+        pts = np.zeros((n, max_points, 9), dtype=np.float32)
+        status = np.zeros(n, dtype=np.uint8)
+        lib().pb2o_contact_manifolds_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, s1.ctypes.data, s2.ctypes.data,
+                                           p1.ctypes.data, p2.ctypes.data, prediction, n, max_points, threads, normals.ctypes.data,
+                                           counts.ctypes.data, pts.ctypes.data, status.ctypes.data)
+        return normals, counts, pts, status
 
     def distance(self, shape1, pos1, shape2, pos2, threads=1):
         """query::distance per pair: (dist (n,), status (n,): 0 Ok, 2 Unsupported, 3 cuboid-cuboid)."""

@@ -251,6 +251,17 @@ int pb2_compound_contact_shapes(pb2_ctx* ctx, const pb2_compounds* compounds, co
                                 const uint32_t* shape_ids, const float* shape_poses7, uint32_t n, float prediction, int compound_second,
                                 pb2_contact* out, uint8_t* status, uint32_t* part, int mem);
 
+/* QueryDispatcher::contact_manifolds for n Ball / Cuboid pairs, first frame (empty incoming manifolds), pos12 =
+ * pos1.inv_mul(pos2) (default_query_dispatcher.rs:629-835 -> contact_manifolds_ball_ball.rs:17-57,
+ * contact_manifolds_convex_ball.rs:42-145, contact_manifolds_cuboid_cuboid.rs:19-107 + sat_cuboid_cuboid.rs +
+ * polygonal_feature3d.rs:215-439). normals: n x 6 {ContactManifold::local_n1, local_n2}; counts: points per manifold;
+ * points: n x max_points x 9 words {TrackedContact::local_p1 (3 f32), local_p2 (3 f32), dist (f32), fid1, fid2
+ * (PackedFeatureId bits, u32)} in the reference's order; status: 0 ok, 2 unsupported pair (a ConvexPolyhedron or an unknown
+ * shape id: Err(Unsupported) / host), 4 more than max_points contacts (two quads yield at most 16; 8 is the observed max). */
+int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
+                                const float* pos1 /* n x 7 */, const float* pos2, float prediction, uint32_t n, uint32_t max_points,
+                                float* normals, uint32_t* counts, float* points, uint8_t* status, int mem);
+
 /* query::cast_shapes for n pairs (query/shape_cast/shape_cast.rs:268-286 -> DefaultQueryDispatcher::cast_shapes,
  * default_query_dispatcher.rs:434-515: ball-ball shape_cast_ball_ball.rs:10-69, every other Ball / Cuboid / ConvexPolyhedron
  * pair shape_cast_support_map_support_map.rs:11-69 + gjk::directional_distance gjk.rs:632-795). vel1 / vel2: n x 3

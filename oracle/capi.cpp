@@ -230,6 +230,7 @@ extern "C" void pb2o_shape_aabbs(const uint8_t* kinds, const float* params /* n 
 // ---------------- query::contact ----------------
 #include "contact.hpp"
 #include "shape_cast.hpp"
+#include "manifold.hpp"
 
 static inline ShapeRef make_shape(const uint8_t* kinds, const float* params4, const float* points, uint32_t id) {
     ShapeRef s; s.kind = kinds[id]; s.radius = params4[4 * id]; s.half_extents = ld3(params4 + 4 * id); s.points = nullptr; s.num_points = 0;
@@ -286,6 +287,34 @@ void pb2o_compound_contact_batch(const uint8_t* kinds, const float* params4, con
             float* o = out + 13 * k;
             if (st == CONTACT_SOME) { st3(o, ct.point1); st3(o + 3, ct.point2); st3(o + 6, ct.normal1); st3(o + 9, ct.normal2); o[12] = ct.dist; }
             else for (int i = 0; i < 13; ++i) o[i] = 0.0f;
+        }
+    });
+}
+// QueryDispatcher::contact_manifolds for n pairs of Ball / Cuboid shapes, first frame (empty incoming manifolds), with
+// pos12 = pos1.inv_mul(pos2). normals: n x 6 (local_n1, local_n2); counts: n; pts: n x max_points x 9 words {local_p1, local_p2,
+// dist, fid1, fid2 (PackedFeatureId bits)}; status: 0 ok, 2 unsupported pair (a ConvexPolyhedron), 4 more than max_points.
+void pb2o_contact_manifolds_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* shape1,
+                                  const uint32_t* shape2, const float* pos1, const float* pos2, float prediction, uint32_t n,
+                                  uint32_t max_points, int nthreads, float* normals, uint32_t* counts, float* pts, uint8_t* status) {
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        Manifold m;
+        for (size_t k = lo; k < hi; ++k) {
+            ShapeRef s1 = make_shape(kinds, params4, points, shape1[k]), s2 = make_shape(kinds, params4, points, shape2[k]);
+            Iso pos12 = Iso::from7(pos1 + 7 * k).inv_mul(Iso::from7(pos2 + 7 * k));
+            int st = dispatch_manifold(pos12, s1, s2, prediction, m);
+            uint32_t cnt = (uint32_t)m.points.size();
+            if (cnt > max_points) { st = 4; cnt = max_points; }
+            if (cnt) { st3(normals + 6 * k, m.local_n1); st3(normals + 6 * k + 3, m.local_n2); }
+            else for (int i = 0; i < 6; ++i) normals[6 * k + i] = 0.0f;
+            counts[k] = cnt; status[k] = (uint8_t)st;
+            float* q = pts + (size_t)k * max_points * 9;
+            for (uint32_t i = 0; i < max_points; ++i) {
+                float* o = q + 9 * i;
+                if (i < cnt) {
+                    const TrackedContact& t = m.points[i];
+                    st3(o, t.local_p1); st3(o + 3, t.local_p2); o[6] = t.dist; memcpy(o + 7, &t.fid1, 4); memcpy(o + 8, &t.fid2, 4);
+                } else for (int j = 0; j < 9; ++j) o[j] = 0.0f;
+            }
         }
     });
 }

@@ -2308,3 +2308,292 @@ int pb2_compound_contact_shapes(pb2_ctx* ctx, const pb2_compounds* compounds, co
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------- contact manifolds (closed-form arms)
+// QueryDispatcher::contact_manifolds for Ball / Cuboid pairs, first frame (empty incoming manifold, so try_update_contacts
+// and match_contacts are no-ops): DefaultQueryDispatcher::contact_manifold_convex_convex (default_query_dispatcher.rs:748-782)
+// -> contact_manifolds_ball_ball.rs:17-57, contact_manifolds_convex_ball.rs:42-145 (Cuboid as shape 1),
+// contact_manifolds_cuboid_cuboid.rs:19-107 + sat_cuboid_cuboid.rs:5-110 + Cuboid::support_face (cuboid.rs:267-354) +
+// PolygonalFeature::contacts_face_face / closest_points_line2d (polygonal_feature3d.rs:215-439) + Vector3::orthonormal_basis
+// (utils/wops.rs:92-110). Pairs with a ConvexPolyhedron need its face/edge topology (pfm_pfm) and get status 2.
+enum { MAN_OK = 0, MAN_UNSUPPORTED = 2, MAN_OVERFLOW = 4 };
+#define PK_VERTEX(c) ((1u << 30) | (c))
+#define PK_EDGE(c) ((2u << 30) | (c))
+#define PK_FACE(c) ((3u << 30) | (c))
+
+struct ManifoldOut {
+    float* pts;         // this pair's max_points x 9 words
+    uint32_t max_points, count;
+    bool overflow;
+    __device__ __forceinline__ void push(V3 p1, V3 p2, uint32_t f1, uint32_t f2, float dist, bool flipped) {
+        if (count >= max_points) { overflow = true; return; }
+        float* o = pts + 9ull * count;
+        if (flipped) { V3 t = p1; p1 = p2; p2 = t; uint32_t u = f1; f1 = f2; f2 = u; }   // TrackedContact::flipped
+        o[0] = p1.x; o[1] = p1.y; o[2] = p1.z; o[3] = p2.x; o[4] = p2.y; o[5] = p2.z; o[6] = dist;
+        o[7] = __uint_as_float(f1); o[8] = __uint_as_float(f2);
+        count++;
+    }
+};
+
+__device__ __forceinline__ V3 cub_support(V3 he, V3 d) { return mk3(copysignf(he.x, d.x), copysignf(he.y, d.y), copysignf(he.z, d.z)); }
+
+// sat_cuboid_cuboid.rs:79-110
+__device__ __forceinline__ void sat_normal_oneway(V3 he1, V3 he2, const Iso7& pos12, float& best_sep, V3& best_dir) {
+    best_sep = -FLT_MAX; best_dir = mk3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float sign = copysignf(1.0f, comp(pos12.t, i));
+        V3 axis1 = mk3(0.f, 0.f, 0.f);
+        setc(axis1, i, sign);
+        V3 axis2 = iso_inv_vec(pos12, -axis1);
+        V3 pt2 = iso_point(pos12, cub_support(he2, axis2));
+        float sep = comp(pt2, i) * sign - comp(he1, i);
+        if (sep > best_sep) { best_sep = sep; best_dir = axis1; }
+    }
+}
+// sat_cuboid_cuboid.rs:5-77
+__device__ __forceinline__ void sat_edge_twoway(V3 he1, V3 he2, const Iso7& pos12, float& best_sep, V3& best_dir) {
+    best_sep = -FLT_MAX; best_dir = mk3(0.f, 0.f, 0.f);
+    V3 c2[3] = {iso_vec(pos12, mk3(1.f, 0.f, 0.f)), iso_vec(pos12, mk3(0.f, 1.f, 0.f)), iso_vec(pos12, mk3(0.f, 0.f, 1.f))};
+    for (int k = 0; k < 9; ++k) {
+        V3 u = c2[k / 3];
+        int a = k % 3;
+        V3 axis = a == 0 ? mk3(0.0f, -u.z, u.y) : (a == 1 ? mk3(u.z, 0.0f, -u.x) : mk3(-u.y, u.x, 0.0f));
+        float n = nrm(axis);
+        if (n > PB2_EPS) {
+            V3 ax = axis / n;
+            float signum = copysignf(1.0f, dot3(pos12.t, ax));
+            V3 axis1 = ax * signum;
+            V3 axis2 = iso_inv_vec(pos12, -axis1);
+            V3 lp1 = cub_support(he1, axis1);
+            V3 pt2 = iso_point(pos12, cub_support(he2, axis2));
+            float sep = dot3(pt2 - lp1, axis1);
+            if (sep > best_sep) { best_sep = sep; best_dir = axis1; }
+        }
+    }
+}
+
+struct PolyFace { V3 v[4]; uint32_t vids[4], eids[4], fid; };
+__constant__ uint8_t c_face_vids[3][2][4] = {{{0, 2, 3, 1}, {4, 6, 7, 5}}, {{0, 4, 5, 1}, {2, 6, 7, 3}}, {{0, 2, 6, 4}, {1, 3, 7, 5}}};
+__constant__ uint8_t c_face_eids[3][2][4] = {{{0xD0, 0xDA, 0xD9, 0xC8}, {0xF4, 0xFE, 0xFD, 0xEC}},
+                                             {{0xE0, 0xEC, 0xE9, 0xC8}, {0xF2, 0xFE, 0xFB, 0xDA}},
+                                             {{0xD0, 0xF2, 0xF4, 0xE0}, {0xD9, 0xFB, 0xFD, 0xE9}}};
+// Cuboid::support_face (cuboid.rs:267-354); the id tables are the reference's literals, [axis][sign_index]
+__device__ __forceinline__ void cuboid_support_face(V3 he, V3 dir, PolyFace& f) {
+    int iamax = 0;
+    float best = fabsf(dir.x);
+    if (fabsf(dir.y) > best) { best = fabsf(dir.y); iamax = 1; }
+    if (fabsf(dir.z) > best) iamax = 2;
+    float sign = copysignf(1.0f, comp(dir, iamax));
+    if (iamax == 0) { f.v[0] = mk3(he.x * sign, he.y, he.z); f.v[1] = mk3(he.x * sign, -he.y, he.z); f.v[2] = mk3(he.x * sign, -he.y, -he.z); f.v[3] = mk3(he.x * sign, he.y, -he.z); }
+    else if (iamax == 1) { f.v[0] = mk3(he.x, he.y * sign, he.z); f.v[1] = mk3(-he.x, he.y * sign, he.z); f.v[2] = mk3(-he.x, he.y * sign, -he.z); f.v[3] = mk3(he.x, he.y * sign, -he.z); }
+    else { f.v[0] = mk3(he.x, he.y, he.z * sign); f.v[1] = mk3(he.x, -he.y, he.z * sign); f.v[2] = mk3(-he.x, -he.y, he.z * sign); f.v[3] = mk3(-he.x, he.y, he.z * sign); }
+    int si = sign > 0.0f ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { f.vids[k] = PK_VERTEX((uint32_t)c_face_vids[iamax][si][k] * 2u); f.eids[k] = PK_EDGE((uint32_t)c_face_eids[iamax][si][k]); }
+    f.fid = PK_FACE((uint32_t)(iamax + si * 3 + 10));
+}
+
+__device__ __forceinline__ float perp2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
+// approx::ulps_eq! defaults for f32 (epsilon = f32::EPSILON, max_ulps = 4)
+__device__ __forceinline__ bool ulps_eq4(float a, float b) {
+    if (fabsf(a - b) <= PB2_EPS) return true;
+    if (signbit(a) != signbit(b)) return false;
+    long long d = (long long)__float_as_int(a) - (long long)__float_as_int(b);
+    if (d < 0) d = -d;
+    return d <= 4;
+}
+// polygonal_feature3d.rs:398-439
+__device__ __forceinline__ bool closest_points_line2d(float2 a0, float2 a1, float2 c0, float2 c1, float& s_out, float& t_out) {
+    float d1x = a1.x - a0.x, d1y = a1.y - a0.y, d2x = c1.x - c0.x, d2y = c1.y - c0.y, rx = a0.x - c0.x, ry = a0.y - c0.y;
+    float a = d1x * d1x + d1y * d1y, e = d2x * d2x + d2y * d2y, f = d2x * rx + d2y * ry;
+    const float eps = PB2_EPS;
+    if (a <= eps && e <= eps) { s_out = 0.f; t_out = 0.f; return true; }
+    if (a <= eps) { s_out = 0.f; t_out = f / e; return true; }
+    float c = d1x * rx + d1y * ry;
+    if (e <= eps) { s_out = -c / a; t_out = 0.f; return true; }
+    float b = d1x * d2x + d1y * d2y;
+    float ae = a * e, bb = b * b, denom = ae - bb;
+    if (denom <= eps || ulps_eq4(ae, bb)) return false;
+    float sv = (b * f - c * e) / denom;
+    s_out = sv; t_out = (b * sv + f) / e;
+    return true;
+}
+
+// PolygonalFeature::contacts_face_face (polygonal_feature3d.rs:215-396) for two quads
+__device__ __forceinline__ void contacts_face_face(const Iso7& pos12, const PolyFace& f1, V3 sep, const PolyFace& f2, ManifoldOut& m) {
+    float sign = copysignf(1.0f, sep.z);
+    float a = -1.0f / (sign + sep.z);
+    float b = sep.x * sep.y * a;
+    V3 b0 = mk3(1.0f + sign * sep.x * sep.x * a, sign * b, -sign * sep.x);
+    V3 b1 = mk3(b, sign + sep.y * sep.y * a, -sep.y);
+    float2 pf1[4], pf2[4];
+    V3 v21[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pf1[i] = make_float2(dot3(f1.v[i], b0), dot3(f1.v[i], b1)); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v21[i] = iso_point(pos12, f2.v[i]); pf2[i] = make_float2(dot3(v21[i], b0), dot3(v21[i], b1)); }
+    {
+        V3 normal2_1 = cross3(v21[2] - v21[1], v21[0] - v21[1]);
+        float denom = dot3(normal2_1, sep);
+        if (!rel_eq(denom, 0.0f, PB2_EPS, PB2_EPS)) {
+            for (int i = 0; i < 4; ++i) {
+                float2 p = pf1[i];
+                float sg = perp2(pf2[0].x - pf2[3].x, pf2[0].y - pf2[3].y, p.x - pf2[3].x, p.y - pf2[3].y);
+                bool outside = false;
+                for (int j = 0; j < 3; ++j) {
+                    float ns = perp2(pf2[j + 1].x - pf2[j].x, pf2[j + 1].y - pf2[j].y, p.x - pf2[j].x, p.y - pf2[j].y);
+                    if (sg == 0.0f) sg = ns;
+                    else if (sg * ns < 0.0f) { outside = true; break; }
+                }
+                if (outside) continue;
+                float dist = dot3(v21[0] - f1.v[i], normal2_1) / denom;
+                V3 lp1 = f1.v[i];
+                V3 lp2_1 = f1.v[i] + sep * dist;
+                m.push(lp1, iso_inv_point(pos12, lp2_1), f1.vids[i], f2.fid, dist, false);
+            }
+        }
+    }
+    {
+        V3 normal1 = cross3(f1.v[2] - f1.v[1], f1.v[0] - f1.v[1]);
+        float denom = -dot3(normal1, sep);
+        if (!rel_eq(denom, 0.0f, PB2_EPS, PB2_EPS)) {
+            for (int i = 0; i < 4; ++i) {
+                float2 p = pf2[i];
+                float sg = perp2(pf1[0].x - pf1[3].x, pf1[0].y - pf1[3].y, p.x - pf1[3].x, p.y - pf1[3].y);
+                bool outside = false;
+                for (int j = 0; j < 3; ++j) {
+                    float ns = perp2(pf1[j + 1].x - pf1[j].x, pf1[j + 1].y - pf1[j].y, p.x - pf1[j].x, p.y - pf1[j].y);
+                    if (sg == 0.0f) sg = ns;
+                    else if (sg * ns < 0.0f) { outside = true; break; }
+                }
+                if (outside) continue;
+                float dist = dot3(f1.v[0] - v21[i], normal1) / denom;
+                V3 lp2_1 = v21[i];
+                V3 lp1 = v21[i] - sep * dist;
+                m.push(lp1, iso_inv_point(pos12, lp2_1), f1.fid, f2.vids[i], dist, false);
+            }
+        }
+    }
+    for (int j = 0; j < 4; ++j) {
+        for (int i = 0; i < 4; ++i) {
+            float sv, tv;
+            if (!closest_points_line2d(pf1[i], pf1[(i + 1) & 3], pf2[j], pf2[(j + 1) & 3], sv, tv)) continue;
+            if (sv > 0.0f && sv < 1.0f && tv > 0.0f && tv < 1.0f) {
+                V3 lp1 = f1.v[i] * (1.0f - sv) + f1.v[(i + 1) & 3] * sv;
+                V3 lp2_1 = v21[j] * (1.0f - tv) + v21[(j + 1) & 3] * tv;
+                float dist = dot3(lp2_1 - lp1, sep);
+                m.push(lp1, iso_inv_point(pos12, lp2_1), f1.eids[i], f2.eids[j], dist, false);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_contact_manifolds(const uint8_t* __restrict__ kinds, const float4* __restrict__ params, uint32_t n_shapes,
+                              const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2, const float* __restrict__ pos1,
+                              const float* __restrict__ pos2, float prediction, uint32_t n, uint32_t max_points, float* __restrict__ normals,
+                              uint32_t* __restrict__ counts, float* __restrict__ pts, uint8_t* __restrict__ status) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    ManifoldOut m;
+    m.pts = pts + (size_t)k * max_points * 9;
+    m.max_points = max_points; m.count = 0; m.overflow = false;
+    V3 n1 = mk3(0.f, 0.f, 0.f), n2 = n1;
+    int st = MAN_OK;
+    uint32_t s1 = shape1[k], s2 = shape2[k];
+    if (s1 >= n_shapes || s2 >= n_shapes || kinds[s1] > PB2_SHAPE_CUBOID || kinds[s2] > PB2_SHAPE_CUBOID) st = MAN_UNSUPPORTED;
+    else {
+        Iso7 pos12 = iso_inv_mul(load_iso(pos1 + 7ull * k), load_iso(pos2 + 7ull * k));
+        bool b1 = kinds[s1] == PB2_SHAPE_BALL, b2 = kinds[s2] == PB2_SHAPE_BALL;
+        float4 pr1 = params[s1], pr2 = params[s2];
+        if (b1 && b2) {
+            // contact_manifolds_ball_ball.rs:17-57
+            V3 dcenter = pos12.t;
+            float center_dist = nrm(dcenter);
+            float dist = center_dist - pr1.x - pr2.x;
+            if (dist < prediction) {
+                n1 = center_dist != 0.0f ? dcenter / center_dist : mk3(0.f, 1.f, 0.f);
+                n2 = iso_inv_vec(pos12, -n1);
+                m.push(n1 * pr1.x, n2 * pr2.x, PK_FACE(0u), PK_FACE(0u), dist, false);
+            }
+        } else if (b1 != b2) {
+            // contact_manifolds_convex_ball.rs:18-145: the ball is shape 2 of the inner call (pos12 inverted when it is shape 1)
+            bool flipped = b1;
+            Iso7 p12 = flipped ? iso_inverse(pos12) : pos12;
+            V3 he = flipped ? mk3(pr2.x, pr2.y, pr2.z) : mk3(pr1.x, pr1.y, pr1.z);
+            float radius = flipped ? pr1.x : pr2.x;
+            V3 proj; bool inside; Feat f;
+            d_cuboid_project(he, p12.t, proj, inside, f);
+            V3 dpos = p12.t - proj;
+            V3 ln1; float dist;
+            if (!try_normalize_get(dpos, 0.0f, ln1, dist)) {
+                float nn;
+                if (!try_normalize_get(p12.t, 0.0f, ln1, nn)) ln1 = mk3(1.f, 0.f, 0.f);
+                dist = 0.0f;
+            }
+            if (inside) { ln1 = -ln1; dist = -dist; }
+            if (dist <= radius + prediction) {
+                V3 ln2 = iso_inv_vec(p12, -ln1);
+                uint32_t fid1 = f.kind == 0 ? PK_VERTEX(f.id) : (f.kind == 1 ? PK_EDGE(f.id) : (f.kind == 2 ? PK_FACE(f.id) : 0u));
+                m.push(proj, ln2 * radius, fid1, PK_FACE(0u), dist - radius, flipped);
+                if (flipped) { n1 = ln2; n2 = ln1; } else { n1 = ln1; n2 = ln2; }
+            }
+        } else {
+            // contact_manifolds_cuboid_cuboid.rs:19-107
+            V3 he1 = mk3(pr1.x, pr1.y, pr1.z), he2 = mk3(pr2.x, pr2.y, pr2.z);
+            Iso7 pos21 = iso_inverse(pos12);
+            float sp1, sp2, sp3; V3 d1, d2, d3;
+            sat_normal_oneway(he1, he2, pos12, sp1, d1);
+            bool sepd = sp1 > prediction;
+            if (!sepd) { sat_normal_oneway(he2, he1, pos21, sp2, d2); sepd = sp2 > prediction; }
+            if (!sepd) { sat_edge_twoway(he1, he2, pos12, sp3, d3); sepd = sp3 > prediction; }
+            if (!sepd) {
+                V3 best = d1;
+                if (sp2 > sp1 && sp2 > sp3) best = iso_vec(pos12, -d2);
+                else if (sp3 > sp1) best = d3;
+                V3 ln2 = iso_vec(pos21, -best);
+                PolyFace f1, f2;
+                cuboid_support_face(he1, best, f1);
+                cuboid_support_face(he2, ln2, f2);
+                contacts_face_face(pos12, f1, best, f2, m);
+                n1 = best; n2 = ln2;
+            }
+        }
+    }
+    if (m.overflow) st = MAN_OVERFLOW;
+    if (m.count == 0) { n1 = mk3(0.f, 0.f, 0.f); n2 = n1; }
+    float* nq = normals + 6ull * k;
+    nq[0] = n1.x; nq[1] = n1.y; nq[2] = n1.z; nq[3] = n2.x; nq[4] = n2.y; nq[5] = n2.z;
+    for (uint32_t i = m.count; i < max_points; ++i) { float* o = m.pts + 9ull * i; for (int j = 0; j < 9; ++j) o[j] = 0.0f; }
+    counts[k] = m.count;
+    status[k] = (uint8_t)st;
+}
+
+extern "C" int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
+                                           const float* pos2, float prediction, uint32_t n, uint32_t max_points, float* normals, uint32_t* counts,
+                                           float* points, uint8_t* status, int mem) {
+    if (!ctx || !shapes || max_points == 0 || (n && (!shape1 || !shape2 || !pos1 || !pos2 || !normals || !counts || !points || !status))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_s1, *d_s2, *d_p1, *d_p2;
+    void *d_nr, *d_ct, *d_pt, *d_st;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape1, (size_t)n * 4, mem, &d_s1));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape2, (size_t)n * 4, mem, &d_s2));
+    PB2_CHECK(pb2_stage_in(ctx, 2, pos1, (size_t)n * 28, mem, &d_p1));
+    PB2_CHECK(pb2_stage_in(ctx, 3, pos2, (size_t)n * 28, mem, &d_p2));
+    PB2_CHECK(pb2_stage_out(ctx, 4, normals, (size_t)n * 24, mem, &d_nr));
+    PB2_CHECK(pb2_stage_out(ctx, 5, counts, (size_t)n * 4, mem, &d_ct));
+    PB2_CHECK(pb2_stage_out(ctx, 6, points, (size_t)n * max_points * 36, mem, &d_pt));
+    PB2_CHECK(pb2_stage_out(ctx, 7, status, (size_t)n, mem, &d_st));
+    k_contact_manifolds<<<pb2_blocks(n, 128), 128, 0, ctx->stream>>>(shapes->kinds, shapes->params, shapes->n, (const uint32_t*)d_s1, (const uint32_t*)d_s2,
+                                                                      (const float*)d_p1, (const float*)d_p2, prediction, n, max_points, (float*)d_nr,
+                                                                      (uint32_t*)d_ct, (float*)d_pt, (uint8_t*)d_st);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(pb2_stage_back(ctx, normals, d_nr, (size_t)n * 24, mem));
+    PB2_CHECK(pb2_stage_back(ctx, counts, d_ct, (size_t)n * 4, mem));
+    PB2_CHECK(pb2_stage_back(ctx, points, d_pt, (size_t)n * max_points * 36, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_st, (size_t)n, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB2_OK;
+}

@@ -648,3 +648,22 @@ def cast_shapes(shapes, shape1, pos1, vel1, shape2, pos2, vel2, options=None):
     ctx.check(ctx._lib.pb2_cast_shapes_batch(ctx.h, shapes.h, ps1, ps2, p1, v1, p2, v2, o.max_time_of_impact, o.target_distance,
                                              int(o.stop_at_penetration), int(o.compute_impact_geometry_on_penetration), n, po, pst, mem))
     return out, status
+
+
+def contact_manifolds(shapes, shape1, pos1, shape2, pos2, prediction, max_points=8):
+    """QueryDispatcher::contact_manifolds(pos1.inv_mul(pos2), g1, g2, prediction, ..) on empty manifolds, batched, for Ball /
+    Cuboid pairs. Returns (normals (n, 6) = local_n1, local_n2; counts (n,) u32; points (n, max_points, 9) f32 = local_p1,
+    local_p2, dist, fid1, fid2 (the last two are PackedFeatureId bit patterns: view as u32); status (n,) u8: 0 ok,
+    2 unsupported pair, 4 more than max_points contacts)."""
+    ctx = shapes.ctx
+    n = int(pos1.shape[0])
+    k1, p1, mem = _prep(pos1, np.float32)
+    k2, p2, _ = _prep(pos2, np.float32, mem)
+    ks1, ps1, _ = _prep(shape1, np.uint32, mem)
+    ks2, ps2, _ = _prep(shape2, np.uint32, mem)
+    normals, pn = _empty((n, 6), np.float32, mem, ctx.torch_device)
+    counts, pc = _empty((n,), np.uint32, mem, ctx.torch_device)
+    points, pp = _empty((n, int(max_points), 9), np.float32, mem, ctx.torch_device)
+    status, pst = _empty((n,), np.uint8, mem, ctx.torch_device)
+    ctx.check(ctx._lib.pb2_contact_manifolds_batch(ctx.h, shapes.h, ps1, ps2, p1, p2, float(prediction), n, int(max_points), pn, pc, pp, pst, mem))
+    return normals, counts, points, status

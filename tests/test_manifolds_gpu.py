@@ -1,0 +1,70 @@
+"""GPU parity of the closed-form contact-manifold arms (ball-ball, ball-cuboid, cuboid-cuboid SAT + face
+clipping) through pb2_contact_manifolds_batch against the CPU oracle: statuses, point counts and feature ids exact, normals /
+points / distances within 1e-5 (bit-identical in practice)."""
+import numpy as np
+import pytest
+
+from harness import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def make_scene(n, seed):
+    g = scenes.rng(seed)
+    spec = [("ball", 0.4), ("ball", 0.25), ("cuboid", [0.3, 0.5, 0.4]), ("cuboid", [0.6, 0.2, 0.2]), ("cuboid", [0.5, 0.5, 0.5])]
+    s1, s2 = g.integers(0, 5, n).astype(np.uint32), g.integers(0, 5, n).astype(np.uint32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 1.3 + 0.2)], axis=1).astype(np.float32)
+    p2[::5, :4] = p1[::5, :4]          # same orientation: face-face stacks with 4 - 8 points
+    p2[::25, 4:] = p1[::25, 4:] + np.array([0.0, 0.7, 0.0], np.float32)   # exactly aligned offsets
+    p2[::50, 4:] = p1[::50, 4:]        # coincident centres (degenerate normals)
+    return spec, s1, p1, s2, p2
+
+
+def tables(ctx, oracle, spec):
+    import parry_b200
+    T = oracle.ShapeTable(spec)
+    G = parry_b200.Shapes(ctx, [parry_b200.Ball(v) if k == "ball" else parry_b200.Cuboid(v) if k == "cuboid" else parry_b200.ConvexPolyhedron(v)
+                                for k, v in spec])
+    return T, G
+
+
+@pytest.mark.parametrize("prediction", [0.05, 0.3])
+def test_manifolds_vs_oracle(ctx, oracle, prediction):
+    import parry_b200
+    spec, s1, p1, s2, p2 = make_scene(30000, seed=7)
+    T, G = tables(ctx, oracle, spec)
+    rn, rc, rp, rs = T.contact_manifolds(s1, p1, s2, p2, prediction, max_points=8, threads=8)
+    gn, gc, gp, gs = parry_b200.contact_manifolds(G, s1, p1, s2, p2, prediction, max_points=8)
+    assert (rs == 0).all() and (gs == rs).all()
+    assert (gc == rc).all(), np.nonzero(gc != rc)[0][:10]
+    assert (rc > 0).mean() > 0.4 and (rc >= 4).mean() > 0.1 and rc.max() >= 6
+    assert (gp[:, :, 7:].view(np.uint32) == rp[:, :, 7:].view(np.uint32)).all()      # feature ids, in the reference's point order
+    np.testing.assert_allclose(gn, rn, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gp[:, :, :7], rp[:, :, :7], rtol=1e-5, atol=2e-6)
+
+
+def test_manifold_statuses_and_capacity(ctx, oracle):
+    import torch
+    import parry_b200
+    spec, s1, p1, s2, p2 = make_scene(5000, seed=9)
+    pts, _ = scenes.hull_pool(1, 16, seed=3)
+    spec = spec + [("convex", pts[0])]
+    T, G = tables(ctx, oracle, spec)
+    s1 = s1.copy()
+    s1[::7] = 5                                 # a ConvexPolyhedron: pfm arm, not built
+    gn, gc, gp, gs = parry_b200.contact_manifolds(G, s1, p1, s2, p2, 0.05, max_points=8)
+    rn, rc, rp, rs = T.contact_manifolds(s1, p1, s2, p2, 0.05, max_points=8)
+    assert (gs == rs).all() and (gs[::7] == 2).all() and (gc[::7] == 0).all() and (gc == rc).all()
+    # capacity: with room for 4 points, richer manifolds report status 4 and keep the first four points
+    g4 = parry_b200.contact_manifolds(G, s1, p1, s2, p2, 0.05, max_points=4)
+    over = rc > 4
+    assert over.sum() > 50 and (g4[3][over] == 4).all() and (g4[1][over] == 4).all() and (g4[3][~over] == gs[~over]).all()
+    assert (g4[2][over].view(np.uint32) == gp[over][:, :4].view(np.uint32)).all()
+    # device-resident inputs give the same bits
+    dev = lambda x: torch.from_numpy(x.view(np.int32) if x.dtype == np.uint32 else x).cuda()
+    dn, dc, dp, ds = parry_b200.contact_manifolds(G, dev(s1), dev(p1), dev(s2), dev(p2), 0.05, max_points=8)
+    ctx.synchronize()
+    assert (dp.cpu().numpy().view(np.uint32) == gp.view(np.uint32)).all() and (dc.cpu().numpy().view(np.uint32) == gc).all()
