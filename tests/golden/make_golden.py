@@ -121,9 +121,58 @@ def shape_rays():
                         aabbs=aabbs, rays=rays, **res)
 
 
+def siblings():
+    """cast_shapes (two option sets), Compound contacts (both orders) and ball / cuboid contact manifolds on one mixed scene."""
+    g = scenes.rng(301)
+    pts, _ = scenes.hull_pool(6, 16, seed=302)
+    spec = [("ball", 0.4), ("ball", 0.25), ("cuboid", [0.3, 0.5, 0.4]), ("cuboid", [0.6, 0.2, 0.2])] + [("convex", np.asarray(p, np.float32) * 0.6) for p in pts]
+    T = oracle.ShapeTable(spec)
+    ns, n = len(spec), 3000
+    s1, s2 = g.integers(0, ns, n).astype(np.uint32), g.integers(0, ns, n).astype(np.uint32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - 0.5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    sep = np.where(g.random(n) < 0.25, g.random(n) * 0.9, 1.0 + g.random(n) * 3.0)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * sep[:, None]], axis=1).astype(np.float32)
+    v1 = (d * (0.5 + g.random((n, 1)) * 3.0) + g.standard_normal((n, 3)) * 0.5).astype(np.float32)
+    v2 = (g.standard_normal((n, 3)) * 0.3).astype(np.float32)
+    out = dict(kinds=T.kinds, params=T.params, points=T.points, shape1=s1, shape2=s2, pos1=p1, pos2=p2, vel1=v1, vel2=v2)
+    o, st = T.cast_shapes(s1, p1, v1, s2, p2, v2)
+    out.update(cast_default=o, cast_default_status=st)
+    o, st = T.cast_shapes(s1, p1, v1, s2, p2, v2, target_distance=0.05, stop_at_penetration=False)
+    out.update(cast_target=o, cast_target_status=st)
+    # compounds: 24 of 1-5 parts
+    first, count, psid, ppose = [], [], [], []
+    for c in range(24):
+        k = int(g.integers(1, 6))
+        first.append(len(psid)); count.append(k)
+        psid += [int(x) for x in g.integers(0, ns, k)]
+        ppose.append(np.concatenate([scenes.random_unit_quaternions(g, k), (g.random((k, 3)) - 0.5) * 1.6], axis=1))
+    first, count, psid = np.asarray(first, np.uint32), np.asarray(count, np.uint32), np.asarray(psid, np.uint32)
+    ppose = np.concatenate(ppose).astype(np.float32)
+    cid = g.integers(0, 24, n).astype(np.uint32)
+    p2c = p2.copy()
+    p2c[:, 4:] = p1[:, 4:] + d * (g.random((n, 1)) * 2.2 + 0.1)
+    out.update(comp_first=first, comp_count=count, part_shape=psid, part_pose=ppose, compound_id=cid, pos2_compound=p2c)
+    for second in (False, True):
+        o, st, part = T.contact_compound(first, count, psid, ppose, cid, p1, s2, p2c, 0.05, compound_second=second)
+        tag = "compound_second" if second else "compound_first"
+        out.update({tag: o, tag + "_status": st, tag + "_part": part})
+    # manifolds on the ball / cuboid subset of the pair list, closer together
+    m1, m2 = (s1 % 4).astype(np.uint32), (s2 % 4).astype(np.uint32)
+    p2m = p2.copy()
+    p2m[:, 4:] = p1[:, 4:] + d * (g.random((n, 1)) * 1.2 + 0.2)
+    p2m[::4, :4] = p1[::4, :4]
+    nr, cnt, mp, st = T.contact_manifolds(m1, p1, m2, p2m, 0.05, max_points=8)
+    out.update(man_shape1=m1, man_shape2=m2, man_pos2=p2m, man_normals=nr, man_counts=cnt, man_points=mp, man_status=st)
+    np.savez_compressed(os.path.join(HERE, "siblings_3000.npz"), **out)
+
+
 if __name__ == "__main__":
     import sys
     if "shape_rays" in sys.argv:
         shape_rays()
+    elif "siblings" in sys.argv:
+        siblings()
     else:
         main()
