@@ -62,6 +62,7 @@ def lib():
         l.pb2o_cast_shapes_batch.argtypes = [P, P, P, P, P, P, P, P, P, f32, f32, i32, i32, u32, i32, P, P]
         l.pb2o_compound_contact_batch.argtypes = [P, P, P, P, P, P, P, P, P, P, P, f32, i32, u32, i32, P, P, P]
         l.pb2o_contact_manifolds_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, u32, i32, P, P, P, P]
+        l.pb2o_closest_points_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, P, P, P]
         l.pb2o_convex_cast_ray.restype = i32
         l.pb2o_convex_cast_ray.argtypes = [P, u32, P, P, f32, i32, P, P]
         l.pb2o_shape_cast_ray.restype = i32
@@ -385,6 +386,18 @@ class ShapeTable:
                                            p1.ctypes.data, p2.ctypes.data, prediction, n, max_points, threads, normals.ctypes.data,
                                            counts.ctypes.data, pts.ctypes.data, status.ctypes.data)
         return normals, counts, pts, status
+
+    def closest_points(self, shape1, pos1, shape2, pos2, max_dist, threads=1):
+        """query::closest_points per pair: (points (n,6) world-space p1, p2; kind (n,): 0 Disjoint, 1 WithinMargin, 2 Intersecting;
+        status (n,): 1 ok, 3 needs hull topology)."""
+        s1, s2, p1, p2 = _u32(shape1), _u32(shape2), _f32(pos1), _f32(pos2)
+        n = len(s1)
+        out = np.zeros((n, 6), dtype=np.float32)
+        kind = np.zeros(n, dtype=np.uint8)
+        status = np.zeros(n, dtype=np.uint8)
+        lib().pb2o_closest_points_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, s1.ctypes.data, s2.ctypes.data,
+                                        p1.ctypes.data, p2.ctypes.data, max_dist, n, threads, out.ctypes.data, kind.ctypes.data, status.ctypes.data)
+        return out, kind, status
 
     def distance(self, shape1, pos1, shape2, pos2, threads=1):
         """query::distance per pair: (dist (n,), status (n,): 0 Ok, 2 Unsupported, 3 cuboid-cuboid)."""

@@ -251,6 +251,14 @@ int pb2_compound_contact_shapes(pb2_ctx* ctx, const pb2_compounds* compounds, co
                                 const uint32_t* shape_ids, const float* shape_poses7, uint32_t n, float prediction, int compound_second,
                                 pb2_contact* out, uint8_t* status, uint32_t* part, int mem);
 
+/* query::closest_points for n pairs (closest_points/closest_points_shape_shape.rs:220-231 -> default_query_dispatcher.rs:358-424:
+ * closest_points_ball_ball.rs:7-36, closest_points_ball_convex_polyhedron.rs:7-44, closest_points_support_map_support_map.rs:8-69).
+ * kind: 0 ClosestPoints::Disjoint, 1 WithinMargin (points[k] = p1, p2 in world space), 2 Intersecting. status: 1 ok, 2 unknown
+ * shape id, 3 host fallback (ball centre on a hull's surface). */
+int pb2_closest_points_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
+                             const float* pos1 /* n x 7 */, const float* pos2, float max_dist, uint32_t n, float* points /* n x 6 */,
+                             uint8_t* kind, uint8_t* status, int mem);
+
 /* QueryDispatcher::contact_manifolds for n Ball / Cuboid pairs, first frame (empty incoming manifolds), pos12 =
  * pos1.inv_mul(pos2) (default_query_dispatcher.rs:629-835 -> contact_manifolds_ball_ball.rs:17-57,
  * contact_manifolds_convex_ball.rs:42-145, contact_manifolds_cuboid_cuboid.rs:19-107 + sat_cuboid_cuboid.rs +
@@ -272,7 +280,8 @@ int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const ui
 #define PB2_CAST_CONVERGED 1       /* ShapeCastStatus::Converged */
 #define PB2_CAST_PENETRATING 2     /* ShapeCastStatus::PenetratingOrWithinTargetDist */
 #define PB2_CAST_UNSUPPORTED 3     /* shape id out of range */
-#define PB2_CAST_NEEDS_HOST 4      /* the penetration contact overflowed the EPA arena */
+#define PB2_CAST_NEEDS_HOST 4      /* the penetration contact overflowed the EPA arena (256 faces; seen with Ball support maps, whose
+                                    * EPA runs converge slowly): run this pair on the host dispatcher */
 int pb2_cast_shapes_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
                           const float* pos1 /* n x 7 */, const float* vel1 /* n x 3 */, const float* pos2, const float* vel2,
                           float max_time_of_impact, float target_distance, int stop_at_penetration,

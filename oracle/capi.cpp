@@ -290,6 +290,21 @@ void pb2o_compound_contact_batch(const uint8_t* kinds, const float* params4, con
         }
     });
 }
+// query::closest_points for n pairs. out: n x 6 (p1, p2 in world space, zeros unless WithinMargin); kind: 0 Disjoint,
+// 1 WithinMargin, 2 Intersecting; status: 1 ok, 3 needs hull topology.
+void pb2o_closest_points_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* shape1, const uint32_t* shape2,
+                               const float* pos1, const float* pos2, float max_dist, uint32_t n, int nthreads, float* out, uint8_t* kind,
+                               uint8_t* status) {
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            ShapeRef s1 = make_shape(kinds, params4, points, shape1[k]), s2 = make_shape(kinds, params4, points, shape2[k]);
+            Vec3 p1, p2; int qs;
+            int kd = query_closest_points(Iso::from7(pos1 + 7 * k), s1, Iso::from7(pos2 + 7 * k), s2, max_dist, p1, p2, qs);
+            kind[k] = (uint8_t)kd; status[k] = (uint8_t)qs;
+            st3(out + 6 * k, p1); st3(out + 6 * k + 3, p2);
+        }
+    });
+}
 // QueryDispatcher::contact_manifolds for n pairs of Ball / Cuboid shapes, first frame (empty incoming manifolds), with
 // pos12 = pos1.inv_mul(pos2). normals: n x 6 (local_n1, local_n2); counts: n; pts: n x max_points x 9 words {local_p1, local_p2,
 // dist, fid1, fid2 (PackedFeatureId bits)}; status: 0 ok, 2 unsupported pair (a ConvexPolyhedron), 4 more than max_points.

@@ -328,6 +328,55 @@ static inline int contact_trimesh_shape(const Iso& pos12, const TriMesh& mesh, c
     return have ? CONTACT_SOME : CONTACT_NONE;
 }
 
+// query::closest_points (closest_points_shape_shape.rs:220-231) -> DefaultQueryDispatcher::closest_points
+// (default_query_dispatcher.rs:358-424) for Ball / Cuboid / ConvexPolyhedron: closest_points_ball_ball.rs:7-36,
+// closest_points_ball_convex_polyhedron.rs:7-44 (through the contact arms), closest_points_support_map_support_map.rs:8-69
+// (GJK only, started toward -pos12.translation). Returns 0 Disjoint, 1 WithinMargin(p1, p2) in world space, 2 Intersecting;
+// qstatus CONTACT_NEEDS_TOPOLOGY when the ball arm needs a hull feature normal.
+enum ClosestPointsKind { CP_DISJOINT = 0, CP_WITHIN_MARGIN = 1, CP_INTERSECTING = 2 };
+static inline int query_closest_points(const Iso& pos1, const ShapeRef& s1, const Iso& pos2, const ShapeRef& s2, Real margin, Vec3& p1, Vec3& p2,
+                                       int& qstatus) {
+    Iso pos12 = pos1.inv_mul(pos2);
+    qstatus = CONTACT_SOME;
+    int kind;
+    p1 = Vec3(); p2 = Vec3();
+    if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_BALL) {
+        Real r1 = s1.radius, r2 = s2.radius;
+        Vec3 delta = pos12.tra;
+        Real distance = norm(delta), sum = r1 + r2;
+        if (distance - margin <= sum) {
+            if (distance <= sum) kind = CP_INTERSECTING;
+            else {
+                Vec3 n = normalize(delta);
+                p1 = n * r1;
+                p2 = pos12.inverse_transform_vector(n) * (-r2);
+                kind = CP_WITHIN_MARGIN;
+            }
+        } else kind = CP_DISJOINT;
+    } else if (s1.kind == SHAPE_BALL || s2.kind == SHAPE_BALL) {
+        Contact c = Contact();
+        int st = s1.kind == SHAPE_BALL ? contact_ball_convex_polyhedron(pos12, s1.radius, s2, margin, c)
+                                       : contact_convex_polyhedron_ball(pos12, s1, s2.radius, margin, c);
+        if (st == CONTACT_SOME) {
+            if (c.dist <= 0.0f) kind = CP_INTERSECTING;
+            else { kind = CP_WITHIN_MARGIN; p1 = c.point1; p2 = c.point2; }
+        } else if (st == CONTACT_NONE) kind = CP_DISJOINT;
+        else { qstatus = st; return CP_DISJOINT; }
+    } else {
+        SupportShape g1 = s1.support(), g2 = s2.support();
+        VoronoiSimplex simplex;
+        Vec3 dir;
+        if (!try_normalize(-pos12.tra, DEFAULT_EPSILON, dir)) dir = Vec3(1, 0, 0);
+        simplex.reset(CSOPoint::from_shapes(pos12, g1, g2, dir));
+        GJKResult r = gjk_closest_points(pos12, g1, g2, margin, simplex);
+        if (r.kind == GJKResult::CLOSEST_POINTS) { kind = CP_WITHIN_MARGIN; p1 = r.p1; p2 = pos12.inverse_transform_point(r.p2); }
+        else if (r.kind == GJKResult::NO_INTERSECTION) kind = CP_DISJOINT;
+        else kind = CP_INTERSECTING;
+    }
+    if (kind == CP_WITHIN_MARGIN) { p1 = pos1.transform_point(p1); p2 = pos2.transform_point(p2); }   // ClosestPoints::transform_by
+    return kind;
+}
+
 // CompositeShapeRef::contact_with_shape for a Compound (contact_composite_shape_shape.rs:14-45, shape/compound.rs:113-144,
 // map_part_at :181-193): parts whose AABB (part shape at its pose) intersects shape2's loosened AABB are dispatched with
 // part_pos1.inv_mul(pose12); the first strictly smaller dist wins and is moved to the compound's frame with

@@ -2597,3 +2597,99 @@ extern "C" int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shape
     if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB2_OK;
 }
+
+// ------------------------------------------------------------------------------------------- query::closest_points
+// query::closest_points (closest_points_shape_shape.rs:220-231) -> DefaultQueryDispatcher::closest_points
+// (default_query_dispatcher.rs:358-424): closest_points_ball_ball.rs:7-36; ball <-> convex through the contact arms
+// (closest_points_ball_convex_polyhedron.rs:7-44: dist <= 0 => Intersecting); everything else
+// closest_points_support_map_support_map.rs:8-69 (GJK started toward -pos12.translation, no EPA: Intersection => Intersecting).
+// kind: 0 Disjoint, 1 WithinMargin (out = p1, p2 in world space, ClosestPoints::transform_by), 2 Intersecting.
+// status: 1 ok, 2 unknown shape id, 3 host fallback (ball centre on a hull's surface: needs the hull's feature normal).
+__global__ void __launch_bounds__(128) k_closest_points(const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float4* __restrict__ pts,
+                              uint32_t n_shapes, PairSrc src, float max_dist, uint32_t n, float* __restrict__ out, uint8_t* __restrict__ kind_out,
+                              uint8_t* __restrict__ status) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float* o = out + 6ull * k;
+    V3 p1 = mk3(0.f, 0.f, 0.f), p2 = p1;
+    int kind = 0, st = ST_SOME;
+    if (src.shape1[k] >= n_shapes || src.shape2[k] >= n_shapes) st = ST_UNSUPPORTED;
+    else {
+        PairSetup ps;
+        pair_setup(kinds, params, pts, src, k, ps);
+        bool b1 = ps.k1 == PB2_SHAPE_BALL, b2 = ps.k2 == PB2_SHAPE_BALL;
+        ContactOut c;
+        int cst = -1;   // >= 0: a contact-arm outcome to map
+        if (b1 && b2) {
+            float r1 = ps.pr1.x, r2 = ps.pr2.x;
+            V3 delta = ps.pos12.t;
+            float distance = nrm(delta), sum = r1 + r2;
+            if (distance - max_dist <= sum) {
+                if (distance <= sum) kind = 2;
+                else {
+                    V3 nrm1 = delta / distance;
+                    p1 = nrm1 * r1;
+                    p2 = iso_inv_vec(ps.pos12, nrm1) * (-r2);
+                    kind = 1;
+                }
+            }
+        } else if (ps.mode == 0) {
+            cst = closed_form_pair(ps, max_dist, c);
+        } else if (ps.mode == 1) {
+            Simplex s;
+            V3 dir; float nn;
+            if (!try_normalize_get(-ps.pos12.t, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
+            sx_reset(s, cso_from_shapes(ps.gpos12, ps.g1, ps.g2, dir));
+            V3 q1, q2, n1;
+            int r = gjk_closest_points<true>(ps.gpos12, ps.g1, ps.g2, max_dist, s, q1, q2, n1);
+            if (r == GJK_CLOSEST_POINTS) { kind = 1; p1 = q1; p2 = iso_inv_point(ps.pos12, q2); }
+            else if (r == GJK_NO_INTERSECTION) kind = 0;
+            else kind = 2;
+        } else {
+            Simplex s;
+            gjk_start(ps, s);
+            V3 q1, q2, n1;
+            int r = gjk_closest_points<true>(ps.gpos12, ps.g1, ps.g2, FLT_MAX, s, q1, q2, n1);
+            if (r == GJK_INTERSECTION) kind = 2;   // centre inside the hull: the contact has dist < 0
+            else if (r == GJK_CLOSEST_POINTS) cst = finish_gjk_pair(ps, false, q1, q2, n1, max_dist, c);
+            else kind = 0;
+        }
+        if (cst == ST_SOME) {
+            if (c.dist <= 0.0f) kind = 2;
+            else { kind = 1; p1 = c.p1; p2 = c.p2; }
+        } else if (cst == ST_NEEDS_HOST) st = ST_NEEDS_HOST;
+        if (kind == 1) { p1 = iso_point(ps.pos1, p1); p2 = iso_point(ps.pos2, p2); }
+    }
+    if (kind != 1) { p1 = mk3(0.f, 0.f, 0.f); p2 = p1; }
+    o[0] = p1.x; o[1] = p1.y; o[2] = p1.z; o[3] = p2.x; o[4] = p2.y; o[5] = p2.z;
+    kind_out[k] = (uint8_t)kind;
+    status[k] = (uint8_t)st;
+}
+
+extern "C" int pb2_closest_points_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
+                                        const float* pos2, float max_dist, uint32_t n, float* points, uint8_t* kind, uint8_t* status, int mem) {
+    if (!ctx || !shapes || (n && (!shape1 || !shape2 || !pos1 || !pos2 || !points || !kind || !status))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_s1, *d_s2, *d_p1, *d_p2;
+    void *d_out, *d_kind, *d_st;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape1, (size_t)n * 4, mem, &d_s1));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape2, (size_t)n * 4, mem, &d_s2));
+    PB2_CHECK(pb2_stage_in(ctx, 2, pos1, (size_t)n * 28, mem, &d_p1));
+    PB2_CHECK(pb2_stage_in(ctx, 3, pos2, (size_t)n * 28, mem, &d_p2));
+    PB2_CHECK(pb2_stage_out(ctx, 4, points, (size_t)n * 24, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, kind, (size_t)n, mem, &d_kind));
+    PB2_CHECK(pb2_stage_out(ctx, 6, status, (size_t)n, mem, &d_st));
+    PairSrc src;
+    src.shape1 = (const uint32_t*)d_s1; src.shape2 = (const uint32_t*)d_s2; src.pos1 = (const float*)d_p1; src.pos2 = (const float*)d_p2;
+    src.ab = nullptr; src.mesh_tris = nullptr; src.n_first = src.n_second = 0;
+    k_closest_points<<<pb2_blocks(n, 128), 128, 0, ctx->stream>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, src, max_dist, n, (float*)d_out,
+                                                                   (uint8_t*)d_kind, (uint8_t*)d_st);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(pb2_stage_back(ctx, points, d_out, (size_t)n * 24, mem));
+    PB2_CHECK(pb2_stage_back(ctx, kind, d_kind, (size_t)n, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_st, (size_t)n, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB2_OK;
+}

@@ -667,3 +667,20 @@ def contact_manifolds(shapes, shape1, pos1, shape2, pos2, prediction, max_points
     status, pst = _empty((n,), np.uint8, mem, ctx.torch_device)
     ctx.check(ctx._lib.pb2_contact_manifolds_batch(ctx.h, shapes.h, ps1, ps2, p1, p2, float(prediction), n, int(max_points), pn, pc, pp, pst, mem))
     return normals, counts, points, status
+
+
+def closest_points(shapes, shape1, pos1, shape2, pos2, max_dist):
+    """query::closest_points(pos1, g1, pos2, g2, max_dist), batched (closest_points_shape_shape.rs:220-231). Returns (points (n, 6)
+    f32 = world-space p1, p2 (zeros unless WithinMargin); kind (n,) u8: 0 Disjoint, 1 WithinMargin, 2 Intersecting; status (n,)
+    u8: 1 ok, 2 unknown shape, 3 host fallback)."""
+    ctx = shapes.ctx
+    n = int(pos1.shape[0])
+    k1, p1, mem = _prep(pos1, np.float32)
+    k2, p2, _ = _prep(pos2, np.float32, mem)
+    ks1, ps1, _ = _prep(shape1, np.uint32, mem)
+    ks2, ps2, _ = _prep(shape2, np.uint32, mem)
+    out, po = _empty((n, 6), np.float32, mem, ctx.torch_device)
+    kind, pk = _empty((n,), np.uint8, mem, ctx.torch_device)
+    status, pst = _empty((n,), np.uint8, mem, ctx.torch_device)
+    ctx.check(ctx._lib.pb2_closest_points_batch(ctx.h, shapes.h, ps1, ps2, p1, p2, float(max_dist), n, po, pk, pst, mem))
+    return out, kind, status

@@ -84,3 +84,40 @@ def test_distance_device_resident(ctx, oracle):
     d = parry_b200.distance(G, T(a), T(p1), T(b), T(p2))
     ctx.synchronize()
     assert (d[0].cpu().numpy().view(np.uint32) == h[0].view(np.uint32)).all() and (d[1].cpu().numpy() == h[1]).all()
+
+
+@pytest.mark.gpu
+def test_closest_points_vs_oracle(ctx, oracle):
+    """query::closest_points (closest_points_shape_shape.rs:220-231): kinds exact, points 1e-5; the doc examples of that file as
+    known answers (balls 0.5 at x = 0 / 12 within 15 -> (0.5, 0, 0), (11.5, 0, 0); ball 2 at x = 5 vs unit cuboid -> (3, 0, 0),
+    (1, 0, 0))."""
+    import parry_b200
+    I = [0, 0, 0, 1]
+    pose = lambda t: np.array(I + list(t), np.float32)
+    G = parry_b200.Shapes(ctx, [parry_b200.Ball(0.5), parry_b200.Ball(2.0), parry_b200.Cuboid([1, 1, 1])])
+    o, k, s = parry_b200.closest_points(G, np.array([0, 1], np.uint32), np.stack([pose([0, 0, 0]), pose([5, 0, 0])]), np.array([0, 2], np.uint32),
+                                        np.stack([pose([12, 0, 0]), pose([0, 0, 0])]), 15.0)
+    assert (k == 1).all() and (s == 1).all()
+    np.testing.assert_allclose(o, [[0.5, 0, 0, 11.5, 0, 0], [3, 0, 0, 1, 0, 0]], rtol=0, atol=1e-6)
+    g = scenes.rng(5)
+    pts, _ = scenes.hull_pool(6, 16, seed=6)
+    spec = [("ball", 0.4), ("ball", 0.25), ("cuboid", [0.3, 0.5, 0.4])] + [("convex", np.asarray(p, np.float32) * 0.6) for p in pts]
+    T = oracle.ShapeTable(spec)
+    G = parry_b200.Shapes(ctx, [parry_b200.Ball(v) if kk == "ball" else parry_b200.Cuboid(v) if kk == "cuboid" else parry_b200.ConvexPolyhedron(v)
+                                for kk, v in spec])
+    n = 30000
+    s1, s2 = g.integers(0, len(spec), n).astype(np.uint32), g.integers(0, len(spec), n).astype(np.uint32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 2.5 + 0.2)], axis=1).astype(np.float32)
+    for margin in (0.8, 0.0):
+        ro, rk, rs = T.closest_points(s1, p1, s2, p2, margin, threads=8)
+        go, gk, gs = parry_b200.closest_points(G, s1, p1, s2, p2, margin)
+        assert (rs == 1).all() and (gs == 1).all() and (gk == rk).all()
+        assert (np.bincount(rk, minlength=3) > (0 if margin == 0.0 else 2000))[[0, 2]].all()
+        np.testing.assert_allclose(go, ro, rtol=1e-5, atol=2e-6)
+    bad = s1.copy()
+    bad[11] = 10 ** 6
+    _, bk, bs = parry_b200.closest_points(G, bad, p1, s2, p2, 0.8)
+    assert bs[11] == 2 and bk[11] == 0

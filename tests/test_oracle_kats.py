@@ -346,3 +346,31 @@ def test_manifold_restatement_properties(oracle):
                 assert ok1 and ok2
             checked += 1
     assert checked > 2000
+
+
+def test_closest_points_doc_examples_and_consistency(oracle):
+    """Doc examples of closest_points_shape_shape.rs:136-200 and consistency with query::distance: WithinMargin points are
+    `distance` apart, Intersecting pairs have distance 0, Disjoint pairs are farther apart than the margin."""
+    pose = lambda t: np.array([0, 0, 0, 1] + list(t), np.float32)
+    T = oracle.ShapeTable([("ball", 0.5), ("ball", 2.0), ("cuboid", [1, 1, 1])])
+    o, k, s = T.closest_points([0], [pose([0, 0, 0])], [0], [pose([12, 0, 0])], 15.0)
+    assert k[0] == 1 and np.allclose(o[0], [0.5, 0, 0, 11.5, 0, 0], atol=1e-6)
+    o, k, s = T.closest_points([0], [pose([0, 0, 0])], [0], [pose([12, 0, 0])], 5.0)
+    assert k[0] == 0
+    o, k, s = T.closest_points([1], [pose([5, 0, 0])], [2], [pose([0, 0, 0])], 10.0)
+    assert k[0] == 1 and np.allclose(o[0], [3, 0, 0, 1, 0, 0], atol=1e-6)
+    g = scenes.rng(5)
+    pts, _ = scenes.hull_pool(4, 16, seed=6)
+    T = oracle.ShapeTable([("ball", 0.4), ("cuboid", [0.3, 0.5, 0.4])] + [("convex", p * 0.6) for p in pts])
+    n = 5000
+    s1, s2 = g.integers(0, 6, n).astype(np.uint32), g.integers(0, 6, n).astype(np.uint32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 2.5 + 0.2)], axis=1).astype(np.float32)
+    o, k, s = T.closest_points(s1, p1, s2, p2, 0.8)
+    dist, ds = T.distance(s1, p1, s2, p2)
+    assert (s == 1).all() and (np.bincount(k) > 500).all()
+    w = (k == 1) & (ds == 0)
+    assert np.abs(np.linalg.norm(o[w, :3] - o[w, 3:], axis=1) - dist[w]).max() < 5e-6
+    assert (dist[(k == 2) & (ds == 0)] == 0).all() and (dist[(k == 0) & (ds == 0)] > 0.8 - 1e-5).all()
