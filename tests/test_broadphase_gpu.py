@@ -347,3 +347,25 @@ def test_bvh_cast_ray_convex_leaves(ctx, oracle):
             np.testing.assert_allclose(g[2][same], r[2][same], rtol=1e-5, atol=1e-6)
             assert (g[3][same] == r[3][same]).all()
             assert (g[3][same & hit & (kinds[np.minimum(r[1], n - 1)] == 2)] == 0xFFFFFFFE).all()
+
+
+def test_bvh_api_mirrors(ctx, oracle):
+    """from_iter with gaps, refit_without_opt, optimize_incremental: the pair set always equals the brute-force set of the
+    leaves that are present."""
+    import parry_b200
+    n = 600
+    kinds, params, poses = make_colliders(n, seed=71)
+    shapes = make_shapes(ctx, kinds, params)
+    aabbs = shapes.compute_aabbs(np.arange(n, dtype=np.uint32), poses)
+    keep = np.ones(n, bool)
+    keep[::7] = False
+    bvh = parry_b200.Bvh.from_iter(ctx, 0, ((i, aabbs[i]) for i in range(n) if keep[i]))
+    assert bvh.leaf_count() <= n
+    idx = np.nonzero(keep)[0]
+    expect = brute_pairs(aabbs[idx])
+    expect = np.sort(idx[expect], axis=1)
+    key = lambda p: np.sort(np.sort(p.astype(np.int64), axis=1)[:, 0] * n + np.sort(p.astype(np.int64), axis=1)[:, 1])
+    for step in (lambda: None, bvh.refit_without_opt, bvh.optimize_incremental):
+        step()
+        got = bvh.traverse_bvtt_single_tree()
+        assert (key(got) == key(expect)).all()

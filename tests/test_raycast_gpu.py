@@ -184,3 +184,13 @@ def test_full_size_config1_properties(ctx, oracle):
     p = rays[hit, :3].astype(np.float64) + rays[hit, 3:].astype(np.float64) * g[0][hit, None].astype(np.float64)
     rad = np.linalg.norm(p, axis=1)
     assert rad.max() <= 1.0 + 1e-5 and rad.min() >= 1.0 - 3e-4
+
+
+def test_intersects_ray(sphere):
+    """RayCast::intersects_ray == cast_ray(..).is_some()"""
+    v, i, gm, om = sphere
+    rays = scenes.sphere_rays(3000, seed=31)
+    pose = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    hit = gm.intersects_ray(pose, rays, FMAX)
+    toi, tri = om.cast_rays(pose, rays, FMAX)[:2]
+    assert hit.dtype == bool and (hit == (tri != INVALID)).all() and 0.1 < hit.mean() < 1.0
