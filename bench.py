@@ -578,7 +578,81 @@ def also_manifolds(ctx, stream, timed, flush, hbm_peak):
             "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
 
 
-EXTRA_ALSO = [("contact_pairs_4M_hulls", also_contacts), ("manifolds_4M_ball_cuboid_pairs", also_manifolds), ("broadphase_1M_colliders", also_broadphase),
+def _mixed_table(ctx, n_hulls=64, seed=31):
+    import parry_b200
+    from harness import scenes
+    pts, _ = scenes.hull_pool(n_hulls, 32, seed=seed)
+    spec = [parry_b200.Ball(0.4), parry_b200.Ball(0.25), parry_b200.Cuboid([0.3, 0.5, 0.4]), parry_b200.Cuboid([0.6, 0.2, 0.2])]
+    spec += [parry_b200.ConvexPolyhedron(np.asarray(p, np.float32) * 0.6) for p in pts]
+    return parry_b200.Shapes(ctx, spec), len(spec)
+
+
+def _mixed_pairs(n, ns, seed, spread=2.5):
+    from harness import scenes
+    g = scenes.rng(seed)
+    s1, s2 = g.integers(0, ns, n).astype(np.int32), g.integers(0, ns, n).astype(np.int32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 20], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * spread + 0.2)], axis=1).astype(np.float32)
+    return g, d, s1, p1, s2, p2
+
+
+def also_siblings(ctx, stream, timed, flush, hbm_peak):
+    """SURVEY §8 f2/f3 queries on 2^21 mixed ball / cuboid / 32-vertex-hull pairs, device resident: cast_shapes (default
+    options, a quarter of the pairs start overlapping), distance, closest_points; compound contacts (2^20 compounds of 1-5 parts)."""
+    import torch
+    import parry_b200
+    G, ns = _mixed_table(ctx)
+    n = 1 << 21
+    g, d, s1, p1, s2, p2 = _mixed_pairs(n, ns, seed=32, spread=3.5)
+    v1 = (d * (0.5 + g.random((n, 1)) * 3.0) + g.standard_normal((n, 3)) * 0.5).astype(np.float32)
+    v2 = (g.standard_normal((n, 3)) * 0.3).astype(np.float32)
+    T = lambda x: torch.from_numpy(x).cuda()
+    ds1, dp1, ds2, dp2, dv1, dv2 = T(s1), T(p1), T(s2), T(p2), T(v1), T(v2)
+    res, out = {}, {}
+
+    def run_cast():
+        res["cast"] = parry_b200.cast_shapes(G, ds1, dp1, dv1, ds2, dp2, dv2)
+    ms = timed(run_cast, steps=5, warmup=2, flush=flush)
+    st = res["cast"][1]
+    out["cast_shapes"] = {"value": n / (ms * 1e-3), "unit": "pairs/s", "ms": ms, "hits": float((st == 1).float().mean().item()),
+                          "penetrating_starts": float((st == 2).float().mean().item())}
+
+    def run_dist():
+        res["dist"] = parry_b200.distance(G, ds1, dp1, ds2, dp2)
+    ms = timed(run_dist, steps=5, warmup=2, flush=flush)
+    out["distance"] = {"value": n / (ms * 1e-3), "unit": "pairs/s", "ms": ms}
+
+    def run_cp():
+        res["cp"] = parry_b200.closest_points(G, ds1, dp1, ds2, dp2, 1.0)
+    ms = timed(run_cp, steps=5, warmup=2, flush=flush)
+    out["closest_points"] = {"value": n / (ms * 1e-3), "unit": "pairs/s", "ms": ms,
+                             "within_margin": float((res["cp"][1] == 1).float().mean().item())}
+    # compounds: 4096 of 1-5 parts, 2^20 (compound, shape) pairs
+    nc = 4096
+    compounds = []
+    for c in range(nc):
+        k = int(g.integers(1, 6))
+        from harness import scenes
+        pp = np.concatenate([scenes.random_unit_quaternions(g, k), (g.random((k, 3)) - 0.5) * 1.6], axis=1).astype(np.float32)
+        compounds.append([(pp[i], int(g.integers(0, ns))) for i in range(k)])
+    Cc = parry_b200.Compounds(ctx, G, compounds)
+    m = 1 << 20
+    cid = T(g.integers(0, nc, m).astype(np.int32))
+
+    def run_comp():
+        res["comp"] = Cc.contact_shapes(cid, dp1[:m], ds2[:m], dp2[:m], 0.05)
+    ms = timed(run_comp, steps=5, warmup=2, flush=flush)
+    out["compound_contacts"] = {"value": m / (ms * 1e-3), "unit": "pairs/s", "ms": ms,
+                                "contacts_fraction": float((res["comp"][1] == 1).float().mean().item())}
+    out["pairs"] = n
+    out["l2"] = "flushed between iterations"
+    return out
+
+
+EXTRA_ALSO = [("contact_pairs_4M_hulls", also_contacts), ("manifolds_4M_ball_cuboid_pairs", also_manifolds),
+              ("sibling_queries_2M_mixed_pairs", also_siblings), ("broadphase_1M_colliders", also_broadphase),
               ("mixed_2M_colliders_pipeline", also_mixed), ("trimesh_contacts_1M_colliders", also_mesh_contacts)]
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ import bench
 import parry_b200
 
 FN = {"contacts": lambda *a: bench.also_contacts(*a, e2e=False), "broadphase": bench.also_broadphase, "mixed": bench.also_mixed,
-      "mesh_contacts": bench.also_mesh_contacts}
+      "mesh_contacts": bench.also_mesh_contacts, "siblings": bench.also_siblings, "manifolds": bench.also_manifolds}
 ctx = parry_b200.Context(0)
 stream = ctx.torch_stream()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -23,6 +23,6 @@ for setting in ["-"] + sys.argv[2:] + ["-"]:
             os.environ[k] = v
             keys.append(k)
     r = FN[sys.argv[1]](ctx, stream, bench.make_timed(ctx, stream), flush, 6553.6)
-    print(setting, json.dumps({k: v for k, v in r.items() if k in ("ms", "value", "contacts_fraction", "pairs_per_frame", "contacts_per_frame")}), flush=True)
+    print(setting, json.dumps({k: v for k, v in r.items() if k in ("ms", "value", "contacts_fraction", "pairs_per_frame", "contacts_per_frame") or isinstance(v, dict)}), flush=True)
     for k in keys:
         del os.environ[k]
