@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
     g1.kind = g2.kind = DS_ORIGIN; g1.n = g2.n = 0; g1.pts = g2.pts = nullptr; g1.he = g2.he = mk3(0.f, 0.f, 0.f);
     gpos12.q.i = gpos12.q.j = gpos12.q.k = 0.f; gpos12.q.w = 1.f; gpos12.t = mk3(0.f, 0.f, 0.f);
     int dim = 0, nverts = 0, nfaces = 0, nheap = 0, niter = 0;
-    float max_dist = FLT_MAX, old_dist = 0.0f, best_neg = 0.0f;
+    float max_dist = FLT_MAX, old_dist = 0.0f;
     uint32_t best_id = 0;
     bool exhausted = false;
 
@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
         if (run_step) {
             V3 fnormal = v3of(face);
             float candidate = dot3(sp_point, fnormal);
-            if (candidate < max_dist) { best_id = face_id; best_neg = face_neg; max_dist = candidate; }
+            if (candidate < max_dist) { best_id = face_id; max_dist = candidate; }
             curr_dist = -face_neg;
             if (max_dist - curr_dist < eps_tol || (fabsf(curr_dist - old_dist) < eps && candidate < max_dist)) {
                 fin = FIN_FACE; fin_face = best_id; run_step = false;
@@ -969,7 +969,7 @@ __global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restri
                 if (state == E2_INIT) {
                     // `*self.heap.peek()?` and the "failed to project the origin on the initial simplex" exit
                     if (nheap == 0) fin = FIN_NONE;
-                    else { float2 top = H.get(0); best_id = __float_as_uint(top.y); best_neg = top.x; state = E2_RUN; }
+                    else { float2 top = H.get(0); best_id = __float_as_uint(top.y); state = E2_RUN; }
                 } else {
                     if (first_new == nfaces) fin = FIN_NONE;
                     else {
