@@ -58,3 +58,15 @@ def test_fails_loudly_without_a_gpu():
         pytest.skip("a CUDA device is present")
     with pytest.raises(parry_b200.Pb2Error):
         parry_b200.Context(0)
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md's Rust extern block stays in step with include/parry_b200.h."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "parry_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"\b(pb2_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) > 40
+    missing = sorted(d for d in declared if ("pub fn %s(" % d) not in doc)
+    assert not missing, missing
