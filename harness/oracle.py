@@ -62,6 +62,7 @@ def lib():
         l.pb2o_cast_shapes_batch.argtypes = [P, P, P, P, P, P, P, P, P, f32, f32, i32, i32, u32, i32, P, P]
         l.pb2o_compound_contact_batch.argtypes = [P, P, P, P, P, P, P, P, P, P, P, f32, i32, u32, i32, P, P, P]
         l.pb2o_contact_manifolds_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, u32, i32, P, P, P, P]
+        l.pb2o_contact_manifolds_batch2.argtypes = [P, P, P, P, P, P, P, P, P, P, P, P, P, P, f32, u32, u32, i32, P, P, P, P]
         l.pb2o_closest_points_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, P, P, P]
         l.pb2o_convex_cast_ray.restype = i32
         l.pb2o_convex_cast_ray.argtypes = [P, u32, P, P, f32, i32, P, P]
@@ -373,7 +374,24 @@ class ShapeTable:
                                           prediction, int(compound_second), n, threads, out.ctypes.data, status.ctypes.data, part.ctypes.data)
         return out, status, part
 
-    def contact_manifolds(self, shape1, pos1, shape2, pos2, prediction, max_points=16, threads=1):
+    def hull_topology(self):
+        """Face topology of every ConvexPolyhedron of the table (harness/hull_topology.py), indexed per table entry:
+        dict(hull_face_first, hull_face_count (both len(kinds)), face_normal, face_first, face_count, vertices_adj_to_face,
+        edges_adj_to_face). Cached."""
+        if getattr(self, "_topo", None) is None:
+            from harness import hull_topology as ht
+            pu = self.params.view(np.uint32)
+            conv = np.nonzero(self.kinds == 2)[0]
+            t = ht.hull_table([self.points[pu[i, 0]:pu[i, 0] + pu[i, 1]] for i in conv]) if len(conv) else None
+            hf, hc = np.zeros(len(self.kinds), np.uint32), np.zeros(len(self.kinds), np.uint32)
+            if t is not None:
+                hf[conv], hc[conv] = t["hull_face_first"], t["hull_face_count"]
+                t = dict(t)
+                t["hull_face_first"], t["hull_face_count"] = hf, hc
+            self._topo = t
+        return self._topo
+
+    def contact_manifolds(self, shape1, pos1, shape2, pos2, prediction, max_points=16, threads=1, topology=None):
         """contact_manifolds per pair, first frame: (normals (n,6), counts (n,), points (n,max_points,9) f32 with fid1/fid2 as u32 bit
         patterns in the last two columns, status (n,): 0 ok, 2 unsupported pair, 4 more than max_points)."""
         s1, s2, p1, p2 = _u32(shape1), _u32(shape2), _f32(pos1), _f32(pos2)
@@ -382,9 +400,13 @@ class ShapeTable:
         counts = np.zeros(n, dtype=np.uint32)
         pts = np.zeros((n, max_points, 9), dtype=np.float32)
         status = np.zeros(n, dtype=np.uint8)
-        lib().pb2o_contact_manifolds_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, s1.ctypes.data, s2.ctypes.data,
-                                           p1.ctypes.data, p2.ctypes.data, prediction, n, max_points, threads, normals.ctypes.data,
-                                           counts.ctypes.data, pts.ctypes.data, status.ctypes.data)
+        t = topology
+        tp = [None] * 7 if t is None else [np.ascontiguousarray(t[k]).ctypes.data for k in
+                                           ("hull_face_first", "hull_face_count", "face_normal", "face_first", "face_count",
+                                            "vertices_adj_to_face", "edges_adj_to_face")]
+        lib().pb2o_contact_manifolds_batch2(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, *tp, s1.ctypes.data,
+                                            s2.ctypes.data, p1.ctypes.data, p2.ctypes.data, prediction, n, max_points, threads,
+                                            normals.ctypes.data, counts.ctypes.data, pts.ctypes.data, status.ctypes.data)
         return normals, counts, pts, status
 
     def closest_points(self, shape1, pos1, shape2, pos2, max_dist, threads=1):

@@ -175,6 +175,16 @@ int pb2_shapes_create(pb2_ctx* ctx, const uint8_t* kinds, const float* params, u
                       uint32_t np, pb2_shapes** out);
 int pb2_shapes_destroy(pb2_ctx* ctx, pb2_shapes* shapes);
 
+/* Face topology of the table's ConvexPolyhedron entries, as parry builds it when such a shape is created
+ * (ConvexPolyhedron::from_convex_mesh, shape/convex_polyhedron.rs:390-637; accessors faces(), vertices_adj_to_face(),
+ * edges_adj_to_face()): hull_face_first / hull_face_count per table entry (ignored for balls and cuboids) select the hull's
+ * faces in face_normal (nf x 3), face_first / face_count (nf; ranges of the two adjacency arrays, rebased to the concatenated
+ * arrays); vertices_adj_to_face holds vertex ids local to the hull, edges_adj_to_face the hull's edge ids. Only the pfm_pfm
+ * contact-manifold arm needs it (PolygonalFeatureMap::local_support_feature, :959-991). HOST pointers; set at most once. */
+int pb2_shapes_set_hull_topology(pb2_ctx* ctx, pb2_shapes* shapes, const uint32_t* hull_face_first, const uint32_t* hull_face_count,
+                                 const float* face_normal, const uint32_t* face_first, const uint32_t* face_count, uint32_t nf,
+                                 const uint32_t* vertices_adj_to_face, const uint32_t* edges_adj_to_face, uint32_t nadj);
+
 /* Shape::compute_aabb(pos) for n colliders (shape/shape.rs:369; aabb_ball.rs:25, aabb_cuboid.rs:9-16,
  * aabb_convex_polyhedron.rs:8) -> aabbs (n x 6). */
 int pb2_shapes_compute_aabbs(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape_ids, const float* poses7,
@@ -259,13 +269,17 @@ int pb2_closest_points_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint3
                              const float* pos1 /* n x 7 */, const float* pos2, float max_dist, uint32_t n, float* points /* n x 6 */,
                              uint8_t* kind, uint8_t* status, int mem);
 
-/* QueryDispatcher::contact_manifolds for n Ball / Cuboid pairs, first frame (empty incoming manifolds), pos12 =
+/* QueryDispatcher::contact_manifolds for n pairs, first frame (empty incoming manifolds), pos12 =
  * pos1.inv_mul(pos2) (default_query_dispatcher.rs:629-835 -> contact_manifolds_ball_ball.rs:17-57,
  * contact_manifolds_convex_ball.rs:42-145, contact_manifolds_cuboid_cuboid.rs:19-107 + sat_cuboid_cuboid.rs +
  * polygonal_feature3d.rs:215-439). normals: n x 6 {ContactManifold::local_n1, local_n2}; counts: points per manifold;
  * points: n x max_points x 9 words {TrackedContact::local_p1 (3 f32), local_p2 (3 f32), dist (f32), fid1, fid2
- * (PackedFeatureId bits, u32)} in the reference's order; status: 0 ok, 2 unsupported pair (a ConvexPolyhedron or an unknown
- * shape id: Err(Unsupported) / host), 4 more than max_points contacts (two quads yield at most 16; 8 is the observed max). */
+ * (PackedFeatureId bits, u32)} in the reference's order. Pairs with a ConvexPolyhedron (against a Cuboid or another one) take
+ * the pfm_pfm arm (contact_manifolds_pfm_pfm.rs:42-162: GJK/EPA contact, support faces along its normals, the same face
+ * clipping, plus the witness pair as a feature-less point) once pb2_shapes_set_hull_topology has been called. status: 0 ok,
+ * 2 unsupported pair (a ConvexPolyhedron without topology, ball vs ConvexPolyhedron, or an unknown shape id:
+ * Err(Unsupported) / host), 3 host fallback (EPA arena overflow), 4 more than max_points contacts (two quads yield at most
+ * 16; 9 is the observed max). */
 int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
                                 const float* pos1 /* n x 7 */, const float* pos2, float prediction, uint32_t n, uint32_t max_points,
                                 float* normals, uint32_t* counts, float* points, uint8_t* status, int mem);

@@ -308,15 +308,26 @@ void pb2o_closest_points_batch(const uint8_t* kinds, const float* params4, const
 // QueryDispatcher::contact_manifolds for n pairs of Ball / Cuboid shapes, first frame (empty incoming manifolds), with
 // pos12 = pos1.inv_mul(pos2). normals: n x 6 (local_n1, local_n2); counts: n; pts: n x max_points x 9 words {local_p1, local_p2,
 // dist, fid1, fid2 (PackedFeatureId bits)}; status: 0 ok, 2 unsupported pair (a ConvexPolyhedron), 4 more than max_points.
-void pb2o_contact_manifolds_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* shape1,
-                                  const uint32_t* shape2, const float* pos1, const float* pos2, float prediction, uint32_t n,
-                                  uint32_t max_points, int nthreads, float* normals, uint32_t* counts, float* pts, uint8_t* status) {
+void pb2o_contact_manifolds_batch2(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* hull_face_first,
+                                   const uint32_t* hull_face_count, const float* face_normal, const uint32_t* face_first,
+                                   const uint32_t* face_count, const uint32_t* vertices_adj_to_face, const uint32_t* edges_adj_to_face,
+                                   const uint32_t* shape1, const uint32_t* shape2, const float* pos1, const float* pos2, float prediction,
+                                   uint32_t n, uint32_t max_points, int nthreads, float* normals, uint32_t* counts, float* pts, uint8_t* status) {
+    // hull_face_first / hull_face_count: per shape-table entry (ignored for balls and cuboids), NULL = no topology supplied
+    auto topo = [=](uint32_t sid, HullTopology& t) -> const HullTopology* {
+        if (!hull_face_first || kinds[sid] != 2) return nullptr;
+        uint32_t f0 = hull_face_first[sid];
+        t.face_normal = face_normal + 3 * (size_t)f0; t.face_first = face_first + f0; t.face_count = face_count + f0;
+        t.vertices_adj_to_face = vertices_adj_to_face; t.edges_adj_to_face = edges_adj_to_face; t.num_faces = hull_face_count[sid];
+        return t.num_faces ? &t : nullptr;
+    };
     parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
         Manifold m;
         for (size_t k = lo; k < hi; ++k) {
             ShapeRef s1 = make_shape(kinds, params4, points, shape1[k]), s2 = make_shape(kinds, params4, points, shape2[k]);
             Iso pos12 = Iso::from7(pos1 + 7 * k).inv_mul(Iso::from7(pos2 + 7 * k));
-            int st = dispatch_manifold(pos12, s1, s2, prediction, m);
+            HullTopology ta, tb;
+            int st = dispatch_manifold(pos12, s1, s2, prediction, m, topo(shape1[k], ta), topo(shape2[k], tb));
             uint32_t cnt = (uint32_t)m.points.size();
             if (cnt > max_points) { st = 4; cnt = max_points; }
             if (cnt) { st3(normals + 6 * k, m.local_n1); st3(normals + 6 * k + 3, m.local_n2); }
@@ -332,6 +343,12 @@ void pb2o_contact_manifolds_batch(const uint8_t* kinds, const float* params4, co
             }
         }
     });
+}
+void pb2o_contact_manifolds_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* shape1,
+                                  const uint32_t* shape2, const float* pos1, const float* pos2, float prediction, uint32_t n,
+                                  uint32_t max_points, int nthreads, float* normals, uint32_t* counts, float* pts, uint8_t* status) {
+    pb2o_contact_manifolds_batch2(kinds, params4, points, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, shape1, shape2, pos1, pos2,
+                                  prediction, n, max_points, nthreads, normals, counts, pts, status);
 }
 // query::cast_shapes for n pairs (shape_cast.rs:268-286). vel1/vel2: n x 3. out: n x 13 floats {witness1, witness2, normal1,
 // normal2, time_of_impact} (witness/normal i in the local frame of shape i, as the reference returns them);

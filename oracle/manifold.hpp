@@ -260,15 +260,68 @@ static inline void manifold_cuboid_cuboid(const Iso& pos12, const Vec3& he1, con
     m.local_n1 = best_d; m.local_n2 = local_n2;
 }
 
+// ---- PolygonalFeatureMap (shape/polygonal_feature_map.rs) for Cuboid (cuboid.rs: support_face) and ConvexPolyhedron
+// (convex_polyhedron.rs:959-991: the face whose normal has the first maximal dot with dir, its first <= 4 vertices). The hull's
+// face topology (ConvexPolyhedron::from_convex_mesh, :390-637) is an INPUT: parry builds it when the shape is created.
+struct HullTopology {
+    const float* face_normal;      // nf x 3
+    const uint32_t* face_first;    // into the two adjacency arrays
+    const uint32_t* face_count;
+    const uint32_t* vertices_adj_to_face;   // vertex ids local to the hull
+    const uint32_t* edges_adj_to_face;
+    uint32_t num_faces;
+};
+static inline PolyFeature hull_local_support_feature(const ShapeRef& s, const HullTopology& t, const Vec3& dir) {
+    uint32_t best = 0;
+    Real best_dot = dot(ld3(t.face_normal), dir);
+    for (uint32_t f = 1; f < t.num_faces; ++f) {
+        Real d = dot(ld3(t.face_normal + 3 * f), dir);
+        if (d > best_dot) { best = f; best_dot = d; }
+    }
+    PolyFeature out;
+    for (int i = 0; i < 4; ++i) { out.v[i] = Vec3(); out.vids[i] = 0; out.eids[i] = 0; }
+    uint32_t i1 = t.face_first[best], nv = t.face_count[best] < 4 ? t.face_count[best] : 4;
+    for (uint32_t i = 0; i < nv; ++i) {
+        uint32_t vid = t.vertices_adj_to_face[i1 + i];
+        out.v[i] = ld3(s.points + 3 * vid);
+        out.vids[i] = packed_vertex(vid);
+        out.eids[i] = packed_edge(t.edges_adj_to_face[i1 + i]);
+    }
+    out.fid = packed_face(best);
+    out.n = (int)nv;
+    return out;
+}
+
+// contact_manifolds_pfm_pfm.rs:42-162, empty incoming manifold (init_dir = None), no normal constraints, border radii 0.
+// Returns false when the GJK/EPA contact is not ClosestPoints (manifold stays empty).
+static inline bool manifold_pfm_pfm(const Iso& pos12, const ShapeRef& s1, const HullTopology* t1, const ShapeRef& s2, const HullTopology* t2,
+                                    Real prediction, Manifold& m) {
+    m.clear();
+    Contact c;
+    if (contact_support_map_support_map(pos12, s1.support(), s2.support(), prediction, c) != CONTACT_SOME) return false;
+    // c: point1 = p1, point2 = pos12^-1 p2_1, normal1 = dir, normal2 = pos12^-1 (-dir), dist = (p2_1 - p1) . dir
+    Vec3 local_n1 = c.normal1, local_n2 = c.normal2;
+    PolyFeature f1 = s1.kind == SHAPE_CUBOID ? cuboid_support_face(s1.half_extents, local_n1) : hull_local_support_feature(s1, *t1, local_n1);
+    PolyFeature f2 = s2.kind == SHAPE_CUBOID ? cuboid_support_face(s2.half_extents, local_n2) : hull_local_support_feature(s2, *t2, local_n2);
+    contacts_face_face(pos12, f1, local_n1, f2, m, false);   // PolygonalFeature::contacts: faces have 3 or 4 vertices here
+    m.push_flipped(c.point1, c.point2, 0u, 0u, c.dist, false);   // the GJK/EPA witness pair itself (:108-122), PackedFeatureId::UNKNOWN
+    m.local_n1 = local_n1; m.local_n2 = local_n2;
+    return true;
+}
+
 enum ManifoldStatus { MANIFOLD_OK = 0, MANIFOLD_UNSUPPORTED = 2 };
 // DefaultQueryDispatcher::contact_manifold_convex_convex arms for Ball / Cuboid (default_query_dispatcher.rs:760-782); pairs with
-// a ConvexPolyhedron need its face/edge topology (pfm_pfm, support_feature_id_toward) and are reported unsupported.
-static inline int dispatch_manifold(const Iso& pos12, const ShapeRef& s1, const ShapeRef& s2, Real prediction, Manifold& m) {
+// a ConvexPolyhedron go through pfm_pfm when the hull's face topology is supplied, and are reported unsupported otherwise.
+static inline int dispatch_manifold(const Iso& pos12, const ShapeRef& s1, const ShapeRef& s2, Real prediction, Manifold& m,
+                                    const HullTopology* t1 = nullptr, const HullTopology* t2 = nullptr) {
     m.clear(); m.local_n1 = Vec3(); m.local_n2 = Vec3();
     if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_BALL) { manifold_ball_ball(pos12, s1.radius, s2.radius, prediction, m); return MANIFOLD_OK; }
     if (s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_CUBOID) { manifold_cuboid_cuboid(pos12, s1.half_extents, s2.half_extents, prediction, m); return MANIFOLD_OK; }
     if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_CUBOID) { manifold_cuboid_ball(pos12.inverse(), s2.half_extents, s1.radius, prediction, true, m); return MANIFOLD_OK; }
     if (s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_BALL) { manifold_cuboid_ball(pos12, s1.half_extents, s2.radius, prediction, false, m); return MANIFOLD_OK; }
+    // _ => contact_manifold_pfm_pfm (default_query_dispatcher.rs:818-831): Cuboid and ConvexPolyhedron are PolygonalFeatureMaps
+    bool ok1 = s1.kind == SHAPE_CUBOID || (s1.kind == SHAPE_CONVEX && t1), ok2 = s2.kind == SHAPE_CUBOID || (s2.kind == SHAPE_CONVEX && t2);
+    if (ok1 && ok2) { manifold_pfm_pfm(pos12, s1, t1, s2, t2, prediction, m); return MANIFOLD_OK; }
     return MANIFOLD_UNSUPPORTED;
 }
 

@@ -2373,7 +2373,7 @@ __device__ __forceinline__ void sat_edge_twoway(V3 he1, V3 he2, const Iso7& pos1
     }
 }
 
-struct PolyFace { V3 v[4]; uint32_t vids[4], eids[4], fid; };
+struct PolyFace { V3 v[4]; uint32_t vids[4], eids[4], fid; int n; };
 __constant__ uint8_t c_face_vids[3][2][4] = {{{0, 2, 3, 1}, {4, 6, 7, 5}}, {{0, 4, 5, 1}, {2, 6, 7, 3}}, {{0, 2, 6, 4}, {1, 3, 7, 5}}};
 __constant__ uint8_t c_face_eids[3][2][4] = {{{0xD0, 0xDA, 0xD9, 0xC8}, {0xF4, 0xFE, 0xFD, 0xEC}},
                                              {{0xE0, 0xEC, 0xE9, 0xC8}, {0xF2, 0xFE, 0xFB, 0xDA}},
@@ -2392,6 +2392,7 @@ __device__ __forceinline__ void cuboid_support_face(V3 he, V3 dir, PolyFace& f) 
 #pragma unroll
     for (int k = 0; k < 4; ++k) { f.vids[k] = PK_VERTEX((uint32_t)c_face_vids[iamax][si][k] * 2u); f.eids[k] = PK_EDGE((uint32_t)c_face_eids[iamax][si][k]); }
     f.fid = PK_FACE((uint32_t)(iamax + si * 3 + 10));
+    f.n = 4;
 }
 
 __device__ __forceinline__ float perp2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
@@ -2420,7 +2421,8 @@ __device__ __forceinline__ bool closest_points_line2d(float2 a0, float2 a1, floa
     return true;
 }
 
-// PolygonalFeature::contacts_face_face (polygonal_feature3d.rs:215-396) for two quads
+// PolygonalFeature::contacts_face_face (polygonal_feature3d.rs:215-396) for faces of 3 or 4 vertices (unused slots are zero, as
+// PolygonalFeature::default leaves them)
 __device__ __forceinline__ void contacts_face_face(const Iso7& pos12, const PolyFace& f1, V3 sep, const PolyFace& f2, ManifoldOut& m) {
     float sign = copysignf(1.0f, sep.z);
     float a = -1.0f / (sign + sep.z);
@@ -2429,19 +2431,20 @@ __device__ __forceinline__ void contacts_face_face(const Iso7& pos12, const Poly
     V3 b1 = mk3(b, sign + sep.y * sep.y * a, -sep.y);
     float2 pf1[4], pf2[4];
     V3 v21[4];
+    const int n1 = f1.n, n2 = f2.n, last1 = f1.n - 1, last2 = f2.n - 1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { pf1[i] = make_float2(dot3(f1.v[i], b0), dot3(f1.v[i], b1)); }
 #pragma unroll
     for (int i = 0; i < 4; ++i) { v21[i] = iso_point(pos12, f2.v[i]); pf2[i] = make_float2(dot3(v21[i], b0), dot3(v21[i], b1)); }
-    {
+    if (n2 > 2) {
         V3 normal2_1 = cross3(v21[2] - v21[1], v21[0] - v21[1]);
         float denom = dot3(normal2_1, sep);
         if (!rel_eq(denom, 0.0f, PB2_EPS, PB2_EPS)) {
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < n1; ++i) {
                 float2 p = pf1[i];
-                float sg = perp2(pf2[0].x - pf2[3].x, pf2[0].y - pf2[3].y, p.x - pf2[3].x, p.y - pf2[3].y);
+                float sg = perp2(pf2[0].x - pf2[last2].x, pf2[0].y - pf2[last2].y, p.x - pf2[last2].x, p.y - pf2[last2].y);
                 bool outside = false;
-                for (int j = 0; j < 3; ++j) {
+                for (int j = 0; j < last2; ++j) {
                     float ns = perp2(pf2[j + 1].x - pf2[j].x, pf2[j + 1].y - pf2[j].y, p.x - pf2[j].x, p.y - pf2[j].y);
                     if (sg == 0.0f) sg = ns;
                     else if (sg * ns < 0.0f) { outside = true; break; }
@@ -2454,15 +2457,15 @@ __device__ __forceinline__ void contacts_face_face(const Iso7& pos12, const Poly
             }
         }
     }
-    {
+    if (n1 > 2) {
         V3 normal1 = cross3(f1.v[2] - f1.v[1], f1.v[0] - f1.v[1]);
         float denom = -dot3(normal1, sep);
         if (!rel_eq(denom, 0.0f, PB2_EPS, PB2_EPS)) {
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < n2; ++i) {
                 float2 p = pf2[i];
-                float sg = perp2(pf1[0].x - pf1[3].x, pf1[0].y - pf1[3].y, p.x - pf1[3].x, p.y - pf1[3].y);
+                float sg = perp2(pf1[0].x - pf1[last1].x, pf1[0].y - pf1[last1].y, p.x - pf1[last1].x, p.y - pf1[last1].y);
                 bool outside = false;
-                for (int j = 0; j < 3; ++j) {
+                for (int j = 0; j < last1; ++j) {
                     float ns = perp2(pf1[j + 1].x - pf1[j].x, pf1[j + 1].y - pf1[j].y, p.x - pf1[j].x, p.y - pf1[j].y);
                     if (sg == 0.0f) sg = ns;
                     else if (sg * ns < 0.0f) { outside = true; break; }
@@ -2475,13 +2478,15 @@ __device__ __forceinline__ void contacts_face_face(const Iso7& pos12, const Poly
             }
         }
     }
-    for (int j = 0; j < 4; ++j) {
-        for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < n2; ++j) {
+        const int jn = j + 1 == n2 ? 0 : j + 1;
+        for (int i = 0; i < n1; ++i) {
+            const int in = i + 1 == n1 ? 0 : i + 1;
             float sv, tv;
-            if (!closest_points_line2d(pf1[i], pf1[(i + 1) & 3], pf2[j], pf2[(j + 1) & 3], sv, tv)) continue;
+            if (!closest_points_line2d(pf1[i], pf1[in], pf2[j], pf2[jn], sv, tv)) continue;
             if (sv > 0.0f && sv < 1.0f && tv > 0.0f && tv < 1.0f) {
-                V3 lp1 = f1.v[i] * (1.0f - sv) + f1.v[(i + 1) & 3] * sv;
-                V3 lp2_1 = v21[j] * (1.0f - tv) + v21[(j + 1) & 3] * tv;
+                V3 lp1 = f1.v[i] * (1.0f - sv) + f1.v[in] * sv;
+                V3 lp2_1 = v21[j] * (1.0f - tv) + v21[jn] * tv;
                 float dist = dot3(lp2_1 - lp1, sep);
                 m.push(lp1, iso_inv_point(pos12, lp2_1), f1.eids[i], f2.eids[j], dist, false);
             }
@@ -2489,12 +2494,52 @@ __device__ __forceinline__ void contacts_face_face(const Iso7& pos12, const Poly
     }
 }
 
+// PolygonalFeatureMap::local_support_feature: Cuboid = support_face; ConvexPolyhedron = the face whose normal has the first
+// maximal dot with dir, its first <= 4 vertices (convex_polyhedron.rs:959-991)
+struct HullTopo { const uint32_t *hull_face_first, *hull_face_count, *face_first, *face_count, *va, *ea; const float* face_normal; };
+__device__ __forceinline__ void pfm_support_feature(uint8_t kind, float4 pr, uint32_t sid, const float4* __restrict__ pts, const HullTopo& t, V3 dir,
+                                                    PolyFace& f) {
+    if (kind == PB2_SHAPE_CUBOID) { cuboid_support_face(mk3(pr.x, pr.y, pr.z), dir, f); return; }
+    const uint32_t f0 = t.hull_face_first[sid], nf = t.hull_face_count[sid];
+    const float* fn = t.face_normal + 3ull * f0;
+    uint32_t best = 0;
+    float best_dot = dot3(mk3(fn[0], fn[1], fn[2]), dir);
+    for (uint32_t k = 1; k < nf; ++k) {
+        float d = dot3(mk3(fn[3 * k], fn[3 * k + 1], fn[3 * k + 2]), dir);
+        if (d > best_dot) { best = k; best_dot = d; }
+    }
+    const uint32_t i1 = t.face_first[f0 + best], cnt = t.face_count[f0 + best];
+    const uint32_t nv = cnt < 4u ? cnt : 4u;
+    const float4* hp = pts + __float_as_uint(pr.x);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if ((uint32_t)i < nv) {
+            uint32_t vid = t.va[i1 + i];
+            float4 q = hp[vid];
+            f.v[i] = mk3(q.x, q.y, q.z);
+            f.vids[i] = PK_VERTEX(vid);
+            f.eids[i] = PK_EDGE(t.ea[i1 + i]);
+        } else { f.v[i] = mk3(0.f, 0.f, 0.f); f.vids[i] = 0u; f.eids[i] = 0u; }
+    }
+    f.fid = PK_FACE(best);
+    f.n = (int)nv;
+}
+
 __global__ void __launch_bounds__(128) k_contact_manifolds(const uint8_t* __restrict__ kinds, const float4* __restrict__ params, uint32_t n_shapes,
                               const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2, const float* __restrict__ pos1,
                               const float* __restrict__ pos2, float prediction, uint32_t n, uint32_t max_points, float* __restrict__ normals,
-                              uint32_t* __restrict__ counts, float* __restrict__ pts, uint8_t* __restrict__ status) {
+                              uint32_t* __restrict__ counts, float* __restrict__ pts, uint8_t* __restrict__ status, bool have_topology,
+                              uint32_t* __restrict__ parked, unsigned long long* parked_count) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
+    {   // pairs for the pfm_pfm arm (a ConvexPolyhedron with topology on at least one side, a Cuboid or such a hull on the other)
+        uint32_t a = shape1[k], b = shape2[k];
+        if (have_topology && a < n_shapes && b < n_shapes) {
+            uint8_t ka = kinds[a], kb = kinds[b];
+            bool pfm = (ka == PB2_SHAPE_CONVEX || kb == PB2_SHAPE_CONVEX) && ka != PB2_SHAPE_BALL && kb != PB2_SHAPE_BALL;
+            if (pfm) { parked[warp_append1(parked_count)] = k; return; }   // outputs written by k_manifold_pfm
+        }
+    }
     ManifoldOut m;
     m.pts = pts + (size_t)k * max_points * 9;
     m.max_points = max_points; m.count = 0; m.overflow = false;
@@ -2569,6 +2614,43 @@ __global__ void __launch_bounds__(128) k_contact_manifolds(const uint8_t* __rest
     status[k] = (uint8_t)st;
 }
 
+// contact_manifolds_pfm_pfm.rs:42-162 after the GJK/EPA contact (first frame, no normal constraints, no border radius): support
+// features along the contact normals, face clipping, and the witness pair itself as one more (feature-less) point.
+__global__ void __launch_bounds__(128) k_manifold_pfm(const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float4* __restrict__ hull_pts,
+                              HullTopo topo, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2, const float* __restrict__ pos1,
+                              const float* __restrict__ pos2, const uint32_t* __restrict__ parked, uint32_t count, const float* __restrict__ contacts,
+                              const uint8_t* __restrict__ cstatus, uint32_t max_points, float* __restrict__ normals, uint32_t* __restrict__ counts,
+                              float* __restrict__ pts, uint8_t* __restrict__ status) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t k = parked[i];
+    ManifoldOut m;
+    m.pts = pts + (size_t)k * max_points * 9;
+    m.max_points = max_points; m.count = 0; m.overflow = false;
+    V3 n1 = mk3(0.f, 0.f, 0.f), n2 = n1;
+    int st = MAN_OK;
+    if (cstatus[i] == ST_NEEDS_HOST) st = 3;
+    else if (cstatus[i] == ST_SOME) {
+        const float* c = contacts + 13ull * i;
+        n1 = mk3(c[6], c[7], c[8]);
+        n2 = mk3(c[9], c[10], c[11]);
+        uint32_t a = shape1[k], b = shape2[k];
+        Iso7 pos12 = iso_inv_mul(load_iso(pos1 + 7ull * k), load_iso(pos2 + 7ull * k));
+        PolyFace f1, f2;
+        pfm_support_feature(kinds[a], params[a], a, hull_pts, topo, n1, f1);
+        pfm_support_feature(kinds[b], params[b], b, hull_pts, topo, n2, f2);
+        contacts_face_face(pos12, f1, n1, f2, m);
+        m.push(mk3(c[0], c[1], c[2]), mk3(c[3], c[4], c[5]), 0u, 0u, c[12], false);   // PackedFeatureId::UNKNOWN
+    }
+    if (m.overflow) st = MAN_OVERFLOW;
+    if (m.count == 0) { n1 = mk3(0.f, 0.f, 0.f); n2 = n1; }
+    float* nq = normals + 6ull * k;
+    nq[0] = n1.x; nq[1] = n1.y; nq[2] = n1.z; nq[3] = n2.x; nq[4] = n2.y; nq[5] = n2.z;
+    for (uint32_t j = m.count; j < max_points; ++j) { float* o = m.pts + 9ull * j; for (int q = 0; q < 9; ++q) o[q] = 0.0f; }
+    counts[k] = m.count;
+    status[k] = (uint8_t)st;
+}
+
 extern "C" int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
                                            const float* pos2, float prediction, uint32_t n, uint32_t max_points, float* normals, uint32_t* counts,
                                            float* points, uint8_t* status, int mem) {
@@ -2585,10 +2667,55 @@ extern "C" int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shape
     PB2_CHECK(pb2_stage_out(ctx, 5, counts, (size_t)n * 4, mem, &d_ct));
     PB2_CHECK(pb2_stage_out(ctx, 6, points, (size_t)n * max_points * 36, mem, &d_pt));
     PB2_CHECK(pb2_stage_out(ctx, 7, status, (size_t)n, mem, &d_st));
-    k_contact_manifolds<<<pb2_blocks(n, 128), 128, 0, ctx->stream>>>(shapes->kinds, shapes->params, shapes->n, (const uint32_t*)d_s1, (const uint32_t*)d_s2,
-                                                                      (const float*)d_p1, (const float*)d_p2, prediction, n, max_points, (float*)d_nr,
-                                                                      (uint32_t*)d_ct, (float*)d_pt, (uint8_t*)d_st);
+    cudaStream_t st = ctx->stream;
+    const bool have_topology = shapes->face_normal != nullptr;
+    uint32_t *d_parked = nullptr, *d_ab = nullptr;
+    float* d_c = nullptr;
+    uint8_t* d_cst = nullptr;
+    unsigned long long* parked_count = (unsigned long long*)(ctx->d_counters + 10);
+    int rc = PB2_OK;
+    if (have_topology) {
+        if (cudaMallocAsync((void**)&d_parked, (size_t)n * 4, st) != cudaSuccess) PB2_FAIL(ctx, PB2_ERR_CUDA, "contact_manifolds: out of device memory");
+        cudaMemsetAsync(parked_count, 0, 8, st);
+    }
+    k_contact_manifolds<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->n, (const uint32_t*)d_s1, (const uint32_t*)d_s2,
+                                                             (const float*)d_p1, (const float*)d_p2, prediction, n, max_points, (float*)d_nr,
+                                                             (uint32_t*)d_ct, (float*)d_pt, (uint8_t*)d_st, have_topology, d_parked, parked_count);
     PB2_LAUNCHED(ctx);
+    if (have_topology) {
+        cudaMemcpyAsync(ctx->h_counters + 10, parked_count, 8, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = PB2_ERR_CUDA;
+        uint32_t cnt = rc == PB2_OK ? (uint32_t)ctx->h_counters[10] : 0u;
+        if (cnt) {
+            if (cudaMallocAsync((void**)&d_ab, (size_t)cnt * 8, st) != cudaSuccess || cudaMallocAsync((void**)&d_c, (size_t)cnt * 52, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_cst, cnt, st) != cudaSuccess) rc = PB2_ERR_CUDA;
+            if (rc == PB2_OK) {
+                k_pair_up<<<pb2_blocks(cnt, 256), 256, 0, st>>>(d_parked, cnt, d_ab);
+                PB2_LAUNCHED(ctx);
+                OutSinks sinks;
+                sinks.dense = d_c; sinks.status = d_cst; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
+                sinks.compact_count = nullptr; sinks.some_count = nullptr;
+                // contact_support_map_support_map_with_params(pos12, pfm1, pfm2, prediction, .., None): the contact kernels, local frames
+                rc = run_contacts(ctx, shapes, (const uint32_t*)d_s1, (const uint32_t*)d_s2, (const float*)d_p1, (const float*)d_p2, prediction, cnt, sinks,
+                                  d_ab, n, nullptr, 0, PAIR_LOCAL_FRAMES);
+            }
+            if (rc == PB2_OK) {
+                HullTopo topo;
+                topo.hull_face_first = shapes->hull_face_first; topo.hull_face_count = shapes->hull_face_count; topo.face_first = shapes->face_first;
+                topo.face_count = shapes->face_count; topo.va = shapes->verts_adj_to_face; topo.ea = shapes->edges_adj_to_face;
+                topo.face_normal = shapes->face_normal;
+                k_manifold_pfm<<<pb2_blocks(cnt, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, topo, (const uint32_t*)d_s1,
+                                                                    (const uint32_t*)d_s2, (const float*)d_p1, (const float*)d_p2, d_parked, cnt, d_c, d_cst,
+                                                                    max_points, (float*)d_nr, (uint32_t*)d_ct, (float*)d_pt, (uint8_t*)d_st);
+                PB2_LAUNCHED(ctx);
+            }
+        }
+        if (d_parked) cudaFreeAsync(d_parked, st);
+        if (d_ab) cudaFreeAsync(d_ab, st);
+        if (d_c) cudaFreeAsync(d_c, st);
+        if (d_cst) cudaFreeAsync(d_cst, st);
+        if (rc != PB2_OK) { snprintf(ctx->err, sizeof(ctx->err), "contact_manifolds: pfm_pfm phase failed"); return rc; }
+    }
     PB2_CUDA(ctx, cudaGetLastError());
     PB2_CHECK(pb2_stage_back(ctx, normals, d_nr, (size_t)n * 24, mem));
     PB2_CHECK(pb2_stage_back(ctx, counts, d_ct, (size_t)n * 4, mem));

@@ -5,6 +5,8 @@
 // Bvh::cast_ray (bvh_queries.rs:260-271) with leaves = RayCast for Ball (query/ray/ray_ball.rs:8-98) and
 // Cuboid (ray_cuboid.rs:6-25 -> ray_aabb.rs:12-92 -> query/clip/clip_aabb_line.rs:79-187).
 #include "shapes.cuh"
+#include <string.h>
+#include <stdlib.h>
 #include "gjk.cuh"
 #include "traverse.cuh"
 
@@ -214,6 +216,8 @@ int pb2_shapes_create(pb2_ctx* ctx, const uint8_t* kinds, const float* params, u
     }
     pb2_shapes* s = new pb2_shapes();
     s->n = n; s->np = np; s->has_convex = has_convex;
+    s->h_npoints = (uint32_t*)calloc(n ? n : 1, sizeof(uint32_t));
+    for (uint32_t i = 0; i < n; ++i) if (kinds[i] == PB2_SHAPE_CONVEX) memcpy(&s->h_npoints[i], params + 4 * i + 1, 4);
     size_t nn = n ? n : 1, npp = np ? np : 1;
     cudaError_t e = cudaMalloc((void**)&s->kinds, nn);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->params, nn * 16);
@@ -245,7 +249,42 @@ int pb2_shapes_destroy(pb2_ctx* ctx, pb2_shapes* s) {
     if (s->params) cudaFree(s->params);
     if (s->points) cudaFree(s->points);
     if (s->points4) cudaFree(s->points4);
+    cudaFree(s->hull_face_first); cudaFree(s->hull_face_count); cudaFree(s->face_normal); cudaFree(s->face_first); cudaFree(s->face_count);
+    cudaFree(s->verts_adj_to_face); cudaFree(s->edges_adj_to_face);
+    free(s->h_npoints);
     delete s;
+    return PB2_OK;
+}
+
+int pb2_shapes_set_hull_topology(pb2_ctx* ctx, pb2_shapes* s, const uint32_t* hull_face_first, const uint32_t* hull_face_count,
+                                 const float* face_normal, const uint32_t* face_first, const uint32_t* face_count, uint32_t nf,
+                                 const uint32_t* vertices_adj_to_face, const uint32_t* edges_adj_to_face, uint32_t nadj) {
+    if (!ctx || !s || !hull_face_first || !hull_face_count || !face_normal || !face_first || !face_count || !vertices_adj_to_face ||
+        !edges_adj_to_face || nf == 0 || nadj == 0)
+        return PB2_ERR_INVALID;
+    if (s->face_normal) PB2_FAIL(ctx, PB2_ERR_INVALID, "shapes_set_hull_topology: topology already set");
+    for (uint32_t i = 0; i < s->n; ++i) {
+        const uint32_t npts = s->h_npoints[i];
+        if (npts == 0) continue;   // not a ConvexPolyhedron
+        if (hull_face_count[i] == 0 || (uint64_t)hull_face_first[i] + hull_face_count[i] > nf)
+            PB2_FAIL(ctx, PB2_ERR_INVALID, "shapes_set_hull_topology: face range of a hull out of bounds");
+        for (uint32_t f = hull_face_first[i]; f < hull_face_first[i] + hull_face_count[i]; ++f) {
+            if (face_count[f] < 3 || (uint64_t)face_first[f] + face_count[f] > nadj)
+                PB2_FAIL(ctx, PB2_ERR_INVALID, "shapes_set_hull_topology: face with fewer than 3 vertices or adjacency range out of bounds");
+            for (uint32_t k = face_first[f]; k < face_first[f] + face_count[f]; ++k)
+                if (vertices_adj_to_face[k] >= npts) PB2_FAIL(ctx, PB2_ERR_INVALID, "shapes_set_hull_topology: vertex id out of range");
+        }
+    }
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto up = [&](const void* src, size_t bytes, void** dst) -> bool {
+        return cudaMalloc(dst, bytes) == cudaSuccess && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    bool ok = up(hull_face_first, (size_t)s->n * 4, (void**)&s->hull_face_first) && up(hull_face_count, (size_t)s->n * 4, (void**)&s->hull_face_count) &&
+              up(face_normal, (size_t)nf * 12, (void**)&s->face_normal) && up(face_first, (size_t)nf * 4, (void**)&s->face_first) &&
+              up(face_count, (size_t)nf * 4, (void**)&s->face_count) && up(vertices_adj_to_face, (size_t)nadj * 4, (void**)&s->verts_adj_to_face) &&
+              up(edges_adj_to_face, (size_t)nadj * 4, (void**)&s->edges_adj_to_face);
+    if (!ok) PB2_FAIL(ctx, PB2_ERR_CUDA, "shapes_set_hull_topology: device allocation or upload failed");
+    s->nf = nf; s->nadj = nadj;
     return PB2_OK;
 }
 

@@ -9,6 +9,14 @@ struct pb2_shapes {
     float4* params = nullptr;   // ball {r}; cuboid {hx,hy,hz}; convex {first point, point count} (u32 bit patterns)
     float* points = nullptr;    // ConvexPolyhedron::points(), xyz packed
     float4* points4 = nullptr;  // same points padded to 16 B for vector loads in the support-map loop
+    // optional face topology of the hulls (ConvexPolyhedron::faces / vertices_adj_to_face / edges_adj_to_face as parry builds
+    // them, shape/convex_polyhedron.rs:390-637), needed by the pfm_pfm contact-manifold arm only
+    uint32_t *hull_face_first = nullptr, *hull_face_count = nullptr;   // per table entry
+    float* face_normal = nullptr;                                      // nf x 3
+    uint32_t *face_first = nullptr, *face_count = nullptr;             // nf, into the adjacency arrays
+    uint32_t *verts_adj_to_face = nullptr, *edges_adj_to_face = nullptr;   // vertex ids local to the hull, edge ids
+    uint32_t nf = 0, nadj = 0;
+    uint32_t* h_npoints = nullptr;   // host mirror: point count per entry (0 unless convex), for validating the topology
 };
 
 // Shape::compute_aabb(pos) (shape/shape.rs:369): aabb_ball.rs:8-33, aabb_cuboid.rs:9-16 + utils/isometry_ops.rs:16-18,

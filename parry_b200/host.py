@@ -488,6 +488,18 @@ class Shapes:
         self.h = h
         return self
 
+    def set_hull_topology(self, topology):
+        """Face topology of the ConvexPolyhedron entries (what ConvexPolyhedron::faces() / vertices_adj_to_face() /
+        edges_adj_to_face() hold in parry): dict(hull_face_first, hull_face_count (per table entry), face_normal (nf, 3),
+        face_first, face_count (nf), vertices_adj_to_face, edges_adj_to_face). Enables the pfm_pfm arm of contact_manifolds."""
+        t = {k: np.ascontiguousarray(topology[k], dtype=np.float32 if k == "face_normal" else np.uint32) for k in
+             ("hull_face_first", "hull_face_count", "face_normal", "face_first", "face_count", "vertices_adj_to_face", "edges_adj_to_face")}
+        assert len(t["hull_face_first"]) == self.n and len(t["hull_face_count"]) == self.n
+        self.ctx.check(self.ctx._lib.pb2_shapes_set_hull_topology(
+            self.ctx.h, self.h, t["hull_face_first"].ctypes.data, t["hull_face_count"].ctypes.data, t["face_normal"].ctypes.data,
+            t["face_first"].ctypes.data, t["face_count"].ctypes.data, len(t["face_first"]), t["vertices_adj_to_face"].ctypes.data,
+            t["edges_adj_to_face"].ctypes.data, len(t["vertices_adj_to_face"])))
+
     def compute_aabbs(self, shape_ids, poses):
         """Shape::compute_aabb(pos), batched (shape/shape.rs:369)."""
         n = int(poses.shape[0])
@@ -683,10 +695,11 @@ def cast_shapes(shapes, shape1, pos1, vel1, shape2, pos2, vel2, options=None):
 
 
 def contact_manifolds(shapes, shape1, pos1, shape2, pos2, prediction, max_points=8):
-    """QueryDispatcher::contact_manifolds(pos1.inv_mul(pos2), g1, g2, prediction, ..) on empty manifolds, batched, for Ball /
-    Cuboid pairs. Returns (normals (n, 6) = local_n1, local_n2; counts (n,) u32; points (n, max_points, 9) f32 = local_p1,
+    """QueryDispatcher::contact_manifolds(pos1.inv_mul(pos2), g1, g2, prediction, ..) on empty manifolds, batched: Ball / Cuboid
+    pairs through the closed-form arms, pairs with a ConvexPolyhedron (vs Cuboid / ConvexPolyhedron) through pfm_pfm once
+    Shapes.set_hull_topology was called. Returns (normals (n, 6) = local_n1, local_n2; counts (n,) u32; points (n, max_points, 9) f32 = local_p1,
     local_p2, dist, fid1, fid2 (the last two are PackedFeatureId bit patterns: view as u32); status (n,) u8: 0 ok,
-    2 unsupported pair, 4 more than max_points contacts)."""
+    2 unsupported pair, 3 host fallback, 4 more than max_points contacts)."""
     ctx = shapes.ctx
     n = int(pos1.shape[0])
     k1, p1, mem = _prep(pos1, np.float32)

@@ -68,3 +68,43 @@ def test_manifold_statuses_and_capacity(ctx, oracle):
     dn, dc, dp, ds = parry_b200.contact_manifolds(G, dev(s1), dev(p1), dev(s2), dev(p2), 0.05, max_points=8)
     ctx.synchronize()
     assert (dp.cpu().numpy().view(np.uint32) == gp.view(np.uint32)).all() and (dc.cpu().numpy().view(np.uint32) == gc).all()
+
+
+def test_pfm_manifolds_vs_oracle(ctx, oracle):
+    """contact_manifolds_pfm_pfm.rs:42-162 on the GPU: pairs of 16-point hulls, hulls of cuboid corners (quad faces) and cuboids,
+    with the hull topology supplied through pb2_shapes_set_hull_topology. Counts, statuses and feature ids exact, values 1e-5."""
+    import parry_b200
+    g = scenes.rng(13)
+    pts, _ = scenes.hull_pool(12, 16, seed=14)
+    hes = [np.array([0.3, 0.5, 0.4], np.float32), np.array([0.6, 0.2, 0.2], np.float32)]
+    corners = lambda he: np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float32) * he
+    spec = [("ball", 0.3), ("cuboid", hes[0]), ("cuboid", hes[1]), ("convex", corners(hes[0])), ("convex", corners(hes[1]))]
+    spec += [("convex", np.asarray(p, np.float32) * 0.6) for p in pts]
+    T, G = tables(ctx, oracle, spec)
+    topo = T.hull_topology()
+    G.set_hull_topology(topo)
+    n = 20000
+    ns = len(spec)
+    s1, s2 = g.integers(0, ns, n).astype(np.uint32), g.integers(0, ns, n).astype(np.uint32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 1.2 + 0.2)], axis=1).astype(np.float32)
+    p2[::4, :4] = p1[::4, :4]
+    rn, rc, rp, rs = T.contact_manifolds(s1, p1, s2, p2, 0.05, max_points=12, threads=8, topology=topo)
+    gn, gc, gp, gs = parry_b200.contact_manifolds(G, s1, p1, s2, p2, 0.05, max_points=12)
+    kinds = np.array([0 if k == "ball" else 1 if k == "cuboid" else 2 for k, _ in spec])
+    pfm = ((kinds[s1] == 2) | (kinds[s2] == 2)) & (kinds[s1] != 0) & (kinds[s2] != 0)
+    ballhull = ((kinds[s1] == 2) | (kinds[s2] == 2)) & ~pfm
+    assert pfm.mean() > 0.5 and (rs[pfm] == 0).all() and (rs[ballhull] == 2).all() and (rc[pfm] > 0).mean() > 0.3
+    host = gs == 3                                   # EPA arena overflow on the GPU: documented host fallback
+    assert host.sum() <= 5
+    ok = ~host
+    assert (gs[ok] == rs[ok]).all() and (gc[ok] == rc[ok]).all(), np.nonzero((gc != rc) & ok)[0][:10]
+    assert (gp[ok][:, :, 7:].view(np.uint32) == rp[ok][:, :, 7:].view(np.uint32)).all()
+    np.testing.assert_allclose(gn[ok], rn[ok], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gp[ok][:, :, :7], rp[ok][:, :, :7], rtol=1e-5, atol=2e-6)
+    # without topology the same pairs are status 2
+    G2 = tables(ctx, oracle, spec)[1]
+    _, c2, _, st2 = parry_b200.contact_manifolds(G2, s1, p1, s2, p2, 0.05, max_points=12)
+    assert (st2[pfm] == 2).all() and (c2[pfm] == 0).all() and (st2[~pfm & ~ballhull] == 0).all()
