@@ -573,9 +573,31 @@ def also_manifolds(ctx, stream, timed, flush, hbm_peak):
     cnt = res["o"][1]
     npts = int(cnt.to(torch.int64).sum().item())
     alg = n * (8 + 56 + 24 + 4 + 1) + npts * 36
-    return {"value": n / (ms * 1e-3), "unit": "pairs/s (ball / cuboid contact manifolds)", "ms": ms, "pairs": n,
-            "manifolds_with_points": float((cnt > 0).float().mean().item()), "points": npts, "l2": "flushed between iterations",
-            "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+    out = {"value": n / (ms * 1e-3), "unit": "pairs/s (ball / cuboid contact manifolds)", "ms": ms, "pairs": n,
+           "manifolds_with_points": float((cnt > 0).float().mean().item()), "points": npts, "l2": "flushed between iterations",
+           "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+    # pfm_pfm arm: 2^20 pairs of 32-vertex hulls / cuboids (hull topology built on the host by the test-side restatement of
+    # ConvexPolyhedron::from_convex_mesh; parry would hand over its own)
+    from harness import hull_topology as ht
+    pts, _ = scenes.hull_pool(64, 32, seed=22)
+    hulls = [np.asarray(p, np.float32) * 0.6 for p in pts]
+    G2 = parry_b200.Shapes(ctx, [parry_b200.Cuboid([0.3, 0.5, 0.4]), parry_b200.Cuboid([0.6, 0.2, 0.2])] + [parry_b200.ConvexPolyhedron(h) for h in hulls])
+    t = ht.hull_table(hulls)
+    hf, hc = np.zeros(66, np.uint32), np.zeros(66, np.uint32)
+    hf[2:], hc[2:] = t["hull_face_first"], t["hull_face_count"]
+    t = dict(t, hull_face_first=hf, hull_face_count=hc)
+    G2.set_hull_topology(t)
+    m = 1 << 20
+    h1, h2 = g.integers(0, 66, m).astype(np.int32), g.integers(2, 66, m).astype(np.int32)
+    dh1, dh2 = torch.from_numpy(h1).cuda(), torch.from_numpy(h2).cuda()
+
+    def run_pfm():
+        res["p"] = parry_b200.contact_manifolds(G2, dh1, dp1[:m], dh2, dp2[:m], 0.05, max_points=12)
+    ms2 = timed(run_pfm, steps=5, warmup=2, flush=flush)
+    c2, st2 = res["p"][1], res["p"][3]
+    out["pfm_pfm_1M_hull_pairs"] = {"value": m / (ms2 * 1e-3), "unit": "pairs/s", "ms": ms2, "manifolds_with_points": float((c2 > 0).float().mean().item()),
+                                    "host_fallback": int((st2 == 3).sum().item())}
+    return out
 
 
 def _mixed_table(ctx, n_hulls=64, seed=31):
