@@ -168,9 +168,33 @@ def siblings():
     np.savez_compressed(os.path.join(HERE, "siblings_3000.npz"), **out)
 
 
+def pfm():
+    """pfm_pfm contact manifolds: cuboids, hulls of cuboid corners and 16-point hulls, with their face topology."""
+    g = scenes.rng(401)
+    pts, _ = scenes.hull_pool(8, 16, seed=402)
+    hes = [np.array([0.3, 0.5, 0.4], np.float32), np.array([0.6, 0.2, 0.2], np.float32)]
+    corners = lambda he: np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float32) * he
+    spec = [("cuboid", hes[0]), ("cuboid", hes[1]), ("convex", corners(hes[0])), ("convex", corners(hes[1]))]
+    spec += [("convex", np.asarray(p, np.float32) * 0.6) for p in pts]
+    T = oracle.ShapeTable(spec)
+    topo = T.hull_topology()
+    n, ns = 2000, len(spec)
+    s1, s2 = g.integers(0, ns, n).astype(np.uint32), g.integers(2, ns, n).astype(np.uint32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 1.2 + 0.2)], axis=1).astype(np.float32)
+    p2[::4, :4] = p1[::4, :4]
+    nr, cnt, mp, st = T.contact_manifolds(s1, p1, s2, p2, 0.05, max_points=12, topology=topo)
+    np.savez_compressed(os.path.join(HERE, "manifolds_pfm_2000.npz"), kinds=T.kinds, params=T.params, points=T.points, shape1=s1, shape2=s2, pos1=p1,
+                        pos2=p2, normals=nr, counts=cnt, man_points=mp, status=st, **{"topo_" + k: v for k, v in topo.items()})
+
+
 if __name__ == "__main__":
     import sys
-    if "shape_rays" in sys.argv:
+    if "pfm" in sys.argv:
+        pfm()
+    elif "shape_rays" in sys.argv:
         shape_rays()
     elif "siblings" in sys.argv:
         siblings()
