@@ -107,22 +107,54 @@ def from_convex_mesh(points, indices):
             break
     if not faces:
         return None
-    return {"face_normal": np.stack([f["normal"] for f in faces]).astype(np.float32),
+    # vertices: adjacent faces / edges (convex_polyhedron.rs:569-617)
+    nv = len(pts)
+    vcount = np.zeros(nv, np.uint32)
+    for f in faces:
+        for v in vertices_adj_to_face[f["first"]:f["first"] + f["count"]]:
+            vcount[v] += 1
+    vfirst = np.concatenate([[0], np.cumsum(vcount)[:-1]]).astype(np.uint32)
+    total = int(vcount.sum())
+    faces_adj_to_vertex, edges_adj_to_vertex = np.zeros(total, np.uint32), np.zeros(total, np.uint32)
+    fill = np.zeros(nv, np.uint32)
+    for fid, f in enumerate(faces):
+        for k in range(f["first"], f["first"] + f["count"]):
+            v = vertices_adj_to_face[k]
+            faces_adj_to_vertex[vfirst[v] + fill[v]] = fid
+            edges_adj_to_vertex[vfirst[v] + fill[v]] = edges_adj_to_face[k]
+            fill[v] += 1
+    edge_dir = np.zeros((len(edges), 3), np.float32)
+    for k, e in enumerate(edges):
+        d = (pts[e["vertices"][1]] - pts[e["vertices"][0]]).astype(np.float32)
+        u, n = _unit(d)
+        edge_dir[k] = u if n > EPS else [1.0, 0.0, 0.0]   # Unit::try_new(.., DEFAULT_EPSILON).unwrap_or(x_axis)
+    return {"vert_first": vfirst, "vert_count": vcount, "faces_adj_to_vertex": faces_adj_to_vertex, "edges_adj_to_vertex": edges_adj_to_vertex,
+            "edge_dir": edge_dir,
+            "face_normal": np.stack([f["normal"] for f in faces]).astype(np.float32),
             "face_first": np.array([f["first"] for f in faces], np.uint32), "face_count": np.array([f["count"] for f in faces], np.uint32),
             "vertices_adj_to_face": np.array(vertices_adj_to_face, np.uint32), "edges_adj_to_face": np.array(edges_adj_to_face, np.uint32),
             "num_edges": len(edges)}
 
 
 def hull_table(hulls):
-    """Concatenated topology of several hulls (list of (n_i, 3) point arrays), vertex ids local to each hull:
-    dict(hull_face_first, hull_face_count, face_normal, face_first, face_count, vertices_adj_to_face, edges_adj_to_face)."""
+    """Concatenated topology of several hulls (list of (n_i, 3) point arrays), vertex / face / edge ids local to each hull:
+    dict(hull_face_first, hull_face_count, face_normal, face_first, face_count, vertices_adj_to_face, edges_adj_to_face) plus the
+    vertex side: vert_first / vert_count (one entry per point, hull after hull), faces_adj_to_vertex, edges_adj_to_vertex,
+    hull_edge_first (per hull), edge_dir."""
     hf, hc, fn, ff, fc, va, ea = [], [], [], [], [], [], []
+    vf, vc, fav, eav, ed, hef = [], [], [], [], [], []
     for p in hulls:
         t = from_convex_mesh(p, hull_triangles(p))
         assert t is not None
         hf.append(len(ff))
         hc.append(len(t["face_first"]))
         base = len(va)
+        vf += [int(x) + len(fav) for x in t["vert_first"]]
+        vc += [int(x) for x in t["vert_count"]]
+        fav += [int(x) for x in t["faces_adj_to_vertex"]]
+        eav += [int(x) for x in t["edges_adj_to_vertex"]]
+        hef.append(sum(len(e) for e in ed))
+        ed.append(t["edge_dir"])
         fn.append(t["face_normal"])
         ff += [int(x) + base for x in t["face_first"]]
         fc += [int(x) for x in t["face_count"]]
@@ -130,4 +162,7 @@ def hull_table(hulls):
         ea += [int(x) for x in t["edges_adj_to_face"]]
     return {"hull_face_first": np.array(hf, np.uint32), "hull_face_count": np.array(hc, np.uint32),
             "face_normal": np.concatenate(fn).astype(np.float32), "face_first": np.array(ff, np.uint32), "face_count": np.array(fc, np.uint32),
-            "vertices_adj_to_face": np.array(va, np.uint32), "edges_adj_to_face": np.array(ea, np.uint32)}
+            "vertices_adj_to_face": np.array(va, np.uint32), "edges_adj_to_face": np.array(ea, np.uint32),
+            # vertex side (support_feature_id_toward): per point of the concatenated hull points, in hull order
+            "vert_first": np.array(vf, np.uint32), "vert_count": np.array(vc, np.uint32), "faces_adj_to_vertex": np.array(fav, np.uint32),
+            "edges_adj_to_vertex": np.array(eav, np.uint32), "hull_edge_first": np.array(hef, np.uint32), "edge_dir": np.concatenate(ed).astype(np.float32)}

@@ -62,7 +62,7 @@ def lib():
         l.pb2o_cast_shapes_batch.argtypes = [P, P, P, P, P, P, P, P, P, f32, f32, i32, i32, u32, i32, P, P]
         l.pb2o_compound_contact_batch.argtypes = [P, P, P, P, P, P, P, P, P, P, P, f32, i32, u32, i32, P, P, P]
         l.pb2o_contact_manifolds_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, u32, i32, P, P, P, P]
-        l.pb2o_contact_manifolds_batch2.argtypes = [P, P, P, P, P, P, P, P, P, P, P, P, P, P, f32, u32, u32, i32, P, P, P, P]
+        l.pb2o_contact_manifolds_batch2.argtypes = [P] * 20 + [f32, u32, u32, i32, P, P, P, P]
         l.pb2o_closest_points_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, P, P, P]
         l.pb2o_convex_cast_ray.restype = i32
         l.pb2o_convex_cast_ray.argtypes = [P, u32, P, P, f32, i32, P, P]
@@ -388,6 +388,18 @@ class ShapeTable:
                 hf[conv], hc[conv] = t["hull_face_first"], t["hull_face_count"]
                 t = dict(t)
                 t["hull_face_first"], t["hull_face_count"] = hf, hc
+                # vertex-side arrays are indexed by the table's global point index, the edge offset per table entry
+                npnt = len(self.points)
+                vfirst, vcount = np.zeros(npnt, np.uint32), np.zeros(npnt, np.uint32)
+                hef = np.zeros(len(self.kinds), np.uint32)
+                at = 0
+                for j, i in enumerate(conv):
+                    f0, c = int(pu[i, 0]), int(pu[i, 1])
+                    vfirst[f0:f0 + c] = t["vert_first"][at:at + c]
+                    vcount[f0:f0 + c] = t["vert_count"][at:at + c]
+                    at += c
+                    hef[i] = t["hull_edge_first"][j]
+                t["vert_first"], t["vert_count"], t["hull_edge_first"] = vfirst, vcount, hef
             self._topo = t
         return self._topo
 
@@ -401,9 +413,10 @@ class ShapeTable:
         pts = np.zeros((n, max_points, 9), dtype=np.float32)
         status = np.zeros(n, dtype=np.uint8)
         t = topology
-        tp = [None] * 7 if t is None else [np.ascontiguousarray(t[k]).ctypes.data for k in
-                                           ("hull_face_first", "hull_face_count", "face_normal", "face_first", "face_count",
-                                            "vertices_adj_to_face", "edges_adj_to_face")]
+        keys = ("hull_face_first", "hull_face_count", "face_normal", "face_first", "face_count", "vertices_adj_to_face", "edges_adj_to_face",
+                "vert_first", "vert_count", "faces_adj_to_vertex", "edges_adj_to_vertex", "hull_edge_first", "edge_dir")
+        keep = None if t is None else [np.ascontiguousarray(t[k]) if k in t else None for k in keys]
+        tp = [None] * 13 if t is None else [None if a is None else a.ctypes.data for a in keep]
         lib().pb2o_contact_manifolds_batch2(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, *tp, s1.ctypes.data,
                                             s2.ctypes.data, p1.ctypes.data, p2.ctypes.data, prediction, n, max_points, threads,
                                             normals.ctypes.data, counts.ctypes.data, pts.ctypes.data, status.ctypes.data)

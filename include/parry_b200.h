@@ -185,6 +185,14 @@ int pb2_shapes_set_hull_topology(pb2_ctx* ctx, pb2_shapes* shapes, const uint32_
                                  const float* face_normal, const uint32_t* face_first, const uint32_t* face_count, uint32_t nf,
                                  const uint32_t* vertices_adj_to_face, const uint32_t* edges_adj_to_face, uint32_t nadj);
 
+/* Vertex side of the same topology, for ConvexPolyhedron::support_feature_id_toward (convex_polyhedron.rs:885-922; the feature id
+ * of the ball-vs-hull manifold arm): vert_first / vert_count per point of the table (parry's Vertex::first_adj_face_or_edge /
+ * num_adj_faces_or_edge, rebased to the concatenated arrays), faces_adj_to_vertex / edges_adj_to_vertex (ids local to the hull),
+ * hull_edge_first per table entry into edge_dir (ne x 3, Edge::dir). Call after pb2_shapes_set_hull_topology. */
+int pb2_shapes_set_hull_vertex_topology(pb2_ctx* ctx, pb2_shapes* shapes, const uint32_t* vert_first, const uint32_t* vert_count,
+                                        const uint32_t* faces_adj_to_vertex, const uint32_t* edges_adj_to_vertex, uint32_t nadj,
+                                        const uint32_t* hull_edge_first, const float* edge_dir, uint32_t ne);
+
 /* Shape::compute_aabb(pos) for n colliders (shape/shape.rs:369; aabb_ball.rs:25, aabb_cuboid.rs:9-16,
  * aabb_convex_polyhedron.rs:8) -> aabbs (n x 6). */
 int pb2_shapes_compute_aabbs(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape_ids, const float* poses7,
@@ -276,8 +284,9 @@ int pb2_closest_points_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint3
  * points: n x max_points x 9 words {TrackedContact::local_p1 (3 f32), local_p2 (3 f32), dist (f32), fid1, fid2
  * (PackedFeatureId bits, u32)} in the reference's order. Pairs with a ConvexPolyhedron (against a Cuboid or another one) take
  * the pfm_pfm arm (contact_manifolds_pfm_pfm.rs:42-162: GJK/EPA contact, support faces along its normals, the same face
- * clipping, plus the witness pair as a feature-less point) once pb2_shapes_set_hull_topology has been called. status: 0 ok,
- * 2 unsupported pair (a ConvexPolyhedron without topology, ball vs ConvexPolyhedron, or an unknown shape id:
+ * clipping, plus the witness pair as a feature-less point) once pb2_shapes_set_hull_topology has been called; Ball vs
+ * ConvexPolyhedron (contact_manifolds_convex_ball.rs) additionally needs pb2_shapes_set_hull_vertex_topology. status: 0 ok,
+ * 2 unsupported pair (a ConvexPolyhedron without topology — ball vs ConvexPolyhedron needs the vertex side too —, or an unknown shape id:
  * Err(Unsupported) / host), 3 host fallback (EPA arena overflow), 4 more than max_points contacts (two quads yield at most
  * 16; 9 is the observed max). */
 int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,

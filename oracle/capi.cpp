@@ -311,6 +311,8 @@ void pb2o_closest_points_batch(const uint8_t* kinds, const float* params4, const
 void pb2o_contact_manifolds_batch2(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* hull_face_first,
                                    const uint32_t* hull_face_count, const float* face_normal, const uint32_t* face_first,
                                    const uint32_t* face_count, const uint32_t* vertices_adj_to_face, const uint32_t* edges_adj_to_face,
+                                   const uint32_t* vert_first, const uint32_t* vert_count, const uint32_t* faces_adj_to_vertex,
+                                   const uint32_t* edges_adj_to_vertex, const uint32_t* hull_edge_first, const float* edge_dir,
                                    const uint32_t* shape1, const uint32_t* shape2, const float* pos1, const float* pos2, float prediction,
                                    uint32_t n, uint32_t max_points, int nthreads, float* normals, uint32_t* counts, float* pts, uint8_t* status) {
     // hull_face_first / hull_face_count: per shape-table entry (ignored for balls and cuboids), NULL = no topology supplied
@@ -319,6 +321,11 @@ void pb2o_contact_manifolds_batch2(const uint8_t* kinds, const float* params4, c
         uint32_t f0 = hull_face_first[sid];
         t.face_normal = face_normal + 3 * (size_t)f0; t.face_first = face_first + f0; t.face_count = face_count + f0;
         t.vertices_adj_to_face = vertices_adj_to_face; t.edges_adj_to_face = edges_adj_to_face; t.num_faces = hull_face_count[sid];
+        if (vert_first) {   // vertex-side arrays are indexed by the table's global point index; edges per table entry
+            uint32_t p0; memcpy(&p0, params4 + 4 * (size_t)sid, 4);
+            t.vert_first = vert_first + p0; t.vert_count = vert_count + p0; t.faces_adj_to_vertex = faces_adj_to_vertex;
+            t.edges_adj_to_vertex = edges_adj_to_vertex; t.edge_dir = edge_dir + 3 * (size_t)hull_edge_first[sid];
+        }
         return t.num_faces ? &t : nullptr;
     };
     parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
@@ -347,7 +354,8 @@ void pb2o_contact_manifolds_batch2(const uint8_t* kinds, const float* params4, c
 void pb2o_contact_manifolds_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* shape1,
                                   const uint32_t* shape2, const float* pos1, const float* pos2, float prediction, uint32_t n,
                                   uint32_t max_points, int nthreads, float* normals, uint32_t* counts, float* pts, uint8_t* status) {
-    pb2o_contact_manifolds_batch2(kinds, params4, points, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, shape1, shape2, pos1, pos2,
+    pb2o_contact_manifolds_batch2(kinds, params4, points, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                  nullptr, nullptr, nullptr, shape1, shape2, pos1, pos2,
                                   prediction, n, max_points, nthreads, normals, counts, pts, status);
 }
 // query::cast_shapes for n pairs (shape_cast.rs:268-286). vel1/vel2: n x 3. out: n x 13 floats {witness1, witness2, normal1,

@@ -270,6 +270,12 @@ struct HullTopology {
     const uint32_t* vertices_adj_to_face;   // vertex ids local to the hull
     const uint32_t* edges_adj_to_face;
     uint32_t num_faces;
+    // vertex side, for support_feature_id_toward (NULL when not supplied): per vertex of THIS hull
+    const uint32_t* vert_first = nullptr;            // into the two arrays below
+    const uint32_t* vert_count = nullptr;
+    const uint32_t* faces_adj_to_vertex = nullptr;   // face ids local to the hull
+    const uint32_t* edges_adj_to_vertex = nullptr;   // edge ids local to the hull
+    const float* edge_dir = nullptr;                 // this hull's edges, ne x 3
 };
 static inline PolyFeature hull_local_support_feature(const ShapeRef& s, const HullTopology& t, const Vec3& dir) {
     uint32_t best = 0;
@@ -290,6 +296,51 @@ static inline PolyFeature hull_local_support_feature(const ShapeRef& s, const Hu
     out.fid = packed_face(best);
     out.n = (int)nv;
     return out;
+}
+
+// ConvexPolyhedron::support_feature_id_toward (convex_polyhedron.rs:885-922), eps = 1 degree: faces adjacent to the support
+// vertex whose normal is within eps of dir, then adjacent edges perpendicular to dir within eps, else the vertex.
+#define PB2O_SIN_1DEG 0.017452406f   // (PI / 180 as f32).sin_cos()
+#define PB2O_COS_1DEG 0.99984770f
+static inline Feature hull_support_feature_id_toward(const ShapeRef& s, const HullTopology& t, const Vec3& dir) {
+    uint32_t best = 0;
+    Real best_dot = dot(ld3(s.points), dir);
+    for (uint32_t i = 1; i < s.num_points; ++i) { Real d = dot(ld3(s.points + 3 * i), dir); if (d > best_dot) { best_dot = d; best = i; } }
+    uint32_t first = t.vert_first[best], cnt = t.vert_count[best];
+    for (uint32_t i = 0; i < cnt; ++i) {
+        uint32_t f = t.faces_adj_to_vertex[first + i];
+        if (dot(ld3(t.face_normal + 3 * f), dir) >= PB2O_COS_1DEG) return Feature{2, f};
+    }
+    for (uint32_t i = 0; i < cnt; ++i) {
+        uint32_t e = t.edges_adj_to_vertex[first + i];
+        if (fabsf(dot(ld3(t.edge_dir + 3 * e), dir)) <= PB2O_SIN_1DEG) return Feature{1, e};
+    }
+    return Feature{0, best};
+}
+
+// contact_manifolds_convex_ball.rs:42-145 with shape1 = ConvexPolyhedron (project_local_point_and_get_feature:
+// point_support_map.rs:62-76), no normal constraints; pos12 = pose of the ball in the hull's frame.
+static inline void manifold_hull_ball(const Iso& pos12, const ShapeRef& hull, const HullTopology& t, Real radius, Real prediction, bool flipped,
+                                      Manifold& m) {
+    Vec3 local_p2_1 = pos12.tra;
+    Vec3 proj; bool inside;
+    hull_project_point(hull.support(), local_p2_1, proj, inside);
+    Vec3 dpt = local_p2_1 - proj;
+    Vec3 local_dir = inside ? -dpt : dpt, ud;
+    Feature f{3, 0};
+    if (try_normalize(local_dir, DEFAULT_EPSILON, ud)) f = hull_support_feature_id_toward(hull, t, ud);
+    Vec3 n1; Real dist;
+    if (!try_normalize_and_get(dpt, 0.0f, n1, dist)) {
+        if (!try_normalize(pos12.tra, 0.0f, n1)) n1 = Vec3(1, 0, 0);
+        dist = 0.0f;
+    }
+    if (inside) { n1 = -n1; dist = -dist; }
+    m.clear();
+    if (dist <= radius + prediction) {
+        Vec3 n2 = pos12.inverse_transform_vector(-n1);
+        m.push_flipped(proj, n2 * radius, packed_from_feature(f), packed_face(0), dist - radius, flipped);
+        if (flipped) { m.local_n1 = n2; m.local_n2 = n1; } else { m.local_n1 = n1; m.local_n2 = n2; }
+    }
 }
 
 // contact_manifolds_pfm_pfm.rs:42-162, empty incoming manifold (init_dir = None), no normal constraints, border radii 0.
@@ -319,6 +370,10 @@ static inline int dispatch_manifold(const Iso& pos12, const ShapeRef& s1, const 
     if (s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_CUBOID) { manifold_cuboid_cuboid(pos12, s1.half_extents, s2.half_extents, prediction, m); return MANIFOLD_OK; }
     if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_CUBOID) { manifold_cuboid_ball(pos12.inverse(), s2.half_extents, s1.radius, prediction, true, m); return MANIFOLD_OK; }
     if (s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_BALL) { manifold_cuboid_ball(pos12, s1.half_extents, s2.radius, prediction, false, m); return MANIFOLD_OK; }
+    // (_, Ball) | (Ball, _) with a ConvexPolyhedron: contact_manifold_convex_ball, needs the vertex side of the topology
+    if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_CONVEX && t2 && t2->vert_first) { manifold_hull_ball(pos12.inverse(), s2, *t2, s1.radius, prediction, true, m); return MANIFOLD_OK; }
+    if (s1.kind == SHAPE_CONVEX && s2.kind == SHAPE_BALL && t1 && t1->vert_first) { manifold_hull_ball(pos12, s1, *t1, s2.radius, prediction, false, m); return MANIFOLD_OK; }
+    if (s1.kind == SHAPE_BALL || s2.kind == SHAPE_BALL) return MANIFOLD_UNSUPPORTED;
     // _ => contact_manifold_pfm_pfm (default_query_dispatcher.rs:818-831): Cuboid and ConvexPolyhedron are PolygonalFeatureMaps
     bool ok1 = s1.kind == SHAPE_CUBOID || (s1.kind == SHAPE_CONVEX && t1), ok2 = s2.kind == SHAPE_CUBOID || (s2.kind == SHAPE_CONVEX && t2);
     if (ok1 && ok2) { manifold_pfm_pfm(pos12, s1, t1, s2, t2, prediction, m); return MANIFOLD_OK; }

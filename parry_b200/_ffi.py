@@ -59,6 +59,7 @@ SIGNATURES = {
     "pb2_compounds_destroy": (c_int, [c_void_p, c_void_p]),
     "pb2_compound_contact_shapes": (c_int, [c_void_p, c_void_p, P, P, P, P, c_u32, c_float, c_int, P, P, P, c_int]),
     "pb2_shapes_set_hull_topology": (c_int, [c_void_p, c_void_p, P, P, P, P, P, c_u32, P, P, c_u32]),
+    "pb2_shapes_set_hull_vertex_topology": (c_int, [c_void_p, c_void_p, P, P, P, P, c_u32, P, P, c_u32]),
     "pb2_contact_manifolds_batch": (c_int, [c_void_p, c_void_p, P, P, P, P, c_float, c_u32, c_u32, P, P, P, P, c_int]),
     "pb2_closest_points_batch": (c_int, [c_void_p, c_void_p, P, P, P, P, c_float, c_u32, P, P, P, c_int]),
     "pb2_cast_shapes_batch": (c_int, [c_void_p, c_void_p, P, P, P, P, P, P, c_float, c_float, c_int, c_int, c_u32, P, P, c_int]),

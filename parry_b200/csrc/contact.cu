@@ -2496,7 +2496,34 @@ __device__ __forceinline__ void contacts_face_face(const Iso7& pos12, const Poly
 
 // PolygonalFeatureMap::local_support_feature: Cuboid = support_face; ConvexPolyhedron = the face whose normal has the first
 // maximal dot with dir, its first <= 4 vertices (convex_polyhedron.rs:959-991)
-struct HullTopo { const uint32_t *hull_face_first, *hull_face_count, *face_first, *face_count, *va, *ea; const float* face_normal; };
+struct HullTopo {
+    const uint32_t *hull_face_first, *hull_face_count, *face_first, *face_count, *va, *ea;
+    const float* face_normal;
+    const uint32_t *vert_first, *vert_count, *fav, *eav, *hull_edge_first;   // vertex side (may be NULL)
+    const float* edge_dir;
+};
+#define PB2_SIN_1DEG 0.017452406f   // (PI / 180 as f32).sin_cos()
+#define PB2_COS_1DEG 0.99984770f
+// ConvexPolyhedron::support_feature_id_toward (convex_polyhedron.rs:885-922) -> PackedFeatureId
+__device__ __forceinline__ uint32_t hull_support_feature_id(float4 pr, uint32_t sid, const float4* __restrict__ pts, const HullTopo& t, V3 dir) {
+    const uint32_t p0 = __float_as_uint(pr.x), np_ = __float_as_uint(pr.y);
+    const float4* hp = pts + p0;
+    uint32_t best = 0;
+    float best_dot = dot3(mk3(hp[0].x, hp[0].y, hp[0].z), dir);
+    for (uint32_t i = 1; i < np_; ++i) { float4 q = hp[i]; float d = dot3(mk3(q.x, q.y, q.z), dir); if (d > best_dot) { best_dot = d; best = i; } }
+    const uint32_t first = t.vert_first[p0 + best], cnt = t.vert_count[p0 + best];
+    const float* fn = t.face_normal + 3ull * t.hull_face_first[sid];
+    for (uint32_t i = 0; i < cnt; ++i) {
+        uint32_t f = t.fav[first + i];
+        if (dot3(mk3(fn[3 * f], fn[3 * f + 1], fn[3 * f + 2]), dir) >= PB2_COS_1DEG) return PK_FACE(f);
+    }
+    const float* ed = t.edge_dir + 3ull * t.hull_edge_first[sid];
+    for (uint32_t i = 0; i < cnt; ++i) {
+        uint32_t e = t.eav[first + i];
+        if (fabsf(dot3(mk3(ed[3 * e], ed[3 * e + 1], ed[3 * e + 2]), dir)) <= PB2_SIN_1DEG) return PK_EDGE(e);
+    }
+    return PK_VERTEX(best);
+}
 __device__ __forceinline__ void pfm_support_feature(uint8_t kind, float4 pr, uint32_t sid, const float4* __restrict__ pts, const HullTopo& t, V3 dir,
                                                     PolyFace& f) {
     if (kind == PB2_SHAPE_CUBOID) { cuboid_support_face(mk3(pr.x, pr.y, pr.z), dir, f); return; }
@@ -2529,15 +2556,16 @@ __global__ void __launch_bounds__(128) k_contact_manifolds(const uint8_t* __rest
                               const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2, const float* __restrict__ pos1,
                               const float* __restrict__ pos2, float prediction, uint32_t n, uint32_t max_points, float* __restrict__ normals,
                               uint32_t* __restrict__ counts, float* __restrict__ pts, uint8_t* __restrict__ status, bool have_topology,
-                              uint32_t* __restrict__ parked, unsigned long long* parked_count) {
+                              bool have_vertex_topology, uint32_t* __restrict__ parked, unsigned long long* parked_count) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     {   // pairs for the pfm_pfm arm (a ConvexPolyhedron with topology on at least one side, a Cuboid or such a hull on the other)
         uint32_t a = shape1[k], b = shape2[k];
         if (have_topology && a < n_shapes && b < n_shapes) {
             uint8_t ka = kinds[a], kb = kinds[b];
-            bool pfm = (ka == PB2_SHAPE_CONVEX || kb == PB2_SHAPE_CONVEX) && ka != PB2_SHAPE_BALL && kb != PB2_SHAPE_BALL;
-            if (pfm) { parked[warp_append1(parked_count)] = k; return; }   // outputs written by k_manifold_pfm
+            bool hull = ka == PB2_SHAPE_CONVEX || kb == PB2_SHAPE_CONVEX, ball = ka == PB2_SHAPE_BALL || kb == PB2_SHAPE_BALL;
+            // hull vs hull / cuboid: pfm_pfm; hull vs ball: convex_ball (needs the vertex side for the feature id)
+            if (hull && (!ball || have_vertex_topology)) { parked[warp_append1(parked_count)] = k; return; }   // outputs written by k_manifold_pfm
         }
     }
     ManifoldOut m;
@@ -2635,12 +2663,21 @@ __global__ void __launch_bounds__(128) k_manifold_pfm(const uint8_t* __restrict_
         n1 = mk3(c[6], c[7], c[8]);
         n2 = mk3(c[9], c[10], c[11]);
         uint32_t a = shape1[k], b = shape2[k];
-        Iso7 pos12 = iso_inv_mul(load_iso(pos1 + 7ull * k), load_iso(pos2 + 7ull * k));
-        PolyFace f1, f2;
-        pfm_support_feature(kinds[a], params[a], a, hull_pts, topo, n1, f1);
-        pfm_support_feature(kinds[b], params[b], b, hull_pts, topo, n2, f2);
-        contacts_face_face(pos12, f1, n1, f2, m);
-        m.push(mk3(c[0], c[1], c[2]), mk3(c[3], c[4], c[5]), 0u, 0u, c[12], false);   // PackedFeatureId::UNKNOWN
+        if (kinds[a] == PB2_SHAPE_BALL || kinds[b] == PB2_SHAPE_BALL) {
+            // contact_manifolds_convex_ball.rs:42-145 with a ConvexPolyhedron: the contact arm computed the same projection, normals
+            // and dist (contact_ball_convex_polyhedron.rs); what the manifold adds is the hull feature under the contact,
+            // support_feature_id_toward(the outward normal in the hull's frame) (point_support_map.rs:62-76)
+            const bool ball_first = kinds[a] == PB2_SHAPE_BALL;
+            uint32_t hf = ball_first ? hull_support_feature_id(params[b], b, hull_pts, topo, n2) : hull_support_feature_id(params[a], a, hull_pts, topo, n1);
+            m.push(mk3(c[0], c[1], c[2]), mk3(c[3], c[4], c[5]), ball_first ? PK_FACE(0u) : hf, ball_first ? hf : PK_FACE(0u), c[12], false);
+        } else {
+            Iso7 pos12 = iso_inv_mul(load_iso(pos1 + 7ull * k), load_iso(pos2 + 7ull * k));
+            PolyFace f1, f2;
+            pfm_support_feature(kinds[a], params[a], a, hull_pts, topo, n1, f1);
+            pfm_support_feature(kinds[b], params[b], b, hull_pts, topo, n2, f2);
+            contacts_face_face(pos12, f1, n1, f2, m);
+            m.push(mk3(c[0], c[1], c[2]), mk3(c[3], c[4], c[5]), 0u, 0u, c[12], false);   // PackedFeatureId::UNKNOWN
+        }
     }
     if (m.overflow) st = MAN_OVERFLOW;
     if (m.count == 0) { n1 = mk3(0.f, 0.f, 0.f); n2 = n1; }
@@ -2680,7 +2717,8 @@ extern "C" int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shape
     }
     k_contact_manifolds<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->n, (const uint32_t*)d_s1, (const uint32_t*)d_s2,
                                                              (const float*)d_p1, (const float*)d_p2, prediction, n, max_points, (float*)d_nr,
-                                                             (uint32_t*)d_ct, (float*)d_pt, (uint8_t*)d_st, have_topology, d_parked, parked_count);
+                                                             (uint32_t*)d_ct, (float*)d_pt, (uint8_t*)d_st, have_topology, shapes->vert_first != nullptr,
+                                                             d_parked, parked_count);
     PB2_LAUNCHED(ctx);
     if (have_topology) {
         cudaMemcpyAsync(ctx->h_counters + 10, parked_count, 8, cudaMemcpyDeviceToHost, st);
@@ -2704,6 +2742,8 @@ extern "C" int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shape
                 topo.hull_face_first = shapes->hull_face_first; topo.hull_face_count = shapes->hull_face_count; topo.face_first = shapes->face_first;
                 topo.face_count = shapes->face_count; topo.va = shapes->verts_adj_to_face; topo.ea = shapes->edges_adj_to_face;
                 topo.face_normal = shapes->face_normal;
+                topo.vert_first = shapes->vert_first; topo.vert_count = shapes->vert_count; topo.fav = shapes->faces_adj_to_vertex;
+                topo.eav = shapes->edges_adj_to_vertex; topo.hull_edge_first = shapes->hull_edge_first; topo.edge_dir = shapes->edge_dir;
                 k_manifold_pfm<<<pb2_blocks(cnt, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, topo, (const uint32_t*)d_s1,
                                                                     (const uint32_t*)d_s2, (const float*)d_p1, (const float*)d_p2, d_parked, cnt, d_c, d_cst,
                                                                     max_points, (float*)d_nr, (uint32_t*)d_ct, (float*)d_pt, (uint8_t*)d_st);

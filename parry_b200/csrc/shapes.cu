@@ -251,6 +251,8 @@ int pb2_shapes_destroy(pb2_ctx* ctx, pb2_shapes* s) {
     if (s->points4) cudaFree(s->points4);
     cudaFree(s->hull_face_first); cudaFree(s->hull_face_count); cudaFree(s->face_normal); cudaFree(s->face_first); cudaFree(s->face_count);
     cudaFree(s->verts_adj_to_face); cudaFree(s->edges_adj_to_face);
+    cudaFree(s->vert_first); cudaFree(s->vert_count); cudaFree(s->faces_adj_to_vertex); cudaFree(s->edges_adj_to_vertex);
+    cudaFree(s->hull_edge_first); cudaFree(s->edge_dir);
     free(s->h_npoints);
     delete s;
     return PB2_OK;
@@ -285,6 +287,29 @@ int pb2_shapes_set_hull_topology(pb2_ctx* ctx, pb2_shapes* s, const uint32_t* hu
               up(edges_adj_to_face, (size_t)nadj * 4, (void**)&s->edges_adj_to_face);
     if (!ok) PB2_FAIL(ctx, PB2_ERR_CUDA, "shapes_set_hull_topology: device allocation or upload failed");
     s->nf = nf; s->nadj = nadj;
+    return PB2_OK;
+}
+
+int pb2_shapes_set_hull_vertex_topology(pb2_ctx* ctx, pb2_shapes* s, const uint32_t* vert_first, const uint32_t* vert_count,
+                                        const uint32_t* faces_adj_to_vertex, const uint32_t* edges_adj_to_vertex, uint32_t nadj,
+                                        const uint32_t* hull_edge_first, const float* edge_dir, uint32_t ne) {
+    if (!ctx || !s || !vert_first || !vert_count || !faces_adj_to_vertex || !edges_adj_to_vertex || !hull_edge_first || !edge_dir || ne == 0 || nadj == 0)
+        return PB2_ERR_INVALID;
+    if (!s->face_normal) PB2_FAIL(ctx, PB2_ERR_INVALID, "shapes_set_hull_vertex_topology: set the face topology first");
+    if (s->vert_first) PB2_FAIL(ctx, PB2_ERR_INVALID, "shapes_set_hull_vertex_topology: already set");
+    for (uint32_t i = 0; i < s->np; ++i)
+        if ((uint64_t)vert_first[i] + vert_count[i] > nadj) PB2_FAIL(ctx, PB2_ERR_INVALID, "shapes_set_hull_vertex_topology: adjacency range out of bounds");
+    for (uint32_t i = 0; i < s->n; ++i)
+        if (s->h_npoints[i] && hull_edge_first[i] >= ne) PB2_FAIL(ctx, PB2_ERR_INVALID, "shapes_set_hull_vertex_topology: edge offset out of bounds");
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto up = [&](const void* src, size_t bytes, void** dst) -> bool {
+        return cudaMalloc(dst, bytes) == cudaSuccess && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    size_t npp = s->np ? s->np : 1;
+    bool ok = up(vert_first, npp * 4, (void**)&s->vert_first) && up(vert_count, npp * 4, (void**)&s->vert_count) &&
+              up(faces_adj_to_vertex, (size_t)nadj * 4, (void**)&s->faces_adj_to_vertex) && up(edges_adj_to_vertex, (size_t)nadj * 4, (void**)&s->edges_adj_to_vertex) &&
+              up(hull_edge_first, (size_t)s->n * 4, (void**)&s->hull_edge_first) && up(edge_dir, (size_t)ne * 12, (void**)&s->edge_dir);
+    if (!ok) PB2_FAIL(ctx, PB2_ERR_CUDA, "shapes_set_hull_vertex_topology: device allocation or upload failed");
     return PB2_OK;
 }
 

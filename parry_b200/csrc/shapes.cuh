@@ -16,6 +16,9 @@ struct pb2_shapes {
     uint32_t *face_first = nullptr, *face_count = nullptr;             // nf, into the adjacency arrays
     uint32_t *verts_adj_to_face = nullptr, *edges_adj_to_face = nullptr;   // vertex ids local to the hull, edge ids
     uint32_t nf = 0, nadj = 0;
+    // vertex side of the topology (support_feature_id_toward): per point of the table; edge directions per table entry
+    uint32_t *vert_first = nullptr, *vert_count = nullptr, *faces_adj_to_vertex = nullptr, *edges_adj_to_vertex = nullptr, *hull_edge_first = nullptr;
+    float* edge_dir = nullptr;
     uint32_t* h_npoints = nullptr;   // host mirror: point count per entry (0 unless convex), for validating the topology
 };
 

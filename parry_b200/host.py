@@ -499,6 +499,14 @@ class Shapes:
             self.ctx.h, self.h, t["hull_face_first"].ctypes.data, t["hull_face_count"].ctypes.data, t["face_normal"].ctypes.data,
             t["face_first"].ctypes.data, t["face_count"].ctypes.data, len(t["face_first"]), t["vertices_adj_to_face"].ctypes.data,
             t["edges_adj_to_face"].ctypes.data, len(t["vertices_adj_to_face"])))
+        if "vert_first" in topology:   # vertex side (ball-vs-hull arm): per-point adjacency, edge directions
+            v = {k: np.ascontiguousarray(topology[k], dtype=np.float32 if k == "edge_dir" else np.uint32) for k in
+                 ("vert_first", "vert_count", "faces_adj_to_vertex", "edges_adj_to_vertex", "hull_edge_first", "edge_dir")}
+            assert len(v["hull_edge_first"]) == self.n
+            self.ctx.check(self.ctx._lib.pb2_shapes_set_hull_vertex_topology(
+                self.ctx.h, self.h, v["vert_first"].ctypes.data, v["vert_count"].ctypes.data, v["faces_adj_to_vertex"].ctypes.data,
+                v["edges_adj_to_vertex"].ctypes.data, len(v["faces_adj_to_vertex"]), v["hull_edge_first"].ctypes.data, v["edge_dir"].ctypes.data,
+                len(v["edge_dir"])))
 
     def compute_aabbs(self, shape_ids, poses):
         """Shape::compute_aabb(pos), batched (shape/shape.rs:369)."""

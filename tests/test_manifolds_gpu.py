@@ -95,8 +95,11 @@ def test_pfm_manifolds_vs_oracle(ctx, oracle):
     gn, gc, gp, gs = parry_b200.contact_manifolds(G, s1, p1, s2, p2, 0.05, max_points=12)
     kinds = np.array([0 if k == "ball" else 1 if k == "cuboid" else 2 for k, _ in spec])
     pfm = ((kinds[s1] == 2) | (kinds[s2] == 2)) & (kinds[s1] != 0) & (kinds[s2] != 0)
-    ballhull = ((kinds[s1] == 2) | (kinds[s2] == 2)) & ~pfm
-    assert pfm.mean() > 0.5 and (rs[pfm] == 0).all() and (rs[ballhull] == 2).all() and (rc[pfm] > 0).mean() > 0.3
+    ballhull = ((kinds[s1] == 2) | (kinds[s2] == 2)) & ~pfm      # contact_manifolds_convex_ball.rs with a ConvexPolyhedron
+    assert pfm.mean() > 0.5 and (rs == 0).all() and (rc[pfm] > 0).mean() > 0.3
+    assert ballhull.sum() > 1000 and (rc[ballhull] > 0).mean() > 0.2 and (rc[ballhull] <= 1).all()
+    hull_feat = np.where(kinds[s1[ballhull]] == 2, rp[ballhull, 0, 7].view(np.uint32), rp[ballhull, 0, 8].view(np.uint32))[rc[ballhull] > 0] >> 30
+    assert (np.bincount(hull_feat, minlength=4)[1:] > 10).all()      # vertex, edge and face features all occur
     host = gs == 3                                   # EPA arena overflow on the GPU: documented host fallback
     assert host.sum() <= 5
     ok = ~host
@@ -107,4 +110,4 @@ def test_pfm_manifolds_vs_oracle(ctx, oracle):
     # without topology the same pairs are status 2
     G2 = tables(ctx, oracle, spec)[1]
     _, c2, _, st2 = parry_b200.contact_manifolds(G2, s1, p1, s2, p2, 0.05, max_points=12)
-    assert (st2[pfm] == 2).all() and (c2[pfm] == 0).all() and (st2[~pfm & ~ballhull] == 0).all()
+    assert (st2[pfm | ballhull] == 2).all() and (c2[pfm | ballhull] == 0).all() and (st2[~pfm & ~ballhull] == 0).all()

@@ -416,3 +416,34 @@ def test_pfm_manifold_matches_cuboid_sat_manifold(oracle):
     for k in idx[:500]:
         np.testing.assert_allclose(rows(ph[k, :cc[k], :7]), rows(pc[k, :cc[k], :7]), rtol=0, atol=2.1e-3)
         assert (ph[k, cc[k], 7:].view(np.uint32) == 0).all()
+
+
+def test_ball_hull_manifold_matches_cuboid_closed_form(oracle):
+    """contact_manifolds_convex_ball.rs with a ConvexPolyhedron (GJK/EPA projection + support_feature_id_toward) against the same
+    arm with a Cuboid (closed-form projection, point_aabb.rs): on the hull of the cuboid's corners both give the same contact, and
+    the same kind of feature (vertex / edge / face) away from the 1-degree thresholds; and it agrees with query::contact."""
+    g = scenes.rng(17)
+    pts, _ = scenes.hull_pool(6, 16, seed=18)
+    he = np.array([0.3, 0.5, 0.4], np.float32)
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float32) * he
+    T = oracle.ShapeTable([("ball", 0.3), ("cuboid", he), ("convex", corners)] + [("convex", p * 0.6) for p in pts])
+    topo = T.hull_topology()
+    n = 6000
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 1.0 + 0.05)], axis=1).astype(np.float32)
+    z = np.zeros(n, np.uint32)
+    nb, cb, pb, sb = T.contact_manifolds(z, p1, z + 1, p2, 0.05)
+    nh, ch, ph, sh = T.contact_manifolds(z, p1, z + 2, p2, 0.05, topology=topo)
+    assert (sb == 0).all() and (sh == 0).all() and (cb == ch).all() and (cb > 0).sum() > 2000
+    both = cb > 0
+    assert np.abs(nb[both] - nh[both]).max() < 3e-3 and np.abs(pb[both, 0, :7] - ph[both, 0, :7]).max() < 1e-3
+    kb, kh = pb[both, 0, 8].view(np.uint32) >> 30, ph[both, 0, 8].view(np.uint32) >> 30      # flipped call: the solid's feature is fid2
+    assert (kb == kh).mean() > 0.98 and (np.bincount(kh, minlength=4)[1:] > 50).all()
+    s1 = g.integers(3, 9, n).astype(np.uint32)
+    nr, cr, pr, sr = T.contact_manifolds(s1, p1, z, p2, 0.05, topology=topo)
+    co, cs = T.contact(s1, p1, z, p2, 0.05)
+    assert (sr == 0).all() and ((cr > 0) == (cs == 1)).all()
+    b2 = cr > 0
+    assert (pr[b2, 0, 6] == co[b2, 12]).all()
