@@ -509,9 +509,46 @@ def also_mixed(ctx, stream, timed, flush, hbm_peak):
     ms = timed(frame, steps=5, warmup=2, flush=flush)
     P, Cn = state["pairs"], state["contacts"]
     alg = 24 * n + 8 * P + P * 8 + Cn * 56
-    return {"value": n / (ms * 1e-3), "unit": "colliders/s (frame: AABBs + Bvh build + self pairs + contacts)", "ms": ms,
-            "colliders": n, "pairs_per_frame": P, "contacts_per_frame": Cn, "pairs_per_s": P / (ms * 1e-3),
-            "l2": "flushed between iterations", "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+    out = {"value": n / (ms * 1e-3), "unit": "colliders/s (frame: AABBs + Bvh build + self pairs + contacts)", "ms": ms,
+           "colliders": n, "pairs_per_frame": P, "contacts_per_frame": Cn, "pairs_per_s": P / (ms * 1e-3),
+           "l2": "flushed between iterations", "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+    # the same frame ending in per-pair contact MANIFOLDS (BASELINE config[4] as worded): the pair list is expanded to per-pair
+    # shape / pose arrays on the device, then pb2_contact_manifolds_batch (all arms; first-frame manifolds). Hull topology for the
+    # pool comes from the test-side restatement of ConvexPolyhedron::from_convex_mesh, so this variant uses the first 256 pool hulls.
+    try:
+        from harness import hull_topology as ht
+        H2 = 256
+        hulls = [pts[h] for h in range(H2)]
+        t = ht.hull_table(hulls)
+        nsh = H + n
+        hf, hc, hef = np.zeros(nsh, np.uint32), np.zeros(nsh, np.uint32), np.zeros(nsh, np.uint32)
+        hf[:H2], hc[:H2], hef[:H2] = t["hull_face_first"], t["hull_face_count"], t["hull_edge_first"]
+        hf[H2:H], hc[H2:H] = t["hull_face_first"][0], t["hull_face_count"][0]     # unused pool entries: any valid range
+        npnt = H * 32
+        vf, vc = np.zeros(npnt, np.uint32), np.zeros(npnt, np.uint32)
+        vf[:H2 * 32], vc[:H2 * 32] = t["vert_first"], t["vert_count"]
+        G.set_hull_topology(dict(t, hull_face_first=hf, hull_face_count=hc, hull_edge_first=hef, vert_first=vf, vert_count=vc))
+        cs2 = torch.where(cs < H, cs % H2, cs)     # hull colliders draw from the 256 hulls that have topology
+        torch.cuda.synchronize()
+
+        def frame_manifolds():
+            # the gathers are torch kernels: they must run on the library's stream, or the library would read the per-pair arrays
+            # before torch has written them
+            with torch.cuda.stream(stream):
+                a = G.compute_aabbs(cs2, dposes)
+                bvh.insert_or_update_partially(a, torch.arange(n, dtype=torch.int32, device="cuda"), 0.0)
+                bvh.rebuild()
+                pr = bvh.traverse_bvtt_single_tree(capacity=16 * n, like=a).to(torch.int64)
+                i1, i2 = pr[:, 0], pr[:, 1]
+                state["m"] = parry_b200.contact_manifolds(G, cs2[i1], dposes[i1], cs2[i2], dposes[i2], 0.01, max_points=10)
+        ms2 = timed(frame_manifolds, steps=3, warmup=2, flush=flush)
+        cnt, st = state["m"][1], state["m"][3]
+        out["with_manifolds"] = {"ms": ms2, "value": n / (ms2 * 1e-3), "pairs_per_s": int(cnt.shape[0]) / (ms2 * 1e-3), "pairs_per_frame": int(cnt.shape[0]),
+                                 "manifolds_with_points": int((cnt > 0).sum().item()), "points": int(cnt.to(torch.int64).sum().item()),
+                                 "status_counts": torch.bincount(st.to(torch.int64), minlength=5).tolist()}
+    except Exception as e:
+        out["with_manifolds"] = {"error": repr(e)}
+    return out
 
 
 def also_mesh_contacts(ctx, stream, timed, flush, hbm_peak):
