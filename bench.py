@@ -620,9 +620,10 @@ def also_manifolds(ctx, stream, timed, flush, hbm_peak):
     hulls = [np.asarray(p, np.float32) * 0.6 for p in pts]
     G2 = parry_b200.Shapes(ctx, [parry_b200.Cuboid([0.3, 0.5, 0.4]), parry_b200.Cuboid([0.6, 0.2, 0.2])] + [parry_b200.ConvexPolyhedron(h) for h in hulls])
     t = ht.hull_table(hulls)
-    hf, hc = np.zeros(66, np.uint32), np.zeros(66, np.uint32)
-    hf[2:], hc[2:] = t["hull_face_first"], t["hull_face_count"]
-    t = dict(t, hull_face_first=hf, hull_face_count=hc)
+    hf, hc, hef = np.zeros(66, np.uint32), np.zeros(66, np.uint32), np.zeros(66, np.uint32)
+    hf[2:], hc[2:], hef[2:] = t["hull_face_first"], t["hull_face_count"], t["hull_edge_first"]
+    # per table entry; the vertex-side arrays are per point, and the table's points are exactly the hulls' points in order
+    t = dict(t, hull_face_first=hf, hull_face_count=hc, hull_edge_first=hef)
     G2.set_hull_topology(t)
     m = 1 << 20
     h1, h2 = g.integers(0, 66, m).astype(np.int32), g.integers(2, 66, m).astype(np.int32)
