@@ -447,3 +447,36 @@ def test_ball_hull_manifold_matches_cuboid_closed_form(oracle):
     assert (sr == 0).all() and ((cr > 0) == (cs == 1)).all()
     b2 = cr > 0
     assert (pr[b2, 0, 6] == co[b2, 12]).all()
+
+
+def test_hull_topology_builder_invariants():
+    """harness/hull_topology.py (restatement of ConvexPolyhedron::from_convex_mesh over Qhull triangles): Euler's formula on the
+    merged faces, outward unit normals, consistent vertex <-> face / edge adjacency; a cube gives 6 quads and 12 live edges."""
+    from harness import hull_topology as ht
+    he = np.array([0.7, 0.4, 1.1], np.float32)
+    cube = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float32) * he
+    t = ht.from_convex_mesh(cube, ht.hull_triangles(cube))
+    assert len(t["face_first"]) == 6 and (t["face_count"] == 4).all() and t["num_edges"] == 18
+    assert len(set(t["edges_adj_to_face"].tolist())) == 12          # the 6 face diagonals are deleted edges
+    assert sorted(np.abs(t["face_normal"]).argmax(axis=1).tolist()) == [0, 0, 1, 1, 2, 2]
+    pts, _ = scenes.hull_pool(6, 24, seed=77)
+    for p in pts:
+        t = ht.from_convex_mesh(p, ht.hull_triangles(p))
+        nf, live = len(t["face_first"]), len(set(t["edges_adj_to_face"].tolist()))
+        assert len(p) - live + nf == 2                                # V - E + F = 2 on the merged faces
+        assert np.abs(np.linalg.norm(t["face_normal"], axis=1) - 1).max() < 1e-5
+        for f in range(nf):
+            vs = t["vertices_adj_to_face"][t["face_first"][f]:t["face_first"][f] + t["face_count"][f]]
+            c = p[vs].mean(axis=0)
+            assert np.dot(t["face_normal"][f], c) > 0                 # outward (the hull contains the origin)
+            # coplanar within what the reference's merge rule lets through (adjacent triangle normals within ~1.5 degrees, chained)
+            assert np.abs((p[vs] - c) @ t["face_normal"][f]).max() < 5e-2
+        # vertex side: every (vertex, face) incidence appears exactly once, with the face's edge leaving that vertex
+        assert int(t["vert_count"].sum()) == len(t["vertices_adj_to_face"])
+        for v in range(len(p)):
+            fs = t["faces_adj_to_vertex"][t["vert_first"][v]:t["vert_first"][v] + t["vert_count"][v]]
+            assert len(fs) >= 3
+            for f in fs:
+                vs = t["vertices_adj_to_face"][t["face_first"][f]:t["face_first"][f] + t["face_count"][f]]
+                assert v in vs
+        assert np.abs(np.linalg.norm(t["edge_dir"], axis=1) - 1).max() < 1e-5
