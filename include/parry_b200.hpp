@@ -203,6 +203,53 @@ inline void cast_shapes(const Context& c, const pb2_shapes* shapes, const std::v
                                   o.max_time_of_impact, o.target_distance, o.stop_at_penetration, o.compute_impact_geometry_on_penetration,
                                   (uint32_t)g1.size(), out[0].witness1, status.data(), PB2_MEM_HOST));
 }
+// query::closest_points(pos1, g1, pos2, g2, max_dist) for n pairs (closest_points_shape_shape.rs:220-231)
+enum class ClosestPointsKind : uint8_t { Disjoint = 0, WithinMargin = 1, Intersecting = 2 };   // query::ClosestPoints
+struct ClosestPoints { float p1[3], p2[3]; };   // world-space points, meaningful for WithinMargin
+inline void closest_points(const Context& c, const pb2_shapes* shapes, const std::vector<uint32_t>& g1, const std::vector<Isometry>& pos1,
+                           const std::vector<uint32_t>& g2, const std::vector<Isometry>& pos2, float max_dist, std::vector<ClosestPoints>& out,
+                           std::vector<ClosestPointsKind>& kind, std::vector<uint8_t>& status) {
+    out.resize(g1.size()); kind.resize(g1.size()); status.resize(g1.size());
+    c.check(pb2_closest_points_batch(c.get(), shapes, g1.data(), g2.data(), pos1[0].rotation, pos2[0].rotation, max_dist, (uint32_t)g1.size(),
+                                     out[0].p1, reinterpret_cast<uint8_t*>(kind.data()), status.data(), PB2_MEM_HOST));
+}
+// query::distance / query::intersection_test for n pairs (distance.rs:89-97, intersection_test.rs:88-96); status 3 = host (cuboid-cuboid SAT arm)
+inline void distance(const Context& c, const pb2_shapes* shapes, const std::vector<uint32_t>& g1, const std::vector<Isometry>& pos1,
+                     const std::vector<uint32_t>& g2, const std::vector<Isometry>& pos2, std::vector<float>& dist, std::vector<uint8_t>& status) {
+    dist.resize(g1.size()); status.resize(g1.size());
+    c.check(pb2_distance_batch(c.get(), shapes, g1.data(), g2.data(), pos1[0].rotation, pos2[0].rotation, (uint32_t)g1.size(), dist.data(),
+                               status.data(), PB2_MEM_HOST));
+}
+inline void intersection_test(const Context& c, const pb2_shapes* shapes, const std::vector<uint32_t>& g1, const std::vector<Isometry>& pos1,
+                              const std::vector<uint32_t>& g2, const std::vector<Isometry>& pos2, std::vector<uint8_t>& hit,
+                              std::vector<uint8_t>& status) {
+    hit.resize(g1.size()); status.resize(g1.size());
+    c.check(pb2_intersection_test_batch(c.get(), shapes, g1.data(), g2.data(), pos1[0].rotation, pos2[0].rotation, (uint32_t)g1.size(), hit.data(),
+                                        status.data(), PB2_MEM_HOST));
+}
+// contact_manifolds(pos1.inv_mul(pos2), g1, g2, prediction, ..) on empty manifolds for n pairs (default_query_dispatcher.rs:629-835)
+struct TrackedContact { float local_p1[3], local_p2[3], dist; uint32_t fid1, fid2; };   // contact_manifold.rs; fids are PackedFeatureId bits
+struct ManifoldNormals { float local_n1[3], local_n2[3]; };
+inline void contact_manifolds(const Context& c, const pb2_shapes* shapes, const std::vector<uint32_t>& g1, const std::vector<Isometry>& pos1,
+                              const std::vector<uint32_t>& g2, const std::vector<Isometry>& pos2, float prediction, uint32_t max_points,
+                              std::vector<ManifoldNormals>& normals, std::vector<uint32_t>& counts, std::vector<TrackedContact>& points,
+                              std::vector<uint8_t>& status) {
+    size_t n = g1.size();
+    normals.resize(n); counts.resize(n); points.resize(n * max_points); status.resize(n);
+    static_assert(sizeof(TrackedContact) == 36 && sizeof(ManifoldNormals) == 24, "layout of pb2_contact_manifolds_batch");
+    c.check(pb2_contact_manifolds_batch(c.get(), shapes, g1.data(), g2.data(), pos1[0].rotation, pos2[0].rotation, prediction, (uint32_t)n, max_points,
+                                        normals[0].local_n1, counts.data(), points[0].local_p1, status.data(), PB2_MEM_HOST));
+}
+// query::contact with a Compound on one side (contact_composite_shape_shape.rs:14-76)
+inline void contact_compound(const Context& c, const pb2_compounds* compounds, const std::vector<uint32_t>& compound_ids,
+                             const std::vector<Isometry>& compound_poses, const std::vector<uint32_t>& shape_ids, const std::vector<Isometry>& shape_poses,
+                             float prediction, bool compound_second, std::vector<pb2_contact>& out, std::vector<uint8_t>& status,
+                             std::vector<uint32_t>& part) {
+    size_t n = compound_ids.size();
+    out.resize(n); status.resize(n); part.resize(n);
+    c.check(pb2_compound_contact_shapes(c.get(), compounds, compound_ids.data(), compound_poses[0].rotation, shape_ids.data(), shape_poses[0].rotation,
+                                        (uint32_t)n, prediction, compound_second ? 1 : 0, out.data(), status.data(), part.data(), PB2_MEM_HOST));
+}
 }  // namespace query
 
 }  // namespace pb2

@@ -70,3 +70,12 @@ def test_integration_doc_lists_every_entry_point():
     assert len(declared) > 40
     missing = sorted(d for d in declared if ("pub fn %s(" % d) not in doc)
     assert not missing, missing
+
+
+def test_cpp_mirror_header_compiles(tmp_path):
+    """include/parry_b200.hpp (the header-only C++ host mirror) compiles against include/parry_b200.h with a plain host compiler."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hpp_check.cpp"
+    src.write_text('#include "parry_b200.hpp"\nint main() { return 0; }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
