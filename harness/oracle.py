@@ -64,6 +64,7 @@ def lib():
         l.pb2o_contact_manifolds_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, u32, i32, P, P, P, P]
         l.pb2o_contact_manifolds_batch2.argtypes = [P] * 20 + [f32, u32, u32, i32, P, P, P, P]
         l.pb2o_closest_points_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, P, P, P]
+        l.pb2o_manifolds_try_update.argtypes = [P, P, u32, u32, P, P, P, P]
         l.pb2o_convex_cast_ray.restype = i32
         l.pb2o_convex_cast_ray.argtypes = [P, u32, P, P, f32, i32, P, P]
         l.pb2o_shape_cast_ray.restype = i32
@@ -373,6 +374,19 @@ class ShapeTable:
                                           psid.ctypes.data, pp.ctypes.data, cid.ctypes.data, pc.ctypes.data, sid.ctypes.data, ps.ctypes.data,
                                           prediction, int(compound_second), n, threads, out.ctypes.data, status.ctypes.data, part.ctypes.data)
         return out, status, part
+
+    @staticmethod
+    def manifolds_try_update(pos1, pos2, normals, counts, points):
+        """ContactManifold::try_update_contacts on manifolds as returned by contact_manifolds; returns (kept (n,) u8, points') with
+        dists / local_p1 refreshed for the points visited before a rejection (in-place semantics of the reference)."""
+        p1, p2 = _f32(pos1), _f32(pos2)
+        n, mp = len(counts), points.shape[1]
+        nr = np.ascontiguousarray(normals, dtype=np.float32).copy()
+        ct = np.ascontiguousarray(counts, dtype=np.uint32)
+        pts = np.ascontiguousarray(points, dtype=np.float32).copy()
+        kept = np.zeros(n, dtype=np.uint8)
+        lib().pb2o_manifolds_try_update(p1.ctypes.data, p2.ctypes.data, n, mp, nr.ctypes.data, ct.ctypes.data, pts.ctypes.data, kept.ctypes.data)
+        return kept, pts
 
     def hull_topology(self):
         """Face topology of every ConvexPolyhedron of the table (harness/hull_topology.py), indexed per table entry:

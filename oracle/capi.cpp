@@ -358,6 +358,24 @@ void pb2o_contact_manifolds_batch(const uint8_t* kinds, const float* params4, co
                                   nullptr, nullptr, nullptr, shape1, shape2, pos1, pos2,
                                   prediction, n, max_points, nthreads, normals, counts, pts, status);
 }
+// ContactManifold::try_update_contacts on n manifolds in the layout of pb2o_contact_manifolds_batch (normals n x 6, counts n,
+// pts n x max_points x 9), in place; kept[k] = 1 when the manifold survives under pos1[k].inv_mul(pos2[k]).
+void pb2o_manifolds_try_update(const float* pos1, const float* pos2, uint32_t n, uint32_t max_points, float* normals, const uint32_t* counts,
+                               float* pts, uint8_t* kept) {
+    for (uint32_t k = 0; k < n; ++k) {
+        Manifold m;
+        m.local_n1 = ld3(normals + 6 * (size_t)k); m.local_n2 = ld3(normals + 6 * (size_t)k + 3);
+        float* q = pts + (size_t)k * max_points * 9;
+        for (uint32_t i = 0; i < counts[k]; ++i) {
+            TrackedContact t; t.local_p1 = ld3(q + 9 * i); t.local_p2 = ld3(q + 9 * i + 3); t.dist = q[9 * i + 6];
+            memcpy(&t.fid1, q + 9 * i + 7, 4); memcpy(&t.fid2, q + 9 * i + 8, 4);
+            m.points.push_back(t);
+        }
+        Iso pos12 = Iso::from7(pos1 + 7 * (size_t)k).inv_mul(Iso::from7(pos2 + 7 * (size_t)k));
+        kept[k] = manifold_try_update_contacts(m, pos12) ? 1 : 0;
+        for (uint32_t i = 0; i < counts[k]; ++i) { st3(q + 9 * i, m.points[i].local_p1); q[9 * i + 6] = m.points[i].dist; }
+    }
+}
 // query::cast_shapes for n pairs (shape_cast.rs:268-286). vel1/vel2: n x 3. out: n x 13 floats {witness1, witness2, normal1,
 // normal2, time_of_impact} (witness/normal i in the local frame of shape i, as the reference returns them);
 // status: 0 None, 1 Converged, 2 PenetratingOrWithinTargetDist.

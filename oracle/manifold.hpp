@@ -360,11 +360,44 @@ static inline bool manifold_pfm_pfm(const Iso& pos12, const ShapeRef& s1, const 
     return true;
 }
 
+// ContactManifold::try_update_contacts[_eps] (contact_manifold.rs:652-699): keep last frame's manifold under the new pos12 if its
+// normal turned by less than the angle threshold and every point, re-projected along local_n1, stayed within sqrt(dist_sq_threshold)
+// of where it was without switching between penetrating and separated; dists and local_p1 are refreshed. Points already
+// updated stay updated when a later point rejects the manifold (the reference mutates in place, then recomputes everything).
+#define PB2O_COS_1_DEGREES 0.99984769515f   // utils::COS_1_DEGREES
+static inline bool manifold_try_update_contacts(Manifold& m, const Iso& pos12, Real angle_dot_threshold = PB2O_COS_1_DEGREES,
+                                                Real dist_sq_threshold = 1.0e-6f) {
+    if (m.points.empty()) return false;
+    Vec3 local_n2 = pos12.transform_vector(m.local_n2);
+    if (-dot(m.local_n1, local_n2) < angle_dot_threshold) return false;
+    for (auto& pt : m.points) {
+        Vec3 local_p2 = pos12.transform_point(pt.local_p2);
+        Vec3 dpt = local_p2 - pt.local_p1;
+        Real dist = dot(dpt, m.local_n1);
+        if (dist * pt.dist < 0.0f) return false;
+        Vec3 new_local_p1 = local_p2 - m.local_n1 * dist;
+        Vec3 dd = pt.local_p1 - new_local_p1;
+        if (norm_squared(dd) > dist_sq_threshold) return false;
+        pt.dist = dist;
+        pt.local_p1 = new_local_p1;
+    }
+    return true;
+}
+
 enum ManifoldStatus { MANIFOLD_OK = 0, MANIFOLD_UNSUPPORTED = 2 };
 // DefaultQueryDispatcher::contact_manifold_convex_convex arms for Ball / Cuboid (default_query_dispatcher.rs:760-782); pairs with
 // a ConvexPolyhedron go through pfm_pfm when the hull's face topology is supplied, and are reported unsupported otherwise.
+// `m` carries last frame's manifold when persistent != 0 (QueryDispatcher::contact_manifolds is called with the same manifold
+// object every frame): the cuboid-cuboid and pfm_pfm arms first try to keep it (contact_manifolds_cuboid_cuboid.rs:30,
+// contact_manifolds_pfm_pfm.rs:64); *kept = true when they did. The ball arms always recompute.
 static inline int dispatch_manifold(const Iso& pos12, const ShapeRef& s1, const ShapeRef& s2, Real prediction, Manifold& m,
-                                    const HullTopology* t1 = nullptr, const HullTopology* t2 = nullptr) {
+                                    const HullTopology* t1 = nullptr, const HullTopology* t2 = nullptr, bool persistent = false,
+                                    bool* kept = nullptr) {
+    if (kept) *kept = false;
+    if (persistent && s1.kind != SHAPE_BALL && s2.kind != SHAPE_BALL) {
+        bool pfm_ok = (s1.kind == SHAPE_CUBOID || t1) && (s2.kind == SHAPE_CUBOID || t2);
+        if (pfm_ok && manifold_try_update_contacts(m, pos12)) { if (kept) *kept = true; return MANIFOLD_OK; }
+    }
     m.clear(); m.local_n1 = Vec3(); m.local_n2 = Vec3();
     if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_BALL) { manifold_ball_ball(pos12, s1.radius, s2.radius, prediction, m); return MANIFOLD_OK; }
     if (s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_CUBOID) { manifold_cuboid_cuboid(pos12, s1.half_extents, s2.half_extents, prediction, m); return MANIFOLD_OK; }

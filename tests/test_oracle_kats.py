@@ -480,3 +480,44 @@ def test_hull_topology_builder_invariants():
                 vs = t["vertices_adj_to_face"][t["face_first"][f]:t["face_first"][f] + t["face_count"][f]]
                 assert v in vs
         assert np.abs(np.linalg.norm(t["edge_dir"], axis=1) - 1).max() < 1e-5
+
+
+def test_manifold_try_update_contacts(oracle):
+    """ContactManifold::try_update_contacts (contact_manifold.rs:652-699), oracle groundwork for manifold persistence: an unchanged
+    pose keeps every manifold (values re-derived within a few ulps); a 1e-4 drift keeps most of them and the refreshed dists track a fresh computation; a
+    5-degree turn drops them all; empty manifolds are never kept."""
+    g = scenes.rng(23)
+    T = oracle.ShapeTable([("cuboid", [0.3, 0.5, 0.4]), ("cuboid", [0.6, 0.2, 0.2]), ("cuboid", [0.5, 0.5, 0.5])])
+    n = 4000
+    s1, s2 = g.integers(0, 3, n).astype(np.uint32), g.integers(0, 3, n).astype(np.uint32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 1.0 + 0.3)], axis=1).astype(np.float32)
+    p2[::3, :4] = p1[::3, :4]
+    nr, cnt, pts, st = T.contact_manifolds(s1, p1, s2, p2, 0.05)
+    has = cnt > 0
+    kept, q = oracle.ShapeTable.manifolds_try_update(p1, p2, nr, cnt, pts)
+    assert (kept[has] == 1).all() and (kept[~has] == 0).all()
+    # (dist and local_p1 are re-derived from local_p2 and the normal: same values up to a few ulps of the coordinates)
+    assert np.abs(q[has] - pts[has])[:, :, :7].max() < 2e-5 and (q[:, :, 7:].view(np.uint32) == pts[:, :, 7:].view(np.uint32)).all()
+    moved = p2.copy()
+    moved[:, 4:] += (d * 1.0e-4).astype(np.float32)
+    kept2, q2 = oracle.ShapeTable.manifolds_try_update(p1, moved, nr, cnt, pts)
+    assert kept2[has].mean() > 0.9
+    nr3, cnt3, pts3, _ = T.contact_manifolds(s1, p1, s2, moved, 0.05)
+    k = (kept2 == 1) & (cnt3 == cnt)
+    valid = np.arange(pts.shape[1])[None, :] < cnt[:, None]
+    # (a fresh computation may pick another separating axis near a tie, hence a quantile and not the maximum)
+    assert np.quantile(np.abs((q2[:, :, 6] - pts3[:, :, 6])[k][valid[k]]), 0.99) < 2e-4
+    c5, s5 = np.cos(np.radians(2.5)), np.sin(np.radians(2.5))
+    turn = np.array([s5, 0.0, 0.0, c5])                      # 5 degrees about x, composed onto every pose of shape 2
+    def qmul(a, b):
+        ai, aj, ak, aw = a[:, 0], a[:, 1], a[:, 2], a[:, 3]
+        bi, bj, bk, bw = b
+        return np.stack([aw * bi + ai * bw + aj * bk - ak * bj, aw * bj - ai * bk + aj * bw + ak * bi,
+                         aw * bk + ai * bj - aj * bi + ak * bw, aw * bw - ai * bi - aj * bj - ak * bk], axis=1)
+    turned = p2.copy()
+    turned[:, :4] = qmul(p2[:, :4].astype(np.float64), turn).astype(np.float32)
+    kept5, _ = oracle.ShapeTable.manifolds_try_update(p1, turned, nr, cnt, pts)
+    assert kept5[has].mean() < 0.35      # only manifolds whose normal is (nearly) the turn axis survive
