@@ -65,6 +65,7 @@ def lib():
         l.pb2o_contact_manifolds_batch2.argtypes = [P] * 20 + [f32, u32, u32, i32, P, P, P, P]
         l.pb2o_closest_points_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, P, P, P]
         l.pb2o_manifolds_try_update.argtypes = [P, P, u32, u32, P, P, P, P]
+        l.pb2o_compound_compound_contact_batch.argtypes = [P, P, P, P, P, P, P, P, P, P, P, f32, u32, i32, P, P, P]
         l.pb2o_convex_cast_ray.restype = i32
         l.pb2o_convex_cast_ray.argtypes = [P, u32, P, P, f32, i32, P, P]
         l.pb2o_shape_cast_ray.restype = i32
@@ -447,6 +448,20 @@ class ShapeTable:
         lib().pb2o_closest_points_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, s1.ctypes.data, s2.ctypes.data,
                                         p1.ctypes.data, p2.ctypes.data, max_dist, n, threads, out.ctypes.data, kind.ctypes.data, status.ctypes.data)
         return out, kind, status
+
+    def contact_compound_compound(self, comp_first, comp_count, part_shape, part_pose, id1, pos1, id2, pos2, prediction, threads=1):
+        """query::contact(pos1, Compound id1, pos2, Compound id2) per pair (oracle groundwork; no GPU path yet): (out (n,13),
+        status, parts (n,2) winning part of each compound)."""
+        cf, cc, psid, a, b = _u32(comp_first), _u32(comp_count), _u32(part_shape), _u32(id1), _u32(id2)
+        pp, p1, p2 = _f32(part_pose), _f32(pos1), _f32(pos2)
+        n = len(a)
+        out = np.zeros((n, 13), dtype=np.float32)
+        status = np.zeros(n, dtype=np.uint8)
+        parts = np.zeros((n, 2), dtype=np.uint32)
+        lib().pb2o_compound_compound_contact_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, cf.ctypes.data,
+                                                   cc.ctypes.data, psid.ctypes.data, pp.ctypes.data, a.ctypes.data, p1.ctypes.data, b.ctypes.data,
+                                                   p2.ctypes.data, prediction, n, threads, out.ctypes.data, status.ctypes.data, parts.ctypes.data)
+        return out, status, parts
 
     def distance(self, shape1, pos1, shape2, pos2, threads=1):
         """query::distance per pair: (dist (n,), status (n,): 0 Ok, 2 Unsupported, 3 cuboid-cuboid)."""

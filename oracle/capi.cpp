@@ -376,6 +376,34 @@ void pb2o_manifolds_try_update(const float* pos1, const float* pos2, uint32_t n,
         for (uint32_t i = 0; i < counts[k]; ++i) { st3(q + 9 * i, m.points[i].local_p1); q[9 * i + 6] = m.points[i].dist; }
     }
 }
+// query::contact between two Compounds (ids into the same compound table) for n pairs; result in world space; parts: n x 2.
+void pb2o_compound_compound_contact_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* comp_first,
+                                          const uint32_t* comp_count, const uint32_t* part_shape, const float* part_pose7, const uint32_t* id1,
+                                          const float* pos1, const uint32_t* id2, const float* pos2, float prediction, uint32_t n, int nthreads,
+                                          float* out, uint8_t* status, uint32_t* parts) {
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        std::vector<ShapeRef> s1, s2; std::vector<Iso> q1, q2;
+        auto load = [&](uint32_t c, std::vector<ShapeRef>& ss, std::vector<Iso>& qq) {
+            uint32_t f = comp_first[c], cnt = comp_count[c];
+            ss.resize(cnt); qq.resize(cnt);
+            for (uint32_t i = 0; i < cnt; ++i) { ss[i] = make_shape(kinds, params4, points, part_shape[f + i]); qq[i] = Iso::from7(part_pose7 + 7 * (size_t)(f + i)); }
+        };
+        for (size_t k = lo; k < hi; ++k) {
+            load(id1[k], s1, q1); load(id2[k], s2, q2);
+            CompoundRef a{s1.data(), q1.data(), (uint32_t)s1.size()}, b{s2.data(), q2.data(), (uint32_t)s2.size()};
+            Iso p1 = Iso::from7(pos1 + 7 * k), p2 = Iso::from7(pos2 + 7 * k);
+            Contact ct = Contact(); uint32_t i1 = UINT32_MAX, i2 = UINT32_MAX;
+            int st = contact_compound_compound(p1.inv_mul(p2), a, b, prediction, ct, i1, i2);
+            status[k] = (uint8_t)st; parts[2 * k] = st == CONTACT_SOME ? i1 : UINT32_MAX; parts[2 * k + 1] = st == CONTACT_SOME ? i2 : UINT32_MAX;
+            float* o = out + 13 * k;
+            if (st == CONTACT_SOME) {
+                ct.point1 = p1.transform_point(ct.point1); ct.point2 = p2.transform_point(ct.point2);
+                ct.normal1 = p1.transform_vector(ct.normal1); ct.normal2 = p2.transform_vector(ct.normal2);
+                st3(o, ct.point1); st3(o + 3, ct.point2); st3(o + 6, ct.normal1); st3(o + 9, ct.normal2); o[12] = ct.dist;
+            } else for (int i = 0; i < 13; ++i) o[i] = 0.0f;
+        }
+    });
+}
 // query::cast_shapes for n pairs (shape_cast.rs:268-286). vel1/vel2: n x 3. out: n x 13 floats {witness1, witness2, normal1,
 // normal2, time_of_impact} (witness/normal i in the local frame of shape i, as the reference returns them);
 // status: 0 None, 1 Converged, 2 PenetratingOrWithinTargetDist.

@@ -401,6 +401,43 @@ static inline int contact_compound_shape(const Iso& pos12, const CompoundRef& co
     }
     return have ? CONTACT_SOME : CONTACT_NONE;
 }
+// Compound vs Compound through the same dispatcher arms (default_query_dispatcher.rs:338-351): shape1 composite =>
+// contact_composite_shape_shape(pos12, c1, shape2 = the other compound): every part of c1 whose AABB meets the loosened AABB of
+// compound 2 (Shape::compute_aabb default = local_aabb.transform_by(pos), aabb.rs:492-498; Compound::local_aabb = merge of the
+// part AABBs, compound.rs:120-126) is dispatched against the whole compound 2, which lands in contact_shape_composite_shape
+// (:63-76): pose.inverse(), compound 2 as the composite, the part as the shape, flipped(). Oracle groundwork (no GPU path yet).
+static inline Aabb compound_local_aabb(const CompoundRef& c) {
+    Aabb a(Vec3(REAL_MAX, REAL_MAX, REAL_MAX), Vec3(-REAL_MAX, -REAL_MAX, -REAL_MAX));
+    for (uint32_t i = 0; i < c.n; ++i) { Aabb b = shape_compute_aabb(c.shapes[i], c.poses[i]); a.mins = vinf(a.mins, b.mins); a.maxs = vsup(a.maxs, b.maxs); }
+    return a;
+}
+static inline Aabb aabb_transform_by(const Aabb& a, const Iso& m) {
+    Vec3 c = m.transform_point(center(a.mins, a.maxs));
+    Vec3 he = m.absolute_transform_vector((a.maxs - a.mins) * 0.5f);
+    return Aabb(c + (-he), c + he);
+}
+static inline int contact_compound_compound(const Iso& pos12, const CompoundRef& c1, const CompoundRef& c2, Real prediction, Contact& best,
+                                            uint32_t& part1, uint32_t& part2) {
+    Aabb ls = aabb_transform_by(compound_local_aabb(c2), pos12);
+    ls.mins = ls.mins - Vec3(prediction, prediction, prediction);
+    ls.maxs = ls.maxs + Vec3(prediction, prediction, prediction);
+    bool have = false;
+    for (uint32_t i = 0; i < c1.n; ++i) {
+        if (!shape_compute_aabb(c1.shapes[i], c1.poses[i]).intersects(ls)) continue;
+        Iso pos_i2 = c1.poses[i].inv_mul(pos12);          // pose of compound 2 in part i's frame
+        Contact c = Contact(); uint32_t j = UINT32_MAX;
+        // dispatcher.contact(pos_i2, part_i, compound2) -> contact_shape_composite_shape: inverse pose, flipped result
+        if (contact_compound_shape(pos_i2.inverse(), c2, c1.shapes[i], prediction, c, j) != CONTACT_SOME) continue;
+        std::swap(c.point1, c.point2); std::swap(c.normal1, c.normal2);
+        if (!have || c.dist < best.dist) {
+            c.point1 = c1.poses[i].transform_point(c.point1);
+            c.normal1 = c1.poses[i].transform_vector(c.normal1);
+            best = c; part1 = i; part2 = j; have = true;
+        }
+    }
+    return have ? CONTACT_SOME : CONTACT_NONE;
+}
+
 // query::contact with a Compound on one side (default_query_dispatcher.rs:338-351): compound first = composite arm; compound
 // second (flipped) = contact_shape_composite_shape (contact_composite_shape_shape.rs:63-76): pose12.inverse(), then flipped().
 static inline int query_contact_compound(const Iso& pos1, const Iso& pos2, const CompoundRef& comp, const ShapeRef& shape, bool compound_second,

@@ -521,3 +521,59 @@ def test_manifold_try_update_contacts(oracle):
     turned[:, :4] = qmul(p2[:, :4].astype(np.float64), turn).astype(np.float32)
     kept5, _ = oracle.ShapeTable.manifolds_try_update(p1, turned, nr, cnt, pts)
     assert kept5[has].mean() < 0.35      # only manifolds whose normal is (nearly) the turn axis survive
+
+
+def test_compound_compound_contact_against_part_pairs(oracle):
+    """Compound vs Compound (oracle groundwork, default_query_dispatcher.rs:338-351 nested through contact_shape_composite_shape): the
+    result must be the closest of the contacts between all part pairs — computed here with plain query::contact on composed poses —
+    and single identity-part compounds on both sides must reproduce the plain contact."""
+    g = scenes.rng(31)
+    pts, _ = scenes.hull_pool(4, 16, seed=32)
+    spec = [("ball", 0.3), ("ball", 0.2), ("cuboid", [0.25, 0.4, 0.3]), ("cuboid", [0.5, 0.15, 0.2])] + [("convex", p * 0.5) for p in pts]
+    T = oracle.ShapeTable(spec)
+    ns = len(spec)
+    first, count, psid, ppose = [], [], [], []
+    for c in range(16):
+        k = int(g.integers(1, 4))
+        first.append(len(psid)); count.append(k)
+        psid += [int(x) for x in g.integers(0, ns, k)]
+        ppose.append(np.concatenate([scenes.random_unit_quaternions(g, k), (g.random((k, 3)) - 0.5) * 1.2], axis=1))
+    first, count, psid = np.asarray(first, np.uint32), np.asarray(count, np.uint32), np.asarray(psid, np.uint32)
+    ppose = np.concatenate(ppose).astype(np.float32)
+    n = 1500
+    a, b = g.integers(0, 16, n).astype(np.uint32), g.integers(0, 16, n).astype(np.uint32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 2.0 + 0.2)], axis=1).astype(np.float32)
+    out, st, parts = T.contact_compound_compound(first, count, psid, ppose, a, p1, b, p2, 0.05, threads=4)
+    assert 0.15 < (st == 1).mean() < 0.9
+
+    def compose(p, q):       # world pose of a part: p * q, float64
+        def rot(qt, v):
+            u, w = qt[:3], qt[3]
+            t = 2.0 * np.cross(u, v)
+            return v + w * t + np.cross(u, t)
+        pq, pt, qq, qt = p[:4].astype(np.float64), p[4:].astype(np.float64), q[:4].astype(np.float64), q[4:].astype(np.float64)
+        w = pq[3] * qq[3] - np.dot(pq[:3], qq[:3])
+        v = pq[3] * qq[:3] + qq[3] * pq[:3] + np.cross(pq[:3], qq[:3])
+        return np.concatenate([v, [w], pt + rot(pq, qt)]).astype(np.float32)
+    for k in range(0, n, 5):
+        best = None
+        for i in range(count[a[k]]):
+            for j in range(count[b[k]]):
+                gi, gj = first[a[k]] + i, first[b[k]] + j
+                o, s = T.contact([psid[gi]], [compose(p1[k], ppose[gi])], [psid[gj]], [compose(p2[k], ppose[gj])], 0.05)
+                if s[0] == 1 and (best is None or o[0, 12] < best):
+                    best = o[0, 12]
+        if best is None or st[k] != 1:
+            # borderline pairs (dist within rounding of the prediction) may flip between the two ways of composing the poses
+            assert (best is None) == (st[k] != 1) or abs((best if best is not None else out[k, 12]) - 0.05) < 1e-4
+        else:
+            assert abs(out[k, 12] - best) < 2e-5
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    cf, cc = np.arange(ns, dtype=np.uint32), np.ones(ns, np.uint32)
+    o1, s1, _ = T.contact_compound_compound(cf, cc, np.arange(ns, dtype=np.uint32), np.tile(ident, (ns, 1)), a % ns, p1, b % ns, p2, 0.05)
+    o2, s2 = T.contact(a % ns, p1, b % ns, p2, 0.05)
+    assert (s1 == s2).all()
+    np.testing.assert_allclose(o1[s2 == 1], o2[s2 == 1], rtol=1e-4, atol=2e-5)
