@@ -65,6 +65,7 @@ def lib():
         l.pb2o_contact_manifolds_batch2.argtypes = [P] * 20 + [f32, u32, u32, i32, P, P, P, P]
         l.pb2o_closest_points_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, P, P, P]
         l.pb2o_manifolds_try_update.argtypes = [P, P, u32, u32, P, P, P, P]
+        l.pb2o_contact_manifolds_update_batch.argtypes = [P] * 20 + [f32, u32, u32, i32, i32, P, P, P, P, P, P]
         l.pb2o_compound_compound_contact_batch.argtypes = [P, P, P, P, P, P, P, P, P, P, P, f32, u32, i32, P, P, P]
         l.pb2o_convex_cast_ray.restype = i32
         l.pb2o_convex_cast_ray.argtypes = [P, u32, P, P, f32, i32, P, P]
@@ -436,6 +437,30 @@ class ShapeTable:
                                             s2.ctypes.data, p1.ctypes.data, p2.ctypes.data, prediction, n, max_points, threads,
                                             normals.ctypes.data, counts.ctypes.data, pts.ctypes.data, status.ctypes.data)
         return normals, counts, pts, status
+
+    def contact_manifolds_update(self, shape1, pos1, shape2, pos2, prediction, normals, counts, points, threads=1, topology=None,
+                                 seed_gjk=False):
+        """contact_manifolds called again with last frame's manifolds (as returned by contact_manifolds): (normals, counts, points,
+        status, kept (n,) u8, match (n,max_points) i32). seed_gjk: the pfm_pfm recomputation starts GJK from last frame's normal
+        like the reference (contact_manifolds_pfm_pfm.rs:66); False restates the GPU path (default first direction)."""
+        s1, s2, p1, p2 = _u32(shape1), _u32(shape2), _f32(pos1), _f32(pos2)
+        n, max_points = len(s1), points.shape[1]
+        normals = np.ascontiguousarray(normals, dtype=np.float32).copy()
+        counts = np.ascontiguousarray(counts, dtype=np.uint32).copy()
+        pts = np.ascontiguousarray(points, dtype=np.float32).copy()
+        status = np.zeros(n, dtype=np.uint8)
+        kept = np.zeros(n, dtype=np.uint8)
+        match = np.full((n, max_points), -1, dtype=np.int32)
+        t = topology
+        keys = ("hull_face_first", "hull_face_count", "face_normal", "face_first", "face_count", "vertices_adj_to_face", "edges_adj_to_face",
+                "vert_first", "vert_count", "faces_adj_to_vertex", "edges_adj_to_vertex", "hull_edge_first", "edge_dir")
+        keep = None if t is None else [np.ascontiguousarray(t[k]) if k in t else None for k in keys]
+        tp = [None] * 13 if t is None else [None if a is None else a.ctypes.data for a in keep]
+        lib().pb2o_contact_manifolds_update_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, *tp, s1.ctypes.data,
+                                                  s2.ctypes.data, p1.ctypes.data, p2.ctypes.data, prediction, n, max_points, threads,
+                                                  int(bool(seed_gjk)), normals.ctypes.data, counts.ctypes.data, pts.ctypes.data,
+                                                  status.ctypes.data, kept.ctypes.data, match.ctypes.data)
+        return normals, counts, pts, status, kept, match
 
     def closest_points(self, shape1, pos1, shape2, pos2, max_dist, threads=1):
         """query::closest_points per pair: (points (n,6) world-space p1, p2; kind (n,): 0 Disjoint, 1 WithinMargin, 2 Intersecting;

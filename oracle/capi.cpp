@@ -308,13 +308,14 @@ void pb2o_closest_points_batch(const uint8_t* kinds, const float* params4, const
 // QueryDispatcher::contact_manifolds for n pairs of Ball / Cuboid shapes, first frame (empty incoming manifolds), with
 // pos12 = pos1.inv_mul(pos2). normals: n x 6 (local_n1, local_n2); counts: n; pts: n x max_points x 9 words {local_p1, local_p2,
 // dist, fid1, fid2 (PackedFeatureId bits)}; status: 0 ok, 2 unsupported pair (a ConvexPolyhedron), 4 more than max_points.
-void pb2o_contact_manifolds_batch2(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* hull_face_first,
-                                   const uint32_t* hull_face_count, const float* face_normal, const uint32_t* face_first,
-                                   const uint32_t* face_count, const uint32_t* vertices_adj_to_face, const uint32_t* edges_adj_to_face,
-                                   const uint32_t* vert_first, const uint32_t* vert_count, const uint32_t* faces_adj_to_vertex,
-                                   const uint32_t* edges_adj_to_vertex, const uint32_t* hull_edge_first, const float* edge_dir,
-                                   const uint32_t* shape1, const uint32_t* shape2, const float* pos1, const float* pos2, float prediction,
-                                   uint32_t n, uint32_t max_points, int nthreads, float* normals, uint32_t* counts, float* pts, uint8_t* status) {
+static void manifolds_batch_impl(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* hull_face_first,
+                                 const uint32_t* hull_face_count, const float* face_normal, const uint32_t* face_first,
+                                 const uint32_t* face_count, const uint32_t* vertices_adj_to_face, const uint32_t* edges_adj_to_face,
+                                 const uint32_t* vert_first, const uint32_t* vert_count, const uint32_t* faces_adj_to_vertex,
+                                 const uint32_t* edges_adj_to_vertex, const uint32_t* hull_edge_first, const float* edge_dir,
+                                 const uint32_t* shape1, const uint32_t* shape2, const float* pos1, const float* pos2, float prediction,
+                                 uint32_t n, uint32_t max_points, int nthreads, float* normals, uint32_t* counts, float* pts, uint8_t* status,
+                                 bool persistent, bool seed_gjk, uint8_t* kept, int32_t* match) {
     // hull_face_first / hull_face_count: per shape-table entry (ignored for balls and cuboids), NULL = no topology supplied
     auto topo = [=](uint32_t sid, HullTopology& t) -> const HullTopology* {
         if (!hull_face_first || kinds[sid] != 2) return nullptr;
@@ -334,7 +335,31 @@ void pb2o_contact_manifolds_batch2(const uint8_t* kinds, const float* params4, c
             ShapeRef s1 = make_shape(kinds, params4, points, shape1[k]), s2 = make_shape(kinds, params4, points, shape2[k]);
             Iso pos12 = Iso::from7(pos1 + 7 * k).inv_mul(Iso::from7(pos2 + 7 * k));
             HullTopology ta, tb;
-            int st = dispatch_manifold(pos12, s1, s2, prediction, m, topo(shape1[k], ta), topo(shape2[k], tb));
+            float* q0 = pts + (size_t)k * max_points * 9;
+            std::vector<TrackedContact> old;
+            m.clear(); m.local_n1 = Vec3(); m.local_n2 = Vec3();
+            if (persistent) {   // the caller's ContactManifold as last frame left it
+                m.local_n1 = ld3(normals + 6 * k); m.local_n2 = ld3(normals + 6 * k + 3);
+                for (uint32_t i = 0; i < counts[k] && i < max_points; ++i) {
+                    TrackedContact t; t.local_p1 = ld3(q0 + 9 * i); t.local_p2 = ld3(q0 + 9 * i + 3); t.dist = q0[9 * i + 6];
+                    memcpy(&t.fid1, q0 + 9 * i + 7, 4); memcpy(&t.fid2, q0 + 9 * i + 8, 4);
+                    m.points.push_back(t);
+                }
+                old = m.points;
+            }
+            bool was_kept = false;
+            int st = dispatch_manifold(pos12, s1, s2, prediction, m, topo(shape1[k], ta), topo(shape2[k], tb), persistent, &was_kept, seed_gjk);
+            if (kept) kept[k] = was_kept ? 1 : 0;
+            if (match) {   // ContactManifold::match_contacts (contact_manifold.rs:761-770): the last old contact with both feature ids equal
+                for (uint32_t i = 0; i < max_points; ++i) {
+                    int32_t j = -1;
+                    if (i < m.points.size()) {
+                        if (was_kept) j = (int32_t)i;
+                        else for (size_t o = 0; o < old.size(); ++o) if (old[o].fid1 == m.points[i].fid1 && old[o].fid2 == m.points[i].fid2) j = (int32_t)o;
+                    }
+                    match[(size_t)k * max_points + i] = j;
+                }
+            }
             uint32_t cnt = (uint32_t)m.points.size();
             if (cnt > max_points) { st = 4; cnt = max_points; }
             if (cnt) { st3(normals + 6 * k, m.local_n1); st3(normals + 6 * k + 3, m.local_n2); }
@@ -350,6 +375,34 @@ void pb2o_contact_manifolds_batch2(const uint8_t* kinds, const float* params4, c
             }
         }
     });
+}
+void pb2o_contact_manifolds_batch2(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* hull_face_first,
+                                   const uint32_t* hull_face_count, const float* face_normal, const uint32_t* face_first,
+                                   const uint32_t* face_count, const uint32_t* vertices_adj_to_face, const uint32_t* edges_adj_to_face,
+                                   const uint32_t* vert_first, const uint32_t* vert_count, const uint32_t* faces_adj_to_vertex,
+                                   const uint32_t* edges_adj_to_vertex, const uint32_t* hull_edge_first, const float* edge_dir,
+                                   const uint32_t* shape1, const uint32_t* shape2, const float* pos1, const float* pos2, float prediction,
+                                   uint32_t n, uint32_t max_points, int nthreads, float* normals, uint32_t* counts, float* pts, uint8_t* status) {
+    manifolds_batch_impl(kinds, params4, points, hull_face_first, hull_face_count, face_normal, face_first, face_count, vertices_adj_to_face,
+                         edges_adj_to_face, vert_first, vert_count, faces_adj_to_vertex, edges_adj_to_vertex, hull_edge_first, edge_dir, shape1, shape2,
+                         pos1, pos2, prediction, n, max_points, nthreads, normals, counts, pts, status, false, false, nullptr, nullptr);
+}
+// QueryDispatcher::contact_manifolds called again with last frame's manifolds (normals / counts / pts hold them on entry and the
+// new ones on return): the cuboid-cuboid and pfm_pfm arms keep a manifold that passes try_update_contacts (kept[k] = 1), everything
+// else is recomputed; match: n x max_points, for each new point the index of the old point match_contacts would take its data from
+// (kept manifolds: the identity), -1 = none. seed_gjk != 0: the pfm_pfm recomputation starts GJK from last frame's normal
+// (contact_manifolds_pfm_pfm.rs:66), as the reference does; 0: from the default direction, as the GPU path does.
+void pb2o_contact_manifolds_update_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* hull_face_first,
+                                         const uint32_t* hull_face_count, const float* face_normal, const uint32_t* face_first,
+                                         const uint32_t* face_count, const uint32_t* vertices_adj_to_face, const uint32_t* edges_adj_to_face,
+                                         const uint32_t* vert_first, const uint32_t* vert_count, const uint32_t* faces_adj_to_vertex,
+                                         const uint32_t* edges_adj_to_vertex, const uint32_t* hull_edge_first, const float* edge_dir,
+                                         const uint32_t* shape1, const uint32_t* shape2, const float* pos1, const float* pos2, float prediction,
+                                         uint32_t n, uint32_t max_points, int nthreads, int seed_gjk, float* normals, uint32_t* counts, float* pts,
+                                         uint8_t* status, uint8_t* kept, int32_t* match) {
+    manifolds_batch_impl(kinds, params4, points, hull_face_first, hull_face_count, face_normal, face_first, face_count, vertices_adj_to_face,
+                         edges_adj_to_face, vert_first, vert_count, faces_adj_to_vertex, edges_adj_to_vertex, hull_edge_first, edge_dir, shape1, shape2,
+                         pos1, pos2, prediction, n, max_points, nthreads, normals, counts, pts, status, true, seed_gjk != 0, kept, match);
 }
 void pb2o_contact_manifolds_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* shape1,
                                   const uint32_t* shape2, const float* pos1, const float* pos2, float prediction, uint32_t n,

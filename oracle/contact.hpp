@@ -163,11 +163,14 @@ static inline int contact_ball_convex_polyhedron(const Iso& pos12, Real radius1,
 struct GjkEpaStats { int gjk_iters = 0; bool used_epa = false; EpaStats epa; };
 
 // contact_support_map_support_map.rs:10-77
+// (with_params, :40-61: a caller-supplied init_dir — contact_manifolds_pfm_pfm.rs:66 passes last frame's manifold normal — replaces
+// the default first direction)
 static inline int contact_support_map_support_map(const Iso& pos12, const SupportShape& g1, const SupportShape& g2, Real prediction, Contact& c,
-                                                  GjkEpaStats* stats = nullptr) {
+                                                  GjkEpaStats* stats = nullptr, const Vec3* init_dir = nullptr) {
     VoronoiSimplex simplex;
     Vec3 dir;
-    if (!try_normalize(pos12.tra, DEFAULT_EPSILON, dir)) dir = Vec3(1, 0, 0);
+    if (init_dir) dir = *init_dir;
+    else if (!try_normalize(pos12.tra, DEFAULT_EPSILON, dir)) dir = Vec3(1, 0, 0);
     simplex.reset(CSOPoint::from_shapes(pos12, g1, g2, dir));
     GJKResult r = gjk_closest_points(pos12, g1, g2, prediction, simplex);
     if (stats) stats->gjk_iters = r.niter;

@@ -346,10 +346,10 @@ static inline void manifold_hull_ball(const Iso& pos12, const ShapeRef& hull, co
 // contact_manifolds_pfm_pfm.rs:42-162, empty incoming manifold (init_dir = None), no normal constraints, border radii 0.
 // Returns false when the GJK/EPA contact is not ClosestPoints (manifold stays empty).
 static inline bool manifold_pfm_pfm(const Iso& pos12, const ShapeRef& s1, const HullTopology* t1, const ShapeRef& s2, const HullTopology* t2,
-                                    Real prediction, Manifold& m) {
+                                    Real prediction, Manifold& m, const Vec3* init_dir = nullptr) {
     m.clear();
     Contact c;
-    if (contact_support_map_support_map(pos12, s1.support(), s2.support(), prediction, c) != CONTACT_SOME) return false;
+    if (contact_support_map_support_map(pos12, s1.support(), s2.support(), prediction, c, nullptr, init_dir) != CONTACT_SOME) return false;
     // c: point1 = p1, point2 = pos12^-1 p2_1, normal1 = dir, normal2 = pos12^-1 (-dir), dist = (p2_1 - p1) . dir
     Vec3 local_n1 = c.normal1, local_n2 = c.normal2;
     PolyFeature f1 = s1.kind == SHAPE_CUBOID ? cuboid_support_face(s1.half_extents, local_n1) : hull_local_support_feature(s1, *t1, local_n1);
@@ -392,11 +392,15 @@ enum ManifoldStatus { MANIFOLD_OK = 0, MANIFOLD_UNSUPPORTED = 2 };
 // contact_manifolds_pfm_pfm.rs:64); *kept = true when they did. The ball arms always recompute.
 static inline int dispatch_manifold(const Iso& pos12, const ShapeRef& s1, const ShapeRef& s2, Real prediction, Manifold& m,
                                     const HullTopology* t1 = nullptr, const HullTopology* t2 = nullptr, bool persistent = false,
-                                    bool* kept = nullptr) {
+                                    bool* kept = nullptr, bool seed_gjk = false) {
     if (kept) *kept = false;
+    Vec3 seed; bool have_seed = false;
     if (persistent && s1.kind != SHAPE_BALL && s2.kind != SHAPE_BALL) {
         bool pfm_ok = (s1.kind == SHAPE_CUBOID || t1) && (s2.kind == SHAPE_CUBOID || t2);
         if (pfm_ok && manifold_try_update_contacts(m, pos12)) { if (kept) *kept = true; return MANIFOLD_OK; }
+        // contact_manifolds_pfm_pfm.rs:66: init_dir = Unit::try_new(manifold.local_n1, DEFAULT_EPSILON) seeds the GJK of the recomputation
+        // (seed_gjk = false restates the GPU path, which restarts GJK from the default direction)
+        have_seed = seed_gjk && try_normalize(m.local_n1, DEFAULT_EPSILON, seed);
     }
     m.clear(); m.local_n1 = Vec3(); m.local_n2 = Vec3();
     if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_BALL) { manifold_ball_ball(pos12, s1.radius, s2.radius, prediction, m); return MANIFOLD_OK; }
@@ -409,7 +413,7 @@ static inline int dispatch_manifold(const Iso& pos12, const ShapeRef& s1, const 
     if (s1.kind == SHAPE_BALL || s2.kind == SHAPE_BALL) return MANIFOLD_UNSUPPORTED;
     // _ => contact_manifold_pfm_pfm (default_query_dispatcher.rs:818-831): Cuboid and ConvexPolyhedron are PolygonalFeatureMaps
     bool ok1 = s1.kind == SHAPE_CUBOID || (s1.kind == SHAPE_CONVEX && t1), ok2 = s2.kind == SHAPE_CUBOID || (s2.kind == SHAPE_CONVEX && t2);
-    if (ok1 && ok2) { manifold_pfm_pfm(pos12, s1, t1, s2, t2, prediction, m); return MANIFOLD_OK; }
+    if (ok1 && ok2) { manifold_pfm_pfm(pos12, s1, t1, s2, t2, prediction, m, have_seed ? &seed : nullptr); return MANIFOLD_OK; }
     return MANIFOLD_UNSUPPORTED;
 }
 

@@ -577,3 +577,67 @@ def test_compound_compound_contact_against_part_pairs(oracle):
     o2, s2 = T.contact(a % ns, p1, b % ns, p2, 0.05)
     assert (s1 == s2).all()
     np.testing.assert_allclose(o1[s2 == 1], o2[s2 == 1], rtol=1e-4, atol=2e-5)
+
+
+def _two_frame_scene(oracle, n, seed, drift=2.0e-4):
+    """Mixed Ball / Cuboid / ConvexPolyhedron pairs in two consecutive frames: half of the pairs drift by `drift`, the rest jump."""
+    g = scenes.rng(seed)
+    pts, _ = scenes.hull_pool(4, 16, seed=seed + 1)
+    spec = [("ball", 0.3), ("cuboid", [0.3, 0.5, 0.4]), ("cuboid", [0.6, 0.2, 0.2])] + [("convex", p * 0.5) for p in pts]
+    T = oracle.ShapeTable(spec)
+    s1, s2 = g.integers(0, len(spec), n).astype(np.uint32), g.integers(0, len(spec), n).astype(np.uint32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 0.9 + 0.3)], axis=1).astype(np.float32)
+    p2[::3, :4] = p1[::3, :4]
+    step = np.where(g.random((n, 1)) < 0.5, drift, 0.05)
+    p2b = p2.copy()
+    p2b[:, 4:] += (g.standard_normal((n, 3)) * step).astype(np.float32)
+    return T, s1, s2, p1, p2, p2b
+
+
+def test_persistent_manifold_dispatch(oracle):
+    """QueryDispatcher::contact_manifolds on a second frame (contact_manifolds_cuboid_cuboid.rs:28, contact_manifolds_pfm_pfm.rs:63-66,
+    match_contacts contact_manifold.rs:761-770): kept manifolds equal try_update_contacts of last frame's, everything else equals a
+    first-frame computation of the new poses (GJK not seeded) — seeded from last frame's normal the pfm_pfm arm lands within GJK's
+    own convergence tolerance of it —, ball pairs are never kept, and match pairs new points with old ones by feature ids."""
+    T, s1, s2, p1, p2, p2b = _two_frame_scene(oracle, 6000, 41)
+    topo = T.hull_topology()
+    nr, cnt, pts, st = T.contact_manifolds(s1, p1, s2, p2, 0.05, topology=topo)
+    assert (st == 0).all() and 0.2 < (cnt > 0).mean() < 0.95
+    nr2, cnt2, pts2, st2, kept, match = T.contact_manifolds_update(s1, p1, s2, p2b, 0.05, nr, cnt, pts, topology=topo)
+    ball = (T.kinds[s1] == 0) | (T.kinds[s2] == 0)
+    assert (kept[ball] == 0).all() and (kept[cnt == 0] == 0).all() and (st2 == 0).all()
+    assert 0.15 < kept[~ball & (cnt > 0)].mean() < 0.85
+    # kept: exactly ContactManifold::try_update_contacts of the old manifold
+    k0, q = oracle.ShapeTable.manifolds_try_update(p1, p2b, nr, cnt, pts)
+    assert (k0[~ball] == kept[~ball]).all()
+    kp = kept == 1
+    assert (pts2[kp].view(np.uint32) == q[kp].view(np.uint32)).all() and (cnt2[kp] == cnt[kp]).all()
+    assert (nr2[kp].view(np.uint32) == nr[kp].view(np.uint32)).all()
+    # recomputed: exactly the first-frame result at the new poses
+    nr3, cnt3, pts3, _ = T.contact_manifolds(s1, p1, s2, p2b, 0.05, topology=topo)
+    assert (cnt2[~kp] == cnt3[~kp]).all() and (pts2[~kp].view(np.uint32) == pts3[~kp].view(np.uint32)).all()
+    assert (nr2[~kp].view(np.uint32) == nr3[~kp].view(np.uint32)).all()
+    # match: identity on kept manifolds; on recomputed ones the last old point with both feature ids equal, else -1
+    mp = pts.shape[1]
+    valid2 = np.arange(mp)[None, :] < cnt2[:, None]
+    assert (match[kp] == np.where(valid2[kp], np.arange(mp)[None, :], -1)).all() and (match[~valid2] == -1).all()
+    f_old, f_new = pts[:, :, 7:].view(np.uint32), pts2[:, :, 7:].view(np.uint32)
+    matched = 0
+    for k in np.nonzero(~kp & (cnt2 > 0))[0][:1500]:
+        for i in range(cnt2[k]):
+            js = [j for j in range(cnt[k]) if (f_old[k, j] == f_new[k, i]).all()]
+            assert match[k, i] == (js[-1] if js else -1)
+            matched += bool(js)
+    assert matched > 100
+    # the reference seeds the pfm_pfm recomputation with last frame's normal: same manifolds up to GJK's convergence tolerance
+    nr4, cnt4, pts4, st4, kept4, _ = T.contact_manifolds_update(s1, p1, s2, p2b, 0.05, nr, cnt, pts, topology=topo, seed_gjk=True)
+    assert (kept4 == kept).all()
+    pfm = ~ball & ~kp & ~((T.kinds[s1] == 1) & (T.kinds[s2] == 1))
+    assert (pts4[~pfm].view(np.uint32) == pts2[~pfm].view(np.uint32)).all()
+    both = pfm & (cnt4 > 0) & (cnt2 > 0)
+    assert ((cnt4 > 0) == (cnt2 > 0))[pfm].mean() > 0.99 and both.sum() > 100
+    deepest = lambda p, c: np.where(np.arange(mp)[None, :] < c[:, None], p[:, :, 6], np.inf).min(axis=1)
+    assert np.quantile(np.abs(deepest(pts4[both], cnt4[both]) - deepest(pts2[both], cnt2[both])), 0.99) < 2e-3
