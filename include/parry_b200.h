@@ -293,6 +293,29 @@ int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const ui
                                 const float* pos1 /* n x 7 */, const float* pos2, float prediction, uint32_t n, uint32_t max_points,
                                 float* normals, uint32_t* counts, float* points, uint8_t* status, int mem);
 
+/* ContactManifold::try_update_contacts_eps (query/contact_manifolds/contact_manifold.rs:662-699) on n manifolds in the layout of
+ * pb2_contact_manifolds_batch, under the new pos12 = pos1.inv_mul(pos2): kept[k] = 1 when the manifold's normal turned by less
+ * than acos(angle_dot_threshold) and no point drifted by more than sqrt(dist_sq_threshold) or switched between penetrating and
+ * separated; dist and local_p1 of the visited points are refreshed in place (points: in / out). try_update_contacts (:652-658)
+ * = thresholds COS_1_DEGREES (0.99984769515) and 1.0e-6. */
+int pb2_manifolds_try_update(pb2_ctx* ctx, const float* pos1 /* n x 7 */, const float* pos2, uint32_t n, uint32_t max_points,
+                             float angle_dot_threshold, float dist_sq_threshold, const float* normals, const uint32_t* counts,
+                             float* points, uint8_t* kept, int mem);
+
+/* QueryDispatcher::contact_manifolds called again with last frame's manifolds (PersistentQueryDispatcher::contact_manifold_convex_convex,
+ * default_query_dispatcher.rs:760-831): normals / counts / points are in / out, in the layout of pb2_contact_manifolds_batch.
+ * Cuboid-cuboid (contact_manifolds_cuboid_cuboid.rs:28) and pfm_pfm pairs (contact_manifolds_pfm_pfm.rs:63) whose manifold
+ * passes try_update_contacts keep it (kept[k] = 1, status 0); every other pair is recomputed exactly as pb2_contact_manifolds_batch
+ * would (the ball arms never keep). match (optional, n x max_points): for each new point the index of last frame's point
+ * ContactManifold::match_contacts (contact_manifold.rs:761-770) would copy the ContactData from — the last one with both feature
+ * ids equal — or -1; kept manifolds map onto themselves. One documented difference: the reference seeds the GJK of a pfm_pfm
+ * recomputation with last frame's normal (contact_manifolds_pfm_pfm.rs:66); this path restarts from the default direction, so
+ * those manifolds agree with the reference's within GJK's convergence tolerance rather than bit for bit. */
+int pb2_contact_manifolds_update_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
+                                       const float* pos1 /* n x 7 */, const float* pos2, float prediction, uint32_t n, uint32_t max_points,
+                                       float* normals, uint32_t* counts, float* points, uint8_t* status, uint8_t* kept, int32_t* match,
+                                       int mem);
+
 /* query::cast_shapes for n pairs (query/shape_cast/shape_cast.rs:268-286 -> DefaultQueryDispatcher::cast_shapes,
  * default_query_dispatcher.rs:434-515: ball-ball shape_cast_ball_ball.rs:10-69, every other Ball / Cuboid / ConvexPolyhedron
  * pair shape_cast_support_map_support_map.rs:11-69 + gjk::directional_distance gjk.rs:632-795). vel1 / vel2: n x 3

@@ -240,6 +240,19 @@ inline void contact_manifolds(const Context& c, const pb2_shapes* shapes, const 
     c.check(pb2_contact_manifolds_batch(c.get(), shapes, g1.data(), g2.data(), pos1[0].rotation, pos2[0].rotation, prediction, (uint32_t)n, max_points,
                                         normals[0].local_n1, counts.data(), points[0].local_p1, status.data(), PB2_MEM_HOST));
 }
+// contact_manifolds on the manifolds of the previous frame (in / out): manifolds that pass ContactManifold::try_update_contacts are kept
+// (kept[k] = 1), the rest recomputed; match[k * max_points + i] = index of the old point whose ContactData match_contacts hands to point i
+inline void contact_manifolds_update(const Context& c, const pb2_shapes* shapes, const std::vector<uint32_t>& g1, const std::vector<Isometry>& pos1,
+                                     const std::vector<uint32_t>& g2, const std::vector<Isometry>& pos2, float prediction, uint32_t max_points,
+                                     std::vector<ManifoldNormals>& normals, std::vector<uint32_t>& counts, std::vector<TrackedContact>& points,
+                                     std::vector<uint8_t>& status, std::vector<uint8_t>& kept, std::vector<int32_t>& match) {
+    size_t n = g1.size();
+    if (normals.size() != n || counts.size() != n || points.size() != n * max_points) throw std::invalid_argument("contact_manifolds_update: last frame's manifolds have another shape");
+    status.resize(n); kept.resize(n); match.resize(n * max_points);
+    c.check(pb2_contact_manifolds_update_batch(c.get(), shapes, g1.data(), g2.data(), pos1[0].rotation, pos2[0].rotation, prediction, (uint32_t)n,
+                                               max_points, normals[0].local_n1, counts.data(), points[0].local_p1, status.data(), kept.data(),
+                                               match.data(), PB2_MEM_HOST));
+}
 // query::contact with a Compound on one side (contact_composite_shape_shape.rs:14-76)
 inline void contact_compound(const Context& c, const pb2_compounds* compounds, const std::vector<uint32_t>& compound_ids,
                              const std::vector<Isometry>& compound_poses, const std::vector<uint32_t>& shape_ids, const std::vector<Isometry>& shape_poses,

@@ -124,22 +124,22 @@ struct Iso7 {
     Q4 q;
     V3 t;
 };
-__device__ __forceinline__ Iso7 load_iso(const float* p) {
+__host__ __device__ __forceinline__ Iso7 load_iso(const float* p) {
     Iso7 m;
     m.q.i = p[0]; m.q.j = p[1]; m.q.k = p[2]; m.q.w = p[3];
     m.t = mk3(p[4], p[5], p[6]);
     return m;
 }
-__device__ __forceinline__ Q4 qconj(Q4 q) { Q4 r; r.i = -q.i; r.j = -q.j; r.k = -q.k; r.w = q.w; return r; }
+__host__ __device__ __forceinline__ Q4 qconj(Q4 q) { Q4 r; r.i = -q.i; r.j = -q.j; r.k = -q.k; r.w = q.w; return r; }
 // UnitQuaternion * Vector3: t = (q.xyz x v) * 2 ; t * w + (q.xyz x t) + v
-__device__ __forceinline__ V3 qrot(Q4 q, V3 v) {
+__host__ __device__ __forceinline__ V3 qrot(Q4 q, V3 v) {
     V3 u = mk3(q.i, q.j, q.k);
     V3 t = cross3(u, v) * 2.0f;
     V3 c = cross3(u, t);
     return (t * q.w + c) + v;
 }
-__device__ __forceinline__ V3 qirot(Q4 q, V3 v) { return qrot(qconj(q), v); }
-__device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
+__host__ __device__ __forceinline__ V3 qirot(Q4 q, V3 v) { return qrot(qconj(q), v); }
+__host__ __device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
     Q4 r;
     r.i = a.w * b.i + a.i * b.w + a.j * b.k - a.k * b.j;
     r.j = a.w * b.j - a.i * b.k + a.j * b.w + a.k * b.i;
@@ -147,11 +147,11 @@ __device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
     r.w = a.w * b.w - a.i * b.i - a.j * b.j - a.k * b.k;
     return r;
 }
-__device__ __forceinline__ V3 iso_point(const Iso7& m, V3 p) { return qrot(m.q, p) + m.t; }
-__device__ __forceinline__ V3 iso_vec(const Iso7& m, V3 v) { return qrot(m.q, v); }
+__host__ __device__ __forceinline__ V3 iso_point(const Iso7& m, V3 p) { return qrot(m.q, p) + m.t; }
+__host__ __device__ __forceinline__ V3 iso_vec(const Iso7& m, V3 v) { return qrot(m.q, v); }
 __device__ __forceinline__ V3 iso_inv_point(const Iso7& m, V3 p) { return qirot(m.q, p - m.t); }
 __device__ __forceinline__ V3 iso_inv_vec(const Iso7& m, V3 v) { return qirot(m.q, v); }
-__device__ __forceinline__ Iso7 iso_inv_mul(const Iso7& a, const Iso7& b) {
+__host__ __device__ __forceinline__ Iso7 iso_inv_mul(const Iso7& a, const Iso7& b) {
     Iso7 r;
     Q4 inv = qconj(a.q);
     r.t = qrot(inv, b.t - a.t);

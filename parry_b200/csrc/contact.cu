@@ -18,6 +18,7 @@
 // and TriMesh-vs-shape candidates (shape 1 = a mesh triangle), see PairSrc.
 #include "gjk.cuh"
 #include "trimesh.cuh"
+#include "manifold_update.cuh"
 #include <stdlib.h>
 #include <cub/cub.cuh>
 
@@ -2556,9 +2557,11 @@ __global__ void __launch_bounds__(128) k_contact_manifolds(const uint8_t* __rest
                               const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2, const float* __restrict__ pos1,
                               const float* __restrict__ pos2, float prediction, uint32_t n, uint32_t max_points, float* __restrict__ normals,
                               uint32_t* __restrict__ counts, float* __restrict__ pts, uint8_t* __restrict__ status, bool have_topology,
-                              bool have_vertex_topology, uint32_t* __restrict__ parked, unsigned long long* parked_count) {
+                              bool have_vertex_topology, uint32_t* __restrict__ parked, unsigned long long* parked_count,
+                              const uint8_t* __restrict__ skip) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
+    if (skip && skip[k]) return;   // persistent dispatch: last frame's manifold was kept (k_manifold_try_update)
     {   // pairs for the pfm_pfm arm (a ConvexPolyhedron with topology on at least one side, a Cuboid or such a hull on the other)
         uint32_t a = shape1[k], b = shape2[k];
         if (have_topology && a < n_shapes && b < n_shapes) {
@@ -2688,22 +2691,9 @@ __global__ void __launch_bounds__(128) k_manifold_pfm(const uint8_t* __restrict_
     status[k] = (uint8_t)st;
 }
 
-extern "C" int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
-                                           const float* pos2, float prediction, uint32_t n, uint32_t max_points, float* normals, uint32_t* counts,
-                                           float* points, uint8_t* status, int mem) {
-    if (!ctx || !shapes || max_points == 0 || (n && (!shape1 || !shape2 || !pos1 || !pos2 || !normals || !counts || !points || !status))) return PB2_ERR_INVALID;
-    if (n == 0) return PB2_OK;
-    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
-    const void *d_s1, *d_s2, *d_p1, *d_p2;
-    void *d_nr, *d_ct, *d_pt, *d_st;
-    PB2_CHECK(pb2_stage_in(ctx, 0, shape1, (size_t)n * 4, mem, &d_s1));
-    PB2_CHECK(pb2_stage_in(ctx, 1, shape2, (size_t)n * 4, mem, &d_s2));
-    PB2_CHECK(pb2_stage_in(ctx, 2, pos1, (size_t)n * 28, mem, &d_p1));
-    PB2_CHECK(pb2_stage_in(ctx, 3, pos2, (size_t)n * 28, mem, &d_p2));
-    PB2_CHECK(pb2_stage_out(ctx, 4, normals, (size_t)n * 24, mem, &d_nr));
-    PB2_CHECK(pb2_stage_out(ctx, 5, counts, (size_t)n * 4, mem, &d_ct));
-    PB2_CHECK(pb2_stage_out(ctx, 6, points, (size_t)n * max_points * 36, mem, &d_pt));
-    PB2_CHECK(pb2_stage_out(ctx, 7, status, (size_t)n, mem, &d_st));
+// The device side of pb2_contact_manifolds_batch on device-resident arrays; pairs with skip[k] != 0 (optional) are left untouched.
+static int manifolds_device(pb2_ctx* ctx, const pb2_shapes* shapes, const void* d_s1, const void* d_s2, const void* d_p1, const void* d_p2,
+                            float prediction, uint32_t n, uint32_t max_points, void* d_nr, void* d_ct, void* d_pt, void* d_st, const uint8_t* d_skip) {
     cudaStream_t st = ctx->stream;
     const bool have_topology = shapes->face_normal != nullptr;
     uint32_t *d_parked = nullptr, *d_ab = nullptr;
@@ -2718,7 +2708,7 @@ extern "C" int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shape
     k_contact_manifolds<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->n, (const uint32_t*)d_s1, (const uint32_t*)d_s2,
                                                              (const float*)d_p1, (const float*)d_p2, prediction, n, max_points, (float*)d_nr,
                                                              (uint32_t*)d_ct, (float*)d_pt, (uint8_t*)d_st, have_topology, shapes->vert_first != nullptr,
-                                                             d_parked, parked_count);
+                                                             d_parked, parked_count, d_skip);
     PB2_LAUNCHED(ctx);
     if (have_topology) {
         cudaMemcpyAsync(ctx->h_counters + 10, parked_count, 8, cudaMemcpyDeviceToHost, st);
@@ -2757,6 +2747,184 @@ extern "C" int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shape
         if (rc != PB2_OK) { snprintf(ctx->err, sizeof(ctx->err), "contact_manifolds: pfm_pfm phase failed"); return rc; }
     }
     PB2_CUDA(ctx, cudaGetLastError());
+    return PB2_OK;
+}
+
+extern "C" int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
+                                           const float* pos2, float prediction, uint32_t n, uint32_t max_points, float* normals, uint32_t* counts,
+                                           float* points, uint8_t* status, int mem) {
+    if (!ctx || !shapes || max_points == 0 || (n && (!shape1 || !shape2 || !pos1 || !pos2 || !normals || !counts || !points || !status))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_s1, *d_s2, *d_p1, *d_p2;
+    void *d_nr, *d_ct, *d_pt, *d_st;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape1, (size_t)n * 4, mem, &d_s1));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape2, (size_t)n * 4, mem, &d_s2));
+    PB2_CHECK(pb2_stage_in(ctx, 2, pos1, (size_t)n * 28, mem, &d_p1));
+    PB2_CHECK(pb2_stage_in(ctx, 3, pos2, (size_t)n * 28, mem, &d_p2));
+    PB2_CHECK(pb2_stage_out(ctx, 4, normals, (size_t)n * 24, mem, &d_nr));
+    PB2_CHECK(pb2_stage_out(ctx, 5, counts, (size_t)n * 4, mem, &d_ct));
+    PB2_CHECK(pb2_stage_out(ctx, 6, points, (size_t)n * max_points * 36, mem, &d_pt));
+    PB2_CHECK(pb2_stage_out(ctx, 7, status, (size_t)n, mem, &d_st));
+    PB2_CHECK(manifolds_device(ctx, shapes, d_s1, d_s2, d_p1, d_p2, prediction, n, max_points, d_nr, d_ct, d_pt, d_st, nullptr));
+    PB2_CHECK(pb2_stage_back(ctx, normals, d_nr, (size_t)n * 24, mem));
+    PB2_CHECK(pb2_stage_back(ctx, counts, d_ct, (size_t)n * 4, mem));
+    PB2_CHECK(pb2_stage_back(ctx, points, d_pt, (size_t)n * max_points * 36, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_st, (size_t)n, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB2_OK;
+}
+
+// ------------------------------------------------------------------------------------------- manifold persistence
+// ContactManifold::try_update_contacts_eps (contact_manifold.rs:662-699) per manifold, in place. dispatch != 0: only the pairs whose
+// dispatcher arm tries to keep last frame's manifold (contact_manifolds_cuboid_cuboid.rs:28, contact_manifolds_pfm_pfm.rs:63: neither
+// shape a Ball, hulls with face topology); kept pairs get status 0. old_fids / old_counts (optional): last frame's feature ids,
+// saved for match_contacts before the recomputation overwrites them.
+__global__ void __launch_bounds__(128) k_manifold_try_update(const uint8_t* __restrict__ kinds, uint32_t n_shapes, const uint32_t* __restrict__ shape1,
+                                                             const uint32_t* __restrict__ shape2, bool dispatch, bool have_topology,
+                                                             const float* __restrict__ pos1, const float* __restrict__ pos2, uint32_t n,
+                                                             uint32_t max_points, float angle_dot_threshold, float dist_sq_threshold,
+                                                             const float* __restrict__ normals, const uint32_t* __restrict__ counts,
+                                                             float* __restrict__ pts, uint8_t* __restrict__ kept, uint8_t* __restrict__ status,
+                                                             uint32_t* __restrict__ old_fids, uint32_t* __restrict__ old_counts) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t cnt = counts[k];
+    if (cnt > max_points) cnt = max_points;
+    float* q = pts + (size_t)k * max_points * 9;
+    if (old_fids) {
+        old_counts[k] = cnt;
+        uint32_t* f = old_fids + (size_t)k * max_points * 2;
+        for (uint32_t i = 0; i < cnt; ++i) { f[2 * i] = __float_as_uint(q[9 * i + 7]); f[2 * i + 1] = __float_as_uint(q[9 * i + 8]); }
+    }
+    bool tries = true;
+    if (dispatch) {
+        uint32_t a = shape1[k], b = shape2[k];
+        tries = a < n_shapes && b < n_shapes;
+        if (tries) {
+            uint8_t ka = kinds[a], kb = kinds[b];
+            bool ok1 = ka == PB2_SHAPE_CUBOID || (ka == PB2_SHAPE_CONVEX && have_topology);
+            bool ok2 = kb == PB2_SHAPE_CUBOID || (kb == PB2_SHAPE_CONVEX && have_topology);
+            tries = ok1 && ok2;
+        }
+    }
+    bool keep = false;
+    if (tries && cnt) {
+        Iso7 pos12 = iso_inv_mul(load_iso(pos1 + 7ull * k), load_iso(pos2 + 7ull * k));
+        keep = manifold_try_update_core(pos12, normals + 6ull * k, cnt, q, angle_dot_threshold, dist_sq_threshold);
+    }
+    kept[k] = keep ? 1 : 0;
+    if (keep && status) status[k] = 0;
+}
+
+// ContactManifold::match_contacts (contact_manifold.rs:761-770) as an index: match[k][i] = the last old point of pair k whose two
+// feature ids equal those of new point i (the one whose ContactData the reference's loop leaves in place), -1 = none; kept
+// manifolds map onto themselves.
+__global__ void __launch_bounds__(128) k_manifold_match(const uint8_t* __restrict__ kept, const uint32_t* __restrict__ old_fids,
+                                                        const uint32_t* __restrict__ old_counts, const uint32_t* __restrict__ counts,
+                                                        const float* __restrict__ pts, uint32_t n, uint32_t max_points, int32_t* __restrict__ match) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t cnt = counts[k], oc = old_counts[k];
+    if (cnt > max_points) cnt = max_points;
+    const float* q = pts + (size_t)k * max_points * 9;
+    const uint32_t* f = old_fids + (size_t)k * max_points * 2;
+    int32_t* m = match + (size_t)k * max_points;
+    bool keep = kept[k] != 0;
+    for (uint32_t i = 0; i < max_points; ++i) {
+        int32_t j = -1;
+        if (i < cnt) {
+            if (keep) j = (int32_t)i;
+            else {
+                uint32_t f1 = __float_as_uint(q[9 * i + 7]), f2 = __float_as_uint(q[9 * i + 8]);
+                for (uint32_t o = 0; o < oc; ++o) if (f[2 * o] == f1 && f[2 * o + 1] == f2) j = (int32_t)o;
+            }
+        }
+        m[i] = j;
+    }
+}
+
+extern "C" int pb2_manifolds_try_update(pb2_ctx* ctx, const float* pos1, const float* pos2, uint32_t n, uint32_t max_points,
+                                        float angle_dot_threshold, float dist_sq_threshold, const float* normals, const uint32_t* counts,
+                                        float* points, uint8_t* kept, int mem) {
+    if (!ctx || max_points == 0 || (n && (!pos1 || !pos2 || !normals || !counts || !points || !kept))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_p1, *d_p2, *d_nr, *d_ct, *d_pt;
+    void* d_kp;
+    PB2_CHECK(pb2_stage_in(ctx, 2, pos1, (size_t)n * 28, mem, &d_p1));
+    PB2_CHECK(pb2_stage_in(ctx, 3, pos2, (size_t)n * 28, mem, &d_p2));
+    PB2_CHECK(pb2_stage_in(ctx, 4, normals, (size_t)n * 24, mem, &d_nr));
+    PB2_CHECK(pb2_stage_in(ctx, 5, counts, (size_t)n * 4, mem, &d_ct));
+    PB2_CHECK(pb2_stage_in(ctx, 6, points, (size_t)n * max_points * 36, mem, &d_pt));   // in / out: uploaded here, read back below
+    PB2_CHECK(pb2_stage_out(ctx, 7, kept, (size_t)n, mem, &d_kp));
+    k_manifold_try_update<<<pb2_blocks(n, 128), 128, 0, ctx->stream>>>(nullptr, 0u, nullptr, nullptr, false, false, (const float*)d_p1, (const float*)d_p2, n,
+                                                                       max_points, angle_dot_threshold, dist_sq_threshold, (const float*)d_nr,
+                                                                       (const uint32_t*)d_ct, (float*)d_pt, (uint8_t*)d_kp, nullptr, nullptr, nullptr);
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(pb2_stage_back(ctx, points, d_pt, (size_t)n * max_points * 36, mem));
+    PB2_CHECK(pb2_stage_back(ctx, kept, d_kp, (size_t)n, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB2_OK;
+}
+
+extern "C" int pb2_contact_manifolds_update_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
+                                                  const float* pos1, const float* pos2, float prediction, uint32_t n, uint32_t max_points,
+                                                  float* normals, uint32_t* counts, float* points, uint8_t* status, uint8_t* kept, int32_t* match,
+                                                  int mem) {
+    if (!ctx || !shapes || max_points == 0 || (n && (!shape1 || !shape2 || !pos1 || !pos2 || !normals || !counts || !points || !status || !kept)))
+        return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_s1, *d_s2, *d_p1, *d_p2, *c_nr, *c_ct, *c_pt;
+    void* d_st;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape1, (size_t)n * 4, mem, &d_s1));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape2, (size_t)n * 4, mem, &d_s2));
+    PB2_CHECK(pb2_stage_in(ctx, 2, pos1, (size_t)n * 28, mem, &d_p1));
+    PB2_CHECK(pb2_stage_in(ctx, 3, pos2, (size_t)n * 28, mem, &d_p2));
+    // in / out arrays: last frame's manifolds go up (host mode) into the staging slots the results come back from
+    PB2_CHECK(pb2_stage_in(ctx, 4, normals, (size_t)n * 24, mem, &c_nr));
+    PB2_CHECK(pb2_stage_in(ctx, 5, counts, (size_t)n * 4, mem, &c_ct));
+    PB2_CHECK(pb2_stage_in(ctx, 6, points, (size_t)n * max_points * 36, mem, &c_pt));
+    PB2_CHECK(pb2_stage_out(ctx, 7, status, (size_t)n, mem, &d_st));
+    void *d_nr = const_cast<void*>(c_nr), *d_ct = const_cast<void*>(c_ct), *d_pt = const_cast<void*>(c_pt);
+    // kept / match / saved feature ids: stream-ordered temporaries in host mode, the caller's arrays in device mode
+    uint8_t* d_kp = kept;
+    int32_t* d_mt = match;
+    uint32_t *d_of = nullptr, *d_oc = nullptr;
+    int rc = PB2_OK;
+    if (mem == PB2_MEM_HOST) {
+        d_kp = nullptr; d_mt = nullptr;
+        if (cudaMallocAsync((void**)&d_kp, (size_t)n, st) != cudaSuccess) rc = PB2_ERR_CUDA;
+        if (rc == PB2_OK && match && cudaMallocAsync((void**)&d_mt, (size_t)n * max_points * 4, st) != cudaSuccess) rc = PB2_ERR_CUDA;
+    }
+    if (rc == PB2_OK && match) {
+        if (cudaMallocAsync((void**)&d_of, (size_t)n * max_points * 8, st) != cudaSuccess || cudaMallocAsync((void**)&d_oc, (size_t)n * 4, st) != cudaSuccess)
+            rc = PB2_ERR_CUDA;
+    }
+    if (rc == PB2_OK) {
+        k_manifold_try_update<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->n, (const uint32_t*)d_s1, (const uint32_t*)d_s2, true,
+                                                                  shapes->face_normal != nullptr, (const float*)d_p1, (const float*)d_p2, n, max_points,
+                                                                  PB2_COS_1_DEGREES, PB2_UPDATE_DIST_SQ, (const float*)d_nr, (const uint32_t*)d_ct,
+                                                                  (float*)d_pt, d_kp, (uint8_t*)d_st, d_of, d_oc);
+        PB2_LAUNCHED(ctx);
+        rc = manifolds_device(ctx, shapes, d_s1, d_s2, d_p1, d_p2, prediction, n, max_points, d_nr, d_ct, d_pt, d_st, d_kp);
+    }
+    if (rc == PB2_OK && match) {
+        k_manifold_match<<<pb2_blocks(n, 128), 128, 0, st>>>(d_kp, d_of, d_oc, (const uint32_t*)d_ct, (const float*)d_pt, n, max_points, d_mt);
+        PB2_LAUNCHED(ctx);
+        if (cudaGetLastError() != cudaSuccess) rc = PB2_ERR_CUDA;
+    }
+    if (rc == PB2_OK && mem == PB2_MEM_HOST) {
+        if (cudaMemcpyAsync(kept, d_kp, (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = PB2_ERR_CUDA;
+        if (rc == PB2_OK && match && cudaMemcpyAsync(match, d_mt, (size_t)n * max_points * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = PB2_ERR_CUDA;
+    }
+    if (mem == PB2_MEM_HOST) { if (d_kp) cudaFreeAsync(d_kp, st); if (d_mt) cudaFreeAsync(d_mt, st); }
+    if (d_of) cudaFreeAsync(d_of, st);
+    if (d_oc) cudaFreeAsync(d_oc, st);
+    if (rc != PB2_OK) { if (!ctx->err[0]) snprintf(ctx->err, sizeof(ctx->err), "contact_manifolds_update: device phase failed"); return rc; }
     PB2_CHECK(pb2_stage_back(ctx, normals, d_nr, (size_t)n * 24, mem));
     PB2_CHECK(pb2_stage_back(ctx, counts, d_ct, (size_t)n * 4, mem));
     PB2_CHECK(pb2_stage_back(ctx, points, d_pt, (size_t)n * max_points * 36, mem));

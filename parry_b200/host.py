@@ -48,7 +48,7 @@ def _prep(x, dtype, mem=None):
 
 def _empty(shape, dtype, mem, device):
     if mem == MEM_DEVICE:
-        tdt = {np.float32: torch.float32, np.uint32: torch.int32, np.uint8: torch.uint8}[dtype]
+        tdt = {np.float32: torch.float32, np.uint32: torch.int32, np.uint8: torch.uint8, np.int32: torch.int32}[dtype]
         t = torch.empty(shape, dtype=tdt, device=device)
         return t, t.data_ptr()
     a = np.empty(shape, dtype=dtype)
@@ -720,6 +720,56 @@ def contact_manifolds(shapes, shape1, pos1, shape2, pos2, prediction, max_points
     status, pst = _empty((n,), np.uint8, mem, ctx.torch_device)
     ctx.check(ctx._lib.pb2_contact_manifolds_batch(ctx.h, shapes.h, ps1, ps2, p1, p2, float(prediction), n, int(max_points), pn, pc, pp, pst, mem))
     return normals, counts, points, status
+
+
+def _inout(x, dtype, mem):
+    """A private copy of an in / out array in the memory space of the call: (array, address)."""
+    if mem == MEM_DEVICE:
+        tdt = {np.float32: torch.float32, np.uint32: torch.int32}[dtype]
+        t = (x if _is_torch(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=dtype).view(np.int32 if dtype is np.uint32 else dtype)))
+        t = t.to(device=None if t.is_cuda else "cuda", dtype=tdt).contiguous().clone()
+        return t, t.data_ptr()
+    a = np.array(x.cpu().numpy() if _is_torch(x) else x, dtype=dtype, order="C", copy=True)
+    return a, a.ctypes.data
+
+
+def manifolds_try_update(ctx, pos1, pos2, normals, counts, points, angle_dot_threshold=0.99984769515, dist_sq_threshold=1.0e-6):
+    """ContactManifold::try_update_contacts[_eps](pos1.inv_mul(pos2)) (contact_manifold.rs:652-699) on manifolds in the layout
+    contact_manifolds returns. Returns (kept (n,) u8, points'): points' carries the refreshed dist / local_p1 (for a rejected
+    manifold the points visited before the rejecting one, as the reference leaves them)."""
+    n = int(pos1.shape[0])
+    max_points = int(points.shape[1])
+    k1, p1, mem = _prep(pos1, np.float32)
+    k2, p2, _ = _prep(pos2, np.float32, mem)
+    kn, pn, _ = _prep(normals, np.float32, mem)
+    kc, pc, _ = _prep(counts, np.uint32, mem)
+    pts, pp = _inout(points, np.float32, mem)
+    kept, pk = _empty((n,), np.uint8, mem, ctx.torch_device)
+    ctx.check(ctx._lib.pb2_manifolds_try_update(ctx.h, p1, p2, n, max_points, float(angle_dot_threshold), float(dist_sq_threshold), pn, pc, pp, pk, mem))
+    return kept, pts
+
+
+def contact_manifolds_update(shapes, shape1, pos1, shape2, pos2, prediction, normals, counts, points, with_match=True):
+    """QueryDispatcher::contact_manifolds called with last frame's manifolds (normals, counts, points as contact_manifolds returned
+    them): the cuboid-cuboid and pfm_pfm arms keep a manifold that passes try_update_contacts, everything else is recomputed.
+    Returns (normals, counts, points, status, kept (n,) u8, match (n, max_points) i32 or None): match[k, i] = index of last
+    frame's point whose ContactData ContactManifold::match_contacts would hand to new point i (-1: none)."""
+    ctx = shapes.ctx
+    n = int(pos1.shape[0])
+    max_points = int(points.shape[1])
+    k1, p1, mem = _prep(pos1, np.float32)
+    k2, p2, _ = _prep(pos2, np.float32, mem)
+    ks1, ps1, _ = _prep(shape1, np.uint32, mem)
+    ks2, ps2, _ = _prep(shape2, np.uint32, mem)
+    nr, pn = _inout(normals, np.float32, mem)
+    ct, pc = _inout(counts, np.uint32, mem)
+    pts, pp = _inout(points, np.float32, mem)
+    status, pst = _empty((n,), np.uint8, mem, ctx.torch_device)
+    kept, pk = _empty((n,), np.uint8, mem, ctx.torch_device)
+    match, pm = _empty((n, max_points), np.int32, mem, ctx.torch_device) if with_match else (None, None)
+    ctx.check(ctx._lib.pb2_contact_manifolds_update_batch(ctx.h, shapes.h, ps1, ps2, p1, p2, float(prediction), n, max_points, pn, pc, pp, pst, pk,
+                                                          pm, mem))
+    return nr, ct, pts, status, kept, match
 
 
 def closest_points(shapes, shape1, pos1, shape2, pos2, max_dist):
