@@ -65,6 +65,7 @@ def lib():
         l.pb2o_contact_manifolds_batch2.argtypes = [P] * 20 + [f32, u32, u32, i32, P, P, P, P]
         l.pb2o_closest_points_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, P, P, P]
         l.pb2o_manifolds_try_update.argtypes = [P, P, u32, u32, P, P, P, P]
+        l.pb2o_contact_local_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, P, P]
         l.pb2o_contact_manifolds_update_batch.argtypes = [P] * 20 + [f32, u32, u32, i32, i32, P, P, P, P, P, P]
         l.pb2o_compound_compound_contact_batch.argtypes = [P, P, P, P, P, P, P, P, P, P, P, f32, u32, i32, P, P, P]
         l.pb2o_convex_cast_ray.restype = i32
@@ -346,6 +347,16 @@ class ShapeTable:
                                  p1.ctypes.data, p2.ctypes.data, prediction, n, threads, out.ctypes.data, status.ctypes.data,
                                  None if stats is None else stats.ctypes.data)
         return (out, status, stats) if with_stats else (out, status)
+
+    def contact_local(self, shape1, pos1, shape2, pos2, prediction, threads=1):
+        """QueryDispatcher::contact(pos1.inv_mul(pos2), ..) per pair, result left in the shapes' local frames: (out (n,13), status)."""
+        s1, s2, p1, p2 = _u32(shape1), _u32(shape2), _f32(pos1), _f32(pos2)
+        n = len(s1)
+        out = np.zeros((n, 13), dtype=np.float32)
+        status = np.zeros(n, dtype=np.uint8)
+        lib().pb2o_contact_local_batch(self.kinds.ctypes.data, self.params.ctypes.data, self.points.ctypes.data, s1.ctypes.data, s2.ctypes.data,
+                                       p1.ctypes.data, p2.ctypes.data, prediction, n, threads, out.ctypes.data, status.ctypes.data)
+        return out, status
 
     def cast_shapes(self, shape1, pos1, vel1, shape2, pos2, vel2, max_time_of_impact=float(np.finfo(np.float32).max), target_distance=0.0,
                     stop_at_penetration=True, compute_impact_geometry_on_penetration=True, threads=1):

@@ -269,6 +269,15 @@ int pb2_compound_contact_shapes(pb2_ctx* ctx, const pb2_compounds* compounds, co
                                 const uint32_t* shape_ids, const float* shape_poses7, uint32_t n, float prediction, int compound_second,
                                 pb2_contact* out, uint8_t* status, uint32_t* part, int mem);
 
+/* query::contact between two Compounds of the table, n pairs (default_query_dispatcher.rs:338-351, the composite arm nested through
+ * contact_shape_composite_shape, contact_composite_shape_shape.rs:14-76; Compound::local_aabb compound.rs:120-127, Aabb::transform_by
+ * aabb.rs:492-498): pair k = compound ids1[k] at poses1[k] vs compound ids2[k] at poses2[k]. out / status as pb2_contact_batch
+ * (status 2: unknown compound id); parts: n x 2 = winning part of each compound (equal dists: smallest (part1, part2)) or
+ * 0xFFFFFFFF. */
+int pb2_compound_contact_compounds(pb2_ctx* ctx, const pb2_compounds* compounds, const uint32_t* ids1, const float* poses1 /* n x 7 */,
+                                   const uint32_t* ids2, const float* poses2, uint32_t n, float prediction, pb2_contact* out, uint8_t* status,
+                                   uint32_t* parts /* n x 2 */, int mem);
+
 /* query::closest_points for n pairs (closest_points/closest_points_shape_shape.rs:220-231 -> default_query_dispatcher.rs:358-424:
  * closest_points_ball_ball.rs:7-36, closest_points_ball_convex_polyhedron.rs:7-44, closest_points_support_map_support_map.rs:8-69).
  * kind: 0 ClosestPoints::Disjoint, 1 WithinMargin (points[k] = p1, p2 in world space), 2 Intersecting. status: 1 ok, 2 unknown

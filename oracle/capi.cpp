@@ -263,6 +263,22 @@ void pb2o_contact_batch(const uint8_t* kinds, const float* params4, const float*
         }
     });
 }
+// QueryDispatcher::contact(pos1.inv_mul(pos2), g1, g2, prediction) for n pairs: the same dispatch without Contact::transform_by_mut,
+// i.e. the contact in the two shapes' local frames (what the composite arms consume).
+void pb2o_contact_local_batch(const uint8_t* kinds, const float* params4, const float* points, const uint32_t* shape1, const uint32_t* shape2,
+                              const float* pos1, const float* pos2, float prediction, uint32_t n, int nthreads, float* out, uint8_t* status) {
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            ShapeRef s1 = make_shape(kinds, params4, points, shape1[k]), s2 = make_shape(kinds, params4, points, shape2[k]);
+            Contact c = Contact();
+            int st = dispatch_contact(Iso::from7(pos1 + 7 * k).inv_mul(Iso::from7(pos2 + 7 * k)), s1, s2, prediction, c);
+            status[k] = (uint8_t)st;
+            float* o = out + 13 * k;
+            if (st == CONTACT_SOME) { st3(o, c.point1); st3(o + 3, c.point2); st3(o + 6, c.normal1); st3(o + 9, c.normal2); o[12] = c.dist; }
+            else for (int i = 0; i < 13; ++i) o[i] = 0.0f;
+        }
+    });
+}
 // query::contact between Compound compound_id[k] (parts comp_first[c] .. + comp_count[c] of the part table: part_shape = index
 // into the shape table, part_pose7) and shape[k]. pos_c / pos_s: poses of the compound and of the shape. compound_second != 0:
 // the call was contact(pos_s, shape, pos_c, compound) (result flipped accordingly). part[k] = winning part (index within

@@ -113,9 +113,18 @@ __host__ __device__ __forceinline__ V3 cross3(V3 a, V3 b) {
 __host__ __device__ __forceinline__ float nrm2(V3 a) { return dot3(a, a); }
 __device__ __forceinline__ float nrm(V3 a) { return sqrtf(dot3(a, a)); }
 __device__ __forceinline__ V3 normalize3(V3 a) { return a / nrm(a); }
-__device__ __forceinline__ V3 vmin3(V3 a, V3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
-__device__ __forceinline__ V3 vmax3(V3 a, V3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+__host__ __device__ __forceinline__ V3 vmin3(V3 a, V3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
+__host__ __device__ __forceinline__ V3 vmax3(V3 a, V3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
 __device__ __forceinline__ float comp(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+// bit pattern of a float (shape tables keep u32 fields in float4 params); __float_as_uint on the device
+__host__ __device__ __forceinline__ uint32_t pb2_f2u(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
 
 struct Q4 {
     float i, j, k, w;
@@ -149,8 +158,8 @@ __host__ __device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
 }
 __host__ __device__ __forceinline__ V3 iso_point(const Iso7& m, V3 p) { return qrot(m.q, p) + m.t; }
 __host__ __device__ __forceinline__ V3 iso_vec(const Iso7& m, V3 v) { return qrot(m.q, v); }
-__device__ __forceinline__ V3 iso_inv_point(const Iso7& m, V3 p) { return qirot(m.q, p - m.t); }
-__device__ __forceinline__ V3 iso_inv_vec(const Iso7& m, V3 v) { return qirot(m.q, v); }
+__host__ __device__ __forceinline__ V3 iso_inv_point(const Iso7& m, V3 p) { return qirot(m.q, p - m.t); }
+__host__ __device__ __forceinline__ V3 iso_inv_vec(const Iso7& m, V3 v) { return qirot(m.q, v); }
 __host__ __device__ __forceinline__ Iso7 iso_inv_mul(const Iso7& a, const Iso7& b) {
     Iso7 r;
     Q4 inv = qconj(a.q);
@@ -158,7 +167,7 @@ __host__ __device__ __forceinline__ Iso7 iso_inv_mul(const Iso7& a, const Iso7& 
     r.q = qmul(inv, b.q);
     return r;
 }
-__device__ __forceinline__ Iso7 iso_inverse(const Iso7& a) {
+__host__ __device__ __forceinline__ Iso7 iso_inverse(const Iso7& a) {
     Iso7 r;
     r.q = qconj(a.q);
     r.t = -qrot(r.q, a.t);

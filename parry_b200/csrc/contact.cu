@@ -19,6 +19,7 @@
 #include "gjk.cuh"
 #include "trimesh.cuh"
 #include "manifold_update.cuh"
+#include "compound_pair.cuh"
 #include <stdlib.h>
 #include <cub/cub.cuh>
 
@@ -2309,6 +2310,123 @@ int pb2_compound_contact_shapes(pb2_ctx* ctx, const pb2_compounds* compounds, co
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------- Compound vs Compound
+// query::contact between two Compounds of one table (nested composite arms, see compound_pair.cuh): candidates = (part of compound
+// 1, part of compound 2) pairs passing the two AABB tests of the reference, materialised as plain leaf problems for the contact
+// kernels (local frames), then reduced per pair. pass 0 counts, pass 1 fills.
+static CompoundTable compound_table(const pb2_compounds* c) {
+    CompoundTable T;
+    T.first = c->first; T.count = c->count; T.part_shape = c->part_shape; T.part_pose = c->part_pose; T.part_aabb = c->part_aabb; T.nc = c->nc;
+    return T;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_cc_candidates(const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float* __restrict__ points,
+                                                       CompoundTable T, const uint32_t* __restrict__ id1, const float* __restrict__ pos1,
+                                                       const uint32_t* __restrict__ id2, const float* __restrict__ pos2, uint32_t n, float prediction,
+                                                       uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ ij,
+                                                       uint32_t* __restrict__ cs1, uint32_t* __restrict__ cs2, float* __restrict__ cp1,
+                                                       float* __restrict__ cp2) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t a = id1[k], b = id2[k], cnt = 0;
+    if (a < T.nc && b < T.nc) {
+        Iso7 pos12 = iso_inv_mul(load_iso(pos1 + 7ull * k), load_iso(pos2 + 7ull * k));   // contact_shape_shape.rs:130
+        cnt = cc_candidates<FILL>(kinds, params, points, T, a, b, pos12, prediction, FILL ? offsets[k] : 0u, ij, cs1, cs2, cp1, cp2);
+    }
+    if (!FILL) counts[k] = cnt;
+}
+
+__global__ void __launch_bounds__(128) k_cc_reduce(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ij, const float* __restrict__ cand,
+                                                   const uint8_t* __restrict__ cst, CompoundTable T, const uint32_t* __restrict__ id1,
+                                                   const float* __restrict__ pos1, const uint32_t* __restrict__ id2, const float* __restrict__ pos2,
+                                                   uint32_t n, float* __restrict__ out, uint8_t* __restrict__ status, uint32_t* __restrict__ parts) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t a = id1[k], b = id2[k];
+    float* o = out + 13ull * k;
+    if (a >= T.nc || b >= T.nc) {
+        for (int d = 0; d < 13; ++d) o[d] = 0.0f;
+        parts[2ull * k] = PB2_INVALID_U32; parts[2ull * k + 1] = PB2_INVALID_U32;
+        status[k] = ST_UNSUPPORTED;
+        return;
+    }
+    status[k] = (uint8_t)cc_reduce(ij, cand, cst, offsets[k], offsets[k + 1], T, a, b, load_iso(pos1 + 7ull * k), load_iso(pos2 + 7ull * k), o,
+                                   parts + 2ull * k);
+}
+
+extern "C" int pb2_compound_contact_compounds(pb2_ctx* ctx, const pb2_compounds* compounds, const uint32_t* ids1, const float* poses1,
+                                              const uint32_t* ids2, const float* poses2, uint32_t n, float prediction, pb2_contact* out,
+                                              uint8_t* status, uint32_t* parts, int mem) {
+    if (!ctx || !compounds || (n && (!ids1 || !poses1 || !ids2 || !poses2 || !out || !status || !parts))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    const pb2_shapes* shapes = compounds->shapes;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_i1, *d_p1, *d_i2, *d_p2;
+    void *d_out, *d_status, *d_parts;
+    PB2_CHECK(pb2_stage_in(ctx, 0, ids1, (size_t)n * 4, mem, &d_i1));
+    PB2_CHECK(pb2_stage_in(ctx, 1, ids2, (size_t)n * 4, mem, &d_i2));
+    PB2_CHECK(pb2_stage_in(ctx, 2, poses1, (size_t)n * 28, mem, &d_p1));
+    PB2_CHECK(pb2_stage_in(ctx, 3, poses2, (size_t)n * 28, mem, &d_p2));
+    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_status));
+    PB2_CHECK(pb2_stage_out(ctx, 6, parts, (size_t)n * 8, mem, &d_parts));
+    CompoundTable T = compound_table(compounds);
+    uint32_t *d_cnt = nullptr, *d_off = nullptr, *d_ij = nullptr, *d_cs1 = nullptr, *d_cs2 = nullptr;
+    float *d_cp1 = nullptr, *d_cp2 = nullptr, *d_cand = nullptr;
+    uint8_t* d_cst = nullptr;
+    void* d_tmp = nullptr;
+    int rc = PB2_OK;
+    do {
+        size_t cub_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n + 1, st);
+        if (cudaMallocAsync((void**)&d_cnt, ((size_t)n + 1) * 4, st) != cudaSuccess || cudaMallocAsync((void**)&d_off, ((size_t)n + 1) * 4, st) != cudaSuccess ||
+            cudaMallocAsync(&d_tmp, cub_bytes, st) != cudaSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), "compound_contact_compounds: out of memory"); rc = PB2_ERR_CUDA; break;
+        }
+        cudaMemsetAsync(d_cnt + n, 0, 4, st);
+        k_cc_candidates<false><<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points, T, (const uint32_t*)d_i1, (const float*)d_p1,
+                                                                   (const uint32_t*)d_i2, (const float*)d_p2, n, prediction, d_cnt, nullptr, nullptr, nullptr,
+                                                                   nullptr, nullptr, nullptr);
+        PB2_LAUNCHED(ctx);
+        cub::DeviceScan::ExclusiveSum(d_tmp, cub_bytes, (const uint32_t*)d_cnt, d_off, (int)n + 1, st);
+        ctx->launches += 1;
+        uint32_t total = 0;
+        cudaMemcpyAsync(&total, d_off + n, 4, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "compound_contact_compounds: candidate pass failed"); rc = PB2_ERR_CUDA; break; }
+        if (total) {
+            if (cudaMallocAsync((void**)&d_ij, (size_t)total * 8, st) != cudaSuccess || cudaMallocAsync((void**)&d_cs1, (size_t)total * 4, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_cs2, (size_t)total * 4, st) != cudaSuccess || cudaMallocAsync((void**)&d_cp1, (size_t)total * 28, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_cp2, (size_t)total * 28, st) != cudaSuccess || cudaMallocAsync((void**)&d_cand, (size_t)total * 52, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_cst, total, st) != cudaSuccess) {
+                snprintf(ctx->err, sizeof(ctx->err), "compound_contact_compounds: out of memory (%u candidates)", total); rc = PB2_ERR_CUDA; break;
+            }
+            k_cc_candidates<true><<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points, T, (const uint32_t*)d_i1,
+                                                                      (const float*)d_p1, (const uint32_t*)d_i2, (const float*)d_p2, n, prediction, nullptr,
+                                                                      d_off, d_ij, d_cs1, d_cs2, d_cp1, d_cp2);
+            PB2_LAUNCHED(ctx);
+            OutSinks sinks;
+            sinks.dense = d_cand; sinks.status = d_cst; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
+            sinks.compact_count = nullptr; sinks.some_count = nullptr;
+            // each candidate is a plain pair: contact(part_pos2[j].inv_mul(pose), part_j, part_i), left in the parts' frames
+            if ((rc = run_contacts(ctx, shapes, d_cs1, d_cs2, d_cp1, d_cp2, prediction, total, sinks, nullptr, 0, nullptr, 0, PAIR_LOCAL_FRAMES)) != PB2_OK) break;
+        }
+        k_cc_reduce<<<pb2_blocks(n, 128), 128, 0, st>>>(d_off, d_ij, d_cand, d_cst, T, (const uint32_t*)d_i1, (const float*)d_p1, (const uint32_t*)d_i2,
+                                                        (const float*)d_p2, n, (float*)d_out, (uint8_t*)d_status, (uint32_t*)d_parts);
+        PB2_LAUNCHED(ctx);
+        if (cudaGetLastError() != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "compound_contact_compounds: launch failed"); rc = PB2_ERR_CUDA; break; }
+    } while (0);
+    void* frees[] = {d_cnt, d_off, d_tmp, d_ij, d_cs1, d_cs2, d_cp1, d_cp2, d_cand, d_cst};
+    for (void* f : frees) if (f) cudaFreeAsync(f, st);
+    if (rc != PB2_OK) return rc;
+    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_status, (size_t)n, mem));
+    PB2_CHECK(pb2_stage_back(ctx, parts, d_parts, (size_t)n * 8, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(st));
+    return PB2_OK;
+}
 
 // ------------------------------------------------------------------------------------------- contact manifolds (closed-form arms)
 // QueryDispatcher::contact_manifolds for Ball / Cuboid pairs, first frame (empty incoming manifold, so try_update_contacts

@@ -24,7 +24,7 @@ struct pb2_shapes {
 
 // Shape::compute_aabb(pos) (shape/shape.rs:369): aabb_ball.rs:8-33, aabb_cuboid.rs:9-16 + utils/isometry_ops.rs:16-18,
 // aabb_convex_polyhedron.rs:8-16 + aabb_utils.rs:66-87.
-__device__ __forceinline__ void shape_aabb_dev(uint8_t kind, float4 pr, const float* __restrict__ points, const Iso7& pos, V3& mn, V3& mx) {
+__host__ __device__ __forceinline__ void shape_aabb_dev(uint8_t kind, float4 pr, const float* __restrict__ points, const Iso7& pos, V3& mn, V3& mx) {
     if (kind == PB2_SHAPE_BALL) {
         // ball_aabb: center + repeat(-r), center + repeat(r)
         float r = pr.x;
@@ -44,7 +44,7 @@ __device__ __forceinline__ void shape_aabb_dev(uint8_t kind, float4 pr, const fl
         mn = pos.t - he;  // Aabb::from_half_extents(center, he)
         mx = pos.t + he;
     } else {
-        uint32_t first = __float_as_uint(pr.x), cnt = __float_as_uint(pr.y);
+        uint32_t first = pb2_f2u(pr.x), cnt = pb2_f2u(pr.y);
         const float* p = points + 3ull * first;
         V3 w0 = iso_point(pos, mk3(p[0], p[1], p[2]));
         mn = w0; mx = w0;

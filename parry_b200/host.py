@@ -568,6 +568,22 @@ class Compounds:
                                                                  po, pst, ppart, mem))
         return out, status, part
 
+    def contact_compounds(self, ids1, poses1, ids2, poses2, prediction):
+        """query::contact(poses1[k], compound ids1[k], poses2[k], compound ids2[k], prediction) for every k (the composite arm of
+        DefaultQueryDispatcher::contact nested through contact_shape_composite_shape). Returns (contacts (n, 13), status (n,),
+        parts (n, 2) winning part of each compound)."""
+        n = int(poses1.shape[0])
+        k1, p1, mem = _prep(poses1, np.float32)
+        k2, p2, _ = _prep(poses2, np.float32, mem)
+        ki1, pi1, _ = _prep(ids1, np.uint32, mem)
+        ki2, pi2, _ = _prep(ids2, np.uint32, mem)
+        dev = self.ctx.torch_device
+        out, po = _empty((n, 13), np.float32, mem, dev)
+        status, pst = _empty((n,), np.uint8, mem, dev)
+        parts, pp = _empty((n, 2), np.uint32, mem, dev)
+        self.ctx.check(self.ctx._lib.pb2_compound_contact_compounds(self.ctx.h, self.h, pi1, p1, pi2, p2, n, float(prediction), po, pst, pp, mem))
+        return out, status, parts
+
     def close(self):
         if self.h:
             self.ctx._lib.pb2_compounds_destroy(self.ctx.h, self.h)

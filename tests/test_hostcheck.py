@@ -1,6 +1,7 @@
-"""CPU check of device code that is written __host__ __device__: the core of the manifold-persistence kernel
-(parry_b200/csrc/manifold_update.cuh) is compiled for the host by nvcc with the library's floating-point flags and must reproduce
-the oracle's ContactManifold::try_update_contacts bit for bit. (The kernel around it is covered by tests/test_manifold_update_gpu.py.)"""
+"""CPU check of device code that is written __host__ __device__: the per-manifold core of the persistence kernel
+(parry_b200/csrc/manifold_update.cuh) and the per-pair candidate enumeration / reduction of Compound-vs-Compound contacts
+(parry_b200/csrc/compound_pair.cuh) are compiled for the host by nvcc with the library's floating-point flags and must reproduce
+the oracle bit for bit. (The kernels around them are covered by the GPU tests; this file needs no GPU.)"""
 import ctypes as C
 import os
 import subprocess
@@ -16,11 +17,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 @pytest.fixture(scope="module")
 def hostlib():
     from parry_b200 import build as b
-    src = os.path.join(HERE, "hostcheck", "manifold_update_host.cu")
+    src = os.path.join(HERE, "hostcheck", "host_device_cores.cu")
     out_dir = os.path.join(HERE, "hostcheck", "_build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libhostcheck.so")
-    deps = [src, os.path.join(b.CSRC, "manifold_update.cuh"), os.path.join(b.CSRC, "common.cuh")]
+    deps = [src] + [os.path.join(b.CSRC, f) for f in ("manifold_update.cuh", "compound_pair.cuh", "shapes.cuh", "common.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call([b._nvcc()] + b.NVCC_FLAGS + ["-shared", src, "-o", so])
     return C.CDLL(so)
@@ -59,3 +60,60 @@ def test_try_update_core_matches_oracle(hostlib, oracle):
     assert 0.2 < kept_o[has].mean() < 0.9                  # both outcomes exercised
     assert (kept_h == kept_o).all()
     assert (q_h.view(np.uint32) == q_o.view(np.uint32)).all()   # including the partially refreshed points of rejected manifolds
+
+
+def test_compound_compound_cores_match_oracle(hostlib, oracle):
+    """compound_pair.cuh on the CPU: candidates (two nested AABB tests) -> leaf contacts (here from the oracle's dispatcher on the
+    materialised leaf problems, on the GPU from the contact kernels) -> reduction; against the oracle's contact_compound_compound."""
+    g = scenes.rng(31)
+    pts, _ = scenes.hull_pool(4, 16, seed=32)
+    spec = [("ball", 0.3), ("ball", 0.2), ("cuboid", [0.25, 0.4, 0.3]), ("cuboid", [0.5, 0.15, 0.2])] + [("convex", p * 0.5) for p in pts]
+    T = oracle.ShapeTable(spec)
+    ns, nc = len(spec), 24
+    first, count, psid, ppose = [], [], [], []
+    for c in range(nc):
+        k = int(g.integers(1, 5))
+        first.append(len(psid)); count.append(k)
+        psid += [int(x) for x in g.integers(0, ns, k)]
+        ppose.append(np.concatenate([scenes.random_unit_quaternions(g, k), (g.random((k, 3)) - 0.5) * 1.2], axis=1))
+    first, count, psid = np.asarray(first, np.uint32), np.asarray(count, np.uint32), np.asarray(psid, np.uint32)
+    ppose = np.ascontiguousarray(np.concatenate(ppose), dtype=np.float32)
+    n = 20000
+    a, b = g.integers(0, nc, n).astype(np.uint32), g.integers(0, nc, n).astype(np.uint32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 2.0 + 0.2)], axis=1).astype(np.float32)
+    pred = 0.05
+    ref_out, ref_st, ref_parts = T.contact_compound_compound(first, count, psid, ppose, a, p1, b, p2, pred, threads=8)
+    assert 0.15 < (ref_st == 1).mean() < 0.9
+
+    P, u32 = C.c_void_p, C.c_uint32
+    tab = [T.kinds.ctypes.data, T.params.ctypes.data, T.points.ctypes.data]
+    np_parts = len(psid)
+    aabb = np.zeros((np_parts, 6), np.float32)
+    hostlib.hostcheck_part_aabbs.argtypes = [P] * 5 + [u32, P]
+    hostlib.hostcheck_part_aabbs(*tab, psid.ctypes.data, ppose.ctypes.data, np_parts, aabb.ctypes.data)
+    comp = [first.ctypes.data, count.ctypes.data, psid.ctypes.data, ppose.ctypes.data, aabb.ctypes.data]
+    pairs = [a.ctypes.data, p1.ctypes.data, b.ctypes.data, p2.ctypes.data]
+    hostlib.hostcheck_cc_candidates.argtypes = [P] * 8 + [u32] + [P] * 4 + [u32, C.c_float, C.c_int] + [P] * 7
+    counts = np.zeros(n + 1, np.uint32)
+    hostlib.hostcheck_cc_candidates(*tab, *comp, nc, *pairs, n, pred, 0, counts.ctypes.data, None, None, None, None, None, None)
+    offsets = np.concatenate([[0], np.cumsum(counts[:n])]).astype(np.uint32)
+    total = int(offsets[n])
+    assert total > n // 4
+    ij, cs1, cs2 = np.zeros((total, 2), np.uint32), np.zeros(total, np.uint32), np.zeros(total, np.uint32)
+    cp1, cp2 = np.zeros((total, 7), np.float32), np.zeros((total, 7), np.float32)
+    hostlib.hostcheck_cc_candidates(*tab, *comp, nc, *pairs, n, pred, 1, None, offsets.ctypes.data, ij.ctypes.data, cs1.ctypes.data, cs2.ctypes.data,
+                                    cp1.ctypes.data, cp2.ctypes.data)
+    assert (cs1 == psid[ij[:, 1]]).all() and (cs2 == psid[ij[:, 0]]).all() and (cp1 == ppose[ij[:, 1]]).all()
+    cand, cst = T.contact_local(cs1, cp1, cs2, cp2, pred, threads=8)       # the contact kernels' job on the GPU
+    out = np.zeros((n, 13), np.float32)
+    st = np.zeros(n, np.uint8)
+    parts = np.zeros((n, 2), np.uint32)
+    hostlib.hostcheck_cc_reduce.argtypes = [P] * 9 + [u32] + [P] * 4 + [u32, P, P, P]
+    hostlib.hostcheck_cc_reduce(offsets.ctypes.data, ij.ctypes.data, cand.ctypes.data, cst.ctypes.data, *comp, nc, *pairs, n, out.ctypes.data,
+                                st.ctypes.data, parts.ctypes.data)
+    assert (st == ref_st).all()
+    assert (parts == ref_parts).all()
+    assert (out.view(np.uint32) == ref_out.view(np.uint32)).all()
