@@ -33,6 +33,7 @@ def _prep(x, dtype, mem=None):
         return None, None, mem
     if _is_torch(x):
         tdt = {np.float32: torch.float32, np.uint32: torch.int32, np.uint8: torch.uint8}[dtype]
+        x0 = x
         if x.dtype != tdt:
             if dtype is np.uint32 and x.dtype in (torch.int64, torch.uint32):
                 x = x.to(torch.int32)
@@ -40,6 +41,9 @@ def _prep(x, dtype, mem=None):
                 x = x.to(tdt)
         x = x.contiguous()
         if x.is_cuda:
+            if x is not x0:
+                # a conversion kernel ran on torch's current stream; the library's stream is non-blocking and would not wait for it
+                torch.cuda.current_stream(x.device).synchronize()
             return x, x.data_ptr(), MEM_DEVICE
         x = x.numpy()
     a = np.ascontiguousarray(x, dtype=dtype)
@@ -56,7 +60,10 @@ def _empty(shape, dtype, mem, device):
 
 
 class Context:
-    """One CUDA device + one stream (pb2_ctx). With `stream=` (a torch.cuda.Stream) work is enqueued there."""
+    """One CUDA device + one stream (pb2_ctx). With `stream=` (a torch.cuda.Stream) work is enqueued there.
+    The context's own stream is non-blocking: device tensors handed to a call must already be complete with respect to it
+    (produce them under `torch.cuda.stream(ctx.torch_stream())`, or synchronize the producing stream first), and results are
+    ordered on it (`ctx.synchronize()` before reading them from another stream)."""
 
     def __init__(self, device=0, stream=None):
         self._lib = _ffi.lib()
@@ -744,6 +751,8 @@ def _inout(x, dtype, mem):
         tdt = {np.float32: torch.float32, np.uint32: torch.int32}[dtype]
         t = (x if _is_torch(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=dtype).view(np.int32 if dtype is np.uint32 else dtype)))
         t = t.to(device=None if t.is_cuda else "cuda", dtype=tdt).contiguous().clone()
+        # the copy is a kernel on torch's current stream; the library's stream is non-blocking and would not wait for it
+        torch.cuda.current_stream(t.device).synchronize()
         return t, t.data_ptr()
     a = np.array(x.cpu().numpy() if _is_torch(x) else x, dtype=dtype, order="C", copy=True)
     return a, a.ctypes.data
