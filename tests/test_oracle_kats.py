@@ -641,3 +641,31 @@ def test_persistent_manifold_dispatch(oracle):
     assert ((cnt4 > 0) == (cnt2 > 0))[pfm].mean() > 0.99 and both.sum() > 100
     deepest = lambda p, c: np.where(np.arange(mp)[None, :] < c[:, None], p[:, :, 6], np.inf).min(axis=1)
     assert np.quantile(np.abs(deepest(pts4[both], cnt4[both]) - deepest(pts2[both], cnt2[both])), 0.99) < 2e-3
+
+
+def test_manifold_doc_examples(oracle):
+    """The doc examples of query/contact_manifolds/contact_manifold.rs, the only places the reference pins manifold values:
+    :270-297 (two unit balls 1.5 apart, prediction 0: one contact), :305-329 (2.1 apart, prediction 0.2: a predicted contact with
+    dist > 0) and :719-758 (frames at 1.9 and 1.85: match_contacts hands the old point's ContactData to the new point, i.e. the
+    new point matches old point 0 by its feature ids; ball manifolds are always recomputed, never kept)."""
+    T = oracle.ShapeTable([("ball", 1.0)])
+    z = np.zeros(3, np.uint32)
+    ident = np.tile(np.array([0, 0, 0, 1, 0, 0, 0], np.float32), (3, 1))
+    p2 = ident.copy()
+    p2[:, 4] = [1.5, 2.1, 1.9]
+    pred = 0.0
+    nr, cnt, pts, st = T.contact_manifolds(z[:1], ident[:1], z[:1], p2[:1], pred)
+    assert st[0] == 0 and cnt[0] == 1 and pts[0, 0, 6] == np.float32(-0.5)
+    assert (nr[0] == np.array([1, 0, 0, -1, 0, 0], np.float32)).all()
+    assert (pts[0, 0, :6] == np.array([1, 0, 0, -1, 0, 0], np.float32)).all()
+    nr, cnt, pts, st = T.contact_manifolds(z[1:2], ident[1:2], z[1:2], p2[1:2], 0.2)
+    assert cnt[0] == 1 and pts[0, 0, 6] > 0 and abs(pts[0, 0, 6] - 0.1) < 1e-6
+    nr, cnt, pts, st = T.contact_manifolds(z[1:2], ident[1:2], z[1:2], p2[1:2], 0.0)
+    assert cnt[0] == 0                                              # without prediction the separated balls give no contact
+    nr, cnt, pts, st = T.contact_manifolds(z[2:], ident[2:], z[2:], p2[2:], 0.0)
+    assert cnt[0] == 1
+    p2b = p2[2:].copy()
+    p2b[:, 4] = 1.85
+    rn, rc, rp, rs, rk, rm = T.contact_manifolds_update(z[2:], ident[2:], z[2:], p2b, 0.0, nr, cnt, pts)
+    assert rk[0] == 0 and rc[0] == 1 and rm[0, 0] == 0 and (rm[0, 1:] == -1).all()
+    assert abs(rp[0, 0, 6] - (1.85 - 2.0)) < 1e-6

@@ -120,3 +120,19 @@ def test_manifolds_update_device_resident(ctx, oracle):
     e = parry_b200.contact_manifolds_update(G, np.zeros(0, np.uint32), z, np.zeros(0, np.uint32), z, 0.05, np.zeros((0, 6), np.float32),
                                             np.zeros(0, np.uint32), np.zeros((0, 12, 9), np.float32))
     assert len(e[1]) == 0
+
+
+def test_match_contacts_doc_example(ctx):
+    """contact_manifold.rs:719-758, the reference's own pin for match_contacts: unit balls at 1.9 then 1.85 apart; the recomputed
+    point carries the old point's feature ids, so it matches old point 0 (whose ContactData the reference hands over)."""
+    import parry_b200
+    G = parry_b200.Shapes(ctx, [parry_b200.Ball(1.0)])
+    z = np.zeros(1, np.uint32)
+    ident = np.array([[0, 0, 0, 1, 0, 0, 0]], np.float32)
+    f1, f2 = ident.copy(), ident.copy()
+    f1[0, 4], f2[0, 4] = 1.9, 1.85
+    nr, cnt, pts, st = parry_b200.contact_manifolds(G, z, ident, z, f1, 0.0, max_points=4)
+    assert cnt[0] == 1
+    gn, gc, gp, gs, gk, gm = parry_b200.contact_manifolds_update(G, z, ident, z, f2, 0.0, nr, cnt, pts)
+    assert gk[0] == 0 and gc[0] == 1 and gm[0, 0] == 0 and (gm[0, 1:] == -1).all()
+    assert abs(gp[0, 0, 6] - (1.85 - 2.0)) < 1e-6
