@@ -1,6 +1,6 @@
 // Known-answer program for the C++ host mirror (include/parry_b200.hpp) above the C ABI: the reference's own exact pins run through
 // the C++ types a maintainer would use. Exit code 0 = all checks passed, 1 = a check failed, 3 = no CUDA device (there is no CPU
-// fallback). Built and run by tests/test_cpp_mirror.py.
+// fallback). Built and run by tests/test_zx_cpp_mirror.py.
 //   crates/parry3d/tests/geometry/epa3.rs:8-23      cuboid (2,1,1) vs itself: dist == -0.5, normal1 == -x; dist == -1.8, normal1 == -y
 //   crates/parry3d/tests/geometry/ball_ball_toi.rs  time_of_impact == 0.9
 //   a unit square of two triangles, three boxes: hand-checkable ray hit, pair set, intersect_aabb
