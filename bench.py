@@ -379,7 +379,11 @@ def bench_also(ctx, stream, args, hbm_peak):
     out["rays_1M_vs_100k_tri_sphere"] = {"value": m / (ms * 1e-3), "unit": "rays/s", "ms": ms, "l2": "flushed between iterations",
                                          "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
     del mesh, mesh2
-    for name, fn in EXTRA_ALSO:
+    extra = list(EXTRA_ALSO)
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        # paths that have not run on hardware yet: last, and never in a multi-rank job (a device fault must not reach a collective)
+        extra.append(("first_hardware_runs", also_first_hardware_runs))
+    for name, fn in extra:
         try:
             out[name] = fn(ctx, stream, timed, flush, hbm_peak)
         except Exception as e:  # a secondary workload must not take the headline down
@@ -707,6 +711,66 @@ def also_siblings(ctx, stream, timed, flush, hbm_peak):
     out["compound_contacts"] = {"value": m / (ms * 1e-3), "unit": "pairs/s", "ms": ms,
                                 "contacts_fraction": float((res["comp"][1] == 1).float().mean().item())}
     out["pairs"] = n
+    out["l2"] = "flushed between iterations"
+    return out
+
+
+def also_first_hardware_runs(ctx, stream, timed, flush, hbm_peak):
+    """The two SURVEY §8 (f) paths written after this round's GPU budget was spent, run LAST so that a
+    failure cannot touch any other entry: manifold persistence (second frame of 2^22 ball / cuboid pairs, half of them drifting by
+    2e-4 — most of those keep their manifold — and half by 0.05) and Compound vs Compound contacts (2^20 pairs of 1-5 parts)."""
+    import torch
+    import parry_b200
+    from harness import scenes
+    out = {}
+    T = lambda x: torch.from_numpy(x).cuda()
+    n = 1 << 22
+    g = scenes.rng(41)
+    G = parry_b200.Shapes(ctx, [parry_b200.Ball(0.4), parry_b200.Ball(0.25), parry_b200.Cuboid([0.3, 0.5, 0.4]), parry_b200.Cuboid([0.6, 0.2, 0.2]),
+                                parry_b200.Cuboid([0.5, 0.5, 0.5])])
+    s1, s2 = g.integers(0, 5, n).astype(np.int32), g.integers(0, 5, n).astype(np.int32)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 20], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 1.3 + 0.2)], axis=1).astype(np.float32)
+    p2b = p2.copy()
+    p2b[:, 4:] += (g.standard_normal((n, 3)) * np.where(g.random((n, 1)) < 0.5, 2.0e-4, 0.05)).astype(np.float32)
+    ds1, ds2, dp1, dp2, dp2b = T(s1), T(s2), T(p1), T(p2), T(p2b)
+    nr, cnt, pts, st = parry_b200.contact_manifolds(G, ds1, dp1, ds2, dp2, 0.05, max_points=8)
+    ctx.synchronize()
+    res = {}
+
+    def run_update():
+        res["u"] = parry_b200.contact_manifolds_update(G, ds1, dp1, ds2, dp2b, 0.05, nr, cnt, pts)
+    ms = timed(run_update, steps=5, warmup=2, flush=flush)
+    kept, cnt2 = res["u"][4], res["u"][1]
+    out["manifold_persistence_4M_ball_cuboid_pairs"] = {
+        "value": n / (ms * 1e-3), "unit": "pairs/s (second frame: try_update_contacts, recompute the rest, match_contacts)", "ms": ms,
+        "kept_fraction_of_nonempty": float((kept[cnt > 0] != 0).float().mean().item()),
+        "manifolds_with_points": float((cnt2 > 0).float().mean().item()),
+        "note": "includes the wrapper's private copy of last frame's manifolds (1.2 GB)"}
+    del res["u"], nr, cnt, pts, st
+    G2, ns = _mixed_table(ctx)
+    nc = 4096
+    compounds = []
+    for c in range(nc):
+        k = int(g.integers(1, 6))
+        pp = np.concatenate([scenes.random_unit_quaternions(g, k), (g.random((k, 3)) - 0.5) * 1.6], axis=1).astype(np.float32)
+        compounds.append([(pp[i], int(g.integers(0, ns))) for i in range(k)])
+    Cc = parry_b200.Compounds(ctx, G2, compounds)
+    m = 1 << 20
+    c1, c2 = T(g.integers(0, nc, m).astype(np.int32)), T(g.integers(0, nc, m).astype(np.int32))
+    q2 = p2[:m].copy()
+    q2[:, 4:] = p1[:m, 4:] + d[:m] * (g.random((m, 1)) * 3.0 + 0.2).astype(np.float32)
+    dq2 = T(q2)
+
+    def run_cc():
+        res["cc"] = Cc.contact_compounds(c1, dp1[:m], c2, dq2, 0.05)
+    ms = timed(run_cc, steps=5, warmup=2, flush=flush)
+    stc = res["cc"][1]
+    out["compound_vs_compound_1M_pairs"] = {"value": m / (ms * 1e-3), "unit": "pairs/s", "ms": ms,
+                                            "contacts_fraction": float((stc == 1).float().mean().item()),
+                                            "host_fallback": int((stc == 3).sum().item())}
     out["l2"] = "flushed between iterations"
     return out
 
