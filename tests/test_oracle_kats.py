@@ -249,6 +249,14 @@ def test_cast_shapes_reference_tests(oracle):
     T = oracle.ShapeTable([("cuboid", [.5, .5, .5])])
     got = [T.cast_shapes([0], [_pose([0, 1.1, 0])], [[0, vy, 0]], [0], [_pose([0, 0, 0])], [[0, 0, 0]])[1][0] for vy in (0.0, 1.0, -1.0)]
     assert got[0] == 0 and got[1] == 0 and got[2] != 0
+    # ball_triangle_toi.rs (issue #123, once an infinite loop): a denormal velocity is "too small", the cast answers None. The
+    # Triangle is given as a 3-point ConvexPolyhedron (same support function up to ties, which play no role here).
+    tri = np.array([[0.5, -0.5, 0], [-0.5, -0.5, 0], [-0.5, 0.5, 0]], np.float32)
+    T = oracle.ShapeTable([("ball", 0.375), ("convex", tri)])
+    vel = np.array([[0.0, 6.925e-42, 0.0]], np.float32)
+    assert vel[0, 1] > 0                                            # still a (denormal) non-zero f32
+    out, st = T.cast_shapes([0], [_pose([0, 0, 0])], vel, [1], [_pose([11.5, 5.5, 0])], [[0, 0, 0]])
+    assert st[0] == 0
 
 
 def test_cast_shapes_hit_configuration_touches(oracle):
