@@ -285,6 +285,18 @@ def shape_cast_ray_toi(kind, params, pose, ray, max_toi, solid=True):
     return toi.value if hit else None
 
 
+_EXTRA.append(("pb2o_clip_aabb_line", i32, [P, P, P, P]))
+
+
+def clip_aabb_line(mins, maxs, origin, direction):
+    """query::details::clip_aabb_line (clip_aabb_line.rs:79-187). Returns None or (near t, far t)."""
+    box = _f32(list(mins) + list(maxs)).ravel()
+    o, d = _f32(origin).ravel(), _f32(direction).ravel()
+    nf = np.zeros(2, dtype=np.float32)
+    hit = lib().pb2o_clip_aabb_line(box.ctypes.data, o.ctypes.data, d.ctypes.data, nf.ctypes.data)
+    return (nf[0], nf[1]) if hit else None
+
+
 _EXTRA.append(("pb2o_shape_aabbs", None, [P, P, P, P, P, P, u32, P]))
 
 

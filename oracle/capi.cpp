@@ -203,6 +203,15 @@ int pb2o_shape_cast_ray_toi(int kind, const float* p, const float* pose7, const 
     *toi = ri.time_of_impact; return 1;
 }
 
+// clip_aabb_line (clip_aabb_line.rs:79-187) on one box and one line, so that the reference's own unit test (:192-206) can be run on
+// the restatement. returns 1 when the line meets the box; near_far[0..1] = the two parameters.
+int pb2o_clip_aabb_line(const float* aabb6, const float* origin3, const float* dir3, float* near_far) {
+    ClipHit near, far;
+    if (!clip_aabb_line(Aabb(ld3(aabb6), ld3(aabb6 + 3)), ld3(origin3), ld3(dir3), near, far)) return 0;
+    if (near_far) { near_far[0] = near.t; near_far[1] = far.t; }
+    return 1;
+}
+
 }  // extern "C"
 
 // ---------------- per-shape AABBs (Shape::compute_aabb) ----------------

@@ -677,3 +677,13 @@ def test_manifold_doc_examples(oracle):
     rn, rc, rp, rs, rk, rm = T.contact_manifolds_update(z[2:], ident[2:], z[2:], p2b, 0.0, nr, cnt, pts)
     assert rk[0] == 0 and rc[0] == 1 and rm[0, 0] == 0 and (rm[0, 1:] == -1).all()
     assert abs(rp[0, 0, 6] - (1.85 - 2.0)) < 1e-6
+
+
+def test_clip_empty_aabb_line(oracle):
+    """query/clip/clip_aabb_line.rs:192-206, the reference's unit test of the function under Cuboid ray casts with normals: a
+    zero direction clips to Some exactly when the origin lies in the (here degenerate) box."""
+    assert oracle.clip_aabb_line([0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0]) is not None
+    assert oracle.clip_aabb_line([1, 1, 1], [2, 2, 2], [0, 0, 0], [0, 0, 0]) is None
+    # and a hand-checkable clip: the x axis through the unit box enters at 1 and leaves at 2 from the origin
+    nf = oracle.clip_aabb_line([1, -1, -1], [2, 1, 1], [0, 0, 0], [1, 0, 0])
+    assert nf is not None and nf[0] == 1.0 and nf[1] == 2.0
