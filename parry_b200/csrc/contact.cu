@@ -2894,10 +2894,8 @@ extern "C" int pb2_contact_manifolds_batch(pb2_ctx* ctx, const pb2_shapes* shape
 }
 
 // ------------------------------------------------------------------------------------------- manifold persistence
-// ContactManifold::try_update_contacts_eps (contact_manifold.rs:662-699) per manifold, in place. dispatch != 0: only the pairs whose
-// dispatcher arm tries to keep last frame's manifold (contact_manifolds_cuboid_cuboid.rs:28, contact_manifolds_pfm_pfm.rs:63: neither
-// shape a Ball, hulls with face topology); kept pairs get status 0. old_fids / old_counts (optional): last frame's feature ids,
-// saved for match_contacts before the recomputation overwrites them.
+// ContactManifold::try_update_contacts_eps (contact_manifold.rs:662-699) per manifold, in place; the per-pair bodies are
+// __host__ __device__ functions in manifold_update.cuh (tests/hostcheck runs them on the CPU against the oracle).
 __global__ void __launch_bounds__(128) k_manifold_try_update(const uint8_t* __restrict__ kinds, uint32_t n_shapes, const uint32_t* __restrict__ shape1,
                                                              const uint32_t* __restrict__ shape2, bool dispatch, bool have_topology,
                                                              const float* __restrict__ pos1, const float* __restrict__ pos2, uint32_t n,
@@ -2907,59 +2905,16 @@ __global__ void __launch_bounds__(128) k_manifold_try_update(const uint8_t* __re
                                                              uint32_t* __restrict__ old_fids, uint32_t* __restrict__ old_counts) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    uint32_t cnt = counts[k];
-    if (cnt > max_points) cnt = max_points;
-    float* q = pts + (size_t)k * max_points * 9;
-    if (old_fids) {
-        old_counts[k] = cnt;
-        uint32_t* f = old_fids + (size_t)k * max_points * 2;
-        for (uint32_t i = 0; i < cnt; ++i) { f[2 * i] = __float_as_uint(q[9 * i + 7]); f[2 * i + 1] = __float_as_uint(q[9 * i + 8]); }
-    }
-    bool tries = true;
-    if (dispatch) {
-        uint32_t a = shape1[k], b = shape2[k];
-        tries = a < n_shapes && b < n_shapes;
-        if (tries) {
-            uint8_t ka = kinds[a], kb = kinds[b];
-            bool ok1 = ka == PB2_SHAPE_CUBOID || (ka == PB2_SHAPE_CONVEX && have_topology);
-            bool ok2 = kb == PB2_SHAPE_CUBOID || (kb == PB2_SHAPE_CONVEX && have_topology);
-            tries = ok1 && ok2;
-        }
-    }
-    bool keep = false;
-    if (tries && cnt) {
-        Iso7 pos12 = iso_inv_mul(load_iso(pos1 + 7ull * k), load_iso(pos2 + 7ull * k));
-        keep = manifold_try_update_core(pos12, normals + 6ull * k, cnt, q, angle_dot_threshold, dist_sq_threshold);
-    }
-    kept[k] = keep ? 1 : 0;
-    if (keep && status) status[k] = 0;
+    manifold_try_update_pair(k, kinds, n_shapes, shape1, shape2, dispatch, have_topology, pos1, pos2, max_points, angle_dot_threshold,
+                             dist_sq_threshold, normals, counts, pts, kept, status, old_fids, old_counts);
 }
 
-// ContactManifold::match_contacts (contact_manifold.rs:761-770) as an index: match[k][i] = the last old point of pair k whose two
-// feature ids equal those of new point i (the one whose ContactData the reference's loop leaves in place), -1 = none; kept
-// manifolds map onto themselves.
 __global__ void __launch_bounds__(128) k_manifold_match(const uint8_t* __restrict__ kept, const uint32_t* __restrict__ old_fids,
                                                         const uint32_t* __restrict__ old_counts, const uint32_t* __restrict__ counts,
                                                         const float* __restrict__ pts, uint32_t n, uint32_t max_points, int32_t* __restrict__ match) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    uint32_t cnt = counts[k], oc = old_counts[k];
-    if (cnt > max_points) cnt = max_points;
-    const float* q = pts + (size_t)k * max_points * 9;
-    const uint32_t* f = old_fids + (size_t)k * max_points * 2;
-    int32_t* m = match + (size_t)k * max_points;
-    bool keep = kept[k] != 0;
-    for (uint32_t i = 0; i < max_points; ++i) {
-        int32_t j = -1;
-        if (i < cnt) {
-            if (keep) j = (int32_t)i;
-            else {
-                uint32_t f1 = __float_as_uint(q[9 * i + 7]), f2 = __float_as_uint(q[9 * i + 8]);
-                for (uint32_t o = 0; o < oc; ++o) if (f[2 * o] == f1 && f[2 * o + 1] == f2) j = (int32_t)o;
-            }
-        }
-        m[i] = j;
-    }
+    manifold_match_pair(k, kept, old_fids, old_counts, counts, pts, max_points, match);
 }
 
 extern "C" int pb2_manifolds_try_update(pb2_ctx* ctx, const float* pos1, const float* pos2, uint32_t n, uint32_t max_points,

@@ -57,3 +57,18 @@ extern "C" void hostcheck_cc_reduce(const uint32_t* offsets, const uint32_t* ij,
         status[k] = (uint8_t)cc_reduce(ij, cand, cst, offsets[k], offsets[k + 1], T, id1[k], id2[k], load_iso(pos1 + 7ull * k), load_iso(pos2 + 7ull * k),
                                        out + 13ull * k, parts + 2ull * k);
 }
+
+// ---- Second-frame dispatch: one "thread" of k_manifold_try_update / k_manifold_match per pair (manifold_update.cuh), so that the
+// dispatch rule (which arms try to keep a manifold), the saved feature ids and the match index are checked on the CPU as well.
+extern "C" void hostcheck_manifold_try_update_pairs(const uint8_t* kinds, uint32_t n_shapes, const uint32_t* shape1, const uint32_t* shape2, int dispatch,
+                                                    int have_topology, const float* pos1, const float* pos2, uint32_t n, uint32_t max_points,
+                                                    const float* normals, const uint32_t* counts, float* pts, uint8_t* kept, uint8_t* status,
+                                                    uint32_t* old_fids, uint32_t* old_counts) {
+    for (uint32_t k = 0; k < n; ++k)
+        manifold_try_update_pair(k, kinds, n_shapes, shape1, shape2, dispatch != 0, have_topology != 0, pos1, pos2, max_points, PB2_COS_1_DEGREES,
+                                 PB2_UPDATE_DIST_SQ, normals, counts, pts, kept, status, old_fids, old_counts);
+}
+extern "C" void hostcheck_manifold_match_pairs(const uint8_t* kept, const uint32_t* old_fids, const uint32_t* old_counts, const uint32_t* counts,
+                                               const float* pts, uint32_t n, uint32_t max_points, int32_t* match) {
+    for (uint32_t k = 0; k < n; ++k) manifold_match_pair(k, kept, old_fids, old_counts, counts, pts, max_points, match);
+}

@@ -117,3 +117,61 @@ def test_compound_compound_cores_match_oracle(hostlib, oracle):
     assert (st == ref_st).all()
     assert (parts == ref_parts).all()
     assert (out.view(np.uint32) == ref_out.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("hulls", [False, True])
+def test_second_frame_dispatch_matches_oracle(hostlib, oracle, hulls):
+    """pb2_contact_manifolds_update_batch step by step on the CPU: the per-pair bodies of k_manifold_try_update (dispatch rule, saved
+    feature ids, kept / status) and k_manifold_match (manifold_update.cuh, compiled for the host), with the recomputation of the
+    pairs that were not kept taken from the oracle's first-frame manifolds (what the manifold kernels compute behind the skip mask),
+    must give the oracle's persistent dispatch: kept flags, counts, points bit for bit, match indices."""
+    g = scenes.rng(91)
+    spec = [("ball", 0.3), ("cuboid", [0.3, 0.5, 0.4]), ("cuboid", [0.6, 0.2, 0.2]), ("cuboid", [0.5, 0.5, 0.5])]
+    if hulls:
+        hp, _ = scenes.hull_pool(5, 16, seed=92)
+        spec += [("convex", np.asarray(p, np.float32) * 0.6) for p in hp]
+    T = oracle.ShapeTable(spec)
+    topo = T.hull_topology() if hulls else None
+    n, mp = 12000, 12
+    ns = len(spec)
+    s1, s2 = g.integers(0, ns, n).astype(np.uint32), g.integers(0, ns, n).astype(np.uint32)
+    s1[::101] = 1000                                       # unknown shape ids: never kept, status from the recomputation
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), (g.random((n, 3)) - .5) * 2], axis=1).astype(np.float32)
+    d = g.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p2 = np.concatenate([scenes.random_unit_quaternions(g, n), p1[:, 4:] + d * (g.random((n, 1)) * 1.0 + 0.3)], axis=1).astype(np.float32)
+    p2[::3, :4] = p1[::3, :4]
+    p2b = p2.copy()
+    p2b[:, 4:] += (g.standard_normal((n, 3)) * np.where(g.random((n, 1)) < 0.5, 2.0e-4, 0.05)).astype(np.float32)
+    nr, cnt, pts, st = T.contact_manifolds(s1, p1, s2, p2, 0.05, max_points=mp, threads=4, topology=topo)
+    rn, rc, rp, rs, rk, rm = T.contact_manifolds_update(s1, p1, s2, p2b, 0.05, nr, cnt, pts, threads=4, topology=topo)
+    # 1. k_manifold_try_update with dispatch
+    hn, hc, hp_, hs = nr.copy(), cnt.copy(), pts.copy(), np.full(n, 255, np.uint8)
+    kept = np.zeros(n, np.uint8)
+    old_f, old_c = np.zeros((n, mp, 2), np.uint32), np.zeros(n, np.uint32)
+    kinds = np.ascontiguousarray(T.kinds, dtype=np.uint8)
+    P, u32, i32 = C.c_void_p, C.c_uint32, C.c_int
+    hostlib.hostcheck_manifold_try_update_pairs.argtypes = [P, u32, P, P, i32, i32, P, P, u32, u32, P, P, P, P, P, P, P]
+    hostlib.hostcheck_manifold_try_update_pairs(kinds.ctypes.data, ns, s1.ctypes.data, s2.ctypes.data, 1, int(hulls), p1.ctypes.data, p2b.ctypes.data,
+                                                n, mp, hn.ctypes.data, hc.ctypes.data, hp_.ctypes.data, kept.ctypes.data, hs.ctypes.data,
+                                                old_f.ctypes.data, old_c.ctypes.data)
+    assert (kept == rk).all(), np.nonzero(kept != rk)[0][:10]
+    assert (hs[kept == 1] == 0).all() and (hs[kept == 0] == 255).all()
+    assert (old_c == np.minimum(cnt, mp)).all()
+    valid = np.arange(mp)[None, :] < old_c[:, None]
+    assert (old_f[valid] == pts[:, :, 7:].view(np.uint32)[valid]).all()
+    # 2. the manifold kernels behind the skip mask = a first-frame computation of the pairs that were not kept
+    fn, fc, fp, fs = T.contact_manifolds(s1, p1, s2, p2b, 0.05, max_points=mp, threads=4, topology=topo)
+    rec = kept == 0
+    hn[rec], hc[rec], hp_[rec], hs[rec] = fn[rec], fc[rec], fp[rec], fs[rec]
+    # 3. k_manifold_match
+    match = np.full((n, mp), -7, np.int32)
+    hostlib.hostcheck_manifold_match_pairs.argtypes = [P, P, P, P, P, u32, u32, P]
+    hostlib.hostcheck_manifold_match_pairs(kept.ctypes.data, old_f.ctypes.data, old_c.ctypes.data, hc.ctypes.data, hp_.ctypes.data, n, mp,
+                                           match.ctypes.data)
+    assert (hs == rs).all() and (hc == rc).all()
+    assert (hp_.view(np.uint32) == rp.view(np.uint32)).all() and (hn.view(np.uint32) == rn.view(np.uint32)).all()
+    assert (match == rm).all(), np.nonzero((match != rm).any(axis=1))[0][:10]
+    ball = (kinds[np.minimum(s1, ns - 1)] == 0) | (kinds[np.minimum(s2, ns - 1)] == 0) | (s1 >= ns)
+    assert (kept[ball] == 0).all() and 0.15 < kept[~ball & (cnt > 0)].mean() < 0.85
+    assert (match >= 0).any(axis=1)[rec & (rc > 0) & (cnt > 0)].mean() > 0.3        # recomputed manifolds do find old points again
