@@ -111,21 +111,3 @@ def test_pfm_manifolds_vs_oracle(ctx, oracle):
     G2 = tables(ctx, oracle, spec)[1]
     _, c2, _, st2 = parry_b200.contact_manifolds(G2, s1, p1, s2, p2, 0.05, max_points=12)
     assert (st2[pfm | ballhull] == 2).all() and (c2[pfm | ballhull] == 0).all() and (st2[~pfm & ~ballhull] == 0).all()
-
-
-def test_manifold_doc_examples(ctx):
-    """contact_manifold.rs:270-297 and :305-329, the reference's own pins (same checks as tests/test_oracle_kats.py on the oracle):
-    unit balls 1.5 apart give one contact of dist -0.5 along +x; 2.1 apart with prediction 0.2 a predicted contact of dist 0.1."""
-    import parry_b200
-    G = parry_b200.Shapes(ctx, [parry_b200.Ball(1.0)])
-    z = np.zeros(3, np.uint32)
-    ident = np.tile(np.array([0, 0, 0, 1, 0, 0, 0], np.float32), (3, 1))
-    p2 = ident.copy()
-    p2[:, 4] = [1.5, 2.1, 2.1]
-    nr, cnt, pts, st = parry_b200.contact_manifolds(G, z[:1], ident[:1], z[:1], p2[:1], 0.0, max_points=4)
-    assert st[0] == 0 and cnt[0] == 1 and pts[0, 0, 6] == np.float32(-0.5)
-    assert (nr[0] == np.array([1, 0, 0, -1, 0, 0], np.float32)).all() and (pts[0, 0, :6] == np.array([1, 0, 0, -1, 0, 0], np.float32)).all()
-    nr, cnt, pts, st = parry_b200.contact_manifolds(G, z[1:2], ident[1:2], z[1:2], p2[1:2], 0.2, max_points=4)
-    assert cnt[0] == 1 and pts[0, 0, 6] > 0 and abs(pts[0, 0, 6] - 0.1) < 1e-6
-    nr, cnt, pts, st = parry_b200.contact_manifolds(G, z[2:], ident[2:], z[2:], p2[2:], 0.0, max_points=4)
-    assert cnt[0] == 0

@@ -55,18 +55,6 @@ def test_reference_shape_cast_tests_on_gpu(ctx):
     assert st[4] == 0 and st[5] == 0 and st[6] == 1                           # still_objects_toi.rs
 
 
-def test_ball_triangle_toi_issue_123(ctx):
-    """crates/parry3d/tests/geometry/ball_triangle_toi.rs: a denormal velocity must answer None (and terminate); the Triangle is a
-    3-point ConvexPolyhedron here, as in tests/test_oracle_kats.py."""
-    import parry_b200
-    tri = np.array([[0.5, -0.5, 0], [-0.5, -0.5, 0], [-0.5, 0.5, 0]], np.float32)
-    G = parry_b200.Shapes(ctx, [parry_b200.Ball(0.375), parry_b200.ConvexPolyhedron(tri)])
-    vel = np.array([[0.0, 6.925e-42, 0.0]], np.float32)
-    out, st = parry_b200.cast_shapes(G, np.array([0], np.uint32), _pose([0, 0, 0])[None], vel, np.array([1], np.uint32),
-                                     _pose([11.5, 5.5, 0])[None], np.zeros((1, 3), np.float32))
-    assert st[0] == 0
-
-
 @pytest.mark.parametrize("opts", [dict(), dict(stop_at_penetration=False), dict(compute_impact_geometry_on_penetration=False),
                                   dict(target_distance=0.05), dict(max_time_of_impact=0.4),
                                   dict(stop_at_penetration=False, compute_impact_geometry_on_penetration=False, target_distance=0.02)])
