@@ -13,7 +13,7 @@ from harness import scenes
 
 FMAX = float(np.finfo(np.float32).max)
 ctx = parry_b200.Context(0)
-what = set(sys.argv[1:]) or {"rays", "pieces", "contacts", "siblings"}
+what = set(sys.argv[1:]) or {"rays", "pieces", "contacts", "siblings", "persistence"}
 if "rays" in what or "pieces" in what:
     v, i = scenes.terrain(65, 65)
     mesh = parry_b200.TriMesh(ctx, v, i)
@@ -50,4 +50,26 @@ if "siblings" in what:
     nr, cnt, mp, st3 = parry_b200.contact_manifolds(G, z["man_shape1"], z["pos1"], z["man_shape2"], z["man_pos2"], 0.05)
     cp, kind, st4 = parry_b200.closest_points(G, z["shape1"], z["pos1"], z["shape2"], z["pos2"], 0.5)
     print("siblings:", int((st != 0).sum()), int((st2 == 1).sum()), int(cnt.sum()), np.bincount(kind).tolist(), flush=True)
+if "persistence" in what:
+    # the paths that first run on hardware in round 2: second-frame manifolds (host and device arrays) and Compound vs Compound
+    z = np.load(os.path.join(ROOT, "tests", "golden", "siblings_3000.npz"))
+    pu = z["params"].view(np.uint32)
+    spec = [parry_b200.Ball(p[0]) if k == 0 else parry_b200.Cuboid(p[:3]) if k == 1 else parry_b200.ConvexPolyhedron(z["points"][u[0]:u[0] + u[1]])
+            for k, p, u in zip(z["kinds"], z["params"], pu)]
+    G = parry_b200.Shapes(ctx, spec)
+    nr, cnt, mp, st3 = parry_b200.contact_manifolds(G, z["man_shape1"], z["pos1"], z["man_shape2"], z["man_pos2"], 0.05)
+    moved = z["man_pos2"].copy()
+    moved[::2, 4:] += np.float32(2.0e-4)
+    moved[1::2, 4:] += np.float32(0.03)
+    u = parry_b200.contact_manifolds_update(G, z["man_shape1"], z["pos1"], z["man_shape2"], moved, 0.05, nr, cnt, mp)
+    dev = lambda x: torch.from_numpy(x.view(np.int32) if x.dtype == np.uint32 else x).cuda()
+    ud = parry_b200.contact_manifolds_update(G, dev(z["man_shape1"]), dev(z["pos1"]), dev(z["man_shape2"]), dev(moved), 0.05, dev(nr), dev(cnt), dev(mp))
+    ctx.synchronize()
+    kept, q = parry_b200.manifolds_try_update(ctx, z["pos1"], moved, nr, cnt, mp)
+    compounds = [[(z["part_pose"][f + i], int(z["part_shape"][f + i])) for i in range(c)] for f, c in zip(z["comp_first"], z["comp_count"])]
+    Cc = parry_b200.Compounds(ctx, G, compounds)
+    ids2 = np.roll(z["compound_id"], 1)
+    o5, st5, parts = Cc.contact_compounds(z["compound_id"], z["pos1"], ids2, z["pos2_compound"], 0.05)
+    print("persistence:", int(u[4].sum()), "kept,", int((ud[4].cpu().numpy() == u[4]).all()), "device == host,", int(kept.sum()), "try_update kept,",
+          int((st5 == 1).sum()), "compound-compound contacts", flush=True)
 print("done", flush=True)
