@@ -190,9 +190,35 @@ def pfm():
                         pos2=p2, normals=nr, counts=cnt, man_points=mp, status=st, **{"topo_" + k: v for k, v in topo.items()})
 
 
+def second_frame():
+    """Second-frame manifolds (persistent dispatch, match_contacts) on the pfm golden's scene and first-frame manifolds, and Compound
+    vs Compound contacts on the sibling golden's compounds; inputs are read from those two files, only the new poses / ids and
+    the oracle's outputs are stored."""
+    z = np.load(os.path.join(HERE, "manifolds_pfm_2000.npz"))
+    T = oracle.ShapeTable([])
+    T.kinds, T.params, T.points = z["kinds"].copy(), z["params"].copy(), np.ascontiguousarray(z["points"])
+    topo = {k[5:]: z[k] for k in z.files if k.startswith("topo_")}
+    g = scenes.rng(501)
+    n = len(z["shape1"])
+    moved = z["pos2"].copy()
+    moved[:, 4:] += (g.standard_normal((n, 3)) * np.where(g.random((n, 1)) < 0.5, 2.0e-4, 0.05)).astype(np.float32)
+    rn, rc, rp, rs, rk, rm = T.contact_manifolds_update(z["shape1"], z["pos1"], z["shape2"], moved, 0.05, z["normals"], z["counts"], z["man_points"],
+                                                        topology=topo)
+    y = np.load(os.path.join(HERE, "siblings_3000.npz"))
+    T2 = oracle.ShapeTable([])
+    T2.kinds, T2.params, T2.points = y["kinds"].copy(), y["params"].copy(), np.ascontiguousarray(y["points"])
+    ids2 = g.integers(0, len(y["comp_first"]), len(y["compound_id"])).astype(np.uint32)
+    co, cs, cp = T2.contact_compound_compound(y["comp_first"], y["comp_count"], y["part_shape"], y["part_pose"], y["compound_id"], y["pos1"], ids2,
+                                              y["pos2_compound"], 0.05)
+    np.savez_compressed(os.path.join(HERE, "second_frame_2000.npz"), moved_pos2=moved, normals=rn, counts=rc, man_points=rp, status=rs, kept=rk,
+                        match=rm, compound_id2=ids2, cc_contacts=co, cc_status=cs, cc_parts=cp)
+
+
 if __name__ == "__main__":
     import sys
-    if "pfm" in sys.argv:
+    if "second_frame" in sys.argv:
+        second_frame()
+    elif "pfm" in sys.argv:
         pfm()
     elif "shape_rays" in sys.argv:
         shape_rays()

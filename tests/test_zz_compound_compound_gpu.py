@@ -78,3 +78,25 @@ def test_single_part_compounds_equal_plain_contact(ctx, oracle):
     ctx.synchronize()
     assert (d[0].cpu().numpy().view(np.uint32) == go.view(np.uint32)).all() and (d[1].cpu().numpy() == gs).all()
     assert (d[2].cpu().numpy().view(np.uint32) == gp).all()
+
+
+def test_gpu_reproduces_compound_compound_golden(ctx):
+    """tests/golden/second_frame_2000.npz (frozen oracle output) on the sibling golden's compounds."""
+    import os
+    import parry_b200
+    gd = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    y, w = np.load(os.path.join(gd, "siblings_3000.npz")), np.load(os.path.join(gd, "second_frame_2000.npz"))
+    pu = y["params"].view(np.uint32)
+    spec = [parry_b200.Ball(p[0]) if k == 0 else parry_b200.Cuboid(p[:3]) if k == 1 else parry_b200.ConvexPolyhedron(y["points"][u[0]:u[0] + u[1]])
+            for k, p, u in zip(y["kinds"], y["params"], pu)]
+    G = parry_b200.Shapes(ctx, spec)
+    compounds = [[(y["part_pose"][f + i], int(y["part_shape"][f + i])) for i in range(c)] for f, c in zip(y["comp_first"], y["comp_count"])]
+    Cc = parry_b200.Compounds(ctx, G, compounds)
+    go, gs, gp = Cc.contact_compounds(y["compound_id"], y["pos1"], w["compound_id2"], y["pos2_compound"], 0.05)
+    ok = gs != 3
+    assert (~ok).sum() <= 2
+    assert (gs[ok] == w["cc_status"][ok]).all()
+    some = ok & (gs == 1)
+    same = (gp[some] == w["cc_parts"][some]).all(axis=1)
+    assert same.mean() > 0.999
+    np.testing.assert_allclose(go[some][same], w["cc_contacts"][some][same], rtol=1e-5, atol=2e-6)

@@ -136,3 +136,27 @@ def test_match_contacts_doc_example(ctx):
     gn, gc, gp, gs, gk, gm = parry_b200.contact_manifolds_update(G, z, ident, z, f2, 0.0, nr, cnt, pts)
     assert gk[0] == 0 and gc[0] == 1 and gm[0, 0] == 0 and (gm[0, 1:] == -1).all()
     assert abs(gp[0, 0, 6] - (1.85 - 2.0)) < 1e-6
+
+
+def test_gpu_reproduces_second_frame_golden(ctx):
+    """tests/golden/second_frame_2000.npz (frozen oracle output, tests/golden/make_golden.py second_frame) on the pfm golden's scene."""
+    import os
+    import parry_b200
+    gd = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z, w = np.load(os.path.join(gd, "manifolds_pfm_2000.npz")), np.load(os.path.join(gd, "second_frame_2000.npz"))
+    pu = z["params"].view(np.uint32)
+    spec = [parry_b200.Ball(p[0]) if k == 0 else parry_b200.Cuboid(p[:3]) if k == 1 else parry_b200.ConvexPolyhedron(z["points"][u[0]:u[0] + u[1]])
+            for k, p, u in zip(z["kinds"], z["params"], pu)]
+    G = parry_b200.Shapes(ctx, spec)
+    G.set_hull_topology({k[5:]: z[k] for k in z.files if k.startswith("topo_")})
+    gn, gc, gp, gs, gk, gm = parry_b200.contact_manifolds_update(G, z["shape1"], z["pos1"], z["shape2"], w["moved_pos2"], 0.05, z["normals"],
+                                                                 z["counts"], z["man_points"])
+    ok = gs != 3
+    assert (~ok).sum() <= 2
+    assert (gk[ok] == w["kept"][ok]).all() and (gc[ok] == w["counts"][ok]).all() and (gs[ok] == w["status"][ok]).all()
+    assert (gm[ok] == w["match"][ok]).all()
+    assert (gp[ok][:, :, 7:].view(np.uint32) == w["man_points"][ok][:, :, 7:].view(np.uint32)).all()
+    kp = ok & (gk == 1)
+    assert (gp[kp].view(np.uint32) == w["man_points"][kp].view(np.uint32)).all()
+    np.testing.assert_allclose(gn[ok], w["normals"][ok], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gp[ok][:, :, :7], w["man_points"][ok][:, :, :7], rtol=1e-5, atol=2e-6)
