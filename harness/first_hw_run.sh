@@ -7,7 +7,7 @@ out=gpurun_out/first_hw
 mkdir -p "$out"
 # 1. the late test files, most trusted first (no -x: see every result)
 timeout 600 python -m pytest tests/test_zx_cpp_mirror.py tests/test_zy_reference_pins_gpu.py tests/test_zz_manifold_update_gpu.py \
-    tests/test_zz_compound_compound_gpu.py -m gpu -q > "$out/pytest.log" 2>&1
+    tests/test_zzz_compound_compound_gpu.py -m gpu -q > "$out/pytest.log" 2>&1
 echo "pytest rc=$?" >> "$out/pytest.log"
 # 2. memcheck of the new kernels on the small golden scene
 timeout 300 compute-sanitizer --tool memcheck python harness/sanitize_probe.py persistence > "$out/memcheck.log" 2>&1
