@@ -38,6 +38,8 @@ def lib():
         l.pb2o_trimesh_cast_rays.argtypes = [P, P, P, u32, f32, i32, i32, i32, P, P, P, P]
         l.pb2o_trimesh_contact_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, i32, P, P, P]
         l.pb2o_trimesh_contact_batch.restype = None
+        l.pb2o_compound_trimesh_contact_batch.argtypes = [P] * 11 + [f32, u32, i32, i32, i32, P, P, P]
+        l.pb2o_compound_trimesh_contact_batch.restype = None
         l.pb2o_trimesh_project_points.argtypes = [P, P, P, u32, i32, i32, i32, P, P, P]
         l.pb2o_trimesh_project_points.restype = None
         l.pb2o_bvh_create.restype = P
@@ -151,6 +153,22 @@ class TriMesh:
                                          s2.ctypes.data, p2.ctypes.data, prediction, n, threads, int(min_index_ties), out.ctypes.data,
                                          status.ctypes.data, part.ctypes.data)
         return out, status, part
+
+    def contact_compounds(self, mesh_pose, table, comp_first, comp_count, part_shape, part_pose, ids, poses, prediction, trimesh_first=False,
+                          threads=1, min_index_ties=False):
+        """query::contact between Compound ids[k] at poses[k] and this mesh at mesh_pose (oracle groundwork, no GPU path yet);
+        trimesh_first: the mesh is shape 1. Returns (contacts (n,13), status, parts (n,2) = winning {compound part, triangle})."""
+        cf, cc, psid, a = _u32(comp_first), _u32(comp_count), _u32(part_shape), _u32(ids)
+        pp, p, mp = _f32(part_pose), _f32(poses), _f32(mesh_pose)
+        n = len(a)
+        out = np.zeros((n, 13), dtype=np.float32)
+        status = np.zeros(n, dtype=np.uint8)
+        parts = np.zeros((n, 2), dtype=np.uint32)
+        lib().pb2o_compound_trimesh_contact_batch(self.h, mp.ctypes.data, table.kinds.ctypes.data, table.params.ctypes.data, table.points.ctypes.data,
+                                                  cf.ctypes.data, cc.ctypes.data, psid.ctypes.data, pp.ctypes.data, a.ctypes.data, p.ctypes.data,
+                                                  prediction, n, threads, int(trimesh_first), int(min_index_ties), out.ctypes.data,
+                                                  status.ctypes.data, parts.ctypes.data)
+        return out, status, parts
 
     def __del__(self):
         try:

@@ -534,6 +534,37 @@ void pb2o_trimesh_contact_batch(void* mesh, const float* mesh_pose7, const uint8
         }
     });
 }
+// query::contact between Compounds of a table and one TriMesh (oracle groundwork, no GPU path yet). trimesh_first == 0:
+// contact(poses[k], Compound ids[k], mesh_pose, &TriMesh); != 0: contact(mesh_pose, &TriMesh, poses[k], Compound ids[k]). World-space
+// result; parts[k] = {winning compound part, winning triangle} or u32::MAX. ties as in pb2o_trimesh_contact_batch.
+void pb2o_compound_trimesh_contact_batch(void* mesh, const float* mesh_pose7, const uint8_t* kinds, const float* params4, const float* points,
+                                         const uint32_t* comp_first, const uint32_t* comp_count, const uint32_t* part_shape, const float* part_pose7,
+                                         const uint32_t* ids, const float* poses, float prediction, uint32_t n, int nthreads, int trimesh_first,
+                                         int ties, float* out, uint8_t* status, uint32_t* parts) {
+    const TriMesh* tm = (const TriMesh*)mesh;
+    Iso pm = Iso::from7(mesh_pose7);
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        std::vector<ShapeRef> ss; std::vector<Iso> qq;
+        for (size_t k = lo; k < hi; ++k) {
+            uint32_t f = comp_first[ids[k]], cnt = comp_count[ids[k]];
+            ss.resize(cnt); qq.resize(cnt);
+            for (uint32_t i = 0; i < cnt; ++i) { ss[i] = make_shape(kinds, params4, points, part_shape[f + i]); qq[i] = Iso::from7(part_pose7 + 7 * (size_t)(f + i)); }
+            CompoundRef comp{ss.data(), qq.data(), cnt};
+            Iso pc = Iso::from7(poses + 7 * k);
+            Iso p1 = trimesh_first ? pm : pc, p2 = trimesh_first ? pc : pm;
+            Contact c = Contact(); uint32_t part = UINT32_MAX, tri = UINT32_MAX;
+            int st = trimesh_first ? contact_trimesh_compound(p1.inv_mul(p2), *tm, comp, prediction, c, tri, part, ties != 0)
+                                   : contact_compound_trimesh(p1.inv_mul(p2), comp, *tm, prediction, c, part, tri, ties != 0);
+            status[k] = (uint8_t)st; parts[2 * k] = st == CONTACT_SOME ? part : UINT32_MAX; parts[2 * k + 1] = st == CONTACT_SOME ? tri : UINT32_MAX;
+            float* o = out + 13 * k;
+            if (st == CONTACT_SOME) {
+                c.point1 = p1.transform_point(c.point1); c.point2 = p2.transform_point(c.point2);
+                c.normal1 = p1.transform_vector(c.normal1); c.normal2 = p2.transform_vector(c.normal2);
+                st3(o, c.point1); st3(o + 3, c.point2); st3(o + 6, c.normal1); st3(o + 9, c.normal2); o[12] = c.dist;
+            } else for (int i = 0; i < 13; ++i) o[i] = 0.0f;
+        }
+    });
+}
 // PointQuery::project_point(m, pt, solid) / project_local_point on a TriMesh (query/point/point_query.rs:147-151: local projection
 // of m^-1 * pt, transformed back). mode 0: reference traversal; mode 1: brute force, ties to the smallest triangle index.
 void pb2o_trimesh_project_points(void* mesh, const float* pose7, const float* points, uint32_t n, int solid, int mode, int nthreads,

@@ -441,6 +441,66 @@ static inline int contact_compound_compound(const Iso& pos12, const CompoundRef&
     return have ? CONTACT_SOME : CONTACT_NONE;
 }
 
+// Compound vs TriMesh, both orders, through the same dispatcher arms (default_query_dispatcher.rs:338-351 takes shape1's composite
+// view first). Oracle groundwork (no GPU path yet).
+// Bvh::root_aabb (bvh_tree.rs:1991-2000) = TriMesh::local_aabb (trimesh.rs:1793-1795); TriMesh::compute_aabb(pos) = root_aabb().transform_by(pos)
+static inline Aabb bvh_root_aabb(const Bvh& b) {
+    if (b.nodes.empty()) return Aabb(Vec3(REAL_MAX, REAL_MAX, REAL_MAX), Vec3(-REAL_MAX, -REAL_MAX, -REAL_MAX));
+    uint32_t lc = b.nodes[0].leaf_count();
+    if (lc == 0) return Aabb(Vec3(REAL_MAX, REAL_MAX, REAL_MAX), Vec3(-REAL_MAX, -REAL_MAX, -REAL_MAX));
+    if (lc == 1) return b.nodes[0].left.aabb();
+    Aabb l = b.nodes[0].left.aabb(), r = b.nodes[0].right.aabb();
+    return Aabb(vinf(l.mins, r.mins), vsup(l.maxs, r.maxs));
+}
+// contact_composite_shape_shape(pos12, compound1, trimesh2): every part i of the compound whose AABB meets the mesh's loosened AABB
+// is dispatched as contact(part_pos1[i].inv_mul(pos12), part_i, trimesh), i.e. contact_shape_composite_shape (:63-76): the mesh as
+// the composite under the inverse pose, flipped(); then transform1_by_mut(part_pos1[i]). part / tri = the winning part and triangle.
+static inline int contact_compound_trimesh(const Iso& pos12, const CompoundRef& c1, const TriMesh& mesh, Real prediction, Contact& best,
+                                           uint32_t& part, uint32_t& tri, bool min_index_ties = false) {
+    Aabb ls = aabb_transform_by(bvh_root_aabb(mesh.bvh), pos12);
+    ls.mins = ls.mins - Vec3(prediction, prediction, prediction);
+    ls.maxs = ls.maxs + Vec3(prediction, prediction, prediction);
+    bool have = false;
+    for (uint32_t i = 0; i < c1.n; ++i) {
+        if (!shape_compute_aabb(c1.shapes[i], c1.poses[i]).intersects(ls)) continue;
+        Iso pos_i2 = c1.poses[i].inv_mul(pos12);          // pose of the mesh in part i's frame
+        Contact c = Contact(); uint32_t t = UINT32_MAX;
+        if (contact_trimesh_shape(pos_i2.inverse(), mesh, c1.shapes[i], prediction, c, t, min_index_ties) != CONTACT_SOME) continue;
+        std::swap(c.point1, c.point2); std::swap(c.normal1, c.normal2);
+        if (!have || c.dist < best.dist) {
+            c.point1 = c1.poses[i].transform_point(c.point1);
+            c.normal1 = c1.poses[i].transform_vector(c.normal1);
+            best = c; part = i; tri = t; have = true;
+        }
+    }
+    return have ? CONTACT_SOME : CONTACT_NONE;
+}
+// contact_composite_shape_shape(pos12, trimesh1, compound2): every triangle whose leaf AABB meets the compound's loosened AABB
+// (Shape::compute_aabb default on Compound::local_aabb) is dispatched as contact(pos12, triangle, compound2) (TriMesh parts have
+// no part pose), i.e. contact_shape_composite_shape: the compound as the composite under pos12.inverse(), flipped().
+static inline int contact_trimesh_compound(const Iso& pos12, const TriMesh& mesh, const CompoundRef& c2, Real prediction, Contact& best,
+                                           uint32_t& tri, uint32_t& part, bool min_index_ties = false) {
+    Aabb ls = aabb_transform_by(compound_local_aabb(c2), pos12);
+    ls.mins = ls.mins - Vec3(prediction, prediction, prediction);
+    ls.maxs = ls.maxs + Vec3(prediction, prediction, prediction);
+    std::vector<uint32_t> ids;
+    mesh.bvh.intersect_aabb(ls, ids);
+    Iso pos21 = pos12.inverse();
+    bool have = false;
+    for (uint32_t id : ids) {
+        float tv[9];
+        const uint32_t* t = &mesh.indices[3 * id];
+        for (int k = 0; k < 3; ++k) { tv[3 * k] = mesh.vertices[t[k]].x; tv[3 * k + 1] = mesh.vertices[t[k]].y; tv[3 * k + 2] = mesh.vertices[t[k]].z; }
+        ShapeRef s1; s1.kind = SHAPE_TRIANGLE; s1.radius = 0; s1.points = tv; s1.num_points = 3;
+        Contact c = Contact(); uint32_t j = UINT32_MAX;
+        if (contact_compound_shape(pos21, c2, s1, prediction, c, j) != CONTACT_SOME) continue;
+        std::swap(c.point1, c.point2); std::swap(c.normal1, c.normal2);
+        bool replace = !have || c.dist < best.dist || (min_index_ties && c.dist == best.dist && id < tri);
+        if (replace) { best = c; tri = id; part = j; have = true; }
+    }
+    return have ? CONTACT_SOME : CONTACT_NONE;
+}
+
 // query::contact with a Compound on one side (default_query_dispatcher.rs:338-351): compound first = composite arm; compound
 // second (flipped) = contact_shape_composite_shape (contact_composite_shape_shape.rs:63-76): pose12.inverse(), then flipped().
 static inline int query_contact_compound(const Iso& pos1, const Iso& pos2, const CompoundRef& comp, const ShapeRef& shape, bool compound_second,

@@ -687,3 +687,76 @@ def test_clip_empty_aabb_line(oracle):
     # and a hand-checkable clip: the x axis through the unit box enters at 1 and leaves at 2 from the origin
     nf = oracle.clip_aabb_line([1, -1, -1], [2, 1, 1], [0, 0, 0], [1, 0, 0])
     assert nf is not None and nf[0] == 1.0 and nf[1] == 2.0
+
+
+def test_compound_trimesh_contact_against_parts(oracle):
+    """Compound vs TriMesh in both orders (oracle groundwork for SURVEY §8 f2's last open item; default_query_dispatcher.rs:338-351
+    nested through contact_shape_composite_shape): the result must be the closest of the contacts of the mesh with every part
+    placed at its composed world pose (TriMesh-vs-shape, already checked against brute force), with that part and its triangle as
+    the winners; the two orders are each other's flipped()."""
+    g = scenes.rng(37)
+    v, idx = scenes.terrain(17, 17)
+    mesh = oracle.TriMesh(v, idx)
+    lo, hi = np.asarray(v).min(axis=0), np.asarray(v).max(axis=0)
+    pts, _ = scenes.hull_pool(4, 16, seed=38)
+    sc = float((hi - lo)[:2].max()) / 16.0            # shapes about the size of a terrain cell
+    spec = [("ball", 0.5 * sc), ("cuboid", [0.4 * sc, 0.6 * sc, 0.5 * sc])] + [("convex", np.asarray(p, np.float32) * 0.8 * sc) for p in pts]
+    T = oracle.ShapeTable(spec)
+    ns = len(spec)
+    first, count, psid, ppose = [], [], [], []
+    for c in range(12):
+        k = int(g.integers(1, 4))
+        first.append(len(psid)); count.append(k)
+        psid += [int(x) for x in g.integers(0, ns, k)]
+        ppose.append(np.concatenate([scenes.random_unit_quaternions(g, k), (g.random((k, 3)) - 0.5) * 2.0 * sc], axis=1))
+    first, count, psid = np.asarray(first, np.uint32), np.asarray(count, np.uint32), np.asarray(psid, np.uint32)
+    ppose = np.concatenate(ppose).astype(np.float32)
+    n = 600
+    ids = g.integers(0, 12, n).astype(np.uint32)
+    # compound centres scattered over the terrain, within a shape size of its surface on average
+    up = int(np.argmin((hi - lo)))                    # the height axis of the generated terrain
+    plane = [a for a in range(3) if a != up]
+    ctr = np.zeros((n, 3))
+    ctr[:, plane] = lo[plane] + g.random((n, 2)) * (hi - lo)[plane]
+    ctr[:, up] = lo[up] + g.random(n) * ((hi - lo)[up] + 2.0 * sc) - 0.5 * sc
+    poses = np.concatenate([scenes.random_unit_quaternions(g, n), ctr], axis=1).astype(np.float32)
+    mpose = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    pred = 0.1 * sc
+    out, st, parts = mesh.contact_compounds(mpose, T, first, count, psid, ppose, ids, poses, pred, threads=4, min_index_ties=True)
+    assert 0.15 < (st == 1).mean() < 0.95
+
+    def compose(p, q):
+        def rot(qt, x):
+            u, w = qt[:3], qt[3]
+            t = 2.0 * np.cross(u, x)
+            return x + w * t + np.cross(u, t)
+        pq, pt, qq, qt = p[:4].astype(np.float64), p[4:].astype(np.float64), q[:4].astype(np.float64), q[4:].astype(np.float64)
+        w = pq[3] * qq[3] - np.dot(pq[:3], qq[:3])
+        vv = pq[3] * qq[:3] + qq[3] * pq[:3] + np.cross(pq[:3], qq[:3])
+        return np.concatenate([vv, [w], pt + rot(pq, qt)]).astype(np.float32)
+    checked = same_tri = 0
+    for k in range(0, n, 3):
+        best, bi, bt = None, None, None
+        for i in range(count[ids[k]]):
+            gi = first[ids[k]] + i
+            o, s, t = mesh.contact_shapes(mpose, T, [psid[gi]], [compose(poses[k], ppose[gi])], pred, min_index_ties=True)
+            if s[0] == 1 and (best is None or o[0, 12] < best):
+                best, bi, bt = o[0, 12], i, t[0]
+        if best is None or st[k] != 1:
+            assert (best is None) == (st[k] != 1) or abs((best if best is not None else out[k, 12]) - pred) < 1e-4 * sc + 1e-5
+        else:
+            assert abs(out[k, 12] - best) < 2e-5 * max(1.0, sc)
+            same_tri += int(parts[k, 0] == bi and parts[k, 1] == bt)
+            checked += 1
+    # (a shape resting on two triangles has two equal dists; composing the poses in float64 here can tip such ties the other way)
+    assert checked > 30 and same_tri > 0.85 * checked
+    # the other order is the flipped contact (same dist; points and normals swapped)
+    out2, st2, parts2 = mesh.contact_compounds(mpose, T, first, count, psid, ppose, ids, poses, pred, trimesh_first=True, threads=4,
+                                               min_index_ties=True)
+    both = (st == 1) & (st2 == 1)
+    assert (st == st2).mean() > 0.99 and both.sum() > 50
+    np.testing.assert_allclose(out2[both][:, 12], out[both][:, 12], rtol=0, atol=3e-5 * max(1.0, sc))
+    agree = both & (parts == parts2).all(axis=1)
+    assert agree.sum() > 0.9 * both.sum()
+    np.testing.assert_allclose(out2[agree][:, 0:3], out[agree][:, 3:6], rtol=0, atol=2e-4 * max(1.0, sc))
+    np.testing.assert_allclose(out2[agree][:, 6:9], out[agree][:, 9:12], rtol=0, atol=2e-3)
