@@ -40,6 +40,8 @@ def lib():
         l.pb2o_trimesh_contact_batch.restype = None
         l.pb2o_compound_trimesh_contact_batch.argtypes = [P] * 11 + [f32, u32, i32, i32, i32, P, P, P]
         l.pb2o_compound_trimesh_contact_batch.restype = None
+        l.pb2o_trimesh_cast_shapes.argtypes = [P, P, P, P, P, P, P, u32, P, P, i32, f32, f32, i32, i32, P, P]
+        l.pb2o_trimesh_cast_shapes.restype = i32
         l.pb2o_trimesh_project_points.argtypes = [P, P, P, u32, i32, i32, i32, P, P, P]
         l.pb2o_trimesh_project_points.restype = None
         l.pb2o_bvh_create.restype = P
@@ -169,6 +171,22 @@ class TriMesh:
                                                   prediction, n, threads, int(trimesh_first), int(min_index_ties), out.ctypes.data,
                                                   status.ctypes.data, parts.ctypes.data)
         return out, status, parts
+
+    def cast_shapes(self, mesh_pose, mesh_vel, pose, vel, other_mesh=None, table=None, shape=0, mesh_second=False, max_toi=None,
+                    target_distance=0.0, stop_at_penetration=True, compute_impact_geometry_on_penetration=True):
+        """query::cast_shapes with this mesh as shape 1 (or 2 with mesh_second) against another TriMesh or table.shape (oracle
+        groundwork, no GPU path yet). Returns None or (out (13,), status, part)."""
+        mp, mv, po, ve = _f32(mesh_pose), _f32(mesh_vel), _f32(pose), _f32(vel)
+        out = np.zeros(13, dtype=np.float32)
+        part = C.c_uint32(0)
+        tk = table.kinds.ctypes.data if table is not None else None
+        tp = table.params.ctypes.data if table is not None else None
+        tq = table.points.ctypes.data if table is not None else None
+        st = lib().pb2o_trimesh_cast_shapes(self.h, mp.ctypes.data, mv.ctypes.data, other_mesh.h if other_mesh is not None else None, tk, tp, tq,
+                                            int(shape), po.ctypes.data, ve.ctypes.data, int(mesh_second),
+                                            float(np.finfo(np.float32).max) if max_toi is None else max_toi, target_distance,
+                                            int(stop_at_penetration), int(compute_impact_geometry_on_penetration), out.ctypes.data, C.byref(part))
+        return None if st == 0 else (out, st, part.value)
 
     def __del__(self):
         try:

@@ -508,6 +508,29 @@ void pb2o_cast_shapes_batch(const uint8_t* kinds, const float* params4, const fl
         }
     });
 }
+// query::cast_shapes with a TriMesh on either side, one pair (oracle groundwork; shape_cast_composite_shape_shape.rs). The mesh is
+// shape 1 (mesh_second == 0) or shape 2; the other shape is mesh_other when non-null, else entry `shape` of the table. out: 13 floats
+// as pb2o_cast_shapes_batch; part = winning triangle of the outer mesh when it is shape 1. Returns the status (0 = None).
+int pb2o_trimesh_cast_shapes(void* mesh, const float* mesh_pose7, const float* mesh_vel3, void* mesh_other, const uint8_t* kinds,
+                             const float* params4, const float* points, uint32_t shape, const float* pose7, const float* vel3, int mesh_second,
+                             float max_toi, float target_distance, int stop_at_penetration, int compute_impact_geometry_on_penetration, float* out,
+                             uint32_t* part) {
+    ShapeCastOptions o;
+    o.max_time_of_impact = max_toi; o.target_distance = target_distance; o.stop_at_penetration = stop_at_penetration != 0;
+    o.compute_impact_geometry_on_penetration = compute_impact_geometry_on_penetration != 0;
+    ShapeRef sr;
+    CastShape m{nullptr, (const TriMesh*)mesh}, other{nullptr, (const TriMesh*)mesh_other};
+    if (!mesh_other) { sr = make_shape(kinds, params4, points, shape); other.shape = &sr; }
+    Iso pm = Iso::from7(mesh_pose7), po = Iso::from7(pose7);
+    Vec3 vm = ld3(mesh_vel3), vo = ld3(vel3);
+    ShapeCastHit h;
+    uint32_t p1 = UINT32_MAX;
+    bool some = mesh_second ? cast_shapes_any(po, vo, other, pm, vm, m, o, h, &p1) : cast_shapes_any(pm, vm, m, po, vo, other, o, h, &p1);
+    if (part) *part = p1;
+    if (!some) { for (int i = 0; i < 13; ++i) out[i] = 0.0f; return 0; }
+    st3(out, h.witness1); st3(out + 3, h.witness2); st3(out + 6, h.normal1); st3(out + 9, h.normal2); out[12] = h.time_of_impact;
+    return h.status == CAST_PENETRATING ? 2 : 1;
+}
 // query::contact(pos1, &TriMesh, pos2[k], shape2[k], prediction) for n shapes against one mesh (composite arm of
 // DefaultQueryDispatcher::contact -> contact_composite_shape_shape). mesh_pose7: one pose. part[k] = winning triangle or
 // u32::MAX. ties != 0: equal-dist ties go to the smallest triangle index (the GPU's documented rule) instead of BVH order.

@@ -760,3 +760,45 @@ def test_compound_trimesh_contact_against_parts(oracle):
     assert agree.sum() > 0.9 * both.sum()
     np.testing.assert_allclose(out2[agree][:, 0:3], out[agree][:, 3:6], rtol=0, atol=2e-4 * max(1.0, sc))
     np.testing.assert_allclose(out2[agree][:, 6:9], out[agree][:, 9:12], rtol=0, atol=2e-3)
+
+
+def test_trimesh_trimesh_toi_issue_194(oracle):
+    """crates/parry3d/tests/geometry/trimesh_trimesh_toi.rs: two pyramids 1000 apart, one moving at 100000 along x:
+    `assert_eq!(time_of_impact, Some(0.00998))`, exact. Pins the restatement of the composite shape casts
+    (shape_cast_composite_shape_shape.rs: find_best over Minkowski-summed node boxes, nested through cast_shapes_shape_composite_shape),
+    oracle groundwork for SURVEY §8 f3's open item. Also: a mesh against a plain shape equals the earliest of the per-triangle casts,
+    and the mesh as second shape gives the swapped hit."""
+    pts = np.array([[0, 1, 0], [-1, -0.5, 0], [0, -0.5, -1], [1, -0.5, 0]], np.float32)
+    idx = np.array([[0, 1, 2], [0, 2, 3], [0, 3, 1]], np.uint32)
+    a, b = oracle.TriMesh(pts, idx), oracle.TriMesh(pts, idx)
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    r = a.cast_shapes(ident, [100000.0, 0, 0], _pose([1000.0, 0, 0]), [0, 0, 0], other_mesh=b)
+    assert r is not None and r[1] == 1 and r[0][12] == np.float32(0.00998)
+    assert (r[0][:6] == np.array([1, -0.5, 0, -1, -0.5, 0], np.float32)).all()          # the two base corners that meet
+    # moving away: None
+    assert a.cast_shapes(ident, [-100000.0, 0, 0], _pose([1000.0, 0, 0]), [0, 0, 0], other_mesh=b) is None
+    # mesh vs plain shapes: the earliest per-triangle cast (triangles as 3-point hulls differ from shape::Triangle only on ties)
+    g = scenes.rng(43)
+    hp, _ = scenes.hull_pool(2, 16, seed=44)
+    spec = [("ball", 0.3), ("cuboid", [0.3, 0.2, 0.4])] + [("convex", np.asarray(p, np.float32) * 0.4) for p in hp]
+    tris = [pts[t] for t in idx]
+    T = oracle.ShapeTable(spec + [("convex", t) for t in tris])
+    n_some = 0
+    for k in range(120):
+        sid = int(g.integers(0, len(spec)))
+        d = g.standard_normal(3); d /= np.linalg.norm(d)
+        pose = np.concatenate([scenes.random_unit_quaternions(g, 1)[0], d * 4.0]).astype(np.float32)
+        vel = (-d * 3.0 + g.standard_normal(3) * 0.6).astype(np.float32)
+        r = a.cast_shapes(ident, [0, 0, 0], pose, vel, table=T, shape=sid)
+        per = [T.cast_shapes([len(spec) + t], [ident], [[0, 0, 0]], [sid], [pose], [vel]) for t in range(3)]
+        tois = [o[0, 12] for o, s in per if s[0] != 0]
+        assert (r is None) == (len(tois) == 0)
+        if r is not None:
+            n_some += 1
+            assert abs(r[0][12] - min(tois)) <= 1e-5 * max(1.0, min(tois))
+            r2 = a.cast_shapes(ident, [0, 0, 0], pose, vel, table=T, shape=sid, mesh_second=True)
+            # (the two orders run different GJK ray casts, each converged to gjk.rs's relative tolerance sqrt(10 eps) ~ 1e-3)
+            assert r2 is not None and abs(r2[0][12] - r[0][12]) <= 1e-3 * max(1.0, r[0][12])
+            np.testing.assert_allclose(r2[0][0:3], r[0][3:6], atol=5e-3)
+            np.testing.assert_allclose(r2[0][3:6], r[0][0:3], atol=5e-3)
+    assert n_some > 30
