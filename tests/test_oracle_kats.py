@@ -802,3 +802,13 @@ def test_trimesh_trimesh_toi_issue_194(oracle):
             np.testing.assert_allclose(r2[0][0:3], r[0][3:6], atol=5e-3)
             np.testing.assert_allclose(r2[0][3:6], r[0][0:3], atol=5e-3)
     assert n_some > 30
+
+
+def test_getting_started_example(oracle):
+    """crates/parry3d/examples/getting_started.rs: a ray from (0, 0, -1) along +z intersects the unit cube (origin on its face:
+    solid cast, toi 0)."""
+    FMAX = float(np.finfo(np.float32).max)
+    toi = oracle.shape_cast_ray_toi(1, [1.0, 1.0, 1.0], None, [0, 0, -1, 0, 0, 1], FMAX, solid=True)
+    assert toi is not None and toi == 0.0
+    hit = oracle.shape_cast_ray(1, [1.0, 1.0, 1.0], None, [0, 0, -3, 0, 0, 1], FMAX, solid=True)
+    assert hit is not None and hit[0] == 2.0 and tuple(hit[1]) == (0.0, 0.0, -1.0)
