@@ -812,3 +812,17 @@ def test_getting_started_example(oracle):
     assert toi is not None and toi == 0.0
     hit = oracle.shape_cast_ray(1, [1.0, 1.0, 1.0], None, [0, 0, -3, 0, 0, 1], FMAX, solid=True)
     assert hit is not None and hit[0] == 2.0 and tuple(hit[1]) == (0.0, 0.0, -1.0)
+
+
+def test_ray_and_shape_cast_doc_examples(oracle):
+    """Doc examples with exact values: query/ray/ray.rs:40-66 (ball at x = 5, toi == 4.0), :255-285 (cuboid from x = -5: toi == 4.0,
+    normal == -x), query/shape_cast/shape_cast.rs:196-252 (unit balls 10 apart at speed 2: time_of_impact == 4.0; overlapping
+    balls: 0.0 with PenetratingOrWithinTargetDist)."""
+    toi = oracle.shape_cast_ray_toi(0, [1.0], _pose([5, 0, 0]), [0, 0, 0, 1, 0, 0], 100.0, solid=True)
+    assert toi == 4.0
+    hit = oracle.shape_cast_ray(1, [1.0, 1.0, 1.0], None, [-5, 0, 0, 1, 0, 0], 100.0, solid=True)
+    assert hit is not None and hit[0] == 4.0 and tuple(hit[1]) == (-1.0, 0.0, 0.0)
+    T = oracle.ShapeTable([("ball", 1.0), ("ball", 2.0)])
+    out, st = T.cast_shapes([0, 1], [_pose([0, 0, 0])] * 2, [[2, 0, 0], [1, 0, 0]], [0, 1], [_pose([10, 0, 0]), _pose([3, 0, 0])], [[0, 0, 0]] * 2)
+    assert st[0] == 1 and out[0, 12] == 4.0
+    assert st[1] == 2 and out[1, 12] == 0.0

@@ -39,3 +39,17 @@ def test_ball_triangle_toi_issue_123(ctx):
     out, st = parry_b200.cast_shapes(G, np.array([0], np.uint32), _pose([0, 0, 0])[None], vel, np.array([1], np.uint32),
                                      _pose([11.5, 5.5, 0])[None], np.zeros((1, 3), np.float32))
     assert st[0] == 0
+
+
+def test_shape_cast_doc_examples(ctx):
+    """query/shape_cast/shape_cast.rs:196-252: unit balls 10 apart at speed 2 meet at exactly 4.0; overlapping balls answer 0.0 with
+    PenetratingOrWithinTargetDist (status 2)."""
+    import parry_b200
+    G = parry_b200.Shapes(ctx, [parry_b200.Ball(1.0), parry_b200.Ball(2.0)])
+    s = np.array([0, 1], np.uint32)
+    p1 = np.stack([_pose([0, 0, 0])] * 2)
+    p2 = np.stack([_pose([10, 0, 0]), _pose([3, 0, 0])])
+    v1 = np.array([[2, 0, 0], [1, 0, 0]], np.float32)
+    out, st = parry_b200.cast_shapes(G, s, p1, v1, s, p2, np.zeros((2, 3), np.float32))
+    assert st[0] == 1 and out[0, 12] == 4.0
+    assert st[1] == 2 and out[1, 12] == 0.0
