@@ -826,3 +826,14 @@ def test_ray_and_shape_cast_doc_examples(oracle):
     out, st = T.cast_shapes([0, 1], [_pose([0, 0, 0])] * 2, [[2, 0, 0], [1, 0, 0]], [0, 1], [_pose([10, 0, 0]), _pose([3, 0, 0])], [[0, 0, 0]] * 2)
     assert st[0] == 1 and out[0, 12] == 4.0
     assert st[1] == 2 and out[1, 12] == 0.0
+
+
+def test_bvh_traverse_doc_examples(oracle):
+    """partitioning/bvh/bvh_traverse.rs:170-243: three unit boxes at x = 0, 5, 10; the region [-1, 7] x [-1, 2]^2 reaches the first
+    two leaves (count == 2), and the point (5.5, 0.5, 0.5) lies in leaf 1 (a degenerate box query is the same prune rule)."""
+    boxes = np.array([[0, 0, 0, 1, 1, 1], [5, 0, 0, 6, 1, 1], [10, 0, 0, 11, 1, 1]], np.float32)
+    for strategy in (0, 1):
+        bvh = oracle.Bvh(boxes, strategy)
+        offs, ids = bvh.intersect_aabbs(np.array([[-1, -1, -1, 7, 2, 2], [5.5, 0.5, 0.5, 5.5, 0.5, 0.5]], np.float32))
+        assert offs[1] - offs[0] == 2 and sorted(ids[offs[0]:offs[1]]) == [0, 1]
+        assert offs[2] - offs[1] == 1 and ids[offs[1]] == 1
