@@ -837,3 +837,16 @@ def test_bvh_traverse_doc_examples(oracle):
         offs, ids = bvh.intersect_aabbs(np.array([[-1, -1, -1, 7, 2, 2], [5.5, 0.5, 0.5, 5.5, 0.5, 0.5]], np.float32))
         assert offs[1] - offs[0] == 2 and sorted(ids[offs[0]:offs[1]]) == [0, 1]
         assert offs[2] - offs[1] == 1 and ids[offs[1]] == 1
+
+
+def test_solid_point_query_example_through_the_ball_arm(oracle):
+    """crates/parry3d/examples/solid_point_query3d.rs pins Cuboid(1, 2, 2) point projection: the origin is at (non-solid) distance
+    -1.0, the point (2, 2, 2) at 1.0. The contact path reaches the same function (point_aabb.rs:9-132, via
+    project_local_point_and_get_feature) in its ball-convex arm, so a Ball of radius 0 at those points must report exactly these
+    distances (contact_ball_convex_polyhedron.rs:37-51: dist = -len - r inside, len - r outside)."""
+    T = oracle.ShapeTable([("cuboid", [1.0, 2.0, 2.0]), ("ball", 0.0)])
+    ident = _pose([0, 0, 0])
+    out, st = T.contact([0, 0, 1], [ident, ident, _pose([2, 2, 2])], [1, 1, 0], [ident, _pose([2, 2, 2]), ident], 2.0)
+    assert (st == 1).all()
+    assert out[0, 12] == -1.0 and out[1, 12] == 1.0 and out[2, 12] == 1.0          # third: the ball-first (flipped) arm
+    assert tuple(out[1, 0:3]) == (1.0, 2.0, 2.0)                                    # the projection on the cuboid

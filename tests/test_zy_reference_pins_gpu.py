@@ -53,3 +53,16 @@ def test_shape_cast_doc_examples(ctx):
     out, st = parry_b200.cast_shapes(G, s, p1, v1, s, p2, np.zeros((2, 3), np.float32))
     assert st[0] == 1 and out[0, 12] == 4.0
     assert st[1] == 2 and out[1, 12] == 0.0
+
+
+def test_solid_point_query_example_through_the_ball_arm(ctx):
+    """examples/solid_point_query3d.rs through the ball-convex contact arm (see tests/test_oracle_kats.py): Cuboid(1, 2, 2) and a
+    Ball of radius 0 at the origin / at (2, 2, 2): dist exactly -1.0 / 1.0, in both argument orders."""
+    import parry_b200
+    G = parry_b200.Shapes(ctx, [parry_b200.Cuboid([1.0, 2.0, 2.0]), parry_b200.Ball(0.0)])
+    ident = _pose([0, 0, 0])
+    out, st = parry_b200.contact(G, np.array([0, 0, 1], np.uint32), np.stack([ident, ident, _pose([2, 2, 2])]), np.array([1, 1, 0], np.uint32),
+                                 np.stack([ident, _pose([2, 2, 2]), ident]), 2.0)
+    assert (st == 1).all()
+    assert out[0, 12] == -1.0 and out[1, 12] == 1.0 and out[2, 12] == 1.0
+    assert tuple(out[1, 0:3]) == (1.0, 2.0, 2.0)
