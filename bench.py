@@ -137,7 +137,11 @@ def main():
     ap.add_argument("--rays-log2", type=int, default=23, help="rays per GPU = 2^k")
     ap.add_argument("--skip-also", action="store_true", help="only the headline workload")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--first-hw-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.first_hw_child:
+        first_hw_child()
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
@@ -379,16 +383,37 @@ def bench_also(ctx, stream, args, hbm_peak):
     out["rays_1M_vs_100k_tri_sphere"] = {"value": m / (ms * 1e-3), "unit": "rays/s", "ms": ms, "l2": "flushed between iterations",
                                          "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
     del mesh, mesh2
-    extra = list(EXTRA_ALSO)
-    if int(os.environ.get("WORLD_SIZE", "1")) == 1:
-        # paths that have not run on hardware yet: last, and never in a multi-rank job (a device fault must not reach a collective)
-        extra.append(("first_hardware_runs", also_first_hardware_runs))
-    for name, fn in extra:
+    for name, fn in EXTRA_ALSO:
         try:
             out[name] = fn(ctx, stream, timed, flush, hbm_peak)
         except Exception as e:  # a secondary workload must not take the headline down
             out[name] = {"error": repr(e)}
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        # paths that have not run on hardware yet: last, never in a multi-rank job, and in a child process with a timeout, so that
+        # neither a device fault nor a crash or hang there can reach this process and its JSON line
+        try:
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(ctx.device)))
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--first-hw-child"], capture_output=True, text=True, timeout=420, env=env)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            out["first_hardware_runs"] = json.loads(lines[-1]) if lines else {"error": "child rc=%d: %s" % (r.returncode, r.stderr[-300:])}
+        except Exception as e:
+            out["first_hardware_runs"] = {"error": repr(e)}
     return out
+
+
+def first_hw_child():
+    """Child process of bench_also: times the not-yet-run paths on device 0 of its own CUDA context and prints one JSON object."""
+    try:
+        import torch
+        import parry_b200
+        hbm_peak, _ = load_peaks()
+        torch.cuda.set_device(0)
+        ctx = parry_b200.Context(0)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        res = also_first_hardware_runs(ctx, ctx.torch_stream(), make_timed(ctx, ctx.torch_stream()), flush, hbm_peak)
+    except Exception as e:
+        res = {"error": repr(e)}
+    print(json.dumps(res), flush=True)
 
 
 def also_contacts(ctx, stream, timed, flush, hbm_peak, seed=4, e2e=True):
