@@ -108,6 +108,7 @@ def run_reference(args):
     sample = 1 << 19
     rays = scenes.terrain_rays(sample, seed=6)
     om = oracle.TriMesh(v, i)
+    args.warmup = max(args.warmup, 1)   # a cold first pass (page faults on the 8M-triangle tree) would understate the reference
     for _ in range(args.warmup):
         om.cast_rays(None, rays, FMAX, threads=threads)
     t0 = time.perf_counter()
