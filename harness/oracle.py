@@ -25,8 +25,7 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            build()
+        build()   # no-op unless a source under oracle/ is newer than the library
         l = C.CDLL(LIB_PATH)
         l.pb2o_hardware_threads.restype = i32
         l.pb2o_trimesh_create.restype = P
@@ -55,6 +54,7 @@ def lib():
         l.pb2o_bvh_update_leaves.argtypes = [P, P, P, u32, f32]
         l.pb2o_bvh_refit.argtypes = [P]
         l.pb2o_bvh_refit_without_opt.argtypes = [P]
+        l.pb2o_bvh_rebuild.argtypes = [P, C.c_int]
         l.pb2o_bvh_intersect_aabbs.restype = u64
         l.pb2o_bvh_intersect_aabbs.argtypes = [P, P, u32, i32, P, P, u64]
         l.pb2o_bvh_self_pairs.restype = u64
@@ -231,6 +231,10 @@ class Bvh:
 
     def refit_without_opt(self):
         lib().pb2o_bvh_refit_without_opt(self.h)
+
+    def rebuild(self, strategy=0):
+        """Bvh::rebuild (bvh_binned_build.rs:11-36): leaves keep their change flags, nothing is resolved."""
+        lib().pb2o_bvh_rebuild(self.h, int(strategy))
 
     def intersect_aabbs(self, queries, threads=1):
         q = _f32(queries).reshape(-1, 6)

@@ -134,6 +134,22 @@ struct Bvh {
         return r;
     }
 
+    // bvh_binned_build.rs:11-36: same leaves (copied verbatim, change flags included), new internal nodes; nothing is refitted
+    // or resolved here.
+    void rebuild(BuildStrategy strategy) {
+        if (nodes.size() < 2) return;
+        std::vector<BvhNode> leaves;
+        for (const BvhNodeWide& n : nodes) {
+            if (n.left.is_leaf()) leaves.push_back(n.left);
+            if (n.right.is_leaf()) leaves.push_back(n.right);
+        }
+        nodes.clear(); parents.clear();
+        nodes.push_back(BvhNodeWide::zeros());
+        parents.push_back(BvhNodeIndex());
+        if (strategy == PLOC) rebuild_range_ploc(0, leaves);
+        else rebuild_range_binned(0, leaves.data(), leaves.size());
+    }
+
     // bvh_binned_build.rs:39-176
     void rebuild_range_binned(uint32_t target, BvhNode* leaves, size_t len) {
         const size_t NUM_BINS = 8;

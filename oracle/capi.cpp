@@ -86,6 +86,7 @@ void pb2o_bvh_update_leaves(void* b, const uint32_t* ids, const float* aabbs, ui
 }
 void pb2o_bvh_refit(void* b) { ((Bvh*)b)->refit(); }
 void pb2o_bvh_refit_without_opt(void* b) { ((Bvh*)b)->refit_without_opt(); }
+void pb2o_bvh_rebuild(void* b, int strategy) { ((Bvh*)b)->rebuild(strategy == 1 ? PLOC : BINNED); }
 
 // Bvh::intersect_aabb for a batch. offsets has m+1 entries. Returns total count (leaf_ids filled up to cap,
 // in the reference's iteration order per query).

@@ -15,6 +15,19 @@ int pb2_scratch_reserve(pb2_ctx* ctx, Scratch* s, size_t bytes) {
     return PB2_OK;
 }
 
+int pb2_fetch_fault(pb2_ctx* ctx) {
+    PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + PB2_FAULT_SLOT, ctx->d_counters + PB2_FAULT_SLOT, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return PB2_OK;
+}
+int pb2_check_fault(pb2_ctx* ctx) {
+    uint32_t f = *(uint32_t*)(ctx->h_counters + PB2_FAULT_SLOT);
+    if (f == 0) return PB2_OK;
+    ctx->h_counters[PB2_FAULT_SLOT] = 0;
+    cudaMemsetAsync(ctx->d_counters + PB2_FAULT_SLOT, 0, 8, ctx->stream);
+    if (f & PB2_FAULT_BAD_ID) PB2_FAIL(ctx, PB2_ERR_INVALID, "a shape id in a device-resident array was out of range: the leaf was skipped");
+    PB2_FAIL(ctx, PB2_ERR_OVERFLOW, "traversal stack overflow (tree deeper than %d levels): results of the calls since the last synchronisation are incomplete", PB2_STACK);
+}
+
 int pb2_pipeline_init(pb2_ctx* ctx) {
     if (ctx->copy_in) return PB2_OK;
     PB2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
@@ -60,6 +73,8 @@ static int ctx_init(int device, cudaStream_t stream, bool own, pb2_ctx** out) {
     if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sm > 0) ctx->sm_count = sm;
     if (cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(uint64_t)) != cudaSuccess) { delete ctx; return PB2_ERR_CUDA; }
     if (cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(uint64_t)) != cudaSuccess) { delete ctx; return PB2_ERR_CUDA; }
+    if (cudaMemset(ctx->d_counters, 0, 16 * sizeof(uint64_t)) != cudaSuccess) { delete ctx; return PB2_ERR_CUDA; }
+    memset(ctx->h_counters, 0, 16 * sizeof(uint64_t));
     {   // temporaries of the pair / candidate lists come from the stream-ordered pool: keep what it has grown to across
         // synchronisations (the default threshold of 0 gives the memory back at every sync and re-maps it on the next call,
         // which showed up as 3-8 ms of idle GPU per TriMesh-contact call); trimmed again in pb2_ctx_destroy
@@ -96,8 +111,9 @@ int pb2_ctx_destroy(pb2_ctx* ctx) {
 
 int pb2_ctx_synchronize(pb2_ctx* ctx) {
     if (!ctx) return PB2_ERR_INVALID;
+    PB2_CHECK(pb2_fetch_fault(ctx));
     PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return PB2_OK;
+    return pb2_check_fault(ctx);   // device-resident calls report a traversal-stack overflow here
 }
 
 void* pb2_ctx_stream(pb2_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

@@ -153,8 +153,11 @@ __global__ void k_tiny_tree(const float* __restrict__ aabbs, uint32_t n, NodeWid
 }
 
 // One thread per leaf: copy its box into its slot.
+// leaf_data != NULL (Bvh::rebuild): the leaf keeps the data word it had before the rebuild — the reference copies the leaf
+// BvhNodes verbatim, change flags included (bvh_binned_build.rs:18-26); NULL (from_leaves): BvhNode::leaf = pending change.
 __global__ void k_init_leaf_boxes(const float* __restrict__ aabbs, uint32_t n, const uint32_t* __restrict__ order,
-                                  const uint32_t* __restrict__ leaf_slot, NodeWide* __restrict__ nodes) {
+                                  const uint32_t* __restrict__ leaf_slot, NodeWide* __restrict__ nodes,
+                                  const uint32_t* __restrict__ leaf_data) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     uint32_t id = order[p];
@@ -162,7 +165,7 @@ __global__ void k_init_leaf_boxes(const float* __restrict__ aabbs, uint32_t n, c
     NodeHalf* h = (slot & 1u) ? &nodes[slot >> 1].right : &nodes[slot >> 1].left;
     const float* a = aabbs + 6ull * id;
     float4 lo = make_float4(a[0], a[1], a[2], __uint_as_float(p));
-    float4 hi = make_float4(a[3], a[4], a[5], __uint_as_float(1u | PB2_CHANGE_PENDING));
+    float4 hi = make_float4(a[3], a[4], a[5], __uint_as_float(leaf_data ? leaf_data[id] : (1u | PB2_CHANGE_PENDING)));
     reinterpret_cast<float4*>(h)[0] = lo;
     reinterpret_cast<float4*>(h)[1] = hi;
 }
@@ -199,6 +202,9 @@ __device__ __forceinline__ uint32_t resolve_pending(uint32_t data) {
 // Bottom-up refit (Bvh::refit, bvh_refit.rs:170-320, minus the DFS re-layout which is a CPU cache optimisation).
 // One thread per leaf; the second thread to arrive at a wide node merges its two halves into the parent's slot
 // (BvhNode::merged, bvh_tree.rs:610-618: inf/sup of the boxes, leaf counts added, change bits OR-ed).
+// RESOLVE = false is the fitting pass of Bvh::rebuild: the builders merge the leaves' flags upward as they are
+// (BvhNodeData::merged, bvh_tree.rs:200-204) and resolve nothing.
+template <bool RESOLVE>
 __global__ void k_refit(uint32_t n, const uint32_t* __restrict__ leaf_slot, const uint32_t* __restrict__ parents,
                         NodeWide* nodes, uint32_t* counters) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,7 +213,7 @@ __global__ void k_refit(uint32_t n, const uint32_t* __restrict__ leaf_slot, cons
     uint32_t node = slot >> 1;
     {
         NodeHalf* h = (slot & 1u) ? &nodes[node].right : &nodes[node].left;
-        h->data = resolve_pending(h->data);
+        if (RESOLVE) h->data = resolve_pending(h->data);
     }
     for (;;) {
         __threadfence();
@@ -264,7 +270,7 @@ static void bvh_free(pb2_bvh* b) {
     b->nodes = nullptr; b->parents = nullptr; b->counters = nullptr; b->leaf_slot = nullptr; b->leaf_order = nullptr;
 }
 
-static int bvh_refit_device(pb2_ctx* ctx, pb2_bvh* b) {
+static int bvh_refit_device(pb2_ctx* ctx, pb2_bvh* b, bool resolve = true) {
     if (b->n_leaves <= 2) {
         // refit_buffers <=2-leaf branch (bvh_refit.rs:192-201): only resolves the change flags.
         if (b->n_leaves == 0) return PB2_OK;
@@ -273,14 +279,16 @@ static int bvh_refit_device(pb2_ctx* ctx, pb2_bvh* b) {
     if (b->n_leaves <= 2) {
         // a single wide node: resolving flags == running k_refit (each leaf resolves its own half, root returns)
     }
-    k_refit<<<pb2_blocks(b->n_leaves, 256), 256, 0, ctx->stream>>>(b->n_leaves, b->leaf_slot, b->parents, b->nodes, b->counters);
+    if (resolve) k_refit<true><<<pb2_blocks(b->n_leaves, 256), 256, 0, ctx->stream>>>(b->n_leaves, b->leaf_slot, b->parents, b->nodes, b->counters);
+    else k_refit<false><<<pb2_blocks(b->n_leaves, 256), 256, 0, ctx->stream>>>(b->n_leaves, b->leaf_slot, b->parents, b->nodes, b->counters);
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
     return PB2_OK;
 }
 
 // Builds topology + boxes from device-resident aabbs (n x 6).
-int pb2_bvh_build_device(pb2_ctx* ctx, pb2_bvh* b, const float* d_aabbs, uint32_t n, bool resolve_flags) {
+// leaf_data (device, per leaf id) != NULL: rebuild of an existing tree, flags carried over and not resolved.
+int pb2_bvh_build_device(pb2_ctx* ctx, pb2_bvh* b, const float* d_aabbs, uint32_t n, bool resolve_flags, const uint32_t* leaf_data) {
     cudaStream_t st = ctx->stream;
     if (n == 0) return PB2_OK;
     if (n <= 2) {
@@ -321,11 +329,10 @@ int pb2_bvh_build_device(pb2_ctx* ctx, pb2_bvh* b, const float* d_aabbs, uint32_
     ctx->launches += 4;  // histogram + onesweep passes (library kernels)
     k_karras<<<pb2_blocks(n - 1, 256), 256, 0, st>>>(keys_out, b->leaf_order, (int)n, b->nodes, b->parents, b->leaf_slot);
     PB2_LAUNCHED(ctx);
-    k_init_leaf_boxes<<<pb2_blocks(n, 256), 256, 0, st>>>(d_aabbs, n, b->leaf_order, b->leaf_slot, b->nodes);
+    k_init_leaf_boxes<<<pb2_blocks(n, 256), 256, 0, st>>>(d_aabbs, n, b->leaf_order, b->leaf_slot, b->nodes, leaf_data);
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
-    (void)resolve_flags;
-    return bvh_refit_device(ctx, b);
+    return bvh_refit_device(ctx, b, resolve_flags);
 }
 
 // Stage a host array into device staging slot `slot`; returns device pointer (or the pointer itself in device mode).
@@ -360,7 +367,7 @@ int pb2_bvh_build(pb2_ctx* ctx, const float* aabbs, uint32_t n, int strategy, in
     int s = bvh_alloc(ctx, b, n);
     const void* d_aabbs = nullptr;
     if (s == PB2_OK) s = pb2_stage_in(ctx, 0, aabbs, (size_t)n * 24, mem, &d_aabbs);
-    if (s == PB2_OK) s = pb2_bvh_build_device(ctx, b, (const float*)d_aabbs, n, true);
+    if (s == PB2_OK) s = pb2_bvh_build_device(ctx, b, (const float*)d_aabbs, n, true, nullptr);
     if (s == PB2_OK && mem == PB2_MEM_HOST) {
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "sync: %s", cudaGetErrorString(e)); s = PB2_ERR_CUDA; }
@@ -404,13 +411,14 @@ int pb2_bvh_refit(pb2_ctx* ctx, pb2_bvh* bvh) {
 }
 
 __global__ void k_gather_leaf_aabbs(const NodeWide* __restrict__ nodes, const uint32_t* __restrict__ leaf_slot, uint32_t n,
-                                    float* __restrict__ aabbs) {
+                                    float* __restrict__ aabbs, uint32_t* __restrict__ leaf_data) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n) return;
     uint32_t slot = leaf_slot[id];
     const NodeHalf* h = (slot & 1u) ? &nodes[slot >> 1].right : &nodes[slot >> 1].left;
     float* a = aabbs + 6ull * id;
     a[0] = h->mnx; a[1] = h->mny; a[2] = h->mnz; a[3] = h->mxx; a[4] = h->mxy; a[5] = h->mxz;
+    if (leaf_data) leaf_data[id] = h->data;
 }
 
 int pb2_bvh_rebuild(pb2_ctx* ctx, pb2_bvh* bvh, int strategy) {
@@ -419,22 +427,26 @@ int pb2_bvh_rebuild(pb2_ctx* ctx, pb2_bvh* bvh, int strategy) {
     bvh->strategy = strategy;
     uint32_t n = bvh->n_leaves;
     if (n < 3) return PB2_OK;  // bvh_binned_build.rs:12-16: nothing to rebuild
-    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[1], (size_t)n * 24));
+    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[1], (size_t)n * 28));
     float* aabbs = (float*)ctx->scratch[1].ptr;
-    k_gather_leaf_aabbs<<<pb2_blocks(n, 256), 256, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_slot, n, aabbs);
+    uint32_t* leaf_data = (uint32_t*)(aabbs + 6ull * n);
+    k_gather_leaf_aabbs<<<pb2_blocks(n, 256), 256, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_slot, n, aabbs, leaf_data);
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
-    return pb2_bvh_build_device(ctx, bvh, aabbs, n, true);
+    // the leaves keep their change flags and nothing is resolved (bvh_binned_build.rs:11-36): change detection still sees
+    // exactly the leaves flagged by the last refit
+    return pb2_bvh_build_device(ctx, bvh, aabbs, n, false, leaf_data);
 }
 
 // Leaves that are not (or no longer) part of the tree keep a slot with Aabb::new_invalid() (mins = +MAX, maxs = -MAX):
 // the neutral element of the box merge, never overlapped, never hit by a ray — inert in every query.
-__global__ void k_fill_invalid_aabbs(float* __restrict__ aabbs, uint32_t lo, uint32_t hi) {
+__global__ void k_fill_invalid_aabbs(float* __restrict__ aabbs, uint32_t lo, uint32_t hi, uint32_t* __restrict__ leaf_data) {
     uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= hi) return;
     float* a = aabbs + 6ull * i;
     a[0] = a[1] = a[2] = FLT_MAX;
     a[3] = a[4] = a[5] = -FLT_MAX;
+    leaf_data[i] = 1u | PB2_CHANGE_PENDING;   // a leaf that did not exist before: BvhNode::leaf (bvh_tree.rs:520-527)
 }
 __global__ void k_invalidate_leaves(const uint32_t* __restrict__ ids, uint32_t n, const uint32_t* __restrict__ leaf_slot, uint32_t n_leaves,
                                     NodeWide* __restrict__ nodes) {
@@ -474,19 +486,21 @@ int pb2_bvh_resize(pb2_ctx* ctx, pb2_bvh* bvh, uint32_t new_n) {
     if (new_n == bvh->n_leaves) return PB2_OK;
     PB2_CUDA(ctx, cudaSetDevice(ctx->device));
     uint32_t old_n = bvh->n_leaves;
-    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[1], (size_t)new_n * 24));
+    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[1], (size_t)new_n * 28));
     float* aabbs = (float*)ctx->scratch[1].ptr;
+    uint32_t* leaf_data = (uint32_t*)(aabbs + 6ull * new_n);
     if (old_n) {
-        k_gather_leaf_aabbs<<<pb2_blocks(old_n, 256), 256, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_slot, old_n, aabbs);
+        k_gather_leaf_aabbs<<<pb2_blocks(old_n, 256), 256, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_slot, old_n, aabbs, leaf_data);
         PB2_LAUNCHED(ctx);
     }
-    k_fill_invalid_aabbs<<<pb2_blocks(new_n - old_n, 256), 256, 0, ctx->stream>>>(aabbs, old_n, new_n);
+    k_fill_invalid_aabbs<<<pb2_blocks(new_n - old_n, 256), 256, 0, ctx->stream>>>(aabbs, old_n, new_n, leaf_data);
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
     PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     bvh_free(bvh);
     PB2_CHECK(bvh_alloc(ctx, bvh, new_n));
-    return pb2_bvh_build_device(ctx, bvh, aabbs, new_n, true);
+    // existing leaves keep their flags; the new (still inert) ones are pending until the next refit resolves them
+    return pb2_bvh_build_device(ctx, bvh, aabbs, new_n, false, leaf_data);
 }
 
 int pb2_bvh_download(pb2_ctx* ctx, const pb2_bvh* bvh, void* nodes64, uint32_t* parents, uint32_t* leaf_node_indices, int mem) {

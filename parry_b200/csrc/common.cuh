@@ -66,6 +66,25 @@ static inline cudaEvent_t pb2_next_event(pb2_ctx* ctx) { cudaEvent_t e = ctx->ev
     } while (0)
 
 int pb2_scratch_reserve(pb2_ctx* ctx, Scratch* s, size_t bytes);
+
+// Sticky device-side fault word (d_counters slot 15). The binary-tree walks keep a fixed per-thread stack; the reference's
+// SmallVec grows instead (bvh_traverse.rs:343). A Karras tree over 63-bit Morton keys with the index tie-break is at most
+// 63 + 32 levels deep, which PB2_STACK covers, so the flag can only fire for trees linked another way (PLOC) on adversarial
+// input. A full stack never drops work silently: the push sets the flag and the next synchronising call (or
+// pb2_ctx_synchronize) returns PB2_ERR_OVERFLOW.
+#define PB2_FAULT_SLOT 15
+#define PB2_FAULT_STACK 1u
+#define PB2_FAULT_BAD_ID 2u   // an id read from a device-resident array was out of range (nothing was dereferenced)
+#define PB2_STACK 96
+#define PB2_FAULT_PTR(ctx) ((unsigned int*)((ctx)->d_counters + PB2_FAULT_SLOT))
+int pb2_check_fault(pb2_ctx* ctx);   // after a stream synchronisation that followed pb2_fetch_fault
+int pb2_fetch_fault(pb2_ctx* ctx);   // enqueues the 4-byte read-back of the fault word
+#ifdef __CUDACC__
+__device__ __forceinline__ void pb2_push(uint32_t* stack, int& sp, uint32_t v, unsigned int* fault) {
+    if (sp < PB2_STACK) stack[sp++] = v;
+    else atomicOr(fault, PB2_FAULT_STACK);
+}
+#endif
 static inline unsigned pb2_blocks(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 #define PB2_LAUNCHED(ctx) ((ctx)->launches++)
 

@@ -15,7 +15,7 @@ int pb2_stage_in(pb2_ctx* ctx, int slot, const void* src, size_t bytes, int mem,
 int pb2_stage_out(pb2_ctx* ctx, int slot, void* dst, size_t bytes, int mem, void** out);
 int pb2_stage_back(pb2_ctx* ctx, void* dst, const void* dev, size_t bytes, int mem);
 
-#define PB2_PSTACK 64
+#define PB2_PSTACK PB2_STACK
 
 struct Box {
     float mnx, mny, mnz, mxx, mxy, mxz;
@@ -39,7 +39,7 @@ __device__ __forceinline__ unsigned long long warp_append(unsigned long long* co
 template <bool WRITE>
 __global__ void k_intersect_aabbs(const NodeWide* __restrict__ nodes, const uint32_t* __restrict__ order, uint32_t n_leaves,
                                   const float* __restrict__ queries, uint32_t m, uint32_t* __restrict__ counts,
-                                  const uint32_t* __restrict__ offsets, uint32_t* __restrict__ out, uint64_t cap) {
+                                  const uint32_t* __restrict__ offsets, uint32_t* __restrict__ out, uint64_t cap, unsigned int* fault) {
     uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= m) return;
     const float* qp = queries + 6ull * qi;
@@ -71,7 +71,7 @@ __global__ void k_intersect_aabbs(const NodeWide* __restrict__ nodes, const uint
             }
             if (rh) {
                 if (rleaf) emit(__float_as_uint(r0.w));
-                else if (next) { if (sp < PB2_PSTACK) stack[sp++] = __float_as_uint(r0.w); }
+                else if (next) pb2_push(stack, sp, __float_as_uint(r0.w), fault);
                 else { curr = __float_as_uint(r0.w); next = true; }
             }
             if (!next) {
@@ -90,7 +90,7 @@ __global__ void k_intersect_aabbs(const NodeWide* __restrict__ nodes, const uint
 template <bool CD>
 __global__ void __launch_bounds__(128) k_self_pairs(const NodeWide* __restrict__ nodes, const uint32_t* __restrict__ order,
                              const uint32_t* __restrict__ leaf_slot, uint32_t n_leaves, uint2* __restrict__ pairs,
-                             uint64_t cap, unsigned long long* __restrict__ counter) {
+                             uint64_t cap, unsigned long long* __restrict__ counter, unsigned int* fault) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_leaves) return;
     uint32_t my_id = order[p];
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128) k_self_pairs(const NodeWide* __restrict__
         }
         if (rh) {
             if (rleaf) emit(rc);
-            else if (next) { if (sp < PB2_PSTACK) stack[sp++] = rc; }
+            else if (next) pb2_push(stack, sp, rc, fault);
             else { curr = rc; next = true; }
         }
         if (!next) {
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128) k_self_pairs(const NodeWide* __restrict__
 __global__ void __launch_bounds__(128) k_leaf_pairs(const NodeWide* __restrict__ nodes_a, const uint32_t* __restrict__ order_a,
                              const uint32_t* __restrict__ slot_a, uint32_t na, const NodeWide* __restrict__ nodes_b,
                              const uint32_t* __restrict__ order_b, uint32_t nb, uint2* __restrict__ pairs, uint64_t cap,
-                             unsigned long long* __restrict__ counter) {
+                             unsigned long long* __restrict__ counter, unsigned int* fault) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= na) return;
     uint32_t my_id = order_a[p];
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(128) k_leaf_pairs(const NodeWide* __restrict__
         }
         if (rh) {
             if (rleaf) emit(__float_as_uint(r0.w));
-            else if (next) { if (sp < PB2_PSTACK) stack[sp++] = __float_as_uint(r0.w); }
+            else if (next) pb2_push(stack, sp, __float_as_uint(r0.w), fault);
             else { curr = __float_as_uint(r0.w); next = true; }
         }
         if (!next) {
@@ -194,9 +194,10 @@ __global__ void __launch_bounds__(128) k_leaf_pairs(const NodeWide* __restrict__
 
 static int read_counter(pb2_ctx* ctx, uint64_t* count) {
     PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PB2_CHECK(pb2_fetch_fault(ctx));
     PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *count = ctx->h_counters[0];
-    return PB2_OK;
+    return pb2_check_fault(ctx);
 }
 
 extern "C" {
@@ -216,18 +217,20 @@ int pb2_intersect_csr_device(pb2_ctx* ctx, const pb2_bvh* bvh, const float* d_qu
     uint32_t* counts = (uint32_t*)ctx->scratch[2].ptr;
     void* cub_tmp = (char*)ctx->scratch[2].ptr + counts_bytes;
     PB2_CUDA(ctx, cudaMemsetAsync(counts + m, 0, 4, st));
-    k_intersect_aabbs<false><<<pb2_blocks(m, 128), 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->n_leaves, d_queries, m, counts, nullptr, nullptr, 0);
+    k_intersect_aabbs<false><<<pb2_blocks(m, 128), 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->n_leaves, d_queries, m, counts, nullptr, nullptr, 0, PB2_FAULT_PTR(ctx));
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, counts, d_offsets, (int)(m + 1), st));
     ctx->launches += 2;
     PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, d_offsets + m, 4, cudaMemcpyDeviceToHost, st));
+    PB2_CHECK(pb2_fetch_fault(ctx));
     PB2_CUDA(ctx, cudaStreamSynchronize(st));
+    PB2_CHECK(pb2_check_fault(ctx));
     uint64_t total = *(uint32_t*)ctx->h_counters;
     *total_out = total;
     if (total == 0) return PB2_OK;
     PB2_CUDA(ctx, cudaMallocAsync((void**)d_items, total * 4, st));
     k_intersect_aabbs<true><<<pb2_blocks(m, 128), 128, 0, st>>>(bvh->nodes, positions ? nullptr : bvh->leaf_order, bvh->n_leaves, d_queries, m,
-                                                               nullptr, d_offsets, *d_items, total);
+                                                               nullptr, d_offsets, *d_items, total, PB2_FAULT_PTR(ctx));
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
     return PB2_OK;
@@ -255,18 +258,20 @@ int pb2_bvh_intersect_aabbs(pb2_ctx* ctx, const pb2_bvh* bvh, const float* queri
     PB2_CUDA(ctx, cudaMemsetAsync(counts + m, 0, 4, st));
     if (m) {
         k_intersect_aabbs<false><<<pb2_blocks(m, 128), 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->n_leaves, (const float*)d_q, m,
-                                                                    counts, nullptr, nullptr, 0);
+                                                                    counts, nullptr, nullptr, 0, PB2_FAULT_PTR(ctx));
         PB2_LAUNCHED(ctx);
     }
     PB2_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, counts, (uint32_t*)d_off, (int)(m + 1), st));
     ctx->launches += 2;
     PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, (uint32_t*)d_off + m, 4, cudaMemcpyDeviceToHost, st));
+    PB2_CHECK(pb2_fetch_fault(ctx));
     PB2_CUDA(ctx, cudaStreamSynchronize(st));
+    PB2_CHECK(pb2_check_fault(ctx));
     uint64_t total = *(uint32_t*)ctx->h_counters;
     *count = total;
     if (m && cap) {
         k_intersect_aabbs<true><<<pb2_blocks(m, 128), 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->n_leaves, (const float*)d_q, m,
-                                                                   nullptr, (const uint32_t*)d_off, (uint32_t*)d_ids, cap);
+                                                                   nullptr, (const uint32_t*)d_off, (uint32_t*)d_ids, cap, PB2_FAULT_PTR(ctx));
         PB2_LAUNCHED(ctx);
         PB2_CUDA(ctx, cudaGetLastError());
     }
@@ -291,9 +296,9 @@ int pb2_bvh_self_pairs(pb2_ctx* ctx, const pb2_bvh* bvh, int change_detection, u
     PB2_CUDA(ctx, cudaMemsetAsync(counter, 0, 8, st));
     unsigned blocks = pb2_blocks(bvh->n_leaves, 128);
     if (change_detection)
-        k_self_pairs<true><<<blocks, 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->leaf_slot, bvh->n_leaves, (uint2*)d_pairs, cap, counter);
+        k_self_pairs<true><<<blocks, 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->leaf_slot, bvh->n_leaves, (uint2*)d_pairs, cap, counter, PB2_FAULT_PTR(ctx));
     else
-        k_self_pairs<false><<<blocks, 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->leaf_slot, bvh->n_leaves, (uint2*)d_pairs, cap, counter);
+        k_self_pairs<false><<<blocks, 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->leaf_slot, bvh->n_leaves, (uint2*)d_pairs, cap, counter, PB2_FAULT_PTR(ctx));
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
     PB2_CHECK(read_counter(ctx, count));
@@ -316,7 +321,7 @@ int pb2_bvh_leaf_pairs(pb2_ctx* ctx, const pb2_bvh* a, const pb2_bvh* b, uint32_
     unsigned long long* counter = (unsigned long long*)ctx->d_counters;
     PB2_CUDA(ctx, cudaMemsetAsync(counter, 0, 8, st));
     k_leaf_pairs<<<pb2_blocks(a->n_leaves, 128), 128, 0, st>>>(a->nodes, a->leaf_order, a->leaf_slot, a->n_leaves, b->nodes, b->leaf_order,
-                                                              b->n_leaves, (uint2*)d_pairs, cap, counter);
+                                                              b->n_leaves, (uint2*)d_pairs, cap, counter, PB2_FAULT_PTR(ctx));
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
     PB2_CHECK(read_counter(ctx, count));

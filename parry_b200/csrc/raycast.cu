@@ -13,7 +13,7 @@
 #include <stdlib.h>
 #include <cub/device/device_radix_sort.cuh>
 
-int pb2_bvh_build_device(pb2_ctx* ctx, pb2_bvh* b, const float* d_aabbs, uint32_t n, bool resolve_flags);
+int pb2_bvh_build_device(pb2_ctx* ctx, pb2_bvh* b, const float* d_aabbs, uint32_t n, bool resolve_flags, const uint32_t* leaf_data);
 int pb2_stage_in(pb2_ctx* ctx, int slot, const void* src, size_t bytes, int mem, const void** out);
 int pb2_stage_out(pb2_ctx* ctx, int slot, void* dst, size_t bytes, int mem, void** out);
 int pb2_stage_back(pb2_ctx* ctx, void* dst, const void* dev, size_t bytes, int mem);
@@ -51,7 +51,7 @@ template <bool WITH_NORMAL>
 __global__ void __launch_bounds__(128) k_raycast_trimesh(const NodeWide* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_leaves,
                                   uint32_t nt, const float* __restrict__ pose7, const float* __restrict__ rays, uint32_t m,
                                   float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
-                                  float* __restrict__ out_normal, uint32_t* __restrict__ out_feature, uint32_t cull) {
+                                  float* __restrict__ out_normal, uint32_t* __restrict__ out_feature, uint32_t cull, unsigned int* fault) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     V3 o = mk3(rays[6ull * r], rays[6ull * r + 1], rays[6ull * r + 2]);
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) k_raycast_trimesh(const NodeWide* __restr
         }
     };
 
-    bvh_find_best(nodes, n_leaves, o, d, inv, max_toi, best, found, leaf_test);
+    bvh_find_best(nodes, n_leaves, o, d, inv, max_toi, best, found, leaf_test, fault);
 
     // CompositeShapeRef::cast_local_ray post-filter `toi < max_toi` holds by construction (strict accept vs
     // the initial best = max_toi).
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128) k_raycast_trimesh_persistent(const NodeWi
                                   uint32_t nt, const float* __restrict__ pose7, const float* __restrict__ rays,
                                   const uint32_t* __restrict__ perm, uint32_t m, float max_toi, float* __restrict__ out_toi,
                                   uint32_t* __restrict__ out_tri, float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
-                                  unsigned int* __restrict__ next_ray, int steps, int refill, uint32_t cull) {
+                                  unsigned int* __restrict__ next_ray, int steps, int refill, uint32_t cull, unsigned int* fault) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     Iso7 pose;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128) k_raycast_trimesh_persistent(const NodeWi
                 }
                 bool go0 = !f0 && s0 != FLT_MAX && (s0 < best || (found && s0 == best));
                 bool go1 = !f1 && s1 != FLT_MAX && (s1 < best || (found && s1 == best));
-                if (go0 && go1 && sp < PB2_STACK) stack[sp++] = c1;
+                if (go0 && go1) pb2_push(stack, sp, c1, fault);
                 uint32_t nxt = go0 ? c0 : c1;
                 if (!(go0 || go1)) {
                     nxt = PB2_INVALID_U32;
@@ -269,7 +269,7 @@ __device__ __forceinline__ float aabb_point_dist(float4 lo, float4 hi, V3 p) {
 
 __global__ void __launch_bounds__(128) k_project_points_trimesh(const NodeWide* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n_leaves,
                                   const float* __restrict__ pose7, const float* __restrict__ points, uint32_t m,
-                                  float* __restrict__ out_proj, uint8_t* __restrict__ out_inside, uint32_t* __restrict__ out_tri) {
+                                  float* __restrict__ out_proj, uint8_t* __restrict__ out_inside, uint32_t* __restrict__ out_tri, unsigned int* fault) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
     V3 p = mk3(points[3ull * k], points[3ull * k + 1], points[3ull * k + 2]);
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(128) k_project_points_trimesh(const NodeWide* 
             }
             if (rs != FLT_MAX && (rs < best || (found && rs == best))) {
                 if (rleaf) leaf(rc);
-                else if (next) { if (sp < PB2_STACK) stack[sp++] = rc; }
+                else if (next) pb2_push(stack, sp, rc, fault);
                 else { curr = rc; next = true; }
             }
             if (!next) { if (sp == 0) break; curr = stack[--sp]; }
@@ -342,11 +342,11 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
         if (with_normal)
             k_raycast_trimesh<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
                                                                      (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
-                                                                     (float*)d_n, (uint32_t*)d_f, cull);
+                                                                     (float*)d_n, (uint32_t*)d_f, cull, PB2_FAULT_PTR(ctx));
         else
             k_raycast_trimesh<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, b->n_leaves, mesh->nt, (const float*)d_pose,
                                                                       (const float*)d_rays, m, max_toi, (float*)d_toi, (uint32_t*)d_tri,
-                                                                      nullptr, nullptr, cull);
+                                                                      nullptr, nullptr, cull, PB2_FAULT_PTR(ctx));
     } else {
         unsigned int* next_ray = (unsigned int*)(ctx->d_counters + ctx->ray_slot);
         PB2_CUDA(ctx, cudaMemsetAsync(next_ray, 0, 4, ctx->stream));
@@ -379,10 +379,10 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
                                     (float*)d_n, (uint32_t*)d_f, with_normal, steps, refill, cull, variant >= 5, pieces));
         else if (with_normal)
             k_raycast_trimesh_persistent<true><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
-                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, (float*)d_n, (uint32_t*)d_f, next_ray, steps, refill, cull);
+                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, (float*)d_n, (uint32_t*)d_f, next_ray, steps, refill, cull, PB2_FAULT_PTR(ctx));
         else
             k_raycast_trimesh_persistent<false><<<blocks, 128, 0, ctx->stream>>>(b->nodes, mesh->tris, mesh->nt, (const float*)d_pose,
-                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, nullptr, nullptr, next_ray, steps, refill, cull);
+                (const float*)d_rays, perm, m, max_toi, (float*)d_toi, (uint32_t*)d_tri, nullptr, nullptr, next_ray, steps, refill, cull, PB2_FAULT_PTR(ctx));
     }
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
@@ -425,7 +425,7 @@ int pb2_trimesh_create(pb2_ctx* ctx, const float* vertices, uint32_t nv, const u
     if (e == cudaSuccess) e = cudaMalloc((void**)&mesh->tris, (size_t)nt * 48);
     int s = PB2_OK;
     if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh alloc: %s", cudaGetErrorString(e)); s = PB2_ERR_CUDA; }
-    if (s == PB2_OK) s = pb2_bvh_build_device(ctx, b, aabbs, nt, true);
+    if (s == PB2_OK) s = pb2_bvh_build_device(ctx, b, aabbs, nt, true, nullptr);
     if (s == PB2_OK) {
         k_gather_triangles<<<pb2_blocks(nt, 256), 256, 0, ctx->stream>>>((const float*)d_v, (const uint32_t*)d_i, nt, b->leaf_order, mesh->tris);
         PB2_LAUNCHED(ctx);
@@ -528,8 +528,9 @@ static int trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float*
     if (rc != PB2_OK) { cudaStreamSynchronize(ctx->copy_out); cudaStreamSynchronize(main_stream); if (dual) cudaStreamSynchronize(ctx->compute2); return rc; }
     PB2_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
     if (dual) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->compute2));
+    PB2_CHECK(pb2_fetch_fault(ctx));
     PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return PB2_OK;
+    return pb2_check_fault(ctx);
 }
 
 int pb2_trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays, uint32_t m,
@@ -648,13 +649,17 @@ int pb2_trimesh_project_points(pb2_ctx* ctx, const pb2_trimesh* mesh, const floa
     PB2_CHECK(pb2_stage_out(ctx, 3, inside, (size_t)m, mem, &d_in));
     PB2_CHECK(pb2_stage_out(ctx, 4, tri, (size_t)m * 4, mem, &d_tri));
     k_project_points_trimesh<<<pb2_blocks(m, 128), 128, 0, ctx->stream>>>(mesh->bvh.nodes, mesh->tris, mesh->bvh.n_leaves, (const float*)d_pose,
-                                                                         (const float*)d_pts, m, (float*)d_proj, (uint8_t*)d_in, (uint32_t*)d_tri);
+                                                                         (const float*)d_pts, m, (float*)d_proj, (uint8_t*)d_in, (uint32_t*)d_tri, PB2_FAULT_PTR(ctx));
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
     PB2_CHECK(pb2_stage_back(ctx, proj, d_proj, (size_t)m * 12, mem));
     PB2_CHECK(pb2_stage_back(ctx, inside, d_in, (size_t)m, mem));
     PB2_CHECK(pb2_stage_back(ctx, tri, d_tri, (size_t)m * 4, mem));
-    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (mem == PB2_MEM_HOST) {
+        PB2_CHECK(pb2_fetch_fault(ctx));
+        PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return pb2_check_fault(ctx);
+    }
     return PB2_OK;
 }
 

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(128) k_raycast_shapes(const NodeWide* __restri
                                  const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float4* __restrict__ pts,
                                  const uint32_t* __restrict__ shape_ids, const float* __restrict__ poses, const float* __restrict__ rays,
                                  uint32_t m, float max_toi, bool solid, float* __restrict__ out_toi, uint32_t* __restrict__ out_leaf,
-                                 float* __restrict__ out_normal, uint32_t* __restrict__ out_feature) {
+                                 float* __restrict__ out_normal, uint32_t* __restrict__ out_feature, uint32_t n_shapes, unsigned int* fault) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     V3 o = mk3(rays[6ull * r], rays[6ull * r + 1], rays[6ull * r + 2]);
@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(128) k_raycast_shapes(const NodeWide* __restri
     auto leaf = [&](uint32_t pos) {
         uint32_t id = order[pos];
         uint32_t sid = shape_ids ? shape_ids[id] : id;
+        if (sid >= n_shapes) { atomicOr(fault, PB2_FAULT_BAD_ID); return; }   // reported as PB2_ERR_INVALID at the next synchronisation
         Iso7 pose = load_iso(poses + 7ull * id);
         V3 lo = iso_inv_point(pose, o), ld = iso_inv_vec(pose, d);  // RayCast::cast_ray (ray.rs:381-390)
         float4 pr = params[sid];
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(128) k_raycast_shapes(const NodeWide* __restri
             if (WITH_NORMAL) { best_n = iso_vec(pose, n); best_feat = feat; }
         }
     };
-    bvh_find_best(nodes, n_leaves, o, d, inv, max_toi, best, found, leaf);
+    bvh_find_best(nodes, n_leaves, o, d, inv, max_toi, best, found, leaf, fault);
     out_toi[r] = found ? best : 0.0f;
     out_leaf[r] = best_id;
     if (WITH_NORMAL) {
@@ -359,18 +360,22 @@ int pb2_bvh_cast_rays_shapes(pb2_ctx* ctx, const pb2_bvh* bvh, const pb2_shapes*
         k_raycast_shapes<true><<<blocks, 128, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_order, nl, shapes->kinds, shapes->params, shapes->points4,
                                                                 (const uint32_t*)d_ids, (const float*)d_poses, (const float*)d_rays, m,
                                                                 max_toi, solid != 0, (float*)d_toi, (uint32_t*)d_leaf, (float*)d_n,
-                                                                (uint32_t*)d_f);
+                                                                (uint32_t*)d_f, shapes->n, PB2_FAULT_PTR(ctx));
     else
         k_raycast_shapes<false><<<blocks, 128, 0, ctx->stream>>>(bvh->nodes, bvh->leaf_order, nl, shapes->kinds, shapes->params, shapes->points4,
                                                                  (const uint32_t*)d_ids, (const float*)d_poses, (const float*)d_rays, m,
-                                                                 max_toi, solid != 0, (float*)d_toi, (uint32_t*)d_leaf, nullptr, nullptr);
+                                                                 max_toi, solid != 0, (float*)d_toi, (uint32_t*)d_leaf, nullptr, nullptr, shapes->n, PB2_FAULT_PTR(ctx));
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
     PB2_CHECK(pb2_stage_back(ctx, toi, d_toi, (size_t)m * 4, mem));
     PB2_CHECK(pb2_stage_back(ctx, leaf, d_leaf, (size_t)m * 4, mem));
     PB2_CHECK(pb2_stage_back(ctx, normal, d_n, (size_t)m * 12, mem));
     PB2_CHECK(pb2_stage_back(ctx, feature, d_f, (size_t)m * 4, mem));
-    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (mem == PB2_MEM_HOST) {
+        PB2_CHECK(pb2_fetch_fault(ctx));
+        PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return pb2_check_fault(ctx);
+    }
     return PB2_OK;
 }
 

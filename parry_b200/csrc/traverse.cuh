@@ -5,14 +5,13 @@
 #pragma once
 #include "common.cuh"
 
-#define PB2_STACK 64
 
 // `leaf(pos)` tests the primitive at sorted position `pos` and updates `best` / `found` itself.
 // Deviation from the reference (documented tie rule): once a hit exists, nodes whose score == best are
 // still visited so that every bit-equal tie is seen and the smallest leaf id can win.
 template <class Leaf>
 __device__ __forceinline__ void bvh_find_best(const NodeWide* __restrict__ nodes, uint32_t n_leaves, V3 o, V3 d, V3 inv,
-                                              float max_toi, float& best, bool& found, Leaf leaf) {
+                                              float max_toi, float& best, bool& found, Leaf leaf, unsigned int* fault) {
     if (n_leaves == 1) {
         // partial root (bvh_traverse.rs:349-358)
         const float4* np = reinterpret_cast<const float4*>(&nodes[0]);
@@ -48,7 +47,7 @@ __device__ __forceinline__ void bvh_find_best(const NodeWide* __restrict__ nodes
         }
         if (rs != FLT_MAX && (rs < best || (found && rs == best))) {
             if (rleaf) leaf(rc);
-            else if (found_next) { if (sp < PB2_STACK) stack[sp++] = rc; }
+            else if (found_next) pb2_push(stack, sp, rc, fault);
             else { curr = rc; found_next = true; }
         }
         if (!found_next) {
