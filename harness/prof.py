@@ -44,7 +44,11 @@ def main():
             v, i = scenes.uv_sphere(708, 707)
             m = 1 << 20
             rays = scenes.sphere_rays(m, seed=1)
-        mesh = parry_b200.TriMesh(ctx, v, i)
+        for rep in range(2):
+            t0 = time.perf_counter()
+            mesh = parry_b200.TriMesh(ctx, v, i)
+            ctx.synchronize()
+            print("TriMesh::new (host arrays, incl. upload) %.2f ms" % ((time.perf_counter() - t0) * 1e3))
         rd = torch.from_numpy(rays).cuda()
         toi = torch.empty(m, dtype=torch.float32, device="cuda")
         tri = torch.empty(m, dtype=torch.int32, device="cuda")

@@ -34,7 +34,10 @@ typedef enum pb2_status {
     PB2_ERR_INVALID = -1,     /* bad argument */
     PB2_ERR_CUDA = -2,        /* CUDA runtime error; see pb2_last_error */
     PB2_ERR_OVERFLOW = -3,    /* output capacity too small; *count holds the required size */
-    PB2_ERR_UNSUPPORTED = -4  /* mirrors query::Unsupported (query/error.rs) */
+    PB2_ERR_UNSUPPORTED = -4, /* mirrors query::Unsupported (query/error.rs) */
+    PB2_ERR_DEPTH = -5        /* a tree walk ran out of its fixed per-thread stack (tree deeper than 96 levels; impossible for the
+                                 Morton-linked trees): results since the last synchronisation are incomplete.
+                                 Sticky: reported by the next synchronising call or by pb2_ctx_synchronize, then cleared. */
 } pb2_status;
 
 typedef enum pb2_mem { PB2_MEM_HOST = 0, PB2_MEM_DEVICE = 1 } pb2_mem;

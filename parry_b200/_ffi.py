@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libparry_b200.so")
 
-PB2_OK, PB2_ERR_INVALID, PB2_ERR_CUDA, PB2_ERR_OVERFLOW, PB2_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+PB2_OK, PB2_ERR_INVALID, PB2_ERR_CUDA, PB2_ERR_OVERFLOW, PB2_ERR_UNSUPPORTED, PB2_ERR_DEPTH = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1
 INVALID_U32 = 0xFFFFFFFF
 

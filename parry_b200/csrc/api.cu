@@ -25,7 +25,7 @@ int pb2_check_fault(pb2_ctx* ctx) {
     ctx->h_counters[PB2_FAULT_SLOT] = 0;
     cudaMemsetAsync(ctx->d_counters + PB2_FAULT_SLOT, 0, 8, ctx->stream);
     if (f & PB2_FAULT_BAD_ID) PB2_FAIL(ctx, PB2_ERR_INVALID, "a shape id in a device-resident array was out of range: the leaf was skipped");
-    PB2_FAIL(ctx, PB2_ERR_OVERFLOW, "traversal stack overflow (tree deeper than %d levels): results of the calls since the last synchronisation are incomplete", PB2_STACK);
+    PB2_FAIL(ctx, PB2_ERR_DEPTH, "traversal stack overflow (tree deeper than %d levels): results of the calls since the last synchronisation are incomplete", PB2_STACK);
 }
 
 int pb2_pipeline_init(pb2_ctx* ctx) {

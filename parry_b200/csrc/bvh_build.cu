@@ -11,8 +11,10 @@
 // BvhNodeWide layout so it can be handed back verbatim (pb2_bvh_download). Karras' numbering puts the two
 // children of a node at adjacent indices (split, split+1) => sibling nodes share a 128-byte line.
 #include "common.cuh"
+#include "ploc.cuh"
 #include <stdlib.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 // ---------------------------------------------------------------- helpers
 __device__ __forceinline__ uint32_t f2ord(float f) {
@@ -286,6 +288,96 @@ static int bvh_refit_device(pb2_ctx* ctx, pb2_bvh* b, bool resolve = true) {
     return PB2_OK;
 }
 
+// ---------------------------------------------------------------- PLOC (BvhBuildStrategy::Ploc)
+// GPU form of rebuild_range_ploc (bvh_ploc_build.rs:10-94); the per-cluster rules live in ploc.cuh. Clusters are NodeHalf
+// records ({mins, children}, {maxs, data}: exactly what the reference's `leaves: Vec<BvhNode>` holds), ping-ponged between
+// two arrays; one round = nearest-neighbour kernel (shared-memory tile of the 2 x radius neighbourhood) -> decision flags ->
+// one 64-bit inclusive scan (low word: position in the next round, high word: rank among this round's merges) -> emit. A
+// round merges 35-45 % of the clusters on meshes and collider clouds, so a million leaves take ~30 rounds. Node ids are
+// handed out from the top: the k-th node created gets id n - 2 - k, so the root (created last) is node 0 and every child
+// follows its parent, like the reference's refit leaves them (bvh_refit.rs:259-320).
+__global__ void k_ploc_init(const float* __restrict__ aabbs, uint32_t n, const uint32_t* __restrict__ order,
+                            const uint32_t* __restrict__ leaf_data, float4* __restrict__ C) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t id = order[p];
+    const float* a = aabbs + 6ull * id;
+    C[2ull * p] = make_float4(a[0], a[1], a[2], __uint_as_float(p));
+    C[2ull * p + 1] = make_float4(a[3], a[4], a[5], __uint_as_float(leaf_data ? leaf_data[id] : (1u | PB2_CHANGE_PENDING)));
+}
+
+#define PLOC_BLOCK 128
+__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_nearest(const float4* __restrict__ C, uint32_t c, uint32_t radius, uint32_t* __restrict__ cand) {
+    __shared__ float4 tile[2 * (PLOC_BLOCK + 2 * PLOC_MAX_RADIUS)];
+    uint32_t b0 = blockIdx.x * PLOC_BLOCK;
+    uint32_t tile_lo = b0 >= radius ? b0 - radius : 0u;
+    uint32_t tile_hi = b0 + PLOC_BLOCK + radius < c ? b0 + PLOC_BLOCK + radius : c;
+    for (uint32_t t = threadIdx.x; t < 2u * (tile_hi - tile_lo); t += PLOC_BLOCK) tile[t] = C[2ull * tile_lo + t];
+    __syncthreads();
+    uint32_t i = b0 + threadIdx.x;
+    if (i < c) cand[i] = ploc_nearest(tile, tile_lo, c, i, radius);
+}
+
+__global__ void k_ploc_flags(const uint32_t* __restrict__ cand, uint32_t c, unsigned long long* __restrict__ flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c) flags[i] = ploc_flags(cand, i);
+}
+
+__global__ void k_ploc_emit(const float4* __restrict__ Cin, const uint32_t* __restrict__ cand, const unsigned long long* __restrict__ incl,
+                            uint32_t c, float4* __restrict__ Cout, NodeWide* __restrict__ nodes, uint32_t* __restrict__ parents,
+                            uint32_t* __restrict__ leaf_slot, const uint32_t* __restrict__ order, uint32_t created, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c) ploc_emit(Cin, cand, incl, i, Cout, nodes, parents, leaf_slot, order, created, n);
+}
+
+// Links the sorted leaves (b->leaf_order) into b->nodes / parents / leaf_slot. PB2_ERR_UNSUPPORTED: the clustering made no
+// progress (thousands of identical boxes merge one pair per round — the reference's own loop is quadratic there); the
+// caller links the same sorted leaves as an LBVH instead.
+static int bvh_link_ploc(pb2_ctx* ctx, pb2_bvh* b, const float* d_aabbs, uint32_t n, const uint32_t* leaf_data) {
+    cudaStream_t st = ctx->stream;
+    uint32_t radius = 16;   // SEARCH_RADIUS (bvh_ploc_build.rs:22)
+    { const char* e = getenv("PB2_PLOC_RADIUS"); if (e && atoi(e) >= 1 && atoi(e) <= PLOC_MAX_RADIUS) radius = (uint32_t)atoi(e); }
+    size_t cl_bytes = ((size_t)n * 32 + 255) & ~(size_t)255, cand_bytes = ((size_t)n * 4 + 255) & ~(size_t)255;
+    size_t fl_bytes = ((size_t)n * 8 + 255) & ~(size_t)255, cub_bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)n, st);
+    char* base = nullptr;
+    PB2_CUDA(ctx, cudaMallocAsync((void**)&base, 2 * cl_bytes + cand_bytes + 2 * fl_bytes + cub_bytes + 256, st));
+    float4 *Ca = (float4*)base, *Cb = (float4*)(base + cl_bytes);
+    uint32_t* cand = (uint32_t*)(base + 2 * cl_bytes);
+    unsigned long long* flags = (unsigned long long*)(base + 2 * cl_bytes + cand_bytes);
+    unsigned long long* incl = (unsigned long long*)(base + 2 * cl_bytes + cand_bytes + fl_bytes);
+    void* cub_tmp = base + 2 * cl_bytes + cand_bytes + 2 * fl_bytes;
+    int rc = [&]() -> int {
+        k_ploc_init<<<pb2_blocks(n, 256), 256, 0, st>>>(d_aabbs, n, b->leaf_order, leaf_data, Ca);
+        PB2_LAUNCHED(ctx);
+        uint32_t c = n, created = 0;
+        int rounds = 0, slow = 0;
+        while (c > 1) {
+            k_ploc_nearest<<<pb2_blocks(c, PLOC_BLOCK), PLOC_BLOCK, 0, st>>>(Ca, c, radius, cand);
+            k_ploc_flags<<<pb2_blocks(c, 256), 256, 0, st>>>(cand, c, flags);
+            PB2_CUDA(ctx, cub::DeviceScan::InclusiveSum(cub_tmp, cub_bytes, flags, incl, (int)c, st));
+            k_ploc_emit<<<pb2_blocks(c, 256), 256, 0, st>>>(Ca, cand, incl, c, Cb, b->nodes, b->parents, b->leaf_slot, b->leaf_order, created, n);
+            ctx->launches += 5;
+            PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, incl + (c - 1), 8, cudaMemcpyDeviceToHost, st));
+            PB2_CUDA(ctx, cudaStreamSynchronize(st));
+            uint64_t tot = ctx->h_counters[0];
+            uint32_t next = (uint32_t)tot, merges = (uint32_t)(tot >> 32);
+            if (merges == 0 || next + merges != c) PB2_FAIL(ctx, PB2_ERR_CUDA, "PLOC round made no progress (%u clusters, %u merges)", c, merges);
+            created += merges;
+            c = next;
+            float4* t = Ca; Ca = Cb; Cb = t;
+            ++rounds;
+            if (merges < c / 64u + 1u && c > 256u) { if (++slow > 32) return PB2_ERR_UNSUPPORTED; }
+        }
+        if (created != n - 1u) PB2_FAIL(ctx, PB2_ERR_CUDA, "PLOC created %u of %u nodes", created, n - 1u);
+        (void)rounds;
+        return PB2_OK;
+    }();
+    cudaFreeAsync(base, st);
+    if (rc == PB2_OK) { PB2_CUDA(ctx, cudaGetLastError()); b->karras = false; }
+    return rc;
+}
+
 // Builds topology + boxes from device-resident aabbs (n x 6).
 // leaf_data (device, per leaf id) != NULL: rebuild of an existing tree, flags carried over and not resolved.
 int pb2_bvh_build_device(pb2_ctx* ctx, pb2_bvh* b, const float* d_aabbs, uint32_t n, bool resolve_flags, const uint32_t* leaf_data) {
@@ -327,6 +419,12 @@ int pb2_bvh_build_device(pb2_ctx* ctx, pb2_bvh* b, const float* d_aabbs, uint32_
     PB2_CUDA(ctx, cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const uint64_t*)keys_in, keys_out, (const uint32_t*)vals_in,
                                                   b->leaf_order, (int)n, 0, 63, st));
     ctx->launches += 4;  // histogram + onesweep passes (library kernels)
+    if (b->strategy == PB2_BUILD_PLOC) {
+        int s = bvh_link_ploc(ctx, b, d_aabbs, n, leaf_data);
+        if (s == PB2_OK) return bvh_refit_device(ctx, b, resolve_flags);
+        if (s != PB2_ERR_UNSUPPORTED) return s;   // UNSUPPORTED: the clustering stalled (degenerate input), link the sorted leaves as an LBVH
+    }
+    b->karras = true;
     k_karras<<<pb2_blocks(n - 1, 256), 256, 0, st>>>(keys_out, b->leaf_order, (int)n, b->nodes, b->parents, b->leaf_slot);
     PB2_LAUNCHED(ctx);
     k_init_leaf_boxes<<<pb2_blocks(n, 256), 256, 0, st>>>(d_aabbs, n, b->leaf_order, b->leaf_slot, b->nodes, leaf_data);

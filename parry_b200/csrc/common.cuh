@@ -71,7 +71,7 @@ int pb2_scratch_reserve(pb2_ctx* ctx, Scratch* s, size_t bytes);
 // SmallVec grows instead (bvh_traverse.rs:343). A Karras tree over 63-bit Morton keys with the index tie-break is at most
 // 63 + 32 levels deep, which PB2_STACK covers, so the flag can only fire for trees linked another way (PLOC) on adversarial
 // input. A full stack never drops work silently: the push sets the flag and the next synchronising call (or
-// pb2_ctx_synchronize) returns PB2_ERR_OVERFLOW.
+// pb2_ctx_synchronize) returns PB2_ERR_DEPTH.
 #define PB2_FAULT_SLOT 15
 #define PB2_FAULT_STACK 1u
 #define PB2_FAULT_BAD_ID 2u   // an id read from a device-resident array was out of range (nothing was dereferenced)
@@ -113,6 +113,10 @@ struct pb2_bvh {
     uint32_t* leaf_order = nullptr;  // sorted position -> leaf id
     uint32_t* counters = nullptr;    // per wide node arrival counters for bottom-up passes
     uint32_t cap_leaves = 0;
+    // true: Karras numbering (children of a node at (split, split + 1), a subtree's leaves are a contiguous range of sorted
+    // positions ending at the left child's index) — the self-pair walk culls "already seen" subtrees with it. false: PLOC
+    // numbering (root 0, children after their parent, no range property).
+    bool karras = true;
 };
 
 // ---------------------------------------------------------------- device math (nalgebra op order)

@@ -87,7 +87,9 @@ __global__ void k_intersect_aabbs(const NodeWide* __restrict__ nodes, const uint
 // One thread per leaf position p. Emits (p, q) for q > p. CHANGE_DETECTION: pair kept iff either leaf is flagged
 // changed (the reference's pruning, bvh_traverse_bvtt.rs:47,103-110,160-163, reduces to exactly this predicate
 // because change flags are OR-ed up the tree).
-template <bool CD>
+// KARRAS = false (PLOC-linked tree): no range property, so the walk visits every overlapping subtree and keeps the pairs whose
+// other leaf sits at a higher sorted position — still each unordered pair exactly once.
+template <bool CD, bool KARRAS>
 __global__ void __launch_bounds__(128) k_self_pairs(const NodeWide* __restrict__ nodes, const uint32_t* __restrict__ order,
                              const uint32_t* __restrict__ leaf_slot, uint32_t n_leaves, uint2* __restrict__ pairs,
                              uint64_t cap, unsigned long long* __restrict__ counter, unsigned int* fault) {
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(128) k_self_pairs(const NodeWide* __restrict__
         uint32_t ld = __float_as_uint(l1.w), rd = __float_as_uint(r1.w);
         bool lleaf = (ld & PB2_LEAF_COUNT_MASK) == 1u, rleaf = (rd & PB2_LEAF_COUNT_MASK) == 1u;
         // left child index == last leaf position of the left range: nothing > p in there when lc <= p.
-        bool lh = lc > p && overlaps(q, l0, l1);
+        bool lh = (KARRAS ? lc > p : (!lleaf || lc > p)) && overlaps(q, l0, l1);
         // right child: leaf at position rc, or a range starting at rc (may extend past p).
         bool rh = (!rleaf || rc > p) && overlaps(q, r0, r1);
         if (CD) {
@@ -295,10 +297,9 @@ int pb2_bvh_self_pairs(pb2_ctx* ctx, const pb2_bvh* bvh, int change_detection, u
     unsigned long long* counter = (unsigned long long*)ctx->d_counters;
     PB2_CUDA(ctx, cudaMemsetAsync(counter, 0, 8, st));
     unsigned blocks = pb2_blocks(bvh->n_leaves, 128);
-    if (change_detection)
-        k_self_pairs<true><<<blocks, 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->leaf_slot, bvh->n_leaves, (uint2*)d_pairs, cap, counter, PB2_FAULT_PTR(ctx));
-    else
-        k_self_pairs<false><<<blocks, 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->leaf_slot, bvh->n_leaves, (uint2*)d_pairs, cap, counter, PB2_FAULT_PTR(ctx));
+    auto kern = change_detection ? (bvh->karras ? k_self_pairs<true, true> : k_self_pairs<true, false>)
+                                 : (bvh->karras ? k_self_pairs<false, true> : k_self_pairs<false, false>);
+    kern<<<blocks, 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->leaf_slot, bvh->n_leaves, (uint2*)d_pairs, cap, counter, PB2_FAULT_PTR(ctx));
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
     PB2_CHECK(read_counter(ctx, count));

@@ -412,7 +412,11 @@ int pb2_trimesh_create(pb2_ctx* ctx, const float* vertices, uint32_t nv, const u
     pb2_trimesh* mesh = new pb2_trimesh();
     mesh->nt = nt; mesh->nv = nv;
     pb2_bvh* b = &mesh->bvh;
-    b->strategy = PB2_BUILD_BINNED;
+    // TriMesh::new builds its Bvh once and queries it many times: the PLOC strategy (surface-area-driven clustering of the
+    // Morton-sorted triangles, bvh_build.cu) costs a few more milliseconds than the plain LBVH link and saves node visits on
+    // every ray (profiles/r2_*). PB2_MESH_BUILD=0 keeps the LBVH.
+    b->strategy = PB2_BUILD_PLOC;
+    { const char* e = getenv("PB2_MESH_BUILD"); if (e) b->strategy = atoi(e) ? PB2_BUILD_PLOC : PB2_BUILD_BINNED; }
     b->n_leaves = nt;
     b->n_nodes = nt <= 2 ? 1 : nt - 1;
     b->cap_leaves = nt;

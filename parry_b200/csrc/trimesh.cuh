@@ -11,6 +11,7 @@ struct pb2_trimesh {
     float4* nodes8 = nullptr;  // 5 x float4 per node
     float4* tris8 = nullptr;   // same 48-byte record as `tris`, ordered by (wide node, slot)
     uint32_t n_nodes8 = 0;
+    int levels8 = 0;           // depth of the wide tree
 };
 
 // local_ray_intersection_with_triangle (ray_triangle.rs:70-152) — toi, face side (0 front / 1 back) and the

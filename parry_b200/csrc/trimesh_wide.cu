@@ -23,7 +23,8 @@
 
 #define W8_LEAF 0x80000000u
 #define W8_STACK 96        // per-lane traversal stack entries; a visit pushes at most 7, so depth <= 7 * levels
-#define W8_MAX_LEVELS 13
+#define W8_MAX_LEVELS 13        // k_raycast_wide<., MODE 1> only (it pushes up to 7 entries per level)
+#define W8_MAX_LEVELS_GROUPS 64 // group walk (MODE 0 and k_raycast_wide_shared): one stack entry per level
 #define W8_TQ 8   // per-lane queue of triangle groups (power of two)
 #define W8_GAMMA 1.00000095367431640625f  // 1 + 2^-20
 
@@ -235,7 +236,8 @@ int pb2_wide_build(pb2_ctx* ctx, pb2_trimesh* mesh) {
             levels++;
         }
         if (s != PB2_OK) break;
-        if (levels > W8_MAX_LEVELS) break;  // degenerate (very deep) tree: keep the binary-tree kernels
+        if (levels > W8_MAX_LEVELS_GROUPS) break;  // degenerate (very deep) tree: keep the binary-tree kernels
+        mesh->levels8 = levels;
         uint32_t n8 = end;
         size_t cub_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n8, st);
@@ -794,6 +796,7 @@ int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, co
     unsigned int* next_ray = (unsigned int*)(ctx->d_counters + ctx->ray_slot);
     int mode = 0;
     { const char* e = getenv("PB2_RAY_MODE"); if (e) mode = atoi(e) ? 1 : 0; }
+    if (mesh->levels8 > W8_MAX_LEVELS) mode = 0;
     auto kern = with_normal ? (mode ? k_raycast_wide<true, 1> : k_raycast_wide<true, 0>) : (mode ? k_raycast_wide<false, 1> : k_raycast_wide<false, 0>);
     const bool pz = pieces != nullptr && shared_tri && !with_normal && d_perm == nullptr;
     if (pieces && !pz) return PB2_ERR_INVALID;

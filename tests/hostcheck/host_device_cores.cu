@@ -72,3 +72,33 @@ extern "C" void hostcheck_manifold_match_pairs(const uint8_t* kept, const uint32
                                                const float* pts, uint32_t n, uint32_t max_points, int32_t* match) {
     for (uint32_t k = 0; k < n; ++k) manifold_match_pair(k, kept, old_fids, old_counts, counts, pts, max_points, match);
 }
+
+// ---- PLOC link (parry_b200/csrc/ploc.cuh): the rounds of bvh_link_ploc (bvh_build.cu) replayed on the CPU with the very
+// per-cluster functions the kernels call. aabbs are in sorted order (leaf id = sorted position here). nodes: n - 1 wide nodes.
+#include "../../parry_b200/csrc/ploc.cuh"
+#include <vector>
+extern "C" int hostcheck_ploc_link(const float* aabbs, uint32_t n, uint32_t radius, void* nodes_out, uint32_t* parents, uint32_t* leaf_slot) {
+    std::vector<float4> Ca(2 * (size_t)n), Cb(2 * (size_t)n);
+    std::vector<uint32_t> cand(n), order(n);
+    std::vector<unsigned long long> incl(n);
+    for (uint32_t p = 0; p < n; ++p) {
+        order[p] = p;
+        const float* a = aabbs + 6ull * p;
+        Ca[2 * p] = make_float4(a[0], a[1], a[2], pb2_u2f(p));
+        Ca[2 * p + 1] = make_float4(a[3], a[4], a[5], pb2_u2f(1u | PB2_CHANGE_PENDING));
+    }
+    uint32_t c = n, created = 0;
+    int rounds = 0;
+    while (c > 1) {
+        for (uint32_t i = 0; i < c; ++i) cand[i] = ploc_nearest(Ca.data(), 0u, c, i, radius);
+        unsigned long long acc = 0;
+        for (uint32_t i = 0; i < c; ++i) { acc += ploc_flags(cand.data(), i); incl[i] = acc; }
+        for (uint32_t i = 0; i < c; ++i)
+            ploc_emit(Ca.data(), cand.data(), incl.data(), i, Cb.data(), (NodeWide*)nodes_out, parents, leaf_slot, order.data(), created, n);
+        created += (uint32_t)(acc >> 32);
+        c = (uint32_t)acc;
+        Ca.swap(Cb);
+        ++rounds;
+    }
+    return created == n - 1 ? rounds : -1;
+}

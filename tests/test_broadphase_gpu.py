@@ -314,11 +314,68 @@ def test_bvh_cast_ray_ball_cuboid_leaves(ctx, oracle):
         adjudicate(g2, r2, 2.0, solid)
 
 
+@pytest.mark.parametrize("n", [3, 4, 7, 100, 1000, 20000])
+def test_ploc_strategy(ctx, oracle, n):
+    """BvhBuildStrategy::Ploc (bvh_ploc_build.rs:10-94) built on the GPU (bvh_build.cu: bvh_link_ploc): a well-formed tree whose
+    queries answer like the reference's (pair sets, intersect_aabb, change detection, refit). The linking rule itself is checked
+    against the oracle's PLOC topology on the CPU (tests/test_hostcheck.py::test_ploc_link_builds_the_reference_topology)."""
+    import parry_b200
+    kinds, params, poses = make_colliders(n, seed=400 + n)
+    shapes = make_shapes(ctx, kinds, params)
+    ids = np.arange(n, dtype=np.uint32)
+    aabbs = shapes.compute_aabbs(ids, poses)
+    gb = parry_b200.Bvh.from_leaves(ctx, parry_b200.BvhBuildStrategy.Ploc, aabbs)
+    ob = oracle.Bvh(aabbs, strategy=1)
+    nodes, parents, leaf_idx = gb.download()
+    assert_well_formed(nodes, parents, leaf_idx)
+    assert (sorted_pairs(gb.traverse_bvtt_single_tree()) == sorted_pairs(ob.self_pairs())).all()
+    assert (sorted_pairs(gb.traverse_bvtt_single_tree(True)) == sorted_pairs(ob.self_pairs(True))).all()
+    q = aabbs[:: max(1, n // 200)]
+    goff, gids = gb.intersect_aabb(q)
+    ooff, oids = ob.intersect_aabbs(q)
+    assert (np.asarray(goff) == np.asarray(ooff)).all()
+    for k in range(len(q)):
+        assert (np.sort(np.asarray(gids)[goff[k]:goff[k + 1]]) == np.sort(np.asarray(oids)[ooff[k]:ooff[k + 1]])).all()
+    # one frame: move a tenth of the leaves, refit, change detection, then a PLOC rebuild keeps the flags
+    g0 = scenes.rng(500 + n)
+    moved = g0.random(n) < 0.1
+    poses = poses.copy()
+    poses[moved, 4:] += (g0.random((int(moved.sum()), 3)).astype(np.float32) - 0.5) * 0.5
+    aabbs2 = shapes.compute_aabbs(ids, poses)
+    gb.insert_or_update_partially(aabbs2, ids, 0.05)
+    gb.refit()
+    ob.update_leaves(aabbs2, ids, 0.05)
+    ob.refit()
+    want_cd, want_all = sorted_pairs(ob.self_pairs(True)), sorted_pairs(ob.self_pairs(False))
+    assert (sorted_pairs(gb.traverse_bvtt_single_tree(True)) == want_cd).all()
+    assert (sorted_pairs(gb.traverse_bvtt_single_tree(False)) == want_all).all()
+    gb.rebuild(parry_b200.BvhBuildStrategy.Ploc)
+    nodes, parents, leaf_idx = gb.download()
+    assert_well_formed(nodes, parents, leaf_idx)
+    assert (sorted_pairs(gb.traverse_bvtt_single_tree(True)) == want_cd).all()
+    assert (sorted_pairs(gb.traverse_bvtt_single_tree(False)) == want_all).all()
+
+
+def test_ploc_degenerate_input_falls_back(ctx, oracle):
+    """Thousands of identical boxes merge one pair per PLOC round (the reference's own loop is quadratic there): the GPU build
+    notices the stall and links the same sorted leaves as an LBVH; every query still answers exactly."""
+    import parry_b200
+    n = 1500
+    aabbs = np.tile(np.array([[0, 0, 0, 1, 1, 1]], np.float32), (n, 1))
+    aabbs[-3:] += 5.0
+    gb = parry_b200.Bvh.from_leaves(ctx, parry_b200.BvhBuildStrategy.Ploc, aabbs)
+    nodes, parents, leaf_idx = gb.download()
+    assert_well_formed(nodes, parents, leaf_idx)
+    gp = gb.traverse_bvtt_single_tree()
+    assert len(gp) == (n - 3) * (n - 4) // 2 + 3
+    assert len(np.unique(sorted_pairs(gp))) == len(gp)
+
+
 def test_deep_tree_no_silent_drops(ctx, oracle):
     """A Karras tree over clustered / duplicated centroids is up to 63 + log2(n) levels deep: 64 clusters whose Morton keys are
     powers of two link into a 63-level chain, 40 duplicates per cluster add the index tie-break levels below it. Round 1's
     64-entry stacks dropped pushes silently there (VERDICT weak #10); now the stacks hold any Karras tree (PB2_STACK = 96 >= 63 +
-    32) and a full stack raises PB2_ERR_OVERFLOW at the next synchronisation instead of losing work."""
+    32) and a full stack raises PB2_ERR_DEPTH at the next synchronisation instead of losing work."""
     import parry_b200
     pts = []
     for j in range(63):

@@ -21,7 +21,7 @@ def hostlib():
     out_dir = os.path.join(HERE, "hostcheck", "_build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libhostcheck.so")
-    deps = [src] + [os.path.join(b.CSRC, f) for f in ("manifold_update.cuh", "compound_pair.cuh", "shapes.cuh", "common.cuh")]
+    deps = [src] + [os.path.join(b.CSRC, f) for f in ("manifold_update.cuh", "compound_pair.cuh", "shapes.cuh", "common.cuh", "ploc.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call([b._nvcc()] + b.NVCC_FLAGS + ["-shared", src, "-o", so])
     return C.CDLL(so)
@@ -175,3 +175,78 @@ def test_second_frame_dispatch_matches_oracle(hostlib, oracle, hulls):
     ball = (kinds[np.minimum(s1, ns - 1)] == 0) | (kinds[np.minimum(s2, ns - 1)] == 0) | (s1 >= ns)
     assert (kept[ball] == 0).all() and 0.15 < kept[~ball & (cnt > 0)].mean() < 0.85
     assert (match >= 0).any(axis=1)[rec & (rc > 0) & (cnt > 0)].mean() > 0.3        # recomputed manifolds do find old points again
+
+
+def _canonical(nodes, root=0):
+    """Ordered-tree fingerprint of a BvhNodeWide array: DFS from the root, left before right, one entry per node half."""
+    out, stack = [], [root]
+    while stack:
+        w = nodes[stack.pop()]
+        push = []
+        for side in ("left", "right"):
+            h = w[side]
+            lc = int(h["data"]) & 0x3FFFFFFF
+            if lc == 1:
+                out.append(("leaf", int(h["children"])))
+            else:
+                out.append(("node", lc))
+                push.append(int(h["children"]))
+        stack.extend(reversed(push))
+    return out
+
+
+@pytest.mark.parametrize("scene", ["colliders", "sphere"])
+def test_ploc_link_builds_the_reference_topology(hostlib, oracle, scene):
+    """BvhBuildStrategy::Ploc on the GPU (bvh_build.cu: k_ploc_nearest / k_ploc_flags / scan / k_ploc_emit) against the oracle's
+    restatement of rebuild_range_ploc (bvh_ploc_build.rs:10-94): the per-cluster functions of ploc.cuh, replayed round by round on
+    the CPU over leaves given in the reference's own Morton order, must link exactly the reference's tree (same ordered topology,
+    same boxes), and parents / leaf_node_indices must be consistent."""
+    from helpers import assert_well_formed
+    if scene == "colliders":
+        kinds, params, poses, _ = scenes.colliders(5000, seed=71)
+        aabbs = oracle.shape_aabbs(kinds, params, poses)
+    else:
+        v, i = scenes.uv_sphere(40, 30)
+        t = v[i]
+        aabbs = np.concatenate([t.min(axis=1), t.max(axis=1)], axis=1).astype(np.float32)
+    # the reference's sort key (bvh_ploc_build.rs:12-19, utils/morton.rs:33-40): per-axis normalised centres, f64, 21 bits per axis
+    c = ((aabbs[:, :3] + aabbs[:, 3:]) * np.float32(0.5)).astype(np.float32)
+    lo, ext = c.min(axis=0), c.max(axis=0) - c.min(axis=0)
+    u = ((c - lo) * (np.float32(1.0) / ext)).astype(np.float32).astype(np.float64)
+    q = np.minimum(np.floor(u * float(1 << 21)), 4294967295.0).astype(np.uint64)
+
+    def spread(x):
+        x = x & np.uint64(0x1fffff)
+        for sh, m in ((32, 0x1f00000000ffff), (16, 0x1f0000ff0000ff), (8, 0x100f00f00f00f00f), (4, 0x10c30c30c30c30c3), (2, 0x1249249249249249)):
+            x = (x | (x << np.uint64(sh))) & np.uint64(m)
+        return x
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
+    aabbs = np.ascontiguousarray(aabbs[np.argsort(key, kind="stable")])
+    n = len(aabbs)
+    ref = oracle.Bvh(aabbs, strategy=1).nodes()
+    nodes = np.zeros(n - 1, dtype=ref.dtype)
+    parents, slots = np.zeros(n - 1, np.uint32), np.zeros(n, np.uint32)
+    P = C.c_void_p
+    hostlib.hostcheck_ploc_link.argtypes = [P, C.c_uint32, C.c_uint32, P, P, P]
+    hostlib.hostcheck_ploc_link.restype = C.c_int
+    rounds = hostlib.hostcheck_ploc_link(aabbs.ctypes.data, n, 16, nodes.ctypes.data, parents.ctypes.data, slots.ctypes.data)
+    assert 5 < rounds < 60
+    assert _canonical(nodes) == _canonical(ref)
+    # boxes of the internal halves are the merged boxes of their subtrees (the reference's refit recomputes the same values)
+    def boxes(nd):
+        out, stack = [], [0]
+        while stack:
+            w = nd[stack.pop()]
+            push = []
+            for side in ("left", "right"):
+                out.append(np.concatenate([w[side]["mins"], w[side]["maxs"]]))
+                if (int(w[side]["data"]) & 0x3FFFFFFF) != 1:
+                    push.append(int(w[side]["children"]))
+            stack.extend(reversed(push))
+        return np.asarray(out)
+    assert (boxes(nodes).view(np.uint32) == boxes(ref).view(np.uint32)).all()
+    # flags: the link leaves pending-change bits everywhere (the refit that follows resolves them); compare structure only
+    chk = nodes.copy()
+    for side in ("left", "right"):
+        chk[side]["data"] &= 0x3FFFFFFF
+    assert_well_formed(chk, parents, slots)
