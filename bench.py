@@ -26,9 +26,25 @@ sys.path.insert(0, ROOT)
 
 FMAX = float(np.finfo(np.float32).max)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full captures
-# (profiles/*.json); None when no capture of the current kernel version exists.
-PROFILED_TRAFFIC = {"rays_terrain": 4502166952}  # profiles/r1_rays_v8_shared_tri_terrain8M_full.json (k_raycast_wide_shared<false>, this workload)
+# Names of the dominant kernels as they are built now. roofline.traffic (ncu dram__bytes_read.sum + dram__bytes_write.sum per
+# launch) is read from profiles/r2_traffic.json and only used when the capture there was taken from a kernel of the same name AND
+# version string; otherwise it is null (a stale capture must not stand in for the current code).
+RAY_KERNEL = "k_raycast_wide_shared<false>"
+RAY_KERNEL_VERSION = "r2.1 staged 32-ray refill; 96 B nodes / 64 B triangles read with LDG.E.256"
+EPA_KERNEL = "k_contact_epa2"
+EPA_KERNEL_VERSION = "r1.8 reconverged phases, finishing kernel split off"
+
+
+def profiled_traffic(kernel, version):
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        with open(p) as f:
+            for e in json.load(f):
+                if e.get("kernel") == kernel and e.get("kernel_version") == version:
+                    return int(e["dram_bytes_per_launch"]), e.get("source")
+    except Exception:
+        pass
+    return None, None
 
 
 def load_peaks():
@@ -95,9 +111,18 @@ def cpu_rays(v, i, rays, threads, repeat=1):
     return len(rays) / best, best, t_build, om
 
 
+def bench_config(args, nt):
+    """`config` is the same object in both arms (ours and --impl reference) so that the driver's same_config holds."""
+    m = 1 << args.rays_log2
+    return {"workload": "2^%d incoherent rays per GPU vs 8,000,000-triangle terrain TriMesh (BASELINE config[3] shard), BVH replicated per GPU"
+                        % args.rays_log2,
+            "triangles": int(nt), "rays_per_gpu": m, "ray_seed": "6 + rank",
+            "l2": "inputs larger than L2 (rays %d MB + results %d MB per step, scene > 600 MB)" % (m * 24 >> 20, m * 8 >> 20)}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; parry3d itself cannot be built offline: no cargo,
-    nalgebra not vendored) with all host threads, each step a bounded sample of the workload."""
+    nalgebra not vendored) with all host threads. Each step casts the SAME 2^23 rays as one step of our arm on rank 0."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -105,8 +130,8 @@ def run_reference(args):
     oracle.build()
     threads = oracle.hardware_threads()
     v, i = terrain_scene()
-    sample = 1 << 19
-    rays = scenes.terrain_rays(sample, seed=6)
+    m = 1 << args.rays_log2
+    rays = scenes.terrain_rays(m, seed=6)
     om = oracle.TriMesh(v, i)
     args.warmup = max(args.warmup, 1)   # a cold first pass (page faults on the 8M-triangle tree) would understate the reference
     for _ in range(args.warmup):
@@ -115,18 +140,72 @@ def run_reference(args):
     for _ in range(args.steps):
         om.cast_rays(None, rays, FMAX, threads=threads)
     dt = (time.perf_counter() - t0) / args.steps
-    val = sample / dt
+    val = m / dt
     line = {
         "impl": "reference", "metric": "rays/s (TriMesh::cast_ray)", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "2^23 incoherent rays per GPU vs 8,000,000-triangle terrain TriMesh (BASELINE config[3] shard)",
-                   "triangles": int(len(i)), "sample_rays_per_step": sample},
+        "config": bench_config(args, len(i)),
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
-                         "sample": "%d rays of the same seeded ray set per step, all host threads" % sample},
+                         "sample": "all %d rays of rank 0's shard per step, all host threads (C++ restatement of parry3d's TriMesh::cast_ray)" % m},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def oracle_slice_check(om, oracle, rays_h, toi, tri, k):
+    """Checks the first k rays of the TIMED device output against the CPU oracle (bit-exact toi + id; the two order-dependent cases
+    of DESIGN.md section 3 are adjudicated by brute force over all triangles). Raises on any unexplained difference."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import check_ray_parity
+    r = om.cast_rays(None, rays_h[:k], FMAX, threads=oracle.hardware_threads())
+
+    def brute(idx):
+        t, i, _, _ = om.cast_rays(None, rays_h[:k][idx], FMAX, with_normal=True, mode=1, threads=oracle.hardware_threads())
+        return t, i
+    g = (toi[:k], tri[:k])
+    adjudicated = check_ray_parity(g, r, brute, max_ulp_cases=1e-4)
+    same = int(((np.asarray(g[1]).astype(np.uint32) == np.asarray(r[1]).astype(np.uint32)) &
+                (np.asarray(g[0]).view(np.uint32) == np.asarray(r[0]).view(np.uint32))).sum())
+    return {"checker": "CPU oracle (reference-order traversal) on the first %d rays of the timed output" % k, "rays": k, "bit_exact": same,
+            "adjudicated_by_brute_force": int(adjudicated), "hits": int((np.asarray(r[1]) != 0xFFFFFFFF).sum())}
+
+
+def cpu_side_baselines(oracle, threads):
+    """CPU (oracle port) figures for the other two named workloads, on bounded samples: query::contact on hull pairs of the 4M-pair
+    scene (1 thread and all threads) and one broad-phase frame on 2^20 colliders (sequential in the reference: 1 thread)."""
+    from harness import scenes
+    out = {}
+    pts, radii = scenes.hull_pool(4096)
+    T = oracle.ShapeTable([("convex", p) for p in pts])
+    n_all, n_one = 1 << 18, 1 << 15
+    a, b, p1, p2 = scenes.hull_pairs(n_all, radii, seed=4)
+    t0 = time.perf_counter()
+    T.contact(a, p1, b, p2, 0.01, threads=threads)
+    dt_all = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    T.contact(a[:n_one], p1[:n_one], b[:n_one], p2[:n_one], 0.01, threads=1)
+    dt_one = time.perf_counter() - t0
+    out["contacts"] = {"value": n_all / dt_all, "unit": "pairs/s", "cores": threads, "one_thread_value": n_one / dt_one, "kind": "port",
+                       "sample": "first %d (all threads) / %d (1 thread) pairs of the 2^22-pair scene (seed 4), 32-vertex hulls, prediction 0.01"
+                                 % (n_all, n_one)}
+    n = 1 << 20
+    kinds, params, poses, _ = scenes.colliders(n, seed=2)
+    t0 = time.perf_counter()
+    aabbs = oracle.shape_aabbs(kinds, params, poses)
+    ob = oracle.Bvh(aabbs)
+    t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    aabbs = oracle.shape_aabbs(kinds, params, poses)
+    ob.update_leaves(aabbs, np.arange(n, dtype=np.uint32), 0.0)
+    ob.refit()
+    pr = ob.self_pairs()
+    dt = time.perf_counter() - t0
+    out["broadphase"] = {"value": n / dt, "unit": "AABBs/s (frame: leaf AABBs + update + refit + traverse_bvtt_single_tree)", "cores": 1, "kind": "port",
+                         "pairs_per_frame": int(len(pr)), "pairs_per_s": len(pr) / dt, "frame_ms": dt * 1e3,
+                         "build_from_leaves_ms": t_build * 1e3,
+                         "sample": "one frame on the full 2^20-collider scene (seed 2); the reference's Bvh is sequential (bvh_tree.rs:24)"}
+    return out
 
 
 def main():
@@ -228,6 +307,8 @@ def main():
     def step_kernel():
         mesh.cast_local_ray(rays_d, FMAX, out=(toi_d, tri_d))
     ms_kernel, _ = timed(step_kernel, args.steps, 1)
+    toi_timed = toi_d.cpu().numpy().copy()          # what the timed kernel launches wrote (checked against the oracle below)
+    tri_timed = tri_d.cpu().numpy().view(np.uint32).copy()
 
     # end-to-end: host (pinned) buffers through the C ABI, copies inside the timed region
     rays_pin = torch.from_numpy(rays_h).pin_memory()
@@ -252,11 +333,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt_e2e = float(t.item())
     e2e_val = world * m / dt_e2e
-    # sanity: device-resident and host paths agree
-    toi_chk = (gather.local()[0] if peer else gather.toi) if world > 1 else toi_d
-    assert (toi_chk.cpu().numpy().view(np.uint32) == toi_np.view(np.uint32)).all()
+    # the host path returns the same bits as the device path
+    assert (toi_timed.view(np.uint32) == toi_np.view(np.uint32)).all() and (tri_timed == tri_np).all()
     if world > 1:
-        # every rank must hold every rank's results: compare per-shard checksums of the gathered arrays with the owners' own
+        # every rank must hold every rank's results, element by element: each rank checks the shard of its right-hand neighbour
+        # against that neighbour's own local results (toi bits and triangle ids), plus per-shard checksums of all shards
         ft, fk = gather.full()
         torch.cuda.synchronize()
         mine = torch.tensor([int(fk[rank * m:(rank + 1) * m].to(torch.int64).sum().item())], device="cuda")
@@ -264,53 +345,107 @@ def main():
         dist.all_gather_into_tensor(owners, mine)
         seen = torch.stack([fk[r * m:(r + 1) * m].to(torch.int64).sum() for r in range(world)])
         assert bool((seen == owners).all()), "gathered results differ from the owners' results"
+        nb = (rank + 1) % world
+        loc_t, loc_k = torch.from_numpy(toi_timed).cuda(), torch.from_numpy(tri_timed.view(np.int32)).cuda()
+        all_t = [torch.empty_like(loc_t) for _ in range(world)]
+        all_k = [torch.empty_like(loc_k) for _ in range(world)]
+        dist.all_gather(all_t, loc_t)
+        dist.all_gather(all_k, loc_k)
+        assert bool((ft[nb * m:(nb + 1) * m].view(torch.int32) == all_t[nb].view(torch.int32)).all()), "gathered toi differs from the owner's"
+        assert bool((fk[nb * m:(nb + 1) * m].view(torch.int32) == all_k[nb]).all()), "gathered triangle ids differ from the owner's"
+        del all_t, all_k, loc_t, loc_k
 
     nt, nv = len(i), len(v)
-    scene_bytes = 64 * (nt - 1) + 48 * nt  # node array + pre-gathered triangles, read at least once per launch
-    alg_bytes = m * 32 + scene_bytes       # 24 B ray in + 8 B (toi, id) out per ray
-    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    # Algorithmic (compulsory) bytes per launch. Contract figure: 32 B per ray (24 in + 8 out) + the scene read once in
+    # the reference's own layout: 64 (T - 1) node bytes + 12 V vertex bytes + 12 T index bytes. Also reported: the same with this
+    # library's scene layout (96-byte wide nodes + 64-byte pre-gathered triangles), which is what the kernel actually has to touch.
+    alg_contract = m * 32 + 64 * (nt - 1) + 12 * nv + 12 * nt
+    alg_own = m * 32 + mesh.wide_bytes() if hasattr(mesh, "wide_bytes") else None
+    achieved = alg_contract / (ms_kernel * 1e-3) / 1e9
+    traffic, traffic_src = profiled_traffic(RAY_KERNEL, RAY_KERNEL_VERSION)
     line = {
         "metric": "rays/s (TriMesh::cast_ray)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "2^%d incoherent rays per GPU vs 8,000,000-triangle terrain TriMesh (BASELINE config[3] shard), "
-                               "BVH replicated per GPU" % args.rays_log2,
-                   "triangles": nt, "rays_per_gpu": m, "l2": "inputs larger than L2 (rays %d MB, scene %d MB)" % (m * 24 >> 20, scene_bytes >> 20),
-                   "collective": gather_kind},
+        "config": bench_config(args, nt),
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": m * 24, "d2h_bytes_per_step": m * 8,
                 "ms_per_step": dt_e2e * 1e3},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": PROFILED_TRAFFIC.get("rays_terrain"), "kernel": "k_raycast_wide_shared<false>", "kernel_ms": ms_kernel,
-                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": RAY_KERNEL, "kernel_version": RAY_KERNEL_VERSION,
+                     "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_contract,
+                     "algorithmic_bytes_rule": "SURVEY 8(d): 32 B/ray x 2^%d + 64(T-1) + 12V + 12T (the reference's own scene layout)" % args.rays_log2,
+                     "peak_source": peak_src, "collective": gather_kind},
     }
+    if alg_own:
+        line["roofline"]["own_layout"] = {"algorithmic_bytes_per_launch": alg_own, "achieved": alg_own / (ms_kernel * 1e-3) / 1e9,
+                                          "frac": alg_own / (ms_kernel * 1e-3) / 1e9 / hbm_peak}
 
+    # ------------------------------------------------------------------ the second named metric: contact pairs/s (BASELINE config[2])
+    timed_also = make_timed(ctx, stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if not args.skip_also else None   # > 126 MB L2
     also = {}
     if not args.skip_also:
-        if world > 1:
-            # the second named metric (contact pairs/s) at N GPUs: every rank runs its own 2^22-pair shard (weak scaling,
-            # no data-path collective), device time = max over ranks
-            r = also_contacts(ctx, stream, make_timed(ctx, stream), None, hbm_peak, seed=4 + rank, e2e=False)
-            t = torch.tensor([r["ms"]], device="cuda")
+        r = also_contacts(ctx, stream, timed_also, None, hbm_peak, seed=4 + rank, e2e=(world == 1))
+        ms_c = r["ms"]
+        if world > 1:   # every rank its own 2^22-pair shard (weak scaling, no data-path collective), device time = max over ranks
+            t = torch.tensor([ms_c], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            also["contact_pairs_4M_hulls_per_gpu_all_ranks"] = {"value": world * r["pairs"] / (ms * 1e-3), "unit": "pairs/s", "ms": ms,
-                                                                "pairs_per_gpu": r["pairs"], "n_gpus": world, "scaling": "weak"}
+            ms_c = float(t.item())
+        pairs_s = world * r["pairs"] / (ms_c * 1e-3)
+        line["roofline"]["second_metric"] = {
+            "metric": "contact pairs/s (query::contact, 2^22 ConvexPolyhedron pairs per GPU, 32-vertex hulls, prediction 0.01; BASELINE config[2])",
+            "value": pairs_s, "unit": "pairs/s", "ms_per_step": ms_c, "n_gpus": world, "scaling": "weak",
+            "e2e_value": r.get("e2e_value"), "contacts_fraction": r["contacts_fraction"],
+            "kernel": EPA_KERNEL, "kernel_version": EPA_KERNEL_VERSION, "kernel_ms": r.get("epa_ms"), "gjk_kernel_ms": r.get("gjk_ms"),
+            "epa_runs": r.get("epa_runs"), "algorithmic_bytes_per_launch": r["pairs"] * 120,
+            "algorithmic_bytes_rule": "SURVEY 8(d): 120 B/pair (64 in + 56 out), hull pool L2-resident",
+            "achieved": r["pairs"] * 120 / (ms_c * 1e-3) / 1e9, "frac": r["pairs"] * 120 / (ms_c * 1e-3) / 1e9 / hbm_peak,
+            "dominant_kernel_frac": (r["pairs"] * 120 / (r["epa_ms"] * 1e-3) / 1e9 / hbm_peak) if r.get("epa_ms") else None,
+            "traffic": profiled_traffic(EPA_KERNEL, EPA_KERNEL_VERSION)[0],
+            "shallow_mix_value": (r.get("shallow_mix") or {}).get("value")}
+        also["contact_pairs_4M_hulls"] = r
+        if world > 1:
+            for name, fn in MULTI_GPU_ALSO:
+                try:
+                    also[name] = fn(ctx, stream, timed_also, flush, hbm_peak, dist, rank, world)
+                except Exception as e:
+                    also[name] = {"error": repr(e)}
         if rank == 0:
-            also.update(bench_also(ctx, stream, args, hbm_peak))
-    if also and rank == 0:
-        line["also"] = also
+            also.update(bench_also(ctx, stream, args, hbm_peak, flush))
 
     if rank == 0 and not args.skip_cpu:
         from harness import oracle
         oracle.build()
         threads = oracle.hardware_threads()
-        sample = min(m, 1 << 23)
-        val, secs, t_build, _ = cpu_rays(v, i, rays_h[:sample], threads)
+        val, secs, t_build, om = cpu_rays(v, i, rays_h, threads)
+        one = 1 << 18
+        t0 = time.perf_counter()
+        om.cast_rays(None, rays_h[:one], FMAX, threads=1)
+        dt_one = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
-                                "sample": "first %d rays of rank 0's shard, same mesh; %.2f s cast + %.2f s Bvh build (1 thread)"
-                                          % (sample, secs, t_build)}
+                                "sample": "all %d rays of rank 0's shard, same mesh, all host threads: %.2f s cast (+ %.2f s Bvh build, 1 thread); "
+                                          "C++ restatement of parry3d (no Rust toolchain on the box)" % (m, secs, t_build),
+                                "one_thread_value": one / dt_one, "one_thread_sample": "first %d rays" % one}
+        # the timed device output against the oracle (not against itself)
+        line["parity"] = oracle_slice_check(om, oracle, rays_h, toi_timed, tri_timed, 1 << 16)
+        del om
+        if not args.skip_also:
+            try:
+                line["cpu_baseline"].update(cpu_side_baselines(oracle, threads))
+            except Exception as e:
+                line["cpu_baseline"]["also_error"] = repr(e)
+    if also and rank == 0:
+        # details of the secondary workloads go to a side file; the line keeps one number per workload so that it stays readable
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "bench_also_n%d.json" % world), "w") as f:
+                json.dump(also, f, indent=1)
+        except Exception:
+            pass
+        line["also"] = {k: ({kk: vv for kk, vv in val.items() if kk in ("value", "unit", "ms", "error", "n_gpus", "efficiency_note")} if isinstance(val, dict) else val)
+                        for k, val in also.items()}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -340,7 +475,7 @@ def make_timed(ctx, stream):
     return timed
 
 
-def bench_also(ctx, stream, args, hbm_peak):
+def bench_also(ctx, stream, args, hbm_peak, flush=None):
     """Secondary single-GPU configurations, device-timed the same way (inputs resident, CUDA events)."""
     import torch
     import parry_b200
@@ -364,7 +499,8 @@ def bench_also(ctx, stream, args, hbm_peak):
             tot += e0.elapsed_time(e1)
         return tot / steps
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    if flush is None:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     # 1M rays vs 1M-triangle sphere (north_star target configuration); inputs fit in L2 => flush between iterations
     v, i = scenes.uv_sphere(708, 707)
@@ -374,13 +510,13 @@ def bench_also(ctx, stream, args, hbm_peak):
     toi = torch.empty(m, dtype=torch.float32, device="cuda")
     tri = torch.empty(m, dtype=torch.int32, device="cuda")
     ms = timed(lambda: mesh.cast_local_ray(rays, FMAX, out=(toi, tri)), flush=flush)
-    alg = m * 32 + 64 * (len(i) - 1) + 48 * len(i)
+    alg = m * 32 + 64 * (len(i) - 1) + 12 * len(v) + 12 * len(i)
     out["rays_1M_vs_1M_tri_sphere"] = {"value": m / (ms * 1e-3), "unit": "rays/s", "ms": ms, "l2": "flushed between iterations",
                                        "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
     v, i = scenes.uv_sphere(224, 224)
     mesh2 = parry_b200.TriMesh(ctx, v, i)
     ms = timed(lambda: mesh2.cast_local_ray(rays, FMAX, out=(toi, tri)), flush=flush)
-    alg = m * 32 + 64 * (len(i) - 1) + 48 * len(i)
+    alg = m * 32 + 64 * (len(i) - 1) + 12 * len(v) + 12 * len(i)
     out["rays_1M_vs_100k_tri_sphere"] = {"value": m / (ms * 1e-3), "unit": "rays/s", "ms": ms, "l2": "flushed between iterations",
                                          "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
     del mesh, mesh2
@@ -433,12 +569,22 @@ def also_contacts(ctx, stream, timed, flush, hbm_peak, seed=4, e2e=True):
     def run():
         res["out"] = parry_b200.contact(G, da, dp1, db, dp2, 0.01)
     ms = timed(run, steps=5, warmup=3)  # inputs+outputs = 2^22 * 120 B = 503 MB > L2
+    phase = None
+    try:   # per-kernel durations of one more call (CUDA events on the library's stream around the GJK / EPA / finishing kernels)
+        ctx.enable_phase_timing(True)
+        run()
+        phase = ctx.contact_phase_times()
+        ctx.enable_phase_timing(False)
+    except Exception:
+        pass
     st = res["out"][1]
     frac_some = float((st == 1).float().mean().item())
     alg = n * 120
     r = {"value": n / (ms * 1e-3), "unit": "pairs/s", "ms": ms, "pairs": n, "contacts_fraction": frac_some,
          "l2": "inputs+outputs (503 MB) larger than L2", "roofline_frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
          "algorithmic_bytes_per_pair": 120}
+    if phase:
+        r.update({"gjk_ms": phase[0], "epa_ms": phase[1], "finish_ms": phase[2], "epa_runs": phase[3]})
     if not e2e:
         return r
     # same batch size with the separations of a settled scene (18 % of the pairs penetrate instead of 67 %): GJK-only
@@ -801,7 +947,9 @@ def also_first_hardware_runs(ctx, stream, timed, flush, hbm_peak):
     return out
 
 
-EXTRA_ALSO = [("contact_pairs_4M_hulls", also_contacts), ("manifolds_4M_ball_cuboid_pairs", also_manifolds),
+MULTI_GPU_ALSO = []   # (name, fn(ctx, stream, timed, flush, hbm_peak, dist, rank, world)): filled below
+
+EXTRA_ALSO = [("manifolds_4M_ball_cuboid_pairs", also_manifolds),
               ("sibling_queries_2M_mixed_pairs", also_siblings), ("broadphase_1M_colliders", also_broadphase),
               ("mixed_2M_colliders_pipeline", also_mixed), ("trimesh_contacts_1M_colliders", also_mesh_contacts)]
 

@@ -42,7 +42,7 @@ def main():
             rays = scenes.terrain_rays(m, seed=6)
         else:
             v, i = scenes.uv_sphere(708, 707)
-            m = 1 << 20
+            m = 1 << int(os.environ.get("PB2_PROF_RAYS_LOG2", "20"))
             rays = scenes.sphere_rays(m, seed=1)
         for rep in range(2):
             t0 = time.perf_counter()

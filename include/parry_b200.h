@@ -81,6 +81,11 @@ void* pb2_ctx_stream(pb2_ctx* ctx);
 const char* pb2_last_error(pb2_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py `gpu_launches`). */
 uint64_t pb2_ctx_launch_count(pb2_ctx* ctx);
+/* Measurement aid (no reference counterpart): with phase timing on, every contact-family call records CUDA events on the context's
+ * stream around its GJK kernel, its EPA kernel and its finishing kernel; pb2_contact_phase_times waits for the last such call and
+ * returns the three durations in milliseconds and the number of pairs GJK handed to EPA. */
+int pb2_ctx_enable_phase_timing(pb2_ctx* ctx, int on);
+int pb2_contact_phase_times(pb2_ctx* ctx, float* gjk_ms, float* epa_ms, float* finish_ms, uint64_t* epa_runs);
 
 /* ------------------------------------------------------------------ Bvh (partitioning/bvh) */
 /* Bvh::from_leaves(strategy, &[Aabb]) — bvh_tree.rs:1835 (leaf id = index). n may be 0, 1, 2 (special-cased like
@@ -131,6 +136,9 @@ int pb2_bvh_leaf_pairs(pb2_ctx* ctx, const pb2_bvh* a, const pb2_bvh* b, uint32_
 int pb2_trimesh_create(pb2_ctx* ctx, const float* vertices /* nv x 3 */, uint32_t nv, const uint32_t* indices /* nt x 3 */,
                        uint32_t nt, int mem, pb2_trimesh** out);
 int pb2_trimesh_destroy(pb2_ctx* ctx, pb2_trimesh* mesh);
+/* Bytes of the arrays a ray cast walks (wide nodes + pre-gathered triangles): what one launch has to read at least once when
+ * every part of the mesh is hit. Measurement aid for roofline figures in this library's own layout. */
+uint64_t pb2_trimesh_traversal_bytes(const pb2_trimesh* mesh);
 /* TriMesh::bvh() — borrowed handle, owned by the mesh. */
 const pb2_bvh* pb2_trimesh_bvh(const pb2_trimesh* mesh);
 /* RayCast::cast_ray / cast_ray_and_get_normal for TriMesh over m rays — query/ray/ray.rs:381-411,

@@ -26,6 +26,9 @@ SIGNATURES = {
     "pb2_ctx_stream": (c_void_p, [c_void_p]),
     "pb2_last_error": (C.c_char_p, [c_void_p]),
     "pb2_ctx_launch_count": (c_u64, [c_void_p]),
+    "pb2_trimesh_traversal_bytes": (c_u64, [c_void_p]),
+    "pb2_ctx_enable_phase_timing": (c_int, [c_void_p, c_int]),
+    "pb2_contact_phase_times": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pb2_bvh_build": (c_int, [c_void_p, P, c_u32, c_int, c_int, C.POINTER(c_void_p)]),
     "pb2_bvh_destroy": (c_int, [c_void_p, c_void_p]),
     "pb2_bvh_leaf_count": (c_u32, [c_void_p]),

@@ -103,6 +103,7 @@ int pb2_ctx_destroy(pb2_ctx* ctx) {
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_pieces) cudaFree(ctx->d_pieces);
+    for (int i = 0; i < 4; ++i) if (ctx->phase_ev[i]) cudaEventDestroy(ctx->phase_ev[i]);
     if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); cudaStreamDestroy(ctx->copy_out); if (ctx->compute2) cudaStreamDestroy(ctx->compute2); for (int i = 0; i < 6; ++i) if (ctx->copy_peer[i]) cudaStreamDestroy(ctx->copy_peer[i]); for (int i = 0; i < 64; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -114,6 +115,33 @@ int pb2_ctx_synchronize(pb2_ctx* ctx) {
     PB2_CHECK(pb2_fetch_fault(ctx));
     PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return pb2_check_fault(ctx);   // device-resident calls report a traversal-stack overflow here
+}
+
+int pb2_ctx_enable_phase_timing(pb2_ctx* ctx, int on) {
+    if (!ctx) return PB2_ERR_INVALID;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (on) for (int i = 0; i < 4; ++i) if (!ctx->phase_ev[i]) PB2_CUDA(ctx, cudaEventCreate(&ctx->phase_ev[i]));
+    ctx->phase_timing = on != 0;
+    ctx->phase_marks = 0;
+    return PB2_OK;
+}
+
+int pb2_contact_phase_times(pb2_ctx* ctx, float* gjk_ms, float* epa_ms, float* finish_ms, uint64_t* epa_runs) {
+    if (!ctx) return PB2_ERR_INVALID;
+    if (!ctx->phase_timing || ctx->phase_marks < 4) PB2_FAIL(ctx, PB2_ERR_INVALID, "no timed contact call since pb2_ctx_enable_phase_timing");
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    PB2_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 4, ctx->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PB2_CUDA(ctx, cudaEventSynchronize(ctx->phase_ev[3]));
+    PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float a = 0.f, b = 0.f, c = 0.f;
+    PB2_CUDA(ctx, cudaEventElapsedTime(&a, ctx->phase_ev[0], ctx->phase_ev[1]));
+    PB2_CUDA(ctx, cudaEventElapsedTime(&b, ctx->phase_ev[1], ctx->phase_ev[2]));
+    PB2_CUDA(ctx, cudaEventElapsedTime(&c, ctx->phase_ev[2], ctx->phase_ev[3]));
+    if (gjk_ms) *gjk_ms = a;
+    if (epa_ms) *epa_ms = b;
+    if (finish_ms) *finish_ms = c;
+    if (epa_runs) *epa_runs = ctx->h_counters[4];
+    return PB2_OK;
 }
 
 void* pb2_ctx_stream(pb2_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

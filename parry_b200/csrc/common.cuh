@@ -36,6 +36,11 @@ struct pb2_ctx {
     int ray_slot = 8;                 // d_counters slot of the persistent ray kernels' fetch counter (8 or 12, one per compute stream)
     cudaEvent_t ev[64] = {nullptr};
     int ev_next = 0;
+    // optional phase timing of the contact pipeline (pb2_ctx_enable_phase_timing): events on the launching stream around the
+    // GJK kernel, the EPA kernel and the finishing kernel of the last run_contacts call (bench.py's per-kernel roofline)
+    bool phase_timing = false;
+    cudaEvent_t phase_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int phase_marks = 0;
     unsigned int* d_pieces = nullptr;  // 2 x 32 u32: per-piece retired-ray counters and completion flags of a piece-signalling ray cast
     void* wait_value32 = nullptr;      // cuStreamWaitValue32, resolved once (NULL: not available -> piece-wise launches)
 };
@@ -87,6 +92,9 @@ __device__ __forceinline__ void pb2_push(uint32_t* stack, int& sp, uint32_t v, u
 #endif
 static inline unsigned pb2_blocks(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 #define PB2_LAUNCHED(ctx) ((ctx)->launches++)
+static inline void pb2_phase_mark(pb2_ctx* ctx, int i) {
+    if (ctx->phase_timing && ctx->phase_ev[i]) { cudaEventRecord(ctx->phase_ev[i], ctx->stream); if (ctx->phase_marks < i + 1) ctx->phase_marks = i + 1; }
+}
 
 // ---------------------------------------------------------------- node layout (== BvhNodeWide, 64 B)
 // child = { mins.xyz, children:u32, maxs.xyz, data:u32 }; data low 30 bits = leaf_count, top 2 = change flags.

@@ -1446,6 +1446,8 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
     int gjk_minb = 4;  // 128 registers, 4 CTAs per SM: 0.7 ms faster than the unconstrained 151-register build on the 4M-pair config
     { const char* e = getenv("PB2_GJK_MINB"); if (e) gjk_minb = atoi(e); }
     auto gjk = gjk_minb >= 5 ? k_contact_gjk<5> : (gjk_minb == 4 ? k_contact_gjk<4> : k_contact_gjk<3>);
+    ctx->phase_marks = 0;
+    pb2_phase_mark(ctx, 0);
     int gjk_persistent = 0, gjk_refill = 12;  // measured: no gain on hull pairs (31.9 vs 31.4 ms), 2.7x slower on TriMesh candidates
     { const char* e = getenv("PB2_GJK_PERSISTENT"); if (e) gjk_persistent = atoi(e); }
     { const char* e = getenv("PB2_GJK_REFILL"); if (e) gjk_refill = atoi(e); }
@@ -1464,6 +1466,7 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
         gjk<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, shapes->n, src, prediction, n, sinks, jobs, job_count);
     }
     PB2_LAUNCHED(ctx);
+    pb2_phase_mark(ctx, 1);
     if (epa_variant == 3) {
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contact_epac, 128, 0);
@@ -1475,6 +1478,7 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
         PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[2], (size_t)128 * epa_blocks * sizeof(EpaCArena)));
         k_contact_epac<<<epa_blocks, 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction, sinks,
                                                   jobs, job_count, next_job, (EpaCArena*)ctx->scratch[2].ptr, refill);
+        pb2_phase_mark(ctx, 2);
     } else {
         int per_sm = 0;
         PB2_CUDA(ctx, cudaFuncSetAttribute(k_contact_epa2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E2_SMEM_BYTES));
@@ -1493,6 +1497,7 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
         }
         k_contact_epa2<<<epa_blocks, 128, E2_SMEM_BYTES, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction, sinks,
                                                   jobs, job_count, next_job, (Epa2Arena*)ctx->scratch[2].ptr, refill, fin_recs, fin_count);
+        pb2_phase_mark(ctx, 2);
         if (split_finish) {
             PB2_LAUNCHED(ctx);
             // grid sized for the worst case (every pair went to EPA); blocks past the record count exit on their first load
@@ -1501,6 +1506,7 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
         }
     }
     PB2_LAUNCHED(ctx);
+    pb2_phase_mark(ctx, 3);
     PB2_CUDA(ctx, cudaGetLastError());
 #ifdef PB2_EPA_DEBUG
     {

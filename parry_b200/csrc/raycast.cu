@@ -329,7 +329,7 @@ static int cast_rays_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const void* d
     // 5 = 3 with the warp-shared triangle phase, 6 = 5 + ray reordering
     bool big = (size_t)b->n_nodes * sizeof(NodeWide) > (size_t)(100u << 20);
     int variant = mesh->n_nodes8 ? 5 : (big ? 2 : 1), steps = 16, refill = 8;
-    if (variant >= 3) { steps = 8; refill = 6; }  // wide kernel: `steps` = lanes with queued triangles that trigger a triangle pass
+    if (variant >= 3) { steps = 8; refill = 4; }  // wide kernel: `steps` = lanes with queued triangles that trigger a triangle pass
     {   // tuning knobs (read per call; cheap)
         const char* e = getenv("PB2_RAY_VARIANT");
         if (e) variant = atoi(e);
@@ -412,10 +412,11 @@ int pb2_trimesh_create(pb2_ctx* ctx, const float* vertices, uint32_t nv, const u
     pb2_trimesh* mesh = new pb2_trimesh();
     mesh->nt = nt; mesh->nv = nv;
     pb2_bvh* b = &mesh->bvh;
-    // TriMesh::new builds its Bvh once and queries it many times: the PLOC strategy (surface-area-driven clustering of the
-    // Morton-sorted triangles, bvh_build.cu) costs a few more milliseconds than the plain LBVH link and saves node visits on
-    // every ray (profiles/r2_*). PB2_MESH_BUILD=0 keeps the LBVH.
-    b->strategy = PB2_BUILD_PLOC;
+    // Link of the Morton-sorted triangles: Karras LBVH by default. The PLOC strategy (surface-area-driven clustering,
+    // bvh_build.cu) is available with PB2_MESH_BUILD=1; measured on the two bench meshes it does not pay: both are regular
+    // tessellations on which the cubic-cell Morton splits are already near-optimal (terrain 10.9 wide-node visits per ray with
+    // the LBVH against 11.5 with PLOC radius 16, 1M-triangle sphere 13.8 against 15.5; gpurun_out/r2b).
+    b->strategy = PB2_BUILD_BINNED;
     { const char* e = getenv("PB2_MESH_BUILD"); if (e) b->strategy = atoi(e) ? PB2_BUILD_PLOC : PB2_BUILD_BINNED; }
     b->n_leaves = nt;
     b->n_nodes = nt <= 2 ? 1 : nt - 1;
@@ -461,6 +462,12 @@ int pb2_trimesh_destroy(pb2_ctx* ctx, pb2_trimesh* mesh) {
 }
 
 const pb2_bvh* pb2_trimesh_bvh(const pb2_trimesh* mesh) { return mesh ? &mesh->bvh : nullptr; }
+
+uint64_t pb2_trimesh_traversal_bytes(const pb2_trimesh* mesh) {
+    if (!mesh) return 0;
+    if (mesh->n_nodes8) return (uint64_t)mesh->n_nodes8 * 96ull + (uint64_t)mesh->nt * 64ull;   // W8_NODE_F4 / W8_TRI_F4 records (trimesh_wide.cu)
+    return (uint64_t)mesh->bvh.n_nodes * 64ull + (uint64_t)mesh->nt * 48ull;
+}
 
 static int trimesh_cast_rays(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays, uint32_t m,
                              float max_toi, uint32_t cull, float* toi, uint32_t* tri, float* normal, uint32_t* feature, int mem) {

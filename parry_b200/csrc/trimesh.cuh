@@ -8,8 +8,8 @@ struct pb2_trimesh {
     uint32_t nt = 0, nv = 0;
     float4* tris = nullptr;    // [3 * sorted position]: {a, id}, {b, -}, {c, -}
     // Compressed 8-wide traversal tree (trimesh_wide.cu): 80-byte nodes, triangles re-gathered in wide-leaf order.
-    float4* nodes8 = nullptr;  // 5 x float4 per node
-    float4* tris8 = nullptr;   // same 48-byte record as `tris`, ordered by (wide node, slot)
+    float4* nodes8 = nullptr;  // W8_NODE_F4 (6) x float4 per node: 80 bytes of payload in a 96-byte, 32-byte-aligned record
+    float4* tris8 = nullptr;   // the 48-byte record of `tris` padded to 64 bytes (W8_TRI_F4), ordered by (wide node, slot)
     uint32_t n_nodes8 = 0;
     int levels8 = 0;           // depth of the wide tree
 };

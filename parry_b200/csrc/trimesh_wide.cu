@@ -22,6 +22,21 @@
 #include <cub/device/device_scan.cuh>
 
 #define W8_LEAF 0x80000000u
+// Record sizes in float4. Round 1 kept 80-byte nodes read with five LDG.128 and 48-byte triangles read with three. A node-fetch
+// microbenchmark (profiles/r2_ldg_bench.txt: one random node per lane, 28 warps per SM) shows that what such a
+// fetch costs is the number of load instructions, not the bytes: L1-resident 88 G nodes/s (5 x LDG.128 on 80 B) against 161 G
+// (3 x LDG.E.256 on 96 B), L2-resident 60 against 97, HBM 15 against 15. So both records are padded to a multiple of 32 bytes,
+// 32-byte aligned, and read with 256-bit loads (sm_100+): 3 per node, 2 per triangle. The aligned records also touch fewer
+// 32-byte sectors than before (a 16-byte-aligned 80-byte node straddles 3.5 sectors on average, a 48-byte triangle 2.5).
+#define W8_NODE_F4 6
+#define W8_TRI_F4 4
+struct F8 { float4 a, b; };
+__device__ __forceinline__ F8 ldg256(const float4* p) {   // p 32-byte aligned; read-only path
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    return r;
+}
 #define W8_STACK 96        // per-lane traversal stack entries; a visit pushes at most 7, so depth <= 7 * levels
 #define W8_MAX_LEVELS 13        // k_raycast_wide<., MODE 1> only (it pushes up to 7 entries per level)
 #define W8_MAX_LEVELS_GROUPS 64 // group walk (MODE 0 and k_raycast_wide_shared): one stack entry per level
@@ -165,7 +180,7 @@ __global__ void k_collapse8(const NodeWide* __restrict__ nodes, uint32_t* __rest
     }
     nleaf[w] = (uint32_t)__popc(lmask);
     auto pack4 = [](const uint32_t* q) { return q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24); };
-    float4* out = nodes8 + 5ull * w;
+    float4* out = nodes8 + (size_t)W8_NODE_F4 * w;
     out[0] = make_float4((float)plo[0], (float)plo[1], (float)plo[2],
                          __uint_as_float(ebits[0] | (ebits[1] << 8) | (ebits[2] << 16) | (imask << 24)));
     // .w = 1.0f: the kernel ORs the quantised bytes into this word's mantissa; reading it from the node (instead of an
@@ -177,6 +192,7 @@ __global__ void k_collapse8(const NodeWide* __restrict__ nodes, uint32_t* __rest
                          __uint_as_float(pack4(&qhi[0][0])), __uint_as_float(pack4(&qhi[0][4])));
     out[4] = make_float4(__uint_as_float(pack4(&qhi[1][0])), __uint_as_float(pack4(&qhi[1][4])),
                          __uint_as_float(pack4(&qhi[2][0])), __uint_as_float(pack4(&qhi[2][4])));
+    out[5] = make_float4(0.f, 0.f, 0.f, 0.f);   // padding to 96 bytes (never read by the kernels' arithmetic)
 }
 
 // Writes each node's first-triangle index and gathers the triangles into (wide node, slot) order.
@@ -185,14 +201,14 @@ __global__ void k_finalize8(uint32_t n8, const uint32_t* __restrict__ tri_base, 
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n8) return;
     uint32_t tb = tri_base[w];
-    reinterpret_cast<uint32_t*>(nodes8 + 5ull * w + 1)[1] = tb;
+    reinterpret_cast<uint32_t*>(nodes8 + (size_t)W8_NODE_F4 * w + 1)[1] = tb;
     uint32_t r = 0;
     for (int s = 0; s < 8; ++s) {
         uint32_t pos = leafpos[8ull * w + s];
         if (pos == 0xffffffffu) continue;
         const float4* src = tris + 3ull * pos;
-        float4* dst = tris8 + 3ull * (tb + r);
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        float4* dst = tris8 + (size_t)W8_TRI_F4 * (tb + r);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
         r++;
     }
 }
@@ -219,7 +235,7 @@ int pb2_wide_build(pb2_ctx* ctx, pb2_trimesh* mesh) {
         if (fail(cudaMalloc((void**)&nleaf, (size_t)nn * 4), "alloc")) break;
         if (fail(cudaMalloc((void**)&tbase, (size_t)nn * 4), "alloc")) break;
         if (fail(cudaMalloc((void**)&total, 4), "alloc")) break;
-        if (fail(cudaMalloc((void**)&tmp8, (size_t)nn * 80), "alloc")) break;
+        if (fail(cudaMalloc((void**)&tmp8, (size_t)nn * 16 * W8_NODE_F4), "alloc")) break;
         uint32_t one = 1, zero = 0;
         if (fail(cudaMemcpyAsync(total, &one, 4, cudaMemcpyHostToDevice, st), "init")) break;
         if (fail(cudaMemcpyAsync(wroot, &zero, 4, cudaMemcpyHostToDevice, st), "init")) break;
@@ -244,9 +260,9 @@ int pb2_wide_build(pb2_ctx* ctx, pb2_trimesh* mesh) {
         if (fail(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 1), "alloc")) break;
         if (fail(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, nleaf, tbase, (int)n8, st), "scan")) break;
         ctx->launches += 2;
-        if (fail(cudaMalloc((void**)&mesh->nodes8, (size_t)n8 * 80), "alloc")) break;
-        if (fail(cudaMalloc((void**)&mesh->tris8, (size_t)mesh->nt * 48), "alloc")) break;
-        if (fail(cudaMemcpyAsync(mesh->nodes8, tmp8, (size_t)n8 * 80, cudaMemcpyDeviceToDevice, st), "copy")) break;
+        if (fail(cudaMalloc((void**)&mesh->nodes8, (size_t)n8 * 16 * W8_NODE_F4), "alloc")) break;
+        if (fail(cudaMalloc((void**)&mesh->tris8, (size_t)mesh->nt * 16 * W8_TRI_F4), "alloc")) break;
+        if (fail(cudaMemcpyAsync(mesh->nodes8, tmp8, (size_t)n8 * 16 * W8_NODE_F4, cudaMemcpyDeviceToDevice, st), "copy")) break;
         k_finalize8<<<pb2_blocks(n8, 128), 128, 0, st>>>(n8, tbase, leafpos, mesh->tris, mesh->nodes8, mesh->tris8);
         PB2_LAUNCHED(ctx);
         if (fail(cudaGetLastError(), "finalize")) break;
@@ -379,8 +395,9 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide(const float4* __restric
             }
         }
         if (cur != PB2_INVALID_U32 && nq < W8_TQ) {
-            const float4* np = nodes8 + 5ull * cur;
-            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            const float4* np = nodes8 + (size_t)W8_NODE_F4 * cur;
+            F8 nA = ldg256(np), nB = ldg256(np + 2), nC = ldg256(np + 4);
+            float4 n0 = nA.a, n1 = nA.b, n2 = nB.a, n3 = nB.b, n4 = nC.a;
             uint32_t ew = __float_as_uint(n0.w);
             const uint32_t onef = __float_as_uint(n1.w);  // 0x3F800000, see k_collapse8
             AxisK kx = axis_setup(n0.x, o.x, inv.x, oct & 1u, ew & 0xffu);
@@ -475,7 +492,8 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide(const float4* __restric
                             qh++; nq--;
                             tg_base = g.x; tg_bits = g.y;
                         }
-                        float4 ta = __ldg(&tris8[3ull * t]), tb = __ldg(&tris8[3ull * t + 1]), tc = __ldg(&tris8[3ull * t + 2]);
+                        F8 tA = ldg256(tris8 + (size_t)W8_TRI_F4 * t), tB = ldg256(tris8 + (size_t)W8_TRI_F4 * t + 2);
+                        float4 ta = tA.a, tb = tA.b, tc = tB.a;
                         // exact leaf AABB (Triangle::local_aabb) and the reference's node test against the best hit so far
                         float4 blo = make_float4(fminf(fminf(ta.x, tb.x), tc.x), fminf(fminf(ta.y, tb.y), tc.y), fminf(fminf(ta.z, tb.z), tc.z), 0.f);
                         float4 bhi = make_float4(fmaxf(fmaxf(ta.x, tb.x), tc.x), fmaxf(fmaxf(ta.y, tb.y), tc.y), fmaxf(fmaxf(ta.z, tb.z), tc.z), 0.f);
@@ -540,6 +558,8 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __
                                   unsigned int* __restrict__ next_ray, int tri_groups, int refill, uint32_t cull, int blocked_max,
                                   unsigned long long* __restrict__ stats, PieceSignal pieces) {
     __shared__ float s_ray[9][128];                // o, d, 1/d of the ray each thread owns
+    __shared__ float s_stage[9][128];              // per warp: the next <= 32 rays, loaded and divided at full width (see the refill)
+    __shared__ uint32_t s_stage_r[128];            // their ray indices
     __shared__ unsigned long long s_key[128];      // best hit so far: |toi| bits << 32 | triangle id (id INVALID: none yet)
     __shared__ uint2 s_pay[128];                   // {exact toi bits, feature bits} of that hit
     __shared__ float s_nrm[WITH_NORMAL ? 3 : 1][128];
@@ -594,23 +614,48 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __
         }
         if (!active) rp = PB2_INVALID_U32;
     };
+    // Ray staging (round 2). Round 1 handed a new ray to each idle lane straight from global memory: one atomicAdd, six scattered
+    // 4-byte loads and three IEEE divisions executed by the ~8 idle lanes of a refill while the other 24 waited behind them — 11 % of
+    // the instruction stream at 17 lanes and 18 % of the stall samples (profiles/r1_rays_v8_*, source page). Now the warp claims rays
+    // 32 at a time: all 32 lanes load one ray each (768 contiguous bytes), transform it, divide, and park {o, d, 1/d} in shared
+    // memory; idle lanes are then served from that stage with nine shared-memory reads. The global round trips are paid once per 32
+    // rays instead of once per refill, the divisions run at full width, and a refill is cheap enough to run as soon as a few lanes idle.
+    uint32_t st_base = 0, st_count = 0, st_next = 0;   // staged batch: first ray slot, rays staged, rays handed out (warp uniform)
     for (;;) {
         unsigned idle = __ballot_sync(FULL, !active);
-        if (!exhausted && (idle == FULL || __popc(idle) >= refill)) {
+        if ((!exhausted || st_next < st_count) && (idle == FULL || __popc(idle) >= refill)) {
             if (PIECES) { pz_collect(); if (++pz_since >= (uint32_t)pieces_flush_every && (pz_count | pz_count2)) pz_flush(); }
-            unsigned base = 0;
-            int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(next_ray, (unsigned)__popc(idle));
-            base = __shfl_sync(FULL, base, leader);
-            if (base + __popc(idle) >= m) exhausted = true;
-            if (!active) {
-                uint32_t slot = base + __popc(idle & lt);
-                if (slot < m) {
-                    r = perm ? perm[slot] : slot;
-                    o = mk3(rays[6ull * r], rays[6ull * r + 1], rays[6ull * r + 2]);
-                    V3 d = mk3(rays[6ull * r + 3], rays[6ull * r + 4], rays[6ull * r + 5]);
-                    if (pose7) { o = iso_inv_point(pose, o); d = iso_inv_vec(pose, d); }
-                    inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            for (;;) {
+                if (st_next == st_count) {
+                    if (exhausted) break;
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(next_ray, 32u);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base >= m) { exhausted = true; break; }
+                    if (base + 32u >= m) exhausted = true;
+                    const uint32_t cnt = m - base < 32u ? m - base : 32u;
+                    if ((uint32_t)lane < cnt) {
+                        uint32_t rr = perm ? perm[base + lane] : base + lane;
+                        V3 so = mk3(rays[6ull * rr], rays[6ull * rr + 1], rays[6ull * rr + 2]);
+                        V3 sd = mk3(rays[6ull * rr + 3], rays[6ull * rr + 4], rays[6ull * rr + 5]);
+                        if (pose7) { so = iso_inv_point(pose, so); sd = iso_inv_vec(pose, sd); }
+                        s_stage[0][threadIdx.x] = so.x; s_stage[1][threadIdx.x] = so.y; s_stage[2][threadIdx.x] = so.z;
+                        s_stage[3][threadIdx.x] = sd.x; s_stage[4][threadIdx.x] = sd.y; s_stage[5][threadIdx.x] = sd.z;
+                        s_stage[6][threadIdx.x] = 1.0f / sd.x; s_stage[7][threadIdx.x] = 1.0f / sd.y; s_stage[8][threadIdx.x] = 1.0f / sd.z;
+                        s_stage_r[threadIdx.x] = rr;
+                    }
+                    __syncwarp();
+                    st_base = base; st_count = cnt; st_next = 0;
+                }
+                const uint32_t navail = st_count - st_next, nidle = (uint32_t)__popc(idle);
+                const uint32_t take = navail < nidle ? navail : nidle;
+                const uint32_t rank = (uint32_t)__popc(idle & lt);
+                if (!active && rank < take) {
+                    const int sl = wbase + (int)(st_next + rank);
+                    r = s_stage_r[sl];
+                    o = mk3(s_stage[0][sl], s_stage[1][sl], s_stage[2][sl]);
+                    V3 d = mk3(s_stage[3][sl], s_stage[4][sl], s_stage[5][sl]);
+                    inv = mk3(s_stage[6][sl], s_stage[7][sl], s_stage[8][sl]);
                     oct = (__float_as_uint(d.x) >> 31) | ((__float_as_uint(d.y) >> 31) << 1) | ((__float_as_uint(d.z) >> 31) << 2);
                     best = max_toi;
                     sp = 0; active = true; pend = false;
@@ -621,7 +666,12 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __
                     s_key[threadIdx.x] = ((unsigned long long)__float_as_uint(max_toi) << 32) | 0xffffffffull;
                     if (PIECES) rp = r / pieces.size;
                 }
+                st_next += take;
+                idle = __ballot_sync(FULL, !active);
+                if (idle == 0u) break;
+                __syncwarp();   // the stage is about to be overwritten: every lane has read its slot
             }
+            (void)st_base;
             idle = __ballot_sync(FULL, !active);
         }
         if (idle == FULL) break;
@@ -642,8 +692,9 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __
             const int MODE = 0;
             float (*tent)[128] = nullptr;
             (void)tent;
-            const float4* np = nodes8 + 5ull * cur;
-            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            const float4* np = nodes8 + (size_t)W8_NODE_F4 * cur;
+            F8 nA = ldg256(np), nB = ldg256(np + 2), nC = ldg256(np + 4);
+            float4 n0 = nA.a, n1 = nA.b, n2 = nB.a, n3 = nB.b, n4 = nC.a;
             uint32_t ew = __float_as_uint(n0.w);
             const uint32_t onef = __float_as_uint(n1.w);
             AxisK kx = axis_setup(n0.x, o.x, inv.x, oct & 1u, ew & 0xffu);
@@ -724,7 +775,8 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __
                             uint2 ge = s_gq[w][gb + (it >> 3)];
                             own = wbase + (int)(ge.y >> 16);
                             uint32_t t = ge.x + (uint32_t)__popc(ge.y & 0xffu & ((1u << (it & 7u)) - 1u));
-                            float4 ta = __ldg(&tris8[3ull * t]), tb = __ldg(&tris8[3ull * t + 1]), tc = __ldg(&tris8[3ull * t + 2]);
+                            F8 tA = ldg256(tris8 + (size_t)W8_TRI_F4 * t), tB = ldg256(tris8 + (size_t)W8_TRI_F4 * t + 2);
+                        float4 ta = tA.a, tb = tA.b, tc = tB.a;
                             unsigned long long k0 = s_key[own];
                             float sbest = __uint_as_float((uint32_t)(k0 >> 32));
                             uint32_t sid = (uint32_t)k0;
@@ -832,7 +884,7 @@ int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, co
         if (max_persist > 0 && max_window > 0) {
             size_t carve = (size_t)max_persist * (size_t)(l2_pct > 100 ? 100 : l2_pct) / 100;
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
-            size_t bytes = (size_t)mesh->n_nodes8 * 80;
+            size_t bytes = (size_t)mesh->n_nodes8 * 16 * W8_NODE_F4;
             if (bytes > (size_t)max_window) bytes = (size_t)max_window;
             cudaStreamAttrValue attr;
             memset(&attr, 0, sizeof(attr));

@@ -90,6 +90,15 @@ class Context:
     def synchronize(self):
         self.check(self._lib.pb2_ctx_synchronize(self.h))
 
+    def enable_phase_timing(self, on=True):
+        self.check(self._lib.pb2_ctx_enable_phase_timing(self.h, 1 if on else 0))
+
+    def contact_phase_times(self):
+        """(gjk_ms, epa_ms, finish_ms, epa_runs) of the last contact-family call (CUDA events on the library's stream)."""
+        a, b, c, r = C.c_float(0), C.c_float(0), C.c_float(0), C.c_uint64(0)
+        self.check(self._lib.pb2_contact_phase_times(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(r)))
+        return a.value, b.value, c.value, int(r.value)
+
     @property
     def stream_ptr(self):
         return self._lib.pb2_ctx_stream(self.h)
@@ -301,6 +310,10 @@ class TriMesh:
         h = C.c_void_p()
         ctx.check(ctx._lib.pb2_trimesh_create(ctx.h, pv, self.num_vertices, pi, self.num_triangles, mem, C.byref(h)))
         self.h = h
+
+    def wide_bytes(self):
+        """Bytes of the traversal arrays (wide nodes + pre-gathered triangles) a ray cast walks."""
+        return int(self.ctx._lib.pb2_trimesh_traversal_bytes(self.h))
 
     def bvh(self):
         return Bvh(self.ctx, C.c_void_p(self.ctx._lib.pb2_trimesh_bvh(self.h)), owned=False, keep=self)
