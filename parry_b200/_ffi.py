@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libparry_b200.so")
+LIB_PATH = os.environ.get("PB2_LIB_PATH") or os.path.join(HERE, "libparry_b200.so")   # PB2_LIB_PATH: A/B builds of the same library (harness)
 
 PB2_OK, PB2_ERR_INVALID, PB2_ERR_CUDA, PB2_ERR_OVERFLOW, PB2_ERR_UNSUPPORTED, PB2_ERR_DEPTH = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -555,7 +555,12 @@ __global__ void __launch_bounds__(128, MINB) k_contact_gjk_persistent(const uint
 #define E2_MAX_FACES 256
 #define E2_MAX_SIL 64
 #define E2_STACK 96
+#ifndef E2_STACK_SMEM
 #define E2_STACK_SMEM 64   // DFS stack entries kept in shared memory by k_contact_epa2 (deeper walks: status 3)
+#endif
+#ifndef E2_MINB
+#define E2_MINB 4          // resident CTAs per SM the EPA kernel is compiled for (register cap 65536 / (128 * E2_MINB))
+#endif
 
 struct Epa2Arena {
     float4 face[E2_MAX_FACES];   // normal.xyz ; w = pts0 | pts1 << 8 | pts2 << 16 | deleted << 24
@@ -581,7 +586,13 @@ __device__ __forceinline__ int e2_next_ccw(float4 f, uint32_t id) {
 __device__ __forceinline__ bool h2_le(float a, float b) { return !(a > b); }
 // Heap storage of k_contact_epa2: the first E2_HEAP_SMEM entries of every thread's heap sit in shared memory ([entry][thread],
 // f32 key + u8 face id), the rest in the thread's arena. Rust's BinaryHeap sift rules (sift_up / sift_down_to_bottom) below.
-#define E2_HEAP_SMEM 32
+// Round 2: 16 entries instead of 32. The four resident CTAs' shared memory comes out of the same 256 KB as L1; at 52 KB per CTA
+// only ~48 KB of L1 were left for 512 threads' arenas. Sweep on the 2^22 hull-pair batch (gpurun r2, whole contact call):
+// 32 entries 31.7 ms, 16: 26.6, 12: 26.6, 8: 27.1, 4: 28.0, 1: 29.1. More resident CTAs instead (5 / 6 / 7 per SM with the
+// register cap that implies: 96 / 80 / 72 registers, 90-530 bytes of spills) were slower: 36.5 / 39.3 / 39.6 ms.
+#ifndef E2_HEAP_SMEM
+#define E2_HEAP_SMEM 16
+#endif
 #define E2_SMEM_BYTES (E2_HEAP_SMEM * 128 * 5 + (E2_STACK_SMEM + E2_MAX_SIL) * 128 * 2)
 struct Heap2 {
     float (*key)[128];
@@ -707,7 +718,7 @@ __device__ __forceinline__ int epa_result_to_contact(const PairSetup& ps, int fi
     return st;
 }
 
-__global__ void __launch_bounds__(128, 4) k_contact_epa2(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
+__global__ void __launch_bounds__(128, E2_MINB) k_contact_epa2(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
                               const float4* __restrict__ pts, PairSrc src, float prediction, OutSinks out,
                               const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
                               unsigned long long* __restrict__ next_job, Epa2Arena* __restrict__ arenas, int refill,
