@@ -42,8 +42,13 @@ typedef enum pb2_status {
 
 typedef enum pb2_mem { PB2_MEM_HOST = 0, PB2_MEM_DEVICE = 1 } pb2_mem;
 
-/* BvhBuildStrategy (partitioning/bvh/bvh_tree.rs:58-78). Both map onto the GPU builder (Morton LBVH +
- * SAH treelet refinement); the value is recorded so a shim can round-trip it. */
+/* BvhBuildStrategy (partitioning/bvh/bvh_tree.rs:58-78). Both builders sort the leaves by 63-bit Morton code on the device.
+ *  - PB2_BUILD_BINNED (the reference's default, bvh_binned_build.rs:39-176: sequential top-down 8-bin SAH): replaced by a plain
+ *    Karras LBVH link of the sorted leaves (no SAH pass) — the per-frame builder, ~1 ms per million leaves.
+ *  - PB2_BUILD_PLOC (bvh_ploc_build.rs:10-94): the same algorithm on the GPU — rounds of radius-16 nearest-neighbour search by
+ *    half-area of the merged box and merging of mutual pairs; links the reference's own topology from the same sorted leaves
+ *    (tests/test_hostcheck.py). Thousands of identical boxes stall the clustering; the builder then falls back to the LBVH link.
+ * Query results never depend on the strategy. */
 typedef enum pb2_build_strategy { PB2_BUILD_BINNED = 0, PB2_BUILD_PLOC = 1 } pb2_build_strategy;
 
 /* Shape kinds known to the typed-leaf / contact kernels (shape/shape.rs ShapeType subset on the hot path). */

@@ -233,10 +233,156 @@ static inline void project_local_point_solid(const ShapeRef& s, const Vec3& pt, 
     else { proj = pt; inside = true; }
 }
 
+// ---- SAT (sat_cuboid_cuboid.rs)
+static inline Vec3 cuboid_local_support(const Vec3& he, const Vec3& dir) {
+    return Vec3(copysignf(he.x, dir.x), copysignf(he.y, dir.y), copysignf(he.z, dir.z));
+}
+// :5-22
+static inline void sat_separation_wrt_local_line(const Vec3& he1, const Vec3& he2, const Iso& pos12, const Vec3& axis_in, Real& sep, Vec3& axis1) {
+    Real signum = copysignf(1.0f, dot(pos12.tra, axis_in));
+    axis1 = axis_in * signum;
+    Vec3 axis2 = pos12.inverse_transform_vector(-axis1);
+    Vec3 local_pt1 = cuboid_local_support(he1, axis1);
+    Vec3 local_pt2 = cuboid_local_support(he2, axis2);
+    Vec3 pt2 = pos12.transform_point(local_pt2);
+    sep = dot(pt2 - local_pt1, axis1);
+}
+// :24-77
+static inline void sat_find_separating_edge_twoway(const Vec3& he1, const Vec3& he2, const Iso& pos12, Real& best_sep, Vec3& best_dir) {
+    best_sep = -REAL_MAX; best_dir = Vec3();
+    Vec3 x2 = pos12.transform_vector(Vec3(1, 0, 0)), y2 = pos12.transform_vector(Vec3(0, 1, 0)), z2 = pos12.transform_vector(Vec3(0, 0, 1));
+    Vec3 axes[9] = {Vec3(0.0f, -x2.z, x2.y), Vec3(x2.z, 0.0f, -x2.x), Vec3(-x2.y, x2.x, 0.0f),
+                    Vec3(0.0f, -y2.z, y2.y), Vec3(y2.z, 0.0f, -y2.x), Vec3(-y2.y, y2.x, 0.0f),
+                    Vec3(0.0f, -z2.z, z2.y), Vec3(z2.z, 0.0f, -z2.x), Vec3(-z2.y, z2.x, 0.0f)};
+    for (int k = 0; k < 9; ++k) {
+        Real n = norm(axes[k]);
+        if (n > DEFAULT_EPSILON) {
+            Real sep; Vec3 a1;
+            sat_separation_wrt_local_line(he1, he2, pos12, axes[k] / n, sep, a1);
+            if (sep > best_sep) { best_sep = sep; best_dir = a1; }
+        }
+    }
+}
+// :79-110
+static inline void sat_find_separating_normal_oneway(const Vec3& he1, const Vec3& he2, const Iso& pos12, Real& best_sep, Vec3& best_dir) {
+    best_sep = -REAL_MAX; best_dir = Vec3();
+    for (int i = 0; i < 3; ++i) {
+        Real sign = copysignf(1.0f, pos12.tra[i]);
+        Vec3 axis1; axis1[i] = sign;
+        Vec3 axis2 = pos12.inverse_transform_vector(-axis1);
+        Vec3 local_pt2 = cuboid_local_support(he2, axis2);
+        Vec3 pt2 = pos12.transform_point(local_pt2);
+        Real sep = pt2[i] * sign - he1[i];
+        if (sep > best_sep) { best_sep = sep; best_dir = axis1; }
+    }
+}
+
+// approx::ulps_eq! defaults for f32: epsilon = f32::EPSILON, max_ulps = 4
+static inline bool ulps_eq(Real a, Real b) {
+    if (fabsf(a - b) <= FLT_EPSILON) return true;
+    if (std::signbit(a) != std::signbit(b)) return false;
+    int32_t ia, ib; memcpy(&ia, &a, 4); memcpy(&ib, &b, 4);
+    int64_t d = (int64_t)ia - (int64_t)ib; if (d < 0) d = -d;
+    return d <= 4;
+}
+
+// ---- cuboid-cuboid arms of distance / intersection_test (SAT based)
+static inline int iamin3(const Vec3& v) {   // nalgebra iamin: first strict minimum of |x|
+    int i = 0; Real best = fabsf(v.x);
+    if (fabsf(v.y) < best) { best = fabsf(v.y); i = 1; }
+    if (fabsf(v.z) < best) i = 2;
+    return i;
+}
+// Cuboid::local_support_edge_segment (shape/cuboid.rs:249-263)
+static inline void cuboid_local_support_edge_segment(const Vec3& he, const Vec3& dir, Vec3& a, Vec3& b) {
+    int i = iamin3(dir), j = (i + 1) % 3, k = (i + 2) % 3;
+    a = Vec3(); a[i] = he[i]; a[j] = copysignf(he[j], dir[j]); a[k] = copysignf(he[k], dir[k]);
+    b = a; b[i] = -he[i];
+}
+static inline Real na_clamp(Real v, Real lo, Real hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// closest_points_segment_segment_with_locations_nD (closest_points_segment_segment.rs:36-107): parameters s on seg1, t on seg2
+static inline void segment_segment_params(const Vec3& a1, const Vec3& b1, const Vec3& a2, const Vec3& b2, Real& s, Real& t) {
+    Vec3 d1 = b1 - a1, d2 = b2 - a2, r = a1 - a2;
+    Real a = norm_squared(d1), e = norm_squared(d2), f = dot(d2, r);
+    const Real eps = DEFAULT_EPSILON;
+    if (a <= eps && e <= eps) { s = 0.0f; t = 0.0f; }
+    else if (a <= eps) { s = 0.0f; t = na_clamp(f / e, 0.0f, 1.0f); }
+    else {
+        Real c = dot(d1, r);
+        if (e <= eps) { t = 0.0f; s = na_clamp(-c / a, 0.0f, 1.0f); }
+        else {
+            Real b = dot(d1, d2), ae = a * e, bb = b * b, denom = ae - bb;
+            if (denom > eps && !ulps_eq(ae, bb)) s = na_clamp((b * f - c * e) / denom, 0.0f, 1.0f);
+            else s = 0.0f;
+            t = (b * s + f) / e;
+            if (t < 0.0f) { t = 0.0f; s = na_clamp(-c / a, 0.0f, 1.0f); }
+            else if (t > 1.0f) { t = 1.0f; s = na_clamp((b - c) / a, 0.0f, 1.0f); }
+        }
+    }
+}
+// Segment::point_at (shape/segment.rs:410-419) of the location the reference derives from a parameter (:88-104)
+static inline Vec3 segment_point_at_param(const Vec3& a, const Vec3& b, Real s) {
+    if (s == 0.0f) return a;
+    if (s == 1.0f) return b;
+    return a * (1.0f - s) + b * s;
+}
+// intersection_test_cuboid_cuboid (intersection_test_cuboid_cuboid.rs:6-31)
+static inline bool intersection_test_cuboid_cuboid(const Iso& pos12, const Vec3& he1, const Vec3& he2) {
+    Real sep; Vec3 dir;
+    sat_find_separating_normal_oneway(he1, he2, pos12, sep, dir);
+    if (sep > 0.0f) return false;
+    Iso pos21 = pos12.inverse();
+    sat_find_separating_normal_oneway(he2, he1, pos21, sep, dir);
+    if (sep > 0.0f) return false;
+    sat_find_separating_edge_twoway(he1, he2, pos12, sep, dir);
+    return sep <= 0.0f;
+}
+// distance_cuboid_cuboid (distance_cuboid_cuboid.rs:6-12) = closest_points_cuboid_cuboid with margin = Real::MAX
+// (closest_points_cuboid_cuboid.rs:6-84), WithinMargin(p1, p2) -> na::distance(p1, pos12 * p2), anything else -> 0
+static inline Real distance_cuboid_cuboid(const Iso& pos12, const Vec3& he1, const Vec3& he2) {
+    const Real margin = REAL_MAX;
+    Iso pos21 = pos12.inverse();
+    Real s1, s2, s3; Vec3 d1, d2, d3;
+    sat_find_separating_normal_oneway(he1, he2, pos12, s1, d1);
+    if (s1 > margin) return 0.0f;
+    sat_find_separating_normal_oneway(he2, he1, pos21, s2, d2);
+    if (s2 > margin) return 0.0f;
+    sat_find_separating_edge_twoway(he1, he2, pos12, s3, d3);
+    if (s3 > margin) return 0.0f;
+    if (s1 <= 0.0f && s2 <= 0.0f && s3 <= 0.0f) return 0.0f;   // Intersecting
+    ShapeRef c1, c2;
+    c1.kind = SHAPE_CUBOID; c1.half_extents = he1; c2.kind = SHAPE_CUBOID; c2.half_extents = he2;
+    if (s1 >= s2 && s1 >= s3) {
+        // SupportMap::support_point(pos12, -dir) = pos12 * local_support_point(pos12^-1 (-dir))
+        Vec3 pt2_1 = pos12.transform_point(cuboid_local_support(he2, pos12.inverse_transform_vector(-d1)));
+        Vec3 proj; bool inside;
+        project_local_point_solid(c1, pt2_1, proj, inside);
+        if (norm_squared(proj - pt2_1) > margin * margin) return 0.0f;
+        Vec3 p2 = pos21.transform_point(pt2_1);
+        return norm(proj - pos12.transform_point(p2));
+    }
+    if (s2 >= s1 && s2 >= s3) {
+        Vec3 pt1_2 = pos21.transform_point(cuboid_local_support(he1, pos21.inverse_transform_vector(-d2)));
+        Vec3 proj; bool inside;
+        project_local_point_solid(c2, pt1_2, proj, inside);
+        if (norm_squared(proj - pt1_2) > margin * margin) return 0.0f;
+        Vec3 p1 = pos12.transform_point(pt1_2);
+        return norm(p1 - pos12.transform_point(proj));
+    }
+    Vec3 a1, b1, a2, b2;
+    cuboid_local_support_edge_segment(he1, d3, a1, b1);
+    cuboid_local_support_edge_segment(he2, pos21.transform_vector(-d3), a2, b2);
+    Real s, t;
+    segment_segment_params(a1, b1, pos12.transform_point(a2), pos12.transform_point(b2), s, t);
+    Vec3 p1 = segment_point_at_param(a1, b1, s), p2 = segment_point_at_param(a2, b2, t);
+    Vec3 p2w = pos12.transform_point(p2);
+    if (norm_squared(p1 - p2w) <= margin * margin) return norm(p1 - p2w);
+    return 0.0f;
+}
+
 enum QueryStatus { QUERY_OK = 0, QUERY_UNSUPPORTED = 2, QUERY_NEEDS_HOST = 3 };
 
-// DefaultQueryDispatcher::distance (default_query_dispatcher.rs:177-236) for Ball / Cuboid / ConvexPolyhedron. The cuboid-cuboid
-// arm (SAT + segment closest points, distance_cuboid_cuboid.rs) is not restated: QUERY_NEEDS_HOST.
+// DefaultQueryDispatcher::distance (default_query_dispatcher.rs:177-236) for Ball / Cuboid / ConvexPolyhedron.
 static inline int dispatch_distance(const Iso& pos12, const ShapeRef& s1, const ShapeRef& s2, Real& out) {
     out = 0.0f;
     if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_BALL) {  // distance_ball_ball.rs
@@ -255,7 +401,7 @@ static inline int dispatch_distance(const Iso& pos12, const ShapeRef& s1, const 
         out = d > 0.0f ? d : 0.0f;             // .max(0.0)
         return QUERY_OK;
     }
-    if (s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_CUBOID) return QUERY_NEEDS_HOST;
+    if (s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_CUBOID) { out = distance_cuboid_cuboid(pos12, s1.half_extents, s2.half_extents); return QUERY_OK; }
     // distance_support_map_support_map.rs
     SupportShape g1 = s1.support(), g2 = s2.support();
     VoronoiSimplex simplex;
@@ -267,7 +413,7 @@ static inline int dispatch_distance(const Iso& pos12, const ShapeRef& s1, const 
     return QUERY_OK;
 }
 
-// DefaultQueryDispatcher::intersection_test (default_query_dispatcher.rs:104-175), same shapes, same restriction.
+// DefaultQueryDispatcher::intersection_test (default_query_dispatcher.rs:104-175), same shapes.
 static inline int dispatch_intersection_test(const Iso& pos12, const ShapeRef& s1, const ShapeRef& s2, bool& out) {
     out = false;
     if (s1.kind == SHAPE_BALL && s2.kind == SHAPE_BALL) {  // intersection_test_ball_ball.rs
@@ -275,7 +421,7 @@ static inline int dispatch_intersection_test(const Iso& pos12, const ShapeRef& s
         out = d2 <= sum * sum;
         return QUERY_OK;
     }
-    if (s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_CUBOID) return QUERY_NEEDS_HOST;
+    if (s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_CUBOID) { out = intersection_test_cuboid_cuboid(pos12, s1.half_extents, s2.half_extents); return QUERY_OK; }
     if (s1.kind == SHAPE_BALL || s2.kind == SHAPE_BALL) {  // intersection_test_ball_point_query.rs
         bool ball_first = s1.kind == SHAPE_BALL;
         Iso p = ball_first ? pos12.inverse() : pos12;

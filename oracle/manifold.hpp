@@ -72,49 +72,7 @@ static inline void manifold_cuboid_ball(const Iso& pos12, const Vec3& he, Real r
     }
 }
 
-// ---- SAT (sat_cuboid_cuboid.rs)
-static inline Vec3 cuboid_local_support(const Vec3& he, const Vec3& dir) {
-    return Vec3(copysignf(he.x, dir.x), copysignf(he.y, dir.y), copysignf(he.z, dir.z));
-}
-// :5-22
-static inline void sat_separation_wrt_local_line(const Vec3& he1, const Vec3& he2, const Iso& pos12, const Vec3& axis_in, Real& sep, Vec3& axis1) {
-    Real signum = copysignf(1.0f, dot(pos12.tra, axis_in));
-    axis1 = axis_in * signum;
-    Vec3 axis2 = pos12.inverse_transform_vector(-axis1);
-    Vec3 local_pt1 = cuboid_local_support(he1, axis1);
-    Vec3 local_pt2 = cuboid_local_support(he2, axis2);
-    Vec3 pt2 = pos12.transform_point(local_pt2);
-    sep = dot(pt2 - local_pt1, axis1);
-}
-// :24-77
-static inline void sat_find_separating_edge_twoway(const Vec3& he1, const Vec3& he2, const Iso& pos12, Real& best_sep, Vec3& best_dir) {
-    best_sep = -REAL_MAX; best_dir = Vec3();
-    Vec3 x2 = pos12.transform_vector(Vec3(1, 0, 0)), y2 = pos12.transform_vector(Vec3(0, 1, 0)), z2 = pos12.transform_vector(Vec3(0, 0, 1));
-    Vec3 axes[9] = {Vec3(0.0f, -x2.z, x2.y), Vec3(x2.z, 0.0f, -x2.x), Vec3(-x2.y, x2.x, 0.0f),
-                    Vec3(0.0f, -y2.z, y2.y), Vec3(y2.z, 0.0f, -y2.x), Vec3(-y2.y, y2.x, 0.0f),
-                    Vec3(0.0f, -z2.z, z2.y), Vec3(z2.z, 0.0f, -z2.x), Vec3(-z2.y, z2.x, 0.0f)};
-    for (int k = 0; k < 9; ++k) {
-        Real n = norm(axes[k]);
-        if (n > DEFAULT_EPSILON) {
-            Real sep; Vec3 a1;
-            sat_separation_wrt_local_line(he1, he2, pos12, axes[k] / n, sep, a1);
-            if (sep > best_sep) { best_sep = sep; best_dir = a1; }
-        }
-    }
-}
-// :79-110
-static inline void sat_find_separating_normal_oneway(const Vec3& he1, const Vec3& he2, const Iso& pos12, Real& best_sep, Vec3& best_dir) {
-    best_sep = -REAL_MAX; best_dir = Vec3();
-    for (int i = 0; i < 3; ++i) {
-        Real sign = copysignf(1.0f, pos12.tra[i]);
-        Vec3 axis1; axis1[i] = sign;
-        Vec3 axis2 = pos12.inverse_transform_vector(-axis1);
-        Vec3 local_pt2 = cuboid_local_support(he2, axis2);
-        Vec3 pt2 = pos12.transform_point(local_pt2);
-        Real sep = pt2[i] * sign - he1[i];
-        if (sep > best_sep) { best_sep = sep; best_dir = axis1; }
-    }
-}
+// ---- SAT (sat_cuboid_cuboid.rs): in contact.hpp (shared with the cuboid-cuboid distance / intersection_test arms)
 
 // ---- Cuboid::support_face (cuboid.rs:267-354)
 struct PolyFeature { Vec3 v[4]; uint32_t vids[4], eids[4], fid; int n; };
@@ -137,14 +95,6 @@ static inline PolyFeature cuboid_support_face(const Vec3& he, const Vec3& dir) {
 }
 
 static inline Real perp2(Real ax, Real ay, Real bx, Real by) { return ax * by - ay * bx; }
-// approx::ulps_eq! defaults for f32: epsilon = f32::EPSILON, max_ulps = 4
-static inline bool ulps_eq(Real a, Real b) {
-    if (fabsf(a - b) <= FLT_EPSILON) return true;
-    if (std::signbit(a) != std::signbit(b)) return false;
-    int32_t ia, ib; memcpy(&ia, &a, 4); memcpy(&ib, &b, 4);
-    int64_t d = (int64_t)ia - (int64_t)ib; if (d < 0) d = -d;
-    return d <= 4;
-}
 // polygonal_feature3d.rs:398-439
 static inline bool closest_points_line2d(const Real e1[2][2], const Real e2[2][2], Real& s_out, Real& t_out) {
     Real d1x = e1[1][0] - e1[0][0], d1y = e1[1][1] - e1[0][1];

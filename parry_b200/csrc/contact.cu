@@ -118,6 +118,144 @@ __device__ __forceinline__ bool d_cuboid_feature_normal(Feat f, V3& n) {
     return false;
 }
 
+__device__ __forceinline__ V3 cub_support(V3 he, V3 d) { return mk3(copysignf(he.x, d.x), copysignf(he.y, d.y), copysignf(he.z, d.z)); }
+
+// sat_cuboid_cuboid.rs:79-110
+__device__ __forceinline__ void sat_normal_oneway(V3 he1, V3 he2, const Iso7& pos12, float& best_sep, V3& best_dir) {
+    best_sep = -FLT_MAX; best_dir = mk3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float sign = copysignf(1.0f, comp(pos12.t, i));
+        V3 axis1 = mk3(0.f, 0.f, 0.f);
+        setc(axis1, i, sign);
+        V3 axis2 = iso_inv_vec(pos12, -axis1);
+        V3 pt2 = iso_point(pos12, cub_support(he2, axis2));
+        float sep = comp(pt2, i) * sign - comp(he1, i);
+        if (sep > best_sep) { best_sep = sep; best_dir = axis1; }
+    }
+}
+// sat_cuboid_cuboid.rs:5-77
+__device__ __forceinline__ void sat_edge_twoway(V3 he1, V3 he2, const Iso7& pos12, float& best_sep, V3& best_dir) {
+    best_sep = -FLT_MAX; best_dir = mk3(0.f, 0.f, 0.f);
+    V3 c2[3] = {iso_vec(pos12, mk3(1.f, 0.f, 0.f)), iso_vec(pos12, mk3(0.f, 1.f, 0.f)), iso_vec(pos12, mk3(0.f, 0.f, 1.f))};
+    for (int k = 0; k < 9; ++k) {
+        V3 u = c2[k / 3];
+        int a = k % 3;
+        V3 axis = a == 0 ? mk3(0.0f, -u.z, u.y) : (a == 1 ? mk3(u.z, 0.0f, -u.x) : mk3(-u.y, u.x, 0.0f));
+        float n = nrm(axis);
+        if (n > PB2_EPS) {
+            V3 ax = axis / n;
+            float signum = copysignf(1.0f, dot3(pos12.t, ax));
+            V3 axis1 = ax * signum;
+            V3 axis2 = iso_inv_vec(pos12, -axis1);
+            V3 lp1 = cub_support(he1, axis1);
+            V3 pt2 = iso_point(pos12, cub_support(he2, axis2));
+            float sep = dot3(pt2 - lp1, axis1);
+            if (sep > best_sep) { best_sep = sep; best_dir = axis1; }
+        }
+    }
+}
+
+// approx::ulps_eq! defaults for f32 (epsilon = f32::EPSILON, max_ulps = 4)
+__device__ __forceinline__ bool ulps_eq4(float a, float b) {
+    if (fabsf(a - b) <= PB2_EPS) return true;
+    if (signbit(a) != signbit(b)) return false;
+    long long d = (long long)__float_as_int(a) - (long long)__float_as_int(b);
+    if (d < 0) d = -d;
+    return d <= 4;
+}
+
+// ---- cuboid-cuboid arms of query::distance / query::intersection_test (default_query_dispatcher.rs:183-186, :205-207)
+// Cuboid::local_support_edge_segment (shape/cuboid.rs:249-263)
+__device__ __forceinline__ void cub_support_edge(V3 he, V3 dir, V3& a, V3& b) {
+    int i = 0; float best = fabsf(dir.x);   // nalgebra iamin: first strict minimum of |x|
+    if (fabsf(dir.y) < best) { best = fabsf(dir.y); i = 1; }
+    if (fabsf(dir.z) < best) i = 2;
+    int j = (i + 1) % 3, k = (i + 2) % 3;
+    a = mk3(0.f, 0.f, 0.f);
+    setc(a, i, comp(he, i)); setc(a, j, copysignf(comp(he, j), comp(dir, j))); setc(a, k, copysignf(comp(he, k), comp(dir, k)));
+    b = a; setc(b, i, -comp(he, i));
+}
+__device__ __forceinline__ float na_clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+// closest_points_segment_segment_with_locations_nD (closest_points_segment_segment.rs:36-107)
+__device__ __forceinline__ void seg_seg_params(V3 a1, V3 b1, V3 a2, V3 b2, float& s, float& t) {
+    V3 d1 = b1 - a1, d2 = b2 - a2, r = a1 - a2;
+    float a = nrm2(d1), e = nrm2(d2), f = dot3(d2, r);
+    const float eps = PB2_EPS;
+    if (a <= eps && e <= eps) { s = 0.0f; t = 0.0f; }
+    else if (a <= eps) { s = 0.0f; t = na_clamp01(f / e); }
+    else {
+        float c = dot3(d1, r);
+        if (e <= eps) { t = 0.0f; s = na_clamp01(-c / a); }
+        else {
+            float b = dot3(d1, d2), ae = a * e, bb = b * b, denom = ae - bb;
+            if (denom > eps && !ulps_eq4(ae, bb)) s = na_clamp01((b * f - c * e) / denom);
+            else s = 0.0f;
+            t = (b * s + f) / e;
+            if (t < 0.0f) { t = 0.0f; s = na_clamp01(-c / a); }
+            else if (t > 1.0f) { t = 1.0f; s = na_clamp01((b - c) / a); }
+        }
+    }
+}
+__device__ __forceinline__ V3 seg_point_at(V3 a, V3 b, float s) {   // Segment::point_at of the location built from s (:88-104, segment.rs:410-419)
+    if (s == 0.0f) return a;
+    if (s == 1.0f) return b;
+    return a * (1.0f - s) + b * s;
+}
+__device__ __forceinline__ V3 cuboid_project_solid(V3 he, V3 pt) {   // Aabb::project_local_point(pt, true) (point_aabb.rs:9-60)
+    V3 zero = mk3(0.f, 0.f, 0.f);
+    V3 shift = vmax3((-he) - pt, zero) - vmax3(pt - he, zero);
+    bool inside = shift.x == 0.0f && shift.y == 0.0f && shift.z == 0.0f;
+    return inside ? pt : pt + shift;
+}
+// intersection_test_cuboid_cuboid (intersection_test_cuboid_cuboid.rs:6-31)
+__device__ __forceinline__ bool d_intersection_test_cuboid_cuboid(const Iso7& pos12, V3 he1, V3 he2) {
+    float sep; V3 dir;
+    sat_normal_oneway(he1, he2, pos12, sep, dir);
+    if (sep > 0.0f) return false;
+    Iso7 pos21 = iso_inverse(pos12);
+    sat_normal_oneway(he2, he1, pos21, sep, dir);
+    if (sep > 0.0f) return false;
+    sat_edge_twoway(he1, he2, pos12, sep, dir);
+    return sep <= 0.0f;
+}
+// distance_cuboid_cuboid (distance_cuboid_cuboid.rs:6-12) = closest_points_cuboid_cuboid with margin = f32::MAX
+// (closest_points_cuboid_cuboid.rs:6-84); WithinMargin(p1, p2) -> na::distance(p1, pos12 * p2), anything else -> 0.
+__device__ __forceinline__ float d_distance_cuboid_cuboid(const Iso7& pos12, V3 he1, V3 he2) {
+    const float margin = FLT_MAX;
+    Iso7 pos21 = iso_inverse(pos12);
+    float s1, s2, s3; V3 d1, d2, d3;
+    sat_normal_oneway(he1, he2, pos12, s1, d1);
+    if (s1 > margin) return 0.0f;
+    sat_normal_oneway(he2, he1, pos21, s2, d2);
+    if (s2 > margin) return 0.0f;
+    sat_edge_twoway(he1, he2, pos12, s3, d3);
+    if (s3 > margin) return 0.0f;
+    if (s1 <= 0.0f && s2 <= 0.0f && s3 <= 0.0f) return 0.0f;
+    if (s1 >= s2 && s1 >= s3) {
+        V3 pt2_1 = iso_point(pos12, cub_support(he2, iso_inv_vec(pos12, -d1)));
+        V3 proj = cuboid_project_solid(he1, pt2_1);
+        if (nrm2(proj - pt2_1) > margin * margin) return 0.0f;
+        V3 p2 = iso_point(pos21, pt2_1);
+        return nrm(proj - iso_point(pos12, p2));
+    }
+    if (s2 >= s1 && s2 >= s3) {
+        V3 pt1_2 = iso_point(pos21, cub_support(he1, iso_inv_vec(pos21, -d2)));
+        V3 proj = cuboid_project_solid(he2, pt1_2);
+        if (nrm2(proj - pt1_2) > margin * margin) return 0.0f;
+        V3 p1 = iso_point(pos12, pt1_2);
+        return nrm(p1 - iso_point(pos12, proj));
+    }
+    V3 a1, b1, a2, b2;
+    cub_support_edge(he1, d3, a1, b1);
+    cub_support_edge(he2, iso_vec(pos21, -d3), a2, b2);
+    float s, t;
+    seg_seg_params(a1, b1, iso_point(pos12, a2), iso_point(pos12, b2), s, t);
+    V3 p1 = seg_point_at(a1, b1, s), p2w = iso_point(pos12, seg_point_at(a2, b2, t));
+    if (nrm2(p1 - p2w) <= margin * margin) return nrm(p1 - p2w);
+    return 0.0f;
+}
+
 // Tail of contact_convex_polyhedron_ball (contact_ball_convex_polyhedron.rs:34-62) once the projection is known.
 __device__ __forceinline__ V3 v3of4(float4 f) { return mk3(f.x, f.y, f.z); }
 __device__ __forceinline__ int d_convex_ball_finish(const Iso7& pos12, bool is_cuboid, Feat f1, V3 proj, bool inside, float radius2,
@@ -1668,8 +1806,9 @@ int pb2_contact_pairs_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint
 // for ball-ball (distance_ball_ball.rs, intersection_test_ball_ball.rs), point projection with solid = true for ball vs
 // cuboid / hull (distance_ball_convex_polyhedron.rs, intersection_test_ball_point_query.rs, point_aabb.rs:9-60,
 // point_support_map.rs:17-52) and GJK for the support-map pairs (distance_support_map_support_map.rs — initial direction
-// -pos12.translation; intersection_test_support_map_support_map.rs — max_dist 0, exact_dist false). The cuboid-cuboid arm is
-// SAT based in the reference and not built: status 3 (host fallback through the dispatcher chain).
+// -pos12.translation; intersection_test_support_map_support_map.rs — max_dist 0, exact_dist false) and the SAT-based cuboid-cuboid
+// arms (distance_cuboid_cuboid.rs -> closest_points_cuboid_cuboid.rs + closest_points_segment_segment.rs;
+// intersection_test_cuboid_cuboid.rs). No pair of these shapes is handed back to the host.
 template <bool DIST>
 __global__ void __launch_bounds__(128) k_query_pairs(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
                               const float4* __restrict__ pts, uint32_t n_shapes, PairSrc src, uint32_t n, float* __restrict__ out_dist,
@@ -1714,7 +1853,9 @@ __global__ void __launch_bounds__(128) k_query_pairs(const uint8_t* __restrict__
         if (DIST) { float d = nrm(c - proj) - radius; dist = d > 0.0f ? d : 0.0f; }
         else hit = inside || nrm2(c - proj) <= radius * radius;
     } else if (ps.k1 == PB2_SHAPE_CUBOID && ps.k2 == PB2_SHAPE_CUBOID) {
-        st = ST_NEEDS_HOST;
+        V3 he1 = mk3(ps.pr1.x, ps.pr1.y, ps.pr1.z), he2 = mk3(ps.pr2.x, ps.pr2.y, ps.pr2.z);
+        if (DIST) dist = d_distance_cuboid_cuboid(ps.pos12, he1, he2);
+        else hit = d_intersection_test_cuboid_cuboid(ps.pos12, he1, he2);
     } else {
         Simplex s;
         V3 dir; float nn;
@@ -2471,43 +2612,7 @@ struct ManifoldOut {
     }
 };
 
-__device__ __forceinline__ V3 cub_support(V3 he, V3 d) { return mk3(copysignf(he.x, d.x), copysignf(he.y, d.y), copysignf(he.z, d.z)); }
-
-// sat_cuboid_cuboid.rs:79-110
-__device__ __forceinline__ void sat_normal_oneway(V3 he1, V3 he2, const Iso7& pos12, float& best_sep, V3& best_dir) {
-    best_sep = -FLT_MAX; best_dir = mk3(0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        float sign = copysignf(1.0f, comp(pos12.t, i));
-        V3 axis1 = mk3(0.f, 0.f, 0.f);
-        setc(axis1, i, sign);
-        V3 axis2 = iso_inv_vec(pos12, -axis1);
-        V3 pt2 = iso_point(pos12, cub_support(he2, axis2));
-        float sep = comp(pt2, i) * sign - comp(he1, i);
-        if (sep > best_sep) { best_sep = sep; best_dir = axis1; }
-    }
-}
-// sat_cuboid_cuboid.rs:5-77
-__device__ __forceinline__ void sat_edge_twoway(V3 he1, V3 he2, const Iso7& pos12, float& best_sep, V3& best_dir) {
-    best_sep = -FLT_MAX; best_dir = mk3(0.f, 0.f, 0.f);
-    V3 c2[3] = {iso_vec(pos12, mk3(1.f, 0.f, 0.f)), iso_vec(pos12, mk3(0.f, 1.f, 0.f)), iso_vec(pos12, mk3(0.f, 0.f, 1.f))};
-    for (int k = 0; k < 9; ++k) {
-        V3 u = c2[k / 3];
-        int a = k % 3;
-        V3 axis = a == 0 ? mk3(0.0f, -u.z, u.y) : (a == 1 ? mk3(u.z, 0.0f, -u.x) : mk3(-u.y, u.x, 0.0f));
-        float n = nrm(axis);
-        if (n > PB2_EPS) {
-            V3 ax = axis / n;
-            float signum = copysignf(1.0f, dot3(pos12.t, ax));
-            V3 axis1 = ax * signum;
-            V3 axis2 = iso_inv_vec(pos12, -axis1);
-            V3 lp1 = cub_support(he1, axis1);
-            V3 pt2 = iso_point(pos12, cub_support(he2, axis2));
-            float sep = dot3(pt2 - lp1, axis1);
-            if (sep > best_sep) { best_sep = sep; best_dir = axis1; }
-        }
-    }
-}
+// cub_support / sat_normal_oneway / sat_edge_twoway: near the top of this file (shared with the distance / intersection_test arms)
 
 struct PolyFace { V3 v[4]; uint32_t vids[4], eids[4], fid; int n; };
 __constant__ uint8_t c_face_vids[3][2][4] = {{{0, 2, 3, 1}, {4, 6, 7, 5}}, {{0, 4, 5, 1}, {2, 6, 7, 3}}, {{0, 2, 6, 4}, {1, 3, 7, 5}}};
@@ -2532,14 +2637,6 @@ __device__ __forceinline__ void cuboid_support_face(V3 he, V3 dir, PolyFace& f) 
 }
 
 __device__ __forceinline__ float perp2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
-// approx::ulps_eq! defaults for f32 (epsilon = f32::EPSILON, max_ulps = 4)
-__device__ __forceinline__ bool ulps_eq4(float a, float b) {
-    if (fabsf(a - b) <= PB2_EPS) return true;
-    if (signbit(a) != signbit(b)) return false;
-    long long d = (long long)__float_as_int(a) - (long long)__float_as_int(b);
-    if (d < 0) d = -d;
-    return d <= 4;
-}
 // polygonal_feature3d.rs:398-439
 __device__ __forceinline__ bool closest_points_line2d(float2 a0, float2 a1, float2 c0, float2 c1, float& s_out, float& t_out) {
     float d1x = a1.x - a0.x, d1y = a1.y - a0.y, d2x = c1.x - c0.x, d2y = c1.y - c0.y, rx = a0.x - c0.x, ry = a0.y - c0.y;

@@ -52,6 +52,18 @@ def main():
     print("golden vectors written")
 
 
+def distance_golden():
+    """distance / intersection_test on the contact golden's pairs. Regenerated in round 2 (`python make_golden.py distance`) when the
+    oracle gained the SAT-based cuboid-cuboid arms (distance_cuboid_cuboid.rs, intersection_test_cuboid_cuboid.rs): those pairs used
+    to be recorded as status 3 (host)."""
+    z = np.load(os.path.join(HERE, "contacts_mixed_3000.npz"))
+    T = oracle.ShapeTable([])
+    T.kinds, T.params, T.points = z["kinds"].copy(), z["params"].copy(), np.ascontiguousarray(z["points"])
+    d, ds = T.distance(z["shape1"], z["pos1"], z["shape2"], z["pos2"])
+    h, hs = T.intersection_test(z["shape1"], z["pos1"], z["shape2"], z["pos2"])
+    np.savez_compressed(os.path.join(HERE, "distance_mixed_3000.npz"), dist=d, dist_status=ds, hit=h, hit_status=hs)
+
+
 def more():
     """Later additions (culling ray casts, distance / intersection_test, TriMesh-vs-shape contacts); separate files so that the
     first set stays byte-identical."""
@@ -65,12 +77,7 @@ def more():
         toi, tri, n, f = m.cast_rays(None, rays, FMAX, with_normal=True, mode=1 + mode)
         res.update({name + "_toi": toi, name + "_tri": tri, name + "_normal": n, name + "_feature": f})
     np.savez_compressed(os.path.join(HERE, "rays_culling_sphere24x16.npz"), rays=rays, **res)
-    z = np.load(os.path.join(HERE, "contacts_mixed_3000.npz"))
-    T = oracle.ShapeTable([])
-    T.kinds, T.params, T.points = z["kinds"].copy(), z["params"].copy(), np.ascontiguousarray(z["points"])
-    d, ds = T.distance(z["shape1"], z["pos1"], z["shape2"], z["pos2"])
-    h, hs = T.intersection_test(z["shape1"], z["pos1"], z["shape2"], z["pos2"])
-    np.savez_compressed(os.path.join(HERE, "distance_mixed_3000.npz"), dist=d, dist_status=ds, hit=h, hit_status=hs)
+    distance_golden()
     # TriMesh-vs-shape contacts on a small terrain
     v, i = scenes.terrain(17, 17, extent=12.0)
     v = v.copy(); v[:, 1] *= 0.1
@@ -216,7 +223,9 @@ def second_frame():
 
 if __name__ == "__main__":
     import sys
-    if "second_frame" in sys.argv:
+    if "distance" in sys.argv:
+        distance_golden()
+    elif "second_frame" in sys.argv:
         second_frame()
     elif "pfm" in sys.argv:
         pfm()

@@ -27,8 +27,11 @@ def test_oracle_pins_from_reference_examples():
     # intersection_test.rs doc-test: two unit balls 1.5 apart intersect, 5 apart do not
     assert T.intersection_test([0], P([0, 0, 0]), [0], P([1.5, 0, 0]))[0][0] == 1
     assert T.intersection_test([0], P([0, 0, 0]), [0], P([5.0, 0, 0]))[0][0] == 0
-    # cuboid-cuboid is the SAT arm: flagged for the host
-    assert T.distance([1], P([0, 0, 0]), [3], P([5, 0, 0]))[1][0] == 3
+    # cuboid-cuboid is the SAT arm (distance_cuboid_cuboid.rs): half extents 1 and 0.5, centres 5 apart on x => 3.5
+    d, st = T.distance([1], P([0, 0, 0]), [3], P([5, 0, 0]))
+    assert st[0] == 0 and d[0] == np.float32(3.5)
+    assert T.intersection_test([1], P([0, 0, 0]), [3], P([1.4, 0, 0]))[0][0] == 1
+    assert T.intersection_test([1], P([0, 0, 0]), [3], P([1.6, 0, 0]))[0][0] == 0
 
 
 def make_pairs(seed, n):
@@ -55,7 +58,11 @@ def test_distance_and_intersection_match_oracle(ctx, oracle):
     od, ods = O.distance(a, p1, b, p2, threads=8)
     assert (np.asarray(gds) == ods).all()
     ok = ods == 0
-    assert 0.05 < (ods == 3).mean() < 0.2           # cuboid-cuboid pairs are flagged for the host
+    assert ok.all()                                  # no pair of these shapes goes back to the host (round 1: cuboid-cuboid did)
+    kinds = np.array([0 if k == "ball" else 1 if k == "cuboid" else 2 for k, _ in spec])
+    cc = (kinds[a] == 1) & (kinds[b] == 1)           # the SAT-based arm (distance_cuboid_cuboid.rs, intersection_test_cuboid_cuboid.rs)
+    assert 0.05 < cc.mean() < 0.2 and 0.2 < (od[cc] > 0).mean() < 0.9
+    assert (np.asarray(gd)[cc].view(np.uint32) == od[cc].view(np.uint32)).mean() > 0.999
     assert 0.2 < (od[ok] > 0).mean() < 0.9
     np.testing.assert_allclose(np.asarray(gd)[ok], od[ok], rtol=1e-5, atol=1e-6)
     assert (np.asarray(gd)[ok].view(np.uint32) == od[ok].view(np.uint32)).mean() > 0.999
