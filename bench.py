@@ -254,18 +254,28 @@ def main():
     toi_d = torch.empty(m, dtype=torch.float32, device="cuda")
     tri_d = torch.empty(m, dtype=torch.int32, device="cuda")
     gather, gather_kind, peer = None, "none (N=1)", False
+    # the C ABI's own exchange layer (pb2_comm_*: NCCL + CUDA IPC peer buffers); torch.distributed only carries the 128-byte id
+    comm = parry_b200.Comm.from_torch_distributed(ctx) if world > 1 else parry_b200.Comm(ctx, parry_b200.Comm.unique_id(), 0, 1)
     if world > 1:
         from parry_b200 import sharding
+        chunks = int(os.environ.get("PB2_BENCH_GATHER_CHUNKS", "4"))
         try:
-            if os.environ.get("PB2_BENCH_NCCL_GATHER"):
+            if os.environ.get("PB2_BENCH_NCCL_GATHER") or os.environ.get("PB2_BENCH_SYMM_GATHER"):
                 raise RuntimeError("forced")
-            gather = sharding.PeerHitGather(m, torch.device("cuda", local_rank), chunks=int(os.environ.get("PB2_BENCH_GATHER_CHUNKS", "4" if world <= 2 else "8")))
-            gather_kind = ("all-gather of the (toi,id) results inside the timed region: pieces pushed into every peer's symmetric-memory "
-                           "buffer by copy engines over NVLink while the next piece is traversed, then a cross-rank barrier")
-        except Exception as e:  # no symmetric memory on this box: NCCL all_gather per piece on a side stream
-            gather = sharding.OverlappedHitGather(m, "cuda", chunks=4)
-            gather_kind = "all_gather (NCCL) of the (toi,id) results inside the timed region, 4 pieces on a side stream (%s)" % type(e).__name__
-        peer = isinstance(gather, sharding.PeerHitGather)
+            gather = sharding.CommHitGather(comm, m, torch.device("cuda", local_rank), chunks=chunks)
+            gather_kind = ("all-gather of the (toi,id) results inside the timed region through the C ABI: finished result ranges are pushed into every "
+                           "peer's buffer (pb2_comm_peer_alloc: CUDA IPC) by copy engines over NVLink while the traversal kernel runs, then pb2_comm_barrier")
+        except Exception as e0:
+            try:
+                if os.environ.get("PB2_BENCH_NCCL_GATHER"):
+                    raise RuntimeError("forced")
+                gather = sharding.PeerHitGather(m, torch.device("cuda", local_rank), chunks=chunks)
+                gather_kind = ("all-gather of the (toi,id) results inside the timed region: pieces pushed into every peer's symmetric-memory "
+                               "buffer by copy engines over NVLink while the next piece is traversed, then a cross-rank barrier (%s)" % type(e0).__name__)
+            except Exception as e:  # no peer mappings on this box: NCCL all_gather per piece on a side stream
+                gather = sharding.OverlappedHitGather(m, "cuda", chunks=4)
+                gather_kind = "all_gather (NCCL) of the (toi,id) results inside the timed region, 4 pieces on a side stream (%s)" % type(e).__name__
+        peer = isinstance(gather, (sharding.PeerHitGather, sharding.CommHitGather))
 
     def step_device():
         if world == 1:
@@ -406,12 +416,15 @@ def main():
             "traffic": profiled_traffic(EPA_KERNEL, EPA_KERNEL_VERSION)[0],
             "shallow_mix_value": (r.get("shallow_mix") or {}).get("value")}
         also["contact_pairs_4M_hulls"] = r
-        if world > 1:
-            for name, fn in MULTI_GPU_ALSO:
-                try:
-                    also[name] = fn(ctx, stream, timed_also, flush, hbm_peak, dist, rank, world)
-                except Exception as e:
-                    also[name] = {"error": repr(e)}
+        for name, fn in MULTI_GPU_ALSO:   # collective: every rank runs these, at every N (N = 1 gives the series its first point)
+            try:
+                also[name] = fn(ctx, stream, timed_also, flush, hbm_peak, comm, dist, rank, world)
+            except Exception as e:
+                also[name] = {"error": repr(e)}
+            # BASELINE config[4] at N GPUs, where the driver keeps it (N2 had no kept record)
+            line["roofline"].setdefault("multi_gpu", {})[name] = {k: also[name].get(k) for k in (
+                "value", "unit", "ms", "n_gpus", "scaling", "pairs_per_frame", "contacts_per_frame", "pairs_per_s", "gathered_bytes_per_rank",
+                "all_ranks_agree", "error") if k in also[name]}
         if rank == 0:
             also.update(bench_also(ctx, stream, args, hbm_peak, flush))
 
@@ -947,7 +960,77 @@ def also_first_hardware_runs(ctx, stream, timed, flush, hbm_peak):
     return out
 
 
-MULTI_GPU_ALSO = []   # (name, fn(ctx, stream, timed, flush, hbm_peak, dist, rank, world)): filled below
+def also_mixed_sharded(ctx, stream, timed, flush, hbm_peak, comm, dist, rank, world):
+    """BASELINE config[4] split over the GPUs of the box (strong scaling: the same 2^21 colliders at every N): every rank computes
+    all leaf AABBs and rebuilds the (replicated, deterministic) Bvh, walks the tree only for its interleaved share of the leaves
+    (pb2_bvh_self_pairs_shard), runs query::contact on its own pairs, and the compacted contacts (52-byte records + the pair they
+    belong to) are gathered on every rank with pb2_comm_allgatherv — all inside the timed region. Cross-rank check after the run: every
+    rank holds the same gathered set (checksums), and its size is the same at every N."""
+    import torch
+    import parry_b200
+    from harness import scenes
+    n, H = 1 << 21, 4096
+    kinds, params, poses, hull_ids = scenes.colliders(n, seed=8, hull_fraction=1.0 / 3.0, n_hulls=H)
+    pts, _ = scenes.hull_pool(H, 32, seed=9)
+    pts = np.asarray(pts, dtype=np.float32) * 0.5
+    tk = np.concatenate([np.full(H, 2, np.uint8), np.where(kinds == 2, 0, kinds).astype(np.uint8)])
+    tp = np.concatenate([np.zeros((H, 3), np.float32), params])
+    first = np.concatenate([np.arange(H, dtype=np.uint32) * 32, np.zeros(n, np.uint32)])
+    count = np.concatenate([np.full(H, 32, np.uint32), np.zeros(n, np.uint32)])
+    G = parry_b200.Shapes.from_arrays(ctx, tk, tp, pts.reshape(-1, 3), first, count)
+    with torch.cuda.stream(stream):
+        cs = torch.from_numpy(np.where(kinds == 2, hull_ids, H + np.arange(n)).astype(np.uint32).view(np.int32)).cuda()
+        dposes = torch.from_numpy(poses).cuda()
+        all_ids = torch.arange(n, dtype=torch.int32, device="cuda")
+    ctx.synchronize()
+    aabbs = G.compute_aabbs(cs, dposes)
+    bvh = parry_b200.Bvh.from_leaves(ctx, 0, aabbs)
+    state = {}
+
+    def frame():
+        a = G.compute_aabbs(cs, dposes)
+        bvh.insert_or_update_partially(a, all_ids, 0.0)
+        bvh.rebuild()
+        pr = bvh.traverse_bvtt_single_tree_shard(rank, world, capacity=(16 * n) // world + 4096, like=a)
+        out, idx = parry_b200.contact_pairs_compact(G, cs, dposes, pr, 0.01)
+        with torch.cuda.stream(stream):
+            owners = pr[idx.to(torch.int64)]                  # the pair each compacted contact belongs to
+        g_out, c1 = comm.allgatherv(out, capacity=state.get("cap", 1 << 22))
+        g_pair, c2 = comm.allgatherv(owners, capacity=state.get("cap", 1 << 22))
+        state.update(pairs=int(pr.shape[0]), contacts=int(out.shape[0]), g_out=g_out, g_pair=g_pair, counts=c1, cap=int(g_out.shape[0]) + 4096)
+
+    ms = timed(frame, steps=5, warmup=2, flush=flush)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ctx.synchronize()
+    g_pair = state["g_pair"].to(torch.int64)
+    key = (g_pair[:, 0] << 32) | (g_pair[:, 1] & 0xFFFFFFFF)
+    chk = torch.stack([key.sum(), (key * 31 + 7).remainder(1000003).sum(), torch.tensor(int(key.shape[0]), device=key.device)])
+    dsum = state["g_out"][:, 12].double().sum().reshape(1)
+    same = True
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool((lo == hi).all())
+    pairs_total = state["pairs"]
+    if world > 1:
+        t = torch.tensor([pairs_total], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        pairs_total = int(t.item())
+    assert same, "ranks hold different gathered contact sets"
+    C_total = int(key.shape[0])
+    return {"value": n / (ms * 1e-3), "unit": "colliders/s (frame: AABBs + Bvh rebuild [replicated] + sharded self pairs + contacts + all-gather-v of the contacts)",
+            "ms": ms, "n_gpus": world, "scaling": "strong", "colliders": n, "pairs_per_frame": pairs_total, "contacts_per_frame": C_total,
+            "contacts_per_rank": state["counts"], "pairs_per_s": pairs_total / (ms * 1e-3),
+            "gathered_bytes_per_rank": C_total * 60, "checksum": [int(x) for x in chk.tolist()], "dist_sum": float(dsum.item()),
+            "all_ranks_agree": same, "l2": "flushed between iterations",
+            "exchange": "pb2_comm_allgatherv (NCCL grouped broadcasts, exact sizes) x2: 52-byte contacts and their 8-byte pair ids"}
+
+
+MULTI_GPU_ALSO = [("mixed_2M_colliders_sharded", also_mixed_sharded)]   # (name, fn(ctx, stream, timed, flush, hbm_peak, comm, dist, rank, world))
 
 EXTRA_ALSO = [("manifolds_4M_ball_cuboid_pairs", also_manifolds),
               ("sibling_queries_2M_mixed_pairs", also_siblings), ("broadphase_1M_colliders", also_broadphase),

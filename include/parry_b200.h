@@ -59,6 +59,7 @@ typedef struct pb2_bvh pb2_bvh;
 typedef struct pb2_trimesh pb2_trimesh;
 typedef struct pb2_shapes pb2_shapes;
 typedef struct pb2_compounds pb2_compounds;
+typedef struct pb2_comm pb2_comm;
 
 #define PB2_INVALID_U32 0xffffffffu
 
@@ -131,6 +132,11 @@ int pb2_bvh_intersect_aabbs(pb2_ctx* ctx, const pb2_bvh* bvh, const float* queri
  * overlapping leaf pair exactly once as (min id, max id); order unspecified. `count` is a HOST pointer. */
 int pb2_bvh_self_pairs(pb2_ctx* ctx, const pb2_bvh* bvh, int change_detection, uint32_t* pairs /* cap x 2 */,
                        uint64_t cap, uint64_t* count, int mem);
+/* Shard of the same pair set for a broad phase split over `n_shards` GPUs with the Bvh replicated: only the
+ * leaves at sorted positions p = shard (mod n_shards) walk the tree (interleaved ownership balances the "other leaf comes later"
+ * filter). The union of the n_shards outputs is exactly pb2_bvh_self_pairs' set, each pair in exactly one shard. */
+int pb2_bvh_self_pairs_shard(pb2_ctx* ctx, const pb2_bvh* bvh, int change_detection, uint32_t shard, uint32_t n_shards,
+                             uint32_t* pairs /* cap x 2 */, uint64_t cap, uint64_t* count, int mem);
 /* Bvh::leaf_pairs(&other, |a, b| a.intersects(b)) — bvh_traverse_bvtt.rs:210-316 (leaf of a, leaf of b). */
 int pb2_bvh_leaf_pairs(pb2_ctx* ctx, const pb2_bvh* a, const pb2_bvh* b, uint32_t* pairs, uint64_t cap,
                        uint64_t* count, int mem);
@@ -173,6 +179,33 @@ int pb2_trimesh_project_points(pb2_ctx* ctx, const pb2_trimesh* mesh, const floa
 int pb2_trimesh_cast_rays_allgather(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* pose7, const float* rays /* m x 6, device */,
                                     uint32_t m, float max_toi, void* const* peer_toi, void* const* peer_tri, int n_peers, int self,
                                     uint64_t elem_offset, int chunks);
+
+/* ---- Multi-GPU exchange, one process per GPU, one pb2_comm per context; NCCL underneath (resolved with
+ * dlopen at the first call: PB2_ERR_UNSUPPORTED when libnccl.so.2 is absent). The reference has no counterpart: its callers
+ * parallelise with rayon on one host. Rendezvous: rank 0 calls pb2_comm_unique_id and the host carries the PB2_COMM_ID_BYTES bytes
+ * to the other ranks by whatever transport it has; then every rank calls pb2_comm_create (collective). All data pointers are
+ * device memory; everything is enqueued on the context's stream unless stated otherwise. */
+#define PB2_COMM_ID_BYTES 128
+int pb2_comm_unique_id(void* id128);
+int pb2_comm_create(pb2_ctx* ctx, const void* id128, int rank, int nranks, pb2_comm** out);
+int pb2_comm_destroy(pb2_comm* comm);
+int pb2_comm_rank(const pb2_comm* comm);
+int pb2_comm_size(const pb2_comm* comm);
+/* Fixed-size all-gather (per-ray hit records): recv = nranks x bytes_per_rank, rank-major; in place when send == recv + rank * bytes. */
+int pb2_comm_allgather(pb2_comm* comm, const void* send, void* recv, uint64_t bytes_per_rank);
+/* All-gather of one count per rank ("compacted hit / pair counts"); `all` is a HOST array of nranks; synchronises the stream. */
+int pb2_comm_allgather_counts(pb2_comm* comm, uint64_t mine, uint64_t* all);
+/* Variable-size gather of compacted records (pairs, contacts): rank r contributes `count` elements of elem_bytes; recv receives
+ * every rank's elements back to back in rank order, counts[r] (HOST) = elements of rank r, *total = their sum. PB2_ERR_OVERFLOW
+ * (nothing written, *total valid) when total > cap_elems. */
+int pb2_comm_allgatherv(pb2_comm* comm, const void* send, uint64_t count, uint32_t elem_bytes, void* recv, uint64_t cap_elems,
+                        uint64_t* counts, uint64_t* total);
+/* Cross-rank barrier on the stream. */
+int pb2_comm_barrier(pb2_comm* comm);
+/* Collective: every rank allocates `bytes` and maps all other ranks' allocations (CUDA IPC, one node): peers[r] is rank r's
+ * buffer as addressable from THIS process (peers[rank] = the local one) — the peer pointers pb2_trimesh_cast_rays_allgather
+ * pushes finished result ranges to. Freed by pb2_comm_destroy. */
+int pb2_comm_peer_alloc(pb2_comm* comm, uint64_t bytes, void** peers /* nranks */);
 
 /* TriMesh::cast_ray_with_culling / cast_local_ray_with_culling (ray_trimesh.rs:139-178, RayCullingMode :50-65): same
  * query, but a triangle is only considered when its scaled normal faces the ray the allowed way. Always the

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("PB2_LIB_PATH") or os.path.join(HERE, "libparry_b200.so")   # PB2_LIB_PATH: A/B builds of the same library (harness)
+LIB_PATH = os.environ.get("PB2_LIB_PATH") or os.path.join(HERE, "libparry_b200.so")   # PB2_LIB_PATH: A/B builds of the same library
 
 PB2_OK, PB2_ERR_INVALID, PB2_ERR_CUDA, PB2_ERR_OVERFLOW, PB2_ERR_UNSUPPORTED, PB2_ERR_DEPTH = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -31,6 +31,17 @@ SIGNATURES = {
     "pb2_contact_phase_times": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pb2_bvh_build": (c_int, [c_void_p, P, c_u32, c_int, c_int, C.POINTER(c_void_p)]),
     "pb2_bvh_destroy": (c_int, [c_void_p, c_void_p]),
+    "pb2_bvh_self_pairs_shard": (c_int, [c_void_p, c_void_p, c_int, c_u32, c_u32, P, c_u64, C.POINTER(c_u64), c_int]),
+    "pb2_comm_unique_id": (c_int, [P]),
+    "pb2_comm_create": (c_int, [c_void_p, P, c_int, c_int, C.POINTER(c_void_p)]),
+    "pb2_comm_destroy": (c_int, [c_void_p]),
+    "pb2_comm_rank": (c_int, [c_void_p]),
+    "pb2_comm_size": (c_int, [c_void_p]),
+    "pb2_comm_allgather": (c_int, [c_void_p, P, P, c_u64]),
+    "pb2_comm_allgather_counts": (c_int, [c_void_p, c_u64, P]),
+    "pb2_comm_allgatherv": (c_int, [c_void_p, P, c_u64, c_u32, P, c_u64, P, C.POINTER(c_u64)]),
+    "pb2_comm_barrier": (c_int, [c_void_p]),
+    "pb2_comm_peer_alloc": (c_int, [c_void_p, c_u64, P]),
     "pb2_bvh_leaf_count": (c_u32, [c_void_p]),
     "pb2_bvh_node_count": (c_u32, [c_void_p]),
     "pb2_bvh_update_leaves": (c_int, [c_void_p, c_void_p, P, P, c_u32, c_float, c_int]),

@@ -92,9 +92,10 @@ __global__ void k_intersect_aabbs(const NodeWide* __restrict__ nodes, const uint
 template <bool CD, bool KARRAS>
 __global__ void __launch_bounds__(128) k_self_pairs(const NodeWide* __restrict__ nodes, const uint32_t* __restrict__ order,
                              const uint32_t* __restrict__ leaf_slot, uint32_t n_leaves, uint2* __restrict__ pairs,
-                             uint64_t cap, unsigned long long* __restrict__ counter, unsigned int* fault) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_leaves) return;
+                             uint64_t cap, unsigned long long* __restrict__ counter, unsigned int* fault, uint32_t shard, uint32_t n_shards) {
+    uint64_t p64 = (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * n_shards + shard;   // interleaved ownership of the walking leaves
+    if (p64 >= n_leaves) return;
+    uint32_t p = (uint32_t)p64;
     uint32_t my_id = order[p];
     uint32_t slot = leaf_slot[my_id];
     const float4* hp = reinterpret_cast<const float4*>((slot & 1u) ? &nodes[slot >> 1].right : &nodes[slot >> 1].left);
@@ -284,8 +285,15 @@ int pb2_bvh_intersect_aabbs(pb2_ctx* ctx, const pb2_bvh* bvh, const float* queri
     return PB2_OK;
 }
 
+int pb2_bvh_self_pairs_shard(pb2_ctx* ctx, const pb2_bvh* bvh, int change_detection, uint32_t shard, uint32_t n_shards, uint32_t* pairs,
+                             uint64_t cap, uint64_t* count, int mem);
 int pb2_bvh_self_pairs(pb2_ctx* ctx, const pb2_bvh* bvh, int change_detection, uint32_t* pairs, uint64_t cap, uint64_t* count, int mem) {
-    if (!ctx || !bvh || !count) return PB2_ERR_INVALID;
+    return pb2_bvh_self_pairs_shard(ctx, bvh, change_detection, 0u, 1u, pairs, cap, count, mem);
+}
+
+int pb2_bvh_self_pairs_shard(pb2_ctx* ctx, const pb2_bvh* bvh, int change_detection, uint32_t shard, uint32_t n_shards, uint32_t* pairs,
+                             uint64_t cap, uint64_t* count, int mem) {
+    if (!ctx || !bvh || !count || n_shards == 0 || shard >= n_shards) return PB2_ERR_INVALID;
     PB2_CUDA(ctx, cudaSetDevice(ctx->device));
     *count = 0;
     // "Not enough nodes for any overlap" (bvh_traverse_bvtt.rs:24-27)
@@ -296,10 +304,11 @@ int pb2_bvh_self_pairs(pb2_ctx* ctx, const pb2_bvh* bvh, int change_detection, u
     if (!d_pairs) cap = 0;
     unsigned long long* counter = (unsigned long long*)ctx->d_counters;
     PB2_CUDA(ctx, cudaMemsetAsync(counter, 0, 8, st));
-    unsigned blocks = pb2_blocks(bvh->n_leaves, 128);
+    unsigned blocks = pb2_blocks((bvh->n_leaves + n_shards - 1) / n_shards, 128);
     auto kern = change_detection ? (bvh->karras ? k_self_pairs<true, true> : k_self_pairs<true, false>)
                                  : (bvh->karras ? k_self_pairs<false, true> : k_self_pairs<false, false>);
-    kern<<<blocks, 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->leaf_slot, bvh->n_leaves, (uint2*)d_pairs, cap, counter, PB2_FAULT_PTR(ctx));
+    kern<<<blocks, 128, 0, st>>>(bvh->nodes, bvh->leaf_order, bvh->leaf_slot, bvh->n_leaves, (uint2*)d_pairs, cap, counter, PB2_FAULT_PTR(ctx),
+                                 shard, n_shards);
     PB2_LAUNCHED(ctx);
     PB2_CUDA(ctx, cudaGetLastError());
     PB2_CHECK(read_counter(ctx, count));

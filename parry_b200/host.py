@@ -248,6 +248,22 @@ class Bvh:
             self.ctx.check(st)
             return pairs[: int(cnt.value)]
 
+    def traverse_bvtt_single_tree_shard(self, shard, n_shards, change_detection=False, capacity=None, like=None):
+        """This rank's part of traverse_bvtt_single_tree when the broad phase is split over n_shards GPUs with the Bvh replicated
+        (SURVEY 8e): the leaves at sorted positions p = shard (mod n_shards) walk the tree; the shards' outputs partition the pair set."""
+        mem = MEM_DEVICE if (like is not None and _is_torch(like) and like.is_cuda) else MEM_HOST
+        cap = int(capacity) if capacity is not None else max(1024, 8 * self.leaf_count() // int(n_shards) + 1024)
+        while True:
+            pairs, pp = _empty((cap, 2), np.uint32, mem, self.ctx.torch_device)
+            cnt = C.c_uint64(0)
+            st = self.ctx._lib.pb2_bvh_self_pairs_shard(self.ctx.h, self.h, int(bool(change_detection)), int(shard), int(n_shards), pp, cap,
+                                                        C.byref(cnt), mem)
+            if st == _ffi.PB2_ERR_OVERFLOW:
+                cap = int(cnt.value)
+                continue
+            self.ctx.check(st)
+            return pairs[: int(cnt.value)]
+
     def leaf_pairs(self, other, capacity=None, like=None):
         """Bvh::leaf_pairs(other, |a, b| a.intersects(b)) (bvh_traverse_bvtt.rs:210)."""
         mem = MEM_DEVICE if (like is not None and _is_torch(like) and like.is_cuda) else MEM_HOST
@@ -616,6 +632,85 @@ class Compounds:
             pass
 
 
+class Comm:
+    """pb2_comm: the multi-GPU exchange of the C ABI (NCCL underneath), one per Context / process. `id128` comes from
+    Comm.unique_id() on rank 0 and reaches the other ranks through the host's own transport; from_torch_distributed() uses an
+    initialised torch.distributed group (any backend) for exactly that and nothing else."""
+
+    def __init__(self, ctx, id128, rank, nranks):
+        self.ctx, self.rank, self.nranks = ctx, int(rank), int(nranks)
+        h = C.c_void_p()
+        buf = (C.c_char * 128).from_buffer_copy(bytes(id128))
+        ctx.check(ctx._lib.pb2_comm_create(ctx.h, buf, self.rank, self.nranks, C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * 128)()
+        st = _ffi.lib().pb2_comm_unique_id(buf)
+        if st != 0:
+            raise Pb2Error("pb2_comm_unique_id failed (%d): is libnccl.so.2 present?" % st)
+        return bytes(buf.raw)
+
+    @staticmethod
+    def from_torch_distributed(ctx, group=None):
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return Comm(ctx, box[0], rank, world)
+
+    def allgather(self, send, recv):
+        """Fixed-size all-gather of device tensors: recv = nranks x send (rank-major)."""
+        nbytes = send.numel() * send.element_size()
+        assert recv.numel() * recv.element_size() == nbytes * self.nranks
+        self.ctx.check(self.ctx._lib.pb2_comm_allgather(self.h, send.data_ptr(), recv.data_ptr(), nbytes))
+        return recv
+
+    def allgather_counts(self, mine):
+        out = (C.c_uint64 * self.nranks)()
+        self.ctx.check(self.ctx._lib.pb2_comm_allgather_counts(self.h, int(mine), out))
+        return [int(x) for x in out]
+
+    def allgatherv(self, rows, capacity=None):
+        """Variable-size gather of compacted records (rows: (count, ...) device tensor): (all rows in rank order, counts per rank)."""
+        count = int(rows.shape[0])
+        rows = rows.contiguous()
+        elem = rows.element_size() * (int(np.prod(rows.shape[1:])) if rows.dim() > 1 else 1)
+        cap = int(capacity) if capacity is not None else max(1, count * self.nranks * 2)
+        counts = (C.c_uint64 * self.nranks)()
+        total = C.c_uint64(0)
+        while True:
+            out = torch.empty((cap,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+            st = self.ctx._lib.pb2_comm_allgatherv(self.h, rows.data_ptr() if count else None, count, elem, out.data_ptr(), cap, counts, C.byref(total))
+            if st == _ffi.PB2_ERR_OVERFLOW:
+                # every rank saw the same total and takes the same branch: the retry stays collective
+                cap = int(total.value)
+                continue
+            self.ctx.check(st)
+            return out[: int(total.value)], [int(x) for x in counts]
+
+    def barrier(self):
+        self.ctx.check(self.ctx._lib.pb2_comm_barrier(self.h))
+
+    def peer_alloc(self, nbytes):
+        """Collective: returns a ctypes array of nranks device pointers (peer buffers mapped in this process; [rank] = local)."""
+        peers = (C.c_void_p * self.nranks)()
+        self.ctx.check(self.ctx._lib.pb2_comm_peer_alloc(self.h, int(nbytes), peers))
+        return peers
+
+    def close(self):
+        if self.h:
+            self.ctx._lib.pb2_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 CONTACT_DTYPE = np.dtype([("point1", np.float32, (3,)), ("point2", np.float32, (3,)), ("normal1", np.float32, (3,)),
                           ("normal2", np.float32, (3,)), ("dist", np.float32)])
 assert CONTACT_DTYPE.itemsize == 52
@@ -694,7 +789,7 @@ def _pair_query(fn_name, out_dtype, shapes, shape1, pos1, shape2, pos2):
 
 def distance(shapes, shape1, pos1, shape2, pos2):
     """query::distance(pos1, g1, pos2, g2), batched (query/distance/distance.rs:89-97): (dist (n,) f32, status (n,) u8: 0 Ok,
-    2 Unsupported, 3 cuboid-cuboid -> host)."""
+    2 Unsupported)."""
     return _pair_query("pb2_distance_batch", np.float32, shapes, shape1, pos1, shape2, pos2)
 
 

@@ -144,3 +144,36 @@ class PeerHitGather:
 
     def full(self):
         return self.toi, self.tri
+
+
+class _DevView:
+    """__cuda_array_interface__ over a raw device pointer (memory owned by the library), so that torch can view it."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": (int(n),), "typestr": typestr, "version": 2}
+
+
+class CommHitGather:
+    """PeerHitGather on the C ABI alone: the gather buffers come from pb2_comm_peer_alloc (CUDA IPC mappings of every rank's
+    buffer), the closing barrier is pb2_comm_barrier. Nothing here needs torch.distributed besides the one-off hand-over of the
+    128-byte NCCL id (parry_b200.Comm.from_torch_distributed); a Rust host does the same through include/parry_b200.h."""
+
+    def __init__(self, comm, m_local, device, chunks=4):
+        self.comm, self.world, self.rank = comm, comm.nranks, comm.rank
+        self.m, self.chunks = int(m_local), int(chunks)
+        n = self.world * self.m
+        self.p_toi = comm.peer_alloc(n * 4)
+        self.p_tri = comm.peer_alloc(n * 4)
+        self.toi = torch.as_tensor(_DevView(self.p_toi[self.rank], n, "<f4"), device=device)
+        self.tri = torch.as_tensor(_DevView(self.p_tri[self.rank], n, "<i4"), device=device)
+
+    def run(self, mesh, rays, max_toi, compute_stream=None):
+        mesh.cast_local_ray_allgather(rays, max_toi, self.p_toi, self.p_tri, self.rank, self.rank * self.m, self.chunks)
+        self.comm.barrier()
+
+    def local(self):
+        lo = self.rank * self.m
+        return self.toi[lo:lo + self.m], self.tri[lo:lo + self.m]
+
+    def full(self):
+        return self.toi, self.tri
