@@ -264,6 +264,12 @@ int pb2_bvh_cast_rays_shapes(pb2_ctx* ctx, const pb2_bvh* bvh, const pb2_shapes*
 int pb2_contact_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
                       const float* pos1 /* n x 7 */, const float* pos2 /* n x 7 */, float prediction, uint32_t n,
                       pb2_contact* out, uint8_t* status, uint64_t* num_contacts, int mem);
+/* QueryDispatcher::contact(pos12, g1, g2, prediction) — query_dispatcher.rs:430-436, the trait method itself: pos12[k] is the pose
+ * of shape 2 relative to shape 1 and the contact stays in the shapes' local frames (point1 / normal1 in shape 1's frame, point2 /
+ * normal2 in shape 2's), which is what a dispatcher inside a QueryDispatcherChain has to return (query::contact applies
+ * Contact::transform_by_mut afterwards, contact_shape_shape.rs:131-135). Same status codes as pb2_contact_batch. */
+int pb2_contact_batch_local(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
+                            const float* pos12 /* n x 7 */, float prediction, uint32_t n, pb2_contact* out, uint8_t* status, int mem);
 /* Compacted variant: writes only the Some(contact) records, each tagged with its pair index, through
  * warp-aggregated atomics (order unspecified). */
 int pb2_contact_batch_compact(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,

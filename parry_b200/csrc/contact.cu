@@ -338,6 +338,7 @@ struct PairSrc {
 #define PAIR_SUPPORT_MAPS_ONLY 1u  // no ball arms: balls take part in GJK/EPA through their support map (what
                                    // cast_shapes_support_map_support_map calls: contact_support_map_support_map on any pair)
 #define PAIR_LOCAL_FRAMES 2u       // leave the contact in the shapes' local frames (no Contact::transform_by_mut)
+#define PAIR_POS12_GIVEN 8u        // pos2[k] already is pos12 (QueryDispatcher::contact's own argument); pos1 is not read. With LOCAL_FRAMES.
 #define PAIR_COMPOUND_SECOND 4u    // Compound mode: the user's call was contact(shape, compound): pose12 = inv_mul(pos2, pos1).inverse()
 #define PB2_SHAPE_TRIANGLE_INTERNAL 3   // a TriMesh part (shape::Triangle), never in a shape table
 
@@ -359,10 +360,11 @@ __device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* p
         uint32_t s1 = src.shape1[i1];
         ps.k1 = kinds[s1];
         ps.pr1 = params[s1];
-        ps.pos1 = load_iso((src.part_pose ? src.part_pose : src.pos1) + 7ull * i1);
+        if (src.flags & PAIR_POS12_GIVEN) { ps.pos1.q.i = ps.pos1.q.j = ps.pos1.q.k = 0.f; ps.pos1.q.w = 1.f; ps.pos1.t = mk3(0.f, 0.f, 0.f); }
+        else ps.pos1 = load_iso((src.part_pose ? src.part_pose : src.pos1) + 7ull * i1);
     }
     ps.tri = tri;
-    ps.pos12 = iso_inv_mul(ps.pos1, ps.pos2);  // contact_shape_shape.rs:130
+    ps.pos12 = (src.flags & PAIR_POS12_GIVEN) ? ps.pos2 : iso_inv_mul(ps.pos1, ps.pos2);  // contact_shape_shape.rs:130
     if (src.part_pose) {
         // contact_composite_shape_shape.rs:27: dispatcher.contact(&part_pos1.inv_mul(pose12), part1, shape2, ..); pose12 is the
         // user's pos12, or its inverse when the compound is the second shape (contact_shape_composite_shape, :74)
@@ -1725,6 +1727,32 @@ int pb2_contact_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* sh
     } else if (mem == PB2_MEM_HOST) {
         PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return PB2_OK;
+}
+
+// QueryDispatcher::contact(pos12, g1, g2, prediction) itself (query_dispatcher.rs:430-436): the relative pose is the input and the
+// contact stays in the shapes' local frames (point1 / normal1 in shape 1's, point2 / normal2 in shape 2's) — what a dispatcher in
+// a QueryDispatcherChain is asked for, as opposed to query::contact which takes two world poses and transforms the result.
+int pb2_contact_batch_local(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos12,
+                            float prediction, uint32_t n, pb2_contact* out, uint8_t* status, int mem) {
+    if (!ctx || !shapes || (n && (!shape1 || !shape2 || !pos12 || !out || !status))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *d_s1, *d_s2, *d_p;
+    void *d_out, *d_st;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape1, (size_t)n * 4, mem, &d_s1));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape2, (size_t)n * 4, mem, &d_s2));
+    PB2_CHECK(pb2_stage_in(ctx, 2, pos12, (size_t)n * 28, mem, &d_p));
+    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_st));
+    OutSinks sinks;
+    sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0; sinks.compact_count = nullptr; sinks.some_count = nullptr;
+    sinks.dense = (float*)d_out; sinks.status = (uint8_t*)d_st;
+    PB2_CHECK(run_contacts(ctx, shapes, (const uint32_t*)d_s1, (const uint32_t*)d_s2, (const float*)d_p, (const float*)d_p, prediction, n, sinks,
+                           nullptr, 0, nullptr, 0, PAIR_LOCAL_FRAMES | PAIR_POS12_GIVEN));
+    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_st, (size_t)n, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB2_OK;
 }
 

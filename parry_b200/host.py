@@ -755,6 +755,20 @@ def contact_compact(shapes, shape1, pos1, shape2, pos2, prediction, capacity=Non
     return out[:c], idx[:c]
 
 
+def contact_local(shapes, shape1, shape2, pos12, prediction):
+    """QueryDispatcher::contact(pos12, g1, g2, prediction), batched (query_dispatcher.rs:430-436): the relative pose is the input and
+    the contact stays in the shapes' local frames. Returns (contacts (n, 13), status (n,))."""
+    ctx = shapes.ctx
+    n = int(pos12.shape[0])
+    kp, pp, mem = _prep(pos12, np.float32)
+    k1, p1, _ = _prep(shape1, np.uint32, mem)
+    k2, p2, _ = _prep(shape2, np.uint32, mem)
+    out, po = _empty((n, 13), np.float32, mem, ctx.torch_device)
+    status, pst = _empty((n,), np.uint8, mem, ctx.torch_device)
+    ctx.check(ctx._lib.pb2_contact_batch_local(ctx.h, shapes.h, p1, p2, pp, float(prediction), n, po, pst, mem))
+    return out, status
+
+
 def contact_pairs_compact(shapes, collider_shape, collider_pose, pairs, prediction, capacity=None):
     """query::contact for every broad-phase pair (a, b) of `pairs` ((n, 2) collider indices, e.g. the output of
     Bvh.traverse_bvtt_single_tree): collider i is shape collider_shape[i] at pose collider_pose[i]. Compacted output:

@@ -60,16 +60,33 @@ def test_fails_loudly_without_a_gpu():
         parry_b200.Context(0)
 
 
-def test_integration_doc_lists_every_entry_point():
-    """INTEGRATION.md's Rust extern block stays in step with include/parry_b200.h."""
+def test_rust_sys_crate_matches_the_header():
+    """rust-shim/parry-b200-sys/src/lib.rs is generated from include/parry_b200.h (rust-shim/gen_sys.py): the committed file must be
+    the generator's output, bind every prototype with the same number of arguments, and the shim crate may only call what exists."""
+    import importlib.util
     import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    header = open(os.path.join(root, "include", "parry_b200.h")).read()
-    doc = open(os.path.join(root, "INTEGRATION.md")).read()
-    declared = set(re.findall(r"\b(pb2_[a-z0-9_]+)\s*\(", header))
-    assert len(declared) > 40
-    missing = sorted(d for d in declared if ("pub fn %s(" % d) not in doc)
-    assert not missing, missing
+    spec = importlib.util.spec_from_file_location("gen_sys", os.path.join(root, "rust-shim", "gen_sys.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text, funcs = gen.generate()
+    committed = open(os.path.join(root, "rust-shim", "parry-b200-sys", "src", "lib.rs")).read()
+    assert committed == text, "run `python rust-shim/gen_sys.py` after changing include/parry_b200.h"
+    declared = header_functions()
+    bound = {name: params for name, params, _ in funcs}
+    assert sorted(bound) == declared
+    from parry_b200 import _ffi
+    for name, params in bound.items():          # same arity as the ctypes table the tests call through
+        assert len(params) == len(_ffi.SIGNATURES[name][1]), name
+    for line in re.findall(r"pub fn (pb2_\w+)\(([^)]*)\)", committed):
+        assert "*const" in line[1] or "*mut" in line[1] or line[1] == "" or ":" in line[1]
+    shim = open(os.path.join(root, "rust-shim", "parry-b200", "src", "lib.rs")).read()
+    used = set(re.findall(r"sys::(pb2_[a-z0-9_]+)\(", shim))
+    assert len(used) > 25 and not [u for u in used if u not in bound], [u for u in used if u not in bound]
+    assert "/* pb2_" not in shim and "todo!" not in shim and "unimplemented!" not in shim      # bodies, not comments
+    # every trait method of QueryDispatcher is implemented (query_dispatcher.rs:408-506)
+    for m in ("fn intersection_test", "fn distance", "fn contact", "fn closest_points", "fn cast_shapes", "fn cast_shapes_nonlinear"):
+        assert m in shim, m
 
 
 def test_cpp_mirror_header_compiles(tmp_path):

@@ -88,6 +88,27 @@ def test_all_dispatch_arms_random(ctx, oracle):
         assert (o[1] < 2).all()
 
 
+def test_dispatcher_level_contact_in_local_frames(ctx, oracle):
+    """pb2_contact_batch_local = QueryDispatcher::contact(pos12, g1, g2, prediction) (query_dispatcher.rs:430-436): what a dispatcher
+    chained in front of DefaultQueryDispatcher must return — relative pose in, contact in the shapes' local frames out."""
+    import parry_b200
+    spec = mixed_spec(40)
+    G, O = build_tables(ctx, oracle, spec)
+    a, b, p1, p2 = random_pairs(40000, len(spec), 47, 1.2)
+    ident = np.tile(np.array(I4 + [0, 0, 0], np.float32), (len(a), 1))
+    pos12 = np.concatenate([p2[:, :4], p2[:, 4:] - p1[:, 4:]], axis=1).astype(np.float32)   # a relative pose per pair
+    g = parry_b200.contact_local(G, a, b, pos12, 0.05)
+    o = O.contact_local(a, ident, b, pos12, 0.05, threads=8)
+    assert 0.05 < (o[1] == 1).mean() < 0.999
+    assert compare(g, o) > 0.999
+    # and query::contact is that result moved to the world frames: consistent with pb2_contact_batch on (identity, pos12) up to the
+    # transform of point2 / normal2
+    w = parry_b200.contact(G, a, ident, b, pos12, 0.05)
+    assert (np.asarray(w[1]) == np.asarray(g[1])).all()
+    some = np.asarray(g[1]) == 1
+    assert (np.asarray(w[0])[some][:, [0, 1, 2, 6, 7, 8, 12]].view(np.uint32) == np.asarray(g[0])[some][:, [0, 1, 2, 6, 7, 8, 12]].view(np.uint32)).all()
+
+
 def test_cuboid_cuboid_goes_through_gjk_epa(ctx, oracle):
     """The SAT arm is commented out in the reference (default_query_dispatcher.rs:314-317): axis-aligned cuboid pairs are
     full of exact ties (EPA heap order, support copy-sign) and must still match."""
