@@ -32,7 +32,7 @@ FMAX = float(np.finfo(np.float32).max)
 RAY_KERNEL = "k_raycast_wide_shared<false>"
 RAY_KERNEL_VERSION = "r2.1 staged 32-ray refill; 96 B nodes / 64 B triangles read with LDG.E.256"
 EPA_KERNEL = "k_contact_epa2"
-EPA_KERNEL_VERSION = "r2.1 reconverged phases, finishing kernel split off, 16-entry shared heap head"
+EPA_KERNEL_VERSION = "r2.2 32-byte face records (one 256-bit load), neighbour records requested with the vertex, 16-entry shared heap head"
 
 
 def profiled_traffic(kernel, version):

@@ -702,9 +702,29 @@ __global__ void __launch_bounds__(128, MINB) k_contact_gjk_persistent(const uint
 #define E2_MINB 4          // resident CTAs per SM the EPA kernel is compiled for (register cap 65536 / (128 * E2_MINB))
 #endif
 
+// One polytope face = one 32-byte, 32-byte-aligned record read with a single 256-bit load (round 2; round 1 kept `face` and `adj` in
+// two arrays: two dependent round trips to L2 wherever both were needed — the kernel is bound by exactly those,
+// profiles/r2_contacts_heap16_full.json: long-scoreboard 8.5 cycles per issue at 4 warps per scheduler).
+struct __align__(32) EFace {
+    float4 f;     // normal.xyz ; w = pts0 | pts1 << 8 | pts2 << 16 | deleted << 24
+    uint2 adj;    // x = adj0 | adj1 << 16 ; y = adj2
+    uint2 pad;
+};
+__device__ __forceinline__ EFace ld_face(const EFace* p) {
+    EFace r;
+    float a0, a1, a2, a3, a4, a5, a6, a7;
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3), "=f"(a4), "=f"(a5), "=f"(a6), "=f"(a7) : "l"(p) : "memory");
+    r.f = make_float4(a0, a1, a2, a3);
+    r.adj = make_uint2(__float_as_uint(a4), __float_as_uint(a5));
+    r.pad = make_uint2(0u, 0u);
+    return r;
+}
+__device__ __forceinline__ void st_face(EFace* p, float4 f, uint2 adj) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w), "f"(__uint_as_float(adj.x)),
+                 "f"(__uint_as_float(adj.y)), "f"(0.0f), "f"(0.0f) : "memory");
+}
 struct Epa2Arena {
-    float4 face[E2_MAX_FACES];   // normal.xyz ; w = pts0 | pts1 << 8 | pts2 << 16 | deleted << 24
-    uint2 adj[E2_MAX_FACES];     // x = adj0 | adj1 << 16 ; y = adj2
+    EFace face[E2_MAX_FACES];
     float2 heap[E2_MAX_FACES];   // neg_dist ; face id (bits)
     float4 vp[E2_MAX_VERTS];     // CSO point
     float4 vo1[E2_MAX_VERTS];    // orig1 (cold)
@@ -948,10 +968,11 @@ __global__ void __launch_bounds__(128, E2_MINB) k_contact_epa2(const uint8_t* __
             while (nheap > 0) {
                 float2 ent = h2_pop(H, nheap);
                 face_id = __float_as_uint(ent.y); face_neg = ent.x;
-                face = A.face[face_id];
+                EFace rec = ld_face(&A.face[face_id]);
+                face = rec.f; face_adj = rec.adj;
                 if (!f_deleted(face)) { got = true; break; }
             }
-            if (got) { need_support = true; run_step = true; sdir = v3of(face); face_adj = A.adj[face_id]; }
+            if (got) { need_support = true; run_step = true; sdir = v3of(face); }
             else { fin = FIN_FACE; fin_face = best_id; }
         } else if (state == E2_INIT) {
             if (dim == 0) fin = FIN_DIM0;
@@ -1003,12 +1024,12 @@ __global__ void __launch_bounds__(128, E2_MINB) k_contact_epa2(const uint8_t* __
                 fin = FIN_FACE; fin_face = best_id; run_step = false;
             } else {
                 old_dist = curr_dist;
-                A.face[face_id].w = __uint_as_float(__float_as_uint(face.w) | (1u << 24));
+                A.face[face_id].f.w = __uint_as_float(__float_as_uint(face.w) | (1u << 24));
                 // three compute_silhouette calls (adj[0], adj[1], adj[2]) as one DFS stack: push in reverse order
 #pragma unroll 1
                 for (int k = 2; k >= 0; --k) {
                     uint32_t af = a_get(face_adj, k);
-                    int opp = e2_next_ccw(A.face[af], f_pts(face, k));
+                    int opp = e2_next_ccw(A.face[af].f, f_pts(face, k));
                     s_stk[sp++][threadIdx.x] = (uint16_t)(af | ((uint32_t)opp << 8));
                 }
                 dfs = true;
@@ -1019,12 +1040,26 @@ __global__ void __launch_bounds__(128, E2_MINB) k_contact_epa2(const uint8_t* __
         const unsigned m_dfs = __ballot_sync(FULL, dfs);
         if (dfs) {
             V3 pt = sp_point;
+            // The visit's loads used to form a chain of four dependent round trips (face -> vertex -> adjacency -> the two neighbour
+            // faces for next_ccw). Now the face record carries its adjacency, the neighbours' records are requested together with
+            // the vertex (speculatively: they are only needed when the face turns out to be visible), and the record of the
+            // neighbour that is visited next stays in registers: one round trip per visit on the critical path.
+            EFace top;
+            uint32_t top_id = PB2_INVALID_U32;
+            top.f = make_float4(0.f, 0.f, 0.f, 0.f); top.adj = make_uint2(0u, 0u); top.pad = make_uint2(0u, 0u);
             while (__any_sync(m_dfs, sp > 0 && !ovf)) {
                 if (sp > 0 && !ovf) {
                     uint32_t e = s_stk[--sp][threadIdx.x];
                     uint32_t fid = e & 0xffu; int fo = (int)(e >> 8);
-                    float4 f = A.face[fid];
+                    EFace rec;
+                    if (top_id == fid) rec = top; else rec = ld_face(&A.face[fid]);
+                    top_id = PB2_INVALID_U32;
+                    const float4 f = rec.f;
                     if (!f_deleted(f)) {
+                        const int i1 = (fo + 2) % 3, i2 = fo;
+                        const uint32_t adj1 = a_get(rec.adj, i1), adj2 = a_get(rec.adj, i2);
+                        const EFace nb1 = ld_face(&A.face[adj1]);
+                        const float4 nb2 = A.face[adj2].f;
                         V3 p0 = v3of(A.vp[f_pts(f, fo)]);
                         bool seen = dot3(pt - p0, v3of(f)) >= -PB2_GJK_EPS_TOL;
                         if (!seen) {
@@ -1036,16 +1071,16 @@ __global__ void __launch_bounds__(128, E2_MINB) k_contact_epa2(const uint8_t* __
                             if (nsil >= E2_MAX_SIL) ovf = true;
                             else s_sil[nsil++][threadIdx.x] = (uint16_t)e;
                         } else {
-                            A.face[fid].w = __uint_as_float(__float_as_uint(f.w) | (1u << 24));
-                            int i1 = (fo + 2) % 3, i2 = fo;
-                            uint2 fa = A.adj[fid];
-                            uint32_t adj1 = a_get(fa, i1), adj2 = a_get(fa, i2);
-                            int o1 = e2_next_ccw(A.face[adj1], f_pts(f, i1));
-                            int o2 = e2_next_ccw(A.face[adj2], f_pts(f, i2));
+                            A.face[fid].f.w = __uint_as_float(__float_as_uint(f.w) | (1u << 24));
+                            int o1 = e2_next_ccw(nb1.f, f_pts(f, i1));
+                            int o2 = e2_next_ccw(nb2, f_pts(f, i2));
                             if (sp + 2 > E2_STACK_SMEM) ovf = true;
                             else {
                                 s_stk[sp++][threadIdx.x] = (uint16_t)(adj2 | ((uint32_t)o2 << 8));
                                 s_stk[sp++][threadIdx.x] = (uint16_t)(adj1 | ((uint32_t)o1 << 8));
+                                // adj1 is popped by the very next visit. Its record was read before this face was marked deleted,
+                                // so it must not be this face itself (degenerate self-adjacency): then the next visit reloads it.
+                                if (adj1 != fid) { top = nb1; top_id = adj1; }
                             }
                         }
                     }
@@ -1081,25 +1116,27 @@ __global__ void __launch_bounds__(128, E2_MINB) k_contact_epa2(const uint8_t* __
                 } else {
                     uint32_t ed = s_sil[e][threadIdx.x];
                     uint32_t efid = ed & 0xffu; int eopp = (int)(ed >> 8);
-                    float4 ef = A.face[efid];
+                    const EFace erec = ld_face(&A.face[efid]);
+                    const float4 ef = erec.f;
                     if (f_deleted(ef)) skip = true;
                     else if (new_id >= E2_MAX_FACES) { fin = FIN_OVERFLOW; skip = true; }
                     else {
                         p0 = (int)f_pts(ef, (eopp + 2) % 3); p1 = (int)f_pts(ef, (eopp + 1) % 3); p2 = (int)support_id;
                         a0 = (int)efid; a1 = new_id + 1; a2 = new_id - 1;
                         dv = p0;
-                        uint2 ea = A.adj[efid];
+                        uint2 ea = erec.adj;
                         a_set(ea, (eopp + 1) % 3, (uint32_t)new_id);
-                        A.adj[efid] = ea;
+                        A.face[efid].adj = ea;
                     }
                 }
                 if (skip) continue;
-                V3 va = v3of(A.vp[p0]), vb = v3of(A.vp[p1]), vc = v3of(A.vp[p2]);
+                // (RUN: the third vertex is the support point of this step, still in registers; the arena holds the same bits)
+                V3 va = v3of(A.vp[p0]), vb = v3of(A.vp[p1]), vc = state == E2_INIT ? v3of(A.vp[p2]) : sp_point;
                 bool inside = e2_face_inside(va, vb, vc);
                 V3 n; float nn;
                 if (!try_normalize_get(cross3(vb - va, vc - va), PB2_EPS, n, nn)) n = mk3(0.f, 0.f, 0.f);
-                A.face[new_id] = make_float4(n.x, n.y, n.z, __uint_as_float((uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16)));
-                A.adj[new_id] = make_uint2((uint32_t)a0 | ((uint32_t)a1 << 16), (uint32_t)a2);
+                st_face(&A.face[new_id], make_float4(n.x, n.y, n.z, __uint_as_float((uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16))),
+                        make_uint2((uint32_t)a0 | ((uint32_t)a1 << 16), (uint32_t)a2));
                 nfaces = new_id + 1;
                 if (state == E2_INIT) {
                     if (npend == 4) {
@@ -1112,7 +1149,7 @@ __global__ void __launch_bounds__(128, E2_MINB) k_contact_epa2(const uint8_t* __
                         h2_push(H, nheap, (uint32_t)new_id, 0.0f);
                     }
                 } else if (inside) {
-                    float dist = dot3(n, v3of(A.vp[dv]));
+                    float dist = dot3(n, va);   // dv == p0 here
                     if (dist < curr_dist) { fin = FIN_FACE; fin_face = face_id; }
                     else if (-dist > PB2_GJK_EPS_TOL) fin = FIN_NONE;
                     else h2_push(H, nheap, (uint32_t)new_id, -dist);
@@ -1126,8 +1163,8 @@ __global__ void __launch_bounds__(128, E2_MINB) k_contact_epa2(const uint8_t* __
                 } else {
                     if (first_new == nfaces) fin = FIN_NONE;
                     else {
-                        uint2 fa = A.adj[first_new]; a_set(fa, 2, (uint32_t)(nfaces - 1)); A.adj[first_new] = fa;
-                        uint2 la = A.adj[nfaces - 1]; a_set(la, 1, (uint32_t)first_new); A.adj[nfaces - 1] = la;
+                        uint2 fa = A.face[first_new].adj; a_set(fa, 2, (uint32_t)(nfaces - 1)); A.face[first_new].adj = fa;
+                        uint2 la = A.face[nfaces - 1].adj; a_set(la, 1, (uint32_t)first_new); A.face[nfaces - 1].adj = la;
                         niter += 1;
                         if (niter > 100) { fin = FIN_FACE; fin_face = best_id; }
                     }
@@ -1139,7 +1176,7 @@ __global__ void __launch_bounds__(128, E2_MINB) k_contact_epa2(const uint8_t* __
         if (fin != FIN_NOT) {
             V3 p1 = mk3(0.f, 0.f, 0.f), p2 = p1, n1 = mk3(0.f, 1.f, 0.f);
             if (fin == FIN_FACE) {
-                float4 f = A.face[fin_face];
+                float4 f = A.face[fin_face].f;
                 uint32_t i0 = f_pts(f, 0), i1 = f_pts(f, 1), i2 = f_pts(f, 2);
                 float bc[3];
                 e2_face_bc(v3of(A.vp[i0]), v3of(A.vp[i1]), v3of(A.vp[i2]), bc);
