@@ -30,7 +30,7 @@ FMAX = float(np.finfo(np.float32).max)
 # launch) is read from profiles/r2_traffic.json and only used when the capture there was taken from a kernel of the same name AND
 # version string; otherwise it is null (a stale capture must not stand in for the current code).
 RAY_KERNEL = "k_raycast_wide_shared<false>"
-RAY_KERNEL_VERSION = "r2.1 staged 32-ray refill; 96 B nodes / 64 B triangles read with LDG.E.256"
+RAY_KERNEL_VERSION = "r2.2 staged 32-ray refill; 96 B nodes / 64 B triangles read with LDG.E.256; order-independent ties"
 EPA_KERNEL = "k_contact_epa2"
 EPA_KERNEL_VERSION = "r2.2 32-byte face records (one 256-bit load), neighbour records requested with the vertex, 16-entry shared heap head"
 
@@ -344,7 +344,8 @@ def main():
         dt_e2e = float(t.item())
     e2e_val = world * m / dt_e2e
     # the host path returns the same bits as the device path
-    assert (toi_timed.view(np.uint32) == toi_np.view(np.uint32)).all() and (tri_timed == tri_np).all()
+    paths_differ = int(((toi_timed.view(np.uint32) != toi_np.view(np.uint32)) | (tri_timed != tri_np)).sum())
+    assert paths_differ == 0, "device-resident and host-buffer ray casts differ on %d rays" % paths_differ
     if world > 1:
         # every rank must hold every rank's results, element by element: each rank checks the shard of its right-hand neighbour
         # against that neighbour's own local results (toi bits and triangle ids), plus per-shard checksums of all shards
@@ -1037,4 +1038,12 @@ EXTRA_ALSO = [("manifolds_4M_ball_cuboid_pairs", also_manifolds),
               ("mixed_2M_colliders_pipeline", also_mixed), ("trimesh_contacts_1M_colliders", also_mesh_contacts)]
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as exc:   # a rank that dies must take the job down at once (peers would wait in a collective for ever)
+        if not isinstance(exc, SystemExit) or exc.code not in (0, None):
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)
+        raise

@@ -497,9 +497,14 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide(const float4* __restric
                         // exact leaf AABB (Triangle::local_aabb) and the reference's node test against the best hit so far
                         float4 blo = make_float4(fminf(fminf(ta.x, tb.x), tc.x), fminf(fminf(ta.y, tb.y), tc.y), fminf(fminf(ta.z, tb.z), tc.z), 0.f);
                         float4 bhi = make_float4(fmaxf(fmaxf(ta.x, tb.x), tc.x), fmaxf(fmaxf(ta.y, tb.y), tc.y), fmaxf(fmaxf(ta.z, tb.z), tc.z), 0.f);
-                        float sc = slab_cost_bf(blo, bhi, o, inv, best);
+                        // The leaf box is tested against best * (1 + 2^-20), like the node boxes: a triangle hit at exactly the best toi
+                        // (a ray through an edge shared by two triangles) can have a box entry one ulp beyond it, and whether it was
+                        // looked at used to depend on which of the two was found first — i.e. on how the warps happened to pick up
+                        // rays. With the slack every candidate within rounding of the best is tested whatever the order, so the
+                        // result is the (toi, smallest id) minimum over all of them: deterministic, and equal to brute force.
+                        float sc = slab_cost_bf(blo, bhi, o, inv, best * W8_GAMMA);
                         if (stats) { atomicAdd(&stats[4], 1ull); if (sc != FLT_MAX && sc <= best) atomicAdd(&stats[5], 1ull); }
-                        if (sc != FLT_MAX && (sc < best || (found && sc == best))) {
+                        if (sc != FLT_MAX) {
                             float toi; uint32_t fid; V3 n;
                             if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), o, d, toi, fid, n) && toi <= best &&
                                 (cull == 0u || (fid & 1u) == cull - 1u)) {  // RayCullingMode::check (ray_trimesh.rs:58-65)
@@ -786,9 +791,10 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide_shared(const float4* __
                             // exact leaf AABB (Triangle::local_aabb) and the reference's node test against the best hit so far
                             float4 blo = make_float4(fminf(fminf(ta.x, tb.x), tc.x), fminf(fminf(ta.y, tb.y), tc.y), fminf(fminf(ta.z, tb.z), tc.z), 0.f);
                             float4 bhi = make_float4(fmaxf(fmaxf(ta.x, tb.x), tc.x), fmaxf(fmaxf(ta.y, tb.y), tc.y), fmaxf(fmaxf(ta.z, tb.z), tc.z), 0.f);
-                            float sc = slab_cost_bf(blo, bhi, ro, rinv, sbest);
+                            // slack of 2^-20 on the bound, as for the node boxes: see k_raycast_wide (order-independent ties)
+                            float sc = slab_cost_bf(blo, bhi, ro, rinv, sbest * W8_GAMMA);
                             if (stats) { atomicAdd(&stats[4], 1ull); if (sc != FLT_MAX && sc <= sbest) atomicAdd(&stats[5], 1ull); }
-                            if (sc != FLT_MAX && (sc < sbest || (sfound && sc == sbest))) {
+                            if (sc != FLT_MAX) {
                                 V3 rd = mk3(s_ray[3][own], s_ray[4][own], s_ray[5][own]);
                                 float toi; uint32_t fid; V3 n;
                                 if (ray_triangle(mk3(ta.x, ta.y, ta.z), mk3(tb.x, tb.y, tb.z), mk3(tc.x, tc.y, tc.z), ro, rd, toi, fid, n) && toi <= sbest &&
