@@ -426,7 +426,9 @@ def main():
             line["roofline"].setdefault("multi_gpu", {})[name] = {k: also[name].get(k) for k in (
                 "value", "unit", "ms", "n_gpus", "scaling", "pairs_per_frame", "contacts_per_frame", "pairs_per_s", "gathered_bytes_per_rank",
                 "all_ranks_agree", "error") if k in also[name]}
-        if rank == 0:
+        if rank == 0 and world == 1:
+            # single-GPU extras (spheres, manifolds, sibling queries, broad phase, TriMesh contacts): measured at N = 1 only, so that
+            # at N > 1 the other ranks do not sit in the closing barrier while rank 0 works through them
             also.update(bench_also(ctx, stream, args, hbm_peak, flush))
 
     if rank == 0 and not args.skip_cpu:
