@@ -103,6 +103,7 @@ int pb2_ctx_destroy(pb2_ctx* ctx) {
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_pieces) cudaFree(ctx->d_pieces);
+    if (ctx->epa_big_arena) cudaFree(ctx->epa_big_arena);
     for (int i = 0; i < 4; ++i) if (ctx->phase_ev[i]) cudaEventDestroy(ctx->phase_ev[i]);
     if (ctx->copy_in) { cudaStreamDestroy(ctx->copy_in); cudaStreamDestroy(ctx->copy_out); if (ctx->compute2) cudaStreamDestroy(ctx->compute2); for (int i = 0; i < 6; ++i) if (ctx->copy_peer[i]) cudaStreamDestroy(ctx->copy_peer[i]); for (int i = 0; i < 64; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -41,6 +41,7 @@ struct pb2_ctx {
     bool phase_timing = false;
     cudaEvent_t phase_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int phase_marks = 0;
+    void* epa_big_arena = nullptr;     // arena of the overflow EPA kernel (contact.cu), allocated at the first contact call
     unsigned int* d_pieces = nullptr;  // 2 x 32 u32: per-piece retired-ray counters and completion flags of a piece-signalling ray cast
     void* wait_value32 = nullptr;      // cuStreamWaitValue32, resolved once (NULL: not available -> piece-wise launches)
 };

@@ -698,6 +698,9 @@ __global__ void __launch_bounds__(128, MINB) k_contact_gjk_persistent(const uint
 #ifndef E2_STACK_SMEM
 #define E2_STACK_SMEM 64   // DFS stack entries kept in shared memory by k_contact_epa2 (deeper walks: status 3)
 #endif
+#ifndef E2_HEAP_SMEM
+#define E2_HEAP_SMEM 16    // heap entries per thread kept in shared memory (sweep: see epa_persistent.inc / DESIGN.md 5.2)
+#endif
 #ifndef E2_MINB
 #define E2_MINB 4          // resident CTAs per SM the EPA kernel is compiled for (register cap 65536 / (128 * E2_MINB))
 #endif
@@ -723,13 +726,7 @@ __device__ __forceinline__ void st_face(EFace* p, float4 f, uint2 adj) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w), "f"(__uint_as_float(adj.x)),
                  "f"(__uint_as_float(adj.y)), "f"(0.0f), "f"(0.0f) : "memory");
 }
-struct Epa2Arena {
-    EFace face[E2_MAX_FACES];
-    float2 heap[E2_MAX_FACES];   // neg_dist ; face id (bits)
-    float4 vp[E2_MAX_VERTS];     // CSO point
-    float4 vo1[E2_MAX_VERTS];    // orig1 (cold)
-    float4 vo2[E2_MAX_VERTS];    // orig2 (cold)
-};
+// struct Epa2Arena: in epa_persistent.inc (one per configuration)
 
 __device__ __forceinline__ uint32_t f_pts(float4 f, int i) { return (__float_as_uint(f.w) >> (8 * i)) & 0xffu; }
 __device__ __forceinline__ bool f_deleted(float4 f) { return (__float_as_uint(f.w) >> 24) != 0u; }
@@ -744,67 +741,7 @@ __device__ __forceinline__ int e2_next_ccw(float4 f, uint32_t id) {
     return 0;
 }
 __device__ __forceinline__ bool h2_le(float a, float b) { return !(a > b); }
-// Heap storage of k_contact_epa2: the first E2_HEAP_SMEM entries of every thread's heap sit in shared memory ([entry][thread],
-// f32 key + u8 face id), the rest in the thread's arena. Rust's BinaryHeap sift rules (sift_up / sift_down_to_bottom) below.
-// Round 2: 16 entries instead of 32. The four resident CTAs' shared memory comes out of the same 256 KB as L1; at 52 KB per CTA
-// only ~48 KB of L1 were left for 512 threads' arenas. Sweep on the 2^22 hull-pair batch (gpurun r2, whole contact call):
-// 32 entries 31.7 ms, 16: 26.6, 12: 26.6, 8: 27.1, 4: 28.0, 1: 29.1. More resident CTAs instead (5 / 6 / 7 per SM with the
-// register cap that implies: 96 / 80 / 72 registers, 90-530 bytes of spills) were slower: 36.5 / 39.3 / 39.6 ms.
-#ifndef E2_HEAP_SMEM
-#define E2_HEAP_SMEM 16
-#endif
-#define E2_SMEM_BYTES (E2_HEAP_SMEM * 128 * 5 + (E2_STACK_SMEM + E2_MAX_SIL) * 128 * 2)
-struct Heap2 {
-    float (*key)[128];
-    uint8_t (*id)[128];
-    float2* spill;
-    __device__ __forceinline__ float2 get(int i) const {
-        if (i < E2_HEAP_SMEM) return make_float2(key[i][threadIdx.x], __uint_as_float((uint32_t)id[i][threadIdx.x]));
-        return spill[i];
-    }
-    __device__ __forceinline__ void set(int i, float2 v) const {
-        if (i < E2_HEAP_SMEM) { key[i][threadIdx.x] = v.x; id[i][threadIdx.x] = (uint8_t)__float_as_uint(v.y); }
-        else spill[i] = v;
-    }
-};
-__device__ __forceinline__ void h2_sift_up(const Heap2& H, int start, int pos) {
-    float2 elt = H.get(pos);
-    while (pos > start) {
-        int parent = (pos - 1) / 2;
-        float2 pe = H.get(parent);
-        if (h2_le(elt.x, pe.x)) break;
-        H.set(pos, pe);
-        pos = parent;
-    }
-    H.set(pos, elt);
-}
-__device__ __forceinline__ void h2_push(const Heap2& H, int& nheap, uint32_t id, float neg_dist) {
-    int old = nheap;
-    H.set(old, make_float2(neg_dist, __uint_as_float(id)));
-    nheap = old + 1;
-    h2_sift_up(H, 0, old);
-}
-__device__ __forceinline__ float2 h2_pop(const Heap2& H, int& nheap) {
-    float2 item = H.get(nheap - 1);
-    nheap -= 1;
-    if (nheap > 0) {
-        float2 t = item; item = H.get(0);
-        int end = nheap, pos = 0;
-        float2 elt = t;
-        int child = 1;
-        while (end >= 2 && child <= end - 2) {
-            float2 c0 = H.get(child), c1 = H.get(child + 1);
-            if (h2_le(c0.x, c1.x)) { child += 1; c0 = c1; }
-            H.set(pos, c0);
-            pos = child;
-            child = 2 * pos + 1;
-        }
-        if (child == end - 1) { H.set(pos, H.get(child)); pos = child; }
-        H.set(pos, elt);
-        h2_sift_up(H, 0, pos);
-    }
-    return item;
-}
+// Heap2 and its sift rules: epa_persistent.inc
 // Barycentric coordinates Face::new would store for (va, vb, vc) + whether the origin projects inside.
 __device__ __forceinline__ bool e2_face_bc(V3 va, V3 vb, V3 vc, float bc[3]) {
     Proj p;
@@ -878,332 +815,68 @@ __device__ __forceinline__ int epa_result_to_contact(const PairSetup& ps, int fi
     return st;
 }
 
-__global__ void __launch_bounds__(128, E2_MINB) k_contact_epa2(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
-                              const float4* __restrict__ pts, PairSrc src, float prediction, OutSinks out,
-                              const EpaJob* __restrict__ jobs, const unsigned long long* __restrict__ job_count,
-                              unsigned long long* __restrict__ next_job, Epa2Arena* __restrict__ arenas, int refill,
-                              float4* __restrict__ fin_recs, unsigned long long* __restrict__ fin_count) {
-    // DFS stack and silhouette list live in shared memory ([entry][thread]: conflict free): they are written and read back
-    // within one trip, and global stores do not allocate in L1, so every pop used to be an L2 round trip
-    extern __shared__ __align__(16) unsigned char e2_smem[];   // E2_SMEM_BYTES, carved below
-    float (*s_hkey)[128] = reinterpret_cast<float (*)[128]>(e2_smem);
-    uint16_t (*s_stk)[128] = reinterpret_cast<uint16_t (*)[128]>(e2_smem + E2_HEAP_SMEM * 128 * 4);   // face | opp << 8
-    uint16_t (*s_sil)[128] = reinterpret_cast<uint16_t (*)[128]>(e2_smem + E2_HEAP_SMEM * 128 * 4 + E2_STACK_SMEM * 128 * 2);
-    uint8_t (*s_hid)[128] = reinterpret_cast<uint8_t (*)[128]>(e2_smem + E2_HEAP_SMEM * 128 * 4 + (E2_STACK_SMEM + E2_MAX_SIL) * 128 * 2);
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    Epa2Arena& A = arenas[blockIdx.x * blockDim.x + threadIdx.x];
-    Heap2 H;
-    H.key = s_hkey; H.id = s_hid; H.spill = A.heap;
-    const unsigned long long total = *job_count;
-    const float eps = PB2_EPS, eps_tol = PB2_EPS * 100.0f;
-
-    int state = E2_IDLE;
-    uint32_t pair = 0;
-    Iso7 gpos12;
-    DShape g1, g2;
-    g1.kind = g2.kind = DS_ORIGIN; g1.n = g2.n = 0; g1.pts = g2.pts = nullptr; g1.he = g2.he = mk3(0.f, 0.f, 0.f);
-    gpos12.q.i = gpos12.q.j = gpos12.q.k = 0.f; gpos12.q.w = 1.f; gpos12.t = mk3(0.f, 0.f, 0.f);
-    int dim = 0, nverts = 0, nfaces = 0, nheap = 0, niter = 0;
-    float max_dist = FLT_MAX, old_dist = 0.0f;
-    uint32_t best_id = 0;
-    bool exhausted = false;
-
-    for (;;) {
-        __syncwarp();
-        unsigned idle = __ballot_sync(FULL, state == E2_IDLE);
-        if (!exhausted && (idle == FULL || __popc(idle) >= refill)) {
-            unsigned long long base = 0;
-            int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(next_job, (unsigned long long)__popc(idle));
-            base = __shfl_sync(FULL, base, leader);
-            if (base >= total) exhausted = true;
-            if (state == E2_IDLE) {
-                unsigned long long j = base + __popc(idle & ((1u << lane) - 1u));
-                if (j < total) {
-                    const EpaJob& job = jobs[j];
-                    pair = job.pair;
-                    PairSetup ps;
-                    pair_setup(kinds, params, pts, src, pair, ps);
-                    gpos12 = ps.gpos12; g1 = ps.g1; g2 = ps.g2;
-                    dim = (int)job.dim;
-                    for (int i = 0; i <= dim; ++i) {
-                        V3 o1 = mk3(job.o1[i][0], job.o1[i][1], job.o1[i][2]), o2 = mk3(job.o2[i][0], job.o2[i][1], job.o2[i][2]);
-                        V3 p = o1 - o2;
-                        A.vp[i] = make_float4(p.x, p.y, p.z, 0.f);
-                        A.vo1[i] = make_float4(o1.x, o1.y, o1.z, 0.f);
-                        A.vo2[i] = make_float4(o2.x, o2.y, o2.z, 0.f);
-                    }
-                    nverts = dim + 1; nfaces = 0; nheap = 0; niter = 0;
-                    max_dist = FLT_MAX; old_dist = 0.0f;
-                    state = E2_INIT;
-                }
-            }
-        }
-        if (!__any_sync(FULL, state != E2_IDLE)) break;
-#ifdef PB2_EPA_DEBUG
-        {
-            unsigned r_ = __ballot_sync(FULL, state == E2_RUN), i_ = __ballot_sync(FULL, state == E2_INIT), d_ = __ballot_sync(FULL, state == E2_IDLE);
-            if (lane == 0) {
-                atomicAdd(&g_epa_dbg[0], 1ull); atomicAdd(&g_epa_dbg[1], (unsigned long long)__popc(r_));
-                atomicAdd(&g_epa_dbg[2], (unsigned long long)__popc(i_)); atomicAdd(&g_epa_dbg[3], (unsigned long long)__popc(d_));
-                if (exhausted) atomicAdd(&g_epa_dbg[4], 1ull);
-            }
-        }
-#endif
-
-        int fin = FIN_NOT;
-        uint32_t fin_face = 0;
-        bool need_support = false, run_step = false;
-        V3 sdir = mk3(0.f, 0.f, 0.f);
-        float4 face = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint2 face_adj = make_uint2(0u, 0u);
-        uint32_t face_id = 0;
-        float face_neg = 0.0f, curr_dist = 0.0f;
-        int npend = 0;
-
-        // ---- phase A: pop the closest live face (RUN) / seed the initial polytope (INIT)
-        if (state == E2_RUN) {
-            bool got = false;
-            while (nheap > 0) {
-                float2 ent = h2_pop(H, nheap);
-                face_id = __float_as_uint(ent.y); face_neg = ent.x;
-                EFace rec = ld_face(&A.face[face_id]);
-                face = rec.f; face_adj = rec.adj;
-                if (!f_deleted(face)) { got = true; break; }
-            }
-            if (got) { need_support = true; run_step = true; sdir = v3of(face); }
-            else { fin = FIN_FACE; fin_face = best_id; }
-        } else if (state == E2_INIT) {
-            if (dim == 0) fin = FIN_DIM0;
-            else if (dim == 3) {
-                V3 v0 = v3of(A.vp[0]), v1 = v3of(A.vp[1]), v2 = v3of(A.vp[2]), v3 = v3of(A.vp[3]);
-                if (dot3(cross3(v1 - v0, v2 - v0), v3 - v0) > 0.0f) {
-                    float4 t = A.vp[1]; A.vp[1] = A.vp[2]; A.vp[2] = t;
-                    t = A.vo1[1]; A.vo1[1] = A.vo1[2]; A.vo1[2] = t;
-                    t = A.vo2[1]; A.vo2[1] = A.vo2[2]; A.vo2[2] = t;
-                }
-                npend = 4;
-            } else {
-                if (dim == 1) {
-                    V3 dpt = v3of(A.vp[1]) - v3of(A.vp[0]);
-                    V3 a = fabsf(dpt.x) > fabsf(dpt.y) ? mk3(dpt.z, 0.0f, -dpt.x) : mk3(0.0f, -dpt.z, dpt.y);
-                    a = normalize3(a);
-                    sdir = cross3(a, dpt);
-                    need_support = true;
-                }
-                npend = 2;
-            }
-        }
-        __syncwarp();  // lanes leave the previous phase's loops at different times: make them walk the next phase together
-        // ---- phase B: one support point of the Minkowski difference
-        uint32_t support_id = 0;
-        V3 sp_point = mk3(0.f, 0.f, 0.f);
-        if (need_support) {
-            if (nverts >= E2_MAX_VERTS) { fin = FIN_OVERFLOW; run_step = false; npend = 0; }
-            else {
-                CSO cso = cso_from_shapes(gpos12, g1, g2, sdir);
-                support_id = (uint32_t)nverts;
-                A.vp[nverts] = make_float4(cso.point.x, cso.point.y, cso.point.z, 0.f);
-                A.vo1[nverts] = make_float4(cso.o1.x, cso.o1.y, cso.o1.z, 0.f);
-                A.vo2[nverts] = make_float4(cso.o2.x, cso.o2.y, cso.o2.z, 0.f);
-                nverts++;
-                sp_point = cso.point;
-            }
-        }
-        __syncwarp();  // lanes leave the previous phase's loops at different times: make them walk the next phase together
-        // ---- phase C/D: convergence test, then the silhouette of the faces visible from the new point
-        int nsil = 0, sp = 0;
-        bool ovf = false, dfs = false;
-        if (run_step) {
-            V3 fnormal = v3of(face);
-            float candidate = dot3(sp_point, fnormal);
-            if (candidate < max_dist) { best_id = face_id; max_dist = candidate; }
-            curr_dist = -face_neg;
-            if (max_dist - curr_dist < eps_tol || (fabsf(curr_dist - old_dist) < eps && candidate < max_dist)) {
-                fin = FIN_FACE; fin_face = best_id; run_step = false;
-            } else {
-                old_dist = curr_dist;
-                A.face[face_id].f.w = __uint_as_float(__float_as_uint(face.w) | (1u << 24));
-                // three compute_silhouette calls (adj[0], adj[1], adj[2]) as one DFS stack: push in reverse order
-#pragma unroll 1
-                for (int k = 2; k >= 0; --k) {
-                    uint32_t af = a_get(face_adj, k);
-                    int opp = e2_next_ccw(A.face[af].f, f_pts(face, k));
-                    s_stk[sp++][threadIdx.x] = (uint16_t)(af | ((uint32_t)opp << 8));
-                }
-                dfs = true;
-            }
-        }
-        // The walk itself, in lockstep: one visit per trip of the loop for every lane that still has entries, so that lanes with
-        // short walks wait at the loop head instead of drifting into their own copies of the loop body.
-        const unsigned m_dfs = __ballot_sync(FULL, dfs);
-        if (dfs) {
-            V3 pt = sp_point;
-            // The visit's loads used to form a chain of four dependent round trips (face -> vertex -> adjacency -> the two neighbour
-            // faces for next_ccw). Now the face record carries its adjacency, the neighbours' records are requested together with
-            // the vertex (speculatively: they are only needed when the face turns out to be visible), and the record of the
-            // neighbour that is visited next stays in registers: one round trip per visit on the critical path.
-            EFace top;
-            uint32_t top_id = PB2_INVALID_U32;
-            top.f = make_float4(0.f, 0.f, 0.f, 0.f); top.adj = make_uint2(0u, 0u); top.pad = make_uint2(0u, 0u);
-            while (__any_sync(m_dfs, sp > 0 && !ovf)) {
-                if (sp > 0 && !ovf) {
-                    uint32_t e = s_stk[--sp][threadIdx.x];
-                    uint32_t fid = e & 0xffu; int fo = (int)(e >> 8);
-                    EFace rec;
-                    if (top_id == fid) rec = top; else rec = ld_face(&A.face[fid]);
-                    top_id = PB2_INVALID_U32;
-                    const float4 f = rec.f;
-                    if (!f_deleted(f)) {
-                        const int i1 = (fo + 2) % 3, i2 = fo;
-                        const uint32_t adj1 = a_get(rec.adj, i1), adj2 = a_get(rec.adj, i2);
-                        const EFace nb1 = ld_face(&A.face[adj1]);
-                        const float4 nb2 = A.face[adj2].f;
-                        V3 p0 = v3of(A.vp[f_pts(f, fo)]);
-                        bool seen = dot3(pt - p0, v3of(f)) >= -PB2_GJK_EPS_TOL;
-                        if (!seen) {
-                            V3 p1 = v3of(A.vp[f_pts(f, (fo + 1) % 3)]), p2 = v3of(A.vp[f_pts(f, (fo + 2) % 3)]);
-                            const float EPS = PB2_EPS * 100.0f;
-                            seen = rel_eq(nrm2(cross3(p2 - p1, pt - p1)), 0.0f, EPS * EPS, PB2_EPS);
-                        }
-                        if (!seen) {
-                            if (nsil >= E2_MAX_SIL) ovf = true;
-                            else s_sil[nsil++][threadIdx.x] = (uint16_t)e;
-                        } else {
-                            A.face[fid].f.w = __uint_as_float(__float_as_uint(f.w) | (1u << 24));
-                            int o1 = e2_next_ccw(nb1.f, f_pts(f, i1));
-                            int o2 = e2_next_ccw(nb2, f_pts(f, i2));
-                            if (sp + 2 > E2_STACK_SMEM) ovf = true;
-                            else {
-                                s_stk[sp++][threadIdx.x] = (uint16_t)(adj2 | ((uint32_t)o2 << 8));
-                                s_stk[sp++][threadIdx.x] = (uint16_t)(adj1 | ((uint32_t)o1 << 8));
-                                // adj1 is popped by the very next visit. Its record was read before this face was marked deleted,
-                                // so it must not be this face itself (degenerate self-adjacency): then the next visit reloads it.
-                                if (adj1 != fid) { top = nb1; top_id = adj1; }
-                            }
-                        }
-                    }
-                }
-            }
-            if (ovf) { fin = FIN_OVERFLOW; run_step = false; }
-            else if (nsil == 0) { fin = FIN_NONE; run_step = false; }
-            else npend = nsil;
-        }
-        __syncwarp();  // lanes leave the previous phase's loops at different times: make them walk the next phase together
-        // ---- phase E: create the pending faces (initial polytope or the fan around the silhouette)
-        int first_new = nfaces;
-        const bool making = fin == FIN_NOT && npend > 0;
-        const unsigned m_mk = __ballot_sync(FULL, making);
-        if (making) {
-#pragma unroll 1
-            for (int e = 0; __any_sync(m_mk, e < npend && fin == FIN_NOT); ++e) {   // lockstep, one face per lane per trip
-                if (!(e < npend && fin == FIN_NOT)) continue;
-                int p0 = 0, p1 = 0, p2 = 0, a0 = 0, a1 = 0, a2 = 0, dv = 0;
-                int new_id = nfaces;
-                bool skip = false;
-                if (state == E2_INIT) {
-                    if (npend == 4) {
-                        // pts {0,1,2},{1,3,2},{0,2,3},{0,3,1}; adj {3,1,2},{3,2,0},{0,1,3},{2,1,0}; dist uses vertex e
-                        p0 = (e == 1) ? 1 : 0; p1 = (e == 0) ? 1 : ((e == 2) ? 2 : 3); p2 = (e == 0) ? 2 : ((e == 1) ? 2 : ((e == 2) ? 3 : 1));
-                        a0 = (e == 0 || e == 1) ? 3 : ((e == 2) ? 0 : 2); a1 = (e == 1) ? 2 : 1; a2 = (e == 0) ? 2 : ((e == 2) ? 3 : 0);
-                        dv = e;
-                    } else {
-                        p0 = 0; p1 = e == 0 ? 1 : 2; p2 = e == 0 ? 2 : 1;
-                        a0 = a1 = a2 = e == 0 ? 1 : 0;
-                        dv = 0;
-                    }
-                } else {
-                    uint32_t ed = s_sil[e][threadIdx.x];
-                    uint32_t efid = ed & 0xffu; int eopp = (int)(ed >> 8);
-                    const EFace erec = ld_face(&A.face[efid]);
-                    const float4 ef = erec.f;
-                    if (f_deleted(ef)) skip = true;
-                    else if (new_id >= E2_MAX_FACES) { fin = FIN_OVERFLOW; skip = true; }
-                    else {
-                        p0 = (int)f_pts(ef, (eopp + 2) % 3); p1 = (int)f_pts(ef, (eopp + 1) % 3); p2 = (int)support_id;
-                        a0 = (int)efid; a1 = new_id + 1; a2 = new_id - 1;
-                        dv = p0;
-                        uint2 ea = erec.adj;
-                        a_set(ea, (eopp + 1) % 3, (uint32_t)new_id);
-                        A.face[efid].adj = ea;
-                    }
-                }
-                if (skip) continue;
-                // (RUN: the third vertex is the support point of this step, still in registers; the arena holds the same bits)
-                V3 va = v3of(A.vp[p0]), vb = v3of(A.vp[p1]), vc = state == E2_INIT ? v3of(A.vp[p2]) : sp_point;
-                bool inside = e2_face_inside(va, vb, vc);
-                V3 n; float nn;
-                if (!try_normalize_get(cross3(vb - va, vc - va), PB2_EPS, n, nn)) n = mk3(0.f, 0.f, 0.f);
-                st_face(&A.face[new_id], make_float4(n.x, n.y, n.z, __uint_as_float((uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16))),
-                        make_uint2((uint32_t)a0 | ((uint32_t)a1 << 16), (uint32_t)a2));
-                nfaces = new_id + 1;
-                if (state == E2_INIT) {
-                    if (npend == 4) {
-                        if (inside) {
-                            float dist = dot3(n, v3of(A.vp[dv]));
-                            if (-dist > PB2_GJK_EPS_TOL) fin = FIN_NONE;
-                            else h2_push(H, nheap, (uint32_t)new_id, -dist);
-                        }
-                    } else {
-                        h2_push(H, nheap, (uint32_t)new_id, 0.0f);
-                    }
-                } else if (inside) {
-                    float dist = dot3(n, va);   // dv == p0 here
-                    if (dist < curr_dist) { fin = FIN_FACE; fin_face = face_id; }
-                    else if (-dist > PB2_GJK_EPS_TOL) fin = FIN_NONE;
-                    else h2_push(H, nheap, (uint32_t)new_id, -dist);
-                }
-            }
-            if (fin == FIN_NOT) {
-                if (state == E2_INIT) {
-                    // `*self.heap.peek()?` and the "failed to project the origin on the initial simplex" exit
-                    if (nheap == 0) fin = FIN_NONE;
-                    else { float2 top = H.get(0); best_id = __float_as_uint(top.y); state = E2_RUN; }
-                } else {
-                    if (first_new == nfaces) fin = FIN_NONE;
-                    else {
-                        uint2 fa = A.face[first_new].adj; a_set(fa, 2, (uint32_t)(nfaces - 1)); A.face[first_new].adj = fa;
-                        uint2 la = A.face[nfaces - 1].adj; a_set(la, 1, (uint32_t)first_new); A.face[nfaces - 1].adj = la;
-                        niter += 1;
-                        if (niter > 100) { fin = FIN_FACE; fin_face = best_id; }
-                    }
-                }
-            }
-        }
-        __syncwarp();  // lanes leave the previous phase's loops at different times: make them walk the next phase together
-        // ---- phase F: finished lanes build the contact and go idle
-        if (fin != FIN_NOT) {
-            V3 p1 = mk3(0.f, 0.f, 0.f), p2 = p1, n1 = mk3(0.f, 1.f, 0.f);
-            if (fin == FIN_FACE) {
-                float4 f = A.face[fin_face].f;
-                uint32_t i0 = f_pts(f, 0), i1 = f_pts(f, 1), i2 = f_pts(f, 2);
-                float bc[3];
-                e2_face_bc(v3of(A.vp[i0]), v3of(A.vp[i1]), v3of(A.vp[i2]), bc);
-                p1 = v3of(A.vo1[i0]) * bc[0] + v3of(A.vo1[i1]) * bc[1] + v3of(A.vo1[i2]) * bc[2];
-                p2 = v3of(A.vo2[i0]) * bc[0] + v3of(A.vo2[i1]) * bc[1] + v3of(A.vo2[i2]) * bc[2];
-                n1 = v3of(f);
-            }
-            if (fin_recs) {
-                // Only ~3 lanes of a warp finish in the same trip, and building the contact (pair setup, two isometry
-                // products, the compacted append) is ~150 instructions: hand the witness points to k_contact_finish,
-                // which does that part with full warps
-                unsigned long long at = warp_append1(fin_count);
-                float4* r = fin_recs + 3ull * at;
-                r[0] = make_float4(__uint_as_float(pair), __uint_as_float((uint32_t)fin), p1.x, p1.y);
-                r[1] = make_float4(p1.z, p2.x, p2.y, p2.z);
-                r[2] = make_float4(n1.x, n1.y, n1.z, 0.0f);
-            } else {
-                PairSetup ps;
-                pair_setup(kinds, params, pts, src, pair, ps);
-                ContactOut c;
-                int st = epa_result_to_contact(ps, fin, p1, p2, n1, prediction, c);
-                emit(out, pair, st, c);
-            }
-            state = E2_IDLE;
-        }
-    }
-}
+// The kernel itself, twice (see epa_persistent.inc): the hot configuration and the overflow configuration.
+#define EPA_N(x) x
+#define EPA_BIG 0
+#define E2_THREADS 128
+#define E2_STACK_CAP E2_STACK_SMEM
+#define E2_ENT_T uint16_t
+#define E2_ENT(face, opp) (uint16_t)((face) | ((uint32_t)(opp) << 8))
+#define E2_ENT_FACE(e) ((e) & 0xffu)
+#define E2_ENT_OPP(e) ((e) >> 8)
+#define E2_SMEM_BYTES (E2_HEAP_SMEM * 128 * 5 + (E2_STACK_SMEM + E2_MAX_SIL) * 128 * 2)
+#include "epa_persistent.inc"
+#undef EPA_N
+#undef EPA_BIG
+#undef E2_THREADS
+#undef E2_STACK_CAP
+#undef E2_ENT_T
+#undef E2_ENT
+#undef E2_ENT_FACE
+#undef E2_ENT_OPP
+#pragma push_macro("E2_MAX_VERTS")
+#pragma push_macro("E2_MAX_FACES")
+#pragma push_macro("E2_MAX_SIL")
+#pragma push_macro("E2_HEAP_SMEM")
+#pragma push_macro("E2_MINB")
+#undef E2_MAX_VERTS
+#undef E2_MAX_FACES
+#undef E2_MAX_SIL
+#undef E2_HEAP_SMEM
+#undef E2_MINB
+#define EPA_N(x) x##_big
+#define EPA_BIG 1
+#define E2_THREADS 32
+#define E2_MINB 1
+#define E2_MAX_VERTS 128      // the reference stops after 100 expansions (epa3.rs:641-646): at most 4 + 2 + 101 vertices
+#define E2_MAX_FACES 4096
+#define E2_MAX_SIL 1024
+#define E2_STACK_CAP 4096
+#define E2_HEAP_SMEM 0
+#define E2_ENT_T uint32_t
+#define E2_ENT(face, opp) ((uint32_t)(face) | ((uint32_t)(opp) << 16))
+#define E2_ENT_FACE(e) ((e) & 0xffffu)
+#define E2_ENT_OPP(e) ((e) >> 16)
+#include "epa_persistent.inc"
+#undef EPA_N
+#undef EPA_BIG
+#undef E2_THREADS
+#undef E2_STACK_CAP
+#undef E2_ENT_T
+#undef E2_ENT
+#undef E2_ENT_FACE
+#undef E2_ENT_OPP
+#undef E2_MAX_VERTS
+#undef E2_MAX_FACES
+#undef E2_MAX_SIL
+#undef E2_HEAP_SMEM
+#undef E2_MINB
+#pragma pop_macro("E2_MINB")
+#pragma pop_macro("E2_HEAP_SMEM")
+#pragma pop_macro("E2_MAX_SIL")
+#pragma pop_macro("E2_MAX_FACES")
+#pragma pop_macro("E2_MAX_VERTS")
+#define E2_BIG_GRID 8   // overflow kernel: 8 single-warp CTAs = 256 runs in flight (~190 KB of arena each)
 
 // Second half of phase F for k_contact_epa2: one thread per finished EPA run.
 __global__ void __launch_bounds__(128) k_contact_finish(const uint8_t* __restrict__ kinds, const float4* __restrict__ params,
@@ -1624,9 +1297,14 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
         if (e) epa_variant = atoi(e);
         if ((e = getenv("PB2_EPA_REFILL"))) refill = atoi(e);
     }
-    size_t jobs_bytes = (size_t)n * sizeof(EpaJob);
-    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[3], jobs_bytes));
+    size_t jobs_bytes = ((size_t)n * sizeof(EpaJob) + 255) & ~(size_t)255;
+    PB2_CHECK(pb2_scratch_reserve(ctx, &ctx->scratch[3], jobs_bytes + (size_t)n * 4));
     EpaJob* jobs = (EpaJob*)ctx->scratch[3].ptr;
+    uint32_t* ovf_list = (uint32_t*)((char*)ctx->scratch[3].ptr + jobs_bytes);   // jobs that outgrow the hot EPA configuration
+    unsigned long long* ovf_count = (unsigned long long*)(ctx->d_counters + 11);
+    unsigned long long* next_job_big = (unsigned long long*)(ctx->d_counters + 13);
+    PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 11, 0, 8, st));
+    PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 13, 0, 8, st));
     unsigned long long* job_count = (unsigned long long*)(ctx->d_counters + 4);
     unsigned long long* next_job = (unsigned long long*)(ctx->d_counters + 5);
     PB2_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 4, 0, 16, st));
@@ -1684,7 +1362,14 @@ static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* 
             fin_recs = (float4*)ctx->scratch[4].ptr;
         }
         k_contact_epa2<<<epa_blocks, 128, E2_SMEM_BYTES, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction, sinks,
-                                                  jobs, job_count, next_job, (Epa2Arena*)ctx->scratch[2].ptr, refill, fin_recs, fin_count);
+                                                  jobs, job_count, next_job, (Epa2Arena*)ctx->scratch[2].ptr, refill, fin_recs, fin_count,
+                                                  nullptr, ovf_list, ovf_count);
+        // Overflow configuration (global-memory arena, 4096 faces): runs the few jobs the hot kernel handed over; its warps find an
+        // empty list and leave at once otherwise. The arena (48 MB) is allocated at the first contact call of the context.
+        if (!ctx->epa_big_arena) PB2_CUDA(ctx, cudaMalloc(&ctx->epa_big_arena, (size_t)E2_BIG_GRID * 32 * sizeof(Epa2Arena_big)));
+        PB2_LAUNCHED(ctx);
+        k_contact_epa2_big<<<E2_BIG_GRID, 32, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, src, prediction, sinks, jobs, ovf_count,
+                                                        next_job_big, (Epa2Arena_big*)ctx->epa_big_arena, 1, fin_recs, fin_count, ovf_list, nullptr, nullptr);
         pb2_phase_mark(ctx, 2);
         if (split_finish) {
             PB2_LAUNCHED(ctx);

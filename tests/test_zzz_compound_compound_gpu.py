@@ -43,8 +43,8 @@ def test_compound_compound_vs_oracle(ctx, oracle):
     ro, rs, rp = T.contact_compound_compound(C.first, C.count, C.part_shape, C.part_pose, a, p1, b, p2, 0.05, threads=8)
     go, gs, gp = C.contact_compounds(a, p1, b, p2, 0.05)
     assert 0.2 < (rs == 1).mean() < 0.9
-    host = gs == 3                                   # EPA arena overflow on the GPU: documented host fallback
-    assert host.sum() <= 5
+    host = gs == 3                                   # none: EPA runs beyond the hot arena go to the overflow kernel
+    assert host.sum() == 0
     ok = ~host
     assert (gs[ok] == rs[ok]).all(), np.nonzero((gs != rs) & ok)[0][:10]
     some = ok & (rs == 1)
