@@ -166,7 +166,9 @@ struct GjkEpaStats { int gjk_iters = 0; bool used_epa = false; EpaStats epa; };
 // (with_params, :40-61: a caller-supplied init_dir — contact_manifolds_pfm_pfm.rs:66 passes last frame's manifold normal — replaces
 // the default first direction)
 static inline int contact_support_map_support_map(const Iso& pos12, const SupportShape& g1, const SupportShape& g2, Real prediction, Contact& c,
-                                                  GjkEpaStats* stats = nullptr, const Vec3* init_dir = nullptr) {
+                                                  GjkEpaStats* stats = nullptr, const Vec3* init_dir = nullptr, Vec3* noint_dir = nullptr) {
+    // noint_dir: the `dir` of GJKResult::NoIntersection(dir) when that is the answer (gjk.rs:387: the last search direction; +x after
+    // 100 iterations or when EPA fails, contact_support_map_support_map.rs:76) — contact_manifolds_pfm_pfm.rs:151-154 caches it
     VoronoiSimplex simplex;
     Vec3 dir;
     if (init_dir) dir = *init_dir;
@@ -179,9 +181,9 @@ static inline int contact_support_map_support_map(const Iso& pos12, const Suppor
         EPA epa;
         bool ok = epa.closest_points(pos12, g1, g2, simplex, p1, p2_1, n1);
         if (stats) { stats->used_epa = true; stats->epa = epa.stats; }
-        if (!ok) return CONTACT_NONE;  // "Everything failed" => NoIntersection => None
+        if (!ok) { if (noint_dir) *noint_dir = Vec3(1, 0, 0); return CONTACT_NONE; }  // "Everything failed" => NoIntersection(+x) => None
     } else if (r.kind == GJKResult::CLOSEST_POINTS) { p1 = r.p1; p2_1 = r.p2; n1 = r.dir; }
-    else return CONTACT_NONE;
+    else { if (noint_dir) *noint_dir = r.dir; return CONTACT_NONE; }
     c.dist = dot(p2_1 - p1, n1);
     c.point1 = p1;
     c.point2 = pos12.inverse_transform_point(p2_1);

@@ -299,7 +299,13 @@ static inline bool manifold_pfm_pfm(const Iso& pos12, const ShapeRef& s1, const 
                                     Real prediction, Manifold& m, const Vec3* init_dir = nullptr) {
     m.clear();
     Contact c;
-    if (contact_support_map_support_map(pos12, s1.support(), s2.support(), prediction, c, nullptr, init_dir) != CONTACT_SOME) return false;
+    Vec3 noint;
+    if (contact_support_map_support_map(pos12, s1.support(), s2.support(), prediction, c, nullptr, init_dir, &noint) != CONTACT_SOME) {
+        // GJKResult::NoIntersection(dir) => manifold.local_n1 = *dir ("use the manifold normal as a cache", :151-154). The reference
+        // leaves local_n2 as it was; nothing reads it on an empty manifold, it is recorded as zero here and on the GPU.
+        m.local_n1 = noint; m.local_n2 = Vec3();
+        return false;
+    }
     // c: point1 = p1, point2 = pos12^-1 p2_1, normal1 = dir, normal2 = pos12^-1 (-dir), dist = (p2_1 - p1) . dir
     Vec3 local_n1 = c.normal1, local_n2 = c.normal2;
     PolyFeature f1 = s1.kind == SHAPE_CUBOID ? cuboid_support_face(s1.half_extents, local_n1) : hull_local_support_feature(s1, *t1, local_n1);
@@ -349,7 +355,7 @@ static inline int dispatch_manifold(const Iso& pos12, const ShapeRef& s1, const 
         bool pfm_ok = (s1.kind == SHAPE_CUBOID || t1) && (s2.kind == SHAPE_CUBOID || t2);
         if (pfm_ok && manifold_try_update_contacts(m, pos12)) { if (kept) *kept = true; return MANIFOLD_OK; }
         // contact_manifolds_pfm_pfm.rs:66: init_dir = Unit::try_new(manifold.local_n1, DEFAULT_EPSILON) seeds the GJK of the recomputation
-        // (seed_gjk = false restates the GPU path, which restarts GJK from the default direction)
+        // (seed_gjk = false restarts GJK from the default direction: kept to measure what the seed changes)
         have_seed = seed_gjk && try_normalize(m.local_n1, DEFAULT_EPSILON, seed);
     }
     m.clear(); m.local_n1 = Vec3(); m.local_n2 = Vec3();

@@ -331,6 +331,9 @@ struct PairSrc {
     const float4* mesh_tris;
     uint32_t n_first, n_second;   // index bounds for ab[2k] / ab[2k+1]
     uint32_t flags = 0;           // PAIR_* below
+    const float* init_dir = nullptr;   // optional GJK seed of the support-map arm (contact_manifolds_pfm_pfm.rs:66: last frame's
+                                       // manifold.local_n1): init_dir[init_stride * i2 .. +3], used when its norm exceeds eps
+    uint32_t init_stride = 3;
     const float* part_pose = nullptr;  // Compound mode (with `ab` = {part, pair}): shape 1 of candidate k is part ab[2k] (shape
                                        // shape1[part] at part_pose[part] inside the compound posed at pos1[pair]); shape 2 is
                                        // shape2[pair] at pos2[pair]. Implies local frames (of the part and of shape 2).
@@ -449,6 +452,7 @@ struct OutSinks {
     unsigned long long cap;
     unsigned long long* compact_count;
     unsigned long long* some_count;
+    float* noint_dir = nullptr;   // n x 3 or NULL: the last search direction of support-map pairs GJK answered NoIntersection for
 };
 
 __device__ __forceinline__ void store_contact(float* o, const ContactOut& c) {
@@ -502,11 +506,18 @@ __device__ __forceinline__ int closed_form_pair(const PairSetup& ps, float predi
 }
 
 // First simplex of the pair's GJK problem.
-__device__ __forceinline__ void gjk_start(const PairSetup& ps, Simplex& s) {
+__device__ __forceinline__ void gjk_start(const PairSetup& ps, Simplex& s, const PairSrc& src, uint32_t k) {
     V3 dir; float nn;
     if (ps.mode == 1) {
-        // contact_support_map_support_map_with_params (contact_support_map_support_map.rs:40-61)
-        if (!try_normalize_get(ps.pos12.t, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
+        // contact_support_map_support_map_with_params (contact_support_map_support_map.rs:40-61): init_dir if the caller has one
+        // (Unit::try_new(manifold.local_n1, eps), contact_manifolds_pfm_pfm.rs:66), else the direction of pos12's translation, else +x
+        bool seeded = false;
+        if (src.init_dir) {
+            uint32_t i2 = src.ab ? src.ab[2ull * k + 1] : k;
+            const float* q = src.init_dir + (size_t)src.init_stride * i2;
+            seeded = try_normalize_get(mk3(q[0], q[1], q[2]), PB2_EPS, dir, nn);
+        }
+        if (!seeded && !try_normalize_get(ps.pos12.t, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
         sx_reset(s, cso_from_shapes(ps.gpos12, ps.g1, ps.g2, dir));
     } else {
         // point_support_map.rs:26-31: dir = normalize(point) or +x; support with m_inv = Isometry(point)
@@ -549,7 +560,7 @@ __global__ void __launch_bounds__(128, MINB) k_contact_gjk(const uint8_t* __rest
         st = closed_form_pair(ps, prediction, c);
     } else {
         Simplex s;
-        gjk_start(ps, s);
+        gjk_start(ps, s, src, k);
         V3 p1, p2, n1;
         float max_dist = ps.mode == 1 ? prediction : FLT_MAX;
         int r = gjk_closest_points(ps.gpos12, ps.g1, ps.g2, max_dist, s, p1, p2, n1);
@@ -560,6 +571,8 @@ __global__ void __launch_bounds__(128, MINB) k_contact_gjk(const uint8_t* __rest
             st = finish_gjk_pair(ps, false, p1, p2, n1, prediction, c);
         } else {
             st = ST_NONE;
+            // GJKResult::NoIntersection(dir): the pfm_pfm manifold arm caches dir for next frame's GJK (contact_manifolds_pfm_pfm.rs:151-154)
+            if (out.noint_dir && ps.mode == 1) { float* q = out.noint_dir + 3ull * k; q[0] = n1.x; q[1] = n1.y; q[2] = n1.z; }
         }
     }
     if (st == ST_SOME) to_world(ps, c);
@@ -638,7 +651,7 @@ __global__ void __launch_bounds__(128, MINB) k_contact_gjk_persistent(const uint
                             if (st == ST_SOME) to_world(ps, c);
                             emit(out, k, st, c);
                         } else {
-                            gjk_start(ps, s);
+                            gjk_start(ps, s, src, k);
                             gpos12 = ps.gpos12; g1 = ps.g1; g2 = ps.g2;
                             max_dist = ps.mode == 1 ? prediction : FLT_MAX;
                             proj = sx_project_origin_and_reduce(s);
@@ -1283,9 +1296,10 @@ __global__ void __launch_bounds__(128, 4) k_contact_epac(const uint8_t* __restri
 static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
                         const float* pos2, float prediction, uint32_t n, OutSinks sinks, const uint32_t* ab = nullptr, uint32_t n_colliders = 0,
                         const float4* mesh_tris = nullptr, uint32_t n_tris = 0, uint32_t flags = 0, const float* part_pose = nullptr,
-                        uint32_t n_parts = 0) {
+                        uint32_t n_parts = 0, const float* init_dir = nullptr, uint32_t init_stride = 3) {
     PairSrc src;
     src.flags = flags;
+    src.init_dir = init_dir; src.init_stride = init_stride;
     src.part_pose = part_pose;
     src.shape1 = shape1; src.shape2 = shape2; src.pos1 = pos1; src.pos2 = pos2; src.ab = ab; src.mesh_tris = mesh_tris;
     src.n_first = mesh_tris ? n_tris : (part_pose ? n_parts : n_colliders); src.n_second = n_colliders;
@@ -2633,7 +2647,7 @@ __global__ void __launch_bounds__(128) k_manifold_pfm(const uint8_t* __restrict_
                               HullTopo topo, const uint32_t* __restrict__ shape1, const uint32_t* __restrict__ shape2, const float* __restrict__ pos1,
                               const float* __restrict__ pos2, const uint32_t* __restrict__ parked, uint32_t count, const float* __restrict__ contacts,
                               const uint8_t* __restrict__ cstatus, uint32_t max_points, float* __restrict__ normals, uint32_t* __restrict__ counts,
-                              float* __restrict__ pts, uint8_t* __restrict__ status) {
+                              float* __restrict__ pts, uint8_t* __restrict__ status, const float* __restrict__ noint_dir) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     uint32_t k = parked[i];
@@ -2665,7 +2679,13 @@ __global__ void __launch_bounds__(128) k_manifold_pfm(const uint8_t* __restrict_
         }
     }
     if (m.overflow) st = MAN_OVERFLOW;
-    if (m.count == 0) { n1 = mk3(0.f, 0.f, 0.f); n2 = n1; }
+    if (m.count == 0) {
+        n1 = mk3(0.f, 0.f, 0.f); n2 = n1;
+        // GJKResult::NoIntersection(dir) => manifold.local_n1 = dir: "use the manifold normal as a cache" for next frame's GJK
+        // (contact_manifolds_pfm_pfm.rs:151-154; EPA's "everything failed" answers NoIntersection(+x), the array's initial value)
+        if (cstatus[i] == ST_NONE && kinds[shape1[k]] != PB2_SHAPE_BALL && kinds[shape2[k]] != PB2_SHAPE_BALL)
+            n1 = mk3(noint_dir[3ull * i], noint_dir[3ull * i + 1], noint_dir[3ull * i + 2]);
+    }
     float* nq = normals + 6ull * k;
     nq[0] = n1.x; nq[1] = n1.y; nq[2] = n1.z; nq[3] = n2.x; nq[4] = n2.y; nq[5] = n2.z;
     for (uint32_t j = m.count; j < max_points; ++j) { float* o = m.pts + 9ull * j; for (int q = 0; q < 9; ++q) o[q] = 0.0f; }
@@ -2674,12 +2694,20 @@ __global__ void __launch_bounds__(128) k_manifold_pfm(const uint8_t* __restrict_
 }
 
 // The device side of pb2_contact_manifolds_batch on device-resident arrays; pairs with skip[k] != 0 (optional) are left untouched.
+__global__ void k_fill_xaxis(float* __restrict__ d, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { d[3ull * i] = 1.0f; d[3ull * i + 1] = 0.0f; d[3ull * i + 2] = 0.0f; }
+}
+
+// d_seed (optional, n x 6): last frame's manifold normals; local_n1 seeds the GJK of the pfm_pfm arm (contact_manifolds_pfm_pfm.rs:66).
+// It may alias d_nr: the contact kernels read it before k_manifold_pfm writes the new normals.
 static int manifolds_device(pb2_ctx* ctx, const pb2_shapes* shapes, const void* d_s1, const void* d_s2, const void* d_p1, const void* d_p2,
-                            float prediction, uint32_t n, uint32_t max_points, void* d_nr, void* d_ct, void* d_pt, void* d_st, const uint8_t* d_skip) {
+                            float prediction, uint32_t n, uint32_t max_points, void* d_nr, void* d_ct, void* d_pt, void* d_st, const uint8_t* d_skip,
+                            const float* d_seed = nullptr) {
     cudaStream_t st = ctx->stream;
     const bool have_topology = shapes->face_normal != nullptr;
     uint32_t *d_parked = nullptr, *d_ab = nullptr;
-    float* d_c = nullptr;
+    float *d_c = nullptr, *d_dir = nullptr;
     uint8_t* d_cst = nullptr;
     unsigned long long* parked_count = (unsigned long long*)(ctx->d_counters + 10);
     int rc = PB2_OK;
@@ -2698,16 +2726,18 @@ static int manifolds_device(pb2_ctx* ctx, const pb2_shapes* shapes, const void* 
         uint32_t cnt = rc == PB2_OK ? (uint32_t)ctx->h_counters[10] : 0u;
         if (cnt) {
             if (cudaMallocAsync((void**)&d_ab, (size_t)cnt * 8, st) != cudaSuccess || cudaMallocAsync((void**)&d_c, (size_t)cnt * 52, st) != cudaSuccess ||
-                cudaMallocAsync((void**)&d_cst, cnt, st) != cudaSuccess) rc = PB2_ERR_CUDA;
+                cudaMallocAsync((void**)&d_cst, cnt, st) != cudaSuccess || cudaMallocAsync((void**)&d_dir, (size_t)cnt * 12, st) != cudaSuccess) rc = PB2_ERR_CUDA;
             if (rc == PB2_OK) {
                 k_pair_up<<<pb2_blocks(cnt, 256), 256, 0, st>>>(d_parked, cnt, d_ab);
-                PB2_LAUNCHED(ctx);
+                k_fill_xaxis<<<pb2_blocks(cnt, 256), 256, 0, st>>>(d_dir, cnt);
+                ctx->launches += 2;
                 OutSinks sinks;
+                sinks.noint_dir = d_dir;
                 sinks.dense = d_c; sinks.status = d_cst; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
                 sinks.compact_count = nullptr; sinks.some_count = nullptr;
                 // contact_support_map_support_map_with_params(pos12, pfm1, pfm2, prediction, .., None): the contact kernels, local frames
                 rc = run_contacts(ctx, shapes, (const uint32_t*)d_s1, (const uint32_t*)d_s2, (const float*)d_p1, (const float*)d_p2, prediction, cnt, sinks,
-                                  d_ab, n, nullptr, 0, PAIR_LOCAL_FRAMES);
+                                  d_ab, n, nullptr, 0, PAIR_LOCAL_FRAMES, nullptr, 0, d_seed, 6);
             }
             if (rc == PB2_OK) {
                 HullTopo topo;
@@ -2718,10 +2748,11 @@ static int manifolds_device(pb2_ctx* ctx, const pb2_shapes* shapes, const void* 
                 topo.eav = shapes->edges_adj_to_vertex; topo.hull_edge_first = shapes->hull_edge_first; topo.edge_dir = shapes->edge_dir;
                 k_manifold_pfm<<<pb2_blocks(cnt, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points4, topo, (const uint32_t*)d_s1,
                                                                     (const uint32_t*)d_s2, (const float*)d_p1, (const float*)d_p2, d_parked, cnt, d_c, d_cst,
-                                                                    max_points, (float*)d_nr, (uint32_t*)d_ct, (float*)d_pt, (uint8_t*)d_st);
+                                                                    max_points, (float*)d_nr, (uint32_t*)d_ct, (float*)d_pt, (uint8_t*)d_st, d_dir);
                 PB2_LAUNCHED(ctx);
             }
         }
+        if (d_dir) cudaFreeAsync(d_dir, st);
         if (d_parked) cudaFreeAsync(d_parked, st);
         if (d_ab) cudaFreeAsync(d_ab, st);
         if (d_c) cudaFreeAsync(d_c, st);
@@ -2847,7 +2878,8 @@ extern "C" int pb2_contact_manifolds_update_batch(pb2_ctx* ctx, const pb2_shapes
                                                                   PB2_COS_1_DEGREES, PB2_UPDATE_DIST_SQ, (const float*)d_nr, (const uint32_t*)d_ct,
                                                                   (float*)d_pt, d_kp, (uint8_t*)d_st, d_of, d_oc);
         PB2_LAUNCHED(ctx);
-        rc = manifolds_device(ctx, shapes, d_s1, d_s2, d_p1, d_p2, prediction, n, max_points, d_nr, d_ct, d_pt, d_st, d_kp);
+        // last frame's normals double as the GJK seed of the pairs that are recomputed
+        rc = manifolds_device(ctx, shapes, d_s1, d_s2, d_p1, d_p2, prediction, n, max_points, d_nr, d_ct, d_pt, d_st, d_kp, (const float*)d_nr);
     }
     if (rc == PB2_OK && match) {
         k_manifold_match<<<pb2_blocks(n, 128), 128, 0, st>>>(d_kp, d_of, d_oc, (const uint32_t*)d_ct, (const float*)d_pt, n, max_points, d_mt);
@@ -2919,7 +2951,7 @@ __global__ void __launch_bounds__(128) k_closest_points(const uint8_t* __restric
             else kind = 2;
         } else {
             Simplex s;
-            gjk_start(ps, s);
+            gjk_start(ps, s, src, k);
             V3 q1, q2, n1;
             int r = gjk_closest_points<true>(ps.gpos12, ps.g1, ps.g2, FLT_MAX, s, q1, q2, n1);
             if (r == GJK_INTERSECTION) kind = 2;   // centre inside the hull: the contact has dist < 0

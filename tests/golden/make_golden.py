@@ -210,7 +210,7 @@ def second_frame():
     moved = z["pos2"].copy()
     moved[:, 4:] += (g.standard_normal((n, 3)) * np.where(g.random((n, 1)) < 0.5, 2.0e-4, 0.05)).astype(np.float32)
     rn, rc, rp, rs, rk, rm = T.contact_manifolds_update(z["shape1"], z["pos1"], z["shape2"], moved, 0.05, z["normals"], z["counts"], z["man_points"],
-                                                        topology=topo)
+                                                        topology=topo, seed_gjk=True)   # round 2: the reference's GJK seed (pfm_pfm.rs:63-66)
     y = np.load(os.path.join(HERE, "siblings_3000.npz"))
     T2 = oracle.ShapeTable([])
     T2.kinds, T2.params, T2.points = y["kinds"].copy(), y["params"].copy(), np.ascontiguousarray(y["points"])
