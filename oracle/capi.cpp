@@ -389,7 +389,12 @@ static void manifolds_batch_impl(const uint8_t* kinds, const float* params4, con
             uint32_t cnt = (uint32_t)m.points.size();
             if (cnt > max_points) { st = 4; cnt = max_points; }
             if (cnt) { st3(normals + 6 * k, m.local_n1); st3(normals + 6 * k + 3, m.local_n2); }
-            else for (int i = 0; i < 6; ++i) normals[6 * k + i] = 0.0f;
+            else {
+                for (int i = 0; i < 6; ++i) normals[6 * k + i] = 0.0f;
+                // an empty pfm_pfm manifold keeps the direction GJK answered NoIntersection with (next frame's seed)
+                bool pfm = st == MANIFOLD_OK && s1.kind != SHAPE_BALL && s2.kind != SHAPE_BALL && !(s1.kind == SHAPE_CUBOID && s2.kind == SHAPE_CUBOID);
+                if (pfm && !was_kept) st3(normals + 6 * k, m.local_n1);
+            }
             counts[k] = cnt; status[k] = (uint8_t)st;
             float* q = pts + (size_t)k * max_points * 9;
             for (uint32_t i = 0; i < max_points; ++i) {
