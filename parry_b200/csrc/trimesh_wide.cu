@@ -44,12 +44,10 @@ __device__ __forceinline__ F8 ldg256(const float4* p) {   // p 32-byte aligned; 
 #define W8_GAMMA 1.00000095367431640625f  // 1 + 2^-20
 
 // ------------------------------------------------------------------------------------------------ build
-// One thread per wide node of the current BFS level. wroot[w] = binary (Karras) node collapsed into wide node w.
-__global__ void k_collapse8(const NodeWide* __restrict__ nodes, uint32_t* __restrict__ wroot, uint32_t w_begin, uint32_t w_end,
+// Collapses the binary subtree rooted at wroot[w] into wide node w (one thread).
+__device__ __forceinline__ void collapse8_node(const NodeWide* __restrict__ nodes, uint32_t* __restrict__ wroot, uint32_t w,
                             uint32_t* __restrict__ total, float4* __restrict__ nodes8, uint32_t* __restrict__ leafpos,
                             uint32_t* __restrict__ nleaf) {
-    uint32_t w = w_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= w_end) return;
     uint32_t ref[8], lc[8];  // lc = leaves below the child; bit 31 = "being flattened" (see below)
     float lo[8][3], hi[8][3];
     int cnt = 0;
@@ -195,6 +193,26 @@ __global__ void k_collapse8(const NodeWide* __restrict__ nodes, uint32_t* __rest
     out[5] = make_float4(0.f, 0.f, 0.f, 0.f);   // padding to 96 bytes (never read by the kernels' arithmetic)
 }
 
+// One thread per wide node of the current BFS level. wroot[w] = binary node collapsed into wide node w.
+// The level loop runs without the host (round 1 read the node count back and synchronised after every level): launch `level` of a
+// fixed series works on the wide nodes [bounds[level], *total) — *total is final when the launch starts because the previous launch
+// has completed — and leaves its own end in bounds[level + 1] for the next one. Launches past the last level find an empty range.
+__global__ void k_collapse8(const NodeWide* __restrict__ nodes, uint32_t* __restrict__ wroot, uint32_t* __restrict__ bounds, uint32_t level,
+                            uint32_t* __restrict__ total, float4* __restrict__ nodes8, uint32_t* __restrict__ leafpos,
+                            uint32_t* __restrict__ nleaf) {
+    const uint32_t w_begin = bounds[level], w_end = bounds[W8_MAX_LEVELS_GROUPS + 2 + level];   // end: snapshot taken by k_collapse8_level
+    for (uint32_t w = w_begin + blockIdx.x * blockDim.x + threadIdx.x; w < w_end; w += gridDim.x * blockDim.x)
+        collapse8_node(nodes, wroot, w, total, nodes8, leafpos, nleaf);
+}
+// Snapshot of the level's range (one thread, between two collapse launches): bounds[level] = begin, bounds[.. + level] = end = *total.
+__global__ void k_collapse8_level(uint32_t* __restrict__ bounds, uint32_t level, const uint32_t* __restrict__ total) {
+    uint32_t begin = level == 0 ? 0u : bounds[W8_MAX_LEVELS_GROUPS + 2 + level - 1];
+    uint32_t end = *total;
+    bounds[level] = begin;
+    bounds[W8_MAX_LEVELS_GROUPS + 2 + level] = end;
+    if (begin < end) bounds[W8_MAX_LEVELS_GROUPS + 1] = level + 1;   // number of non-empty levels so far
+}
+
 // Writes each node's first-triangle index and gathers the triangles into (wide node, slot) order.
 __global__ void k_finalize8(uint32_t n8, const uint32_t* __restrict__ tri_base, const uint32_t* __restrict__ leafpos,
                             const float4* __restrict__ tris, float4* __restrict__ nodes8, float4* __restrict__ tris8) {
@@ -221,44 +239,55 @@ int pb2_wide_build(pb2_ctx* ctx, pb2_trimesh* mesh) {
     if (off && atoi(off)) return PB2_OK;
     cudaStream_t st = ctx->stream;
     uint32_t nn = b->n_nodes;
-    uint32_t *wroot = nullptr, *leafpos = nullptr, *nleaf = nullptr, *tbase = nullptr, *total = nullptr;
-    float4* tmp8 = nullptr;
-    void* cub_tmp = nullptr;
+    // One stream-ordered allocation for every temporary (round 1: six cudaMalloc / cudaFree pairs), no host round trip per level:
+    // a fixed series of W8_MAX_LEVELS_GROUPS launch pairs whose ranges live on the device (see k_collapse8), then ONE
+    // synchronisation to learn the node count the final arrays are sized with.
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)nn, st);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t n_bounds = 2 * (W8_MAX_LEVELS_GROUPS + 2);
+    size_t o_wroot = 0, o_leafpos = o_wroot + up((size_t)nn * 4), o_nleaf = o_leafpos + up((size_t)nn * 32), o_tbase = o_nleaf + up((size_t)nn * 4);
+    size_t o_bounds = o_tbase + up((size_t)nn * 4), o_total = o_bounds + up(n_bounds * 4), o_tmp8 = o_total + 256;
+    size_t o_cub = o_tmp8 + up((size_t)nn * 16 * W8_NODE_F4), bytes = o_cub + up(cub_bytes ? cub_bytes : 1);
+    char* base = nullptr;
+    PB2_CUDA(ctx, cudaMallocAsync((void**)&base, bytes, st));
+    uint32_t *wroot = (uint32_t*)(base + o_wroot), *leafpos = (uint32_t*)(base + o_leafpos), *nleaf = (uint32_t*)(base + o_nleaf);
+    uint32_t *tbase = (uint32_t*)(base + o_tbase), *bounds = (uint32_t*)(base + o_bounds), *total = (uint32_t*)(base + o_total);
+    float4* tmp8 = (float4*)(base + o_tmp8);
     int s = PB2_OK;
     auto fail = [&](cudaError_t e, const char* what) {
         if (e != cudaSuccess && s == PB2_OK) { snprintf(ctx->err, sizeof(ctx->err), "wide build (%s): %s", what, cudaGetErrorString(e)); s = PB2_ERR_CUDA; }
         return e != cudaSuccess;
     };
     do {
-        if (fail(cudaMalloc((void**)&wroot, (size_t)nn * 4), "alloc")) break;
-        if (fail(cudaMalloc((void**)&leafpos, (size_t)nn * 32), "alloc")) break;
-        if (fail(cudaMalloc((void**)&nleaf, (size_t)nn * 4), "alloc")) break;
-        if (fail(cudaMalloc((void**)&tbase, (size_t)nn * 4), "alloc")) break;
-        if (fail(cudaMalloc((void**)&total, 4), "alloc")) break;
-        if (fail(cudaMalloc((void**)&tmp8, (size_t)nn * 16 * W8_NODE_F4), "alloc")) break;
         uint32_t one = 1, zero = 0;
+        if (fail(cudaMemsetAsync(bounds, 0, n_bounds * 4, st), "init")) break;
         if (fail(cudaMemcpyAsync(total, &one, 4, cudaMemcpyHostToDevice, st), "init")) break;
         if (fail(cudaMemcpyAsync(wroot, &zero, 4, cudaMemcpyHostToDevice, st), "init")) break;
-        uint32_t begin = 0, end = 1;
-        int levels = 0;
-        while (begin < end) {
-            k_collapse8<<<pb2_blocks(end - begin, 128), 128, 0, st>>>(b->nodes, wroot, begin, end, total, tmp8, leafpos, nleaf);
-            PB2_LAUNCHED(ctx);
-            uint32_t t = 0;
-            if (fail(cudaMemcpyAsync(&t, total, 4, cudaMemcpyDeviceToHost, st), "level")) break;
-            if (fail(cudaStreamSynchronize(st), "level")) break;
-            begin = end;
-            end = t;
-            levels++;
+        unsigned grid = pb2_blocks(nn, 128);
+        unsigned cap = (unsigned)ctx->sm_count * 16u;
+        if (grid > cap) grid = cap;
+        for (uint32_t level = 0; level < W8_MAX_LEVELS_GROUPS; ++level) {
+            k_collapse8_level<<<1, 1, 0, st>>>(bounds, level, total);
+            // the first levels hold 1, 8, 64 ... nodes: a small grid until the range can be large (8^level nodes at most)
+            unsigned g = level < 8 ? (unsigned)min((unsigned long long)grid, ((1ull << (3 * level)) + 127ull) / 128ull) : grid;
+            k_collapse8<<<g ? g : 1, 128, 0, st>>>(b->nodes, wroot, bounds, level, total, tmp8, leafpos, nleaf);
+            ctx->launches += 2;
         }
-        if (s != PB2_OK) break;
-        if (levels > W8_MAX_LEVELS_GROUPS) break;  // degenerate (very deep) tree: keep the binary-tree kernels
+        uint32_t h[2] = {0, 0};   // {levels, node count}
+        if (fail(cudaMemcpyAsync(&h[0], bounds + W8_MAX_LEVELS_GROUPS + 1, 4, cudaMemcpyDeviceToHost, st), "levels")) break;
+        if (fail(cudaMemcpyAsync(&h[1], total, 4, cudaMemcpyDeviceToHost, st), "levels")) break;
+        if (fail(cudaStreamSynchronize(st), "levels")) break;
+        // did the series end on an empty level? (the last launch pair must have found nothing to do)
+        uint32_t last[2] = {0, 0};
+        if (fail(cudaMemcpyAsync(&last[0], bounds + W8_MAX_LEVELS_GROUPS - 1, 4, cudaMemcpyDeviceToHost, st), "levels")) break;
+        if (fail(cudaMemcpyAsync(&last[1], bounds + W8_MAX_LEVELS_GROUPS + 2 + W8_MAX_LEVELS_GROUPS - 1, 4, cudaMemcpyDeviceToHost, st), "levels")) break;
+        if (fail(cudaStreamSynchronize(st), "levels")) break;
+        if (last[0] < last[1]) break;  // degenerate (very deep) tree: keep the binary-tree kernels
+        const int levels = (int)h[0];
         mesh->levels8 = levels;
-        uint32_t n8 = end;
-        size_t cub_bytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n8, st);
-        if (fail(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 1), "alloc")) break;
-        if (fail(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, nleaf, tbase, (int)n8, st), "scan")) break;
+        uint32_t n8 = h[1];
+        if (fail(cub::DeviceScan::ExclusiveSum(base + o_cub, cub_bytes, nleaf, tbase, (int)n8, st), "scan")) break;
         ctx->launches += 2;
         if (fail(cudaMalloc((void**)&mesh->nodes8, (size_t)n8 * 16 * W8_NODE_F4), "alloc")) break;
         if (fail(cudaMalloc((void**)&mesh->tris8, (size_t)mesh->nt * 16 * W8_TRI_F4), "alloc")) break;
@@ -266,10 +295,10 @@ int pb2_wide_build(pb2_ctx* ctx, pb2_trimesh* mesh) {
         k_finalize8<<<pb2_blocks(n8, 128), 128, 0, st>>>(n8, tbase, leafpos, mesh->tris, mesh->nodes8, mesh->tris8);
         PB2_LAUNCHED(ctx);
         if (fail(cudaGetLastError(), "finalize")) break;
-        if (fail(cudaStreamSynchronize(st), "finalize")) break;
         mesh->n_nodes8 = n8;
     } while (0);
-    cudaFree(wroot); cudaFree(leafpos); cudaFree(nleaf); cudaFree(tbase); cudaFree(total); cudaFree(tmp8); cudaFree(cub_tmp);
+    cudaFreeAsync(base, st);
+    if (s == PB2_OK && mesh->n_nodes8) { if (fail(cudaStreamSynchronize(st), "finalize")) mesh->n_nodes8 = 0; }
     if (s != PB2_OK || mesh->n_nodes8 == 0) {
         if (mesh->nodes8) cudaFree(mesh->nodes8);
         if (mesh->tris8) cudaFree(mesh->tris8);
