@@ -30,7 +30,7 @@ FMAX = float(np.finfo(np.float32).max)
 # launch) is read from profiles/r2_traffic.json and only used when the capture there was taken from a kernel of the same name AND
 # version string; otherwise it is null (a stale capture must not stand in for the current code).
 RAY_KERNEL = "k_raycast_wide_shared<false>"
-RAY_KERNEL_VERSION = "r2.2 staged 32-ray refill; 96 B nodes / 64 B triangles read with LDG.E.256; order-independent ties"
+RAY_KERNEL_VERSION = "r2.3 staged 32-ray refill; 96 B nodes / 64 B triangles read with LDG.E.256; order-independent ties; 8 CTAs per SM"
 EPA_KERNEL = "k_contact_epa2"
 EPA_KERNEL_VERSION = "r2.2 32-byte face records (one 256-bit load), neighbour records requested with the vertex, 16-entry shared heap head"
 
