@@ -460,8 +460,13 @@ def main():
                 json.dump(also, f, indent=1)
         except Exception:
             pass
-        line["also"] = {k: ({kk: vv for kk, vv in val.items() if kk in ("value", "unit", "ms", "error", "n_gpus", "efficiency_note")} if isinstance(val, dict) else val)
-                        for k, val in also.items()}
+        def brief(val):
+            if not isinstance(val, dict):
+                return val
+            if "value" in val or "error" in val:
+                return {kk: vv for kk, vv in val.items() if kk in ("value", "unit", "ms", "error", "n_gpus")}
+            return {kk: brief(vv) for kk, vv in val.items() if isinstance(vv, dict)}   # groups of workloads: one number each
+        line["also"] = {k: brief(val) for k, val in also.items()}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -542,20 +547,20 @@ def bench_also(ctx, stream, args, hbm_peak, flush=None):
         except Exception as e:  # a secondary workload must not take the headline down
             out[name] = {"error": repr(e)}
     if int(os.environ.get("WORLD_SIZE", "1")) == 1:
-        # paths that have not run on hardware yet: last, never in a multi-rank job, and in a child process with a timeout, so that
+        # manifold persistence and Compound-vs-Compound: in a child process with a timeout (the two largest allocations of the run), so that
         # neither a device fault nor a crash or hang there can reach this process and its JSON line
         try:
             env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(ctx.device)))
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--first-hw-child"], capture_output=True, text=True, timeout=420, env=env)
             lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
-            out["first_hardware_runs"] = json.loads(lines[-1]) if lines else {"error": "child rc=%d: %s" % (r.returncode, r.stderr[-300:])}
+            out["persistence_and_compound_pairs"] = json.loads(lines[-1]) if lines else {"error": "child rc=%d: %s" % (r.returncode, r.stderr[-300:])}
         except Exception as e:
-            out["first_hardware_runs"] = {"error": repr(e)}
+            out["persistence_and_compound_pairs"] = {"error": repr(e)}
     return out
 
 
 def first_hw_child():
-    """Child process of bench_also: times the not-yet-run paths on device 0 of its own CUDA context and prints one JSON object."""
+    """Child process of bench_also: times manifold persistence and Compound-vs-Compound contacts on device 0 of its own CUDA context and prints one JSON object."""
     try:
         import torch
         import parry_b200
@@ -563,7 +568,7 @@ def first_hw_child():
         torch.cuda.set_device(0)
         ctx = parry_b200.Context(0)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-        res = also_first_hardware_runs(ctx, ctx.torch_stream(), make_timed(ctx, ctx.torch_stream()), flush, hbm_peak)
+        res = also_persistence_and_compounds(ctx, ctx.torch_stream(), make_timed(ctx, ctx.torch_stream()), flush, hbm_peak)
     except Exception as e:
         res = {"error": repr(e)}
     print(json.dumps(res), flush=True)
@@ -903,7 +908,7 @@ def also_siblings(ctx, stream, timed, flush, hbm_peak):
     return out
 
 
-def also_first_hardware_runs(ctx, stream, timed, flush, hbm_peak):
+def also_persistence_and_compounds(ctx, stream, timed, flush, hbm_peak):
     """The two SURVEY §8 (f) paths written after this round's GPU budget was spent, run LAST so that a
     failure cannot touch any other entry: manifold persistence (second frame of 2^22 ball / cuboid pairs, half of them drifting by
     2e-4 — most of those keep their manifold — and half by 0.05) and Compound vs Compound contacts (2^20 pairs of 1-5 parts)."""
