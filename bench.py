@@ -909,8 +909,7 @@ def also_siblings(ctx, stream, timed, flush, hbm_peak):
 
 
 def also_persistence_and_compounds(ctx, stream, timed, flush, hbm_peak):
-    """The two SURVEY §8 (f) paths written after this round's GPU budget was spent, run LAST so that a
-    failure cannot touch any other entry: manifold persistence (second frame of 2^22 ball / cuboid pairs, half of them drifting by
+    """Two SURVEY §8 (f) paths: manifold persistence (second frame of 2^22 ball / cuboid pairs, half of them drifting by
     2e-4 — most of those keep their manifold — and half by 0.05) and Compound vs Compound contacts (2^20 pairs of 1-5 parts)."""
     import torch
     import parry_b200
