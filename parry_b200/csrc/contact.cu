@@ -1887,13 +1887,13 @@ extern "C" int pb2_intersect_csr_device(pb2_ctx* ctx, const pb2_bvh* bvh, const 
 // shape2.compute_aabb(pose12).loosened(prediction) in the mesh's frame (contact_composite_shape_shape.rs:21)
 __global__ void k_mesh_query_aabbs(const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float* __restrict__ points,
                                    uint32_t n_shapes, const uint32_t* __restrict__ shape_ids, const float* __restrict__ poses,
-                                   const float* __restrict__ mesh_pose, uint32_t n, float prediction, float* __restrict__ out) {
+                                   const float* __restrict__ mesh_pose, uint32_t n, float prediction, bool pos12_given, float* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float* o = out + 6ull * i;
     uint32_t sid = shape_ids[i];
     if (sid >= n_shapes) { o[0] = o[1] = o[2] = FLT_MAX; o[3] = o[4] = o[5] = -FLT_MAX; return; }  // no candidates: reported by the reduce
-    Iso7 pos12 = iso_inv_mul(load_iso(mesh_pose), load_iso(poses + 7ull * i));
+    Iso7 pos12 = pos12_given ? load_iso(poses + 7ull * i) : iso_inv_mul(load_iso(mesh_pose), load_iso(poses + 7ull * i));
     V3 mn, mx;
     shape_aabb_dev(kinds[sid], params[sid], points, pos12, mn, mx);
     o[0] = mn.x + (-prediction); o[1] = mn.y + (-prediction); o[2] = mn.z + (-prediction);
@@ -1937,20 +1937,12 @@ __global__ void k_mesh_reduce(const uint32_t* __restrict__ offsets, const uint32
 
 extern "C" {
 
-int pb2_trimesh_contact_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* mesh_pose7, const pb2_shapes* shapes, const uint32_t* shape_ids,
-                               const float* poses7, uint32_t n, float prediction, pb2_contact* out, uint8_t* status, uint32_t* part, int mem) {
-    if (!ctx || !mesh || !shapes || !mesh_pose7 || (n && (!shape_ids || !poses7 || !out || !status || !part))) return PB2_ERR_INVALID;
-    if (n == 0) return PB2_OK;
-    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+// Device side of TriMesh-vs-shape contacts on device-resident arrays (n queries): loosened shape AABB in the mesh frame -> mesh Bvh
+// intersect_aabb (CSR) -> every candidate triangle through the contact kernels -> per-query reduction to the smallest dist.
+// flags = PAIR_LOCAL_FRAMES leaves the contacts in the frames of the mesh and of each shape (what a nested composite dispatch needs).
+static int trimesh_contact_device(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_mpose, const pb2_shapes* shapes, const uint32_t* d_ids,
+                                  const float* d_poses, uint32_t n, float prediction, float* d_out, uint8_t* d_status, uint32_t* d_part, uint32_t flags) {
     cudaStream_t st = ctx->stream;
-    const void *d_ids, *d_poses, *d_mpose;
-    void *d_out, *d_status, *d_part;
-    PB2_CHECK(pb2_stage_in(ctx, 0, shape_ids, (size_t)n * 4, mem, &d_ids));
-    PB2_CHECK(pb2_stage_in(ctx, 2, poses7, (size_t)n * 28, mem, &d_poses));
-    PB2_CHECK(pb2_stage_in(ctx, 3, mesh_pose7, 28, mem, &d_mpose));
-    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * 52, mem, &d_out));
-    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_status));
-    PB2_CHECK(pb2_stage_out(ctx, 6, part, (size_t)n * 4, mem, &d_part));
     float* d_q = nullptr;
     uint32_t *d_off = nullptr, *d_items = nullptr, *d_ab = nullptr;
     float* d_cand = nullptr;
@@ -1960,8 +1952,8 @@ int pb2_trimesh_contact_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const floa
         if (cudaMallocAsync((void**)&d_q, (size_t)n * 24, st) != cudaSuccess || cudaMallocAsync((void**)&d_off, ((size_t)n + 1) * 4, st) != cudaSuccess) {
             snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_shapes: out of memory"); rc = PB2_ERR_CUDA; break;
         }
-        k_mesh_query_aabbs<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points, shapes->n, (const uint32_t*)d_ids,
-                                                              (const float*)d_poses, (const float*)d_mpose, n, prediction, d_q);
+        k_mesh_query_aabbs<<<pb2_blocks(n, 128), 128, 0, st>>>(shapes->kinds, shapes->params, shapes->points, shapes->n, d_ids, d_poses, d_mpose, n, prediction,
+                                                               (flags & PAIR_POS12_GIVEN) != 0, d_q);
         PB2_LAUNCHED(ctx);
         uint64_t total = 0;
         if ((rc = pb2_intersect_csr_device(ctx, &mesh->bvh, d_q, n, true, d_off, &d_items, &total)) != PB2_OK) break;
@@ -1976,11 +1968,9 @@ int pb2_trimesh_contact_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const floa
             OutSinks sinks;
             sinks.dense = d_cand; sinks.status = d_cst; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
             sinks.compact_count = nullptr; sinks.some_count = nullptr;
-            if ((rc = run_contacts(ctx, shapes, nullptr, (const uint32_t*)d_ids, (const float*)d_mpose, (const float*)d_poses, prediction,
-                                   (uint32_t)total, sinks, d_ab, n, mesh->tris, mesh->nt)) != PB2_OK) break;
+            if ((rc = run_contacts(ctx, shapes, nullptr, d_ids, d_mpose, d_poses, prediction, (uint32_t)total, sinks, d_ab, n, mesh->tris, mesh->nt, flags)) != PB2_OK) break;
         }
-        k_mesh_reduce<<<pb2_blocks(n, 128), 128, 0, st>>>(d_off, d_items, mesh->tris, d_cand, d_cst, (const uint32_t*)d_ids, shapes->n, n,
-                                                         (float*)d_out, (uint8_t*)d_status, (uint32_t*)d_part);
+        k_mesh_reduce<<<pb2_blocks(n, 128), 128, 0, st>>>(d_off, d_items, mesh->tris, d_cand, d_cst, d_ids, shapes->n, n, d_out, d_status, d_part);
         PB2_LAUNCHED(ctx);
         if (cudaGetLastError() != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_shapes: launch failed"); rc = PB2_ERR_CUDA; break; }
     } while (0);
@@ -1990,7 +1980,25 @@ int pb2_trimesh_contact_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const floa
     if (d_ab) cudaFreeAsync(d_ab, st);
     if (d_cand) cudaFreeAsync(d_cand, st);
     if (d_cst) cudaFreeAsync(d_cst, st);
-    if (rc != PB2_OK) return rc;
+    return rc;
+}
+
+int pb2_trimesh_contact_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* mesh_pose7, const pb2_shapes* shapes, const uint32_t* shape_ids,
+                               const float* poses7, uint32_t n, float prediction, pb2_contact* out, uint8_t* status, uint32_t* part, int mem) {
+    if (!ctx || !mesh || !shapes || !mesh_pose7 || (n && (!shape_ids || !poses7 || !out || !status || !part))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_ids, *d_poses, *d_mpose;
+    void *d_out, *d_status, *d_part;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape_ids, (size_t)n * 4, mem, &d_ids));
+    PB2_CHECK(pb2_stage_in(ctx, 2, poses7, (size_t)n * 28, mem, &d_poses));
+    PB2_CHECK(pb2_stage_in(ctx, 3, mesh_pose7, 28, mem, &d_mpose));
+    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_status));
+    PB2_CHECK(pb2_stage_out(ctx, 6, part, (size_t)n * 4, mem, &d_part));
+    PB2_CHECK(trimesh_contact_device(ctx, mesh, (const float*)d_mpose, shapes, (const uint32_t*)d_ids, (const float*)d_poses, n, prediction, (float*)d_out,
+                                     (uint8_t*)d_status, (uint32_t*)d_part, 0u));
     PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
     PB2_CHECK(pb2_stage_back(ctx, status, d_status, (size_t)n, mem));
     PB2_CHECK(pb2_stage_back(ctx, part, d_part, (size_t)n * 4, mem));
@@ -2108,6 +2116,98 @@ __global__ void k_compound_reduce(const uint32_t* __restrict__ offsets, const ui
     }
     status[q] = (uint8_t)st;
 }
+
+// Compound (shape 1) against a TriMesh (shape 2): contact_composite_shape_shape(pos12, compound, trimesh)
+// (contact_composite_shape_shape.rs:12-48). Every part whose AABB meets the mesh's root AABB, moved into the compound's frame and
+// loosened, is one TriMesh-vs-shape query with the part's pose in the MESH frame, (part_pos.inv_mul(pos12)).inverse() (:27 and the
+// inverse of contact_shape_composite_shape, :74). pass 0 counts, pass 1 (offsets given) fills {shape id, pose, owner}.
+template <bool FILL>
+__global__ void k_ct_candidates(const NodeWide* __restrict__ mesh_nodes, uint32_t mesh_leaves, const float* __restrict__ mesh_pose,
+                                const uint32_t* __restrict__ comp_first, const uint32_t* __restrict__ comp_count, uint32_t nc,
+                                const uint32_t* __restrict__ part_shape, const float* __restrict__ part_pose, const float* __restrict__ part_aabb,
+                                const uint32_t* __restrict__ compound_id, const float* __restrict__ pos_c, uint32_t n, float prediction,
+                                uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cand_shape,
+                                float* __restrict__ cand_pose, uint32_t* __restrict__ cand_part) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t c = compound_id[k], cnt = 0;
+    if (c < nc && mesh_leaves) {
+        NodeWide w = mesh_nodes[0];   // Bvh::root_aabb (bvh_tree.rs:1991-1999)
+        V3 amn = mk3(w.left.mnx, w.left.mny, w.left.mnz), amx = mk3(w.left.mxx, w.left.mxy, w.left.mxz);
+        if (mesh_leaves > 1) {
+            amn = vmin3(amn, mk3(w.right.mnx, w.right.mny, w.right.mnz));
+            amx = vmax3(amx, mk3(w.right.mxx, w.right.mxy, w.right.mxz));
+        }
+        Iso7 pos12 = iso_inv_mul(load_iso(pos_c + 7ull * k), load_iso(mesh_pose));
+        V3 ctr = iso_point(pos12, (amn + amx) * 0.5f);   // Aabb::transform_by(pos12).loosened(prediction)
+        V3 he = iso_abs_vec(pos12, (amx - amn) * 0.5f);
+        V3 lmn = ctr + (-he), lmx = ctr + he;
+        lmn = mk3(lmn.x + (-prediction), lmn.y + (-prediction), lmn.z + (-prediction));
+        lmx = mk3(lmx.x + prediction, lmx.y + prediction, lmx.z + prediction);
+        uint32_t f = comp_first[c], m = comp_count[c];
+        uint32_t at = FILL ? offsets[k] : 0;
+        for (uint32_t i = 0; i < m; ++i) {
+            if (!aabb6_intersects(part_aabb + 6ull * (f + i), lmn, lmx)) continue;
+            if (FILL) {
+                size_t j = (size_t)at + cnt;
+                cand_shape[j] = part_shape[f + i];
+                Iso7 pose = iso_inverse(iso_inv_mul(load_iso(part_pose + 7ull * (f + i)), pos12));
+                float* o = cand_pose + 7 * j;
+                o[0] = pose.q.i; o[1] = pose.q.j; o[2] = pose.q.k; o[3] = pose.q.w; o[4] = pose.t.x; o[5] = pose.t.y; o[6] = pose.t.z;
+                cand_part[j] = i;
+            }
+            cnt++;
+        }
+    }
+    if (!FILL) counts[k] = cnt;
+}
+
+// The compound side of the reduction (:29-41): candidates are in part order and the first strictly smaller dist wins; each candidate
+// is the flipped TriMesh-vs-part contact; Contact::transform1_by_mut(part_pos) and the caller's two world poses finish it.
+__global__ void k_ct_reduce(const uint32_t* __restrict__ offsets, const float* __restrict__ cand, const uint8_t* __restrict__ cand_status,
+                            const uint32_t* __restrict__ cand_tri, const uint32_t* __restrict__ cand_part, const uint32_t* __restrict__ comp_first,
+                            uint32_t nc, const float* __restrict__ part_pose, const uint32_t* __restrict__ compound_id,
+                            const float* __restrict__ pos_c, const float* __restrict__ mesh_pose, uint32_t n, float* __restrict__ out,
+                            uint8_t* __restrict__ status, uint32_t* __restrict__ parts) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    uint32_t c = compound_id[q];
+    int st = c >= nc ? ST_UNSUPPORTED : ST_NONE;
+    uint32_t best_j = 0;
+    float best = 0.0f;
+    int worst = ST_NONE;
+    if (st == ST_NONE) {
+        for (uint32_t j = offsets[q]; j < offsets[q + 1]; ++j) {
+            int cs = cand_status[j];
+            if (cs >= ST_UNSUPPORTED && worst == ST_NONE) worst = cs;
+            if (cs != ST_SOME) continue;
+            float d = cand[13ull * j + 12];
+            if (st != ST_SOME || d < best) { best = d; best_j = j; st = ST_SOME; }
+        }
+        if (worst != ST_NONE) st = worst;   // one part could not be decided on the device: neither can the minimum
+    }
+    float* o = out + 13ull * q;
+    if (st == ST_SOME) {
+        const float* cj = cand + 13ull * best_j;
+        uint32_t pi = cand_part[best_j];
+        Iso7 pp = load_iso(part_pose + 7ull * (comp_first[c] + pi));
+        Iso7 pc = load_iso(pos_c + 7ull * q), pm = load_iso(mesh_pose);
+        ContactOut ct;   // flipped: the part is shape 1
+        ct.p1 = iso_point(pc, iso_point(pp, mk3(cj[3], cj[4], cj[5])));
+        ct.n1 = iso_vec(pc, iso_vec(pp, mk3(cj[9], cj[10], cj[11])));
+        ct.p2 = iso_point(pm, mk3(cj[0], cj[1], cj[2]));
+        ct.n2 = iso_vec(pm, mk3(cj[6], cj[7], cj[8]));
+        ct.dist = cj[12];
+        store_contact(o, ct);
+        parts[2ull * q] = pi;
+        parts[2ull * q + 1] = cand_tri[best_j];
+    } else {
+        for (int i = 0; i < 13; ++i) o[i] = 0.0f;
+        parts[2ull * q] = parts[2ull * q + 1] = PB2_INVALID_U32;
+    }
+    status[q] = (uint8_t)st;
+}
+
 
 extern "C" {
 
@@ -2227,6 +2327,76 @@ int pb2_compound_contact_shapes(pb2_ctx* ctx, const pb2_compounds* compounds, co
     PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
     PB2_CHECK(pb2_stage_back(ctx, status, d_status, (size_t)n, mem));
     PB2_CHECK(pb2_stage_back(ctx, part, d_part, (size_t)n * 4, mem));
+    if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(st));
+    return PB2_OK;
+}
+
+int pb2_compound_contact_trimesh(pb2_ctx* ctx, const pb2_compounds* compounds, const uint32_t* compound_ids, const float* compound_poses7,
+                                 const pb2_trimesh* mesh, const float* mesh_pose7, uint32_t n, float prediction, pb2_contact* out, uint8_t* status,
+                                 uint32_t* parts, int mem) {
+    if (!ctx || !compounds || !mesh || !mesh_pose7 || (n && (!compound_ids || !compound_poses7 || !out || !status || !parts))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    const pb2_shapes* shapes = compounds->shapes;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_cid, *d_pc, *d_mpose;
+    void *d_out, *d_status, *d_parts;
+    PB2_CHECK(pb2_stage_in(ctx, 0, compound_ids, (size_t)n * 4, mem, &d_cid));
+    PB2_CHECK(pb2_stage_in(ctx, 2, compound_poses7, (size_t)n * 28, mem, &d_pc));
+    PB2_CHECK(pb2_stage_in(ctx, 3, mesh_pose7, 28, mem, &d_mpose));
+    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_status));
+    PB2_CHECK(pb2_stage_out(ctx, 6, parts, (size_t)n * 8, mem, &d_parts));
+    uint32_t *d_cnt = nullptr, *d_off = nullptr, *d_cs = nullptr, *d_cpart = nullptr, *d_ctri = nullptr;
+    float *d_cpose = nullptr, *d_cand = nullptr, *d_ident = nullptr;
+    uint8_t* d_cst = nullptr;
+    void* d_tmp = nullptr;
+    int rc = PB2_OK;
+    do {
+        size_t cub_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n + 1, st);
+        if (cudaMallocAsync((void**)&d_cnt, ((size_t)n + 1) * 4, st) != cudaSuccess || cudaMallocAsync((void**)&d_off, ((size_t)n + 1) * 4, st) != cudaSuccess ||
+            cudaMallocAsync(&d_tmp, cub_bytes, st) != cudaSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), "compound_contact_trimesh: out of memory"); rc = PB2_ERR_CUDA; break;
+        }
+        cudaMemsetAsync(d_cnt + n, 0, 4, st);
+        k_ct_candidates<false><<<pb2_blocks(n, 128), 128, 0, st>>>(mesh->bvh.nodes, mesh->bvh.n_leaves, (const float*)d_mpose, compounds->first,
+            compounds->count, compounds->nc, compounds->part_shape, compounds->part_pose, compounds->part_aabb, (const uint32_t*)d_cid,
+            (const float*)d_pc, n, prediction, d_cnt, nullptr, nullptr, nullptr, nullptr);
+        PB2_LAUNCHED(ctx);
+        cub::DeviceScan::ExclusiveSum(d_tmp, cub_bytes, (const uint32_t*)d_cnt, d_off, (int)n + 1, st);
+        ctx->launches += 1;
+        uint32_t total = 0;
+        cudaMemcpyAsync(&total, d_off + n, 4, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "compound_contact_trimesh: candidate pass failed"); rc = PB2_ERR_CUDA; break; }
+        if (total) {
+            if (cudaMallocAsync((void**)&d_cs, (size_t)total * 4, st) != cudaSuccess || cudaMallocAsync((void**)&d_cpart, (size_t)total * 4, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_ctri, (size_t)total * 4, st) != cudaSuccess || cudaMallocAsync((void**)&d_cpose, (size_t)total * 28, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_cand, (size_t)total * 52, st) != cudaSuccess || cudaMallocAsync((void**)&d_cst, total, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_ident, 28, st) != cudaSuccess) {
+                snprintf(ctx->err, sizeof(ctx->err), "compound_contact_trimesh: out of memory (%u candidate parts)", total); rc = PB2_ERR_CUDA; break;
+            }
+            k_ct_candidates<true><<<pb2_blocks(n, 128), 128, 0, st>>>(mesh->bvh.nodes, mesh->bvh.n_leaves, (const float*)d_mpose, compounds->first,
+                compounds->count, compounds->nc, compounds->part_shape, compounds->part_pose, compounds->part_aabb, (const uint32_t*)d_cid,
+                (const float*)d_pc, n, prediction, nullptr, d_off, d_cs, d_cpose, d_cpart);
+            PB2_LAUNCHED(ctx);
+            static const float ident[7] = {0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f};
+            cudaMemcpyAsync(d_ident, ident, 28, cudaMemcpyHostToDevice, st);
+            // every (query, part) is one TriMesh-vs-shape query in the mesh's own frame; contacts stay in the mesh / part frames
+            if ((rc = trimesh_contact_device(ctx, mesh, d_ident, shapes, d_cs, d_cpose, total, prediction, d_cand, d_cst, d_ctri,
+                                             PAIR_LOCAL_FRAMES | PAIR_POS12_GIVEN)) != PB2_OK) break;
+        }
+        k_ct_reduce<<<pb2_blocks(n, 128), 128, 0, st>>>(d_off, d_cand, d_cst, d_ctri, d_cpart, compounds->first, compounds->nc, compounds->part_pose,
+            (const uint32_t*)d_cid, (const float*)d_pc, (const float*)d_mpose, n, (float*)d_out, (uint8_t*)d_status, (uint32_t*)d_parts);
+        PB2_LAUNCHED(ctx);
+        if (cudaGetLastError() != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "compound_contact_trimesh: launch failed"); rc = PB2_ERR_CUDA; break; }
+    } while (0);
+    void* frees[] = {d_cnt, d_off, d_tmp, d_cs, d_cpart, d_ctri, d_cpose, d_cand, d_cst, d_ident};
+    for (void* p : frees) if (p) cudaFreeAsync(p, st);
+    if (rc != PB2_OK) return rc;
+    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_status, (size_t)n, mem));
+    PB2_CHECK(pb2_stage_back(ctx, parts, d_parts, (size_t)n * 8, mem));
     if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(st));
     return PB2_OK;
 }
