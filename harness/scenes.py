@@ -91,6 +91,19 @@ def random_unit_quaternions(g, n):
     return q  # (i, j, k, w)
 
 
+def compose_pose(p, q):
+    """p * q for two (quaternion ijkw, translation) poses, in float64, rounded to float32."""
+    pq, pt, qq, qt = (np.asarray(x, np.float64) for x in (p[:4], p[4:], q[:4], q[4:]))
+
+    def rot(u4, x):
+        u, w = u4[:3], u4[3]
+        t = 2.0 * np.cross(u, x)
+        return x + w * t + np.cross(u, t)
+    w = pq[3] * qq[3] - np.dot(pq[:3], qq[:3])
+    v = pq[3] * qq[:3] + qq[3] * pq[:3] + np.cross(pq[:3], qq[:3])
+    return np.concatenate([v, [w], pt + rot(pq, qt)]).astype(np.float32)
+
+
 def colliders(n, side=None, seed=2, hull_fraction=0.0, n_hulls=0):
     """n colliders with centres uniform in a cube (density ~1/unit^3), balls r in [0.2,0.6],
     cuboids h in [0.2,0.6]^3 with random rotations, optional hulls from a pool. Returns (kinds, params(n,3), poses(n,7),

@@ -346,7 +346,7 @@ int pb2_compound_contact_trimesh(pb2_ctx* ctx, const pb2_compounds* compounds, c
 /* query::closest_points for n pairs (closest_points/closest_points_shape_shape.rs:220-231 -> default_query_dispatcher.rs:358-424:
  * closest_points_ball_ball.rs:7-36, closest_points_ball_convex_polyhedron.rs:7-44, closest_points_support_map_support_map.rs:8-69).
  * kind: 0 ClosestPoints::Disjoint, 1 WithinMargin (points[k] = p1, p2 in world space), 2 Intersecting. status: 1 ok, 2 unknown
- * shape id, 3 host fallback (ball centre on a hull's surface). */
+ * shape id (3, host fallback, is reserved: no input of the three shape types produces it). */
 int pb2_closest_points_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2,
                              const float* pos1 /* n x 7 */, const float* pos2, float max_dist, uint32_t n, float* points /* n x 6 */,
                              uint8_t* kind, uint8_t* status, int mem);

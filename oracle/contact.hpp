@@ -140,8 +140,10 @@ static inline int contact_convex_polyhedron_ball(const Iso& pos12, const ShapeRe
                 if (!try_normalize(proj, DEFAULT_EPSILON, normal1)) normal1 = Vec3(0, 1, 0);
             }
         } else {
-        if (shape1.kind != SHAPE_CUBOID) return CONTACT_NEEDS_TOPOLOGY;  // ConvexPolyhedron::feature_normal needs the hull topology
-        if (!cuboid_feature_normal(f1, normal1)) {
+        // ConvexPolyhedron::project_local_point_and_get_feature (point_support_map.rs:62-77) forms the feature from the same vector
+        // (point - proj, negated when inside) with the same Unit::try_new(.., DEFAULT_EPSILON): whenever this branch runs that test has
+        // failed too, the feature is FeatureId::Unknown and feature_normal (convex_polyhedron.rs:925-949) is None — no topology needed
+        if (shape1.kind != SHAPE_CUBOID || !cuboid_feature_normal(f1, normal1)) {
             if (!try_normalize(proj, DEFAULT_EPSILON, normal1)) normal1 = Vec3(0, 1, 0);
         }
         }
@@ -483,7 +485,7 @@ static inline int contact_trimesh_shape(const Iso& pos12, const TriMesh& mesh, c
 // (default_query_dispatcher.rs:358-424) for Ball / Cuboid / ConvexPolyhedron: closest_points_ball_ball.rs:7-36,
 // closest_points_ball_convex_polyhedron.rs:7-44 (through the contact arms), closest_points_support_map_support_map.rs:8-69
 // (GJK only, started toward -pos12.translation). Returns 0 Disjoint, 1 WithinMargin(p1, p2) in world space, 2 Intersecting;
-// qstatus CONTACT_NEEDS_TOPOLOGY when the ball arm needs a hull feature normal.
+// qstatus CONTACT_NEEDS_TOPOLOGY is no longer produced (the hull arm never needs a feature normal, see contact_convex_polyhedron_ball).
 enum ClosestPointsKind { CP_DISJOINT = 0, CP_WITHIN_MARGIN = 1, CP_INTERSECTING = 2 };
 static inline int query_closest_points(const Iso& pos1, const ShapeRef& s1, const Iso& pos2, const ShapeRef& s2, Real margin, Vec3& p1, Vec3& p2,
                                        int& qstatus) {

@@ -274,8 +274,9 @@ __device__ __forceinline__ int d_convex_ball_finish(const Iso7& pos12, bool is_c
                 if (!try_normalize_get(proj, PB2_EPS, normal1, n)) normal1 = mk3(0.f, 1.f, 0.f);
             }
         } else {
-        if (!is_cuboid) return ST_NEEDS_HOST;  // ConvexPolyhedron::feature_normal_at_point needs the hull topology
-        if (!d_cuboid_feature_normal(f1, normal1)) {
+        // a hull's feature here is always FeatureId::Unknown (point_support_map.rs:62-77 normalises the same vector with the same
+        // epsilon and fails like the test above), so ConvexPolyhedron::feature_normal is None and the fall-backs apply
+        if (!is_cuboid || !d_cuboid_feature_normal(f1, normal1)) {
             if (!try_normalize_get(proj, PB2_EPS, normal1, n)) normal1 = mk3(0.f, 1.f, 0.f);
         }
         }

@@ -472,8 +472,8 @@ impl Drop for ShapeTable<'_> {
     }
 }
 
-/// status 0 -> `Ok(None)`, 1 -> `Ok(Some(contact))`, anything else -> `Err(Unsupported)`: 2 is an unknown shape; 3 (a ball centre
-/// exactly on a hull's surface, or an EPA polytope beyond the device arena — both measure-zero on real scenes) makes the chain
+/// status 0 -> `Ok(None)`, 1 -> `Ok(Some(contact))`, anything else -> `Err(Unsupported)`: 2 is an unknown shape; 3 (reserved: an
+/// EPA polytope beyond the device's overflow arena, which the reference's iteration cap does not reach) would make the chain
 /// re-run that one pair on `DefaultQueryDispatcher`.
 fn contact_of_status(status: u8, c: &sys::pb2_contact) -> Result<Option<Contact>, Unsupported> {
     match status {

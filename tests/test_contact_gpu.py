@@ -153,6 +153,53 @@ def test_ball_arms_edge_cases(ctx, oracle):
     assert o[1][0] == 1 and (o[0][0, 6:9] == [1, 0, 0]).all()
 
 
+def test_ball_centre_on_a_hull_needs_no_host(ctx, oracle):
+    """Ball centre exactly on a ConvexPolyhedron's vertex / edge / face (and one ulp around them): the degenerate branch of
+    contact_convex_polyhedron_ball (contact_ball_convex_polyhedron.rs:47-53). The hull's feature there is always
+    FeatureId::Unknown (point_support_map.rs:62-77 fails the same normalisation), so the normal is the normalised projection, else
+    +y — no status 3, identical to the oracle, also through closest_points / distance."""
+    import parry_b200
+    cube = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], np.float32)
+    shifted = cube + np.array([1, 1, 1], np.float32)                     # one vertex at the origin: the +y fall-back
+    spec = [("ball", 0.5), ("convex", cube), ("convex", shifted)]
+    G, O = build_tables(ctx, oracle, spec)
+    spots = [[1, 1, 1], [1, 1, 0.25], [1, 0.5, -0.25], [-1, -1, 1], [1, 0, 0], [0.5, 0.25, 0.125]]
+    cases = [(1, 0, s) for s in spots] + [(0, 1, [-x for x in s]) for s in spots] + [(2, 0, [0, 0, 0]), (2, 0, [2, 2, 2]), (0, 2, [0, 0, 0])]
+    up = np.nextafter(np.float32(1), np.float32(2)); dn = np.nextafter(np.float32(1), np.float32(0))
+    cases += [(1, 0, [up, 1, 1]), (1, 0, [dn, dn, dn]), (1, 0, [up, 0.5, 0.5]), (1, 0, [dn, 0.5, 0.5])]
+    a = np.array([c[0] for c in cases], np.uint32)
+    b = np.array([c[1] for c in cases], np.uint32)
+    p1 = np.tile(np.array(I4 + [0, 0, 0], np.float32), (len(cases), 1))
+    p2 = np.array([I4 + list(map(float, c[2])) for c in cases], np.float32)
+    for pred in (0.0, 0.01):
+        g = parry_b200.contact(G, a, p1, b, p2, pred)
+        o = O.contact(a, p1, b, p2, pred)
+        assert (np.asarray(g[1]) != 3).all() and (o[1] != 3).all()
+        compare(g, o)
+    # centre on a face / an edge: dist = -radius, normal1 = the normalised projection; projection at the origin: +y. (Exactly on a
+    # vertex GJK stops on a 0-dimensional simplex and EPA answers with its placeholder, epa3.rs:451-455: proj = origin, as the oracle.)
+    assert o[1][4] == 1 and o[0][4, 12] == np.float32(-0.5) and (o[0][4, 6:9] == [1, 0, 0]).all()
+    np.testing.assert_allclose(o[0][1, 6:9], np.array([1, 1, 0.25]) / np.linalg.norm([1, 1, 0.25]), atol=1e-6)
+    k = 2 * len(spots)
+    assert o[1][k] == 1 and (o[0][k, 6:9] == [0, 1, 0]).all()
+    # rotated poses too
+    g0 = scenes.rng(77)
+    q = scenes.random_unit_quaternions(g0, len(cases)).astype(np.float32)
+    r1 = np.concatenate([q, (g0.random((len(cases), 3)) * 2).astype(np.float32)], axis=1)
+    hull_first = a == 1
+    sel = np.nonzero(hull_first)[0]
+    # ball pose = hull pose * local spot (exactly representable offsets keep some of the cases degenerate, the others nearly so)
+    from harness.scenes import compose_pose
+    r2 = np.stack([compose_pose(r1[i], p2[i]) for i in sel])
+    g = parry_b200.contact(G, a[sel], r1[sel], b[sel], r2, 0.01)
+    o = O.contact(a[sel], r1[sel], b[sel], r2, 0.01)
+    assert (np.asarray(g[1]) != 3).all() and (o[1] != 3).all()
+    compare(g, o)
+    d_g = parry_b200.distance(G, a, p1, b, p2)
+    d_o = O.distance(a, p1, b, p2)
+    assert (np.asarray(d_g[1]) != 3).all() and (np.asarray(d_g[0]).view(np.uint32) == d_o[0].view(np.uint32)).all()
+
+
 def test_hull_pairs_config3_slice_and_compact(ctx, oracle):
     """BASELINE config[2] inputs (32-vertex hulls, prediction 0.01) on a slice the oracle finishes in seconds."""
     import parry_b200
