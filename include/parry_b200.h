@@ -407,6 +407,19 @@ int pb2_cast_shapes_batch(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t
                           float max_time_of_impact, float target_distance, int stop_at_penetration,
                           int compute_impact_geometry_on_penetration, uint32_t n, float* out /* n x 13 */, uint8_t* status, int mem);
 
+/* query::cast_shapes with a TriMesh on one side, n queries against one mesh (the composite arms of DefaultQueryDispatcher::cast_shapes,
+ * default_query_dispatcher.rs:498-515 -> shape_cast_composite_shape_shape.rs:14-105: Bvh::find_best over the mesh tree with
+ * Minkowski-summed node boxes, every reached triangle cast like a support-map pair). mesh_second = 0:
+ * cast_shapes(mesh_pose, mesh_vel, mesh, poses[k], vels[k], shape_ids[k]); != 0: the shape is shape 1 and the hit is
+ * ShapeCastHit::swapped(). out / status as pb2_cast_shapes_batch (witness / normal of the mesh in the mesh's frame); part[k] = the
+ * triangle that was hit or 0xFFFFFFFF. Equal times of impact resolve to the smallest triangle index (the reference keeps the
+ * first in its own tree's order). stop_at_penetration = 0 is PB2_ERR_UNSUPPORTED (a leaf's answer would depend on its EPA contact). */
+int pb2_trimesh_cast_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* mesh_pose7, const float* mesh_vel3, const pb2_shapes* shapes,
+                            const uint32_t* shape_ids, const float* poses7 /* n x 7 */, const float* vels3 /* n x 3 */, int mesh_second,
+                            float max_time_of_impact, float target_distance, int stop_at_penetration,
+                            int compute_impact_geometry_on_penetration, uint32_t n, float* out /* n x 13 */, uint8_t* status, uint32_t* part,
+                            int mem);
+
 #ifdef __cplusplus
 }
 #endif

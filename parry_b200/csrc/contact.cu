@@ -20,6 +20,7 @@
 #include "trimesh.cuh"
 #include "manifold_update.cuh"
 #include "compound_pair.cuh"
+#include "traverse.cuh"
 #include <stdlib.h>
 #include <cub/cub.cuh>
 
@@ -382,7 +383,8 @@ __device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* p
     if (src.flags & PAIR_SUPPORT_MAPS_ONLY) {
         ps.mode = 1;
         ps.gpos12 = ps.pos12;
-        ps.g1 = make_dshape(ps.k1, ps.pr1, pts);
+        if (tri) { ps.g1.kind = DS_TRIANGLE; ps.g1.he = mk3(0.f, 0.f, 0.f); ps.g1.pts = tri; ps.g1.n = 3; }
+        else ps.g1 = make_dshape(ps.k1, ps.pr1, pts);
         ps.g2 = make_dshape(ps.k2, ps.pr2, pts);
         if (b1) ps.g1.kind = DS_BALL;
         if (b2) ps.g2.kind = DS_BALL;
@@ -1879,6 +1881,189 @@ done:
     if (d_c) cudaFreeAsync(d_c, st);
     if (d_cst) cudaFreeAsync(d_cst, st);
     return rc;
+}
+
+
+// ------------------------------------------------------------------------------- query::cast_shapes with a TriMesh on one side
+// cast_shapes_composite_shape_shape / cast_shapes_shape_composite_shape (shape_cast_composite_shape_shape.rs:65-105, the composite arms
+// of DefaultQueryDispatcher::cast_shapes, default_query_dispatcher.rs:498-515) -> CompositeShapeRef::cast_shape (:14-62): Bvh::find_best
+// over the mesh tree with Minkowski-summed node boxes, every reached triangle cast against the shape like any support-map pair.
+// One thread per query. P / V: pose and velocity of the shape in the MESH frame (the caller's pos12 / vel12 when the mesh is shape 1,
+// pos12.inverse() / -pos12.inverse_transform_vector(vel12) when it is shape 2, :95-99).
+__global__ void k_mesh_cast_frames(const float* __restrict__ mesh_pose, const float* __restrict__ mesh_vel, const float* __restrict__ poses,
+                                   const float* __restrict__ vels, uint32_t n, int mesh_second, float* __restrict__ P, float* __restrict__ V) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Iso7 pm = load_iso(mesh_pose), ps = load_iso(poses + 7ull * k);
+    V3 vm = mk3(mesh_vel[0], mesh_vel[1], mesh_vel[2]), vs = mk3(vels[3ull * k], vels[3ull * k + 1], vels[3ull * k + 2]);
+    Iso7 pose; V3 vel;
+    if (!mesh_second) { pose = iso_inv_mul(pm, ps); vel = iso_inv_vec(pm, vs - vm); }   // shape_cast.rs:279-281
+    else {
+        Iso7 pos12 = iso_inv_mul(ps, pm);
+        V3 vel12 = iso_inv_vec(ps, vm - vs);
+        pose = iso_inverse(pos12);
+        vel = -iso_inv_vec(pos12, vel12);
+    }
+    float* o = P + 7ull * k;
+    o[0] = pose.q.i; o[1] = pose.q.j; o[2] = pose.q.k; o[3] = pose.q.w; o[4] = pose.t.x; o[5] = pose.t.y; o[6] = pose.t.z;
+    V[3ull * k] = vel.x; V[3ull * k + 1] = vel.y; V[3ull * k + 2] = vel.z;
+}
+
+__global__ void __launch_bounds__(128) k_mesh_cast_shapes(const NodeWide* __restrict__ nodes, uint32_t n_leaves, const float4* __restrict__ tris,
+                              const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float4* __restrict__ pts,
+                              const float* __restrict__ points, uint32_t n_shapes, const uint32_t* __restrict__ shape_ids,
+                              const float* __restrict__ P, const float* __restrict__ V, CastOpts o, uint32_t n, float* __restrict__ out,
+                              uint8_t* __restrict__ status, uint32_t* __restrict__ part, uint32_t* __restrict__ parked,
+                              uint32_t* __restrict__ parked_ab, unsigned long long* parked_count, unsigned int* fault) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float* q = out + 13ull * k;
+    uint32_t sid = shape_ids[k];
+    int st = CAST_NONE;
+    V3 w1 = mk3(0.f, 0.f, 0.f), w2 = w1, n1 = w1, n2 = w1;
+    float best = o.max_toi;
+    uint32_t best_id = PB2_INVALID_U32, best_pos = 0;
+    bool found = false;
+    if (sid >= n_shapes) st = CAST_UNSUPPORTED;
+    else {
+        Iso7 pos12 = load_iso(P + 7ull * k);
+        V3 vel12 = mk3(V[3ull * k], V[3ull * k + 1], V[3ull * k + 2]);
+        uint8_t k2 = kinds[sid];
+        float4 pr2 = params[sid];
+        V3 mn, mx;
+        shape_aabb_dev(k2, pr2, points, pos12, mn, mx);   // g2.compute_aabb(pose12), :29
+        V3 shift = -((mn + mx) * 0.5f);
+        V3 margin = (mx - mn) * 0.5f + mk3(o.target_distance, o.target_distance, o.target_distance);
+        V3 inv = mk3(1.0f / vel12.x, 1.0f / vel12.y, 1.0f / vel12.z);
+        DShape g2 = cast_dshape(k2, pr2, pts);
+        const float border = o.target_distance;
+        auto leaf = [&](uint32_t pos) {
+            const float4* tp = tris + 3ull * pos;
+            DShape g1; g1.kind = DS_TRIANGLE; g1.he = mk3(0.f, 0.f, 0.f); g1.pts = tp; g1.n = 3;
+            Simplex s;
+            V3 normal1; float toi;
+            auto cso = [&](V3 dir) {
+                V3 sp1;
+                if (border > 0.0f) { V3 nd = dir / nrm(dir); sp1 = ds_local_support(g1, nd) + nd * border; }
+                else sp1 = ds_local_support(g1, dir);
+                return cso_make(sp1, ds_support_point(g2, pos12, -dir));
+            };
+            if (!minkowski_ray_cast(cso, s, mk3(0.f, 0.f, 0.f), vel12, FLT_MAX, toi, normal1) || toi > o.max_toi) return;
+            uint32_t id = __float_as_uint(__ldg(&tp[0]).w);
+            if (!(toi < best || (found && toi == best && id < best_id))) return;
+            best = toi; best_id = id; best_pos = pos; found = true;
+            if (o.compute_geometry && toi < 1.0e-5f) { st = CAST_PARKED; return; }   // geometry from the contact kernels (second phase)
+            V3 r0 = mk3(0.f, 0.f, 0.f), r1 = r0;
+            if (toi != 0.0f) gjk_witness(s, s.dim == 3, r0, r1);
+            n1 = normal1;
+            n2 = iso_inv_vec(pos12, -normal1);
+            w1 = r0 - normal1 * border;
+            w2 = iso_inv_point(pos12, r1);
+            st = toi == 0.0f ? CAST_PENETRATING : CAST_CONVERGED;
+        };
+        bvh_find_best_msum(nodes, n_leaves, shift, margin, vel12, inv, o.max_toi, best, found, leaf, fault);
+    }
+    if (st == CAST_PARKED) {
+        unsigned long long at = warp_append1(parked_count);
+        parked[at] = k;
+        parked_ab[2 * at] = best_pos; parked_ab[2 * at + 1] = k;
+    }
+    bool some = found && st != CAST_UNSUPPORTED;
+    if (!some || st == CAST_PARKED) { w1 = w2 = n1 = n2 = mk3(0.f, 0.f, 0.f); }
+    q[0] = w1.x; q[1] = w1.y; q[2] = w1.z; q[3] = w2.x; q[4] = w2.y; q[5] = w2.z;
+    q[6] = n1.x; q[7] = n1.y; q[8] = n1.z; q[9] = n2.x; q[10] = n2.y; q[11] = n2.z; q[12] = some ? best : 0.0f;
+    status[k] = (uint8_t)st;
+    part[k] = some ? best_id : PB2_INVALID_U32;
+}
+
+// ShapeCastHit::swapped (shape_cast.rs:71-80) for the shape-first order; hits that lost their contact lose their triangle too
+__global__ void k_mesh_cast_finish(uint32_t n, int mesh_second, float* __restrict__ out, const uint8_t* __restrict__ status, uint32_t* __restrict__ part) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int st = status[k];
+    if (st != CAST_CONVERGED && st != CAST_PENETRATING) { part[k] = PB2_INVALID_U32; return; }
+    if (!mesh_second) return;
+    float* q = out + 13ull * k;
+    for (int j = 0; j < 3; ++j) {
+        float t = q[j]; q[j] = q[3 + j]; q[3 + j] = t;
+        t = q[6 + j]; q[6 + j] = q[9 + j]; q[9 + j] = t;
+    }
+}
+
+extern "C" int pb2_trimesh_cast_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* mesh_pose7, const float* mesh_vel3, const pb2_shapes* shapes,
+                                       const uint32_t* shape_ids, const float* poses7, const float* vels3, int mesh_second, float max_time_of_impact,
+                                       float target_distance, int stop_at_penetration, int compute_impact_geometry_on_penetration, uint32_t n,
+                                       float* out, uint8_t* status, uint32_t* part, int mem) {
+    if (!ctx || !mesh || !shapes || !mesh_pose7 || !mesh_vel3 || (n && (!shape_ids || !poses7 || !vels3 || !out || !status || !part))) return PB2_ERR_INVALID;
+    // with stop_at_penetration off a leaf's answer depends on its EPA contact (shape_cast_support_map_support_map.rs:41-46), which one
+    // thread inside a tree descent cannot run: the reference's default (on) is what this entry offers
+    if (!stop_at_penetration) PB2_FAIL(ctx, PB2_ERR_UNSUPPORTED, "trimesh_cast_shapes: stop_at_penetration = false is not offered on the device");
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_ids, *d_p, *d_v, *d_mp, *d_mv;
+    void *d_out, *d_st, *d_part;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape_ids, (size_t)n * 4, mem, &d_ids));
+    PB2_CHECK(pb2_stage_in(ctx, 1, mesh_vel3, 12, mem, &d_mv));
+    PB2_CHECK(pb2_stage_in(ctx, 2, poses7, (size_t)n * 28, mem, &d_p));
+    PB2_CHECK(pb2_stage_in(ctx, 3, mesh_pose7, 28, mem, &d_mp));
+    PB2_CHECK(pb2_stage_in(ctx, 4, vels3, (size_t)n * 12, mem, &d_v));
+    PB2_CHECK(pb2_stage_out(ctx, 5, out, (size_t)n * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 6, status, (size_t)n, mem, &d_st));
+    PB2_CHECK(pb2_stage_out(ctx, 7, part, (size_t)n * 4, mem, &d_part));
+    float *d_P = nullptr, *d_V = nullptr, *d_c = nullptr;
+    uint32_t *d_parked = nullptr, *d_ab = nullptr;
+    uint8_t* d_cst = nullptr;
+    int rc = PB2_OK;
+    do {
+        if (cudaMallocAsync((void**)&d_P, (size_t)n * 28, st) != cudaSuccess || cudaMallocAsync((void**)&d_V, (size_t)n * 12, st) != cudaSuccess ||
+            cudaMallocAsync((void**)&d_parked, (size_t)n * 4, st) != cudaSuccess || cudaMallocAsync((void**)&d_ab, (size_t)n * 8, st) != cudaSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), "trimesh_cast_shapes: out of device memory"); rc = PB2_ERR_CUDA; break;
+        }
+        unsigned long long* parked_count = (unsigned long long*)(ctx->d_counters + 10);
+        cudaMemsetAsync(parked_count, 0, 8, st);
+        k_mesh_cast_frames<<<pb2_blocks(n, 128), 128, 0, st>>>((const float*)d_mp, (const float*)d_mv, (const float*)d_p, (const float*)d_v, n,
+                                                               mesh_second, d_P, d_V);
+        PB2_LAUNCHED(ctx);
+        CastOpts o;
+        o.max_toi = max_time_of_impact; o.target_distance = target_distance; o.stop_at_penetration = 1;
+        o.compute_geometry = compute_impact_geometry_on_penetration;
+        k_mesh_cast_shapes<<<pb2_blocks(n, 128), 128, 0, st>>>(mesh->bvh.nodes, mesh->bvh.n_leaves, mesh->tris, shapes->kinds, shapes->params,
+            shapes->points4, shapes->points, shapes->n, (const uint32_t*)d_ids, d_P, d_V, o, n, (float*)d_out, (uint8_t*)d_st, (uint32_t*)d_part,
+            d_parked, d_ab, parked_count, PB2_FAULT_PTR(ctx));
+        PB2_LAUNCHED(ctx);
+        cudaMemcpyAsync(ctx->h_counters + 10, parked_count, 8, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh_cast_shapes: kernel failed"); rc = PB2_ERR_CUDA; break; }
+        uint32_t cnt = (uint32_t)ctx->h_counters[10];
+        if (cnt) {
+            if (cudaMallocAsync((void**)&d_c, (size_t)cnt * 52, st) != cudaSuccess || cudaMallocAsync((void**)&d_cst, cnt, st) != cudaSuccess) {
+                snprintf(ctx->err, sizeof(ctx->err), "trimesh_cast_shapes: out of device memory"); rc = PB2_ERR_CUDA; break;
+            }
+            OutSinks sinks;
+            sinks.dense = d_c; sinks.status = d_cst; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
+            sinks.compact_count = nullptr; sinks.some_count = nullptr;
+            // contact_support_map_support_map(pos12, triangle, shape, Real::MAX) of the penetrating winners, in the two local frames
+            if ((rc = run_contacts(ctx, shapes, nullptr, (const uint32_t*)d_ids, (const float*)d_mp, d_P, FLT_MAX, cnt, sinks, d_ab, n, mesh->tris,
+                                   mesh->nt, PAIR_SUPPORT_MAPS_ONLY | PAIR_LOCAL_FRAMES | PAIR_POS12_GIVEN)) != PB2_OK) break;
+            k_cast_merge<<<pb2_blocks(cnt, 128), 128, 0, st>>>(d_parked, cnt, d_c, d_cst, d_P, d_V, d_V, 1, (float*)d_out, (uint8_t*)d_st);
+            PB2_LAUNCHED(ctx);
+        }
+        k_mesh_cast_finish<<<pb2_blocks(n, 128), 128, 0, st>>>(n, mesh_second, (float*)d_out, (const uint8_t*)d_st, (uint32_t*)d_part);
+        PB2_LAUNCHED(ctx);
+        if (cudaGetLastError() != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh_cast_shapes: launch failed"); rc = PB2_ERR_CUDA; break; }
+    } while (0);
+    void* frees[] = {d_P, d_V, d_parked, d_ab, d_c, d_cst};
+    for (void* p : frees) if (p) cudaFreeAsync(p, st);
+    if (rc != PB2_OK) return rc;
+    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_st, (size_t)n, mem));
+    PB2_CHECK(pb2_stage_back(ctx, part, d_part, (size_t)n * 4, mem));
+    if (mem == PB2_MEM_HOST) {
+        PB2_CHECK(pb2_fetch_fault(ctx));
+        PB2_CUDA(ctx, cudaStreamSynchronize(st));
+        return pb2_check_fault(ctx);
+    }
+    return PB2_OK;
 }
 
 

@@ -56,3 +56,54 @@ __device__ __forceinline__ void bvh_find_best(const NodeWide* __restrict__ nodes
         }
     }
 }
+
+// Bvh::find_best with the node cost of CompositeShapeRef::cast_shape (shape_cast_composite_shape_shape.rs:36-45): every node box is
+// Minkowski-summed with the other shape's box — Aabb::new(mins + shift - margin, maxs + shift + margin) — and hit by the ray
+// (origin, d) = (0, vel12), solid. Same descent and tie rule as bvh_find_best.
+template <class Leaf>
+__device__ __forceinline__ void bvh_find_best_msum(const NodeWide* __restrict__ nodes, uint32_t n_leaves, V3 shift, V3 margin, V3 d, V3 inv,
+                                                   float max_toi, float& best, bool& found, Leaf leaf, unsigned int* fault) {
+    const V3 o = mk3(0.f, 0.f, 0.f);
+    auto cost = [&](float4 lo, float4 hi, float bound) {
+        if (lo.x > hi.x) return FLT_MAX;   // inert leaves (Aabb::new_invalid)
+        return slab_cost((lo.x + shift.x) - margin.x, (lo.y + shift.y) - margin.y, (lo.z + shift.z) - margin.z, (hi.x + shift.x) + margin.x,
+                         (hi.y + shift.y) + margin.y, (hi.z + shift.z) + margin.z, o, d, inv, bound);
+    };
+    if (n_leaves == 1) {
+        const float4* np = reinterpret_cast<const float4*>(&nodes[0]);
+        float4 l0 = __ldg(np), l1 = __ldg(np + 1);
+        if (cost(l0, l1, max_toi) < max_toi) leaf(__float_as_uint(l0.w));
+        return;
+    }
+    if (n_leaves < 2) return;
+    uint32_t stack[PB2_STACK];
+    int sp = 0;
+    uint32_t curr = 0;
+    for (;;) {
+        const float4* np = reinterpret_cast<const float4*>(&nodes[curr]);
+        float4 l0 = __ldg(np), l1 = __ldg(np + 1), r0 = __ldg(np + 2), r1 = __ldg(np + 3);
+        float ls = cost(l0, l1, best), rs = cost(r0, r1, best);
+        uint32_t lc = __float_as_uint(l0.w), rc = __float_as_uint(r0.w);
+        bool lleaf = (__float_as_uint(l1.w) & PB2_LEAF_COUNT_MASK) == 1u;
+        bool rleaf = (__float_as_uint(r1.w) & PB2_LEAF_COUNT_MASK) == 1u;
+        if (ls > rs) {
+            float ts = ls; ls = rs; rs = ts;
+            uint32_t tc = lc; lc = rc; rc = tc;
+            bool tl = lleaf; lleaf = rleaf; rleaf = tl;
+        }
+        bool found_next = false;
+        if (ls != FLT_MAX && (ls < best || (found && ls == best))) {
+            if (lleaf) leaf(lc);
+            else { curr = lc; found_next = true; }
+        }
+        if (rs != FLT_MAX && (rs < best || (found && rs == best))) {
+            if (rleaf) leaf(rc);
+            else if (found_next) pb2_push(stack, sp, rc, fault);
+            else { curr = rc; found_next = true; }
+        }
+        if (!found_next) {
+            if (sp == 0) break;
+            curr = stack[--sp];
+        }
+    }
+}

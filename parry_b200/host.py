@@ -434,6 +434,26 @@ class TriMesh:
         self.ctx.check(self.ctx._lib.pb2_trimesh_contact_shapes(self.ctx.h, self.h, pm, shapes.h, ps, pp, n, float(prediction), po, pst, ppart, mem))
         return out, status, part
 
+    def cast_shapes(self, mesh_pose, mesh_vel, shapes, shape_ids, poses, vels, options=None, mesh_second=False):
+        """query::cast_shapes(mesh_pose, mesh_vel, self, poses[k], vels[k], shapes[shape_ids[k]], options) for every k — or, with
+        mesh_second, the shape as shape 1 and the swapped hit (shape_cast_composite_shape_shape.rs:65-105). Returns (hits (n, 13) as
+        parry_b200.cast_shapes, status (n,), part (n,) = the triangle hit)."""
+        o = options or ShapeCastOptions()
+        n = int(poses.shape[0])
+        kp, pp, mem = _prep(poses, np.float32)
+        kv, pv, _ = _prep(vels, np.float32, mem)
+        ks, ps, _ = _prep(shape_ids, np.uint32, mem)
+        km, pm, _ = _prep(mesh_pose, np.float32, mem)
+        kmv, pmv, _ = _prep(mesh_vel, np.float32, mem)
+        dev = self.ctx.torch_device
+        out, po = _empty((n, 13), np.float32, mem, dev)
+        status, pst = _empty((n,), np.uint8, mem, dev)
+        part, ppart = _empty((n,), np.uint32, mem, dev)
+        self.ctx.check(self.ctx._lib.pb2_trimesh_cast_shapes(self.ctx.h, self.h, pm, pmv, shapes.h, ps, pp, pv, int(mesh_second),
+                                                             o.max_time_of_impact, o.target_distance, int(o.stop_at_penetration),
+                                                             int(o.compute_impact_geometry_on_penetration), n, po, pst, ppart, mem))
+        return out, status, part
+
     def close(self):
         if self.h:
             self.ctx._lib.pb2_trimesh_destroy(self.ctx.h, self.h)
