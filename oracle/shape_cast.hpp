@@ -138,8 +138,9 @@ static inline bool dispatch_cast_shapes_any(const Iso& pos12, const Vec3& vel12,
     // cast_shapes_shape_composite_shape: the mesh as shape 1 under the inverse pose and velocity, then swapped()
     Iso pos21 = pos12.inverse();
     ShapeCastHit h;
-    if (!trimesh_cast_shape(*b.mesh, pos21, -pos12.inverse_transform_vector(vel12), a, o, part, h)) return false;
+    if (!trimesh_cast_shape(*b.mesh, pos21, -pos12.inverse_transform_vector(vel12), a, o, part, h)) { if (part1) *part1 = UINT32_MAX; return false; }
     hit = cast_hit_swapped(h);
+    if (part1) *part1 = part;   // (test bookkeeping: the triangle of the mesh that was hit, whichever side the mesh is on)
     return true;
 }
 // query::cast_shapes (shape_cast.rs:268-286) with a TriMesh on either side

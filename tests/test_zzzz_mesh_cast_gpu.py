@@ -49,7 +49,7 @@ def oracle_casts(om, T, mpose, mvel, sid, poses, vel, mesh_second, **opts):
     return out, st, part
 
 
-def check(g, o, min_hits, min_same=0.97):
+def check(g, o, min_hits):
     go, gs, gp = (np.asarray(x) for x in g)
     oo, os_, op = o
     gp = gp.astype(np.uint32)
@@ -61,12 +61,16 @@ def check(g, o, min_hits, min_same=0.97):
     some = ok & (os_ != 0)
     assert (gp[ok & (os_ == 0)] == 0xFFFFFFFF).all() and (go[ok & (os_ == 0)] == 0).all()
     np.testing.assert_allclose(go[some][:, 12], oo[some][:, 12], rtol=1e-5, atol=2e-6)
+    # Equal times of impact are common on a mesh — a shape that starts in touch with several triangles hits all of them at time 0, an
+    # impact on a shared edge is one event for both triangles (measured with harness/mesh_cast_check.py: 18-35 % of the hits here, all
+    # of them bit-equal times) — and resolve to the reference's first-in-tree-order in the oracle, to the smallest index here.
     same = gp[some] == op[some]
-    assert same.mean() > min_same, same.mean()
-    a, b = go[some][same], oo[some][same]
+    assert same.mean() > 0.5, same.mean()
+    assert (go[some][~same][:, 12] == oo[some][~same][:, 12]).all()
+    a, b = go[some], oo[some]
     rows_ok = (np.abs(a[:, :12] - b[:, :12]) < 1e-4).all(axis=1)
-    assert rows_ok.mean() > 0.99, rows_ok.mean()
-    return some, same
+    assert rows_ok[same].mean() > 0.99, rows_ok[same].mean()
+    return some, same, rows_ok
 
 
 @pytest.mark.parametrize("seed,n,lift,mesh_second,opts", [
@@ -88,9 +92,7 @@ def test_trimesh_cast_shapes_vs_oracle(ctx, oracle, seed, n, lift, mesh_second, 
     go = parry_b200.ShapeCastOptions(max_time_of_impact=opts.get("max_toi", FMAX), target_distance=opts.get("target_distance", 0.0),
                                      compute_impact_geometry_on_penetration=opts.get("compute_impact_geometry_on_penetration", True))
     g = gm.cast_shapes(mpose, mvel, G, sid, poses, vel, go, mesh_second=mesh_second)
-    # shapes that start inside several triangles have as many hits at time 0: the reference keeps the first in its tree's order,
-    # this library the smallest index
-    some, same = check(g, o, 0.2, min_same=0.97 if lift[0] > 0 else 0.6)
+    some, same, rows_ok = check(g, o, 0.2)
     if lift[0] < 0:
         assert (o[1][some] == 2).mean() > 0.1               # PenetratingOrWithinTargetDist is exercised
 
