@@ -2067,6 +2067,137 @@ extern "C" int pb2_trimesh_cast_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, co
 }
 
 
+// TriMesh against TriMesh (the nesting behind the reference's tests/geometry/trimesh_trimesh_toi.rs): cast_shapes_composite_shape_shape
+// over mesh 1, whose every reached triangle is cast against mesh 2 through cast_shapes_shape_composite_shape — mesh 2 walked under
+// pos12.inverse() with the triangle's transformed box, each of its triangles cast against the triangle of mesh 1 as a support-map
+// pair, the hit swapped back (shape_cast_composite_shape_shape.rs:65-105). One thread per query, two nested descents.
+__global__ void __launch_bounds__(128) k_mesh_cast_mesh(const NodeWide* __restrict__ nodes1, uint32_t nl1, const float4* __restrict__ tris1,
+                              const NodeWide* __restrict__ nodes2, uint32_t nl2, const float4* __restrict__ tris2, const float* __restrict__ pos1,
+                              const float* __restrict__ vel1, const float* __restrict__ pos2, const float* __restrict__ vel2, CastOpts o, uint32_t n,
+                              float* __restrict__ out, uint8_t* __restrict__ status, uint32_t* __restrict__ parts, unsigned int* fault) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Iso7 p1 = load_iso(pos1 + 7ull * k), p2 = load_iso(pos2 + 7ull * k);
+    Iso7 pos12 = iso_inv_mul(p1, p2);
+    V3 v1 = mk3(vel1[3ull * k], vel1[3ull * k + 1], vel1[3ull * k + 2]), v2 = mk3(vel2[3ull * k], vel2[3ull * k + 1], vel2[3ull * k + 2]);
+    V3 vel12 = iso_inv_vec(p1, v2 - v1);
+    int st = CAST_NONE;
+    V3 w1 = mk3(0.f, 0.f, 0.f), w2 = w1, n1 = w1, n2 = w1;
+    float best = o.max_toi;
+    uint32_t best_id1 = PB2_INVALID_U32, best_id2 = PB2_INVALID_U32;
+    bool found = false;
+    if (nl1 && nl2) {
+        NodeWide r = nodes2[0];   // TriMesh::compute_aabb(pos12) = root_aabb().transform_by(pos12) (trimesh.rs:1763-1765)
+        V3 amn = mk3(r.left.mnx, r.left.mny, r.left.mnz), amx = mk3(r.left.mxx, r.left.mxy, r.left.mxz);
+        if (nl2 > 1) {
+            amn = vmin3(amn, mk3(r.right.mnx, r.right.mny, r.right.mnz));
+            amx = vmax3(amx, mk3(r.right.mxx, r.right.mxy, r.right.mxz));
+        }
+        V3 ctr = iso_point(pos12, (amn + amx) * 0.5f), he = iso_abs_vec(pos12, (amx - amn) * 0.5f);
+        V3 lmn = ctr + (-he), lmx = ctr + he;
+        const V3 tgt = mk3(o.target_distance, o.target_distance, o.target_distance);
+        V3 shift = -((lmn + lmx) * 0.5f), margin = (lmx - lmn) * 0.5f + tgt;
+        V3 inv12 = mk3(1.0f / vel12.x, 1.0f / vel12.y, 1.0f / vel12.z);
+        const Iso7 pos21 = iso_inverse(pos12);
+        const V3 vel21 = -iso_inv_vec(pos12, vel12);
+        const V3 inv21 = mk3(1.0f / vel21.x, 1.0f / vel21.y, 1.0f / vel21.z);
+        const float border = o.target_distance;
+        auto leaf1 = [&](uint32_t pa) {
+            const float4* t1 = tris1 + 3ull * pa;
+            DShape gt1; gt1.kind = DS_TRIANGLE; gt1.he = mk3(0.f, 0.f, 0.f); gt1.pts = t1; gt1.n = 3;
+            // Triangle::compute_aabb(pos21) = the box of the transformed vertices (aabb_triangle.rs:10-30)
+            float4 fa = __ldg(&t1[0]), fb = __ldg(&t1[1]), fc = __ldg(&t1[2]);
+            V3 qa = iso_point(pos21, mk3(fa.x, fa.y, fa.z)), qb = iso_point(pos21, mk3(fb.x, fb.y, fb.z)), qc = iso_point(pos21, mk3(fc.x, fc.y, fc.z));
+            V3 bmn = mk3(fminf(fminf(qa.x, qb.x), qc.x), fminf(fminf(qa.y, qb.y), qc.y), fminf(fminf(qa.z, qb.z), qc.z));
+            V3 bmx = mk3(fmaxf(fmaxf(qa.x, qb.x), qc.x), fmaxf(fmaxf(qa.y, qb.y), qc.y), fmaxf(fmaxf(qa.z, qb.z), qc.z));
+            V3 shift2 = -((bmn + bmx) * 0.5f), margin2 = (bmx - bmn) * 0.5f + tgt;
+            float ibest = o.max_toi;
+            bool ifound = false;
+            uint32_t iid2 = PB2_INVALID_U32;
+            int ist = CAST_NONE;
+            V3 iw1 = mk3(0.f, 0.f, 0.f), iw2 = iw1, in1 = iw1, in2 = iw1;
+            auto leaf2 = [&](uint32_t pb) {
+                const float4* t2 = tris2 + 3ull * pb;
+                DShape gt2; gt2.kind = DS_TRIANGLE; gt2.he = mk3(0.f, 0.f, 0.f); gt2.pts = t2; gt2.n = 3;
+                Simplex s;
+                V3 normal1; float toi;
+                auto cso = [&](V3 dir) {
+                    V3 sp1;
+                    if (border > 0.0f) { V3 nd = dir / nrm(dir); sp1 = ds_local_support(gt2, nd) + nd * border; }
+                    else sp1 = ds_local_support(gt2, dir);
+                    return cso_make(sp1, ds_support_point(gt1, pos21, -dir));
+                };
+                if (!minkowski_ray_cast(cso, s, mk3(0.f, 0.f, 0.f), vel21, FLT_MAX, toi, normal1) || toi > o.max_toi) return;
+                uint32_t id2 = __float_as_uint(__ldg(&t2[0]).w);
+                if (!(toi < ibest || (ifound && toi == ibest && id2 < iid2))) return;
+                ibest = toi; iid2 = id2; ifound = true;
+                if (o.compute_geometry && toi < 1.0e-5f) { ist = CAST_PARKED; return; }
+                V3 r0 = mk3(0.f, 0.f, 0.f), r1 = r0;
+                if (toi != 0.0f) gjk_witness(s, s.dim == 3, r0, r1);
+                in1 = normal1;
+                in2 = iso_inv_vec(pos21, -normal1);
+                iw1 = r0 - normal1 * border;
+                iw2 = iso_inv_point(pos21, r1);
+                ist = toi == 0.0f ? CAST_PENETRATING : CAST_CONVERGED;
+            };
+            bvh_find_best_msum(nodes2, nl2, shift2, margin2, vel21, inv21, o.max_toi, ibest, ifound, leaf2, fault);
+            if (!ifound) return;
+            uint32_t id1 = __float_as_uint(fa.w);
+            if (!(ibest < best || (found && ibest == best && id1 < best_id1))) return;
+            best = ibest; best_id1 = id1; best_id2 = iid2; found = true;
+            st = ist;
+            w1 = iw2; w2 = iw1; n1 = in2; n2 = in1;   // ShapeCastHit::swapped
+        };
+        bvh_find_best_msum(nodes1, nl1, shift, margin, vel12, inv12, o.max_toi, best, found, leaf1, fault);
+    }
+    // a winner that starts in touch wants the triangle-triangle contact for its geometry, which the contact kernels do not take
+    if (st == CAST_PARKED) { st = CAST_NEEDS_HOST; w1 = w2 = n1 = n2 = mk3(0.f, 0.f, 0.f); }
+    float* q = out + 13ull * k;
+    q[0] = w1.x; q[1] = w1.y; q[2] = w1.z; q[3] = w2.x; q[4] = w2.y; q[5] = w2.z;
+    q[6] = n1.x; q[7] = n1.y; q[8] = n1.z; q[9] = n2.x; q[10] = n2.y; q[11] = n2.z; q[12] = found ? best : 0.0f;
+    status[k] = (uint8_t)st;
+    parts[2ull * k] = found ? best_id1 : PB2_INVALID_U32;
+    parts[2ull * k + 1] = found ? best_id2 : PB2_INVALID_U32;
+}
+
+extern "C" int pb2_trimesh_cast_trimesh(pb2_ctx* ctx, const pb2_trimesh* mesh1, const float* pos1, const float* vel1, const pb2_trimesh* mesh2,
+                                        const float* pos2, const float* vel2, float max_time_of_impact, float target_distance,
+                                        int stop_at_penetration, int compute_impact_geometry_on_penetration, uint32_t n, float* out,
+                                        uint8_t* status, uint32_t* parts, int mem) {
+    if (!ctx || !mesh1 || !mesh2 || (n && (!pos1 || !vel1 || !pos2 || !vel2 || !out || !status || !parts))) return PB2_ERR_INVALID;
+    if (!stop_at_penetration) PB2_FAIL(ctx, PB2_ERR_UNSUPPORTED, "trimesh_cast_trimesh: stop_at_penetration = false is not offered on the device");
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_p1, *d_p2, *d_v1, *d_v2;
+    void *d_out, *d_st, *d_parts;
+    PB2_CHECK(pb2_stage_in(ctx, 0, pos1, (size_t)n * 28, mem, &d_p1));
+    PB2_CHECK(pb2_stage_in(ctx, 1, pos2, (size_t)n * 28, mem, &d_p2));
+    PB2_CHECK(pb2_stage_in(ctx, 2, vel1, (size_t)n * 12, mem, &d_v1));
+    PB2_CHECK(pb2_stage_in(ctx, 3, vel2, (size_t)n * 12, mem, &d_v2));
+    PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * 52, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_st));
+    PB2_CHECK(pb2_stage_out(ctx, 6, parts, (size_t)n * 8, mem, &d_parts));
+    CastOpts o;
+    o.max_toi = max_time_of_impact; o.target_distance = target_distance; o.stop_at_penetration = 1;
+    o.compute_geometry = compute_impact_geometry_on_penetration;
+    k_mesh_cast_mesh<<<pb2_blocks(n, 128), 128, 0, st>>>(mesh1->bvh.nodes, mesh1->bvh.n_leaves, mesh1->tris, mesh2->bvh.nodes, mesh2->bvh.n_leaves,
+        mesh2->tris, (const float*)d_p1, (const float*)d_v1, (const float*)d_p2, (const float*)d_v2, o, n, (float*)d_out, (uint8_t*)d_st,
+        (uint32_t*)d_parts, PB2_FAULT_PTR(ctx));
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_st, (size_t)n, mem));
+    PB2_CHECK(pb2_stage_back(ctx, parts, d_parts, (size_t)n * 8, mem));
+    if (mem == PB2_MEM_HOST) {
+        PB2_CHECK(pb2_fetch_fault(ctx));
+        PB2_CUDA(ctx, cudaStreamSynchronize(st));
+        return pb2_check_fault(ctx);
+    }
+    return PB2_OK;
+}
+
+
 extern "C" int pb2_intersect_csr_device(pb2_ctx* ctx, const pb2_bvh* bvh, const float* d_queries, uint32_t m, bool positions,
                                         uint32_t* d_offsets, uint32_t** d_items, uint64_t* total_out);
 

@@ -454,6 +454,24 @@ class TriMesh:
                                                              int(o.compute_impact_geometry_on_penetration), n, po, pst, ppart, mem))
         return out, status, part
 
+    def cast_trimesh(self, poses1, vels1, other, poses2, vels2, options=None):
+        """query::cast_shapes(poses1[k], vels1[k], self, poses2[k], vels2[k], other, options) for every k (two TriMeshes; the
+        reference's trimesh_trimesh_toi.rs). Returns (hits (n, 13), status (n,), parts (n, 2) = the triangle of each mesh)."""
+        o = options or ShapeCastOptions()
+        n = int(poses1.shape[0])
+        k1, p1, mem = _prep(poses1, np.float32)
+        k2, p2, _ = _prep(poses2, np.float32, mem)
+        kv1, v1, _ = _prep(vels1, np.float32, mem)
+        kv2, v2, _ = _prep(vels2, np.float32, mem)
+        dev = self.ctx.torch_device
+        out, po = _empty((n, 13), np.float32, mem, dev)
+        status, pst = _empty((n,), np.uint8, mem, dev)
+        parts, pp = _empty((n, 2), np.uint32, mem, dev)
+        self.ctx.check(self.ctx._lib.pb2_trimesh_cast_trimesh(self.ctx.h, self.h, p1, v1, other.h, p2, v2, o.max_time_of_impact, o.target_distance,
+                                                              int(o.stop_at_penetration), int(o.compute_impact_geometry_on_penetration), n, po,
+                                                              pst, pp, mem))
+        return out, status, parts
+
     def close(self):
         if self.h:
             self.ctx._lib.pb2_trimesh_destroy(self.ctx.h, self.h)

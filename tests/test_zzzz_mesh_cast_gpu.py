@@ -128,3 +128,67 @@ def test_trimesh_cast_shapes_edge_cases(ctx, oracle):
     gq = pm.cast_shapes(ident, zero, G, np.array([0], np.uint32), pose, np.array([[-2.0, 0, 0]], np.float32))
     assert r is not None and np.asarray(gq[1])[0] == r[1]
     np.testing.assert_allclose(np.asarray(gq[0])[0], r[0], rtol=1e-5, atol=1e-6)
+
+
+def pyramid():
+    pts = np.array([[0, 1, 0], [-1, -0.5, 0], [0, -0.5, -1], [1, -0.5, 0]], np.float32)
+    idx = np.array([[0, 1, 2], [0, 2, 3], [0, 3, 1]], np.uint32)
+    return pts, idx
+
+
+def test_trimesh_trimesh_toi_issue_194_on_the_gpu(ctx, oracle):
+    """crates/parry3d/tests/geometry/trimesh_trimesh_toi.rs through pb2_trimesh_cast_trimesh: two pyramids 1000 apart, one moving at
+    100000 along x: `assert_eq!(time_of_impact, Some(0.00998))`, exact; and the opposite direction misses."""
+    import parry_b200
+    pts, idx = pyramid()
+    a, b = parry_b200.TriMesh(ctx, pts, idx), parry_b200.TriMesh(ctx, pts, idx)
+    p1 = np.array([[0, 0, 0, 1, 0, 0, 0]] * 2, np.float32)
+    p2 = np.array([[0, 0, 0, 1, 1000.0, 0, 0]] * 2, np.float32)
+    v1 = np.array([[100000.0, 0, 0], [-100000.0, 0, 0]], np.float32)
+    v2 = np.zeros((2, 3), np.float32)
+    out, st, parts = (np.asarray(x) for x in a.cast_trimesh(p1, v1, b, p2, v2))
+    assert st[0] == 1 and out[0, 12] == np.float32(0.00998)
+    assert (out[0, :6] == np.array([1, -0.5, 0, -1, -0.5, 0], np.float32)).all()          # the two base corners that meet
+    assert st[1] == 0 and (parts[1] == 0xFFFFFFFF).all()
+    oa, ob = oracle.TriMesh(pts, idx), oracle.TriMesh(pts, idx)
+    r = oa.cast_shapes(p1[0], v1[0], p2[0], v2[0], other_mesh=ob)
+    assert r is not None and (r[0].view(np.uint32) == out[0].view(np.uint32)).all()
+
+
+def test_trimesh_cast_trimesh_vs_oracle(ctx, oracle):
+    """Random poses / velocities of two small meshes (a pyramid against a patch of terrain) against the oracle's nested descent."""
+    import parry_b200
+    g = scenes.rng(411)
+    pts, idx = pyramid()
+    v, tidx = scenes.terrain(17, 17, extent=12.0)
+    v = v.copy()
+    v[:, 1] *= 0.2
+    ga, gb = parry_b200.TriMesh(ctx, pts, idx), parry_b200.TriMesh(ctx, v, tidx)
+    oa, ob = oracle.TriMesh(pts, idx), oracle.TriMesh(v, tidx)
+    n = 600
+    lo, hi = v.min(axis=0), v.max(axis=0)
+    t = np.stack([lo[0] + g.random(n) * (hi[0] - lo[0]), hi[1] + 1.6 + g.random(n) * 4.0, lo[2] + g.random(n) * (hi[2] - lo[2])], axis=1)
+    p1 = np.concatenate([scenes.random_unit_quaternions(g, n), t], axis=1).astype(np.float32)
+    p2 = np.tile(np.array([0.02, -0.01, 0.03, 1.0, 0.1, 0.0, -0.1], np.float32), (n, 1))
+    p2[:, :4] /= np.linalg.norm(p2[:, :4], axis=1, keepdims=True)
+    v1 = np.stack([g.standard_normal(n) * 0.5, -(g.random(n) * 2.0 + 0.3), g.standard_normal(n) * 0.5], axis=1).astype(np.float32)
+    v1[g.random(n) < 0.15] *= -1.0
+    v2 = (g.standard_normal((n, 3)) * 0.1).astype(np.float32)
+    for first, second, pa, va, pb, vb, fa, fb in ((ga, gb, p1, v1, p2, v2, oa, ob), (gb, ga, p2, v2, p1, v1, ob, oa)):
+        out, st, parts = (np.asarray(x) for x in first.cast_trimesh(pa, va, second, pb, vb))
+        oo = np.zeros((n, 13), np.float32); os_ = np.zeros(n, np.uint8); op = np.full(n, 0xFFFFFFFF, np.uint32)
+        for k in range(n):
+            r = fa.cast_shapes(pa[k], va[k], pb[k], vb[k], other_mesh=fb)
+            if r is not None:
+                oo[k], os_[k], op[k] = r[0], r[1], r[2]
+        assert 0.3 < (os_ != 0).mean() < 0.95
+        assert ((st != 0) == (os_ != 0)).all()
+        hit = os_ != 0
+        assert (out[hit][:, 12] == oo[hit][:, 12]).mean() > 0.99
+        np.testing.assert_allclose(out[hit][:, 12], oo[hit][:, 12], rtol=1e-5, atol=2e-6)
+        full = hit & (st == os_)                              # status 4 = starts in touch: geometry not offered
+        assert (st[hit & ~full] == 4).all() and full.sum() > 0.9 * hit.sum()
+        same = parts[full][:, 0] == op[full]
+        assert same.mean() > 0.8
+        rows_ok = (np.abs(out[full][same][:, :12] - oo[full][same][:, :12]) < 1e-4).all(axis=1)
+        assert rows_ok.mean() > 0.97, rows_ok.mean()
