@@ -401,6 +401,49 @@ impl<'c> TriMesh<'c> {
     }
 }
 
+impl<'c> TriMesh<'c> {
+    /// `query::cast_shapes(mesh_pose, mesh_vel, &trimesh, poses[k], vels[k], shape k, options)` — the composite arm
+    /// (shape_cast_composite_shape_shape.rs:65-83) — or, with `mesh_second`, the shape as shape 1 and the swapped hit (:86-105):
+    /// `(hit, triangle)` per collider. `options.stop_at_penetration` must be true (the reference's default).
+    pub fn cast_shapes(&self, mesh_pose: &Isometry<Real>, mesh_vel: &Vector<Real>, table: &ShapeTable<'c>, shape_ids: &[u32], poses: &[Isometry<Real>],
+                       vels: &[Vector<Real>], mesh_second: bool, options: ShapeCastOptions)
+                       -> Result<Vec<Result<Option<(ShapeCastHit, u32)>, Unsupported>>, Error> {
+        let n = shape_ids.len();
+        let p7: Vec<[f32; 7]> = poses.iter().map(iso7).collect();
+        let v3: Vec<[f32; 3]> = vels.iter().map(|v| [v.x, v.y, v.z]).collect();
+        let (mp, mv) = (iso7(mesh_pose), [mesh_vel.x, mesh_vel.y, mesh_vel.z]);
+        let (mut out, mut status, mut part) = (vec![0f32; 13 * n], vec![0u8; n], vec![0u32; n]);
+        let (h, t) = (self.h, table.h);
+        self.c.call(|ctx| unsafe {
+            sys::pb2_trimesh_cast_shapes(ctx, h, mp.as_ptr(), mv.as_ptr(), t, shape_ids.as_ptr(), p7.as_ptr() as *const f32, v3.as_ptr() as *const f32,
+                                         mesh_second as i32, options.max_time_of_impact, options.target_distance, options.stop_at_penetration as i32,
+                                         options.compute_impact_geometry_on_penetration as i32, n as u32, out.as_mut_ptr(), status.as_mut_ptr(),
+                                         part.as_mut_ptr(), sys::PB2_MEM_HOST)
+        })?;
+        Ok((0..n).map(|k| cast_of_status(status[k], &out[13 * k..13 * k + 13]).map(|h| h.map(|h| (h, part[k])))).collect())
+    }
+
+    /// `query::cast_shapes(pos1[k], vel1[k], &self, pos2[k], vel2[k], &other, options)` for two TriMeshes (the nesting of the
+    /// reference's tests/geometry/trimesh_trimesh_toi.rs): `(hit, [triangle of self, triangle of other])`. A pair that starts in
+    /// touch while `compute_impact_geometry_on_penetration` is set comes back `Err(Unsupported)` (PB2_CAST_NEEDS_HOST).
+    pub fn cast_trimesh(&self, pos1: &[Isometry<Real>], vel1: &[Vector<Real>], other: &TriMesh<'c>, pos2: &[Isometry<Real>], vel2: &[Vector<Real>],
+                        options: ShapeCastOptions) -> Result<Vec<Result<Option<(ShapeCastHit, [u32; 2])>, Unsupported>>, Error> {
+        let n = pos1.len();
+        let (p1, p2): (Vec<[f32; 7]>, Vec<[f32; 7]>) = (pos1.iter().map(iso7).collect(), pos2.iter().map(iso7).collect());
+        let v1: Vec<[f32; 3]> = vel1.iter().map(|v| [v.x, v.y, v.z]).collect();
+        let v2: Vec<[f32; 3]> = vel2.iter().map(|v| [v.x, v.y, v.z]).collect();
+        let (mut out, mut status, mut parts) = (vec![0f32; 13 * n], vec![0u8; n], vec![[0u32; 2]; n]);
+        let (h1, h2) = (self.h, other.h);
+        self.c.call(|ctx| unsafe {
+            sys::pb2_trimesh_cast_trimesh(ctx, h1, p1.as_ptr() as *const f32, v1.as_ptr() as *const f32, h2, p2.as_ptr() as *const f32,
+                                          v2.as_ptr() as *const f32, options.max_time_of_impact, options.target_distance,
+                                          options.stop_at_penetration as i32, options.compute_impact_geometry_on_penetration as i32, n as u32,
+                                          out.as_mut_ptr(), status.as_mut_ptr(), parts.as_mut_ptr() as *mut u32, sys::PB2_MEM_HOST)
+        })?;
+        Ok((0..n).map(|k| cast_of_status(status[k], &out[13 * k..13 * k + 13]).map(|h| h.map(|h| (h, parts[k])))).collect())
+    }
+}
+
 impl Drop for TriMesh<'_> {
     fn drop(&mut self) {
         let h = self.h;
@@ -469,6 +512,111 @@ impl Drop for ShapeTable<'_> {
     fn drop(&mut self) {
         let h = self.h;
         let _ = self.c.call(|ctx| unsafe { sys::pb2_shapes_destroy(ctx, h) });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ shape::Compound
+/// A table of `Compound`s (`pb2_compounds`, shape/compound.rs:113-144) whose parts are shapes of one [`ShapeTable`]. The composite
+/// arms of `DefaultQueryDispatcher::contact` (default_query_dispatcher.rs:338-351 -> contact_composite_shape_shape.rs:14-76) in
+/// batches; every method returns, next to the contact, the winning part(s) the reference's traversal would have reported.
+pub struct Compounds<'c> {
+    c: &'c B200,
+    h: *mut sys::pb2_compounds,
+}
+unsafe impl Send for Compounds<'_> {}
+unsafe impl Sync for Compounds<'_> {}
+
+impl<'c> Compounds<'c> {
+    /// Every part must be a shape `table` holds (looked up by address, like `ShapeTable::id_of`); otherwise `Error::Unsupported`.
+    pub fn new(c: &'c B200, table: &ShapeTable<'c>, compounds: &[&parry3d::shape::Compound]) -> Result<Self, Error> {
+        let (mut first, mut count, mut part_shape, mut part_pose) = (Vec::<u32>::new(), Vec::<u32>::new(), Vec::<u32>::new(), Vec::<[f32; 7]>::new());
+        for cp in compounds {
+            first.push(part_shape.len() as u32);
+            count.push(cp.shapes().len() as u32);
+            for (pose, shape) in cp.shapes() {
+                part_shape.push(table.id_of(shape.as_ref()).ok_or(Error::Unsupported)?);
+                part_pose.push(iso7(pose));
+            }
+        }
+        let mut h = core::ptr::null_mut();
+        let t = table.h;
+        c.call(|ctx| unsafe {
+            sys::pb2_compounds_create(ctx, t, first.as_ptr(), count.as_ptr(), first.len() as u32, part_shape.as_ptr(), part_pose.as_ptr() as *const f32,
+                                      part_shape.len() as u32, &mut h)
+        })?;
+        Ok(Compounds { c, h })
+    }
+
+    /// `query::contact(compound_poses[k], compound k, shape_poses[k], shape k, prediction)`, or with `compound_second` the shape
+    /// first (contact_shape_composite_shape, :63-76): `(contact, winning part)`.
+    pub fn contact_shapes(&self, compound_ids: &[u32], compound_poses: &[Isometry<Real>], shape_ids: &[u32], shape_poses: &[Isometry<Real>],
+                          prediction: Real, compound_second: bool) -> Result<Vec<Result<Option<(Contact, u32)>, Unsupported>>, Error> {
+        let n = compound_ids.len();
+        let (pc, ps): (Vec<[f32; 7]>, Vec<[f32; 7]>) = (compound_poses.iter().map(iso7).collect(), shape_poses.iter().map(iso7).collect());
+        let (mut out, mut status, mut part) = (vec![sys::pb2_contact::default(); n], vec![0u8; n], vec![0u32; n]);
+        let h = self.h;
+        self.c.call(|ctx| unsafe {
+            sys::pb2_compound_contact_shapes(ctx, h, compound_ids.as_ptr(), pc.as_ptr() as *const f32, shape_ids.as_ptr(), ps.as_ptr() as *const f32,
+                                             n as u32, prediction, compound_second as i32, out.as_mut_ptr(), status.as_mut_ptr(), part.as_mut_ptr(),
+                                             sys::PB2_MEM_HOST)
+        })?;
+        Ok((0..n).map(|k| contact_of_status(status[k], &out[k]).map(|c| c.map(|c| (c, part[k])))).collect())
+    }
+
+    /// `query::contact(poses1[k], compound ids1[k], poses2[k], compound ids2[k], prediction)`: `(contact, [part of 1, part of 2])`.
+    pub fn contact_compounds(&self, ids1: &[u32], poses1: &[Isometry<Real>], ids2: &[u32], poses2: &[Isometry<Real>], prediction: Real)
+                             -> Result<Vec<Result<Option<(Contact, [u32; 2])>, Unsupported>>, Error> {
+        let n = ids1.len();
+        let (p1, p2): (Vec<[f32; 7]>, Vec<[f32; 7]>) = (poses1.iter().map(iso7).collect(), poses2.iter().map(iso7).collect());
+        let (mut out, mut status, mut parts) = (vec![sys::pb2_contact::default(); n], vec![0u8; n], vec![[0u32; 2]; n]);
+        let h = self.h;
+        self.c.call(|ctx| unsafe {
+            sys::pb2_compound_contact_compounds(ctx, h, ids1.as_ptr(), p1.as_ptr() as *const f32, ids2.as_ptr(), p2.as_ptr() as *const f32, n as u32,
+                                                prediction, out.as_mut_ptr(), status.as_mut_ptr(), parts.as_mut_ptr() as *mut u32, sys::PB2_MEM_HOST)
+        })?;
+        Ok((0..n).map(|k| contact_of_status(status[k], &out[k]).map(|c| c.map(|c| (c, parts[k])))).collect())
+    }
+
+    /// `query::contact(poses[k], compound ids[k], mesh_pose, &trimesh, prediction)`: `(contact, [part, triangle])`. The opposite
+    /// argument order nests per triangle in the reference and is not offered on the device.
+    pub fn contact_trimesh(&self, ids: &[u32], poses: &[Isometry<Real>], mesh: &TriMesh<'c>, mesh_pose: &Isometry<Real>, prediction: Real)
+                           -> Result<Vec<Result<Option<(Contact, [u32; 2])>, Unsupported>>, Error> {
+        let n = ids.len();
+        let p7: Vec<[f32; 7]> = poses.iter().map(iso7).collect();
+        let mp = iso7(mesh_pose);
+        let (mut out, mut status, mut parts) = (vec![sys::pb2_contact::default(); n], vec![0u8; n], vec![[0u32; 2]; n]);
+        let (h, m) = (self.h, mesh.h);
+        self.c.call(|ctx| unsafe {
+            sys::pb2_compound_contact_trimesh(ctx, h, ids.as_ptr(), p7.as_ptr() as *const f32, m, mp.as_ptr(), n as u32, prediction, out.as_mut_ptr(),
+                                              status.as_mut_ptr(), parts.as_mut_ptr() as *mut u32, sys::PB2_MEM_HOST)
+        })?;
+        Ok((0..n).map(|k| contact_of_status(status[k], &out[k]).map(|c| c.map(|c| (c, parts[k])))).collect())
+    }
+}
+
+impl Drop for Compounds<'_> {
+    fn drop(&mut self) {
+        let h = self.h;
+        let _ = self.c.call(|ctx| unsafe { sys::pb2_compounds_destroy(ctx, h) });
+    }
+}
+
+/// `PB2_CAST_*` + the 13 floats of one hit -> `cast_shapes`' return value. Unknown shape, or a documented host case: `Unsupported`,
+/// so that a chain re-runs the pair on the CPU.
+fn cast_of_status(status: u8, out: &[f32]) -> Result<Option<ShapeCastHit>, Unsupported> {
+    let hit = |st: ShapeCastStatus| ShapeCastHit {
+        witness1: Point::new(out[0], out[1], out[2]),
+        witness2: Point::new(out[3], out[4], out[5]),
+        normal1: nalgebra::Unit::new_unchecked(Vector::new(out[6], out[7], out[8])),
+        normal2: nalgebra::Unit::new_unchecked(Vector::new(out[9], out[10], out[11])),
+        time_of_impact: out[12],
+        status: st,
+    };
+    match status as usize {
+        sys::PB2_CAST_NONE => Ok(None),
+        sys::PB2_CAST_CONVERGED => Ok(Some(hit(ShapeCastStatus::Converged))),
+        sys::PB2_CAST_PENETRATING => Ok(Some(hit(ShapeCastStatus::PenetratingOrWithinTargetDist))),
+        _ => Err(Unsupported),
     }
 }
 
@@ -679,20 +827,7 @@ impl QueryDispatcher for B200Dispatcher<'_> {
                                        options.stop_at_penetration as i32, options.compute_impact_geometry_on_penetration as i32, 1, out.as_mut_ptr(), &mut status,
                                        sys::PB2_MEM_HOST)
         }).map_err(|_| Unsupported)?;
-        let hit = |st: ShapeCastStatus| ShapeCastHit {
-            witness1: Point::new(out[0], out[1], out[2]),
-            witness2: Point::new(out[3], out[4], out[5]),
-            normal1: nalgebra::Unit::new_unchecked(Vector::new(out[6], out[7], out[8])),
-            normal2: nalgebra::Unit::new_unchecked(Vector::new(out[9], out[10], out[11])),
-            time_of_impact: out[12],
-            status: st,
-        };
-        match status as usize {
-            sys::PB2_CAST_NONE => Ok(None),
-            sys::PB2_CAST_CONVERGED => Ok(Some(hit(ShapeCastStatus::Converged))),
-            sys::PB2_CAST_PENETRATING => Ok(Some(hit(ShapeCastStatus::PenetratingOrWithinTargetDist))),
-            _ => Err(Unsupported),   // unknown shape, or the documented host case: the chain re-runs the pair on the CPU
-        }
+        cast_of_status(status, &out)
     }
 
     /// Not on the device path (SURVEY §8 f3 lists it as open): always `Unsupported`, i.e. `DefaultQueryDispatcher` in a chain.
