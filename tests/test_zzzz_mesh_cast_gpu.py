@@ -188,7 +188,8 @@ def test_trimesh_cast_trimesh_vs_oracle(ctx, oracle):
         np.testing.assert_allclose(out[hit][:, 12], oo[hit][:, 12], rtol=1e-5, atol=2e-6)
         full = hit & (st == os_)                              # status 4 = starts in touch: geometry not offered
         assert (st[hit & ~full] == 4).all() and full.sum() > 0.9 * hit.sum()
-        same = parts[full][:, 0] == op[full]
-        assert same.mean() > 0.8
+        same = parts[full][:, 0] == op[full]                   # (a pyramid's edges and apex belong to 2-3 triangles: ties, see check())
+        assert same.mean() > 0.5
+        assert (out[full][~same][:, 12] == oo[full][~same][:, 12]).mean() > 0.98
         rows_ok = (np.abs(out[full][same][:, :12] - oo[full][same][:, :12]) < 1e-4).all(axis=1)
         assert rows_ok.mean() > 0.97, rows_ok.mean()
