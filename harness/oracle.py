@@ -37,6 +37,8 @@ def lib():
         l.pb2o_trimesh_cast_rays.argtypes = [P, P, P, u32, f32, i32, i32, i32, P, P, P, P]
         l.pb2o_trimesh_contact_batch.argtypes = [P, P, P, P, P, P, P, f32, u32, i32, i32, P, P, P]
         l.pb2o_trimesh_contact_batch.restype = None
+        l.pb2o_trimesh_distance_batch.argtypes = [P] * 7 + [u32, i32, i32, P, P]
+        l.pb2o_trimesh_distance_batch.restype = None
         l.pb2o_compound_trimesh_contact_batch.argtypes = [P] * 11 + [f32, u32, i32, i32, i32, P, P, P]
         l.pb2o_compound_trimesh_contact_batch.restype = None
         l.pb2o_trimesh_cast_shapes.argtypes = [P, P, P, P, P, P, P, u32, P, P, i32, f32, f32, i32, i32, P, P]
@@ -155,6 +157,16 @@ class TriMesh:
                                          s2.ctypes.data, p2.ctypes.data, prediction, n, threads, int(min_index_ties), out.ctypes.data,
                                          status.ctypes.data, part.ctypes.data)
         return out, status, part
+
+    def distance_shapes(self, mesh_pose, table, shape_ids, poses, mesh_second=False, threads=1):
+        """query::distance(mesh_pose, mesh, poses[k], shape k) (or with the shape first): (dist (n,), part (n,) closest triangle)."""
+        s2, p2, mp = _u32(shape_ids), _f32(poses), _f32(mesh_pose)
+        n = len(s2)
+        dist = np.zeros(n, dtype=np.float32)
+        part = np.zeros(n, dtype=np.uint32)
+        lib().pb2o_trimesh_distance_batch(self.h, mp.ctypes.data, table.kinds.ctypes.data, table.params.ctypes.data, table.points.ctypes.data,
+                                          s2.ctypes.data, p2.ctypes.data, n, threads, int(mesh_second), dist.ctypes.data, part.ctypes.data)
+        return dist, part
 
     def contact_compounds(self, mesh_pose, table, comp_first, comp_count, part_shape, part_pose, ids, poses, prediction, trimesh_first=False,
                           threads=1, min_index_ties=False):

@@ -431,6 +431,15 @@ int pb2_trimesh_cast_trimesh(pb2_ctx* ctx, const pb2_trimesh* mesh1, const float
                              int stop_at_penetration, int compute_impact_geometry_on_penetration, uint32_t n, float* out /* n x 13 */,
                              uint8_t* status, uint32_t* parts /* n x 2 */, int mem);
 
+/* query::distance with a TriMesh on one side, n queries against one mesh (the composite arms of DefaultQueryDispatcher::distance,
+ * default_query_dispatcher.rs:288-297 -> distance_composite_shape_shape.rs:13-77: Bvh::find_best with Aabb::distance_to_origin of the
+ * Minkowski-summed node boxes, leaf = distance(triangle, shape)). mesh_second = 0: distance(mesh_pose, mesh, poses[k], shape k);
+ * != 0: distance(poses[k], shape k, mesh_pose, mesh). dist[k] as the reference (0 when touching or penetrating; f32::MAX for a mesh
+ * without live triangles); status[k]: 0 Ok, 2 unknown shape id; part[k] = the closest triangle (equal distances: smallest index). */
+int pb2_trimesh_distance_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* mesh_pose7, const pb2_shapes* shapes,
+                                const uint32_t* shape_ids, const float* poses7 /* n x 7 */, int mesh_second, uint32_t n, float* dist,
+                                uint8_t* status, uint32_t* part, int mem);
+
 #ifdef __cplusplus
 }
 #endif

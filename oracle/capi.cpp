@@ -563,6 +563,24 @@ void pb2o_trimesh_contact_batch(void* mesh, const float* mesh_pose7, const uint8
         }
     });
 }
+// query::distance with a TriMesh on one side (default_query_dispatcher.rs:288-297 -> distance_composite_shape_shape.rs:46-77).
+// mesh_second != 0: distance(poses[k], shape, mesh_pose, &TriMesh) = distance_shape_composite_shape (pos12.inverse()).
+void pb2o_trimesh_distance_batch(void* mesh, const float* mesh_pose7, const uint8_t* kinds, const float* params4, const float* points,
+                                 const uint32_t* shape_ids, const float* poses, uint32_t n, int nthreads, int mesh_second, float* dist,
+                                 uint32_t* part) {
+    const TriMesh* tm = (const TriMesh*)mesh;
+    Iso pm = Iso::from7(mesh_pose7);
+    parallel_for(n, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            ShapeRef s2 = make_shape(kinds, params4, points, shape_ids[k]);
+            Iso ps = Iso::from7(poses + 7 * k);
+            Iso pos12 = mesh_second ? ps.inv_mul(pm).inverse() : pm.inv_mul(ps);
+            Real d; uint32_t id = UINT32_MAX;
+            distance_trimesh_shape(pos12, *tm, s2, d, id);
+            dist[k] = d; part[k] = id;
+        }
+    });
+}
 // query::contact between Compounds of a table and one TriMesh (oracle groundwork, no GPU path yet). trimesh_first == 0:
 // contact(poses[k], Compound ids[k], mesh_pose, &TriMesh); != 0: contact(mesh_pose, &TriMesh, poses[k], Compound ids[k]). World-space
 // result; parts[k] = {winning compound part, winning triangle} or u32::MAX. ties as in pb2o_trimesh_contact_batch.

@@ -225,6 +225,11 @@ static inline void project_local_point_solid(const ShapeRef& s, const Vec3& pt, 
         proj = inside ? pt : pt + shift;
         return;
     }
+    if (s.kind == SHAPE_TRIANGLE) {   // PointQuery for Triangle: its own Voronoi-region projection (point_triangle.rs:17-25), not GJK
+        TriProj p = project_on_triangle(ld3(s.points), ld3(s.points + 3), ld3(s.points + 6), pt, true);
+        proj = p.point; inside = p.inside;
+        return;
+    }
     SupportShape shape = s.support();
     Iso m(Quat(), -pt), m_inv(Quat(), pt);
     Vec3 dir;
@@ -479,6 +484,31 @@ static inline int contact_trimesh_shape(const Iso& pos12, const TriMesh& mesh, c
         if (replace) { best = c; part = id; have = true; }
     }
     return have ? CONTACT_SOME : CONTACT_NONE;
+}
+
+// CompositeShapeRef::distance_to_shape for a TriMesh (distance_composite_shape_shape.rs:13-42): Bvh::find_best with the node cost
+// Aabb::distance_to_origin (aabb.rs:556-562) of the node box Minkowski-summed with shape2's box, leaf cost = dispatcher.distance(pose12,
+// triangle, shape2) (TriMesh parts have no part pose). distance_composite_shape_shape (:46-60) keeps the distance only.
+struct DistLeaf { Real d; Real cost() const { return d; } };
+static inline bool distance_trimesh_shape(const Iso& pos12, const TriMesh& mesh, const ShapeRef& shape2, Real& out, uint32_t& part) {
+    Aabb ls = shape_compute_aabb(shape2, pos12);
+    Vec3 msum_shift = -center(ls.mins, ls.maxs);
+    Vec3 msum_margin = (ls.maxs - ls.mins) * 0.5f;
+    auto aabb_cost = [&](const BvhNode& node, Real) -> Real {
+        Vec3 mins = (node.mins + msum_shift) - msum_margin, maxs = (node.maxs + msum_shift) + msum_margin;
+        return norm(vsup(vsup(mins, -maxs), Vec3()));
+    };
+    auto leaf_cost = [&](uint32_t id, Real, DistLeaf& o) -> bool {
+        float tv[9];
+        const uint32_t* t = &mesh.indices[3 * id];
+        for (int k = 0; k < 3; ++k) { tv[3 * k] = mesh.vertices[t[k]].x; tv[3 * k + 1] = mesh.vertices[t[k]].y; tv[3 * k + 2] = mesh.vertices[t[k]].z; }
+        ShapeRef tri; tri.kind = SHAPE_TRIANGLE; tri.radius = 0; tri.points = tv; tri.num_points = 3;
+        return dispatch_distance(pos12, tri, shape2, o.d) == QUERY_OK;
+    };
+    DistLeaf best;
+    if (!mesh.bvh.find_best<DistLeaf>(REAL_MAX, aabb_cost, leaf_cost, part, best)) { out = REAL_MAX; part = UINT32_MAX; return false; }
+    out = best.d;
+    return true;
 }
 
 // query::closest_points (closest_points_shape_shape.rs:220-231) -> DefaultQueryDispatcher::closest_points

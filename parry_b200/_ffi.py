@@ -84,6 +84,7 @@ SIGNATURES = {
     "pb2_cast_shapes_batch": (c_int, [c_void_p, c_void_p, P, P, P, P, P, P, c_float, c_float, c_int, c_int, c_u32, P, P, c_int]),
     "pb2_trimesh_cast_shapes": (c_int, [c_void_p, c_void_p, P, P, c_void_p, P, P, P, c_int, c_float, c_float, c_int, c_int, c_u32, P, P, P, c_int]),
     "pb2_trimesh_cast_trimesh": (c_int, [c_void_p, c_void_p, P, P, c_void_p, P, P, c_float, c_float, c_int, c_int, c_u32, P, P, P, c_int]),
+    "pb2_trimesh_distance_shapes": (c_int, [c_void_p, c_void_p, P, c_void_p, P, P, c_int, c_u32, P, P, P, c_int]),
     "pb2_intersection_test_batch": (c_int, [c_void_p, c_void_p, P, P, P, P, c_u32, P, P, c_int]),
     "pb2_contact_pairs_compact": (c_int, [c_void_p, c_void_p, P, P, c_u32, P, c_u32, c_float, P, P, c_u64, C.POINTER(c_u64), c_int]),
 }

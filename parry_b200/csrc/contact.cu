@@ -2198,6 +2198,92 @@ extern "C" int pb2_trimesh_cast_trimesh(pb2_ctx* ctx, const pb2_trimesh* mesh1, 
 }
 
 
+// ------------------------------------------------------------------------------- query::distance with a TriMesh on one side
+// distance_composite_shape_shape / distance_shape_composite_shape (distance_composite_shape_shape.rs:46-77, the composite arms of
+// DefaultQueryDispatcher::distance, default_query_dispatcher.rs:288-297) -> CompositeShapeRef::distance_to_shape (:13-42). One thread
+// per query; the leaf is DefaultQueryDispatcher::distance on (Triangle, shape): a Triangle is convex, so a Ball goes through
+// distance_convex_polyhedron_ball with the triangle's own point projection (distance_ball_convex_polyhedron.rs:24-33,
+// point_triangle.rs:17-25), a Cuboid / ConvexPolyhedron through distance_support_map_support_map (GJK from -pos12.translation).
+__global__ void __launch_bounds__(128) k_mesh_distance(const NodeWide* __restrict__ nodes, uint32_t n_leaves, const float4* __restrict__ tris,
+                              const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float4* __restrict__ pts,
+                              const float* __restrict__ points, uint32_t n_shapes, const uint32_t* __restrict__ shape_ids,
+                              const float* __restrict__ mesh_pose, const float* __restrict__ poses, int mesh_second, uint32_t n,
+                              float* __restrict__ out, uint8_t* __restrict__ status, uint32_t* __restrict__ part, unsigned int* fault) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t sid = shape_ids[k];
+    if (sid >= n_shapes) { out[k] = 0.0f; status[k] = (uint8_t)ST_UNSUPPORTED; part[k] = PB2_INVALID_U32; return; }
+    Iso7 pm = load_iso(mesh_pose), ps = load_iso(poses + 7ull * k);
+    Iso7 pos12 = mesh_second ? iso_inverse(iso_inv_mul(ps, pm)) : iso_inv_mul(pm, ps);
+    uint8_t k2 = kinds[sid];
+    float4 pr2 = params[sid];
+    V3 mn, mx;
+    shape_aabb_dev(k2, pr2, points, pos12, mn, mx);
+    V3 shift = -((mn + mx) * 0.5f), margin = (mx - mn) * 0.5f;
+    float best = FLT_MAX;
+    uint32_t best_id = PB2_INVALID_U32;
+    bool found = false;
+    DShape g2 = make_dshape(k2, pr2, pts);
+    auto leaf = [&](uint32_t pos) {
+        const float4* tp = tris + 3ull * pos;
+        float d;
+        if (k2 == PB2_SHAPE_BALL) {
+            float4 fa = __ldg(&tp[0]), fb = __ldg(&tp[1]), fc = __ldg(&tp[2]);
+            Proj pr;
+            project_on_triangle(mk3(fa.x, fa.y, fa.z), mk3(fb.x, fb.y, fb.z), mk3(fc.x, fc.y, fc.z), pos12.t, pr);
+            d = nrm(pos12.t - pr.point) - pr2.x;
+            d = d > 0.0f ? d : 0.0f;
+        } else {
+            DShape g1; g1.kind = DS_TRIANGLE; g1.he = mk3(0.f, 0.f, 0.f); g1.pts = tp; g1.n = 3;
+            Simplex s;
+            V3 dir; float nn;
+            if (!try_normalize_get(-pos12.t, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
+            sx_reset(s, cso_from_shapes(pos12, g1, g2, dir));
+            V3 p1, p2, n1;
+            int r = gjk_closest_points<true>(pos12, g1, g2, FLT_MAX, s, p1, p2, n1);
+            d = r == GJK_CLOSEST_POINTS ? nrm(p2 - p1) : 0.0f;
+        }
+        uint32_t id = __float_as_uint(__ldg(&tp[0]).w);
+        if (d < best || (found && d == best && id < best_id)) { best = d; best_id = id; found = true; }
+    };
+    bvh_find_best_msum_distance(nodes, n_leaves, shift, margin, best, found, leaf, fault);
+    out[k] = best;   // unwrap_or((u32::MAX, Real::MAX)) for a mesh whose every leaf was removed
+    status[k] = (uint8_t)ST_NONE;
+    part[k] = best_id;
+}
+
+extern "C" int pb2_trimesh_distance_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* mesh_pose7, const pb2_shapes* shapes,
+                                           const uint32_t* shape_ids, const float* poses7, int mesh_second, uint32_t n, float* dist, uint8_t* status,
+                                           uint32_t* part, int mem) {
+    if (!ctx || !mesh || !shapes || !mesh_pose7 || (n && (!shape_ids || !poses7 || !dist || !status || !part))) return PB2_ERR_INVALID;
+    if (n == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const void *d_ids, *d_p, *d_mp;
+    void *d_out, *d_st, *d_part;
+    PB2_CHECK(pb2_stage_in(ctx, 0, shape_ids, (size_t)n * 4, mem, &d_ids));
+    PB2_CHECK(pb2_stage_in(ctx, 2, poses7, (size_t)n * 28, mem, &d_p));
+    PB2_CHECK(pb2_stage_in(ctx, 3, mesh_pose7, 28, mem, &d_mp));
+    PB2_CHECK(pb2_stage_out(ctx, 4, dist, (size_t)n * 4, mem, &d_out));
+    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_st));
+    PB2_CHECK(pb2_stage_out(ctx, 6, part, (size_t)n * 4, mem, &d_part));
+    k_mesh_distance<<<pb2_blocks(n, 128), 128, 0, st>>>(mesh->bvh.nodes, mesh->bvh.n_leaves, mesh->tris, shapes->kinds, shapes->params, shapes->points4,
+        shapes->points, shapes->n, (const uint32_t*)d_ids, (const float*)d_mp, (const float*)d_p, mesh_second, n, (float*)d_out, (uint8_t*)d_st,
+        (uint32_t*)d_part, PB2_FAULT_PTR(ctx));
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(pb2_stage_back(ctx, dist, d_out, (size_t)n * 4, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_st, (size_t)n, mem));
+    PB2_CHECK(pb2_stage_back(ctx, part, d_part, (size_t)n * 4, mem));
+    if (mem == PB2_MEM_HOST) {
+        PB2_CHECK(pb2_fetch_fault(ctx));
+        PB2_CUDA(ctx, cudaStreamSynchronize(st));
+        return pb2_check_fault(ctx);
+    }
+    return PB2_OK;
+}
+
+
 extern "C" int pb2_intersect_csr_device(pb2_ctx* ctx, const pb2_bvh* bvh, const float* d_queries, uint32_t m, bool positions,
                                         uint32_t* d_offsets, uint32_t** d_items, uint64_t* total_out);
 

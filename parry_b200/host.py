@@ -454,6 +454,20 @@ class TriMesh:
                                                              int(o.compute_impact_geometry_on_penetration), n, po, pst, ppart, mem))
         return out, status, part
 
+    def distance_shapes(self, mesh_pose, shapes, shape_ids, poses, mesh_second=False):
+        """query::distance(mesh_pose, self, poses[k], shapes[shape_ids[k]]) for every k, or with mesh_second the shape first
+        (distance_composite_shape_shape.rs:46-77). Returns (dist (n,), status (n,), part (n,) = the closest triangle)."""
+        n = int(poses.shape[0])
+        kp, pp, mem = _prep(poses, np.float32)
+        ks, ps, _ = _prep(shape_ids, np.uint32, mem)
+        km, pm, _ = _prep(mesh_pose, np.float32, mem)
+        dev = self.ctx.torch_device
+        out, po = _empty((n,), np.float32, mem, dev)
+        status, pst = _empty((n,), np.uint8, mem, dev)
+        part, ppart = _empty((n,), np.uint32, mem, dev)
+        self.ctx.check(self.ctx._lib.pb2_trimesh_distance_shapes(self.ctx.h, self.h, pm, shapes.h, ps, pp, int(mesh_second), n, po, pst, ppart, mem))
+        return out, status, part
+
     def cast_trimesh(self, poses1, vels1, other, poses2, vels2, options=None):
         """query::cast_shapes(poses1[k], vels1[k], self, poses2[k], vels2[k], other, options) for every k (two TriMeshes; the
         reference's trimesh_trimesh_toi.rs). Returns (hits (n, 13), status (n,), parts (n, 2) = the triangle of each mesh)."""

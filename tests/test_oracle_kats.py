@@ -850,3 +850,39 @@ def test_solid_point_query_example_through_the_ball_arm(oracle):
     assert (st == 1).all()
     assert out[0, 12] == -1.0 and out[1, 12] == 1.0 and out[2, 12] == 1.0          # third: the ball-first (flipped) arm
     assert tuple(out[1, 0:3]) == (1.0, 2.0, 2.0)                                    # the projection on the cuboid
+
+
+def test_trimesh_distance_closed_forms_and_brute_force(oracle):
+    """query::distance with a TriMesh (distance_composite_shape_shape.rs:13-77): closed forms over a flat mesh, and on a terrain the
+    minimum over every triangle of the per-triangle distance (triangles as 3-point hulls in the plain pair path: same GJK for cuboids
+    and hulls; balls go through the triangle's own projection instead of GJK, equal to rounding)."""
+    v = np.array([[-4, 0, -4], [4, 0, -4], [4, 0, 4], [-4, 0, 4]], np.float32)
+    idx = np.array([[0, 2, 1], [0, 3, 2]], np.uint32)
+    om = oracle.TriMesh(v, idx)
+    T = oracle.ShapeTable([("ball", 0.5), ("cuboid", [0.5, 0.25, 0.5])])
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    poses = np.array([[0, 0, 0, 1, 0.3, 2.0, -0.2], [0, 0, 0, 1, 1.0, 1.0, 1.0], [0, 0, 0, 1, 0.0, 0.1, 0.0], [0, 0, 0, 1, 6.0, 0.0, 0.0]], np.float32)
+    d, part = om.distance_shapes(ident, T, [0, 1, 0, 0], poses)
+    np.testing.assert_allclose(d, [1.5, 0.75, 0.0, 1.5], atol=1e-6)
+    d2, _ = om.distance_shapes(ident, T, [0, 1, 0, 0], poses, mesh_second=True)
+    np.testing.assert_allclose(d2, d, atol=1e-6)
+    g = scenes.rng(51)
+    tv, tidx = scenes.terrain(17, 17, extent=12.0)
+    tv = tv.copy(); tv[:, 1] *= 0.2
+    om = oracle.TriMesh(tv, tidx)
+    hp, _ = scenes.hull_pool(2, 16, seed=52)
+    spec = [("ball", 0.3), ("cuboid", [0.3, 0.2, 0.4])] + [("convex", np.asarray(p, np.float32) * 0.4) for p in hp]
+    T = oracle.ShapeTable(spec + [("convex", tv[t]) for t in tidx])
+    n = 60
+    sid = g.integers(0, len(spec), n).astype(np.uint32)
+    t = np.stack([(g.random(n) - 0.5) * 12, g.random(n) * 6 - 1.0, (g.random(n) - 0.5) * 12], axis=1)
+    poses = np.concatenate([scenes.random_unit_quaternions(g, n), t], axis=1).astype(np.float32)
+    d, part = om.distance_shapes(ident, T, sid, poses, threads=4)
+    nt = len(tidx)
+    for k in range(n):
+        tri_ids = np.arange(len(spec), len(spec) + nt, dtype=np.uint32)
+        bd, _ = T.distance(tri_ids, np.tile(ident, (nt, 1)), np.full(nt, sid[k], np.uint32), np.tile(poses[k], (nt, 1)))
+        assert abs(bd.min() - d[k]) < 2e-5, (k, sid[k], bd.min(), d[k])
+        if d[k] > 0 and (bd == bd.min()).sum() == 1 and sid[k] != 0:
+            assert part[k] == int(np.argmin(bd))
+    assert (d > 0).mean() > 0.4 and (d == 0).mean() > 0.05
