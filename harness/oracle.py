@@ -64,6 +64,8 @@ def lib():
         l.pb2o_bvh_leaf_pairs.restype = u64
         l.pb2o_bvh_leaf_pairs.argtypes = [P, P, P, u64]
         l.pb2o_bvh_cast_rays_shapes.argtypes = [P, P, P, P, P, u32, f32, i32, i32, P, P, P, P]
+        l.pb2o_bvh_project_points_shapes.argtypes = [P, P, P, P, P, P, P, P, u32, f32, i32, i32, P, P, P]
+        l.pb2o_bvh_project_points_shapes.restype = None
         l.pb2o_bvh_cast_rays_shapes2.argtypes = [P, P, P, P, P, P, P, P, u32, f32, i32, i32, P, P, P, P]
         l.pb2o_cast_shapes_batch.argtypes = [P, P, P, P, P, P, P, P, P, f32, f32, i32, i32, u32, i32, P, P]
         l.pb2o_compound_contact_batch.argtypes = [P, P, P, P, P, P, P, P, P, P, P, f32, i32, u32, i32, P, P, P]
@@ -294,6 +296,28 @@ class Bvh:
                                          None if normal is None else normal.ctypes.data,
                                          None if feature is None else feature.ctypes.data)
         return (toi, leaf, normal, feature) if with_normal else (toi, leaf)
+
+    def project_points_shapes(self, kinds, params, poses, pts, max_distance, solid=True, threads=1, points=None, first=None, count=None):
+        """Bvh::project_point with typed leaves (as cast_rays_shapes): (proj (m,3) world space, inside (m,), leaf (m,))."""
+        pts = _f32(pts)
+        m = pts.shape[0]
+        kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+        params = _f32(params).reshape(-1, 3)
+        poses = _f32(poses)
+        proj = np.zeros((m, 3), dtype=np.float32)
+        inside = np.zeros(m, dtype=np.uint8)
+        leaf = np.zeros(m, dtype=np.uint32)
+        if points is not None:
+            points = _f32(points).reshape(-1, 3)
+            first = np.ascontiguousarray(first, dtype=np.uint32)
+            count = np.ascontiguousarray(count, dtype=np.uint32)
+        else:
+            assert not (kinds == 2).any()
+        lib().pb2o_bvh_project_points_shapes(self.h, kinds.ctypes.data, params.ctypes.data, None if points is None else points.ctypes.data,
+                                             None if points is None else first.ctypes.data, None if points is None else count.ctypes.data,
+                                             poses.ctypes.data, pts.ctypes.data, m, max_distance, int(solid), threads, proj.ctypes.data,
+                                             inside.ctypes.data, leaf.ctypes.data)
+        return proj, inside, leaf
 
     def __del__(self):
         try:

@@ -256,6 +256,16 @@ int pb2_bvh_cast_rays_shapes(pb2_ctx* ctx, const pb2_bvh* bvh, const pb2_shapes*
                              const float* poses7, const float* rays, uint32_t m, float max_toi, int solid, float* toi,
                              uint32_t* leaf, float* normal, uint32_t* feature, int mem);
 
+/* Bvh::project_point with typed leaves (bvh_queries.rs:213-227: find_best on Aabb::distance_to_local_point, point_aabb.rs:135-146;
+ * leaf check PointQuery::project_point(pose, pt, solid), point_query.rs:147-151, of a Ball point_ball.rs:9-21 / Cuboid point_aabb.rs:9-60
+ * / ConvexPolyhedron point_support_map.rs:17-52): leaf i of `bvh` is shape shape_ids[i] (NULL: shape i) at poses7[i]. proj: m x 3
+ * world-space projections; inside[k] = PointProjection::is_inside; leaf[k] = the leaf projected on (equal distances: smallest index)
+ * or 0xFFFFFFFF; status[k]: 0 nothing within max_distance, 1 found, 3 = solid == 0 and the point lies inside a ConvexPolyhedron
+ * leaf (the reference runs EPA there): host. */
+int pb2_bvh_project_points_shapes(pb2_ctx* ctx, const pb2_bvh* bvh, const pb2_shapes* shapes, const uint32_t* shape_ids, const float* poses7,
+                                  const float* points /* m x 3 */, uint32_t m, float max_distance, int solid, float* proj, uint8_t* inside,
+                                  uint32_t* leaf, uint8_t* status, int mem);
+
 /* ------------------------------------------------------------------ query::contact (query/contact, gjk, epa) */
 /* query::contact(pos1, g1, pos2, g2, prediction) for n pairs — contact_shape_shape.rs:123-138 through
  * DefaultQueryDispatcher::contact (default_query_dispatcher.rs:302-356). Pair k uses shapes shape1[k] /

@@ -563,6 +563,45 @@ void pb2o_trimesh_contact_batch(void* mesh, const float* mesh_pose7, const uint8
         }
     });
 }
+// Bvh::project_point with typed leaves (bvh_queries.rs:213-227; leaves as in pb2o_bvh_cast_rays_shapes2): the leaf check is
+// PointQuery::project_point(pose, pt, solid) (point_query.rs:147-151) of a Ball (point_ball.rs:9-21), a Cuboid (point_cuboid.rs ->
+// point_aabb.rs:9-60) or a ConvexPolyhedron (point_support_map.rs:17-52; EPA when inside and not solid), the cost na::distance of the
+// world-space projection to the point. leaf = UINT32_MAX when nothing lies within max_distance.
+struct ProjLeaf { Real d; Vec3 point; bool inside; Real cost() const { return d; } };
+void pb2o_bvh_project_points_shapes(void* b, const uint8_t* kinds, const float* params, const float* points, const uint32_t* first,
+                                    const uint32_t* count, const float* poses7, const float* pts, uint32_t m, float max_distance, int solid,
+                                    int nthreads, float* proj, uint8_t* inside, uint32_t* leaf) {
+    const Bvh* t = (const Bvh*)b;
+    parallel_for(m, nthreads, [=](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            Vec3 pt = ld3(pts + 3 * i);
+            uint32_t id = UINT32_MAX; ProjLeaf best; best.d = 0; best.inside = false;
+            bool hit = t->find_best<ProjLeaf>(max_distance,
+                [&](const BvhNode& n, Real) { return norm(vsup(vsup(n.mins - pt, pt - n.maxs), Vec3())); },   // Aabb::distance_to_local_point(pt, true)
+                [&](uint32_t prim, Real, ProjLeaf& o) {
+                    Iso pose = Iso::from7(poses7 + 7 * prim);
+                    Vec3 lp = pose.inverse_transform_point(pt), q;
+                    bool in;
+                    if (kinds[prim] == 0) {
+                        Real r = params[3 * prim], d2 = norm_squared(lp);
+                        in = d2 <= r * r;
+                        q = (in && solid) ? lp : lp * (r / sqrtf(d2));
+                    } else {
+                        ShapeRef s;
+                        s.kind = kinds[prim] == 1 ? SHAPE_CUBOID : SHAPE_CONVEX; s.radius = 0; s.half_extents = ld3(params + 3 * prim);
+                        s.points = kinds[prim] == 2 ? points + 3 * (size_t)first[prim] : nullptr; s.num_points = kinds[prim] == 2 ? count[prim] : 0;
+                        if (solid) project_local_point_solid(s, lp, q, in);
+                        else if (kinds[prim] == 1) { Feature f{3, 0}; cuboid_project_point_and_get_feature(s.half_extents, lp, q, in, f); }
+                        else hull_project_point(s.support(), lp, q, in);
+                    }
+                    o.point = pose.transform_point(q); o.inside = in; o.d = norm(pt - o.point);
+                    return true;
+                }, id, best);
+            if (!hit) { st3(proj + 3 * i, Vec3()); inside[i] = 0; leaf[i] = UINT32_MAX; continue; }
+            st3(proj + 3 * i, best.point); inside[i] = best.inside ? 1 : 0; leaf[i] = id;
+        }
+    });
+}
 // query::distance with a TriMesh on one side (default_query_dispatcher.rs:288-297 -> distance_composite_shape_shape.rs:46-77).
 // mesh_second != 0: distance(poses[k], shape, mesh_pose, &TriMesh) = distance_shape_composite_shape (pos12.inverse()).
 void pb2o_trimesh_distance_batch(void* mesh, const float* mesh_pose7, const uint8_t* kinds, const float* params4, const float* points,

@@ -63,6 +63,7 @@ SIGNATURES = {
     "pb2_shapes_destroy": (c_int, [c_void_p, c_void_p]),
     "pb2_shapes_compute_aabbs": (c_int, [c_void_p, c_void_p, P, P, c_u32, P, c_int]),
     "pb2_bvh_cast_rays_shapes": (c_int, [c_void_p, c_void_p, c_void_p, P, P, P, c_u32, c_float, c_int, P, P, P, P, c_int]),
+    "pb2_bvh_project_points_shapes": (c_int, [c_void_p, c_void_p, c_void_p, P, P, P, c_u32, c_float, c_int, P, P, P, P, c_int]),
     "pb2_contact_batch": (c_int, [c_void_p, c_void_p, P, P, P, P, c_float, c_u32, P, P, C.POINTER(c_u64), c_int]),
     "pb2_contact_batch_local": (c_int, [c_void_p, c_void_p, P, P, P, c_float, c_u32, P, P, c_int]),
     "pb2_contact_batch_compact": (c_int, [c_void_p, c_void_p, P, P, P, P, c_float, c_u32, P, P, c_u64, C.POINTER(c_u64), c_int]),

@@ -2284,6 +2284,106 @@ extern "C" int pb2_trimesh_distance_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh
 }
 
 
+// ------------------------------------------------------------------------------- Bvh::project_point with typed leaves
+// Bvh::project_point (bvh_queries.rs:213-227): find_best with node cost Aabb::distance_to_local_point(pt, solid = true)
+// (point_aabb.rs:135-146) and the leaf check PointQuery::project_point(pose, pt, solid) (point_query.rs:147-151) of the leaf's shape:
+// Ball (point_ball.rs:9-21), Cuboid (point_cuboid.rs -> point_aabb.rs:9-60), ConvexPolyhedron (point_support_map.rs:17-52: GJK, the
+// point itself when inside and solid). A point inside a hull with solid = false needs EPA (:39-52), which one thread inside a descent
+// does not run: that query is answered status 3. Leaf cost = na::distance(world-space projection, pt).
+__global__ void __launch_bounds__(128) k_project_points_shapes(const NodeWide* __restrict__ nodes, const uint32_t* __restrict__ order, uint32_t n_leaves,
+                              const uint8_t* __restrict__ kinds, const float4* __restrict__ params, const float4* __restrict__ pts,
+                              uint32_t n_shapes, const uint32_t* __restrict__ shape_ids, const float* __restrict__ poses,
+                              const float* __restrict__ points, uint32_t m, float max_distance, bool solid, float* __restrict__ out_proj,
+                              uint8_t* __restrict__ out_inside, uint32_t* __restrict__ out_leaf, uint8_t* __restrict__ status, unsigned int* fault) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const V3 p = mk3(points[3ull * k], points[3ull * k + 1], points[3ull * k + 2]);
+    float best = max_distance;
+    bool found = false, best_inside = false, needs_host = false;
+    uint32_t best_id = PB2_INVALID_U32;
+    V3 best_pt = mk3(0.f, 0.f, 0.f);
+    auto leaf = [&](uint32_t pos) {
+        uint32_t id = order[pos];
+        uint32_t sid = shape_ids ? shape_ids[id] : id;
+        if (sid >= n_shapes) { atomicOr(fault, PB2_FAULT_BAD_ID); return; }
+        Iso7 pose = load_iso(poses + 7ull * id);
+        V3 lp = iso_inv_point(pose, p), q;
+        bool in;
+        float4 pr = params[sid];
+        uint8_t kind = kinds[sid];
+        if (kind == PB2_SHAPE_BALL) {
+            float d2 = nrm2(lp);
+            in = d2 <= pr.x * pr.x;
+            q = (in && solid) ? lp : lp * (pr.x / sqrtf(d2));
+        } else if (kind == PB2_SHAPE_CUBOID) {
+            Feat f;
+            d_cuboid_project(mk3(pr.x, pr.y, pr.z), lp, q, in, f);   // the non-solid projection
+            if (in && solid) q = lp;
+        } else {
+            DShape g1 = make_dshape(kind, pr, pts), g2 = origin_dshape();
+            Simplex s;
+            V3 dir; float nn;
+            if (!try_normalize_get(lp, PB2_EPS, dir, nn)) dir = mk3(1.f, 0.f, 0.f);
+            Iso7 m_inv; m_inv.q.i = 0.f; m_inv.q.j = 0.f; m_inv.q.k = 0.f; m_inv.q.w = 1.f; m_inv.t = lp;
+            sx_reset(s, cso_from_shapes(m_inv, g1, g2, dir));
+            Iso7 mm; mm.q = m_inv.q; mm.t = -lp;
+            V3 p1, p2, n1;
+            int r = gjk_closest_points<true>(iso_inverse(mm), g1, g2, FLT_MAX, s, p1, p2, n1);
+            in = r != GJK_CLOSEST_POINTS;
+            if (in && !solid) { needs_host = true; return; }
+            q = in ? lp : p1;
+        }
+        V3 w = iso_point(pose, q);
+        float d = nrm(p - w);
+        if (d < best || (found && d == best && id < best_id)) { best = d; best_id = id; best_pt = w; best_inside = in; found = true; }
+    };
+    auto cost = [&](float4 lo, float4 hi, float) {
+        V3 shift = vmax3(vmax3(mk3(lo.x, lo.y, lo.z) - p, p - mk3(hi.x, hi.y, hi.z)), mk3(0.f, 0.f, 0.f));
+        return nrm(shift);
+    };
+    bvh_find_best_cost(nodes, n_leaves, max_distance, best, found, cost, leaf, fault);
+    if (needs_host) { found = false; best_pt = mk3(0.f, 0.f, 0.f); best_inside = false; best_id = PB2_INVALID_U32; }
+    out_proj[3ull * k] = best_pt.x; out_proj[3ull * k + 1] = best_pt.y; out_proj[3ull * k + 2] = best_pt.z;
+    out_inside[k] = best_inside ? 1 : 0;
+    out_leaf[k] = best_id;
+    status[k] = needs_host ? (uint8_t)ST_NEEDS_HOST : (found ? (uint8_t)ST_SOME : (uint8_t)ST_NONE);
+}
+
+extern "C" int pb2_bvh_project_points_shapes(pb2_ctx* ctx, const pb2_bvh* bvh, const pb2_shapes* shapes, const uint32_t* shape_ids, const float* poses7,
+                                             const float* points, uint32_t m, float max_distance, int solid, float* proj, uint8_t* inside,
+                                             uint32_t* leaf, uint8_t* status, int mem) {
+    if (!ctx || !bvh || !shapes || !poses7 || (m && (!points || !proj || !inside || !leaf || !status))) return PB2_ERR_INVALID;
+    if (m == 0) return PB2_OK;
+    PB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint32_t nl = bvh->n_leaves;
+    const void *d_pts, *d_ids = nullptr, *d_poses;
+    void *d_proj, *d_in, *d_leaf, *d_st;
+    PB2_CHECK(pb2_stage_in(ctx, 0, points, (size_t)m * 12, mem, &d_pts));
+    PB2_CHECK(pb2_stage_in(ctx, 1, shape_ids, (size_t)nl * 4, mem, &d_ids));
+    PB2_CHECK(pb2_stage_in(ctx, 6, poses7, (size_t)nl * 28, mem, &d_poses));
+    PB2_CHECK(pb2_stage_out(ctx, 2, proj, (size_t)m * 12, mem, &d_proj));
+    PB2_CHECK(pb2_stage_out(ctx, 3, inside, (size_t)m, mem, &d_in));
+    PB2_CHECK(pb2_stage_out(ctx, 4, leaf, (size_t)m * 4, mem, &d_leaf));
+    PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)m, mem, &d_st));
+    k_project_points_shapes<<<pb2_blocks(m, 128), 128, 0, st>>>(bvh->nodes, bvh->leaf_order, nl, shapes->kinds, shapes->params, shapes->points4,
+        shapes->n, (const uint32_t*)d_ids, (const float*)d_poses, (const float*)d_pts, m, max_distance, solid != 0, (float*)d_proj,
+        (uint8_t*)d_in, (uint32_t*)d_leaf, (uint8_t*)d_st, PB2_FAULT_PTR(ctx));
+    PB2_LAUNCHED(ctx);
+    PB2_CUDA(ctx, cudaGetLastError());
+    PB2_CHECK(pb2_stage_back(ctx, proj, d_proj, (size_t)m * 12, mem));
+    PB2_CHECK(pb2_stage_back(ctx, inside, d_in, (size_t)m, mem));
+    PB2_CHECK(pb2_stage_back(ctx, leaf, d_leaf, (size_t)m * 4, mem));
+    PB2_CHECK(pb2_stage_back(ctx, status, d_st, (size_t)m, mem));
+    if (mem == PB2_MEM_HOST) {
+        PB2_CHECK(pb2_fetch_fault(ctx));
+        PB2_CUDA(ctx, cudaStreamSynchronize(st));
+        return pb2_check_fault(ctx);
+    }
+    return PB2_OK;
+}
+
+
 extern "C" int pb2_intersect_csr_device(pb2_ctx* ctx, const pb2_bvh* bvh, const float* d_queries, uint32_t m, bool positions,
                                         uint32_t* d_offsets, uint32_t** d_items, uint64_t* total_out);
 

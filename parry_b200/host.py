@@ -296,6 +296,22 @@ class Bvh:
                                                              int(bool(solid)), pt, pl, pn, pf, mem))
         return (toi, leaf, normal, feature) if with_normal else (toi, leaf)
 
+    def project_point(self, shapes, shape_ids, poses, points, max_distance, solid=True):
+        """Batched Bvh::project_point with typed leaves (bvh_queries.rs:213-227): leaf i = shapes[shape_ids[i]] at poses[i]. Returns
+        (proj (m, 3) world space, inside (m,), leaf (m,), status (m,): 0 nothing within max_distance, 1 found, 3 host)."""
+        m = int(points.shape[0])
+        kq, pq, mem = _prep(points, np.float32)
+        ks, ps, _ = _prep(shape_ids, np.uint32, mem)
+        kp, pp, _ = _prep(poses, np.float32, mem)
+        dev = self.ctx.torch_device
+        proj, ppr = _empty((m, 3), np.float32, mem, dev)
+        inside, pin = _empty((m,), np.uint8, mem, dev)
+        leaf, pl = _empty((m,), np.uint32, mem, dev)
+        status, pst = _empty((m,), np.uint8, mem, dev)
+        self.ctx.check(self.ctx._lib.pb2_bvh_project_points_shapes(self.ctx.h, self.h, shapes.h, ps, pp, pq, m, float(max_distance),
+                                                                   int(bool(solid)), ppr, pin, pl, pst, mem))
+        return proj, inside, leaf, status
+
     def close(self):
         if self.owned and self.h:
             self.ctx._lib.pb2_bvh_destroy(self.ctx.h, self.h)

@@ -499,6 +499,63 @@ def test_bvh_cast_ray_convex_leaves(ctx, oracle):
             assert (g[3][same & hit & (kinds[np.minimum(r[1], n - 1)] == 2)] == 0xFFFFFFFE).all()
 
 
+def test_bvh_project_point_typed_leaves(ctx, oracle):
+    """SURVEY §8 f3: Bvh::project_point over ball / cuboid / ConvexPolyhedron leaves (bvh_queries.rs:213-227) through
+    pb2_bvh_project_points_shapes: the leaf and the inside flag exact but for equal distances, projections 1e-5; max_distance prunes;
+    solid = false asks the host only for points inside a hull."""
+    import parry_b200
+    n, H = 1500, 64
+    g0 = scenes.rng(63)
+    hulls, _ = scenes.hull_pool(H, 16, seed=64)
+    hulls = (hulls * 0.5).astype(np.float32)
+    kinds = g0.integers(0, 3, n).astype(np.uint8)
+    params = (g0.random((n, 3)) * 0.3 + 0.15).astype(np.float32)
+    hid = g0.integers(0, H, n)
+    side = (n ** (1 / 3)) * 1.2
+    poses = np.concatenate([scenes.random_unit_quaternions(g0, n), g0.random((n, 3)) * side], axis=1).astype(np.float32)
+    shapes = parry_b200.Shapes(ctx, [parry_b200.Ball(p[0]) if k == 0 else parry_b200.Cuboid(p) if k == 1 else parry_b200.ConvexPolyhedron(hulls[h])
+                                     for k, p, h in zip(kinds, params, hid)])
+    ids = np.arange(n, dtype=np.uint32)
+    aabbs = shapes.compute_aabbs(ids, poses)
+    gb, ob = parry_b200.Bvh.from_leaves(ctx, 0, aabbs), oracle.Bvh(aabbs)
+    points = np.concatenate([hulls[h] for h in hid])
+    first = (np.arange(n) * 16).astype(np.uint32)
+    count = np.full(n, 16, np.uint32)
+    m = 20000
+    q = (g0.random((m, 3)) * (side + 2.0) - 1.0).astype(np.float32)
+    # a tenth of the query points sit inside a leaf's shape (near its centre)
+    pick = g0.integers(0, n, m // 10)
+    q[: m // 10] = poses[pick, 4:] + (g0.standard_normal((m // 10, 3)) * 0.05).astype(np.float32)
+    for solid in (True, False):
+        for max_dist in (FMAX, 0.4):
+            g = [np.asarray(x) for x in gb.project_point(shapes, ids, poses, q, max_dist, solid=solid)]
+            r = ob.project_points_shapes(kinds, params, poses, q, max_dist, solid=solid, threads=8, points=points, first=first, count=count)
+            host = g[3] == 3
+            if solid:
+                assert not host.any()
+            else:   # only where the reference ends up inside a hull (its EPA branch)
+                assert 0 < host.sum() < 0.1 * m
+            found = r[2] != INVALID
+            ok = ~host
+            assert ((g[2] != INVALID) == found)[ok].all() and ((g[3] == 1) == found)[ok].all()
+            if max_dist == FMAX:
+                assert found.all()
+            else:
+                assert 0.1 < found.mean() < 0.9
+            same = ok & found & (g[2] == r[2])
+            assert same.sum() > 0.97 * (ok & found).sum()
+            np.testing.assert_allclose(g[0][same], r[0][same], rtol=1e-5, atol=2e-6)
+            assert (g[1][same] == r[1][same]).all()
+            assert r[1][found].mean() > 0.05 and (kinds[r[2][found]] == 2).mean() > 0.15
+            # a different leaf only at (nearly) equal distances: overlapping solids both containing the point, or rounding
+            diff = ok & found & (g[2] != r[2])
+            dg = np.linalg.norm(g[0][diff] - q[diff], axis=1)
+            dr = np.linalg.norm(r[0][diff] - q[diff], axis=1)
+            np.testing.assert_allclose(dg, dr, rtol=1e-5, atol=2e-6)
+            if not solid:   # the hosted queries are exactly those whose answer (or a nearer candidate's) lies inside a hull
+                assert (kinds[r[2][host & found]] == 2).mean() > 0.5
+
+
 def test_bvh_api_mirrors(ctx, oracle):
     """from_iter with gaps, refit_without_opt, optimize_incremental: the pair set always equals the brute-force set of the
     leaves that are present."""

@@ -886,3 +886,24 @@ def test_trimesh_distance_closed_forms_and_brute_force(oracle):
         if d[k] > 0 and (bd == bd.min()).sum() == 1 and sid[k] != 0:
             assert part[k] == int(np.argmin(bd))
     assert (d > 0).mean() > 0.4 and (d == 0).mean() > 0.05
+
+
+def test_bvh_project_point_typed_leaves_closed_forms(oracle):
+    """Bvh::project_point (bvh_queries.rs:213-227) over typed leaves: closed forms for a ball and a cuboid leaf, solid and not, and the
+    max_distance cut-off (strict: find_best only accepts costs below it)."""
+    I = [0.0, 0.0, 0.0, 1.0]
+    poses = np.array([I + [0, 0, 0], I + [5, 0, 0]], np.float32)
+    kinds = np.array([0, 1], np.uint8)
+    params = np.array([[1.0, 0, 0], [0.5, 1.0, 1.0]], np.float32)
+    aabbs = np.array([[-1, -1, -1, 1, 1, 1], [4.5, -1, -1, 5.5, 1, 1]], np.float32)
+    b = oracle.Bvh(aabbs)
+    pts = np.array([[3, 0, 0], [0.5, 0, 0], [5.1, 0.2, 0.3], [2.0, 0, 0], [-4, 0, 0]], np.float32)
+    proj, inside, leaf = b.project_points_shapes(kinds, params, poses, pts, float(np.finfo(np.float32).max), solid=True)
+    assert leaf.tolist() == [1, 0, 1, 0, 0] and inside.tolist() == [0, 1, 1, 0, 0]
+    np.testing.assert_allclose(proj, [[4.5, 0, 0], [0.5, 0, 0], [5.1, 0.2, 0.3], [1, 0, 0], [-1, 0, 0]], atol=1e-6)
+    proj, inside, leaf = b.project_points_shapes(kinds, params, poses, pts, float(np.finfo(np.float32).max), solid=False)
+    assert inside.tolist() == [0, 1, 1, 0, 0]
+    np.testing.assert_allclose(proj[1], [1, 0, 0], atol=1e-6)            # pushed to the sphere
+    np.testing.assert_allclose(proj[2], [5.5, 0.2, 0.3], atol=1e-6)      # pushed to the nearest face
+    proj, inside, leaf = b.project_points_shapes(kinds, params, poses, pts, 1.5, solid=True)
+    assert leaf.tolist() == [0xFFFFFFFF, 0, 1, 0, 0xFFFFFFFF]            # 1.5 away is not < 1.5; 3 away is cut
