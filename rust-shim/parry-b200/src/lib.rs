@@ -295,6 +295,33 @@ impl<'c> Bvh<'c> {
     }
 }
 
+impl<'c> Bvh<'c> {
+    /// `Bvh::project_point(point, max_distance, |leaf, _| shape(leaf).project_point(pose(leaf), point, solid))`
+    /// (bvh_queries.rs:213-227) for a batch of points over typed leaves: `Some((leaf, (distance, projection)))` per point.
+    /// `Err(Unsupported)`: `solid == false` and the point lies inside a ConvexPolyhedron leaf (the reference's EPA branch).
+    pub fn project_points(&self, table: &ShapeTable<'c>, shape_ids: &[u32], poses: &[Isometry<Real>], points: &[Point<Real>], max_distance: Real,
+                          solid: bool) -> Result<Vec<Result<Option<(u32, (Real, parry3d::query::PointProjection))>, Unsupported>>, Error> {
+        let m = points.len();
+        let p7: Vec<[f32; 7]> = poses.iter().map(iso7).collect();
+        let q: Vec<[f32; 3]> = points.iter().map(|p| [p.x, p.y, p.z]).collect();
+        let (mut proj, mut inside, mut leaf, mut status) = (vec![[0f32; 3]; m], vec![0u8; m], vec![0u32; m], vec![0u8; m]);
+        let (h, t) = (self.h, table.h);
+        self.c.call(|ctx| unsafe {
+            sys::pb2_bvh_project_points_shapes(ctx, h, t, shape_ids.as_ptr(), p7.as_ptr() as *const f32, q.as_ptr() as *const f32, m as u32, max_distance,
+                                               solid as i32, proj.as_mut_ptr() as *mut f32, inside.as_mut_ptr(), leaf.as_mut_ptr(), status.as_mut_ptr(),
+                                               sys::PB2_MEM_HOST)
+        })?;
+        Ok((0..m).map(|k| match status[k] {
+            0 => Ok(None),
+            1 => {
+                let pt = Point::new(proj[k][0], proj[k][1], proj[k][2]);
+                Ok(Some((leaf[k], (nalgebra::distance(&pt, &points[k]), parry3d::query::PointProjection::new(inside[k] != 0, pt)))))
+            }
+            _ => Err(Unsupported),
+        }).collect())
+    }
+}
+
 impl Drop for Bvh<'_> {
     fn drop(&mut self) {
         let h = self.h;
