@@ -433,9 +433,9 @@ int pb2_trimesh_cast_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* 
 /* query::cast_shapes between two TriMeshes, n pose / velocity pairs for the same two meshes (the nesting the reference's
  * crates/parry3d/tests/geometry/trimesh_trimesh_toi.rs exercises, issue #194: cast_shapes_composite_shape_shape over mesh 1, every
  * reached triangle through cast_shapes_shape_composite_shape over mesh 2, shape_cast_composite_shape_shape.rs:65-105). out as
- * pb2_cast_shapes_batch; parts: n x 2 = {triangle of mesh 1, triangle of mesh 2} or 0xFFFFFFFF. status PB2_CAST_NEEDS_HOST: the
- * winning pair starts in touch (time < 1e-5) and compute_impact_geometry_on_penetration asks for its triangle-triangle contact —
- * time_of_impact and parts are valid, witnesses / normals are not. stop_at_penetration = 0 is PB2_ERR_UNSUPPORTED. */
+ * pb2_cast_shapes_batch; parts: n x 2 = {triangle of mesh 1, triangle of mesh 2} or 0xFFFFFFFF. A winning pair that starts in touch
+ * (time < 1e-5) takes its witnesses / normals from the triangle-triangle contact, as the reference does when
+ * compute_impact_geometry_on_penetration is set. stop_at_penetration = 0 is PB2_ERR_UNSUPPORTED. */
 int pb2_trimesh_cast_trimesh(pb2_ctx* ctx, const pb2_trimesh* mesh1, const float* pos1 /* n x 7 */, const float* vel1 /* n x 3 */,
                              const pb2_trimesh* mesh2, const float* pos2, const float* vel2, float max_time_of_impact, float target_distance,
                              int stop_at_penetration, int compute_impact_geometry_on_penetration, uint32_t n, float* out /* n x 13 */,

@@ -317,6 +317,7 @@ struct PairSetup {
     Iso7 cb_pos12;  // pos12 seen by contact_convex_polyhedron_ball (mode 2: pos12, mode 3: pos12.inverse())
     DShape g1, g2;
     const float4* tri;  // shape 1 is this TriMesh triangle (k1 == PB2_SHAPE_TRIANGLE_INTERNAL), else NULL
+    const float4* tri2; // shape 2 is this triangle (support-map arm only: TriMesh-vs-TriMesh shape casts), else NULL
     bool local_frames;
 };
 
@@ -331,6 +332,7 @@ struct PairSrc {
     const float* pos2;
     const uint32_t* ab;
     const float4* mesh_tris;
+    const float4* mesh_tris2 = nullptr;   // optional: shape 2 of pair k is the triangle at mesh_tris2[3 * ab[2k+1]] (shape2 is not read)
     uint32_t n_first, n_second;   // index bounds for ab[2k] / ab[2k+1]
     uint32_t flags = 0;           // PAIR_* below
     const float* init_dir = nullptr;   // optional GJK seed of the support-map arm (contact_manifolds_pfm_pfm.rs:66: last frame's
@@ -351,9 +353,16 @@ __device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* p
                                            PairSetup& ps) {
     uint32_t i1 = k, i2 = k;
     if (src.ab) { i1 = src.ab[2ull * k]; i2 = src.ab[2ull * k + 1]; }
-    uint32_t s2 = src.shape2[i2];
-    ps.k2 = kinds[s2];
-    ps.pr2 = params[s2];
+    ps.tri2 = nullptr;
+    if (src.mesh_tris2) {
+        ps.tri2 = src.mesh_tris2 + 3ull * i2;
+        ps.k2 = PB2_SHAPE_TRIANGLE_INTERNAL;
+        ps.pr2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        uint32_t s2 = src.shape2[i2];
+        ps.k2 = kinds[s2];
+        ps.pr2 = params[s2];
+    }
     ps.pos2 = load_iso(src.pos2 + 7ull * i2);
     const float4* tri = nullptr;
     if (src.mesh_tris) {
@@ -385,7 +394,8 @@ __device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* p
         ps.gpos12 = ps.pos12;
         if (tri) { ps.g1.kind = DS_TRIANGLE; ps.g1.he = mk3(0.f, 0.f, 0.f); ps.g1.pts = tri; ps.g1.n = 3; }
         else ps.g1 = make_dshape(ps.k1, ps.pr1, pts);
-        ps.g2 = make_dshape(ps.k2, ps.pr2, pts);
+        if (ps.tri2) { ps.g2.kind = DS_TRIANGLE; ps.g2.he = mk3(0.f, 0.f, 0.f); ps.g2.pts = ps.tri2; ps.g2.n = 3; }
+        else ps.g2 = make_dshape(ps.k2, ps.pr2, pts);
         if (b1) ps.g1.kind = DS_BALL;
         if (b2) ps.g2.kind = DS_BALL;
     } else if (!b1 && !b2) {
@@ -553,7 +563,7 @@ __global__ void __launch_bounds__(128, MINB) k_contact_gjk(const uint8_t* __rest
         uint32_t i1 = k, i2 = k;
         if (src.ab) { i1 = src.ab[2ull * k]; i2 = src.ab[2ull * k + 1]; }
         bool bad = src.ab && (i1 >= src.n_first || i2 >= src.n_second);
-        if (!bad) bad = src.shape2[i2] >= n_shapes || (!src.mesh_tris && src.shape1[i1] >= n_shapes);
+        if (!bad) bad = (!src.mesh_tris2 && src.shape2[i2] >= n_shapes) || (!src.mesh_tris && src.shape1[i1] >= n_shapes);
         if (bad) { emit(out, k, ST_UNSUPPORTED, c); return; }
     }
     PairSetup ps;
@@ -643,7 +653,7 @@ __global__ void __launch_bounds__(128, MINB) k_contact_gjk_persistent(const uint
                     uint32_t i1 = k, i2 = k;
                     if (src.ab) { i1 = src.ab[2ull * k]; i2 = src.ab[2ull * k + 1]; }
                     bool bad = src.ab && (i1 >= src.n_first || i2 >= src.n_second);
-                    if (!bad) bad = src.shape2[i2] >= n_shapes || (!src.mesh_tris && src.shape1[i1] >= n_shapes);
+                    if (!bad) bad = (!src.mesh_tris2 && src.shape2[i2] >= n_shapes) || (!src.mesh_tris && src.shape1[i1] >= n_shapes);
                     if (bad) {
                         emit(out, k, ST_UNSUPPORTED, c);
                     } else {
@@ -1299,9 +1309,10 @@ __global__ void __launch_bounds__(128, 4) k_contact_epac(const uint8_t* __restri
 static int run_contacts(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* shape1, const uint32_t* shape2, const float* pos1,
                         const float* pos2, float prediction, uint32_t n, OutSinks sinks, const uint32_t* ab = nullptr, uint32_t n_colliders = 0,
                         const float4* mesh_tris = nullptr, uint32_t n_tris = 0, uint32_t flags = 0, const float* part_pose = nullptr,
-                        uint32_t n_parts = 0, const float* init_dir = nullptr, uint32_t init_stride = 3) {
+                        uint32_t n_parts = 0, const float* init_dir = nullptr, uint32_t init_stride = 3, const float4* mesh_tris2 = nullptr) {
     PairSrc src;
     src.flags = flags;
+    src.mesh_tris2 = mesh_tris2;
     src.init_dir = init_dir; src.init_stride = init_stride;
     src.part_pose = part_pose;
     src.shape1 = shape1; src.shape2 = shape2; src.pos1 = pos1; src.pos2 = pos2; src.ab = ab; src.mesh_tris = mesh_tris;
@@ -2074,11 +2085,13 @@ extern "C" int pb2_trimesh_cast_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, co
 __global__ void __launch_bounds__(128) k_mesh_cast_mesh(const NodeWide* __restrict__ nodes1, uint32_t nl1, const float4* __restrict__ tris1,
                               const NodeWide* __restrict__ nodes2, uint32_t nl2, const float4* __restrict__ tris2, const float* __restrict__ pos1,
                               const float* __restrict__ vel1, const float* __restrict__ pos2, const float* __restrict__ vel2, CastOpts o, uint32_t n,
-                              float* __restrict__ out, uint8_t* __restrict__ status, uint32_t* __restrict__ parts, unsigned int* fault) {
+                              float* __restrict__ out, uint8_t* __restrict__ status, uint32_t* __restrict__ parts, uint32_t* __restrict__ parked,
+                              uint32_t* __restrict__ parked_pos, unsigned long long* parked_count, unsigned int* fault) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     Iso7 p1 = load_iso(pos1 + 7ull * k), p2 = load_iso(pos2 + 7ull * k);
     Iso7 pos12 = iso_inv_mul(p1, p2);
+    uint32_t best_pa = 0, best_pb = 0;
     V3 v1 = mk3(vel1[3ull * k], vel1[3ull * k + 1], vel1[3ull * k + 2]), v2 = mk3(vel2[3ull * k], vel2[3ull * k + 1], vel2[3ull * k + 2]);
     V3 vel12 = iso_inv_vec(p1, v2 - v1);
     int st = CAST_NONE;
@@ -2113,7 +2126,7 @@ __global__ void __launch_bounds__(128) k_mesh_cast_mesh(const NodeWide* __restri
             V3 shift2 = -((bmn + bmx) * 0.5f), margin2 = (bmx - bmn) * 0.5f + tgt;
             float ibest = o.max_toi;
             bool ifound = false;
-            uint32_t iid2 = PB2_INVALID_U32;
+            uint32_t iid2 = PB2_INVALID_U32, ipb = 0;
             int ist = CAST_NONE;
             V3 iw1 = mk3(0.f, 0.f, 0.f), iw2 = iw1, in1 = iw1, in2 = iw1;
             auto leaf2 = [&](uint32_t pb) {
@@ -2130,7 +2143,7 @@ __global__ void __launch_bounds__(128) k_mesh_cast_mesh(const NodeWide* __restri
                 if (!minkowski_ray_cast(cso, s, mk3(0.f, 0.f, 0.f), vel21, FLT_MAX, toi, normal1) || toi > o.max_toi) return;
                 uint32_t id2 = __float_as_uint(__ldg(&t2[0]).w);
                 if (!(toi < ibest || (ifound && toi == ibest && id2 < iid2))) return;
-                ibest = toi; iid2 = id2; ifound = true;
+                ibest = toi; iid2 = id2; ipb = pb; ifound = true;
                 if (o.compute_geometry && toi < 1.0e-5f) { ist = CAST_PARKED; return; }
                 V3 r0 = mk3(0.f, 0.f, 0.f), r1 = r0;
                 if (toi != 0.0f) gjk_witness(s, s.dim == 3, r0, r1);
@@ -2144,20 +2157,57 @@ __global__ void __launch_bounds__(128) k_mesh_cast_mesh(const NodeWide* __restri
             if (!ifound) return;
             uint32_t id1 = __float_as_uint(fa.w);
             if (!(ibest < best || (found && ibest == best && id1 < best_id1))) return;
-            best = ibest; best_id1 = id1; best_id2 = iid2; found = true;
+            best = ibest; best_id1 = id1; best_id2 = iid2; best_pa = pa; best_pb = ipb; found = true;
             st = ist;
             w1 = iw2; w2 = iw1; n1 = in2; n2 = in1;   // ShapeCastHit::swapped
         };
         bvh_find_best_msum(nodes1, nl1, shift, margin, vel12, inv12, o.max_toi, best, found, leaf1, fault);
     }
-    // a winner that starts in touch wants the triangle-triangle contact for its geometry, which the contact kernels do not take
-    if (st == CAST_PARKED) { st = CAST_NEEDS_HOST; w1 = w2 = n1 = n2 = mk3(0.f, 0.f, 0.f); }
+    // a winner that starts in touch takes its geometry from the triangle-triangle contact (second phase)
+    if (st == CAST_PARKED) {
+        unsigned long long at = warp_append1(parked_count);
+        parked[at] = k;
+        parked_pos[2 * at] = best_pa; parked_pos[2 * at + 1] = best_pb;
+        w1 = w2 = n1 = n2 = mk3(0.f, 0.f, 0.f);
+    }
     float* q = out + 13ull * k;
     q[0] = w1.x; q[1] = w1.y; q[2] = w1.z; q[3] = w2.x; q[4] = w2.y; q[5] = w2.z;
     q[6] = n1.x; q[7] = n1.y; q[8] = n1.z; q[9] = n2.x; q[10] = n2.y; q[11] = n2.z; q[12] = found ? best : 0.0f;
     status[k] = (uint8_t)st;
     parts[2ull * k] = found ? best_id1 : PB2_INVALID_U32;
     parts[2ull * k + 1] = found ? best_id2 : PB2_INVALID_U32;
+}
+
+// Second phase of TriMesh-vs-TriMesh casts that start in touch: the winning triangle pairs as stand-alone records. The inner leaf
+// problem of the reference is (triangle of mesh 2, triangle of mesh 1) under pos21 (shape_cast_composite_shape_shape.rs:95-103).
+__global__ void k_mm_gather(const uint32_t* __restrict__ parked, const uint32_t* __restrict__ ppos, uint32_t cnt, const float4* __restrict__ tris1,
+                            const float4* __restrict__ tris2, const float* __restrict__ pos1, const float* __restrict__ pos2,
+                            float4* __restrict__ ta, float4* __restrict__ tb, float* __restrict__ pose, uint32_t* __restrict__ ab) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    uint32_t k = parked[i], pa = ppos[2ull * i], pb = ppos[2ull * i + 1];
+    for (int j = 0; j < 3; ++j) { ta[3ull * i + j] = tris2[3ull * pb + j]; tb[3ull * i + j] = tris1[3ull * pa + j]; }
+    Iso7 pos21 = iso_inverse(iso_inv_mul(load_iso(pos1 + 7ull * k), load_iso(pos2 + 7ull * k)));
+    float* o = pose + 7ull * i;
+    o[0] = pos21.q.i; o[1] = pos21.q.j; o[2] = pos21.q.k; o[3] = pos21.q.w; o[4] = pos21.t.x; o[5] = pos21.t.y; o[6] = pos21.t.z;
+    ab[2ull * i] = i; ab[2ull * i + 1] = i;
+}
+// ... and their contacts written back as the swapped hit (:100-104); a pair without a contact (EPA failure) loses its hit.
+__global__ void k_mm_merge(const uint32_t* __restrict__ parked, uint32_t cnt, const float* __restrict__ contacts, const uint8_t* __restrict__ cstatus,
+                           float* __restrict__ out, uint8_t* __restrict__ status, uint32_t* __restrict__ parts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    uint32_t k = parked[i];
+    float* q = out + 13ull * k;
+    const float* c = contacts + 13ull * i;
+    if (cstatus[i] == ST_SOME) {
+        for (int j = 0; j < 3; ++j) { q[j] = c[3 + j]; q[3 + j] = c[j]; q[6 + j] = c[9 + j]; q[9 + j] = c[6 + j]; }
+        status[k] = (uint8_t)CAST_PENETRATING;
+    } else {
+        for (int j = 0; j < 13; ++j) q[j] = 0.0f;
+        status[k] = cstatus[i] == ST_NEEDS_HOST ? (uint8_t)CAST_NEEDS_HOST : (uint8_t)CAST_NONE;
+        parts[2ull * k] = parts[2ull * k + 1] = PB2_INVALID_U32;
+    }
 }
 
 extern "C" int pb2_trimesh_cast_trimesh(pb2_ctx* ctx, const pb2_trimesh* mesh1, const float* pos1, const float* vel1, const pb2_trimesh* mesh2,
@@ -2181,11 +2231,48 @@ extern "C" int pb2_trimesh_cast_trimesh(pb2_ctx* ctx, const pb2_trimesh* mesh1, 
     CastOpts o;
     o.max_toi = max_time_of_impact; o.target_distance = target_distance; o.stop_at_penetration = 1;
     o.compute_geometry = compute_impact_geometry_on_penetration;
-    k_mesh_cast_mesh<<<pb2_blocks(n, 128), 128, 0, st>>>(mesh1->bvh.nodes, mesh1->bvh.n_leaves, mesh1->tris, mesh2->bvh.nodes, mesh2->bvh.n_leaves,
-        mesh2->tris, (const float*)d_p1, (const float*)d_v1, (const float*)d_p2, (const float*)d_v2, o, n, (float*)d_out, (uint8_t*)d_st,
-        (uint32_t*)d_parts, PB2_FAULT_PTR(ctx));
-    PB2_LAUNCHED(ctx);
-    PB2_CUDA(ctx, cudaGetLastError());
+    uint32_t *d_parked = nullptr, *d_ppos = nullptr, *d_ab = nullptr;
+    float4 *d_ta = nullptr, *d_tb = nullptr;
+    float *d_pose = nullptr, *d_c = nullptr;
+    uint8_t* d_cst = nullptr;
+    int rc = PB2_OK;
+    do {
+        if (cudaMallocAsync((void**)&d_parked, (size_t)n * 4, st) != cudaSuccess || cudaMallocAsync((void**)&d_ppos, (size_t)n * 8, st) != cudaSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), "trimesh_cast_trimesh: out of device memory"); rc = PB2_ERR_CUDA; break;
+        }
+        unsigned long long* parked_count = (unsigned long long*)(ctx->d_counters + 10);
+        cudaMemsetAsync(parked_count, 0, 8, st);
+        k_mesh_cast_mesh<<<pb2_blocks(n, 128), 128, 0, st>>>(mesh1->bvh.nodes, mesh1->bvh.n_leaves, mesh1->tris, mesh2->bvh.nodes, mesh2->bvh.n_leaves,
+            mesh2->tris, (const float*)d_p1, (const float*)d_v1, (const float*)d_p2, (const float*)d_v2, o, n, (float*)d_out, (uint8_t*)d_st,
+            (uint32_t*)d_parts, d_parked, d_ppos, parked_count, PB2_FAULT_PTR(ctx));
+        PB2_LAUNCHED(ctx);
+        cudaMemcpyAsync(ctx->h_counters + 10, parked_count, 8, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh_cast_trimesh: kernel failed"); rc = PB2_ERR_CUDA; break; }
+        uint32_t cnt = (uint32_t)ctx->h_counters[10];
+        if (cnt) {
+            if (cudaMallocAsync((void**)&d_ta, (size_t)cnt * 48, st) != cudaSuccess || cudaMallocAsync((void**)&d_tb, (size_t)cnt * 48, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_pose, (size_t)cnt * 28, st) != cudaSuccess || cudaMallocAsync((void**)&d_ab, (size_t)cnt * 8, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_c, (size_t)cnt * 52, st) != cudaSuccess || cudaMallocAsync((void**)&d_cst, cnt, st) != cudaSuccess) {
+                snprintf(ctx->err, sizeof(ctx->err), "trimesh_cast_trimesh: out of device memory"); rc = PB2_ERR_CUDA; break;
+            }
+            k_mm_gather<<<pb2_blocks(cnt, 128), 128, 0, st>>>(d_parked, d_ppos, cnt, mesh1->tris, mesh2->tris, (const float*)d_p1, (const float*)d_p2,
+                                                              d_ta, d_tb, d_pose, d_ab);
+            PB2_LAUNCHED(ctx);
+            OutSinks sinks;
+            sinks.dense = d_c; sinks.status = d_cst; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
+            sinks.compact_count = nullptr; sinks.some_count = nullptr;
+            pb2_shapes none;   // no table shape takes part
+            // contact_support_map_support_map(pos21, triangle of mesh 2, triangle of mesh 1, Real::MAX), in the two meshes' frames
+            if ((rc = run_contacts(ctx, &none, nullptr, nullptr, d_pose, d_pose, FLT_MAX, cnt, sinks, d_ab, cnt, d_ta, cnt,
+                                   PAIR_SUPPORT_MAPS_ONLY | PAIR_LOCAL_FRAMES | PAIR_POS12_GIVEN, nullptr, 0, nullptr, 3, d_tb)) != PB2_OK) break;
+            k_mm_merge<<<pb2_blocks(cnt, 128), 128, 0, st>>>(d_parked, cnt, d_c, d_cst, (float*)d_out, (uint8_t*)d_st, (uint32_t*)d_parts);
+            PB2_LAUNCHED(ctx);
+        }
+        if (cudaGetLastError() != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh_cast_trimesh: launch failed"); rc = PB2_ERR_CUDA; break; }
+    } while (0);
+    void* frees[] = {d_parked, d_ppos, d_ab, d_ta, d_tb, d_pose, d_c, d_cst};
+    for (void* p : frees) if (p) cudaFreeAsync(p, st);
+    if (rc != PB2_OK) return rc;
     PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
     PB2_CHECK(pb2_stage_back(ctx, status, d_st, (size_t)n, mem));
     PB2_CHECK(pb2_stage_back(ctx, parts, d_parts, (size_t)n * 8, mem));

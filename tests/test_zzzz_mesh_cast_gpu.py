@@ -155,10 +155,12 @@ def test_trimesh_trimesh_toi_issue_194_on_the_gpu(ctx, oracle):
     assert r is not None and (r[0].view(np.uint32) == out[0].view(np.uint32)).all()
 
 
-def test_trimesh_cast_trimesh_vs_oracle(ctx, oracle):
-    """Random poses / velocities of two small meshes (a pyramid against a patch of terrain) against the oracle's nested descent."""
+@pytest.mark.parametrize("lift,seed", [((2.6, 6.5), 411), ((0.9, 3.0), 412)])
+def test_trimesh_cast_trimesh_vs_oracle(ctx, oracle, lift, seed):
+    """Random poses / velocities of two small meshes (a pyramid against a patch of terrain) against the oracle's nested descent; with
+    the lower lift a good part of the pairs start in touch and take their geometry from the triangle-triangle contact."""
     import parry_b200
-    g = scenes.rng(411)
+    g = scenes.rng(seed)
     pts, idx = pyramid()
     v, tidx = scenes.terrain(17, 17, extent=12.0)
     v = v.copy()
@@ -167,7 +169,8 @@ def test_trimesh_cast_trimesh_vs_oracle(ctx, oracle):
     oa, ob = oracle.TriMesh(pts, idx), oracle.TriMesh(v, tidx)
     n = 600
     lo, hi = v.min(axis=0), v.max(axis=0)
-    t = np.stack([lo[0] + g.random(n) * (hi[0] - lo[0]), hi[1] + 1.6 + g.random(n) * 4.0, lo[2] + g.random(n) * (hi[2] - lo[2])], axis=1)
+    anchor = v[g.integers(0, len(v), n)]
+    t = anchor + np.stack([g.standard_normal(n) * 0.3, lift[0] + g.random(n) * (lift[1] - lift[0]), g.standard_normal(n) * 0.3], axis=1)
     p1 = np.concatenate([scenes.random_unit_quaternions(g, n), t], axis=1).astype(np.float32)
     p2 = np.tile(np.array([0.02, -0.01, 0.03, 1.0, 0.1, 0.0, -0.1], np.float32), (n, 1))
     p2[:, :4] /= np.linalg.norm(p2[:, :4], axis=1, keepdims=True)
@@ -181,42 +184,17 @@ def test_trimesh_cast_trimesh_vs_oracle(ctx, oracle):
             r = fa.cast_shapes(pa[k], va[k], pb[k], vb[k], other_mesh=fb)
             if r is not None:
                 oo[k], os_[k], op[k] = r[0], r[1], r[2]
-        assert 0.3 < (os_ != 0).mean() < 0.95
-        assert ((st != 0) == (os_ != 0)).all()
+        assert 0.3 < (os_ != 0).mean() < 0.98
+        if lift[0] < 2:
+            assert (os_ == 2).mean() > 0.1
+        assert (st == os_).all(), np.nonzero(st != os_)[0][:10]
         hit = os_ != 0
         assert (out[hit][:, 12] == oo[hit][:, 12]).mean() > 0.99
         np.testing.assert_allclose(out[hit][:, 12], oo[hit][:, 12], rtol=1e-5, atol=2e-6)
-        full = hit & (st == os_)                              # status 4 = starts in touch: geometry not offered
-        assert (st[hit & ~full] == 4).all() and full.sum() > 0.9 * hit.sum()
-        same = parts[full][:, 0] == op[full]                   # (a pyramid's edges and apex belong to 2-3 triangles: ties, see check())
-        assert same.mean() > 0.5
-        assert (out[full][~same][:, 12] == oo[full][~same][:, 12]).mean() > 0.98
-        rows_ok = (np.abs(out[full][same][:, :12] - oo[full][same][:, :12]) < 1e-4).all(axis=1)
-        assert rows_ok.mean() > 0.97, rows_ok.mean()
-
-
-@pytest.mark.parametrize("mesh_second", [False, True])
-def test_trimesh_distance_vs_oracle(ctx, oracle, mesh_second):
-    """query::distance with a TriMesh on one side through pb2_trimesh_distance_shapes: the distance is a pure minimum (no tie
-    can change it), so it must be bit-identical to the oracle's descent of the reference's own tree."""
-    import parry_b200
-    v, idx, spec, sid, poses, _ = make_scene(8000, 421, (-0.5, 6.0))
-    T, G = tables(ctx, oracle, spec)
-    gm, om = parry_b200.TriMesh(ctx, v, idx), oracle.TriMesh(v, idx)
-    mq = np.array([0.01, -0.02, 0.015, 1.0]); mq /= np.linalg.norm(mq)
-    mpose = np.concatenate([mq, [0.05, -0.1, 0.08]]).astype(np.float32)
-    od, op = om.distance_shapes(mpose, T, sid, poses, mesh_second=mesh_second, threads=8)
-    gd, gs, gp = (np.asarray(x) for x in gm.distance_shapes(mpose, G, sid, poses, mesh_second=mesh_second))
-    assert (gs == 0).all()
-    assert 0.05 < (od == 0).mean() < 0.6
-    assert (gd.view(np.uint32) == od.view(np.uint32)).all(), np.nonzero(gd != od)[0][:10]
-    pos = od > 0
-    # (query::distance returns no part; the closest point of a convex shape over a terrain is on a shared edge or vertex about half of
-    # the time, where 2-6 triangles are equally close: first in the reference's tree order there, smallest index here)
-    assert (gp.astype(np.uint32)[pos] == op[pos]).mean() > 0.4
-    for lo, hi in ((0, 2), (2, 4), (4, 12)):                          # every arm is exercised
-        m = (sid >= lo) & (sid < hi)
-        assert (od[m] > 0).mean() > 0.3
-    bad = sid[:4].copy(); bad[1] = 9999
-    b = gm.distance_shapes(mpose, G, bad, poses[:4], mesh_second=mesh_second)
-    assert np.asarray(b[1])[1] == 2 and (np.asarray(b[0])[[0, 2, 3]] == gd[[0, 2, 3]]).all()
+        same = parts[hit][:, 0] == op[hit]                     # (a pyramid's edges and apex belong to 2-3 triangles: ties, see check())
+        assert same.mean() > (0.5 if lift[0] > 2 else 0.25)
+        assert (out[hit][~same][:, 12] == oo[hit][~same][:, 12]).mean() > 0.98
+        rows_ok = (np.abs(out[hit][same][:, :12] - oo[hit][same][:, :12]) < 1e-4).all(axis=1)
+        # (the oracle reports the triangle of the first mesh only: an equal-time pair with another triangle of the second mesh passes
+        # `same` with different geometry)
+        assert rows_ok.mean() > (0.9 if lift[0] > 2 else 0.6), rows_ok.mean()
