@@ -451,8 +451,7 @@ impl<'c> TriMesh<'c> {
     }
 
     /// `query::cast_shapes(pos1[k], vel1[k], &self, pos2[k], vel2[k], &other, options)` for two TriMeshes (the nesting of the
-    /// reference's tests/geometry/trimesh_trimesh_toi.rs): `(hit, [triangle of self, triangle of other])`. A pair that starts in
-    /// touch while `compute_impact_geometry_on_penetration` is set comes back `Err(Unsupported)` (PB2_CAST_NEEDS_HOST).
+    /// reference's tests/geometry/trimesh_trimesh_toi.rs): `(hit, [triangle of self, triangle of other])`.
     pub fn cast_trimesh(&self, pos1: &[Isometry<Real>], vel1: &[Vector<Real>], other: &TriMesh<'c>, pos2: &[Isometry<Real>], vel2: &[Vector<Real>],
                         options: ShapeCastOptions) -> Result<Vec<Result<Option<(ShapeCastHit, [u32; 2])>, Unsupported>>, Error> {
         let n = pos1.len();
