@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small single-workload driver for ncu captures / quick timings: python harness/prof.py <workload> [iters]
-workloads: rays_terrain, rays_sphere1m, contacts, broadphase"""
+workloads: rays_terrain, rays_sphere1m, contacts, broadphase, mesh_queries"""
 import os
 import sys
 import time
@@ -98,6 +98,33 @@ def main():
             st["p"] = bvh.traverse_bvtt_single_tree(capacity=16 * n, like=a)
         ms = timeit(frame, wl)
         print("%.1f MAABB/s, %d pairs" % (n / ms / 1e3, st["p"].shape[0]))
+    elif wl == "mesh_queries":
+        # the composite-shape queries against a 2 M-triangle terrain: shapes scattered within a few shape sizes of the surface
+        v, i = scenes.terrain(1001, 1001)
+        mesh = parry_b200.TriMesh(ctx, v, i)
+        g = scenes.rng(9)
+        pts, _ = scenes.hull_pool(64, 32, seed=10)
+        spec = [parry_b200.Ball(0.4), parry_b200.Cuboid([0.3, 0.5, 0.4])] + [parry_b200.ConvexPolyhedron(np.asarray(p, np.float32) * 0.6) for p in pts]
+        G = parry_b200.Shapes(ctx, spec)
+        n = 1 << 20
+        sid = g.integers(0, len(spec), n).astype(np.int32)
+        anchor = np.asarray(v)[g.integers(0, len(v), n)]
+        t = anchor + np.stack([g.standard_normal(n) * 0.3, g.random(n) * 4.0 - 0.3, g.standard_normal(n) * 0.3], axis=1)
+        poses = np.concatenate([scenes.random_unit_quaternions(g, n), t], axis=1).astype(np.float32)
+        vel = np.stack([g.standard_normal(n) * 0.5, -(g.random(n) * 2.0 + 0.2), g.standard_normal(n) * 0.5], axis=1).astype(np.float32)
+        dsid, dposes, dvel = torch.from_numpy(sid).cuda(), torch.from_numpy(poses).cuda(), torch.from_numpy(vel).cuda()
+        ident = torch.tensor([0, 0, 0, 1, 0, 0, 0], dtype=torch.float32, device="cuda")
+        zero = torch.zeros(3, dtype=torch.float32, device="cuda")
+        res = {}
+        ms = timeit(lambda: res.__setitem__("c", mesh.contact_shapes(ident, G, dsid, dposes, 0.05)), "trimesh contact_shapes")
+        print("   %.1f M queries/s, %d contacts" % (n / ms / 1e3, int((res["c"][1] == 1).sum().item())))
+        ms = timeit(lambda: res.__setitem__("s", mesh.cast_shapes(ident, zero, G, dsid, dposes, dvel)), "trimesh cast_shapes")
+        print("   %.1f M queries/s, %d hits" % (n / ms / 1e3, int((res["s"][1] != 0).sum().item())))
+        ms = timeit(lambda: res.__setitem__("d", mesh.distance_shapes(ident, G, dsid, dposes)), "trimesh distance_shapes")
+        print("   %.1f M queries/s, %d apart" % (n / ms / 1e3, int((res["d"][0] > 0).sum().item())))
+        q = torch.from_numpy((t + g.standard_normal((n, 3)) * 0.5).astype(np.float32)).cuda()
+        ms = timeit(lambda: res.__setitem__("p", mesh.project_local_point(q)), "trimesh project_point")
+        print("   %.1f M points/s" % (n / ms / 1e3))
 
 
 if __name__ == "__main__":
