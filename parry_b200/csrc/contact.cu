@@ -1927,7 +1927,8 @@ __global__ void __launch_bounds__(128) k_mesh_cast_shapes(const NodeWide* __rest
                               uint8_t* __restrict__ status, uint32_t* __restrict__ part, uint32_t* __restrict__ parked,
                               uint32_t* __restrict__ parked_ab, unsigned long long* parked_count, unsigned int* fault) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    const bool valid = k < n;   // every lane stays: the descent below is warp-cooperative
+    if (!valid) k = 0;
     float* q = out + 13ull * k;
     uint32_t sid = shape_ids[k];
     int st = CAST_NONE;
@@ -1935,8 +1936,9 @@ __global__ void __launch_bounds__(128) k_mesh_cast_shapes(const NodeWide* __rest
     float best = o.max_toi;
     uint32_t best_id = PB2_INVALID_U32, best_pos = 0;
     bool found = false;
-    if (sid >= n_shapes) st = CAST_UNSUPPORTED;
-    else {
+    const bool known = sid >= n_shapes ? false : true;
+    if (!known) { st = CAST_UNSUPPORTED; sid = 0; }
+    {
         Iso7 pos12 = load_iso(P + 7ull * k);
         V3 vel12 = mk3(V[3ull * k], V[3ull * k + 1], V[3ull * k + 2]);
         uint8_t k2 = kinds[sid];
@@ -1948,7 +1950,7 @@ __global__ void __launch_bounds__(128) k_mesh_cast_shapes(const NodeWide* __rest
         V3 inv = mk3(1.0f / vel12.x, 1.0f / vel12.y, 1.0f / vel12.z);
         DShape g2 = cast_dshape(k2, pr2, pts);
         const float border = o.target_distance;
-        auto leaf = [&](uint32_t pos) {
+        auto leaf = [&](uint32_t pos, unsigned) {
             const float4* tp = tris + 3ull * pos;
             DShape g1; g1.kind = DS_TRIANGLE; g1.he = mk3(0.f, 0.f, 0.f); g1.pts = tp; g1.n = 3;
             Simplex s;
@@ -1972,8 +1974,9 @@ __global__ void __launch_bounds__(128) k_mesh_cast_shapes(const NodeWide* __rest
             w2 = iso_inv_point(pos12, r1);
             st = toi == 0.0f ? CAST_PENETRATING : CAST_CONVERGED;
         };
-        bvh_find_best_msum(nodes, n_leaves, shift, margin, vel12, inv, o.max_toi, best, found, leaf, fault);
+        bvh_find_best_msum(0xffffffffu, valid && known, nodes, n_leaves, shift, margin, vel12, inv, o.max_toi, best, found, leaf, fault);
     }
+    if (!valid) return;
     if (st == CAST_PARKED) {
         unsigned long long at = warp_append1(parked_count);
         parked[at] = k;
@@ -2088,7 +2091,8 @@ __global__ void __launch_bounds__(128) k_mesh_cast_mesh(const NodeWide* __restri
                               float* __restrict__ out, uint8_t* __restrict__ status, uint32_t* __restrict__ parts, uint32_t* __restrict__ parked,
                               uint32_t* __restrict__ parked_pos, unsigned long long* parked_count, unsigned int* fault) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    const bool valid = k < n;   // every lane stays: the descents below are warp-cooperative
+    if (!valid) k = 0;
     Iso7 p1 = load_iso(pos1 + 7ull * k), p2 = load_iso(pos2 + 7ull * k);
     Iso7 pos12 = iso_inv_mul(p1, p2);
     uint32_t best_pa = 0, best_pb = 0;
@@ -2115,7 +2119,7 @@ __global__ void __launch_bounds__(128) k_mesh_cast_mesh(const NodeWide* __restri
         const V3 vel21 = -iso_inv_vec(pos12, vel12);
         const V3 inv21 = mk3(1.0f / vel21.x, 1.0f / vel21.y, 1.0f / vel21.z);
         const float border = o.target_distance;
-        auto leaf1 = [&](uint32_t pa) {
+        auto leaf1 = [&](uint32_t pa, unsigned lanes1) {
             const float4* t1 = tris1 + 3ull * pa;
             DShape gt1; gt1.kind = DS_TRIANGLE; gt1.he = mk3(0.f, 0.f, 0.f); gt1.pts = t1; gt1.n = 3;
             // Triangle::compute_aabb(pos21) = the box of the transformed vertices (aabb_triangle.rs:10-30)
@@ -2129,7 +2133,7 @@ __global__ void __launch_bounds__(128) k_mesh_cast_mesh(const NodeWide* __restri
             uint32_t iid2 = PB2_INVALID_U32, ipb = 0;
             int ist = CAST_NONE;
             V3 iw1 = mk3(0.f, 0.f, 0.f), iw2 = iw1, in1 = iw1, in2 = iw1;
-            auto leaf2 = [&](uint32_t pb) {
+            auto leaf2 = [&](uint32_t pb, unsigned) {
                 const float4* t2 = tris2 + 3ull * pb;
                 DShape gt2; gt2.kind = DS_TRIANGLE; gt2.he = mk3(0.f, 0.f, 0.f); gt2.pts = t2; gt2.n = 3;
                 Simplex s;
@@ -2153,7 +2157,7 @@ __global__ void __launch_bounds__(128) k_mesh_cast_mesh(const NodeWide* __restri
                 iw2 = iso_inv_point(pos21, r1);
                 ist = toi == 0.0f ? CAST_PENETRATING : CAST_CONVERGED;
             };
-            bvh_find_best_msum(nodes2, nl2, shift2, margin2, vel21, inv21, o.max_toi, ibest, ifound, leaf2, fault);
+            bvh_find_best_msum(lanes1, true, nodes2, nl2, shift2, margin2, vel21, inv21, o.max_toi, ibest, ifound, leaf2, fault);
             if (!ifound) return;
             uint32_t id1 = __float_as_uint(fa.w);
             if (!(ibest < best || (found && ibest == best && id1 < best_id1))) return;
@@ -2161,8 +2165,9 @@ __global__ void __launch_bounds__(128) k_mesh_cast_mesh(const NodeWide* __restri
             st = ist;
             w1 = iw2; w2 = iw1; n1 = in2; n2 = in1;   // ShapeCastHit::swapped
         };
-        bvh_find_best_msum(nodes1, nl1, shift, margin, vel12, inv12, o.max_toi, best, found, leaf1, fault);
+        bvh_find_best_msum(0xffffffffu, valid, nodes1, nl1, shift, margin, vel12, inv12, o.max_toi, best, found, leaf1, fault);
     }
+    if (!valid) return;
     // a winner that starts in touch takes its geometry from the triangle-triangle contact (second phase)
     if (st == CAST_PARKED) {
         unsigned long long at = warp_append1(parked_count);
@@ -2297,9 +2302,11 @@ __global__ void __launch_bounds__(128) k_mesh_distance(const NodeWide* __restric
                               const float* __restrict__ mesh_pose, const float* __restrict__ poses, int mesh_second, uint32_t n,
                               float* __restrict__ out, uint8_t* __restrict__ status, uint32_t* __restrict__ part, unsigned int* fault) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    const bool valid = k < n;   // every lane stays: the descent below is warp-cooperative
+    if (!valid) k = 0;
     uint32_t sid = shape_ids[k];
-    if (sid >= n_shapes) { out[k] = 0.0f; status[k] = (uint8_t)ST_UNSUPPORTED; part[k] = PB2_INVALID_U32; return; }
+    const bool known = sid < n_shapes;
+    if (!known) sid = 0;
     Iso7 pm = load_iso(mesh_pose), ps = load_iso(poses + 7ull * k);
     Iso7 pos12 = mesh_second ? iso_inverse(iso_inv_mul(ps, pm)) : iso_inv_mul(pm, ps);
     uint8_t k2 = kinds[sid];
@@ -2311,7 +2318,7 @@ __global__ void __launch_bounds__(128) k_mesh_distance(const NodeWide* __restric
     uint32_t best_id = PB2_INVALID_U32;
     bool found = false;
     DShape g2 = make_dshape(k2, pr2, pts);
-    auto leaf = [&](uint32_t pos) {
+    auto leaf = [&](uint32_t pos, unsigned) {
         const float4* tp = tris + 3ull * pos;
         float d;
         if (k2 == PB2_SHAPE_BALL) {
@@ -2333,7 +2340,9 @@ __global__ void __launch_bounds__(128) k_mesh_distance(const NodeWide* __restric
         uint32_t id = __float_as_uint(__ldg(&tp[0]).w);
         if (d < best || (found && d == best && id < best_id)) { best = d; best_id = id; found = true; }
     };
-    bvh_find_best_msum_distance(nodes, n_leaves, shift, margin, best, found, leaf, fault);
+    bvh_find_best_msum_distance(0xffffffffu, valid && known, nodes, n_leaves, shift, margin, best, found, leaf, fault);
+    if (!valid) return;
+    if (!known) { out[k] = 0.0f; status[k] = (uint8_t)ST_UNSUPPORTED; part[k] = PB2_INVALID_U32; return; }
     out[k] = best;   // unwrap_or((u32::MAX, Real::MAX)) for a mesh whose every leaf was removed
     status[k] = (uint8_t)ST_NONE;
     part[k] = best_id;
@@ -2383,13 +2392,14 @@ __global__ void __launch_bounds__(128) k_project_points_shapes(const NodeWide* _
                               const float* __restrict__ points, uint32_t m, float max_distance, bool solid, float* __restrict__ out_proj,
                               uint8_t* __restrict__ out_inside, uint32_t* __restrict__ out_leaf, uint8_t* __restrict__ status, unsigned int* fault) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= m) return;
+    const bool valid = k < m;   // every lane stays: the descent below is warp-cooperative
+    if (!valid) k = 0;
     const V3 p = mk3(points[3ull * k], points[3ull * k + 1], points[3ull * k + 2]);
     float best = max_distance;
     bool found = false, best_inside = false, needs_host = false;
     uint32_t best_id = PB2_INVALID_U32;
     V3 best_pt = mk3(0.f, 0.f, 0.f);
-    auto leaf = [&](uint32_t pos) {
+    auto leaf = [&](uint32_t pos, unsigned) {
         uint32_t id = order[pos];
         uint32_t sid = shape_ids ? shape_ids[id] : id;
         if (sid >= n_shapes) { atomicOr(fault, PB2_FAULT_BAD_ID); return; }
@@ -2428,7 +2438,8 @@ __global__ void __launch_bounds__(128) k_project_points_shapes(const NodeWide* _
         V3 shift = vmax3(vmax3(mk3(lo.x, lo.y, lo.z) - p, p - mk3(hi.x, hi.y, hi.z)), mk3(0.f, 0.f, 0.f));
         return nrm(shift);
     };
-    bvh_find_best_cost(nodes, n_leaves, max_distance, best, found, cost, leaf, fault);
+    bvh_find_best_cost(0xffffffffu, valid, nodes, n_leaves, max_distance, best, found, cost, leaf, fault);
+    if (!valid) return;
     if (needs_host) { found = false; best_pt = mk3(0.f, 0.f, 0.f); best_inside = false; best_id = PB2_INVALID_U32; }
     out_proj[3ull * k] = best_pt.x; out_proj[3ull * k + 1] = best_pt.y; out_proj[3ull * k + 2] = best_pt.z;
     out_inside[k] = best_inside ? 1 : 0;
