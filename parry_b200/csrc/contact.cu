@@ -1901,6 +1901,15 @@ done:
 // over the mesh tree with Minkowski-summed node boxes, every reached triangle cast against the shape like any support-map pair.
 // One thread per query. P / V: pose and velocity of the shape in the MESH frame (the caller's pos12 / vel12 when the mesh is shape 1,
 // pos12.inverse() / -pos12.inverse_transform_vector(vel12) when it is shape 2, :95-99).
+static void apply_leaf_lanes_knob(pb2_ctx* ctx) {
+    const char* e = getenv("PB2_LEAF_LANES");
+    if (!e) return;
+    int v = atoi(e);
+    if (v < 1) v = 1;
+    if (v > 32) v = 32;
+    cudaMemcpyToSymbolAsync(g_pb2_leaf_lanes, &v, sizeof(int), 0, cudaMemcpyHostToDevice, ctx->stream);
+}
+
 __global__ void k_mesh_cast_frames(const float* __restrict__ mesh_pose, const float* __restrict__ mesh_vel, const float* __restrict__ poses,
                                    const float* __restrict__ vels, uint32_t n, int mesh_second, float* __restrict__ P, float* __restrict__ V) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2042,6 +2051,7 @@ extern "C" int pb2_trimesh_cast_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh, co
         CastOpts o;
         o.max_toi = max_time_of_impact; o.target_distance = target_distance; o.stop_at_penetration = 1;
         o.compute_geometry = compute_impact_geometry_on_penetration;
+        apply_leaf_lanes_knob(ctx);
         k_mesh_cast_shapes<<<pb2_blocks(n, 128), 128, 0, st>>>(mesh->bvh.nodes, mesh->bvh.n_leaves, mesh->tris, shapes->kinds, shapes->params,
             shapes->points4, shapes->points, shapes->n, (const uint32_t*)d_ids, d_P, d_V, o, n, (float*)d_out, (uint8_t*)d_st, (uint32_t*)d_part,
             d_parked, d_ab, parked_count, PB2_FAULT_PTR(ctx));
@@ -2247,6 +2257,7 @@ extern "C" int pb2_trimesh_cast_trimesh(pb2_ctx* ctx, const pb2_trimesh* mesh1, 
         }
         unsigned long long* parked_count = (unsigned long long*)(ctx->d_counters + 10);
         cudaMemsetAsync(parked_count, 0, 8, st);
+        apply_leaf_lanes_knob(ctx);
         k_mesh_cast_mesh<<<pb2_blocks(n, 128), 128, 0, st>>>(mesh1->bvh.nodes, mesh1->bvh.n_leaves, mesh1->tris, mesh2->bvh.nodes, mesh2->bvh.n_leaves,
             mesh2->tris, (const float*)d_p1, (const float*)d_v1, (const float*)d_p2, (const float*)d_v2, o, n, (float*)d_out, (uint8_t*)d_st,
             (uint32_t*)d_parts, d_parked, d_ppos, parked_count, PB2_FAULT_PTR(ctx));
@@ -2363,6 +2374,7 @@ extern "C" int pb2_trimesh_distance_shapes(pb2_ctx* ctx, const pb2_trimesh* mesh
     PB2_CHECK(pb2_stage_out(ctx, 4, dist, (size_t)n * 4, mem, &d_out));
     PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_st));
     PB2_CHECK(pb2_stage_out(ctx, 6, part, (size_t)n * 4, mem, &d_part));
+    apply_leaf_lanes_knob(ctx);
     k_mesh_distance<<<pb2_blocks(n, 128), 128, 0, st>>>(mesh->bvh.nodes, mesh->bvh.n_leaves, mesh->tris, shapes->kinds, shapes->params, shapes->points4,
         shapes->points, shapes->n, (const uint32_t*)d_ids, (const float*)d_mp, (const float*)d_p, mesh_second, n, (float*)d_out, (uint8_t*)d_st,
         (uint32_t*)d_part, PB2_FAULT_PTR(ctx));
@@ -2464,6 +2476,7 @@ extern "C" int pb2_bvh_project_points_shapes(pb2_ctx* ctx, const pb2_bvh* bvh, c
     PB2_CHECK(pb2_stage_out(ctx, 3, inside, (size_t)m, mem, &d_in));
     PB2_CHECK(pb2_stage_out(ctx, 4, leaf, (size_t)m * 4, mem, &d_leaf));
     PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)m, mem, &d_st));
+    apply_leaf_lanes_knob(ctx);
     k_project_points_shapes<<<pb2_blocks(m, 128), 128, 0, st>>>(bvh->nodes, bvh->leaf_order, nl, shapes->kinds, shapes->params, shapes->points4,
         shapes->n, (const uint32_t*)d_ids, (const float*)d_poses, (const float*)d_pts, m, max_distance, solid != 0, (float*)d_proj,
         (uint8_t*)d_in, (uint32_t*)d_leaf, (uint8_t*)d_st, PB2_FAULT_PTR(ctx));

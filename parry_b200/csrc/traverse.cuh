@@ -5,6 +5,10 @@
 #pragma once
 #include "common.cuh"
 
+// lanes that must wait at a leaf before the leaf code runs (bvh_find_best_cost below); one copy per translation unit, the one in
+// contact.cu can be set with PB2_LEAF_LANES (tuning only)
+static __device__ int g_pb2_leaf_lanes = 32;   // measured best: run the leaf code only when no lane can move (4..32 swept)
+
 
 // `leaf(pos)` tests the primitive at sorted position `pos` and updates `best` / `found` itself.
 // Deviation from the reference (documented tie rule): once a hit exists, nodes whose score == best are
@@ -68,7 +72,8 @@ __device__ __forceinline__ void bvh_find_best(const NodeWide* __restrict__ nodes
 // execute the leaf code with it, for nested descents.
 template <class Cost, class Leaf>
 __device__ __forceinline__ void bvh_find_best_cost(unsigned mask, bool active, const NodeWide* __restrict__ nodes, uint32_t n_leaves, float max_cost,
-                                                   float& best, bool& found, Cost cost, Leaf leaf, unsigned int* fault, int min_lanes = 12) {
+                                                   float& best, bool& found, Cost cost, Leaf leaf, unsigned int* fault) {
+    const int min_lanes = g_pb2_leaf_lanes;
     if (n_leaves == 1) {
         bool want = false;
         uint32_t lpos = 0;
