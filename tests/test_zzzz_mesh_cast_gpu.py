@@ -198,3 +198,30 @@ def test_trimesh_cast_trimesh_vs_oracle(ctx, oracle, lift, seed):
         # (the oracle reports the triangle of the first mesh only: an equal-time pair with another triangle of the second mesh passes
         # `same` with different geometry)
         assert rows_ok.mean() > (0.9 if lift[0] > 2 else 0.6), rows_ok.mean()
+
+
+@pytest.mark.parametrize("mesh_second", [False, True])
+def test_trimesh_distance_vs_oracle(ctx, oracle, mesh_second):
+    """query::distance with a TriMesh on one side through pb2_trimesh_distance_shapes: the distance is a pure minimum (no tie
+    can change it), so it must be bit-identical to the oracle's descent of the reference's own tree."""
+    import parry_b200
+    v, idx, spec, sid, poses, _ = make_scene(8000, 421, (-0.5, 6.0))
+    T, G = tables(ctx, oracle, spec)
+    gm, om = parry_b200.TriMesh(ctx, v, idx), oracle.TriMesh(v, idx)
+    mq = np.array([0.01, -0.02, 0.015, 1.0]); mq /= np.linalg.norm(mq)
+    mpose = np.concatenate([mq, [0.05, -0.1, 0.08]]).astype(np.float32)
+    od, op = om.distance_shapes(mpose, T, sid, poses, mesh_second=mesh_second, threads=8)
+    gd, gs, gp = (np.asarray(x) for x in gm.distance_shapes(mpose, G, sid, poses, mesh_second=mesh_second))
+    assert (gs == 0).all()
+    assert 0.05 < (od == 0).mean() < 0.6
+    assert (gd.view(np.uint32) == od.view(np.uint32)).all(), np.nonzero(gd != od)[0][:10]
+    pos = od > 0
+    # (query::distance returns no part; the closest point of a convex shape over a terrain is on a shared edge or vertex about half of
+    # the time, where 2-6 triangles are equally close: first in the reference's tree order there, smallest index here)
+    assert (gp.astype(np.uint32)[pos] == op[pos]).mean() > 0.4
+    for lo, hi in ((0, 2), (2, 4), (4, 12)):                          # every arm is exercised
+        m = (sid >= lo) & (sid < hi)
+        assert (od[m] > 0).mean() > 0.3
+    bad = sid[:4].copy(); bad[1] = 9999
+    b = gm.distance_shapes(mpose, G, bad, poses[:4], mesh_second=mesh_second)
+    assert np.asarray(b[1])[1] == 2 and (np.asarray(b[0])[[0, 2, 3]] == gd[[0, 2, 3]]).all()
