@@ -343,15 +343,17 @@ int pb2_compound_contact_compounds(pb2_ctx* ctx, const pb2_compounds* compounds,
                                    const uint32_t* ids2, const float* poses2, uint32_t n, float prediction, pb2_contact* out, uint8_t* status,
                                    uint32_t* parts /* n x 2 */, int mem);
 
-/* query::contact(compound_poses7[k], Compound compound_ids[k], mesh_pose7, &TriMesh): the composite arm with the Compound first and
- * the TriMesh handled as the composite of the nested dispatch (default_query_dispatcher.rs:338-351; contact_composite_shape_shape.rs
- * :12-48 over the parts, :63-76 + :12-48 over the triangles; Bvh::root_aabb bvh_tree.rs:1991-1999). out / status as
- * pb2_contact_batch (status 2: unknown compound id); parts: n x 2 = {winning part, winning triangle} or 0xFFFFFFFF. Equal dists: the
- * first part in part order, the smallest triangle index (the reference keeps the first in its own tree's order). The opposite
- * argument order, contact(trimesh, compound), nests per triangle and is not offered. */
+/* query::contact between a Compound and a TriMesh, n compounds against one mesh (default_query_dispatcher.rs:338-351: the composite arm
+ * of shape 1, the other composite handled by the nested dispatch). mesh_first = 0: contact(compound_poses7[k], Compound compound_ids[k],
+ * mesh_pose7, &TriMesh) — contact_composite_shape_shape.rs:12-48 over the parts (Bvh::root_aabb bvh_tree.rs:1991-1999 for the mesh's
+ * box), :63-76 + :12-48 over the triangles; mesh_first != 0: contact(mesh_pose7, &TriMesh, compound_poses7[k], Compound) — over the
+ * triangles first (Compound::local_aabb compound.rs:120-127), each against the compound's parts with the part as shape 1 of the leaf
+ * problem. out / status as pb2_contact_batch (status 2: unknown compound id), contact sides in the argument order; parts: n x 2 =
+ * {winning part, winning triangle} or 0xFFFFFFFF. Equal dists: the first part in part order, the smallest triangle index (the
+ * reference keeps the first in its own tree's order). */
 int pb2_compound_contact_trimesh(pb2_ctx* ctx, const pb2_compounds* compounds, const uint32_t* compound_ids, const float* compound_poses7 /* n x 7 */,
-                                 const pb2_trimesh* mesh, const float* mesh_pose7, uint32_t n, float prediction, pb2_contact* out, uint8_t* status,
-                                 uint32_t* parts /* n x 2 */, int mem);
+                                 const pb2_trimesh* mesh, const float* mesh_pose7, uint32_t n, float prediction, int mesh_first, pb2_contact* out,
+                                 uint8_t* status, uint32_t* parts /* n x 2 */, int mem);
 
 /* query::closest_points for n pairs (closest_points/closest_points_shape_shape.rs:220-231 -> default_query_dispatcher.rs:358-424:
  * closest_points_ball_ball.rs:7-36, closest_points_ball_convex_polyhedron.rs:7-44, closest_points_support_map_support_map.rs:8-69).

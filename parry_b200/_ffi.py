@@ -78,7 +78,7 @@ SIGNATURES = {
     "pb2_shapes_set_hull_vertex_topology": (c_int, [c_void_p, c_void_p, P, P, P, P, c_u32, P, P, c_u32]),
     "pb2_contact_manifolds_batch": (c_int, [c_void_p, c_void_p, P, P, P, P, c_float, c_u32, c_u32, P, P, P, P, c_int]),
     "pb2_compound_contact_compounds": (c_int, [c_void_p, c_void_p, P, P, P, P, c_u32, c_float, P, P, P, c_int]),
-    "pb2_compound_contact_trimesh": (c_int, [c_void_p, c_void_p, P, P, c_void_p, P, c_u32, c_float, P, P, P, c_int]),
+    "pb2_compound_contact_trimesh": (c_int, [c_void_p, c_void_p, P, P, c_void_p, P, c_u32, c_float, c_int, P, P, P, c_int]),
     "pb2_manifolds_try_update": (c_int, [c_void_p, P, P, c_u32, c_u32, c_float, c_float, P, P, P, P, c_int]),
     "pb2_contact_manifolds_update_batch": (c_int, [c_void_p, c_void_p, P, P, P, P, c_float, c_u32, c_u32, P, P, P, P, P, P, c_int]),
     "pb2_closest_points_batch": (c_int, [c_void_p, c_void_p, P, P, P, P, c_float, c_u32, P, P, P, c_int]),

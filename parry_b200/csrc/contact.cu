@@ -403,7 +403,8 @@ __device__ __forceinline__ void pair_setup(const uint8_t* kinds, const float4* p
         ps.gpos12 = ps.pos12;
         if (tri) { ps.g1.kind = DS_TRIANGLE; ps.g1.he = mk3(0.f, 0.f, 0.f); ps.g1.pts = tri; ps.g1.n = 3; }
         else ps.g1 = make_dshape(ps.k1, ps.pr1, pts);
-        ps.g2 = make_dshape(ps.k2, ps.pr2, pts);
+        if (ps.tri2) { ps.g2.kind = DS_TRIANGLE; ps.g2.he = mk3(0.f, 0.f, 0.f); ps.g2.pts = ps.tri2; ps.g2.n = 3; }
+        else ps.g2 = make_dshape(ps.k2, ps.pr2, pts);
     } else if (b1 != b2) {
         bool convex_first = b2;
         ps.cb_pos12 = convex_first ? ps.pos12 : iso_inverse(ps.pos12);
@@ -501,14 +502,15 @@ __device__ __forceinline__ int closed_form_pair(const PairSetup& ps, float predi
         float4 prc = convex_first ? ps.pr1 : ps.pr2;
         float radius = convex_first ? ps.pr2.x : ps.pr1.x;
         V3 proj; bool inside; Feat f;
-        if (ps.tri) {
+        const float4* t = convex_first ? ps.tri : ps.tri2;   // the non-ball side is a triangle
+        if (t) {
             // PointQuery for Triangle (point_triangle.rs:27-47: location with solid = true); the feature normal of a
             // triangle is its normal whatever the feature (shape.rs:919-928, triangle.rs:226-228)
-            V3 ta = v3of4(ps.tri[0]), tb = v3of4(ps.tri[1]), tc = v3of4(ps.tri[2]);
+            V3 ta = v3of4(t[0]), tb = v3of4(t[1]), tc = v3of4(t[2]);
             Proj pr;
             project_on_triangle(ta, tb, tc, ps.cb_pos12.t, pr);
             f.kind = 4; f.id = 0;
-            st = d_convex_ball_finish(ps.cb_pos12, false, f, pr.point, pr.inside, radius, prediction, c, ps.tri);
+            st = d_convex_ball_finish(ps.cb_pos12, false, f, pr.point, pr.inside, radius, prediction, c, t);
         } else {
             d_cuboid_project(mk3(prc.x, prc.y, prc.z), ps.cb_pos12.t, proj, inside, f);
             st = d_convex_ball_finish(ps.cb_pos12, true, f, proj, inside, radius, prediction, c);
@@ -2823,6 +2825,194 @@ __global__ void k_ct_reduce(const uint32_t* __restrict__ offsets, const float* _
 }
 
 
+// TriMesh (shape 1) against a Compound (shape 2): contact_composite_shape_shape(pos12, trimesh, compound) (contact_composite_shape_shape.rs
+// :12-48): every triangle whose leaf box meets the compound's local box (Compound::local_aabb, compound.rs:120-127) moved into the mesh
+// frame and loosened is dispatched as contact(pos12, triangle, compound) = contact_shape_composite_shape (:63-76): the compound as the
+// composite under pos12.inverse() — its parts whose box meets the triangle's loosened box, each contact(part_pos.inv_mul(pos21), part,
+// triangle), first strictly smaller dist in part order, transform1_by(part_pos) — flipped; then the smallest dist over the triangles.
+__global__ void k_tc_query_aabbs(const uint32_t* __restrict__ comp_first, const uint32_t* __restrict__ comp_count, uint32_t nc,
+                                 const float* __restrict__ part_aabb, const uint32_t* __restrict__ compound_id, const float* __restrict__ pos_c,
+                                 const float* __restrict__ mesh_pose, uint32_t n, float prediction, float* __restrict__ out) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float* o = out + 6ull * k;
+    uint32_t c = compound_id[k];
+    if (c >= nc) { o[0] = o[1] = o[2] = FLT_MAX; o[3] = o[4] = o[5] = -FLT_MAX; return; }
+    uint32_t f = comp_first[c], m = comp_count[c];
+    V3 amn = mk3(FLT_MAX, FLT_MAX, FLT_MAX), amx = mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (uint32_t j = 0; j < m; ++j) {
+        const float* b = part_aabb + 6ull * (f + j);
+        amn = vmin3(amn, mk3(b[0], b[1], b[2]));
+        amx = vmax3(amx, mk3(b[3], b[4], b[5]));
+    }
+    Iso7 pos12 = iso_inv_mul(load_iso(mesh_pose), load_iso(pos_c + 7ull * k));
+    V3 ctr = iso_point(pos12, (amn + amx) * 0.5f), he = iso_abs_vec(pos12, (amx - amn) * 0.5f);
+    V3 lmn = ctr + (-he), lmx = ctr + he;
+    o[0] = lmn.x + (-prediction); o[1] = lmn.y + (-prediction); o[2] = lmn.z + (-prediction);
+    o[3] = lmx.x + prediction; o[4] = lmx.y + prediction; o[5] = lmx.z + prediction;
+}
+
+// e = one (query, triangle) couple of the CSR (kt[2e] = triangle position, kt[2e+1] = query). pass 0 counts the parts that meet the
+// triangle's loosened box in the compound's frame, pass 1 (offsets given) fills one candidate per such part.
+template <bool FILL>
+__global__ void k_tc_candidates(const uint32_t* __restrict__ kt, uint32_t total, const float4* __restrict__ tris, const uint32_t* __restrict__ comp_first,
+                                const uint32_t* __restrict__ comp_count, const uint32_t* __restrict__ part_shape, const float* __restrict__ part_pose,
+                                const float* __restrict__ part_aabb, const uint32_t* __restrict__ compound_id, const float* __restrict__ pos_c,
+                                const float* __restrict__ mesh_pose, float prediction, uint32_t* __restrict__ counts,
+                                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cand_shape, float4* __restrict__ cand_tri,
+                                float* __restrict__ cand_pose, uint32_t* __restrict__ cand_part, uint32_t* __restrict__ cand_ab) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    uint32_t tp = kt[2ull * e], k = kt[2ull * e + 1];
+    uint32_t c = compound_id[k];
+    Iso7 pos21 = iso_inverse(iso_inv_mul(load_iso(mesh_pose), load_iso(pos_c + 7ull * k)));
+    float4 fa = tris[3ull * tp], fb = tris[3ull * tp + 1], fc = tris[3ull * tp + 2];
+    V3 qa = iso_point(pos21, mk3(fa.x, fa.y, fa.z)), qb = iso_point(pos21, mk3(fb.x, fb.y, fb.z)), qc = iso_point(pos21, mk3(fc.x, fc.y, fc.z));
+    V3 mn = mk3(fminf(fminf(qa.x, qb.x), qc.x), fminf(fminf(qa.y, qb.y), qc.y), fminf(fminf(qa.z, qb.z), qc.z));
+    V3 mx = mk3(fmaxf(fmaxf(qa.x, qb.x), qc.x), fmaxf(fmaxf(qa.y, qb.y), qc.y), fmaxf(fmaxf(qa.z, qb.z), qc.z));
+    mn = mk3(mn.x + (-prediction), mn.y + (-prediction), mn.z + (-prediction));
+    mx = mk3(mx.x + prediction, mx.y + prediction, mx.z + prediction);
+    uint32_t f = comp_first[c], m = comp_count[c], cnt = 0;
+    uint32_t at = FILL ? offsets[e] : 0;
+    for (uint32_t j = 0; j < m; ++j) {
+        if (!aabb6_intersects(part_aabb + 6ull * (f + j), mn, mx)) continue;
+        if (FILL) {
+            size_t ci = (size_t)at + cnt;
+            cand_shape[ci] = part_shape[f + j];
+            cand_tri[3 * ci] = fa; cand_tri[3 * ci + 1] = fb; cand_tri[3 * ci + 2] = fc;
+            Iso7 pose = iso_inv_mul(load_iso(part_pose + 7ull * (f + j)), pos21);
+            float* o = cand_pose + 7 * ci;
+            o[0] = pose.q.i; o[1] = pose.q.j; o[2] = pose.q.k; o[3] = pose.q.w; o[4] = pose.t.x; o[5] = pose.t.y; o[6] = pose.t.z;
+            cand_part[ci] = j;
+            cand_ab[2 * ci] = (uint32_t)ci; cand_ab[2 * ci + 1] = (uint32_t)ci;
+        }
+        cnt++;
+    }
+    if (!FILL) counts[e] = cnt;
+}
+
+__global__ void k_tc_reduce(const uint32_t* __restrict__ q_off, const uint32_t* __restrict__ kt, const uint32_t* __restrict__ e_off,
+                            const float4* __restrict__ tris, const float* __restrict__ cand, const uint8_t* __restrict__ cand_status,
+                            const uint32_t* __restrict__ cand_part, const uint32_t* __restrict__ comp_first, uint32_t nc,
+                            const float* __restrict__ part_pose, const uint32_t* __restrict__ compound_id, const float* __restrict__ pos_c,
+                            const float* __restrict__ mesh_pose, uint32_t n, float* __restrict__ out, uint8_t* __restrict__ status,
+                            uint32_t* __restrict__ parts) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    uint32_t c = compound_id[q];
+    int st = c >= nc ? ST_UNSUPPORTED : ST_NONE, worst = ST_NONE;
+    uint32_t best_j = 0, best_tri = PB2_INVALID_U32;
+    float best = 0.0f;
+    if (st == ST_NONE) {
+        for (uint32_t e = q_off[q]; e < q_off[q + 1]; ++e) {
+            // the compound's answer for this triangle: first strictly smaller dist in part order
+            bool have = false;
+            uint32_t ej = 0;
+            float ed = 0.0f;
+            for (uint32_t j = e_off[e]; j < e_off[e + 1]; ++j) {
+                int cs = cand_status[j];
+                if (cs >= ST_UNSUPPORTED && worst == ST_NONE) worst = cs;
+                if (cs != ST_SOME) continue;
+                float d = cand[13ull * j + 12];
+                if (!have || d < ed) { have = true; ed = d; ej = j; }
+            }
+            if (!have) continue;
+            uint32_t id = __float_as_uint(tris[3ull * kt[2ull * e]].w);
+            if (best_tri == PB2_INVALID_U32 || ed < best || (ed == best && id < best_tri)) { best = ed; best_j = ej; best_tri = id; }
+        }
+        if (best_tri != PB2_INVALID_U32) st = ST_SOME;
+        if (worst != ST_NONE) st = worst;
+    }
+    float* o = out + 13ull * q;
+    if (st == ST_SOME) {
+        const float* cj = cand + 13ull * best_j;   // contact(part, triangle) in the part's and the mesh's frames
+        uint32_t pi = cand_part[best_j];
+        Iso7 pp = load_iso(part_pose + 7ull * (comp_first[c] + pi));
+        Iso7 pc = load_iso(pos_c + 7ull * q), pm = load_iso(mesh_pose);
+        ContactOut ct;   // transform1_by(part_pos), flipped: the mesh is shape 1
+        ct.p1 = iso_point(pm, mk3(cj[3], cj[4], cj[5]));
+        ct.n1 = iso_vec(pm, mk3(cj[9], cj[10], cj[11]));
+        ct.p2 = iso_point(pc, iso_point(pp, mk3(cj[0], cj[1], cj[2])));
+        ct.n2 = iso_vec(pc, iso_vec(pp, mk3(cj[6], cj[7], cj[8])));
+        ct.dist = cj[12];
+        store_contact(o, ct);
+        parts[2ull * q] = pi;
+        parts[2ull * q + 1] = best_tri;
+    } else {
+        for (int i = 0; i < 13; ++i) o[i] = 0.0f;
+        parts[2ull * q] = parts[2ull * q + 1] = PB2_INVALID_U32;
+    }
+    status[q] = (uint8_t)st;
+}
+
+static int trimesh_contact_compounds(pb2_ctx* ctx, const pb2_compounds* compounds, const uint32_t* d_cid, const float* d_pc, const pb2_trimesh* mesh,
+                                     const float* d_mpose, uint32_t n, float prediction, float* d_out, uint8_t* d_status, uint32_t* d_parts) {
+    const pb2_shapes* shapes = compounds->shapes;
+    cudaStream_t st = ctx->stream;
+    float *d_q = nullptr, *d_cpose = nullptr, *d_cand = nullptr;
+    uint32_t *d_off = nullptr, *d_items = nullptr, *d_kt = nullptr, *d_cnt = nullptr, *d_eoff = nullptr, *d_cs = nullptr, *d_cpart = nullptr, *d_cab = nullptr;
+    float4* d_ctri = nullptr;
+    uint8_t* d_cst = nullptr;
+    void* d_tmp = nullptr;
+    int rc = PB2_OK;
+    do {
+        if (cudaMallocAsync((void**)&d_q, (size_t)n * 24, st) != cudaSuccess || cudaMallocAsync((void**)&d_off, ((size_t)n + 1) * 4, st) != cudaSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_compounds: out of memory"); rc = PB2_ERR_CUDA; break;
+        }
+        k_tc_query_aabbs<<<pb2_blocks(n, 128), 128, 0, st>>>(compounds->first, compounds->count, compounds->nc, compounds->part_aabb, d_cid, d_pc, d_mpose,
+                                                             n, prediction, d_q);
+        PB2_LAUNCHED(ctx);
+        uint64_t total64 = 0;
+        if ((rc = pb2_intersect_csr_device(ctx, &mesh->bvh, d_q, n, true, d_off, &d_items, &total64)) != PB2_OK) break;
+        if (total64 > 0x7fffffffull) { snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_compounds: too many candidates"); rc = PB2_ERR_OVERFLOW; break; }
+        const uint32_t total = (uint32_t)total64;
+        uint32_t ncand = 0;
+        if (total) {
+            size_t cub_bytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)total + 1, st);
+            if (cudaMallocAsync((void**)&d_kt, (size_t)total * 8, st) != cudaSuccess || cudaMallocAsync((void**)&d_cnt, ((size_t)total + 1) * 4, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_eoff, ((size_t)total + 1) * 4, st) != cudaSuccess || cudaMallocAsync(&d_tmp, cub_bytes, st) != cudaSuccess) {
+                snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_compounds: out of memory (%u triangle candidates)", total); rc = PB2_ERR_CUDA; break;
+            }
+            k_expand_candidates<<<pb2_blocks(n, 128), 128, 0, st>>>(d_off, d_items, n, d_kt);
+            PB2_LAUNCHED(ctx);
+            cudaMemsetAsync(d_cnt + total, 0, 4, st);
+            k_tc_candidates<false><<<pb2_blocks(total, 128), 128, 0, st>>>(d_kt, total, mesh->tris, compounds->first, compounds->count, compounds->part_shape,
+                compounds->part_pose, compounds->part_aabb, d_cid, d_pc, d_mpose, prediction, d_cnt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+            PB2_LAUNCHED(ctx);
+            cub::DeviceScan::ExclusiveSum(d_tmp, cub_bytes, (const uint32_t*)d_cnt, d_eoff, (int)total + 1, st);
+            ctx->launches += 1;
+            cudaMemcpyAsync(&ncand, d_eoff + total, 4, cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_compounds: candidate pass failed"); rc = PB2_ERR_CUDA; break; }
+        }
+        if (ncand) {
+            if (cudaMallocAsync((void**)&d_cs, (size_t)ncand * 4, st) != cudaSuccess || cudaMallocAsync((void**)&d_cpart, (size_t)ncand * 4, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_cab, (size_t)ncand * 8, st) != cudaSuccess || cudaMallocAsync((void**)&d_ctri, (size_t)ncand * 48, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_cpose, (size_t)ncand * 28, st) != cudaSuccess || cudaMallocAsync((void**)&d_cand, (size_t)ncand * 52, st) != cudaSuccess ||
+                cudaMallocAsync((void**)&d_cst, ncand, st) != cudaSuccess) {
+                snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_compounds: out of memory (%u part candidates)", ncand); rc = PB2_ERR_CUDA; break;
+            }
+            k_tc_candidates<true><<<pb2_blocks(total, 128), 128, 0, st>>>(d_kt, total, mesh->tris, compounds->first, compounds->count, compounds->part_shape,
+                compounds->part_pose, compounds->part_aabb, d_cid, d_pc, d_mpose, prediction, nullptr, d_eoff, d_cs, d_ctri, d_cpose, d_cpart, d_cab);
+            PB2_LAUNCHED(ctx);
+            OutSinks sinks;
+            sinks.dense = d_cand; sinks.status = d_cst; sinks.compact = nullptr; sinks.pair_index = nullptr; sinks.cap = 0;
+            sinks.compact_count = nullptr; sinks.some_count = nullptr;
+            // contact(part_pos.inv_mul(pos21), part, triangle): the part from the shape table, the triangle as shape 2, local frames
+            if ((rc = run_contacts(ctx, shapes, d_cs, nullptr, d_cpose, d_cpose, prediction, ncand, sinks, d_cab, ncand, nullptr, 0,
+                                   PAIR_LOCAL_FRAMES | PAIR_POS12_GIVEN, nullptr, 0, nullptr, 3, d_ctri)) != PB2_OK) break;
+        }
+        k_tc_reduce<<<pb2_blocks(n, 128), 128, 0, st>>>(d_off, d_kt, d_eoff, mesh->tris, d_cand, d_cst, d_cpart, compounds->first, compounds->nc,
+            compounds->part_pose, d_cid, d_pc, d_mpose, n, d_out, d_status, d_parts);
+        PB2_LAUNCHED(ctx);
+        if (cudaGetLastError() != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "trimesh_contact_compounds: launch failed"); rc = PB2_ERR_CUDA; break; }
+    } while (0);
+    void* frees[] = {d_q, d_off, d_items, d_kt, d_cnt, d_eoff, d_tmp, d_cs, d_cpart, d_cab, d_ctri, d_cpose, d_cand, d_cst};
+    for (void* p : frees) if (p) cudaFreeAsync(p, st);
+    return rc;
+}
+
+
 extern "C" {
 
 int pb2_compounds_create(pb2_ctx* ctx, const pb2_shapes* shapes, const uint32_t* comp_first, const uint32_t* comp_count, uint32_t nc,
@@ -2946,8 +3136,8 @@ int pb2_compound_contact_shapes(pb2_ctx* ctx, const pb2_compounds* compounds, co
 }
 
 int pb2_compound_contact_trimesh(pb2_ctx* ctx, const pb2_compounds* compounds, const uint32_t* compound_ids, const float* compound_poses7,
-                                 const pb2_trimesh* mesh, const float* mesh_pose7, uint32_t n, float prediction, pb2_contact* out, uint8_t* status,
-                                 uint32_t* parts, int mem) {
+                                 const pb2_trimesh* mesh, const float* mesh_pose7, uint32_t n, float prediction, int mesh_first, pb2_contact* out,
+                                 uint8_t* status, uint32_t* parts, int mem) {
     if (!ctx || !compounds || !mesh || !mesh_pose7 || (n && (!compound_ids || !compound_poses7 || !out || !status || !parts))) return PB2_ERR_INVALID;
     if (n == 0) return PB2_OK;
     const pb2_shapes* shapes = compounds->shapes;
@@ -2961,6 +3151,15 @@ int pb2_compound_contact_trimesh(pb2_ctx* ctx, const pb2_compounds* compounds, c
     PB2_CHECK(pb2_stage_out(ctx, 4, out, (size_t)n * 52, mem, &d_out));
     PB2_CHECK(pb2_stage_out(ctx, 5, status, (size_t)n, mem, &d_status));
     PB2_CHECK(pb2_stage_out(ctx, 6, parts, (size_t)n * 8, mem, &d_parts));
+    if (mesh_first) {
+        PB2_CHECK(trimesh_contact_compounds(ctx, compounds, (const uint32_t*)d_cid, (const float*)d_pc, mesh, (const float*)d_mpose, n, prediction,
+                                            (float*)d_out, (uint8_t*)d_status, (uint32_t*)d_parts));
+        PB2_CHECK(pb2_stage_back(ctx, out, d_out, (size_t)n * 52, mem));
+        PB2_CHECK(pb2_stage_back(ctx, status, d_status, (size_t)n, mem));
+        PB2_CHECK(pb2_stage_back(ctx, parts, d_parts, (size_t)n * 8, mem));
+        if (mem == PB2_MEM_HOST) PB2_CUDA(ctx, cudaStreamSynchronize(st));
+        return PB2_OK;
+    }
     uint32_t *d_cnt = nullptr, *d_off = nullptr, *d_cs = nullptr, *d_cpart = nullptr, *d_ctri = nullptr;
     float *d_cpose = nullptr, *d_cand = nullptr, *d_ident = nullptr;
     uint8_t* d_cst = nullptr;

@@ -688,10 +688,11 @@ class Compounds:
         self.ctx.check(self.ctx._lib.pb2_compound_contact_compounds(self.ctx.h, self.h, pi1, p1, pi2, p2, n, float(prediction), po, pst, pp, mem))
         return out, status, parts
 
-    def contact_trimesh(self, ids, poses, mesh, mesh_pose, prediction):
+    def contact_trimesh(self, ids, poses, mesh, mesh_pose, prediction, mesh_first=False):
         """query::contact(poses[k], compound ids[k], mesh_pose, mesh, prediction) for every k (the composite arm with the Compound
-        first, contact_composite_shape_shape.rs:12-48 over the parts and :63-76 over the triangles). Returns (contacts (n, 13),
-        status (n,), parts (n, 2) = {winning part, winning triangle})."""
+        first, contact_composite_shape_shape.rs:12-48 over the parts and :63-76 over the triangles) — or, with mesh_first,
+        query::contact(mesh_pose, mesh, poses[k], compound ids[k], prediction). Returns (contacts (n, 13), status (n,), parts (n, 2) =
+        {winning part, winning triangle})."""
         n = int(poses.shape[0])
         kp, pp, mem = _prep(poses, np.float32)
         ki, pi, _ = _prep(ids, np.uint32, mem)
@@ -700,7 +701,8 @@ class Compounds:
         out, po = _empty((n, 13), np.float32, mem, dev)
         status, pst = _empty((n,), np.uint8, mem, dev)
         parts, ppart = _empty((n, 2), np.uint32, mem, dev)
-        self.ctx.check(self.ctx._lib.pb2_compound_contact_trimesh(self.ctx.h, self.h, pi, pp, mesh.h, pm, n, float(prediction), po, pst, ppart, mem))
+        self.ctx.check(self.ctx._lib.pb2_compound_contact_trimesh(self.ctx.h, self.h, pi, pp, mesh.h, pm, n, float(prediction), int(mesh_first),
+                                                                  po, pst, ppart, mem))
         return out, status, parts
 
     def close(self):

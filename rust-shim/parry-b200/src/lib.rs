@@ -603,9 +603,9 @@ impl<'c> Compounds<'c> {
         Ok((0..n).map(|k| contact_of_status(status[k], &out[k]).map(|c| c.map(|c| (c, parts[k])))).collect())
     }
 
-    /// `query::contact(poses[k], compound ids[k], mesh_pose, &trimesh, prediction)`: `(contact, [part, triangle])`. The opposite
-    /// argument order nests per triangle in the reference and is not offered on the device.
-    pub fn contact_trimesh(&self, ids: &[u32], poses: &[Isometry<Real>], mesh: &TriMesh<'c>, mesh_pose: &Isometry<Real>, prediction: Real)
+    /// `query::contact(poses[k], compound ids[k], mesh_pose, &trimesh, prediction)` or, with `mesh_first`,
+    /// `query::contact(mesh_pose, &trimesh, poses[k], compound ids[k], prediction)`: `(contact, [part, triangle])`.
+    pub fn contact_trimesh(&self, ids: &[u32], poses: &[Isometry<Real>], mesh: &TriMesh<'c>, mesh_pose: &Isometry<Real>, prediction: Real, mesh_first: bool)
                            -> Result<Vec<Result<Option<(Contact, [u32; 2])>, Unsupported>>, Error> {
         let n = ids.len();
         let p7: Vec<[f32; 7]> = poses.iter().map(iso7).collect();
@@ -613,8 +613,8 @@ impl<'c> Compounds<'c> {
         let (mut out, mut status, mut parts) = (vec![sys::pb2_contact::default(); n], vec![0u8; n], vec![[0u32; 2]; n]);
         let (h, m) = (self.h, mesh.h);
         self.c.call(|ctx| unsafe {
-            sys::pb2_compound_contact_trimesh(ctx, h, ids.as_ptr(), p7.as_ptr() as *const f32, m, mp.as_ptr(), n as u32, prediction, out.as_mut_ptr(),
-                                              status.as_mut_ptr(), parts.as_mut_ptr() as *mut u32, sys::PB2_MEM_HOST)
+            sys::pb2_compound_contact_trimesh(ctx, h, ids.as_ptr(), p7.as_ptr() as *const f32, m, mp.as_ptr(), n as u32, prediction, mesh_first as i32,
+                                              out.as_mut_ptr(), status.as_mut_ptr(), parts.as_mut_ptr() as *mut u32, sys::PB2_MEM_HOST)
         })?;
         Ok((0..n).map(|k| contact_of_status(status[k], &out[k]).map(|c| c.map(|c| (c, parts[k])))).collect())
     }

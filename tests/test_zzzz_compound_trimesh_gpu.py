@@ -69,6 +69,43 @@ def test_compound_trimesh_vs_oracle(ctx, oracle, seed, n, prediction, mesh_moved
     assert (rp[some][:, 0] > 0).mean() > 0.2            # later parts win too
 
 
+@pytest.mark.parametrize("seed,n,prediction,mesh_moved", [(311, 8000, 0.05, False), (312, 3000, 0.3, True)])
+def test_trimesh_compound_vs_oracle(ctx, oracle, seed, n, prediction, mesh_moved):
+    """The other argument order, query::contact(mesh_pose, &TriMesh, pose, Compound): the reference walks the triangles first and
+    solves every leaf problem with the part as shape 1 and the triangle as shape 2 (contact_composite_shape_shape.rs:12-76 twice);
+    against the oracle's contact_trimesh_compound."""
+    import parry_b200
+    v, idx, spec, compounds, ids, poses = make_scene(n, seed)
+    T, G, C = tables(ctx, oracle, spec, compounds)
+    gm, om = parry_b200.TriMesh(ctx, v, idx), oracle.TriMesh(v, idx)
+    mpose = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    if mesh_moved:
+        mq = np.array([0.01, -0.02, 0.015, 1.0]); mq /= np.linalg.norm(mq)
+        mpose = np.concatenate([mq, [0.05, -0.1, 0.08]]).astype(np.float32)
+    ro, rs, rp = om.contact_compounds(mpose, T, C.first, C.count, C.part_shape, C.part_pose, ids, poses, prediction, trimesh_first=True, threads=8,
+                                      min_index_ties=True)
+    go, gs, gp = C.contact_trimesh(ids, poses, gm, mpose, prediction, mesh_first=True)
+    go, gs, gp = np.asarray(go), np.asarray(gs), np.asarray(gp).astype(np.uint32)
+    assert 0.2 < (rs == 1).mean() < 0.98
+    assert (gs != 3).all()
+    assert (gs == rs).all(), np.nonzero(gs != rs)[0][:10]
+    some = rs == 1
+    assert (gp[~some] == 0xFFFFFFFF).all() and (go[~some] == 0).all()
+    np.testing.assert_allclose(go[some][:, 12], ro[some][:, 12], rtol=1e-5, atol=2e-6)
+    same = (gp[some] == rp[some]).all(axis=1)
+    assert same.mean() > 0.99, same.mean()
+    np.testing.assert_allclose(go[some][same], ro[some][same], rtol=1e-5, atol=3e-6)
+    exact = (go[some].view(np.uint32) == ro[some].view(np.uint32)).all(axis=1).mean()
+    assert exact > 0.98, exact
+    assert (rp[some][:, 0] > 0).mean() > 0.2
+    # and it is the other order's flipped contact up to the leaf problems' swapped roles (same dist to rounding)
+    fo, fs, fp = C.contact_trimesh(ids, poses, gm, mpose, prediction)
+    fo, fs = np.asarray(fo), np.asarray(fs)
+    both = (fs == 1) & (gs == 1)
+    assert (fs == gs).mean() > 0.99
+    np.testing.assert_allclose(fo[both][:, 12], go[both][:, 12], rtol=0, atol=5e-5)
+
+
 def test_compound_trimesh_edge_cases_and_device_memory(ctx, oracle):
     import torch
     import parry_b200
