@@ -896,6 +896,7 @@ int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, co
     if (shared_tri) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_shared, 128, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
     if (per_sm < 1) per_sm = 1;
+    { const char* e = getenv("PB2_RAY_CTAS_PER_SM"); if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e); }
     unsigned blocks = (unsigned)(ctx->sm_count * per_sm);
     unsigned need = pb2_blocks(m, 128);
     if (blocks > need) blocks = need;
