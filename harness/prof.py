@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small single-workload driver for ncu captures / quick timings: python harness/prof.py <workload> [iters]
-workloads: rays_terrain, rays_sphere1m, contacts, broadphase, mesh_queries"""
+workloads: rays_terrain, rays_sphere1m, contacts, broadphase, mesh_queries, rays_colliders"""
 import os
 import sys
 import time
@@ -98,6 +98,31 @@ def main():
             st["p"] = bvh.traverse_bvtt_single_tree(capacity=16 * n, like=a)
         ms = timeit(frame, wl)
         print("%.1f MAABB/s, %d pairs" % (n / ms / 1e3, st["p"].shape[0]))
+    elif wl == "rays_colliders":
+        # Bvh::cast_ray over typed leaves: 2^20 rays against 2^20 colliders, a third of them 32-vertex hulls
+        n = 1 << 20
+        g = scenes.rng(12)
+        pts, _ = scenes.hull_pool(256, 32, seed=13)
+        kinds = g.integers(0, 3, n)
+        base = [parry_b200.Ball(0.4), parry_b200.Cuboid([0.3, 0.5, 0.4])] + [parry_b200.ConvexPolyhedron(np.asarray(p, np.float32) * 0.6) for p in pts]
+        shapes = parry_b200.Shapes(ctx, base)
+        sid = np.where(kinds == 0, 0, np.where(kinds == 1, 1, 2 + g.integers(0, len(pts), n))).astype(np.int32)
+        side = (n ** (1 / 3)) * 1.6
+        poses = np.concatenate([scenes.random_unit_quaternions(g, n), g.random((n, 3)) * side], axis=1).astype(np.float32)
+        dsid, dposes = torch.from_numpy(sid).cuda(), torch.from_numpy(poses).cuda()
+        aabbs = shapes.compute_aabbs(dsid, dposes)
+        bvh = parry_b200.Bvh.from_leaves(ctx, 0, aabbs)
+        o = g.random((n, 3)) * side
+        d = g.standard_normal((n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        rays = torch.from_numpy(np.concatenate([o, d], axis=1).astype(np.float32)).cuda()
+        res = {}
+        for with_normal in (False, True):
+            ms = timeit(lambda: res.__setitem__("r", bvh.cast_ray(shapes, dsid, dposes, rays, FMAX, solid=True, with_normal=with_normal)),
+                        "Bvh::cast_ray typed leaves, normal=%s" % with_normal)
+            print("   %.1f M rays/s, %d hits, checksum %.6f" % (n / ms / 1e3, int((res["r"][1] != -1).sum().item()), float(res["r"][0].double().sum().item())))
+        q = torch.from_numpy((g.random((n, 3)) * side).astype(np.float32)).cuda()
+        ms = timeit(lambda: res.__setitem__("p", bvh.project_point(shapes, dsid, dposes, q, FMAX, solid=True)), "Bvh::project_point typed leaves")
+        print("   %.1f M points/s" % (n / ms / 1e3))
     elif wl == "mesh_queries":
         # the composite-shape queries against a 2 M-triangle terrain: shapes scattered within a few shape sizes of the surface
         v, i = scenes.terrain(1001, 1001)
