@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small single-workload driver for ncu captures / quick timings: python harness/prof.py <workload> [iters]
-workloads: rays_terrain, rays_sphere1m, contacts, broadphase, mesh_queries, rays_colliders"""
+workloads: rays_terrain, rays_sphere1m, contacts, broadphase, mesh_queries, colliders_queries"""
 import os
 import sys
 import time
@@ -98,7 +98,7 @@ def main():
             st["p"] = bvh.traverse_bvtt_single_tree(capacity=16 * n, like=a)
         ms = timeit(frame, wl)
         print("%.1f MAABB/s, %d pairs" % (n / ms / 1e3, st["p"].shape[0]))
-    elif wl == "rays_colliders":
+    elif wl == "colliders_queries":
         # Bvh::cast_ray over typed leaves: 2^20 rays against 2^20 colliders, a third of them 32-vertex hulls
         n = 1 << 20
         g = scenes.rng(12)
