@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(128) k_raycast_shapes(const NodeWide* __restri
                                  uint32_t m, float max_toi, bool solid, float* __restrict__ out_toi, uint32_t* __restrict__ out_leaf,
                                  float* __restrict__ out_normal, uint32_t* __restrict__ out_feature, uint32_t n_shapes, unsigned int* fault) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= m) return;
+    const bool valid = r < m;   // every lane stays: the descent below is warp-cooperative (traverse.cuh)
+    if (!valid) r = 0;
     V3 o = mk3(rays[6ull * r], rays[6ull * r + 1], rays[6ull * r + 2]);
     V3 d = mk3(rays[6ull * r + 3], rays[6ull * r + 4], rays[6ull * r + 5]);
     V3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(128) k_raycast_shapes(const NodeWide* __restri
     bool found = false;
     uint32_t best_id = PB2_INVALID_U32, best_feat = PB2_INVALID_U32;
     V3 best_n = mk3(0.f, 0.f, 0.f);
-    auto leaf = [&](uint32_t pos) {
+    auto leaf = [&](uint32_t pos, unsigned) {
         uint32_t id = order[pos];
         uint32_t sid = shape_ids ? shape_ids[id] : id;
         if (sid >= n_shapes) { atomicOr(fault, PB2_FAULT_BAD_ID); return; }   // reported as PB2_ERR_INVALID at the next synchronisation
@@ -184,7 +185,11 @@ __global__ void __launch_bounds__(128) k_raycast_shapes(const NodeWide* __restri
             if (WITH_NORMAL) { best_n = iso_vec(pose, n); best_feat = feat; }
         }
     };
-    bvh_find_best(nodes, n_leaves, o, d, inv, max_toi, best, found, leaf, fault);
+    // BvhNode::cast_ray (bvh_tree.rs:1177-1181) as the node cost; the leaf query (a GJK ray cast for hull leaves) runs for all
+    // waiting lanes together: 13.7 -> see DESIGN.md section 7 for the measured effect
+    auto cost = [&](float4 lo, float4 hi, float bound) { return slab_cost(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, o, d, inv, bound); };
+    bvh_find_best_cost(0xffffffffu, valid, nodes, n_leaves, max_toi, best, found, cost, leaf, fault);
+    if (!valid) return;
     out_toi[r] = found ? best : 0.0f;
     out_leaf[r] = best_id;
     if (WITH_NORMAL) {
