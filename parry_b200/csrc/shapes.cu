@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128) k_raycast_shapes(const NodeWide* __restri
         }
     };
     // BvhNode::cast_ray (bvh_tree.rs:1177-1181) as the node cost; the leaf query (a GJK ray cast for hull leaves) runs for all
-    // waiting lanes together: 13.7 -> see DESIGN.md section 7 for the measured effect
+    // waiting lanes together: 2^20 rays vs 2^20 mixed colliders 13.7 -> 8.7 ms (22.5 -> 9.9 ms with normals), same results
     auto cost = [&](float4 lo, float4 hi, float bound) { return slab_cost(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, o, d, inv, bound); };
     bvh_find_best_cost(0xffffffffu, valid, nodes, n_leaves, max_toi, best, found, cost, leaf, fault);
     if (!valid) return;
