@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(128, 8) k_raycast_wide_shared(const float4* __
     if (pose7) pose = load_iso(pose7);
     V3 o = mk3(0.f, 0.f, 0.f), inv = o;
     float best = 0.f;
-    uint32_t r = 0, oct = 0, cur = PB2_INVALID_U32;
+    uint32_t r = PB2_INVALID_U32, oct = 0, cur = PB2_INVALID_U32;   // r == INVALID: no ray yet (PIECES: nothing to count)
     uint32_t g_base = 0, g_bits = 0;
     bool active = false, pend = false;
     uint2 stack[W8_STACK];
