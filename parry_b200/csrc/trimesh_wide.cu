@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide(const float4* __restric
 // (cuStreamWaitValue32) to push that range of results to the peer GPUs. One launch keeps the SMs full across range
 // boundaries, which separate launches per range cannot (each boundary cost ~40 us of ramp-down).
 template <bool WITH_NORMAL, bool PIECES>
-__global__ void __launch_bounds__(128, 8) k_raycast_wide_shared(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
+__global__ void __launch_bounds__(128, PIECES ? 7 : 8) k_raycast_wide_shared(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
                                   const float* __restrict__ pose7, const float* __restrict__ rays, const uint32_t* __restrict__ perm,
                                   uint32_t m, float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
                                   float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
