@@ -45,7 +45,7 @@ struct pb2_ctx {
     unsigned int* d_pieces = nullptr;  // 2 x 32 u32: per-piece retired-ray counters and completion flags of a piece-signalling ray cast
     void* wait_value32 = nullptr;      // cuStreamWaitValue32, resolved once (NULL: not available -> piece-wise launches)
 };
-struct PieceSignal { uint32_t size; unsigned int* done; unsigned int* flag; uint32_t flush_every; };
+struct PieceSignal { uint32_t size; unsigned int* done; unsigned int* flag; uint32_t flush_every; uint32_t shift; };   // size == 1 << shift
 int pb2_pipeline_init(pb2_ctx* ctx);
 static inline cudaEvent_t pb2_next_event(pb2_ctx* ctx) { cudaEvent_t e = ctx->ev[ctx->ev_next]; ctx->ev_next = (ctx->ev_next + 1) % 64; return e; }
 

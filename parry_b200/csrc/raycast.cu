@@ -575,6 +575,9 @@ int pb2_trimesh_cast_rays_allgather(pb2_ctx* ctx, const pb2_trimesh* mesh, const
         wait_fn_t wait_value = (wait_fn_t)ctx->wait_value32;
         PieceSignal ps;
         ps.size = (m + (uint32_t)chunks - 1u) / (uint32_t)chunks;
+        ps.shift = 0;   // ranges are rounded up to a power of two so that the kernel finds a ray's range with a shift
+        while ((1u << ps.shift) < ps.size && ps.shift < 31u) ps.shift++;
+        ps.size = 1u << ps.shift;
         ps.done = ctx->d_pieces; ps.flag = ctx->d_pieces + 32;
         ps.flush_every = 32;  // refills between two publications of a warp's retired-ray counts
         { const char* e = getenv("PB2_RAY_PIECE_FLUSH"); if (e && atoi(e) > 0) ps.flush_every = (uint32_t)atoi(e); }

@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide(const float4* __restric
 // (cuStreamWaitValue32) to push that range of results to the peer GPUs. One launch keeps the SMs full across range
 // boundaries, which separate launches per range cannot (each boundary cost ~40 us of ramp-down).
 template <bool WITH_NORMAL, bool PIECES>
-__global__ void __launch_bounds__(128, PIECES ? 7 : 8) k_raycast_wide_shared(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
+__global__ void __launch_bounds__(128, 8) k_raycast_wide_shared(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
                                   const float* __restrict__ pose7, const float* __restrict__ rays, const uint32_t* __restrict__ perm,
                                   uint32_t m, float max_toi, float* __restrict__ out_toi, uint32_t* __restrict__ out_tri,
                                   float* __restrict__ out_normal, uint32_t* __restrict__ out_feature,
@@ -599,6 +599,10 @@ __global__ void __launch_bounds__(128, PIECES ? 7 : 8) k_raycast_wide_shared(con
     __shared__ float s_nrm[WITH_NORMAL ? 3 : 1][128];
     __shared__ uint2 s_gq[4][W8C_GQ];              // {first triangle, leaf mask | hit mask << 8 | owner lane << 16}
     __shared__ uint16_t s_items[4][256];           // queue slot << 3 | child slot, one per triangle to test
+    // PIECES bookkeeping, per warp: {range a, count a, range b, count b, refills since the last publication}. In shared memory so
+    // that the variant keeps the plain kernel's register budget (at 64 registers five more live values spilled inside the hot loop:
+    // 2.40 instead of 2.09 ms on one GPU, harness/pieces_probe.py)
+    __shared__ uint32_t s_pz[PIECES ? 4 : 1][5];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
     const unsigned lt = (1u << lane) - 1u;
@@ -607,7 +611,7 @@ __global__ void __launch_bounds__(128, PIECES ? 7 : 8) k_raycast_wide_shared(con
     if (pose7) pose = load_iso(pose7);
     V3 o = mk3(0.f, 0.f, 0.f), inv = o;
     float best = 0.f;
-    uint32_t r = 0, oct = 0, cur = PB2_INVALID_U32;
+    uint32_t r = PB2_INVALID_U32, oct = 0, cur = PB2_INVALID_U32;   // r == INVALID: no ray yet (PIECES: nothing to count)
     uint32_t g_base = 0, g_bits = 0;
     bool active = false, pend = false;
     uint2 stack[W8_STACK];
@@ -615,38 +619,54 @@ __global__ void __launch_bounds__(128, PIECES ? 7 : 8) k_raycast_wide_shared(con
     uint32_t G = 0;                                // groups in this warp's queue (warp uniform)
     bool exhausted = false;
     // PIECES: retired rays not yet published, for the two ranges a warp can hold rays of around a range boundary
-    uint32_t pz_piece = PB2_INVALID_U32, pz_count = 0, pz_piece2 = PB2_INVALID_U32, pz_count2 = 0, pz_since = 0;
+    if (PIECES) {
+        if (lane == 0) { s_pz[w][0] = PB2_INVALID_U32; s_pz[w][1] = 0; s_pz[w][2] = PB2_INVALID_U32; s_pz[w][3] = 0; s_pz[w][4] = 0; }
+        __syncwarp();
+    }
     auto pz_publish = [&](uint32_t piece, uint32_t count) {   // lane 0, after the warp's fence
         uint32_t lo_r = piece * pieces.size;
         uint32_t total = m - lo_r < pieces.size ? m - lo_r : pieces.size;
         unsigned prev = atomicAdd(&pieces.done[piece], count);
         if (prev + count == total) { __threadfence(); atomicExch(&pieces.flag[piece], 1u); }
     };
-    auto pz_flush = [&]() {
+    auto pz_flush = [&]() {   // every lane of the warp
         __threadfence();   // every lane's result stores are visible before the counts are
         __syncwarp();
         if (lane == 0) {
-            if (pz_count) pz_publish(pz_piece, pz_count);
-            if (pz_count2) pz_publish(pz_piece2, pz_count2);
+            if (s_pz[w][1]) pz_publish(s_pz[w][0], s_pz[w][1]);
+            if (s_pz[w][3]) pz_publish(s_pz[w][2], s_pz[w][3]);
+            s_pz[w][1] = 0; s_pz[w][3] = 0; s_pz[w][4] = 0;
         }
-        pz_count = 0; pz_count2 = 0; pz_since = 0;
+        __syncwarp();
     };
-    // rays retired since the last refill are counted when their lane is handed a new ray (and at exit): nothing per trip
-    uint32_t rp = PB2_INVALID_U32;   // range of the ray this lane holds or has retired but not yet counted
+    // rays retired since the last refill are counted when their lane is handed a new ray (and at exit): nothing per trip. A lane that
+    // has been counted forgets its ray index (r = INVALID), which is what marks it as counted.
     auto pz_collect = [&]() {
-        unsigned cm = __ballot_sync(FULL, !active && rp != PB2_INVALID_U32);
+        uint32_t mine = (!active && r != PB2_INVALID_U32) ? r >> pieces.shift : PB2_INVALID_U32;   // ranges are powers of two
+        unsigned cm = __ballot_sync(FULL, mine != PB2_INVALID_U32);
         while (cm) {   // usually one range
-            uint32_t p0 = __shfl_sync(FULL, rp, __ffs(cm) - 1);
-            unsigned grp = __ballot_sync(FULL, !active && rp == p0);
+            uint32_t p0 = __shfl_sync(FULL, mine, __ffs(cm) - 1);
+            unsigned grp = __ballot_sync(FULL, mine == p0);
             cm &= ~grp;
             uint32_t c = (uint32_t)__popc(grp);
-            if (p0 == pz_piece) pz_count += c;
-            else if (p0 == pz_piece2) pz_count2 += c;
-            else if (pz_count == 0) { pz_piece = p0; pz_count = c; }
-            else if (pz_count2 == 0) { pz_piece2 = p0; pz_count2 = c; }
-            else { pz_flush(); pz_piece = p0; pz_count = c; }
+            const uint32_t pa = s_pz[w][0], ca = s_pz[w][1], pb = s_pz[w][2], cb = s_pz[w][3];   // warp-uniform reads
+            int slot;   // 0 / 1: add to range a / b; 2 / 3: start a / b; 4: publish first, then start a
+            if (p0 == pa) slot = 0;
+            else if (p0 == pb) slot = 1;
+            else if (ca == 0) slot = 2;
+            else if (cb == 0) slot = 3;
+            else slot = 4;
+            if (slot == 4) pz_flush();
+            __syncwarp();
+            if (lane == 0) {
+                if (slot == 0) s_pz[w][1] = ca + c;
+                else if (slot == 1) s_pz[w][3] = cb + c;
+                else if (slot == 3) { s_pz[w][2] = p0; s_pz[w][3] = c; }
+                else { s_pz[w][0] = p0; s_pz[w][1] = c; }
+            }
+            __syncwarp();
         }
-        if (!active) rp = PB2_INVALID_U32;
+        if (!active) r = PB2_INVALID_U32;
     };
     // Ray staging (round 2). Round 1 handed a new ray to each idle lane straight from global memory: one atomicAdd, six scattered
     // 4-byte loads and three IEEE divisions executed by the ~8 idle lanes of a refill while the other 24 waited behind them — 11 % of
@@ -658,7 +678,14 @@ __global__ void __launch_bounds__(128, PIECES ? 7 : 8) k_raycast_wide_shared(con
     for (;;) {
         unsigned idle = __ballot_sync(FULL, !active);
         if ((!exhausted || st_next < st_count) && (idle == FULL || __popc(idle) >= refill)) {
-            if (PIECES) { pz_collect(); if (++pz_since >= (uint32_t)pieces_flush_every && (pz_count | pz_count2)) pz_flush(); }
+            if (PIECES) {
+                pz_collect();
+                const uint32_t since = s_pz[w][4] + 1u;
+                const bool due = since >= (uint32_t)pieces_flush_every && (s_pz[w][1] | s_pz[w][3]) != 0u;
+                __syncwarp();
+                if (due) pz_flush();
+                else { if (lane == 0) s_pz[w][4] = since; __syncwarp(); }
+            }
             for (;;) {
                 if (st_next == st_count) {
                     if (exhausted) break;
@@ -698,7 +725,6 @@ __global__ void __launch_bounds__(128, PIECES ? 7 : 8) k_raycast_wide_shared(con
                     s_ray[3][threadIdx.x] = d.x; s_ray[4][threadIdx.x] = d.y; s_ray[5][threadIdx.x] = d.z;
                     s_ray[6][threadIdx.x] = inv.x; s_ray[7][threadIdx.x] = inv.y; s_ray[8][threadIdx.x] = inv.z;
                     s_key[threadIdx.x] = ((unsigned long long)__float_as_uint(max_toi) << 32) | 0xffffffffull;
-                    if (PIECES) rp = r / pieces.size;
                 }
                 st_next += take;
                 idle = __ballot_sync(FULL, !active);
@@ -874,7 +900,7 @@ __global__ void __launch_bounds__(128, PIECES ? 7 : 8) k_raycast_wide_shared(con
             active = false;
         }
     }
-    if (PIECES) { pz_collect(); if (pz_count | pz_count2) pz_flush(); }
+    if (PIECES) { pz_collect(); if (s_pz[w][1] | s_pz[w][3]) pz_flush(); }
 }
 
 int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, const float* d_rays, const uint32_t* d_perm, uint32_t m,
@@ -888,7 +914,7 @@ int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, co
     const bool pz = pieces != nullptr && shared_tri && !with_normal && d_perm == nullptr;
     if (pieces && !pz) return PB2_ERR_INVALID;
     auto kern_shared = pz ? k_raycast_wide_shared<false, true> : (with_normal ? k_raycast_wide_shared<true, false> : k_raycast_wide_shared<false, false>);
-    PieceSignal no_pieces = {0u, nullptr, nullptr, 0u};
+    PieceSignal no_pieces = {0u, nullptr, nullptr, 0u, 0u};
     int tri_groups = 12, blocked_max = 8;
     { const char* e = getenv("PB2_RAY_TRI_GROUPS"); if (e) tri_groups = atoi(e); }
     { const char* e = getenv("PB2_RAY_BLOCKED"); if (e) blocked_max = atoi(e); }
