@@ -618,11 +618,12 @@ __global__ void __launch_bounds__(128, 8) k_raycast_wide_shared(const float4* __
     int sp = 0;
     uint32_t G = 0;                                // groups in this warp's queue (warp uniform)
     bool exhausted = false;
-    // PIECES: retired rays not yet published, for the two ranges a warp can hold rays of around a range boundary
-    if (PIECES) {
-        if (lane == 0) { s_pz[w][0] = PB2_INVALID_U32; s_pz[w][1] = 0; s_pz[w][2] = PB2_INVALID_U32; s_pz[w][3] = 0; s_pz[w][4] = 0; }
-        __syncwarp();
-    }
+    // PIECES: retired rays not yet published, for the two ranges a warp can hold rays of around a range boundary. The five words are
+    // warp-uniform: every lane computes and stores the same values (volatile, so that they are not carried in registers through the
+    // hot loop; no lane-0 branch). Every read-modify-write is read -> __syncwarp -> write -> __syncwarp, so a lane that runs ahead
+    // can never read a value another lane has already updated.
+    volatile uint32_t* const pz = s_pz[PIECES ? w : 0];
+    if (PIECES) { pz[0] = PB2_INVALID_U32; pz[1] = 0; pz[2] = PB2_INVALID_U32; pz[3] = 0; pz[4] = 0; __syncwarp(); }
     auto pz_publish = [&](uint32_t piece, uint32_t count) {   // lane 0, after the warp's fence
         uint32_t lo_r = piece * pieces.size;
         uint32_t total = m - lo_r < pieces.size ? m - lo_r : pieces.size;
@@ -631,12 +632,13 @@ __global__ void __launch_bounds__(128, 8) k_raycast_wide_shared(const float4* __
     };
     auto pz_flush = [&]() {   // every lane of the warp
         __threadfence();   // every lane's result stores are visible before the counts are
-        __syncwarp();
+        const uint32_t pa = pz[0], ca = pz[1], pb = pz[2], cb = pz[3];
+        __syncwarp();      // every lane has read the counts before anybody clears them
         if (lane == 0) {
-            if (s_pz[w][1]) pz_publish(s_pz[w][0], s_pz[w][1]);
-            if (s_pz[w][3]) pz_publish(s_pz[w][2], s_pz[w][3]);
-            s_pz[w][1] = 0; s_pz[w][3] = 0; s_pz[w][4] = 0;
+            if (ca) pz_publish(pa, ca);
+            if (cb) pz_publish(pb, cb);
         }
+        pz[1] = 0; pz[3] = 0; pz[4] = 0;
         __syncwarp();
     };
     // rays retired since the last refill are counted when their lane is handed a new ray (and at exit): nothing per trip. A lane that
@@ -649,21 +651,13 @@ __global__ void __launch_bounds__(128, 8) k_raycast_wide_shared(const float4* __
             unsigned grp = __ballot_sync(FULL, mine == p0);
             cm &= ~grp;
             uint32_t c = (uint32_t)__popc(grp);
-            const uint32_t pa = s_pz[w][0], ca = s_pz[w][1], pb = s_pz[w][2], cb = s_pz[w][3];   // warp-uniform reads
-            int slot;   // 0 / 1: add to range a / b; 2 / 3: start a / b; 4: publish first, then start a
-            if (p0 == pa) slot = 0;
-            else if (p0 == pb) slot = 1;
-            else if (ca == 0) slot = 2;
-            else if (cb == 0) slot = 3;
-            else slot = 4;
-            if (slot == 4) pz_flush();
+            const uint32_t pa = pz[0], ca = pz[1], pb = pz[2], cb = pz[3];
             __syncwarp();
-            if (lane == 0) {
-                if (slot == 0) s_pz[w][1] = ca + c;
-                else if (slot == 1) s_pz[w][3] = cb + c;
-                else if (slot == 3) { s_pz[w][2] = p0; s_pz[w][3] = c; }
-                else { s_pz[w][0] = p0; s_pz[w][1] = c; }
-            }
+            if (p0 == pa) pz[1] = ca + c;
+            else if (p0 == pb) pz[3] = cb + c;
+            else if (ca == 0) { pz[0] = p0; pz[1] = c; }
+            else if (cb == 0) { pz[2] = p0; pz[3] = c; }
+            else { pz_flush(); pz[0] = p0; pz[1] = c; }
             __syncwarp();
         }
         if (!active) r = PB2_INVALID_U32;
@@ -680,11 +674,11 @@ __global__ void __launch_bounds__(128, 8) k_raycast_wide_shared(const float4* __
         if ((!exhausted || st_next < st_count) && (idle == FULL || __popc(idle) >= refill)) {
             if (PIECES) {
                 pz_collect();
-                const uint32_t since = s_pz[w][4] + 1u;
-                const bool due = since >= (uint32_t)pieces_flush_every && (s_pz[w][1] | s_pz[w][3]) != 0u;
+                const uint32_t since = pz[4] + 1u;
+                const bool due = since >= (uint32_t)pieces_flush_every && (pz[1] | pz[3]) != 0u;
                 __syncwarp();
                 if (due) pz_flush();
-                else { if (lane == 0) s_pz[w][4] = since; __syncwarp(); }
+                else { pz[4] = since; __syncwarp(); }
             }
             for (;;) {
                 if (st_next == st_count) {
@@ -900,7 +894,7 @@ __global__ void __launch_bounds__(128, 8) k_raycast_wide_shared(const float4* __
             active = false;
         }
     }
-    if (PIECES) { pz_collect(); if (s_pz[w][1] | s_pz[w][3]) pz_flush(); }
+    if (PIECES) { pz_collect(); if (pz[1] | pz[3]) pz_flush(); }
 }
 
 int pb2_wide_cast(pb2_ctx* ctx, const pb2_trimesh* mesh, const float* d_pose, const float* d_rays, const uint32_t* d_perm, uint32_t m,
