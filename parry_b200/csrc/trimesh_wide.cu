@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(128, 8) k_raycast_wide_shared(const float4* __
     __shared__ uint16_t s_items[4][256];           // queue slot << 3 | child slot, one per triangle to test
     // PIECES bookkeeping, per warp: {range a, count a, range b, count b, refills since the last publication}. In shared memory so
     // that the variant keeps the plain kernel's register budget (at 64 registers five more live values spilled inside the hot loop:
-    // 2.40 instead of 2.09 ms on one GPU, harness/pieces_probe.py)
+    // 2.40 instead of 2.09 ms on one GPU)
     __shared__ uint32_t s_pz[PIECES ? 4 : 1][5];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wbase = threadIdx.x & ~31;
