@@ -450,6 +450,22 @@ impl<'c> TriMesh<'c> {
         Ok((0..n).map(|k| cast_of_status(status[k], &out[13 * k..13 * k + 13]).map(|h| h.map(|h| (h, part[k])))).collect())
     }
 
+    /// `query::distance(mesh_pose, &trimesh, poses[k], shape k)` — or with `mesh_second` the shape first — for every k: the composite
+    /// arms of `DefaultQueryDispatcher::distance` (distance_composite_shape_shape.rs:46-77). `Err(Unsupported)`: unknown shape id.
+    pub fn distance_shapes(&self, mesh_pose: &Isometry<Real>, table: &ShapeTable<'c>, shape_ids: &[u32], poses: &[Isometry<Real>], mesh_second: bool)
+                           -> Result<Vec<Result<Real, Unsupported>>, Error> {
+        let n = shape_ids.len();
+        let p7: Vec<[f32; 7]> = poses.iter().map(iso7).collect();
+        let mp = iso7(mesh_pose);
+        let (mut dist, mut status, mut part) = (vec![0f32; n], vec![0u8; n], vec![0u32; n]);
+        let (h, t) = (self.h, table.h);
+        self.c.call(|ctx| unsafe {
+            sys::pb2_trimesh_distance_shapes(ctx, h, mp.as_ptr(), t, shape_ids.as_ptr(), p7.as_ptr() as *const f32, mesh_second as i32, n as u32,
+                                             dist.as_mut_ptr(), status.as_mut_ptr(), part.as_mut_ptr(), sys::PB2_MEM_HOST)
+        })?;
+        Ok((0..n).map(|k| if status[k] == 0 { Ok(dist[k]) } else { Err(Unsupported) }).collect())
+    }
+
     /// `query::cast_shapes(pos1[k], vel1[k], &self, pos2[k], vel2[k], &other, options)` for two TriMeshes (the nesting of the
     /// reference's tests/geometry/trimesh_trimesh_toi.rs): `(hit, [triangle of self, triangle of other])`.
     pub fn cast_trimesh(&self, pos1: &[Isometry<Real>], vel1: &[Vector<Real>], other: &TriMesh<'c>, pos2: &[Isometry<Real>], vel2: &[Vector<Real>],
