@@ -263,6 +263,36 @@ inline void contact_compound(const Context& c, const pb2_compounds* compounds, c
     c.check(pb2_compound_contact_shapes(c.get(), compounds, compound_ids.data(), compound_poses[0].rotation, shape_ids.data(), shape_poses[0].rotation,
                                         (uint32_t)n, prediction, compound_second ? 1 : 0, out.data(), status.data(), part.data(), PB2_MEM_HOST));
 }
+// query::contact between a Compound and a TriMesh, either argument order (default_query_dispatcher.rs:338-351 nested through
+// contact_composite_shape_shape.rs:12-76); parts[k] = {winning part, winning triangle}
+inline void contact_compound_trimesh(const Context& c, const pb2_compounds* compounds, const std::vector<uint32_t>& compound_ids,
+                                     const std::vector<Isometry>& compound_poses, const pb2_trimesh* mesh, const Isometry& mesh_pose, float prediction,
+                                     bool mesh_first, std::vector<pb2_contact>& out, std::vector<uint8_t>& status, std::vector<uint32_t>& parts) {
+    size_t n = compound_ids.size();
+    out.resize(n); status.resize(n); parts.resize(2 * n);
+    c.check(pb2_compound_contact_trimesh(c.get(), compounds, compound_ids.data(), compound_poses[0].rotation, mesh, mesh_pose.rotation, (uint32_t)n,
+                                         prediction, mesh_first ? 1 : 0, out.data(), status.data(), parts.data(), PB2_MEM_HOST));
+}
+// query::cast_shapes with a TriMesh on one side (shape_cast_composite_shape_shape.rs:65-105); hits: 13 floats per query as pb2_cast_shapes_batch
+inline void cast_shapes_trimesh(const Context& c, const pb2_trimesh* mesh, const Isometry& mesh_pose, const float mesh_vel[3], const pb2_shapes* shapes,
+                                const std::vector<uint32_t>& shape_ids, const std::vector<Isometry>& poses, const std::vector<float>& vels_xyz,
+                                bool mesh_second, float max_time_of_impact, float target_distance, bool compute_impact_geometry_on_penetration,
+                                std::vector<float>& hits, std::vector<uint8_t>& status, std::vector<uint32_t>& part) {
+    size_t n = shape_ids.size();
+    hits.resize(13 * n); status.resize(n); part.resize(n);
+    c.check(pb2_trimesh_cast_shapes(c.get(), mesh, mesh_pose.rotation, mesh_vel, shapes, shape_ids.data(), poses[0].rotation, vels_xyz.data(),
+                                    mesh_second ? 1 : 0, max_time_of_impact, target_distance, 1, compute_impact_geometry_on_penetration ? 1 : 0,
+                                    (uint32_t)n, hits.data(), status.data(), part.data(), PB2_MEM_HOST));
+}
+// query::distance with a TriMesh on one side (distance_composite_shape_shape.rs:46-77)
+inline void distance_trimesh(const Context& c, const pb2_trimesh* mesh, const Isometry& mesh_pose, const pb2_shapes* shapes,
+                             const std::vector<uint32_t>& shape_ids, const std::vector<Isometry>& poses, bool mesh_second, std::vector<float>& dist,
+                             std::vector<uint8_t>& status, std::vector<uint32_t>& part) {
+    size_t n = shape_ids.size();
+    dist.resize(n); status.resize(n); part.resize(n);
+    c.check(pb2_trimesh_distance_shapes(c.get(), mesh, mesh_pose.rotation, shapes, shape_ids.data(), poses[0].rotation, mesh_second ? 1 : 0, (uint32_t)n,
+                                        dist.data(), status.data(), part.data(), PB2_MEM_HOST));
+}
 }  // namespace query
 
 }  // namespace pb2
