@@ -5,6 +5,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -51,3 +52,33 @@ def test_single_rank_comm_and_shards(ctx):
             assert len(allp) == len(full) and (allp == full).all()
             assert max(len(p) for p in parts) < 1.5 * len(full) / k + 64
     comm.close()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("m,chunks", [(4096, 2), (5000, 3), (100003, 4), (1 << 20, 8), (70000, 16)])
+def test_ray_gather_ranges_on_one_gpu(ctx, m, chunks):
+    """pb2_trimesh_cast_rays_allgather with a second buffer on the same device standing in for the peer: the range-signalling ray
+    kernel (ranges published by per-warp counts while it runs, copy-engine streams waiting on their flags) must give the plain cast's
+    results, and the pushed copy must be complete — for batch sizes that are not multiples of the (power-of-two) range size too."""
+    import ctypes as C
+    import torch
+    import parry_b200
+    from harness import scenes
+    FMAX = float(np.finfo(np.float32).max)
+    v, i = scenes.terrain(257, 257)
+    mesh = parry_b200.TriMesh(ctx, v, i)
+    rays = torch.from_numpy(scenes.terrain_rays(m, seed=21)).cuda()
+    toi = torch.zeros(m, dtype=torch.float32, device="cuda")
+    tri = torch.zeros(m, dtype=torch.int32, device="cuda")
+    ref_toi, ref_tri = mesh.cast_local_ray(rays, FMAX)
+    toi2, tri2 = torch.zeros_like(toi), torch.zeros_like(tri)
+    p_toi = (C.c_void_p * 2)(toi.data_ptr(), toi2.data_ptr())
+    p_tri = (C.c_void_p * 2)(tri.data_ptr(), tri2.data_ptr())
+    for _ in range(2):      # the second call finds the flags of the first one reset
+        toi.zero_(); tri.zero_(); toi2.zero_(); tri2.zero_()
+        torch.cuda.synchronize()
+        mesh.cast_local_ray_allgather(rays, FMAX, p_toi, p_tri, 0, 0, chunks)
+        ctx.synchronize()
+        assert (tri == ref_tri).all() and (toi.view(torch.int32) == ref_toi.view(torch.int32)).all()
+        assert (tri2 == ref_tri).all() and (toi2.view(torch.int32) == ref_toi.view(torch.int32)).all()
+    assert (ref_tri != -1).float().mean() > 0.3
