@@ -584,6 +584,28 @@ __global__ void __launch_bounds__(128, 7) k_raycast_wide(const float4* __restric
 // stores and adds the count to pieces.done[range]; whoever completes a range sets pieces.flag[range], which copy-engine streams wait on
 // (cuStreamWaitValue32) to push that range of results to the peer GPUs. One launch keeps the SMs full across range
 // boundaries, which separate launches per range cannot (each boundary cost ~40 us of ramp-down).
+// Publication of a warp's retired-ray counts (PIECES): rare (every `flush_every` refills), kept out of line so that the traversal
+// loop's instruction footprint stays the plain kernel's. Every lane of the warp calls it.
+static __device__ __noinline__ void pz_flush_warp(volatile uint32_t* pz, PieceSignal pieces, uint32_t m, int lane) {
+    __threadfence();   // every lane's result stores are visible before the counts are
+    const uint32_t pa = pz[0], ca = pz[1], pb = pz[2], cb = pz[3];
+    __syncwarp();      // every lane has read the counts before anybody clears them
+    if (lane == 0) {
+        const uint32_t pc[2][2] = {{pa, ca}, {pb, cb}};
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t piece = pc[i][0], count = pc[i][1];
+            if (!count) continue;
+            uint32_t lo_r = piece * pieces.size;
+            uint32_t total = m - lo_r < pieces.size ? m - lo_r : pieces.size;
+            unsigned prev = atomicAdd(&pieces.done[piece], count);
+            if (prev + count == total) { __threadfence(); atomicExch(&pieces.flag[piece], 1u); }
+        }
+    }
+    pz[1] = 0; pz[3] = 0; pz[4] = 0;
+    __syncwarp();
+}
+
 template <bool WITH_NORMAL, bool PIECES>
 __global__ void __launch_bounds__(128, 8) k_raycast_wide_shared(const float4* __restrict__ nodes8, const float4* __restrict__ tris8, uint32_t nt,
                                   const float* __restrict__ pose7, const float* __restrict__ rays, const uint32_t* __restrict__ perm,
@@ -624,23 +646,7 @@ __global__ void __launch_bounds__(128, 8) k_raycast_wide_shared(const float4* __
     // can never read a value another lane has already updated.
     volatile uint32_t* const pz = s_pz[PIECES ? w : 0];
     if (PIECES) { pz[0] = PB2_INVALID_U32; pz[1] = 0; pz[2] = PB2_INVALID_U32; pz[3] = 0; pz[4] = 0; __syncwarp(); }
-    auto pz_publish = [&](uint32_t piece, uint32_t count) {   // lane 0, after the warp's fence
-        uint32_t lo_r = piece * pieces.size;
-        uint32_t total = m - lo_r < pieces.size ? m - lo_r : pieces.size;
-        unsigned prev = atomicAdd(&pieces.done[piece], count);
-        if (prev + count == total) { __threadfence(); atomicExch(&pieces.flag[piece], 1u); }
-    };
-    auto pz_flush = [&]() {   // every lane of the warp
-        __threadfence();   // every lane's result stores are visible before the counts are
-        const uint32_t pa = pz[0], ca = pz[1], pb = pz[2], cb = pz[3];
-        __syncwarp();      // every lane has read the counts before anybody clears them
-        if (lane == 0) {
-            if (ca) pz_publish(pa, ca);
-            if (cb) pz_publish(pb, cb);
-        }
-        pz[1] = 0; pz[3] = 0; pz[4] = 0;
-        __syncwarp();
-    };
+    auto pz_flush = [&]() { pz_flush_warp(pz, pieces, m, lane); };   // every lane of the warp
     // rays retired since the last refill are counted when their lane is handed a new ray (and at exit): nothing per trip. A lane that
     // has been counted forgets its ray index (r = INVALID), which is what marks it as counted.
     auto pz_collect = [&]() {
